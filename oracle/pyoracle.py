@@ -1,0 +1,187 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes access to the two CPU checkers.
+
+* ``liblongtr_oracle.so``  : plain-C restatement (oracle/longtr_oracle.c)
+* ``_ref/libltr_ref.so``   : the unmodified reference sources compiled in place
+                             (oracle/build_ref.sh), when available.
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import this.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from longtr_b200.flat import FlatLocus
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ORACLE_SO = os.path.join(_HERE, "liblongtr_oracle.so")
+_REF_SO = os.path.join(_HERE, "_ref", "libltr_ref.so")
+
+
+class OracleParams(C.Structure):
+    _fields_ = [("ins_ins", C.c_float), ("ins_match", C.c_float), ("del_del", C.c_float),
+                ("del_match", C.c_float), ("match_match", C.c_float), ("match_ins", C.c_float),
+                ("match_del", C.c_float), ("indel_flank_len", C.c_int32)]
+
+
+def build(force=False):
+    """Compile the restatement (and oracle/_ref when /root/reference exists)."""
+    if force or not os.path.exists(_ORACLE_SO) or \
+            os.path.getmtime(_ORACLE_SO) < os.path.getmtime(os.path.join(_HERE, "longtr_oracle.c")):
+        subprocess.check_call(["make", "-C", _HERE, "liblongtr_oracle.so"], stdout=subprocess.DEVNULL)
+    if os.path.isdir(os.environ.get("LONGTR_REFERENCE", "/root/reference") + "/src"):
+        if force or not os.path.exists(_REF_SO):
+            subprocess.check_call([os.path.join(_HERE, "build_ref.sh")], stdout=subprocess.DEVNULL)
+
+
+_oracle = None
+_ref = None
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+_u32p = C.POINTER(C.c_uint32)
+_u8p = C.POINTER(C.c_uint8)
+
+
+def oracle_lib():
+    global _oracle
+    if _oracle is None:
+        build()
+        lib = C.CDLL(_ORACLE_SO)
+        lib.ltr_oracle_default_params.argtypes = [C.POINTER(OracleParams)]
+        lib.ltr_oracle_viterbi_pair.restype = C.c_double
+        lib.ltr_oracle_viterbi_pair.argtypes = [C.c_char_p, C.c_int32, C.c_char_p, C.c_int32,
+                                                C.POINTER(OracleParams)]
+        lib.ltr_oracle_viterbi_pair_cells.restype = C.c_double
+        lib.ltr_oracle_viterbi_pair_cells.argtypes = [C.c_char_p, C.c_int32, C.c_char_p, C.c_int32,
+                                                      C.POINTER(OracleParams), C.POINTER(C.c_int64)]
+        lib.ltr_oracle_trim_read.restype = C.c_int32
+        lib.ltr_oracle_trim_read.argtypes = [C.POINTER(FlatLocus), C.c_int32, C.c_char_p]
+        lib.ltr_oracle_process_reads.restype = C.c_int
+        lib.ltr_oracle_process_reads.argtypes = [C.POINTER(FlatLocus), _dp, _ip]
+        lib.ltr_oracle_viterbi_batch.restype = C.c_int
+        lib.ltr_oracle_viterbi_batch.argtypes = [C.c_uint32, _u32p, _u32p, _u32p, _u8p, _u32p, _u8p,
+                                                 C.POINTER(OracleParams), _dp, C.POINTER(C.c_int64),
+                                                 C.c_int]
+        lib.ltr_oracle_log_sample_posteriors.restype = C.c_double
+        lib.ltr_oracle_log_sample_posteriors.argtypes = [C.c_int, C.c_int32, C.c_int32, C.c_int32, _dp,
+                                                         _dp, _dp, _ip, _dp, _dp]
+        lib.ltr_oracle_optimal_haplotypes.argtypes = [C.c_int32, C.c_int32, _dp, _ip]
+        _oracle = lib
+    return _oracle
+
+
+def ref_available():
+    build()
+    return os.path.exists(_REF_SO)
+
+
+def ref_lib():
+    global _ref
+    if _ref is None:
+        build()
+        lib = C.CDLL(_REF_SO)
+        lib.ltr_ref_process_reads.restype = C.c_int
+        lib.ltr_ref_process_reads.argtypes = [C.POINTER(FlatLocus), _dp, _ip, _dp]
+        lib.ltr_ref_log_sample_posteriors.restype = C.c_double
+        lib.ltr_ref_log_sample_posteriors.argtypes = [C.c_int, C.c_int, _ip, C.c_int, _dp, _dp, _dp,
+                                                      _dp, _dp, _dp, _ip]
+        _ref = lib
+    return _ref
+
+
+def make_params(aln_params=None, indel_flank_len=5):
+    p = OracleParams()
+    oracle_lib().ltr_oracle_default_params(C.byref(p))
+    if aln_params is not None:
+        (p.ins_ins, p.ins_match, p.del_del, p.del_match, p.match_match, p.match_ins,
+         p.match_del) = [float(x) for x in aln_params]
+    p.indel_flank_len = indel_flank_len
+    return p
+
+
+def _ptr(a, t):
+    return a.ctypes.data_as(t)
+
+
+def viterbi_pair(full_hap, read, aln_params=None, indel_flank_len=5):
+    p = make_params(aln_params, indel_flank_len)
+    cells = C.c_int64(0)
+    h = full_hap if isinstance(full_hap, bytes) else full_hap.encode()
+    r = read if isinstance(read, bytes) else read.encode()
+    v = oracle_lib().ltr_oracle_viterbi_pair_cells(h, len(h), r, len(r), C.byref(p), C.byref(cells))
+    return v, cells.value
+
+
+def process_reads(locus, n_reads, n_alleles, fill=0.0, which="oracle"):
+    """Run HapAligner::process_reads on a FlatLocus. Returns (ll[P,H], seeds[P], seconds)."""
+    ll = np.full((n_reads, n_alleles), fill, dtype=np.float64)
+    seeds = np.full(n_reads, -12345, dtype=np.int32)
+    sec = C.c_double(0.0)
+    if which == "oracle":
+        rc = oracle_lib().ltr_oracle_process_reads(C.byref(locus), _ptr(ll, _dp), _ptr(seeds, _ip))
+    else:
+        rc = ref_lib().ltr_ref_process_reads(C.byref(locus), _ptr(ll, _dp), _ptr(seeds, _ip), C.byref(sec))
+    if rc != 0:
+        raise RuntimeError("process_reads(%s) failed rc=%d" % (which, rc))
+    return ll, seeds, sec.value
+
+
+def trim_read(locus, read_index):
+    n = len(locus.reads[read_index].seq)
+    buf = C.create_string_buffer(n + 16)
+    k = oracle_lib().ltr_oracle_trim_read(C.byref(locus), read_index, buf)
+    if k < 0:
+        raise RuntimeError("trim failed")
+    return buf.value[:k]
+
+
+def viterbi_batch(batch, aln_params=None, indel_flank_len=5, n_threads=1):
+    """batch: dict with numpy arrays locus_hap_begin, locus_read_begin, hap_off, hap_bytes,
+    read_off, read_bytes (see include/longtr_b200.h ltr_viterbi_batch). Returns (ll, cells)."""
+    p = make_params(aln_params, indel_flank_len)
+    lhb = np.ascontiguousarray(batch["locus_hap_begin"], dtype=np.uint32)
+    lrb = np.ascontiguousarray(batch["locus_read_begin"], dtype=np.uint32)
+    n_loci = len(lhb) - 1
+    nout = int(np.sum((lhb[1:] - lhb[:-1]).astype(np.int64) * (lrb[1:] - lrb[:-1]).astype(np.int64)))
+    out = np.zeros(nout, dtype=np.float64)
+    cells = C.c_int64(0)
+    hoff = np.ascontiguousarray(batch["hap_off"], dtype=np.uint32)
+    roff = np.ascontiguousarray(batch["read_off"], dtype=np.uint32)
+    hb = np.ascontiguousarray(batch["hap_bytes"], dtype=np.uint8)
+    rb = np.ascontiguousarray(batch["read_bytes"], dtype=np.uint8)
+    rc = oracle_lib().ltr_oracle_viterbi_batch(n_loci, _ptr(lhb, _u32p), _ptr(lrb, _u32p),
+                                               _ptr(hoff, _u32p), _ptr(hb, _u8p), _ptr(roff, _u32p),
+                                               _ptr(rb, _u8p), C.byref(p), _ptr(out, _dp),
+                                               C.byref(cells), n_threads)
+    if rc != 0:
+        raise RuntimeError("oracle batch failed")
+    return out, cells.value
+
+
+def log_sample_posteriors(ll, log_p1, log_p2, sample_label, n_samples, haploid=False, which="oracle"):
+    """Returns (ll_clamped, post[S,H,H], totals[S], total, best[S,2])."""
+    ll = np.array(ll, dtype=np.float64, order="C", copy=True)
+    R, H = ll.shape
+    p1 = np.ascontiguousarray(log_p1, dtype=np.float64)
+    p2 = np.ascontiguousarray(log_p2, dtype=np.float64)
+    lab = np.ascontiguousarray(sample_label, dtype=np.int32)
+    post = np.zeros((n_samples, H, H), dtype=np.float64)
+    tot = np.zeros(n_samples, dtype=np.float64)
+    best = np.zeros((n_samples, 2), dtype=np.int32)
+    if which == "oracle":
+        total = oracle_lib().ltr_oracle_log_sample_posteriors(int(haploid), n_samples, R, H, _ptr(ll, _dp),
+                                                              _ptr(p1, _dp), _ptr(p2, _dp), _ptr(lab, _ip),
+                                                              _ptr(post, _dp), _ptr(tot, _dp))
+        oracle_lib().ltr_oracle_optimal_haplotypes(n_samples, H, _ptr(post, _dp), _ptr(best, _ip))
+    else:
+        assert np.all(np.diff(lab) >= 0), "reference needs sample-major reads"
+        rps = np.bincount(lab, minlength=n_samples).astype(np.int32)
+        out_ll = np.zeros_like(ll)
+        total = ref_lib().ltr_ref_log_sample_posteriors(int(haploid), n_samples, _ptr(rps, _ip), H,
+                                                        _ptr(ll, _dp), _ptr(p1, _dp), _ptr(p2, _dp),
+                                                        _ptr(out_ll, _dp), _ptr(post, _dp), _ptr(tot, _dp),
+                                                        _ptr(best, _ip))
+        ll = out_ll
+    return ll, post, tot, total, best
