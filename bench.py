@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the LongTR read x haplotype hot path on B200.
+
+One "step" = one pass of the hot path (Viterbi log-likelihoods of every pooled read against
+every candidate haplotype + genotype posteriors) over one batch of synthetic loci
+(BASELINE.json config 3: HiFi STRs, generator of SURVEY.md section 8d).  Loci are sharded over
+the ranks with no data-path collective (weak scaling: every GPU gets --loci loci).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--loci L] [--config 3|4]
+  python bench.py --impl reference ...     # the reference's own CPU code on the host cores
+
+Prints ONE JSON line (rank 0).  value = loci/s with inputs resident in HBM; e2e = the same through
+the C-ABI one-shot path with host buffers (H2D + kernels + D2H inside the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+FP64_OPS_PER_CELL = 17.0  # 10 DADD + 7 compare/select per DP cell
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", type=int, default=3, choices=[3, 4])
+    ap.add_argument("--loci", type=int, default=0, help="loci per GPU per step (default: config size)")
+    ap.add_argument("--cpu-sample-loci", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+CONFIG_LOCI = {3: 100000, 4: 10000}
+CONFIG_NAME = {3: "synthetic HiFi STRs: 1-6 bp motifs, 50-300 bp repeats, 30 reads/locus (BASELINE.json configs[2])",
+               4: "synthetic VNTRs: 500-1000 bp repeats, 2-12 haplotypes, ONT-like params (BASELINE.json configs[3])"}
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_setup(n_gpus):
+    """One process per GPU; NCCL only for the barrier and the max-over-ranks of the timings."""
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+    return torch, rank, world, local
+
+
+def barrier(torch, world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(torch, world, x):
+    if world == 1:
+        return x
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(torch, world, x):
+    if world == 1:
+        return x
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def pinned_copy(torch, d):
+    """Copy a dict of numpy arrays into pinned host memory (e2e inputs come from pinned buffers)."""
+    out, keep = {}, []
+    for k, v in d.items():
+        if v is None:
+            out[k] = None
+            continue
+        t = torch.empty(max(1, v.nbytes), dtype=torch.uint8, pin_memory=True)
+        a = t.numpy()[:v.nbytes].view(v.dtype)
+        a[...] = v
+        out[k] = a
+        keep.append(t)
+    return out, keep
+
+
+def cpu_baseline(work, n_sample, threads):
+    """The reference's CPU path (process_reads + posteriors) on a bounded sample of the same workload.
+    oracle/ is used here only as the measured CPU baseline, never on the product path.
+    Returns (kind, seconds inside the hot path [max over threads], wall seconds)."""
+    from oracle import pyoracle as po
+    sb, sp = work.subset(n_sample)
+    t0 = time.perf_counter()
+    if po.ref_available():
+        kind = "reference"
+        _ll, sec, _post = po.ref_viterbi_batch(sb, work.aln_params, n_threads=threads, post=sp)
+    else:
+        kind = "port"
+        ll, _cells = po.viterbi_batch(sb, aln_params=work.aln_params, n_threads=threads)
+        H = np.diff(sb["locus_hap_begin"]).astype(np.int64)
+        P = np.diff(sb["locus_read_begin"]).astype(np.int64)
+        off, lsb = 0, sp["locus_sread_begin"]
+        for l in range(n_sample):
+            h, p = int(H[l]), int(P[l])
+            mat = ll[off:off + h * p].reshape(p, h)
+            off += h * p
+            r0, r1 = int(lsb[l]), int(lsb[l + 1])
+            po.log_sample_posteriors(mat[sp["pool_index"][r0:r1]], sp["log_p1"][r0:r1], sp["log_p2"][r0:r1],
+                                     sp["sample_label"][r0:r1], 1)
+        sec = time.perf_counter() - t0
+    wall = time.perf_counter() - t0
+    return kind, sec, wall
+
+
+def sample_cells(work, n_sample):
+    b = work.batch
+    hoff, roff = b["hap_off"].astype(np.int64), b["read_off"].astype(np.int64)
+    lhb, lrb = b["locus_hap_begin"], b["locus_read_begin"]
+    cells = 0
+    for l in range(n_sample):
+        n = np.diff(hoff[lhb[l]:lhb[l + 1] + 1]) - 60
+        m = np.diff(roff[lrb[l]:lrb[l + 1] + 1])
+        nm = n[:, None] * m[None, :]
+        nm[np.abs(n[:, None] - m[None, :]) > 600] = 0
+        cells += int(nm[n > 0].sum())
+    return cells
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from longtr_b200 import workloads
+    threads = os.cpu_count() or 1
+    n_sample = args.cpu_sample_loci or (100 * threads if args.config == 3 else max(2, threads))
+    work = workloads.generate(args.config, n_sample)
+    cells = sample_cells(work, n_sample)
+    times = []
+    kind = "port"
+    for it in range(args.warmup + args.steps):
+        kind, sec, wall = cpu_baseline(work, n_sample, threads)
+        if it >= args.warmup:
+            times.append(wall)
+    tot = sum(times)
+    val = n_sample * len(times) / tot
+    line = {
+        "impl": "reference", "metric": "loci_per_sec", "value": val, "unit": "loci/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "gcups": cells * len(times) / tot / 1e9,
+        "config": {"workload": CONFIG_NAME[args.config], "loci_per_step": n_sample,
+                   "note": "bounded sample of the b200 arm's workload (same generator and seeds)"},
+        "cpu_baseline": {"value": val, "unit": "loci/s", "cores": threads, "kind": kind,
+                         "sample": "%d loci per step, wall clock incl. Haplotype construction" % n_sample},
+        "e2e": {"value": val, "unit": "loci/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    torch, rank, world, local = dist_setup(args.gpus)
+    from longtr_b200 import Engine, workloads
+    n_loci = args.loci or CONFIG_LOCI[args.config]
+    eng = Engine(local)
+    # roofline denominator: sustained FP64-pipe issue rate measured on this GPU, right now
+    fp64_rate = max(eng.fp64_issue_rate(0)[0] for _ in range(2))
+    peak_gcups = fp64_rate / FP64_OPS_PER_CELL / 1e9
+    work = workloads.generate(args.config, n_loci, first_locus=rank * n_loci)
+    job = eng.create_job(work.batch, work.post, aln_params=work.aln_params)
+    pinned_b, keep_b = pinned_copy(torch, work.batch)
+    pinned_p, keep_p = pinned_copy(torch, work.post)
+
+    # ---- resident arm -------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        job.run()
+    sampler = ClockSampler(local)
+    barrier(torch, world)
+    if rank == 0:
+        sampler.start()
+    t0 = time.perf_counter()
+    dev_ms = vit_ms = 0.0
+    launches = 0
+    for _ in range(args.steps):
+        st = job.run()
+        dev_ms += st.kernel_ms
+        vit_ms += st.viterbi_ms
+        launches += st.n_launches
+    barrier(torch, world)
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop() if rank == 0 else None
+    st = job.stats()
+    step_ms = max_over_ranks(torch, world, max(dev_ms, 0.0) / args.steps)
+    wall_step_ms = max_over_ranks(torch, world, wall_ms / args.steps)
+    total_loci = sum_over_ranks(torch, world, float(n_loci))
+    total_cells = sum_over_ranks(torch, world, float(st.n_cells))
+    vit_step_ms = max_over_ranks(torch, world, vit_ms / args.steps)
+    ll, post, tot = job.download()
+    checksum = float(np.sum(ll[ll > -600.0]))
+
+    # ---- end-to-end arm: host buffers through the C ABI, copies inside the timed region -------
+    def e2e_step():
+        j = eng.create_job(pinned_b, pinned_p, aln_params=work.aln_params)
+        s = j.run()
+        j.download()
+        s = j.stats()
+        j.close()
+        return s
+    for _ in range(min(args.warmup, 3)):
+        e2e_step()
+    barrier(torch, world)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        es = e2e_step()
+    barrier(torch, world)
+    e2e_ms = max_over_ranks(torch, world, (time.perf_counter() - t0) * 1e3 / args.steps)
+
+    if rank != 0:
+        return
+    achieved = st.n_cells / (vit_ms / args.steps) / 1e6  # GCUPS of the Viterbi kernels on this rank
+    line = {
+        "metric": "loci_per_sec", "value": total_loci / (step_ms * 1e-3), "unit": "loci/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "gcups": total_cells / (vit_step_ms * 1e-3) / 1e9,
+        "config": {"workload": CONFIG_NAME[args.config], "loci_per_gpu": n_loci,
+                   "pairs_per_gpu": int(st.n_pairs), "cells_per_gpu": int(st.n_cells),
+                   "l2": "inputs (%.0f MB) + outputs larger than L2; no flush needed" % (work.input_bytes / 1e6),
+                   "parallelism": "locus-sharded, no collective", "wall_ms_per_step": wall_step_ms,
+                   "fallback_pairs": int(st.n_fallback), "ll_checksum": checksum},
+        "e2e": {"value": total_loci / (e2e_ms * 1e-3), "unit": "loci/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int(es.h2d_bytes), "d2h_bytes_per_step": int(es.d2h_bytes)},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "fp64_issue", "achieved": achieved, "peak": peak_gcups, "unit": "GCUPS",
+                     "frac": achieved / peak_gcups, "traffic": None,
+                     "peak_source": "ltr_fp64_issue_rate (DADD lane-ops/s measured in this run) / 17 FP64 ops per cell",
+                     "fp64_lane_ops_per_s": fp64_rate,
+                     "hbm_gbs_algorithmic": (work.input_bytes + 8.0 * st.n_pairs) / (vit_ms / args.steps) / 1e6},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        n_sample = args.cpu_sample_loci or min(n_loci, 256 * threads if args.config == 3 else 4 * threads)
+        kind, sec, wall = cpu_baseline(work, n_sample, threads)
+        line["cpu_baseline"] = {"value": n_sample / wall, "unit": "loci/s", "cores": threads, "kind": kind,
+                                "gcups": sample_cells(work, n_sample) / sec / 1e9,
+                                "sample": "first %d loci of the same workload, all host threads" % n_sample}
+    print(json.dumps(line), flush=True)
+    job.close()
+    eng.close()
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

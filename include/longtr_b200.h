@@ -1,0 +1,168 @@
+/* longtr_b200.h -- C ABI of the B200-native LongTR hot path.
+ *
+ * Everything the GPU does for LongTR is reached through the entry points below:
+ * plain pointers and sizes, no C++/torch types, no exceptions, no exit().
+ * One ltr_ctx per (host thread, GPU).  Return value: 0 = LTR_OK, negative = error
+ * (ltr_strerror).  There is NO CPU fallback: if no CUDA device is usable,
+ * ltr_ctx_create fails with LTR_ERR_NO_DEVICE.
+ *
+ * What each entry point replaces in the reference (paths relative to the LongTR
+ * tree):
+ *   ltr_viterbi_ll        the (pooled read x candidate haplotype) loop of
+ *                         HapAligner::process_reads / process_read, long path
+ *                         (src/SeqAlignment/HapAligner.cpp:545-581, 812-854) with
+ *                         align_seq_to_hap (:236-343) as the per-pair kernel;
+ *   ltr_posteriors        Genotyper::calc_log_sample_posteriors
+ *                         (src/genotyper.cpp:45-83, priors :21-43);
+ *   ltr_job_*             the same two steps for a whole batch of loci kept resident
+ *                         on the device (what SeqStutterGenotyper::genotype does per
+ *                         locus at src/seq_stutter_genotyper.cpp:634-635, for many
+ *                         loci at once);
+ *   ltr_process_reads_flat  HapAligner::process_reads on one flat locus, through the
+ *                         host-side mirror of the HapAligner class
+ *                         (longtr_b200/csrc/host/), used by bindings and tests.
+ */
+#ifndef LONGTR_B200_H_
+#define LONGTR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "longtr_b200_locus.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LTR_OK 0
+#define LTR_ERR_NO_DEVICE (-1)
+#define LTR_ERR_CUDA (-2)
+#define LTR_ERR_INVALID (-3)
+#define LTR_ERR_OOM (-4)
+#define LTR_ERR_UNSUPPORTED (-5)
+
+typedef struct ltr_ctx ltr_ctx;
+typedef struct ltr_job ltr_job;
+
+/* AlignmentModel (HapAligner.h:12-37) + the constants align_seq_to_hap hard-codes. */
+typedef struct ltr_params {
+  float ins_ins, ins_match, del_del, del_match, match_match, match_ins, match_del;
+  int32_t indel_flank_len; /* INDEL_FLANK_LEN; haplotypes are cut by 35-indel_flank_len
+                              on each side (HapAligner.cpp:245-246)                  */
+} ltr_params;
+
+/* Fills the Dindel defaults of HapAligner.h:118 and indel_flank_len = 5. */
+void ltr_params_default(ltr_params* p);
+
+/* A batch of loci, flattened.  Locus l owns haplotypes [locus_hap_begin[l],
+ * locus_hap_begin[l+1]) and pooled reads [locus_read_begin[l], locus_read_begin[l+1]).
+ * hap_bytes holds Haplotype::get_seq() of every candidate haplotype (flanks included,
+ * column order = gray-code order of Haplotype::next(), Haplotype.cpp:157-196);
+ * read_bytes holds the reads already trimmed by HapAligner::trim_alignment
+ * (HapAligner.cpp:346-465).  Offsets are byte offsets, arrays have n+1 entries.
+ * The log-likelihood of (read p, haplotype h) of locus l is written to
+ *   out_ll[ ll_off(l) + (p - locus_read_begin[l]) * H_l + (h - locus_hap_begin[l]) ],
+ * ll_off(l) = sum_{l'<l} P_l' * H_l'   -- i.e. the reference's aln_probs[read*H + hap]
+ * matrices (HapAligner.cpp:549), one after the other.                              */
+typedef struct ltr_viterbi_batch {
+  uint32_t n_loci;
+  const uint32_t* locus_hap_begin;  /* [n_loci+1] */
+  const uint32_t* locus_read_begin; /* [n_loci+1] */
+  const uint32_t* hap_off;          /* [n_haps+1]  */
+  const uint8_t* hap_bytes;
+  const uint32_t* read_off;         /* [n_reads+1] */
+  const uint8_t* read_bytes;
+} ltr_viterbi_batch;
+
+/* Per-read inputs of the posterior step for the same batch (optional, see ltr_job_create).
+ * Sample-reads of locus l are [locus_sread_begin[l], locus_sread_begin[l+1]); each maps to
+ * a pooled read of its locus (ReadPooler, src/read_pooler.cpp:3-20) through pool_index
+ * (index RELATIVE to the locus' first pooled read), carries the phasing terms log_p1/log_p2
+ * (src/snp_bam_processor.h:16-18) and the index of its sample within the locus.       */
+typedef struct ltr_posterior_batch {
+  const uint32_t* locus_sread_begin; /* [n_loci+1] */
+  const uint32_t* pool_index;        /* [n_sreads]  */
+  const int32_t* sample_label;       /* [n_sreads], 0..n_samples(l)-1 */
+  const double* log_p1;              /* [n_sreads]  */
+  const double* log_p2;              /* [n_sreads]  */
+  const uint32_t* locus_n_samples;   /* [n_loci]    */
+  const uint8_t* locus_haploid;      /* [n_loci] or NULL (all diploid) */
+} ltr_posterior_batch;
+
+typedef struct ltr_job_stats {
+  uint64_t n_pairs;        /* (read, haplotype) pairs                               */
+  uint64_t n_cells;        /* sum over pairs of n*m (SURVEY 8d GCUPS definition)    */
+  uint64_t n_fallback;     /* pairs re-run by the exact row-bail-out kernel          */
+  uint64_t h2d_bytes, d2h_bytes;
+  uint32_t n_launches;     /* kernels launched by the last ltr_job_run               */
+  float kernel_ms;         /* device time of the last ltr_job_run (CUDA events)      */
+  float viterbi_ms;        /* ... of which: Viterbi kernels                          */
+} ltr_job_stats;
+
+/* ---- context --------------------------------------------------------------------- */
+int ltr_ctx_create(int device, ltr_ctx** out);
+void ltr_ctx_destroy(ltr_ctx* ctx);
+const char* ltr_strerror(int code);
+const char* ltr_last_error(const ltr_ctx* ctx); /* CUDA error text of the last failure */
+const char* ltr_version(void);
+
+/* ---- one-shot calls (host buffers in, host buffers out) -------------------------- */
+/* out_ll must hold sum_l P_l*H_l doubles.  Sentinels as in the reference: -1e9 when
+ * the haplotype is <= 60 bp (HapAligner.cpp:241-244), -700 for |n-m| > 600 (:249-252)
+ * and for the per-row bail-out (:300-306).                                            */
+int ltr_viterbi_ll(ltr_ctx* ctx, const ltr_params* params, const ltr_viterbi_batch* batch,
+                   double* out_ll, ltr_job_stats* stats);
+
+/* Genotyper::calc_log_sample_posteriors for one locus.  ll is [n_reads*n_alleles] and is
+ * clamped IN PLACE to >= -600 like the reference (genotyper.cpp:57-58); post receives
+ * [n_samples*H*H] log posteriors, totals [n_samples]; *total_ll their sum.            */
+int ltr_posteriors(ltr_ctx* ctx, int haploid, int32_t n_samples, int32_t n_reads,
+                   int32_t n_alleles, double* ll, const double* log_p1, const double* log_p2,
+                   const int32_t* sample_label, double* post, double* totals, double* total_ll);
+
+/* ---- resident jobs: upload once, run many times, download ------------------------- */
+/* post may be NULL (Viterbi only).  Host arrays may be released after the call.       */
+int ltr_job_create(ltr_ctx* ctx, const ltr_params* params, const ltr_viterbi_batch* batch,
+                   const ltr_posterior_batch* post, ltr_job** out);
+/* Launches every kernel of the job on the context's streams; returns after completion. */
+int ltr_job_run(ltr_ctx* ctx, ltr_job* job);
+/* Sizes of the result arrays (in elements). */
+void ltr_job_sizes(const ltr_job* job, uint64_t* n_ll, uint64_t* n_post, uint64_t* n_totals);
+/* Any output pointer may be NULL. out_post is [sum_l S_l*H_l*H_l], out_totals [sum_l S_l]. */
+int ltr_job_download(ltr_ctx* ctx, ltr_job* job, double* out_ll, double* out_post,
+                     double* out_totals);
+void ltr_job_get_stats(const ltr_job* job, ltr_job_stats* stats);
+void ltr_job_destroy(ltr_ctx* ctx, ltr_job* job);
+
+/* ---- reference-facing convenience (host mirror of HapAligner) --------------------- */
+/* HapAligner(haplotype, realign_to_hap, INDEL_FLANK_LEN, SWITCH_OLD_ALIGN_LEN, params)
+ *   .process_reads(alns, 0, &base_quality, realign_read, out_ll, out_seeds)
+ * (HapAligner.h:94-95, 137-138) on a flat locus.  out_ll is [n_reads*n_alleles]; slots of
+ * reads / haplotypes that are not realigned are left untouched, as in the reference.   */
+int ltr_process_reads_flat(ltr_ctx* ctx, const ltr_flat_locus* locus, double* out_ll,
+                           int32_t* out_seeds);
+
+/* ---- diagnostics --------------------------------------------------------------------- */
+/* Sustained FP64-pipe issue rate of the device in lane-operations per second (the roofline
+ * denominator of SURVEY.md section 8d): kind 0 = DADD, 1 = DSETP, 2 = the DADD,DADD,DSETP,
+ * 2xFSEL pattern of one max-plus term.  ms (optional) = duration of the probe kernel.      */
+int ltr_fp64_issue_rate(int device, int kind, double* lane_ops_per_s, double* ms);
+
+/* ---- synthetic workloads (BASELINE.json configs 3-5) ------------- */
+typedef struct ltr_synth_batch {
+  ltr_viterbi_batch vit;      /* flattened loci                                   */
+  ltr_posterior_batch post;   /* 30 sample-reads per locus, one sample            */
+  uint32_t n_haps, n_reads, n_sreads;
+  uint64_t hap_nbytes, read_nbytes;
+} ltr_synth_batch;
+/* config 3 = HiFi STRs, 4 = VNTRs (ONT-like), 5 = homopolymers; loci [first_locus,
+ * first_locus+n_loci) of the job seeded with base_seed (mt19937_64(base_seed + locus)).      */
+int ltr_synth_generate(int config, uint64_t base_seed, uint32_t first_locus, uint32_t n_loci,
+                       int n_threads, ltr_synth_batch** out);
+void ltr_synth_params(int config, ltr_params* p);
+void ltr_synth_free(ltr_synth_batch* b);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

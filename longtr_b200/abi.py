@@ -1,0 +1,162 @@
+"""ctypes binding of the C ABI in include/longtr_b200.h (liblongtr_b200.so).
+
+This is the Python host side of the drop-in boundary: plain pointers and sizes only.
+The library is built in-tree by ``longtr_b200.build`` (nvcc, sm_100a); importing this
+module never falls back to a CPU implementation -- if the shared library or a CUDA
+device is missing, the calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from .flat import FlatLocus
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "liblongtr_b200.so")
+
+LTR_OK = 0
+
+_u32p = C.POINTER(C.c_uint32)
+_u8p = C.POINTER(C.c_uint8)
+_i32p = C.POINTER(C.c_int32)
+_dp = C.POINTER(C.c_double)
+
+
+class Params(C.Structure):
+    """ltr_params: AlignmentModel of the reference (HapAligner.h:12-37)."""
+    _fields_ = [("ins_ins", C.c_float), ("ins_match", C.c_float), ("del_del", C.c_float),
+                ("del_match", C.c_float), ("match_match", C.c_float), ("match_ins", C.c_float),
+                ("match_del", C.c_float), ("indel_flank_len", C.c_int32)]
+
+
+class ViterbiBatch(C.Structure):
+    _fields_ = [("n_loci", C.c_uint32), ("locus_hap_begin", _u32p), ("locus_read_begin", _u32p),
+                ("hap_off", _u32p), ("hap_bytes", _u8p), ("read_off", _u32p), ("read_bytes", _u8p)]
+
+
+class PosteriorBatch(C.Structure):
+    _fields_ = [("locus_sread_begin", _u32p), ("pool_index", _u32p), ("sample_label", _i32p),
+                ("log_p1", _dp), ("log_p2", _dp), ("locus_n_samples", _u32p), ("locus_haploid", _u8p)]
+
+
+class JobStats(C.Structure):
+    _fields_ = [("n_pairs", C.c_uint64), ("n_cells", C.c_uint64), ("n_fallback", C.c_uint64),
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("n_launches", C.c_uint32),
+                ("kernel_ms", C.c_float), ("viterbi_ms", C.c_float)]
+
+
+DEFAULT_ALN_PARAMS = (-1.0, -0.458675, -1.0, -0.458675, -0.00005800168, -10.448214728, -10.448214728)
+
+
+def make_params(aln_params=None, indel_flank_len=5):
+    p = Params()
+    vals = DEFAULT_ALN_PARAMS if aln_params is None else aln_params
+    (p.ins_ins, p.ins_match, p.del_del, p.del_match, p.match_match, p.match_ins, p.match_del) = \
+        [float(x) for x in vals]
+    p.indel_flank_len = indel_flank_len
+    return p
+
+
+def ptr(a, t):
+    return a.ctypes.data_as(t)
+
+
+def make_viterbi_batch(batch):
+    """dict of numpy arrays -> (ViterbiBatch, keepalive list)."""
+    keep = dict(
+        lhb=np.ascontiguousarray(batch["locus_hap_begin"], dtype=np.uint32),
+        lrb=np.ascontiguousarray(batch["locus_read_begin"], dtype=np.uint32),
+        hoff=np.ascontiguousarray(batch["hap_off"], dtype=np.uint32),
+        roff=np.ascontiguousarray(batch["read_off"], dtype=np.uint32),
+        hb=np.ascontiguousarray(batch["hap_bytes"], dtype=np.uint8),
+        rb=np.ascontiguousarray(batch["read_bytes"], dtype=np.uint8))
+    b = ViterbiBatch()
+    b.n_loci = len(keep["lhb"]) - 1
+    b.locus_hap_begin = ptr(keep["lhb"], _u32p)
+    b.locus_read_begin = ptr(keep["lrb"], _u32p)
+    b.hap_off = ptr(keep["hoff"], _u32p)
+    b.hap_bytes = ptr(keep["hb"], _u8p)
+    b.read_off = ptr(keep["roff"], _u32p)
+    b.read_bytes = ptr(keep["rb"], _u8p)
+    return b, keep
+
+
+def ll_size(batch):
+    lhb = np.asarray(batch["locus_hap_begin"], dtype=np.int64)
+    lrb = np.asarray(batch["locus_read_begin"], dtype=np.int64)
+    return int(np.sum((lhb[1:] - lhb[:-1]) * (lrb[1:] - lrb[:-1])))
+
+
+def make_posterior_batch(post):
+    keep = dict(
+        lsb=np.ascontiguousarray(post["locus_sread_begin"], dtype=np.uint32),
+        pool=np.ascontiguousarray(post["pool_index"], dtype=np.uint32),
+        lab=np.ascontiguousarray(post["sample_label"], dtype=np.int32),
+        p1=np.ascontiguousarray(post["log_p1"], dtype=np.float64),
+        p2=np.ascontiguousarray(post["log_p2"], dtype=np.float64),
+        ns=np.ascontiguousarray(post["locus_n_samples"], dtype=np.uint32))
+    b = PosteriorBatch()
+    b.locus_sread_begin = ptr(keep["lsb"], _u32p)
+    b.pool_index = ptr(keep["pool"], _u32p)
+    b.sample_label = ptr(keep["lab"], _i32p)
+    b.log_p1 = ptr(keep["p1"], _dp)
+    b.log_p2 = ptr(keep["p2"], _dp)
+    b.locus_n_samples = ptr(keep["ns"], _u32p)
+    if post.get("locus_haploid") is not None:
+        keep["hap"] = np.ascontiguousarray(post["locus_haploid"], dtype=np.uint8)
+        b.locus_haploid = ptr(keep["hap"], _u8p)
+    return b, keep
+
+
+_lib = None
+
+
+def load():
+    """Load liblongtr_b200.so and declare every symbol of include/longtr_b200.h."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("liblongtr_b200.so is not built (run `python -m longtr_b200.build`); "
+                           "there is no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    lib.ltr_params_default.argtypes = [C.POINTER(Params)]
+    lib.ltr_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
+    lib.ltr_ctx_create.restype = C.c_int
+    lib.ltr_ctx_destroy.argtypes = [vp]
+    lib.ltr_strerror.argtypes = [C.c_int]
+    lib.ltr_strerror.restype = C.c_char_p
+    lib.ltr_last_error.argtypes = [vp]
+    lib.ltr_last_error.restype = C.c_char_p
+    lib.ltr_version.restype = C.c_char_p
+    lib.ltr_viterbi_ll.argtypes = [vp, C.POINTER(Params), C.POINTER(ViterbiBatch), _dp, C.POINTER(JobStats)]
+    lib.ltr_viterbi_ll.restype = C.c_int
+    lib.ltr_posteriors.argtypes = [vp, C.c_int, C.c_int32, C.c_int32, C.c_int32, _dp, _dp, _dp, _i32p,
+                                   _dp, _dp, _dp]
+    lib.ltr_posteriors.restype = C.c_int
+    lib.ltr_job_create.argtypes = [vp, C.POINTER(Params), C.POINTER(ViterbiBatch), C.POINTER(PosteriorBatch),
+                                   C.POINTER(vp)]
+    lib.ltr_job_create.restype = C.c_int
+    lib.ltr_job_run.argtypes = [vp, vp]
+    lib.ltr_job_run.restype = C.c_int
+    lib.ltr_job_sizes.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    lib.ltr_job_download.argtypes = [vp, vp, _dp, _dp, _dp]
+    lib.ltr_job_download.restype = C.c_int
+    lib.ltr_job_get_stats.argtypes = [vp, C.POINTER(JobStats)]
+    lib.ltr_job_destroy.argtypes = [vp, vp]
+    lib.ltr_process_reads_flat.argtypes = [vp, C.POINTER(FlatLocus), _dp, _i32p]
+    lib.ltr_process_reads_flat.restype = C.c_int
+    lib.ltr_fp64_issue_rate.argtypes = [C.c_int, C.c_int, _dp, _dp]
+    lib.ltr_fp64_issue_rate.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+EXPORTED_SYMBOLS = [
+    "ltr_params_default", "ltr_ctx_create", "ltr_ctx_destroy", "ltr_strerror", "ltr_last_error",
+    "ltr_version", "ltr_viterbi_ll", "ltr_posteriors", "ltr_job_create", "ltr_job_run", "ltr_job_sizes",
+    "ltr_job_download", "ltr_job_get_stats", "ltr_job_destroy", "ltr_process_reads_flat",
+    "ltr_fp64_issue_rate",
+]

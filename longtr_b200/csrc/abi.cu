@@ -1,0 +1,582 @@
+// abi.cu -- implementation of the C ABI declared in include/longtr_b200.h.
+//
+// Host side of the drop-in boundary: validates and plans a flattened batch of loci
+// (viterbi_host.h), keeps it resident in HBM, launches the sm_100a kernels on the context's
+// CUDA streams (one stream per row class so the persistent grids overlap), and moves results
+// back.  There is no CPU fallback anywhere in this file: without a CUDA device the context
+// cannot be created and every entry point fails.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+#include "longtr_b200.h"
+#include "viterbi_host.h"
+
+using namespace ltr;
+
+namespace {
+
+const int kNumStreams = 8;
+
+struct DeviceBuffer {
+  void* p = nullptr;
+  size_t bytes = 0;
+  cudaError_t alloc(size_t n) {
+    free();
+    if (n == 0) n = 8;
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e == cudaSuccess) bytes = n;
+    return e;
+  }
+  void free() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  template <typename T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+}  // namespace
+
+struct ltr_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t main_stream = nullptr;
+  cudaStream_t streams[kNumStreams] = {nullptr};
+  cudaEvent_t ev_start = nullptr, ev_vit = nullptr, ev_end = nullptr;
+  cudaEvent_t ev_stream[kNumStreams] = {nullptr};
+  int blocks_per_sm[2][32] = {{0}};
+  std::string last_error;
+};
+
+struct ClassState {
+  int k = 0;
+  uint32_t n_tasks = 0;
+  uint32_t fail_cap = 0;
+  uint32_t grid_fast = 0, grid_full = 0;
+  DeviceBuffer tasks, fails, ctrl;  // ctrl: [0] fast cursor [1] n_tasks [2] fail count [3] full cursor
+  DeviceBuffer sx, sy, sb;
+  uint32_t scratch_stride = 0;
+  bool force_full = false;
+};
+
+struct ltr_job {
+  ltr_params params;
+  Plan plan;
+  HostConsts hc;
+  uint32_t n_loci = 0, n_haps = 0, n_reads = 0;
+  uint64_t n_ll = 0, n_post = 0, n_tot = 0;
+  DeviceBuffer hap_bytes, hap_off, hap_locus, read_bytes, read_off, lhb, lrb, ll_off, out_ll, tabI, tabD;
+  // posterior inputs
+  bool has_post = false;
+  DeviceBuffer lsb, pool, label, p1, p2, nsamp, haploid, post_off, tot_off, post, totals, int_logs;
+  uint32_t n_int_logs = 0;
+  std::vector<ClassState> classes;
+  ltr_job_stats stats;
+};
+
+namespace {
+
+int fail_cuda(ltr_ctx* ctx, cudaError_t e, const char* what) {
+  if (ctx) ctx->last_error = std::string(what) + ": " + cudaGetErrorString(e);
+  return (e == cudaErrorMemoryAllocation) ? LTR_ERR_OOM : LTR_ERR_CUDA;
+}
+
+#define LTR_CUDA(ctx, call)                                  \
+  do {                                                       \
+    cudaError_t e__ = (call);                                \
+    if (e__ != cudaSuccess) return fail_cuda(ctx, e__, #call); \
+  } while (0)
+
+template <typename T>
+int upload(ltr_ctx* ctx, DeviceBuffer& buf, const T* src, size_t count, size_t pad_bytes, uint64_t* h2d) {
+  const size_t bytes = count * sizeof(T);
+  LTR_CUDA(ctx, buf.alloc(bytes + pad_bytes));
+  if (pad_bytes) LTR_CUDA(ctx, cudaMemsetAsync((char*)buf.p + bytes, 0, pad_bytes, ctx->main_stream));
+  if (bytes) LTR_CUDA(ctx, cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, ctx->main_stream));
+  if (h2d) *h2d += bytes;
+  return LTR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void ltr_params_default(ltr_params* p) {
+  // Dindel defaults, reference HapAligner.h:118
+  p->ins_ins = -1.0f;
+  p->ins_match = (float)-0.458675;
+  p->del_del = -1.0f;
+  p->del_match = (float)-0.458675;
+  p->match_match = (float)-0.00005800168;
+  p->match_ins = (float)-10.448214728;
+  p->match_del = (float)-10.448214728;
+  p->indel_flank_len = 5;
+}
+
+const char* ltr_strerror(int code) {
+  switch (code) {
+    case LTR_OK: return "ok";
+    case LTR_ERR_NO_DEVICE: return "no usable CUDA device (there is no CPU fallback)";
+    case LTR_ERR_CUDA: return "CUDA runtime error (see ltr_last_error)";
+    case LTR_ERR_INVALID: return "invalid argument or malformed batch";
+    case LTR_ERR_OOM: return "out of device memory";
+    case LTR_ERR_UNSUPPORTED: return "unsupported configuration";
+    default: return "unknown error";
+  }
+}
+
+const char* ltr_last_error(const ltr_ctx* ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+
+const char* ltr_version(void) { return "longtr_b200 0.1 (sm_100a)"; }
+
+int ltr_ctx_create(int device, ltr_ctx** out) {
+  if (!out) return LTR_ERR_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+    cudaGetLastError();
+    return LTR_ERR_NO_DEVICE;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) return LTR_ERR_NO_DEVICE;
+  ltr_ctx* ctx = new ltr_ctx();
+  ctx->device = device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+    delete ctx;
+    return LTR_ERR_NO_DEVICE;
+  }
+  ctx->sm_count = prop.multiProcessorCount;
+  cudaError_t e = cudaStreamCreateWithFlags(&ctx->main_stream, cudaStreamNonBlocking);
+  for (int i = 0; i < kNumStreams && e == cudaSuccess; ++i) {
+    e = cudaStreamCreateWithFlags(&ctx->streams[i], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_stream[i], cudaEventDisableTiming);
+  }
+  if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_start);
+  if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_vit);
+  if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_end);
+  if (e != cudaSuccess) {
+    ltr_ctx_destroy(ctx);
+    return LTR_ERR_CUDA;
+  }
+  for (int k = 1; k <= viterbi_max_rows_per_lane(); ++k) {
+    ctx->blocks_per_sm[MODE_FAST][k] = viterbi_blocks_per_sm(k, MODE_FAST);
+    ctx->blocks_per_sm[MODE_FULL][k] = viterbi_blocks_per_sm(k, MODE_FULL);
+    if (ctx->blocks_per_sm[MODE_FAST][k] <= 0 || ctx->blocks_per_sm[MODE_FULL][k] <= 0) {
+      // kernel image not loadable on this device (not sm_100a?)
+      ltr_ctx_destroy(ctx);
+      return LTR_ERR_NO_DEVICE;
+    }
+  }
+  *out = ctx;
+  return LTR_OK;
+}
+
+void ltr_ctx_destroy(ltr_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  for (int i = 0; i < kNumStreams; ++i) {
+    if (ctx->streams[i]) cudaStreamDestroy(ctx->streams[i]);
+    if (ctx->ev_stream[i]) cudaEventDestroy(ctx->ev_stream[i]);
+  }
+  if (ctx->main_stream) cudaStreamDestroy(ctx->main_stream);
+  if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
+  if (ctx->ev_vit) cudaEventDestroy(ctx->ev_vit);
+  if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
+  delete ctx;
+}
+
+void ltr_job_destroy(ltr_ctx* ctx, ltr_job* job) {
+  if (!job) return;
+  if (ctx) cudaSetDevice(ctx->device);
+  DeviceBuffer* bufs[] = {&job->hap_bytes, &job->hap_off, &job->hap_locus, &job->read_bytes, &job->read_off,
+                          &job->lhb, &job->lrb, &job->ll_off, &job->out_ll, &job->tabI, &job->tabD,
+                          &job->lsb, &job->pool, &job->label, &job->p1, &job->p2, &job->nsamp,
+                          &job->haploid, &job->post_off, &job->tot_off, &job->post, &job->totals,
+                          &job->int_logs};
+  for (DeviceBuffer* b : bufs) b->free();
+  for (ClassState& c : job->classes) {
+    c.tasks.free(); c.fails.free(); c.ctrl.free(); c.sx.free(); c.sy.free(); c.sb.free();
+  }
+  delete job;
+}
+
+int ltr_job_create(ltr_ctx* ctx, const ltr_params* params, const ltr_viterbi_batch* b,
+                   const ltr_posterior_batch* post, ltr_job** out) {
+  if (!ctx || !params || !b || !out) return LTR_ERR_INVALID;
+  *out = nullptr;
+  if (b->n_loci && (!b->locus_hap_begin || !b->locus_read_begin || !b->hap_off || !b->read_off))
+    return LTR_ERR_INVALID;
+  if (params->indel_flank_len < 0 || params->indel_flank_len > 35) return LTR_ERR_INVALID;
+  LTR_CUDA(ctx, cudaSetDevice(ctx->device));
+  ltr_job* job = new ltr_job();
+  std::memset(&job->stats, 0, sizeof(job->stats));
+  job->params = *params;
+  const int kmax = viterbi_max_rows_per_lane();
+  static const uint32_t kZero[2] = {0, 0};
+  ltr_viterbi_batch bb = *b;
+  if (bb.n_loci == 0) {
+    bb.locus_hap_begin = bb.locus_read_begin = bb.hap_off = bb.read_off = kZero;
+  }
+  int rc = make_plan(bb, *params, kmax, job->plan);
+  if (rc != LTR_OK) { delete job; return rc; }
+  Plan& plan = job->plan;
+  job->n_loci = bb.n_loci;
+  job->n_haps = bb.locus_hap_begin[bb.n_loci];
+  job->n_reads = bb.locus_read_begin[bb.n_loci];
+  job->n_ll = plan.ll_off[bb.n_loci];
+  job->stats.n_pairs = plan.n_pairs;
+  job->stats.n_cells = plan.n_cells;
+  make_consts(*params, std::max(plan.max_n, plan.max_m) + 2, job->hc);
+  uint64_t* h2d = &job->stats.h2d_bytes;
+
+#define LTR_TRY(expr)                     \
+  do {                                    \
+    int rc__ = (expr);                    \
+    if (rc__ != LTR_OK) {                 \
+      ltr_job_destroy(ctx, job);          \
+      return rc__;                        \
+    }                                     \
+  } while (0)
+#define LTR_CUDA_J(call)                                   \
+  do {                                                     \
+    cudaError_t e__ = (call);                              \
+    if (e__ != cudaSuccess) {                              \
+      int rc__ = fail_cuda(ctx, e__, #call);               \
+      ltr_job_destroy(ctx, job);                           \
+      return rc__;                                         \
+    }                                                      \
+  } while (0)
+
+  const size_t hap_nbytes = bb.hap_off[job->n_haps], read_nbytes = bb.read_off[job->n_reads];
+  LTR_TRY(upload(ctx, job->hap_bytes, bb.hap_bytes, hap_nbytes, 16, h2d));
+  LTR_TRY(upload(ctx, job->read_bytes, bb.read_bytes, read_nbytes, 16, h2d));
+  LTR_TRY(upload(ctx, job->hap_off, bb.hap_off, (size_t)job->n_haps + 1, 0, h2d));
+  LTR_TRY(upload(ctx, job->read_off, bb.read_off, (size_t)job->n_reads + 1, 0, h2d));
+  LTR_TRY(upload(ctx, job->lhb, bb.locus_hap_begin, (size_t)job->n_loci + 1, 0, h2d));
+  LTR_TRY(upload(ctx, job->lrb, bb.locus_read_begin, (size_t)job->n_loci + 1, 0, h2d));
+  LTR_TRY(upload(ctx, job->hap_locus, plan.hap_locus.data(), plan.hap_locus.size(), 0, h2d));
+  LTR_TRY(upload(ctx, job->ll_off, plan.ll_off.data(), plan.ll_off.size(), 0, h2d));
+  LTR_TRY(upload(ctx, job->tabI, job->hc.tabI.data(), job->hc.tabI.size(), 0, h2d));
+  LTR_TRY(upload(ctx, job->tabD, job->hc.tabD.data(), job->hc.tabD.size(), 0, h2d));
+  LTR_CUDA_J(job->out_ll.alloc(job->n_ll * sizeof(double)));
+  job->hc.C.tabI = job->tabI.as<double>();
+  job->hc.C.tabD = job->tabD.as<double>();
+
+  for (int k = 1; k <= kmax; ++k) {
+    if (plan.tasks[k].empty()) continue;
+    ClassState cs;
+    cs.k = k;
+    cs.n_tasks = (uint32_t)plan.tasks[k].size();
+    uint64_t pairs = 0;
+    for (const Task& t : plan.tasks[k]) pairs += t.read_end - t.read_begin;
+    cs.fail_cap = (uint32_t)std::min<uint64_t>(pairs, 1u << 22);
+    const uint32_t warps_per_block = viterbi_block_threads() / 32;
+    const uint32_t want_blocks = (cs.n_tasks + warps_per_block - 1) / warps_per_block;
+    cs.grid_fast = std::min<uint32_t>(want_blocks, (uint32_t)(ctx->sm_count * ctx->blocks_per_sm[MODE_FAST][k]));
+    cs.grid_full = (uint32_t)(ctx->sm_count * std::min(2, ctx->blocks_per_sm[MODE_FULL][k]));
+    const uint32_t grid_max = std::max(cs.grid_fast, cs.grid_full);
+    LTR_TRY(upload(ctx, cs.tasks, plan.tasks[k].data(), plan.tasks[k].size(), 0, h2d));
+    LTR_CUDA_J(cs.fails.alloc((size_t)cs.fail_cap * sizeof(Task)));
+    LTR_CUDA_J(cs.ctrl.alloc(4 * sizeof(uint32_t)));
+    // strip hand-off scratch: needed when a haplotype of this class has more than 32*k rows; the
+    // exact fallback re-runs single pairs of the same haplotypes, so it shares the buffers.
+    if (plan.max_q_multistrip[k] > 0) {
+      cs.scratch_stride = plan.max_q_multistrip[k] + 8;
+      const size_t warps = (size_t)grid_max * warps_per_block;
+      LTR_CUDA_J(cs.sx.alloc(warps * cs.scratch_stride * sizeof(double)));
+      LTR_CUDA_J(cs.sy.alloc(warps * cs.scratch_stride * sizeof(double)));
+      LTR_CUDA_J(cs.sb.alloc(warps * cs.scratch_stride * sizeof(uint32_t)));
+    }
+    job->classes.push_back(cs);
+  }
+
+  if (post) {
+    job->has_post = true;
+    const uint32_t n_sreads = post->locus_sread_begin[bb.n_loci];
+    std::vector<unsigned long long> post_off((size_t)bb.n_loci + 1, 0), tot_off((size_t)bb.n_loci + 1, 0);
+    uint32_t max_h = 1;
+    for (uint32_t l = 0; l < bb.n_loci; ++l) {
+      const uint32_t H = bb.locus_hap_begin[l + 1] - bb.locus_hap_begin[l];
+      const uint32_t S = post->locus_n_samples[l];
+      const uint32_t P = bb.locus_read_begin[l + 1] - bb.locus_read_begin[l];
+      max_h = std::max(max_h, H);
+      post_off[l + 1] = post_off[l] + (unsigned long long)S * H * H;
+      tot_off[l + 1] = tot_off[l] + S;
+      for (uint32_t r = post->locus_sread_begin[l]; r < post->locus_sread_begin[l + 1]; ++r)
+        if (post->pool_index[r] >= P || post->sample_label[r] < 0 || (uint32_t)post->sample_label[r] >= S) {
+          ltr_job_destroy(ctx, job);
+          return LTR_ERR_INVALID;
+        }
+    }
+    job->n_post = post_off[bb.n_loci];
+    job->n_tot = tot_off[bb.n_loci];
+    // INT_LOGS (mathops.cpp:14-22) with the host's libm so the priors match the reference bit for bit
+    std::vector<double> logs((size_t)max_h + 2);
+    logs[0] = -1000.0;
+    for (uint32_t i = 1; i < logs.size(); ++i) logs[i] = log((double)i);
+    job->n_int_logs = (uint32_t)logs.size();
+    LTR_TRY(upload(ctx, job->int_logs, logs.data(), logs.size(), 0, h2d));
+    LTR_TRY(upload(ctx, job->lsb, post->locus_sread_begin, (size_t)bb.n_loci + 1, 0, h2d));
+    LTR_TRY(upload(ctx, job->pool, post->pool_index, n_sreads, 0, h2d));
+    LTR_TRY(upload(ctx, job->label, post->sample_label, n_sreads, 0, h2d));
+    LTR_TRY(upload(ctx, job->p1, post->log_p1, n_sreads, 0, h2d));
+    LTR_TRY(upload(ctx, job->p2, post->log_p2, n_sreads, 0, h2d));
+    LTR_TRY(upload(ctx, job->nsamp, post->locus_n_samples, bb.n_loci, 0, h2d));
+    if (post->locus_haploid) LTR_TRY(upload(ctx, job->haploid, post->locus_haploid, bb.n_loci, 0, h2d));
+    LTR_TRY(upload(ctx, job->post_off, post_off.data(), post_off.size(), 0, h2d));
+    LTR_TRY(upload(ctx, job->tot_off, tot_off.data(), tot_off.size(), 0, h2d));
+    LTR_CUDA_J(job->post.alloc(job->n_post * sizeof(double)));
+    LTR_CUDA_J(job->totals.alloc(job->n_tot * sizeof(double)));
+  }
+  LTR_CUDA_J(cudaStreamSynchronize(ctx->main_stream));
+  *out = job;
+  return LTR_OK;
+#undef LTR_TRY
+#undef LTR_CUDA_J
+}
+
+static int run_classes(ltr_ctx* ctx, ltr_job* job, bool only_forced) {
+  DevBatch B;
+  B.hap_bytes = job->hap_bytes.as<uint8_t>();
+  B.hap_off = job->hap_off.as<uint32_t>();
+  B.hap_locus = job->hap_locus.as<uint32_t>();
+  B.read_bytes = job->read_bytes.as<uint8_t>();
+  B.read_off = job->read_off.as<uint32_t>();
+  B.locus_hap_begin = job->lhb.as<uint32_t>();
+  B.locus_read_begin = job->lrb.as<uint32_t>();
+  B.ll_off = job->ll_off.as<unsigned long long>();
+  B.out_ll = job->out_ll.as<double>();
+  int si = 0;
+  for (ClassState& cs : job->classes) {
+    if (only_forced && !cs.force_full) continue;
+    cudaStream_t st = ctx->streams[si % kNumStreams];
+    ++si;
+    const uint32_t ctrl_init[4] = {0u, cs.n_tasks, 0u, 0u};
+    LTR_CUDA(ctx, cudaMemcpyAsync(cs.ctrl.p, ctrl_init, sizeof(ctrl_init), cudaMemcpyHostToDevice, st));
+    uint32_t* ctrl = cs.ctrl.as<uint32_t>();
+    FailSink sink;
+    sink.items = cs.fails.as<Task>();
+    sink.count = ctrl + 2;
+    sink.capacity = cs.fail_cap;
+    FailSink none;
+    none.items = nullptr;
+    none.count = ctrl + 2;
+    none.capacity = 0;
+    if (cs.force_full) {
+      // witness list overflowed on an earlier run: evaluate every pair with the exact kernel
+      LTR_CUDA(ctx, launch_viterbi(cs.k, MODE_FULL, (int)cs.grid_fast, st, job->hc.C, B, cs.tasks.as<Task>(),
+                                   ctrl + 1, cs.n_tasks, ctrl + 0, none, cs.sx.as<double>(),
+                                   cs.sy.as<double>(), cs.sb.as<uint32_t>(), cs.scratch_stride));
+      job->stats.n_launches += 1;
+    } else {
+      LTR_CUDA(ctx, launch_viterbi(cs.k, MODE_FAST, (int)cs.grid_fast, st, job->hc.C, B, cs.tasks.as<Task>(),
+                                   ctrl + 1, cs.n_tasks, ctrl + 0, sink, cs.sx.as<double>(),
+                                   cs.sy.as<double>(), cs.sb.as<uint32_t>(), cs.scratch_stride));
+      LTR_CUDA(ctx, launch_viterbi(cs.k, MODE_FULL, (int)cs.grid_full, st, job->hc.C, B, cs.fails.as<Task>(),
+                                   ctrl + 2, cs.fail_cap, ctrl + 3, none, cs.sx.as<double>(),
+                                   cs.sy.as<double>(), cs.sb.as<uint32_t>(), cs.scratch_stride));
+      job->stats.n_launches += 2;
+    }
+  }
+  return LTR_OK;
+}
+
+int ltr_job_run(ltr_ctx* ctx, ltr_job* job) {
+  if (!ctx || !job) return LTR_ERR_INVALID;
+  LTR_CUDA(ctx, cudaSetDevice(ctx->device));
+  job->stats.n_launches = 0;
+  job->stats.n_fallback = 0;
+  LTR_CUDA(ctx, cudaEventRecord(ctx->ev_start, ctx->main_stream));
+  for (int i = 0; i < kNumStreams; ++i) LTR_CUDA(ctx, cudaStreamWaitEvent(ctx->streams[i], ctx->ev_start, 0));
+  int rc = run_classes(ctx, job, false);
+  if (rc != LTR_OK) return rc;
+  for (int i = 0; i < kNumStreams; ++i) {
+    LTR_CUDA(ctx, cudaEventRecord(ctx->ev_stream[i], ctx->streams[i]));
+    LTR_CUDA(ctx, cudaStreamWaitEvent(ctx->main_stream, ctx->ev_stream[i], 0));
+  }
+  // fail counts back to the host: fallback statistics + overflow detection
+  std::vector<uint32_t> ctrl(job->classes.size() * 4, 0);
+  for (size_t c = 0; c < job->classes.size(); ++c)
+    LTR_CUDA(ctx, cudaMemcpyAsync(&ctrl[c * 4], job->classes[c].ctrl.p, 4 * sizeof(uint32_t),
+                                  cudaMemcpyDeviceToHost, ctx->main_stream));
+  LTR_CUDA(ctx, cudaStreamSynchronize(ctx->main_stream));
+  bool rerun = false;
+  for (size_t c = 0; c < job->classes.size(); ++c) {
+    ClassState& cs = job->classes[c];
+    if (cs.force_full) continue;
+    job->stats.n_fallback += ctrl[c * 4 + 2];
+    if (ctrl[c * 4 + 2] > cs.fail_cap) {
+      cs.force_full = true;
+      rerun = true;
+    }
+  }
+  if (rerun) {
+    for (int i = 0; i < kNumStreams; ++i) LTR_CUDA(ctx, cudaStreamWaitEvent(ctx->streams[i], ctx->ev_start, 0));
+    rc = run_classes(ctx, job, true);
+    if (rc != LTR_OK) return rc;
+    for (int i = 0; i < kNumStreams; ++i) {
+      LTR_CUDA(ctx, cudaEventRecord(ctx->ev_stream[i], ctx->streams[i]));
+      LTR_CUDA(ctx, cudaStreamWaitEvent(ctx->main_stream, ctx->ev_stream[i], 0));
+    }
+  }
+  LTR_CUDA(ctx, cudaEventRecord(ctx->ev_vit, ctx->main_stream));
+  if (job->has_post) {
+    DevPosterior P;
+    P.n_loci = job->n_loci;
+    P.locus_hap_begin = job->lhb.as<uint32_t>();
+    P.locus_sread_begin = job->lsb.as<uint32_t>();
+    P.pool_index = job->pool.as<uint32_t>();
+    P.sample_label = job->label.as<int32_t>();
+    P.log_p1 = job->p1.as<double>();
+    P.log_p2 = job->p2.as<double>();
+    P.locus_n_samples = job->nsamp.as<uint32_t>();
+    P.locus_haploid = job->haploid.p ? job->haploid.as<uint8_t>() : nullptr;
+    P.ll_off = job->ll_off.as<unsigned long long>();
+    P.post_off = job->post_off.as<unsigned long long>();
+    P.tot_off = job->tot_off.as<unsigned long long>();
+    P.ll = job->out_ll.as<double>();
+    P.int_logs = job->int_logs.as<double>();
+    P.n_int_logs = job->n_int_logs;
+    P.log_one_half = log(0.5);
+    P.post = job->post.as<double>();
+    P.totals = job->totals.as<double>();
+    LTR_CUDA(ctx, launch_posteriors(P, ctx->main_stream));
+    job->stats.n_launches += 1;
+  }
+  LTR_CUDA(ctx, cudaEventRecord(ctx->ev_end, ctx->main_stream));
+  LTR_CUDA(ctx, cudaStreamSynchronize(ctx->main_stream));
+  float ms_total = 0.f, ms_vit = 0.f;
+  LTR_CUDA(ctx, cudaEventElapsedTime(&ms_total, ctx->ev_start, ctx->ev_end));
+  LTR_CUDA(ctx, cudaEventElapsedTime(&ms_vit, ctx->ev_start, ctx->ev_vit));
+  job->stats.kernel_ms = ms_total;
+  job->stats.viterbi_ms = ms_vit;
+  return LTR_OK;
+}
+
+void ltr_job_sizes(const ltr_job* job, uint64_t* n_ll, uint64_t* n_post, uint64_t* n_totals) {
+  if (n_ll) *n_ll = job ? job->n_ll : 0;
+  if (n_post) *n_post = job ? job->n_post : 0;
+  if (n_totals) *n_totals = job ? job->n_tot : 0;
+}
+
+int ltr_job_download(ltr_ctx* ctx, ltr_job* job, double* out_ll, double* out_post, double* out_totals) {
+  if (!ctx || !job) return LTR_ERR_INVALID;
+  LTR_CUDA(ctx, cudaSetDevice(ctx->device));
+  job->stats.d2h_bytes = 0;
+  if (out_ll && job->n_ll) {
+    LTR_CUDA(ctx, cudaMemcpyAsync(out_ll, job->out_ll.p, job->n_ll * sizeof(double), cudaMemcpyDeviceToHost,
+                                  ctx->main_stream));
+    job->stats.d2h_bytes += job->n_ll * sizeof(double);
+  }
+  if (out_post && job->has_post && job->n_post) {
+    LTR_CUDA(ctx, cudaMemcpyAsync(out_post, job->post.p, job->n_post * sizeof(double), cudaMemcpyDeviceToHost,
+                                  ctx->main_stream));
+    job->stats.d2h_bytes += job->n_post * sizeof(double);
+  }
+  if (out_totals && job->has_post && job->n_tot) {
+    LTR_CUDA(ctx, cudaMemcpyAsync(out_totals, job->totals.p, job->n_tot * sizeof(double), cudaMemcpyDeviceToHost,
+                                  ctx->main_stream));
+    job->stats.d2h_bytes += job->n_tot * sizeof(double);
+  }
+  LTR_CUDA(ctx, cudaStreamSynchronize(ctx->main_stream));
+  return LTR_OK;
+}
+
+void ltr_job_get_stats(const ltr_job* job, ltr_job_stats* stats) {
+  if (job && stats) *stats = job->stats;
+}
+
+int ltr_viterbi_ll(ltr_ctx* ctx, const ltr_params* params, const ltr_viterbi_batch* batch, double* out_ll,
+                   ltr_job_stats* stats) {
+  ltr_job* job = nullptr;
+  int rc = ltr_job_create(ctx, params, batch, nullptr, &job);
+  if (rc != LTR_OK) return rc;
+  rc = ltr_job_run(ctx, job);
+  if (rc == LTR_OK) rc = ltr_job_download(ctx, job, out_ll, nullptr, nullptr);
+  if (stats) ltr_job_get_stats(job, stats);
+  ltr_job_destroy(ctx, job);
+  return rc;
+}
+
+int ltr_posteriors(ltr_ctx* ctx, int haploid, int32_t n_samples, int32_t n_reads, int32_t n_alleles,
+                   double* ll, const double* log_p1, const double* log_p2, const int32_t* sample_label,
+                   double* post, double* totals, double* total_ll) {
+  if (!ctx || !ll || !log_p1 || !log_p2 || !sample_label || !post || !totals) return LTR_ERR_INVALID;
+  if (n_samples <= 0 || n_alleles <= 0 || n_reads < 0) return LTR_ERR_INVALID;
+  LTR_CUDA(ctx, cudaSetDevice(ctx->device));
+  for (int r = 0; r < n_reads; ++r)
+    if (sample_label[r] < 0 || sample_label[r] >= n_samples) return LTR_ERR_INVALID;
+  const size_t H = (size_t)n_alleles, R = (size_t)n_reads, S = (size_t)n_samples;
+  DeviceBuffer d_ll, d_p1, d_p2, d_lab, d_pool, d_lhb, d_lsb, d_ns, d_hap, d_off, d_post, d_tot, d_logs;
+  std::vector<uint32_t> pool(R);
+  for (size_t r = 0; r < R; ++r) pool[r] = (uint32_t)r;
+  const uint32_t lhb[2] = {0u, (uint32_t)H}, lsb[2] = {0u, (uint32_t)R}, ns[1] = {(uint32_t)S};
+  const uint8_t hp[1] = {(uint8_t)(haploid ? 1 : 0)};
+  const unsigned long long offs[6] = {0ull, (unsigned long long)(R * H), 0ull, (unsigned long long)(S * H * H),
+                                      0ull, (unsigned long long)S};
+  std::vector<double> logs(H + 2);
+  logs[0] = -1000.0;
+  for (size_t i = 1; i < logs.size(); ++i) logs[i] = log((double)i);
+  int rc = LTR_OK;
+  auto up = [&](DeviceBuffer& b, const void* src, size_t bytes) {
+    if (rc != LTR_OK) return;
+    cudaError_t e = b.alloc(bytes);
+    if (e == cudaSuccess && bytes) e = cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->main_stream);
+    if (e != cudaSuccess) rc = fail_cuda(ctx, e, "ltr_posteriors upload");
+  };
+  up(d_ll, ll, R * H * 8); up(d_p1, log_p1, R * 8); up(d_p2, log_p2, R * 8); up(d_lab, sample_label, R * 4);
+  up(d_pool, pool.data(), R * 4); up(d_lhb, lhb, 8); up(d_lsb, lsb, 8); up(d_ns, ns, 4); up(d_hap, hp, 1);
+  up(d_off, offs, sizeof(offs)); up(d_logs, logs.data(), logs.size() * 8);
+  if (rc == LTR_OK) {
+    cudaError_t e = d_post.alloc(S * H * H * 8);
+    if (e == cudaSuccess) e = d_tot.alloc(S * 8);
+    if (e != cudaSuccess) rc = fail_cuda(ctx, e, "ltr_posteriors alloc");
+  }
+  if (rc == LTR_OK) {
+    DevPosterior P;
+    P.n_loci = 1;
+    P.locus_hap_begin = d_lhb.as<uint32_t>();
+    P.locus_sread_begin = d_lsb.as<uint32_t>();
+    P.pool_index = d_pool.as<uint32_t>();
+    P.sample_label = d_lab.as<int32_t>();
+    P.log_p1 = d_p1.as<double>();
+    P.log_p2 = d_p2.as<double>();
+    P.locus_n_samples = d_ns.as<uint32_t>();
+    P.locus_haploid = d_hap.as<uint8_t>();
+    P.ll_off = d_off.as<unsigned long long>();
+    P.post_off = d_off.as<unsigned long long>() + 2;
+    P.tot_off = d_off.as<unsigned long long>() + 4;
+    P.ll = d_ll.as<double>();
+    P.int_logs = d_logs.as<double>();
+    P.n_int_logs = (uint32_t)logs.size();
+    P.log_one_half = log(0.5);
+    P.post = d_post.as<double>();
+    P.totals = d_tot.as<double>();
+    cudaError_t e = launch_posteriors(P, ctx->main_stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(post, d_post.p, S * H * H * 8, cudaMemcpyDeviceToHost, ctx->main_stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(totals, d_tot.p, S * 8, cudaMemcpyDeviceToHost, ctx->main_stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->main_stream);
+    if (e != cudaSuccess) rc = fail_cuda(ctx, e, "ltr_posteriors run");
+  }
+  DeviceBuffer* all[] = {&d_ll, &d_p1, &d_p2, &d_lab, &d_pool, &d_lhb, &d_lsb, &d_ns, &d_hap, &d_off, &d_post,
+                         &d_tot, &d_logs};
+  for (DeviceBuffer* b : all) b->free();
+  if (rc != LTR_OK) return rc;
+  // the reference clamps log_aln_probs_ in place (genotyper.cpp:57-58); mirror that on the caller's array
+  for (size_t i = 0; i < R * H; ++i)
+    if (ll[i] < -600.0) ll[i] = -600.0;
+  if (total_ll) {
+    double t = 0.0;  // sum(), mathops.cpp:24-29
+    for (size_t s = 0; s < S; ++s) t += totals[s];
+    *total_ll = t;
+  }
+  return LTR_OK;
+}
+
+}  // extern "C"

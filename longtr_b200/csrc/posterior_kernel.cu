@@ -1,0 +1,74 @@
+// posterior_kernel.cu -- genotype posteriors from the read x haplotype LL matrix.
+//
+// Restates Genotyper::calc_log_sample_posteriors (reference src/genotyper.cpp:45-83):
+//   post[s][a][b] = prior(a==b) + sum_{reads r of sample s, in storage order}
+//                   log( exp(LL[r][a] + log_p1[r] + log(1/2)) + exp(LL[r][b] + log_p2[r] + log(1/2)) )
+// with LL clamped to >= -600 (:57-58), then per sample total = log_sum_exp over the H*H
+// entries in storage order (mathops.cpp:45-51) and post -= total.
+// One CTA per locus; each thread owns whole (s,a,b) entries so every sum runs in the
+// reference's order.  Priors use the host's libm log table (genotyper.cpp:21-33 use INT_LOGS).
+// Floating point: CUDA exp/log are within 1 ulp of libm's -> parity tolerance 1e-12 relative.
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdint.h>
+
+#include "kernels.h"
+
+namespace ltr {
+
+__global__ void __launch_bounds__(128) posterior_kernel(const DevPosterior P) {
+  for (uint32_t l = blockIdx.x; l < P.n_loci; l += gridDim.x) {
+    const uint32_t H = P.locus_hap_begin[l + 1] - P.locus_hap_begin[l];
+    const uint32_t S = P.locus_n_samples[l];
+    const uint32_t r0 = P.locus_sread_begin[l], r1 = P.locus_sread_begin[l + 1];
+    const bool haploid = P.locus_haploid ? (P.locus_haploid[l] != 0) : false;
+    const double* ll = P.ll + P.ll_off[l];
+    double* post = P.post + P.post_off[l];
+    double* tot = P.totals + P.tot_off[l];
+    const uint32_t HH = H * H;
+    if (H == 0 || S == 0) continue;
+    double hom, het;
+    const double lH = P.int_logs[H < P.n_int_logs ? H : 0], lH1 = P.int_logs[H + 1 < P.n_int_logs ? H + 1 : 0];
+    if (haploid) {
+      hom = -lH;
+      het = -DBL_MAX / 2;
+    } else {
+      hom = P.int_logs[2] - lH - lH1;
+      het = -lH - lH1;
+    }
+    for (uint32_t idx = threadIdx.x; idx < S * HH; idx += blockDim.x) {
+      const uint32_t s = idx / HH, ab = idx - s * HH, a = ab / H, b = ab - a * H;
+      double acc = (a == b) ? hom : het;
+      for (uint32_t r = r0; r < r1; ++r) {
+        if ((uint32_t)P.sample_label[r] != s) continue;
+        const double* row = ll + (size_t)P.pool_index[r] * H;
+        double la = row[a], lb = row[b];
+        la = (la < -600.0) ? -600.0 : la;
+        lb = (lb < -600.0) ? -600.0 : lb;
+        acc += log(exp(la + P.log_p1[r] + P.log_one_half) + exp(lb + P.log_p2[r] + P.log_one_half));
+      }
+      post[idx] = acc;
+    }
+    __syncthreads();
+    for (uint32_t s = threadIdx.x; s < S; s += blockDim.x) {
+      const double* v = post + (size_t)s * HH;
+      double mx = v[0];
+      for (uint32_t k = 1; k < HH; ++k) mx = (mx < v[k]) ? v[k] : mx;
+      double sum = 0.0;
+      for (uint32_t k = 0; k < HH; ++k) sum += exp(v[k] - mx);
+      tot[s] = mx + log(sum);
+    }
+    __syncthreads();
+    for (uint32_t idx = threadIdx.x; idx < S * HH; idx += blockDim.x) post[idx] -= tot[idx / HH];
+    __syncthreads();
+  }
+}
+
+cudaError_t launch_posteriors(const DevPosterior& P, cudaStream_t stream) {
+  if (P.n_loci == 0) return cudaSuccess;
+  const uint32_t grid = P.n_loci < 148u * 16u ? P.n_loci : 148u * 16u;
+  posterior_kernel<<<grid, 128, 0, stream>>>(P);
+  return cudaGetLastError();
+}
+
+}  // namespace ltr

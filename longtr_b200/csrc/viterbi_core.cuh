@@ -1,0 +1,451 @@
+// viterbi_core.cuh -- per-lane logic of the read-stream Viterbi wavefront.
+//
+// Computes what HapAligner::align_seq_to_hap computes for one (haplotype, read) pair
+// (reference: src/SeqAlignment/HapAligner.cpp:236-343; arithmetic recipe in SURVEY.md
+// Appendix B), reorganised for a GPU warp:
+//
+//  * A warp owns one candidate haplotype (one strip of <= 32*K of its rows); lane t keeps
+//    K (or K-1) consecutive DP rows in registers.  ALL pooled reads of the locus are
+//    streamed through the warp back to back, so the pipeline fill/drain of the wavefront
+//    is paid once per haplotype, not once per pair.  Lane t works on stream position
+//    s - t at step s (skew of one column per lane).
+//  * The three-state recurrence is carried in "pre-added" form.  For a finished cell
+//    (i,j) with values M,I,D the lane forms
+//        X(i,j) = max(M+M2M, max(D+D2M, I+I2M))    -> diagonal input of cell (i+1,j+1)
+//        Y(i,j) = max(M+M2I, I+I2I)                -> upper    input of cell (i+1,j)
+//        Z(i,j) = max(M+M2D, D+D2D)                == D(i,j+1)
+//    so that  M(i,j) = emit + X(i-1,j-1),  I(i,j) = MATCH + Y(i-1,j),  D(i,j) = Z(i,j-1).
+//    These are exactly the additions/maxima of HapAligner.cpp:287-295, evaluated in the
+//    same order on the same doubles, hence bit-identical results; only two doubles
+//    (X,Y) cross a lane boundary per step and only X,Z persist per row.
+//  * Column 0 and row 0 of the reference matrices are closed forms (HapAligner.cpp:263-280)
+//    and enter as boundary values (tables tabI/tabD hold the reference's repeatedly-added
+//    prefix sums so that even non-integer transition parameters round identically).
+//  * Row bail-out (HapAligner.cpp:297-306).  MODE_FULL evaluates it literally.  MODE_FAST
+//    only looks for a cheap *witness* per row (a match-state value that provably keeps
+//    the row above -600) on every CHECK-th step; pairs with an unwitnessed row are
+//    re-run in MODE_FULL, so results are exact either way.
+//
+// The same code is compiled for the device and, with LTR_HOST_EMU, for a host-side
+// lane emulator used ONLY by the CPU unit tests (tests/emu) to check this logic without
+// a GPU.  The product never runs the emulator.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__) && !defined(LTR_HOST_EMU)
+#define LTR_HD __device__ __forceinline__
+#define LTR_DEVICE_CODE 1
+#else
+#define LTR_HD inline
+#include <cmath>
+#include <cstring>
+#endif
+
+namespace ltr {
+
+enum { MODE_FAST = 0, MODE_FULL = 1 };
+
+// Parameters shared by every task of a launch (passed by value as a kernel argument).
+struct VitConsts {
+  double m2m, d2m, i2m, m2i, i2i, m2d, d2d;  // (double)(float) transition log-probs
+  double match, mismatch;                    // (double)(float) emissions, HapAligner.cpp:260-261
+  double imp;                                // IMPOSSIBLE = -1e9, HapAligner.cpp:20
+  float d2d_f;                               // float LOG_DEL_TO_DEL for the int*float band term (:298)
+  int32_t cut;                               // 35 - INDEL_FLANK_LEN (:245-246)
+  int32_t band_w;                            // MODE_FAST: witnesses only within |diag offset| <= band_w
+  uint32_t thr_hi;                           // MODE_FAST: witness iff hi32(M) < thr_hi (M > threshold)
+  const double* tabI;                        // tabI[0] = IMP, tabI[i] = I(i,0)           (:277-279)
+  const double* tabD;                        // tabD[0] = IMP, tabD[j] = D(0,j)           (:270-271)
+  int32_t tab_len;
+};
+
+LTR_HD double vmax(double a, double b) { return (a < b) ? b : a; }  // std::max
+
+LTR_HD uint32_t hi32(double v) {
+#ifdef LTR_DEVICE_CODE
+  return (uint32_t)__double2hiint(v);
+#else
+  uint64_t u;
+  std::memcpy(&u, &v, 8);
+  return (uint32_t)(u >> 32);
+#endif
+}
+
+LTR_HD float fmul_nofma(float a, float b) {
+#ifdef LTR_DEVICE_CODE
+  return __fmul_rn(a, b);
+#else
+  return a * b;
+#endif
+}
+
+LTR_HD double ldg_d(const double* p) {
+#ifdef LTR_DEVICE_CODE
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
+
+template <int K>
+struct Lane {
+  // DP state
+  double Xp[K];  // Xp[r] = X(row r-1, previous column); Xp[0] arrives from the lane above
+  double Z[K];   // Z[r]  = D(row r, current column)
+  int32_t hc[K]; // haplotype characters of the lane's rows (0xFFFF = no row)
+  uint32_t acc[K];    // MODE_FAST: min over checked in-band cells of hi32(M)
+  double rowmax[K];   // MODE_FULL: max_j (best + band penalty)
+  double Xout, Yout;  // X,Y of the lane's last real row at the column just finished
+  uint32_t Bout;      // 1 if some row of this pair, in this or an upper lane, is bad
+  // geometry (fixed per task/strip)
+  int32_t i0;     // DP row index of r = 0
+  int32_t nrows;  // number of real rows (K or K-1; 0 for lanes below the haplotype)
+  // cursor
+  int32_t j;   // column within the current read
+  int32_t m;   // length of the current read
+  int32_t dn;  // n - m
+};
+
+// X,Y,Z of a finished cell.
+struct XYZ {
+  double x, y, z;
+};
+
+LTR_HD XYZ finish_cell(const VitConsts& C, double M, double I, double D) {
+  XYZ o;
+  o.x = vmax(M + C.m2m, vmax(D + C.d2m, I + C.i2m));
+  o.y = vmax(M + C.m2i, I + C.i2i);
+  o.z = vmax(M + C.m2d, D + C.d2d);
+  return o;
+}
+
+// ----------------------------------------------------------------------------------
+// Column 0 of a new read (closed forms, HapAligner.cpp:274-280).  rx = X(i0-1, 0) from
+// the lane above (or the row-0 boundary for the first lane of strip 0).
+//   e1      = emit(h[0], r[1])  (the reference's column-0 emission quirk, :276)
+//   returns max(D,max(I,M)) of the lane's last real row at column 0 (used when m == 1).
+// ----------------------------------------------------------------------------------
+template <int K, int MODE>
+LTR_HD double lane_begin_read(Lane<K>& L, const VitConsts& C, int32_t n, int32_t m, double e1,
+                              double rx) {
+  L.j = 0;
+  L.m = m;
+  L.dn = n - m;
+  L.Xp[0] = rx;
+  double lastbest = C.imp;
+  double xo = rx;
+#pragma unroll
+  for (int r = 0; r < K; ++r) {
+    const int32_t i = L.i0 + r;
+    // table reads are clamped: rows past the haplotype compute garbage nobody consumes
+    const int32_t ia = (i < C.tab_len) ? i : (C.tab_len - 1);
+    const double Ii = ldg_d(C.tabI + ia);
+    const double Mi = (ldg_d(C.tabI + ia - 1) + C.i2m) + e1;
+    const double Di = C.imp;
+    const XYZ o = finish_cell(C, Mi, Ii, Di);
+    if (r + 1 < K) L.Xp[r + 1] = o.x;
+    L.Z[r] = o.z;
+    if (MODE == MODE_FAST) L.acc[r] = 0xFFFFFFFFu;
+    if (MODE == MODE_FULL) L.rowmax[r] = C.imp;
+    if (r == L.nrows - 1) {
+      xo = o.x;
+      lastbest = vmax(Di, vmax(Ii, Mi));
+    }
+  }
+  L.Xout = xo;
+  L.Yout = C.imp;  // Y(.,0) is never consumed: column 0 is not produced by the recurrence
+  return lastbest;
+}
+
+// ----------------------------------------------------------------------------------
+// One DP column (j >= 1) for the lane's rows.  c = read[j]; rx,ry = X(i0-1,j), Y(i0-1,j).
+// Returns max(D,max(I,M)) of the lane's last real row (meaningful at j == m-1).
+// ----------------------------------------------------------------------------------
+template <int K, int MODE, bool CHECK>
+LTR_HD double lane_column(Lane<K>& L, const VitConsts& C, int32_t c, double rx, double ry) {
+  L.j += 1;
+  double yup = ry;
+  double xd = L.Xp[0];
+  L.Xp[0] = rx;
+  // MODE_FAST witness mask for this column: all K rows must lie inside the band
+  uint32_t msk = 0;
+  const int32_t d0 = L.dn - L.i0 + L.j;  // diagonal offset (n-m)-(i-j) of row r = 0
+  if (MODE == MODE_FAST && CHECK) {
+    const int32_t dl = d0 - (K - 1);
+    const int32_t a0 = d0 < 0 ? -d0 : d0, a1 = dl < 0 ? -dl : dl;
+    msk = ((a0 > a1 ? a0 : a1) <= C.band_w) ? 0u : 0xFFFFFFFFu;
+  }
+  double Ma = C.imp, Ia = C.imp, Da = C.imp;  // cell of row K-1
+  double Mb = C.imp, Ib = C.imp, Db = C.imp;  // cell of row K-2
+  double xa = 0, ya = 0, xb = 0, yb = 0;
+#pragma unroll
+  for (int r = 0; r < K; ++r) {
+    const double e = (L.hc[r] == c) ? C.match : C.mismatch;
+    const double M = e + xd;
+    const double I = C.match + yup;
+    const double D = L.Z[r];
+    const XYZ o = finish_cell(C, M, I, D);
+    if (MODE == MODE_FAST && CHECK) {
+      const uint32_t h = hi32(M) | msk;
+      L.acc[r] = (h < L.acc[r]) ? h : L.acc[r];
+    }
+    if (MODE == MODE_FULL) {
+      // literal HapAligner.cpp:297-298: best + (float)(|(n-m)-(i-j)|) * D2D
+      const double best = vmax(D, vmax(I, M));
+      int32_t ad = d0 - r;
+      ad = ad < 0 ? -ad : ad;
+      const float pen = fmul_nofma((float)ad, C.d2d_f);
+      const double v = best + (double)pen;
+      if (v > L.rowmax[r]) L.rowmax[r] = v;
+    }
+    if (r + 1 < K) {
+      xd = L.Xp[r + 1];
+      L.Xp[r + 1] = o.x;
+    }
+    yup = o.y;
+    L.Z[r] = o.z;
+    if (r == K - 1) { Ma = M; Ia = I; Da = D; xa = o.x; ya = o.y; }
+    if (r == K - 2) { Mb = M; Ib = I; Db = D; xb = o.x; yb = o.y; }
+  }
+  const bool full_lane = (L.nrows == K);
+  L.Xout = full_lane ? xa : xb;
+  L.Yout = full_lane ? ya : yb;
+  if (K == 1) return vmax(Da, vmax(Ia, Ma));
+  return full_lane ? vmax(Da, vmax(Ia, Ma)) : vmax(Db, vmax(Ib, Mb));
+}
+
+// True iff one of the lane's real rows fails the per-row test of the finished read.
+template <int K, int MODE>
+LTR_HD bool lane_rows_bad(const Lane<K>& L, const VitConsts& C) {
+  bool bad = false;
+#pragma unroll
+  for (int r = 0; r < K; ++r) {
+    if (r < L.nrows) {
+      if (MODE == MODE_FAST) bad |= !(L.acc[r] < C.thr_hi);
+      if (MODE == MODE_FULL) bad |= (L.rowmax[r] < -600.0);
+    }
+  }
+  return bad;
+}
+
+// Row 0 of the reference matrices as seen by DP row 1 (closed forms, HapAligner.cpp:263-272).
+// hj = h[j] (0 when j >= n: SURVEY 8a-1 policy for the reference's out-of-range read),
+// c0 = read[0].  Produces X(0,j), Y(0,j).
+LTR_HD void row0_boundary(const VitConsts& C, int32_t j, int32_t hj, int32_t c0, double& x, double& y) {
+  const int32_t jj = (j < C.tab_len) ? j : (C.tab_len - 1);
+  const double M0 = (j == 0) ? ((hj == c0) ? C.match : C.mismatch)
+                             : ((ldg_d(C.tabD + jj - 1) + C.d2m) + ((hj == c0) ? C.match : C.mismatch));
+  const double I0 = C.imp;
+  const double D0 = ldg_d(C.tabD + jj);
+  const XYZ o = finish_cell(C, M0, I0, D0);
+  x = o.x;
+  y = o.y;
+}
+
+// Result of a pair whose haplotype has a single row (n == 1): row 0 at column m-1.
+LTR_HD double single_row_result(const VitConsts& C, int32_t m, int32_t h_at_last, int32_t c0, int32_t h0) {
+  if (m == 1) return vmax(C.imp, vmax(C.imp, (h0 == c0) ? C.match : C.mismatch));
+  const int32_t j = m - 1;
+  const int32_t jj = (j < C.tab_len) ? j : (C.tab_len - 1);
+  const double M0 = (ldg_d(C.tabD + jj - 1) + C.d2m) + ((h_at_last == c0) ? C.match : C.mismatch);
+  return vmax(ldg_d(C.tabD + jj), vmax(C.imp, M0));
+}
+
+}  // namespace ltr
+
+// ======================================================================================
+// Stream driver: what one lane does at one step of the read stream.
+// ======================================================================================
+namespace ltr {
+
+struct Task {           // one haplotype against reads [read_begin, read_end) of its locus
+  uint32_t hap;
+  uint32_t read_begin;
+  uint32_t read_end;
+};
+
+struct DevBatch {       // flattened batch, device pointers (layout: include/longtr_b200.h)
+  const uint8_t* hap_bytes;
+  const uint32_t* hap_off;
+  const uint32_t* hap_locus;          // [n_haps] locus of each haplotype
+  const uint8_t* read_bytes;          // padded with >= 8 readable bytes
+  const uint32_t* read_off;
+  const uint32_t* locus_hap_begin;
+  const uint32_t* locus_read_begin;
+  const unsigned long long* ll_off;   // [n_loci+1]
+  double* out_ll;
+};
+
+struct FailSink {       // pairs that MODE_FAST could not certify; consumed by MODE_FULL
+  Task* items;
+  uint32_t* count;
+  uint32_t capacity;
+};
+
+struct StripCtx {       // warp-uniform description of the strip being streamed
+  const uint8_t* hap;   // trimmed haplotype: hap[i] is DP row/column-0 character i
+  const uint8_t* read_bytes;
+  const uint32_t* read_off;
+  double* out_ll;
+  unsigned long long out_base;  // ll_off(locus) + hap index within locus
+  uint32_t H;                   // haplotypes of the locus (row stride of the LL matrix)
+  uint32_t rb0;                 // first pooled read of the locus
+  uint32_t hap_index;
+  uint32_t qs, Q;               // stream = read_bytes[qs, qs+Q)
+  int32_t n, h0;
+  int32_t t_last;               // lane owning the strip's last row
+  bool first_strip, last_strip;
+  double* sx;                   // strip hand-off scratch (X,Y,bad per stream position)
+  double* sy;
+  uint32_t* sb;
+  FailSink fail;
+};
+
+template <int K>
+struct LaneStream {     // per-lane cursor over the stream
+  Lane<K> L;
+  int32_t p;            // current read index
+  uint32_t qe;          // end offset of the current read
+  int32_t c0;           // first character of the current read
+  int32_t cnext;        // prefetched character for the next step
+};
+
+LTR_HD uint32_t fail_append(const FailSink& F, uint32_t hap, uint32_t read) {
+#ifdef LTR_DEVICE_CODE
+  const uint32_t k = atomicAdd(F.count, 1u);
+#else
+  const uint32_t k = (*F.count)++;
+#endif
+  if (k < F.capacity) {
+    F.items[k].hap = hap;
+    F.items[k].read_begin = read;
+    F.items[k].read_end = read + 1;
+  }
+  return k;
+}
+
+template <int K>
+LTR_HD void lane_stream_reset(LaneStream<K>& S, const VitConsts& C, const StripCtx& T, int lane,
+                              int32_t i0, int32_t nrows, uint32_t read_begin) {
+  S.L.i0 = i0;
+  S.L.nrows = nrows;
+#pragma unroll
+  for (int r = 0; r < K; ++r) {
+    S.L.hc[r] = (r < nrows) ? (int32_t)T.hap[i0 + r] : 0xFFFF;
+    S.L.Xp[r] = C.imp;
+    S.L.Z[r] = C.imp;
+    S.L.acc[r] = 0xFFFFFFFFu;
+    S.L.rowmax[r] = C.imp;
+  }
+  S.L.Xout = C.imp;
+  S.L.Yout = C.imp;
+  S.L.Bout = 0;
+  S.L.j = 0;
+  S.L.m = 0x7FFFFFFF;
+  S.L.dn = 0;
+  S.p = (int32_t)read_begin - 1;
+  S.qe = T.qs;
+  S.c0 = 0;
+  S.cnext = (int32_t)T.read_bytes[T.qs];
+  (void)lane;
+}
+
+// One step of lane `lane` at stream position pos (0 <= pos < Q).  rx, ry, rbad are the values
+// the lane above exported at the previous step (ignored by lane 0, which uses the boundary).
+template <int K, int MODE>
+LTR_HD void lane_stream_step(LaneStream<K>& S, const VitConsts& C, const StripCtx& T, int lane,
+                             uint32_t pos, bool check, double rx, double ry, uint32_t rbad) {
+  Lane<K>& L = S.L;
+  const uint32_t q = T.qs + pos;
+  const int32_t c = S.cnext;
+  S.cnext = (int32_t)T.read_bytes[q + 1];
+  double lastbest;
+  if (q == S.qe) {
+    // ---- first character of the next read: column 0 -------------------------------------
+    S.p += 1;
+    S.qe = T.read_off[S.p + 1];
+    const int32_t m = (int32_t)(S.qe - q);
+    S.c0 = c;
+    const int32_t c1 = (m > 1) ? S.cnext : 0;
+    if (lane == 0) {
+      if (T.first_strip) {
+        double yy;
+        row0_boundary(C, 0, T.h0, c, rx, yy);
+      } else {
+        rx = T.sx[pos];
+      }
+    }
+    const double e1 = (T.h0 == c1) ? C.match : C.mismatch;
+    lastbest = lane_begin_read<K, MODE>(L, C, T.n, m, e1, rx);
+  } else {
+    // ---- DP column j >= 1 ------------------------------------------------------------------
+    if (lane == 0) {
+      if (T.first_strip) {
+        const int32_t j = L.j + 1;
+        const int32_t hj = (j < T.n) ? (int32_t)T.hap[j] : 0;
+        row0_boundary(C, j, hj, S.c0, rx, ry);
+      } else {
+        rx = T.sx[pos];
+        ry = T.sy[pos];
+      }
+    }
+    lastbest = check ? lane_column<K, MODE, true>(L, C, c, rx, ry)
+                     : lane_column<K, MODE, false>(L, C, c, rx, ry);
+  }
+  if (L.j == L.m - 1) {
+    // ---- the lane has finished the current read ---------------------------------------------
+    uint32_t bad_in = rbad;
+    if (lane == 0) bad_in = T.first_strip ? 0u : T.sb[pos];
+    const uint32_t bad = (lane_rows_bad<K, MODE>(L, C) ? 1u : 0u) | bad_in;
+    L.Bout = bad;
+    if (lane == T.t_last) {
+      if (T.last_strip) {
+        double* dst = T.out_ll + T.out_base + (unsigned long long)((uint32_t)S.p - T.rb0) * T.H;
+        const int32_t adn = L.dn < 0 ? -L.dn : L.dn;
+        if (adn > 600) {
+          *dst = -700.0;                       // HapAligner.cpp:249-252
+        } else if (MODE == MODE_FULL) {
+          *dst = bad ? -700.0 : lastbest;      // HapAligner.cpp:300-309
+        } else {
+          *dst = lastbest;
+          if (bad) fail_append(T.fail, T.hap_index, (uint32_t)S.p);
+        }
+      } else {
+        T.sb[pos] = bad;
+      }
+    }
+  }
+  if (!T.last_strip && lane == T.t_last) {
+    T.sx[pos] = L.Xout;
+    T.sy[pos] = L.Yout;
+  }
+}
+
+// Row split of a task: R = n-1 DP rows over S strips of <= 32*K rows, lanes get K or K-1 rows.
+struct StripPlan {
+  int32_t strips, base, rem;
+};
+LTR_HD StripPlan plan_strips(int32_t R, int K) {
+  StripPlan P;
+  P.strips = (R + 32 * K - 1) / (32 * K);
+  if (P.strips < 1) P.strips = 1;
+  P.base = R / P.strips;
+  P.rem = R % P.strips;
+  return P;
+}
+// Geometry of lane `lane` in a strip of `rows` rows starting at DP row row_start.
+LTR_HD void lane_geometry(int K, int lane, int32_t rows, int32_t row_start, int32_t& i0, int32_t& nrows,
+                          int32_t& t_last) {
+  if (rows >= 32) {
+    const int32_t a = rows - 32 * (K - 1);  // lanes [0,a) carry K rows, the others K-1
+    nrows = (lane < a) ? K : (K - 1);
+    i0 = row_start + lane * (K - 1) + (lane < a ? lane : a);
+    t_last = 31;
+  } else {
+    nrows = (lane < rows) ? 1 : 0;
+    i0 = row_start + lane;
+    t_last = rows - 1;
+  }
+}
+
+}  // namespace ltr

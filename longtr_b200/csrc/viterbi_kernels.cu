@@ -1,0 +1,167 @@
+// viterbi_kernels.cu -- sm_100a kernels of the LongTR read x haplotype Viterbi
+// (HapAligner::align_seq_to_hap, reference src/SeqAlignment/HapAligner.cpp:236-343).
+//
+// One persistent warp per (haplotype, read stream) task; see viterbi_core.cuh for the
+// per-lane algorithm.  FP64 max-plus on the FP64 pipe, no tensor cores: this is not a
+// contraction.  Per DP cell the fast kernel issues 9 DADD + 4 DSETP (+8 selects); the
+// reference recipe counts 17 FP64 ops per cell -- the 4 ops of the
+// per-row bail-out test are replaced by a sparse integer witness test and an exact
+// fallback kernel (MODE_FULL) for the pairs the witness cannot certify.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.h"
+#include "viterbi_core.cuh"
+
+namespace ltr {
+
+static constexpr unsigned kFullMask = 0xFFFFFFFFu;
+static constexpr int kBlockThreads = 128;
+static constexpr unsigned kCheckMask = 3u;  // MODE_FAST looks for row witnesses every 4th step
+
+template <int K, int MODE>
+__device__ __forceinline__ void run_task(const VitConsts& C, const DevBatch& B, const Task& T,
+                                         const FailSink& fail, double* sx, double* sy, uint32_t* sb,
+                                         int lane) {
+  const uint32_t g = T.hap;
+  const uint32_t hoff = B.hap_off[g];
+  const int32_t hlen = (int32_t)(B.hap_off[g + 1] - hoff);
+  const uint32_t l = B.hap_locus[g];
+  const uint32_t hb0 = B.locus_hap_begin[l];
+  const uint32_t H = B.locus_hap_begin[l + 1] - hb0;
+  const uint32_t rb0 = B.locus_read_begin[l];
+  const unsigned long long out_base = B.ll_off[l] + (g - hb0);
+  const int32_t n = hlen - 2 * C.cut;
+
+  if (hlen <= 60 || n < 1) {  // HapAligner.cpp:241-244
+    for (uint32_t p = T.read_begin + lane; p < T.read_end; p += 32)
+      B.out_ll[out_base + (unsigned long long)(p - rb0) * H] = C.imp;
+    return;
+  }
+  const uint8_t* hap = B.hap_bytes + hoff + C.cut;
+  if (n == 1) {  // no DP rows: the result is row 0 of the reference matrices
+    for (uint32_t p = T.read_begin + lane; p < T.read_end; p += 32) {
+      const uint32_t qb = B.read_off[p];
+      const int32_t m = (int32_t)(B.read_off[p + 1] - qb);
+      const int32_t dn = n - m;
+      double v;
+      if ((dn < 0 ? -dn : dn) > 600)
+        v = -700.0;
+      else
+        v = single_row_result(C, m, (m - 1 < n) ? (int32_t)hap[m - 1] : 0, (int32_t)B.read_bytes[qb],
+                              (int32_t)hap[0]);
+      B.out_ll[out_base + (unsigned long long)(p - rb0) * H] = v;
+    }
+    return;
+  }
+
+  StripCtx S;
+  S.hap = hap;
+  S.read_bytes = B.read_bytes;
+  S.read_off = B.read_off;
+  S.out_ll = B.out_ll;
+  S.out_base = out_base;
+  S.H = H;
+  S.rb0 = rb0;
+  S.hap_index = g;
+  S.qs = B.read_off[T.read_begin];
+  S.Q = B.read_off[T.read_end] - S.qs;
+  S.n = n;
+  S.h0 = (int32_t)hap[0];
+  S.fail = fail;
+  S.sx = sx;
+  S.sy = sy;
+  S.sb = sb;
+
+  const StripPlan P = plan_strips(n - 1, K);
+  int32_t row_start = 1;
+  LaneStream<K> LS;
+  for (int s = 0; s < P.strips; ++s) {
+    const int32_t rows = P.base + (s < P.rem ? 1 : 0);
+    S.first_strip = (s == 0);
+    S.last_strip = (s == P.strips - 1);
+    int32_t i0, nrows, t_last;
+    lane_geometry(K, lane, rows, row_start, i0, nrows, t_last);
+    S.t_last = t_last;
+    lane_stream_reset<K>(LS, C, S, lane, i0, nrows, T.read_begin);
+    const uint32_t nsteps = S.Q + (uint32_t)t_last;
+    for (uint32_t step = 0; step < nsteps; ++step) {
+      const double rx = __shfl_up_sync(kFullMask, LS.L.Xout, 1);
+      const double ry = __shfl_up_sync(kFullMask, LS.L.Yout, 1);
+      const uint32_t rb = __shfl_up_sync(kFullMask, LS.L.Bout, 1);
+      const uint32_t pos = step - (uint32_t)lane;
+      if (pos < S.Q)
+        lane_stream_step<K, MODE>(LS, C, S, lane, pos, (step & kCheckMask) == 0u, rx, ry, rb);
+    }
+    row_start += rows;
+    __syncwarp();  // strip hand-off through global scratch: order lane 31's stores before lane 0's loads
+  }
+}
+
+// ctrl[0] = task cursor, ctrl[1] = number of tasks (for MODE_FULL: the fail count written by
+// the MODE_FAST launch that ran before on the same stream).
+template <int K, int MODE>
+__global__ void __launch_bounds__(kBlockThreads)
+viterbi_stream_kernel(const VitConsts C, const DevBatch B, const Task* __restrict__ tasks,
+                      const uint32_t* __restrict__ ntasks_ptr, uint32_t task_cap, uint32_t* cursor,
+                      const FailSink fail, double* scratch_x, double* scratch_y, uint32_t* scratch_b,
+                      uint32_t scratch_stride) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp_global = (blockIdx.x * (uint32_t)blockDim.x + threadIdx.x) >> 5;
+  uint32_t ntasks = *ntasks_ptr;
+  if (ntasks > task_cap) ntasks = task_cap;
+  double* sx = scratch_x ? scratch_x + (size_t)warp_global * scratch_stride : nullptr;
+  double* sy = scratch_y ? scratch_y + (size_t)warp_global * scratch_stride : nullptr;
+  uint32_t* sb = scratch_b ? scratch_b + (size_t)warp_global * scratch_stride : nullptr;
+  while (true) {
+    uint32_t ti = 0;
+    if (lane == 0) ti = atomicAdd(cursor, 1u);
+    ti = __shfl_sync(kFullMask, ti, 0);
+    if (ti >= ntasks) break;
+    Task T;
+    T.hap = tasks[ti].hap;
+    T.read_begin = tasks[ti].read_begin;
+    T.read_end = tasks[ti].read_end;
+    run_task<K, MODE>(C, B, T, fail, sx, sy, sb, lane);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+typedef void (*VitKernel)(const VitConsts, const DevBatch, const Task*, const uint32_t*, uint32_t,
+                          uint32_t*, const FailSink, double*, double*, uint32_t*, uint32_t);
+
+template <int MODE>
+static VitKernel kernel_for(int k) {
+  switch (k) {
+#define LTR_CASE(KK) case KK: return viterbi_stream_kernel<KK, MODE>;
+    LTR_CASE(1) LTR_CASE(2) LTR_CASE(3) LTR_CASE(4) LTR_CASE(5) LTR_CASE(6) LTR_CASE(7) LTR_CASE(8)
+    LTR_CASE(9) LTR_CASE(10) LTR_CASE(11) LTR_CASE(12) LTR_CASE(13) LTR_CASE(14) LTR_CASE(15) LTR_CASE(16)
+#undef LTR_CASE
+    default: return nullptr;
+  }
+}
+
+int viterbi_max_rows_per_lane() { return 16; }
+
+int viterbi_block_threads() { return kBlockThreads; }
+
+int viterbi_blocks_per_sm(int k, int mode) {
+  VitKernel f = (mode == MODE_FAST) ? kernel_for<MODE_FAST>(k) : kernel_for<MODE_FULL>(k);
+  if (!f) return 0;
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f, kBlockThreads, 0) != cudaSuccess) return 0;
+  return nb;
+}
+
+cudaError_t launch_viterbi(int k, int mode, int grid_blocks, cudaStream_t stream, const VitConsts& C,
+                           const DevBatch& B, const Task* tasks, const uint32_t* ntasks_ptr,
+                           uint32_t task_cap, uint32_t* cursor, const FailSink& fail, double* sx,
+                           double* sy, uint32_t* sb, uint32_t scratch_stride) {
+  VitKernel f = (mode == MODE_FAST) ? kernel_for<MODE_FAST>(k) : kernel_for<MODE_FULL>(k);
+  if (!f) return cudaErrorInvalidValue;
+  f<<<grid_blocks, kBlockThreads, 0, stream>>>(C, B, tasks, ntasks_ptr, task_cap, cursor, fail, sx, sy,
+                                               sb, scratch_stride);
+  return cudaGetLastError();
+}
+
+}  // namespace ltr

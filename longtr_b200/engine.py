@@ -1,0 +1,142 @@
+"""Python host wrapper over the C ABI (include/longtr_b200.h).
+
+``Engine`` owns one ``ltr_ctx`` (one per process and GPU); ``Job`` is a batch of loci kept
+resident in HBM (``ltr_job_*``).  Everything below calls the CUDA library through ctypes;
+nothing here computes on the CPU and nothing falls back to the oracle.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+
+
+class LongTRError(RuntimeError):
+    pass
+
+
+def _check(lib, ctx, rc, what):
+    if rc != abi.LTR_OK:
+        detail = lib.ltr_last_error(ctx).decode() if ctx else ""
+        raise LongTRError("%s failed: %s %s" % (what, lib.ltr_strerror(rc).decode(), detail))
+
+
+class Job:
+    """A flattened batch of loci resident on the GPU (``ltr_job``)."""
+
+    def __init__(self, engine, handle, keep):
+        self._e = engine
+        self._h = handle
+        self._keep = keep
+        n_ll, n_post, n_tot = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        engine.lib.ltr_job_sizes(handle, C.byref(n_ll), C.byref(n_post), C.byref(n_tot))
+        self.n_ll, self.n_post, self.n_totals = n_ll.value, n_post.value, n_tot.value
+
+    def run(self):
+        _check(self._e.lib, self._e.ctx, self._e.lib.ltr_job_run(self._e.ctx, self._h), "ltr_job_run")
+        return self.stats()
+
+    def download(self, want_post=True, out_ll=None, out_post=None, out_totals=None):
+        ll = out_ll if out_ll is not None else np.empty(self.n_ll, dtype=np.float64)
+        post = tot = None
+        pp = tp = None
+        if want_post and self.n_post:
+            post = out_post if out_post is not None else np.empty(self.n_post, dtype=np.float64)
+            tot = out_totals if out_totals is not None else np.empty(self.n_totals, dtype=np.float64)
+            pp, tp = abi.ptr(post, abi._dp), abi.ptr(tot, abi._dp)
+        rc = self._e.lib.ltr_job_download(self._e.ctx, self._h, abi.ptr(ll, abi._dp), pp, tp)
+        _check(self._e.lib, self._e.ctx, rc, "ltr_job_download")
+        return ll, post, tot
+
+    def stats(self):
+        s = abi.JobStats()
+        self._e.lib.ltr_job_get_stats(self._h, C.byref(s))
+        return s
+
+    def close(self):
+        if self._h is not None:
+            self._e.lib.ltr_job_destroy(self._e.ctx, self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Engine:
+    """One GPU context. Raises ``LongTRError`` when no CUDA device is usable (no CPU fallback)."""
+
+    def __init__(self, device=0):
+        self.lib = abi.load()
+        self.ctx = C.c_void_p()
+        self.device = device
+        rc = self.lib.ltr_ctx_create(device, C.byref(self.ctx))
+        if rc != abi.LTR_OK:
+            self.ctx = None
+            raise LongTRError("ltr_ctx_create(%d): %s" % (device, self.lib.ltr_strerror(rc).decode()))
+
+    def close(self):
+        if self.ctx:
+            self.lib.ltr_ctx_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- HapAligner::process_reads, long path, for a flattened batch of loci ------------------
+    def viterbi_ll(self, batch, aln_params=None, indel_flank_len=5):
+        vb, keep = abi.make_viterbi_batch(batch)
+        p = abi.make_params(aln_params, indel_flank_len)
+        out = np.empty(abi.ll_size(batch), dtype=np.float64)
+        st = abi.JobStats()
+        rc = self.lib.ltr_viterbi_ll(self.ctx, C.byref(p), C.byref(vb), abi.ptr(out, abi._dp), C.byref(st))
+        _check(self.lib, self.ctx, rc, "ltr_viterbi_ll")
+        return out, st
+
+    # -- Genotyper::calc_log_sample_posteriors for one locus -----------------------------------
+    def posteriors(self, ll, log_p1, log_p2, sample_label, n_samples, haploid=False):
+        ll = np.array(ll, dtype=np.float64, order="C", copy=True)
+        R, H = ll.shape
+        p1 = np.ascontiguousarray(log_p1, dtype=np.float64)
+        p2 = np.ascontiguousarray(log_p2, dtype=np.float64)
+        lab = np.ascontiguousarray(sample_label, dtype=np.int32)
+        post = np.empty((n_samples, H, H), dtype=np.float64)
+        tot = np.empty(n_samples, dtype=np.float64)
+        total = C.c_double(0.0)
+        rc = self.lib.ltr_posteriors(self.ctx, int(haploid), n_samples, R, H, abi.ptr(ll, abi._dp),
+                                     abi.ptr(p1, abi._dp), abi.ptr(p2, abi._dp), abi.ptr(lab, abi._i32p),
+                                     abi.ptr(post, abi._dp), abi.ptr(tot, abi._dp), C.byref(total))
+        _check(self.lib, self.ctx, rc, "ltr_posteriors")
+        return ll, post, tot, total.value
+
+    def create_job(self, batch, post=None, aln_params=None, indel_flank_len=5):
+        vb, keep = abi.make_viterbi_batch(batch)
+        p = abi.make_params(aln_params, indel_flank_len)
+        pb_ref = None
+        keep2 = None
+        if post is not None:
+            pb, keep2 = abi.make_posterior_batch(post)
+            pb_ref = C.byref(pb)
+        h = C.c_void_p()
+        rc = self.lib.ltr_job_create(self.ctx, C.byref(p), C.byref(vb), pb_ref, C.byref(h))
+        _check(self.lib, self.ctx, rc, "ltr_job_create")
+        return Job(self, h, (keep, keep2))
+
+    def process_reads_flat(self, locus, n_reads, n_alleles, fill=0.0):
+        ll = np.full((n_reads, n_alleles), fill, dtype=np.float64)
+        seeds = np.full(n_reads, -12345, dtype=np.int32)
+        rc = self.lib.ltr_process_reads_flat(self.ctx, C.byref(locus), abi.ptr(ll, abi._dp),
+                                             abi.ptr(seeds, abi._i32p))
+        _check(self.lib, self.ctx, rc, "ltr_process_reads_flat")
+        return ll, seeds
+
+    def fp64_issue_rate(self, kind=0):
+        rate, ms = C.c_double(0.0), C.c_double(0.0)
+        rc = self.lib.ltr_fp64_issue_rate(self.device, kind, C.byref(rate), C.byref(ms))
+        _check(self.lib, self.ctx, rc, "ltr_fp64_issue_rate")
+        return rate.value, ms.value

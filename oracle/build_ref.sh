@@ -32,5 +32,5 @@ done
 $CXX -O2 -g -std=c++11 -fPIC -w -I"$here/shim" -I"$ref/src" -I"$here/../include" \
      -c "$here/ref_driver.cpp" -o "$out/obj/ref_driver.o"
 $CXX -O2 -std=c++11 -fPIC -w -I"$here/shim" -c "$here/shim/hts_stubs.cpp" -o "$out/obj/hts_stubs.o"
-$CXX -shared -o "$out/libltr_ref.so" "$out/obj/ref_driver.o" "$out/obj/hts_stubs.o" $objs -Wl,--no-undefined -lm
+$CXX -shared -o "$out/libltr_ref.so" "$out/obj/ref_driver.o" "$out/obj/hts_stubs.o" $objs -Wl,--no-undefined -lm -lpthread
 echo "built $out/libltr_ref.so"

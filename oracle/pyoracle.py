@@ -87,6 +87,10 @@ def ref_lib():
         lib.ltr_ref_log_sample_posteriors.restype = C.c_double
         lib.ltr_ref_log_sample_posteriors.argtypes = [C.c_int, C.c_int, _ip, C.c_int, _dp, _dp, _dp,
                                                       _dp, _dp, _dp, _ip]
+        lib.ltr_ref_viterbi_batch.restype = C.c_int
+        lib.ltr_ref_viterbi_batch.argtypes = [C.c_uint32, _u32p, _u32p, _u32p, _u8p, _u32p, _u8p, C.c_int,
+                                              C.POINTER(C.c_float), C.c_int, _dp, _dp,
+                                              _u32p, _u32p, _dp, _dp, _dp]
         _ref = lib
     return _ref
 
@@ -158,6 +162,43 @@ def viterbi_batch(batch, aln_params=None, indel_flank_len=5, n_threads=1):
     if rc != 0:
         raise RuntimeError("oracle batch failed")
     return out, cells.value
+
+
+def ref_viterbi_batch(batch, aln_params=None, n_threads=1, post=None):
+    """The reference's own HapAligner::process_reads over a flattened batch (haplotypes must carry
+    35 bp flanks, reads >= 11 bp). Returns (ll, seconds inside process_reads, max over threads)."""
+    lhb = np.ascontiguousarray(batch["locus_hap_begin"], dtype=np.uint32)
+    lrb = np.ascontiguousarray(batch["locus_read_begin"], dtype=np.uint32)
+    nout = int(np.sum((lhb[1:] - lhb[:-1]).astype(np.int64) * (lrb[1:] - lrb[:-1]).astype(np.int64)))
+    out = np.zeros(nout, dtype=np.float64)
+    hoff = np.ascontiguousarray(batch["hap_off"], dtype=np.uint32)
+    roff = np.ascontiguousarray(batch["read_off"], dtype=np.uint32)
+    hb = np.ascontiguousarray(batch["hap_bytes"], dtype=np.uint8)
+    rb = np.ascontiguousarray(batch["read_bytes"], dtype=np.uint8)
+    sec = C.c_double(0.0)
+    if aln_params is None:
+        npar, par = 0, (C.c_float * 7)()
+    else:
+        npar, par = 7, (C.c_float * 7)(*[float(x) for x in aln_params])
+    pargs = [None, None, None, None, None]
+    out_post = None
+    if post is not None:
+        H = (lhb[1:] - lhb[:-1]).astype(np.int64)
+        out_post = np.zeros(int(np.sum(H * H)), dtype=np.float64)
+        keep = [np.ascontiguousarray(post["locus_sread_begin"], dtype=np.uint32),
+                np.ascontiguousarray(post["pool_index"], dtype=np.uint32),
+                np.ascontiguousarray(post["log_p1"], dtype=np.float64),
+                np.ascontiguousarray(post["log_p2"], dtype=np.float64)]
+        pargs = [_ptr(keep[0], _u32p), _ptr(keep[1], _u32p), _ptr(keep[2], _dp), _ptr(keep[3], _dp),
+                 _ptr(out_post, _dp)]
+    rc = ref_lib().ltr_ref_viterbi_batch(len(lhb) - 1, _ptr(lhb, _u32p), _ptr(lrb, _u32p), _ptr(hoff, _u32p),
+                                         _ptr(hb, _u8p), _ptr(roff, _u32p), _ptr(rb, _u8p), npar, par,
+                                         n_threads, _ptr(out, _dp), C.byref(sec), *pargs)
+    if rc != 0:
+        raise RuntimeError("ltr_ref_viterbi_batch failed rc=%d" % rc)
+    if post is not None:
+        return out, sec.value, out_post
+    return out, sec.value
 
 
 def log_sample_posteriors(ll, log_p1, log_p2, sample_label, n_samples, haploid=False, which="oracle"):

@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "SeqAlignment/AlignmentData.h"
@@ -157,6 +158,101 @@ double ltr_ref_log_sample_posteriors(int haploid, int n_samples, const int32_t* 
   }
   PosteriorProbe probe(haploid != 0, names, p1, p2, n_alleles);
   return probe.run(ll_in, ll_out, post, totals, best_pairs);
+}
+
+// Flattened batch (layout of ltr_viterbi_batch) through the reference classes: per locus a
+// three-block Haplotype is rebuilt from the full haplotype strings (35 bp flanks) and every
+// trimmed read becomes an Alignment that exactly covers [repeat_start-5, repeat_end+5), so
+// that HapAligner::trim_alignment leaves it untouched.  Loci are sharded over n_threads
+// std::threads (the reference itself is single-threaded; README.md:78-82 recommends splitting
+// the BED).  *seconds = max over threads of the time spent inside process_reads.
+int ltr_ref_viterbi_batch(uint32_t n_loci, const uint32_t* lhb, const uint32_t* lrb,
+                          const uint32_t* hap_off, const uint8_t* hap_bytes, const uint32_t* read_off,
+                          const uint8_t* read_bytes, int n_aln_params, const float* aln_params,
+                          int n_threads, double* out_ll, double* seconds,
+                          /* optional posterior stage (all NULL to skip): one sample per locus */
+                          const uint32_t* lsb, const uint32_t* pool_index, const double* log_p1,
+                          const double* log_p2, double* out_post) {
+  ensure_tables();
+  std::vector<uint64_t> post_off((size_t)n_loci + 1, 0);
+  for (uint32_t l = 0; l < n_loci; ++l)
+    post_off[l + 1] = post_off[l] + (uint64_t)(lhb[l + 1] - lhb[l]) * (lhb[l + 1] - lhb[l]);
+  std::vector<uint64_t> ll_off((size_t)n_loci + 1, 0);
+  for (uint32_t l = 0; l < n_loci; ++l)
+    ll_off[l + 1] = ll_off[l] + (uint64_t)(lhb[l + 1] - lhb[l]) * (lrb[l + 1] - lrb[l]);
+  if (n_threads < 1) n_threads = 1;
+  std::vector<double> tsec((size_t)n_threads, 0.0);
+  std::vector<int> trc((size_t)n_threads, 0);
+  auto work = [&](int t) {
+    for (uint32_t l = (uint32_t)t; l < n_loci; l += (uint32_t)n_threads) {
+      const uint32_t H = lhb[l + 1] - lhb[l], P = lrb[l + 1] - lrb[l];
+      if (H == 0 || P == 0) continue;
+      std::vector<std::string> haps, reads, quals, cigars;
+      for (uint32_t h = lhb[l]; h < lhb[l + 1]; ++h)
+        haps.push_back(std::string((const char*)hap_bytes + hap_off[h], hap_off[h + 1] - hap_off[h]));
+      bool ok = true;
+      for (const std::string& s : haps) ok = ok && s.size() >= 70 && s.compare(0, 35, haps[0], 0, 35) == 0;
+      if (!ok) { trc[t] = -3; continue; }
+      const std::string lflank = haps[0].substr(0, 35), rflank = haps[0].substr(haps[0].size() - 35);
+      std::vector<std::string> alleles;
+      std::vector<const char*> allele_ptrs;
+      for (const std::string& s : haps) alleles.push_back(s.substr(35, s.size() - 70));
+      for (const std::string& s : alleles) allele_ptrs.push_back(s.c_str());
+      const int32_t rs = 1000, re = rs + (int32_t)alleles[0].size();
+      std::vector<ltr_flat_read> fr(P);
+      for (uint32_t r = 0; r < P; ++r) {
+        const uint32_t g = lrb[l] + r;
+        reads.push_back(std::string((const char*)read_bytes + read_off[g], read_off[g + 1] - read_off[g]));
+        quals.push_back(std::string(reads.back().size(), 'I'));
+        const int m = (int)reads.back().size();
+        if (m < 11) { trc[t] = -3; ok = false; break; }
+        cigars.push_back("5=" + std::to_string(m - 10) + "I5=");
+      }
+      if (!ok) continue;
+      for (uint32_t r = 0; r < P; ++r) {
+        fr[r].start = rs - 5; fr[r].stop = re + 5 - 1;
+        fr[r].seq = reads[r].c_str(); fr[r].qual = quals[r].c_str(); fr[r].cigar = cigars[r].c_str();
+      }
+      ltr_flat_locus L;
+      std::memset(&L, 0, sizeof(L));
+      L.lflank = lflank.c_str(); L.rflank = rflank.c_str();
+      L.repeat_start = rs; L.repeat_end = re; L.period = 2; L.n_alleles = (int32_t)H;
+      L.alleles = allele_ptrs.data();
+      const double st[6] = {0.95, 0.05, 0.05, 0.95, 0.01, 0.01};
+      std::memcpy(L.stutter, st, sizeof(st));
+      L.motif = "AC";
+      L.n_reads = (int32_t)P; L.reads = fr.data();
+      L.indel_flank_len = 5; L.switch_old_align_len = 0;
+      L.n_aln_params = n_aln_params;
+      for (int i = 0; i < n_aln_params && i < 7; ++i) L.aln_params[i] = aln_params[i];
+      std::vector<int32_t> seeds(P, 0);
+      int rc = ltr_ref_process_reads(&L, out_ll + ll_off[l], seeds.data(), &tsec[t]);
+      if (rc != 0) trc[t] = rc;
+      if (lsb != NULL && out_post != NULL) {
+        // per-read LL rows scattered from the pools (seq_stutter_genotyper.cpp:526-538), then
+        // Genotyper::calc_log_sample_posteriors
+        const uint32_t r0 = lsb[l], r1 = lsb[l + 1];
+        const int32_t R = (int32_t)(r1 - r0);
+        std::vector<double> rows((size_t)R * H), clamped((size_t)R * H);
+        for (int32_t r = 0; r < R; ++r)
+          std::memcpy(&rows[(size_t)r * H], out_ll + ll_off[l] + (size_t)pool_index[r0 + r] * H, sizeof(double) * H);
+        double tot = 0.0;
+        auto p0 = std::chrono::steady_clock::now();
+        ltr_ref_log_sample_posteriors(0, 1, &R, (int)H, rows.data(), log_p1 + r0, log_p2 + r0, clamped.data(),
+                                      out_post + post_off[l], &tot, NULL);
+        tsec[t] += std::chrono::duration<double>(std::chrono::steady_clock::now() - p0).count();
+      }
+    }
+  };
+  std::vector<std::thread> th;
+  for (int t = 1; t < n_threads; ++t) th.emplace_back(work, t);
+  work(0);
+  for (auto& x : th) x.join();
+  double mx = 0.0;
+  int rc = 0;
+  for (int t = 0; t < n_threads; ++t) { if (tsec[t] > mx) mx = tsec[t]; if (trc[t]) rc = trc[t]; }
+  if (seconds) *seconds = mx;
+  return rc;
 }
 
 const char* ltr_ref_version(void) { return "LongTR reference sources, compiled in place (oracle/_ref)"; }

@@ -1,0 +1,131 @@
+// TEST INFRASTRUCTURE ONLY.  Host-side emulation of one warp of the Viterbi stream kernel:
+// the very same lane functions as the CUDA kernel (longtr_b200/csrc/viterbi_core.cuh,
+// compiled with LTR_HOST_EMU), with the warp shuffles replaced by array copies.  Lets the
+// CPU test-suite check the wavefront / boundary / strip / witness logic against the oracle
+// without a GPU.  It is not a CPU fallback: nothing in the product links it.
+#define LTR_HOST_EMU 1
+#include "viterbi_host.h"
+
+#include <cstdio>
+#include <vector>
+
+using namespace ltr;
+
+template <int K, int MODE>
+static void emu_task(const VitConsts& C, const DevBatch& B, const Task& T, FailSink fail,
+                     std::vector<double>& sx, std::vector<double>& sy, std::vector<uint32_t>& sb) {
+  const uint32_t g = T.hap;
+  const uint32_t hoff = B.hap_off[g];
+  const int32_t hlen = (int32_t)(B.hap_off[g + 1] - hoff);
+  const uint32_t l = B.hap_locus[g];
+  const uint32_t H = B.locus_hap_begin[l + 1] - B.locus_hap_begin[l];
+  const uint32_t rb0 = B.locus_read_begin[l];
+  const unsigned long long out_base = B.ll_off[l] + (g - B.locus_hap_begin[l]);
+  const int32_t n = hlen - 2 * C.cut;
+  if (hlen <= 60 || n < 1) {
+    for (uint32_t p = T.read_begin; p < T.read_end; ++p)
+      B.out_ll[out_base + (unsigned long long)(p - rb0) * H] = C.imp;
+    return;
+  }
+  const uint8_t* hap = B.hap_bytes + hoff + C.cut;
+  if (n == 1) {
+    for (uint32_t p = T.read_begin; p < T.read_end; ++p) {
+      const uint32_t qb = B.read_off[p];
+      const int32_t m = (int32_t)(B.read_off[p + 1] - qb);
+      double v;
+      if (std::abs(n - m) > 600) v = -700.0;
+      else v = single_row_result(C, m, (m - 1 < n) ? hap[m - 1] : 0, B.read_bytes[qb], hap[0]);
+      B.out_ll[out_base + (unsigned long long)(p - rb0) * H] = v;
+    }
+    return;
+  }
+  StripCtx S;
+  S.hap = hap; S.read_bytes = B.read_bytes; S.read_off = B.read_off; S.out_ll = B.out_ll;
+  S.out_base = out_base; S.H = H; S.rb0 = rb0; S.hap_index = g;
+  S.qs = B.read_off[T.read_begin];
+  S.Q = B.read_off[T.read_end] - S.qs;
+  S.n = n; S.h0 = hap[0];
+  S.fail = fail;
+  sx.assign(S.Q, 0.0); sy.assign(S.Q, 0.0); sb.assign(S.Q, 0);
+  S.sx = sx.data(); S.sy = sy.data(); S.sb = sb.data();
+  const StripPlan P = plan_strips(n - 1, K);
+  int32_t row_start = 1;
+  std::vector<LaneStream<K>> lanes(32);
+  for (int s = 0; s < P.strips; ++s) {
+    const int32_t rows = P.base + (s < P.rem ? 1 : 0);
+    S.first_strip = (s == 0);
+    S.last_strip = (s == P.strips - 1);
+    for (int t = 0; t < 32; ++t) {
+      int32_t i0, nrows, tl;
+      lane_geometry(K, t, rows, row_start, i0, nrows, tl);
+      S.t_last = tl;
+      lane_stream_reset<K>(lanes[t], C, S, t, i0, nrows, T.read_begin);
+    }
+    std::vector<double> ox(32), oy(32);
+    std::vector<uint32_t> ob(32);
+    for (uint32_t step = 0; step < S.Q + (uint32_t)S.t_last; ++step) {
+      for (int t = 0; t < 32; ++t) { ox[t] = lanes[t].L.Xout; oy[t] = lanes[t].L.Yout; ob[t] = lanes[t].L.Bout; }
+      const bool check = (step & 3u) == 0u;
+      for (int t = 0; t < 32; ++t) {
+        const uint32_t pos = step - (uint32_t)t;
+        if (pos < S.Q) {
+          const double rx = t ? ox[t - 1] : 0.0, ry = t ? oy[t - 1] : 0.0;
+          const uint32_t rb = t ? ob[t - 1] : 0u;
+          lane_stream_step<K, MODE>(lanes[t], C, S, t, pos, check, rx, ry, rb);
+        }
+      }
+    }
+    row_start += rows;
+  }
+}
+
+template <int MODE>
+static void emu_dispatch(int k, const VitConsts& C, const DevBatch& B, const Task& T, FailSink fail,
+                         std::vector<double>& sx, std::vector<double>& sy, std::vector<uint32_t>& sb) {
+  switch (k) {
+#define CASE(KK) case KK: emu_task<KK, MODE>(C, B, T, fail, sx, sy, sb); break;
+    CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
+    CASE(9) CASE(10) CASE(11) CASE(12) CASE(13) CASE(14) CASE(15) CASE(16)
+#undef CASE
+    default: std::fprintf(stderr, "emu: bad K %d\n", k); std::abort();
+  }
+}
+
+extern "C" int ltr_emu_viterbi_batch(const ltr_viterbi_batch* b, const ltr_params* p, int kmax,
+                                     int use_fast, double* out_ll, uint64_t* n_fallback) {
+  Plan plan;
+  int rc = make_plan(*b, *p, kmax, plan);
+  if (rc != LTR_OK) return rc;
+  HostConsts hc;
+  make_consts(*p, std::max(plan.max_n, plan.max_m) + 2, hc);
+  hc.C.tabI = hc.tabI.data();
+  hc.C.tabD = hc.tabD.data();
+  // padded copy of the read bytes (the kernel prefetches one byte ahead)
+  const uint32_t nbytes = b->read_off[b->locus_read_begin[b->n_loci]];
+  std::vector<uint8_t> rbytes(nbytes + 8, 0);
+  std::memcpy(rbytes.data(), b->read_bytes, nbytes);
+  DevBatch B;
+  B.hap_bytes = b->hap_bytes; B.hap_off = b->hap_off; B.hap_locus = plan.hap_locus.data();
+  B.read_bytes = rbytes.data(); B.read_off = b->read_off;
+  B.locus_hap_begin = b->locus_hap_begin; B.locus_read_begin = b->locus_read_begin;
+  B.ll_off = plan.ll_off.data(); B.out_ll = out_ll;
+  std::vector<double> sx, sy;
+  std::vector<uint32_t> sb;
+  uint64_t nfall = 0;
+  for (int k = 1; k <= kmax; ++k) {
+    std::vector<Task> fails(plan.n_pairs + 1);
+    uint32_t nfail = 0;
+    FailSink sink;
+    sink.items = fails.data(); sink.count = &nfail; sink.capacity = (uint32_t)fails.size();
+    for (const Task& T : plan.tasks[k]) {
+      if (use_fast) emu_dispatch<MODE_FAST>(k, hc.C, B, T, sink, sx, sy, sb);
+      else emu_dispatch<MODE_FULL>(k, hc.C, B, T, sink, sx, sy, sb);
+    }
+    nfall += nfail;
+    FailSink none; uint32_t zero = 0;
+    none.items = nullptr; none.count = &zero; none.capacity = 0;
+    for (uint32_t f = 0; f < nfail; ++f) emu_dispatch<MODE_FULL>(k, hc.C, B, fails[f], none, sx, sy, sb);
+  }
+  if (n_fallback) *n_fallback = nfall;
+  return LTR_OK;
+}
