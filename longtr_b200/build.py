@@ -21,7 +21,7 @@ CPP_SOURCES = ["host/flat_api.cpp", "synth.cpp"]
 HEADERS = ["viterbi_core.cuh", "viterbi_host.h", "kernels.h"]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC,-ffp-contract=off", "--threads", "8",
               "-I" + INCLUDE, "-I" + CSRC]
 

@@ -60,7 +60,7 @@ struct ClassState {
   uint32_t fail_cap = 0;
   uint32_t grid_fast = 0, grid_full = 0;
   DeviceBuffer tasks, fails, ctrl;  // ctrl: [0] fast cursor [1] n_tasks [2] fail count [3] full cursor
-  DeviceBuffer sx, sy, sb;
+  DeviceBuffer sxy, sb;
   uint32_t scratch_stride = 0;
   bool force_full = false;
 };
@@ -201,7 +201,7 @@ void ltr_job_destroy(ltr_ctx* ctx, ltr_job* job) {
                           &job->int_logs};
   for (DeviceBuffer* b : bufs) b->free();
   for (ClassState& c : job->classes) {
-    c.tasks.free(); c.fails.free(); c.ctrl.free(); c.sx.free(); c.sy.free(); c.sb.free();
+    c.tasks.free(); c.fails.free(); c.ctrl.free(); c.sxy.free(); c.sb.free();
   }
   delete job;
 }
@@ -284,14 +284,13 @@ int ltr_job_create(ltr_ctx* ctx, const ltr_params* params, const ltr_viterbi_bat
     LTR_TRY(upload(ctx, cs.tasks, plan.tasks[k].data(), plan.tasks[k].size(), 0, h2d));
     LTR_CUDA_J(cs.fails.alloc((size_t)cs.fail_cap * sizeof(Task)));
     LTR_CUDA_J(cs.ctrl.alloc(4 * sizeof(uint32_t)));
-    // strip hand-off scratch: needed when a haplotype of this class has more than 32*k rows; the
-    // exact fallback re-runs single pairs of the same haplotypes, so it shares the buffers.
-    if (plan.max_q_multistrip[k] > 0) {
-      cs.scratch_stride = plan.max_q_multistrip[k] + 8;
+    // per-warp scratch line: row-0 boundary of the read stream / strip hand-off (viterbi_core.cuh)
+    {
+      cs.scratch_stride = viterbi_scratch_entries(plan.max_q[k]);
       const size_t warps = (size_t)grid_max * warps_per_block;
-      LTR_CUDA_J(cs.sx.alloc(warps * cs.scratch_stride * sizeof(double)));
-      LTR_CUDA_J(cs.sy.alloc(warps * cs.scratch_stride * sizeof(double)));
+      LTR_CUDA_J(cs.sxy.alloc(warps * cs.scratch_stride * sizeof(XY)));
       LTR_CUDA_J(cs.sb.alloc(warps * cs.scratch_stride * sizeof(uint32_t)));
+      LTR_CUDA_J(cudaMemsetAsync(cs.sxy.p, 0, cs.sxy.bytes, ctx->main_stream));
     }
     job->classes.push_back(cs);
   }
@@ -371,16 +370,16 @@ static int run_classes(ltr_ctx* ctx, ltr_job* job, bool only_forced) {
     if (cs.force_full) {
       // witness list overflowed on an earlier run: evaluate every pair with the exact kernel
       LTR_CUDA(ctx, launch_viterbi(cs.k, MODE_FULL, (int)cs.grid_fast, st, job->hc.C, B, cs.tasks.as<Task>(),
-                                   ctrl + 1, cs.n_tasks, ctrl + 0, none, cs.sx.as<double>(),
-                                   cs.sy.as<double>(), cs.sb.as<uint32_t>(), cs.scratch_stride));
+                                   ctrl + 1, cs.n_tasks, ctrl + 0, none, cs.sxy.as<XY>(),
+                                   cs.sb.as<uint32_t>(), cs.scratch_stride));
       job->stats.n_launches += 1;
     } else {
       LTR_CUDA(ctx, launch_viterbi(cs.k, MODE_FAST, (int)cs.grid_fast, st, job->hc.C, B, cs.tasks.as<Task>(),
-                                   ctrl + 1, cs.n_tasks, ctrl + 0, sink, cs.sx.as<double>(),
-                                   cs.sy.as<double>(), cs.sb.as<uint32_t>(), cs.scratch_stride));
+                                   ctrl + 1, cs.n_tasks, ctrl + 0, sink, cs.sxy.as<XY>(),
+                                   cs.sb.as<uint32_t>(), cs.scratch_stride));
       LTR_CUDA(ctx, launch_viterbi(cs.k, MODE_FULL, (int)cs.grid_full, st, job->hc.C, B, cs.fails.as<Task>(),
-                                   ctrl + 2, cs.fail_cap, ctrl + 3, none, cs.sx.as<double>(),
-                                   cs.sy.as<double>(), cs.sb.as<uint32_t>(), cs.scratch_stride));
+                                   ctrl + 2, cs.fail_cap, ctrl + 3, none, cs.sxy.as<XY>(),
+                                   cs.sb.as<uint32_t>(), cs.scratch_stride));
       job->stats.n_launches += 2;
     }
   }

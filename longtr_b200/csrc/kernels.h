@@ -10,10 +10,11 @@ namespace ltr {
 int viterbi_max_rows_per_lane();
 int viterbi_block_threads();
 int viterbi_blocks_per_sm(int k, int mode);
+uint32_t viterbi_scratch_entries(uint32_t q);
 cudaError_t launch_viterbi(int k, int mode, int grid_blocks, cudaStream_t stream, const VitConsts& C,
                            const DevBatch& B, const Task* tasks, const uint32_t* ntasks_ptr,
-                           uint32_t task_cap, uint32_t* cursor, const FailSink& fail, double* sx,
-                           double* sy, uint32_t* sb, uint32_t scratch_stride);
+                           uint32_t task_cap, uint32_t* cursor, const FailSink& fail, XY* sxy,
+                           uint32_t* sb, uint32_t scratch_stride);
 
 // Posterior step for a batch of loci (Genotyper::calc_log_sample_posteriors, genotyper.cpp:45-83).
 struct DevPosterior {

@@ -25,6 +25,11 @@
 //    only looks for a cheap *witness* per row (a match-state value that provably keeps
 //    the row above -600) on every CHECK-th step; pairs with an unwitnessed row are
 //    re-run in MODE_FULL, so results are exact either way.
+//  * Nothing in the per-step path is computed by a single lane: the row-0 boundary of
+//    the whole read stream is produced by a warp-wide pre-pass into a scratch line that
+//    lane 0 consumes through a double-buffered shared-memory window, and the column-0
+//    state a lane needs when it starts a read comes from per-lane tables in shared
+//    memory (two variants, for the two values of the reference's column-0 emission).
 //
 // The same code is compiled for the device and, with LTR_HOST_EMU, for a host-side
 // lane emulator used ONLY by the CPU unit tests (tests/emu) to check this logic without
@@ -50,13 +55,16 @@ struct VitConsts {
   double m2m, d2m, i2m, m2i, i2i, m2d, d2d;  // (double)(float) transition log-probs
   double match, mismatch;                    // (double)(float) emissions, HapAligner.cpp:260-261
   double imp;                                // IMPOSSIBLE = -1e9, HapAligner.cpp:20
+  double wit_base, wit_slope;                // MODE_FAST: M > wit_base + wit_slope*|diag offset| is a witness
   float d2d_f;                               // float LOG_DEL_TO_DEL for the int*float band term (:298)
   int32_t cut;                               // 35 - INDEL_FLANK_LEN (:245-246)
-  int32_t band_w;                            // MODE_FAST: witnesses only within |diag offset| <= band_w
-  uint32_t thr_hi;                           // MODE_FAST: witness iff hi32(M) < thr_hi (M > threshold)
   const double* tabI;                        // tabI[0] = IMP, tabI[i] = I(i,0)           (:277-279)
   const double* tabD;                        // tabD[0] = IMP, tabD[j] = D(0,j)           (:270-271)
   int32_t tab_len;
+};
+
+struct alignas(16) XY {
+  double x, y;
 };
 
 LTR_HD double vmax(double a, double b) { return (a < b) ? b : a; }  // std::max
@@ -90,10 +98,11 @@ LTR_HD double ldg_d(const double* p) {
 template <int K>
 struct Lane {
   // DP state
-  double Xp[K];  // Xp[r] = X(row r-1, previous column); Xp[0] arrives from the lane above
+  double Xin;    // X(row i0-1, previous column): arrived from the lane above one step ago
+  double X[K];   // X[r]  = X(row r, previous column), updated in place
   double Z[K];   // Z[r]  = D(row r, current column)
   int32_t hc[K]; // haplotype characters of the lane's rows (0xFFFF = no row)
-  uint32_t acc[K];    // MODE_FAST: min over checked in-band cells of hi32(M)
+  int32_t acc[K];     // MODE_FAST: min over checked cells of hi32(M) - hi32(threshold)  (<0: witness)
   double rowmax[K];   // MODE_FULL: max_j (best + band penalty)
   double Xout, Yout;  // X,Y of the lane's last real row at the column just finished
   uint32_t Bout;      // 1 if some row of this pair, in this or an upper lane, is bad
@@ -119,109 +128,91 @@ LTR_HD XYZ finish_cell(const VitConsts& C, double M, double I, double D) {
   return o;
 }
 
-// ----------------------------------------------------------------------------------
-// Column 0 of a new read (closed forms, HapAligner.cpp:274-280).  rx = X(i0-1, 0) from
-// the lane above (or the row-0 boundary for the first lane of strip 0).
-//   e1      = emit(h[0], r[1])  (the reference's column-0 emission quirk, :276)
-//   returns max(D,max(I,M)) of the lane's last real row at column 0 (used when m == 1).
-// ----------------------------------------------------------------------------------
-template <int K, int MODE>
-LTR_HD double lane_begin_read(Lane<K>& L, const VitConsts& C, int32_t n, int32_t m, double e1,
-                              double rx) {
-  L.j = 0;
-  L.m = m;
-  L.dn = n - m;
-  L.Xp[0] = rx;
-  double lastbest = C.imp;
-  double xo = rx;
-#pragma unroll
-  for (int r = 0; r < K; ++r) {
-    const int32_t i = L.i0 + r;
-    // table reads are clamped: rows past the haplotype compute garbage nobody consumes
-    const int32_t ia = (i < C.tab_len) ? i : (C.tab_len - 1);
-    const double Ii = ldg_d(C.tabI + ia);
-    const double Mi = (ldg_d(C.tabI + ia - 1) + C.i2m) + e1;
-    const double Di = C.imp;
-    const XYZ o = finish_cell(C, Mi, Ii, Di);
-    if (r + 1 < K) L.Xp[r + 1] = o.x;
-    L.Z[r] = o.z;
-    if (MODE == MODE_FAST) L.acc[r] = 0xFFFFFFFFu;
-    if (MODE == MODE_FULL) L.rowmax[r] = C.imp;
-    if (r == L.nrows - 1) {
-      xo = o.x;
-      lastbest = vmax(Di, vmax(Ii, Mi));
-    }
-  }
-  L.Xout = xo;
-  L.Yout = C.imp;  // Y(.,0) is never consumed: column 0 is not produced by the recurrence
-  return lastbest;
+// Closed-form column 0 of row i (HapAligner.cpp:274-280) for column-0 emission e1.
+LTR_HD void col0_cell(const VitConsts& C, int32_t i, double e1, double& Mi, double& Ii, double& Di) {
+  const int32_t ia = (i < C.tab_len) ? i : (C.tab_len - 1);  // rows past the haplotype: garbage nobody consumes
+  Ii = ldg_d(C.tabI + ia);
+  Mi = (ldg_d(C.tabI + ia - 1) + C.i2m) + e1;
+  Di = C.imp;
 }
+
+// M,I,D of the lane's last real row at the column just computed (consumed at read ends only).
+struct LastCell {
+  double M, I, D;
+};
 
 // ----------------------------------------------------------------------------------
 // One DP column (j >= 1) for the lane's rows.  c = read[j]; rx,ry = X(i0-1,j), Y(i0-1,j).
-// Returns max(D,max(I,M)) of the lane's last real row (meaningful at j == m-1).
+// Pass 1 forms every M of the column from the previous column's X (no dependence between
+// rows); pass 2 walks the rows top-down for the I chain and rewrites X,Z in place.
 // ----------------------------------------------------------------------------------
-template <int K, int MODE, bool CHECK>
-LTR_HD double lane_column(Lane<K>& L, const VitConsts& C, int32_t c, double rx, double ry) {
+template <int K, int MODE>
+LTR_HD LastCell lane_column(Lane<K>& L, const VitConsts& C, int32_t c, double rx, double ry, bool check) {
   L.j += 1;
-  double yup = ry;
-  double xd = L.Xp[0];
-  L.Xp[0] = rx;
-  // MODE_FAST witness mask for this column: all K rows must lie inside the band
-  uint32_t msk = 0;
-  const int32_t d0 = L.dn - L.i0 + L.j;  // diagonal offset (n-m)-(i-j) of row r = 0
-  if (MODE == MODE_FAST && CHECK) {
-    const int32_t dl = d0 - (K - 1);
-    const int32_t a0 = d0 < 0 ? -d0 : d0, a1 = dl < 0 ? -dl : dl;
-    msk = ((a0 > a1 ? a0 : a1) <= C.band_w) ? 0u : 0xFFFFFFFFu;
-  }
-  double Ma = C.imp, Ia = C.imp, Da = C.imp;  // cell of row K-1
-  double Mb = C.imp, Ib = C.imp, Db = C.imp;  // cell of row K-2
-  double xa = 0, ya = 0, xb = 0, yb = 0;
+  double M[K];
 #pragma unroll
   for (int r = 0; r < K; ++r) {
     const double e = (L.hc[r] == c) ? C.match : C.mismatch;
-    const double M = e + xd;
+    M[r] = e + (r == 0 ? L.Xin : L.X[r - 1]);
+  }
+  L.Xin = rx;
+  const int32_t d0 = L.dn - L.i0 + L.j;  // diagonal offset (n-m)-(i-j) of row r = 0
+  double yup = ry;
+  double ya = 0, yb = 0;
+  LastCell a, b;
+  a.M = a.I = a.D = b.M = b.I = b.D = C.imp;
+#pragma unroll
+  for (int r = 0; r < K; ++r) {
     const double I = C.match + yup;
     const double D = L.Z[r];
-    const XYZ o = finish_cell(C, M, I, D);
-    if (MODE == MODE_FAST && CHECK) {
-      const uint32_t h = hi32(M) | msk;
-      L.acc[r] = (h < L.acc[r]) ? h : L.acc[r];
-    }
+    const XYZ o = finish_cell(C, M[r], I, D);
     if (MODE == MODE_FULL) {
       // literal HapAligner.cpp:297-298: best + (float)(|(n-m)-(i-j)|) * D2D
-      const double best = vmax(D, vmax(I, M));
+      const double best = vmax(D, vmax(I, M[r]));
       int32_t ad = d0 - r;
       ad = ad < 0 ? -ad : ad;
       const float pen = fmul_nofma((float)ad, C.d2d_f);
       const double v = best + (double)pen;
       if (v > L.rowmax[r]) L.rowmax[r] = v;
     }
-    if (r + 1 < K) {
-      xd = L.Xp[r + 1];
-      L.Xp[r + 1] = o.x;
-    }
+    L.X[r] = o.x;
     yup = o.y;
     L.Z[r] = o.z;
-    if (r == K - 1) { Ma = M; Ia = I; Da = D; xa = o.x; ya = o.y; }
-    if (r == K - 2) { Mb = M; Ib = I; Db = D; xb = o.x; yb = o.y; }
+    if (r == K - 1) { a.M = M[r]; a.I = I; a.D = D; ya = o.y; }
+    if (r == K - 2) { b.M = M[r]; b.I = I; b.D = D; yb = o.y; }
   }
   const bool full_lane = (L.nrows == K);
-  L.Xout = full_lane ? xa : xb;
-  L.Yout = full_lane ? ya : yb;
-  if (K == 1) return vmax(Da, vmax(Ia, Ma));
-  return full_lane ? vmax(Da, vmax(Ia, Ma)) : vmax(Db, vmax(Ib, Mb));
+  L.Xout = (K == 1 || full_lane) ? L.X[K - 1] : L.X[K >= 2 ? K - 2 : 0];
+  L.Yout = (K == 1 || full_lane) ? ya : yb;
+  if (MODE == MODE_FAST) {
+    if (check) {
+      // Row witness: a match value M above T = wit_base + wit_slope*|offset| keeps
+      // best + (float)|offset|*D2D >= -600 with a margin of 1; T is taken for the lane's worst row.
+      // Negative doubles order like their high words reversed: M > T  <=  hi32(M) < hi32(T).
+      const int32_t dl = d0 - (K - 1);
+      const int32_t a0 = d0 < 0 ? -d0 : d0, a1 = dl < 0 ? -dl : dl;
+      double T = C.wit_base + C.wit_slope * (double)(a0 > a1 ? a0 : a1);
+      T = (T < -1.0) ? T : -0.0;
+      const uint32_t thr = hi32(T);
+#pragma unroll
+      for (int r = 0; r < K; ++r) {
+        const int32_t diff = (int32_t)(hi32(M[r]) - thr);
+        L.acc[r] = (diff < L.acc[r]) ? diff : L.acc[r];
+      }
+    }
+  }
+  if (K == 1 || full_lane) return a;
+  return b;
 }
 
 // True iff one of the lane's real rows fails the per-row test of the finished read.
 template <int K, int MODE>
-LTR_HD bool lane_rows_bad(const Lane<K>& L, const VitConsts& C) {
+LTR_HD bool lane_rows_bad(const Lane<K>& L) {
   bool bad = false;
 #pragma unroll
   for (int r = 0; r < K; ++r) {
     if (r < L.nrows) {
-      if (MODE == MODE_FAST) bad |= !(L.acc[r] < C.thr_hi);
+      if (MODE == MODE_FAST) bad |= !(L.acc[r] < 0);
       if (MODE == MODE_FULL) bad |= (L.rowmax[r] < -600.0);
     }
   }
@@ -231,15 +222,17 @@ LTR_HD bool lane_rows_bad(const Lane<K>& L, const VitConsts& C) {
 // Row 0 of the reference matrices as seen by DP row 1 (closed forms, HapAligner.cpp:263-272).
 // hj = h[j] (0 when j >= n: SURVEY 8a-1 policy for the reference's out-of-range read),
 // c0 = read[0].  Produces X(0,j), Y(0,j).
-LTR_HD void row0_boundary(const VitConsts& C, int32_t j, int32_t hj, int32_t c0, double& x, double& y) {
+LTR_HD XY row0_boundary(const VitConsts& C, int32_t j, int32_t hj, int32_t c0) {
   const int32_t jj = (j < C.tab_len) ? j : (C.tab_len - 1);
-  const double M0 = (j == 0) ? ((hj == c0) ? C.match : C.mismatch)
-                             : ((ldg_d(C.tabD + jj - 1) + C.d2m) + ((hj == c0) ? C.match : C.mismatch));
+  const double e = (hj == c0) ? C.match : C.mismatch;
+  const double M0 = (j == 0) ? e : ((ldg_d(C.tabD + jj - 1) + C.d2m) + e);
   const double I0 = C.imp;
   const double D0 = ldg_d(C.tabD + jj);
   const XYZ o = finish_cell(C, M0, I0, D0);
-  x = o.x;
-  y = o.y;
+  XY b;
+  b.x = o.x;
+  b.y = o.y;
+  return b;
 }
 
 // Result of a pair whose haplotype has a single row (n == 1): row 0 at column m-1.
@@ -282,6 +275,16 @@ struct FailSink {       // pairs that MODE_FAST could not certify; consumed by M
   uint32_t capacity;
 };
 
+// Per-warp shared memory: boundary window + column-0 tables.
+//   bnd [2][32] XY      double-buffered window of the scratch line read by lane 0
+//   tx  [2][K][32]      X(row r, column 0) for column-0 emission variant v (0 mismatch, 1 match)
+//   tz  [2][K][32]      Z(row r, column 0)
+//   txo [2][32]         X of the lane's last real row at column 0
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline constexpr size_t warp_smem_bytes(int K) { return 2 * 32 * sizeof(XY) + (size_t)(4 * K + 2) * 32 * sizeof(double); }
+
 struct StripCtx {       // warp-uniform description of the strip being streamed
   const uint8_t* hap;   // trimmed haplotype: hap[i] is DP row/column-0 character i
   const uint8_t* read_bytes;
@@ -295,9 +298,13 @@ struct StripCtx {       // warp-uniform description of the strip being streamed
   int32_t n, h0;
   int32_t t_last;               // lane owning the strip's last row
   bool first_strip, last_strip;
-  double* sx;                   // strip hand-off scratch (X,Y,bad per stream position)
-  double* sy;
-  uint32_t* sb;
+  XY* sxy;                      // scratch line: boundary (X,Y) entering the strip's first row, per position;
+                                // the strip's last lane overwrites it in place for the next strip
+  uint32_t* sb;                 // per position: bad flag handed to the next strip (valid at read ends)
+  XY* bnd;                      // shared memory (see warp_smem_bytes)
+  double* tx;
+  double* tz;
+  double* txo;
   FailSink fail;
 };
 
@@ -306,8 +313,8 @@ struct LaneStream {     // per-lane cursor over the stream
   Lane<K> L;
   int32_t p;            // current read index
   uint32_t qe;          // end offset of the current read
-  int32_t c0;           // first character of the current read
   int32_t cnext;        // prefetched character for the next step
+  const uint8_t* rptr;  // address of the character after cnext
 };
 
 LTR_HD uint32_t fail_append(const FailSink& F, uint32_t hap, uint32_t read) {
@@ -324,6 +331,22 @@ LTR_HD uint32_t fail_append(const FailSink& F, uint32_t hap, uint32_t read) {
   return k;
 }
 
+// Warp-wide pre-pass, strip 0: lane `lane` fills the row-0 boundary of stream positions
+// lane, lane+32, ... of every read of the task.
+LTR_HD void prepass_boundary(const VitConsts& C, const StripCtx& T, int lane, uint32_t read_begin,
+                             uint32_t read_end) {
+  for (uint32_t p = read_begin; p < read_end; ++p) {
+    const uint32_t qb = T.read_off[p];
+    const int32_t m = (int32_t)(T.read_off[p + 1] - qb);
+    const int32_t c0 = (int32_t)T.read_bytes[qb];
+    for (int32_t j = lane; j < m; j += 32) {
+      const int32_t hj = (j < T.n) ? (int32_t)T.hap[j] : 0;
+      T.sxy[qb - T.qs + (uint32_t)j] = row0_boundary(C, j, hj, c0);
+    }
+  }
+}
+
+// Per strip: geometry, haplotype characters and the lane's column-0 tables.
 template <int K>
 LTR_HD void lane_stream_reset(LaneStream<K>& S, const VitConsts& C, const StripCtx& T, int lane,
                               int32_t i0, int32_t nrows, uint32_t read_begin) {
@@ -332,11 +355,26 @@ LTR_HD void lane_stream_reset(LaneStream<K>& S, const VitConsts& C, const StripC
 #pragma unroll
   for (int r = 0; r < K; ++r) {
     S.L.hc[r] = (r < nrows) ? (int32_t)T.hap[i0 + r] : 0xFFFF;
-    S.L.Xp[r] = C.imp;
+    S.L.X[r] = C.imp;
     S.L.Z[r] = C.imp;
-    S.L.acc[r] = 0xFFFFFFFFu;
+    S.L.acc[r] = 0x7FFFFFFF;
     S.L.rowmax[r] = C.imp;
   }
+  for (int v = 0; v < 2; ++v) {
+    const double e1 = v ? C.match : C.mismatch;
+    double xo = C.imp;
+#pragma unroll
+    for (int r = 0; r < K; ++r) {
+      double Mi, Ii, Di;
+      col0_cell(C, i0 + r, e1, Mi, Ii, Di);
+      const XYZ o = finish_cell(C, Mi, Ii, Di);
+      T.tx[(v * K + r) * 32 + lane] = o.x;
+      T.tz[(v * K + r) * 32 + lane] = o.z;
+      if (r == nrows - 1) xo = o.x;
+    }
+    T.txo[v * 32 + lane] = xo;
+  }
+  S.L.Xin = C.imp;
   S.L.Xout = C.imp;
   S.L.Yout = C.imp;
   S.L.Bout = 0;
@@ -345,58 +383,58 @@ LTR_HD void lane_stream_reset(LaneStream<K>& S, const VitConsts& C, const StripC
   S.L.dn = 0;
   S.p = (int32_t)read_begin - 1;
   S.qe = T.qs;
-  S.c0 = 0;
   S.cnext = (int32_t)T.read_bytes[T.qs];
-  (void)lane;
+  S.rptr = T.read_bytes + T.qs + 1;
 }
 
 // One step of lane `lane` at stream position pos (0 <= pos < Q).  rx, ry, rbad are the values
-// the lane above exported at the previous step (ignored by lane 0, which uses the boundary).
+// the lane above exported at the previous step; lane 0 takes them from the boundary window.
 template <int K, int MODE>
 LTR_HD void lane_stream_step(LaneStream<K>& S, const VitConsts& C, const StripCtx& T, int lane,
                              uint32_t pos, bool check, double rx, double ry, uint32_t rbad) {
   Lane<K>& L = S.L;
   const uint32_t q = T.qs + pos;
   const int32_t c = S.cnext;
-  S.cnext = (int32_t)T.read_bytes[q + 1];
-  double lastbest;
+  S.cnext = (int32_t)*S.rptr;
+  S.rptr += 1;
+  if (lane == 0) {
+    const XY b = T.bnd[((pos >> 5) & 1u) * 32u + (pos & 31u)];
+    rx = b.x;
+    ry = b.y;
+  }
+  LastCell last;
+  last.M = last.I = last.D = C.imp;
   if (q == S.qe) {
-    // ---- first character of the next read: column 0 -------------------------------------
+    // ---- first character of the next read: column 0 from the lane's tables ------------------
     S.p += 1;
     S.qe = T.read_off[S.p + 1];
     const int32_t m = (int32_t)(S.qe - q);
-    S.c0 = c;
     const int32_t c1 = (m > 1) ? S.cnext : 0;
-    if (lane == 0) {
-      if (T.first_strip) {
-        double yy;
-        row0_boundary(C, 0, T.h0, c, rx, yy);
-      } else {
-        rx = T.sx[pos];
-      }
+    const int v = (T.h0 == c1) ? 1 : 0;  // column-0 emission emit(h[0], r[1]), HapAligner.cpp:276
+    L.j = 0;
+    L.m = m;
+    L.dn = T.n - m;
+    L.Xin = rx;
+#pragma unroll
+    for (int r = 0; r < K; ++r) {
+      L.X[r] = T.tx[(v * K + r) * 32 + lane];
+      L.Z[r] = T.tz[(v * K + r) * 32 + lane];
+      if (MODE == MODE_FAST) L.acc[r] = 0x7FFFFFFF;
+      if (MODE == MODE_FULL) L.rowmax[r] = C.imp;
     }
-    const double e1 = (T.h0 == c1) ? C.match : C.mismatch;
-    lastbest = lane_begin_read<K, MODE>(L, C, T.n, m, e1, rx);
+    L.Xout = T.txo[v * 32 + lane];
+    L.Yout = C.imp;  // Y(.,0) is never consumed: column 0 is not produced by the recurrence
+    if (m == 1 && L.nrows > 0)
+      col0_cell(C, L.i0 + L.nrows - 1, v ? C.match : C.mismatch, last.M, last.I, last.D);
   } else {
     // ---- DP column j >= 1 ------------------------------------------------------------------
-    if (lane == 0) {
-      if (T.first_strip) {
-        const int32_t j = L.j + 1;
-        const int32_t hj = (j < T.n) ? (int32_t)T.hap[j] : 0;
-        row0_boundary(C, j, hj, S.c0, rx, ry);
-      } else {
-        rx = T.sx[pos];
-        ry = T.sy[pos];
-      }
-    }
-    lastbest = check ? lane_column<K, MODE, true>(L, C, c, rx, ry)
-                     : lane_column<K, MODE, false>(L, C, c, rx, ry);
+    last = lane_column<K, MODE>(L, C, c, rx, ry, check);
   }
   if (L.j == L.m - 1) {
     // ---- the lane has finished the current read ---------------------------------------------
     uint32_t bad_in = rbad;
     if (lane == 0) bad_in = T.first_strip ? 0u : T.sb[pos];
-    const uint32_t bad = (lane_rows_bad<K, MODE>(L, C) ? 1u : 0u) | bad_in;
+    const uint32_t bad = (lane_rows_bad<K, MODE>(L) ? 1u : 0u) | bad_in;
     L.Bout = bad;
     if (lane == T.t_last) {
       if (T.last_strip) {
@@ -405,9 +443,9 @@ LTR_HD void lane_stream_step(LaneStream<K>& S, const VitConsts& C, const StripCt
         if (adn > 600) {
           *dst = -700.0;                       // HapAligner.cpp:249-252
         } else if (MODE == MODE_FULL) {
-          *dst = bad ? -700.0 : lastbest;      // HapAligner.cpp:300-309
+          *dst = bad ? -700.0 : vmax(last.D, vmax(last.I, last.M));      // HapAligner.cpp:300-309
         } else {
-          *dst = lastbest;
+          *dst = vmax(last.D, vmax(last.I, last.M));
           if (bad) fail_append(T.fail, T.hap_index, (uint32_t)S.p);
         }
       } else {
@@ -415,9 +453,13 @@ LTR_HD void lane_stream_step(LaneStream<K>& S, const VitConsts& C, const StripCt
       }
     }
   }
-  if (!T.last_strip && lane == T.t_last) {
-    T.sx[pos] = L.Xout;
-    T.sy[pos] = L.Yout;
+  if (!T.last_strip) {  // warp-uniform
+    if (lane == T.t_last) {
+      XY o;
+      o.x = L.Xout;
+      o.y = L.Yout;
+      T.sxy[pos] = o;
+    }
   }
 }
 

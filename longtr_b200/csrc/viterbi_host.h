@@ -50,18 +50,11 @@ inline void make_consts(const ltr_params& p, int tab_len, HostConsts& out) {
     out.tabD[j] = (double)p.match_del + left;
     left += (double)p.del_del;
   }
-  // MODE_FAST witness: a match value M > thr inside |diag offset| <= band_w keeps
-  // best + penalty >= -600 with a margin of 1.0 (band penalty = |offset| * D2D, :298).
-  const double c = std::fabs((double)p.del_del);
-  int band = 1 << 20;
-  if (p.del_del < 0.0f && c * (double)band > 300.0) band = (int)std::floor(300.0 / c);
-  C.band_w = band;
-  double thr = -599.0;
-  if (p.del_del < 0.0f) thr += c * (double)band * (1.0 + 1e-6);
-  if (thr > -1.0) thr = -1.0;
-  uint64_t u;
-  std::memcpy(&u, &thr, 8);
-  C.thr_hi = (uint32_t)(u >> 32);
+  // MODE_FAST witness (viterbi_core.cuh): M > wit_base + wit_slope*|diag offset| keeps
+  // best + (float)|offset|*D2D >= -600 with a margin of 1.0 (band penalty of HapAligner.cpp:298;
+  // the 1e-6 covers the float rounding of the reference's int*float product).
+  C.wit_base = -599.0;
+  C.wit_slope = (p.del_del < 0.0f) ? std::fabs((double)p.del_del) * (1.0 + 1e-6) : 0.0;
   C.tabI = nullptr;
   C.tabD = nullptr;
   C.tab_len = tab_len;
@@ -82,7 +75,7 @@ struct Plan {
   std::vector<unsigned long long> ll_off;  // [n_loci+1]
   uint64_t n_pairs = 0, n_cells = 0;
   int max_n = 0, max_m = 0;
-  std::vector<uint32_t> max_q_multistrip;  // [K] longest stream among multi-strip tasks
+  std::vector<uint32_t> max_q;  // [K] longest read stream among the tasks of class K
 };
 
 // Validates the batch and builds per-class task lists (heaviest first within a class so the
@@ -90,7 +83,7 @@ struct Plan {
 inline int make_plan(const ltr_viterbi_batch& b, const ltr_params& p, int kmax, Plan& out) {
   const int cut = 35 - p.indel_flank_len;
   out.tasks.assign(kmax + 1, std::vector<Task>());
-  out.max_q_multistrip.assign(kmax + 1, 0);
+  out.max_q.assign(kmax + 1, 0);
   const uint32_t n_haps = b.locus_hap_begin[b.n_loci], n_reads = b.locus_read_begin[b.n_loci];
   out.hap_locus.assign(n_haps, 0);
   out.ll_off.assign((size_t)b.n_loci + 1, 0);
@@ -120,7 +113,7 @@ inline int make_plan(const ltr_viterbi_batch& b, const ltr_params& p, int kmax, 
         k = rows_per_lane(n, kmax);
         const int strips = std::max(1, (n - 1 + 32 * k - 1) / (32 * k));
         cost = (uint64_t)k * strips * (q + 32);
-        if (strips > 1) out.max_q_multistrip[k] = std::max<uint32_t>(out.max_q_multistrip[k], (uint32_t)q);
+        out.max_q[k] = std::max<uint32_t>(out.max_q[k], (uint32_t)q);
         for (uint32_t r = r0; r < r1; ++r) {
           const int m = (int)(b.read_off[r + 1] - b.read_off[r]);
           if (std::abs(n - m) <= 600) out.n_cells += (uint64_t)n * (uint64_t)m;

@@ -21,8 +21,8 @@ static constexpr unsigned kCheckMask = 3u;  // MODE_FAST looks for row witnesses
 
 template <int K, int MODE>
 __device__ __forceinline__ void run_task(const VitConsts& C, const DevBatch& B, const Task& T,
-                                         const FailSink& fail, double* sx, double* sy, uint32_t* sb,
-                                         int lane) {
+                                         const FailSink& fail, XY* sxy, uint32_t* sb,
+                                         unsigned char* wsmem, int lane) {
   const uint32_t g = T.hap;
   const uint32_t hoff = B.hap_off[g];
   const int32_t hlen = (int32_t)(B.hap_off[g + 1] - hoff);
@@ -69,9 +69,16 @@ __device__ __forceinline__ void run_task(const VitConsts& C, const DevBatch& B, 
   S.n = n;
   S.h0 = (int32_t)hap[0];
   S.fail = fail;
-  S.sx = sx;
-  S.sy = sy;
+  S.sxy = sxy;
   S.sb = sb;
+  S.bnd = reinterpret_cast<XY*>(wsmem);
+  S.tx = reinterpret_cast<double*>(wsmem + 2 * 32 * sizeof(XY));
+  S.tz = S.tx + 2 * K * 32;
+  S.txo = S.tz + 2 * K * 32;
+
+  // row-0 boundary of the whole stream, produced by all lanes (strip 0 input of lane 0)
+  prepass_boundary(C, S, lane, T.read_begin, T.read_end);
+  __syncwarp();
 
   const StripPlan P = plan_strips(n - 1, K);
   int32_t row_start = 1;
@@ -84,17 +91,30 @@ __device__ __forceinline__ void run_task(const VitConsts& C, const DevBatch& B, 
     lane_geometry(K, lane, rows, row_start, i0, nrows, t_last);
     S.t_last = t_last;
     lane_stream_reset<K>(LS, C, S, lane, i0, nrows, T.read_begin);
+    // boundary window: positions [0,32) -> bnd[0], positions [32,64) prefetched into registers
+    S.bnd[lane] = sxy[lane];
+    XY nxt = sxy[32 + lane];
+    __syncwarp();
     const uint32_t nsteps = S.Q + (uint32_t)t_last;
-    for (uint32_t step = 0; step < nsteps; ++step) {
-      const double rx = __shfl_up_sync(kFullMask, LS.L.Xout, 1);
-      const double ry = __shfl_up_sync(kFullMask, LS.L.Yout, 1);
-      const uint32_t rb = __shfl_up_sync(kFullMask, LS.L.Bout, 1);
-      const uint32_t pos = step - (uint32_t)lane;
-      if (pos < S.Q)
-        lane_stream_step<K, MODE>(LS, C, S, lane, pos, (step & kCheckMask) == 0u, rx, ry, rb);
+    uint32_t step = 0;
+    while (step < nsteps) {
+      const uint32_t chunk_end = (step + 32u < nsteps) ? step + 32u : nsteps;
+      for (; step < chunk_end; ++step) {
+        const double rx = __shfl_up_sync(kFullMask, LS.L.Xout, 1);
+        const double ry = __shfl_up_sync(kFullMask, LS.L.Yout, 1);
+        const uint32_t rb = __shfl_up_sync(kFullMask, LS.L.Bout, 1);
+        const uint32_t pos = step - (uint32_t)lane;
+        if (pos < S.Q)
+          lane_stream_step<K, MODE>(LS, C, S, lane, pos, (step & kCheckMask) == 0u, rx, ry, rb);
+      }
+      if (step < nsteps) {  // next window of the scratch line: positions [step, step+32)
+        S.bnd[((step >> 5) & 1u) * 32u + lane] = nxt;
+        nxt = sxy[step + 32u + lane];
+        __syncwarp();
+      }
     }
     row_start += rows;
-    __syncwarp();  // strip hand-off through global scratch: order lane 31's stores before lane 0's loads
+    __syncwarp();  // strip hand-off through the scratch line: order the last lane's stores before lane 0's loads
   }
 }
 
@@ -104,15 +124,15 @@ template <int K, int MODE>
 __global__ void __launch_bounds__(kBlockThreads)
 viterbi_stream_kernel(const VitConsts C, const DevBatch B, const Task* __restrict__ tasks,
                       const uint32_t* __restrict__ ntasks_ptr, uint32_t task_cap, uint32_t* cursor,
-                      const FailSink fail, double* scratch_x, double* scratch_y, uint32_t* scratch_b,
-                      uint32_t scratch_stride) {
+                      const FailSink fail, XY* scratch_xy, uint32_t* scratch_b, uint32_t scratch_stride) {
+  extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31;
   const uint32_t warp_global = (blockIdx.x * (uint32_t)blockDim.x + threadIdx.x) >> 5;
   uint32_t ntasks = *ntasks_ptr;
   if (ntasks > task_cap) ntasks = task_cap;
-  double* sx = scratch_x ? scratch_x + (size_t)warp_global * scratch_stride : nullptr;
-  double* sy = scratch_y ? scratch_y + (size_t)warp_global * scratch_stride : nullptr;
-  uint32_t* sb = scratch_b ? scratch_b + (size_t)warp_global * scratch_stride : nullptr;
+  XY* sxy = scratch_xy + (size_t)warp_global * scratch_stride;
+  uint32_t* sb = scratch_b + (size_t)warp_global * scratch_stride;
+  unsigned char* wsmem = smem + (size_t)(threadIdx.x >> 5) * warp_smem_bytes(K);
   while (true) {
     uint32_t ti = 0;
     if (lane == 0) ti = atomicAdd(cursor, 1u);
@@ -122,13 +142,13 @@ viterbi_stream_kernel(const VitConsts C, const DevBatch B, const Task* __restric
     T.hap = tasks[ti].hap;
     T.read_begin = tasks[ti].read_begin;
     T.read_end = tasks[ti].read_end;
-    run_task<K, MODE>(C, B, T, fail, sx, sy, sb, lane);
+    run_task<K, MODE>(C, B, T, fail, sxy, sb, wsmem, lane);
   }
 }
 
 // ------------------------------------------------------------------------------------------
 typedef void (*VitKernel)(const VitConsts, const DevBatch, const Task*, const uint32_t*, uint32_t,
-                          uint32_t*, const FailSink, double*, double*, uint32_t*, uint32_t);
+                          uint32_t*, const FailSink, XY*, uint32_t*, uint32_t);
 
 template <int MODE>
 static VitKernel kernel_for(int k) {
@@ -145,22 +165,29 @@ int viterbi_max_rows_per_lane() { return 16; }
 
 int viterbi_block_threads() { return kBlockThreads; }
 
+static size_t block_smem_bytes(int k) { return (size_t)(kBlockThreads / 32) * warp_smem_bytes(k); }
+
 int viterbi_blocks_per_sm(int k, int mode) {
   VitKernel f = (mode == MODE_FAST) ? kernel_for<MODE_FAST>(k) : kernel_for<MODE_FULL>(k);
   if (!f) return 0;
+  const size_t smem = block_smem_bytes(k);
+  if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
   int nb = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f, kBlockThreads, 0) != cudaSuccess) return 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f, kBlockThreads, smem) != cudaSuccess) return 0;
   return nb;
 }
 
+// Scratch entries a warp needs for a stream of q bytes (window prefetch reads ahead of the stream).
+uint32_t viterbi_scratch_entries(uint32_t q) { return q + 128u; }
+
 cudaError_t launch_viterbi(int k, int mode, int grid_blocks, cudaStream_t stream, const VitConsts& C,
                            const DevBatch& B, const Task* tasks, const uint32_t* ntasks_ptr,
-                           uint32_t task_cap, uint32_t* cursor, const FailSink& fail, double* sx,
-                           double* sy, uint32_t* sb, uint32_t scratch_stride) {
+                           uint32_t task_cap, uint32_t* cursor, const FailSink& fail, XY* sxy,
+                           uint32_t* sb, uint32_t scratch_stride) {
   VitKernel f = (mode == MODE_FAST) ? kernel_for<MODE_FAST>(k) : kernel_for<MODE_FULL>(k);
   if (!f) return cudaErrorInvalidValue;
-  f<<<grid_blocks, kBlockThreads, 0, stream>>>(C, B, tasks, ntasks_ptr, task_cap, cursor, fail, sx, sy,
-                                               sb, scratch_stride);
+  f<<<grid_blocks, kBlockThreads, block_smem_bytes(k), stream>>>(C, B, tasks, ntasks_ptr, task_cap, cursor,
+                                                                 fail, sxy, sb, scratch_stride);
   return cudaGetLastError();
 }
 

@@ -11,9 +11,14 @@
 
 using namespace ltr;
 
+struct EmuScratch {
+  std::vector<XY> sxy;
+  std::vector<uint32_t> sb;
+  std::vector<unsigned char> smem;
+};
+
 template <int K, int MODE>
-static void emu_task(const VitConsts& C, const DevBatch& B, const Task& T, FailSink fail,
-                     std::vector<double>& sx, std::vector<double>& sy, std::vector<uint32_t>& sb) {
+static void emu_task(const VitConsts& C, const DevBatch& B, const Task& T, FailSink fail, EmuScratch& E) {
   const uint32_t g = T.hap;
   const uint32_t hoff = B.hap_off[g];
   const int32_t hlen = (int32_t)(B.hap_off[g + 1] - hoff);
@@ -46,8 +51,15 @@ static void emu_task(const VitConsts& C, const DevBatch& B, const Task& T, FailS
   S.Q = B.read_off[T.read_end] - S.qs;
   S.n = n; S.h0 = hap[0];
   S.fail = fail;
-  sx.assign(S.Q, 0.0); sy.assign(S.Q, 0.0); sb.assign(S.Q, 0);
-  S.sx = sx.data(); S.sy = sy.data(); S.sb = sb.data();
+  E.sxy.assign(S.Q + 128, XY());
+  E.sb.assign(S.Q + 128, 0);
+  E.smem.assign(warp_smem_bytes(K), 0);
+  S.sxy = E.sxy.data(); S.sb = E.sb.data();
+  S.bnd = reinterpret_cast<XY*>(E.smem.data());
+  S.tx = reinterpret_cast<double*>(E.smem.data() + 2 * 32 * sizeof(XY));
+  S.tz = S.tx + 2 * K * 32;
+  S.txo = S.tz + 2 * K * 32;
+  for (int t = 0; t < 32; ++t) prepass_boundary(C, S, t, T.read_begin, T.read_end);
   const StripPlan P = plan_strips(n - 1, K);
   int32_t row_start = 1;
   std::vector<LaneStream<K>> lanes(32);
@@ -61,9 +73,13 @@ static void emu_task(const VitConsts& C, const DevBatch& B, const Task& T, FailS
       S.t_last = tl;
       lane_stream_reset<K>(lanes[t], C, S, t, i0, nrows, T.read_begin);
     }
+    std::vector<XY> nxt(32);
+    for (int t = 0; t < 32; ++t) { S.bnd[t] = S.sxy[t]; nxt[t] = S.sxy[32 + t]; }
     std::vector<double> ox(32), oy(32);
     std::vector<uint32_t> ob(32);
     for (uint32_t step = 0; step < S.Q + (uint32_t)S.t_last; ++step) {
+      if ((step & 31u) == 0u && step != 0u)
+        for (int t = 0; t < 32; ++t) { S.bnd[((step >> 5) & 1u) * 32u + t] = nxt[t]; nxt[t] = S.sxy[step + 32u + t]; }
       for (int t = 0; t < 32; ++t) { ox[t] = lanes[t].L.Xout; oy[t] = lanes[t].L.Yout; ob[t] = lanes[t].L.Bout; }
       const bool check = (step & 3u) == 0u;
       for (int t = 0; t < 32; ++t) {
@@ -81,9 +97,9 @@ static void emu_task(const VitConsts& C, const DevBatch& B, const Task& T, FailS
 
 template <int MODE>
 static void emu_dispatch(int k, const VitConsts& C, const DevBatch& B, const Task& T, FailSink fail,
-                         std::vector<double>& sx, std::vector<double>& sy, std::vector<uint32_t>& sb) {
+                         EmuScratch& E) {
   switch (k) {
-#define CASE(KK) case KK: emu_task<KK, MODE>(C, B, T, fail, sx, sy, sb); break;
+#define CASE(KK) case KK: emu_task<KK, MODE>(C, B, T, fail, E); break;
     CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
     CASE(9) CASE(10) CASE(11) CASE(12) CASE(13) CASE(14) CASE(15) CASE(16)
 #undef CASE
@@ -109,8 +125,7 @@ extern "C" int ltr_emu_viterbi_batch(const ltr_viterbi_batch* b, const ltr_param
   B.read_bytes = rbytes.data(); B.read_off = b->read_off;
   B.locus_hap_begin = b->locus_hap_begin; B.locus_read_begin = b->locus_read_begin;
   B.ll_off = plan.ll_off.data(); B.out_ll = out_ll;
-  std::vector<double> sx, sy;
-  std::vector<uint32_t> sb;
+  EmuScratch E;
   uint64_t nfall = 0;
   for (int k = 1; k <= kmax; ++k) {
     std::vector<Task> fails(plan.n_pairs + 1);
@@ -118,13 +133,13 @@ extern "C" int ltr_emu_viterbi_batch(const ltr_viterbi_batch* b, const ltr_param
     FailSink sink;
     sink.items = fails.data(); sink.count = &nfail; sink.capacity = (uint32_t)fails.size();
     for (const Task& T : plan.tasks[k]) {
-      if (use_fast) emu_dispatch<MODE_FAST>(k, hc.C, B, T, sink, sx, sy, sb);
-      else emu_dispatch<MODE_FULL>(k, hc.C, B, T, sink, sx, sy, sb);
+      if (use_fast) emu_dispatch<MODE_FAST>(k, hc.C, B, T, sink, E);
+      else emu_dispatch<MODE_FULL>(k, hc.C, B, T, sink, E);
     }
     nfall += nfail;
     FailSink none; uint32_t zero = 0;
     none.items = nullptr; none.count = &zero; none.capacity = 0;
-    for (uint32_t f = 0; f < nfail; ++f) emu_dispatch<MODE_FULL>(k, hc.C, B, fails[f], none, sx, sy, sb);
+    for (uint32_t f = 0; f < nfail; ++f) emu_dispatch<MODE_FULL>(k, hc.C, B, fails[f], none, E);
   }
   if (n_fallback) *n_fallback = nfall;
   return LTR_OK;
