@@ -121,7 +121,7 @@ __device__ __forceinline__ void run_task(const VitConsts& C, const DevBatch& B, 
 // ctrl[0] = task cursor, ctrl[1] = number of tasks (for MODE_FULL: the fail count written by
 // the MODE_FAST launch that ran before on the same stream).
 template <int K, int MODE>
-__global__ void __launch_bounds__(kBlockThreads)
+__global__ void __launch_bounds__(kBlockThreads, (K <= 10 ? 4 : (K <= 12 ? 3 : 2)))
 viterbi_stream_kernel(const VitConsts C, const DevBatch B, const Task* __restrict__ tasks,
                       const uint32_t* __restrict__ ntasks_ptr, uint32_t task_cap, uint32_t* cursor,
                       const FailSink fail, XY* scratch_xy, uint32_t* scratch_b, uint32_t scratch_stride) {
