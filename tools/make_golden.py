@@ -1,0 +1,153 @@
+#!/usr/bin/env python
+"""Generates tests/golden/*.json from the UNMODIFIED reference sources (oracle/_ref).
+
+Run in the build container (needs /root/reference to build oracle/_ref):
+
+    python tools/make_golden.py
+
+The reference ships no golden vectors for this path, so the fixtures are
+outputs of the reference's own HapAligner::process_reads / Genotyper::calc_log_sample_posteriors
+on seeded inputs.  Doubles are stored as C99 hex-float strings (bit exact).  The inputs are stored
+next to the outputs so the fixtures can be replayed anywhere (GPU box included) without the
+reference tree.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import synth  # noqa: E402
+from longtr_b200.flat import make_flat_locus  # noqa: E402
+from oracle import pyoracle as po  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+ONT = (-1.0, -0.458675, -1.0, -0.458675, -0.0202027, -4.60517, -4.60517)
+ODD = (-0.7, -0.61, -0.35, -1.3, -0.013, -3.9, -4.4)
+
+
+def hexf(a):
+    return [float(x).hex() for x in np.asarray(a, dtype=np.float64).ravel()]
+
+
+def appendix_a():
+    """SURVEY.md Appendix A1-A3 inputs."""
+    lf = "GATTACAGGCTTAACGTGCATCGATCGGATCCATG"
+    rf = "TTGACCGTAGGCTAATCGGATATCGCGTATAGCCA"
+    pr = "GGTCT"
+    out = []
+    pl = "CTGAA"
+    alleles = [pl + "AC" * 10 + pr, pl + "AC" * 8 + pr, pl + "AC" * 12 + pr]
+    seq = "T" * 50 + lf + pl + "AC" * 12 + pr + rf + "G" * 50
+    out.append(dict(name="A1", lflank=lf, rflank=rf, alleles=alleles, repeat_start=1035, repeat_end=1065,
+                    period=2, motif="AC", switch=0, aln_params=None,
+                    reads=[dict(start=950, stop=1149, seq=seq, qual="I" * len(seq), cigar="110=4I90=")]))
+    pl = "CTGAC"
+    alleles = [pl + "A" * 12 + pr, pl + "A" * 11 + pr, pl + "A" * 13 + pr]
+    seq = "T" * 50 + lf + pl + "A" * 13 + pr + rf + "G" * 50
+    for name, sw in (("A2", 0), ("A3", 20)):
+        out.append(dict(name=name, lflank=lf, rflank=rf, alleles=alleles, repeat_start=1035, repeat_end=1057,
+                        period=1, motif="A", switch=sw, aln_params=None,
+                        reads=[dict(start=950, stop=1141, seq=seq, qual="?" * len(seq), cigar="102=1I90=")]))
+    return out
+
+
+def run_ref(case):
+    reads = [(r["start"], r["stop"], r["seq"], r["qual"], r["cigar"]) for r in case["reads"]]
+    L, keep = make_flat_locus(case["lflank"], case["alleles"], case["rflank"], case["repeat_start"],
+                              case["repeat_end"], case["period"], reads, motif=case["motif"],
+                              switch_old_align_len=case["switch"], aln_params=case["aln_params"],
+                              realign_to_hap=case.get("realign_to_hap"), realign_read=case.get("realign_read"))
+    ll, seeds, _ = po.process_reads(L, len(reads), len(case["alleles"]), fill=case.get("fill", 0.0), which="ref")
+    case["ll"] = hexf(ll)
+    case["seeds"] = [int(s) for s in seeds]
+    return case
+
+
+def long_path_cases():
+    cases = []
+    for seed in range(40):
+        kw = dict(n_reads=8)
+        params = None
+        if seed % 4 == 1:
+            kw.update(sub=0.01, indel=0.02)
+            params = ONT
+        if seed % 4 == 2:
+            kw.update(ref_len=int(150 + 10 * seed), n_reads=5)
+        if seed % 4 == 3:
+            params = ODD
+            kw.update(sub=0.03, indel=0.03)
+        if seed % 10 == 9:
+            kw.update(homopolymer=True)
+        loc = synth.make_locus(1000 + seed, **kw)
+        case = dict(name="long%02d" % seed, lflank=loc["lflank"], rflank=loc["rflank"], alleles=loc["alleles"],
+                    repeat_start=loc["repeat_start"], repeat_end=loc["repeat_end"], period=loc["period"],
+                    motif=loc["motif"], switch=0, aln_params=list(params) if params else None, reads=loc["reads"])
+        if seed % 7 == 3:
+            rng = np.random.default_rng(seed)
+            case["realign_to_hap"] = [bool(x) for x in (rng.random(len(loc["alleles"])) < 0.7)]
+            case["realign_read"] = [bool(x) for x in (rng.random(len(loc["reads"])) < 0.7)]
+            case["fill"] = 7.25
+        cases.append(run_ref(case))
+    return cases
+
+
+def posterior_cases():
+    rng = np.random.default_rng(20260117)
+    out = []
+    for t in range(24):
+        S, H = int(rng.integers(1, 4)), int(rng.integers(1, 9))
+        haploid = (t % 5 == 0)
+        rps = rng.integers(1, 15, size=S)
+        lab = np.repeat(np.arange(S), rps).astype(np.int32)
+        R = len(lab)
+        ll = -rng.exponential(20, size=(R, H))
+        ll[rng.random((R, H)) < 0.05] = -700
+        ll[rng.random((R, H)) < 0.02] = -1e9
+        hp = rng.integers(0, 3, size=R)
+        p1 = np.where(hp == 0, -1e-6, np.where(hp == 1, -1000.0, 0.0))
+        p2 = np.where(hp == 0, -1000.0, np.where(hp == 1, -1e-6, 0.0))
+        cl, post, tot, total, best = po.log_sample_posteriors(ll, p1, p2, lab, S, haploid=haploid, which="ref")
+        out.append(dict(name="post%02d" % t, S=S, H=H, haploid=haploid, label=[int(x) for x in lab], ll=hexf(ll),
+                        log_p1=hexf(p1), log_p2=hexf(p2), ll_clamped=hexf(cl), post=hexf(post), totals=hexf(tot),
+                        total=float(total).hex(), best=[int(x) for x in best.ravel()]))
+    return out
+
+
+def pair_batch_cases():
+    """Kernel-level batches (full haplotypes + trimmed reads) through the reference classes."""
+    out = []
+    for seed, kw, params in ((11, dict(n_loci=12, n_lo=20, n_hi=160, flank=30, weird=0.0), None),
+                             (12, dict(n_loci=8, n_lo=100, n_hi=420, flank=30, weird=0.0, sub=0.02, indel=0.03), ONT),
+                             (13, dict(n_loci=10, n_lo=20, n_hi=90, flank=30, weird=0.0, sub=0.05, indel=0.05), ODD)):
+        b = synth.make_pair_batch(seed, **kw)
+        # the reference driver needs reads >= 11 bp and haplotypes with 35 bp flanks (synth flank=30 -> 35)
+        ll, _sec = po.ref_viterbi_batch(b, params, n_threads=4)
+        out.append(dict(name="pairs%d" % seed, aln_params=list(params) if params else None,
+                        locus_hap_begin=[int(x) for x in b["locus_hap_begin"]],
+                        locus_read_begin=[int(x) for x in b["locus_read_begin"]],
+                        haps=b["haps"], reads=b["reads"], ll=hexf(ll)))
+    return out
+
+
+def main():
+    if not po.ref_available():
+        raise SystemExit("oracle/_ref is not built (needs /root/reference)")
+    os.makedirs(GOLD, exist_ok=True)
+    sets = dict(appendix_a=[run_ref(c) for c in appendix_a()], process_reads_long=long_path_cases(),
+                posteriors=posterior_cases(), pair_batches=pair_batch_cases())
+    for name, cases in sets.items():
+        path = os.path.join(GOLD, name + ".json")
+        with open(path, "w") as f:
+            json.dump(dict(generator="tools/make_golden.py", source="oracle/_ref (reference sources compiled in place)",
+                           cases=cases), f, indent=0, separators=(",", ":"))
+        print(path, len(cases), "cases", os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()
