@@ -142,6 +142,42 @@ void ltr_job_destroy(ltr_ctx* ctx, ltr_job* job);
 int ltr_process_reads_flat(ltr_ctx* ctx, const ltr_flat_locus* locus, double* out_ll,
                            int32_t* out_seeds);
 
+/* Genotype calls of one locus from its read x haplotype LL matrix: what SeqStutterGenotyper::genotype +
+ * write_vcf_record obtain from Genotyper::calc_log_sample_posteriors (GPU) followed by
+ * Genotyper::extract_genotypes_and_likelihoods (src/genotyper.cpp:132-256; host, integer / small vectors)
+ * with hap_to_allele = identity (one multi-allele block).  Reads are sample-major: sample s owns
+ * reads_per_sample[s] consecutive rows of ll / log_p1 / log_p2.  ll is clamped in place (genotyper.cpp:57-58).
+ * Output arrays may be NULL.  n_gl = H(H+1)/2 (haploid: H), n_pgl = H*H (haploid: H).                      */
+typedef struct ltr_locus_calls {
+  int32_t* best_gts;                   /* [2*S]  allele pair per sample (GT)                 */
+  double* log_phased_posteriors;       /* [S]    -> PQ = exp(.)                              */
+  double* log_unphased_posteriors;     /* [S]    -> Q  = exp(.)                              */
+  double* hap_log_phased_posteriors;   /* [S]                                                */
+  double* hap_log_unphased_posteriors; /* [S]                                                */
+  double* gls;                         /* [S*n_gl]  log10 genotype likelihoods (GL)          */
+  int32_t* pls;                        /* [S*n_gl]  PL                                       */
+  double* phased_gls;                  /* [S*n_pgl] PHASEDGL                                 */
+  double* gl_diffs;                    /* [S]    GLDIFF                                      */
+  double* sample_total_lls;            /* [S]                                                */
+  double* log_sample_posteriors;       /* [S*H*H]                                            */
+  double total_ll;
+} ltr_locus_calls;
+int ltr_genotype_locus(ltr_ctx* ctx, int haploid, int32_t n_samples, const int32_t* reads_per_sample,
+                       int32_t n_alleles, double* ll, const double* log_p1, const double* log_p2,
+                       ltr_locus_calls* out);
+/* The host half of the above on posteriors that are already computed (no GPU involved). */
+int ltr_extract_calls(int haploid, int32_t n_samples, int32_t n_alleles, const double* post, const double* totals,
+                      ltr_locus_calls* out);
+
+/* Host-only pieces of HapAligner on a flat locus (integer work, no GPU involved):
+ * ltr_trim_read_flat  = HapAligner::trim_alignment (HapAligner.cpp:346-465): writes the NUL-terminated trimmed
+ *                       read into out[cap] and returns its length (0 = the caller substitutes the 10 bp
+ *                       pseudo read of HapAligner.cpp:820-823), negative = error;
+ * ltr_seed_base_flat  = HapAligner::calc_seed_base (HapAligner.cpp:493-542): seed index or -1 (none);
+ *                       LTR_ERR_INVALID for a CIGAR operation the reference dies on.                       */
+int32_t ltr_trim_read_flat(const ltr_flat_locus* locus, int32_t read_index, char* out, int32_t cap);
+int32_t ltr_seed_base_flat(const ltr_flat_locus* locus, int32_t read_index);
+
 /* ---- diagnostics --------------------------------------------------------------------- */
 /* Sustained FP64-pipe issue rate of the device in lane-operations per second (the roofline
  * denominator of SURVEY.md section 8d): kind 0 = DADD, 1 = DSETP, 2 = the DADD,DADD,DSETP,

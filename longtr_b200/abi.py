@@ -46,6 +46,28 @@ class JobStats(C.Structure):
                 ("kernel_ms", C.c_float), ("viterbi_ms", C.c_float)]
 
 
+class LocusCalls(C.Structure):
+    """ltr_locus_calls (include/longtr_b200.h)."""
+    _fields_ = [("best_gts", _i32p), ("log_phased_posteriors", _dp), ("log_unphased_posteriors", _dp),
+                ("hap_log_phased_posteriors", _dp), ("hap_log_unphased_posteriors", _dp), ("gls", _dp),
+                ("pls", _i32p), ("phased_gls", _dp), ("gl_diffs", _dp), ("sample_total_lls", _dp),
+                ("log_sample_posteriors", _dp), ("total_ll", C.c_double)]
+
+
+def make_locus_calls(S, H, haploid):
+    """Allocates every output array of ltr_locus_calls; returns (struct, dict of numpy arrays)."""
+    n_gl = H if haploid else H * (H + 1) // 2
+    n_pgl = H if haploid else H * H
+    a = dict(best_gts=np.zeros((S, 2), np.int32), log_phased_posteriors=np.zeros(S), log_unphased_posteriors=np.zeros(S),
+             hap_log_phased_posteriors=np.zeros(S), hap_log_unphased_posteriors=np.zeros(S), gls=np.zeros((S, n_gl)),
+             pls=np.zeros((S, n_gl), np.int32), phased_gls=np.zeros((S, n_pgl)), gl_diffs=np.zeros(S),
+             sample_total_lls=np.zeros(S), log_sample_posteriors=np.zeros((S, H, H)))
+    c = LocusCalls()
+    for k, v in a.items():
+        setattr(c, k, v.ctypes.data_as(_i32p if v.dtype == np.int32 else _dp))
+    return c, a
+
+
 DEFAULT_ALN_PARAMS = (-1.0, -0.458675, -1.0, -0.458675, -0.00005800168, -10.448214728, -10.448214728)
 
 
@@ -148,6 +170,14 @@ def load():
     lib.ltr_job_destroy.argtypes = [vp, vp]
     lib.ltr_process_reads_flat.argtypes = [vp, C.POINTER(FlatLocus), _dp, _i32p]
     lib.ltr_process_reads_flat.restype = C.c_int
+    lib.ltr_genotype_locus.argtypes = [vp, C.c_int, C.c_int32, _i32p, C.c_int32, _dp, _dp, _dp, C.POINTER(LocusCalls)]
+    lib.ltr_genotype_locus.restype = C.c_int
+    lib.ltr_extract_calls.argtypes = [C.c_int, C.c_int32, C.c_int32, _dp, _dp, C.POINTER(LocusCalls)]
+    lib.ltr_extract_calls.restype = C.c_int
+    lib.ltr_trim_read_flat.argtypes = [C.POINTER(FlatLocus), C.c_int32, C.c_char_p, C.c_int32]
+    lib.ltr_trim_read_flat.restype = C.c_int32
+    lib.ltr_seed_base_flat.argtypes = [C.POINTER(FlatLocus), C.c_int32]
+    lib.ltr_seed_base_flat.restype = C.c_int32
     lib.ltr_fp64_issue_rate.argtypes = [C.c_int, C.c_int, _dp, _dp]
     lib.ltr_fp64_issue_rate.restype = C.c_int
     _lib = lib
@@ -158,5 +188,33 @@ EXPORTED_SYMBOLS = [
     "ltr_params_default", "ltr_ctx_create", "ltr_ctx_destroy", "ltr_strerror", "ltr_last_error",
     "ltr_version", "ltr_viterbi_ll", "ltr_posteriors", "ltr_job_create", "ltr_job_run", "ltr_job_sizes",
     "ltr_job_download", "ltr_job_get_stats", "ltr_job_destroy", "ltr_process_reads_flat",
-    "ltr_fp64_issue_rate",
+    "ltr_fp64_issue_rate", "ltr_genotype_locus", "ltr_extract_calls", "ltr_trim_read_flat", "ltr_seed_base_flat",
 ]
+
+
+def extract_calls(post, totals, haploid=False):
+    """Host-only genotype extraction (Genotyper::extract_genotypes_and_likelihoods) on given posteriors."""
+    lib = load()
+    post = np.ascontiguousarray(post, dtype=np.float64)
+    totals = np.ascontiguousarray(totals, dtype=np.float64)
+    S, H = post.shape[0], post.shape[1]
+    c, arrays = make_locus_calls(S, H, haploid)
+    rc = lib.ltr_extract_calls(int(haploid), S, H, ptr(post, _dp), ptr(totals, _dp), C.byref(c))
+    if rc != LTR_OK:
+        raise RuntimeError("ltr_extract_calls failed: %d" % rc)
+    arrays["total_ll"] = c.total_ll
+    return arrays
+
+
+def trim_read(locus, read_index):
+    lib = load()
+    n = len(locus.reads[read_index].seq)
+    buf = C.create_string_buffer(n + 16)
+    k = lib.ltr_trim_read_flat(C.byref(locus), read_index, buf, n + 16)
+    if k < 0:
+        raise RuntimeError("ltr_trim_read_flat failed: %d" % k)
+    return buf.value[:k]
+
+
+def seed_base(locus, read_index):
+    return load().ltr_seed_base_flat(C.byref(locus), read_index)

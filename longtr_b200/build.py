@@ -17,7 +17,8 @@ OUT = os.path.join(CSRC, "liblongtr_b200.so")
 OBJ = os.path.join(CSRC, "build")
 
 CU_SOURCES = ["viterbi_kernels.cu", "posterior_kernel.cu", "abi.cu", "microbench.cu"]
-CPP_SOURCES = ["host/flat_api.cpp", "synth.cpp"]
+CPP_SOURCES = ["host/flat_api.cpp", "host/host_types.cpp", "host/hap_aligner.cpp", "host/stutter_host.cpp",
+               "host/genotyper.cpp", "synth.cpp"]
 HEADERS = ["viterbi_core.cuh", "viterbi_host.h", "kernels.h"]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -114,6 +114,21 @@ class Engine:
         _check(self.lib, self.ctx, rc, "ltr_posteriors")
         return ll, post, tot, total.value
 
+    # -- posteriors (GPU) + Genotyper::extract_genotypes_and_likelihoods (host) for one locus ----------
+    def genotype_locus(self, ll, log_p1, log_p2, reads_per_sample, haploid=False):
+        ll = np.array(ll, dtype=np.float64, order="C", copy=True)
+        R, H = ll.shape
+        rps = np.ascontiguousarray(reads_per_sample, dtype=np.int32)
+        p1 = np.ascontiguousarray(log_p1, dtype=np.float64)
+        p2 = np.ascontiguousarray(log_p2, dtype=np.float64)
+        c, arrays = abi.make_locus_calls(len(rps), H, haploid)
+        rc = self.lib.ltr_genotype_locus(self.ctx, int(haploid), len(rps), abi.ptr(rps, abi._i32p), H,
+                                         abi.ptr(ll, abi._dp), abi.ptr(p1, abi._dp), abi.ptr(p2, abi._dp), C.byref(c))
+        _check(self.lib, self.ctx, rc, "ltr_genotype_locus")
+        arrays["total_ll"] = c.total_ll
+        arrays["ll_clamped"] = ll
+        return arrays
+
     def create_job(self, batch, post=None, aln_params=None, indel_flank_len=5):
         vb, keep = abi.make_viterbi_batch(batch)
         p = abi.make_params(aln_params, indel_flank_len)

@@ -91,8 +91,40 @@ def ref_lib():
         lib.ltr_ref_viterbi_batch.argtypes = [C.c_uint32, _u32p, _u32p, _u32p, _u8p, _u32p, _u8p, C.c_int,
                                               C.POINTER(C.c_float), C.c_int, _dp, _dp,
                                               _u32p, _u32p, _dp, _dp, _dp]
+        from longtr_b200.abi import LocusCalls
+        lib.ltr_ref_genotype_locus.restype = C.c_int
+        lib.ltr_ref_genotype_locus.argtypes = [C.c_int, C.c_int, _ip, C.c_int, _dp, _dp, _dp, _dp, C.POINTER(LocusCalls)]
+        lib.ltr_ref_seed_bases.restype = C.c_int
+        lib.ltr_ref_seed_bases.argtypes = [C.POINTER(FlatLocus), _ip]
         _ref = lib
     return _ref
+
+
+def ref_genotype_locus(ll, log_p1, log_p2, reads_per_sample, haploid=False):
+    """Reference calc_log_sample_posteriors + extract_genotypes_and_likelihoods (hap_to_allele = identity)."""
+    from longtr_b200.abi import make_locus_calls
+    ll = np.ascontiguousarray(ll, dtype=np.float64)
+    R, H = ll.shape
+    rps = np.ascontiguousarray(reads_per_sample, dtype=np.int32)
+    p1 = np.ascontiguousarray(log_p1, dtype=np.float64)
+    p2 = np.ascontiguousarray(log_p2, dtype=np.float64)
+    out_ll = np.zeros_like(ll)
+    c, arrays = make_locus_calls(len(rps), H, haploid)
+    rc = ref_lib().ltr_ref_genotype_locus(int(haploid), len(rps), _ptr(rps, _ip), H, _ptr(ll, _dp), _ptr(p1, _dp),
+                                          _ptr(p2, _dp), _ptr(out_ll, _dp), C.byref(c))
+    if rc != 0:
+        raise RuntimeError("ltr_ref_genotype_locus failed rc=%d" % rc)
+    arrays["total_ll"] = c.total_ll
+    arrays["ll_clamped"] = out_ll
+    return arrays
+
+
+def ref_seed_bases(locus, n_reads):
+    seeds = np.zeros(n_reads, dtype=np.int32)
+    rc = ref_lib().ltr_ref_seed_bases(C.byref(locus), _ptr(seeds, _ip))
+    if rc != 0:
+        raise RuntimeError("ltr_ref_seed_bases failed")
+    return seeds
 
 
 def make_params(aln_params=None, indel_flank_len=5):

@@ -27,6 +27,7 @@
 #include "mathops.h"
 #include "stutter_model.h"
 
+#include "longtr_b200.h"
 #include "longtr_b200_locus.h"
 
 namespace {
@@ -78,6 +79,36 @@ class PosteriorProbe : public Genotyper {
       }
     }
     return total;
+  }
+  // Genotyper::extract_genotypes_and_likelihoods (src/genotyper.cpp:132-256) with hap_to_allele = identity
+  int calls(int haploid, double total, ltr_locus_calls* out) {
+    const int S = num_samples_, H = num_alleles_;
+    std::vector<int> hap_to_allele(H);
+    for (int a = 0; a < H; ++a) hap_to_allele[a] = a;
+    std::vector<std::pair<int, int> > best_haps, best_gts;
+    std::vector<double> lpp, lup, hlpp, hlup, gl_diffs;
+    std::vector<std::vector<double> > gls, pgls;
+    std::vector<std::vector<int> > pls;
+    extract_genotypes_and_likelihoods(H, hap_to_allele, best_haps, best_gts, lpp, lup, hlpp, hlup, true, gls, gl_diffs,
+                                      true, pls, true, pgls);
+    const size_t n_gl = haploid ? H : H * (H + 1) / 2, n_pgl = haploid ? H : H * H;
+    out->total_ll = total;
+    for (int s = 0; s < S; ++s) {
+      out->best_gts[2 * s] = best_gts[s].first;
+      out->best_gts[2 * s + 1] = best_gts[s].second;
+      out->log_phased_posteriors[s] = lpp[s];
+      out->log_unphased_posteriors[s] = lup[s];
+      out->hap_log_phased_posteriors[s] = hlpp[s];
+      out->hap_log_unphased_posteriors[s] = hlup[s];
+      out->gl_diffs[s] = gl_diffs[s];
+      out->sample_total_lls[s] = sample_total_LLs_[s];
+      if (gls[s].size() != n_gl || pls[s].size() != n_gl || pgls[s].size() != n_pgl) return -1;
+      std::copy(gls[s].begin(), gls[s].end(), out->gls + s * n_gl);
+      std::copy(pls[s].begin(), pls[s].end(), out->pls + s * n_gl);
+      std::copy(pgls[s].begin(), pgls[s].end(), out->phased_gls + s * n_pgl);
+    }
+    std::memcpy(out->log_sample_posteriors, log_sample_posteriors_, sizeof(double) * S * H * H);
+    return 0;
   }
 };
 
@@ -253,6 +284,58 @@ int ltr_ref_viterbi_batch(uint32_t n_loci, const uint32_t* lhb, const uint32_t* 
   for (int t = 0; t < n_threads; ++t) { if (tsec[t] > mx) mx = tsec[t]; if (trc[t]) rc = trc[t]; }
   if (seconds) *seconds = mx;
   return rc;
+}
+
+// calc_log_sample_posteriors + extract_genotypes_and_likelihoods for one locus (all outputs of
+// ltr_locus_calls must be non-NULL here).
+int ltr_ref_genotype_locus(int haploid, int n_samples, const int32_t* reads_per_sample, int n_alleles,
+                           const double* ll_in, const double* log_p1, const double* log_p2, double* ll_out,
+                           ltr_locus_calls* out) {
+  ensure_tables();
+  std::vector<std::string> names;
+  std::vector<std::vector<double> > p1(n_samples), p2(n_samples);
+  int idx = 0;
+  for (int s = 0; s < n_samples; ++s) {
+    names.push_back("S" + std::to_string(s));
+    for (int r = 0; r < reads_per_sample[s]; ++r, ++idx) {
+      p1[s].push_back(log_p1[idx]);
+      p2[s].push_back(log_p2[idx]);
+    }
+  }
+  PosteriorProbe probe(haploid != 0, names, p1, p2, n_alleles);
+  std::vector<double> post((size_t)n_samples * n_alleles * n_alleles), totals(n_samples);
+  const double total = probe.run(ll_in, ll_out, post.data(), totals.data(), NULL);
+  return probe.calls(haploid, total, out);
+}
+
+// HapAligner::calc_seed_base (src/SeqAlignment/HapAligner.cpp:493-542) for every read of a flat locus
+int ltr_ref_seed_bases(const ltr_flat_locus* L, int32_t* out_seeds) {
+  ensure_tables();
+  StutterModel model(L->stutter[0], L->stutter[1], L->stutter[2], L->stutter[3], L->stutter[4], L->stutter[5],
+                     std::string(L->motif));
+  std::string lflank(L->lflank), rflank(L->rflank);
+  std::vector<HapBlock*> blocks;
+  blocks.push_back(new HapBlock(L->repeat_start - (int32_t)lflank.size(), L->repeat_start, lflank));
+  RepeatBlock* rep = new RepeatBlock(L->repeat_start, L->repeat_end, std::string(L->alleles[0]), L->period, &model);
+  for (int a = 1; a < L->n_alleles; ++a)
+    rep->add_alternate(std::pair<std::string, bool>(std::string(L->alleles[a]), false));
+  blocks.push_back(rep);
+  blocks.push_back(new HapBlock(L->repeat_end, L->repeat_end + (int32_t)rflank.size(), rflank));
+  Haplotype* hap = new Haplotype(blocks);
+  std::vector<bool> realign_hap(L->n_alleles, true);
+  std::vector<float> params;
+  {
+    HapAligner aligner(hap, realign_hap, L->indel_flank_len, L->switch_old_align_len, params);
+    for (int r = 0; r < L->n_reads; ++r) {
+      const ltr_flat_read& fr = L->reads[r];
+      Alignment aln(fr.start, fr.stop, false, false, "read", std::string(fr.qual), std::string(fr.seq), std::string(fr.seq));
+      parse_cigar(fr.cigar, aln);
+      out_seeds[r] = aligner.calc_seed_base(aln);
+    }
+  }
+  delete hap;
+  for (size_t i = 0; i < blocks.size(); ++i) delete blocks[i];
+  return 0;
 }
 
 const char* ltr_ref_version(void) { return "LongTR reference sources, compiled in place (oracle/_ref)"; }

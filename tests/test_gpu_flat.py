@@ -1,0 +1,59 @@
+"""GPU parity through the reference-facing entry points: ltr_process_reads_flat (HapAligner::process_reads)
+and ltr_genotype_locus (calc_log_sample_posteriors + extract_genotypes_and_likelihoods) against the values
+recorded from the unmodified reference (tests/golden)."""
+import numpy as np
+import pytest
+
+import golden_util as gu
+import synth
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+
+LONG_CASES = [c for c in gu.load("appendix_a") + gu.load("process_reads_long")
+              if not (c["switch"] != 0 and c["period"] == 1)]
+
+
+@pytest.mark.parametrize("case", LONG_CASES, ids=lambda c: c["name"])
+def test_process_reads_flat_matches_reference(engine, case):
+    L, keep = gu.flat_locus(case)
+    P, H = len(case["reads"]), len(case["alleles"])
+    ll, seeds = engine.process_reads_flat(L, P, H, fill=case.get("fill", 0.0))
+    assert np.array_equal(ll, gu.unhex(case["ll"], (P, H)))  # bit-exact, untouched slots included
+    for r in range(P):
+        if case.get("realign_read") is None or case["realign_read"][r]:
+            assert seeds[r] == case["seeds"][r]
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_process_reads_flat_matches_oracle_on_fresh_loci(engine, seed):
+    loc = synth.make_locus(7000 + seed, n_reads=10, sub=0.01, indel=0.02, ref_len=40 + 25 * seed)
+    L, keep = synth.to_flat(loc)
+    P, H = len(loc["reads"]), len(loc["alleles"])
+    want, wseeds, _ = po.process_reads(L, P, H)
+    got, gseeds = engine.process_reads_flat(L, P, H)
+    assert np.array_equal(got, want)
+    assert np.array_equal(gseeds, wseeds)
+
+
+# posteriors: CUDA exp/log vs glibc (<= 1 ulp each) over sums of <= a few hundred terms
+RTOL, ATOL = 1e-12, 1e-10
+
+
+@pytest.mark.parametrize("case", gu.load("calls"), ids=lambda c: c["name"])
+def test_genotype_locus_matches_reference(engine, case):
+    S, H = case["S"], case["H"]
+    R = sum(case["reads_per_sample"])
+    got = engine.genotype_locus(gu.unhex(case["ll"], (R, H)), gu.unhex(case["log_p1"]), gu.unhex(case["log_p2"]),
+                                case["reads_per_sample"], haploid=case["haploid"])
+    assert np.array_equal(got["ll_clamped"], gu.unhex(case["out_ll_clamped"], (R, H)))
+    assert list(got["best_gts"].ravel()) == case["out_best_gts"]  # GT identical
+    for k in ("log_sample_posteriors", "sample_total_lls", "log_phased_posteriors", "log_unphased_posteriors",
+              "hap_log_phased_posteriors", "gls", "phased_gls", "gl_diffs"):
+        np.testing.assert_allclose(got[k].ravel(), gu.unhex(case["out_" + k]), rtol=RTOL, atol=ATOL, err_msg=k)
+    # the approximate two-argument fast_log_sum_exp is piecewise smooth: same tolerance, looser floor
+    np.testing.assert_allclose(got["hap_log_unphased_posteriors"], gu.unhex(case["out_hap_log_unphased_posteriors"]),
+                               rtol=1e-9, atol=1e-9)
+    # PL = (int)(-10*dGL): an integer boundary can flip on a 1e-12 difference
+    assert np.max(np.abs(got["pls"].ravel() - np.array(case["out_pls"]))) <= 1
+    assert abs(got["total_ll"] - float.fromhex(case["total_ll"])) <= ATOL + RTOL * abs(got["total_ll"])

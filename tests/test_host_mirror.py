@@ -1,0 +1,69 @@
+"""CPU: the host-side (integer / small-vector) half of the drop-in boundary -- no GPU involved.
+trim_alignment, calc_seed_base and extract_genotypes_and_likelihoods of the C++ host mirror
+(longtr_b200/csrc/host) against values recorded from the reference (tests/golden) and the oracle."""
+import numpy as np
+import pytest
+
+import golden_util as gu
+import synth
+from longtr_b200 import abi
+from oracle import pyoracle as po
+
+
+@pytest.mark.parametrize("case", gu.load("appendix_a") + gu.load("process_reads_long"), ids=lambda c: c["name"])
+def test_seed_base_matches_reference(case):
+    L, keep = gu.flat_locus(case)
+    got = [abi.seed_base(L, r) for r in range(len(case["reads"]))]
+    assert got == case["seed_bases"]
+
+
+@pytest.mark.parametrize("case", gu.load("appendix_a") + gu.load("process_reads_long"), ids=lambda c: c["name"])
+def test_trim_matches_oracle(case):
+    L, keep = gu.flat_locus(case)
+    for r in range(len(case["reads"])):
+        want = po.trim_read(L, r)
+        got = abi.trim_read(L, r)
+        if len(got) == 0:  # the oracle helper already substitutes the 10 bp pseudo read
+            got = case["lflank"][-5:].encode() + case["rflank"][:5].encode()
+        assert got == want
+
+
+def test_trim_window_appendix_a():
+    """trimmed read = bases aligned to [block.start-5, block.end+5)."""
+    a1 = [c for c in gu.load("appendix_a") if c["name"] == "A1"][0]
+    L, keep = gu.flat_locus(a1)
+    assert abi.trim_read(L, 0).decode() == a1["lflank"][30:] + "CTGAA" + "AC" * 12 + "GGTCT" + a1["rflank"][:5]
+
+
+@pytest.mark.parametrize("seed", range(30))
+def test_trim_with_indels_near_the_pads(seed):
+    loc = synth.make_locus(9000 + seed, n_reads=6, sub=0.02, indel=0.08, ref_len=30)
+    L, keep = synth.to_flat(loc)
+    for r in range(6):
+        want = po.trim_read(L, r)
+        got = abi.trim_read(L, r)
+        if len(got) == 0:
+            got = loc["lflank"][-5:].encode() + loc["rflank"][:5].encode()
+        assert got == want
+
+
+def test_bad_cigar_is_an_error_not_an_exit():
+    loc = synth.make_locus(1, n_reads=1)
+    loc["reads"][0]["cigar"] = "10Q"
+    L, keep = synth.to_flat(loc)
+    assert abi.load().ltr_seed_base_flat(L, 0) == -3
+    with pytest.raises(RuntimeError):
+        abi.trim_read(L, 0)
+
+
+@pytest.mark.parametrize("case", gu.load("calls"), ids=lambda c: c["name"])
+def test_extract_calls_matches_reference(case):
+    S, H = case["S"], case["H"]
+    post = gu.unhex(case["out_log_sample_posteriors"], (S, H, H))
+    totals = gu.unhex(case["out_sample_total_lls"])
+    got = abi.extract_calls(post, totals, haploid=case["haploid"])
+    assert list(got["best_gts"].ravel()) == case["out_best_gts"]
+    assert list(got["pls"].ravel()) == case["out_pls"]
+    for k in ("log_phased_posteriors", "log_unphased_posteriors", "hap_log_phased_posteriors",
+              "hap_log_unphased_posteriors", "gls", "phased_gls", "gl_diffs"):
+        assert np.array_equal(got[k].ravel(), gu.unhex(case["out_" + k])), k

@@ -66,6 +66,8 @@ def run_ref(case):
     ll, seeds, _ = po.process_reads(L, len(reads), len(case["alleles"]), fill=case.get("fill", 0.0), which="ref")
     case["ll"] = hexf(ll)
     case["seeds"] = [int(s) for s in seeds]
+    # HapAligner::calc_seed_base of every read (used by the homopolymer path; recorded for all loci)
+    case["seed_bases"] = [int(s) for s in po.ref_seed_bases(L, len(reads))]
     return case
 
 
@@ -119,6 +121,35 @@ def posterior_cases():
     return out
 
 
+def calls_cases():
+    """calc_log_sample_posteriors + extract_genotypes_and_likelihoods (GT, Q, PQ, GL, PL, PHASEDGL, GLDIFF)."""
+    rng = np.random.default_rng(20260118)
+    out = []
+    for t in range(30):
+        S, H = int(rng.integers(1, 4)), int(rng.integers(1, 7))
+        haploid = (t % 6 == 0)
+        rps = [int(x) for x in rng.integers(1, 15, size=S)]
+        R = sum(rps)
+        true = rng.integers(0, H, size=(S, 2))
+        lab = np.repeat(np.arange(S), rps)
+        ll = -rng.exponential(25, size=(R, H)) - 5
+        hp = rng.integers(0, 3, size=R)
+        for r in range(R):  # reads support one of the sample's two alleles
+            ll[r, true[lab[r], hp[r] % 2]] = -rng.exponential(0.3)
+        ll[rng.random((R, H)) < 0.03] = -700
+        p1 = np.where(hp == 0, -1e-6, np.where(hp == 1, -1000.0, 0.0))
+        p2 = np.where(hp == 0, -1000.0, np.where(hp == 1, -1e-6, 0.0))
+        ref = po.ref_genotype_locus(ll, p1, p2, rps, haploid=haploid)
+        case = dict(name="calls%02d" % t, S=S, H=H, haploid=haploid, reads_per_sample=rps, ll=hexf(ll),
+                    log_p1=hexf(p1), log_p2=hexf(p2), total_ll=float(ref["total_ll"]).hex())
+        for k, v in ref.items():
+            if k in ("total_ll",):
+                continue
+            case["out_" + k] = [int(x) for x in v.ravel()] if v.dtype == np.int32 else hexf(v)
+        out.append(case)
+    return out
+
+
 def pair_batch_cases():
     """Kernel-level batches (full haplotypes + trimmed reads) through the reference classes."""
     out = []
@@ -140,7 +171,7 @@ def main():
         raise SystemExit("oracle/_ref is not built (needs /root/reference)")
     os.makedirs(GOLD, exist_ok=True)
     sets = dict(appendix_a=[run_ref(c) for c in appendix_a()], process_reads_long=long_path_cases(),
-                posteriors=posterior_cases(), pair_batches=pair_batch_cases())
+                posteriors=posterior_cases(), pair_batches=pair_batch_cases(), calls=calls_cases())
     for name, cases in sets.items():
         path = os.path.join(GOLD, name + ".json")
         with open(path, "w") as f:
