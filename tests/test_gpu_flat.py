@@ -49,11 +49,13 @@ def test_genotype_locus_matches_reference(engine, case):
     assert np.array_equal(got["ll_clamped"], gu.unhex(case["out_ll_clamped"], (R, H)))
     assert list(got["best_gts"].ravel()) == case["out_best_gts"]  # GT identical
     for k in ("log_sample_posteriors", "sample_total_lls", "log_phased_posteriors", "log_unphased_posteriors",
-              "hap_log_phased_posteriors", "gls", "phased_gls", "gl_diffs"):
+              "hap_log_phased_posteriors", "phased_gls"):
         np.testing.assert_allclose(got[k].ravel(), gu.unhex(case["out_" + k]), rtol=RTOL, atol=ATOL, err_msg=k)
-    # the approximate two-argument fast_log_sum_exp is piecewise smooth: same tolerance, looser floor
-    np.testing.assert_allclose(got["hap_log_unphased_posteriors"], gu.unhex(case["out_hap_log_unphased_posteriors"]),
-                               rtol=1e-9, atol=1e-9)
+    # GL / GLDIFF / unphased haplotype posterior go through the reference's approximate two-argument
+    # fast_log_sum_exp (single-precision fastlog(1+fastexp(d)), mathops.cpp:87-96): a 1e-13 change of its
+    # argument can move the result by one float ulp (~6e-8), so the floor is 1e-6 for these fields
+    for k in ("gls", "gl_diffs", "hap_log_unphased_posteriors"):
+        np.testing.assert_allclose(got[k].ravel(), gu.unhex(case["out_" + k]), rtol=1e-9, atol=1e-6, err_msg=k)
     # PL = (int)(-10*dGL): an integer boundary can flip on a 1e-12 difference
     assert np.max(np.abs(got["pls"].ravel() - np.array(case["out_pls"]))) <= 1
     assert abs(got["total_ll"] - float.fromhex(case["total_ll"])) <= ATOL + RTOL * abs(got["total_ll"])
