@@ -229,7 +229,21 @@ int32_t ltr_oracle_trim_read(const ltr_flat_locus* L, int32_t read_index, char* 
  * is simply the allele index.
  * ------------------------------------------------------------------------- */
 int ltr_oracle_process_reads(const ltr_flat_locus* L, double* out_ll, int32_t* out_seeds) {
-  if (L->period == 1 && L->switch_old_align_len != 0) return -2; /* short path: not restated yet */
+  if (L->period == 1 && L->switch_old_align_len != 0) { /* HapAligner.cpp:552, 567-579: homopolymer path */
+    for (int r = 0; r < L->n_reads; ++r) {
+      if (L->realign_read && !L->realign_read[r]) continue;
+      const int32_t seed = ltr_oracle_seed_base(L, r);
+      if (seed == -2) return -1;
+      out_seeds[r] = seed;
+      if (seed == -1) { /* no seed: every haplotype gets LL 0 (:570-574) */
+        for (int a = 0; a < L->n_alleles; ++a) out_ll[(size_t)r * L->n_alleles + a] = 0;
+        continue;
+      }
+      int rc = ltr_oracle_process_read_short(L, r, seed, out_ll + (size_t)r * L->n_alleles);
+      if (rc != 0) return rc;
+    }
+    return 0;
+  }
   ltr_oracle_params p;
   ltr_oracle_default_params(&p);
   if (L->n_aln_params == 7) {

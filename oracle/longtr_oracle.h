@@ -44,9 +44,15 @@ double ltr_oracle_viterbi_pair_cells(const char* full_hap, int32_t hap_len, cons
  * process_read, :820-823).  out must hold strlen(seq)+11 bytes. Returns length. */
 int32_t ltr_oracle_trim_read(const ltr_flat_locus* L, int32_t read_index, char* out);
 
-/* HapAligner::process_reads, HapAligner.cpp:545-581 + process_read :812-991.
- * Returns 0, or -2 if the locus selects the short (stutter) path and that path
- * is not restated in this build.                                                */
+/* HapAligner::calc_seed_base, HapAligner.cpp:467-542: seed index, -1 = none, -2 = bad CIGAR. */
+int32_t ltr_oracle_seed_base(const ltr_flat_locus* L, int32_t read_index);
+
+/* process_read with short_ == 1 (HapAligner.cpp:855-975) for one read with a valid seed: writes
+ * out_row[a] for every allele flagged for realignment (longtr_oracle_short.c).              */
+int ltr_oracle_process_read_short(const ltr_flat_locus* L, int32_t read_index, int32_t seed, double* out_row);
+
+/* HapAligner::process_reads, HapAligner.cpp:545-581 + process_read :812-991 (long path and, for
+ * period-1 loci with switch_old_align_len != 0, the homopolymer path).  Returns 0 on success.  */
 int ltr_oracle_process_reads(const ltr_flat_locus* L, double* out_ll, int32_t* out_seeds);
 
 /* Flattened batch of (trimmed read, full haplotype) loci; same layout as

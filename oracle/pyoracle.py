@@ -28,7 +28,8 @@ class OracleParams(C.Structure):
 def build(force=False):
     """Compile the restatement (and oracle/_ref when /root/reference exists)."""
     if force or not os.path.exists(_ORACLE_SO) or \
-            os.path.getmtime(_ORACLE_SO) < os.path.getmtime(os.path.join(_HERE, "longtr_oracle.c")):
+            os.path.getmtime(_ORACLE_SO) < max(os.path.getmtime(os.path.join(_HERE, f)) for f in
+                                              ("longtr_oracle.c", "longtr_oracle_short.c", "longtr_oracle.h")):
         subprocess.check_call(["make", "-C", _HERE, "liblongtr_oracle.so"], stdout=subprocess.DEVNULL)
     if os.path.isdir(os.environ.get("LONGTR_REFERENCE", "/root/reference") + "/src"):
         if force or not os.path.exists(_REF_SO):

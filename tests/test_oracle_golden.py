@@ -39,6 +39,21 @@ def test_process_reads_matches_reference(case):
                 assert seeds[r] == case["seeds"][r]
 
 
+SHORT_CASES = [c for c in gu.load("appendix_a") if c["switch"] != 0] + gu.load("process_reads_short")
+
+
+@pytest.mark.parametrize("case", SHORT_CASES, ids=lambda c: c["name"])
+def test_process_reads_short_path_matches_reference(case):
+    """Homopolymer / --stutter-align-len path: same doubles, same float bit tricks -> bit equality."""
+    L, keep = gu.flat_locus(case)
+    P, H = len(case["reads"]), len(case["alleles"])
+    ll, seeds, _ = po.process_reads(L, P, H, fill=case.get("fill", 0.0))
+    assert np.array_equal(ll, gu.unhex(case["ll"], (P, H)))
+    for r in range(P):
+        if case.get("realign_read") is None or case["realign_read"][r]:
+            assert seeds[r] == case["seeds"][r]
+
+
 @pytest.mark.parametrize("case", gu.load("pair_batches"), ids=lambda c: c["name"])
 def test_pair_batches_match_reference(case):
     b = gu.pair_batch(case)

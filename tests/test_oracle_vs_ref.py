@@ -24,6 +24,19 @@ def test_process_reads_long_path(seed):
     assert np.array_equal(gseeds, wseeds)
 
 
+@pytest.mark.parametrize("seed", range(16))
+def test_process_reads_short_path(seed):
+    params = ONT if seed % 4 == 3 else None
+    loc = synth.make_locus(6000 + seed, n_reads=5, homopolymer=True, ref_len=int(9 + (7 * seed) % 28),
+                           sub=0.005 * (seed % 3), indel=0.01 * (seed % 4))
+    L, keep = synth.to_flat(loc, aln_params=params, switch_old_align_len=20)
+    P, H = len(loc["reads"]), len(loc["alleles"])
+    want, wseeds, _ = po.process_reads(L, P, H, which="ref")
+    got, gseeds, _ = po.process_reads(L, P, H)
+    assert np.array_equal(got, want)
+    assert np.array_equal(gseeds, wseeds)
+
+
 @pytest.mark.parametrize("seed,params", [(21, None), (22, ONT), (23, ODD)])
 def test_pair_batch(seed, params):
     b = synth.make_pair_batch(seed, n_loci=10, n_lo=20, n_hi=250, flank=30, weird=0.0, sub=0.02, indel=0.02)

@@ -99,6 +99,31 @@ def long_path_cases():
     return cases
 
 
+def short_path_cases():
+    """Homopolymer loci with --stutter-align-len (HapAligner::process_reads short path, SURVEY Q3)."""
+    cases = []
+    for seed in range(24):
+        kw = dict(n_reads=6, homopolymer=True, ref_len=int(8 + (5 * seed) % 30), sub=0.004 * (seed % 3),
+                  indel=0.01 * (seed % 4), ctx=40 + 10 * (seed % 5))
+        params = ONT if seed % 5 == 4 else None
+        loc = synth.make_locus(3000 + seed, **kw)
+        case = dict(name="short%02d" % seed, lflank=loc["lflank"], rflank=loc["rflank"], alleles=loc["alleles"],
+                    repeat_start=loc["repeat_start"], repeat_end=loc["repeat_end"], period=1, motif=loc["motif"],
+                    switch=20, aln_params=list(params) if params else None, reads=loc["reads"])
+        if seed % 6 == 5:
+            rng = np.random.default_rng(seed)
+            case["realign_to_hap"] = [bool(x) for x in (rng.random(len(loc["alleles"])) < 0.7)]
+            case["realign_read"] = [bool(x) for x in (rng.random(len(loc["reads"])) < 0.7)]
+            case["fill"] = 7.25
+        if seed % 8 == 7:  # a read without any '=' run long enough -> no seed -> all-zero row
+            r = case["reads"][0]
+            n = len(r["seq"])
+            r["cigar"] = "%dX" % n
+            r["stop"] = r["start"] + n - 1
+        cases.append(run_ref(case))
+    return cases
+
+
 def posterior_cases():
     rng = np.random.default_rng(20260117)
     out = []
@@ -171,6 +196,7 @@ def main():
         raise SystemExit("oracle/_ref is not built (needs /root/reference)")
     os.makedirs(GOLD, exist_ok=True)
     sets = dict(appendix_a=[run_ref(c) for c in appendix_a()], process_reads_long=long_path_cases(),
+                process_reads_short=short_path_cases(),
                 posteriors=posterior_cases(), pair_batches=pair_batch_cases(), calls=calls_cases())
     for name, cases in sets.items():
         path = os.path.join(GOLD, name + ".json")
