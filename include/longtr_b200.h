@@ -120,6 +120,41 @@ int ltr_posteriors(ltr_ctx* ctx, int haploid, int32_t n_samples, int32_t n_reads
                    int32_t n_alleles, double* ll, const double* log_p1, const double* log_p2,
                    const int32_t* sample_label, double* post, double* totals, double* total_ll);
 
+/* ---- homopolymer / --stutter-align-len path ------------------------------------------- */
+/* What HapAligner::process_reads does when block 1 has period 1 and SWITCH_OLD_ALIGN_LEN != 0
+ * (HapAligner.cpp:552, 567-579, 855-975): per (pooled read, haplotype) two quality-aware flank
+ * alignments around a seed base (align_seq_to_hap_short, :27-163) with the repeat block marginalised over
+ * PCR stutter artifacts of -6..+6 bases (StutterAlignerClass), joined by compute_aln_logprob (:165-233).
+ * Reads are the WHOLE pooled reads (not trimmed) with their Phred+33 qualities and the seed index of
+ * HapAligner::calc_seed_base (ltr_seed_base_flat); read_seed < 0 gives the reference's all-zero row.
+ * Loci have one left flank, one right flank and their repeat-block alleles (all non-empty); the stutter
+ * model of locus l is stutter[6*l..6*l+5] = (inframe_geom, inframe_up, inframe_down, outframe_geom,
+ * outframe_up, outframe_down) with motif length motif_len[l] (StutterModel, src/stutter_model.h:34-60).
+ * Output layout as ltr_viterbi_batch: out_ll[ll_off(l) + p*H_l + h].                                   */
+typedef struct ltr_stutter_batch {
+  uint32_t n_loci;
+  const uint32_t* locus_allele_begin; /* [n_loci+1] */
+  const uint32_t* locus_read_begin;   /* [n_loci+1] */
+  const uint32_t* lflank_off;         /* [n_loci+1] */
+  const uint8_t* lflank_bytes;
+  const uint32_t* rflank_off;         /* [n_loci+1] */
+  const uint8_t* rflank_bytes;
+  const uint32_t* allele_off;         /* [n_alleles+1] */
+  const uint8_t* allele_bytes;
+  const double* stutter;              /* [6*n_loci] */
+  const int32_t* motif_len;           /* [n_loci]   */
+  const uint32_t* read_off;           /* [n_reads+1] */
+  const uint8_t* read_bytes;
+  const uint8_t* qual_bytes;
+  const int32_t* read_seed;           /* [n_reads]  */
+  const uint8_t* realign_allele;      /* [n_alleles] or NULL (all): 0 leaves the column untouched */
+  const uint8_t* realign_read;        /* [n_reads]   or NULL (all): 0 leaves the row untouched    */
+} ltr_stutter_batch;
+/* params->indel_flank_len is ignored on this path.  stats->n_cells counts cell-equivalents as defined in
+ * SURVEY.md section 8d (flank rows x columns + 13 x block length per column, both flanks).            */
+int ltr_stutter_ll(ltr_ctx* ctx, const ltr_params* params, const ltr_stutter_batch* batch, double* out_ll,
+                   ltr_job_stats* stats);
+
 /* ---- resident jobs: upload once, run many times, download ------------------------- */
 /* post may be NULL (Viterbi only).  Host arrays may be released after the call.       */
 int ltr_job_create(ltr_ctx* ctx, const ltr_params* params, const ltr_viterbi_batch* batch,

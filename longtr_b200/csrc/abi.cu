@@ -18,41 +18,7 @@
 
 using namespace ltr;
 
-namespace {
-
-const int kNumStreams = 8;
-
-struct DeviceBuffer {
-  void* p = nullptr;
-  size_t bytes = 0;
-  cudaError_t alloc(size_t n) {
-    free();
-    if (n == 0) n = 8;
-    cudaError_t e = cudaMalloc(&p, n);
-    if (e == cudaSuccess) bytes = n;
-    return e;
-  }
-  void free() {
-    if (p) cudaFree(p);
-    p = nullptr;
-    bytes = 0;
-  }
-  template <typename T>
-  T* as() const { return reinterpret_cast<T*>(p); }
-};
-
-}  // namespace
-
-struct ltr_ctx {
-  int device = 0;
-  int sm_count = 0;
-  cudaStream_t main_stream = nullptr;
-  cudaStream_t streams[kNumStreams] = {nullptr};
-  cudaEvent_t ev_start = nullptr, ev_vit = nullptr, ev_end = nullptr;
-  cudaEvent_t ev_stream[kNumStreams] = {nullptr};
-  int blocks_per_sm[2][32] = {{0}};
-  std::string last_error;
-};
+#include "ctx.h"
 
 struct ClassState {
   int k = 0;
@@ -81,17 +47,6 @@ struct ltr_job {
 };
 
 namespace {
-
-int fail_cuda(ltr_ctx* ctx, cudaError_t e, const char* what) {
-  if (ctx) ctx->last_error = std::string(what) + ": " + cudaGetErrorString(e);
-  return (e == cudaErrorMemoryAllocation) ? LTR_ERR_OOM : LTR_ERR_CUDA;
-}
-
-#define LTR_CUDA(ctx, call)                                  \
-  do {                                                       \
-    cudaError_t e__ = (call);                                \
-    if (e__ != cudaSuccess) return fail_cuda(ctx, e__, #call); \
-  } while (0)
 
 template <typename T>
 int upload(ltr_ctx* ctx, DeviceBuffer& buf, const T* src, size_t count, size_t pad_bytes, uint64_t* h2d) {

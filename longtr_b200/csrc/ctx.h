@@ -1,0 +1,58 @@
+// ctx.h -- private definitions shared by the C-ABI translation units (abi.cu, stutter_abi.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+
+#include "longtr_b200.h"
+
+namespace ltr {
+
+const int kNumStreams = 8;
+
+struct DeviceBuffer {
+  void* p = nullptr;
+  size_t bytes = 0;
+  cudaError_t alloc(size_t n) {
+    free();
+    if (n == 0) n = 8;
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e == cudaSuccess) bytes = n;
+    return e;
+  }
+  void free() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  template <typename T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+}  // namespace ltr
+
+struct ltr_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t main_stream = nullptr;
+  cudaStream_t streams[ltr::kNumStreams] = {nullptr};
+  cudaEvent_t ev_start = nullptr, ev_vit = nullptr, ev_end = nullptr;
+  cudaEvent_t ev_stream[ltr::kNumStreams] = {nullptr};
+  int blocks_per_sm[2][32] = {{0}};
+  std::string last_error;
+};
+
+namespace ltr {
+
+inline int fail_cuda(ltr_ctx* ctx, cudaError_t e, const char* what) {
+  if (ctx) ctx->last_error = std::string(what) + ": " + cudaGetErrorString(e);
+  return (e == cudaErrorMemoryAllocation) ? LTR_ERR_OOM : LTR_ERR_CUDA;
+}
+
+}  // namespace ltr
+
+#define LTR_CUDA(ctx, call)                                          \
+  do {                                                               \
+    cudaError_t e__ = (call);                                        \
+    if (e__ != cudaSuccess) return ltr::fail_cuda(ctx, e__, #call);  \
+  } while (0)

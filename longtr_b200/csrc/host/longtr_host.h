@@ -99,6 +99,9 @@ class StutterModel {
     return StutterModel(in_geom_, in_up_, in_down_, out_geom_, out_up_, out_down_, motif_);
   }
   bool valid() const { return valid_; }
+  void get_parameters(double out[6]) const {  // constructor order
+    out[0] = in_geom_; out[1] = in_up_; out[2] = in_down_; out[3] = out_geom_; out[4] = out_up_; out[5] = out_down_;
+  }
 
  private:
   double in_geom_, in_up_, in_down_, out_geom_, out_up_, out_down_;

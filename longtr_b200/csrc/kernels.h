@@ -39,4 +39,30 @@ struct DevPosterior {
 };
 cudaError_t launch_posteriors(const DevPosterior& P, cudaStream_t stream);
 
+// Homopolymer / --stutter-align-len path (stutter_kernel.cu): one warp per (read, allele) pair.
+struct StutConsts;
+struct StutterTask {
+  uint32_t locus, read, allele;
+  unsigned long long out_index;  // position in out_ll
+};
+struct StutterDevBatch {
+  uint32_t n_tasks;
+  const StutterTask* tasks;
+  const uint32_t* read_off;     // [n_reads+1] whole (untrimmed) pooled reads
+  const uint8_t* read_bytes;
+  const uint8_t* qual_bytes;    // Phred+33, same offsets
+  const int32_t* read_seed;     // [n_reads] HapAligner::calc_seed_base
+  const uint32_t* lflank_off;   // [n_loci+1]
+  const uint8_t* lflank_bytes;
+  const uint32_t* rflank_off;   // [n_loci+1]
+  const uint8_t* rflank_bytes;
+  const uint32_t* allele_off;   // [n_alleles+1]
+  const uint8_t* allele_bytes;
+  const double* allele_artifact_lp;  // [n_alleles*13] log_prob_pcr_artifact(allele, D), D = -6..6
+  double* out_ll;
+  uint32_t max_flank, max_block, max_hap;  // shared-memory sizing
+};
+size_t stutter_block_smem_bytes(uint32_t max_flank, uint32_t max_block, uint32_t max_hap);
+cudaError_t launch_stutter(const StutConsts& C, const StutterDevBatch& B, cudaStream_t stream);
+
 }  // namespace ltr
