@@ -34,16 +34,18 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", type=int, default=3, choices=[3, 4])
+    ap.add_argument("--config", type=int, default=3, choices=[3, 4, 5])
     ap.add_argument("--loci", type=int, default=0, help="loci per GPU per step (default: config size)")
     ap.add_argument("--cpu-sample-loci", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
 
-CONFIG_LOCI = {3: 100000, 4: 10000}
+CONFIG_LOCI = {3: 100000, 4: 10000, 5: 50000}
 CONFIG_NAME = {3: "synthetic HiFi STRs: 1-6 bp motifs, 50-300 bp repeats, 30 reads/locus (BASELINE.json configs[2])",
-               4: "synthetic VNTRs: 500-1000 bp repeats, 2-12 haplotypes, ONT-like params (BASELINE.json configs[3])"}
+               4: "synthetic VNTRs: 500-1000 bp repeats, 2-12 haplotypes, ONT-like params (BASELINE.json configs[3])",
+               5: "homopolymer stutter path: --stutter-align-len 20, synthetic homopolymer loci (BASELINE.json configs[4])"}
+FP64_OPS_PER_CELL_SHORT = 13.0  # flank-row cell of align_seq_to_hap_short: 9 add + 4 max (HapAligner.cpp:141-156)
 
 
 class ClockSampler:
@@ -227,10 +229,129 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def cpu_baseline_stutter(work, n_sample, threads):
+    """Reference HapAligner::process_reads (homopolymer path) over the first n_sample loci, one locus per task on a
+    thread pool (ctypes releases the GIL; the README's 'split the BED' parallelisation).  Returns wall seconds."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import pyoracle as po
+    which = "ref" if po.ref_available() else "oracle"
+    loci = [work.flat_locus(l) for l in range(n_sample)]
+    po.process_reads(loci[0][0][0], loci[0][1][0], loci[0][1][1], which=which)  # one-time table init outside the clock
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        list(ex.map(lambda x: po.process_reads(x[0][0], x[1][0], x[1][1], which=which), loci))
+    return ("reference" if which == "ref" else "port"), time.perf_counter() - t0
+
+
+def run_reference_stutter(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from longtr_b200 import workloads
+    threads = os.cpu_count() or 1
+    n_sample = args.cpu_sample_loci or 8 * threads
+    work = workloads.generate_stutter(n_sample)
+    cells = work.cells(n_sample)
+    times, kind = [], "port"
+    for it in range(args.warmup + args.steps):
+        kind, wall = cpu_baseline_stutter(work, n_sample, threads)
+        if it >= args.warmup:
+            times.append(wall)
+    tot = sum(times)
+    val = n_sample * len(times) / tot
+    print(json.dumps({
+        "impl": "reference", "metric": "loci_per_sec", "value": val, "unit": "loci/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "gcups": cells * len(times) / tot / 1e9,
+        "config": {"workload": CONFIG_NAME[5], "loci_per_step": n_sample,
+                   "note": "bounded sample of the b200 arm's workload (same generator and seeds)"},
+        "cpu_baseline": {"value": val, "unit": "loci/s", "cores": threads, "kind": kind,
+                         "sample": "%d loci per step, wall clock incl. Haplotype construction" % n_sample},
+        "e2e": {"value": val, "unit": "loci/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}), flush=True)
+
+
+def run_stutter(args):
+    """--config 5: the homopolymer / --stutter-align-len path (kernel 2) at the process_reads boundary."""
+    torch, rank, world, local = dist_setup(args.gpus)
+    from longtr_b200 import Engine, workloads
+    n_loci = args.loci or CONFIG_LOCI[5]
+    eng = Engine(local)
+    fp64_rate = max(eng.fp64_issue_rate(0)[0] for _ in range(2))
+    work = workloads.generate_stutter(n_loci, first_locus=rank * n_loci)
+    pinned_b, keep_b = pinned_copy(torch, work.batch)
+    out = np.zeros(abi_ll_size(work.batch), dtype=np.float64)
+    for _ in range(args.warmup):
+        eng.stutter_ll(pinned_b, out=out)
+    sampler = ClockSampler(local)
+    barrier(torch, world)
+    if rank == 0:
+        sampler.start()
+    t0 = time.perf_counter()
+    dev_ms, launches = 0.0, 0
+    for _ in range(args.steps):
+        out, st = eng.stutter_ll(pinned_b, out=out)
+        dev_ms += st.kernel_ms
+        launches += st.n_launches
+    barrier(torch, world)
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop() if rank == 0 else None
+    step_ms = max_over_ranks(torch, world, dev_ms / args.steps)
+    e2e_ms = max_over_ranks(torch, world, wall_ms / args.steps)
+    total_loci = sum_over_ranks(torch, world, float(n_loci))
+    total_cells = sum_over_ranks(torch, world, float(st.n_cells))
+    if rank != 0:
+        return
+    achieved = st.n_cells / (dev_ms / args.steps) / 1e6
+    peak = fp64_rate / FP64_OPS_PER_CELL_SHORT / 1e9
+    line = {
+        "metric": "loci_per_sec", "value": total_loci / (step_ms * 1e-3), "unit": "loci/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "gcups": total_cells / (step_ms * 1e-3) / 1e9,
+        "config": {"workload": CONFIG_NAME[5], "loci_per_gpu": n_loci, "pairs_per_gpu": int(st.n_pairs),
+                   "cell_equivalents_per_gpu": int(st.n_cells),
+                   "l2": "inputs (%.0f MB) streamed once per step; per-warp working set lives in shared memory" %
+                         (work.input_bytes / 1e6),
+                   "parallelism": "locus-sharded, no collective", "ll_checksum": float(np.sum(out))},
+        "e2e": {"value": total_loci / (e2e_ms * 1e-3), "unit": "loci/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int(st.h2d_bytes), "d2h_bytes_per_step": int(st.d2h_bytes)},
+        "gpu_launches": launches, "clocks": clocks,
+        "roofline": {"bound": "fp64_issue", "achieved": achieved, "peak": peak, "unit": "GCUPS", "frac": achieved / peak,
+                     "traffic": None,
+                     "peak_source": "ltr_fp64_issue_rate (DADD lane-ops/s measured in this run) / 13 FP64 ops per "
+                                    "flank cell; cell-equivalents as defined in SURVEY.md 8d",
+                     "fp64_lane_ops_per_s": fp64_rate}}
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        n_sample = args.cpu_sample_loci or min(n_loci, 8 * threads)
+        kind, wall = cpu_baseline_stutter(work, n_sample, threads)
+        line["cpu_baseline"] = {"value": n_sample / wall, "unit": "loci/s", "cores": threads, "kind": kind,
+                                "gcups": work.cells(n_sample) / wall / 1e9,
+                                "sample": "first %d loci of the same workload, all host threads" % n_sample}
+    print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def abi_ll_size(batch):
+    from longtr_b200 import abi
+    return abi.stutter_ll_size(batch)
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
-        run_reference(args)
+        if args.config == 5:
+            run_reference_stutter(args)
+        else:
+            run_reference(args)
+        return
+    if args.config == 5:
+        run_stutter(args)
         return
     torch, rank, world, local = dist_setup(args.gpus)
     from longtr_b200 import Engine, workloads

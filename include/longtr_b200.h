@@ -233,6 +233,24 @@ int ltr_synth_generate(int config, uint64_t base_seed, uint32_t first_locus, uin
 void ltr_synth_params(int config, ltr_params* p);
 void ltr_synth_free(ltr_synth_batch* b);
 
+/* config 5 (homopolymers, --stutter-align-len path): an ltr_stutter_batch with whole pooled reads, median
+ * qualities and calc_seed_base seeds, plus what is needed to replay the same loci as flat loci
+ * (include/longtr_b200_locus.h): per-read reference coordinates and CIGAR, per-locus repeat coordinates. */
+typedef struct ltr_synth_stutter_batch {
+  ltr_stutter_batch batch;
+  ltr_posterior_batch post;      /* 30 sample-reads per locus, one sample */
+  const int32_t* read_start;     /* [n_reads] */
+  const int32_t* read_stop;      /* [n_reads] */
+  const uint32_t* cigar_off;     /* [n_reads+1] */
+  const uint8_t* cigar_bytes;
+  const int32_t* repeat_start;   /* [n_loci] */
+  const int32_t* repeat_end;     /* [n_loci] */
+  uint32_t n_alleles, n_reads, n_sreads;
+} ltr_synth_stutter_batch;
+int ltr_synth_stutter_generate(uint64_t base_seed, uint32_t first_locus, uint32_t n_loci, int n_threads,
+                               ltr_synth_stutter_batch** out);
+void ltr_synth_stutter_free(ltr_synth_stutter_batch* b);
+
 #ifdef __cplusplus
 }
 #endif

@@ -178,6 +178,8 @@ def load():
     lib.ltr_trim_read_flat.restype = C.c_int32
     lib.ltr_seed_base_flat.argtypes = [C.POINTER(FlatLocus), C.c_int32]
     lib.ltr_seed_base_flat.restype = C.c_int32
+    lib.ltr_stutter_ll.argtypes = [vp, C.POINTER(Params), C.c_void_p, _dp, C.POINTER(JobStats)]
+    lib.ltr_stutter_ll.restype = C.c_int
     lib.ltr_fp64_issue_rate.argtypes = [C.c_int, C.c_int, _dp, _dp]
     lib.ltr_fp64_issue_rate.restype = C.c_int
     _lib = lib
@@ -189,6 +191,7 @@ EXPORTED_SYMBOLS = [
     "ltr_version", "ltr_viterbi_ll", "ltr_posteriors", "ltr_job_create", "ltr_job_run", "ltr_job_sizes",
     "ltr_job_download", "ltr_job_get_stats", "ltr_job_destroy", "ltr_process_reads_flat",
     "ltr_fp64_issue_rate", "ltr_genotype_locus", "ltr_extract_calls", "ltr_trim_read_flat", "ltr_seed_base_flat",
+    "ltr_stutter_ll",
 ]
 
 
@@ -218,3 +221,36 @@ def trim_read(locus, read_index):
 
 def seed_base(locus, read_index):
     return load().ltr_seed_base_flat(C.byref(locus), read_index)
+
+
+class StutterBatch(C.Structure):
+    """ltr_stutter_batch (include/longtr_b200.h)."""
+    _fields_ = [("n_loci", C.c_uint32), ("locus_allele_begin", _u32p), ("locus_read_begin", _u32p),
+                ("lflank_off", _u32p), ("lflank_bytes", _u8p), ("rflank_off", _u32p), ("rflank_bytes", _u8p),
+                ("allele_off", _u32p), ("allele_bytes", _u8p), ("stutter", _dp), ("motif_len", _i32p),
+                ("read_off", _u32p), ("read_bytes", _u8p), ("qual_bytes", _u8p), ("read_seed", _i32p),
+                ("realign_allele", _u8p), ("realign_read", _u8p)]
+
+
+STUTTER_FIELDS = [("locus_allele_begin", np.uint32), ("locus_read_begin", np.uint32), ("lflank_off", np.uint32),
+                  ("lflank_bytes", np.uint8), ("rflank_off", np.uint32), ("rflank_bytes", np.uint8),
+                  ("allele_off", np.uint32), ("allele_bytes", np.uint8), ("stutter", np.float64),
+                  ("motif_len", np.int32), ("read_off", np.uint32), ("read_bytes", np.uint8), ("qual_bytes", np.uint8),
+                  ("read_seed", np.int32)]
+
+
+def make_stutter_batch(batch):
+    """dict of numpy arrays (keys of STUTTER_FIELDS) -> (StutterBatch, keepalive)."""
+    keep = {k: np.ascontiguousarray(batch[k], dtype=dt) for k, dt in STUTTER_FIELDS}
+    b = StutterBatch()
+    b.n_loci = len(keep["locus_allele_begin"]) - 1
+    for k, dt in STUTTER_FIELDS:
+        t = {np.uint32: _u32p, np.uint8: _u8p, np.float64: _dp, np.int32: _i32p}[dt]
+        setattr(b, k, ptr(keep[k], t))
+    return b, keep
+
+
+def stutter_ll_size(batch):
+    a = np.asarray(batch["locus_allele_begin"], dtype=np.int64)
+    r = np.asarray(batch["locus_read_begin"], dtype=np.int64)
+    return int(np.sum((a[1:] - a[:-1]) * (r[1:] - r[:-1])))

@@ -114,6 +114,17 @@ class Engine:
         _check(self.lib, self.ctx, rc, "ltr_posteriors")
         return ll, post, tot, total.value
 
+    # -- HapAligner::process_reads, homopolymer / --stutter-align-len path, for a batch of loci ---------
+    def stutter_ll(self, batch, aln_params=None, out=None):
+        sb, keep = abi.make_stutter_batch(batch)
+        p = abi.make_params(aln_params, 5)
+        if out is None:
+            out = np.zeros(abi.stutter_ll_size(batch), dtype=np.float64)
+        st = abi.JobStats()
+        rc = self.lib.ltr_stutter_ll(self.ctx, C.byref(p), C.byref(sb), abi.ptr(out, abi._dp), C.byref(st))
+        _check(self.lib, self.ctx, rc, "ltr_stutter_ll")
+        return out, st
+
     # -- posteriors (GPU) + Genotyper::extract_genotypes_and_likelihoods (host) for one locus ----------
     def genotype_locus(self, ll, log_p1, log_p2, reads_per_sample, haploid=False):
         ll = np.array(ll, dtype=np.float64, order="C", copy=True)

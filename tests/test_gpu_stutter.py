@@ -35,3 +35,18 @@ def test_short_path_matches_oracle_on_fresh_loci(engine, seed):
     got, gseeds = engine.process_reads_flat(L, P, H)
     assert np.array_equal(got, want)
     assert np.array_equal(gseeds, wseeds)
+
+
+def test_stutter_batch_config5_matches_oracle(engine):
+    """A batch of BASELINE config-5 loci through ltr_stutter_ll (one launch) against the oracle, locus by locus."""
+    from longtr_b200 import workloads
+    work = workloads.generate_stutter(48)
+    got, st = engine.stutter_ll(work.batch)
+    assert st.n_pairs > 0 and st.n_launches == 1
+    off = 0
+    for l in range(work.n_loci):
+        (L, keep), (P, H) = work.flat_locus(l)
+        want, _seeds, _ = po.process_reads(L, P, H)
+        assert np.array_equal(got[off:off + P * H].reshape(P, H), want), l
+        off += P * H
+    assert off == len(got)
