@@ -227,6 +227,7 @@ int ltr_job_create(ltr_ctx* ctx, const ltr_params* params, const ltr_viterbi_bat
     if (plan.tasks[k].empty()) continue;
     ClassState cs;
     cs.k = k;
+    cs.force_full = !fast_certificate_valid(*params);  // parameters outside the certificate's condition: exact kernel only
     cs.n_tasks = (uint32_t)plan.tasks[k].size();
     uint64_t pairs = 0;
     for (const Task& t : plan.tasks[k]) pairs += t.read_end - t.read_begin;

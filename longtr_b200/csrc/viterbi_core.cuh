@@ -22,9 +22,15 @@
 //    and enter as boundary values (tables tabI/tabD hold the reference's repeatedly-added
 //    prefix sums so that even non-integer transition parameters round identically).
 //  * Row bail-out (HapAligner.cpp:297-306).  MODE_FULL evaluates it literally.  MODE_FAST
-//    only looks for a cheap *witness* per row (a match-state value that provably keeps
-//    the row above -600) on every CHECK-th step; pairs with an unwitnessed row are
-//    re-run in MODE_FULL, so results are exact either way.
+//    does not evaluate it at all: when the final score F of a pair exceeds
+//    fast_thr = -600 + slack, no row can fail the test (every row holds a cell of an optimal
+//    path whose value minus the band penalty is >= F - slack; proof and the parameter
+//    condition it needs in DESIGN.md section 4), so the pair is certified from F alone;
+//    the remaining pairs are re-run in MODE_FULL.  Results are exact either way.
+//  * The stream loop is event driven: as long as no lane of the warp is at a read start /
+//    read end (lane_plain_distance), the warp runs lane_fast_step -- shuffle, one character,
+//    one DP column, nothing else -- and falls back to the general lane_stream_step for the
+//    ~33 of every |read| steps in which some lane crosses a read boundary.
 //  * Nothing in the per-step path is computed by a single lane: the row-0 boundary of
 //    the whole read stream is produced by a warp-wide pre-pass into a scratch line that
 //    lane 0 consumes through a double-buffered shared-memory window, and the column-0
@@ -55,7 +61,7 @@ struct VitConsts {
   double m2m, d2m, i2m, m2i, i2i, m2d, d2d;  // (double)(float) transition log-probs
   double match, mismatch;                    // (double)(float) emissions, HapAligner.cpp:260-261
   double imp;                                // IMPOSSIBLE = -1e9, HapAligner.cpp:20
-  double wit_base, wit_slope;                // MODE_FAST: M > wit_base + wit_slope*|diag offset| is a witness
+  double fast_thr;                           // MODE_FAST: a pair with final score > fast_thr cannot bail out
   float d2d_f;                               // float LOG_DEL_TO_DEL for the int*float band term (:298)
   int32_t cut;                               // 35 - INDEL_FLANK_LEN (:245-246)
   const double* tabI;                        // tabI[0] = IMP, tabI[i] = I(i,0)           (:277-279)
@@ -102,7 +108,6 @@ struct Lane {
   double X[K];   // X[r]  = X(row r, previous column), updated in place
   double Z[K];   // Z[r]  = D(row r, current column)
   int32_t hc[K]; // haplotype characters of the lane's rows (0xFFFF = no row)
-  int32_t acc[K];     // MODE_FAST: min over checked cells of hi32(M) - hi32(threshold)  (<0: witness)
   double rowmax[K];   // MODE_FULL: max_j (best + band penalty)
   double Xout, Yout;  // X,Y of the lane's last real row at the column just finished
   uint32_t Bout;      // 1 if some row of this pair, in this or an upper lane, is bad
@@ -147,7 +152,7 @@ struct LastCell {
 // rows); pass 2 walks the rows top-down for the I chain and rewrites X,Z in place.
 // ----------------------------------------------------------------------------------
 template <int K, int MODE>
-LTR_HD LastCell lane_column(Lane<K>& L, const VitConsts& C, int32_t c, double rx, double ry, bool check) {
+LTR_HD LastCell lane_column(Lane<K>& L, const VitConsts& C, int32_t c, double rx, double ry) {
   L.j += 1;
   double M[K];
 #pragma unroll
@@ -184,23 +189,6 @@ LTR_HD LastCell lane_column(Lane<K>& L, const VitConsts& C, int32_t c, double rx
   const bool full_lane = (L.nrows == K);
   L.Xout = (K == 1 || full_lane) ? L.X[K - 1] : L.X[K >= 2 ? K - 2 : 0];
   L.Yout = (K == 1 || full_lane) ? ya : yb;
-  if (MODE == MODE_FAST) {
-    if (check) {
-      // Row witness: a match value M above T = wit_base + wit_slope*|offset| keeps
-      // best + (float)|offset|*D2D >= -600 with a margin of 1; T is taken for the lane's worst row.
-      // Negative doubles order like their high words reversed: M > T  <=  hi32(M) < hi32(T).
-      const int32_t dl = d0 - (K - 1);
-      const int32_t a0 = d0 < 0 ? -d0 : d0, a1 = dl < 0 ? -dl : dl;
-      double T = C.wit_base + C.wit_slope * (double)(a0 > a1 ? a0 : a1);
-      T = (T < -1.0) ? T : -0.0;
-      const uint32_t thr = hi32(T);
-#pragma unroll
-      for (int r = 0; r < K; ++r) {
-        const int32_t diff = (int32_t)(hi32(M[r]) - thr);
-        L.acc[r] = (diff < L.acc[r]) ? diff : L.acc[r];
-      }
-    }
-  }
   if (K == 1 || full_lane) return a;
   return b;
 }
@@ -212,7 +200,6 @@ LTR_HD bool lane_rows_bad(const Lane<K>& L) {
 #pragma unroll
   for (int r = 0; r < K; ++r) {
     if (r < L.nrows) {
-      if (MODE == MODE_FAST) bad |= !(L.acc[r] < 0);
       if (MODE == MODE_FULL) bad |= (L.rowmax[r] < -600.0);
     }
   }
@@ -357,7 +344,6 @@ LTR_HD void lane_stream_reset(LaneStream<K>& S, const VitConsts& C, const StripC
     S.L.hc[r] = (r < nrows) ? (int32_t)T.hap[i0 + r] : 0xFFFF;
     S.L.X[r] = C.imp;
     S.L.Z[r] = C.imp;
-    S.L.acc[r] = 0x7FFFFFFF;
     S.L.rowmax[r] = C.imp;
   }
   for (int v = 0; v < 2; ++v) {
@@ -391,7 +377,7 @@ LTR_HD void lane_stream_reset(LaneStream<K>& S, const VitConsts& C, const StripC
 // the lane above exported at the previous step; lane 0 takes them from the boundary window.
 template <int K, int MODE>
 LTR_HD void lane_stream_step(LaneStream<K>& S, const VitConsts& C, const StripCtx& T, int lane,
-                             uint32_t pos, bool check, double rx, double ry, uint32_t rbad) {
+                             uint32_t pos, double rx, double ry, uint32_t rbad) {
   Lane<K>& L = S.L;
   const uint32_t q = T.qs + pos;
   const int32_t c = S.cnext;
@@ -419,7 +405,6 @@ LTR_HD void lane_stream_step(LaneStream<K>& S, const VitConsts& C, const StripCt
     for (int r = 0; r < K; ++r) {
       L.X[r] = T.tx[(v * K + r) * 32 + lane];
       L.Z[r] = T.tz[(v * K + r) * 32 + lane];
-      if (MODE == MODE_FAST) L.acc[r] = 0x7FFFFFFF;
       if (MODE == MODE_FULL) L.rowmax[r] = C.imp;
     }
     L.Xout = T.txo[v * 32 + lane];
@@ -428,7 +413,7 @@ LTR_HD void lane_stream_step(LaneStream<K>& S, const VitConsts& C, const StripCt
       col0_cell(C, L.i0 + L.nrows - 1, v ? C.match : C.mismatch, last.M, last.I, last.D);
   } else {
     // ---- DP column j >= 1 ------------------------------------------------------------------
-    last = lane_column<K, MODE>(L, C, c, rx, ry, check);
+    last = lane_column<K, MODE>(L, C, c, rx, ry);
   }
   if (L.j == L.m - 1) {
     // ---- the lane has finished the current read ---------------------------------------------
@@ -445,8 +430,10 @@ LTR_HD void lane_stream_step(LaneStream<K>& S, const VitConsts& C, const StripCt
         } else if (MODE == MODE_FULL) {
           *dst = bad ? -700.0 : vmax(last.D, vmax(last.I, last.M));      // HapAligner.cpp:300-309
         } else {
-          *dst = vmax(last.D, vmax(last.I, last.M));
-          if (bad) fail_append(T.fail, T.hap_index, (uint32_t)S.p);
+          const double F = vmax(last.D, vmax(last.I, last.M));
+          *dst = F;
+          // certified by the final score alone (needs a column j >= 1, i.e. m >= 2); else exact re-run
+          if (!(L.m >= 2 && F > C.fast_thr)) fail_append(T.fail, T.hap_index, (uint32_t)S.p);
         }
       } else {
         T.sb[pos] = bad;
@@ -458,6 +445,39 @@ LTR_HD void lane_stream_step(LaneStream<K>& S, const VitConsts& C, const StripCt
       XY o;
       o.x = L.Xout;
       o.y = L.Yout;
+      T.sxy[pos] = o;
+    }
+  }
+}
+
+// Number of consecutive steps, starting with the one that processes stream position pos, in which this lane
+// only computes plain DP columns (no read start, no read end).  0 for lanes outside the stream.
+template <int K>
+LTR_HD uint32_t lane_plain_distance(const LaneStream<K>& S, const StripCtx& T, uint32_t pos) {
+  if (pos >= T.Q) return 0u;  // not started yet (pos wrapped below 0) or finished
+  const uint32_t q = T.qs + pos;
+  if (q == S.qe) return 0u;   // first character of a read
+  return S.qe - 1u - q;       // the column at qe-1 finishes the read
+}
+
+// One plain DP column (the caller guarantees lane_plain_distance >= 1 for every lane of the warp).
+template <int K, int MODE>
+LTR_HD void lane_fast_step(LaneStream<K>& S, const VitConsts& C, const StripCtx& T, int lane, uint32_t pos,
+                           double rx, double ry) {
+  const int32_t c = S.cnext;
+  S.cnext = (int32_t)*S.rptr;
+  S.rptr += 1;
+  if (lane == 0) {
+    const XY b = T.bnd[((pos >> 5) & 1u) * 32u + (pos & 31u)];
+    rx = b.x;
+    ry = b.y;
+  }
+  lane_column<K, MODE>(S.L, C, c, rx, ry);
+  if (!T.last_strip) {  // warp-uniform
+    if (lane == T.t_last) {
+      XY o;
+      o.x = S.L.Xout;
+      o.y = S.L.Yout;
       T.sxy[pos] = o;
     }
   }

@@ -50,14 +50,25 @@ inline void make_consts(const ltr_params& p, int tab_len, HostConsts& out) {
     out.tabD[j] = (double)p.match_del + left;
     left += (double)p.del_del;
   }
-  // MODE_FAST witness (viterbi_core.cuh): M > wit_base + wit_slope*|diag offset| keeps
-  // best + (float)|offset|*D2D >= -600 with a margin of 1.0 (band penalty of HapAligner.cpp:298;
-  // the 1e-6 covers the float rounding of the reference's int*float product).
-  C.wit_base = -599.0;
-  C.wit_slope = (p.del_del < 0.0f) ? std::fabs((double)p.del_del) * (1.0 + 1e-6) : 0.0;
+  // MODE_FAST certificate (viterbi_core.cuh): final score > -600 + slack
+  //   slack = 2|MISMATCH| + |M2M| + |I2M| + 2|D2D| + 0.01
+  C.fast_thr = -600.0 + (2.0 * 9.0 + std::fabs((double)p.match_match) + std::fabs((double)p.ins_match) +
+                         2.0 * std::fabs((double)p.del_del) + 0.01);
   C.tabI = nullptr;
   C.tabD = nullptr;
   C.tab_len = tab_len;
+}
+
+// The final-score certificate of MODE_FAST holds when every unit of band offset costs the path at least |D2D|:
+// all parameters <= 0 and |I2I|, |M2I|, |M2D| >= |D2D| (Dindel defaults and the ONT-like set satisfy it).
+// Otherwise every pair is evaluated by the exact kernel.
+inline bool fast_certificate_valid(const ltr_params& p) {
+  const float v[7] = {p.ins_ins, p.ins_match, p.del_del, p.del_match, p.match_match, p.match_ins, p.match_del};
+  for (int i = 0; i < 7; ++i)
+    if (!(v[i] <= 0.0f)) return false;
+  const double d = std::fabs((double)p.del_del);
+  return std::fabs((double)p.ins_ins) >= d && std::fabs((double)p.match_ins) >= d && std::fabs((double)p.match_del) >= d &&
+         d * 4096.0 < 1e6;
 }
 
 // Row class of a haplotype with n DP rows/columns (n = trimmed length): K rows per lane.

@@ -3,10 +3,10 @@
 //
 // One persistent warp per (haplotype, read stream) task; see viterbi_core.cuh for the
 // per-lane algorithm.  FP64 max-plus on the FP64 pipe, no tensor cores: this is not a
-// contraction.  Per DP cell the fast kernel issues 9 DADD + 4 DSETP (+8 selects); the
+// contraction.  Per DP cell the fast kernel issues 9 DADD + 4 DSETP (+10 selects); the
 // reference recipe counts 17 FP64 ops per cell -- the 4 ops of the
-// per-row bail-out test are replaced by a sparse integer witness test and an exact
-// fallback kernel (MODE_FULL) for the pairs the witness cannot certify.
+// per-row bail-out test are not evaluated: a pair is certified from its final score
+// (viterbi_core.cuh) and the exact kernel (MODE_FULL) re-runs the rest.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -17,7 +17,6 @@ namespace ltr {
 
 static constexpr unsigned kFullMask = 0xFFFFFFFFu;
 static constexpr int kBlockThreads = 128;
-static constexpr unsigned kCheckMask = 3u;  // MODE_FAST looks for row witnesses every 4th step
 
 template <int K, int MODE>
 __device__ __forceinline__ void run_task(const VitConsts& C, const DevBatch& B, const Task& T,
@@ -99,13 +98,27 @@ __device__ __forceinline__ void run_task(const VitConsts& C, const DevBatch& B, 
     uint32_t step = 0;
     while (step < nsteps) {
       const uint32_t chunk_end = (step + 32u < nsteps) ? step + 32u : nsteps;
-      for (; step < chunk_end; ++step) {
-        const double rx = __shfl_up_sync(kFullMask, LS.L.Xout, 1);
-        const double ry = __shfl_up_sync(kFullMask, LS.L.Yout, 1);
-        const uint32_t rb = __shfl_up_sync(kFullMask, LS.L.Bout, 1);
-        const uint32_t pos = step - (uint32_t)lane;
-        if (pos < S.Q)
-          lane_stream_step<K, MODE>(LS, C, S, lane, pos, (step & kCheckMask) == 0u, rx, ry, rb);
+      while (step < chunk_end) {
+        // event-driven: plain columns for as many steps as every lane of the warp allows, else one general step
+        const uint32_t d = lane_plain_distance<K>(LS, S, step - (uint32_t)lane);
+        uint32_t nfast = __reduce_min_sync(kFullMask, d);
+        nfast = (nfast < chunk_end - step) ? nfast : (chunk_end - step);
+        if (nfast > 0u) {
+          const uint32_t fast_end = step + nfast;
+#pragma unroll 1
+          for (; step < fast_end; ++step) {
+            const double rx = __shfl_up_sync(kFullMask, LS.L.Xout, 1);
+            const double ry = __shfl_up_sync(kFullMask, LS.L.Yout, 1);
+            lane_fast_step<K, MODE>(LS, C, S, lane, step - (uint32_t)lane, rx, ry);
+          }
+        } else {
+          const double rx = __shfl_up_sync(kFullMask, LS.L.Xout, 1);
+          const double ry = __shfl_up_sync(kFullMask, LS.L.Yout, 1);
+          const uint32_t rb = __shfl_up_sync(kFullMask, LS.L.Bout, 1);
+          const uint32_t pos = step - (uint32_t)lane;
+          if (pos < S.Q) lane_stream_step<K, MODE>(LS, C, S, lane, pos, rx, ry, rb);
+          ++step;
+        }
       }
       if (step < nsteps) {  // next window of the scratch line: positions [step, step+32)
         S.bnd[((step >> 5) & 1u) * 32u + lane] = nxt;

@@ -77,19 +77,29 @@ static void emu_task(const VitConsts& C, const DevBatch& B, const Task& T, FailS
     for (int t = 0; t < 32; ++t) { S.bnd[t] = S.sxy[t]; nxt[t] = S.sxy[32 + t]; }
     std::vector<double> ox(32), oy(32);
     std::vector<uint32_t> ob(32);
-    for (uint32_t step = 0; step < S.Q + (uint32_t)S.t_last; ++step) {
-      if ((step & 31u) == 0u && step != 0u)
-        for (int t = 0; t < 32; ++t) { S.bnd[((step >> 5) & 1u) * 32u + t] = nxt[t]; nxt[t] = S.sxy[step + 32u + t]; }
-      for (int t = 0; t < 32; ++t) { ox[t] = lanes[t].L.Xout; oy[t] = lanes[t].L.Yout; ob[t] = lanes[t].L.Bout; }
-      const bool check = (step & 3u) == 0u;
-      for (int t = 0; t < 32; ++t) {
-        const uint32_t pos = step - (uint32_t)t;
-        if (pos < S.Q) {
-          const double rx = t ? ox[t - 1] : 0.0, ry = t ? oy[t - 1] : 0.0;
-          const uint32_t rb = t ? ob[t - 1] : 0u;
-          lane_stream_step<K, MODE>(lanes[t], C, S, t, pos, check, rx, ry, rb);
+    const uint32_t nsteps = S.Q + (uint32_t)S.t_last;
+    uint32_t step = 0;
+    while (step < nsteps) {  // same event-driven schedule as viterbi_stream_kernel
+      const uint32_t chunk_end = (step + 32u < nsteps) ? step + 32u : nsteps;
+      while (step < chunk_end) {
+        uint32_t nfast = 0xFFFFFFFFu;
+        for (int t = 0; t < 32; ++t) nfast = std::min(nfast, lane_plain_distance<K>(lanes[t], S, step - (uint32_t)t));
+        nfast = std::min(nfast, chunk_end - step);
+        for (int t = 0; t < 32; ++t) { ox[t] = lanes[t].L.Xout; oy[t] = lanes[t].L.Yout; ob[t] = lanes[t].L.Bout; }
+        if (nfast > 0u) {
+          for (int t = 0; t < 32; ++t)
+            lane_fast_step<K, MODE>(lanes[t], C, S, t, step - (uint32_t)t, t ? ox[t - 1] : 0.0, t ? oy[t - 1] : 0.0);
+        } else {
+          for (int t = 0; t < 32; ++t) {
+            const uint32_t pos = step - (uint32_t)t;
+            if (pos < S.Q)
+              lane_stream_step<K, MODE>(lanes[t], C, S, t, pos, t ? ox[t - 1] : 0.0, t ? oy[t - 1] : 0.0, t ? ob[t - 1] : 0u);
+          }
         }
+        ++step;
       }
+      if (step < nsteps)
+        for (int t = 0; t < 32; ++t) { S.bnd[((step >> 5) & 1u) * 32u + t] = nxt[t]; nxt[t] = S.sxy[step + 32u + t]; }
     }
     row_start += rows;
   }
@@ -127,6 +137,7 @@ extern "C" int ltr_emu_viterbi_batch(const ltr_viterbi_batch* b, const ltr_param
   B.ll_off = plan.ll_off.data(); B.out_ll = out_ll;
   EmuScratch E;
   uint64_t nfall = 0;
+  if (!fast_certificate_valid(*p)) use_fast = 0;  // as ltr_job_create does
   for (int k = 1; k <= kmax; ++k) {
     std::vector<Task> fails(plan.n_pairs + 1);
     uint32_t nfail = 0;

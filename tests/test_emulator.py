@@ -51,3 +51,38 @@ def test_emulator_matches_oracle(emu, seed, kw, kmax, params, fast):
     assert len(bad) == 0, (bad[:10], out[bad[:10]], want[bad[:10]])
     if not fast:
         assert nf.value == 0
+
+
+@pytest.mark.parametrize("seed", range(9))
+def test_final_score_certificate_near_the_bailout_threshold(emu, seed):
+    """MODE_FAST certifies 'no row bails out' from the final score alone.  Unrelated reads of
+    a length chosen so that scores land around -600 exercise exactly the pairs where that matters: the reference's
+    per-row bail-out (-700) and near-threshold scores must come out identical to the oracle."""
+    rng = np.random.default_rng(9100 + seed)
+    params, per_base = [(None, 2.056), (ONT, 1.732), (ODD, 1.060)][seed % 3]  # -score per base of unrelated pairs
+    n0 = int(585.0 / per_base)
+    lhb, lrb, hoff, roff, hb, rb = [0], [0], [0], [0], [], []
+    for _l in range(6):
+        n = n0 + int(rng.integers(-25, 26))
+        hap = synth.rand_seq(rng, n + 60)
+        hb.append(hap)
+        hoff.append(hoff[-1] + len(hap))
+        for _r in range(4):
+            m = max(2, n + int(rng.integers(-30, 31)))
+            s = (hap[30:30 + int(rng.integers(0, 40))] + synth.rand_seq(rng, m))[:m]
+            rb.append(s)
+            roff.append(roff[-1] + len(s))
+        lhb.append(len(hb))
+        lrb.append(len(rb))
+    b = dict(locus_hap_begin=np.array(lhb, np.uint32), locus_read_begin=np.array(lrb, np.uint32),
+             hap_off=np.array(hoff, np.uint32), read_off=np.array(roff, np.uint32),
+             hap_bytes=np.frombuffer("".join(hb).encode(), np.uint8).copy(),
+             read_bytes=np.frombuffer("".join(rb).encode(), np.uint8).copy())
+    want, _ = po.viterbi_batch(b, aln_params=params, n_threads=4)
+    assert np.sum((want > -640) & (want < -540)) + np.sum(want == -700) >= 6  # the case is on target
+    vb, keep = abi.make_viterbi_batch(b)
+    p = abi.make_params(params)
+    out = np.full(len(want), 123.0)
+    nf = C.c_uint64(0)
+    assert emu.ltr_emu_viterbi_batch(C.byref(vb), C.byref(p), 16, 1, abi.ptr(out, abi._dp), C.byref(nf)) == 0
+    assert np.array_equal(out, want)
