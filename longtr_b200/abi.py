@@ -13,7 +13,7 @@ import numpy as np
 from .flat import FlatLocus
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "liblongtr_b200.so")
+LIB_PATH = os.environ.get("LONGTR_B200_LIB") or os.path.join(_HERE, "csrc", "liblongtr_b200.so")
 
 LTR_OK = 0
 

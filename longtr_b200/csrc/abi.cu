@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -310,7 +311,8 @@ static int run_classes(ltr_ctx* ctx, ltr_job* job, bool only_forced) {
   int si = 0;
   for (ClassState& cs : job->classes) {
     if (only_forced && !cs.force_full) continue;
-    cudaStream_t st = ctx->streams[si % kNumStreams];
+    static const bool serial = getenv("LTR_SERIAL_CLASSES") != nullptr;  // diagnostics: one row class at a time
+    cudaStream_t st = ctx->streams[serial ? 0 : (si % kNumStreams)];
     ++si;
     const uint32_t ctrl_init[4] = {0u, cs.n_tasks, 0u, 0u};
     LTR_CUDA(ctx, cudaMemcpyAsync(cs.ctrl.p, ctrl_init, sizeof(ctrl_init), cudaMemcpyHostToDevice, st));
