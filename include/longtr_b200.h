@@ -97,6 +97,9 @@ typedef struct ltr_job_stats {
   uint32_t n_launches;     /* kernels launched by the last ltr_job_run               */
   float kernel_ms;         /* device time of the last ltr_job_run (CUDA events)      */
   float viterbi_ms;        /* ... of which: Viterbi kernels                          */
+  uint64_t n_pairs_computed; /* pairs actually aligned: identical trimmed reads of a locus are aligned
+                                once and fanned out (results are a pure function of the two strings) */
+  uint64_t n_cells_computed; /* ... and their n*m cells                                              */
 } ltr_job_stats;
 
 /* ---- context --------------------------------------------------------------------- */

@@ -43,7 +43,8 @@ class PosteriorBatch(C.Structure):
 class JobStats(C.Structure):
     _fields_ = [("n_pairs", C.c_uint64), ("n_cells", C.c_uint64), ("n_fallback", C.c_uint64),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("n_launches", C.c_uint32),
-                ("kernel_ms", C.c_float), ("viterbi_ms", C.c_float)]
+                ("kernel_ms", C.c_float), ("viterbi_ms", C.c_float), ("n_pairs_computed", C.c_uint64),
+                ("n_cells_computed", C.c_uint64)]
 
 
 class LocusCalls(C.Structure):

@@ -39,6 +39,7 @@ struct ltr_job {
   uint32_t n_loci = 0, n_haps = 0, n_reads = 0;
   uint64_t n_ll = 0, n_post = 0, n_tot = 0;
   DeviceBuffer hap_bytes, hap_off, hap_locus, read_bytes, read_off, lhb, lrb, ll_off, out_ll, tabI, tabD;
+  DeviceBuffer lub, r2u, rlocus, ull_off, uniq_ll;  // unique-read bookkeeping (Plan)
   // posterior inputs
   bool has_post = false;
   DeviceBuffer lsb, pool, label, p1, p2, nsamp, haploid, post_off, tot_off, post, totals, int_logs;
@@ -152,6 +153,7 @@ void ltr_job_destroy(ltr_ctx* ctx, ltr_job* job) {
   if (ctx) cudaSetDevice(ctx->device);
   DeviceBuffer* bufs[] = {&job->hap_bytes, &job->hap_off, &job->hap_locus, &job->read_bytes, &job->read_off,
                           &job->lhb, &job->lrb, &job->ll_off, &job->out_ll, &job->tabI, &job->tabD,
+                          &job->lub, &job->r2u, &job->rlocus, &job->ull_off, &job->uniq_ll,
                           &job->lsb, &job->pool, &job->label, &job->p1, &job->p2, &job->nsamp,
                           &job->haploid, &job->post_off, &job->tot_off, &job->post, &job->totals,
                           &job->int_logs};
@@ -188,6 +190,8 @@ int ltr_job_create(ltr_ctx* ctx, const ltr_params* params, const ltr_viterbi_bat
   job->n_ll = plan.ll_off[bb.n_loci];
   job->stats.n_pairs = plan.n_pairs;
   job->stats.n_cells = plan.n_cells;
+  job->stats.n_pairs_computed = plan.n_pairs_computed;
+  job->stats.n_cells_computed = plan.n_cells_computed;
   make_consts(*params, std::max(plan.max_n, plan.max_m) + 2, job->hc);
   uint64_t* h2d = &job->stats.h2d_bytes;
 
@@ -209,15 +213,22 @@ int ltr_job_create(ltr_ctx* ctx, const ltr_params* params, const ltr_viterbi_bat
     }                                                      \
   } while (0)
 
-  const size_t hap_nbytes = bb.hap_off[job->n_haps], read_nbytes = bb.read_off[job->n_reads];
+  // Only the distinct trimmed reads of each locus travel to the device (Plan, viterbi_host.h); the kernels fill the
+  // unique LL matrices and expand_ll_kernel fans them out to the caller-visible aln_probs layout.
+  const size_t hap_nbytes = bb.hap_off[job->n_haps];
   LTR_TRY(upload(ctx, job->hap_bytes, bb.hap_bytes, hap_nbytes, 16, h2d));
-  LTR_TRY(upload(ctx, job->read_bytes, bb.read_bytes, read_nbytes, 16, h2d));
+  LTR_TRY(upload(ctx, job->read_bytes, plan.uread_bytes.data(), plan.uread_bytes.size(), 16, h2d));
   LTR_TRY(upload(ctx, job->hap_off, bb.hap_off, (size_t)job->n_haps + 1, 0, h2d));
-  LTR_TRY(upload(ctx, job->read_off, bb.read_off, (size_t)job->n_reads + 1, 0, h2d));
+  LTR_TRY(upload(ctx, job->read_off, plan.uread_off.data(), plan.uread_off.size(), 0, h2d));
   LTR_TRY(upload(ctx, job->lhb, bb.locus_hap_begin, (size_t)job->n_loci + 1, 0, h2d));
   LTR_TRY(upload(ctx, job->lrb, bb.locus_read_begin, (size_t)job->n_loci + 1, 0, h2d));
+  LTR_TRY(upload(ctx, job->lub, plan.locus_uread_begin.data(), plan.locus_uread_begin.size(), 0, h2d));
+  LTR_TRY(upload(ctx, job->r2u, plan.read_to_uread.data(), plan.read_to_uread.size(), 0, h2d));
+  LTR_TRY(upload(ctx, job->rlocus, plan.read_locus.data(), plan.read_locus.size(), 0, h2d));
   LTR_TRY(upload(ctx, job->hap_locus, plan.hap_locus.data(), plan.hap_locus.size(), 0, h2d));
   LTR_TRY(upload(ctx, job->ll_off, plan.ll_off.data(), plan.ll_off.size(), 0, h2d));
+  LTR_TRY(upload(ctx, job->ull_off, plan.ull_off.data(), plan.ull_off.size(), 0, h2d));
+  LTR_CUDA_J(job->uniq_ll.alloc(plan.ull_off[bb.n_loci] * sizeof(double)));
   LTR_TRY(upload(ctx, job->tabI, job->hc.tabI.data(), job->hc.tabI.size(), 0, h2d));
   LTR_TRY(upload(ctx, job->tabD, job->hc.tabD.data(), job->hc.tabD.size(), 0, h2d));
   LTR_CUDA_J(job->out_ll.alloc(job->n_ll * sizeof(double)));
@@ -305,9 +316,9 @@ static int run_classes(ltr_ctx* ctx, ltr_job* job, bool only_forced) {
   B.read_bytes = job->read_bytes.as<uint8_t>();
   B.read_off = job->read_off.as<uint32_t>();
   B.locus_hap_begin = job->lhb.as<uint32_t>();
-  B.locus_read_begin = job->lrb.as<uint32_t>();
-  B.ll_off = job->ll_off.as<unsigned long long>();
-  B.out_ll = job->out_ll.as<double>();
+  B.locus_read_begin = job->lub.as<uint32_t>();            // unique reads
+  B.ll_off = job->ull_off.as<unsigned long long>();
+  B.out_ll = job->uniq_ll.as<double>();
   int si = 0;
   for (ClassState& cs : job->classes) {
     if (only_forced && !cs.force_full) continue;
@@ -381,6 +392,21 @@ int ltr_job_run(ltr_ctx* ctx, ltr_job* job) {
       LTR_CUDA(ctx, cudaEventRecord(ctx->ev_stream[i], ctx->streams[i]));
       LTR_CUDA(ctx, cudaStreamWaitEvent(ctx->main_stream, ctx->ev_stream[i], 0));
     }
+  }
+  {
+    ExpandArgs E;
+    E.n_reads = job->n_reads;
+    E.read_locus = job->rlocus.as<uint32_t>();
+    E.read_to_uread = job->r2u.as<uint32_t>();
+    E.locus_hap_begin = job->lhb.as<uint32_t>();
+    E.locus_read_begin = job->lrb.as<uint32_t>();
+    E.locus_uread_begin = job->lub.as<uint32_t>();
+    E.ll_off = job->ll_off.as<unsigned long long>();
+    E.ull_off = job->ull_off.as<unsigned long long>();
+    E.uniq_ll = job->uniq_ll.as<double>();
+    E.out_ll = job->out_ll.as<double>();
+    LTR_CUDA(ctx, launch_expand_ll(E, ctx->main_stream));
+    if (job->n_reads) job->stats.n_launches += 1;
   }
   LTR_CUDA(ctx, cudaEventRecord(ctx->ev_vit, ctx->main_stream));
   if (job->has_post) {

@@ -16,6 +16,22 @@ cudaError_t launch_viterbi(int k, int mode, int grid_blocks, cudaStream_t stream
                            uint32_t task_cap, uint32_t* cursor, const FailSink& fail, XY* sxy,
                            uint32_t* sb, uint32_t scratch_stride);
 
+// Fan-out of the unique LL matrices (one row per distinct trimmed read of a locus) to the reference's
+// aln_probs[read*H + hap] layout (HapAligner.cpp:549): out[ll_off(l) + (p-rb0)*H + h] = uniq[ull_off(l) + u(p)*H + h].
+struct ExpandArgs {
+  uint32_t n_reads;
+  const uint32_t* read_locus;
+  const uint32_t* read_to_uread;
+  const uint32_t* locus_hap_begin;
+  const uint32_t* locus_read_begin;
+  const uint32_t* locus_uread_begin;
+  const unsigned long long* ll_off;
+  const unsigned long long* ull_off;
+  const double* uniq_ll;
+  double* out_ll;
+};
+cudaError_t launch_expand_ll(const ExpandArgs& E, cudaStream_t stream);
+
 // Posterior step for a batch of loci (Genotyper::calc_log_sample_posteriors, genotyper.cpp:45-83).
 struct DevPosterior {
   uint32_t n_loci;

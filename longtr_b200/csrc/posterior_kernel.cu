@@ -64,6 +64,26 @@ __global__ void __launch_bounds__(128) posterior_kernel(const DevPosterior P) {
   }
 }
 
+// 8 lanes per pooled read walk its H haplotype columns (H is 2-12 in practice): coalesced within the row.
+__global__ void __launch_bounds__(256) expand_ll_kernel(const ExpandArgs E) {
+  const uint32_t sub = threadIdx.x & 7u;
+  for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; r < E.n_reads; r += (gridDim.x * blockDim.x) >> 3) {
+    const uint32_t l = E.read_locus[r];
+    const uint32_t H = E.locus_hap_begin[l + 1] - E.locus_hap_begin[l];
+    const double* src = E.uniq_ll + E.ull_off[l] + (size_t)(E.read_to_uread[r] - E.locus_uread_begin[l]) * H;
+    double* dst = E.out_ll + E.ll_off[l] + (size_t)(r - E.locus_read_begin[l]) * H;
+    for (uint32_t h = sub; h < H; h += 8u) dst[h] = src[h];
+  }
+}
+
+cudaError_t launch_expand_ll(const ExpandArgs& E, cudaStream_t stream) {
+  if (E.n_reads == 0) return cudaSuccess;
+  const uint64_t want = ((uint64_t)E.n_reads * 8u + 255u) / 256u;
+  const uint32_t grid = (uint32_t)(want < 148u * 32u ? want : 148u * 32u);
+  expand_ll_kernel<<<grid, 256, 0, stream>>>(E);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_posteriors(const DevPosterior& P, cudaStream_t stream) {
   if (P.n_loci == 0) return cudaSuccess;
   const uint32_t grid = P.n_loci < 148u * 16u ? P.n_loci : 148u * 16u;

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "longtr_b200.h"
@@ -81,44 +82,143 @@ inline int rows_per_lane(int n, int kmax) {
 }
 
 struct Plan {
-  std::vector<std::vector<Task>> tasks;  // [K] -> tasks of class K (index 0 unused)
+  std::vector<std::vector<Task>> tasks;  // [K] -> tasks of class K (index 0 unused); read ranges index UNIQUE reads
   std::vector<uint32_t> hap_locus;       // [n_haps]
-  std::vector<unsigned long long> ll_off;  // [n_loci+1]
-  uint64_t n_pairs = 0, n_cells = 0;
+  std::vector<unsigned long long> ll_off;  // [n_loci+1] offsets of the caller-visible LL matrices (P_l x H_l)
+  uint64_t n_pairs = 0, n_cells = 0;     // as the reference counts them (every pooled read x haplotype)
+  uint64_t n_pairs_computed = 0, n_cells_computed = 0;  // after collapsing identical trimmed reads of a locus
   int max_n = 0, max_m = 0;
-  std::vector<uint32_t> max_q;  // [K] longest read stream among the tasks of class K
+  std::vector<uint32_t> max_q;  // [K] longest (unique) read stream among the tasks of class K
+  // Identical trimmed reads of a locus give identical log-likelihoods against every haplotype (the kernel is a
+  // pure function of the two strings), so each distinct sequence is aligned once and the result fanned out.
+  // LongTR pools reads by their +-200 bp sequence (ReadPooler, src/read_pooler.cpp:3-20) but aligns the +-5 bp
+  // trim of it (HapAligner.cpp:346-465), so pools that differ only outside the trim window collapse here.
+  std::vector<uint32_t> locus_uread_begin;  // [n_loci+1]
+  std::vector<uint32_t> uread_off;          // [n_ureads+1]
+  std::vector<uint8_t> uread_bytes;
+  std::vector<uint32_t> read_to_uread;      // [n_reads] global unique-read index of every pooled read
+  std::vector<uint32_t> read_locus;         // [n_reads]
+  std::vector<unsigned long long> ull_off;  // [n_loci+1] offsets of the unique LL matrices (U_l x H_l)
 };
 
-// Validates the batch and builds per-class task lists (heaviest first within a class so the
-// persistent warps finish together).  Returns LTR_OK or LTR_ERR_INVALID.
-inline int make_plan(const ltr_viterbi_batch& b, const ltr_params& p, int kmax, Plan& out) {
+inline uint64_t plan_hash_bytes(const uint8_t* p, uint32_t n) {  // FNV-1a, 64 bit
+  uint64_t h = 1469598103934665603ull;
+  for (uint32_t i = 0; i < n; ++i) h = (h ^ p[i]) * 1099511628211ull;
+  return h;
+}
+
+// Validates the batch, collapses duplicate reads per locus and builds per-class task lists (heaviest first within a
+// class so the persistent warps finish together).  Returns LTR_OK or LTR_ERR_INVALID.
+inline int make_plan(const ltr_viterbi_batch& b, const ltr_params& p, int kmax, Plan& out, int n_threads = 0) {
   const int cut = 35 - p.indel_flank_len;
   out.tasks.assign(kmax + 1, std::vector<Task>());
   out.max_q.assign(kmax + 1, 0);
-  const uint32_t n_haps = b.locus_hap_begin[b.n_loci], n_reads = b.locus_read_begin[b.n_loci];
+  const uint32_t n_loci = b.n_loci;
+  const uint32_t n_haps = b.locus_hap_begin[n_loci], n_reads = b.locus_read_begin[n_loci];
   out.hap_locus.assign(n_haps, 0);
-  out.ll_off.assign((size_t)b.n_loci + 1, 0);
+  out.ll_off.assign((size_t)n_loci + 1, 0);
+  out.ull_off.assign((size_t)n_loci + 1, 0);
+  out.locus_uread_begin.assign((size_t)n_loci + 1, 0);
+  out.read_to_uread.assign(n_reads, 0);
+  out.read_locus.assign(n_reads, 0);
+  for (uint32_t l = 0; l < n_loci; ++l)
+    if (b.locus_hap_begin[l + 1] < b.locus_hap_begin[l] || b.locus_read_begin[l + 1] < b.locus_read_begin[l])
+      return LTR_ERR_INVALID;
   for (uint32_t r = 0; r < n_reads; ++r) {
     if (b.read_off[r + 1] <= b.read_off[r]) return LTR_ERR_INVALID;  // empty read
     out.max_m = std::max<int>(out.max_m, (int)(b.read_off[r + 1] - b.read_off[r]));
   }
+  for (uint32_t h = 0; h < n_haps; ++h)
+    if (b.hap_off[h + 1] < b.hap_off[h]) return LTR_ERR_INVALID;
+
+  // ---- pass 1 (parallel over loci): local unique index of every read, unique count / bytes per locus ----
+  std::vector<uint32_t> local_u(n_reads, 0), ucount(n_loci, 0), ubytes(n_loci, 0);
+  if (n_threads <= 0) n_threads = (n_loci >= 4096) ? (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency())) : 1;
+  auto dedupe = [&](uint32_t l0, uint32_t l1) {
+    std::vector<uint64_t> hashes;
+    std::vector<uint32_t> reps;  // representative read of each unique sequence of the locus
+    for (uint32_t l = l0; l < l1; ++l) {
+      const uint32_t r0 = b.locus_read_begin[l], r1 = b.locus_read_begin[l + 1];
+      hashes.clear();
+      reps.clear();
+      uint32_t bytes = 0;
+      for (uint32_t r = r0; r < r1; ++r) {
+        const uint8_t* s = b.read_bytes + b.read_off[r];
+        const uint32_t len = b.read_off[r + 1] - b.read_off[r];
+        const uint64_t h = plan_hash_bytes(s, len);
+        uint32_t u = 0;
+        for (; u < reps.size(); ++u) {
+          if (hashes[u] != h) continue;
+          const uint32_t q = reps[u];
+          if (b.read_off[q + 1] - b.read_off[q] == len && std::memcmp(b.read_bytes + b.read_off[q], s, len) == 0) break;
+        }
+        if (u == reps.size()) {
+          reps.push_back(r);
+          hashes.push_back(h);
+          bytes += len;
+        }
+        local_u[r] = u;
+        out.read_locus[r] = l;
+      }
+      ucount[l] = (uint32_t)reps.size();
+      ubytes[l] = bytes;
+    }
+  };
+  if (n_threads > 1) {
+    std::vector<std::thread> th;
+    const uint32_t chunk = (n_loci + (uint32_t)n_threads - 1) / (uint32_t)n_threads;
+    for (int t = 0; t < n_threads; ++t) {
+      const uint32_t l0 = std::min(n_loci, (uint32_t)t * chunk), l1 = std::min(n_loci, l0 + chunk);
+      if (l0 < l1) th.emplace_back(dedupe, l0, l1);
+    }
+    for (auto& x : th) x.join();
+  } else {
+    dedupe(0, n_loci);
+  }
+  // ---- pass 2: prefix sums, unique read bytes ----------------------------------------------------------------
+  std::vector<uint64_t> ubyte_off((size_t)n_loci + 1, 0);
+  for (uint32_t l = 0; l < n_loci; ++l) {
+    out.locus_uread_begin[l + 1] = out.locus_uread_begin[l] + ucount[l];
+    ubyte_off[l + 1] = ubyte_off[l] + ubytes[l];
+  }
+  if (ubyte_off[n_loci] > 0xFFFFFFF0ull) return LTR_ERR_INVALID;
+  const uint32_t n_ureads = out.locus_uread_begin[n_loci];
+  out.uread_off.assign((size_t)n_ureads + 1, 0);
+  out.uread_bytes.assign((size_t)ubyte_off[n_loci], 0);
+  for (uint32_t l = 0; l < n_loci; ++l) {
+    const uint32_t r0 = b.locus_read_begin[l], r1 = b.locus_read_begin[l + 1], u0 = out.locus_uread_begin[l];
+    uint32_t next = 0, off = (uint32_t)ubyte_off[l];
+    for (uint32_t r = r0; r < r1; ++r) {
+      out.read_to_uread[r] = u0 + local_u[r];
+      if (local_u[r] == next) {  // first occurrence (unique indices are handed out in read order)
+        const uint32_t len = b.read_off[r + 1] - b.read_off[r];
+        std::memcpy(out.uread_bytes.data() + off, b.read_bytes + b.read_off[r], len);
+        out.uread_off[u0 + next] = off;
+        off += len;
+        ++next;
+      }
+    }
+  }
+  out.uread_off[n_ureads] = (uint32_t)ubyte_off[n_loci];
+
+  // ---- tasks -------------------------------------------------------------------------------------------------
   struct Key { uint64_t cost; Task t; int k; };
   std::vector<Key> keys;
   keys.reserve(n_haps);
-  for (uint32_t l = 0; l < b.n_loci; ++l) {
+  for (uint32_t l = 0; l < n_loci; ++l) {
     const uint32_t h0 = b.locus_hap_begin[l], h1 = b.locus_hap_begin[l + 1];
     const uint32_t r0 = b.locus_read_begin[l], r1 = b.locus_read_begin[l + 1];
-    if (h1 < h0 || r1 < r0) return LTR_ERR_INVALID;
+    const uint32_t u0 = out.locus_uread_begin[l], u1 = out.locus_uread_begin[l + 1];
     out.ll_off[l + 1] = out.ll_off[l] + (unsigned long long)(h1 - h0) * (r1 - r0);
-    const uint64_t q = (uint64_t)b.read_off[r1] - b.read_off[r0];
+    out.ull_off[l + 1] = out.ull_off[l] + (unsigned long long)(h1 - h0) * (u1 - u0);
+    const uint64_t q = (uint64_t)out.uread_off[u1] - out.uread_off[u0];
     for (uint32_t h = h0; h < h1; ++h) {
       out.hap_locus[h] = l;
-      if (b.hap_off[h + 1] < b.hap_off[h]) return LTR_ERR_INVALID;
       const int hlen = (int)(b.hap_off[h + 1] - b.hap_off[h]);
       const int n = hlen - 2 * cut;
       if (r1 == r0) continue;
       int k = 1;
-      uint64_t cost = r1 - r0;
+      uint64_t cost = u1 - u0;
       if (hlen > 60 && n >= 1) {
         out.max_n = std::max(out.max_n, n);
         k = rows_per_lane(n, kmax);
@@ -129,17 +229,35 @@ inline int make_plan(const ltr_viterbi_batch& b, const ltr_params& p, int kmax, 
           const int m = (int)(b.read_off[r + 1] - b.read_off[r]);
           if (std::abs(n - m) <= 600) out.n_cells += (uint64_t)n * (uint64_t)m;
         }
+        for (uint32_t u = u0; u < u1; ++u) {
+          const int m = (int)(out.uread_off[u + 1] - out.uread_off[u]);
+          if (std::abs(n - m) <= 600) out.n_cells_computed += (uint64_t)n * (uint64_t)m;
+        }
       }
       out.n_pairs += r1 - r0;
+      out.n_pairs_computed += u1 - u0;
       Key key;
       key.cost = cost; key.k = k;
-      key.t.hap = h; key.t.read_begin = r0; key.t.read_end = r1;
+      key.t.hap = h; key.t.read_begin = u0; key.t.read_end = u1;
       keys.push_back(key);
     }
   }
   std::stable_sort(keys.begin(), keys.end(), [](const Key& a, const Key& c) { return a.cost > c.cost; });
   for (const Key& k : keys) out.tasks[k.k].push_back(k.t);
   return LTR_OK;
+}
+
+// Fan the unique LL matrices (U_l x H_l) out to the caller-visible ones (P_l x H_l); host version for the CPU emulator
+// (the product does this on the device, expand_ll_kernel).
+inline void expand_ll_host(const ltr_viterbi_batch& b, const Plan& plan, const double* uniq_ll, double* out_ll) {
+  const uint32_t n_reads = b.locus_read_begin[b.n_loci];
+  for (uint32_t r = 0; r < n_reads; ++r) {
+    const uint32_t l = plan.read_locus[r];
+    const uint32_t H = b.locus_hap_begin[l + 1] - b.locus_hap_begin[l];
+    const double* src = uniq_ll + plan.ull_off[l] + (size_t)(plan.read_to_uread[r] - plan.locus_uread_begin[l]) * H;
+    double* dst = out_ll + plan.ll_off[l] + (size_t)(r - b.locus_read_begin[l]) * H;
+    for (uint32_t h = 0; h < H; ++h) dst[h] = src[h];
+  }
 }
 
 }  // namespace ltr

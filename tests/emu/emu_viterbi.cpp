@@ -126,15 +126,15 @@ extern "C" int ltr_emu_viterbi_batch(const ltr_viterbi_batch* b, const ltr_param
   make_consts(*p, std::max(plan.max_n, plan.max_m) + 2, hc);
   hc.C.tabI = hc.tabI.data();
   hc.C.tabD = hc.tabD.data();
-  // padded copy of the read bytes (the kernel prefetches one byte ahead)
-  const uint32_t nbytes = b->read_off[b->locus_read_begin[b->n_loci]];
-  std::vector<uint8_t> rbytes(nbytes + 8, 0);
-  std::memcpy(rbytes.data(), b->read_bytes, nbytes);
+  // the warps see the distinct trimmed reads of each locus (Plan); padded copy: the kernel prefetches one byte ahead
+  std::vector<uint8_t> rbytes(plan.uread_bytes.size() + 8, 0);
+  if (!plan.uread_bytes.empty()) std::memcpy(rbytes.data(), plan.uread_bytes.data(), plan.uread_bytes.size());
+  std::vector<double> uniq_ll((size_t)plan.ull_off[b->n_loci] + 1, 123.0);
   DevBatch B;
   B.hap_bytes = b->hap_bytes; B.hap_off = b->hap_off; B.hap_locus = plan.hap_locus.data();
-  B.read_bytes = rbytes.data(); B.read_off = b->read_off;
-  B.locus_hap_begin = b->locus_hap_begin; B.locus_read_begin = b->locus_read_begin;
-  B.ll_off = plan.ll_off.data(); B.out_ll = out_ll;
+  B.read_bytes = rbytes.data(); B.read_off = plan.uread_off.data();
+  B.locus_hap_begin = b->locus_hap_begin; B.locus_read_begin = plan.locus_uread_begin.data();
+  B.ll_off = plan.ull_off.data(); B.out_ll = uniq_ll.data();
   EmuScratch E;
   uint64_t nfall = 0;
   if (!fast_certificate_valid(*p)) use_fast = 0;  // as ltr_job_create does
@@ -152,6 +152,7 @@ extern "C" int ltr_emu_viterbi_batch(const ltr_viterbi_batch* b, const ltr_param
     none.items = nullptr; none.count = &zero; none.capacity = 0;
     for (uint32_t f = 0; f < nfail; ++f) emu_dispatch<MODE_FULL>(k, hc.C, B, fails[f], none, E);
   }
+  expand_ll_host(*b, plan, uniq_ll.data(), out_ll);
   if (n_fallback) *n_fallback = nfall;
   return LTR_OK;
 }
