@@ -393,12 +393,25 @@ def main():
     checksum = float(np.sum(ll[ll > -600.0]))
 
     # ---- end-to-end arm: host buffers through the C ABI, copies inside the timed region -------
+    # results land in pinned host buffers allocated once (the caller of the C ABI owns its output arrays)
+    n_ll, n_post, n_tot = job.n_ll, job.n_post, job.n_totals
+    pin_out, keep_o = pinned_copy(torch, dict(ll=np.zeros(n_ll), post=np.zeros(max(1, n_post)), tot=np.zeros(max(1, n_tot))))
+    timing = os.environ.get("LTR_TIMING") is not None
+
     def e2e_step():
+        t = [time.perf_counter()]
         j = eng.create_job(pinned_b, pinned_p, aln_params=work.aln_params)
+        t.append(time.perf_counter())
         s = j.run()
-        j.download()
+        t.append(time.perf_counter())
+        j.download(out_ll=pin_out["ll"], out_post=pin_out["post"][:n_post], out_totals=pin_out["tot"][:n_tot])
+        t.append(time.perf_counter())
         s = j.stats()
         j.close()
+        t.append(time.perf_counter())
+        if timing and rank == 0:
+            print("[bench] e2e step: create %.1f run %.1f download %.1f close %.1f ms" %
+                  tuple(1e3 * (b - a) for a, b in zip(t[:-1], t[1:])), file=sys.stderr)
         return s
     for _ in range(min(args.warmup, 3)):
         e2e_step()

@@ -7,6 +7,7 @@
 // cannot be created and every entry point fails.
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -145,6 +146,7 @@ void ltr_ctx_destroy(ltr_ctx* ctx) {
   if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
   if (ctx->ev_vit) cudaEventDestroy(ctx->ev_vit);
   if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
+  if (ctx->stage) cudaFreeHost(ctx->stage);
   delete ctx;
 }
 
@@ -181,7 +183,29 @@ int ltr_job_create(ltr_ctx* ctx, const ltr_params* params, const ltr_viterbi_bat
   if (bb.n_loci == 0) {
     bb.locus_hap_begin = bb.locus_read_begin = bb.hap_off = bb.read_off = kZero;
   }
-  int rc = make_plan(bb, *params, kmax, job->plan);
+  // unique read bytes are staged in pinned host memory owned by the context (grow-only, reused by the next job)
+  struct Stage {
+    static uint8_t* get(size_t bytes, void* user) {
+      ltr_ctx* c = static_cast<ltr_ctx*>(user);
+      if (bytes > c->stage_bytes) {
+        if (c->stage) cudaFreeHost(c->stage);
+        c->stage = nullptr;
+        c->stage_bytes = 0;
+        const size_t want = bytes + bytes / 4 + (1u << 20);
+        if (cudaHostAlloc(&c->stage, want, cudaHostAllocDefault) != cudaSuccess) {
+          cudaGetLastError();
+          c->stage = nullptr;
+          return nullptr;  // make_plan falls back to pageable memory
+        }
+        c->stage_bytes = want;
+      }
+      return static_cast<uint8_t*>(c->stage);
+    }
+  };
+  static const bool timing = getenv("LTR_TIMING") != nullptr;  // diagnostics: host-side phases of job creation on stderr
+  const auto t_begin = std::chrono::steady_clock::now();
+  int rc = make_plan(bb, *params, kmax, job->plan, 0, &Stage::get, ctx);
+  const auto t_plan = std::chrono::steady_clock::now();
   if (rc != LTR_OK) { delete job; return rc; }
   Plan& plan = job->plan;
   job->n_loci = bb.n_loci;
@@ -217,7 +241,7 @@ int ltr_job_create(ltr_ctx* ctx, const ltr_params* params, const ltr_viterbi_bat
   // unique LL matrices and expand_ll_kernel fans them out to the caller-visible aln_probs layout.
   const size_t hap_nbytes = bb.hap_off[job->n_haps];
   LTR_TRY(upload(ctx, job->hap_bytes, bb.hap_bytes, hap_nbytes, 16, h2d));
-  LTR_TRY(upload(ctx, job->read_bytes, plan.uread_bytes.data(), plan.uread_bytes.size(), 16, h2d));
+  LTR_TRY(upload(ctx, job->read_bytes, plan.uread_bytes, plan.uread_nbytes, 16, h2d));
   LTR_TRY(upload(ctx, job->hap_off, bb.hap_off, (size_t)job->n_haps + 1, 0, h2d));
   LTR_TRY(upload(ctx, job->read_off, plan.uread_off.data(), plan.uread_off.size(), 0, h2d));
   LTR_TRY(upload(ctx, job->lhb, bb.locus_hap_begin, (size_t)job->n_loci + 1, 0, h2d));
@@ -301,7 +325,15 @@ int ltr_job_create(ltr_ctx* ctx, const ltr_params* params, const ltr_viterbi_bat
     LTR_CUDA_J(job->post.alloc(job->n_post * sizeof(double)));
     LTR_CUDA_J(job->totals.alloc(job->n_tot * sizeof(double)));
   }
+  const auto t_enq = std::chrono::steady_clock::now();
   LTR_CUDA_J(cudaStreamSynchronize(ctx->main_stream));
+  if (timing) {
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+      return std::chrono::duration<double, std::milli>(b - a).count();
+    };
+    fprintf(stderr, "[ltr] job_create: plan %.1f ms, alloc+enqueue %.1f ms, copy drain %.1f ms (h2d %.1f MB)\n",
+            ms(t_begin, t_plan), ms(t_plan, t_enq), ms(t_enq, std::chrono::steady_clock::now()), *h2d / 1e6);
+  }
   *out = job;
   return LTR_OK;
 #undef LTR_TRY

@@ -40,6 +40,8 @@ struct ltr_ctx {
   cudaEvent_t ev_stream[ltr::kNumStreams] = {nullptr};
   int blocks_per_sm[2][32] = {{0}};
   std::string last_error;
+  void* stage = nullptr;  // pinned host staging for the plan's unique read bytes (grow-only)
+  size_t stage_bytes = 0;
 };
 
 namespace ltr {

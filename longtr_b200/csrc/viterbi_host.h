@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <memory>
 #include <thread>
 #include <vector>
 
@@ -95,21 +96,50 @@ struct Plan {
   // trim of it (HapAligner.cpp:346-465), so pools that differ only outside the trim window collapse here.
   std::vector<uint32_t> locus_uread_begin;  // [n_loci+1]
   std::vector<uint32_t> uread_off;          // [n_ureads+1]
-  std::vector<uint8_t> uread_bytes;
+  uint8_t* uread_bytes = nullptr;           // uread_nbytes bytes: caller-provided staging (pinned) or uread_owned
+  size_t uread_nbytes = 0;
+  std::unique_ptr<uint8_t[]> uread_owned;   // uninitialised on purpose: first touched by the parallel copy
   std::vector<uint32_t> read_to_uread;      // [n_reads] global unique-read index of every pooled read
   std::vector<uint32_t> read_locus;         // [n_reads]
   std::vector<unsigned long long> ull_off;  // [n_loci+1] offsets of the unique LL matrices (U_l x H_l)
 };
 
-inline uint64_t plan_hash_bytes(const uint8_t* p, uint32_t n) {  // FNV-1a, 64 bit
-  uint64_t h = 1469598103934665603ull;
-  for (uint32_t i = 0; i < n; ++i) h = (h ^ p[i]) * 1099511628211ull;
-  return h;
+inline uint64_t plan_hash_bytes(const uint8_t* p, uint32_t n) {  // 8 bytes per round, multiply-xorshift mixing
+  uint64_t h = 0x9E3779B97F4A7C15ull ^ ((uint64_t)n * 0xD6E8FEB86659FD93ull);
+  uint32_t i = 0;
+  for (; i + 8 <= n; i += 8) {
+    uint64_t w;
+    std::memcpy(&w, p + i, 8);
+    h = (h ^ w) * 0xFF51AFD7ED558CCDull;
+    h ^= h >> 32;
+  }
+  uint64_t w = 0;
+  if (i < n) std::memcpy(&w, p + i, n - i);
+  h = (h ^ w) * 0xC4CEB9FE1A85EC53ull;
+  return h ^ (h >> 29);
+}
+
+template <typename F>
+inline void plan_parallel_for(uint32_t n, int n_threads, F f) {  // f(begin, end, thread)
+  if (n_threads <= 1 || n < 2) {
+    f(0u, n, 0);
+    return;
+  }
+  std::vector<std::thread> th;
+  const uint32_t chunk = (n + (uint32_t)n_threads - 1) / (uint32_t)n_threads;
+  for (int t = 0; t < n_threads; ++t) {
+    const uint32_t b0 = std::min(n, (uint32_t)t * chunk), b1 = std::min(n, b0 + chunk);
+    if (b0 < b1) th.emplace_back(f, b0, b1, t);
+  }
+  for (auto& x : th) x.join();
 }
 
 // Validates the batch, collapses duplicate reads per locus and builds per-class task lists (heaviest first within a
 // class so the persistent warps finish together).  Returns LTR_OK or LTR_ERR_INVALID.
-inline int make_plan(const ltr_viterbi_batch& b, const ltr_params& p, int kmax, Plan& out, int n_threads = 0) {
+// stage(bytes, user) may provide the buffer for the unique read bytes (the C ABI hands out pinned host memory).
+typedef uint8_t* (*PlanStageFn)(size_t bytes, void* user);
+inline int make_plan(const ltr_viterbi_batch& b, const ltr_params& p, int kmax, Plan& out, int n_threads = 0,
+                     PlanStageFn stage = nullptr, void* stage_user = nullptr) {
   const int cut = 35 - p.indel_flank_len;
   out.tasks.assign(kmax + 1, std::vector<Task>());
   out.max_q.assign(kmax + 1, 0);
@@ -134,7 +164,7 @@ inline int make_plan(const ltr_viterbi_batch& b, const ltr_params& p, int kmax, 
   // ---- pass 1 (parallel over loci): local unique index of every read, unique count / bytes per locus ----
   std::vector<uint32_t> local_u(n_reads, 0), ucount(n_loci, 0), ubytes(n_loci, 0);
   if (n_threads <= 0) n_threads = (n_loci >= 4096) ? (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency())) : 1;
-  auto dedupe = [&](uint32_t l0, uint32_t l1) {
+  auto dedupe = [&](uint32_t l0, uint32_t l1, int) {
     std::vector<uint64_t> hashes;
     std::vector<uint32_t> reps;  // representative read of each unique sequence of the locus
     for (uint32_t l = l0; l < l1; ++l) {
@@ -164,17 +194,7 @@ inline int make_plan(const ltr_viterbi_batch& b, const ltr_params& p, int kmax, 
       ubytes[l] = bytes;
     }
   };
-  if (n_threads > 1) {
-    std::vector<std::thread> th;
-    const uint32_t chunk = (n_loci + (uint32_t)n_threads - 1) / (uint32_t)n_threads;
-    for (int t = 0; t < n_threads; ++t) {
-      const uint32_t l0 = std::min(n_loci, (uint32_t)t * chunk), l1 = std::min(n_loci, l0 + chunk);
-      if (l0 < l1) th.emplace_back(dedupe, l0, l1);
-    }
-    for (auto& x : th) x.join();
-  } else {
-    dedupe(0, n_loci);
-  }
+  plan_parallel_for(n_loci, n_threads, dedupe);
   // ---- pass 2: prefix sums, unique read bytes ----------------------------------------------------------------
   std::vector<uint64_t> ubyte_off((size_t)n_loci + 1, 0);
   for (uint32_t l = 0; l < n_loci; ++l) {
@@ -183,64 +203,92 @@ inline int make_plan(const ltr_viterbi_batch& b, const ltr_params& p, int kmax, 
   }
   if (ubyte_off[n_loci] > 0xFFFFFFF0ull) return LTR_ERR_INVALID;
   const uint32_t n_ureads = out.locus_uread_begin[n_loci];
-  out.uread_off.assign((size_t)n_ureads + 1, 0);
-  out.uread_bytes.assign((size_t)ubyte_off[n_loci], 0);
-  for (uint32_t l = 0; l < n_loci; ++l) {
+  out.uread_off.resize((size_t)n_ureads + 1);
+  out.uread_nbytes = (size_t)ubyte_off[n_loci];
+  out.uread_bytes = stage ? stage(out.uread_nbytes + 16, stage_user) : nullptr;
+  if (out.uread_bytes == nullptr) {
+    out.uread_owned.reset(new uint8_t[out.uread_nbytes + 16]);
+    out.uread_bytes = out.uread_owned.get();
+  }
+  plan_parallel_for(n_loci, n_threads, [&](uint32_t l0, uint32_t l1, int) {
+   for (uint32_t l = l0; l < l1; ++l) {
     const uint32_t r0 = b.locus_read_begin[l], r1 = b.locus_read_begin[l + 1], u0 = out.locus_uread_begin[l];
     uint32_t next = 0, off = (uint32_t)ubyte_off[l];
     for (uint32_t r = r0; r < r1; ++r) {
       out.read_to_uread[r] = u0 + local_u[r];
       if (local_u[r] == next) {  // first occurrence (unique indices are handed out in read order)
         const uint32_t len = b.read_off[r + 1] - b.read_off[r];
-        std::memcpy(out.uread_bytes.data() + off, b.read_bytes + b.read_off[r], len);
+        std::memcpy(out.uread_bytes + off, b.read_bytes + b.read_off[r], len);
         out.uread_off[u0 + next] = off;
         off += len;
         ++next;
       }
     }
-  }
+   }
+  });
   out.uread_off[n_ureads] = (uint32_t)ubyte_off[n_loci];
 
   // ---- tasks -------------------------------------------------------------------------------------------------
   struct Key { uint64_t cost; Task t; int k; };
+  for (uint32_t l = 0; l < n_loci; ++l) {
+    const uint32_t H = b.locus_hap_begin[l + 1] - b.locus_hap_begin[l];
+    out.ll_off[l + 1] = out.ll_off[l] + (unsigned long long)H * (b.locus_read_begin[l + 1] - b.locus_read_begin[l]);
+    out.ull_off[l + 1] = out.ull_off[l] + (unsigned long long)H * (out.locus_uread_begin[l + 1] - out.locus_uread_begin[l]);
+  }
+  struct Part {
+    std::vector<Key> keys;
+    std::vector<uint32_t> max_q;
+    uint64_t n_pairs = 0, n_cells = 0, n_pairs_c = 0, n_cells_c = 0;
+    int max_n = 0;
+  };
+  std::vector<Part> parts((size_t)std::max(1, n_threads));
+  plan_parallel_for(n_loci, n_threads, [&](uint32_t l0, uint32_t l1, int t) {
+    Part& P = parts[(size_t)t];
+    P.max_q.assign(kmax + 1, 0);
+    for (uint32_t l = l0; l < l1; ++l) {
+      const uint32_t h0 = b.locus_hap_begin[l], h1 = b.locus_hap_begin[l + 1];
+      const uint32_t r0 = b.locus_read_begin[l], r1 = b.locus_read_begin[l + 1];
+      const uint32_t u0 = out.locus_uread_begin[l], u1 = out.locus_uread_begin[l + 1];
+      const uint64_t q = (uint64_t)out.uread_off[u1] - out.uread_off[u0];
+      for (uint32_t h = h0; h < h1; ++h) {
+        out.hap_locus[h] = l;
+        const int hlen = (int)(b.hap_off[h + 1] - b.hap_off[h]);
+        const int n = hlen - 2 * cut;
+        if (r1 == r0) continue;
+        int k = 1;
+        uint64_t cost = u1 - u0;
+        if (hlen > 60 && n >= 1) {
+          P.max_n = std::max(P.max_n, n);
+          k = rows_per_lane(n, kmax);
+          const int strips = std::max(1, (n - 1 + 32 * k - 1) / (32 * k));
+          cost = (uint64_t)k * strips * (q + 32);
+          P.max_q[k] = std::max<uint32_t>(P.max_q[k], (uint32_t)q);
+          for (uint32_t r = r0; r < r1; ++r) {
+            const int m = (int)(b.read_off[r + 1] - b.read_off[r]);
+            if (std::abs(n - m) <= 600) P.n_cells += (uint64_t)n * (uint64_t)m;
+          }
+          for (uint32_t u = u0; u < u1; ++u) {
+            const int m = (int)(out.uread_off[u + 1] - out.uread_off[u]);
+            if (std::abs(n - m) <= 600) P.n_cells_c += (uint64_t)n * (uint64_t)m;
+          }
+        }
+        P.n_pairs += r1 - r0;
+        P.n_pairs_c += u1 - u0;
+        Key key;
+        key.cost = cost; key.k = k;
+        key.t.hap = h; key.t.read_begin = u0; key.t.read_end = u1;
+        P.keys.push_back(key);
+      }
+    }
+  });
   std::vector<Key> keys;
   keys.reserve(n_haps);
-  for (uint32_t l = 0; l < n_loci; ++l) {
-    const uint32_t h0 = b.locus_hap_begin[l], h1 = b.locus_hap_begin[l + 1];
-    const uint32_t r0 = b.locus_read_begin[l], r1 = b.locus_read_begin[l + 1];
-    const uint32_t u0 = out.locus_uread_begin[l], u1 = out.locus_uread_begin[l + 1];
-    out.ll_off[l + 1] = out.ll_off[l] + (unsigned long long)(h1 - h0) * (r1 - r0);
-    out.ull_off[l + 1] = out.ull_off[l] + (unsigned long long)(h1 - h0) * (u1 - u0);
-    const uint64_t q = (uint64_t)out.uread_off[u1] - out.uread_off[u0];
-    for (uint32_t h = h0; h < h1; ++h) {
-      out.hap_locus[h] = l;
-      const int hlen = (int)(b.hap_off[h + 1] - b.hap_off[h]);
-      const int n = hlen - 2 * cut;
-      if (r1 == r0) continue;
-      int k = 1;
-      uint64_t cost = u1 - u0;
-      if (hlen > 60 && n >= 1) {
-        out.max_n = std::max(out.max_n, n);
-        k = rows_per_lane(n, kmax);
-        const int strips = std::max(1, (n - 1 + 32 * k - 1) / (32 * k));
-        cost = (uint64_t)k * strips * (q + 32);
-        out.max_q[k] = std::max<uint32_t>(out.max_q[k], (uint32_t)q);
-        for (uint32_t r = r0; r < r1; ++r) {
-          const int m = (int)(b.read_off[r + 1] - b.read_off[r]);
-          if (std::abs(n - m) <= 600) out.n_cells += (uint64_t)n * (uint64_t)m;
-        }
-        for (uint32_t u = u0; u < u1; ++u) {
-          const int m = (int)(out.uread_off[u + 1] - out.uread_off[u]);
-          if (std::abs(n - m) <= 600) out.n_cells_computed += (uint64_t)n * (uint64_t)m;
-        }
-      }
-      out.n_pairs += r1 - r0;
-      out.n_pairs_computed += u1 - u0;
-      Key key;
-      key.cost = cost; key.k = k;
-      key.t.hap = h; key.t.read_begin = u0; key.t.read_end = u1;
-      keys.push_back(key);
-    }
+  for (const Part& P : parts) {
+    keys.insert(keys.end(), P.keys.begin(), P.keys.end());
+    out.n_pairs += P.n_pairs; out.n_cells += P.n_cells;
+    out.n_pairs_computed += P.n_pairs_c; out.n_cells_computed += P.n_cells_c;
+    out.max_n = std::max(out.max_n, P.max_n);
+    for (size_t k = 0; k < P.max_q.size(); ++k) out.max_q[k] = std::max(out.max_q[k], P.max_q[k]);
   }
   std::stable_sort(keys.begin(), keys.end(), [](const Key& a, const Key& c) { return a.cost > c.cost; });
   for (const Key& k : keys) out.tasks[k.k].push_back(k.t);

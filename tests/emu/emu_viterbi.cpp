@@ -127,8 +127,8 @@ extern "C" int ltr_emu_viterbi_batch(const ltr_viterbi_batch* b, const ltr_param
   hc.C.tabI = hc.tabI.data();
   hc.C.tabD = hc.tabD.data();
   // the warps see the distinct trimmed reads of each locus (Plan); padded copy: the kernel prefetches one byte ahead
-  std::vector<uint8_t> rbytes(plan.uread_bytes.size() + 8, 0);
-  if (!plan.uread_bytes.empty()) std::memcpy(rbytes.data(), plan.uread_bytes.data(), plan.uread_bytes.size());
+  std::vector<uint8_t> rbytes(plan.uread_nbytes + 8, 0);
+  if (plan.uread_nbytes) std::memcpy(rbytes.data(), plan.uread_bytes, plan.uread_nbytes);
   std::vector<double> uniq_ll((size_t)plan.ull_off[b->n_loci] + 1, 123.0);
   DevBatch B;
   B.hap_bytes = b->hap_bytes; B.hap_off = b->hap_off; B.hap_locus = plan.hap_locus.data();
