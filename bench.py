@@ -110,6 +110,7 @@ def dist_setup(n_gpus):
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the single JSON line (NCCL prints its version banner there)
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
     return torch, rank, world, local
 
