@@ -34,3 +34,46 @@ $CXX -O2 -g -std=c++11 -fPIC -w -I"$here/shim" -I"$ref/src" -I"$here/../include"
 $CXX -O2 -std=c++11 -fPIC -w -I"$here/shim" -c "$here/shim/hts_stubs.cpp" -o "$out/obj/hts_stubs.o"
 $CXX -shared -o "$out/libltr_ref.so" "$out/obj/ref_driver.o" "$out/obj/hts_stubs.o" $objs -Wl,--no-undefined -lm -lpthread
 echo "built $out/libltr_ref.so"
+
+# ---- IO-less per-locus genotyper (SeqStutterGenotyper ctor -> genotype -> write_vcf_record), twice ------------
+#   ltr_ref_full : every object is the reference's own (golden VCF records)
+#   ltr_ref_gpu  : HapAligner::process_reads and Genotyper::calc_log_sample_posteriors are taken from
+#                        integration/reference_binding.cpp (C ABI -> liblongtr_b200.so); the reference's own
+#                        definitions are weakened in COPIES of its objects under oracle/_ref/obj.
+FULL_TUS="seq_stutter_genotyper SeqAlignment/HaplotypeGenerator SeqAlignment/AlignmentOps vcf_writer vcf_input
+          debruijn_graph directed_graph extract_indels zalgorithm"
+fobjs=""
+for tu in $FULL_TUS; do
+  o="$out/obj/$(basename "$tu").o"
+  if [ ! -f "$o" ] || [ "$ref/src/$tu.cpp" -nt "$o" ]; then
+    $CXX $FLAGS -I"$here/shim" -c "$ref/src/$tu.cpp" -o "$o"
+  fi
+  fobjs="$fobjs $o"
+done
+$CXX -O2 -g -std=c++11 -fPIC -w -DLTR_FULL_MAIN -I"$here/shim" -I"$ref/src" -I"$here" -c "$here/full_driver.cpp" -o "$out/obj/full_driver.o"
+base_objs=""
+for o in $objs; do case "$o" in *fasta_reader.o) ;; *) base_objs="$base_objs $o";; esac; done
+$CXX -o "$out/ltr_ref_full" "$out/obj/full_driver.o" "$out/obj/hts_stubs.o" "$out/obj/fasta_reader.o" \
+     $base_objs $fobjs -lm -lpthread
+echo "built $out/ltr_ref_full"
+lib="$here/../longtr_b200/csrc"
+if [ -f "$lib/liblongtr_b200.so" ]; then
+  objcopy --weaken-symbol=_ZN10HapAligner13process_readsERKSt6vectorI9AlignmentSaIS1_EEiPK11BaseQualityRKS0_IbSaIbEEPdPi \
+          "$out/obj/HapAligner.o" "$out/obj/HapAligner_weak.o"
+  objcopy --weaken-symbol=_ZN9Genotyper26calc_log_sample_posteriorsERSt6vectorIiSaIiEE \
+          "$out/obj/genotyper.o" "$out/obj/genotyper_weak.o"
+  $CXX -O2 -g -std=c++11 -fPIC -w -I"$here/shim" -I"$ref/src" -I"$here/../include" \
+       -c "$here/../integration/reference_binding.cpp" -o "$out/obj/reference_binding.o"
+  gpu_objs=""
+  for o in $base_objs; do
+    case "$o" in
+      *HapAligner.o) gpu_objs="$gpu_objs $out/obj/HapAligner_weak.o";;
+      *genotyper.o) gpu_objs="$gpu_objs $out/obj/genotyper_weak.o";;
+      *) gpu_objs="$gpu_objs $o";;
+    esac
+  done
+  $CXX -o "$out/ltr_ref_gpu" "$out/obj/reference_binding.o" "$out/obj/full_driver.o" "$out/obj/hts_stubs.o" \
+       "$out/obj/fasta_reader.o" $gpu_objs $fobjs -L"$lib" -llongtr_b200 \
+       -Wl,-rpath,'$ORIGIN/../../longtr_b200/csrc' -lm -lpthread
+  echo "built $out/ltr_ref_gpu"
+fi

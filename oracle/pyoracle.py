@@ -259,3 +259,44 @@ def log_sample_posteriors(ll, log_p1, log_p2, sample_label, n_samples, haploid=F
                                                         _ptr(best, _ip))
         ll = out_ll
     return ll, post, tot, total, best
+
+
+# ---- IO-less per-locus genotyper of the reference (full_driver.cpp): VCF record text ---------------------------
+def full_available(which):
+    """which = 'full' (all-CPU reference) or 'gpu' (reference + integration/reference_binding.cpp -> GPU)."""
+    return os.path.exists(os.path.join(_HERE, "_ref", "ltr_ref_%s" % which))
+
+
+def _case_text(case):
+    st = case.get("stutter", (0.95, 0.05, 0.05, 0.95, 0.01, 0.01))
+    params = case.get("aln_params")
+    t = [case["chrom_name"], case["chrom_seq"], case["region_start"], case["region_stop"], case["motif"],
+         case["region_name"], len(case["samples"])] + list(case["samples"]) + list(case["n_p1s"]) + list(case["n_p2s"])
+    t += ["%.17g" % x for x in st] + [case.get("stutter_motif", "A"), case.get("stutter_period", len(case["motif"])),
+                                     int(case.get("haploid", False)), case.get("indel_flank_len", 5), case.get("switch", 0)]
+    t += [0] if params is None else [7] + ["%.9g" % x for x in params]
+    t.append(len(case["reads"]))
+    for r in case["reads"]:
+        t += [r["start"], r["stop"], int(r["rev"]), r["sample"], r["name"], r["seq"], r["qual"], r["aln"], r["cigar"],
+              "%.17g" % r["log_p1"], "%.17g" % r["log_p2"]]
+    return " ".join(str(x) for x in t) + "\n"
+
+
+def full_locus_records(cases, which="full"):
+    """SeqStutterGenotyper ctor -> genotype -> write_vcf_record for every case; returns the VCF record texts
+    ('' where genotype() failed)."""
+    build()
+    exe = os.path.join(_HERE, "_ref", "ltr_ref_%s" % which)
+    p = subprocess.run([exe], input="".join(_case_text(c) for c in cases).encode(), stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, timeout=600)
+    if p.returncode != 0:
+        raise RuntimeError("ltr_ref_%s failed rc=%d: %s" % (which, p.returncode, p.stderr.decode()[-400:]))
+    out, recs, pos = p.stdout.decode(), [], 0
+    while pos < len(out):
+        assert out.startswith("RECORD ", pos)
+        nl = out.index("\n", pos)
+        n = int(out[pos + 7:nl])
+        recs.append(out[nl + 1:nl + 1 + n].rstrip("\n"))
+        pos = nl + 1 + n + 1
+    assert len(recs) == len(cases)
+    return recs

@@ -191,13 +191,22 @@ def pair_batch_cases():
     return out
 
 
+def vcf_record_cases():
+    """Whole loci through the reference's SeqStutterGenotyper (ctor -> genotype -> write_vcf_record), IO-less."""
+    import dropin_cases as dc
+    cases = [dc.case_a4()] + dc.seeded_cases()
+    recs = po.full_locus_records(cases, "full")
+    assert recs[0] == dc.A4_RECORD, "SURVEY Appendix A4 not reproduced"
+    return [dict(name=c["name"], record=r) for c, r in zip(cases, recs)]
+
+
 def main():
     if not po.ref_available():
         raise SystemExit("oracle/_ref is not built (needs /root/reference)")
     os.makedirs(GOLD, exist_ok=True)
     sets = dict(appendix_a=[run_ref(c) for c in appendix_a()], process_reads_long=long_path_cases(),
                 process_reads_short=short_path_cases(),
-                posteriors=posterior_cases(), pair_batches=pair_batch_cases(), calls=calls_cases())
+                posteriors=posterior_cases(), pair_batches=pair_batch_cases(), calls=calls_cases(), vcf_records=vcf_record_cases())
     for name, cases in sets.items():
         path = os.path.join(GOLD, name + ".json")
         with open(path, "w") as f:
