@@ -18,3 +18,14 @@ def test_reference_reproduces_appendix_a4_and_golden_records():
     for c, r in zip(cases, recs):
         assert r == gold[c["name"]], c["name"]
         assert r, "genotype() failed for " + c["name"]
+
+
+@pytest.mark.skipif(not po.full_available("gpu"), reason="oracle/_ref/ltr_ref_gpu not built")
+def test_gpu_binding_is_linked_and_refuses_to_run_without_a_gpu():
+    """The drop-in build really routes HapAligner::process_reads through the C ABI: without a CUDA device it dies
+    through LongTR's own printErrorAndDie instead of silently using the reference's CPU code."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError, match="no usable CUDA device"):
+        po.full_locus_records([dc.case_a4()], "gpu")
