@@ -62,10 +62,12 @@ __device__ __forceinline__ WarpSmem carve(unsigned char* base, uint32_t max_flan
 // first_type is the type of the very first row (ROW_FIRST / ROW_AFTER_STUTTER); every other row is ROW_NORMAL.
 // lineM/lineD hold the row above on entry (unused for ROW_FIRST / ROW_AFTER_STUTTER beyond M) and the last
 // row on exit.  last[] receives M at the last column of every row.  Returns left_prob when first_type == ROW_FIRST.
-template <typename HapChar>
-__device__ __forceinline__ double wavefront_rows(const StutConsts& C, const FlankView& F, WarpSmem& W, double* last,
-                                                 int32_t row0, int32_t nrows, int32_t first_type, HapChar hapc,
-                                                 int lane) {
+// The haplotype character of row r of the block is chars[r * dir] (dir = -1 walks a reversed block).
+// One copy in the binary (noinline): the whole kernel has to stay inside the instruction caches -- the first
+// version inlined this four times and stalled ~10 cycles per issue on instruction fetch (profiles/r1i).
+__device__ __noinline__ double wavefront_rows(const StutConsts& C, const FlankView& F, WarpSmem& W, double* last,
+                                              int32_t row0, int32_t nrows, int32_t first_type, const uint8_t* chars,
+                                              int32_t dir, int lane) {
   double left_prob = 0.0;
   const int32_t per_strip = 32 * kStutRows;
   for (int32_t s0 = 0; s0 < nrows; s0 += per_strip) {
@@ -78,7 +80,7 @@ __device__ __forceinline__ double wavefront_rows(const StutConsts& C, const Flan
       const int32_t r = lane * kStutRows + k;
       if (r < rows) {
         Ln.type[k] = (s0 + r == 0) ? first_type : ROW_NORMAL;
-        Ln.hc[k] = hapc(s0 + r);
+        Ln.hc[k] = (int32_t)chars[(s0 + r) * dir];
       }
     }
     const int32_t nsteps = F.L + t_last;
@@ -122,8 +124,8 @@ struct SideGeom {  // one flank of one pair
 
 // Runs one flank (side 0 = left of the seed against the forward haplotype, side 1 = right of the seed, reversed,
 // against the reversed haplotype).  Fills last[] (last-column M of every reachable hap row), returns left_prob.
-__device__ __forceinline__ double run_side(const StutConsts& C, const SideGeom& G, int side, const double* art_lp,
-                                           WarpSmem& W, double* last, int lane) {
+__device__ __noinline__ double run_side(const StutConsts& C, const SideGeom& G, int side, const double* art_lp,
+                                        WarpSmem& W, double* last, int lane) {
   const int32_t L = side == 0 ? G.seed : (G.N - G.seed - 1);
   const int32_t B = G.B;
   // ---- stage the flank, the allele and the tables ---------------------------------------------------------
@@ -164,9 +166,10 @@ __device__ __forceinline__ double run_side(const StutConsts& C, const SideGeom& 
   const int32_t na = side == 0 ? G.n0 : G.n2, nc = side == 0 ? G.n2 : G.n0;
   const uint8_t* fa = side == 0 ? G.lflank : G.rflank;
   const uint8_t* fc = side == 0 ? G.rflank : G.lflank;
-  auto hap_a = [&](int32_t r) { return (int32_t)(side == 0 ? fa[r] : fa[na - 1 - r]); };
-  auto hap_c = [&](int32_t r) { return (int32_t)(side == 0 ? fc[r] : fc[nc - 1 - r]); };
-  const double left_prob = wavefront_rows(C, F, W, last, 0, na, ROW_FIRST, hap_a, lane);
+  const int32_t dir = side == 0 ? 1 : -1;
+  const uint8_t* chars_a = side == 0 ? fa : fa + (na - 1);
+  const uint8_t* chars_c = side == 0 ? fc : fc + (nc - 1);
+  const double left_prob = wavefront_rows(C, F, W, last, 0, na, ROW_FIRST, chars_a, dir, lane);
   // ---- phase B: the stutter row, one column per lane (HapAligner.cpp:64-111) ----------------------------------
   for (int32_t j = lane; j < L; j += 32) W.lineD[j] = stutter_row_cell(C, F, W.lineM, j);
   __syncwarp();
@@ -177,7 +180,7 @@ __device__ __forceinline__ double run_side(const StutConsts& C, const SideGeom& 
   }
   if (lane == 0) last[na + B - 1] = W.lineM[L - 1];
   // ---- phase C: rows of the second flank block -----------------------------------------------------------------
-  wavefront_rows(C, F, W, last, na + B, nc, ROW_AFTER_STUTTER, hap_c, lane);
+  wavefront_rows(C, F, W, last, na + B, nc, ROW_AFTER_STUTTER, chars_c, dir, lane);
   return left_prob;
 }
 
@@ -203,8 +206,10 @@ __global__ void __launch_bounds__(kStutWarps * 32) stutter_pair_kernel(const Stu
   G.B = (int32_t)(Bt.allele_off[T.allele + 1] - Bt.allele_off[T.allele]);
   const double* art_lp = Bt.allele_artifact_lp + (size_t)T.allele * 13;
 
-  const double l_prob = run_side(C, G, 0, art_lp, W, W.lastL, lane);
-  const double r_prob = run_side(C, G, 1, art_lp, W, W.lastR, lane);
+  double side_prob[2];
+#pragma unroll 1
+  for (int side = 0; side < 2; ++side) side_prob[side] = run_side(C, G, side, art_lp, W, side ? W.lastR : W.lastL, lane);
+  const double l_prob = side_prob[0], r_prob = side_prob[1];
   __syncwarp();
 
   // ---- seed join (compute_aln_logprob, HapAligner.cpp:165-233) ----------------------------------------------------
