@@ -195,30 +195,11 @@ struct SumVisit {
   LTS_HD void operator()(double v) { total += lse_term(*C, v, mx); }
 };
 
-struct StoreVisit {
-  double* buf;
-  int32_t n;
-  LTS_HD void operator()(double v) { buf[n++] = v; }
-};
-enum { kStutMaxTerms = 72 };  // terms of one (column, artifact) pair kept on the thread's stack (<= block length + 2)
-
 // align_stutter_region_reverse for (column j, artifact D).  The reference collects the terms in a vector and
-// reduces them with fast_log_sum_exp (max, then sum of fasterexp): one pass into a small per-thread buffer, or --
-// for blocks too long for the buffer -- two passes over the same term sequence.
+// reduces them with fast_log_sum_exp (max, then sum of fasterexp): two passes over the same term sequence, so that
+// no per-thread buffer (local memory) is needed.
 LTS_HD double stutter_region_ll(const StutConsts& C, const FlankView& F, int32_t base_len, int32_t j, int32_t D) {
   if (D == 0) return F.match[j];
-  if (F.B + 3 <= kStutMaxTerms) {
-    double terms[kStutMaxTerms];
-    StoreVisit st;
-    st.buf = terms;
-    st.n = 0;
-    stutter_region_terms(C, F, base_len, j, D, st);
-    double mx = terms[0];
-    for (int32_t k = 1; k < st.n; ++k) mx = smax(mx, terms[k]);
-    double total = 0.0;
-    for (int32_t k = 0; k < st.n; ++k) total += lse_term(C, terms[k], mx);
-    return lse_finish(mx, total);
-  }
   MaxVisit mv;
   mv.mx = 0.0;
   mv.any = false;

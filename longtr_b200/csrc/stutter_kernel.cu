@@ -7,6 +7,13 @@
 // reversed right flank, and joins the two at the seed base.  FP64 max-plus + a float bit-trick log-sum-exp; no
 // tensor cores (not a contraction).  The matrices of the reference are never materialised: only one row
 // (hand-off between phases / strips) and the last column (consumed by the seed join) are kept.
+//
+// Code layout follows two measurements (profiles/r1i, r1j): (1) the phases are single noinline functions so
+// that the kernel stays inside the instruction caches (the fully inlined first version stalled ~10 cycles per
+// issue on instruction fetch); (2) nothing is passed to them by reference on the thread stack -- with ~55 KB of
+// shared memory per CTA there is almost no L1 left, so local-memory traffic goes to L2 (5.5 cycles of
+// long-scoreboard stall per issue in the second version).  All per-warp context lives in shared memory and is
+// copied into registers at the top of each phase; the constants and the log table are staged per CTA.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -18,7 +25,17 @@ namespace ltr {
 static constexpr unsigned kFull = 0xFFFFFFFFu;
 static constexpr int kStutWarps = 4;
 
-struct WarpSmem {  // carved out of dynamic shared memory, per warp
+struct SideGeom {  // one pair
+  const uint8_t* read;  // whole read
+  const uint8_t* qual;
+  int32_t N, seed;
+  const uint8_t* lflank;
+  const uint8_t* rflank;
+  const uint8_t* allele;
+  int32_t n0, n2, B;  // |lflank|, |rflank|, |allele|
+};
+
+struct WarpCtx {  // per warp, in shared memory
   double* lc;
   double* lw;
   double* match;
@@ -26,48 +43,61 @@ struct WarpSmem {  // carved out of dynamic shared memory, per warp
   double* lineD;
   double* lastL;
   double* lastR;
+  double* probs;  // [13][32] artifact terms of the stutter row, one column per lane
   int32_t* um;
   uint8_t* seq;
   uint8_t* blk;
+  double art_lp[13];
+  SideGeom G;
+  FlankView F;
 };
 
 __host__ __device__ inline size_t stutter_warp_smem_bytes(uint32_t max_flank, uint32_t max_block, uint32_t max_hap) {
-  size_t b = 0;
+  size_t b = (sizeof(WarpCtx) + 15) / 16 * 16;
   b += 5 * (size_t)max_flank * sizeof(double);  // lc lw match lineM lineD
   b += 2 * (size_t)max_hap * sizeof(double);    // lastL lastR
+  b += 13 * 32 * sizeof(double);                // probs
   b += 6 * (size_t)max_block * sizeof(int32_t); // um
   b += ((size_t)max_flank + 15) / 16 * 16;      // seq
   b += ((size_t)max_block + 15) / 16 * 16;      // blk
   return (b + 15) / 16 * 16;
 }
-
-__device__ __forceinline__ WarpSmem carve(unsigned char* base, uint32_t max_flank, uint32_t max_block, uint32_t max_hap) {
-  WarpSmem W;
-  double* d = reinterpret_cast<double*>(base);
-  W.lc = d; d += max_flank;
-  W.lw = d; d += max_flank;
-  W.match = d; d += max_flank;
-  W.lineM = d; d += max_flank;
-  W.lineD = d; d += max_flank;
-  W.lastL = d; d += max_hap;
-  W.lastR = d; d += max_hap;
-  W.um = reinterpret_cast<int32_t*>(d);
-  uint8_t* u = reinterpret_cast<uint8_t*>(W.um + 6 * (size_t)max_block);
-  W.seq = u;
-  W.blk = u + ((size_t)max_flank + 15) / 16 * 16;
-  return W;
+__host__ __device__ inline size_t stutter_cta_smem_bytes(uint32_t n_logs) {
+  return (sizeof(StutConsts) + (size_t)n_logs * sizeof(double) + 15) / 16 * 16;
 }
 
-// Wavefront over `nrows` consecutive flank rows whose first hap row is row0; chars come from hapc(row).
-// first_type is the type of the very first row (ROW_FIRST / ROW_AFTER_STUTTER); every other row is ROW_NORMAL.
-// lineM/lineD hold the row above on entry (unused for ROW_FIRST / ROW_AFTER_STUTTER beyond M) and the last
-// row on exit.  last[] receives M at the last column of every row.  Returns left_prob when first_type == ROW_FIRST.
-// The haplotype character of row r of the block is chars[r * dir] (dir = -1 walks a reversed block).
-// One copy in the binary (noinline): the whole kernel has to stay inside the instruction caches -- the first
-// version inlined this four times and stalled ~10 cycles per issue on instruction fetch (profiles/r1i).
-__device__ __noinline__ double wavefront_rows(const StutConsts& C, const FlankView& F, WarpSmem& W, double* last,
-                                              int32_t row0, int32_t nrows, int32_t first_type, const uint8_t* chars,
-                                              int32_t dir, int lane) {
+__device__ __forceinline__ WarpCtx* carve(unsigned char* base, uint32_t max_flank, uint32_t max_block, uint32_t max_hap,
+                                          int lane) {
+  WarpCtx* X = reinterpret_cast<WarpCtx*>(base);
+  if (lane == 0) {
+    double* d = reinterpret_cast<double*>(base + (sizeof(WarpCtx) + 15) / 16 * 16);
+    X->lc = d; d += max_flank;
+    X->lw = d; d += max_flank;
+    X->match = d; d += max_flank;
+    X->lineM = d; d += max_flank;
+    X->lineD = d; d += max_flank;
+    X->lastL = d; d += max_hap;
+    X->lastR = d; d += max_hap;
+    X->probs = d; d += 13 * 32;
+    X->um = reinterpret_cast<int32_t*>(d);
+    uint8_t* u = reinterpret_cast<uint8_t*>(X->um + 6 * (size_t)max_block);
+    X->seq = u;
+    X->blk = u + ((size_t)max_flank + 15) / 16 * 16;
+  }
+  return X;
+}
+
+// Wavefront over `nrows` consecutive flank rows whose first hap row is row0.  The haplotype character of row r of
+// the block is chars[r * dir] (dir = -1 walks a reversed block).  first_type is the type of the very first row
+// (ROW_FIRST / ROW_AFTER_STUTTER); every other row is ROW_NORMAL.  lineM/lineD hold the row above on entry and the
+// last row on exit; last[] receives M at the last column of every row.  Returns left_prob for ROW_FIRST.
+__device__ __noinline__ double wavefront_rows(const StutConsts* Cs, const WarpCtx* X, double* last, int32_t row0,
+                                              int32_t nrows, int32_t first_type, const uint8_t* chars, int32_t dir,
+                                              int lane) {
+  const StutConsts C = *Cs;  // registers
+  const FlankView F = X->F;
+  double* lineM = X->lineM;
+  double* lineD = X->lineD;
   double left_prob = 0.0;
   const int32_t per_strip = 32 * kStutRows;
   for (int32_t s0 = 0; s0 < nrows; s0 += per_strip) {
@@ -90,14 +120,14 @@ __device__ __noinline__ double wavefront_rows(const StutConsts& C, const FlankVi
       const int32_t j = step - lane;
       if (lane <= t_last && j >= 0 && j < F.L) {
         if (lane == 0) {
-          aM = W.lineM[j];
-          aD = W.lineD[j];
+          aM = lineM[j];
+          aD = lineD[j];
         }
         double Mout[kStutRows];
         flank_lane_column(Ln, C, F, j, aM, aD, Mout);
         if (lane == t_last) {  // hand-off line for the next strip / phase (written after lane 0 consumed entry j)
-          W.lineM[j] = Ln.outM;
-          W.lineD[j] = Ln.outD;
+          lineM[j] = Ln.outM;
+          lineD[j] = Ln.outD;
         }
         if (j == F.L - 1) {
 #pragma unroll
@@ -112,112 +142,172 @@ __device__ __noinline__ double wavefront_rows(const StutConsts& C, const FlankVi
   return left_prob;
 }
 
-struct SideGeom {  // one flank of one pair
-  const uint8_t* read;  // whole read
-  const uint8_t* qual;
-  int32_t N, seed;
-  const uint8_t* lflank;
-  const uint8_t* rflank;
-  const uint8_t* allele;
-  int32_t n0, n2, B;  // |lflank|, |rflank|, |allele|
-};
+// The stutter row (HapAligner.cpp:64-111): one read column per lane, 13 artifact sizes each; prevM = lineM,
+// result -> lineD.
+__device__ __noinline__ void stutter_row(const StutConsts* Cs, const WarpCtx* X, int lane) {
+  const StutConsts C = *Cs;
+  const FlankView F = X->F;
+  const double* prevM = X->lineM;
+  double* out = X->lineD;
+  double* probs = X->probs + lane;  // stride 32: conflict free
+  for (int32_t j = lane; j < F.L; j += 32) {
+#pragma unroll 1
+    for (int32_t a = 0; a < 13; ++a) {
+      const int32_t D = a - 6;
+      int32_t base_len = F.B + D;
+      base_len = (base_len < j + 1) ? base_len : (j + 1);
+      double v = kStutImpossible;
+      if (base_len >= 0) {
+        const double prob = stutter_region_ll(C, F, base_len, j, D);
+        const double pre = (j - base_len < 0) ? 0.0 : prevM[j - base_len];
+        v = (F.art_lp[a] + prob) + pre;
+      }
+      probs[a * 32] = v;
+    }
+    double mx = probs[0];
+#pragma unroll
+    for (int32_t a = 1; a < 13; ++a) mx = smax(mx, probs[a * 32]);
+    double total = 0.0;
+#pragma unroll
+    for (int32_t a = 0; a < 13; ++a) total += lse_term(C, probs[a * 32], mx);
+    out[j] = lse_finish(mx, total);
+  }
+}
 
 // Runs one flank (side 0 = left of the seed against the forward haplotype, side 1 = right of the seed, reversed,
 // against the reversed haplotype).  Fills last[] (last-column M of every reachable hap row), returns left_prob.
-__device__ __noinline__ double run_side(const StutConsts& C, const SideGeom& G, int side, const double* art_lp,
-                                        WarpSmem& W, double* last, int lane) {
+__device__ __noinline__ double run_side(const StutConsts* Cs, WarpCtx* X, int side, int lane) {
+  const SideGeom G = X->G;
   const int32_t L = side == 0 ? G.seed : (G.N - G.seed - 1);
   const int32_t B = G.B;
+  double* last = side ? X->lastR : X->lastL;
   // ---- stage the flank, the allele and the tables ---------------------------------------------------------
-  for (int32_t j = lane; j < L; j += 32) {
-    const int32_t p = side == 0 ? j : (G.N - 1 - j);
-    const uint8_t q = G.qual[p];
-    W.seq[j] = G.read[p];
-    W.lc[j] = C.qual_lc[q];
-    W.lw[j] = C.qual_lw[q];
+  {
+    uint8_t* seq = X->seq;
+    double* lc = X->lc;
+    double* lw = X->lw;
+    const double* qlc = Cs->qual_lc;
+    const double* qlw = Cs->qual_lw;
+    for (int32_t j = lane; j < L; j += 32) {
+      const int32_t p = side == 0 ? j : (G.N - 1 - j);
+      const uint8_t q = G.qual[p];
+      seq[j] = G.read[p];
+      lc[j] = qlc[q];
+      lw[j] = qlw[q];
+    }
+    uint8_t* blk = X->blk;
+    for (int32_t i = lane; i < B; i += 32) blk[i] = side == 0 ? G.allele[i] : G.allele[B - 1 - i];
   }
-  for (int32_t i = lane; i < B; i += 32) W.blk[i] = side == 0 ? G.allele[i] : G.allele[B - 1 - i];
   __syncwarp();
   const int32_t n_del = B < 6 ? B : 6;
   if (lane < n_del) {  // num_upstream_matches at lag lane+1 (StutterAlignerClass.h:35-42)
     const int32_t lag = lane + 1;
-    int32_t* ml = W.um + (size_t)lane * B;
+    const uint8_t* blk = X->blk;
+    int32_t* ml = X->um + (size_t)lane * B;
     int32_t run = 0;
     for (int32_t i = 0; i < B; ++i) {
       if (i < lag) run = 0;
-      else run = (W.blk[i - lag] != W.blk[i]) ? 0 : run + 1;
+      else run = (blk[i - lag] != blk[i]) ? 0 : run + 1;
       ml[i] = run;
     }
   }
-  FlankView F;
-  F.seq = W.seq;
-  F.lc = W.lc;
-  F.lw = W.lw;
-  F.L = L;
-  F.blk = W.blk;
-  F.B = B;
-  F.um = W.um;
-  F.n_del = n_del;
-  F.match = W.match;
-  F.art_lp = art_lp;
-  for (int32_t p = lane; p < L; p += 32) W.match[p] = stutter_match_prob(F, p);
+  if (lane == 0) {
+    FlankView F;
+    F.seq = X->seq;
+    F.lc = X->lc;
+    F.lw = X->lw;
+    F.L = L;
+    F.blk = X->blk;
+    F.B = B;
+    F.um = X->um;
+    F.n_del = n_del;
+    F.match = X->match;
+    F.art_lp = X->art_lp;
+    X->F = F;
+  }
+  __syncwarp();
+  {
+    const FlankView F = X->F;
+    double* match = X->match;
+    for (int32_t p = lane; p < L; p += 32) match[p] = stutter_match_prob(F, p);
+  }
   __syncwarp();
   // ---- phase A: rows of the first flank block ----------------------------------------------------------------
   const int32_t na = side == 0 ? G.n0 : G.n2, nc = side == 0 ? G.n2 : G.n0;
   const uint8_t* fa = side == 0 ? G.lflank : G.rflank;
   const uint8_t* fc = side == 0 ? G.rflank : G.lflank;
   const int32_t dir = side == 0 ? 1 : -1;
-  const uint8_t* chars_a = side == 0 ? fa : fa + (na - 1);
-  const uint8_t* chars_c = side == 0 ? fc : fc + (nc - 1);
-  const double left_prob = wavefront_rows(C, F, W, last, 0, na, ROW_FIRST, chars_a, dir, lane);
-  // ---- phase B: the stutter row, one column per lane (HapAligner.cpp:64-111) ----------------------------------
-  for (int32_t j = lane; j < L; j += 32) W.lineD[j] = stutter_row_cell(C, F, W.lineM, j);
+  const double left_prob = wavefront_rows(Cs, X, last, 0, na, ROW_FIRST, side == 0 ? fa : fa + (na - 1), dir, lane);
+  // ---- phase B: the stutter row ----------------------------------------------------------------------------------
+  stutter_row(Cs, X, lane);
   __syncwarp();
-  {
-    double* t = W.lineM;  // the stutter row becomes the row above phase C; its I and D are IMPOSSIBLE (:104-105)
-    W.lineM = W.lineD;
-    W.lineD = t;
+  if (lane == 0) {
+    double* t = X->lineM;  // the stutter row becomes the row above phase C; its I and D are IMPOSSIBLE (:104-105)
+    X->lineM = X->lineD;
+    X->lineD = t;
+    last[na + B - 1] = X->lineM[L - 1];
   }
-  if (lane == 0) last[na + B - 1] = W.lineM[L - 1];
+  __syncwarp();
   // ---- phase C: rows of the second flank block -----------------------------------------------------------------
-  wavefront_rows(C, F, W, last, na + B, nc, ROW_AFTER_STUTTER, chars_c, dir, lane);
+  wavefront_rows(Cs, X, last, na + B, nc, ROW_AFTER_STUTTER, side == 0 ? fc : fc + (nc - 1), dir, lane);
   return left_prob;
 }
 
-__global__ void __launch_bounds__(kStutWarps * 32) stutter_pair_kernel(const StutConsts C, const StutterDevBatch Bt) {
+__global__ void __launch_bounds__(kStutWarps * 32) stutter_pair_kernel(const StutConsts C, const StutterDevBatch Bt,
+                                                                        uint32_t n_logs) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // ---- per-CTA constants: StutConsts with the log table redirected into shared memory -----------------------------
+  StutConsts* Cs = reinterpret_cast<StutConsts*>(smem);
+  double* logs = reinterpret_cast<double*>(smem + sizeof(StutConsts));
+  for (uint32_t i = threadIdx.x; i < n_logs; i += blockDim.x) logs[i] = C.int_logs[i];
+  if (threadIdx.x == 0) {
+    StutConsts c = C;
+    c.int_logs = logs;
+    *Cs = c;
+  }
+  __syncthreads();
   const uint32_t ti = blockIdx.x * kStutWarps + warp;
   if (ti >= Bt.n_tasks) return;
   const StutterTask T = Bt.tasks[ti];
-  WarpSmem W = carve(smem + (size_t)warp * stutter_warp_smem_bytes(Bt.max_flank, Bt.max_block, Bt.max_hap), Bt.max_flank,
-                     Bt.max_block, Bt.max_hap);
-  SideGeom G;
-  const uint32_t ro = Bt.read_off[T.read];
-  G.read = Bt.read_bytes + ro;
-  G.qual = Bt.qual_bytes + ro;
-  G.N = (int32_t)(Bt.read_off[T.read + 1] - ro);
-  G.seed = Bt.read_seed[T.read];
-  G.lflank = Bt.lflank_bytes + Bt.lflank_off[T.locus];
-  G.n0 = (int32_t)(Bt.lflank_off[T.locus + 1] - Bt.lflank_off[T.locus]);
-  G.rflank = Bt.rflank_bytes + Bt.rflank_off[T.locus];
-  G.n2 = (int32_t)(Bt.rflank_off[T.locus + 1] - Bt.rflank_off[T.locus]);
-  G.allele = Bt.allele_bytes + Bt.allele_off[T.allele];
-  G.B = (int32_t)(Bt.allele_off[T.allele + 1] - Bt.allele_off[T.allele]);
-  const double* art_lp = Bt.allele_artifact_lp + (size_t)T.allele * 13;
+  WarpCtx* X = carve(smem + stutter_cta_smem_bytes(n_logs) +
+                         (size_t)warp * stutter_warp_smem_bytes(Bt.max_flank, Bt.max_block, Bt.max_hap),
+                     Bt.max_flank, Bt.max_block, Bt.max_hap, lane);
+  if (lane == 0) {
+    SideGeom G;
+    const uint32_t ro = Bt.read_off[T.read];
+    G.read = Bt.read_bytes + ro;
+    G.qual = Bt.qual_bytes + ro;
+    G.N = (int32_t)(Bt.read_off[T.read + 1] - ro);
+    G.seed = Bt.read_seed[T.read];
+    G.lflank = Bt.lflank_bytes + Bt.lflank_off[T.locus];
+    G.n0 = (int32_t)(Bt.lflank_off[T.locus + 1] - Bt.lflank_off[T.locus]);
+    G.rflank = Bt.rflank_bytes + Bt.rflank_off[T.locus];
+    G.n2 = (int32_t)(Bt.rflank_off[T.locus + 1] - Bt.rflank_off[T.locus]);
+    G.allele = Bt.allele_bytes + Bt.allele_off[T.allele];
+    G.B = (int32_t)(Bt.allele_off[T.allele + 1] - Bt.allele_off[T.allele]);
+    X->G = G;
+  }
+  if (lane < 13) X->art_lp[lane] = Bt.allele_artifact_lp[(size_t)T.allele * 13 + lane];
+  __syncwarp();
 
-  double side_prob[2];
-#pragma unroll 1
-  for (int side = 0; side < 2; ++side) side_prob[side] = run_side(C, G, side, art_lp, W, side ? W.lastR : W.lastL, lane);
-  const double l_prob = side_prob[0], r_prob = side_prob[1];
+  const double l_prob = run_side(Cs, X, 0, lane);
+  __syncwarp();
+  const double r_prob = run_side(Cs, X, 1, lane);
   __syncwarp();
 
   // ---- seed join (compute_aln_logprob, HapAligner.cpp:165-233) ----------------------------------------------------
+  const SideGeom G = X->G;
+  const double* lastL = X->lastL;
+  const double* lastR = X->lastR;
+  const double log_thresh = Cs->log_thresh;
+  StutConsts Cj;  // only log_thresh is used by lse_term
+  Cj.log_thresh = log_thresh;
   const int32_t hapsize = G.n0 + G.B + G.n2;
   const int32_t seed_char = (int32_t)G.read[G.seed];
   const uint8_t sq = G.qual[G.seed];
-  const double sc = C.qual_lc[sq], sw = C.qual_lw[sq];
-  const double prior = -C.int_logs[G.n0 + G.n2];
+  const double sc = Cs->qual_lc[sq], sw = Cs->qual_lw[sq];
+  const double prior = -logs[G.n0 + G.n2];
   // term index u: 0 and 1 are the two "flank entirely outside" configurations, u >= 2 <-> hap position u-1
   double mx = 0.0;
   bool any = false;
@@ -226,24 +316,24 @@ __global__ void __launch_bounds__(kStutWarps * 32) stutter_pair_kernel(const Stu
     for (int32_t u = lane; u < hapsize; u += 32) {
       double v;
       if (u == 0) {
-        v = ((prior + (seed_char == (int32_t)G.lflank[0] ? sc : sw)) + l_prob) + W.lastR[hapsize - 2];
+        v = ((prior + (seed_char == (int32_t)G.lflank[0] ? sc : sw)) + l_prob) + lastR[hapsize - 2];
       } else if (u == 1) {
-        v = ((prior + (seed_char == (int32_t)G.rflank[G.n2 - 1] ? sc : sw)) + r_prob) + W.lastL[hapsize - 2];
+        v = ((prior + (seed_char == (int32_t)G.rflank[G.n2 - 1] ? sc : sw)) + r_prob) + lastL[hapsize - 2];
       } else {
         const int32_t i = u - 1;  // 1 .. hapsize-2
         if (i >= G.n0 && i < G.n0 + G.B) continue;
         const int32_t hc = (int32_t)(i < G.n0 ? G.lflank[i] : G.rflank[i - G.n0 - G.B]);
-        v = ((prior + (seed_char == hc ? sc : sw)) + W.lastL[i - 1]) + W.lastR[hapsize - 2 - i];
+        v = ((prior + (seed_char == hc ? sc : sw)) + lastL[i - 1]) + lastR[hapsize - 2 - i];
       }
       if (pass == 0) {
         mx = any ? smax(mx, v) : v;
         any = true;
       } else {
-        total += lse_term(C, v, mx);
+        total += lse_term(Cj, v, mx);
       }
     }
     if (pass == 0) {
-      // every lane < min(32, hapsize) has at least one term only if it is not inside the repeat block: reduce with flags
+      // a lane may hold no term (all its positions inside the repeat block): reduce with flags
       for (int off = 16; off > 0; off >>= 1) {
         const double omx = __shfl_xor_sync(kFull, mx, off);
         const int oany = __shfl_xor_sync(kFull, (int)any, off);
@@ -260,16 +350,17 @@ __global__ void __launch_bounds__(kStutWarps * 32) stutter_pair_kernel(const Stu
 }
 
 size_t stutter_block_smem_bytes(uint32_t max_flank, uint32_t max_block, uint32_t max_hap) {
-  return (size_t)kStutWarps * stutter_warp_smem_bytes(max_flank, max_block, max_hap);
+  return stutter_cta_smem_bytes(max_hap + 16) + (size_t)kStutWarps * stutter_warp_smem_bytes(max_flank, max_block, max_hap);
 }
 
 cudaError_t launch_stutter(const StutConsts& C, const StutterDevBatch& B, cudaStream_t stream) {
   if (B.n_tasks == 0) return cudaSuccess;
+  const uint32_t n_logs = B.max_hap + 16;  // log table entries used: <= max(block)+2 and <= hap length (stutter_abi.cu sizes it)
   const size_t smem = stutter_block_smem_bytes(B.max_flank, B.max_block, B.max_hap);
   cudaError_t e = cudaFuncSetAttribute(stutter_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const uint32_t grid = (B.n_tasks + kStutWarps - 1) / kStutWarps;
-  stutter_pair_kernel<<<grid, kStutWarps * 32, smem, stream>>>(C, B);
+  stutter_pair_kernel<<<grid, kStutWarps * 32, smem, stream>>>(C, B, n_logs);
   return cudaGetLastError();
 }
 
