@@ -110,6 +110,14 @@ int ltr_ctx_create(int device, ltr_ctx** out) {
     return LTR_ERR_NO_DEVICE;
   }
   ctx->sm_count = prop.multiProcessorCount;
+  {
+    cudaMemPool_t pool = nullptr;  // keep freed blocks cached: job create/destroy never goes back to the driver
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+  }
   cudaError_t e = cudaStreamCreateWithFlags(&ctx->main_stream, cudaStreamNonBlocking);
   for (int i = 0; i < kNumStreams && e == cudaSuccess; ++i) {
     e = cudaStreamCreateWithFlags(&ctx->streams[i], cudaStreamNonBlocking);
@@ -174,6 +182,7 @@ int ltr_job_create(ltr_ctx* ctx, const ltr_params* params, const ltr_viterbi_bat
     return LTR_ERR_INVALID;
   if (params->indel_flank_len < 0 || params->indel_flank_len > 35) return LTR_ERR_INVALID;
   LTR_CUDA(ctx, cudaSetDevice(ctx->device));
+  AllocScope alloc_scope(ctx->main_stream);
   ltr_job* job = new ltr_job();
   std::memset(&job->stats, 0, sizeof(job->stats));
   job->params = *params;
@@ -392,11 +401,12 @@ int ltr_job_run(ltr_ctx* ctx, ltr_job* job) {
   LTR_CUDA(ctx, cudaSetDevice(ctx->device));
   job->stats.n_launches = 0;
   job->stats.n_fallback = 0;
+  const int n_used = (int)std::min<size_t>(kNumStreams, job->classes.size());  // streams run_classes touches
   LTR_CUDA(ctx, cudaEventRecord(ctx->ev_start, ctx->main_stream));
-  for (int i = 0; i < kNumStreams; ++i) LTR_CUDA(ctx, cudaStreamWaitEvent(ctx->streams[i], ctx->ev_start, 0));
+  for (int i = 0; i < n_used; ++i) LTR_CUDA(ctx, cudaStreamWaitEvent(ctx->streams[i], ctx->ev_start, 0));
   int rc = run_classes(ctx, job, false);
   if (rc != LTR_OK) return rc;
-  for (int i = 0; i < kNumStreams; ++i) {
+  for (int i = 0; i < n_used; ++i) {
     LTR_CUDA(ctx, cudaEventRecord(ctx->ev_stream[i], ctx->streams[i]));
     LTR_CUDA(ctx, cudaStreamWaitEvent(ctx->main_stream, ctx->ev_stream[i], 0));
   }
@@ -525,6 +535,7 @@ int ltr_posteriors(ltr_ctx* ctx, int haploid, int32_t n_samples, int32_t n_reads
   if (!ctx || !ll || !log_p1 || !log_p2 || !sample_label || !post || !totals) return LTR_ERR_INVALID;
   if (n_samples <= 0 || n_alleles <= 0 || n_reads < 0) return LTR_ERR_INVALID;
   LTR_CUDA(ctx, cudaSetDevice(ctx->device));
+  AllocScope alloc_scope(ctx->main_stream);
   for (int r = 0; r < n_reads; ++r)
     if (sample_label[r] < 0 || sample_label[r] >= n_samples) return LTR_ERR_INVALID;
   const size_t H = (size_t)n_alleles, R = (size_t)n_reads, S = (size_t)n_samples;

@@ -10,18 +10,39 @@ namespace ltr {
 
 const int kNumStreams = 8;
 
+// Device allocations are stream ordered (cudaMallocAsync on the context's main stream, pool never trimmed):
+// creating and destroying a job costs no device synchronisation, which matters for the per-locus entry points.
+// The entry points name the stream with an AllocScope; without one (never in this library) cudaMalloc is used.
+inline cudaStream_t& alloc_stream_slot() {
+  static thread_local cudaStream_t s = nullptr;
+  return s;
+}
+struct AllocScope {
+  cudaStream_t prev;
+  explicit AllocScope(cudaStream_t s) : prev(alloc_stream_slot()) { alloc_stream_slot() = s; }
+  ~AllocScope() { alloc_stream_slot() = prev; }
+};
+
 struct DeviceBuffer {
   void* p = nullptr;
   size_t bytes = 0;
+  cudaStream_t stream = nullptr;
+  bool async = false;
   cudaError_t alloc(size_t n) {
     free();
     if (n == 0) n = 8;
-    cudaError_t e = cudaMalloc(&p, n);
+    stream = alloc_stream_slot();
+    async = (stream != nullptr);
+    cudaError_t e = async ? cudaMallocAsync(&p, n, stream) : cudaMalloc(&p, n);
     if (e == cudaSuccess) bytes = n;
+    else p = nullptr;
     return e;
   }
   void free() {
-    if (p) cudaFree(p);
+    if (p) {
+      if (async) cudaFreeAsync(p, stream);
+      else cudaFree(p);
+    }
     p = nullptr;
     bytes = 0;
   }

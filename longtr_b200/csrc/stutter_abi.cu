@@ -49,6 +49,7 @@ extern "C" int ltr_stutter_ll(ltr_ctx* ctx, const ltr_params* params, const ltr_
       !b->stutter || !b->motif_len || !b->read_off || !b->read_seed)
     return LTR_ERR_INVALID;
   LTR_CUDA(ctx, cudaSetDevice(ctx->device));
+  AllocScope alloc_scope(ctx->main_stream);
   const uint32_t n_loci = b->n_loci;
   const uint32_t n_alleles = b->locus_allele_begin[n_loci], n_reads = b->locus_read_begin[n_loci];
 

@@ -290,6 +290,26 @@ inline int make_plan(const ltr_viterbi_batch& b, const ltr_params& p, int kmax, 
     out.max_n = std::max(out.max_n, P.max_n);
     for (size_t k = 0; k < P.max_q.size(); ++k) out.max_q[k] = std::max(out.max_q[k], P.max_q[k]);
   }
+  // Small batches (the per-locus entry points): a task streams ALL reads of its locus through one warp, which leaves
+  // most of the GPU idle and makes the call latency the length of that stream.  Cut the read ranges so that there
+  // are enough tasks to occupy the device; every piece still pays the 31-step pipeline fill once.
+  const size_t kWantTasks = 2048;
+  if (!keys.empty() && keys.size() < kWantTasks) {
+    const uint32_t pieces = (uint32_t)((kWantTasks + keys.size() - 1) / keys.size());
+    std::vector<Key> split;
+    for (const Key& k : keys) {
+      const uint32_t nr = k.t.read_end - k.t.read_begin;
+      const uint32_t np = std::max(1u, std::min(pieces, nr));
+      for (uint32_t c = 0; c < np; ++c) {
+        Key part = k;
+        part.t.read_begin = k.t.read_begin + (uint32_t)((uint64_t)nr * c / np);
+        part.t.read_end = k.t.read_begin + (uint32_t)((uint64_t)nr * (c + 1) / np);
+        part.cost = k.cost / np + 1;
+        if (part.t.read_end > part.t.read_begin) split.push_back(part);
+      }
+    }
+    keys.swap(split);
+  }
   std::stable_sort(keys.begin(), keys.end(), [](const Key& a, const Key& c) { return a.cost > c.cost; });
   for (const Key& k : keys) out.tasks[k.k].push_back(k.t);
   return LTR_OK;
