@@ -35,3 +35,49 @@ def test_posteriors_match_oracle(engine):
         np.testing.assert_allclose(g_post, w_post, rtol=RTOL, atol=ATOL)
         np.testing.assert_allclose(g_tot, w_tot, rtol=RTOL, atol=ATOL)
         assert abs(g_total - w_total) <= ATOL + RTOL * abs(w_total)
+
+
+def test_job_posteriors_multi_sample_trio(engine):
+    """Resident-job path with three samples per locus (the trio configuration of BASELINE.json configs[1]):
+    Viterbi LLs of the pooled reads -> per-sample posteriors, against the oracle locus by locus."""
+    import synth
+    rng = np.random.default_rng(2026)
+    b = synth.make_pair_batch(31, n_loci=40, n_lo=30, n_hi=160, reads_lo=4, reads_hi=9, haps_lo=2, haps_hi=6, weird=0.05)
+    lrb = b["locus_read_begin"].astype(np.int64)
+    lhb = b["locus_hap_begin"].astype(np.int64)
+    lsb, pool, lab, p1, p2, nsamp, hap = [0], [], [], [], [], [], []
+    for l in range(40):
+        P = int(lrb[l + 1] - lrb[l])
+        S = 3
+        for s in range(S):                       # sample-major reads, each pointing at a pooled read of the locus
+            k = int(rng.integers(2, 12))
+            pool += [int(x) for x in rng.integers(0, P, size=k)]
+            lab += [s] * k
+            hp = rng.integers(0, 3, size=k)
+            p1 += [(-1e-6, -1000.0, 0.0)[h] for h in hp]
+            p2 += [(-1000.0, -1e-6, 0.0)[h] for h in hp]
+        lsb.append(len(pool))
+        nsamp.append(S)
+        hap.append(1 if l % 7 == 0 else 0)
+    post = dict(locus_sread_begin=np.array(lsb, np.uint32), pool_index=np.array(pool, np.uint32),
+                sample_label=np.array(lab, np.int32), log_p1=np.array(p1), log_p2=np.array(p2),
+                locus_n_samples=np.array(nsamp, np.uint32), locus_haploid=np.array(hap, np.uint8))
+    job = engine.create_job(b, post)
+    job.run()
+    ll, gpost, gtot = job.download()
+    job.close()
+    want_ll, _ = po.viterbi_batch(b)
+    assert np.array_equal(ll, want_ll)
+    off = np.concatenate([[0], np.cumsum((lhb[1:] - lhb[:-1]) * (lrb[1:] - lrb[:-1]))])
+    po_off, t_off = 0, 0
+    for l in range(40):
+        H, P = int(lhb[l + 1] - lhb[l]), int(lrb[l + 1] - lrb[l])
+        mat = want_ll[off[l]:off[l + 1]].reshape(P, H)
+        r0, r1 = lsb[l], lsb[l + 1]
+        _cl, wpost, wtot, _total, _best = po.log_sample_posteriors(mat[post["pool_index"][r0:r1]], post["log_p1"][r0:r1],
+                                                                   post["log_p2"][r0:r1], post["sample_label"][r0:r1], 3,
+                                                                   haploid=bool(hap[l]))
+        np.testing.assert_allclose(gpost[po_off:po_off + 3 * H * H], wpost.ravel(), rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(gtot[t_off:t_off + 3], wtot, rtol=RTOL, atol=ATOL)
+        po_off += 3 * H * H
+        t_off += 3
