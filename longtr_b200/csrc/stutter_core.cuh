@@ -93,8 +93,9 @@ LTS_HD double lse_finish(double mx, double total) { return mx + (double)faster_l
 // ---- one flank of one pair, as the warp sees it -------------------------------------------------------
 struct FlankView {
   const uint8_t* seq;   // read flank, left to right in alignment order (right flank: already reversed)
-  const double* lc;     // per-column log P(correct), same order
-  const double* lw;     // per-column log P(error)
+  const uint8_t* qual;  // per-column Phred+33 byte, same order
+  const double* tlc;    // [256] log P(correct) by quality byte (BaseQuality, src/base_quality.h:29-75): a byte per column
+  const double* tlw;    // [256] log P(error)     plus two small tables instead of two double arrays keeps more warps resident
   int32_t L;            // columns
   const uint8_t* blk;   // repeat-block allele in alignment order (reversed for the right flank)
   int32_t B;            // its length (>= 1)
@@ -104,7 +105,10 @@ struct FlankView {
   const double* art_lp; // [13] log_prob_pcr_artifact(allele, D), D = -6..6 (RepeatStutterInfo.h:53-61)
 };
 
-LTS_HD double emit_at(const FlankView& F, int32_t p, int32_t c) { return ((int32_t)F.seq[p] == c) ? F.lc[p] : F.lw[p]; }
+LTS_HD double emit_at(const FlankView& F, int32_t p, int32_t c) {
+  const double* t = ((int32_t)F.seq[p] == c) ? F.tlc : F.tlw;
+  return t[F.qual[p]];
+}
 
 // match[p] (load_read): the read walked backwards from p against the block walked backwards from its end.
 LTS_HD double stutter_match_prob(const FlankView& F, int32_t p) {
@@ -268,7 +272,8 @@ LTS_HD void flank_lane_reset(FlankLane& Ln) {
 LTS_HD void flank_lane_column(FlankLane& Ln, const StutConsts& C, const FlankView& F, int32_t j, double aboveM,
                               double aboveD, double* Mout) {
   const int32_t c = (int32_t)F.seq[j];
-  const double lcj = F.lc[j], lwj = F.lw[j];
+  const int32_t qj = (int32_t)F.qual[j];
+  const double lcj = F.tlc[qj], lwj = F.tlw[qj];
   double upM = aboveM, upD = aboveD;        // row above, this column
   double ulM = Ln.upM, ulD = Ln.upD;        // row above, previous column
 #pragma unroll

@@ -36,8 +36,6 @@ struct SideGeom {  // one pair
 };
 
 struct WarpCtx {  // per warp, in shared memory
-  double* lc;
-  double* lw;
   double* match;
   double* lineM;
   double* lineD;
@@ -46,6 +44,7 @@ struct WarpCtx {  // per warp, in shared memory
   double* probs;  // [13][32] artifact terms of the stutter row, one column per lane
   int32_t* um;
   uint8_t* seq;
+  uint8_t* qual;
   uint8_t* blk;
   double art_lp[13];
   SideGeom G;
@@ -54,16 +53,16 @@ struct WarpCtx {  // per warp, in shared memory
 
 __host__ __device__ inline size_t stutter_warp_smem_bytes(uint32_t max_flank, uint32_t max_block, uint32_t max_hap) {
   size_t b = (sizeof(WarpCtx) + 15) / 16 * 16;
-  b += 5 * (size_t)max_flank * sizeof(double);  // lc lw match lineM lineD
+  b += 3 * (size_t)max_flank * sizeof(double);  // match lineM lineD
   b += 2 * (size_t)max_hap * sizeof(double);    // lastL lastR
   b += 13 * 32 * sizeof(double);                // probs
   b += 6 * (size_t)max_block * sizeof(int32_t); // um
-  b += ((size_t)max_flank + 15) / 16 * 16;      // seq
+  b += 2 * (((size_t)max_flank + 15) / 16 * 16);  // seq, qual
   b += ((size_t)max_block + 15) / 16 * 16;      // blk
   return (b + 15) / 16 * 16;
 }
-__host__ __device__ inline size_t stutter_cta_smem_bytes(uint32_t n_logs) {
-  return (sizeof(StutConsts) + (size_t)n_logs * sizeof(double) + 15) / 16 * 16;
+__host__ __device__ inline size_t stutter_cta_smem_bytes(uint32_t n_logs) {  // constants, log table, 2 quality tables
+  return (sizeof(StutConsts) + ((size_t)n_logs + 512) * sizeof(double) + 15) / 16 * 16;
 }
 
 __device__ __forceinline__ WarpCtx* carve(unsigned char* base, uint32_t max_flank, uint32_t max_block, uint32_t max_hap,
@@ -71,8 +70,6 @@ __device__ __forceinline__ WarpCtx* carve(unsigned char* base, uint32_t max_flan
   WarpCtx* X = reinterpret_cast<WarpCtx*>(base);
   if (lane == 0) {
     double* d = reinterpret_cast<double*>(base + (sizeof(WarpCtx) + 15) / 16 * 16);
-    X->lc = d; d += max_flank;
-    X->lw = d; d += max_flank;
     X->match = d; d += max_flank;
     X->lineM = d; d += max_flank;
     X->lineD = d; d += max_flank;
@@ -82,7 +79,8 @@ __device__ __forceinline__ WarpCtx* carve(unsigned char* base, uint32_t max_flan
     X->um = reinterpret_cast<int32_t*>(d);
     uint8_t* u = reinterpret_cast<uint8_t*>(X->um + 6 * (size_t)max_block);
     X->seq = u;
-    X->blk = u + ((size_t)max_flank + 15) / 16 * 16;
+    X->qual = u + ((size_t)max_flank + 15) / 16 * 16;
+    X->blk = X->qual + ((size_t)max_flank + 15) / 16 * 16;
   }
   return X;
 }
@@ -184,16 +182,11 @@ __device__ __noinline__ double run_side(const StutConsts* Cs, WarpCtx* X, int si
   // ---- stage the flank, the allele and the tables ---------------------------------------------------------
   {
     uint8_t* seq = X->seq;
-    double* lc = X->lc;
-    double* lw = X->lw;
-    const double* qlc = Cs->qual_lc;
-    const double* qlw = Cs->qual_lw;
+    uint8_t* qual = X->qual;
     for (int32_t j = lane; j < L; j += 32) {
       const int32_t p = side == 0 ? j : (G.N - 1 - j);
-      const uint8_t q = G.qual[p];
       seq[j] = G.read[p];
-      lc[j] = qlc[q];
-      lw[j] = qlw[q];
+      qual[j] = G.qual[p];
     }
     uint8_t* blk = X->blk;
     for (int32_t i = lane; i < B; i += 32) blk[i] = side == 0 ? G.allele[i] : G.allele[B - 1 - i];
@@ -214,8 +207,9 @@ __device__ __noinline__ double run_side(const StutConsts* Cs, WarpCtx* X, int si
   if (lane == 0) {
     FlankView F;
     F.seq = X->seq;
-    F.lc = X->lc;
-    F.lw = X->lw;
+    F.qual = X->qual;
+    F.tlc = Cs->qual_lc;
+    F.tlw = Cs->qual_lw;
     F.L = L;
     F.blk = X->blk;
     F.B = B;
@@ -260,10 +254,18 @@ __global__ void __launch_bounds__(kStutWarps * 32) stutter_pair_kernel(const Stu
   // ---- per-CTA constants: StutConsts with the log table redirected into shared memory -----------------------------
   StutConsts* Cs = reinterpret_cast<StutConsts*>(smem);
   double* logs = reinterpret_cast<double*>(smem + sizeof(StutConsts));
+  double* tlc = logs + n_logs;
+  double* tlw = tlc + 256;
   for (uint32_t i = threadIdx.x; i < n_logs; i += blockDim.x) logs[i] = C.int_logs[i];
+  for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
+    tlc[i] = C.qual_lc[i];
+    tlw[i] = C.qual_lw[i];
+  }
   if (threadIdx.x == 0) {
     StutConsts c = C;
     c.int_logs = logs;
+    c.qual_lc = tlc;
+    c.qual_lw = tlw;
     *Cs = c;
   }
   __syncthreads();

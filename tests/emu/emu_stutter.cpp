@@ -22,7 +22,8 @@ struct Emu {
   StutConsts C;
   std::vector<double> int_logs, qlc, qlw;
   // "shared memory" of the warp
-  std::vector<double> lc, lw, match, lineM, lineD;
+  std::vector<double> match, lineM, lineD;
+  std::vector<uint8_t> qual;
   std::vector<int32_t> um;
   std::vector<uint8_t> seq, blk;
 };
@@ -78,16 +79,14 @@ double run_side(Emu& E, int side, const std::string& read, const std::string& qu
                 const std::string& rf, const std::string& allele, const double* art_lp, std::vector<double>& last) {
   const int32_t N = (int32_t)read.size(), L = side == 0 ? seed : N - seed - 1, B = (int32_t)allele.size();
   E.seq.assign(L, 0);
-  E.lc.assign(L, 0);
-  E.lw.assign(L, 0);
+  E.qual.assign(L, 0);
   E.match.assign(L, 0);
   E.lineM.assign(L, nan(""));
   E.lineD.assign(L, nan(""));
   for (int32_t j = 0; j < L; ++j) {
     const int32_t p = side == 0 ? j : N - 1 - j;
     E.seq[j] = (uint8_t)read[p];
-    E.lc[j] = E.qlc[(uint8_t)qual[p]];
-    E.lw[j] = E.qlw[(uint8_t)qual[p]];
+    E.qual[j] = (uint8_t)qual[p];
   }
   E.blk.assign(B, 0);
   for (int32_t i = 0; i < B; ++i) E.blk[i] = (uint8_t)(side == 0 ? allele[i] : allele[B - 1 - i]);
@@ -101,7 +100,7 @@ double run_side(Emu& E, int side, const std::string& read, const std::string& qu
     }
   }
   FlankView F;
-  F.seq = E.seq.data(); F.lc = E.lc.data(); F.lw = E.lw.data(); F.L = L;
+  F.seq = E.seq.data(); F.qual = E.qual.data(); F.tlc = E.qlc.data(); F.tlw = E.qlw.data(); F.L = L;
   F.blk = E.blk.data(); F.B = B; F.um = E.um.data(); F.n_del = n_del; F.match = E.match.data(); F.art_lp = art_lp;
   for (int32_t p = 0; p < L; ++p) E.match[p] = stutter_match_prob(F, p);
   const std::string& fa = side == 0 ? lf : rf;
