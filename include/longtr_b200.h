@@ -203,6 +203,16 @@ typedef struct ltr_locus_calls {
 int ltr_genotype_locus(ltr_ctx* ctx, int haploid, int32_t n_samples, const int32_t* reads_per_sample,
                        int32_t n_alleles, double* ll, const double* log_p1, const double* log_p2,
                        ltr_locus_calls* out);
+/* The same followed by what SeqStutterGenotyper::genotype does next (src/seq_stutter_genotyper.cpp:636-645):
+ * non-reference alleles that are in no sample's optimal haplotype pair are dropped (get_unused_alleles, :250-311;
+ * samples whose reads all have seed_positions < 0 do not vote; seed_positions may be NULL = all aligned), the LL
+ * columns of the kept alleles are carried over (:317-409) and the posteriors are recomputed on them.
+ * kept_alleles[0..*n_kept) receives the original indices of the kept alleles (always includes 0); the arrays of
+ * `out` are filled for H' = *n_kept alleles (allocate them for H).                                       */
+int ltr_genotype_locus_pruned(ltr_ctx* ctx, int haploid, int32_t n_samples, const int32_t* reads_per_sample,
+                              int32_t n_alleles, double* ll, const double* log_p1, const double* log_p2,
+                              const int32_t* seed_positions, int32_t* kept_alleles, int32_t* n_kept,
+                              ltr_locus_calls* out);
 /* The host half of the above on posteriors that are already computed (no GPU involved). */
 int ltr_extract_calls(int haploid, int32_t n_samples, int32_t n_alleles, const double* post, const double* totals,
                       ltr_locus_calls* out);

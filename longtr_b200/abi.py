@@ -173,6 +173,9 @@ def load():
     lib.ltr_process_reads_flat.restype = C.c_int
     lib.ltr_genotype_locus.argtypes = [vp, C.c_int, C.c_int32, _i32p, C.c_int32, _dp, _dp, _dp, C.POINTER(LocusCalls)]
     lib.ltr_genotype_locus.restype = C.c_int
+    lib.ltr_genotype_locus_pruned.argtypes = [vp, C.c_int, C.c_int32, _i32p, C.c_int32, _dp, _dp, _dp, _i32p, _i32p, _i32p,
+                                              C.POINTER(LocusCalls)]
+    lib.ltr_genotype_locus_pruned.restype = C.c_int
     lib.ltr_extract_calls.argtypes = [C.c_int, C.c_int32, C.c_int32, _dp, _dp, C.POINTER(LocusCalls)]
     lib.ltr_extract_calls.restype = C.c_int
     lib.ltr_trim_read_flat.argtypes = [C.POINTER(FlatLocus), C.c_int32, C.c_char_p, C.c_int32]
@@ -192,7 +195,7 @@ EXPORTED_SYMBOLS = [
     "ltr_version", "ltr_viterbi_ll", "ltr_posteriors", "ltr_job_create", "ltr_job_run", "ltr_job_sizes",
     "ltr_job_download", "ltr_job_get_stats", "ltr_job_destroy", "ltr_process_reads_flat",
     "ltr_fp64_issue_rate", "ltr_genotype_locus", "ltr_extract_calls", "ltr_trim_read_flat", "ltr_seed_base_flat",
-    "ltr_stutter_ll",
+    "ltr_stutter_ll", "ltr_genotype_locus_pruned",
 ]
 
 

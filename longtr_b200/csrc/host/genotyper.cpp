@@ -261,6 +261,67 @@ extern "C" int ltr_genotype_locus(ltr_ctx* ctx, int haploid, int32_t n_samples, 
   return fill_calls(g, haploid, n_samples, n_alleles, total, out);
 }
 
+// SeqStutterGenotyper::genotype after the first posterior pass (reference src/seq_stutter_genotyper.cpp:636-645):
+// alleles that are in no sample's optimal haplotype pair are dropped (get_unused_alleles with check_called, :250-311;
+// only samples with at least one aligned read vote, :262-266; the reference allele always stays), the LL columns of
+// the kept alleles are carried over (add_and_remove_alleles, :317-409 -- no realignment when nothing is added) and
+// the posteriors are recomputed on the reduced allele set.
+extern "C" int ltr_genotype_locus_pruned(ltr_ctx* ctx, int haploid, int32_t n_samples, const int32_t* reads_per_sample,
+                                         int32_t n_alleles, double* ll, const double* log_p1, const double* log_p2,
+                                         const int32_t* seed_positions, int32_t* kept_alleles, int32_t* n_kept,
+                                         ltr_locus_calls* out) {
+  using namespace ltr;
+  if (!ctx || !reads_per_sample || !ll || !log_p1 || !log_p2 || !out || !kept_alleles || !n_kept || n_samples < 1 ||
+      n_alleles < 1)
+    return LTR_ERR_INVALID;
+  std::vector<std::string> names;
+  std::vector<std::vector<double> > p1((size_t)n_samples), p2((size_t)n_samples);
+  std::vector<bool> aligned_read((size_t)n_samples, false);
+  size_t idx = 0;
+  for (int s = 0; s < n_samples; ++s) {
+    names.push_back("S" + std::to_string(s));
+    if (reads_per_sample[s] < 0) return LTR_ERR_INVALID;
+    for (int r = 0; r < reads_per_sample[s]; ++r, ++idx) {
+      p1[s].push_back(log_p1[idx]);
+      p2[s].push_back(log_p2[idx]);
+      if (seed_positions == NULL || seed_positions[idx] >= 0) aligned_read[s] = true;
+    }
+  }
+  const size_t R = idx;
+  // first pass on the full allele set
+  Genotyper g(haploid != 0, names, p1, p2, ctx);
+  if (g.status() != LTR_OK) return g.status();
+  g.set_num_alleles(n_alleles);
+  std::copy(ll, ll + R * n_alleles, g.log_aln_probs());
+  g.calc_log_sample_posteriors();
+  if (g.status() != LTR_OK) return g.status();
+  std::copy(g.log_aln_probs(), g.log_aln_probs() + R * n_alleles, ll);  // clamped in place
+  std::vector<std::pair<int, int> > haps;
+  g.get_optimal_haplotypes(haps);
+  std::vector<bool> called((size_t)n_alleles, false);
+  for (int s = 0; s < n_samples; ++s)
+    if (aligned_read[s]) {
+      called[haps[s].first] = true;
+      called[haps[s].second] = true;
+    }
+  int kept = 0;
+  for (int a = 0; a < n_alleles; ++a)
+    if (a == 0 || called[a]) kept_alleles[kept++] = a;
+  *n_kept = kept;
+  if (kept == n_alleles) {  // nothing to remove: the first pass stands (seq_stutter_genotyper.cpp:641)
+    double total = 0.0;
+    for (int s = 0; s < n_samples; ++s) total += g.sample_total_LLs()[s];
+    return fill_calls(g, haploid, n_samples, n_alleles, total, out);
+  }
+  Genotyper g2(haploid != 0, names, p1, p2, ctx);
+  g2.set_num_alleles(kept);
+  for (size_t r = 0; r < R; ++r)
+    for (int k = 0; k < kept; ++k) g2.log_aln_probs()[r * kept + k] = ll[r * n_alleles + kept_alleles[k]];
+  const double total = g2.calc_log_sample_posteriors();
+  if (g2.status() != LTR_OK) return g2.status();
+  return fill_calls(g2, haploid, n_samples, kept, total, out);
+}
+
 // ---- C ABI: host-only helpers of HapAligner (no GPU needed) ------------------------------------------------
 namespace {
 struct FlatView {  // the three blocks + one read of a flat locus as host-mirror objects

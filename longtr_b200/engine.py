@@ -140,6 +140,26 @@ class Engine:
         arrays["ll_clamped"] = ll
         return arrays
 
+    def genotype_locus_pruned(self, ll, log_p1, log_p2, reads_per_sample, haploid=False, seeds=None):
+        """genotype_locus + the reference's removal of uncalled alleles and second posterior pass."""
+        ll = np.array(ll, dtype=np.float64, order="C", copy=True)
+        R, H = ll.shape
+        rps = np.ascontiguousarray(reads_per_sample, dtype=np.int32)
+        p1 = np.ascontiguousarray(log_p1, dtype=np.float64)
+        p2 = np.ascontiguousarray(log_p2, dtype=np.float64)
+        sd = None if seeds is None else np.ascontiguousarray(seeds, dtype=np.int32)
+        kept = np.zeros(H, dtype=np.int32)
+        nk = C.c_int32(0)
+        c, arrays = abi.make_locus_calls(len(rps), H, haploid)
+        rc = self.lib.ltr_genotype_locus_pruned(self.ctx, int(haploid), len(rps), abi.ptr(rps, abi._i32p), H,
+                                                abi.ptr(ll, abi._dp), abi.ptr(p1, abi._dp), abi.ptr(p2, abi._dp),
+                                                None if sd is None else abi.ptr(sd, abi._i32p), abi.ptr(kept, abi._i32p),
+                                                C.byref(nk), C.byref(c))
+        _check(self.lib, self.ctx, rc, "ltr_genotype_locus_pruned")
+        arrays["total_ll"] = c.total_ll
+        arrays["kept"] = kept[:nk.value].copy()
+        return arrays
+
     def create_job(self, batch, post=None, aln_params=None, indel_flank_len=5):
         vb, keep = abi.make_viterbi_batch(batch)
         p = abi.make_params(aln_params, indel_flank_len)

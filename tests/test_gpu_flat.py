@@ -59,3 +59,36 @@ def test_genotype_locus_matches_reference(engine, case):
     # PL = (int)(-10*dGL): an integer boundary can flip on a 1e-12 difference
     assert np.max(np.abs(got["pls"].ravel() - np.array(case["out_pls"]))) <= 1
     assert abs(got["total_ll"] - float.fromhex(case["total_ll"])) <= ATOL + RTOL * abs(got["total_ll"])
+
+
+def test_genotype_locus_pruned_drops_uncalled_alleles(engine):
+    """SeqStutterGenotyper::genotype's second stage: uncalled non-reference alleles are removed and the posteriors
+    recomputed on the kept LL columns (checked against the oracle's posteriors on the pruned matrix)."""
+    rng = np.random.default_rng(77)
+    for t in range(20):
+        S, H = int(rng.integers(1, 4)), int(rng.integers(2, 8))
+        rps = [int(x) for x in rng.integers(3, 12, size=S)]
+        R = sum(rps)
+        lab = np.repeat(np.arange(S), rps).astype(np.int32)
+        true = rng.integers(0, H, size=(S, 2))
+        ll = -rng.exponential(30, size=(R, H)) - 8
+        hp = rng.integers(0, 2, size=R)
+        for r in range(R):
+            ll[r, true[lab[r], hp[r]]] = -rng.exponential(0.2)
+        p1 = np.where(hp == 0, -1e-6, -1000.0)
+        p2 = np.where(hp == 0, -1000.0, -1e-6)
+        seeds = np.full(R, 10, np.int32)
+        if t % 5 == 0 and S > 1:
+            seeds[lab == S - 1] = -1                    # a sample without aligned reads does not vote
+        got = engine.genotype_locus_pruned(ll, p1, p2, rps, seeds=seeds)
+        # expected kept set from the oracle's first pass
+        _cl, _post, _tot, _total, best = po.log_sample_posteriors(ll, p1, p2, lab, S)
+        voters = [s for s in range(S) if np.any(seeds[lab == s] >= 0)]
+        called = {0} | {int(a) for s in voters for a in best[s]}
+        kept = sorted(called)
+        assert list(got["kept"]) == kept
+        sub = np.maximum(ll, -600.0)[:, kept]
+        _cl2, wpost, wtot, _t2, wbest = po.log_sample_posteriors(sub, p1, p2, lab, S)
+        K = len(kept)
+        np.testing.assert_allclose(got["log_sample_posteriors"].ravel()[:S * K * K], wpost.ravel(), rtol=RTOL, atol=ATOL)
+        assert list(got["best_gts"].ravel()) == list(wbest.ravel())
