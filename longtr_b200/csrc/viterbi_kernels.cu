@@ -17,10 +17,16 @@ namespace ltr {
 
 static constexpr unsigned kFullMask = 0xFFFFFFFFu;
 static constexpr int kBlockThreads = 128;
-#ifndef LTR_FAST_UNROLL
-#define LTR_FAST_UNROLL 1  // the hot loop of the larger row classes just fits the ~6 KB L0 instruction cache
+// Unroll factor of the fast loop.  Unrolling twice removes the ~4 register moves per cell ptxas puts on the loop's
+// back edge, but the loop has to stay inside the ~6 KB L0 instruction cache: K = 9 unrolled twice is 9 KB and
+// measured 9 % slower; unrolling only the small row classes (K <= 5) measured -0.3 % on config 3.  Default: none.
+#ifndef LTR_FAST_UNROLL_MAX_K
+#define LTR_FAST_UNROLL_MAX_K 0
 #endif
-static constexpr int kFastUnroll = LTR_FAST_UNROLL;
+template <int K>
+struct FastUnroll {
+  static constexpr int value = (K <= LTR_FAST_UNROLL_MAX_K) ? 2 : 1;
+};
 
 template <int K, int MODE>
 __device__ __forceinline__ void run_task(const VitConsts& C, const DevBatch& B, const Task& T,
@@ -109,7 +115,7 @@ __device__ __forceinline__ void run_task(const VitConsts& C, const DevBatch& B, 
         nfast = (nfast < chunk_end - step) ? nfast : (chunk_end - step);
         if (nfast > 0u) {
           const uint32_t fast_end = step + nfast;
-#pragma unroll kFastUnroll
+#pragma unroll FastUnroll<K>::value
           for (; step < fast_end; ++step) {
             const double rx = __shfl_up_sync(kFullMask, LS.L.Xout, 1);
             const double ry = __shfl_up_sync(kFullMask, LS.L.Yout, 1);
