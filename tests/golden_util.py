@@ -35,3 +35,11 @@ def pair_batch(case):
                 hap_off=hoff, read_off=roff,
                 hap_bytes=np.frombuffer("".join(haps).encode(), dtype=np.uint8).copy(),
                 read_bytes=np.frombuffer("".join(reads).encode(), dtype=np.uint8).copy())
+
+
+def load_real_cases():
+    """Per-locus inputs cut from the reference's shipped HG002/HG003/HG004 reads + the VCF records the reference's own
+    per-locus genotyper writes for them (tools/real_cases.py)."""
+    import gzip
+    with gzip.open(os.path.join(GOLD, "real_cases.json.gz"), "rt") as f:
+        return json.load(f)["cases"]

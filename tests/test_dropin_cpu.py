@@ -29,3 +29,13 @@ def test_gpu_binding_is_linked_and_refuses_to_run_without_a_gpu():
         pytest.skip("a GPU is present")
     with pytest.raises(RuntimeError, match="no usable CUDA device"):
         po.full_locus_records([dc.case_a4()], "gpu")
+
+
+def test_reference_reproduces_real_data_records():
+    """BASELINE.json configs[0] / [1] as parity cases: HG002 alone and the HG002+HG003+HG004 trio on the shipped BED
+    regions (reads decoded by tools/real_cases.py), through the all-CPU reference genotyper."""
+    cases = gu.load_real_cases()
+    assert len(cases) >= 40
+    recs = po.full_locus_records(cases, "full")
+    for c, r in zip(cases, recs):
+        assert r == c["record"], c["name"]

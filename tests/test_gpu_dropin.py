@@ -20,3 +20,13 @@ def test_vcf_records_identical_to_reference():
     assert recs[0] == dc.A4_RECORD
     for c, r in zip(cases, recs):
         assert r == gold[c["name"]], (c["name"], r, gold[c["name"]])
+
+
+def test_real_data_vcf_records_identical_to_reference():
+    """The shipped trio reads (BASELINE.json configs[0]: HG002; configs[1]: HG002+HG003+HG004 joint genotyping, the
+    multi-sample posterior path) on the shipped BED regions: LongTR's genotyper on top of the GPU library writes
+    the same VCF records, character for character, as the all-CPU reference (fixtures: tools/real_cases.py)."""
+    cases = gu.load_real_cases()
+    recs = po.full_locus_records(cases, "gpu")
+    bad = [c["name"] for c, r in zip(cases, recs) if r != c["record"]]
+    assert not bad, bad
