@@ -287,7 +287,8 @@ int ltr_job_create(ltr_ctx* ctx, const ltr_params* params, const ltr_viterbi_bat
     LTR_CUDA_J(cs.ctrl.alloc(4 * sizeof(uint32_t)));
     // per-warp scratch line: row-0 boundary of the read stream / strip hand-off (viterbi_core.cuh)
     {
-      cs.scratch_stride = viterbi_scratch_entries(plan.max_q[k]);
+      // only haplotypes cut into several strips hand rows over through the scratch line (row class kmax only)
+      cs.scratch_stride = plan.multi_strip[k] ? viterbi_scratch_entries(plan.max_q[k]) : 1u;
       const size_t warps = (size_t)grid_max * warps_per_block;
       LTR_CUDA_J(cs.sxy.alloc(warps * cs.scratch_stride * sizeof(XY)));
       LTR_CUDA_J(cs.sb.alloc(warps * cs.scratch_stride * sizeof(uint32_t)));

@@ -32,8 +32,8 @@
 //    one DP column, nothing else -- and falls back to the general lane_stream_step for the
 //    ~33 of every |read| steps in which some lane crosses a read boundary.
 //  * Nothing in the per-step path is computed by a single lane: the row-0 boundary of
-//    the whole read stream is produced by a warp-wide pre-pass into a scratch line that
-//    lane 0 consumes through a double-buffered shared-memory window, and the column-0
+//    the read stream is produced 32 positions at a time by all lanes (boundary_at) into a
+//    double-buffered shared-memory window that lane 0 consumes, and the column-0
 //    state a lane needs when it starts a read comes from per-lane tables in shared
 //    memory (two variants, for the two values of the reference's column-0 emission).
 //
@@ -267,10 +267,13 @@ struct FailSink {       // pairs that MODE_FAST could not certify; consumed by M
 //   tx  [2][K][32]      X(row r, column 0) for column-0 emission variant v (0 mismatch, 1 match)
 //   tz  [2][K][32]      Z(row r, column 0)
 //   txo [2][32]         X of the lane's last real row at column 0
+//   cur [32]            per-lane BoundaryCursor (kept out of the register file: it is touched once per 32 steps)
 #if defined(__CUDACC__)
 __host__ __device__
 #endif
-inline constexpr size_t warp_smem_bytes(int K) { return 2 * 32 * sizeof(XY) + (size_t)(4 * K + 2) * 32 * sizeof(double); }
+inline constexpr size_t warp_smem_bytes(int K) {
+  return 2 * 32 * sizeof(XY) + (size_t)(4 * K + 2) * 32 * sizeof(double) + 32 * 4 * sizeof(uint32_t);
+}
 
 struct StripCtx {       // warp-uniform description of the strip being streamed
   const uint8_t* hap;   // trimmed haplotype: hap[i] is DP row/column-0 character i
@@ -318,19 +321,37 @@ LTR_HD uint32_t fail_append(const FailSink& F, uint32_t hap, uint32_t read) {
   return k;
 }
 
-// Warp-wide pre-pass, strip 0: lane `lane` fills the row-0 boundary of stream positions
-// lane, lane+32, ... of every read of the task.
-LTR_HD void prepass_boundary(const VitConsts& C, const StripCtx& T, int lane, uint32_t read_begin,
-                             uint32_t read_end) {
-  for (uint32_t p = read_begin; p < read_end; ++p) {
-    const uint32_t qb = T.read_off[p];
-    const int32_t m = (int32_t)(T.read_off[p + 1] - qb);
-    const int32_t c0 = (int32_t)T.read_bytes[qb];
-    for (int32_t j = lane; j < m; j += 32) {
-      const int32_t hj = (j < T.n) ? (int32_t)T.hap[j] : 0;
-      T.sxy[qb - T.qs + (uint32_t)j] = row0_boundary(C, j, hj, c0);
-    }
+// Row-0 boundary of the stream for strip 0, produced on the fly: every 32 steps each lane evaluates the closed form
+// for ONE stream position (window position = lane) straight into the shared-memory window that lane 0 consumes --
+// nothing goes through global memory.  The cursor remembers which read the lane's next position falls into
+// (positions of a lane grow by 32 per refill, reads are >= 1 base long).
+struct alignas(16) BoundaryCursor {
+  uint32_t p;       // read index
+  uint32_t qb, qe;  // its byte range
+  uint32_t pad;
+};
+LTR_HD void boundary_cursor_reset(BoundaryCursor& bc, const StripCtx& T, uint32_t read_begin) {
+  bc.p = read_begin;
+  bc.qb = T.read_off[read_begin];
+  bc.qe = T.read_off[read_begin + 1];
+}
+LTR_HD XY boundary_at(const VitConsts& C, const StripCtx& T, BoundaryCursor& slot, uint32_t pos) {
+  XY b;
+  b.x = C.imp;
+  b.y = C.imp;
+  if (pos >= T.Q) return b;  // window slots past the end of the stream are never consumed
+  const uint32_t q = T.qs + pos;
+  BoundaryCursor bc = slot;
+  while (q >= bc.qe) {
+    bc.p += 1;
+    bc.qb = bc.qe;
+    bc.qe = T.read_off[bc.p + 1];
   }
+  slot = bc;
+  const int32_t j = (int32_t)(q - bc.qb);
+  const int32_t c0 = (int32_t)T.read_bytes[bc.qb];
+  const int32_t hj = (j < T.n) ? (int32_t)T.hap[j] : 0;
+  return row0_boundary(C, j, hj, c0);
 }
 
 // Per strip: geometry, haplotype characters and the lane's column-0 tables.

@@ -90,6 +90,7 @@ struct Plan {
   uint64_t n_pairs_computed = 0, n_cells_computed = 0;  // after collapsing identical trimmed reads of a locus
   int max_n = 0, max_m = 0;
   std::vector<uint32_t> max_q;  // [K] longest (unique) read stream among the tasks of class K
+  std::vector<uint8_t> multi_strip;  // [K] some task of the class needs more than one strip (scratch line hand-off)
   // Identical trimmed reads of a locus give identical log-likelihoods against every haplotype (the kernel is a
   // pure function of the two strings), so each distinct sequence is aligned once and the result fanned out.
   // LongTR pools reads by their +-200 bp sequence (ReadPooler, src/read_pooler.cpp:3-20) but aligns the +-5 bp
@@ -143,6 +144,7 @@ inline int make_plan(const ltr_viterbi_batch& b, const ltr_params& p, int kmax, 
   const int cut = 35 - p.indel_flank_len;
   out.tasks.assign(kmax + 1, std::vector<Task>());
   out.max_q.assign(kmax + 1, 0);
+  out.multi_strip.assign(kmax + 1, 0);
   const uint32_t n_loci = b.n_loci;
   const uint32_t n_haps = b.locus_hap_begin[n_loci], n_reads = b.locus_read_begin[n_loci];
   out.hap_locus.assign(n_haps, 0);
@@ -238,6 +240,7 @@ inline int make_plan(const ltr_viterbi_batch& b, const ltr_params& p, int kmax, 
   struct Part {
     std::vector<Key> keys;
     std::vector<uint32_t> max_q;
+    std::vector<uint8_t> multi;
     uint64_t n_pairs = 0, n_cells = 0, n_pairs_c = 0, n_cells_c = 0;
     int max_n = 0;
   };
@@ -245,6 +248,7 @@ inline int make_plan(const ltr_viterbi_batch& b, const ltr_params& p, int kmax, 
   plan_parallel_for(n_loci, n_threads, [&](uint32_t l0, uint32_t l1, int t) {
     Part& P = parts[(size_t)t];
     P.max_q.assign(kmax + 1, 0);
+    P.multi.assign(kmax + 1, 0);
     for (uint32_t l = l0; l < l1; ++l) {
       const uint32_t h0 = b.locus_hap_begin[l], h1 = b.locus_hap_begin[l + 1];
       const uint32_t r0 = b.locus_read_begin[l], r1 = b.locus_read_begin[l + 1];
@@ -263,6 +267,7 @@ inline int make_plan(const ltr_viterbi_batch& b, const ltr_params& p, int kmax, 
           const int strips = std::max(1, (n - 1 + 32 * k - 1) / (32 * k));
           cost = (uint64_t)k * strips * (q + 32);
           P.max_q[k] = std::max<uint32_t>(P.max_q[k], (uint32_t)q);
+          if (strips > 1) P.multi[k] = 1;
           for (uint32_t r = r0; r < r1; ++r) {
             const int m = (int)(b.read_off[r + 1] - b.read_off[r]);
             if (std::abs(n - m) <= 600) P.n_cells += (uint64_t)n * (uint64_t)m;
@@ -288,7 +293,10 @@ inline int make_plan(const ltr_viterbi_batch& b, const ltr_params& p, int kmax, 
     out.n_pairs += P.n_pairs; out.n_cells += P.n_cells;
     out.n_pairs_computed += P.n_pairs_c; out.n_cells_computed += P.n_cells_c;
     out.max_n = std::max(out.max_n, P.max_n);
-    for (size_t k = 0; k < P.max_q.size(); ++k) out.max_q[k] = std::max(out.max_q[k], P.max_q[k]);
+    for (size_t k = 0; k < P.max_q.size(); ++k) {
+      out.max_q[k] = std::max(out.max_q[k], P.max_q[k]);
+      out.multi_strip[k] |= P.multi[k];
+    }
   }
   // Small batches (the per-locus entry points): a task streams ALL reads of its locus through one warp, which leaves
   // most of the GPU idle and makes the call latency the length of that stream.  Cut the read ranges so that there

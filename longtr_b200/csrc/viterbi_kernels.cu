@@ -85,10 +85,6 @@ __device__ __forceinline__ void run_task(const VitConsts& C, const DevBatch& B, 
   S.tz = S.tx + 2 * K * 32;
   S.txo = S.tz + 2 * K * 32;
 
-  // row-0 boundary of the whole stream, produced by all lanes (strip 0 input of lane 0)
-  prepass_boundary(C, S, lane, T.read_begin, T.read_end);
-  __syncwarp();
-
   const StripPlan P = plan_strips(n - 1, K);
   int32_t row_start = 1;
   LaneStream<K> LS;
@@ -100,9 +96,18 @@ __device__ __forceinline__ void run_task(const VitConsts& C, const DevBatch& B, 
     lane_geometry(K, lane, rows, row_start, i0, nrows, t_last);
     S.t_last = t_last;
     lane_stream_reset<K>(LS, C, S, lane, i0, nrows, T.read_begin);
-    // boundary window: positions [0,32) -> bnd[0], positions [32,64) prefetched into registers
-    S.bnd[lane] = sxy[lane];
-    XY nxt = sxy[32 + lane];
+    // boundary window: positions [0,32) -> bnd[0], positions [32,64) prefetched into registers.  Strip 0 evaluates
+    // the row-0 closed form on the fly; later strips read what the previous strip's last lane left in the scratch line.
+    BoundaryCursor& bc = reinterpret_cast<BoundaryCursor*>(S.txo + 2 * 32)[lane];  // shared memory, see warp_smem_bytes
+    boundary_cursor_reset(bc, S, T.read_begin);
+    XY nxt;
+    if (s == 0) {
+      S.bnd[lane] = boundary_at(C, S, bc, (uint32_t)lane);
+      nxt = boundary_at(C, S, bc, 32u + (uint32_t)lane);
+    } else {
+      S.bnd[lane] = sxy[lane];
+      nxt = sxy[32 + lane];
+    }
     __syncwarp();
     const uint32_t nsteps = S.Q + (uint32_t)t_last;
     uint32_t step = 0;
@@ -132,7 +137,7 @@ __device__ __forceinline__ void run_task(const VitConsts& C, const DevBatch& B, 
       }
       if (step < nsteps) {  // next window of the scratch line: positions [step, step+32)
         S.bnd[((step >> 5) & 1u) * 32u + lane] = nxt;
-        nxt = sxy[step + 32u + lane];
+        nxt = (s == 0) ? boundary_at(C, S, bc, step + 32u + (uint32_t)lane) : sxy[step + 32u + lane];
         __syncwarp();
       }
     }

@@ -59,7 +59,6 @@ static void emu_task(const VitConsts& C, const DevBatch& B, const Task& T, FailS
   S.tx = reinterpret_cast<double*>(E.smem.data() + 2 * 32 * sizeof(XY));
   S.tz = S.tx + 2 * K * 32;
   S.txo = S.tz + 2 * K * 32;
-  for (int t = 0; t < 32; ++t) prepass_boundary(C, S, t, T.read_begin, T.read_end);
   const StripPlan P = plan_strips(n - 1, K);
   int32_t row_start = 1;
   std::vector<LaneStream<K>> lanes(32);
@@ -74,7 +73,12 @@ static void emu_task(const VitConsts& C, const DevBatch& B, const Task& T, FailS
       lane_stream_reset<K>(lanes[t], C, S, t, i0, nrows, T.read_begin);
     }
     std::vector<XY> nxt(32);
-    for (int t = 0; t < 32; ++t) { S.bnd[t] = S.sxy[t]; nxt[t] = S.sxy[32 + t]; }
+    std::vector<BoundaryCursor> bc(32);
+    for (int t = 0; t < 32; ++t) {
+      boundary_cursor_reset(bc[t], S, T.read_begin);
+      if (s == 0) { S.bnd[t] = boundary_at(C, S, bc[t], (uint32_t)t); nxt[t] = boundary_at(C, S, bc[t], 32u + (uint32_t)t); }
+      else { S.bnd[t] = S.sxy[t]; nxt[t] = S.sxy[32 + t]; }
+    }
     std::vector<double> ox(32), oy(32);
     std::vector<uint32_t> ob(32);
     const uint32_t nsteps = S.Q + (uint32_t)S.t_last;
@@ -99,7 +103,10 @@ static void emu_task(const VitConsts& C, const DevBatch& B, const Task& T, FailS
         ++step;
       }
       if (step < nsteps)
-        for (int t = 0; t < 32; ++t) { S.bnd[((step >> 5) & 1u) * 32u + t] = nxt[t]; nxt[t] = S.sxy[step + 32u + t]; }
+        for (int t = 0; t < 32; ++t) {
+          S.bnd[((step >> 5) & 1u) * 32u + t] = nxt[t];
+          nxt[t] = (s == 0) ? boundary_at(C, S, bc[t], step + 32u + (uint32_t)t) : S.sxy[step + 32u + t];
+        }
     }
     row_start += rows;
   }
