@@ -122,6 +122,15 @@ def barrier(torch, world):
     torch.cuda.synchronize()
 
 
+def ncu_traffic(key):
+    """DRAM bytes of the dominant kernel from the committed `ncu --set full` capture (profiles/traffic.json)."""
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")) as f:
+            return json.load(f).get(key)
+    except OSError:
+        return None
+
+
 def max_over_ranks(torch, world, x):
     if world == 1:
         return x
@@ -466,7 +475,8 @@ def main():
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "fp64_issue", "achieved": achieved, "peak": peak_gcups, "unit": "GCUPS",
-                     "frac": achieved / peak_gcups, "traffic": None,
+                     "frac": achieved / peak_gcups, "traffic": ncu_traffic("traffic"),
+                     "traffic_source": ncu_traffic("source"), "traffic_kernel": ncu_traffic("kernel"),
                      "peak_source": "ltr_fp64_issue_rate (DADD lane-ops/s measured in this run) / 17 FP64 ops per cell",
                      "fp64_lane_ops_per_s": fp64_rate,
                      "hbm_gbs_algorithmic": (work.input_bytes + 8.0 * st.n_pairs) / (vit_ms / args.steps) / 1e6},
