@@ -99,12 +99,19 @@ typedef struct ltr_job_stats {
   float viterbi_ms;        /* ... of which: Viterbi kernels                          */
   uint64_t n_pairs_computed; /* pairs actually aligned: identical trimmed reads of a locus are aligned
                                 once and fanned out (results are a pure function of the two strings) */
-  uint64_t n_cells_computed; /* ... and their n*m cells                                              */
+  uint64_t n_cells_computed; /* ... and the cells evaluated for them: n*m over the full matrix, the cells
+                                inside the band for pairs certified by the banded kernel                 */
+  uint64_t n_band_pairs;       /* pairs sent to the banded kernel (band_core.cuh) ...                    */
+  uint64_t n_band_uncertified; /* ... of which the band could not certify (re-run over the full matrix)  */
 } ltr_job_stats;
 
 /* ---- context --------------------------------------------------------------------- */
 int ltr_ctx_create(int device, ltr_ctx** out);
 void ltr_ctx_destroy(ltr_ctx* ctx);
+/* Banded evaluation of the Viterbi score (exact: a pair is accepted only when its banded score proves the band was
+ * wide enough, otherwise it is re-run over the full matrix).  half_width < 0: off; 0 (default): automatic margin;
+ * > 0: minimum number of diagonals kept on either side of the diagonals 0 .. m-n.  Results do not depend on it. */
+int ltr_ctx_set_band(ltr_ctx* ctx, int32_t half_width);
 const char* ltr_strerror(int code);
 const char* ltr_last_error(const ltr_ctx* ctx); /* CUDA error text of the last failure */
 const char* ltr_version(void);

@@ -44,7 +44,7 @@ class JobStats(C.Structure):
     _fields_ = [("n_pairs", C.c_uint64), ("n_cells", C.c_uint64), ("n_fallback", C.c_uint64),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("n_launches", C.c_uint32),
                 ("kernel_ms", C.c_float), ("viterbi_ms", C.c_float), ("n_pairs_computed", C.c_uint64),
-                ("n_cells_computed", C.c_uint64)]
+                ("n_cells_computed", C.c_uint64), ("n_band_pairs", C.c_uint64), ("n_band_uncertified", C.c_uint64)]
 
 
 class LocusCalls(C.Structure):
@@ -149,6 +149,8 @@ def load():
     lib.ltr_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
     lib.ltr_ctx_create.restype = C.c_int
     lib.ltr_ctx_destroy.argtypes = [vp]
+    lib.ltr_ctx_set_band.argtypes = [vp, C.c_int32]
+    lib.ltr_ctx_set_band.restype = C.c_int
     lib.ltr_strerror.argtypes = [C.c_int]
     lib.ltr_strerror.restype = C.c_char_p
     lib.ltr_last_error.argtypes = [vp]
@@ -191,7 +193,7 @@ def load():
 
 
 EXPORTED_SYMBOLS = [
-    "ltr_params_default", "ltr_ctx_create", "ltr_ctx_destroy", "ltr_strerror", "ltr_last_error",
+    "ltr_params_default", "ltr_ctx_create", "ltr_ctx_destroy", "ltr_ctx_set_band", "ltr_strerror", "ltr_last_error",
     "ltr_version", "ltr_viterbi_ll", "ltr_posteriors", "ltr_job_create", "ltr_job_run", "ltr_job_sizes",
     "ltr_job_download", "ltr_job_get_stats", "ltr_job_destroy", "ltr_process_reads_flat",
     "ltr_fp64_issue_rate", "ltr_genotype_locus", "ltr_extract_calls", "ltr_trim_read_flat", "ltr_seed_base_flat",

@@ -16,11 +16,11 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 OUT = os.path.join(CSRC, "liblongtr_b200.so")
 OBJ = os.path.join(CSRC, "build")
 
-CU_SOURCES = ["viterbi_kernels.cu", "posterior_kernel.cu", "stutter_kernel.cu", "abi.cu", "stutter_abi.cu",
+CU_SOURCES = ["viterbi_kernels.cu", "band_kernel.cu", "posterior_kernel.cu", "stutter_kernel.cu", "abi.cu", "stutter_abi.cu",
               "microbench.cu"]
 CPP_SOURCES = ["host/flat_api.cpp", "host/host_types.cpp", "host/hap_aligner.cpp", "host/stutter_host.cpp",
                "host/genotyper.cpp", "synth.cpp", "synth_stutter.cpp"]
-HEADERS = ["viterbi_core.cuh", "viterbi_host.h", "kernels.h", "stutter_core.cuh", "ctx.h"]
+HEADERS = ["viterbi_core.cuh", "band_core.cuh", "viterbi_host.h", "kernels.h", "stutter_core.cuh", "ctx.h"]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",

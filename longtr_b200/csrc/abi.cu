@@ -24,7 +24,8 @@ using namespace ltr;
 
 struct ClassState {
   int k = 0;
-  uint32_t n_tasks = 0;
+  uint32_t n_tasks = 0;   // tasks of the plan; band_collect_kernel may append up to task_cap
+  uint32_t task_cap = 0;
   uint32_t fail_cap = 0;
   uint32_t grid_fast = 0, grid_full = 0;
   DeviceBuffer tasks, fails, ctrl;  // ctrl: [0] fast cursor [1] n_tasks [2] fail count [3] full cursor
@@ -46,8 +47,18 @@ struct ltr_job {
   DeviceBuffer lsb, pool, label, p1, p2, nsamp, haploid, post_off, tot_off, post, totals, int_logs;
   uint32_t n_int_logs = 0;
   std::vector<ClassState> classes;
+  // banded kernel (band_kernel.cu): tasks of all band classes back to back, their pair lists, control words
+  struct BandClass {
+    int k = 0;
+    uint32_t task_begin = 0, n_tasks = 0, pair_begin = 0, n_pairs = 0, grid = 0;
+  };
+  std::vector<BandClass> band_classes;
+  uint32_t n_band_tasks = 0;
+  DeviceBuffer band_tasks, band_cum, band_pairs, band_ctrl;  // band_ctrl: u32[8] cursors, u32[2] counters, pad, u64[2] stats
+  uint64_t plan_cells_computed = 0;
   ltr_job_stats stats;
 };
+static const size_t kBandCtrlBytes = 64;
 
 namespace {
 
@@ -126,6 +137,8 @@ int ltr_ctx_create(int device, ltr_ctx** out) {
   if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_start);
   if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_vit);
   if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_end);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_init, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_collect, cudaEventDisableTiming);
   if (e != cudaSuccess) {
     ltr_ctx_destroy(ctx);
     return LTR_ERR_CUDA;
@@ -139,7 +152,22 @@ int ltr_ctx_create(int device, ltr_ctx** out) {
       return LTR_ERR_NO_DEVICE;
     }
   }
+  for (int c = 0; c < kBandClasses; ++c) {
+    const int k = band_class_k(c);
+    ctx->band_blocks_per_sm[k] = band_blocks_per_sm(k);
+    if (ctx->band_blocks_per_sm[k] <= 0) {
+      ltr_ctx_destroy(ctx);
+      return LTR_ERR_NO_DEVICE;
+    }
+  }
+  if (const char* env = getenv("LTR_BAND")) ctx->band_w = atoi(env);  // diagnostics: initial ltr_ctx_set_band value
   *out = ctx;
+  return LTR_OK;
+}
+
+int ltr_ctx_set_band(ltr_ctx* ctx, int32_t half_width) {
+  if (!ctx) return LTR_ERR_INVALID;
+  ctx->band_w = half_width;
   return LTR_OK;
 }
 
@@ -154,6 +182,8 @@ void ltr_ctx_destroy(ltr_ctx* ctx) {
   if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
   if (ctx->ev_vit) cudaEventDestroy(ctx->ev_vit);
   if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
+  if (ctx->ev_init) cudaEventDestroy(ctx->ev_init);
+  if (ctx->ev_collect) cudaEventDestroy(ctx->ev_collect);
   if (ctx->stage) cudaFreeHost(ctx->stage);
   delete ctx;
 }
@@ -166,7 +196,7 @@ void ltr_job_destroy(ltr_ctx* ctx, ltr_job* job) {
                           &job->lub, &job->r2u, &job->rlocus, &job->ull_off, &job->uniq_ll,
                           &job->lsb, &job->pool, &job->label, &job->p1, &job->p2, &job->nsamp,
                           &job->haploid, &job->post_off, &job->tot_off, &job->post, &job->totals,
-                          &job->int_logs};
+                          &job->int_logs, &job->band_tasks, &job->band_cum, &job->band_pairs, &job->band_ctrl};
   for (DeviceBuffer* b : bufs) b->free();
   for (ClassState& c : job->classes) {
     c.tasks.free(); c.fails.free(); c.ctrl.free(); c.sxy.free(); c.sb.free();
@@ -213,7 +243,7 @@ int ltr_job_create(ltr_ctx* ctx, const ltr_params* params, const ltr_viterbi_bat
   };
   static const bool timing = getenv("LTR_TIMING") != nullptr;  // diagnostics: host-side phases of job creation on stderr
   const auto t_begin = std::chrono::steady_clock::now();
-  int rc = make_plan(bb, *params, kmax, job->plan, 0, &Stage::get, ctx);
+  int rc = make_plan(bb, *params, kmax, job->plan, 0, &Stage::get, ctx, ctx->band_w);
   const auto t_plan = std::chrono::steady_clock::now();
   if (rc != LTR_OK) { delete job; return rc; }
   Plan& plan = job->plan;
@@ -225,6 +255,8 @@ int ltr_job_create(ltr_ctx* ctx, const ltr_params* params, const ltr_viterbi_bat
   job->stats.n_cells = plan.n_cells;
   job->stats.n_pairs_computed = plan.n_pairs_computed;
   job->stats.n_cells_computed = plan.n_cells_computed;
+  job->plan_cells_computed = plan.n_cells_computed;
+  job->stats.n_band_pairs = plan.n_band_pairs;
   make_consts(*params, std::max(plan.max_n, plan.max_m) + 2, job->hc);
   uint64_t* h2d = &job->stats.h2d_bytes;
 
@@ -249,8 +281,9 @@ int ltr_job_create(ltr_ctx* ctx, const ltr_params* params, const ltr_viterbi_bat
   // Only the distinct trimmed reads of each locus travel to the device (Plan, viterbi_host.h); the kernels fill the
   // unique LL matrices and expand_ll_kernel fans them out to the caller-visible aln_probs layout.
   const size_t hap_nbytes = bb.hap_off[job->n_haps];
-  LTR_TRY(upload(ctx, job->hap_bytes, bb.hap_bytes, hap_nbytes, 16, h2d));
-  LTR_TRY(upload(ctx, job->read_bytes, plan.uread_bytes, plan.uread_nbytes, 16, h2d));
+  // padding: the stream kernel prefetches one byte, the band kernel's character windows run up to W/2 + K bytes ahead
+  LTR_TRY(upload(ctx, job->hap_bytes, bb.hap_bytes, hap_nbytes, 256, h2d));
+  LTR_TRY(upload(ctx, job->read_bytes, plan.uread_bytes, plan.uread_nbytes, 256, h2d));
   LTR_TRY(upload(ctx, job->hap_off, bb.hap_off, (size_t)job->n_haps + 1, 0, h2d));
   LTR_TRY(upload(ctx, job->read_off, plan.uread_off.data(), plan.uread_off.size(), 0, h2d));
   LTR_TRY(upload(ctx, job->lhb, bb.locus_hap_begin, (size_t)job->n_loci + 1, 0, h2d));
@@ -269,20 +302,28 @@ int ltr_job_create(ltr_ctx* ctx, const ltr_params* params, const ltr_viterbi_bat
   job->hc.C.tabD = job->tabD.as<double>();
 
   for (int k = 1; k <= kmax; ++k) {
-    if (plan.tasks[k].empty()) continue;
+    const uint64_t band_extra = plan.band_pairs_by_rows[k];  // tasks band_collect_kernel may append (<= pairs)
+    if (plan.tasks[k].empty() && band_extra == 0) continue;
+    if (plan.tasks[k].size() + band_extra > 0xFFFFFFF0ull) { ltr_job_destroy(ctx, job); return LTR_ERR_INVALID; }
     ClassState cs;
     cs.k = k;
     cs.force_full = !fast_certificate_valid(*params);  // parameters outside the certificate's condition: exact kernel only
     cs.n_tasks = (uint32_t)plan.tasks[k].size();
-    uint64_t pairs = 0;
+    cs.task_cap = (uint32_t)(plan.tasks[k].size() + band_extra);
+    uint64_t pairs = band_extra;
     for (const Task& t : plan.tasks[k]) pairs += t.read_end - t.read_begin;
     cs.fail_cap = (uint32_t)std::min<uint64_t>(pairs, 1u << 22);
     const uint32_t warps_per_block = viterbi_block_threads() / 32;
-    const uint32_t want_blocks = (cs.n_tasks + warps_per_block - 1) / warps_per_block;
-    cs.grid_fast = std::min<uint32_t>(want_blocks, (uint32_t)(ctx->sm_count * ctx->blocks_per_sm[MODE_FAST][k]));
+    const uint64_t want_blocks = ((uint64_t)cs.n_tasks + band_extra + warps_per_block - 1) / warps_per_block;
+    cs.grid_fast = (uint32_t)std::min<uint64_t>(want_blocks, (uint64_t)(ctx->sm_count * ctx->blocks_per_sm[MODE_FAST][k]));
     cs.grid_full = (uint32_t)(ctx->sm_count * std::min(2, ctx->blocks_per_sm[MODE_FULL][k]));
     const uint32_t grid_max = std::max(cs.grid_fast, cs.grid_full);
-    LTR_TRY(upload(ctx, cs.tasks, plan.tasks[k].data(), plan.tasks[k].size(), 0, h2d));
+    LTR_CUDA_J(cs.tasks.alloc((size_t)cs.task_cap * sizeof(Task)));
+    if (cs.n_tasks) {
+      LTR_CUDA_J(cudaMemcpyAsync(cs.tasks.p, plan.tasks[k].data(), (size_t)cs.n_tasks * sizeof(Task),
+                                 cudaMemcpyHostToDevice, ctx->main_stream));
+      *h2d += (size_t)cs.n_tasks * sizeof(Task);
+    }
     LTR_CUDA_J(cs.fails.alloc((size_t)cs.fail_cap * sizeof(Task)));
     LTR_CUDA_J(cs.ctrl.alloc(4 * sizeof(uint32_t)));
     // per-warp scratch line: row-0 boundary of the read stream / strip hand-off (viterbi_core.cuh)
@@ -295,6 +336,40 @@ int ltr_job_create(ltr_ctx* ctx, const ltr_params* params, const ltr_viterbi_bat
       LTR_CUDA_J(cudaMemsetAsync(cs.sxy.p, 0, cs.sxy.bytes, ctx->main_stream));
     }
     job->classes.push_back(cs);
+  }
+
+  if (plan.n_band_pairs) {
+    std::vector<BandTask> all;
+    std::vector<uint32_t> cum;
+    uint64_t npairs = 0;
+    for (int c = 0; c < kBandClasses; ++c) {
+      const std::vector<BandTask>& v = plan.band_tasks[(size_t)c];
+      if (v.empty()) continue;
+      ltr_job::BandClass bc;
+      bc.k = band_class_k(c);
+      bc.task_begin = (uint32_t)all.size();
+      bc.n_tasks = (uint32_t)v.size();
+      bc.pair_begin = (uint32_t)npairs;
+      for (const BandTask& t : v) {
+        all.push_back(t);
+        cum.push_back((uint32_t)npairs);
+        npairs += t.read_end - t.read_begin;
+      }
+      if (npairs > 0xFFFFFFF0ull) { ltr_job_destroy(ctx, job); return LTR_ERR_INVALID; }
+      bc.n_pairs = (uint32_t)npairs - bc.pair_begin;
+      const uint32_t warps_per_block = (uint32_t)band_block_threads() / 32;
+      const uint32_t rounds = (bc.n_pairs + 3) / 4;
+      bc.grid = std::min<uint32_t>((rounds + warps_per_block - 1) / warps_per_block,
+                                   (uint32_t)(ctx->sm_count * ctx->band_blocks_per_sm[bc.k]));
+      job->band_classes.push_back(bc);
+    }
+    job->n_band_tasks = (uint32_t)all.size();
+    LTR_TRY(upload(ctx, job->band_tasks, all.data(), all.size(), 0, h2d));
+    LTR_TRY(upload(ctx, job->band_cum, cum.data(), cum.size(), 0, h2d));
+    LTR_CUDA_J(job->band_pairs.alloc((size_t)npairs * sizeof(uint2)));
+    LTR_CUDA_J(job->band_ctrl.alloc(kBandCtrlBytes));
+    LTR_CUDA_J(launch_band_expand(job->band_tasks.as<BandTask>(), job->band_cum.as<uint32_t>(), job->n_band_tasks,
+                                  job->band_pairs.as<uint2>(), ctx->main_stream));
   }
 
   if (post) {
@@ -350,7 +425,7 @@ int ltr_job_create(ltr_ctx* ctx, const ltr_params* params, const ltr_viterbi_bat
 #undef LTR_CUDA_J
 }
 
-static int run_classes(ltr_ctx* ctx, ltr_job* job, bool only_forced) {
+static DevBatch job_dev_batch(const ltr_job* job) {
   DevBatch B;
   B.hap_bytes = job->hap_bytes.as<uint8_t>();
   B.hap_off = job->hap_off.as<uint32_t>();
@@ -361,14 +436,26 @@ static int run_classes(ltr_ctx* ctx, ltr_job* job, bool only_forced) {
   B.locus_read_begin = job->lub.as<uint32_t>();            // unique reads
   B.ll_off = job->ull_off.as<unsigned long long>();
   B.out_ll = job->uniq_ll.as<double>();
+  return B;
+}
+
+// Launches the stream kernels of every row class on its stream.  init_ctrl: write the control words first (on the
+// class stream); otherwise the caller has initialised them (band phase: band_collect_kernel appends tasks).
+// only_forced: re-run of the classes whose fail list overflowed; ntasks_override[c] = tasks incl. appended ones.
+static int run_classes(ltr_ctx* ctx, ltr_job* job, bool only_forced, bool init_ctrl,
+                       const std::vector<uint32_t>* ntasks_override) {
+  const DevBatch B = job_dev_batch(job);
   int si = 0;
-  for (ClassState& cs : job->classes) {
+  for (size_t ci = 0; ci < job->classes.size(); ++ci) {
+    ClassState& cs = job->classes[ci];
     if (only_forced && !cs.force_full) continue;
     static const bool serial = getenv("LTR_SERIAL_CLASSES") != nullptr;  // diagnostics: one row class at a time
     cudaStream_t st = ctx->streams[serial ? 0 : (si % kNumStreams)];
     ++si;
-    const uint32_t ctrl_init[4] = {0u, cs.n_tasks, 0u, 0u};
-    LTR_CUDA(ctx, cudaMemcpyAsync(cs.ctrl.p, ctrl_init, sizeof(ctrl_init), cudaMemcpyHostToDevice, st));
+    if (init_ctrl) {
+      const uint32_t ctrl_init[4] = {0u, ntasks_override ? (*ntasks_override)[ci] : cs.n_tasks, 0u, 0u};
+      LTR_CUDA(ctx, cudaMemcpyAsync(cs.ctrl.p, ctrl_init, sizeof(ctrl_init), cudaMemcpyHostToDevice, st));
+    }
     uint32_t* ctrl = cs.ctrl.as<uint32_t>();
     FailSink sink;
     sink.items = cs.fails.as<Task>();
@@ -379,14 +466,14 @@ static int run_classes(ltr_ctx* ctx, ltr_job* job, bool only_forced) {
     none.count = ctrl + 2;
     none.capacity = 0;
     if (cs.force_full) {
-      // witness list overflowed on an earlier run: evaluate every pair with the exact kernel
+      // parameters outside the certificate's condition, or the fail list overflowed on an earlier run: exact kernel only
       LTR_CUDA(ctx, launch_viterbi(cs.k, MODE_FULL, (int)cs.grid_fast, st, job->hc.C, B, cs.tasks.as<Task>(),
-                                   ctrl + 1, cs.n_tasks, ctrl + 0, none, cs.sxy.as<XY>(),
+                                   ctrl + 1, cs.task_cap, ctrl + 0, none, cs.sxy.as<XY>(),
                                    cs.sb.as<uint32_t>(), cs.scratch_stride));
       job->stats.n_launches += 1;
     } else {
       LTR_CUDA(ctx, launch_viterbi(cs.k, MODE_FAST, (int)cs.grid_fast, st, job->hc.C, B, cs.tasks.as<Task>(),
-                                   ctrl + 1, cs.n_tasks, ctrl + 0, sink, cs.sxy.as<XY>(),
+                                   ctrl + 1, cs.task_cap, ctrl + 0, sink, cs.sxy.as<XY>(),
                                    cs.sb.as<uint32_t>(), cs.scratch_stride));
       LTR_CUDA(ctx, launch_viterbi(cs.k, MODE_FULL, (int)cs.grid_full, st, job->hc.C, B, cs.fails.as<Task>(),
                                    ctrl + 2, cs.fail_cap, ctrl + 3, none, cs.sxy.as<XY>(),
@@ -397,15 +484,71 @@ static int run_classes(ltr_ctx* ctx, ltr_job* job, bool only_forced) {
   return LTR_OK;
 }
 
+// Band phase: the banded kernels of every band class, then band_collect_kernel, all ordered before the stream kernels.
+static int run_band_phase(ltr_ctx* ctx, ltr_job* job) {
+  const DevBatch B = job_dev_batch(job);
+  for (ClassState& cs : job->classes) {
+    const uint32_t ctrl_init[4] = {0u, cs.n_tasks, 0u, 0u};
+    LTR_CUDA(ctx, cudaMemcpyAsync(cs.ctrl.p, ctrl_init, sizeof(ctrl_init), cudaMemcpyHostToDevice, ctx->main_stream));
+  }
+  LTR_CUDA(ctx, cudaMemsetAsync(job->band_ctrl.p, 0, kBandCtrlBytes, ctx->main_stream));
+  LTR_CUDA(ctx, cudaEventRecord(ctx->ev_init, ctx->main_stream));
+  uint32_t* bctrl = job->band_ctrl.as<uint32_t>();
+  static const bool no_abandon = getenv("LTR_BAND_NO_ABANDON") != nullptr;  // diagnostics
+  for (size_t i = 0; i < job->band_classes.size(); ++i) {
+    const ltr_job::BandClass& bc = job->band_classes[i];
+    cudaStream_t st = ctx->streams[i % kNumStreams];
+    LTR_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_init, 0));
+    BandArgs A;
+    A.pairs = job->band_pairs.as<uint2>() + bc.pair_begin;
+    A.n_pairs = bc.n_pairs;
+    A.cursor = bctrl + i;
+    A.counters = bctrl + 8;
+    A.gap = job->plan.band.gap;
+    A.abandon_after = no_abandon ? 0u : 4096u;
+    LTR_CUDA(ctx, launch_band(bc.k, (int)bc.grid, st, job->hc.C, B, A));
+    job->stats.n_launches += 1;
+    LTR_CUDA(ctx, cudaEventRecord(ctx->ev_stream[i % kNumStreams], st));
+    LTR_CUDA(ctx, cudaStreamWaitEvent(ctx->main_stream, ctx->ev_stream[i % kNumStreams], 0));
+  }
+  BandCollect S;
+  for (int k = 0; k < 17; ++k) {
+    S.tasks[k] = nullptr;
+    S.count[k] = bctrl + 10;  // never read: capacity 0
+    S.cap[k] = 0;
+  }
+  for (ClassState& cs : job->classes) {
+    S.tasks[cs.k] = cs.tasks.as<Task>();
+    S.count[cs.k] = cs.ctrl.as<uint32_t>() + 1;
+    S.cap[cs.k] = cs.task_cap;
+  }
+  S.kmax = viterbi_max_rows_per_lane();
+  S.n_uncertified = reinterpret_cast<unsigned long long*>(job->band_ctrl.as<char>() + 48);
+  S.cells_uncertified = reinterpret_cast<unsigned long long*>(job->band_ctrl.as<char>() + 56);
+  LTR_CUDA(ctx, launch_band_collect(job->hc.C, B, job->band_tasks.as<BandTask>(), job->n_band_tasks, S,
+                                    ctx->main_stream));
+  job->stats.n_launches += 1;
+  LTR_CUDA(ctx, cudaEventRecord(ctx->ev_collect, ctx->main_stream));
+  return LTR_OK;
+}
+
 int ltr_job_run(ltr_ctx* ctx, ltr_job* job) {
   if (!ctx || !job) return LTR_ERR_INVALID;
   LTR_CUDA(ctx, cudaSetDevice(ctx->device));
   job->stats.n_launches = 0;
   job->stats.n_fallback = 0;
+  job->stats.n_band_uncertified = 0;
   const int n_used = (int)std::min<size_t>(kNumStreams, job->classes.size());  // streams run_classes touches
+  const bool band = !job->band_classes.empty();
   LTR_CUDA(ctx, cudaEventRecord(ctx->ev_start, ctx->main_stream));
-  for (int i = 0; i < n_used; ++i) LTR_CUDA(ctx, cudaStreamWaitEvent(ctx->streams[i], ctx->ev_start, 0));
-  int rc = run_classes(ctx, job, false);
+  if (band) {
+    int rcb = run_band_phase(ctx, job);
+    if (rcb != LTR_OK) return rcb;
+    for (int i = 0; i < n_used; ++i) LTR_CUDA(ctx, cudaStreamWaitEvent(ctx->streams[i], ctx->ev_collect, 0));
+  } else {
+    for (int i = 0; i < n_used; ++i) LTR_CUDA(ctx, cudaStreamWaitEvent(ctx->streams[i], ctx->ev_start, 0));
+  }
+  int rc = run_classes(ctx, job, false, !band, nullptr);
   if (rc != LTR_OK) return rc;
   for (int i = 0; i < n_used; ++i) {
     LTR_CUDA(ctx, cudaEventRecord(ctx->ev_stream[i], ctx->streams[i]));
@@ -416,10 +559,17 @@ int ltr_job_run(ltr_ctx* ctx, ltr_job* job) {
   for (size_t c = 0; c < job->classes.size(); ++c)
     LTR_CUDA(ctx, cudaMemcpyAsync(&ctrl[c * 4], job->classes[c].ctrl.p, 4 * sizeof(uint32_t),
                                   cudaMemcpyDeviceToHost, ctx->main_stream));
+  unsigned long long band_words[kBandCtrlBytes / 8] = {0};
+  if (band)
+    LTR_CUDA(ctx, cudaMemcpyAsync(band_words, job->band_ctrl.p, kBandCtrlBytes, cudaMemcpyDeviceToHost, ctx->main_stream));
   LTR_CUDA(ctx, cudaStreamSynchronize(ctx->main_stream));
+  job->stats.n_band_uncertified = band_words[6];
+  job->stats.n_cells_computed = job->plan_cells_computed + band_words[7];
   bool rerun = false;
+  std::vector<uint32_t> ntasks(job->classes.size(), 0);
   for (size_t c = 0; c < job->classes.size(); ++c) {
     ClassState& cs = job->classes[c];
+    ntasks[c] = std::min(ctrl[c * 4 + 1], cs.task_cap);
     if (cs.force_full) continue;
     job->stats.n_fallback += ctrl[c * 4 + 2];
     if (ctrl[c * 4 + 2] > cs.fail_cap) {
@@ -429,7 +579,7 @@ int ltr_job_run(ltr_ctx* ctx, ltr_job* job) {
   }
   if (rerun) {
     for (int i = 0; i < kNumStreams; ++i) LTR_CUDA(ctx, cudaStreamWaitEvent(ctx->streams[i], ctx->ev_start, 0));
-    rc = run_classes(ctx, job, true);
+    rc = run_classes(ctx, job, true, true, &ntasks);
     if (rc != LTR_OK) return rc;
     for (int i = 0; i < kNumStreams; ++i) {
       LTR_CUDA(ctx, cudaEventRecord(ctx->ev_stream[i], ctx->streams[i]));

@@ -1,0 +1,259 @@
+// band_core.cuh -- per-lane logic of the banded anti-diagonal Viterbi (kernel 1b).
+//
+// Same function as viterbi_core.cuh -- the score of HapAligner::align_seq_to_hap for one (haplotype, read) pair,
+// reference src/SeqAlignment/HapAligner.cpp:236-343 -- evaluated only on the diagonals d = j - i of a band
+// [dlo, dlo + W) that contains the origin's diagonal 0 and the end cell's diagonal de = m - n with a margin of w
+// diagonals on either side, and accepted only when the result PROVES that the band was wide enough:
+//
+//  * Every value of the reference's matrices is the maximum over chains of cells (a chain starts at the origin,
+//    may run along row 0 or column 0 through the closed-form boundary cells, then through the interior) of the
+//    chain's sequentially rounded sum; max and "+ constant" commute under round-to-nearest, so restricting the DP to
+//    a band yields exactly max{chains inside the band}.
+//  * A chain that leaves the band and still ends in (n-1, m-1) makes at least |de| + 2w + 2 horizontal/vertical
+//    moves; all of them but at most one (the M cell of the boundary row/column, HapAligner.cpp:266-279) cost at least
+//    g = min(|M2I|, |I2I|, |M2D|, |D2D|) when all transition parameters are <= 0 (emissions are < 0).  Its value is
+//    therefore <= U = -g (|de| + 2w) (+1e-3 for the rounding of at most ~1e4 additions of magnitude < 1e4).
+//  * Hence F_band > U  =>  F = F_band bit for bit; and F > fast_thr additionally certifies that the reference's
+//    per-row bail-out (HapAligner.cpp:297-306) cannot fire (viterbi_core.cuh).  Pairs that are not certified are
+//    marked and re-run over the full matrix by viterbi_stream_kernel.  Results are exact either way.
+//
+// Mapping: a group of 8 lanes owns one pair; lane l keeps 2K consecutive diagonals (W = 16 K).  All lanes advance
+// along the anti-diagonals s = i + j in lock step: at step s the lane evaluates its K cells with d = s (mod 2), which
+// are independent of each other (X comes from the same diagonal two steps back, Y from diagonal d+1 and Z from
+// diagonal d-1 one step back), so one double crosses a lane boundary per step (SHFL.UP on even steps, SHFL.DOWN on
+// odd steps).  Steps that may touch a boundary cell, cells outside the matrix or the end cell run band_general_step;
+// all others run the branch-free band_fast_even / band_fast_odd pair on characters kept in register windows.
+//
+// Compiled for the device and, with LTR_HOST_EMU, for the CPU lane emulator of the unit tests (tests/emu).
+#pragma once
+#include "viterbi_core.cuh"
+
+namespace ltr {
+
+static constexpr int kBandGroupLanes = 8;
+static constexpr int kBandMaxK = 8;                  // widest class: W = 128 diagonals
+static constexpr double kBandUncertified = 2.0;      // marker in the LL matrix (log-likelihoods are <= 0)
+
+// Band classes (cells per lane per step); W = 16 * K diagonals.
+LTR_HHD int band_class_k(int c) {
+  return c == 0 ? 2 : c == 1 ? 3 : c == 2 ? 4 : c == 3 ? 6 : 8;
+}
+static constexpr int kBandClasses = 5;
+
+struct BandGeom {
+  int32_t dlo;  // lowest diagonal of the band (even)
+  int32_t w;    // guaranteed margin: [min(0,de) - w, max(0,de) + w] lies inside the band (negative: band too narrow)
+};
+
+LTR_HHD BandGeom band_geometry(int32_t n, int32_t m, int32_t W) {
+  const int32_t de = m - n;
+  const int32_t lo = de < 0 ? de : 0, hi = de < 0 ? 0 : de;
+  const int32_t slack = W - 1 - (hi - lo);
+  BandGeom g;
+  int32_t half = slack / 2;
+  if (slack < 0) half = 0;
+  g.dlo = lo - half;
+  if (g.dlo & 1) g.dlo -= 1;  // even: the step parity of a lane's cells is the same for every pair of a warp
+  const int32_t dhi = g.dlo + W - 1;
+  const int32_t wl = lo - g.dlo, wh = dhi - hi;
+  g.w = (slack < 0) ? -1 : (wl < wh ? wl : wh);
+  return g;
+}
+
+// Number of interior cells (i >= 1, j >= 1) of the n x m matrix that lie inside the band: what the band kernel has to
+// evaluate for the pair (statistics / roofline accounting).
+LTR_HHD unsigned long long band_cells(int32_t n, int32_t m, int32_t W, int32_t dlo) {
+  const long long dhi = (long long)dlo + W - 1;
+  long long total = (long long)(n - 1) * W;
+  // rows whose band starts left of column 1: i + dlo < 1  ->  i in [1, min(n-1, -dlo)], each loses 1 - (i + dlo)
+  long long a = -(long long)dlo;
+  if (a > n - 1) a = n - 1;
+  if (a >= 1) total -= a * (1 - (long long)dlo) - a * (a + 1) / 2;
+  // rows whose band ends right of column m-1: i + dhi > m-1 -> i in [max(1, m - dhi), n-1], each loses i + dhi - (m-1)
+  long long b0 = (long long)m - dhi;
+  if (b0 < 1) b0 = 1;
+  if (b0 <= n - 1) {
+    const long long cnt = (long long)(n - 1) - b0 + 1;
+    total -= cnt * (dhi - (m - 1)) + (b0 + (n - 1)) * cnt / 2;
+  }
+  return total > 0 ? (unsigned long long)total : 0ull;
+}
+
+// Pair certified from its banded score?  thr = max(fast_thr, -g(|de| + 2w) + 1e-3), see the header comment.
+LTR_HD double band_threshold(const VitConsts& C, double gap, int32_t n, int32_t m, int32_t w) {
+  int32_t de = m - n;
+  if (de < 0) de = -de;
+  const double u = -gap * (double)(de + 2 * w) + 1e-3;
+  return u > C.fast_thr ? u : C.fast_thr;
+}
+
+struct BandPair {       // one (haplotype, read) pair as seen by a lane of its group
+  const uint8_t* hap;   // trimmed haplotype: hap[i] is the character of DP row i
+  const uint8_t* read;  // read[j] is the character of DP column j
+  int32_t n, m;
+  int32_t d0;           // first of the lane's 2K diagonals
+};
+
+template <int K>
+struct BandLane {
+  double X[2 * K];  // X of the latest cell on local diagonal q
+  double A[K];      // Y slots: after an even step A[k] = Y(diag 2k), after an odd step A[k] = Y(diag 2k+1)
+  double B[K];      // Z slots: after an even step B[k] = Z(diag 2k), after an odd step B[k] = Z(diag 2k+1)
+  int32_t hw[K];      // fast loop: hw[k] = hap[ib - k]
+  int32_t rw[K + 1];  // fast loop: rw[k] = read[jb + k]
+};
+
+// Closed-form boundary cell of local diagonal q (row 0 for d >= 0, column 0 for d < 0): bx = X, bv = Y (row 0) or Z
+// (column 0) -- the two values interior cells consume (HapAligner.cpp:263-280).
+LTR_HD void band_boundary(const VitConsts& C, const BandPair& R, int32_t d, double& bx, double& bv) {
+  if (d >= 0) {
+    const int32_t j = d;
+    const int32_t hj = (j < R.n) ? (int32_t)R.hap[j] : 0;
+    const XY b = row0_boundary(C, j, hj, (int32_t)R.read[0]);
+    bx = b.x;
+    bv = b.y;
+  } else {
+    const int32_t c1 = (R.m > 1) ? (int32_t)R.read[1] : 0;
+    const double e1 = ((int32_t)R.hap[0] == c1) ? C.match : C.mismatch;  // emit(h[0], r[1]), HapAligner.cpp:276
+    double Mi, Ii, Di;
+    col0_cell(C, -d, e1, Mi, Ii, Di);
+    const XYZ o = finish_cell(C, Mi, Ii, Di);
+    bx = o.x;
+    bv = o.z;
+  }
+}
+
+template <int K>
+LTR_HD void band_lane_reset(BandLane<K>& L, const VitConsts& C) {
+#pragma unroll
+  for (int q = 0; q < 2 * K; ++q) L.X[q] = C.imp;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    L.A[k] = C.imp;
+    L.B[k] = C.imp;
+    L.hw[k] = 0;
+    L.rw[k] = 0;
+  }
+  L.rw[K] = 0;
+}
+
+// One anti-diagonal step with every special case: cells before the matrix (imp), boundary cells (tbx/tbv: the
+// lane's closed forms, indexed by local diagonal), interior cells by the recurrence with characters fetched from
+// memory, and the end cell (n-1, m-1), whose max(D, max(I, M)) is the pair's score (HapAligner.cpp:308-309).
+// P = parity of the step (the lane's cells are the local diagonals q = 2k + P); nb = Z of the lower neighbour's last
+// diagonal (P == 0) or Y of the upper neighbour's first diagonal (P == 1), imp at the edges of the band.
+template <int K, int P, typename TB>
+LTR_HD void band_general_step(BandLane<K>& L, const VitConsts& C, const BandPair& R, const TB& tb, int32_t s,
+                              double nb, double& F, bool& got) {
+#pragma unroll
+  for (int kk = 0; kk < K; ++kk) {
+    const int k = (P == 0) ? (K - 1 - kk) : kk;  // order matters: the Y/Z slots are updated in place
+    const int q = 2 * k + P;
+    const int32_t d = R.d0 + q;
+    const int32_t ad = d < 0 ? -d : d;
+    const double yin = (P == 0) ? L.A[k] : ((k == K - 1) ? nb : L.A[k + 1 < K ? k + 1 : k]);
+    const double zin = (P == 0) ? ((k == 0) ? nb : L.B[k >= 1 ? k - 1 : 0]) : L.B[k];
+    const double xin = L.X[q];
+    double x, y, z;
+    if (s < ad) {
+      x = C.imp;
+      y = C.imp;
+      z = C.imp;
+    } else if (s == ad) {
+      x = tb.x(q);
+      y = (d >= 0) ? tb.v(q) : C.imp;
+      z = (d >= 0) ? C.imp : tb.v(q);
+    } else {
+      const int32_t i = (s - d) >> 1, j = (s + d) >> 1;
+      const int32_t ii = (i < R.n) ? i : (R.n - 1), jj = (j < R.m) ? j : (R.m - 1);
+      const double e = ((int32_t)R.hap[ii] == (int32_t)R.read[jj]) ? C.match : C.mismatch;
+      const double M = e + xin;
+      const double I = C.match + yin;
+      const double D = zin;
+      const XYZ o = finish_cell(C, M, I, D);
+      x = o.x;
+      y = o.y;
+      z = o.z;
+      if (i == R.n - 1 && j == R.m - 1) {
+        F = vmax(D, vmax(I, M));
+        got = true;
+      }
+    }
+    L.X[q] = x;
+    L.A[k] = y;
+    L.B[k] = z;
+  }
+}
+
+// Fill the character windows for an even step s: ib = (s - d0)/2, jb = (s + d0)/2.
+template <int K>
+LTR_HD void band_windows_init(BandLane<K>& L, const BandPair& R, int32_t s) {
+  const int32_t ib = (s - R.d0) >> 1, jb = (s + R.d0) >> 1;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    int32_t i = ib - k;
+    i = i < 0 ? 0 : (i < R.n ? i : R.n - 1);
+    L.hw[k] = (int32_t)R.hap[i];
+  }
+#pragma unroll
+  for (int k = 0; k <= K; ++k) {
+    int32_t j = jb + k;
+    j = j < 0 ? 0 : (j < R.m ? j : R.m - 1);
+    L.rw[k] = (int32_t)R.read[j];
+  }
+}
+
+// Plain even step: cells q = 2k (i = ib - k, j = jb + k).  zl = Z of diagonal -1 (lower neighbour lane).
+template <int K>
+LTR_HD void band_fast_even(BandLane<K>& L, const VitConsts& C, double zl) {
+#pragma unroll
+  for (int k = K - 1; k >= 0; --k) {
+    const double e = (L.hw[k] == L.rw[k]) ? C.match : C.mismatch;
+    const double M = e + L.X[2 * k];
+    const double I = C.match + L.A[k];
+    const double D = (k == 0) ? zl : L.B[k >= 1 ? k - 1 : 0];
+    const XYZ o = finish_cell(C, M, I, D);
+    L.X[2 * k] = o.x;
+    L.A[k] = o.y;
+    L.B[k] = o.z;
+  }
+}
+
+// Plain odd step: cells q = 2k+1 (i = ib - k, j = jb + k + 1).  yr = Y of diagonal 2K (upper neighbour lane).
+// Then the windows move on by one row and one column; nh, nr are the characters hap[ib + 1], read[jb + K + 1].
+template <int K>
+LTR_HD void band_fast_odd(BandLane<K>& L, const VitConsts& C, double yr, int32_t nh, int32_t nr) {
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const double e = (L.hw[k] == L.rw[k + 1]) ? C.match : C.mismatch;
+    const double M = e + L.X[2 * k + 1];
+    const double I = C.match + ((k == K - 1) ? yr : L.A[k + 1 < K ? k + 1 : k]);
+    const double D = L.B[k];
+    const XYZ o = finish_cell(C, M, I, D);
+    L.X[2 * k + 1] = o.x;
+    L.A[k] = o.y;
+    L.B[k] = o.z;
+  }
+#pragma unroll
+  for (int k = K - 1; k >= 1; --k) L.hw[k] = L.hw[k - 1];
+  L.hw[0] = nh;
+#pragma unroll
+  for (int k = 0; k < K; ++k) L.rw[k] = L.rw[k + 1];
+  L.rw[K] = nr;
+}
+
+// First even step from which every cell of the band is interior (s >= |d| + 2 for every diagonal of the band).
+LTR_HHD int32_t band_prologue_steps(int32_t dlo, int32_t W) {
+  const int32_t dhi = dlo + W - 1;
+  const int32_t a = (-dlo > dhi) ? -dlo : dhi;
+  const int32_t s = a + 2;
+  return s + (s & 1);
+}
+
+struct BandTask {  // one haplotype against the unique reads [read_begin, read_end) of its locus, all of one band class
+  uint32_t hap;
+  uint32_t read_begin;
+  uint32_t read_end;
+};
+
+}  // namespace ltr

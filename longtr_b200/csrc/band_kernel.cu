@@ -1,0 +1,239 @@
+// band_kernel.cu -- kernel 1b: banded anti-diagonal Viterbi with an exactness certificate (band_core.cuh).
+//
+// viterbi_band_kernel<K>: persistent warps; a warp takes a round of four consecutive pairs of its band class (one
+// per group of 8 lanes; consecutive pairs share the haplotype and their reads are sorted by length, so the four
+// groups run almost the same number of anti-diagonals) and walks them in lock step: general steps while some band
+// cell is a boundary cell or lies before the matrix, the branch-free double step in between, general steps around
+// the end cells.  FP64 max-plus on the FP64 pipe like viterbi_stream_kernel: 9 DADD + 4 DSETP per cell.
+// band_expand_kernel turns the plan's (haplotype, read range) tasks into the pair list; band_collect_kernel turns
+// the pairs the band could not certify into tasks of viterbi_stream_kernel (runs of consecutive reads stay one task).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "band_core.cuh"
+#include "kernels.h"
+
+namespace ltr {
+
+static constexpr unsigned kFull = 0xFFFFFFFFu;
+static constexpr int kBandBlockThreads = 128;
+
+struct SmemTable {  // the lane's closed-form boundary cells, [2K][2][32] doubles per warp
+  const double* base;
+  __device__ __forceinline__ double x(int q) const { return base[(2 * q) * 32]; }
+  __device__ __forceinline__ double v(int q) const { return base[(2 * q + 1) * 32]; }
+};
+
+template <int K>
+__global__ void __launch_bounds__(kBandBlockThreads, (K <= 4 ? 4 : 3))
+viterbi_band_kernel(const VitConsts C, const DevBatch B, const BandArgs A) {
+  extern __shared__ __align__(16) double band_smem[];
+  const int lane = threadIdx.x & 31;
+  const int lg = lane & (kBandGroupLanes - 1);
+  const int grp = lane >> 3;
+  double* tb = band_smem + (size_t)(threadIdx.x >> 5) * (4 * K * 32) + lane;
+  SmemTable T;
+  T.base = tb;
+  constexpr int W = 16 * K;
+  const uint32_t n_rounds = (A.n_pairs + 3u) >> 2;
+  while (true) {
+    uint32_t round = 0, att = 0, fl = 0;
+    if (lane == 0) {
+      round = atomicAdd(A.cursor, 1u);
+      att = *(volatile uint32_t*)(A.counters + 0);
+      fl = *(volatile uint32_t*)(A.counters + 1);
+    }
+    round = __shfl_sync(kFull, round, 0);
+    if (round >= n_rounds) break;
+    att = __shfl_sync(kFull, att, 0);
+    fl = __shfl_sync(kFull, fl, 0);
+    const uint32_t base = round * 4u;
+    const bool active = (base + (uint32_t)grp) < A.n_pairs;
+    const uint2 pr = A.pairs[active ? base + (uint32_t)grp : base];  // idle groups shadow the round's first pair
+    const uint32_t g = pr.x, u = pr.y;
+    const uint32_t hoff = B.hap_off[g];
+    const int32_t hlen = (int32_t)(B.hap_off[g + 1] - hoff);
+    const uint32_t qb = B.read_off[u];
+    BandPair R;
+    R.n = hlen - 2 * C.cut;
+    R.m = (int32_t)(B.read_off[u + 1] - qb);
+    R.hap = B.hap_bytes + hoff + C.cut;
+    R.read = B.read_bytes + qb;
+    const BandGeom geo = band_geometry(R.n, R.m, W);
+    R.d0 = geo.dlo + 2 * K * lg;
+    const uint32_t l = B.hap_locus[g];
+    const uint32_t hb0 = B.locus_hap_begin[l];
+    const uint32_t H = B.locus_hap_begin[l + 1] - hb0;
+    double* out = B.out_ll + B.ll_off[l] + (unsigned long long)(u - B.locus_read_begin[l]) * H + (g - hb0);
+    // Most pairs so far could not be certified (noisy reads, band too narrow): stop trying, hand the rest to the
+    // full-matrix kernel.  Performance heuristic only -- both routes give the reference's bits.
+    if (A.abandon_after && att >= A.abandon_after && 2u * fl > att) {
+      if (active && lg == 0) *out = kBandUncertified;
+      continue;
+    }
+    // ---- per-lane closed forms of the boundary cells of its diagonals, initial state -----------------------------
+#pragma unroll
+    for (int q = 0; q < 2 * K; ++q) {
+      double bx, bv;
+      band_boundary(C, R, R.d0 + q, bx, bv);
+      tb[(2 * q) * 32] = bx;
+      tb[(2 * q + 1) * 32] = bv;
+    }
+    BandLane<K> L;
+    band_lane_reset<K>(L, C);
+    const int32_t s_end = R.n + R.m - 2;
+    const int32_t s_pro = (int32_t)__reduce_max_sync(kFull, (uint32_t)band_prologue_steps(geo.dlo, W));
+    const int32_t s_end_min = (int32_t)__reduce_min_sync(kFull, (uint32_t)s_end);
+    const int32_t s_end_max = (int32_t)__reduce_max_sync(kFull, (uint32_t)s_end);
+    double F = C.imp;
+    bool got = false;
+    int32_t s = 0;
+#define LTR_BAND_GENERAL_STEP()                                              \
+  do {                                                                       \
+    if (s & 1) {                                                             \
+      double yr = __shfl_down_sync(kFull, L.A[0], 1);                        \
+      if (lg == kBandGroupLanes - 1) yr = C.imp;                             \
+      band_general_step<K, 1>(L, C, R, T, s, yr, F, got);                    \
+    } else {                                                                 \
+      double zl = __shfl_up_sync(kFull, L.B[K - 1], 1);                      \
+      if (lg == 0) zl = C.imp;                                               \
+      band_general_step<K, 0>(L, C, R, T, s, zl, F, got);                    \
+    }                                                                        \
+    ++s;                                                                     \
+  } while (0)
+    while (s < s_pro && s <= s_end_max) LTR_BAND_GENERAL_STEP();
+    if (s + 1 < s_end_min) {  // s is even here (s_pro is)
+      band_windows_init<K>(L, R, s);
+      const uint8_t* hp = R.hap + ((s - R.d0) >> 1) + 1;
+      const uint8_t* rp = R.read + ((s + R.d0) >> 1) + K + 1;
+#pragma unroll 1
+      for (; s + 1 < s_end_min; s += 2) {
+        const int32_t nh = (int32_t)*hp, nr = (int32_t)*rp;  // consumed after both steps
+        ++hp;
+        ++rp;
+        double zl = __shfl_up_sync(kFull, L.B[K - 1], 1);
+        if (lg == 0) zl = C.imp;
+        band_fast_even<K>(L, C, zl);
+        double yr = __shfl_down_sync(kFull, L.A[0], 1);
+        if (lg == kBandGroupLanes - 1) yr = C.imp;
+        band_fast_odd<K>(L, C, yr, nh, nr);
+      }
+    }
+    while (s <= s_end_max) LTR_BAND_GENERAL_STEP();
+#undef LTR_BAND_GENERAL_STEP
+    // ---- result: the lane that owns diagonal de holds the score ----------------------------------------------------
+    const double thr = band_threshold(C, A.gap, R.n, R.m, geo.w);
+    const bool mine = got && active;
+    const bool ok = mine && (F > thr);
+    if (mine) *out = ok ? F : kBandUncertified;
+    const unsigned done = __ballot_sync(kFull, mine), good = __ballot_sync(kFull, ok);
+    if (lane == 0) {
+      atomicAdd(A.counters + 0, (uint32_t)__popc(done));
+      if (done != good) atomicAdd(A.counters + 1, (uint32_t)__popc(done & ~good));
+    }
+  }
+}
+
+// pairs[cum[t] + i] = (task t's haplotype, read_begin + i)
+__global__ void band_expand_kernel(const BandTask* __restrict__ tasks, const uint32_t* __restrict__ cum,
+                                   uint32_t n_tasks, uint2* __restrict__ pairs) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tasks) return;
+  const BandTask bt = tasks[t];
+  uint2* dst = pairs + cum[t];
+  for (uint32_t r = bt.read_begin; r < bt.read_end; ++r) dst[r - bt.read_begin] = make_uint2(bt.hap, r);
+}
+
+// One thread per band task: runs of uncertified pairs become tasks of the stream kernel of the haplotype's row class.
+__global__ void band_collect_kernel(const VitConsts C, const DevBatch B, const BandTask* __restrict__ tasks,
+                                    uint32_t n_tasks, const BandCollect S) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tasks) return;
+  const BandTask bt = tasks[t];
+  const uint32_t g = bt.hap;
+  const uint32_t l = B.hap_locus[g];
+  const uint32_t hb0 = B.locus_hap_begin[l];
+  const uint32_t H = B.locus_hap_begin[l + 1] - hb0;
+  const uint32_t rb0 = B.locus_read_begin[l];
+  const int32_t n = (int32_t)(B.hap_off[g + 1] - B.hap_off[g]) - 2 * C.cut;
+  const int kr = rows_per_lane_hd(n, S.kmax);
+  const double* col = B.out_ll + B.ll_off[l] + (g - hb0);
+  uint32_t run_begin = 0, n_bad = 0;
+  unsigned long long cells = 0;
+  bool in_run = false;
+  for (uint32_t r = bt.read_begin; r <= bt.read_end; ++r) {
+    const bool bad = (r < bt.read_end) && (col[(unsigned long long)(r - rb0) * H] == kBandUncertified);
+    if (bad) {
+      ++n_bad;
+      cells += (unsigned long long)n * (unsigned long long)(B.read_off[r + 1] - B.read_off[r]);
+      if (!in_run) {
+        in_run = true;
+        run_begin = r;
+      }
+    } else if (in_run) {
+      in_run = false;
+      const uint32_t k = atomicAdd(S.count[kr], 1u);
+      if (k < S.cap[kr]) {
+        Task T;
+        T.hap = g;
+        T.read_begin = run_begin;
+        T.read_end = r;
+        S.tasks[kr][k] = T;
+      }
+    }
+  }
+  if (n_bad) {
+    atomicAdd(S.n_uncertified, (unsigned long long)n_bad);
+    atomicAdd(S.cells_uncertified, cells);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+typedef void (*BandKernel)(const VitConsts, const DevBatch, const BandArgs);
+
+static BandKernel band_kernel_for(int k) {
+  switch (k) {
+    case 2: return viterbi_band_kernel<2>;
+    case 3: return viterbi_band_kernel<3>;
+    case 4: return viterbi_band_kernel<4>;
+    case 6: return viterbi_band_kernel<6>;
+    case 8: return viterbi_band_kernel<8>;
+    default: return nullptr;
+  }
+}
+
+static size_t band_block_smem(int k) { return (size_t)(kBandBlockThreads / 32) * 4 * k * 32 * sizeof(double); }
+
+int band_block_threads() { return kBandBlockThreads; }
+
+int band_blocks_per_sm(int k) {
+  BandKernel f = band_kernel_for(k);
+  if (!f) return 0;
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f, kBandBlockThreads, band_block_smem(k)) != cudaSuccess) return 0;
+  return nb;
+}
+
+cudaError_t launch_band(int k, int grid_blocks, cudaStream_t stream, const VitConsts& C, const DevBatch& B,
+                        const BandArgs& A) {
+  BandKernel f = band_kernel_for(k);
+  if (!f) return cudaErrorInvalidValue;
+  f<<<grid_blocks, kBandBlockThreads, band_block_smem(k), stream>>>(C, B, A);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_band_expand(const BandTask* tasks, const uint32_t* cum, uint32_t n_tasks, uint2* pairs,
+                               cudaStream_t stream) {
+  if (n_tasks == 0) return cudaSuccess;
+  band_expand_kernel<<<(n_tasks + 127) / 128, 128, 0, stream>>>(tasks, cum, n_tasks, pairs);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_band_collect(const VitConsts& C, const DevBatch& B, const BandTask* tasks, uint32_t n_tasks,
+                                const BandCollect& S, cudaStream_t stream) {
+  if (n_tasks == 0) return cudaSuccess;
+  band_collect_kernel<<<(n_tasks + 127) / 128, 128, 0, stream>>>(C, B, tasks, n_tasks, S);
+  return cudaGetLastError();
+}
+
+}  // namespace ltr

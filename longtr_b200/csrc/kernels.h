@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "band_core.cuh"
 #include "viterbi_core.cuh"
 
 namespace ltr {
@@ -15,6 +16,32 @@ cudaError_t launch_viterbi(int k, int mode, int grid_blocks, cudaStream_t stream
                            const DevBatch& B, const Task* tasks, const uint32_t* ntasks_ptr,
                            uint32_t task_cap, uint32_t* cursor, const FailSink& fail, XY* sxy,
                            uint32_t* sb, uint32_t scratch_stride);
+
+// Banded anti-diagonal Viterbi (band_kernel.cu, band_core.cuh): rounds of four pairs per warp.
+struct BandArgs {
+  const uint2* pairs;       // (haplotype, unique read) pairs of one band class, haplotype-major
+  uint32_t n_pairs;
+  uint32_t* cursor;         // round cursor of the persistent grid
+  uint32_t* counters;       // [0] pairs evaluated, [1] of which not certified (shared by all band classes of a job)
+  double gap;               // g = min(|M2I|, |I2I|, |M2D|, |D2D|)
+  uint32_t abandon_after;   // 0: never; else stop banding once this many pairs were evaluated and most failed
+};
+struct BandCollect {        // where band_collect_kernel appends the uncertified runs: task list of each row class
+  Task* tasks[17];
+  uint32_t* count[17];
+  uint32_t cap[17];
+  int kmax;
+  unsigned long long* n_uncertified;
+  unsigned long long* cells_uncertified;
+};
+int band_block_threads();
+int band_blocks_per_sm(int k);
+cudaError_t launch_band(int k, int grid_blocks, cudaStream_t stream, const VitConsts& C, const DevBatch& B,
+                        const BandArgs& A);
+cudaError_t launch_band_expand(const BandTask* tasks, const uint32_t* cum, uint32_t n_tasks, uint2* pairs,
+                               cudaStream_t stream);
+cudaError_t launch_band_collect(const VitConsts& C, const DevBatch& B, const BandTask* tasks, uint32_t n_tasks,
+                                const BandCollect& S, cudaStream_t stream);
 
 // Fan-out of the unique LL matrices (one row per distinct trimmed read of a locus) to the reference's
 // aln_probs[read*H + hap] layout (HapAligner.cpp:549): out[ll_off(l) + (p-rb0)*H + h] = uniq[ull_off(l) + u(p)*H + h].

@@ -45,9 +45,11 @@
 
 #if defined(__CUDACC__) && !defined(LTR_HOST_EMU)
 #define LTR_HD __device__ __forceinline__
+#define LTR_HHD __host__ __device__ inline
 #define LTR_DEVICE_CODE 1
 #else
 #define LTR_HD inline
+#define LTR_HHD inline
 #include <cmath>
 #include <cstring>
 #endif
@@ -502,6 +504,16 @@ LTR_HD void lane_fast_step(LaneStream<K>& S, const VitConsts& C, const StripCtx&
       T.sxy[pos] = o;
     }
   }
+}
+
+// Row class of a haplotype with n DP rows/columns (n = trimmed length): K rows per lane, K <= kmax.
+LTR_HHD int rows_per_lane_hd(int n, int kmax) {
+  const int R = n - 1;
+  if (R <= 32) return 1;
+  const int strips = (R + 32 * kmax - 1) / (32 * kmax);
+  const int per = (R + strips - 1) / strips;
+  const int k = (per + 31) / 32;
+  return k < 1 ? 1 : k;
 }
 
 // Row split of a task: R = n-1 DP rows over S strips of <= 32*K rows, lanes get K or K-1 rows.

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "longtr_b200.h"
+#include "band_core.cuh"
 #include "viterbi_core.cuh"
 
 namespace ltr {
@@ -74,15 +75,45 @@ inline bool fast_certificate_valid(const ltr_params& p) {
 }
 
 // Row class of a haplotype with n DP rows/columns (n = trimmed length): K rows per lane.
-inline int rows_per_lane(int n, int kmax) {
-  const int R = n - 1;
-  if (R <= 32) return 1;
-  const int strips = (R + 32 * kmax - 1) / (32 * kmax);
-  const int per = (R + strips - 1) / strips;
-  return std::max(1, (per + 31) / 32);
+inline int rows_per_lane(int n, int kmax) { return rows_per_lane_hd(n, kmax); }
+
+// Banded evaluation (band_core.cuh): which pairs go to the band kernel, and with which band class.
+struct BandPolicy {
+  bool on = false;
+  double gap = 0.0;  // g = min(|M2I|, |I2I|, |M2D|, |D2D|)
+  int w_need = 0;    // minimum margin (diagonals) a pair's band class must guarantee
+};
+// band_w < 0: banding off; 0: automatic margin (about 34 log units of slack: two indels or three mismatches more than
+// the length difference explains); > 0: that many diagonals.  The band certificate needs every transition parameter
+// <= 0 and the same parameter condition as the final-score certificate (the bail-out is certified from F as well).
+inline BandPolicy band_policy(const ltr_params& p, int band_w) {
+  BandPolicy b;
+  if (band_w < 0 || !fast_certificate_valid(p)) return b;
+  b.gap = std::min(std::min(std::fabs((double)p.match_ins), std::fabs((double)p.ins_ins)),
+                   std::min(std::fabs((double)p.match_del), std::fabs((double)p.del_del)));
+  if (!(b.gap >= 0.05)) return b;
+  b.w_need = band_w > 0 ? band_w : (int)std::ceil(17.0 / b.gap);
+  b.on = true;
+  return b;
+}
+// Band class of a pair (index into band_class_k) or -1: not banded (too short, band not narrower than ~half the matrix,
+// length difference beyond the widest class).
+inline int band_class_of(int hlen, int n, int m, const BandPolicy& bp) {
+  if (!bp.on || hlen <= 60 || n < 2 || m < 2) return -1;
+  for (int c = 0; c < kBandClasses; ++c) {
+    const int K = band_class_k(c);
+    if (band_geometry(n, m, 16 * K).w < bp.w_need) continue;
+    return ((uint64_t)(n + m) * 8u * (uint64_t)K * 100u <= 55ull * (uint64_t)n * (uint64_t)m) ? c : -1;
+  }
+  return -1;
 }
 
 struct Plan {
+  std::vector<std::vector<BandTask>> band_tasks;  // [kBandClasses] tasks of the band kernel; read ranges index unique reads
+  std::vector<uint64_t> band_pairs_by_rows;       // [K] band pairs whose haplotype has row class K (capacity of the
+                                                  // stream-kernel tasks band_collect_kernel may append)
+  uint64_t n_band_pairs = 0, n_band_cells = 0;    // pairs sent to the band kernel, interior cells inside their bands
+  BandPolicy band;
   std::vector<std::vector<Task>> tasks;  // [K] -> tasks of class K (index 0 unused); read ranges index UNIQUE reads
   std::vector<uint32_t> hap_locus;       // [n_haps]
   std::vector<unsigned long long> ll_off;  // [n_loci+1] offsets of the caller-visible LL matrices (P_l x H_l)
@@ -140,8 +171,11 @@ inline void plan_parallel_for(uint32_t n, int n_threads, F f) {  // f(begin, end
 // stage(bytes, user) may provide the buffer for the unique read bytes (the C ABI hands out pinned host memory).
 typedef uint8_t* (*PlanStageFn)(size_t bytes, void* user);
 inline int make_plan(const ltr_viterbi_batch& b, const ltr_params& p, int kmax, Plan& out, int n_threads = 0,
-                     PlanStageFn stage = nullptr, void* stage_user = nullptr) {
+                     PlanStageFn stage = nullptr, void* stage_user = nullptr, int band_w = -1) {
   const int cut = 35 - p.indel_flank_len;
+  out.band = band_policy(p, band_w);
+  out.band_tasks.assign(kBandClasses, std::vector<BandTask>());
+  out.band_pairs_by_rows.assign(kmax + 1, 0);
   out.tasks.assign(kmax + 1, std::vector<Task>());
   out.max_q.assign(kmax + 1, 0);
   out.multi_strip.assign(kmax + 1, 0);
@@ -164,11 +198,15 @@ inline int make_plan(const ltr_viterbi_batch& b, const ltr_params& p, int kmax, 
     if (b.hap_off[h + 1] < b.hap_off[h]) return LTR_ERR_INVALID;
 
   // ---- pass 1 (parallel over loci): local unique index of every read, unique count / bytes per locus ----
+  // The distinct reads of a locus are numbered by increasing length (ties: first occurrence): the band kernel works on
+  // rounds of consecutive pairs in lock step and runs of equal band class become one task.
   std::vector<uint32_t> local_u(n_reads, 0), ucount(n_loci, 0), ubytes(n_loci, 0);
+  std::vector<uint8_t> is_rep(n_reads, 0);
   if (n_threads <= 0) n_threads = (n_loci >= 4096) ? (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency())) : 1;
   auto dedupe = [&](uint32_t l0, uint32_t l1, int) {
     std::vector<uint64_t> hashes;
     std::vector<uint32_t> reps;  // representative read of each unique sequence of the locus
+    std::vector<uint32_t> order, rank;
     for (uint32_t l = l0; l < l1; ++l) {
       const uint32_t r0 = b.locus_read_begin[l], r1 = b.locus_read_begin[l + 1];
       hashes.clear();
@@ -194,6 +232,15 @@ inline int make_plan(const ltr_viterbi_batch& b, const ltr_params& p, int kmax, 
       }
       ucount[l] = (uint32_t)reps.size();
       ubytes[l] = bytes;
+      order.resize(reps.size());
+      rank.resize(reps.size());
+      for (uint32_t u = 0; u < reps.size(); ++u) order[u] = u;
+      std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
+        return b.read_off[reps[x] + 1] - b.read_off[reps[x]] < b.read_off[reps[y] + 1] - b.read_off[reps[y]];
+      });
+      for (uint32_t k = 0; k < order.size(); ++k) rank[order[k]] = k;
+      for (uint32_t r = r0; r < r1; ++r) local_u[r] = rank[local_u[r]];
+      for (uint32_t u = 0; u < reps.size(); ++u) is_rep[reps[u]] = 1;
     }
   };
   plan_parallel_for(n_loci, n_threads, dedupe);
@@ -215,17 +262,21 @@ inline int make_plan(const ltr_viterbi_batch& b, const ltr_params& p, int kmax, 
   plan_parallel_for(n_loci, n_threads, [&](uint32_t l0, uint32_t l1, int) {
    for (uint32_t l = l0; l < l1; ++l) {
     const uint32_t r0 = b.locus_read_begin[l], r1 = b.locus_read_begin[l + 1], u0 = out.locus_uread_begin[l];
-    uint32_t next = 0, off = (uint32_t)ubyte_off[l];
+    const uint32_t nu = out.locus_uread_begin[l + 1] - u0;
     for (uint32_t r = r0; r < r1; ++r) {
       out.read_to_uread[r] = u0 + local_u[r];
-      if (local_u[r] == next) {  // first occurrence (unique indices are handed out in read order)
-        const uint32_t len = b.read_off[r + 1] - b.read_off[r];
-        std::memcpy(out.uread_bytes + off, b.read_bytes + b.read_off[r], len);
-        out.uread_off[u0 + next] = off;
-        off += len;
-        ++next;
-      }
+      if (is_rep[r]) out.uread_off[u0 + local_u[r]] = b.read_off[r + 1] - b.read_off[r];  // length, for now
     }
+    uint32_t off = (uint32_t)ubyte_off[l];
+    for (uint32_t u = 0; u < nu; ++u) {
+      const uint32_t len = out.uread_off[u0 + u];
+      out.uread_off[u0 + u] = off;
+      off += len;
+    }
+    for (uint32_t r = r0; r < r1; ++r)
+      if (is_rep[r])
+        std::memcpy(out.uread_bytes + out.uread_off[u0 + local_u[r]], b.read_bytes + b.read_off[r],
+                    b.read_off[r + 1] - b.read_off[r]);
    }
   });
   out.uread_off[n_ureads] = (uint32_t)ubyte_off[n_loci];
@@ -239,50 +290,86 @@ inline int make_plan(const ltr_viterbi_batch& b, const ltr_params& p, int kmax, 
   }
   struct Part {
     std::vector<Key> keys;
+    std::vector<std::vector<BandTask>> band;
+    std::vector<uint64_t> band_by_rows;
     std::vector<uint32_t> max_q;
     std::vector<uint8_t> multi;
-    uint64_t n_pairs = 0, n_cells = 0, n_pairs_c = 0, n_cells_c = 0;
+    uint64_t n_pairs = 0, n_cells = 0, n_pairs_c = 0, n_cells_c = 0, n_band_pairs = 0, n_band_cells = 0;
     int max_n = 0;
   };
   std::vector<Part> parts((size_t)std::max(1, n_threads));
+  const BandPolicy& bp = out.band;
   plan_parallel_for(n_loci, n_threads, [&](uint32_t l0, uint32_t l1, int t) {
     Part& P = parts[(size_t)t];
     P.max_q.assign(kmax + 1, 0);
     P.multi.assign(kmax + 1, 0);
+    P.band.assign(kBandClasses, std::vector<BandTask>());
+    P.band_by_rows.assign(kmax + 1, 0);
     for (uint32_t l = l0; l < l1; ++l) {
       const uint32_t h0 = b.locus_hap_begin[l], h1 = b.locus_hap_begin[l + 1];
       const uint32_t r0 = b.locus_read_begin[l], r1 = b.locus_read_begin[l + 1];
       const uint32_t u0 = out.locus_uread_begin[l], u1 = out.locus_uread_begin[l + 1];
-      const uint64_t q = (uint64_t)out.uread_off[u1] - out.uread_off[u0];
       for (uint32_t h = h0; h < h1; ++h) {
         out.hap_locus[h] = l;
         const int hlen = (int)(b.hap_off[h + 1] - b.hap_off[h]);
         const int n = hlen - 2 * cut;
         if (r1 == r0) continue;
-        int k = 1;
-        uint64_t cost = u1 - u0;
-        if (hlen > 60 && n >= 1) {
+        P.n_pairs += r1 - r0;
+        P.n_pairs_c += u1 - u0;
+        const bool real = (hlen > 60 && n >= 1);
+        int k = 1, strips = 1;
+        if (real) {
           P.max_n = std::max(P.max_n, n);
           k = rows_per_lane(n, kmax);
-          const int strips = std::max(1, (n - 1 + 32 * k - 1) / (32 * k));
-          cost = (uint64_t)k * strips * (q + 32);
-          P.max_q[k] = std::max<uint32_t>(P.max_q[k], (uint32_t)q);
-          if (strips > 1) P.multi[k] = 1;
+          strips = std::max(1, (n - 1 + 32 * k - 1) / (32 * k));
           for (uint32_t r = r0; r < r1; ++r) {
             const int m = (int)(b.read_off[r + 1] - b.read_off[r]);
             if (std::abs(n - m) <= 600) P.n_cells += (uint64_t)n * (uint64_t)m;
           }
-          for (uint32_t u = u0; u < u1; ++u) {
-            const int m = (int)(out.uread_off[u + 1] - out.uread_off[u]);
-            if (std::abs(n - m) <= 600) P.n_cells_c += (uint64_t)n * (uint64_t)m;
+        }
+        // runs of consecutive unique reads (sorted by length) with the same band class; class -1 = stream kernel
+        uint32_t run_begin = u0;
+        int run_class = -2;
+        auto close_run = [&](uint32_t run_end) {
+          if (run_class == -2 || run_end == run_begin) return;
+          if (run_class >= 0) {
+            BandTask bt;
+            bt.hap = h; bt.read_begin = run_begin; bt.read_end = run_end;
+            P.band[(size_t)run_class].push_back(bt);
+            P.band_by_rows[(size_t)k] += run_end - run_begin;
+            P.n_band_pairs += run_end - run_begin;
+            // uncertified pairs come back as stream-kernel tasks over sub-ranges of this run: size its scratch for them
+            P.max_q[k] = std::max<uint32_t>(P.max_q[k], out.uread_off[run_end] - out.uread_off[run_begin]);
+            if (strips > 1) P.multi[k] = 1;
+          } else {
+            const uint64_t q = (uint64_t)out.uread_off[run_end] - out.uread_off[run_begin];
+            Key key;
+            key.cost = real ? (uint64_t)k * strips * (q + 32) : (uint64_t)(run_end - run_begin);
+            key.k = k;
+            key.t.hap = h; key.t.read_begin = run_begin; key.t.read_end = run_end;
+            P.keys.push_back(key);
+            if (real) {
+              P.max_q[k] = std::max<uint32_t>(P.max_q[k], (uint32_t)q);
+              if (strips > 1) P.multi[k] = 1;
+            }
+          }
+        };
+        for (uint32_t u = u0; u < u1; ++u) {
+          const int m = (int)(out.uread_off[u + 1] - out.uread_off[u]);
+          const int c = real ? band_class_of(hlen, n, m, bp) : -1;
+          if (c >= 0) {
+            const int W = 16 * band_class_k(c);
+            P.n_band_cells += band_cells(n, m, W, band_geometry(n, m, W).dlo);
+          } else if (real && std::abs(n - m) <= 600) {
+            P.n_cells_c += (uint64_t)n * (uint64_t)m;
+          }
+          if (c != run_class) {
+            close_run(u);
+            run_begin = u;
+            run_class = c;
           }
         }
-        P.n_pairs += r1 - r0;
-        P.n_pairs_c += u1 - u0;
-        Key key;
-        key.cost = cost; key.k = k;
-        key.t.hap = h; key.t.read_begin = u0; key.t.read_end = u1;
-        P.keys.push_back(key);
+        close_run(u1);
       }
     }
   });
@@ -291,7 +378,12 @@ inline int make_plan(const ltr_viterbi_batch& b, const ltr_params& p, int kmax, 
   for (const Part& P : parts) {
     keys.insert(keys.end(), P.keys.begin(), P.keys.end());
     out.n_pairs += P.n_pairs; out.n_cells += P.n_cells;
-    out.n_pairs_computed += P.n_pairs_c; out.n_cells_computed += P.n_cells_c;
+    out.n_pairs_computed += P.n_pairs_c; out.n_cells_computed += P.n_cells_c + P.n_band_cells;
+    out.n_band_pairs += P.n_band_pairs; out.n_band_cells += P.n_band_cells;
+    if (!P.band.empty())
+      for (int c = 0; c < kBandClasses; ++c)
+        out.band_tasks[(size_t)c].insert(out.band_tasks[(size_t)c].end(), P.band[(size_t)c].begin(), P.band[(size_t)c].end());
+    for (size_t k = 0; k < P.band_by_rows.size(); ++k) out.band_pairs_by_rows[k] += P.band_by_rows[k];
     out.max_n = std::max(out.max_n, P.max_n);
     for (size_t k = 0; k < P.max_q.size(); ++k) {
       out.max_q[k] = std::max(out.max_q[k], P.max_q[k]);

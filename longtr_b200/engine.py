@@ -82,6 +82,11 @@ class Engine:
             self.lib.ltr_ctx_destroy(self.ctx)
             self.ctx = None
 
+    def set_band(self, half_width):
+        """ltr_ctx_set_band: < 0 disables the banded kernel, 0 = automatic margin, > 0 = margin in diagonals.
+        Results never depend on it (uncertified pairs are re-run over the full matrix)."""
+        _check(self.lib, self.ctx, self.lib.ltr_ctx_set_band(self.ctx, int(half_width)), "ltr_ctx_set_band")
+
     def __del__(self):
         try:
             self.close()

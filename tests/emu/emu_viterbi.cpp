@@ -6,6 +6,7 @@
 #define LTR_HOST_EMU 1
 #include "viterbi_host.h"
 
+#include <array>
 #include <cstdio>
 #include <vector>
 
@@ -124,17 +125,141 @@ static void emu_dispatch(int k, const VitConsts& C, const DevBatch& B, const Tas
   }
 }
 
+// ---- band kernel (band_core.cuh): one round = four pairs in lock step, eight lanes per pair --------------------------
+struct EmuTable {
+  const double* t;  // [2K][2]
+  double x(int q) const { return t[2 * q]; }
+  double v(int q) const { return t[2 * q + 1]; }
+};
+
+template <int K>
+static void emu_band_round(const VitConsts& C, const DevBatch& B, const uint32_t (*pairs)[2], uint32_t n_pairs,
+                           uint32_t base, double gap, uint64_t* n_uncert) {
+  constexpr int W = 16 * K, G = kBandGroupLanes;
+  BandPair R[4][G];
+  BandLane<K> L[4][G];
+  double tab[4][G][4 * K];
+  BandGeom geo[4];
+  bool active[4];
+  double* out[4];
+  int32_t s_pro = 0, s_end_min = 0x7FFFFFFF, s_end_max = 0;
+  for (int g = 0; g < 4; ++g) {
+    active[g] = base + g < n_pairs;
+    const uint32_t pi = active[g] ? base + g : base;
+    const uint32_t h = pairs[pi][0], u = pairs[pi][1];
+    const uint32_t hoff = B.hap_off[h];
+    const int32_t hlen = (int32_t)(B.hap_off[h + 1] - hoff);
+    const uint32_t qb = B.read_off[u];
+    const int32_t n = hlen - 2 * C.cut, m = (int32_t)(B.read_off[u + 1] - qb);
+    geo[g] = band_geometry(n, m, W);
+    const uint32_t l = B.hap_locus[h];
+    const uint32_t hb0 = B.locus_hap_begin[l], H = B.locus_hap_begin[l + 1] - hb0;
+    out[g] = B.out_ll + B.ll_off[l] + (unsigned long long)(u - B.locus_read_begin[l]) * H + (h - hb0);
+    for (int t = 0; t < G; ++t) {
+      R[g][t].n = n; R[g][t].m = m;
+      R[g][t].hap = B.hap_bytes + hoff + C.cut;
+      R[g][t].read = B.read_bytes + qb;
+      R[g][t].d0 = geo[g].dlo + 2 * K * t;
+      for (int q = 0; q < 2 * K; ++q) band_boundary(C, R[g][t], R[g][t].d0 + q, tab[g][t][2 * q], tab[g][t][2 * q + 1]);
+      band_lane_reset<K>(L[g][t], C);
+    }
+    s_pro = std::max(s_pro, band_prologue_steps(geo[g].dlo, W));
+    s_end_min = std::min(s_end_min, n + m - 2);
+    s_end_max = std::max(s_end_max, n + m - 2);
+  }
+  double F[4][G];
+  bool got[4][G];
+  for (int g = 0; g < 4; ++g) for (int t = 0; t < G; ++t) { F[g][t] = C.imp; got[g][t] = false; }
+  int32_t s = 0;
+  auto general = [&]() {
+    for (int g = 0; g < 4; ++g) {
+      double nb[G];
+      for (int t = 0; t < G; ++t) {
+        if (s & 1) nb[t] = (t == G - 1) ? C.imp : L[g][t + 1].A[0];
+        else nb[t] = (t == 0) ? C.imp : L[g][t - 1].B[K - 1];
+      }
+      for (int t = 0; t < G; ++t) {
+        EmuTable T{tab[g][t]};
+        if (s & 1) band_general_step<K, 1>(L[g][t], C, R[g][t], T, s, nb[t], F[g][t], got[g][t]);
+        else band_general_step<K, 0>(L[g][t], C, R[g][t], T, s, nb[t], F[g][t], got[g][t]);
+      }
+    }
+    ++s;
+  };
+  while (s < s_pro && s <= s_end_max) general();
+  if (s + 1 < s_end_min) {
+    int32_t hi[4][G], ri[4][G];
+    for (int g = 0; g < 4; ++g)
+      for (int t = 0; t < G; ++t) {
+        band_windows_init<K>(L[g][t], R[g][t], s);
+        hi[g][t] = ((s - R[g][t].d0) >> 1) + 1;
+        ri[g][t] = ((s + R[g][t].d0) >> 1) + K + 1;
+      }
+    for (; s + 1 < s_end_min; s += 2) {
+      for (int g = 0; g < 4; ++g) {
+        double nb[G];
+        int32_t nh[G], nr[G];
+        for (int t = 0; t < G; ++t) {
+          // the device reads up to ~W/2 + K bytes past the strings (padded buffers); values only reach cells outside the matrix
+          nh[t] = (int32_t)R[g][t].hap[hi[g][t]++];
+          nr[t] = (int32_t)R[g][t].read[ri[g][t]++];
+          nb[t] = (t == 0) ? C.imp : L[g][t - 1].B[K - 1];
+        }
+        for (int t = 0; t < G; ++t) band_fast_even<K>(L[g][t], C, nb[t]);
+        for (int t = 0; t < G; ++t) nb[t] = (t == G - 1) ? C.imp : L[g][t + 1].A[0];
+        for (int t = 0; t < G; ++t) band_fast_odd<K>(L[g][t], C, nb[t], nh[t], nr[t]);
+      }
+    }
+  }
+  while (s <= s_end_max) general();
+  for (int g = 0; g < 4; ++g) {
+    if (!active[g]) continue;
+    int owners = 0;
+    for (int t = 0; t < G; ++t) {
+      if (!got[g][t]) continue;
+      ++owners;
+      const double thr = band_threshold(C, gap, R[g][t].n, R[g][t].m, geo[g].w);
+      const bool ok = F[g][t] > thr;
+      *out[g] = ok ? F[g][t] : kBandUncertified;
+      if (!ok) ++*n_uncert;
+    }
+    if (owners != 1) { std::fprintf(stderr, "emu band: %d owners\n", owners); std::abort(); }
+  }
+}
+
+static void emu_band_dispatch(int k, const VitConsts& C, const DevBatch& B, const uint32_t (*pairs)[2], uint32_t n_pairs,
+                              uint32_t base, double gap, uint64_t* n_uncert) {
+  switch (k) {
+    case 2: emu_band_round<2>(C, B, pairs, n_pairs, base, gap, n_uncert); break;
+    case 3: emu_band_round<3>(C, B, pairs, n_pairs, base, gap, n_uncert); break;
+    case 4: emu_band_round<4>(C, B, pairs, n_pairs, base, gap, n_uncert); break;
+    case 6: emu_band_round<6>(C, B, pairs, n_pairs, base, gap, n_uncert); break;
+    case 8: emu_band_round<8>(C, B, pairs, n_pairs, base, gap, n_uncert); break;
+    default: std::abort();
+  }
+}
+
+extern "C" int ltr_emu_viterbi_batch_band(const ltr_viterbi_batch* b, const ltr_params* p, int kmax, int use_fast,
+                                          int band_w, double* out_ll, uint64_t* n_fallback, uint64_t* band_stats);
+
 extern "C" int ltr_emu_viterbi_batch(const ltr_viterbi_batch* b, const ltr_params* p, int kmax,
                                      int use_fast, double* out_ll, uint64_t* n_fallback) {
+  return ltr_emu_viterbi_batch_band(b, p, kmax, use_fast, -1, out_ll, n_fallback, nullptr);
+}
+
+// band_w as ltr_ctx_set_band; band_stats (may be NULL): [0] pairs sent to the band kernel, [1] of which uncertified,
+// [2] stream-kernel tasks created for them.
+extern "C" int ltr_emu_viterbi_batch_band(const ltr_viterbi_batch* b, const ltr_params* p, int kmax, int use_fast,
+                                          int band_w, double* out_ll, uint64_t* n_fallback, uint64_t* band_stats) {
   Plan plan;
-  int rc = make_plan(*b, *p, kmax, plan);
+  int rc = make_plan(*b, *p, kmax, plan, 0, nullptr, nullptr, use_fast ? band_w : -1);
   if (rc != LTR_OK) return rc;
   HostConsts hc;
   make_consts(*p, std::max(plan.max_n, plan.max_m) + 2, hc);
   hc.C.tabI = hc.tabI.data();
   hc.C.tabD = hc.tabD.data();
   // the warps see the distinct trimmed reads of each locus (Plan); padded copy: the kernel prefetches one byte ahead
-  std::vector<uint8_t> rbytes(plan.uread_nbytes + 8, 0);
+  std::vector<uint8_t> rbytes(plan.uread_nbytes + 256, 0);
   if (plan.uread_nbytes) std::memcpy(rbytes.data(), plan.uread_bytes, plan.uread_nbytes);
   std::vector<double> uniq_ll((size_t)plan.ull_off[b->n_loci] + 1, 123.0);
   DevBatch B;
@@ -145,6 +270,40 @@ extern "C" int ltr_emu_viterbi_batch(const ltr_viterbi_batch* b, const ltr_param
   EmuScratch E;
   uint64_t nfall = 0;
   if (!fast_certificate_valid(*p)) use_fast = 0;  // as ltr_job_create does
+  // ---- band kernel first; what it cannot certify goes to the stream kernel's task lists (band_collect_kernel) ------
+  std::vector<uint8_t> hbytes((size_t)b->hap_off[b->locus_hap_begin[b->n_loci]] + 256, 0);  // padded like the device copy
+  std::memcpy(hbytes.data(), b->hap_bytes, hbytes.size() - 256);
+  B.hap_bytes = hbytes.data();
+  uint64_t bstats[3] = {plan.n_band_pairs, 0, 0};
+  for (int c = 0; c < kBandClasses; ++c) {
+    std::vector<std::array<uint32_t, 2>> pairs;
+    for (const BandTask& bt : plan.band_tasks[(size_t)c])
+      for (uint32_t r = bt.read_begin; r < bt.read_end; ++r) pairs.push_back({bt.hap, r});
+    const uint32_t np = (uint32_t)pairs.size();
+    for (uint32_t base = 0; base < np; base += 4)
+      emu_band_dispatch(band_class_k(c), hc.C, B, reinterpret_cast<const uint32_t(*)[2]>(pairs.data()), np, base,
+                        plan.band.gap, &bstats[1]);
+    for (const BandTask& bt : plan.band_tasks[(size_t)c]) {  // as band_collect_kernel
+      const uint32_t l = plan.hap_locus[bt.hap];
+      const uint32_t hb0 = b->locus_hap_begin[l], H = b->locus_hap_begin[l + 1] - hb0, rb0 = plan.locus_uread_begin[l];
+      const int n = (int)(b->hap_off[bt.hap + 1] - b->hap_off[bt.hap]) - 2 * hc.C.cut;
+      const int kr = rows_per_lane_hd(n, kmax);
+      const double* col = uniq_ll.data() + plan.ull_off[l] + (bt.hap - hb0);
+      bool in_run = false;
+      uint32_t run_begin = 0;
+      for (uint32_t r = bt.read_begin; r <= bt.read_end; ++r) {
+        const bool bad = r < bt.read_end && col[(size_t)(r - rb0) * H] == kBandUncertified;
+        if (bad && !in_run) { in_run = true; run_begin = r; }
+        if (!bad && in_run) {
+          in_run = false;
+          Task T; T.hap = bt.hap; T.read_begin = run_begin; T.read_end = r;
+          plan.tasks[(size_t)kr].push_back(T);
+          ++bstats[2];
+        }
+      }
+    }
+  }
+  if (band_stats) std::memcpy(band_stats, bstats, sizeof(bstats));
   for (int k = 1; k <= kmax; ++k) {
     std::vector<Task> fails(plan.n_pairs + 1);
     uint32_t nfail = 0;
@@ -162,4 +321,11 @@ extern "C" int ltr_emu_viterbi_batch(const ltr_viterbi_batch* b, const ltr_param
   expand_ll_host(*b, plan, uniq_ll.data(), out_ll);
   if (n_fallback) *n_fallback = nfall;
   return LTR_OK;
+}
+
+extern "C" void ltr_emu_band_geometry(int n, int m, int W, int* dlo, int* w, uint64_t* cells) {
+  const BandGeom g = band_geometry(n, m, W);
+  *dlo = g.dlo;
+  *w = g.w;
+  *cells = band_cells(n, m, W, g.dlo);
 }

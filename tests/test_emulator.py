@@ -23,7 +23,22 @@ def emu():
     lib.ltr_emu_viterbi_batch.argtypes = [C.POINTER(abi.ViterbiBatch), C.POINTER(abi.Params), C.c_int, C.c_int,
                                           abi._dp, C.POINTER(C.c_uint64)]
     lib.ltr_emu_viterbi_batch.restype = C.c_int
+    lib.ltr_emu_viterbi_batch_band.argtypes = [C.POINTER(abi.ViterbiBatch), C.POINTER(abi.Params), C.c_int, C.c_int,
+                                               C.c_int, abi._dp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    lib.ltr_emu_viterbi_batch_band.restype = C.c_int
     return lib
+
+
+def run_band(emu, b, params, kmax, band_w):
+    """Emulated band kernel + collect + stream kernels; returns (LL, [band pairs, uncertified, appended tasks])."""
+    vb, keep = abi.make_viterbi_batch(b)
+    p = abi.make_params(params)
+    out = np.full(abi.ll_size(b), 123.0)
+    nf = C.c_uint64(0)
+    bs = (C.c_uint64 * 3)()
+    rc = emu.ltr_emu_viterbi_batch_band(C.byref(vb), C.byref(p), kmax, 1, band_w, abi.ptr(out, abi._dp), C.byref(nf), bs)
+    assert rc == 0
+    return out, list(bs)
 
 
 CASES = [
@@ -86,3 +101,88 @@ def test_final_score_certificate_near_the_bailout_threshold(emu, seed):
     nf = C.c_uint64(0)
     assert emu.ltr_emu_viterbi_batch(C.byref(vb), C.byref(p), 16, 1, abi.ptr(out, abi._dp), C.byref(nf)) == 0
     assert np.array_equal(out, want)
+
+
+@pytest.mark.parametrize("seed,kw,kmax,params", [c for c in CASES if c[0] in (1, 2, 3, 6)])
+@pytest.mark.parametrize("band_w", [0, 2, 8, 40])
+def test_band_emulator_matches_oracle(emu, seed, kw, kmax, params, band_w):
+    """Banded anti-diagonal kernel (band_core.cuh) + re-run of the uncertified pairs == oracle, bit for bit, whatever
+    the requested margin (0 = automatic)."""
+    b = synth.make_pair_batch(seed, **kw)
+    want, _ = po.viterbi_batch(b, aln_params=params)
+    out, stats = run_band(emu, b, params, kmax, band_w)
+    assert np.array_equal(out, want)
+    if band_w in (0, 2, 8):
+        assert stats[0] > 0  # the case does exercise the band kernel
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_band_certificate_adversarial(emu, seed):
+    """Reads whose best alignment leaves a narrow band (block insertions / deletions / duplications of up to 30 bases
+    in low-complexity haplotypes) under three parameter sets: the certificate F_band > -g(|de| + 2w) must reject
+    every pair whose banded score is not the reference's score."""
+    rng = np.random.default_rng(777 + seed)
+    params = [None, ONT, (-0.5, -0.4, -0.25, -0.3, -0.01, -2.0, -1.5)][seed % 3]
+    lhb, lrb, hoff, roff, hb, rb = [0], [0], [0], [0], [], []
+    for _l in range(8):
+        n = int(rng.integers(60, 200))
+        hap = synth.rand_seq(rng, n + 60)
+        if rng.random() < 0.5:  # low complexity: off-diagonal paths are competitive
+            motif = synth.rand_seq(rng, int(rng.integers(1, 5)))
+            hap = hap[:30] + (motif * 400)[:n] + hap[30 + n:]
+        hb.append(hap)
+        hoff.append(hoff[-1] + len(hap))
+        for _r in range(6):
+            core = list(hap[30:30 + n])
+            for _e in range(int(rng.integers(0, 4))):
+                k, pos = int(rng.integers(1, 30)), int(rng.integers(0, max(1, len(core))))
+                if rng.random() < 0.5:
+                    core[pos:pos] = list(synth.rand_seq(rng, k)) if rng.random() < 0.5 else core[max(0, pos - k):pos]
+                else:
+                    del core[pos:pos + k]
+            for _e in range(int(rng.integers(0, 4))):
+                if core:
+                    core[int(rng.integers(0, len(core)))] = "ACGT"[int(rng.integers(0, 4))]
+            s = "".join(core)
+            if len(s) < 2:
+                s = "AC"
+            rb.append(s)
+            roff.append(roff[-1] + len(s))
+        lhb.append(len(hb))
+        lrb.append(len(rb))
+    b = dict(locus_hap_begin=np.array(lhb, np.uint32), locus_read_begin=np.array(lrb, np.uint32),
+             hap_off=np.array(hoff, np.uint32), read_off=np.array(roff, np.uint32),
+             hap_bytes=np.frombuffer("".join(hb).encode(), np.uint8).copy(),
+             read_bytes=np.frombuffer("".join(rb).encode(), np.uint8).copy())
+    want, _ = po.viterbi_batch(b, aln_params=params, n_threads=4)
+    n_band = n_unc = 0
+    for band_w in (1, 3, 6):
+        out, stats = run_band(emu, b, params, 16, band_w)
+        assert np.array_equal(out, want)
+        n_band += stats[0]
+        n_unc += stats[1]
+    assert n_band > 0 and 0 < n_unc < n_band  # both outcomes of the certificate occur
+
+
+def test_band_geometry_properties():
+    """band_geometry / band_cells (band_core.cuh) against brute force, through the emulator library's helpers."""
+    lib = C.CDLL(os.path.join(HERE, "emu", "libltr_emu.so"))
+    lib.ltr_emu_band_geometry.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                          C.POINTER(C.c_uint64)]
+    rng = np.random.default_rng(5)
+    for _ in range(400):
+        n, m = int(rng.integers(2, 400)), int(rng.integers(2, 400))
+        W = 16 * int(rng.choice([2, 3, 4, 6, 8]))
+        dlo, w, cells = C.c_int(), C.c_int(), C.c_uint64()
+        lib.ltr_emu_band_geometry(n, m, W, C.byref(dlo), C.byref(w), C.byref(cells))
+        de = m - n
+        if W - 1 - abs(de) < 0 or w.value < 0:
+            assert w.value < 0 and W - 1 - abs(de) <= 1  # no margin left (the even alignment may cost one diagonal)
+            continue
+        dhi = dlo.value + W - 1
+        assert dlo.value % 2 == 0
+        assert dlo.value <= min(0, de) - w.value and dhi >= max(0, de) + w.value and w.value >= 0
+        assert w.value >= (W - 1 - abs(de)) // 2 - 1  # at most one diagonal lost to the even alignment
+        i = np.arange(1, n)[:, None]
+        j = np.arange(1, m)[None, :]
+        assert cells.value == int(np.sum((j - i >= dlo.value) & (j - i <= dhi)))
