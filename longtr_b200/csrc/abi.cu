@@ -58,7 +58,7 @@ struct ltr_job {
   uint64_t plan_cells_computed = 0;
   ltr_job_stats stats;
 };
-static const size_t kBandCtrlBytes = 64;
+static const size_t kBandCtrlBytes = 72;  // u32[12], u64 uncertified pairs, u64 their n*m cells, u64 band cells evaluated
 
 namespace {
 
@@ -243,22 +243,31 @@ int ltr_job_create(ltr_ctx* ctx, const ltr_params* params, const ltr_viterbi_bat
   };
   static const bool timing = getenv("LTR_TIMING") != nullptr;  // diagnostics: host-side phases of job creation on stderr
   const auto t_begin = std::chrono::steady_clock::now();
-  int rc = make_plan(bb, *params, kmax, job->plan, 0, &Stage::get, ctx, ctx->band_w);
-  const auto t_plan = std::chrono::steady_clock::now();
-  if (rc != LTR_OK) { delete job; return rc; }
-  Plan& plan = job->plan;
+  if (!plan_offsets_valid(bb)) { delete job; return LTR_ERR_INVALID; }
   job->n_loci = bb.n_loci;
   job->n_haps = bb.locus_hap_begin[bb.n_loci];
   job->n_reads = bb.locus_read_begin[bb.n_loci];
+  uint64_t* h2d = &job->stats.h2d_bytes;
+  // Uploads that do not depend on the plan are enqueued first: with pinned caller buffers they overlap make_plan.
+  {
+    int rc_up = upload(ctx, job->hap_bytes, bb.hap_bytes, (size_t)bb.hap_off[job->n_haps], 256, h2d);
+    if (rc_up == LTR_OK) rc_up = upload(ctx, job->hap_off, bb.hap_off, (size_t)job->n_haps + 1, 0, h2d);
+    if (rc_up == LTR_OK) rc_up = upload(ctx, job->lhb, bb.locus_hap_begin, (size_t)job->n_loci + 1, 0, h2d);
+    if (rc_up == LTR_OK) rc_up = upload(ctx, job->lrb, bb.locus_read_begin, (size_t)job->n_loci + 1, 0, h2d);
+    if (rc_up != LTR_OK) { ltr_job_destroy(ctx, job); return rc_up; }
+  }
+  int rc = make_plan(bb, *params, kmax, job->plan, 0, &Stage::get, ctx, ctx->band_w);
+  const auto t_plan = std::chrono::steady_clock::now();
+  if (rc != LTR_OK) { ltr_job_destroy(ctx, job); return rc; }
+  Plan& plan = job->plan;
   job->n_ll = plan.ll_off[bb.n_loci];
   job->stats.n_pairs = plan.n_pairs;
   job->stats.n_cells = plan.n_cells;
   job->stats.n_pairs_computed = plan.n_pairs_computed;
   job->stats.n_cells_computed = plan.n_cells_computed;
-  job->plan_cells_computed = plan.n_cells_computed;
+  job->plan_cells_computed = plan.n_cells_computed - plan.n_band_cells;  // stream-kernel pairs of the plan
   job->stats.n_band_pairs = plan.n_band_pairs;
   make_consts(*params, std::max(plan.max_n, plan.max_m) + 2, job->hc);
-  uint64_t* h2d = &job->stats.h2d_bytes;
 
 #define LTR_TRY(expr)                     \
   do {                                    \
@@ -280,14 +289,10 @@ int ltr_job_create(ltr_ctx* ctx, const ltr_params* params, const ltr_viterbi_bat
 
   // Only the distinct trimmed reads of each locus travel to the device (Plan, viterbi_host.h); the kernels fill the
   // unique LL matrices and expand_ll_kernel fans them out to the caller-visible aln_probs layout.
-  const size_t hap_nbytes = bb.hap_off[job->n_haps];
-  // padding: the stream kernel prefetches one byte, the band kernel's character windows run up to W/2 + K bytes ahead
-  LTR_TRY(upload(ctx, job->hap_bytes, bb.hap_bytes, hap_nbytes, 256, h2d));
+  // padding (here and for hap_bytes above): the stream kernel prefetches one byte, the band kernel's character
+  // windows run up to W/2 + K bytes ahead
   LTR_TRY(upload(ctx, job->read_bytes, plan.uread_bytes, plan.uread_nbytes, 256, h2d));
-  LTR_TRY(upload(ctx, job->hap_off, bb.hap_off, (size_t)job->n_haps + 1, 0, h2d));
   LTR_TRY(upload(ctx, job->read_off, plan.uread_off.data(), plan.uread_off.size(), 0, h2d));
-  LTR_TRY(upload(ctx, job->lhb, bb.locus_hap_begin, (size_t)job->n_loci + 1, 0, h2d));
-  LTR_TRY(upload(ctx, job->lrb, bb.locus_read_begin, (size_t)job->n_loci + 1, 0, h2d));
   LTR_TRY(upload(ctx, job->lub, plan.locus_uread_begin.data(), plan.locus_uread_begin.size(), 0, h2d));
   LTR_TRY(upload(ctx, job->r2u, plan.read_to_uread.data(), plan.read_to_uread.size(), 0, h2d));
   LTR_TRY(upload(ctx, job->rlocus, plan.read_locus.data(), plan.read_locus.size(), 0, h2d));
@@ -504,6 +509,7 @@ static int run_band_phase(ltr_ctx* ctx, ltr_job* job) {
     A.n_pairs = bc.n_pairs;
     A.cursor = bctrl + i;
     A.counters = bctrl + 8;
+    A.cells_evaluated = reinterpret_cast<unsigned long long*>(job->band_ctrl.as<char>() + 64);
     A.gap = job->plan.band.gap;
     A.abandon_after = no_abandon ? 0u : 4096u;
     LTR_CUDA(ctx, launch_band(bc.k, (int)bc.grid, st, job->hc.C, B, A));
@@ -564,7 +570,8 @@ int ltr_job_run(ltr_ctx* ctx, ltr_job* job) {
     LTR_CUDA(ctx, cudaMemcpyAsync(band_words, job->band_ctrl.p, kBandCtrlBytes, cudaMemcpyDeviceToHost, ctx->main_stream));
   LTR_CUDA(ctx, cudaStreamSynchronize(ctx->main_stream));
   job->stats.n_band_uncertified = band_words[6];
-  job->stats.n_cells_computed = job->plan_cells_computed + band_words[7];
+  // cells evaluated: full matrices of the stream-kernel pairs (planned + uncertified) + the bands actually evaluated
+  job->stats.n_cells_computed = job->plan_cells_computed + band_words[7] + band_words[8];
   bool rerun = false;
   std::vector<uint32_t> ntasks(job->classes.size(), 0);
   for (size_t c = 0; c < job->classes.size(); ++c) {

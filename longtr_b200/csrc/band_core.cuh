@@ -142,7 +142,7 @@ LTR_HD void band_lane_reset(BandLane<K>& L, const VitConsts& C) {
 // memory, and the end cell (n-1, m-1), whose max(D, max(I, M)) is the pair's score (HapAligner.cpp:308-309).
 // P = parity of the step (the lane's cells are the local diagonals q = 2k + P); nb = Z of the lower neighbour's last
 // diagonal (P == 0) or Y of the upper neighbour's first diagonal (P == 1), imp at the edges of the band.
-template <int K, int P, typename TB>
+template <int K, int P, bool SYM, typename TB>
 LTR_HD void band_general_step(BandLane<K>& L, const VitConsts& C, const BandPair& R, const TB& tb, int32_t s,
                               double nb, double& F, bool& got) {
 #pragma unroll
@@ -154,30 +154,23 @@ LTR_HD void band_general_step(BandLane<K>& L, const VitConsts& C, const BandPair
     const double yin = (P == 0) ? L.A[k] : ((k == K - 1) ? nb : L.A[k + 1 < K ? k + 1 : k]);
     const double zin = (P == 0) ? ((k == 0) ? nb : L.B[k >= 1 ? k - 1 : 0]) : L.B[k];
     const double xin = L.X[q];
-    double x, y, z;
-    if (s < ad) {
-      x = C.imp;
-      y = C.imp;
-      z = C.imp;
-    } else if (s == ad) {
-      x = tb.x(q);
-      y = (d >= 0) ? tb.v(q) : C.imp;
-      z = (d >= 0) ? C.imp : tb.v(q);
-    } else {
-      const int32_t i = (s - d) >> 1, j = (s + d) >> 1;
-      const int32_t ii = (i < R.n) ? i : (R.n - 1), jj = (j < R.m) ? j : (R.m - 1);
-      const double e = ((int32_t)R.hap[ii] == (int32_t)R.read[jj]) ? C.match : C.mismatch;
-      const double M = e + xin;
-      const double I = C.match + yin;
-      const double D = zin;
-      const XYZ o = finish_cell(C, M, I, D);
-      x = o.x;
-      y = o.y;
-      z = o.z;
-      if (i == R.n - 1 && j == R.m - 1) {
-        F = vmax(D, vmax(I, M));
-        got = true;
-      }
+    // branch-free: the recurrence is evaluated for every cell (clamped characters) and replaced by imp / the closed form
+    // where the cell lies before the matrix / on its boundary -- lanes of a warp are in all three cases at once
+    const int32_t i = (s - d) >> 1, j = (s + d) >> 1;
+    const int32_t ii = i < 0 ? 0 : (i < R.n ? i : R.n - 1), jj = j < 0 ? 0 : (j < R.m ? j : R.m - 1);
+    const double e = ((int32_t)R.hap[ii] == (int32_t)R.read[jj]) ? C.match : C.mismatch;
+    const double M = e + xin;
+    const double I = C.match + yin;
+    const double D = zin;
+    const XYZ o = finish_cell_t<SYM>(C, M, I, D);
+    const bool before = s < ad, bnd = s == ad;
+    const double bx = tb.x(q), bv = tb.v(q);
+    const double x = before ? C.imp : (bnd ? bx : o.x);
+    const double y = before ? C.imp : (bnd ? ((d >= 0) ? bv : C.imp) : o.y);
+    const double z = before ? C.imp : (bnd ? ((d >= 0) ? C.imp : bv) : o.z);
+    if (s > ad && i == R.n - 1 && j == R.m - 1) {
+      F = vmax(D, vmax(I, M));
+      got = true;
     }
     L.X[q] = x;
     L.A[k] = y;
@@ -204,7 +197,7 @@ LTR_HD void band_windows_init(BandLane<K>& L, const BandPair& R, int32_t s) {
 }
 
 // Plain even step: cells q = 2k (i = ib - k, j = jb + k).  zl = Z of diagonal -1 (lower neighbour lane).
-template <int K>
+template <int K, bool SYM>
 LTR_HD void band_fast_even(BandLane<K>& L, const VitConsts& C, double zl) {
 #pragma unroll
   for (int k = K - 1; k >= 0; --k) {
@@ -212,7 +205,7 @@ LTR_HD void band_fast_even(BandLane<K>& L, const VitConsts& C, double zl) {
     const double M = e + L.X[2 * k];
     const double I = C.match + L.A[k];
     const double D = (k == 0) ? zl : L.B[k >= 1 ? k - 1 : 0];
-    const XYZ o = finish_cell(C, M, I, D);
+    const XYZ o = finish_cell_t<SYM>(C, M, I, D);
     L.X[2 * k] = o.x;
     L.A[k] = o.y;
     L.B[k] = o.z;
@@ -221,7 +214,7 @@ LTR_HD void band_fast_even(BandLane<K>& L, const VitConsts& C, double zl) {
 
 // Plain odd step: cells q = 2k+1 (i = ib - k, j = jb + k + 1).  yr = Y of diagonal 2K (upper neighbour lane).
 // Then the windows move on by one row and one column; nh, nr are the characters hap[ib + 1], read[jb + K + 1].
-template <int K>
+template <int K, bool SYM>
 LTR_HD void band_fast_odd(BandLane<K>& L, const VitConsts& C, double yr, int32_t nh, int32_t nr) {
 #pragma unroll
   for (int k = 0; k < K; ++k) {
@@ -229,7 +222,7 @@ LTR_HD void band_fast_odd(BandLane<K>& L, const VitConsts& C, double yr, int32_t
     const double M = e + L.X[2 * k + 1];
     const double I = C.match + ((k == K - 1) ? yr : L.A[k + 1 < K ? k + 1 : k]);
     const double D = L.B[k];
-    const XYZ o = finish_cell(C, M, I, D);
+    const XYZ o = finish_cell_t<SYM>(C, M, I, D);
     L.X[2 * k + 1] = o.x;
     L.A[k] = o.y;
     L.B[k] = o.z;

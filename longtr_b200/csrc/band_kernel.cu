@@ -24,8 +24,11 @@ struct SmemTable {  // the lane's closed-form boundary cells, [2K][2][32] double
   __device__ __forceinline__ double v(int q) const { return base[(2 * q + 1) * 32]; }
 };
 
-template <int K>
-__global__ void __launch_bounds__(kBandBlockThreads, (K <= 4 ? 4 : 3))
+#ifndef LTR_BAND_MINBLOCKS
+#define LTR_BAND_MINBLOCKS 4
+#endif
+template <int K, bool SYM>
+__global__ void __launch_bounds__(kBandBlockThreads, (K <= 4 ? LTR_BAND_MINBLOCKS : (K <= 6 ? 3 : 2)))
 viterbi_band_kernel(const VitConsts C, const DevBatch B, const BandArgs A) {
   extern __shared__ __align__(16) double band_smem[];
   const int lane = threadIdx.x & 31;
@@ -93,11 +96,11 @@ viterbi_band_kernel(const VitConsts C, const DevBatch B, const BandArgs A) {
     if (s & 1) {                                                             \
       double yr = __shfl_down_sync(kFull, L.A[0], 1);                        \
       if (lg == kBandGroupLanes - 1) yr = C.imp;                             \
-      band_general_step<K, 1>(L, C, R, T, s, yr, F, got);                    \
+      band_general_step<K, 1, SYM>(L, C, R, T, s, yr, F, got);                    \
     } else {                                                                 \
       double zl = __shfl_up_sync(kFull, L.B[K - 1], 1);                      \
       if (lg == 0) zl = C.imp;                                               \
-      band_general_step<K, 0>(L, C, R, T, s, zl, F, got);                    \
+      band_general_step<K, 0, SYM>(L, C, R, T, s, zl, F, got);                    \
     }                                                                        \
     ++s;                                                                     \
   } while (0)
@@ -113,10 +116,10 @@ viterbi_band_kernel(const VitConsts C, const DevBatch B, const BandArgs A) {
         ++rp;
         double zl = __shfl_up_sync(kFull, L.B[K - 1], 1);
         if (lg == 0) zl = C.imp;
-        band_fast_even<K>(L, C, zl);
+        band_fast_even<K, SYM>(L, C, zl);
         double yr = __shfl_down_sync(kFull, L.A[0], 1);
         if (lg == kBandGroupLanes - 1) yr = C.imp;
-        band_fast_odd<K>(L, C, yr, nh, nr);
+        band_fast_odd<K, SYM>(L, C, yr, nh, nr);
       }
     }
     while (s <= s_end_max) LTR_BAND_GENERAL_STEP();
@@ -127,7 +130,9 @@ viterbi_band_kernel(const VitConsts C, const DevBatch B, const BandArgs A) {
     const bool ok = mine && (F > thr);
     if (mine) *out = ok ? F : kBandUncertified;
     const unsigned done = __ballot_sync(kFull, mine), good = __ballot_sync(kFull, ok);
+    const uint32_t cells = __reduce_add_sync(kFull, mine ? (uint32_t)band_cells(R.n, R.m, W, geo.dlo) : 0u);
     if (lane == 0) {
+      atomicAdd(A.cells_evaluated, (unsigned long long)cells);
       atomicAdd(A.counters + 0, (uint32_t)__popc(done));
       if (done != good) atomicAdd(A.counters + 1, (uint32_t)__popc(done & ~good));
     }
@@ -191,13 +196,13 @@ __global__ void band_collect_kernel(const VitConsts C, const DevBatch B, const B
 // ------------------------------------------------------------------------------------------------------------------
 typedef void (*BandKernel)(const VitConsts, const DevBatch, const BandArgs);
 
-static BandKernel band_kernel_for(int k) {
+static BandKernel band_kernel_for(int k, bool sym) {
   switch (k) {
-    case 2: return viterbi_band_kernel<2>;
-    case 3: return viterbi_band_kernel<3>;
-    case 4: return viterbi_band_kernel<4>;
-    case 6: return viterbi_band_kernel<6>;
-    case 8: return viterbi_band_kernel<8>;
+    case 2: return sym ? viterbi_band_kernel<2, true> : viterbi_band_kernel<2, false>;
+    case 3: return sym ? viterbi_band_kernel<3, true> : viterbi_band_kernel<3, false>;
+    case 4: return sym ? viterbi_band_kernel<4, true> : viterbi_band_kernel<4, false>;
+    case 6: return sym ? viterbi_band_kernel<6, true> : viterbi_band_kernel<6, false>;
+    case 8: return sym ? viterbi_band_kernel<8, true> : viterbi_band_kernel<8, false>;
     default: return nullptr;
   }
 }
@@ -207,16 +212,19 @@ static size_t band_block_smem(int k) { return (size_t)(kBandBlockThreads / 32) *
 int band_block_threads() { return kBandBlockThreads; }
 
 int band_blocks_per_sm(int k) {
-  BandKernel f = band_kernel_for(k);
-  if (!f) return 0;
-  int nb = 0;
+  BandKernel f = band_kernel_for(k, true), f2 = band_kernel_for(k, false);
+  if (!f || !f2) return 0;
+  int nb = 0, nb2 = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, f2, kBandBlockThreads, band_block_smem(k)) != cudaSuccess) return 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f, kBandBlockThreads, band_block_smem(k)) != cudaSuccess) return 0;
-  return nb;
+  return nb < nb2 ? nb : nb2;
 }
 
 cudaError_t launch_band(int k, int grid_blocks, cudaStream_t stream, const VitConsts& C, const DevBatch& B,
                         const BandArgs& A) {
-  BandKernel f = band_kernel_for(k);
+  // symmetric parameters (D2M == I2M, M2I == M2D): two additions per cell fewer, same bits (finish_cell_sym)
+  const bool sym = (C.d2m == C.i2m) && (C.m2i == C.m2d);
+  BandKernel f = band_kernel_for(k, sym);
   if (!f) return cudaErrorInvalidValue;
   f<<<grid_blocks, kBandBlockThreads, band_block_smem(k), stream>>>(C, B, A);
   return cudaGetLastError();

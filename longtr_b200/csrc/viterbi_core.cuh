@@ -135,6 +135,21 @@ LTR_HD XYZ finish_cell(const VitConsts& C, double M, double I, double D) {
   return o;
 }
 
+// Same values when D2M == I2M and M2I == M2D (Dindel defaults, ONT-like set): max(D + c, I + c) == max(D, I) + c bit
+// for bit (rounding is monotone) and M + M2I is M + M2D, so the cell needs 5 additions instead of 7.
+LTR_HD XYZ finish_cell_sym(const VitConsts& C, double M, double I, double D) {
+  XYZ o;
+  const double t = M + C.m2i;
+  o.x = vmax(M + C.m2m, vmax(D, I) + C.d2m);
+  o.y = vmax(t, I + C.i2i);
+  o.z = vmax(t, D + C.d2d);
+  return o;
+}
+template <bool SYM>
+LTR_HD XYZ finish_cell_t(const VitConsts& C, double M, double I, double D) {
+  return SYM ? finish_cell_sym(C, M, I, D) : finish_cell(C, M, I, D);
+}
+
 // Closed-form column 0 of row i (HapAligner.cpp:274-280) for column-0 emission e1.
 LTR_HD void col0_cell(const VitConsts& C, int32_t i, double e1, double& Mi, double& Ii, double& Di) {
   const int32_t ia = (i < C.tab_len) ? i : (C.tab_len - 1);  // rows past the haplotype: garbage nobody consumes

@@ -3,6 +3,9 @@
 #pragma once
 #include <stdint.h>
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cmath>
 #include <cstring>
 #include <memory>
@@ -77,6 +80,22 @@ inline bool fast_certificate_valid(const ltr_params& p) {
 // Row class of a haplotype with n DP rows/columns (n = trimmed length): K rows per lane.
 inline int rows_per_lane(int n, int kmax) { return rows_per_lane_hd(n, kmax); }
 
+// Array of PODs whose elements are all written before they are read: no zero fill (these are tens of MB per batch).
+template <typename T>
+struct PodArray {
+  std::unique_ptr<T[]> p;
+  size_t n = 0;
+  void resize_uninit(size_t count) {
+    p.reset(new T[count ? count : 1]);
+    n = count;
+  }
+  T* data() { return p.get(); }
+  const T* data() const { return p.get(); }
+  size_t size() const { return n; }
+  T& operator[](size_t i) { return p[i]; }
+  const T& operator[](size_t i) const { return p[i]; }
+};
+
 // Banded evaluation (band_core.cuh): which pairs go to the band kernel, and with which band class.
 struct BandPolicy {
   bool on = false;
@@ -112,10 +131,10 @@ struct Plan {
   std::vector<std::vector<BandTask>> band_tasks;  // [kBandClasses] tasks of the band kernel; read ranges index unique reads
   std::vector<uint64_t> band_pairs_by_rows;       // [K] band pairs whose haplotype has row class K (capacity of the
                                                   // stream-kernel tasks band_collect_kernel may append)
-  uint64_t n_band_pairs = 0, n_band_cells = 0;    // pairs sent to the band kernel, interior cells inside their bands
+  uint64_t n_band_pairs = 0, n_band_cells = 0;    // pairs sent to the band kernel (n_band_cells: unused, the kernel counts)
   BandPolicy band;
   std::vector<std::vector<Task>> tasks;  // [K] -> tasks of class K (index 0 unused); read ranges index UNIQUE reads
-  std::vector<uint32_t> hap_locus;       // [n_haps]
+  PodArray<uint32_t> hap_locus;          // [n_haps]
   std::vector<unsigned long long> ll_off;  // [n_loci+1] offsets of the caller-visible LL matrices (P_l x H_l)
   uint64_t n_pairs = 0, n_cells = 0;     // as the reference counts them (every pooled read x haplotype)
   uint64_t n_pairs_computed = 0, n_cells_computed = 0;  // after collapsing identical trimmed reads of a locus
@@ -131,24 +150,31 @@ struct Plan {
   uint8_t* uread_bytes = nullptr;           // uread_nbytes bytes: caller-provided staging (pinned) or uread_owned
   size_t uread_nbytes = 0;
   std::unique_ptr<uint8_t[]> uread_owned;   // uninitialised on purpose: first touched by the parallel copy
-  std::vector<uint32_t> read_to_uread;      // [n_reads] global unique-read index of every pooled read
-  std::vector<uint32_t> read_locus;         // [n_reads]
+  PodArray<uint32_t> read_to_uread;         // [n_reads] global unique-read index of every pooled read
+  PodArray<uint32_t> read_locus;            // [n_reads]
   std::vector<unsigned long long> ull_off;  // [n_loci+1] offsets of the unique LL matrices (U_l x H_l)
 };
 
-inline uint64_t plan_hash_bytes(const uint8_t* p, uint32_t n) {  // 8 bytes per round, multiply-xorshift mixing
-  uint64_t h = 0x9E3779B97F4A7C15ull ^ ((uint64_t)n * 0xD6E8FEB86659FD93ull);
+inline uint64_t plan_mix(uint64_t a, uint64_t b) {  // 64x64 -> 128 bit multiply, folded
+  const unsigned __int128 r = (unsigned __int128)a * b;
+  return (uint64_t)r ^ (uint64_t)(r >> 64);
+}
+// 32 bytes per round on two independent multiply chains (equality is always confirmed with memcmp).
+inline uint64_t plan_hash_bytes(const uint8_t* p, uint32_t n) {
+  const uint64_t k0 = 0x9E3779B97F4A7C15ull, k1 = 0xD6E8FEB86659FD93ull, k2 = 0xFF51AFD7ED558CCDull, k3 = 0xC4CEB9FE1A85EC53ull;
+  uint64_t s0 = k0 ^ n, s1 = k1;
   uint32_t i = 0;
-  for (; i + 8 <= n; i += 8) {
-    uint64_t w;
-    std::memcpy(&w, p + i, 8);
-    h = (h ^ w) * 0xFF51AFD7ED558CCDull;
-    h ^= h >> 32;
+  for (; i + 32 <= n; i += 32) {
+    uint64_t w[4];
+    std::memcpy(w, p + i, 32);
+    s0 = plan_mix(w[0] ^ k2, w[1] ^ s0);
+    s1 = plan_mix(w[2] ^ k3, w[3] ^ s1);
   }
-  uint64_t w = 0;
-  if (i < n) std::memcpy(&w, p + i, n - i);
-  h = (h ^ w) * 0xC4CEB9FE1A85EC53ull;
-  return h ^ (h >> 29);
+  uint64_t w[4] = {0, 0, 0, 0};
+  if (i < n) std::memcpy(w, p + i, n - i);
+  s0 = plan_mix(w[0] ^ k2, w[1] ^ s0);
+  s1 = plan_mix(w[2] ^ k3, w[3] ^ s1);
+  return plan_mix(s0 ^ k1, s1 ^ k0);
 }
 
 template <typename F>
@@ -166,6 +192,18 @@ inline void plan_parallel_for(uint32_t n, int n_threads, F f) {  // f(begin, end
   for (auto& x : th) x.join();
 }
 
+// Offsets monotone (nothing else in the batch is trusted before this holds): lets the C ABI start the uploads that do not
+// depend on the plan while make_plan runs.
+inline bool plan_offsets_valid(const ltr_viterbi_batch& b) {
+  const uint32_t n_loci = b.n_loci;
+  for (uint32_t l = 0; l < n_loci; ++l)
+    if (b.locus_hap_begin[l + 1] < b.locus_hap_begin[l] || b.locus_read_begin[l + 1] < b.locus_read_begin[l]) return false;
+  const uint32_t n_haps = b.locus_hap_begin[n_loci];
+  for (uint32_t h = 0; h < n_haps; ++h)
+    if (b.hap_off[h + 1] < b.hap_off[h]) return false;
+  return true;
+}
+
 // Validates the batch, collapses duplicate reads per locus and builds per-class task lists (heaviest first within a
 // class so the persistent warps finish together).  Returns LTR_OK or LTR_ERR_INVALID.
 // stage(bytes, user) may provide the buffer for the unique read bytes (the C ABI hands out pinned host memory).
@@ -173,6 +211,14 @@ typedef uint8_t* (*PlanStageFn)(size_t bytes, void* user);
 inline int make_plan(const ltr_viterbi_batch& b, const ltr_params& p, int kmax, Plan& out, int n_threads = 0,
                      PlanStageFn stage = nullptr, void* stage_user = nullptr, int band_w = -1) {
   const int cut = 35 - p.indel_flank_len;
+  static const bool plan_timing = std::getenv("LTR_TIMING") != nullptr;  // diagnostics: phases on stderr
+  auto tick = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!plan_timing) return;
+    const auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[ltr] plan: %s %.1f ms\n", what, std::chrono::duration<double, std::milli>(now - tick).count());
+    tick = now;
+  };
   out.band = band_policy(p, band_w);
   out.band_tasks.assign(kBandClasses, std::vector<BandTask>());
   out.band_pairs_by_rows.assign(kmax + 1, 0);
@@ -181,18 +227,31 @@ inline int make_plan(const ltr_viterbi_batch& b, const ltr_params& p, int kmax, 
   out.multi_strip.assign(kmax + 1, 0);
   const uint32_t n_loci = b.n_loci;
   const uint32_t n_haps = b.locus_hap_begin[n_loci], n_reads = b.locus_read_begin[n_loci];
-  out.hap_locus.assign(n_haps, 0);
+  out.hap_locus.resize_uninit(n_haps);
   out.ll_off.assign((size_t)n_loci + 1, 0);
   out.ull_off.assign((size_t)n_loci + 1, 0);
   out.locus_uread_begin.assign((size_t)n_loci + 1, 0);
-  out.read_to_uread.assign(n_reads, 0);
-  out.read_locus.assign(n_reads, 0);
+  out.read_to_uread.resize_uninit(n_reads);
+  out.read_locus.resize_uninit(n_reads);
   for (uint32_t l = 0; l < n_loci; ++l)
     if (b.locus_hap_begin[l + 1] < b.locus_hap_begin[l] || b.locus_read_begin[l + 1] < b.locus_read_begin[l])
       return LTR_ERR_INVALID;
-  for (uint32_t r = 0; r < n_reads; ++r) {
-    if (b.read_off[r + 1] <= b.read_off[r]) return LTR_ERR_INVALID;  // empty read
-    out.max_m = std::max<int>(out.max_m, (int)(b.read_off[r + 1] - b.read_off[r]));
+  if (n_threads <= 0) n_threads = (n_loci >= 4096) ? (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency())) : 1;
+  {  // offsets must be monotone (reads non-empty); longest read
+    std::vector<int> bad((size_t)std::max(1, n_threads), 0), mx((size_t)std::max(1, n_threads), 0);
+    plan_parallel_for(n_reads, n_threads, [&](uint32_t r0, uint32_t r1, int t) {
+      int m = 0, bd = 0;
+      for (uint32_t r = r0; r < r1; ++r) {
+        if (b.read_off[r + 1] <= b.read_off[r]) bd = 1;  // empty read
+        else m = std::max<int>(m, (int)(b.read_off[r + 1] - b.read_off[r]));
+      }
+      bad[(size_t)t] = bd;
+      mx[(size_t)t] = m;
+    });
+    for (size_t t = 0; t < bad.size(); ++t) {
+      if (bad[t]) return LTR_ERR_INVALID;
+      out.max_m = std::max(out.max_m, mx[t]);
+    }
   }
   for (uint32_t h = 0; h < n_haps; ++h)
     if (b.hap_off[h + 1] < b.hap_off[h]) return LTR_ERR_INVALID;
@@ -200,9 +259,10 @@ inline int make_plan(const ltr_viterbi_batch& b, const ltr_params& p, int kmax, 
   // ---- pass 1 (parallel over loci): local unique index of every read, unique count / bytes per locus ----
   // The distinct reads of a locus are numbered by increasing length (ties: first occurrence): the band kernel works on
   // rounds of consecutive pairs in lock step and runs of equal band class become one task.
-  std::vector<uint32_t> local_u(n_reads, 0), ucount(n_loci, 0), ubytes(n_loci, 0);
-  std::vector<uint8_t> is_rep(n_reads, 0);
-  if (n_threads <= 0) n_threads = (n_loci >= 4096) ? (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency())) : 1;
+  PodArray<uint32_t> local_u;  // bit 31: the read is the representative (first occurrence) of its sequence
+  local_u.resize_uninit(n_reads);
+  const uint32_t kRep = 0x80000000u;
+  std::vector<uint32_t> ucount(n_loci, 0), ubytes(n_loci, 0);
   auto dedupe = [&](uint32_t l0, uint32_t l1, int) {
     std::vector<uint64_t> hashes;
     std::vector<uint32_t> reps;  // representative read of each unique sequence of the locus
@@ -240,10 +300,12 @@ inline int make_plan(const ltr_viterbi_batch& b, const ltr_params& p, int kmax, 
       });
       for (uint32_t k = 0; k < order.size(); ++k) rank[order[k]] = k;
       for (uint32_t r = r0; r < r1; ++r) local_u[r] = rank[local_u[r]];
-      for (uint32_t u = 0; u < reps.size(); ++u) is_rep[reps[u]] = 1;
+      for (uint32_t u = 0; u < reps.size(); ++u) local_u[reps[u]] |= kRep;
     }
   };
+  lap("validate");
   plan_parallel_for(n_loci, n_threads, dedupe);
+  lap("dedupe");
   // ---- pass 2: prefix sums, unique read bytes ----------------------------------------------------------------
   std::vector<uint64_t> ubyte_off((size_t)n_loci + 1, 0);
   for (uint32_t l = 0; l < n_loci; ++l) {
@@ -264,8 +326,8 @@ inline int make_plan(const ltr_viterbi_batch& b, const ltr_params& p, int kmax, 
     const uint32_t r0 = b.locus_read_begin[l], r1 = b.locus_read_begin[l + 1], u0 = out.locus_uread_begin[l];
     const uint32_t nu = out.locus_uread_begin[l + 1] - u0;
     for (uint32_t r = r0; r < r1; ++r) {
-      out.read_to_uread[r] = u0 + local_u[r];
-      if (is_rep[r]) out.uread_off[u0 + local_u[r]] = b.read_off[r + 1] - b.read_off[r];  // length, for now
+      out.read_to_uread[r] = u0 + (local_u[r] & ~kRep);
+      if (local_u[r] & kRep) out.uread_off[u0 + (local_u[r] & ~kRep)] = b.read_off[r + 1] - b.read_off[r];  // length, for now
     }
     uint32_t off = (uint32_t)ubyte_off[l];
     for (uint32_t u = 0; u < nu; ++u) {
@@ -274,12 +336,13 @@ inline int make_plan(const ltr_viterbi_batch& b, const ltr_params& p, int kmax, 
       off += len;
     }
     for (uint32_t r = r0; r < r1; ++r)
-      if (is_rep[r])
-        std::memcpy(out.uread_bytes + out.uread_off[u0 + local_u[r]], b.read_bytes + b.read_off[r],
+      if (local_u[r] & kRep)
+        std::memcpy(out.uread_bytes + out.uread_off[u0 + (local_u[r] & ~kRep)], b.read_bytes + b.read_off[r],
                     b.read_off[r + 1] - b.read_off[r]);
    }
   });
   out.uread_off[n_ureads] = (uint32_t)ubyte_off[n_loci];
+  lap("unique bytes");
 
   // ---- tasks -------------------------------------------------------------------------------------------------
   struct Key { uint64_t cost; Task t; int k; };
@@ -309,6 +372,14 @@ inline int make_plan(const ltr_viterbi_batch& b, const ltr_params& p, int kmax, 
       const uint32_t h0 = b.locus_hap_begin[l], h1 = b.locus_hap_begin[l + 1];
       const uint32_t r0 = b.locus_read_begin[l], r1 = b.locus_read_begin[l + 1];
       const uint32_t u0 = out.locus_uread_begin[l], u1 = out.locus_uread_begin[l + 1];
+      uint64_t sum_m = 0;
+      int min_m = 0x7FFFFFFF, max_m = 0;
+      for (uint32_t r = r0; r < r1; ++r) {
+        const int m = (int)(b.read_off[r + 1] - b.read_off[r]);
+        sum_m += (uint64_t)m;
+        min_m = std::min(min_m, m);
+        max_m = std::max(max_m, m);
+      }
       for (uint32_t h = h0; h < h1; ++h) {
         out.hap_locus[h] = l;
         const int hlen = (int)(b.hap_off[h + 1] - b.hap_off[h]);
@@ -322,9 +393,13 @@ inline int make_plan(const ltr_viterbi_batch& b, const ltr_params& p, int kmax, 
           P.max_n = std::max(P.max_n, n);
           k = rows_per_lane(n, kmax);
           strips = std::max(1, (n - 1 + 32 * k - 1) / (32 * k));
-          for (uint32_t r = r0; r < r1; ++r) {
-            const int m = (int)(b.read_off[r + 1] - b.read_off[r]);
-            if (std::abs(n - m) <= 600) P.n_cells += (uint64_t)n * (uint64_t)m;
+          if (n - min_m <= 600 && max_m - n <= 600) {
+            P.n_cells += (uint64_t)n * sum_m;
+          } else {
+            for (uint32_t r = r0; r < r1; ++r) {
+              const int m = (int)(b.read_off[r + 1] - b.read_off[r]);
+              if (std::abs(n - m) <= 600) P.n_cells += (uint64_t)n * (uint64_t)m;
+            }
           }
         }
         // runs of consecutive unique reads (sorted by length) with the same band class; class -1 = stream kernel
@@ -354,15 +429,15 @@ inline int make_plan(const ltr_viterbi_batch& b, const ltr_params& p, int kmax, 
             }
           }
         };
+        int last_m = -1, c = -1;
         for (uint32_t u = u0; u < u1; ++u) {
           const int m = (int)(out.uread_off[u + 1] - out.uread_off[u]);
-          const int c = real ? band_class_of(hlen, n, m, bp) : -1;
-          if (c >= 0) {
-            const int W = 16 * band_class_k(c);
-            P.n_band_cells += band_cells(n, m, W, band_geometry(n, m, W).dlo);
-          } else if (real && std::abs(n - m) <= 600) {
-            P.n_cells_c += (uint64_t)n * (uint64_t)m;
+          if (m != last_m) {  // reads are sorted by length: equal lengths are neighbours
+            c = real ? band_class_of(hlen, n, m, bp) : -1;
+            last_m = m;
           }
+          // (the cells of banded pairs are counted by the kernel: band_cells of the pairs it evaluated)
+          if (c < 0 && real && std::abs(n - m) <= 600) P.n_cells_c += (uint64_t)n * (uint64_t)m;
           if (c != run_class) {
             close_run(u);
             run_begin = u;
@@ -373,12 +448,13 @@ inline int make_plan(const ltr_viterbi_batch& b, const ltr_params& p, int kmax, 
       }
     }
   });
+  lap("tasks");
   std::vector<Key> keys;
   keys.reserve(n_haps);
   for (const Part& P : parts) {
     keys.insert(keys.end(), P.keys.begin(), P.keys.end());
     out.n_pairs += P.n_pairs; out.n_cells += P.n_cells;
-    out.n_pairs_computed += P.n_pairs_c; out.n_cells_computed += P.n_cells_c + P.n_band_cells;
+    out.n_pairs_computed += P.n_pairs_c; out.n_cells_computed += P.n_cells_c;
     out.n_band_pairs += P.n_band_pairs; out.n_band_cells += P.n_band_cells;
     if (!P.band.empty())
       for (int c = 0; c < kBandClasses; ++c)
@@ -412,6 +488,7 @@ inline int make_plan(const ltr_viterbi_batch& b, const ltr_params& p, int kmax, 
   }
   std::stable_sort(keys.begin(), keys.end(), [](const Key& a, const Key& c) { return a.cost > c.cost; });
   for (const Key& k : keys) out.tasks[k.k].push_back(k.t);
+  lap("merge + sort");
   return LTR_OK;
 }
 

@@ -5,6 +5,7 @@ resident in HBM (``ltr_job_*``).  Everything below calls the CUDA library throug
 nothing here computes on the CPU and nothing falls back to the oracle.
 """
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -28,6 +29,7 @@ class Job:
         self._e = engine
         self._h = handle
         self._keep = keep
+        engine._jobs.add(self)  # the engine closes its live jobs before destroying the context
         n_ll, n_post, n_tot = C.c_uint64(), C.c_uint64(), C.c_uint64()
         engine.lib.ltr_job_sizes(handle, C.byref(n_ll), C.byref(n_post), C.byref(n_tot))
         self.n_ll, self.n_post, self.n_totals = n_ll.value, n_post.value, n_tot.value
@@ -55,8 +57,10 @@ class Job:
 
     def close(self):
         if self._h is not None:
-            self._e.lib.ltr_job_destroy(self._e.ctx, self._h)
+            if self._e.ctx:
+                self._e.lib.ltr_job_destroy(self._e.ctx, self._h)
             self._h = None
+            self._e._jobs.discard(self)
 
     def __del__(self):
         try:
@@ -72,6 +76,7 @@ class Engine:
         self.lib = abi.load()
         self.ctx = C.c_void_p()
         self.device = device
+        self._jobs = weakref.WeakSet()
         rc = self.lib.ltr_ctx_create(device, C.byref(self.ctx))
         if rc != abi.LTR_OK:
             self.ctx = None
@@ -79,6 +84,8 @@ class Engine:
 
     def close(self):
         if self.ctx:
+            for job in list(self._jobs):
+                job.close()
             self.lib.ltr_ctx_destroy(self.ctx)
             self.ctx = None
 

@@ -132,7 +132,7 @@ struct EmuTable {
   double v(int q) const { return t[2 * q + 1]; }
 };
 
-template <int K>
+template <int K, bool SYM>
 static void emu_band_round(const VitConsts& C, const DevBatch& B, const uint32_t (*pairs)[2], uint32_t n_pairs,
                            uint32_t base, double gap, uint64_t* n_uncert) {
   constexpr int W = 16 * K, G = kBandGroupLanes;
@@ -180,8 +180,8 @@ static void emu_band_round(const VitConsts& C, const DevBatch& B, const uint32_t
       }
       for (int t = 0; t < G; ++t) {
         EmuTable T{tab[g][t]};
-        if (s & 1) band_general_step<K, 1>(L[g][t], C, R[g][t], T, s, nb[t], F[g][t], got[g][t]);
-        else band_general_step<K, 0>(L[g][t], C, R[g][t], T, s, nb[t], F[g][t], got[g][t]);
+        if (s & 1) band_general_step<K, 1, SYM>(L[g][t], C, R[g][t], T, s, nb[t], F[g][t], got[g][t]);
+        else band_general_step<K, 0, SYM>(L[g][t], C, R[g][t], T, s, nb[t], F[g][t], got[g][t]);
       }
     }
     ++s;
@@ -205,9 +205,9 @@ static void emu_band_round(const VitConsts& C, const DevBatch& B, const uint32_t
           nr[t] = (int32_t)R[g][t].read[ri[g][t]++];
           nb[t] = (t == 0) ? C.imp : L[g][t - 1].B[K - 1];
         }
-        for (int t = 0; t < G; ++t) band_fast_even<K>(L[g][t], C, nb[t]);
+        for (int t = 0; t < G; ++t) band_fast_even<K, SYM>(L[g][t], C, nb[t]);
         for (int t = 0; t < G; ++t) nb[t] = (t == G - 1) ? C.imp : L[g][t + 1].A[0];
-        for (int t = 0; t < G; ++t) band_fast_odd<K>(L[g][t], C, nb[t], nh[t], nr[t]);
+        for (int t = 0; t < G; ++t) band_fast_odd<K, SYM>(L[g][t], C, nb[t], nh[t], nr[t]);
       }
     }
   }
@@ -229,12 +229,13 @@ static void emu_band_round(const VitConsts& C, const DevBatch& B, const uint32_t
 
 static void emu_band_dispatch(int k, const VitConsts& C, const DevBatch& B, const uint32_t (*pairs)[2], uint32_t n_pairs,
                               uint32_t base, double gap, uint64_t* n_uncert) {
+  const bool sym = (C.d2m == C.i2m) && (C.m2i == C.m2d);  // as launch_band
   switch (k) {
-    case 2: emu_band_round<2>(C, B, pairs, n_pairs, base, gap, n_uncert); break;
-    case 3: emu_band_round<3>(C, B, pairs, n_pairs, base, gap, n_uncert); break;
-    case 4: emu_band_round<4>(C, B, pairs, n_pairs, base, gap, n_uncert); break;
-    case 6: emu_band_round<6>(C, B, pairs, n_pairs, base, gap, n_uncert); break;
-    case 8: emu_band_round<8>(C, B, pairs, n_pairs, base, gap, n_uncert); break;
+    case 2: if (sym) emu_band_round<2, true>(C, B, pairs, n_pairs, base, gap, n_uncert); else emu_band_round<2, false>(C, B, pairs, n_pairs, base, gap, n_uncert); break;
+    case 3: if (sym) emu_band_round<3, true>(C, B, pairs, n_pairs, base, gap, n_uncert); else emu_band_round<3, false>(C, B, pairs, n_pairs, base, gap, n_uncert); break;
+    case 4: if (sym) emu_band_round<4, true>(C, B, pairs, n_pairs, base, gap, n_uncert); else emu_band_round<4, false>(C, B, pairs, n_pairs, base, gap, n_uncert); break;
+    case 6: if (sym) emu_band_round<6, true>(C, B, pairs, n_pairs, base, gap, n_uncert); else emu_band_round<6, false>(C, B, pairs, n_pairs, base, gap, n_uncert); break;
+    case 8: if (sym) emu_band_round<8, true>(C, B, pairs, n_pairs, base, gap, n_uncert); else emu_band_round<8, false>(C, B, pairs, n_pairs, base, gap, n_uncert); break;
     default: std::abort();
   }
 }

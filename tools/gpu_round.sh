@@ -12,6 +12,6 @@ python bench.py --config 5 --steps 3 --warmup 3 > $out/${tag}_bench_c5.json 2> $
 python bench.py --impl reference --steps 2 --warmup 1 > $out/${tag}_bench_ref_c3.json 2> $out/${tag}_bench_ref_c3.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches.csv \
     python bench.py --steps 2 --warmup 1 --loci 20000 --no-cpu-baseline > $out/${tag}_launches_bench.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:viterbi_stream_kernel -s 10 -c 2 -f -o $out/${tag}_full \
+ncu --set full --clock-control none --import-source on -k regex:viterbi_band_kernel -c 3 -f -o $out/${tag}_full \
     python bench.py --steps 1 --warmup 1 --loci 20000 --no-cpu-baseline > $out/${tag}_full_bench.log 2>&1
 tail -3 $out/${tag}_pytest.log; cat $out/${tag}_bench_c3.json $out/${tag}_bench_c4.json $out/${tag}_bench_c5.json $out/${tag}_bench_ref_c3.json
