@@ -236,7 +236,12 @@ inline int make_plan(const ltr_viterbi_batch& b, const ltr_params& p, int kmax, 
   for (uint32_t l = 0; l < n_loci; ++l)
     if (b.locus_hap_begin[l + 1] < b.locus_hap_begin[l] || b.locus_read_begin[l + 1] < b.locus_read_begin[l])
       return LTR_ERR_INVALID;
-  if (n_threads <= 0) n_threads = (n_loci >= 4096) ? (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency())) : 1;
+  if (n_threads <= 0) {
+    // host threads of the plan: up to 16; LTR_PLAN_THREADS caps it (several ranks / batches in flight on one host)
+    unsigned cap = 16u;
+    if (const char* env = std::getenv("LTR_PLAN_THREADS")) cap = (unsigned)std::max(1, std::atoi(env));
+    n_threads = (n_loci >= 4096) ? (int)std::min<unsigned>(cap, std::max(1u, std::thread::hardware_concurrency())) : 1;
+  }
   {  // offsets must be monotone (reads non-empty); longest read
     std::vector<int> bad((size_t)std::max(1, n_threads), 0), mx((size_t)std::max(1, n_threads), 0);
     plan_parallel_for(n_reads, n_threads, [&](uint32_t r0, uint32_t r1, int t) {
