@@ -107,8 +107,9 @@ def dist_setup(n_gpus):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
-    # host threads of ltr_job_create's plan: the ranks of one node share its cores
-    os.environ.setdefault("LTR_PLAN_THREADS", str(max(2, min(16, (os.cpu_count() or 16) // world))))
+    # host threads of ltr_job_create's plan: the ranks of one node and the batches in flight share its cores
+    # (8 measured best with three batches in flight on the 16-core box: profiles/r1r notes)
+    os.environ.setdefault("LTR_PLAN_THREADS", str(max(2, min(8, (os.cpu_count() or 16) // world))))
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -410,13 +411,17 @@ def main():
     pin_out, keep_o = pinned_copy(torch, dict(ll=np.zeros(n_ll), post=np.zeros(max(1, n_post)), tot=np.zeros(max(1, n_tot))))
     timing = os.environ.get("LTR_TIMING") is not None
 
+    import threading
+    gpu_turn = threading.Lock()  # batches in flight take turns on the GPU: while one runs, the next is planned / uploaded
+
     def e2e_step(engine=None, out=None):
         engine = engine or eng
         out = out or pin_out
         t = [time.perf_counter()]
         j = engine.create_job(pinned_b, pinned_p, aln_params=work.aln_params)
         t.append(time.perf_counter())
-        s = j.run()
+        with gpu_turn:
+            s = j.run()
         t.append(time.perf_counter())
         j.download(out_ll=out["ll"], out_post=out["post"][:n_post], out_totals=out["tot"][:n_tot])
         t.append(time.perf_counter())

@@ -56,6 +56,10 @@ struct ltr_job {
   uint32_t n_band_tasks = 0;
   DeviceBuffer band_tasks, band_cum, band_pairs, band_ctrl;  // band_ctrl: u32[8] cursors, u32[2] counters, pad, u64[2] stats
   uint64_t plan_cells_computed = 0;
+  // Memsets and kernels of ltr_job_create are issued AFTER every host-to-device copy: they execute on the SMs / in
+  // stream order behind whatever another context's persistent kernels are doing, and a pageable copy enqueued behind
+  // them would block the calling thread for that long (batches in flight on other host threads).
+  std::vector<std::pair<void*, size_t>> deferred_zero;
   ltr_job_stats stats;
 };
 static const size_t kBandCtrlBytes = 72;  // u32[12], u64 uncertified pairs, u64 their n*m cells, u64 band cells evaluated
@@ -63,10 +67,14 @@ static const size_t kBandCtrlBytes = 72;  // u32[12], u64 uncertified pairs, u64
 namespace {
 
 template <typename T>
-int upload(ltr_ctx* ctx, DeviceBuffer& buf, const T* src, size_t count, size_t pad_bytes, uint64_t* h2d) {
+int upload(ltr_ctx* ctx, DeviceBuffer& buf, const T* src, size_t count, size_t pad_bytes, uint64_t* h2d,
+           std::vector<std::pair<void*, size_t>>* deferred_zero = nullptr) {
   const size_t bytes = count * sizeof(T);
   LTR_CUDA(ctx, buf.alloc(bytes + pad_bytes));
-  if (pad_bytes) LTR_CUDA(ctx, cudaMemsetAsync((char*)buf.p + bytes, 0, pad_bytes, ctx->main_stream));
+  if (pad_bytes) {
+    if (deferred_zero) deferred_zero->push_back(std::make_pair((void*)((char*)buf.p + bytes), pad_bytes));
+    else LTR_CUDA(ctx, cudaMemsetAsync((char*)buf.p + bytes, 0, pad_bytes, ctx->main_stream));
+  }
   if (bytes) LTR_CUDA(ctx, cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, ctx->main_stream));
   if (h2d) *h2d += bytes;
   return LTR_OK;
@@ -250,7 +258,7 @@ int ltr_job_create(ltr_ctx* ctx, const ltr_params* params, const ltr_viterbi_bat
   uint64_t* h2d = &job->stats.h2d_bytes;
   // Uploads that do not depend on the plan are enqueued first: with pinned caller buffers they overlap make_plan.
   {
-    int rc_up = upload(ctx, job->hap_bytes, bb.hap_bytes, (size_t)bb.hap_off[job->n_haps], 256, h2d);
+    int rc_up = upload(ctx, job->hap_bytes, bb.hap_bytes, (size_t)bb.hap_off[job->n_haps], 256, h2d, &job->deferred_zero);
     if (rc_up == LTR_OK) rc_up = upload(ctx, job->hap_off, bb.hap_off, (size_t)job->n_haps + 1, 0, h2d);
     if (rc_up == LTR_OK) rc_up = upload(ctx, job->lhb, bb.locus_hap_begin, (size_t)job->n_loci + 1, 0, h2d);
     if (rc_up == LTR_OK) rc_up = upload(ctx, job->lrb, bb.locus_read_begin, (size_t)job->n_loci + 1, 0, h2d);
@@ -291,7 +299,7 @@ int ltr_job_create(ltr_ctx* ctx, const ltr_params* params, const ltr_viterbi_bat
   // unique LL matrices and expand_ll_kernel fans them out to the caller-visible aln_probs layout.
   // padding (here and for hap_bytes above): the stream kernel prefetches one byte, the band kernel's character
   // windows run up to W/2 + K bytes ahead
-  LTR_TRY(upload(ctx, job->read_bytes, plan.uread_bytes, plan.uread_nbytes, 256, h2d));
+  LTR_TRY(upload(ctx, job->read_bytes, plan.uread_bytes, plan.uread_nbytes, 256, h2d, &job->deferred_zero));
   LTR_TRY(upload(ctx, job->read_off, plan.uread_off.data(), plan.uread_off.size(), 0, h2d));
   LTR_TRY(upload(ctx, job->lub, plan.locus_uread_begin.data(), plan.locus_uread_begin.size(), 0, h2d));
   LTR_TRY(upload(ctx, job->r2u, plan.read_to_uread.data(), plan.read_to_uread.size(), 0, h2d));
@@ -338,7 +346,7 @@ int ltr_job_create(ltr_ctx* ctx, const ltr_params* params, const ltr_viterbi_bat
       const size_t warps = (size_t)grid_max * warps_per_block;
       LTR_CUDA_J(cs.sxy.alloc(warps * cs.scratch_stride * sizeof(XY)));
       LTR_CUDA_J(cs.sb.alloc(warps * cs.scratch_stride * sizeof(uint32_t)));
-      LTR_CUDA_J(cudaMemsetAsync(cs.sxy.p, 0, cs.sxy.bytes, ctx->main_stream));
+      job->deferred_zero.push_back(std::make_pair(cs.sxy.p, cs.sxy.bytes));
     }
     job->classes.push_back(cs);
   }
@@ -373,8 +381,6 @@ int ltr_job_create(ltr_ctx* ctx, const ltr_params* params, const ltr_viterbi_bat
     LTR_TRY(upload(ctx, job->band_cum, cum.data(), cum.size(), 0, h2d));
     LTR_CUDA_J(job->band_pairs.alloc((size_t)npairs * sizeof(uint2)));
     LTR_CUDA_J(job->band_ctrl.alloc(kBandCtrlBytes));
-    LTR_CUDA_J(launch_band_expand(job->band_tasks.as<BandTask>(), job->band_cum.as<uint32_t>(), job->n_band_tasks,
-                                  job->band_pairs.as<uint2>(), ctx->main_stream));
   }
 
   if (post) {
@@ -415,8 +421,16 @@ int ltr_job_create(ltr_ctx* ctx, const ltr_params* params, const ltr_viterbi_bat
     LTR_CUDA_J(job->post.alloc(job->n_post * sizeof(double)));
     LTR_CUDA_J(job->totals.alloc(job->n_tot * sizeof(double)));
   }
+  // every copy from host memory is enqueued: wait for those only (the caller may release its arrays when we return)
+  LTR_CUDA_J(cudaEventRecord(ctx->ev_init, ctx->main_stream));
+  for (const std::pair<void*, size_t>& z : job->deferred_zero)
+    LTR_CUDA_J(cudaMemsetAsync(z.first, 0, z.second, ctx->main_stream));
+  job->deferred_zero.clear();
+  if (job->n_band_tasks)
+    LTR_CUDA_J(launch_band_expand(job->band_tasks.as<BandTask>(), job->band_cum.as<uint32_t>(), job->n_band_tasks,
+                                  job->band_pairs.as<uint2>(), ctx->main_stream));
   const auto t_enq = std::chrono::steady_clock::now();
-  LTR_CUDA_J(cudaStreamSynchronize(ctx->main_stream));
+  LTR_CUDA_J(cudaEventSynchronize(ctx->ev_init));
   if (timing) {
     auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
       return std::chrono::duration<double, std::milli>(b - a).count();
