@@ -63,6 +63,8 @@ struct ltr_job {
   ltr_job_stats stats;
 };
 static const size_t kBandCtrlBytes = 72;  // u32[12], u64 uncertified pairs, u64 their n*m cells, u64 band cells evaluated
+static const size_t kBandBucketOff = 128, kBandBucketWords = 17 * 32;  // then count / base / fill of band_collect_kernel
+static const size_t kBandCtrlAlloc = kBandBucketOff + 3 * kBandBucketWords * sizeof(uint32_t);
 
 namespace {
 
@@ -380,7 +382,7 @@ int ltr_job_create(ltr_ctx* ctx, const ltr_params* params, const ltr_viterbi_bat
     LTR_TRY(upload(ctx, job->band_tasks, all.data(), all.size(), 0, h2d));
     LTR_TRY(upload(ctx, job->band_cum, cum.data(), cum.size(), 0, h2d));
     LTR_CUDA_J(job->band_pairs.alloc((size_t)npairs * sizeof(uint2)));
-    LTR_CUDA_J(job->band_ctrl.alloc(kBandCtrlBytes));
+    LTR_CUDA_J(job->band_ctrl.alloc(kBandCtrlAlloc));
   }
 
   if (post) {
@@ -510,7 +512,7 @@ static int run_band_phase(ltr_ctx* ctx, ltr_job* job) {
     const uint32_t ctrl_init[4] = {0u, cs.n_tasks, 0u, 0u};
     LTR_CUDA(ctx, cudaMemcpyAsync(cs.ctrl.p, ctrl_init, sizeof(ctrl_init), cudaMemcpyHostToDevice, ctx->main_stream));
   }
-  LTR_CUDA(ctx, cudaMemsetAsync(job->band_ctrl.p, 0, kBandCtrlBytes, ctx->main_stream));
+  LTR_CUDA(ctx, cudaMemsetAsync(job->band_ctrl.p, 0, kBandCtrlAlloc, ctx->main_stream));
   LTR_CUDA(ctx, cudaEventRecord(ctx->ev_init, ctx->main_stream));
   uint32_t* bctrl = job->band_ctrl.as<uint32_t>();
   static const bool no_abandon = getenv("LTR_BAND_NO_ABANDON") != nullptr;  // diagnostics
@@ -545,9 +547,12 @@ static int run_band_phase(ltr_ctx* ctx, ltr_job* job) {
   S.kmax = viterbi_max_rows_per_lane();
   S.n_uncertified = reinterpret_cast<unsigned long long*>(job->band_ctrl.as<char>() + 48);
   S.cells_uncertified = reinterpret_cast<unsigned long long*>(job->band_ctrl.as<char>() + 56);
+  S.bucket_count = reinterpret_cast<uint32_t*>(job->band_ctrl.as<char>() + kBandBucketOff);
+  S.bucket_base = S.bucket_count + kBandBucketWords;
+  S.bucket_fill = S.bucket_base + kBandBucketWords;
   LTR_CUDA(ctx, launch_band_collect(job->hc.C, B, job->band_tasks.as<BandTask>(), job->n_band_tasks, S,
                                     ctx->main_stream));
-  job->stats.n_launches += 1;
+  job->stats.n_launches += 3;
   LTR_CUDA(ctx, cudaEventRecord(ctx->ev_collect, ctx->main_stream));
   return LTR_OK;
 }

@@ -150,8 +150,11 @@ __global__ void band_expand_kernel(const BandTask* __restrict__ tasks, const uin
 }
 
 // One thread per band task: runs of uncertified pairs become tasks of the stream kernel of the haplotype's row class.
+// Two passes so that the appended tasks end up heaviest first (the persistent warps of the stream kernel then finish
+// together, like on the plan's own sorted list): pass 0 counts the runs per (row class, cost bucket = floor(log2 cost)),
+// band_bucket_scan_kernel turns the counts into list positions, pass 1 writes the tasks.
 __global__ void band_collect_kernel(const VitConsts C, const DevBatch B, const BandTask* __restrict__ tasks,
-                                    uint32_t n_tasks, const BandCollect S) {
+                                    uint32_t n_tasks, const BandCollect S, int pass) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_tasks) return;
   const BandTask bt = tasks[t];
@@ -162,6 +165,8 @@ __global__ void band_collect_kernel(const VitConsts C, const DevBatch B, const B
   const uint32_t rb0 = B.locus_read_begin[l];
   const int32_t n = (int32_t)(B.hap_off[g + 1] - B.hap_off[g]) - 2 * C.cut;
   const int kr = rows_per_lane_hd(n, S.kmax);
+  int strips = (n - 1 + 32 * kr - 1) / (32 * kr);
+  if (strips < 1) strips = 1;
   const double* col = B.out_ll + B.ll_off[l] + (g - hb0);
   uint32_t run_begin = 0, n_bad = 0;
   unsigned long long cells = 0;
@@ -177,20 +182,42 @@ __global__ void band_collect_kernel(const VitConsts C, const DevBatch B, const B
       }
     } else if (in_run) {
       in_run = false;
-      const uint32_t k = atomicAdd(S.count[kr], 1u);
-      if (k < S.cap[kr]) {
-        Task T;
-        T.hap = g;
-        T.read_begin = run_begin;
-        T.read_end = r;
-        S.tasks[kr][k] = T;
+      // same cost model as the plan (viterbi_host.h): rows per lane x strips x stream length
+      const unsigned long long cost =
+          (unsigned long long)kr * (unsigned long long)strips * ((unsigned long long)(B.read_off[r] - B.read_off[run_begin]) + 32ull);
+      int bucket = 63 - __clzll((long long)cost);
+      bucket = bucket > 31 ? 31 : bucket;
+      const int slot = kr * 32 + bucket;
+      if (pass == 0) {
+        atomicAdd(S.bucket_count + slot, 1u);
+      } else {
+        const uint32_t k = S.bucket_base[slot] + atomicAdd(S.bucket_fill + slot, 1u);
+        if (k < S.cap[kr]) {
+          Task T;
+          T.hap = g;
+          T.read_begin = run_begin;
+          T.read_end = r;
+          S.tasks[kr][k] = T;
+        }
       }
     }
   }
-  if (n_bad) {
+  if (pass == 0 && n_bad) {
     atomicAdd(S.n_uncertified, (unsigned long long)n_bad);
     atomicAdd(S.cells_uncertified, cells);
   }
+}
+
+// One thread per row class: positions of the cost buckets behind the plan's tasks, heaviest bucket first; new task count.
+__global__ void band_bucket_scan_kernel(const BandCollect S) {
+  const int kr = threadIdx.x;
+  if (kr > 16) return;
+  uint32_t running = *S.count[kr];
+  for (int bkt = 31; bkt >= 0; --bkt) {
+    S.bucket_base[kr * 32 + bkt] = running;
+    running += S.bucket_count[kr * 32 + bkt];
+  }
+  if (S.cap[kr]) *S.count[kr] = running < S.cap[kr] ? running : S.cap[kr];
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -240,7 +267,9 @@ cudaError_t launch_band_expand(const BandTask* tasks, const uint32_t* cum, uint3
 cudaError_t launch_band_collect(const VitConsts& C, const DevBatch& B, const BandTask* tasks, uint32_t n_tasks,
                                 const BandCollect& S, cudaStream_t stream) {
   if (n_tasks == 0) return cudaSuccess;
-  band_collect_kernel<<<(n_tasks + 127) / 128, 128, 0, stream>>>(C, B, tasks, n_tasks, S);
+  band_collect_kernel<<<(n_tasks + 127) / 128, 128, 0, stream>>>(C, B, tasks, n_tasks, S, 0);
+  band_bucket_scan_kernel<<<1, 32, 0, stream>>>(S);
+  band_collect_kernel<<<(n_tasks + 127) / 128, 128, 0, stream>>>(C, B, tasks, n_tasks, S, 1);
   return cudaGetLastError();
 }
 

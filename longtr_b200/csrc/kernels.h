@@ -34,6 +34,9 @@ struct BandCollect {        // where band_collect_kernel appends the uncertified
   int kmax;
   unsigned long long* n_uncertified;
   unsigned long long* cells_uncertified;
+  uint32_t* bucket_count;   // [17*32] runs per (row class, floor(log2 cost)); zeroed before the collect
+  uint32_t* bucket_base;    // [17*32] list position of each bucket (band_bucket_scan_kernel)
+  uint32_t* bucket_fill;    // [17*32] zeroed before the collect
 };
 int band_block_threads();
 int band_blocks_per_sm(int k);
