@@ -10,9 +10,11 @@
 //    chain's sequentially rounded sum; max and "+ constant" commute under round-to-nearest, so restricting the DP to
 //    a band yields exactly max{chains inside the band}.
 //  * A chain that leaves the band and still ends in (n-1, m-1) makes at least |de| + 2w + 2 horizontal/vertical
-//    moves; all of them but at most one (the M cell of the boundary row/column, HapAligner.cpp:266-279) cost at least
-//    g = min(|M2I|, |I2I|, |M2D|, |D2D|) when all transition parameters are <= 0 (emissions are < 0).  Its value is
-//    therefore <= U = -g (|de| + 2w) (+1e-3 for the rounding of at most ~1e4 additions of magnitude < 1e4).
+//    moves in at least two runs (one out, one back; runs are separated by M cells because D is only reached from M
+//    or D and I from M or I).  Each run pays open = min(|M2D|, |M2I|) for its first move and at least
+//    ext = min(|D2D|, |I2I|) for every further one (all transition parameters <= 0, emissions < 0), except for at most
+//    one move, the M cell of the boundary row/column (HapAligner.cpp:266-279).  Its value is therefore
+//    <= U = -(2 open + (|de| + 2w - 1) ext) (+1e-3 for the rounding of at most ~1e4 additions of magnitude < 1e4).
 //  * Hence F_band > U  =>  F = F_band bit for bit; and F > fast_thr additionally certifies that the reference's
 //    per-row bail-out (HapAligner.cpp:297-306) cannot fire (viterbi_core.cuh).  Pairs that are not certified are
 //    marked and re-run over the full matrix by viterbi_stream_kernel.  Results are exact either way.
@@ -79,11 +81,22 @@ LTR_HHD unsigned long long band_cells(int32_t n, int32_t m, int32_t W, int32_t d
   return total > 0 ? (unsigned long long)total : 0ull;
 }
 
-// Pair certified from its banded score?  thr = max(fast_thr, -g(|de| + 2w) + 1e-3), see the header comment.
-LTR_HD double band_threshold(const VitConsts& C, double gap, int32_t n, int32_t m, int32_t w) {
+// Cost of the gap moves a chain cannot avoid (see the header comment): every maximal run of horizontal (or of vertical)
+// moves is opened from an M cell (D comes from M or D, I from M or I: HapAligner.cpp:289-292), so its first move costs at
+// least `open` = min(|M2D|, |M2I|) and every further one at least `ext` = min(|D2D|, |I2I|); open >= ext is enforced.
+struct BandGap {
+  double open, ext;
+};
+
+// Pair certified from its banded score?  A chain that leaves the band [lo - w, hi + w] and ends on diagonal de makes
+// T >= |de| + 2w + 2 gap moves in at least two runs (out and back, an M cell between them); at most one of them is the
+// cheap M cell of the boundary row / column (D2M / I2M instead of a gap cost, HapAligner.cpp:266-279), and that one sits in
+// a run that still pays its opening.  Its value is therefore <= U = -(2 open + (|de| + 2w - 1) ext) + 1e-3.
+// thr = max(fast_thr, U).
+LTR_HD double band_threshold(const VitConsts& C, const BandGap& gap, int32_t n, int32_t m, int32_t w) {
   int32_t de = m - n;
   if (de < 0) de = -de;
-  const double u = -gap * (double)(de + 2 * w) + 1e-3;
+  const double u = -(2.0 * gap.open + gap.ext * (double)(de + 2 * w - 1)) + 1e-3;
   return u > C.fast_thr ? u : C.fast_thr;
 }
 

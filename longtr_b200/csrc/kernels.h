@@ -24,7 +24,7 @@ struct BandArgs {
   uint32_t* cursor;         // round cursor of the persistent grid
   uint32_t* counters;       // [0] pairs evaluated, [1] of which not certified (shared by all band classes of a job)
   unsigned long long* cells_evaluated;  // interior band cells of the pairs evaluated (statistics)
-  double gap;               // g = min(|M2I|, |I2I|, |M2D|, |D2D|)
+  BandGap gap;              // unavoidable gap costs of the certificate (band_core.cuh)
   uint32_t abandon_after;   // 0: never; else stop banding once this many pairs were evaluated and most failed
 };
 struct BandCollect {        // where band_collect_kernel appends the uncertified runs: task list of each row class

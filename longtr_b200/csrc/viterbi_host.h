@@ -99,19 +99,23 @@ struct PodArray {
 // Banded evaluation (band_core.cuh): which pairs go to the band kernel, and with which band class.
 struct BandPolicy {
   bool on = false;
-  double gap = 0.0;  // g = min(|M2I|, |I2I|, |M2D|, |D2D|)
+  BandGap gap = {0.0, 0.0};  // open = min(|M2D|, |M2I|), ext = min(|D2D|, |I2I|) (open >= ext enforced)
   int w_need = 0;    // minimum margin (diagonals) a pair's band class must guarantee
 };
-// band_w < 0: banding off; 0: automatic margin (about 34 log units of slack: two indels or three mismatches more than
-// the length difference explains); > 0: that many diagonals.  The band certificate needs every transition parameter
+// band_w < 0: banding off; 0: automatic margin; > 0: that many diagonals.  The band certificate needs every transition parameter
 // <= 0 and the same parameter condition as the final-score certificate (the bail-out is certified from F as well).
 inline BandPolicy band_policy(const ltr_params& p, int band_w) {
   BandPolicy b;
   if (band_w < 0 || !fast_certificate_valid(p)) return b;
-  b.gap = std::min(std::min(std::fabs((double)p.match_ins), std::fabs((double)p.ins_ins)),
-                   std::min(std::fabs((double)p.match_del), std::fabs((double)p.del_del)));
-  if (!(b.gap >= 0.05)) return b;
-  b.w_need = band_w > 0 ? band_w : (int)std::ceil(17.0 / b.gap);
+  b.gap.open = std::min(std::fabs((double)p.match_del), std::fabs((double)p.match_ins));
+  b.gap.ext = std::min(std::fabs((double)p.del_del), std::fabs((double)p.ins_ins));
+  if (b.gap.open < b.gap.ext) b.gap.open = b.gap.ext;
+  if (!(b.gap.ext >= 0.05)) return b;
+  // automatic margin: the band must be certifiable for a path that pays, beyond the gap the length difference forces
+  // (open + |de| ext), about 27 log units of errors (three mismatches, or two more indels):
+  //   2 open + (|de| + 2w - 1) ext >= open + |de| ext + 27   <=>   w >= ((27 - open) / ext + 1) / 2
+  const int w_auto = std::max(2, (int)std::ceil(((27.0 - b.gap.open) / b.gap.ext + 1.0) / 2.0));
+  b.w_need = band_w > 0 ? band_w : w_auto;
   b.on = true;
   return b;
 }

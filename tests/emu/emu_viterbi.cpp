@@ -134,7 +134,7 @@ struct EmuTable {
 
 template <int K, bool SYM>
 static void emu_band_round(const VitConsts& C, const DevBatch& B, const uint32_t (*pairs)[2], uint32_t n_pairs,
-                           uint32_t base, double gap, uint64_t* n_uncert) {
+                           uint32_t base, const BandGap& gap, uint64_t* n_uncert) {
   constexpr int W = 16 * K, G = kBandGroupLanes;
   BandPair R[4][G];
   BandLane<K> L[4][G];
@@ -228,7 +228,7 @@ static void emu_band_round(const VitConsts& C, const DevBatch& B, const uint32_t
 }
 
 static void emu_band_dispatch(int k, const VitConsts& C, const DevBatch& B, const uint32_t (*pairs)[2], uint32_t n_pairs,
-                              uint32_t base, double gap, uint64_t* n_uncert) {
+                              uint32_t base, const BandGap& gap, uint64_t* n_uncert) {
   const bool sym = (C.d2m == C.i2m) && (C.m2i == C.m2d);  // as launch_band
   switch (k) {
     case 2: if (sym) emu_band_round<2, true>(C, B, pairs, n_pairs, base, gap, n_uncert); else emu_band_round<2, false>(C, B, pairs, n_pairs, base, gap, n_uncert); break;

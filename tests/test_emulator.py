@@ -164,6 +164,63 @@ def test_band_certificate_adversarial(emu, seed):
     assert n_band > 0 and 0 < n_unc < n_band  # both outcomes of the certificate occur
 
 
+CHEAP = (-0.5, -0.4, -0.25, -0.3, -0.01, -0.6, -0.55)  # opening a gap barely dearer than extending it
+P4 = (-0.3, -0.05, -0.3, -0.05, -0.001, -1.2, -1.2)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_band_certificate_out_and_back(emu, seed):
+    """The certificate charges a chain that leaves the band two gap openings (out and back).  Reads made of noisy tandem
+    repeats with a block deleted at one place and (almost) the same block re-inserted elsewhere are exactly the inputs
+    whose best path makes two long gap runs far from the diagonal; margins 1-7 and the automatic one, four parameter
+    sets including one whose gap opening is barely dearer than its extension."""
+    rng = np.random.default_rng(31337 + seed)
+    params = [None, ONT, CHEAP, P4][seed % 4]
+    lhb, lrb, hoff, roff, hb, rb = [0], [0], [0], [0], [], []
+    for _l in range(6):
+        n = int(rng.integers(70, 260))
+        motif = synth.rand_seq(rng, int(rng.integers(1, 7)))
+        core = list((motif * 400)[:n])
+        for i in range(n):
+            if rng.random() < 0.06:
+                core[i] = "ACGT"[int(rng.integers(0, 4))]
+        hap = synth.rand_seq(rng, 30) + "".join(core) + synth.rand_seq(rng, 30)
+        hb.append(hap)
+        hoff.append(hoff[-1] + len(hap))
+        for _r in range(8):
+            c = list(core)
+            for _e in range(int(rng.integers(1, 3))):
+                k = int(rng.integers(1, 40))
+                a = int(rng.integers(0, max(1, len(c) - k)))
+                seg = c[a:a + k]
+                del c[a:a + k]
+                k2 = max(0, k + int(rng.integers(-3, 4)))
+                bpos = int(rng.integers(0, len(c) + 1))
+                c[bpos:bpos] = seg[:k2] if rng.random() < 0.5 else list((motif * 50)[:k2])
+            for _e in range(int(rng.integers(0, 3))):
+                if c:
+                    c[int(rng.integers(0, len(c)))] = "ACGT"[int(rng.integers(0, 4))]
+            s = "".join(c)
+            if len(s) < 2:
+                s = "AC"
+            rb.append(s)
+            roff.append(roff[-1] + len(s))
+        lhb.append(len(hb))
+        lrb.append(len(rb))
+    b = dict(locus_hap_begin=np.array(lhb, np.uint32), locus_read_begin=np.array(lrb, np.uint32),
+             hap_off=np.array(hoff, np.uint32), read_off=np.array(roff, np.uint32),
+             hap_bytes=np.frombuffer("".join(hb).encode(), np.uint8).copy(),
+             read_bytes=np.frombuffer("".join(rb).encode(), np.uint8).copy())
+    want, _ = po.viterbi_batch(b, aln_params=params, n_threads=4)
+    n_band = n_unc = 0
+    for band_w in (1, 2, 4, 7, 0):
+        out, stats = run_band(emu, b, params, 16, band_w)
+        assert np.array_equal(out, want)
+        n_band += stats[0]
+        n_unc += stats[1]
+    assert n_band > 0 and 0 < n_unc < n_band
+
+
 def test_band_geometry_properties():
     """band_geometry / band_cells (band_core.cuh) against brute force, through the emulator library's helpers."""
     lib = C.CDLL(os.path.join(HERE, "emu", "libltr_emu.so"))
