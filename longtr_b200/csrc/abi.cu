@@ -68,16 +68,27 @@ static const size_t kBandCtrlAlloc = kBandBucketOff + 3 * kBandBucketWords * siz
 
 namespace {
 
+// The string buffers (haplotypes, reads) carry kStringPad readable bytes on either side: the stream kernel prefetches one
+// byte ahead, the band kernel's character windows run up to W/2 + K bytes ahead of a string's end and, during the
+// prologue, up to W/2 bytes in front of its start (values that only reach cells outside the matrix).
+static const size_t kStringPad = 256;
+
 template <typename T>
 int upload(ltr_ctx* ctx, DeviceBuffer& buf, const T* src, size_t count, size_t pad_bytes, uint64_t* h2d,
            std::vector<std::pair<void*, size_t>>* deferred_zero = nullptr) {
   const size_t bytes = count * sizeof(T);
-  LTR_CUDA(ctx, buf.alloc(bytes + pad_bytes));
+  const size_t front = pad_bytes;  // padded buffers are padded on both sides; data starts at p + pad_bytes
+  LTR_CUDA(ctx, buf.alloc(front + bytes + pad_bytes));
   if (pad_bytes) {
-    if (deferred_zero) deferred_zero->push_back(std::make_pair((void*)((char*)buf.p + bytes), pad_bytes));
-    else LTR_CUDA(ctx, cudaMemsetAsync((char*)buf.p + bytes, 0, pad_bytes, ctx->main_stream));
+    if (deferred_zero) {
+      deferred_zero->push_back(std::make_pair(buf.p, front));
+      deferred_zero->push_back(std::make_pair((void*)((char*)buf.p + front + bytes), pad_bytes));
+    } else {
+      LTR_CUDA(ctx, cudaMemsetAsync(buf.p, 0, front, ctx->main_stream));
+      LTR_CUDA(ctx, cudaMemsetAsync((char*)buf.p + front + bytes, 0, pad_bytes, ctx->main_stream));
+    }
   }
-  if (bytes) LTR_CUDA(ctx, cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, ctx->main_stream));
+  if (bytes) LTR_CUDA(ctx, cudaMemcpyAsync((char*)buf.p + front, src, bytes, cudaMemcpyHostToDevice, ctx->main_stream));
   if (h2d) *h2d += bytes;
   return LTR_OK;
 }
@@ -260,7 +271,7 @@ int ltr_job_create(ltr_ctx* ctx, const ltr_params* params, const ltr_viterbi_bat
   uint64_t* h2d = &job->stats.h2d_bytes;
   // Uploads that do not depend on the plan are enqueued first: with pinned caller buffers they overlap make_plan.
   {
-    int rc_up = upload(ctx, job->hap_bytes, bb.hap_bytes, (size_t)bb.hap_off[job->n_haps], 256, h2d, &job->deferred_zero);
+    int rc_up = upload(ctx, job->hap_bytes, bb.hap_bytes, (size_t)bb.hap_off[job->n_haps], kStringPad, h2d, &job->deferred_zero);
     if (rc_up == LTR_OK) rc_up = upload(ctx, job->hap_off, bb.hap_off, (size_t)job->n_haps + 1, 0, h2d);
     if (rc_up == LTR_OK) rc_up = upload(ctx, job->lhb, bb.locus_hap_begin, (size_t)job->n_loci + 1, 0, h2d);
     if (rc_up == LTR_OK) rc_up = upload(ctx, job->lrb, bb.locus_read_begin, (size_t)job->n_loci + 1, 0, h2d);
@@ -301,7 +312,7 @@ int ltr_job_create(ltr_ctx* ctx, const ltr_params* params, const ltr_viterbi_bat
   // unique LL matrices and expand_ll_kernel fans them out to the caller-visible aln_probs layout.
   // padding (here and for hap_bytes above): the stream kernel prefetches one byte, the band kernel's character
   // windows run up to W/2 + K bytes ahead
-  LTR_TRY(upload(ctx, job->read_bytes, plan.uread_bytes, plan.uread_nbytes, 256, h2d, &job->deferred_zero));
+  LTR_TRY(upload(ctx, job->read_bytes, plan.uread_bytes, plan.uread_nbytes, kStringPad, h2d, &job->deferred_zero));
   LTR_TRY(upload(ctx, job->read_off, plan.uread_off.data(), plan.uread_off.size(), 0, h2d));
   LTR_TRY(upload(ctx, job->lub, plan.locus_uread_begin.data(), plan.locus_uread_begin.size(), 0, h2d));
   LTR_TRY(upload(ctx, job->r2u, plan.read_to_uread.data(), plan.read_to_uread.size(), 0, h2d));
@@ -448,10 +459,10 @@ int ltr_job_create(ltr_ctx* ctx, const ltr_params* params, const ltr_viterbi_bat
 
 static DevBatch job_dev_batch(const ltr_job* job) {
   DevBatch B;
-  B.hap_bytes = job->hap_bytes.as<uint8_t>();
+  B.hap_bytes = job->hap_bytes.as<uint8_t>() + kStringPad;
   B.hap_off = job->hap_off.as<uint32_t>();
   B.hap_locus = job->hap_locus.as<uint32_t>();
-  B.read_bytes = job->read_bytes.as<uint8_t>();
+  B.read_bytes = job->read_bytes.as<uint8_t>() + kStringPad;
   B.read_off = job->read_off.as<uint32_t>();
   B.locus_hap_begin = job->lhb.as<uint32_t>();
   B.locus_read_begin = job->lub.as<uint32_t>();            // unique reads

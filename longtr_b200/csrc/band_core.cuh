@@ -116,15 +116,16 @@ struct BandLane {
   int32_t rw[K + 1];  // fast loop: rw[k] = read[jb + k]
 };
 
-// Closed-form boundary cell of local diagonal q (row 0 for d >= 0, column 0 for d < 0): bx = X, bv = Y (row 0) or Z
-// (column 0) -- the two values interior cells consume (HapAligner.cpp:263-280).
-LTR_HD void band_boundary(const VitConsts& C, const BandPair& R, int32_t d, double& bx, double& bv) {
+// Closed-form boundary cell of diagonal d (row 0 for d >= 0, column 0 for d < 0): the X, Y, Z interior cells consume
+// (HapAligner.cpp:263-280).  Z of a row-0 cell and Y of a column-0 cell only feed other boundary cells: imp.
+LTR_HD void band_boundary(const VitConsts& C, const BandPair& R, int32_t d, double& bx, double& by, double& bz) {
   if (d >= 0) {
     const int32_t j = d;
     const int32_t hj = (j < R.n) ? (int32_t)R.hap[j] : 0;
     const XY b = row0_boundary(C, j, hj, (int32_t)R.read[0]);
     bx = b.x;
-    bv = b.y;
+    by = b.y;
+    bz = C.imp;
   } else {
     const int32_t c1 = (R.m > 1) ? (int32_t)R.read[1] : 0;
     const double e1 = ((int32_t)R.hap[0] == c1) ? C.match : C.mismatch;  // emit(h[0], r[1]), HapAligner.cpp:276
@@ -132,7 +133,8 @@ LTR_HD void band_boundary(const VitConsts& C, const BandPair& R, int32_t d, doub
     col0_cell(C, -d, e1, Mi, Ii, Di);
     const XYZ o = finish_cell(C, Mi, Ii, Di);
     bx = o.x;
-    bv = o.z;
+    by = C.imp;
+    bz = o.z;
   }
 }
 
@@ -150,9 +152,8 @@ LTR_HD void band_lane_reset(BandLane<K>& L, const VitConsts& C) {
   L.rw[K] = 0;
 }
 
-// One anti-diagonal step with every special case: cells before the matrix (imp), boundary cells (tbx/tbv: the
-// lane's closed forms, indexed by local diagonal), interior cells by the recurrence with characters fetched from
-// memory, and the end cell (n-1, m-1), whose max(D, max(I, M)) is the pair's score (HapAligner.cpp:308-309).
+// One anti-diagonal step with every special case: boundary cells (tb: the lane's closed forms, indexed by local
+// diagonal), interior cells by the recurrence with characters fetched from memory, and the end cell (n-1, m-1), whose max(D, max(I, M)) is the pair's score (HapAligner.cpp:308-309).
 // P = parity of the step (the lane's cells are the local diagonals q = 2k + P); nb = Z of the lower neighbour's last
 // diagonal (P == 0) or Y of the upper neighbour's first diagonal (P == 1), imp at the edges of the band.
 template <int K, int P, bool SYM, typename TB>
@@ -176,11 +177,12 @@ LTR_HD void band_general_step(BandLane<K>& L, const VitConsts& C, const BandPair
     const double I = C.match + yin;
     const double D = zin;
     const XYZ o = finish_cell_t<SYM>(C, M, I, D);
-    const bool before = s < ad, bnd = s == ad;
-    const double bx = tb.x(q), bv = tb.v(q);
-    const double x = before ? C.imp : (bnd ? bx : o.x);
-    const double y = before ? C.imp : (bnd ? ((d >= 0) ? bv : C.imp) : o.y);
-    const double z = before ? C.imp : (bnd ? ((d >= 0) ? C.imp : bv) : o.z);
+    // cells before the matrix (s < |d|) keep whatever the recurrence makes of the imp-initialised state: they only feed
+    // boundary cells (replaced here) and other cells before the matrix, never an interior cell
+    const bool bnd = s == ad;
+    const double x = bnd ? tb.x(q) : o.x;
+    const double y = bnd ? tb.y(q) : o.y;
+    const double z = bnd ? tb.z(q) : o.z;
     if (s > ad && i == R.n - 1 && j == R.m - 1) {
       F = vmax(D, vmax(I, M));
       got = true;
@@ -250,6 +252,24 @@ LTR_HD void band_fast_odd(BandLane<K>& L, const VitConsts& C, double yr, int32_t
 #pragma unroll
   for (int k = 0; k < K; ++k) L.rw[k] = L.rw[k + 1];
   L.rw[K] = nr;
+}
+
+// Prologue: after a plain step of parity P at step s, the cells that are boundary cells at this step (s == |d|) take
+// their closed forms.  Cells before the matrix were computed from the imp-initialised state and garbage characters;
+// they are never consumed by an interior cell.
+template <int K, int P, typename TB>
+LTR_HD void band_fixup(BandLane<K>& L, const BandPair& R, const TB& tb, int32_t s) {
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const int q = 2 * k + P;
+    const int32_t d = R.d0 + q;
+    const int32_t ad = d < 0 ? -d : d;
+    if (s == ad) {
+      L.X[q] = tb.x(q);
+      L.A[k] = tb.y(q);
+      L.B[k] = tb.z(q);
+    }
+  }
 }
 
 // First even step from which every cell of the band is interior (s >= |d| + 2 for every diagonal of the band).

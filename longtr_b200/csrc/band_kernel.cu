@@ -18,10 +18,11 @@ namespace ltr {
 static constexpr unsigned kFull = 0xFFFFFFFFu;
 static constexpr int kBandBlockThreads = 128;
 
-struct SmemTable {  // the lane's closed-form boundary cells, [2K][2][32] doubles per warp
+struct SmemTable {  // the lane's closed-form boundary cells, [2K][3][32] doubles per warp
   const double* base;
-  __device__ __forceinline__ double x(int q) const { return base[(2 * q) * 32]; }
-  __device__ __forceinline__ double v(int q) const { return base[(2 * q + 1) * 32]; }
+  __device__ __forceinline__ double x(int q) const { return base[(3 * q) * 32]; }
+  __device__ __forceinline__ double y(int q) const { return base[(3 * q + 1) * 32]; }
+  __device__ __forceinline__ double z(int q) const { return base[(3 * q + 2) * 32]; }
 };
 
 #ifndef LTR_BAND_MINBLOCKS
@@ -34,7 +35,7 @@ viterbi_band_kernel(const VitConsts C, const DevBatch B, const BandArgs A) {
   const int lane = threadIdx.x & 31;
   const int lg = lane & (kBandGroupLanes - 1);
   const int grp = lane >> 3;
-  double* tb = band_smem + (size_t)(threadIdx.x >> 5) * (4 * K * 32) + lane;
+  double* tb = band_smem + (size_t)(threadIdx.x >> 5) * (6 * K * 32) + lane;
   SmemTable T;
   T.base = tb;
   constexpr int W = 16 * K;
@@ -77,10 +78,11 @@ viterbi_band_kernel(const VitConsts C, const DevBatch B, const BandArgs A) {
     // ---- per-lane closed forms of the boundary cells of its diagonals, initial state -----------------------------
 #pragma unroll
     for (int q = 0; q < 2 * K; ++q) {
-      double bx, bv;
-      band_boundary(C, R, R.d0 + q, bx, bv);
-      tb[(2 * q) * 32] = bx;
-      tb[(2 * q + 1) * 32] = bv;
+      double bx, by, bz;
+      band_boundary(C, R, R.d0 + q, bx, by, bz);
+      tb[(3 * q) * 32] = bx;
+      tb[(3 * q + 1) * 32] = by;
+      tb[(3 * q + 2) * 32] = bz;
     }
     BandLane<K> L;
     band_lane_reset<K>(L, C);
@@ -104,11 +106,27 @@ viterbi_band_kernel(const VitConsts C, const DevBatch B, const BandArgs A) {
     }                                                                        \
     ++s;                                                                     \
   } while (0)
-    while (s < s_pro && s <= s_end_max) LTR_BAND_GENERAL_STEP();
-    if (s + 1 < s_end_min) {  // s is even here (s_pro is)
+    // Prologue and steady state share one loop body: plain double steps on the register windows; during the prologue
+    // (s < s_pro) the cells that are boundary cells at the step are then replaced by their closed forms.  The windows of
+    // lanes whose cells still lie before the matrix read up to W/2 bytes in front of the strings (padded buffers).
+    if (s + 1 < s_end_min) {
       band_windows_init<K>(L, R, s);
       const uint8_t* hp = R.hap + ((s - R.d0) >> 1) + 1;
       const uint8_t* rp = R.read + ((s + R.d0) >> 1) + K + 1;
+#pragma unroll 1
+      for (; s < s_pro && s + 1 < s_end_min; s += 2) {
+        const int32_t nh = (int32_t)*hp, nr = (int32_t)*rp;
+        ++hp;
+        ++rp;
+        double zl = __shfl_up_sync(kFull, L.B[K - 1], 1);
+        if (lg == 0) zl = C.imp;
+        band_fast_even<K, SYM>(L, C, zl);
+        band_fixup<K, 0>(L, R, T, s);
+        double yr = __shfl_down_sync(kFull, L.A[0], 1);
+        if (lg == kBandGroupLanes - 1) yr = C.imp;
+        band_fast_odd<K, SYM>(L, C, yr, nh, nr);
+        band_fixup<K, 1>(L, R, T, s + 1);
+      }
 #pragma unroll 1
       for (; s + 1 < s_end_min; s += 2) {
         const int32_t nh = (int32_t)*hp, nr = (int32_t)*rp;  // consumed after both steps
@@ -234,7 +252,7 @@ static BandKernel band_kernel_for(int k, bool sym) {
   }
 }
 
-static size_t band_block_smem(int k) { return (size_t)(kBandBlockThreads / 32) * 4 * k * 32 * sizeof(double); }
+static size_t band_block_smem(int k) { return (size_t)(kBandBlockThreads / 32) * 6 * k * 32 * sizeof(double); }
 
 int band_block_threads() { return kBandBlockThreads; }
 

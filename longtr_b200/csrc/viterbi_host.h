@@ -112,9 +112,10 @@ inline BandPolicy band_policy(const ltr_params& p, int band_w) {
   if (b.gap.open < b.gap.ext) b.gap.open = b.gap.ext;
   if (!(b.gap.ext >= 0.05)) return b;
   // automatic margin: the band must be certifiable for a path that pays, beyond the gap the length difference forces
-  // (open + |de| ext), about 27 log units of errors (three mismatches, or two more indels):
-  //   2 open + (|de| + 2w - 1) ext >= open + |de| ext + 27   <=>   w >= ((27 - open) / ext + 1) / 2
-  const int w_auto = std::max(2, (int)std::ceil(((27.0 - b.gap.open) / b.gap.ext + 1.0) / 2.0));
+  // (open + |de| ext), about 23 log units of errors (two mismatches and a bit, or two more indels):
+  //   2 open + (|de| + 2w - 1) ext >= open + |de| ext + 23   <=>   w >= ((23 - open) / ext + 1) / 2
+  // (config 3 on a B200: margins of 4 / 7 / 9 / 12 diagonals give 1.89 / 1.84 / 1.78 / 1.60 M loci/s -- flat; 7 it is)
+  const int w_auto = std::max(2, (int)std::ceil(((23.0 - b.gap.open) / b.gap.ext + 1.0) / 2.0));
   b.w_need = band_w > 0 ? band_w : w_auto;
   b.on = true;
   return b;

@@ -127,9 +127,10 @@ static void emu_dispatch(int k, const VitConsts& C, const DevBatch& B, const Tas
 
 // ---- band kernel (band_core.cuh): one round = four pairs in lock step, eight lanes per pair --------------------------
 struct EmuTable {
-  const double* t;  // [2K][2]
-  double x(int q) const { return t[2 * q]; }
-  double v(int q) const { return t[2 * q + 1]; }
+  const double* t;  // [2K][3]
+  double x(int q) const { return t[3 * q]; }
+  double y(int q) const { return t[3 * q + 1]; }
+  double z(int q) const { return t[3 * q + 2]; }
 };
 
 template <int K, bool SYM>
@@ -138,7 +139,7 @@ static void emu_band_round(const VitConsts& C, const DevBatch& B, const uint32_t
   constexpr int W = 16 * K, G = kBandGroupLanes;
   BandPair R[4][G];
   BandLane<K> L[4][G];
-  double tab[4][G][4 * K];
+  double tab[4][G][6 * K];
   BandGeom geo[4];
   bool active[4];
   double* out[4];
@@ -160,7 +161,7 @@ static void emu_band_round(const VitConsts& C, const DevBatch& B, const uint32_t
       R[g][t].hap = B.hap_bytes + hoff + C.cut;
       R[g][t].read = B.read_bytes + qb;
       R[g][t].d0 = geo[g].dlo + 2 * K * t;
-      for (int q = 0; q < 2 * K; ++q) band_boundary(C, R[g][t], R[g][t].d0 + q, tab[g][t][2 * q], tab[g][t][2 * q + 1]);
+      for (int q = 0; q < 2 * K; ++q) band_boundary(C, R[g][t], R[g][t].d0 + q, tab[g][t][3 * q], tab[g][t][3 * q + 1], tab[g][t][3 * q + 2]);
       band_lane_reset<K>(L[g][t], C);
     }
     s_pro = std::max(s_pro, band_prologue_steps(geo[g].dlo, W));
@@ -186,8 +187,7 @@ static void emu_band_round(const VitConsts& C, const DevBatch& B, const uint32_t
     }
     ++s;
   };
-  while (s < s_pro && s <= s_end_max) general();
-  if (s + 1 < s_end_min) {
+  if (s + 1 < s_end_min) {  // same schedule as viterbi_band_kernel: plain double steps, fix-ups during the prologue
     int32_t hi[4][G], ri[4][G];
     for (int g = 0; g < 4; ++g)
       for (int t = 0; t < G; ++t) {
@@ -196,18 +196,26 @@ static void emu_band_round(const VitConsts& C, const DevBatch& B, const uint32_t
         ri[g][t] = ((s + R[g][t].d0) >> 1) + K + 1;
       }
     for (; s + 1 < s_end_min; s += 2) {
+      const bool prologue = s < s_pro;
       for (int g = 0; g < 4; ++g) {
         double nb[G];
         int32_t nh[G], nr[G];
         for (int t = 0; t < G; ++t) {
-          // the device reads up to ~W/2 + K bytes past the strings (padded buffers); values only reach cells outside the matrix
+          // the device reads up to ~W/2 + K bytes past and up to W/2 bytes in front of the strings (padded buffers);
+          // those values only reach cells outside the matrix
           nh[t] = (int32_t)R[g][t].hap[hi[g][t]++];
           nr[t] = (int32_t)R[g][t].read[ri[g][t]++];
           nb[t] = (t == 0) ? C.imp : L[g][t - 1].B[K - 1];
         }
-        for (int t = 0; t < G; ++t) band_fast_even<K, SYM>(L[g][t], C, nb[t]);
+        for (int t = 0; t < G; ++t) {
+          band_fast_even<K, SYM>(L[g][t], C, nb[t]);
+          if (prologue) band_fixup<K, 0>(L[g][t], R[g][t], EmuTable{tab[g][t]}, s);
+        }
         for (int t = 0; t < G; ++t) nb[t] = (t == G - 1) ? C.imp : L[g][t + 1].A[0];
-        for (int t = 0; t < G; ++t) band_fast_odd<K, SYM>(L[g][t], C, nb[t], nh[t], nr[t]);
+        for (int t = 0; t < G; ++t) {
+          band_fast_odd<K, SYM>(L[g][t], C, nb[t], nh[t], nr[t]);
+          if (prologue) band_fixup<K, 1>(L[g][t], R[g][t], EmuTable{tab[g][t]}, s + 1);
+        }
       }
     }
   }
@@ -260,21 +268,22 @@ extern "C" int ltr_emu_viterbi_batch_band(const ltr_viterbi_batch* b, const ltr_
   hc.C.tabI = hc.tabI.data();
   hc.C.tabD = hc.tabD.data();
   // the warps see the distinct trimmed reads of each locus (Plan); padded copy: the kernel prefetches one byte ahead
-  std::vector<uint8_t> rbytes(plan.uread_nbytes + 256, 0);
-  if (plan.uread_nbytes) std::memcpy(rbytes.data(), plan.uread_bytes, plan.uread_nbytes);
+  const size_t kPad = 256;  // as the device buffers: readable bytes on both sides of the strings
+  std::vector<uint8_t> rbytes(kPad + plan.uread_nbytes + kPad, 0);
+  if (plan.uread_nbytes) std::memcpy(rbytes.data() + kPad, plan.uread_bytes, plan.uread_nbytes);
   std::vector<double> uniq_ll((size_t)plan.ull_off[b->n_loci] + 1, 123.0);
   DevBatch B;
   B.hap_bytes = b->hap_bytes; B.hap_off = b->hap_off; B.hap_locus = plan.hap_locus.data();
-  B.read_bytes = rbytes.data(); B.read_off = plan.uread_off.data();
+  B.read_bytes = rbytes.data() + kPad; B.read_off = plan.uread_off.data();
   B.locus_hap_begin = b->locus_hap_begin; B.locus_read_begin = plan.locus_uread_begin.data();
   B.ll_off = plan.ull_off.data(); B.out_ll = uniq_ll.data();
   EmuScratch E;
   uint64_t nfall = 0;
   if (!fast_certificate_valid(*p)) use_fast = 0;  // as ltr_job_create does
   // ---- band kernel first; what it cannot certify goes to the stream kernel's task lists (band_collect_kernel) ------
-  std::vector<uint8_t> hbytes((size_t)b->hap_off[b->locus_hap_begin[b->n_loci]] + 256, 0);  // padded like the device copy
-  std::memcpy(hbytes.data(), b->hap_bytes, hbytes.size() - 256);
-  B.hap_bytes = hbytes.data();
+  std::vector<uint8_t> hbytes(kPad + (size_t)b->hap_off[b->locus_hap_begin[b->n_loci]] + kPad, 0);  // padded like the device copy
+  std::memcpy(hbytes.data() + kPad, b->hap_bytes, hbytes.size() - 2 * kPad);
+  B.hap_bytes = hbytes.data() + kPad;
   uint64_t bstats[3] = {plan.n_band_pairs, 0, 0};
   for (int c = 0; c < kBandClasses; ++c) {
     std::vector<std::array<uint32_t, 2>> pairs;
