@@ -480,6 +480,7 @@ def main():
         "config": {"workload": CONFIG_NAME[args.config], "loci_per_gpu": n_loci,
                    "pairs_per_gpu": int(st.n_pairs), "cells_per_gpu": int(st.n_cells),
                    "pairs_aligned_per_gpu": int(st.n_pairs_computed), "cells_evaluated_per_gpu": int(st.n_cells_computed),
+                   "pairs_banded_per_gpu": int(st.n_band_pairs), "pairs_band_uncertified_per_gpu": int(st.n_band_uncertified),
                    "gcups_note": "gcups = reference-defined cells (every pooled read x haplotype) / Viterbi time; "
                                  "roofline.achieved = cells actually evaluated / Viterbi time",
                    "l2": "inputs (%.0f MB) + outputs larger than L2; no flush needed" % (work.input_bytes / 1e6),

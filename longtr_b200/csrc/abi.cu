@@ -49,7 +49,7 @@ struct ltr_job {
   std::vector<ClassState> classes;
   // banded kernel (band_kernel.cu): tasks of all band classes back to back, their pair lists, control words
   struct BandClass {
-    int k = 0;
+    int cls = 0;  // band class index (band_class_k / band_class_g)
     uint32_t task_begin = 0, n_tasks = 0, pair_begin = 0, n_pairs = 0, grid = 0;
   };
   std::vector<BandClass> band_classes;
@@ -174,9 +174,8 @@ int ltr_ctx_create(int device, ltr_ctx** out) {
     }
   }
   for (int c = 0; c < kBandClasses; ++c) {
-    const int k = band_class_k(c);
-    ctx->band_blocks_per_sm[k] = band_blocks_per_sm(k);
-    if (ctx->band_blocks_per_sm[k] <= 0) {
+    ctx->band_blocks_per_sm[c] = band_blocks_per_sm(c);
+    if (ctx->band_blocks_per_sm[c] <= 0) {
       ltr_ctx_destroy(ctx);
       return LTR_ERR_NO_DEVICE;
     }
@@ -372,7 +371,7 @@ int ltr_job_create(ltr_ctx* ctx, const ltr_params* params, const ltr_viterbi_bat
       const std::vector<BandTask>& v = plan.band_tasks[(size_t)c];
       if (v.empty()) continue;
       ltr_job::BandClass bc;
-      bc.k = band_class_k(c);
+      bc.cls = c;
       bc.task_begin = (uint32_t)all.size();
       bc.n_tasks = (uint32_t)v.size();
       bc.pair_begin = (uint32_t)npairs;
@@ -384,9 +383,10 @@ int ltr_job_create(ltr_ctx* ctx, const ltr_params* params, const ltr_viterbi_bat
       if (npairs > 0xFFFFFFF0ull) { ltr_job_destroy(ctx, job); return LTR_ERR_INVALID; }
       bc.n_pairs = (uint32_t)npairs - bc.pair_begin;
       const uint32_t warps_per_block = (uint32_t)band_block_threads() / 32;
-      const uint32_t rounds = (bc.n_pairs + 3) / 4;
+      const uint32_t ppr = 32u / (uint32_t)band_class_g(c);
+      const uint32_t rounds = (bc.n_pairs + ppr - 1) / ppr;
       bc.grid = std::min<uint32_t>((rounds + warps_per_block - 1) / warps_per_block,
-                                   (uint32_t)(ctx->sm_count * ctx->band_blocks_per_sm[bc.k]));
+                                   (uint32_t)(ctx->sm_count * ctx->band_blocks_per_sm[bc.cls]));
       job->band_classes.push_back(bc);
     }
     job->n_band_tasks = (uint32_t)all.size();
@@ -539,7 +539,7 @@ static int run_band_phase(ltr_ctx* ctx, ltr_job* job) {
     A.cells_evaluated = reinterpret_cast<unsigned long long*>(job->band_ctrl.as<char>() + 64);
     A.gap = job->plan.band.gap;
     A.abandon_after = no_abandon ? 0u : 4096u;
-    LTR_CUDA(ctx, launch_band(bc.k, (int)bc.grid, st, job->hc.C, B, A));
+    LTR_CUDA(ctx, launch_band(bc.cls, (int)bc.grid, st, job->hc.C, B, A));
     job->stats.n_launches += 1;
     LTR_CUDA(ctx, cudaEventRecord(ctx->ev_stream[i % kNumStreams], st));
     LTR_CUDA(ctx, cudaStreamWaitEvent(ctx->main_stream, ctx->ev_stream[i % kNumStreams], 0));

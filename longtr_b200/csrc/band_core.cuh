@@ -19,7 +19,8 @@
 //    per-row bail-out (HapAligner.cpp:297-306) cannot fire (viterbi_core.cuh).  Pairs that are not certified are
 //    marked and re-run over the full matrix by viterbi_stream_kernel.  Results are exact either way.
 //
-// Mapping: a group of 8 lanes owns one pair; lane l keeps 2K consecutive diagonals (W = 16 K).  All lanes advance
+// Mapping: a group of G lanes (8, or 4 for the narrowest class) owns one pair; lane l keeps 2K consecutive diagonals
+// (W = 2 K G).  All lanes advance
 // along the anti-diagonals s = i + j in lock step: at step s the lane evaluates its K cells with d = s (mod 2), which
 // are independent of each other (X comes from the same diagonal two steps back, Y from diagonal d+1 and Z from
 // diagonal d-1 one step back), so one double crosses a lane boundary per step (SHFL.UP on even steps, SHFL.DOWN on
@@ -32,15 +33,15 @@
 
 namespace ltr {
 
-static constexpr int kBandGroupLanes = 8;
 static constexpr int kBandMaxK = 8;                  // widest class: W = 128 diagonals
 static constexpr double kBandUncertified = 2.0;      // marker in the LL matrix (log-likelihoods are <= 0)
 
-// Band classes (cells per lane per step); W = 16 * K diagonals.
-LTR_HHD int band_class_k(int c) {
-  return c == 0 ? 2 : c == 1 ? 3 : c == 2 ? 4 : c == 3 ? 6 : 8;
-}
+// Band classes: G lanes per pair, K cells per lane per step, W = 2 K G diagonals.  The narrowest class spreads its 32
+// diagonals over 4 lanes (8 pairs per warp) so that the loop overhead of a double step is shared by 8 cells.
 static constexpr int kBandClasses = 5;
+LTR_HHD int band_class_k(int c) { return c == 0 ? 4 : c == 1 ? 3 : c == 2 ? 4 : c == 3 ? 6 : 8; }
+LTR_HHD int band_class_g(int c) { return c == 0 ? 4 : 8; }
+LTR_HHD int band_class_w(int c) { return 2 * band_class_k(c) * band_class_g(c); }
 
 struct BandGeom {
   int32_t dlo;  // lowest diagonal of the band (even)

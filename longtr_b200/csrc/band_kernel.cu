@@ -28,18 +28,22 @@ struct SmemTable {  // the lane's closed-form boundary cells, [2K][3][32] double
 #ifndef LTR_BAND_MINBLOCKS
 #define LTR_BAND_MINBLOCKS 4
 #endif
-template <int K, bool SYM>
-__global__ void __launch_bounds__(kBandBlockThreads, (K <= 4 ? LTR_BAND_MINBLOCKS : (K <= 6 ? 3 : 2)))
+#ifndef LTR_BAND_MINBLOCKS_G4
+#define LTR_BAND_MINBLOCKS_G4 4
+#endif
+template <int K, int G, bool SYM>
+__global__ void __launch_bounds__(kBandBlockThreads, (G == 4 ? LTR_BAND_MINBLOCKS_G4 : (K <= 4 ? LTR_BAND_MINBLOCKS : (K <= 6 ? 3 : 2))))
 viterbi_band_kernel(const VitConsts C, const DevBatch B, const BandArgs A) {
+  constexpr int PPR = 32 / G;  // pairs per round
   extern __shared__ __align__(16) double band_smem[];
   const int lane = threadIdx.x & 31;
-  const int lg = lane & (kBandGroupLanes - 1);
-  const int grp = lane >> 3;
+  const int lg = lane & (G - 1);
+  const int grp = lane / G;
   double* tb = band_smem + (size_t)(threadIdx.x >> 5) * (6 * K * 32) + lane;
   SmemTable T;
   T.base = tb;
-  constexpr int W = 16 * K;
-  const uint32_t n_rounds = (A.n_pairs + 3u) >> 2;
+  constexpr int W = 2 * K * G;
+  const uint32_t n_rounds = (A.n_pairs + (uint32_t)PPR - 1u) / (uint32_t)PPR;
   while (true) {
     uint32_t round = 0, att = 0, fl = 0;
     if (lane == 0) {
@@ -51,7 +55,7 @@ viterbi_band_kernel(const VitConsts C, const DevBatch B, const BandArgs A) {
     if (round >= n_rounds) break;
     att = __shfl_sync(kFull, att, 0);
     fl = __shfl_sync(kFull, fl, 0);
-    const uint32_t base = round * 4u;
+    const uint32_t base = round * (uint32_t)PPR;
     const bool active = (base + (uint32_t)grp) < A.n_pairs;
     const uint2 pr = A.pairs[active ? base + (uint32_t)grp : base];  // idle groups shadow the round's first pair
     const uint32_t g = pr.x, u = pr.y;
@@ -97,7 +101,7 @@ viterbi_band_kernel(const VitConsts C, const DevBatch B, const BandArgs A) {
   do {                                                                       \
     if (s & 1) {                                                             \
       double yr = __shfl_down_sync(kFull, L.A[0], 1);                        \
-      if (lg == kBandGroupLanes - 1) yr = C.imp;                             \
+      if (lg == G - 1) yr = C.imp;                             \
       band_general_step<K, 1, SYM>(L, C, R, T, s, yr, F, got);                    \
     } else {                                                                 \
       double zl = __shfl_up_sync(kFull, L.B[K - 1], 1);                      \
@@ -123,7 +127,7 @@ viterbi_band_kernel(const VitConsts C, const DevBatch B, const BandArgs A) {
         band_fast_even<K, SYM>(L, C, zl);
         band_fixup<K, 0>(L, R, T, s);
         double yr = __shfl_down_sync(kFull, L.A[0], 1);
-        if (lg == kBandGroupLanes - 1) yr = C.imp;
+        if (lg == G - 1) yr = C.imp;
         band_fast_odd<K, SYM>(L, C, yr, nh, nr);
         band_fixup<K, 1>(L, R, T, s + 1);
       }
@@ -136,7 +140,7 @@ viterbi_band_kernel(const VitConsts C, const DevBatch B, const BandArgs A) {
         if (lg == 0) zl = C.imp;
         band_fast_even<K, SYM>(L, C, zl);
         double yr = __shfl_down_sync(kFull, L.A[0], 1);
-        if (lg == kBandGroupLanes - 1) yr = C.imp;
+        if (lg == G - 1) yr = C.imp;
         band_fast_odd<K, SYM>(L, C, yr, nh, nr);
       }
     }
@@ -241,22 +245,23 @@ __global__ void band_bucket_scan_kernel(const BandCollect S) {
 // ------------------------------------------------------------------------------------------------------------------
 typedef void (*BandKernel)(const VitConsts, const DevBatch, const BandArgs);
 
-static BandKernel band_kernel_for(int k, bool sym) {
-  switch (k) {
-    case 2: return sym ? viterbi_band_kernel<2, true> : viterbi_band_kernel<2, false>;
-    case 3: return sym ? viterbi_band_kernel<3, true> : viterbi_band_kernel<3, false>;
-    case 4: return sym ? viterbi_band_kernel<4, true> : viterbi_band_kernel<4, false>;
-    case 6: return sym ? viterbi_band_kernel<6, true> : viterbi_band_kernel<6, false>;
-    case 8: return sym ? viterbi_band_kernel<8, true> : viterbi_band_kernel<8, false>;
+static BandKernel band_kernel_for(int cls, bool sym) {  // cls: band class index (band_class_k / band_class_g)
+  switch (cls) {
+    case 0: return sym ? viterbi_band_kernel<4, 4, true> : viterbi_band_kernel<4, 4, false>;
+    case 1: return sym ? viterbi_band_kernel<3, 8, true> : viterbi_band_kernel<3, 8, false>;
+    case 2: return sym ? viterbi_band_kernel<4, 8, true> : viterbi_band_kernel<4, 8, false>;
+    case 3: return sym ? viterbi_band_kernel<6, 8, true> : viterbi_band_kernel<6, 8, false>;
+    case 4: return sym ? viterbi_band_kernel<8, 8, true> : viterbi_band_kernel<8, 8, false>;
     default: return nullptr;
   }
 }
 
-static size_t band_block_smem(int k) { return (size_t)(kBandBlockThreads / 32) * 6 * k * 32 * sizeof(double); }
+static size_t band_block_smem(int cls) { return (size_t)(kBandBlockThreads / 32) * 6 * band_class_k(cls) * 32 * sizeof(double); }
 
 int band_block_threads() { return kBandBlockThreads; }
 
-int band_blocks_per_sm(int k) {
+int band_blocks_per_sm(int cls) {
+  const int k = cls;
   BandKernel f = band_kernel_for(k, true), f2 = band_kernel_for(k, false);
   if (!f || !f2) return 0;
   int nb = 0, nb2 = 0;
@@ -265,8 +270,9 @@ int band_blocks_per_sm(int k) {
   return nb < nb2 ? nb : nb2;
 }
 
-cudaError_t launch_band(int k, int grid_blocks, cudaStream_t stream, const VitConsts& C, const DevBatch& B,
+cudaError_t launch_band(int cls, int grid_blocks, cudaStream_t stream, const VitConsts& C, const DevBatch& B,
                         const BandArgs& A) {
+  const int k = cls;
   // symmetric parameters (D2M == I2M, M2I == M2D): two additions per cell fewer, same bits (finish_cell_sym)
   const bool sym = (C.d2m == C.i2m) && (C.m2i == C.m2d);
   BandKernel f = band_kernel_for(k, sym);

@@ -61,7 +61,7 @@ struct ltr_ctx {
   cudaEvent_t ev_stream[ltr::kNumStreams] = {nullptr};
   cudaEvent_t ev_init = nullptr, ev_collect = nullptr;  // band phase ordering (no timing)
   int blocks_per_sm[2][32] = {{0}};
-  int band_blocks_per_sm[16] = {0};  // by cells per lane (band_class_k)
+  int band_blocks_per_sm[16] = {0};  // by band class index
   int band_w = 0;                    // ltr_ctx_set_band: < 0 off, 0 automatic margin, > 0 margin in diagonals
   std::string last_error;
   void* stage = nullptr;  // pinned host staging for the plan's unique read bytes (grow-only)

@@ -17,7 +17,7 @@ cudaError_t launch_viterbi(int k, int mode, int grid_blocks, cudaStream_t stream
                            uint32_t task_cap, uint32_t* cursor, const FailSink& fail, XY* sxy,
                            uint32_t* sb, uint32_t scratch_stride);
 
-// Banded anti-diagonal Viterbi (band_kernel.cu, band_core.cuh): rounds of four pairs per warp.
+// Banded anti-diagonal Viterbi (band_kernel.cu, band_core.cuh): rounds of 32 / G pairs per warp.
 struct BandArgs {
   const uint2* pairs;       // (haplotype, unique read) pairs of one band class, haplotype-major
   uint32_t n_pairs;
@@ -39,8 +39,8 @@ struct BandCollect {        // where band_collect_kernel appends the uncertified
   uint32_t* bucket_fill;    // [17*32] zeroed before the collect
 };
 int band_block_threads();
-int band_blocks_per_sm(int k);
-cudaError_t launch_band(int k, int grid_blocks, cudaStream_t stream, const VitConsts& C, const DevBatch& B,
+int band_blocks_per_sm(int cls);  // cls: band class index (band_core.cuh)
+cudaError_t launch_band(int cls, int grid_blocks, cudaStream_t stream, const VitConsts& C, const DevBatch& B,
                         const BandArgs& A);
 cudaError_t launch_band_expand(const BandTask* tasks, const uint32_t* cum, uint32_t n_tasks, uint2* pairs,
                                cudaStream_t stream);

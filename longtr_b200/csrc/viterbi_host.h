@@ -125,9 +125,9 @@ inline BandPolicy band_policy(const ltr_params& p, int band_w) {
 inline int band_class_of(int hlen, int n, int m, const BandPolicy& bp) {
   if (!bp.on || hlen <= 60 || n < 2 || m < 2) return -1;
   for (int c = 0; c < kBandClasses; ++c) {
-    const int K = band_class_k(c);
-    if (band_geometry(n, m, 16 * K).w < bp.w_need) continue;
-    return ((uint64_t)(n + m) * 8u * (uint64_t)K * 100u <= 55ull * (uint64_t)n * (uint64_t)m) ? c : -1;
+    const int W = band_class_w(c);
+    if (band_geometry(n, m, W).w < bp.w_need) continue;
+    return ((uint64_t)(n + m) * (uint64_t)(W / 2) * 100u <= 55ull * (uint64_t)n * (uint64_t)m) ? c : -1;
   }
   return -1;
 }

@@ -133,18 +133,18 @@ struct EmuTable {
   double z(int q) const { return t[3 * q + 2]; }
 };
 
-template <int K, bool SYM>
+template <int K, int G, bool SYM>
 static void emu_band_round(const VitConsts& C, const DevBatch& B, const uint32_t (*pairs)[2], uint32_t n_pairs,
                            uint32_t base, const BandGap& gap, uint64_t* n_uncert) {
-  constexpr int W = 16 * K, G = kBandGroupLanes;
-  BandPair R[4][G];
-  BandLane<K> L[4][G];
-  double tab[4][G][6 * K];
-  BandGeom geo[4];
-  bool active[4];
-  double* out[4];
+  constexpr int W = 2 * K * G, NG = 32 / G;  // NG pairs per round
+  BandPair R[NG][G];
+  BandLane<K> L[NG][G];
+  double tab[NG][G][6 * K];
+  BandGeom geo[NG];
+  bool active[NG];
+  double* out[NG];
   int32_t s_pro = 0, s_end_min = 0x7FFFFFFF, s_end_max = 0;
-  for (int g = 0; g < 4; ++g) {
+  for (int g = 0; g < NG; ++g) {
     active[g] = base + g < n_pairs;
     const uint32_t pi = active[g] ? base + g : base;
     const uint32_t h = pairs[pi][0], u = pairs[pi][1];
@@ -168,12 +168,12 @@ static void emu_band_round(const VitConsts& C, const DevBatch& B, const uint32_t
     s_end_min = std::min(s_end_min, n + m - 2);
     s_end_max = std::max(s_end_max, n + m - 2);
   }
-  double F[4][G];
-  bool got[4][G];
-  for (int g = 0; g < 4; ++g) for (int t = 0; t < G; ++t) { F[g][t] = C.imp; got[g][t] = false; }
+  double F[NG][G];
+  bool got[NG][G];
+  for (int g = 0; g < NG; ++g) for (int t = 0; t < G; ++t) { F[g][t] = C.imp; got[g][t] = false; }
   int32_t s = 0;
   auto general = [&]() {
-    for (int g = 0; g < 4; ++g) {
+    for (int g = 0; g < NG; ++g) {
       double nb[G];
       for (int t = 0; t < G; ++t) {
         if (s & 1) nb[t] = (t == G - 1) ? C.imp : L[g][t + 1].A[0];
@@ -188,8 +188,8 @@ static void emu_band_round(const VitConsts& C, const DevBatch& B, const uint32_t
     ++s;
   };
   if (s + 1 < s_end_min) {  // same schedule as viterbi_band_kernel: plain double steps, fix-ups during the prologue
-    int32_t hi[4][G], ri[4][G];
-    for (int g = 0; g < 4; ++g)
+    int32_t hi[NG][G], ri[NG][G];
+    for (int g = 0; g < NG; ++g)
       for (int t = 0; t < G; ++t) {
         band_windows_init<K>(L[g][t], R[g][t], s);
         hi[g][t] = ((s - R[g][t].d0) >> 1) + 1;
@@ -197,7 +197,7 @@ static void emu_band_round(const VitConsts& C, const DevBatch& B, const uint32_t
       }
     for (; s + 1 < s_end_min; s += 2) {
       const bool prologue = s < s_pro;
-      for (int g = 0; g < 4; ++g) {
+      for (int g = 0; g < NG; ++g) {
         double nb[G];
         int32_t nh[G], nr[G];
         for (int t = 0; t < G; ++t) {
@@ -220,7 +220,7 @@ static void emu_band_round(const VitConsts& C, const DevBatch& B, const uint32_t
     }
   }
   while (s <= s_end_max) general();
-  for (int g = 0; g < 4; ++g) {
+  for (int g = 0; g < NG; ++g) {
     if (!active[g]) continue;
     int owners = 0;
     for (int t = 0; t < G; ++t) {
@@ -235,17 +235,23 @@ static void emu_band_round(const VitConsts& C, const DevBatch& B, const uint32_t
   }
 }
 
-static void emu_band_dispatch(int k, const VitConsts& C, const DevBatch& B, const uint32_t (*pairs)[2], uint32_t n_pairs,
+static void emu_band_dispatch(int cls, const VitConsts& C, const DevBatch& B, const uint32_t (*pairs)[2], uint32_t n_pairs,
                               uint32_t base, const BandGap& gap, uint64_t* n_uncert) {
   const bool sym = (C.d2m == C.i2m) && (C.m2i == C.m2d);  // as launch_band
-  switch (k) {
-    case 2: if (sym) emu_band_round<2, true>(C, B, pairs, n_pairs, base, gap, n_uncert); else emu_band_round<2, false>(C, B, pairs, n_pairs, base, gap, n_uncert); break;
-    case 3: if (sym) emu_band_round<3, true>(C, B, pairs, n_pairs, base, gap, n_uncert); else emu_band_round<3, false>(C, B, pairs, n_pairs, base, gap, n_uncert); break;
-    case 4: if (sym) emu_band_round<4, true>(C, B, pairs, n_pairs, base, gap, n_uncert); else emu_band_round<4, false>(C, B, pairs, n_pairs, base, gap, n_uncert); break;
-    case 6: if (sym) emu_band_round<6, true>(C, B, pairs, n_pairs, base, gap, n_uncert); else emu_band_round<6, false>(C, B, pairs, n_pairs, base, gap, n_uncert); break;
-    case 8: if (sym) emu_band_round<8, true>(C, B, pairs, n_pairs, base, gap, n_uncert); else emu_band_round<8, false>(C, B, pairs, n_pairs, base, gap, n_uncert); break;
+#define EMU_BAND(KK, GG)                                                                 \
+  do {                                                                                   \
+    if (sym) emu_band_round<KK, GG, true>(C, B, pairs, n_pairs, base, gap, n_uncert);    \
+    else emu_band_round<KK, GG, false>(C, B, pairs, n_pairs, base, gap, n_uncert);       \
+  } while (0)
+  switch (cls) {  // as band_kernel_for
+    case 0: EMU_BAND(4, 4); break;
+    case 1: EMU_BAND(3, 8); break;
+    case 2: EMU_BAND(4, 8); break;
+    case 3: EMU_BAND(6, 8); break;
+    case 4: EMU_BAND(8, 8); break;
     default: std::abort();
   }
+#undef EMU_BAND
 }
 
 extern "C" int ltr_emu_viterbi_batch_band(const ltr_viterbi_batch* b, const ltr_params* p, int kmax, int use_fast,
@@ -290,8 +296,8 @@ extern "C" int ltr_emu_viterbi_batch_band(const ltr_viterbi_batch* b, const ltr_
     for (const BandTask& bt : plan.band_tasks[(size_t)c])
       for (uint32_t r = bt.read_begin; r < bt.read_end; ++r) pairs.push_back({bt.hap, r});
     const uint32_t np = (uint32_t)pairs.size();
-    for (uint32_t base = 0; base < np; base += 4)
-      emu_band_dispatch(band_class_k(c), hc.C, B, reinterpret_cast<const uint32_t(*)[2]>(pairs.data()), np, base,
+    for (uint32_t base = 0; base < np; base += 32u / (uint32_t)band_class_g(c))
+      emu_band_dispatch(c, hc.C, B, reinterpret_cast<const uint32_t(*)[2]>(pairs.data()), np, base,
                         plan.band.gap, &bstats[1]);
     for (const BandTask& bt : plan.band_tasks[(size_t)c]) {  // as band_collect_kernel
       const uint32_t l = plan.hap_locus[bt.hap];
