@@ -69,9 +69,9 @@ static const size_t kBandCtrlAlloc = kBandBucketOff + 3 * kBandBucketWords * siz
 namespace {
 
 // The string buffers (haplotypes, reads) carry kStringPad readable bytes on either side: the stream kernel prefetches one
-// byte ahead, the band kernel's character windows run up to W/2 + K bytes ahead of a string's end and, during the
-// prologue, up to W/2 bytes in front of its start (values that only reach cells outside the matrix).
-static const size_t kStringPad = 256;
+// byte ahead, the band kernel's character windows run up to W/2 + K bytes (W <= 512) ahead of a string's end and,
+// during the prologue, up to W/2 bytes in front of its start (values that only reach cells outside the matrix).
+static const size_t kStringPad = 512;
 
 template <typename T>
 int upload(ltr_ctx* ctx, DeviceBuffer& buf, const T* src, size_t count, size_t pad_bytes, uint64_t* h2d,

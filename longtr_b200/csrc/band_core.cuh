@@ -33,14 +33,15 @@
 
 namespace ltr {
 
-static constexpr int kBandMaxK = 8;                  // widest class: W = 128 diagonals
+static constexpr int kBandMaxK = 8;                  // cells per lane per step of the widest classes
 static constexpr double kBandUncertified = 2.0;      // marker in the LL matrix (log-likelihoods are <= 0)
 
 // Band classes: G lanes per pair, K cells per lane per step, W = 2 K G diagonals.  The narrowest class spreads its 32
 // diagonals over 4 lanes (8 pairs per warp) so that the loop overhead of a double step is shared by 8 cells.
-static constexpr int kBandClasses = 5;
-LTR_HHD int band_class_k(int c) { return c == 0 ? 4 : c == 1 ? 3 : c == 2 ? 4 : c == 3 ? 6 : 8; }
-LTR_HHD int band_class_g(int c) { return c == 0 ? 4 : 8; }
+// The three widest classes give a whole warp to one pair (noisy reads, long repeats: W = 256, 384, 512).
+static constexpr int kBandClasses = 8;
+LTR_HHD int band_class_k(int c) { return c == 0 ? 4 : c == 1 ? 3 : c == 2 ? 4 : c == 3 ? 6 : c == 4 ? 8 : c == 5 ? 4 : c == 6 ? 6 : 8; }
+LTR_HHD int band_class_g(int c) { return c == 0 ? 4 : (c <= 4 ? 8 : 32); }
 LTR_HHD int band_class_w(int c) { return 2 * band_class_k(c) * band_class_g(c); }
 
 struct BandGeom {

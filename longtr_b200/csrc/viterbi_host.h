@@ -100,10 +100,11 @@ struct PodArray {
 struct BandPolicy {
   bool on = false;
   BandGap gap = {0.0, 0.0};  // open = min(|M2D|, |M2I|), ext = min(|D2D|, |I2I|) (open >= ext enforced)
-  int w_need = 0;    // minimum margin (diagonals) a pair's band class must guarantee
+  int w_fixed = 0;           // > 0: margin requested with ltr_ctx_set_band
+  double budget0 = 0.0, budget_per_row = 0.0;  // automatic margin: error budget B(n) = budget0 + n * budget_per_row
 };
-// band_w < 0: banding off; 0: automatic margin; > 0: that many diagonals.  The band certificate needs every transition parameter
-// <= 0 and the same parameter condition as the final-score certificate (the bail-out is certified from F as well).
+// band_w < 0: banding off; 0: automatic margin; > 0: that many diagonals.  The band certificate needs every transition
+// parameter <= 0 and the same parameter condition as the final-score certificate (the bail-out is certified from F as well).
 inline BandPolicy band_policy(const ltr_params& p, int band_w) {
   BandPolicy b;
   if (band_w < 0 || !fast_certificate_valid(p)) return b;
@@ -111,22 +112,36 @@ inline BandPolicy band_policy(const ltr_params& p, int band_w) {
   b.gap.ext = std::min(std::fabs((double)p.del_del), std::fabs((double)p.ins_ins));
   if (b.gap.open < b.gap.ext) b.gap.open = b.gap.ext;
   if (!(b.gap.ext >= 0.05)) return b;
-  // automatic margin: the band must be certifiable for a path that pays, beyond the gap the length difference forces
-  // (open + |de| ext), about 23 log units of errors (two mismatches and a bit, or two more indels):
-  //   2 open + (|de| + 2w - 1) ext >= open + |de| ext + 23   <=>   w >= ((23 - open) / ext + 1) / 2
-  // (config 3 on a B200: margins of 4 / 7 / 9 / 12 diagonals give 1.89 / 1.84 / 1.78 / 1.60 M loci/s -- flat; 7 it is)
-  const int w_auto = std::max(2, (int)std::ceil(((23.0 - b.gap.open) / b.gap.ext + 1.0) / 2.0));
-  b.w_need = band_w > 0 ? band_w : w_auto;
+  // Automatic margin (performance heuristic, results never depend on it): the band must be certifiable for a path that
+  // pays, beyond the gap the length difference forces (open + |de| ext), an error budget B(n):
+  //   2 open + (|de| + 2w - 1) ext >= open + |de| ext + B   <=>   w >= ((B - open) / ext + 1) / 2.
+  // B(n) = 23 log units (two mismatches and a bit; config 3 on a B200: margins of 4 / 7 / 9 / 12 diagonals give
+  // 1.89 / 1.84 / 1.78 / 1.60 M loci/s -- flat; 7 it is) + n * 0.6 * r, where r is the error cost per base the
+  // transition parameters themselves announce: gaps open with probability 1 - exp(M2M) per base and cost about
+  // open + close + ext, and substitutions (cost 9) are assumed as frequent as gaps.  r is 0.002 for the Dindel defaults
+  // and 0.30 for the ONT-like set (config 4: margin ~80 for a 760-base haplotype, the measured optimum is 64-96).
+  const double p_gap = 1.0 - std::exp((double)p.match_match);
+  const double close = std::min(std::fabs((double)p.del_match), std::fabs((double)p.ins_match));
+  b.budget0 = 23.0;
+  b.budget_per_row = 0.6 * p_gap * (b.gap.open + close + b.gap.ext + 9.0);
+  b.w_fixed = band_w > 0 ? band_w : 0;
   b.on = true;
   return b;
+}
+inline int band_margin_needed(const BandPolicy& bp, int n) {
+  if (bp.w_fixed > 0) return bp.w_fixed;
+  const double B = bp.budget0 + bp.budget_per_row * (double)n;
+  const int w = (int)std::ceil(((B - bp.gap.open) / bp.gap.ext + 1.0) / 2.0);
+  return std::max(2, std::min(w, 255));
 }
 // Band class of a pair (index into band_class_k) or -1: not banded (too short, band not narrower than ~half the matrix,
 // length difference beyond the widest class).
 inline int band_class_of(int hlen, int n, int m, const BandPolicy& bp) {
   if (!bp.on || hlen <= 60 || n < 2 || m < 2) return -1;
+  const int w_need = band_margin_needed(bp, n);
   for (int c = 0; c < kBandClasses; ++c) {
     const int W = band_class_w(c);
-    if (band_geometry(n, m, W).w < bp.w_need) continue;
+    if (band_geometry(n, m, W).w < w_need) continue;
     return ((uint64_t)(n + m) * (uint64_t)(W / 2) * 100u <= 55ull * (uint64_t)n * (uint64_t)m) ? c : -1;
   }
   return -1;

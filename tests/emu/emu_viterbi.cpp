@@ -249,6 +249,9 @@ static void emu_band_dispatch(int cls, const VitConsts& C, const DevBatch& B, co
     case 2: EMU_BAND(4, 8); break;
     case 3: EMU_BAND(6, 8); break;
     case 4: EMU_BAND(8, 8); break;
+    case 5: EMU_BAND(4, 32); break;
+    case 6: EMU_BAND(6, 32); break;
+    case 7: EMU_BAND(8, 32); break;
     default: std::abort();
   }
 #undef EMU_BAND
@@ -274,7 +277,7 @@ extern "C" int ltr_emu_viterbi_batch_band(const ltr_viterbi_batch* b, const ltr_
   hc.C.tabI = hc.tabI.data();
   hc.C.tabD = hc.tabD.data();
   // the warps see the distinct trimmed reads of each locus (Plan); padded copy: the kernel prefetches one byte ahead
-  const size_t kPad = 256;  // as the device buffers: readable bytes on both sides of the strings
+  const size_t kPad = 512;  // as the device buffers: readable bytes on both sides of the strings
   std::vector<uint8_t> rbytes(kPad + plan.uread_nbytes + kPad, 0);
   if (plan.uread_nbytes) std::memcpy(rbytes.data() + kPad, plan.uread_bytes, plan.uread_nbytes);
   std::vector<double> uniq_ll((size_t)plan.ull_off[b->n_loci] + 1, 123.0);

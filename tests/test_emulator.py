@@ -116,6 +116,17 @@ def test_band_emulator_matches_oracle(emu, seed, kw, kmax, params, band_w):
         assert stats[0] > 0  # the case does exercise the band kernel
 
 
+@pytest.mark.parametrize("band_w", [70, 110, 150, 0])
+def test_band_wide_classes(emu, band_w):
+    """Whole-warp band classes (W = 256, 384, 512) on long noisy pairs with ONT-like parameters (0 = the automatic
+    margin, which grows with the haplotype length for such parameters)."""
+    b = synth.make_pair_batch(61, n_loci=3, n_lo=500, n_hi=900, reads_hi=3, haps_hi=3, sub=0.02, indel=0.03)
+    want, _ = po.viterbi_batch(b, aln_params=ONT, n_threads=4)
+    out, stats = run_band(emu, b, ONT, 16, band_w)
+    assert np.array_equal(out, want)
+    assert stats[0] > 0
+
+
 @pytest.mark.parametrize("seed", range(12))
 def test_band_certificate_adversarial(emu, seed):
     """Reads whose best alignment leaves a narrow band (block insertions / deletions / duplications of up to 30 bases

@@ -24,7 +24,7 @@ def band_engine(engine):
     (3, dict(n_loci=40, n_lo=200, n_hi=520, reads_hi=4, haps_hi=3), ONT),
     (6, dict(n_loci=6, n_lo=600, n_hi=1100, reads_hi=3, haps_hi=3, sub=0.02, indel=0.03), ONT),
 ])
-@pytest.mark.parametrize("band_w", [-1, 0, 1, 5, 24, 60])
+@pytest.mark.parametrize("band_w", [-1, 0, 1, 5, 24, 60, 110, 180])
 def test_band_bit_exact(band_engine, seed, kw, params, band_w):
     b = synth.make_pair_batch(seed, **kw)
     want, _cells = po.viterbi_batch(b, aln_params=params, n_threads=4)
