@@ -56,7 +56,11 @@
 
 namespace ltr {
 
-enum { MODE_FAST = 0, MODE_FULL = 1 };
+// Kernel modes.  Bit 0: the per-row bail-out is evaluated literally (MODE_FULL) or certified from the final score
+// (MODE_FAST); bit 1 (MODE_SYM): D2M == I2M and M2I == M2D, the cell is evaluated by finish_cell_sym (same bits, two
+// additions fewer).  The launcher picks the SYM variants from the parameters.
+enum { MODE_FAST = 0, MODE_FULL = 1, MODE_SYM = 2 };
+#define LTR_MODE_IS_FULL(MODE) (((MODE) & 1) != 0)
 
 // Parameters shared by every task of a launch (passed by value as a kernel argument).
 struct VitConsts {
@@ -187,8 +191,8 @@ LTR_HD LastCell lane_column(Lane<K>& L, const VitConsts& C, int32_t c, double rx
   for (int r = 0; r < K; ++r) {
     const double I = C.match + yup;
     const double D = L.Z[r];
-    const XYZ o = finish_cell(C, M[r], I, D);
-    if (MODE == MODE_FULL) {
+    const XYZ o = finish_cell_t<(MODE & MODE_SYM) != 0>(C, M[r], I, D);
+    if (LTR_MODE_IS_FULL(MODE)) {
       // literal HapAligner.cpp:297-298: best + (float)(|(n-m)-(i-j)|) * D2D
       const double best = vmax(D, vmax(I, M[r]));
       int32_t ad = d0 - r;
@@ -217,7 +221,7 @@ LTR_HD bool lane_rows_bad(const Lane<K>& L) {
 #pragma unroll
   for (int r = 0; r < K; ++r) {
     if (r < L.nrows) {
-      if (MODE == MODE_FULL) bad |= (L.rowmax[r] < -600.0);
+      if (LTR_MODE_IS_FULL(MODE)) bad |= (L.rowmax[r] < -600.0);
     }
   }
   return bad;
@@ -443,7 +447,7 @@ LTR_HD void lane_stream_step(LaneStream<K>& S, const VitConsts& C, const StripCt
     for (int r = 0; r < K; ++r) {
       L.X[r] = T.tx[(v * K + r) * 32 + lane];
       L.Z[r] = T.tz[(v * K + r) * 32 + lane];
-      if (MODE == MODE_FULL) L.rowmax[r] = C.imp;
+      if (LTR_MODE_IS_FULL(MODE)) L.rowmax[r] = C.imp;
     }
     L.Xout = T.txo[v * 32 + lane];
     L.Yout = C.imp;  // Y(.,0) is never consumed: column 0 is not produced by the recurrence
@@ -465,7 +469,7 @@ LTR_HD void lane_stream_step(LaneStream<K>& S, const VitConsts& C, const StripCt
         const int32_t adn = L.dn < 0 ? -L.dn : L.dn;
         if (adn > 600) {
           *dst = -700.0;                       // HapAligner.cpp:249-252
-        } else if (MODE == MODE_FULL) {
+        } else if (LTR_MODE_IS_FULL(MODE)) {
           *dst = bad ? -700.0 : vmax(last.D, vmax(last.I, last.M));      // HapAligner.cpp:300-309
         } else {
           const double F = vmax(last.D, vmax(last.I, last.M));

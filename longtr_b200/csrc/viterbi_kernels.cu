@@ -189,6 +189,16 @@ static VitKernel kernel_for(int k) {
   }
 }
 
+static VitKernel kernel_for_mode(int k, int mode) {
+  switch (mode) {
+    case MODE_FAST: return kernel_for<MODE_FAST>(k);
+    case MODE_FULL: return kernel_for<MODE_FULL>(k);
+    case MODE_FAST | MODE_SYM: return kernel_for<MODE_FAST | MODE_SYM>(k);
+    case MODE_FULL | MODE_SYM: return kernel_for<MODE_FULL | MODE_SYM>(k);
+    default: return nullptr;
+  }
+}
+
 int viterbi_max_rows_per_lane() { return 16; }
 
 int viterbi_block_threads() { return kBlockThreads; }
@@ -196,13 +206,18 @@ int viterbi_block_threads() { return kBlockThreads; }
 static size_t block_smem_bytes(int k) { return (size_t)(kBlockThreads / 32) * warp_smem_bytes(k); }
 
 int viterbi_blocks_per_sm(int k, int mode) {
-  VitKernel f = (mode == MODE_FAST) ? kernel_for<MODE_FAST>(k) : kernel_for<MODE_FULL>(k);
-  if (!f) return 0;
-  const size_t smem = block_smem_bytes(k);
-  if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
-  int nb = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f, kBlockThreads, smem) != cudaSuccess) return 0;
-  return nb;
+  // the smaller of the general and the symmetric-parameter instance (the launcher picks one from the parameters)
+  int best = 1 << 30;
+  for (int sym = 0; sym < 2; ++sym) {
+    VitKernel f = kernel_for_mode(k, mode | (sym ? MODE_SYM : 0));
+    if (!f) return 0;
+    const size_t smem = block_smem_bytes(k);
+    if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f, kBlockThreads, smem) != cudaSuccess) return 0;
+    best = nb < best ? nb : best;
+  }
+  return best;
 }
 
 // Scratch entries a warp needs for a stream of q bytes (window prefetch reads ahead of the stream).
@@ -212,7 +227,9 @@ cudaError_t launch_viterbi(int k, int mode, int grid_blocks, cudaStream_t stream
                            const DevBatch& B, const Task* tasks, const uint32_t* ntasks_ptr,
                            uint32_t task_cap, uint32_t* cursor, const FailSink& fail, XY* sxy,
                            uint32_t* sb, uint32_t scratch_stride) {
-  VitKernel f = (mode == MODE_FAST) ? kernel_for<MODE_FAST>(k) : kernel_for<MODE_FULL>(k);
+  // symmetric parameters (D2M == I2M, M2I == M2D): two additions per cell fewer, same bits (finish_cell_sym)
+  const bool sym = (C.d2m == C.i2m) && (C.m2i == C.m2d);
+  VitKernel f = kernel_for_mode(k, mode | (sym ? MODE_SYM : 0));
   if (!f) return cudaErrorInvalidValue;
   f<<<grid_blocks, kBlockThreads, block_smem_bytes(k), stream>>>(C, B, tasks, ntasks_ptr, task_cap, cursor,
                                                                  fail, sxy, sb, scratch_stride);

@@ -323,19 +323,23 @@ extern "C" int ltr_emu_viterbi_batch_band(const ltr_viterbi_batch* b, const ltr_
     }
   }
   if (band_stats) std::memcpy(band_stats, bstats, sizeof(bstats));
+  const bool sym = (hc.C.d2m == hc.C.i2m) && (hc.C.m2i == hc.C.m2d);  // as launch_viterbi
   for (int k = 1; k <= kmax; ++k) {
     std::vector<Task> fails(plan.n_pairs + 1);
     uint32_t nfail = 0;
     FailSink sink;
     sink.items = fails.data(); sink.count = &nfail; sink.capacity = (uint32_t)fails.size();
     for (const Task& T : plan.tasks[k]) {
-      if (use_fast) emu_dispatch<MODE_FAST>(k, hc.C, B, T, sink, E);
-      else emu_dispatch<MODE_FULL>(k, hc.C, B, T, sink, E);
+      if (use_fast) { if (sym) emu_dispatch<MODE_FAST | MODE_SYM>(k, hc.C, B, T, sink, E); else emu_dispatch<MODE_FAST>(k, hc.C, B, T, sink, E); }
+      else { if (sym) emu_dispatch<MODE_FULL | MODE_SYM>(k, hc.C, B, T, sink, E); else emu_dispatch<MODE_FULL>(k, hc.C, B, T, sink, E); }
     }
     nfall += nfail;
     FailSink none; uint32_t zero = 0;
     none.items = nullptr; none.count = &zero; none.capacity = 0;
-    for (uint32_t f = 0; f < nfail; ++f) emu_dispatch<MODE_FULL>(k, hc.C, B, fails[f], none, E);
+    for (uint32_t f = 0; f < nfail; ++f) {
+      if (sym) emu_dispatch<MODE_FULL | MODE_SYM>(k, hc.C, B, fails[f], none, E);
+      else emu_dispatch<MODE_FULL>(k, hc.C, B, fails[f], none, E);
+    }
   }
   expand_ll_host(*b, plan, uniq_ll.data(), out_ll);
   if (n_fallback) *n_fallback = nfall;
