@@ -447,7 +447,8 @@ def main():
     from concurrent.futures import ThreadPoolExecutor
     slots = [(eng, pin_out)]
     e2e_by_slots = {1: e2e_serial_ms}
-    for n_slots in (2, 3):
+    max_slots = int(os.environ.get("LTR_BENCH_SLOTS", "3"))  # diagnostics: more batches in flight
+    for n_slots in range(2, max_slots + 1):
         e_new = Engine(local)
         pin_new, keep_new = pinned_copy(torch, dict(ll=np.zeros(n_ll), post=np.zeros(max(1, n_post)), tot=np.zeros(max(1, n_tot))))
         slots.append((e_new, pin_new))
@@ -489,7 +490,8 @@ def main():
         "e2e": {"value": total_loci / (e2e_ms * 1e-3), "unit": "loci/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(es.h2d_bytes), "d2h_bytes_per_step": int(es.d2h_bytes),
                 "batches_in_flight": in_flight, "ms_per_step_one_in_flight": e2e_serial_ms,
-                "ms_per_step_two_in_flight": e2e_pipe_ms, "ms_per_step_three_in_flight": e2e_by_slots[3]},
+                "ms_per_step_two_in_flight": e2e_pipe_ms, "ms_per_step_three_in_flight": e2e_by_slots[3],
+                "ms_per_step_by_batches_in_flight": {str(k): v for k, v in e2e_by_slots.items()}},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "fp64_issue", "achieved": achieved, "peak": peak_gcups, "unit": "GCUPS",
