@@ -20,7 +20,8 @@
  *                         loci at once);
  *   ltr_process_reads_flat  HapAligner::process_reads on one flat locus, through the
  *                         host-side mirror of the HapAligner class
- *                         (longtr_b200/csrc/host/), used by bindings and tests.
+ *                         (longtr_b200/csrc/host/), used by bindings and tests;
+ *   ltr_process_reads_flat_batch  the same for many loci in one GPU job.
  */
 #ifndef LONGTR_B200_H_
 #define LONGTR_B200_H_
@@ -186,6 +187,13 @@ void ltr_job_destroy(ltr_ctx* ctx, ltr_job* job);
  * reads / haplotypes that are not realigned are left untouched, as in the reference.   */
 int ltr_process_reads_flat(ltr_ctx* ctx, const ltr_flat_locus* locus, double* out_ll,
                            int32_t* out_seeds);
+/* The same for n_loci flat loci in one call: what a host that keeps many regions open (the pipelined replacement of
+ * the serial loop in src/genotyper_bam_processor.cpp:227-351) hands over.  The long-path loci
+ * that share their alignment parameters become ONE flattened GPU job (one plan, one upload, one set of launches);
+ * loci on the homopolymer path (HapAligner.cpp:552) are processed one by one.  out_ll[l] / out_seeds[l] are locus l's
+ * arrays as in ltr_process_reads_flat; results are identical to n_loci separate calls.                              */
+int ltr_process_reads_flat_batch(ltr_ctx* ctx, int32_t n_loci, const ltr_flat_locus* loci, double* const* out_ll,
+                                 int32_t* const* out_seeds);
 
 /* Genotype calls of one locus from its read x haplotype LL matrix: what SeqStutterGenotyper::genotype +
  * write_vcf_record obtain from Genotyper::calc_log_sample_posteriors (GPU) followed by

@@ -173,6 +173,8 @@ def load():
     lib.ltr_job_destroy.argtypes = [vp, vp]
     lib.ltr_process_reads_flat.argtypes = [vp, C.POINTER(FlatLocus), _dp, _i32p]
     lib.ltr_process_reads_flat.restype = C.c_int
+    lib.ltr_process_reads_flat_batch.argtypes = [vp, C.c_int32, C.POINTER(FlatLocus), C.POINTER(_dp), C.POINTER(_i32p)]
+    lib.ltr_process_reads_flat_batch.restype = C.c_int
     lib.ltr_genotype_locus.argtypes = [vp, C.c_int, C.c_int32, _i32p, C.c_int32, _dp, _dp, _dp, C.POINTER(LocusCalls)]
     lib.ltr_genotype_locus.restype = C.c_int
     lib.ltr_genotype_locus_pruned.argtypes = [vp, C.c_int, C.c_int32, _i32p, C.c_int32, _dp, _dp, _dp, _i32p, _i32p, _i32p,
@@ -196,6 +198,7 @@ EXPORTED_SYMBOLS = [
     "ltr_params_default", "ltr_ctx_create", "ltr_ctx_destroy", "ltr_ctx_set_band", "ltr_strerror", "ltr_last_error",
     "ltr_version", "ltr_viterbi_ll", "ltr_posteriors", "ltr_job_create", "ltr_job_run", "ltr_job_sizes",
     "ltr_job_download", "ltr_job_get_stats", "ltr_job_destroy", "ltr_process_reads_flat",
+    "ltr_process_reads_flat_batch",
     "ltr_fp64_issue_rate", "ltr_genotype_locus", "ltr_extract_calls", "ltr_trim_read_flat", "ltr_seed_base_flat",
     "ltr_stutter_ll", "ltr_genotype_locus_pruned",
 ]

@@ -210,52 +210,66 @@ void HapAligner::process_reads(const std::vector<Alignment>& alignments, int ini
     return;
   }
   // HapAligner.cpp:552: the homopolymer path is chosen per locus, by the period of block 1
-  const RepeatStutterInfo* info = fw_haplotype_->get_block(1)->get_repeat_info();
-  const bool short_path = info != NULL && info->get_period() == 1 && SWITCH_OLD_ALIGN_LEN_ != 0;
-  if (short_path)
+  if (uses_short_path())
     process_reads_short(alignments, init_read_index, base_quality, realign_read, aln_probs, seed_positions);
   else
     process_reads_long(alignments, init_read_index, realign_read, aln_probs, seed_positions);
 }
 
-// Long path (HapAligner.cpp:556-566, 812-854): one GPU batch for the whole locus.
-void HapAligner::process_reads_long(const std::vector<Alignment>& alns, int init_read_index,
-                                    const std::vector<bool>& realign_read, double* aln_probs, int* seed_positions) {
-  const int ncombs = fw_haplotype_->num_combs();
+bool HapAligner::uses_short_path() const {
+  const RepeatStutterInfo* info = fw_haplotype_->get_block(1)->get_repeat_info();
+  return info != NULL && info->get_period() == 1 && SWITCH_OLD_ALIGN_LEN_ != 0;
+}
+
+void HapAligner::fill_params(ltr_params& p) const {
+  p.ins_ins = model_.LOG_INS_TO_INS;
+  p.ins_match = model_.LOG_INS_TO_MATCH;
+  p.del_del = model_.LOG_DEL_TO_DEL;
+  p.del_match = model_.LOG_DEL_TO_MATCH;
+  p.match_match = model_.LOG_MATCH_TO_MATCH;
+  p.match_ins = model_.LOG_MATCH_TO_INS;
+  p.match_del = model_.LOG_MATCH_TO_DEL;
+  p.indel_flank_len = INDEL_FLANK_LEN_;
+}
+
+// Long path, first half (HapAligner.cpp:556-566, 812-854): the locus' haplotypes and trimmed reads, flattened.
+bool HapAligner::prepare_long(const std::vector<Alignment>& alns, int init_read_index, const std::vector<bool>& realign_read,
+                              int* seed_positions, LongPart& part, std::string& hap_bytes, std::vector<uint32_t>& hap_off,
+                              std::string& read_bytes, std::vector<uint32_t>& read_off) {
+  if (status_ != LTR_OK) return false;
+  if (alns.size() != realign_read.size()) {
+    status_ = LTR_ERR_INVALID;
+    return false;
+  }
   // haplotypes in column order; only the ones flagged for realignment travel to the GPU
-  std::vector<int> hap_cols;
-  std::vector<uint32_t> hap_off(1, 0);
-  std::string hap_bytes;
   fw_haplotype_->reset();
   do {
     const int c = fw_haplotype_->cur_index();
     if (!realign_to_hap_[c]) continue;  // HapAligner.cpp:841-845: slot left untouched
-    hap_cols.push_back(c);
+    part.hap_cols.push_back(c);
     hap_bytes += fw_haplotype_->get_seq();
     hap_off.push_back((uint32_t)hap_bytes.size());
   } while (fw_haplotype_->next());
   fw_haplotype_->reset();
 
-  std::vector<int> read_rows;
-  std::vector<uint32_t> read_off(1, 0);
-  std::string read_bytes, trimmed;
+  std::string trimmed;
   for (size_t i = 0; i < alns.size(); ++i) {
     if (!realign_read[i]) continue;
     if (alns[i].get_sequence().size() != alns[i].get_base_qualities().size() && !alns[i].get_base_qualities().empty()) {
       status_ = LTR_ERR_INVALID;  // the reference asserts (HapAligner.cpp:816)
-      return;
+      return false;
     }
     seed_positions[init_read_index + i] = (int)alns[i].get_sequence().size() - 1;  // HapAligner.cpp:562-563
     if (!trim_alignment(alns[i], trimmed)) {
       status_ = LTR_ERR_INVALID;
-      return;
+      return false;
     }
     if (trimmed.empty()) {  // HapAligner.cpp:820-823: 10 bp pseudo read from the flank blocks
       const std::string& lf = fw_haplotype_->get_first_block()->get_seq(0);
       const std::string& rf = fw_haplotype_->get_last_block()->get_seq(0);
       if (lf.size() < 5 || rf.size() < 5) {
         status_ = LTR_ERR_INVALID;
-        return;
+        return false;
       }
       trimmed = lf.substr(lf.size() - 5, 5) + rf.substr(0, 5);
     }
@@ -263,15 +277,34 @@ void HapAligner::process_reads_long(const std::vector<Alignment>& alns, int init
     if (nul != std::string::npos) trimmed.resize(nul);
     if (trimmed.empty()) {
       status_ = LTR_ERR_INVALID;
-      return;
+      return false;
     }
-    read_rows.push_back((int)i);
+    part.read_rows.push_back((int)i);
     read_bytes += trimmed;
     read_off.push_back((uint32_t)read_bytes.size());
   }
-  if (hap_cols.empty() || read_rows.empty()) return;
+  return true;
+}
 
-  const uint32_t lhb[2] = {0u, (uint32_t)hap_cols.size()}, lrb[2] = {0u, (uint32_t)read_rows.size()};
+// Long path, second half: aln_probs[(init_read_index + read) * num_combs + column] (HapAligner.cpp:549).
+void HapAligner::scatter_long(const LongPart& part, const double* ll, int init_read_index, double* aln_probs) const {
+  const int ncombs = fw_haplotype_->num_combs();
+  for (size_t r = 0; r < part.read_rows.size(); ++r) {
+    double* row = aln_probs + (size_t)(init_read_index + part.read_rows[r]) * ncombs;
+    for (size_t h = 0; h < part.hap_cols.size(); ++h) row[part.hap_cols[h]] = ll[r * part.hap_cols.size() + h];
+  }
+}
+
+// Long path for one locus: one GPU batch for the whole locus.
+void HapAligner::process_reads_long(const std::vector<Alignment>& alns, int init_read_index,
+                                    const std::vector<bool>& realign_read, double* aln_probs, int* seed_positions) {
+  LongPart part;
+  std::vector<uint32_t> hap_off(1, 0), read_off(1, 0);
+  std::string hap_bytes, read_bytes;
+  if (!prepare_long(alns, init_read_index, realign_read, seed_positions, part, hap_bytes, hap_off, read_bytes, read_off))
+    return;
+  if (part.hap_cols.empty() || part.read_rows.empty()) return;
+  const uint32_t lhb[2] = {0u, (uint32_t)part.hap_cols.size()}, lrb[2] = {0u, (uint32_t)part.read_rows.size()};
   ltr_viterbi_batch b;
   b.n_loci = 1;
   b.locus_hap_begin = lhb;
@@ -281,21 +314,11 @@ void HapAligner::process_reads_long(const std::vector<Alignment>& alns, int init
   b.read_off = read_off.data();
   b.read_bytes = reinterpret_cast<const uint8_t*>(read_bytes.data());
   ltr_params p;
-  p.ins_ins = model_.LOG_INS_TO_INS;
-  p.ins_match = model_.LOG_INS_TO_MATCH;
-  p.del_del = model_.LOG_DEL_TO_DEL;
-  p.del_match = model_.LOG_DEL_TO_MATCH;
-  p.match_match = model_.LOG_MATCH_TO_MATCH;
-  p.match_ins = model_.LOG_MATCH_TO_INS;
-  p.match_del = model_.LOG_MATCH_TO_DEL;
-  p.indel_flank_len = INDEL_FLANK_LEN_;
-  std::vector<double> ll(hap_cols.size() * read_rows.size());
+  fill_params(p);
+  std::vector<double> ll(part.hap_cols.size() * part.read_rows.size());
   status_ = ltr_viterbi_ll(ctx_, &p, &b, ll.data(), NULL);
   if (status_ != LTR_OK) return;
-  for (size_t r = 0; r < read_rows.size(); ++r) {
-    double* row = aln_probs + (size_t)(init_read_index + read_rows[r]) * ncombs;
-    for (size_t h = 0; h < hap_cols.size(); ++h) row[hap_cols[h]] = ll[r * hap_cols.size() + h];
-  }
+  scatter_long(part, ll.data(), init_read_index, aln_probs);
 }
 
 }  // namespace ltr

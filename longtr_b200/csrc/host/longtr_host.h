@@ -232,6 +232,21 @@ class HapAligner {
   int status() const { return status_; }
   const AlignmentModel& model() const { return model_; }
 
+  // The long path in two halves, so that many loci can share ONE GPU job (ltr_process_reads_flat_batch):
+  // prepare_long appends the locus' haplotypes (column order, only the ones flagged for realignment) and trimmed
+  // reads to the flattened strings and sets seed_positions like process_reads; scatter_long writes the job's
+  // P x H log-likelihood matrix of the locus into aln_probs.  uses_short_path(): the locus takes the homopolymer
+  // path instead (HapAligner.cpp:552).
+  struct LongPart {
+    std::vector<int> hap_cols, read_rows;
+  };
+  bool uses_short_path() const;
+  bool prepare_long(const std::vector<Alignment>& alns, int init_read_index, const std::vector<bool>& realign_read,
+                    int* seed_positions, LongPart& part, std::string& hap_bytes, std::vector<uint32_t>& hap_off,
+                    std::string& read_bytes, std::vector<uint32_t>& read_off);
+  void scatter_long(const LongPart& part, const double* ll, int init_read_index, double* aln_probs) const;
+  void fill_params(ltr_params& p) const;
+
  private:
   void calc_best_seed_position(int32_t region_start, int32_t region_end, int32_t& best_dist, int32_t& best_pos) const;
   void process_reads_long(const std::vector<Alignment>& alns, int init_read_index, const std::vector<bool>& realign_read,

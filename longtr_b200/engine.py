@@ -193,6 +193,20 @@ class Engine:
         _check(self.lib, self.ctx, rc, "ltr_process_reads_flat")
         return ll, seeds
 
+    def process_reads_flat_batch(self, loci, shapes, fill=0.0):
+        """ltr_process_reads_flat_batch: ``loci`` = list of FlatLocus, ``shapes`` = [(n_reads, n_alleles)];
+        returns ([ll], [seeds]) per locus.  All long-path loci run as ONE GPU job."""
+        n = len(loci)
+        arr = (abi.FlatLocus * max(1, n))(*loci)
+        fills = fill if isinstance(fill, (list, tuple)) else [fill] * n
+        lls = [np.full(sh, f, dtype=np.float64) for sh, f in zip(shapes, fills)]
+        seeds = [np.full(sh[0], -12345, dtype=np.int32) for sh in shapes]
+        ll_ptrs = (abi._dp * max(1, n))(*[abi.ptr(a, abi._dp) for a in lls])
+        seed_ptrs = (abi._i32p * max(1, n))(*[abi.ptr(a, abi._i32p) for a in seeds])
+        rc = self.lib.ltr_process_reads_flat_batch(self.ctx, n, arr, ll_ptrs, seed_ptrs)
+        _check(self.lib, self.ctx, rc, "ltr_process_reads_flat_batch")
+        return lls, seeds
+
     def fp64_issue_rate(self, kind=0):
         rate, ms = C.c_double(0.0), C.c_double(0.0)
         rc = self.lib.ltr_fp64_issue_rate(self.device, kind, C.byref(rate), C.byref(ms))

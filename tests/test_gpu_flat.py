@@ -36,6 +36,41 @@ def test_process_reads_flat_matches_oracle_on_fresh_loci(engine, seed):
     assert np.array_equal(gseeds, wseeds)
 
 
+def test_process_reads_flat_batch_matches_single_calls(engine):
+    """ltr_process_reads_flat_batch: golden long-path cases (several parameter sets, untouched slots), a homopolymer
+    locus on the stutter path and fresh loci in ONE call == the reference's values / the per-locus entry point."""
+    cases = list(LONG_CASES) + [c for c in gu.load("process_reads_short")][:2]
+    loci, keeps, shapes, fills = [], [], [], []
+    for c in cases:
+        L, keep = gu.flat_locus(c)
+        loci.append(L)
+        keeps.append(keep)
+        shapes.append((len(c["reads"]), len(c["alleles"])))
+        fills.append(c.get("fill", 0.0))
+    fresh = []
+    for seed in range(40):
+        loc = synth.make_locus(9100 + seed, n_reads=12, sub=0.01, indel=0.02, ref_len=40 + 11 * seed)
+        L, keep = synth.to_flat(loc)
+        loci.append(L)
+        keeps.append(keep)
+        shapes.append((len(loc["reads"]), len(loc["alleles"])))
+        fills.append(0.0)
+        fresh.append(loc)
+    lls, seeds = engine.process_reads_flat_batch(loci, shapes, fill=fills)
+    for i, c in enumerate(cases):
+        P, H = shapes[i]
+        assert np.array_equal(lls[i], gu.unhex(c["ll"], (P, H))), c["name"]
+        for r in range(P):
+            if c.get("realign_read") is None or c["realign_read"][r]:
+                assert seeds[i][r] == c["seeds"][r]
+    for k in range(len(fresh)):
+        i = len(cases) + k
+        want, wseeds = engine.process_reads_flat(loci[i], *shapes[i])
+        assert np.array_equal(lls[i], want) and np.array_equal(seeds[i], wseeds)
+    empty_ll, empty_seeds = engine.process_reads_flat_batch([], [])
+    assert empty_ll == [] and empty_seeds == []
+
+
 # posteriors: CUDA exp/log vs glibc (<= 1 ulp each) over sums of <= a few hundred terms
 RTOL, ATOL = 1e-12, 1e-10
 

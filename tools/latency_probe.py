@@ -24,3 +24,12 @@ for rep in range(2):
         eng.genotype_locus(ll, p1, p2, [24])
     dt = (time.perf_counter() - t0) / 100
     print("genotype_locus: %.3f ms per locus" % (dt * 1e3), flush=True)
+# the same loci handed over in ONE call (ltr_process_reads_flat_batch): one flattened GPU job for all of them
+many = (loci * 34)[:2000]
+flat = [x[0][0] for x in many]
+shapes = [(x[1], x[2]) for x in many]
+for rep in range(3):
+    t0 = time.perf_counter()
+    eng.process_reads_flat_batch(flat, shapes)
+    dt = (time.perf_counter() - t0) / len(many)
+    print("process_reads_flat_batch (2000 loci per call): %.4f ms per locus (%.0f loci/s)" % (dt * 1e3, 1 / dt), flush=True)
