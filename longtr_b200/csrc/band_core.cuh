@@ -98,7 +98,10 @@ struct BandGap {
 LTR_HD double band_threshold(const VitConsts& C, const BandGap& gap, int32_t n, int32_t m, int32_t w) {
   int32_t de = m - n;
   if (de < 0) de = -de;
-  const double u = -(2.0 * gap.open + gap.ext * (double)(de + 2 * w - 1)) + 1e-3;
+  // rounding allowance: 1e-3 plus the worst case of ~4(n+m) additions on magnitudes <= ~12(n+m) (only matters for
+  // strings of 10^5 bases and more)
+  const double len = (double)n + (double)m;
+  const double u = -(2.0 * gap.open + gap.ext * (double)(de + 2 * w - 1)) + 1e-3 + 1e-14 * len * len;
   return u > C.fast_thr ? u : C.fast_thr;
 }
 

@@ -352,3 +352,9 @@ extern "C" void ltr_emu_band_geometry(int n, int m, int W, int* dlo, int* w, uin
   *w = g.w;
   *cells = band_cells(n, m, W, g.dlo);
 }
+
+// Margin (diagonals) the plan asks of a pair's band class for a haplotype of n rows, or -1 when banding is off.
+extern "C" int ltr_emu_band_margin(const ltr_params* p, int band_w, int n) {
+  const BandPolicy bp = band_policy(*p, band_w);
+  return bp.on ? band_margin_needed(bp, n) : -1;
+}

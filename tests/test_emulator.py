@@ -254,3 +254,21 @@ def test_band_geometry_properties():
         i = np.arange(1, n)[:, None]
         j = np.arange(1, m)[None, :]
         assert cells.value == int(np.sum((j - i >= dlo.value) & (j - i <= dhi)))
+
+
+def test_band_policy_margins(emu):
+    """band_policy / band_margin_needed (viterbi_host.h): off when the certificate's parameter condition fails, explicit
+    margins honoured, automatic margin 7 for the Dindel defaults and growing with the haplotype for ONT-like parameters."""
+    emu.ltr_emu_band_margin.argtypes = [C.POINTER(abi.Params), C.c_int, C.c_int]
+    emu.ltr_emu_band_margin.restype = C.c_int
+    dindel, ont = abi.make_params(None), abi.make_params(ONT)
+    assert emu.ltr_emu_band_margin(C.byref(dindel), -1, 200) == -1            # switched off
+    assert emu.ltr_emu_band_margin(C.byref(dindel), 33, 200) == 33            # explicit
+    assert emu.ltr_emu_band_margin(C.byref(dindel), 0, 200) == 7              # automatic, HiFi-like parameters
+    assert emu.ltr_emu_band_margin(C.byref(dindel), 0, 600) in (7, 8)
+    w300, w760 = emu.ltr_emu_band_margin(C.byref(ont), 0, 300), emu.ltr_emu_band_margin(C.byref(ont), 0, 760)
+    assert 30 <= w300 < w760 and 70 <= w760 <= 90                            # ONT-like: margin follows the expected errors
+    bad = abi.make_params((-1.0, -0.4, -1.0, -0.4, 0.01, -10.0, -10.0))       # a positive parameter: no certificate
+    assert emu.ltr_emu_band_margin(C.byref(bad), 0, 200) == -1
+    odd = abi.make_params(ODD)                                                # |I2I| < |D2D| ... condition of section 4 fails?
+    assert emu.ltr_emu_band_margin(C.byref(odd), 0, 200) in (-1,) + tuple(range(2, 256))
