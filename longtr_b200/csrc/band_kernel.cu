@@ -1,10 +1,11 @@
 // band_kernel.cu -- kernel 1b: banded anti-diagonal Viterbi with an exactness certificate (band_core.cuh).
 //
-// viterbi_band_kernel<K>: persistent warps; a warp takes a round of four consecutive pairs of its band class (one
-// per group of 8 lanes; consecutive pairs share the haplotype and their reads are sorted by length, so the four
-// groups run almost the same number of anti-diagonals) and walks them in lock step: general steps while some band
-// cell is a boundary cell or lies before the matrix, the branch-free double step in between, general steps around
-// the end cells.  FP64 max-plus on the FP64 pipe like viterbi_stream_kernel: 9 DADD + 4 DSETP per cell.
+// viterbi_band_kernel<K, G, SYM>: persistent warps; a warp takes a round of 32 / G consecutive pairs of its band class
+// (one per group of G lanes; consecutive pairs share the haplotype and their reads are sorted by length, so the
+// groups run almost the same number of anti-diagonals) and walks them in lock step: the branch-free double step from
+// the first anti-diagonal on -- followed, during the prologue, by a fix-up that gives the boundary cells of the step
+// their closed forms -- and a general step around the end cells.  FP64 max-plus on the FP64 pipe like
+// viterbi_stream_kernel: 9 DADD + 4 DSETP per cell (7 + 4 for symmetric parameters).
 // band_expand_kernel turns the plan's (haplotype, read range) tasks into the pair list; band_collect_kernel turns
 // the pairs the band could not certify into tasks of viterbi_stream_kernel (runs of consecutive reads stay one task).
 #include <cuda_runtime.h>
@@ -263,24 +264,23 @@ static size_t band_block_smem(int cls) { return (size_t)(kBandBlockThreads / 32)
 
 int band_block_threads() { return kBandBlockThreads; }
 
+// Resident CTAs per SM of band class cls: the smaller of the symmetric-parameter and the general instance.
 int band_blocks_per_sm(int cls) {
-  const int k = cls;
-  BandKernel f = band_kernel_for(k, true), f2 = band_kernel_for(k, false);
-  if (!f || !f2) return 0;
-  int nb = 0, nb2 = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, f2, kBandBlockThreads, band_block_smem(k)) != cudaSuccess) return 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f, kBandBlockThreads, band_block_smem(k)) != cudaSuccess) return 0;
-  return nb < nb2 ? nb : nb2;
+  BandKernel f_sym = band_kernel_for(cls, true), f_gen = band_kernel_for(cls, false);
+  if (!f_sym || !f_gen) return 0;
+  int nb_sym = 0, nb_gen = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_gen, f_gen, kBandBlockThreads, band_block_smem(cls)) != cudaSuccess) return 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_sym, f_sym, kBandBlockThreads, band_block_smem(cls)) != cudaSuccess) return 0;
+  return nb_sym < nb_gen ? nb_sym : nb_gen;
 }
 
 cudaError_t launch_band(int cls, int grid_blocks, cudaStream_t stream, const VitConsts& C, const DevBatch& B,
                         const BandArgs& A) {
-  const int k = cls;
   // symmetric parameters (D2M == I2M, M2I == M2D): two additions per cell fewer, same bits (finish_cell_sym)
   const bool sym = (C.d2m == C.i2m) && (C.m2i == C.m2d);
-  BandKernel f = band_kernel_for(k, sym);
+  BandKernel f = band_kernel_for(cls, sym);
   if (!f) return cudaErrorInvalidValue;
-  f<<<grid_blocks, kBandBlockThreads, band_block_smem(k), stream>>>(C, B, A);
+  f<<<grid_blocks, kBandBlockThreads, band_block_smem(cls), stream>>>(C, B, A);
   return cudaGetLastError();
 }
 
