@@ -358,3 +358,80 @@ extern "C" int ltr_emu_band_margin(const ltr_params* p, int band_w, int n) {
   const BandPolicy bp = band_policy(*p, band_w);
   return bp.on ? band_margin_needed(bp, n) : -1;
 }
+
+// Plan invariants (viterbi_host.h) for the CPU tests.  Returns 0 when all hold, otherwise the number of the first
+// violated one:
+//  1 every pooled read maps to a distinct read of its own locus with the same bytes;
+//  2 the distinct reads of a locus are numbered by non-decreasing length and are pairwise different;
+//  3 every (haplotype, distinct read) pair is covered exactly once by the band tasks and the stream tasks together;
+//  4 every pair of a band task has the band class of its list and a certifiable margin; task row classes are right.
+// counts: [0] distinct reads, [1] band pairs, [2] stream pairs.
+extern "C" int ltr_emu_plan_check(const ltr_viterbi_batch* b, const ltr_params* p, int kmax, int band_w, uint64_t* counts) {
+  Plan plan;
+  if (make_plan(*b, *p, kmax, plan, 0, nullptr, nullptr, band_w) != LTR_OK) return -1;
+  const int cut = 35 - p->indel_flank_len;
+  const uint32_t n_loci = b->n_loci;
+  const uint32_t n_reads = b->locus_read_begin[n_loci];
+  for (uint32_t r = 0; r < n_reads; ++r) {
+    const uint32_t l = plan.read_locus[r], u = plan.read_to_uread[r];
+    if (!(b->locus_read_begin[l] <= r && r < b->locus_read_begin[l + 1])) return 1;
+    if (!(plan.locus_uread_begin[l] <= u && u < plan.locus_uread_begin[l + 1])) return 1;
+    const uint32_t len = b->read_off[r + 1] - b->read_off[r];
+    if (plan.uread_off[u + 1] - plan.uread_off[u] != len) return 1;
+    if (std::memcmp(plan.uread_bytes + plan.uread_off[u], b->read_bytes + b->read_off[r], len) != 0) return 1;
+  }
+  for (uint32_t l = 0; l < n_loci; ++l)
+    for (uint32_t u = plan.locus_uread_begin[l]; u + 1 < plan.locus_uread_begin[l + 1]; ++u) {
+      const uint32_t la = plan.uread_off[u + 1] - plan.uread_off[u], lb = plan.uread_off[u + 2] - plan.uread_off[u + 1];
+      if (la > lb) return 2;
+      for (uint32_t v = u + 1; v < plan.locus_uread_begin[l + 1]; ++v) {
+        const uint32_t lv = plan.uread_off[v + 1] - plan.uread_off[v];
+        if (lv != la) break;
+        if (std::memcmp(plan.uread_bytes + plan.uread_off[u], plan.uread_bytes + plan.uread_off[v], la) == 0) return 2;
+      }
+    }
+  const uint32_t n_haps = b->locus_hap_begin[n_loci];
+  std::vector<std::vector<uint8_t> > seen(n_haps);
+  for (uint32_t h = 0; h < n_haps; ++h) {
+    const uint32_t l = plan.hap_locus[h];
+    seen[h].assign(plan.locus_uread_begin[l + 1] - plan.locus_uread_begin[l], 0);
+  }
+  uint64_t band_pairs = 0, stream_pairs = 0;
+  for (int c = 0; c < kBandClasses; ++c)
+    for (const BandTask& t : plan.band_tasks[(size_t)c]) {
+      const uint32_t l = plan.hap_locus[t.hap];
+      const int hlen = (int)(b->hap_off[t.hap + 1] - b->hap_off[t.hap]), n = hlen - 2 * cut;
+      for (uint32_t u = t.read_begin; u < t.read_end; ++u) {
+        if (u < plan.locus_uread_begin[l] || u >= plan.locus_uread_begin[l + 1]) return 3;
+        if (seen[t.hap][u - plan.locus_uread_begin[l]]++) return 3;
+        const int m = (int)(plan.uread_off[u + 1] - plan.uread_off[u]);
+        if (band_class_of(hlen, n, m, plan.band) != c) return 4;
+        if (band_geometry(n, m, band_class_w(c)).w < band_margin_needed(plan.band, n)) return 4;
+        ++band_pairs;
+      }
+    }
+  for (int k = 1; k <= kmax; ++k)
+    for (const Task& t : plan.tasks[(size_t)k]) {
+      const uint32_t l = plan.hap_locus[t.hap];
+      const int hlen = (int)(b->hap_off[t.hap + 1] - b->hap_off[t.hap]), n = hlen - 2 * cut;
+      if (hlen > 60 && n >= 1 && rows_per_lane(n, kmax) != k) return 4;
+      for (uint32_t u = t.read_begin; u < t.read_end; ++u) {
+        if (u < plan.locus_uread_begin[l] || u >= plan.locus_uread_begin[l + 1]) return 3;
+        if (seen[t.hap][u - plan.locus_uread_begin[l]]++) return 3;
+        ++stream_pairs;
+      }
+    }
+  for (uint32_t h = 0; h < n_haps; ++h) {
+    const uint32_t l = plan.hap_locus[h];
+    if (b->locus_read_begin[l + 1] == b->locus_read_begin[l]) continue;
+    for (uint8_t s : seen[h])
+      if (s != 1) return 3;
+  }
+  if (band_pairs != plan.n_band_pairs || band_pairs + stream_pairs != plan.n_pairs_computed) return 3;
+  if (counts) {
+    counts[0] = plan.locus_uread_begin[n_loci];
+    counts[1] = band_pairs;
+    counts[2] = stream_pairs;
+  }
+  return 0;
+}

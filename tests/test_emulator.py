@@ -272,3 +272,37 @@ def test_band_policy_margins(emu):
     assert emu.ltr_emu_band_margin(C.byref(bad), 0, 200) == -1
     odd = abi.make_params(ODD)                                                # |I2I| < |D2D| ... condition of section 4 fails?
     assert emu.ltr_emu_band_margin(C.byref(odd), 0, 200) in (-1,) + tuple(range(2, 256))
+
+
+@pytest.mark.parametrize("seed,kw,kmax,params", CASES)
+@pytest.mark.parametrize("band_w", [-1, 0, 3, 90])
+def test_plan_invariants(emu, seed, kw, kmax, params, band_w):
+    """make_plan (viterbi_host.h): read de-duplication, length order of the distinct reads, and the partition of all
+    (haplotype, distinct read) pairs into band tasks and stream tasks -- each pair exactly once, classes consistent."""
+    emu.ltr_emu_plan_check.argtypes = [C.POINTER(abi.ViterbiBatch), C.POINTER(abi.Params), C.c_int, C.c_int,
+                                       C.POINTER(C.c_uint64)]
+    emu.ltr_emu_plan_check.restype = C.c_int
+    b = synth.make_pair_batch(seed, **kw)
+    # duplicate some reads inside their locus so that the de-duplication has something to do
+    vb, keep = abi.make_viterbi_batch(b)
+    p = abi.make_params(params)
+    counts = (C.c_uint64 * 3)()
+    assert emu.ltr_emu_plan_check(C.byref(vb), C.byref(p), kmax, band_w, counts) == 0
+    if band_w < 0:
+        assert counts[1] == 0
+
+
+def test_plan_invariants_with_duplicate_reads(emu):
+    emu.ltr_emu_plan_check.argtypes = [C.POINTER(abi.ViterbiBatch), C.POINTER(abi.Params), C.c_int, C.c_int,
+                                       C.POINTER(C.c_uint64)]
+    emu.ltr_emu_plan_check.restype = C.c_int
+    from longtr_b200 import workloads
+    w = workloads.generate(3, 150)   # config-3 loci: about half of the pooled reads are duplicates after trimming
+    b, _ = w.subset(150)
+    vb, keep = abi.make_viterbi_batch(b)
+    p = abi.make_params(w.aln_params)
+    counts = (C.c_uint64 * 3)()
+    assert emu.ltr_emu_plan_check(C.byref(vb), C.byref(p), 16, 0, counts) == 0
+    n_reads = int(b["locus_read_begin"][-1])
+    assert counts[0] < 0.8 * n_reads and counts[1] > 10 * counts[2]
+    w.close()
