@@ -36,7 +36,8 @@ struct ClassState {
 
 struct ltr_job {
   ltr_params params;
-  Plan plan;
+  Plan plan;  // its large arrays (unique read bytes, read maps, offsets) live in the context's pinned staging buffers
+              // and are valid during ltr_job_create only; afterwards only the scalars and task lists are used
   HostConsts hc;
   uint32_t n_loci = 0, n_haps = 0, n_reads = 0;
   uint64_t n_ll = 0, n_post = 0, n_tot = 0;
@@ -204,7 +205,8 @@ void ltr_ctx_destroy(ltr_ctx* ctx) {
   if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
   if (ctx->ev_init) cudaEventDestroy(ctx->ev_init);
   if (ctx->ev_collect) cudaEventDestroy(ctx->ev_collect);
-  if (ctx->stage) cudaFreeHost(ctx->stage);
+  for (int i = 0; i < 4; ++i)
+    if (ctx->stage[i]) cudaFreeHost(ctx->stage[i]);
   delete ctx;
 }
 
@@ -244,21 +246,22 @@ int ltr_job_create(ltr_ctx* ctx, const ltr_params* params, const ltr_viterbi_bat
   }
   // unique read bytes are staged in pinned host memory owned by the context (grow-only, reused by the next job)
   struct Stage {
-    static uint8_t* get(size_t bytes, void* user) {
+    static uint8_t* get(size_t bytes, int slot, void* user) {
       ltr_ctx* c = static_cast<ltr_ctx*>(user);
-      if (bytes > c->stage_bytes) {
-        if (c->stage) cudaFreeHost(c->stage);
-        c->stage = nullptr;
-        c->stage_bytes = 0;
+      if (slot < 0 || slot >= 4) return nullptr;
+      if (bytes > c->stage_bytes[slot]) {
+        if (c->stage[slot]) cudaFreeHost(c->stage[slot]);
+        c->stage[slot] = nullptr;
+        c->stage_bytes[slot] = 0;
         const size_t want = bytes + bytes / 4 + (1u << 20);
-        if (cudaHostAlloc(&c->stage, want, cudaHostAllocDefault) != cudaSuccess) {
+        if (cudaHostAlloc(&c->stage[slot], want, cudaHostAllocDefault) != cudaSuccess) {
           cudaGetLastError();
-          c->stage = nullptr;
+          c->stage[slot] = nullptr;
           return nullptr;  // make_plan falls back to pageable memory
         }
-        c->stage_bytes = want;
+        c->stage_bytes[slot] = want;
       }
-      return static_cast<uint8_t*>(c->stage);
+      return static_cast<uint8_t*>(c->stage[slot]);
     }
   };
   static const bool timing = getenv("LTR_TIMING") != nullptr;  // diagnostics: host-side phases of job creation on stderr

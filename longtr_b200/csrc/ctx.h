@@ -64,8 +64,8 @@ struct ltr_ctx {
   int band_blocks_per_sm[16] = {0};  // by band class index
   int band_w = 0;                    // ltr_ctx_set_band: < 0 off, 0 automatic margin, > 0 margin in diagonals
   std::string last_error;
-  void* stage = nullptr;  // pinned host staging for the plan's unique read bytes (grow-only)
-  size_t stage_bytes = 0;
+  void* stage[4] = {nullptr, nullptr, nullptr, nullptr};  // pinned host staging for the plan's large arrays (grow-only)
+  size_t stage_bytes[4] = {0, 0, 0, 0};
 };
 
 namespace ltr {

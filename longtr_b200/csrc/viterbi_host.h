@@ -85,15 +85,17 @@ template <typename T>
 struct PodArray {
   std::unique_ptr<T[]> p;
   size_t n = 0;
-  void resize_uninit(size_t count) {
-    p.reset(new T[count ? count : 1]);
+  T* ext = nullptr;  // caller-provided storage (the C ABI hands out pinned host memory), not owned
+  void resize_uninit(size_t count, void* storage = nullptr) {
+    ext = static_cast<T*>(storage);
+    if (!ext) p.reset(new T[count ? count : 1]);
     n = count;
   }
-  T* data() { return p.get(); }
-  const T* data() const { return p.get(); }
+  T* data() { return ext ? ext : p.get(); }
+  const T* data() const { return ext ? ext : p.get(); }
   size_t size() const { return n; }
-  T& operator[](size_t i) { return p[i]; }
-  const T& operator[](size_t i) const { return p[i]; }
+  T& operator[](size_t i) { return data()[i]; }
+  const T& operator[](size_t i) const { return data()[i]; }
 };
 
 // Banded evaluation (band_core.cuh): which pairs go to the band kernel, and with which band class.
@@ -166,7 +168,7 @@ struct Plan {
   // LongTR pools reads by their +-200 bp sequence (ReadPooler, src/read_pooler.cpp:3-20) but aligns the +-5 bp
   // trim of it (HapAligner.cpp:346-465), so pools that differ only outside the trim window collapse here.
   std::vector<uint32_t> locus_uread_begin;  // [n_loci+1]
-  std::vector<uint32_t> uread_off;          // [n_ureads+1]
+  PodArray<uint32_t> uread_off;             // [n_ureads+1]
   uint8_t* uread_bytes = nullptr;           // uread_nbytes bytes: caller-provided staging (pinned) or uread_owned
   size_t uread_nbytes = 0;
   std::unique_ptr<uint8_t[]> uread_owned;   // uninitialised on purpose: first touched by the parallel copy
@@ -226,8 +228,10 @@ inline bool plan_offsets_valid(const ltr_viterbi_batch& b) {
 
 // Validates the batch, collapses duplicate reads per locus and builds per-class task lists (heaviest first within a
 // class so the persistent warps finish together).  Returns LTR_OK or LTR_ERR_INVALID.
-// stage(bytes, user) may provide the buffer for the unique read bytes (the C ABI hands out pinned host memory).
-typedef uint8_t* (*PlanStageFn)(size_t bytes, void* user);
+// stage(bytes, slot, user) may provide the buffers of the plan's large arrays (the C ABI hands out pinned host memory so
+// that their uploads are asynchronous DMA instead of staged pageable copies); NULL = plain heap memory.
+enum { PLAN_SLOT_UREAD_BYTES = 0, PLAN_SLOT_READ_TO_UREAD = 1, PLAN_SLOT_READ_LOCUS = 2, PLAN_SLOT_UREAD_OFF = 3, PLAN_SLOTS = 4 };
+typedef uint8_t* (*PlanStageFn)(size_t bytes, int slot, void* user);
 inline int make_plan(const ltr_viterbi_batch& b, const ltr_params& p, int kmax, Plan& out, int n_threads = 0,
                      PlanStageFn stage = nullptr, void* stage_user = nullptr, int band_w = -1) {
   const int cut = 35 - p.indel_flank_len;
@@ -251,8 +255,8 @@ inline int make_plan(const ltr_viterbi_batch& b, const ltr_params& p, int kmax, 
   out.ll_off.assign((size_t)n_loci + 1, 0);
   out.ull_off.assign((size_t)n_loci + 1, 0);
   out.locus_uread_begin.assign((size_t)n_loci + 1, 0);
-  out.read_to_uread.resize_uninit(n_reads);
-  out.read_locus.resize_uninit(n_reads);
+  out.read_to_uread.resize_uninit(n_reads, stage ? stage((size_t)n_reads * 4 + 16, PLAN_SLOT_READ_TO_UREAD, stage_user) : nullptr);
+  out.read_locus.resize_uninit(n_reads, stage ? stage((size_t)n_reads * 4 + 16, PLAN_SLOT_READ_LOCUS, stage_user) : nullptr);
   for (uint32_t l = 0; l < n_loci; ++l)
     if (b.locus_hap_begin[l + 1] < b.locus_hap_begin[l] || b.locus_read_begin[l + 1] < b.locus_read_begin[l])
       return LTR_ERR_INVALID;
@@ -339,9 +343,10 @@ inline int make_plan(const ltr_viterbi_batch& b, const ltr_params& p, int kmax, 
   }
   if (ubyte_off[n_loci] > 0xFFFFFFF0ull) return LTR_ERR_INVALID;
   const uint32_t n_ureads = out.locus_uread_begin[n_loci];
-  out.uread_off.resize((size_t)n_ureads + 1);
+  out.uread_off.resize_uninit((size_t)n_ureads + 1,
+                              stage ? stage(((size_t)n_ureads + 1) * 4 + 16, PLAN_SLOT_UREAD_OFF, stage_user) : nullptr);
   out.uread_nbytes = (size_t)ubyte_off[n_loci];
-  out.uread_bytes = stage ? stage(out.uread_nbytes + 16, stage_user) : nullptr;
+  out.uread_bytes = stage ? stage(out.uread_nbytes + 16, PLAN_SLOT_UREAD_BYTES, stage_user) : nullptr;
   if (out.uread_bytes == nullptr) {
     out.uread_owned.reset(new uint8_t[out.uread_nbytes + 16]);
     out.uread_bytes = out.uread_owned.get();
