@@ -98,18 +98,18 @@ viterbi_band_kernel(const VitConsts C, const DevBatch B, const BandArgs A) {
     double F = C.imp;
     bool got = false;
     int32_t s = 0;
-#define LTR_BAND_GENERAL_STEP()                                              \
-  do {                                                                       \
-    if (s & 1) {                                                             \
-      double yr = __shfl_down_sync(kFull, L.A[0], 1);                        \
-      if (lg == G - 1) yr = C.imp;                             \
-      band_general_step<K, 1, SYM>(L, C, R, T, s, yr, F, got);                    \
-    } else {                                                                 \
-      double zl = __shfl_up_sync(kFull, L.B[K - 1], 1);                      \
-      if (lg == 0) zl = C.imp;                                               \
-      band_general_step<K, 0, SYM>(L, C, R, T, s, zl, F, got);                    \
-    }                                                                        \
-    ++s;                                                                     \
+#define LTR_BAND_GENERAL_STEP()                                    \
+  do {                                                             \
+    if (s & 1) {                                                   \
+      double yr = __shfl_down_sync(kFull, L.A[0], 1);              \
+      if (lg == G - 1) yr = C.imp;                                 \
+      band_general_step<K, 1, SYM>(L, C, R, T, s, yr, F, got);     \
+    } else {                                                       \
+      double zl = __shfl_up_sync(kFull, L.B[K - 1], 1);            \
+      if (lg == 0) zl = C.imp;                                     \
+      band_general_step<K, 0, SYM>(L, C, R, T, s, zl, F, got);     \
+    }                                                              \
+    ++s;                                                           \
   } while (0)
     // Prologue and steady state share one loop body: plain double steps on the register windows; during the prologue
     // (s < s_pro) the cells that are boundary cells at the step are then replaced by their closed forms.  The windows of
