@@ -125,6 +125,14 @@ static void emu_dispatch(int k, const VitConsts& C, const DevBatch& B, const Tas
   }
 }
 
+// Study hook (tools only): when set, every banded pair appends (n, m, W, w, F_band, certified).
+static std::vector<double>* g_band_dump = nullptr;
+extern "C" void ltr_emu_band_dump_begin() { delete g_band_dump; g_band_dump = new std::vector<double>(); }
+extern "C" uint64_t ltr_emu_band_dump_size() { return g_band_dump ? g_band_dump->size() / 6 : 0; }
+extern "C" void ltr_emu_band_dump_get(double* out) {
+  if (g_band_dump) std::memcpy(out, g_band_dump->data(), g_band_dump->size() * sizeof(double));
+}
+
 // ---- band kernel (band_core.cuh): one round = four pairs in lock step, eight lanes per pair --------------------------
 struct EmuTable {
   const double* t;  // [2K][3]
@@ -228,6 +236,10 @@ static void emu_band_round(const VitConsts& C, const DevBatch& B, const uint32_t
       ++owners;
       const double thr = band_threshold(C, gap, R[g][t].n, R[g][t].m, geo[g].w);
       const bool ok = F[g][t] > thr;
+      if (g_band_dump) {
+        const double rec[6] = {(double)R[g][t].n, (double)R[g][t].m, (double)W, (double)geo[g].w, F[g][t], ok ? 1.0 : 0.0};
+        g_band_dump->insert(g_band_dump->end(), rec, rec + 6);
+      }
       *out[g] = ok ? F[g][t] : kBandUncertified;
       if (!ok) ++*n_uncert;
     }
