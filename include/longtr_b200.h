@@ -195,6 +195,27 @@ int ltr_process_reads_flat(ltr_ctx* ctx, const ltr_flat_locus* locus, double* ou
 int ltr_process_reads_flat_batch(ltr_ctx* ctx, int32_t n_loci, const ltr_flat_locus* loci, double* const* out_ll,
                                  int32_t* const* out_seeds);
 
+/* ---- many loci in flight for a host that produces loci one at a time ------------------------------------------ */
+/* LongTR's region loop (src/genotyper_bam_processor.cpp:227-351) decodes a region, builds its haplotypes and calls
+ * HapAligner::process_reads before it looks at the next one.  The pipeline lets that loop hand each locus over and carry
+ * on: ltr_pipeline_submit deep-copies the flat locus (the caller may release it at once); loci are collected into
+ * batches of batch_loci and run through ltr_process_reads_flat_batch on `slots` worker threads, each with its own
+ * ltr_ctx on `device`, so that decoding the next regions overlaps the plan / upload / kernels of the previous ones.
+ * Results come back by tag in completion order:
+ *   ltr_pipeline_next returns 1 and the locus' aln_probs (n_reads x n_alleles, slots that are not realigned hold `fill`),
+ *   seed positions and status (LTR_OK or the error of that locus); the pointers stay valid until the next call of
+ *   ltr_pipeline_next / ltr_pipeline_destroy.  It returns 0 when nothing is finished (with wait != 0: when nothing is
+ *   pending either; waiting also sends a partially filled batch on its way).
+ * submit blocks while 2*slots batches are queued (back-pressure).  One producer / consumer thread at a time per call
+ * family is assumed (the functions are internally locked).  No CPU fallback: ltr_pipeline_create fails without a device. */
+typedef struct ltr_pipeline ltr_pipeline;
+int ltr_pipeline_create(int device, int32_t batch_loci, int32_t slots, ltr_pipeline** out);
+int ltr_pipeline_submit(ltr_pipeline* p, const ltr_flat_locus* locus, uint64_t tag, const int32_t* in_seeds, double fill);
+int ltr_pipeline_flush(ltr_pipeline* p);
+int ltr_pipeline_next(ltr_pipeline* p, int wait, uint64_t* tag, int32_t* n_reads, int32_t* n_alleles, const double** ll,
+                      const int32_t** seeds, int* status);
+void ltr_pipeline_destroy(ltr_pipeline* p);
+
 /* Genotype calls of one locus from its read x haplotype LL matrix: what SeqStutterGenotyper::genotype +
  * write_vcf_record obtain from Genotyper::calc_log_sample_posteriors (GPU) followed by
  * Genotyper::extract_genotypes_and_likelihoods (src/genotyper.cpp:132-256; host, integer / small vectors)

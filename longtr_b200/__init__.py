@@ -4,4 +4,4 @@ The package holds only what that path needs: ``csrc/`` (CUDA kernels, the C ABI 
 C++ host mirror of LongTR's HapAligner / Genotyper interfaces) and thin ctypes bindings.
 """
 from .abi import DEFAULT_ALN_PARAMS, EXPORTED_SYMBOLS, LIB_PATH  # noqa: F401
-from .engine import Engine, Job, LongTRError  # noqa: F401
+from .engine import Engine, Job, LongTRError, Pipeline  # noqa: F401

@@ -175,6 +175,17 @@ def load():
     lib.ltr_process_reads_flat.restype = C.c_int
     lib.ltr_process_reads_flat_batch.argtypes = [vp, C.c_int32, C.POINTER(FlatLocus), C.POINTER(_dp), C.POINTER(_i32p)]
     lib.ltr_process_reads_flat_batch.restype = C.c_int
+    lib.ltr_pipeline_create.argtypes = [C.c_int, C.c_int32, C.c_int32, C.POINTER(vp)]
+    lib.ltr_pipeline_create.restype = C.c_int
+    lib.ltr_pipeline_submit.argtypes = [vp, C.POINTER(FlatLocus), C.c_uint64, _i32p, C.c_double]
+    lib.ltr_pipeline_submit.restype = C.c_int
+    lib.ltr_pipeline_flush.argtypes = [vp]
+    lib.ltr_pipeline_flush.restype = C.c_int
+    lib.ltr_pipeline_next.argtypes = [vp, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                      C.POINTER(_dp), C.POINTER(_i32p), C.POINTER(C.c_int)]
+    lib.ltr_pipeline_next.restype = C.c_int
+    lib.ltr_pipeline_destroy.argtypes = [vp]
+    lib.ltr_pipeline_destroy.restype = None
     lib.ltr_genotype_locus.argtypes = [vp, C.c_int, C.c_int32, _i32p, C.c_int32, _dp, _dp, _dp, C.POINTER(LocusCalls)]
     lib.ltr_genotype_locus.restype = C.c_int
     lib.ltr_genotype_locus_pruned.argtypes = [vp, C.c_int, C.c_int32, _i32p, C.c_int32, _dp, _dp, _dp, _i32p, _i32p, _i32p,
@@ -198,7 +209,8 @@ EXPORTED_SYMBOLS = [
     "ltr_params_default", "ltr_ctx_create", "ltr_ctx_destroy", "ltr_ctx_set_band", "ltr_strerror", "ltr_last_error",
     "ltr_version", "ltr_viterbi_ll", "ltr_posteriors", "ltr_job_create", "ltr_job_run", "ltr_job_sizes",
     "ltr_job_download", "ltr_job_get_stats", "ltr_job_destroy", "ltr_process_reads_flat",
-    "ltr_process_reads_flat_batch",
+    "ltr_process_reads_flat_batch", "ltr_pipeline_create", "ltr_pipeline_submit", "ltr_pipeline_flush", "ltr_pipeline_next",
+    "ltr_pipeline_destroy",
     "ltr_fp64_issue_rate", "ltr_genotype_locus", "ltr_extract_calls", "ltr_trim_read_flat", "ltr_seed_base_flat",
     "ltr_stutter_ll", "ltr_genotype_locus_pruned",
 ]

@@ -105,7 +105,7 @@ extern "C" int ltr_process_reads_flat_batch(ltr_ctx* ctx, int32_t n_loci, const 
   std::vector<std::string> hap_bytes((size_t)n_loci), read_bytes((size_t)n_loci);
   std::vector<std::vector<uint32_t> > hap_off((size_t)n_loci), read_off((size_t)n_loci);
   std::vector<ltr_params> params((size_t)n_loci);
-  std::vector<int> state((size_t)n_loci, 0);  // 0 = long path prepared, 1 = short path, 2 = nothing to align, < 0 = error
+  std::vector<int> state((size_t)n_loci, 0);  // 0 = long path prepared, 1 = short path, 2 = nothing to align, < 0 = error code
   // ---- build the reference objects and flatten every locus (host threads) ---------------------------------------
   {
     unsigned n_threads = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
@@ -113,16 +113,16 @@ extern "C" int ltr_process_reads_flat_batch(ltr_ctx* ctx, int32_t n_loci, const 
     if ((unsigned)n_loci < 4 * n_threads) n_threads = 1;
     auto work = [&](int l0, int l1) {
       for (int l = l0; l < l1; ++l) {
-        if (!out_ll[l] || !out_seeds[l]) { state[(size_t)l] = -LTR_ERR_INVALID; continue; }
+        if (!out_ll[l] || !out_seeds[l]) { state[(size_t)l] = LTR_ERR_INVALID; continue; }
         int rc = build_flat_locus(ctx, &loci[l], out_seeds[l], objs[(size_t)l]);
-        if (rc != LTR_OK) { state[(size_t)l] = -rc; continue; }
+        if (rc != LTR_OK) { state[(size_t)l] = rc; continue; }
         HapAligner& al = *objs[(size_t)l].aligner;
         if (al.uses_short_path()) { state[(size_t)l] = 1; continue; }
         hap_off[(size_t)l].assign(1, 0);
         read_off[(size_t)l].assign(1, 0);
         if (!al.prepare_long(objs[(size_t)l].alns, 0, objs[(size_t)l].realign_read, objs[(size_t)l].seeds.data(), parts[(size_t)l],
                              hap_bytes[(size_t)l], hap_off[(size_t)l], read_bytes[(size_t)l], read_off[(size_t)l])) {
-          state[(size_t)l] = -al.status();
+          state[(size_t)l] = al.status() < 0 ? al.status() : LTR_ERR_INVALID;
           continue;
         }
         al.fill_params(params[(size_t)l]);
@@ -142,7 +142,7 @@ extern "C" int ltr_process_reads_flat_batch(ltr_ctx* ctx, int32_t n_loci, const 
     }
   }
   for (int l = 0; l < n_loci; ++l)
-    if (state[(size_t)l] < 0) return -state[(size_t)l];
+    if (state[(size_t)l] < 0) return state[(size_t)l];  // error codes are negative
   // ---- one job per distinct parameter set ------------------------------------------------------------------------
   std::vector<char> done((size_t)n_loci, 0);
   for (int first = 0; first < n_loci; ++first) {

@@ -69,6 +69,51 @@ class Job:
             pass
 
 
+class Pipeline:
+    """``ltr_pipeline``: loci handed over one at a time, processed in batches on worker threads (each with its own
+    context); results come back by tag."""
+
+    def __init__(self, device=0, batch_loci=256, slots=2):
+        self.lib = abi.load()
+        self.h = C.c_void_p()
+        rc = self.lib.ltr_pipeline_create(device, batch_loci, slots, C.byref(self.h))
+        if rc != abi.LTR_OK:
+            self.h = None
+            raise LongTRError("ltr_pipeline_create: %s" % self.lib.ltr_strerror(rc).decode())
+
+    def submit(self, locus, tag, fill=0.0):
+        rc = self.lib.ltr_pipeline_submit(self.h, C.byref(locus), tag, None, fill)
+        if rc != abi.LTR_OK:
+            raise LongTRError("ltr_pipeline_submit: %s" % self.lib.ltr_strerror(rc).decode())
+
+    def flush(self):
+        self.lib.ltr_pipeline_flush(self.h)
+
+    def next(self, wait=True):
+        """(tag, ll[n_reads, n_alleles], seeds, status) of the next finished locus, or None."""
+        tag, nr, na, st = C.c_uint64(), C.c_int32(), C.c_int32(), C.c_int()
+        ll, seeds = abi._dp(), abi._i32p()
+        got = self.lib.ltr_pipeline_next(self.h, 1 if wait else 0, C.byref(tag), C.byref(nr), C.byref(na), C.byref(ll),
+                                         C.byref(seeds), C.byref(st))
+        if got <= 0:
+            return None
+        n = nr.value * na.value
+        a = np.ctypeslib.as_array(ll, (max(1, n),))[:n].reshape(nr.value, na.value).copy()
+        s = np.ctypeslib.as_array(seeds, (max(1, nr.value),))[:nr.value].copy()
+        return tag.value, a, s, st.value
+
+    def close(self):
+        if self.h:
+            self.lib.ltr_pipeline_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Engine:
     """One GPU context. Raises ``LongTRError`` when no CUDA device is usable (no CPU fallback)."""
 

@@ -69,6 +69,12 @@ def test_process_reads_flat_batch_matches_single_calls(engine):
         assert np.array_equal(lls[i], want) and np.array_equal(seeds[i], wseeds)
     empty_ll, empty_seeds = engine.process_reads_flat_batch([], [])
     assert empty_ll == [] and empty_seeds == []
+    # one malformed locus: the call fails as a whole, loudly (the pipeline then retries the loci one by one)
+    from longtr_b200 import LongTRError
+    bad, keep_bad = synth.to_flat(fresh[0])
+    bad.period = 0
+    with pytest.raises(LongTRError):
+        engine.process_reads_flat_batch([loci[-1], bad, loci[-2]], [shapes[-1], shapes[-1], shapes[-2]])
 
 
 # posteriors: CUDA exp/log vs glibc (<= 1 ulp each) over sums of <= a few hundred terms
