@@ -48,6 +48,13 @@ def test_no_cpu_fallback():
     from longtr_b200.engine import LongTRError
     with pytest.raises(LongTRError):
         Engine(0)
+    # the many-loci entry points need a device as well: no worker thread is started without one
+    pipe = C.c_void_p()
+    assert lib.ltr_pipeline_create(0, 64, 2, C.byref(pipe)) == -1 and not pipe.value
+    from longtr_b200 import Pipeline
+    with pytest.raises(LongTRError):
+        Pipeline(0)
+    assert lib.ltr_process_reads_flat_batch(None, 0, None, None, None) == -3  # LTR_ERR_INVALID without a context
 
 
 def test_product_does_not_import_oracle():
