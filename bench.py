@@ -49,18 +49,56 @@ FP64_OPS_PER_CELL_SHORT = 13.0  # flank-row cell of align_seq_to_hap_short: 9 ad
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """Samples SM clocks / throttle reasons during the timed region (B200_PROFILING.md): NVML every 5 ms when the
+    binding is available (the timed region of config 3 is only ~0.2 s long), else `nvidia-smi -lms 100`."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    # nvmlClocksThrottleReason* / nvmlClocksEventReason* bits
+    REASON_BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, index):
         self.index = index
         self.rows = []
         self.proc = None
+        self.nvml = None
+        self.samples = []  # (sm_mhz, reasons bitmask) from NVML
+        self.max_mhz = None
+        self.stop_flag = False
+        self.thread = None
+
+    def _nvml_open(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            self.nvml = (pynvml, h)
+            return True
+        except Exception:
+            self.nvml = None
+            return False
+
+    def _nvml_loop(self):
+        pynvml, h = self.nvml
+        reasons_fn = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(pynvml, "nvmlDeviceGetCurrentClocksThrottleReasons", None)
+        while not self.stop_flag:
+            try:
+                mhz = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                bits = int(reasons_fn(h)) if reasons_fn else 0
+                self.samples.append((mhz, bits))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
+        if self._nvml_open():
+            self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -75,8 +113,18 @@ class ClockSampler:
             self.rows.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            sm = [s[0] for s in self.samples]
+            bits = 0
+            for s in self.samples:
+                bits |= s[1]
+            reasons = sorted(nm for nm, b in self.REASON_BITS.items() if bits & b)
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "samples": len(sm),
+                    "reasons": reasons, "source": "nvml"}
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -97,7 +145,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi"}
 
 
 def dist_setup(n_gpus):
