@@ -187,3 +187,39 @@ def make_pair_batch(seed, n_loci, n_lo=20, n_hi=200, reads_lo=1, reads_hi=6, hap
                 hap_bytes=np.frombuffer("".join(hbytes).encode(), dtype=np.uint8).copy(),
                 read_bytes=np.frombuffer("".join(rbytes).encode(), dtype=np.uint8).copy(),
                 haps=hbytes, reads=rbytes)
+
+
+def make_pathological_batch(seed):
+    """Loci without reads or without haplotypes, haplotypes of 0..62 bases next to 700-base ones, duplicated / one-base /
+    1 500-base reads (kernel-level batch like make_pair_batch)."""
+    rng = np.random.default_rng(99 + seed)
+    lhb, lrb, hoff, roff, hb, rb = [0], [0], [0], [0], [], []
+    for _l in range(int(rng.integers(1, 8))):
+        H, R = int(rng.integers(0, 4)), int(rng.integers(0, 7))
+        n = int(rng.choice([0, 1, 2, 5, 40, 61, 62, 90, 200, 700]))
+        base = rand_seq(rng, n + 60) if n > 0 else rand_seq(rng, int(rng.integers(0, 61)))
+        for _h in range(H):
+            s = base if rng.random() < 0.6 else rand_seq(rng, int(rng.integers(0, 130)))
+            hb.append(s)
+            hoff.append(hoff[-1] + len(s))
+        pool = []
+        for _r in range(R):
+            u = rng.random()
+            if pool and u < 0.4:
+                s = pool[int(rng.integers(0, len(pool)))]
+            elif u < 0.5:
+                s = "A"
+            elif u < 0.6:
+                s = rand_seq(rng, int(rng.integers(700, 1500)))
+            else:
+                core = base[30:30 + max(1, n)] if len(base) > 60 else "ACGT"
+                s = core[:max(1, len(core) - int(rng.integers(0, 5)))] + rand_seq(rng, int(rng.integers(0, 4)))
+            pool.append(s)
+            rb.append(s)
+            roff.append(roff[-1] + len(s))
+        lhb.append(len(hb))
+        lrb.append(len(rb))
+    return dict(locus_hap_begin=np.array(lhb, np.uint32), locus_read_begin=np.array(lrb, np.uint32),
+                hap_off=np.array(hoff, np.uint32), read_off=np.array(roff, np.uint32),
+                hap_bytes=np.frombuffer("".join(hb).encode(), np.uint8).copy() if hb else np.zeros(0, np.uint8),
+                read_bytes=np.frombuffer("".join(rb).encode(), np.uint8).copy() if rb else np.zeros(0, np.uint8))

@@ -315,37 +315,7 @@ def test_pathological_batches(emu, seed):
     emu.ltr_emu_plan_check.argtypes = [C.POINTER(abi.ViterbiBatch), C.POINTER(abi.Params), C.c_int, C.c_int,
                                        C.POINTER(C.c_uint64)]
     emu.ltr_emu_plan_check.restype = C.c_int
-    rng = np.random.default_rng(99 + seed)
-    lhb, lrb, hoff, roff, hb, rb = [0], [0], [0], [0], [], []
-    for _l in range(int(rng.integers(1, 8))):
-        H, R = int(rng.integers(0, 4)), int(rng.integers(0, 7))
-        n = int(rng.choice([0, 1, 2, 5, 40, 61, 62, 90, 200, 700]))
-        base = synth.rand_seq(rng, n + 60) if n > 0 else synth.rand_seq(rng, int(rng.integers(0, 61)))
-        for _h in range(H):
-            s = base if rng.random() < 0.6 else synth.rand_seq(rng, int(rng.integers(0, 130)))
-            hb.append(s)
-            hoff.append(hoff[-1] + len(s))
-        pool = []
-        for _r in range(R):
-            u = rng.random()
-            if pool and u < 0.4:
-                s = pool[int(rng.integers(0, len(pool)))]
-            elif u < 0.5:
-                s = "A"
-            elif u < 0.6:
-                s = synth.rand_seq(rng, int(rng.integers(700, 1500)))
-            else:
-                core = base[30:30 + max(1, n)] if len(base) > 60 else "ACGT"
-                s = core[:max(1, len(core) - int(rng.integers(0, 5)))] + synth.rand_seq(rng, int(rng.integers(0, 4)))
-            pool.append(s)
-            rb.append(s)
-            roff.append(roff[-1] + len(s))
-        lhb.append(len(hb))
-        lrb.append(len(rb))
-    b = dict(locus_hap_begin=np.array(lhb, np.uint32), locus_read_begin=np.array(lrb, np.uint32),
-             hap_off=np.array(hoff, np.uint32), read_off=np.array(roff, np.uint32),
-             hap_bytes=np.frombuffer("".join(hb).encode(), np.uint8).copy() if hb else np.zeros(0, np.uint8),
-             read_bytes=np.frombuffer("".join(rb).encode(), np.uint8).copy() if rb else np.zeros(0, np.uint8))
+    b = synth.make_pathological_batch(seed)
     vb, keep = abi.make_viterbi_batch(b)
     p = abi.make_params(None)
     for band_w in (-1, 0, 3):

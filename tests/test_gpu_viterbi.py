@@ -49,3 +49,12 @@ def test_job_rerun_is_idempotent(engine):
         ll, _, _ = job.download()
         assert np.array_equal(ll, want)
     job.close()
+
+
+@pytest.mark.parametrize("seed", range(15))
+def test_pathological_batches(engine, seed):
+    """Loci without reads or haplotypes, tiny and long haplotypes side by side, duplicated / one-base / huge reads."""
+    b = synth.make_pathological_batch(seed)
+    want, _ = po.viterbi_batch(b)
+    got, st = engine.viterbi_ll(b)
+    assert np.array_equal(got, want)
