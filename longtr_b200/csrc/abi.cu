@@ -288,7 +288,7 @@ int ltr_job_create(ltr_ctx* ctx, const ltr_params* params, const ltr_viterbi_bat
   job->stats.n_cells = plan.n_cells;
   job->stats.n_pairs_computed = plan.n_pairs_computed;
   job->stats.n_cells_computed = plan.n_cells_computed;
-  job->plan_cells_computed = plan.n_cells_computed - plan.n_band_cells;  // stream-kernel pairs of the plan
+  job->plan_cells_computed = plan.n_cells_computed;  // stream-kernel pairs of the plan (banded pairs: counted by the kernel)
   job->stats.n_band_pairs = plan.n_band_pairs;
   make_consts(*params, std::max(plan.max_n, plan.max_m) + 2, job->hc);
 

@@ -33,7 +33,6 @@
 
 namespace ltr {
 
-static constexpr int kBandMaxK = 8;                  // cells per lane per step of the widest classes
 static constexpr double kBandUncertified = 2.0;      // marker in the LL matrix (log-likelihoods are <= 0)
 
 // Band classes: G lanes per pair, K cells per lane per step, W = 2 K G diagonals.  The narrowest class spreads its 32

@@ -153,7 +153,7 @@ struct Plan {
   std::vector<std::vector<BandTask>> band_tasks;  // [kBandClasses] tasks of the band kernel; read ranges index unique reads
   std::vector<uint64_t> band_pairs_by_rows;       // [K] band pairs whose haplotype has row class K (capacity of the
                                                   // stream-kernel tasks band_collect_kernel may append)
-  uint64_t n_band_pairs = 0, n_band_cells = 0;    // pairs sent to the band kernel (n_band_cells: unused, the kernel counts)
+  uint64_t n_band_pairs = 0;                      // pairs sent to the band kernel (their cells are counted by the kernel)
   BandPolicy band;
   std::vector<std::vector<Task>> tasks;  // [K] -> tasks of class K (index 0 unused); read ranges index UNIQUE reads
   PodArray<uint32_t> hap_locus;          // [n_haps]
@@ -387,7 +387,7 @@ inline int make_plan(const ltr_viterbi_batch& b, const ltr_params& p, int kmax, 
     std::vector<uint64_t> band_by_rows;
     std::vector<uint32_t> max_q;
     std::vector<uint8_t> multi;
-    uint64_t n_pairs = 0, n_cells = 0, n_pairs_c = 0, n_cells_c = 0, n_band_pairs = 0, n_band_cells = 0;
+    uint64_t n_pairs = 0, n_cells = 0, n_pairs_c = 0, n_cells_c = 0, n_band_pairs = 0;
     int max_n = 0;
   };
   std::vector<Part> parts((size_t)std::max(1, n_threads));
@@ -485,7 +485,7 @@ inline int make_plan(const ltr_viterbi_batch& b, const ltr_params& p, int kmax, 
     keys.insert(keys.end(), P.keys.begin(), P.keys.end());
     out.n_pairs += P.n_pairs; out.n_cells += P.n_cells;
     out.n_pairs_computed += P.n_pairs_c; out.n_cells_computed += P.n_cells_c;
-    out.n_band_pairs += P.n_band_pairs; out.n_band_cells += P.n_band_cells;
+    out.n_band_pairs += P.n_band_pairs;
     if (!P.band.empty())
       for (int c = 0; c < kBandClasses; ++c)
         out.band_tasks[(size_t)c].insert(out.band_tasks[(size_t)c].end(), P.band[(size_t)c].begin(), P.band[(size_t)c].end());
