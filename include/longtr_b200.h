@@ -195,6 +195,21 @@ int ltr_process_reads_flat(ltr_ctx* ctx, const ltr_flat_locus* locus, double* ou
 int ltr_process_reads_flat_batch(ltr_ctx* ctx, int32_t n_loci, const ltr_flat_locus* loci, double* const* out_ll,
                                  int32_t* const* out_seeds);
 
+/* The flattening half of the batch call on its own (host only, no GPU): the haplotypes (column order, only those flagged
+ * for realignment) and trimmed reads (HapAligner::trim_alignment, only those flagged) of n_loci long-path flat loci as
+ * the arrays of an ltr_viterbi_batch, ready for ltr_job_create together with an ltr_posterior_batch of the caller.
+ * hap_col[h] / read_row[r] give the column / row of flattened haplotype h / read r in its locus' aln_probs matrix;
+ * params_out (optional) receives the alignment parameters of the loci (they must all agree).  Loci on the homopolymer
+ * path give LTR_ERR_UNSUPPORTED (ltr_stutter_ll has its own batch form).  Free with ltr_flat_batch_free.            */
+typedef struct ltr_flat_batch {
+  ltr_viterbi_batch vit;
+  const int32_t* hap_col;   /* [n_haps]  */
+  const int32_t* read_row;  /* [n_reads] */
+  uint32_t n_haps, n_reads;
+} ltr_flat_batch;
+int ltr_flatten_loci(int32_t n_loci, const ltr_flat_locus* loci, ltr_params* params_out, ltr_flat_batch** out);
+void ltr_flat_batch_free(ltr_flat_batch* batch);
+
 /* ---- many loci in flight for a host that produces loci one at a time ------------------------------------------ */
 /* LongTR's region loop (src/genotyper_bam_processor.cpp:227-351) decodes a region, builds its haplotypes and calls
  * HapAligner::process_reads before it looks at the next one.  The pipeline lets that loop hand each locus over and carry

@@ -210,7 +210,7 @@ EXPORTED_SYMBOLS = [
     "ltr_version", "ltr_viterbi_ll", "ltr_posteriors", "ltr_job_create", "ltr_job_run", "ltr_job_sizes",
     "ltr_job_download", "ltr_job_get_stats", "ltr_job_destroy", "ltr_process_reads_flat",
     "ltr_process_reads_flat_batch", "ltr_pipeline_create", "ltr_pipeline_submit", "ltr_pipeline_flush", "ltr_pipeline_next",
-    "ltr_pipeline_destroy",
+    "ltr_pipeline_destroy", "ltr_flatten_loci", "ltr_flat_batch_free",
     "ltr_fp64_issue_rate", "ltr_genotype_locus", "ltr_extract_calls", "ltr_trim_read_flat", "ltr_seed_base_flat",
     "ltr_stutter_ll", "ltr_genotype_locus_pruned",
 ]
@@ -242,6 +242,45 @@ def trim_read(locus, read_index):
 
 def seed_base(locus, read_index):
     return load().ltr_seed_base_flat(C.byref(locus), read_index)
+
+
+class FlatBatch(C.Structure):
+    """ltr_flat_batch (include/longtr_b200.h)."""
+    _fields_ = [("vit", ViterbiBatch), ("hap_col", _i32p), ("read_row", _i32p), ("n_haps", C.c_uint32),
+                ("n_reads", C.c_uint32)]
+
+
+def flatten_loci(loci):
+    """ltr_flatten_loci (host only): returns (batch dict as for make_viterbi_batch, hap_col, read_row, aln params)."""
+    lib = load()
+    lib.ltr_flatten_loci.argtypes = [C.c_int32, C.POINTER(FlatLocus), C.POINTER(Params), C.POINTER(C.POINTER(FlatBatch))]
+    lib.ltr_flatten_loci.restype = C.c_int
+    lib.ltr_flat_batch_free.argtypes = [C.POINTER(FlatBatch)]
+    lib.ltr_flat_batch_free.restype = None
+    n = len(loci)
+    arr = (FlatLocus * max(1, n))(*loci)
+    p = Params()
+    h = C.POINTER(FlatBatch)()
+    rc = lib.ltr_flatten_loci(n, arr, C.byref(p), C.byref(h))
+    if rc != LTR_OK:
+        raise RuntimeError("ltr_flatten_loci failed: %d" % rc)
+    fb = h.contents
+    as_arr = np.ctypeslib.as_array
+
+    def take(ptr, count, dtype):
+        return as_arr(ptr, (max(1, count),))[:count].astype(dtype).copy()
+    nh, nr = fb.n_haps, fb.n_reads
+    hap_off = take(fb.vit.hap_off, nh + 1, np.uint32)
+    read_off = take(fb.vit.read_off, nr + 1, np.uint32)
+    batch = dict(locus_hap_begin=take(fb.vit.locus_hap_begin, n + 1, np.uint32),
+                 locus_read_begin=take(fb.vit.locus_read_begin, n + 1, np.uint32), hap_off=hap_off, read_off=read_off,
+                 hap_bytes=take(fb.vit.hap_bytes, int(hap_off[-1]), np.uint8),
+                 read_bytes=take(fb.vit.read_bytes, int(read_off[-1]), np.uint8))
+    hap_col, read_row = take(fb.hap_col, nh, np.int32), take(fb.read_row, nr, np.int32)
+    params = (p.ins_ins, p.ins_match, p.del_del, p.del_match, p.match_match, p.match_ins, p.match_del)
+    flank = p.indel_flank_len
+    lib.ltr_flat_batch_free(h)
+    return batch, hap_col, read_row, params, flank
 
 
 class StutterBatch(C.Structure):

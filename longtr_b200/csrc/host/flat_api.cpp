@@ -196,3 +196,72 @@ extern "C" int ltr_process_reads_flat_batch(ltr_ctx* ctx, int32_t n_loci, const 
   }
   return LTR_OK;
 }
+
+// ---- ltr_flatten_loci: the flattening half of the batch call, on its own (host only, no GPU) ------------------------
+namespace {
+struct FlatBatchOwner {
+  ltr_flat_batch pub;
+  std::vector<uint32_t> lhb, lrb, hoff, roff;
+  std::string hb, rb;
+  std::vector<int32_t> hap_col, read_row;
+};
+}  // namespace
+
+extern "C" int ltr_flatten_loci(int32_t n_loci, const ltr_flat_locus* loci, ltr_params* params_out, ltr_flat_batch** out) {
+  if (!out || n_loci < 0 || (n_loci > 0 && !loci)) return LTR_ERR_INVALID;
+  *out = nullptr;
+  std::unique_ptr<FlatBatchOwner> B(new FlatBatchOwner());
+  B->lhb.assign(1, 0);
+  B->lrb.assign(1, 0);
+  B->hoff.assign(1, 0);
+  B->roff.assign(1, 0);
+  ltr_params first_params;
+  memset(&first_params, 0, sizeof(first_params));
+  for (int l = 0; l < n_loci; ++l) {
+    FlatLocusObjects o;
+    std::vector<int32_t> no_seeds((size_t)std::max(0, loci[l].n_reads), -1);
+    const int rc = build_flat_locus(nullptr, &loci[l], no_seeds.data(), o);
+    if (rc != LTR_OK) return rc;
+    if (o.aligner->uses_short_path()) return LTR_ERR_UNSUPPORTED;  // homopolymer path: ltr_stutter_ll has its own batch form
+    HapAligner::LongPart part;
+    std::vector<uint32_t> hap_off(1, 0), read_off(1, 0);
+    std::string hap_bytes, read_bytes;
+    if (!o.aligner->prepare_long(o.alns, 0, o.realign_read, o.seeds.data(), part, hap_bytes, hap_off, read_bytes, read_off))
+      return o.aligner->status() < 0 ? o.aligner->status() : LTR_ERR_INVALID;
+    ltr_params p;
+    o.aligner->fill_params(p);
+    if (l == 0) first_params = p;
+    else if (!same_params(p, first_params)) return LTR_ERR_UNSUPPORTED;  // one job = one parameter set
+    const uint32_t hbase = (uint32_t)B->hb.size(), rbase = (uint32_t)B->rb.size();
+    if ((uint64_t)hbase + hap_bytes.size() > 0xFFFFFFF0ull || (uint64_t)rbase + read_bytes.size() > 0xFFFFFFF0ull) return LTR_ERR_INVALID;
+    B->hb += hap_bytes;
+    B->rb += read_bytes;
+    for (size_t i = 1; i < hap_off.size(); ++i) B->hoff.push_back(hbase + hap_off[i]);
+    for (size_t i = 1; i < read_off.size(); ++i) B->roff.push_back(rbase + read_off[i]);
+    for (int c : part.hap_cols) B->hap_col.push_back(c);
+    for (int r : part.read_rows) B->read_row.push_back(r);
+    B->lhb.push_back((uint32_t)B->hoff.size() - 1);
+    B->lrb.push_back((uint32_t)B->roff.size() - 1);
+  }
+  if (params_out) {
+    if (n_loci > 0) *params_out = first_params;
+    else ltr_params_default(params_out);
+  }
+  B->pub.vit.n_loci = (uint32_t)n_loci;
+  B->pub.vit.locus_hap_begin = B->lhb.data();
+  B->pub.vit.locus_read_begin = B->lrb.data();
+  B->pub.vit.hap_off = B->hoff.data();
+  B->pub.vit.hap_bytes = reinterpret_cast<const uint8_t*>(B->hb.data());
+  B->pub.vit.read_off = B->roff.data();
+  B->pub.vit.read_bytes = reinterpret_cast<const uint8_t*>(B->rb.data());
+  B->pub.hap_col = B->hap_col.data();
+  B->pub.read_row = B->read_row.data();
+  B->pub.n_haps = (uint32_t)B->hap_col.size();
+  B->pub.n_reads = (uint32_t)B->read_row.size();
+  *out = &B.release()->pub;  // pub is the first member: the owner is recovered from it in ltr_flat_batch_free
+  return LTR_OK;
+}
+
+extern "C" void ltr_flat_batch_free(ltr_flat_batch* b) {
+  if (b) delete reinterpret_cast<FlatBatchOwner*>(b);
+}

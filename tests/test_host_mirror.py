@@ -67,3 +67,43 @@ def test_extract_calls_matches_reference(case):
     for k in ("log_phased_posteriors", "log_unphased_posteriors", "hap_log_phased_posteriors",
               "hap_log_unphased_posteriors", "gls", "phased_gls", "gl_diffs"):
         assert np.array_equal(got[k].ravel(), gu.unhex(case["out_" + k])), k
+
+
+def test_flatten_loci_feeds_the_oracle_to_the_reference_values():
+    """ltr_flatten_loci (host mirror: Haplotype column order, realign masks, trim_alignment, 10 bp pseudo reads) on the
+    golden long-path loci: the oracle's Viterbi on the flattened batch, scattered by hap_col / read_row, reproduces the
+    aln_probs matrices recorded from the unmodified reference bit for bit -- one locus at a time and all loci that share
+    their parameters in one batch."""
+    from longtr_b200 import abi
+    from oracle import pyoracle as po
+    cases = [c for c in gu.load("appendix_a") + gu.load("process_reads_long") if not (c["switch"] != 0 and c["period"] == 1)]
+    assert len(cases) >= 30
+
+    def check(group):
+        loci, keeps = [], []
+        for c in group:
+            L, keep = gu.flat_locus(c)
+            loci.append(L)
+            keeps.append(keep)
+        batch, hap_col, read_row, params, flank = abi.flatten_loci(loci)
+        ll, _ = po.viterbi_batch(batch, aln_params=params, indel_flank_len=flank)
+        pos = 0
+        for i, c in enumerate(group):
+            P, H = len(c["reads"]), len(c["alleles"])
+            h0, h1 = int(batch["locus_hap_begin"][i]), int(batch["locus_hap_begin"][i + 1])
+            r0, r1 = int(batch["locus_read_begin"][i]), int(batch["locus_read_begin"][i + 1])
+            got = np.full((P, H), c.get("fill", 0.0))
+            block = ll[pos:pos + (h1 - h0) * (r1 - r0)].reshape(r1 - r0, h1 - h0)
+            pos += (h1 - h0) * (r1 - r0)
+            for rr in range(r1 - r0):
+                for hh in range(h1 - h0):
+                    got[read_row[r0 + rr], hap_col[h0 + hh]] = block[rr, hh]
+            assert np.array_equal(got, gu.unhex(c["ll"], (P, H))), c["name"]
+
+    for c in cases:
+        check([c])
+    groups = {}
+    for c in cases:
+        groups.setdefault((tuple(c.get("aln_params") or ()), c.get("indel_flank_len", 5)), []).append(c)
+    for g in groups.values():
+        check(g)
