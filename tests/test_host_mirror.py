@@ -107,3 +107,33 @@ def test_flatten_loci_feeds_the_oracle_to_the_reference_values():
         groups.setdefault((tuple(c.get("aln_params") or ()), c.get("indel_flank_len", 5)), []).append(c)
     for g in groups.values():
         check(g)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_flatten_loci_matches_the_oracle_flattening_on_fresh_loci(seed):
+    """Same check against the oracle's own per-locus restatement (trim + haplotype order + Viterbi) on seeded loci with
+    indels near the repeat boundaries, so that trim_alignment's un-trimming rules matter."""
+    from longtr_b200 import abi
+    from oracle import pyoracle as po
+    loci, shapes, keeps = [], [], []
+    for k in range(6):
+        loc = synth.make_locus(20000 + 10 * seed + k, n_reads=10, sub=0.01, indel=0.03, ref_len=30 + 17 * k)
+        L, keep = synth.to_flat(loc)
+        loci.append(L)
+        keeps.append(keep)
+        shapes.append((len(loc["reads"]), len(loc["alleles"])))
+    batch, hap_col, read_row, params, flank = abi.flatten_loci(loci)
+    ll, _ = po.viterbi_batch(batch, aln_params=params, indel_flank_len=flank)
+    pos = 0
+    for i, (P, H) in enumerate(shapes):
+        want, _seeds, _ = po.process_reads(loci[i], P, H)
+        h0, h1 = int(batch["locus_hap_begin"][i]), int(batch["locus_hap_begin"][i + 1])
+        r0, r1 = int(batch["locus_read_begin"][i]), int(batch["locus_read_begin"][i + 1])
+        assert (h1 - h0, r1 - r0) == (H, P)
+        got = np.zeros((P, H))
+        block = ll[pos:pos + H * P].reshape(P, H)
+        pos += H * P
+        for rr in range(P):
+            for hh in range(H):
+                got[read_row[r0 + rr], hap_col[h0 + hh]] = block[rr, hh]
+        assert np.array_equal(got, want)
