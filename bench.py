@@ -9,8 +9,10 @@ the ranks with no data-path collective (weak scaling: every GPU gets --loci loci
   python bench.py [--gpus N] [--steps K] [--warmup W] [--loci L] [--config 3|4]
   python bench.py --impl reference ...     # the reference's own CPU code on the host cores
 
-Prints ONE JSON line (rank 0).  value = loci/s with inputs resident in HBM; e2e = the same through
-the C-ABI one-shot path with host buffers (H2D + kernels + D2H inside the timed region).
+Prints ONE JSON line (rank 0).  value = loci/s with inputs resident in HBM (plan kernels included every step); e2e = the
+same through ltr_job_submit / ltr_job_wait with pinned HOST buffers on ONE host thread (H2D + plan + kernels + D2H inside
+the timed region, up to three jobs in flight).  The default run appends extra.c4 / extra.c5: BASELINE.json configs[3] and
+configs[4] timed the same way.
 """
 import argparse
 import json
@@ -38,6 +40,7 @@ def parse_args():
     ap.add_argument("--loci", type=int, default=0, help="loci per GPU per step (default: config size)")
     ap.add_argument("--cpu-sample-loci", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra.c4 / extra.c5 sub-lines of the default run")
     return ap.parse_args()
 
 
@@ -155,13 +158,9 @@ def dist_setup(n_gpus):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
-    # host threads of ltr_job_create's plan: the ranks of one node and the batches in flight share its cores
-    # (8 measured best with three batches in flight on the 16-core box: profiles/r1r notes)
-    os.environ.setdefault("LTR_PLAN_THREADS", str(max(2, min(8, (os.cpu_count() or 16) // world))))
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the single JSON line (NCCL prints its version banner there)
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
     return torch, rank, world, local
 
@@ -333,17 +332,14 @@ def run_reference_stutter(args):
         "gpu_launches": 0}), flush=True)
 
 
-def run_stutter(args):
+def run_stutter(args, torch, rank, world, local, eng, n_loci, steps, warmup, with_cpu_baseline):
     """--config 5: the homopolymer / --stutter-align-len path (kernel 2) at the process_reads boundary."""
-    torch, rank, world, local = dist_setup(args.gpus)
-    from longtr_b200 import Engine, workloads
-    n_loci = args.loci or CONFIG_LOCI[5]
-    eng = Engine(local)
+    from longtr_b200 import workloads
     fp64_rate = max(eng.fp64_issue_rate(0)[0] for _ in range(2))
     work = workloads.generate_stutter(n_loci, first_locus=rank * n_loci)
     pinned_b, keep_b = pinned_copy(torch, work.batch)
     out = np.zeros(abi_ll_size(work.batch), dtype=np.float64)
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         eng.stutter_ll(pinned_b, out=out)
     sampler = ClockSampler(local)
     barrier(torch, world)
@@ -351,24 +347,24 @@ def run_stutter(args):
         sampler.start()
     t0 = time.perf_counter()
     dev_ms, launches = 0.0, 0
-    for _ in range(args.steps):
+    for _ in range(steps):
         out, st = eng.stutter_ll(pinned_b, out=out)
         dev_ms += st.kernel_ms
         launches += st.n_launches
     barrier(torch, world)
     wall_ms = (time.perf_counter() - t0) * 1e3
     clocks = sampler.stop() if rank == 0 else None
-    step_ms = max_over_ranks(torch, world, dev_ms / args.steps)
-    e2e_ms = max_over_ranks(torch, world, wall_ms / args.steps)
+    step_ms = max_over_ranks(torch, world, dev_ms / steps)
+    e2e_ms = max_over_ranks(torch, world, wall_ms / steps)
     total_loci = sum_over_ranks(torch, world, float(n_loci))
     total_cells = sum_over_ranks(torch, world, float(st.n_cells))
     if rank != 0:
-        return
-    achieved = st.n_cells / (dev_ms / args.steps) / 1e6
+        return None
+    achieved = st.n_cells / (dev_ms / steps) / 1e6
     peak = fp64_rate / FP64_OPS_PER_CELL_SHORT / 1e9
     line = {
         "metric": "loci_per_sec", "value": total_loci / (step_ms * 1e-3), "unit": "loci/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
+        "steps": steps, "warmup": warmup, "ms_per_step": step_ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "gcups": total_cells / (step_ms * 1e-3) / 1e9,
         "config": {"workload": CONFIG_NAME[5], "loci_per_gpu": n_loci, "pairs_per_gpu": int(st.n_pairs),
@@ -384,23 +380,191 @@ def run_stutter(args):
                      "peak_source": "ltr_fp64_issue_rate (DADD lane-ops/s measured in this run) / 13 FP64 ops per "
                                     "flank cell; cell-equivalents as defined in SURVEY.md 8d",
                      "fp64_lane_ops_per_s": fp64_rate}}
-    if world == 1 and not args.no_cpu_baseline:
+    if with_cpu_baseline:
         threads = os.cpu_count() or 1
         n_sample = args.cpu_sample_loci or min(n_loci, 8 * threads)
         kind, wall = cpu_baseline_stutter(work, n_sample, threads)
         line["cpu_baseline"] = {"value": n_sample / wall, "unit": "loci/s", "cores": threads, "kind": kind,
                                 "gcups": work.cells(n_sample) / wall / 1e9,
                                 "sample": "first %d loci of the same workload, all host threads" % n_sample}
-    print(json.dumps(line), flush=True)
-    eng.close()
-    if world > 1:
-        import torch.distributed as dist
-        dist.destroy_process_group()
+    work.close()
+    return line
 
 
 def abi_ll_size(batch):
     from longtr_b200 import abi
     return abi.stutter_ll_size(batch)
+
+
+def bench_sample_parity(work, n_sample, ref_ll, ref_post, ll, post):
+    """The reference's results on the CPU-baseline sample (the first n_sample loci of the timed workload) against what the
+    GPU job produced for the same loci: log-likelihoods bit for bit, posteriors to 1e-12 relative (CUDA exp/log vs libm)."""
+    b, p = work.batch, work.post
+    H = np.diff(b["locus_hap_begin"][:n_sample + 1]).astype(np.int64)
+    n_post = int(np.sum(p["locus_n_samples"][:n_sample].astype(np.int64) * H * H))
+    out = {"loci": int(n_sample), "pairs": int(len(ref_ll)),
+           "ll_bit_exact": bool(np.array_equal(ref_ll, ll[:len(ref_ll)]))}
+    if ref_post is not None and post is not None and n_post == len(ref_post):
+        g = post[:n_post]
+        ok = np.isfinite(ref_post) & (np.abs(ref_post) > 1e-300)
+        rel = float(np.max(np.abs(g[ok] - ref_post[ok]) / np.abs(ref_post[ok]))) if ok.any() else 0.0
+        out["post_max_rel_err"] = rel
+        out["post_within_1e-12"] = bool(rel <= 1e-12)
+    return out
+
+
+def measure_long(args, config, n_loci, steps, warmup, torch, rank, world, local, eng, peak_gcups, fp64_rate,
+                 with_cpu_baseline):
+    """Configs 3 / 4 (long path): resident arm (value), asynchronous end-to-end arm (e2e), roofline, CPU baseline."""
+    import collections
+    from longtr_b200 import abi, workloads
+    work = workloads.generate(config, n_loci, first_locus=rank * n_loci)
+    pinned_b, keep_b = pinned_copy(torch, work.batch)
+    pinned_p, keep_p = pinned_copy(torch, work.post)
+    job = eng.create_job(pinned_b, pinned_p, aln_params=work.aln_params)
+
+    # ---- resident arm: inputs in HBM; every step = plan kernels + Viterbi kernels + fan-out + posteriors -------------
+    for _ in range(warmup):
+        job.run()
+    sampler = ClockSampler(local)
+    barrier(torch, world)
+    if rank == 0:
+        sampler.start()
+    t0 = time.perf_counter()
+    dev_ms = vit_ms = plan_ms = 0.0
+    launches = 0
+    for _ in range(steps):
+        st = job.run()
+        dev_ms += st.kernel_ms
+        vit_ms += st.viterbi_ms
+        plan_ms += st.plan_ms
+        launches += st.n_launches
+    barrier(torch, world)
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop() if rank == 0 else None
+    st = job.stats()
+    step_ms = max_over_ranks(torch, world, max(dev_ms, 0.0) / steps)
+    wall_step_ms = max_over_ranks(torch, world, wall_ms / steps)
+    total_loci = sum_over_ranks(torch, world, float(n_loci))
+    total_cells = sum_over_ranks(torch, world, float(st.n_cells))
+    vit_step_ms = max_over_ranks(torch, world, vit_ms / steps)
+    ll, post, tot = job.download()
+    checksum = float(np.sum(ll[ll > -600.0]))
+    n_ll, n_post, n_tot = job.n_ll, job.n_post, job.n_totals
+    job.close()
+
+    # ---- end-to-end arm: ONE host thread, host buffers through ltr_job_submit / ltr_job_wait ---------------------------
+    # Every step moves its inputs from pinned host memory to the device and its results back inside the timed region; with
+    # `depth` jobs in flight the upload of step k+1 and the download of step k-1 overlap the kernels of step k.
+    vb, keep_vb = abi.make_viterbi_batch(pinned_b)
+    pb, keep_pb = abi.make_posterior_batch(pinned_p)
+    prepared = (vb, pb, (keep_vb, keep_pb))
+    max_depth = int(os.environ.get("LTR_BENCH_DEPTH", "3"))
+    outs = []
+    for _ in range(max_depth):
+        o, keep_o = pinned_copy(torch, dict(ll=np.zeros(n_ll), post=np.zeros(max(1, n_post)), tot=np.zeros(max(1, n_tot))))
+        outs.append((o, keep_o))
+
+    def e2e_run(depth, n_steps):
+        inflight = collections.deque()
+        last, acc = None, 0.0
+        for i in range(n_steps + depth):
+            if len(inflight) == depth or i >= n_steps:
+                if not inflight:
+                    break
+                j, o = inflight.popleft()
+                last = j.wait()
+                acc += float(o["tot"][0])  # the host reads the step's result
+                j.close()
+            if i < n_steps:
+                o = outs[i % depth][0]
+                j = eng.submit_job(None, None, aln_params=work.aln_params, out_ll=o["ll"], out_post=o["post"][:n_post],
+                                   out_totals=o["tot"][:n_tot], prepared=prepared)
+                inflight.append((j, o))
+        return last, acc
+    e2e_by_depth = {}
+    es = None
+    for depth in range(1, max_depth + 1):
+        e2e_run(depth, max(2, min(warmup, 3)))
+        barrier(torch, world)
+        t0 = time.perf_counter()
+        es, _ = e2e_run(depth, steps)
+        barrier(torch, world)
+        e2e_by_depth[depth] = max_over_ranks(torch, world, (time.perf_counter() - t0) * 1e3 / steps)
+    e2e_same = bool(np.array_equal(outs[0][0]["ll"], ll))  # the asynchronous path delivers the resident job's bits
+    in_flight = min(e2e_by_depth, key=e2e_by_depth.get)
+    e2e_ms = e2e_by_depth[in_flight]
+    if rank != 0:
+        work.close()
+        return None
+    # roofline: cells the kernels actually evaluated (identical trimmed reads of a locus are aligned once)
+    achieved = st.n_cells_computed / (vit_ms / steps) / 1e6
+    line = {
+        "metric": "loci_per_sec", "value": total_loci / (step_ms * 1e-3), "unit": "loci/s",
+        "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": step_ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "gcups": total_cells / (vit_step_ms * 1e-3) / 1e9,
+        "config": {"workload": CONFIG_NAME[config], "loci_per_gpu": n_loci,
+                   "pairs_per_gpu": int(st.n_pairs), "cells_per_gpu": int(st.n_cells),
+                   "pairs_aligned_per_gpu": int(st.n_pairs_computed), "cells_evaluated_per_gpu": int(st.n_cells_computed),
+                   "pairs_banded_per_gpu": int(st.n_band_pairs), "pairs_band_uncertified_per_gpu": int(st.n_band_uncertified),
+                   "value_includes": "device plan (read de-duplication, band classes, task lists) + Viterbi kernels + "
+                                     "fan-out + posteriors, every step; results start as NaN every step",
+                   "plan_ms_per_step": plan_ms / steps, "viterbi_ms_per_step": vit_ms / steps,
+                   "gcups_note": "gcups = reference-defined cells (every pooled read x haplotype) / Viterbi time; "
+                                 "roofline.achieved = cells actually evaluated / Viterbi time",
+                   "l2": "inputs (%.0f MB) + outputs larger than L2; no flush needed" % (work.input_bytes / 1e6),
+                   "parallelism": "locus-sharded, no collective", "wall_ms_per_step": wall_step_ms,
+                   "fallback_pairs": int(st.n_fallback), "ll_checksum": checksum},
+        "e2e": {"value": total_loci / (e2e_ms * 1e-3), "unit": "loci/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int(es.h2d_bytes), "d2h_bytes_per_step": int(es.d2h_bytes),
+                "host_threads_per_gpu": 1, "api": "ltr_job_submit / ltr_job_wait",
+                "jobs_in_flight": in_flight, "results_equal_resident_job": e2e_same,
+                "ms_per_step_by_jobs_in_flight": {str(k): v for k, v in e2e_by_depth.items()}},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "fp64_issue", "achieved": achieved, "peak": peak_gcups, "unit": "GCUPS",
+                     "frac": achieved / peak_gcups, "traffic": ncu_traffic("traffic"),
+                     "traffic_source": ncu_traffic("source"), "traffic_kernel": ncu_traffic("kernel"),
+                     "peak_source": "ltr_fp64_issue_rate (DADD lane-ops/s measured in this run) / 17 FP64 ops per cell",
+                     "fp64_lane_ops_per_s": fp64_rate,
+                     "hbm_gbs_algorithmic": (work.input_bytes + 8.0 * st.n_pairs) / (vit_ms / steps) / 1e6},
+    }
+    if with_cpu_baseline:
+        from oracle import pyoracle as po
+        threads = os.cpu_count() or 1
+        n_sample = args.cpu_sample_loci or min(n_loci, 256 * threads if config == 3 else 4 * threads)
+        sb, sp = work.subset(n_sample)
+        t0 = time.perf_counter()
+        if po.ref_available():
+            kind = "reference"
+            ref_ll, sec, ref_post = po.ref_viterbi_batch(sb, work.aln_params, n_threads=threads, post=sp)
+        else:
+            kind = "port"
+            ref_ll, _cells = po.viterbi_batch(sb, aln_params=work.aln_params, n_threads=threads)
+            ref_post = None
+            sec = time.perf_counter() - t0
+        wall = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": n_sample / wall, "unit": "loci/s", "cores": threads, "kind": kind,
+                                "gcups": sample_cells(work, n_sample) / sec / 1e9,
+                                "sample": "first %d loci of the same workload, all host threads" % n_sample}
+        line["parity_on_bench_sample"] = bench_sample_parity(work, n_sample, ref_ll, ref_post, ll, post)
+    work.close()
+    return line
+
+
+def compact(line):
+    """Sub-line of another configuration inside the default run (extra.c4 / extra.c5)."""
+    if line is None:
+        return None
+    keep = ("metric", "value", "unit", "ms_per_step", "gcups", "steps", "warmup", "e2e", "roofline", "cpu_baseline",
+            "parity_on_bench_sample", "gpu_launches", "clocks")
+    out = {k: line[k] for k in keep if k in line}
+    out["config"] = {k: line["config"][k] for k in ("workload", "loci_per_gpu", "pairs_per_gpu", "pairs_aligned_per_gpu",
+                                                     "cells_evaluated_per_gpu", "pairs_banded_per_gpu",
+                                                     "pairs_band_uncertified_per_gpu", "cell_equivalents_per_gpu")
+                     if k in line["config"]}
+    return out
 
 
 def main():
@@ -411,153 +575,32 @@ def main():
         else:
             run_reference(args)
         return
-    if args.config == 5:
-        run_stutter(args)
-        return
     torch, rank, world, local = dist_setup(args.gpus)
-    from longtr_b200 import Engine, workloads
-    n_loci = args.loci or CONFIG_LOCI[args.config]
+    from longtr_b200 import Engine
     eng = Engine(local)
-    # roofline denominator: sustained FP64-pipe issue rate measured on this GPU, right now
-    fp64_rate = max(eng.fp64_issue_rate(0)[0] for _ in range(2))
-    peak_gcups = fp64_rate / FP64_OPS_PER_CELL / 1e9
-    work = workloads.generate(args.config, n_loci, first_locus=rank * n_loci)
-    job = eng.create_job(work.batch, work.post, aln_params=work.aln_params)
-    pinned_b, keep_b = pinned_copy(torch, work.batch)
-    pinned_p, keep_p = pinned_copy(torch, work.post)
-
-    # ---- resident arm -------------------------------------------------------------------------
-    for _ in range(args.warmup):
-        job.run()
-    sampler = ClockSampler(local)
-    barrier(torch, world)
-    if rank == 0:
-        sampler.start()
-    t0 = time.perf_counter()
-    dev_ms = vit_ms = 0.0
-    launches = 0
-    for _ in range(args.steps):
-        st = job.run()
-        dev_ms += st.kernel_ms
-        vit_ms += st.viterbi_ms
-        launches += st.n_launches
-    barrier(torch, world)
-    wall_ms = (time.perf_counter() - t0) * 1e3
-    clocks = sampler.stop() if rank == 0 else None
-    st = job.stats()
-    step_ms = max_over_ranks(torch, world, max(dev_ms, 0.0) / args.steps)
-    wall_step_ms = max_over_ranks(torch, world, wall_ms / args.steps)
-    total_loci = sum_over_ranks(torch, world, float(n_loci))
-    total_cells = sum_over_ranks(torch, world, float(st.n_cells))
-    vit_step_ms = max_over_ranks(torch, world, vit_ms / args.steps)
-    ll, post, tot = job.download()
-    checksum = float(np.sum(ll[ll > -600.0]))
-
-    # ---- end-to-end arm: host buffers through the C ABI, copies inside the timed region -------
-    # results land in pinned host buffers allocated once (the caller of the C ABI owns its output arrays)
-    n_ll, n_post, n_tot = job.n_ll, job.n_post, job.n_totals
-    pin_out, keep_o = pinned_copy(torch, dict(ll=np.zeros(n_ll), post=np.zeros(max(1, n_post)), tot=np.zeros(max(1, n_tot))))
-    timing = os.environ.get("LTR_TIMING") is not None
-
-    import threading
-    gpu_turn = threading.Lock()  # batches in flight take turns on the GPU: while one runs, the next is planned / uploaded
-
-    def e2e_step(engine=None, out=None):
-        engine = engine or eng
-        out = out or pin_out
-        t = [time.perf_counter()]
-        j = engine.create_job(pinned_b, pinned_p, aln_params=work.aln_params)
-        t.append(time.perf_counter())
-        with gpu_turn:
-            s = j.run()
-        t.append(time.perf_counter())
-        j.download(out_ll=out["ll"], out_post=out["post"][:n_post], out_totals=out["tot"][:n_tot])
-        t.append(time.perf_counter())
-        s = j.stats()
-        j.close()
-        t.append(time.perf_counter())
-        if timing and rank == 0:
-            print("[bench] e2e step: create %.1f run %.1f download %.1f close %.1f ms" %
-                  tuple(1e3 * (b - a) for a, b in zip(t[:-1], t[1:])), file=sys.stderr)
-        return s
-    for _ in range(min(args.warmup, 3)):
-        e2e_step()
-    barrier(torch, world)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        es = e2e_step()
-    barrier(torch, world)
-    e2e_serial_ms = max_over_ranks(torch, world, (time.perf_counter() - t0) * 1e3 / args.steps)
-    # Several batches in flight (the pipelined host of INTEGRATION.md section 3): one host thread + one ltr_ctx + one set
-    # of pinned output buffers per slot, so that the plan / H2D of batch k+1 overlaps the kernels of batch k.  Every
-    # step still moves its inputs from pinned host memory and its results back inside the timed region.  With the
-    # banded kernel a batch spends about as long in ltr_job_create as on the GPU, so two and three slots are timed.
-    from concurrent.futures import ThreadPoolExecutor
-    slots = [(eng, pin_out)]
-    e2e_by_slots = {1: e2e_serial_ms}
-    max_slots = int(os.environ.get("LTR_BENCH_SLOTS", "3"))  # diagnostics: more batches in flight
-    for n_slots in range(2, max_slots + 1):
-        e_new = Engine(local)
-        pin_new, keep_new = pinned_copy(torch, dict(ll=np.zeros(n_ll), post=np.zeros(max(1, n_post)), tot=np.zeros(max(1, n_tot))))
-        slots.append((e_new, pin_new))
-
-        def slot_loop(k, n_steps, n_slots=n_slots):  # slot k takes steps k, k + n_slots, ...
-            for _ in range(k, n_steps, n_slots):
-                e2e_step(*slots[k])
-        with ThreadPoolExecutor(max_workers=n_slots) as ex:
-            list(ex.map(lambda k: slot_loop(k, 2 * n_slots), range(n_slots)))  # warm the new context
-            barrier(torch, world)
-            t0 = time.perf_counter()
-            list(ex.map(lambda k: slot_loop(k, args.steps), range(n_slots)))
-            barrier(torch, world)
-        e2e_by_slots[n_slots] = max_over_ranks(torch, world, (time.perf_counter() - t0) * 1e3 / args.steps)
-    for e_x, _ in slots[1:]:
-        e_x.close()
-    e2e_pipe_ms = e2e_by_slots[2]
-    in_flight = min(e2e_by_slots, key=e2e_by_slots.get)
-    e2e_ms = e2e_by_slots[in_flight]
-
-    if rank != 0:
-        return
-    # roofline: cells the kernels actually evaluated (identical trimmed reads of a locus are aligned once)
-    achieved = st.n_cells_computed / (vit_ms / args.steps) / 1e6
-    line = {
-        "metric": "loci_per_sec", "value": total_loci / (step_ms * 1e-3), "unit": "loci/s",
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "gcups": total_cells / (vit_step_ms * 1e-3) / 1e9,
-        "config": {"workload": CONFIG_NAME[args.config], "loci_per_gpu": n_loci,
-                   "pairs_per_gpu": int(st.n_pairs), "cells_per_gpu": int(st.n_cells),
-                   "pairs_aligned_per_gpu": int(st.n_pairs_computed), "cells_evaluated_per_gpu": int(st.n_cells_computed),
-                   "pairs_banded_per_gpu": int(st.n_band_pairs), "pairs_band_uncertified_per_gpu": int(st.n_band_uncertified),
-                   "gcups_note": "gcups = reference-defined cells (every pooled read x haplotype) / Viterbi time; "
-                                 "roofline.achieved = cells actually evaluated / Viterbi time",
-                   "l2": "inputs (%.0f MB) + outputs larger than L2; no flush needed" % (work.input_bytes / 1e6),
-                   "parallelism": "locus-sharded, no collective", "wall_ms_per_step": wall_step_ms,
-                   "fallback_pairs": int(st.n_fallback), "ll_checksum": checksum},
-        "e2e": {"value": total_loci / (e2e_ms * 1e-3), "unit": "loci/s", "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": int(es.h2d_bytes), "d2h_bytes_per_step": int(es.d2h_bytes),
-                "batches_in_flight": in_flight, "ms_per_step_one_in_flight": e2e_serial_ms,
-                "ms_per_step_two_in_flight": e2e_pipe_ms, "ms_per_step_three_in_flight": e2e_by_slots[3],
-                "ms_per_step_by_batches_in_flight": {str(k): v for k, v in e2e_by_slots.items()}},
-        "gpu_launches": launches,
-        "clocks": clocks,
-        "roofline": {"bound": "fp64_issue", "achieved": achieved, "peak": peak_gcups, "unit": "GCUPS",
-                     "frac": achieved / peak_gcups, "traffic": ncu_traffic("traffic"),
-                     "traffic_source": ncu_traffic("source"), "traffic_kernel": ncu_traffic("kernel"),
-                     "peak_source": "ltr_fp64_issue_rate (DADD lane-ops/s measured in this run) / 17 FP64 ops per cell",
-                     "fp64_lane_ops_per_s": fp64_rate,
-                     "hbm_gbs_algorithmic": (work.input_bytes + 8.0 * st.n_pairs) / (vit_ms / args.steps) / 1e6},
-    }
-    if world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        n_sample = args.cpu_sample_loci or min(n_loci, 256 * threads if args.config == 3 else 4 * threads)
-        kind, sec, wall = cpu_baseline(work, n_sample, threads)
-        line["cpu_baseline"] = {"value": n_sample / wall, "unit": "loci/s", "cores": threads, "kind": kind,
-                                "gcups": sample_cells(work, n_sample) / sec / 1e9,
-                                "sample": "first %d loci of the same workload, all host threads" % n_sample}
-    print(json.dumps(line), flush=True)
-    job.close()
+    if args.config == 5:
+        line = run_stutter(args, torch, rank, world, local, eng, args.loci or CONFIG_LOCI[5], args.steps, args.warmup,
+                           world == 1 and not args.no_cpu_baseline)
+    else:
+        # roofline denominator: sustained FP64-pipe issue rate measured on this GPU, right now
+        fp64_rate = max(eng.fp64_issue_rate(0)[0] for _ in range(2))
+        peak_gcups = fp64_rate / FP64_OPS_PER_CELL / 1e9
+        line = measure_long(args, args.config, args.loci or CONFIG_LOCI[args.config], args.steps, args.warmup, torch, rank,
+                            world, local, eng, peak_gcups, fp64_rate, world == 1 and not args.no_cpu_baseline)
+        # The default single-GPU run also times the other two synthetic configurations (shorter runs, bounded CPU
+        # samples) so that their numbers are driver-run too: extra.c4 (VNTRs, ONT-like) and extra.c5 (homopolymer path).
+        if args.config == 3 and world == 1 and not args.loci and not args.no_extra:
+            extra = {}
+            try:
+                extra["c4"] = compact(measure_long(args, 4, CONFIG_LOCI[4], 2, 3, torch, rank, world, local, eng, peak_gcups,
+                                                   fp64_rate, not args.no_cpu_baseline))
+                extra["c5"] = compact(run_stutter(args, torch, rank, world, local, eng, CONFIG_LOCI[5], 2, 3,
+                                                  not args.no_cpu_baseline))
+            except Exception as e:  # the headline line must not be lost to a sub-line
+                extra["error"] = repr(e)
+            line["extra"] = extra
+    if rank == 0 and line is not None:
+        print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:
         import torch.distributed as dist

@@ -104,6 +104,8 @@ typedef struct ltr_job_stats {
                                 inside the band for pairs certified by the banded kernel                 */
   uint64_t n_band_pairs;       /* pairs sent to the banded kernel (band_core.cuh) ...                    */
   uint64_t n_band_uncertified; /* ... of which the band could not certify (re-run over the full matrix)  */
+  float plan_ms;               /* device time of the plan kernels (de-duplication of the trimmed reads, band classes,
+                                  task lists: plan_kernels.cu) inside kernel_ms; 0 when the plan was built on the host */
 } ltr_job_stats;
 
 /* ---- context --------------------------------------------------------------------- */
@@ -113,6 +115,10 @@ void ltr_ctx_destroy(ltr_ctx* ctx);
  * wide enough, otherwise it is re-run over the full matrix).  half_width < 0: off; 0 (default): automatic margin;
  * > 0: minimum number of diagonals kept on either side of the diagonals 0 .. m-n.  Results do not depend on it. */
 int ltr_ctx_set_band(ltr_ctx* ctx, int32_t half_width);
+/* Where the plan of a job (de-duplication of the trimmed reads of each locus, band classes, task lists) is built:
+ * 0 (default) on the device for batches of >= 4096 pooled reads and on the host below that (per-locus calls: fewer
+ * launches), 1 always on the host, 2 always on the device.  Results do not depend on it. */
+int ltr_ctx_set_plan(ltr_ctx* ctx, int32_t mode);
 const char* ltr_strerror(int code);
 const char* ltr_last_error(const ltr_ctx* ctx); /* CUDA error text of the last failure */
 const char* ltr_version(void);
@@ -179,6 +185,23 @@ int ltr_job_download(ltr_ctx* ctx, ltr_job* job, double* out_ll, double* out_pos
                      double* out_totals);
 void ltr_job_get_stats(const ltr_job* job, ltr_job_stats* stats);
 void ltr_job_destroy(ltr_ctx* ctx, ltr_job* job);
+
+/* ---- asynchronous jobs: many batches in flight from ONE host thread ------------------------------------------------ */
+/* ltr_job_submit enqueues a whole job -- upload of the batch, plan, kernels, posteriors, download of the results into
+ * out_ll / out_post / out_totals (any may be NULL) -- on the streams of the context and returns without waiting; jobs
+ * submitted one after the other overlap (the upload of job k+1 and the download of job k-1 run beside the kernels of
+ * job k).  The caller's input AND output arrays must stay valid and untouched until ltr_job_wait returns; page-locked
+ * (pinned) host memory makes the copies truly asynchronous, pageable memory works but blocks inside submit.
+ * ltr_job_wait blocks until the job is complete and returns its status: a malformed batch that is only detected on the
+ * device (read offsets, sample-read indices) is reported here as LTR_ERR_INVALID.  ltr_job_poll: 1 = complete,
+ * 0 = still running, negative = error.  Statistics are valid after ltr_job_wait; finish with ltr_job_destroy.
+ * (the submit / wait pair the pipelined host of SeqStutterGenotyper::genotype calls at
+ * src/seq_stutter_genotyper.cpp:634-635.)                                                                            */
+int ltr_job_submit(ltr_ctx* ctx, const ltr_params* params, const ltr_viterbi_batch* batch,
+                   const ltr_posterior_batch* post, double* out_ll, double* out_post, double* out_totals,
+                   ltr_job** out);
+int ltr_job_wait(ltr_ctx* ctx, ltr_job* job);
+int ltr_job_poll(ltr_ctx* ctx, ltr_job* job);
 
 /* ---- reference-facing convenience (host mirror of HapAligner) --------------------- */
 /* HapAligner(haplotype, realign_to_hap, INDEL_FLANK_LEN, SWITCH_OLD_ALIGN_LEN, params)
@@ -283,20 +306,7 @@ int32_t ltr_seed_base_flat(const ltr_flat_locus* locus, int32_t read_index);
  * 2xFSEL pattern of one max-plus term.  ms (optional) = duration of the probe kernel.      */
 int ltr_fp64_issue_rate(int device, int kind, double* lane_ops_per_s, double* ms);
 
-/* ---- synthetic workloads (BASELINE.json configs 3-5) ------------- */
-typedef struct ltr_synth_batch {
-  ltr_viterbi_batch vit;      /* flattened loci                                   */
-  ltr_posterior_batch post;   /* 30 sample-reads per locus, one sample            */
-  uint32_t n_haps, n_reads, n_sreads;
-  uint64_t hap_nbytes, read_nbytes;
-} ltr_synth_batch;
-/* config 3 = HiFi STRs, 4 = VNTRs (ONT-like), 5 = homopolymers; loci [first_locus,
- * first_locus+n_loci) of the job seeded with base_seed (mt19937_64(base_seed + locus)).      */
-int ltr_synth_generate(int config, uint64_t base_seed, uint32_t first_locus, uint32_t n_loci,
-                       int n_threads, ltr_synth_batch** out);
-void ltr_synth_params(int config, ltr_params* p);
-void ltr_synth_free(ltr_synth_batch* b);
-
+/* ---- synthetic workload of BASELINE.json config 5 (configs 3 and 4: longtr_b200/synth/longtr_synth.h, a library of its own) ---- */
 /* config 5 (homopolymers, --stutter-align-len path): an ltr_stutter_batch with whole pooled reads, median
  * qualities and calc_seed_base seeds, plus what is needed to replay the same loci as flat loci
  * (include/longtr_b200_locus.h): per-read reference coordinates and CIGAR, per-locus repeat coordinates. */

@@ -44,7 +44,8 @@ class JobStats(C.Structure):
     _fields_ = [("n_pairs", C.c_uint64), ("n_cells", C.c_uint64), ("n_fallback", C.c_uint64),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("n_launches", C.c_uint32),
                 ("kernel_ms", C.c_float), ("viterbi_ms", C.c_float), ("n_pairs_computed", C.c_uint64),
-                ("n_cells_computed", C.c_uint64), ("n_band_pairs", C.c_uint64), ("n_band_uncertified", C.c_uint64)]
+                ("n_cells_computed", C.c_uint64), ("n_band_pairs", C.c_uint64), ("n_band_uncertified", C.c_uint64),
+                ("plan_ms", C.c_float)]
 
 
 class LocusCalls(C.Structure):
@@ -171,6 +172,15 @@ def load():
     lib.ltr_job_download.restype = C.c_int
     lib.ltr_job_get_stats.argtypes = [vp, C.POINTER(JobStats)]
     lib.ltr_job_destroy.argtypes = [vp, vp]
+    lib.ltr_ctx_set_plan.argtypes = [vp, C.c_int32]
+    lib.ltr_ctx_set_plan.restype = C.c_int
+    lib.ltr_job_submit.argtypes = [vp, C.POINTER(Params), C.POINTER(ViterbiBatch), C.POINTER(PosteriorBatch), _dp, _dp, _dp,
+                                   C.POINTER(vp)]
+    lib.ltr_job_submit.restype = C.c_int
+    lib.ltr_job_wait.argtypes = [vp, vp]
+    lib.ltr_job_wait.restype = C.c_int
+    lib.ltr_job_poll.argtypes = [vp, vp]
+    lib.ltr_job_poll.restype = C.c_int
     lib.ltr_process_reads_flat.argtypes = [vp, C.POINTER(FlatLocus), _dp, _i32p]
     lib.ltr_process_reads_flat.restype = C.c_int
     lib.ltr_process_reads_flat_batch.argtypes = [vp, C.c_int32, C.POINTER(FlatLocus), C.POINTER(_dp), C.POINTER(_i32p)]
@@ -212,7 +222,7 @@ EXPORTED_SYMBOLS = [
     "ltr_process_reads_flat_batch", "ltr_pipeline_create", "ltr_pipeline_submit", "ltr_pipeline_flush", "ltr_pipeline_next",
     "ltr_pipeline_destroy", "ltr_flatten_loci", "ltr_flat_batch_free",
     "ltr_fp64_issue_rate", "ltr_genotype_locus", "ltr_extract_calls", "ltr_trim_read_flat", "ltr_seed_base_flat",
-    "ltr_stutter_ll", "ltr_genotype_locus_pruned",
+    "ltr_stutter_ll", "ltr_genotype_locus_pruned", "ltr_ctx_set_plan", "ltr_job_submit", "ltr_job_wait", "ltr_job_poll",
 ]
 
 

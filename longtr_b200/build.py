@@ -14,13 +14,15 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 OUT = os.path.join(CSRC, "liblongtr_b200.so")
+SYNTH_DIR = os.path.join(HERE, "synth")
+SYNTH_OUT = os.path.join(SYNTH_DIR, "libltr_synth.so")  # workload generator of configs 3 / 4: its own library, no product code
 OBJ = os.path.join(CSRC, "build")
 
-CU_SOURCES = ["viterbi_kernels.cu", "band_kernel.cu", "posterior_kernel.cu", "stutter_kernel.cu", "abi.cu", "stutter_abi.cu",
+CU_SOURCES = ["viterbi_kernels.cu", "band_kernel.cu", "plan_kernels.cu", "posterior_kernel.cu", "stutter_kernel.cu", "abi.cu", "stutter_abi.cu",
               "microbench.cu"]
 CPP_SOURCES = ["host/flat_api.cpp", "host/host_types.cpp", "host/hap_aligner.cpp", "host/stutter_host.cpp",
-               "host/genotyper.cpp", "host/pipeline.cpp", "synth.cpp", "synth_stutter.cpp"]
-HEADERS = ["viterbi_core.cuh", "band_core.cuh", "viterbi_host.h", "kernels.h", "stutter_core.cuh", "ctx.h"]
+               "host/genotyper.cpp", "host/pipeline.cpp", "synth_stutter.cpp"]
+HEADERS = ["viterbi_core.cuh", "band_core.cuh", "viterbi_host.h", "kernels.h", "stutter_core.cuh", "ctx.h", "plan_device.cuh"]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
@@ -65,6 +67,10 @@ def build(force=False, verbose=False):
         list(ex.map(run, jobs))
     if jobs or force or not os.path.exists(OUT):
         run([NVCC, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"])
+    synth_src = [os.path.join(SYNTH_DIR, "synth.cpp"), os.path.join(SYNTH_DIR, "longtr_synth.h")]
+    if force or _stale(SYNTH_OUT, synth_src + [os.path.join(INCLUDE, "longtr_b200.h")]):
+        run([os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-I" + INCLUDE,
+             "-I" + SYNTH_DIR, "-o", SYNTH_OUT, synth_src[0]])
     return OUT
 
 

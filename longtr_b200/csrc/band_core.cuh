@@ -89,6 +89,34 @@ struct BandGap {
   double open, ext;
 };
 
+// Banded evaluation: which pairs go to the band kernel, and with which band class (set up by band_policy(),
+// viterbi_host.h; used by the host plan and by the device plan, plan_device.cuh).
+struct BandPolicy {
+  bool on = false;
+  BandGap gap = {0.0, 0.0};  // open = min(|M2D|, |M2I|), ext = min(|D2D|, |I2I|) (open >= ext enforced)
+  int w_fixed = 0;           // > 0: margin requested with ltr_ctx_set_band
+  double budget0 = 0.0, budget_per_row = 0.0;  // automatic margin: error budget B(n) = budget0 + n * budget_per_row
+};
+LTR_HHD int band_margin_needed(const BandPolicy& bp, int n) {
+  if (bp.w_fixed > 0) return bp.w_fixed;
+  const double B = bp.budget0 + bp.budget_per_row * (double)n;
+  int w = (int)ceil(((B - bp.gap.open) / bp.gap.ext + 1.0) / 2.0);
+  w = w < 255 ? w : 255;
+  return w > 2 ? w : 2;
+}
+// Band class of a pair (index into band_class_k) or -1: not banded (too short, band not narrower than ~half the matrix,
+// length difference beyond the widest class).
+LTR_HHD int band_class_of(int hlen, int n, int m, const BandPolicy& bp) {
+  if (!bp.on || hlen <= 60 || n < 2 || m < 2) return -1;
+  const int w_need = band_margin_needed(bp, n);
+  for (int c = 0; c < kBandClasses; ++c) {
+    const int W = band_class_w(c);
+    if (band_geometry(n, m, W).w < w_need) continue;
+    return ((unsigned long long)(n + m) * (unsigned long long)(W / 2) * 100ull <= 55ull * (unsigned long long)n * (unsigned long long)m) ? c : -1;
+  }
+  return -1;
+}
+
 // Pair certified from its banded score?  A chain that leaves the band [lo - w, hi + w] and ends on diagonal de makes
 // T >= |de| + 2w + 2 gap moves in at least two runs (out and back, an M cell between them); at most one of them is the
 // cheap M cell of the boundary row / column (D2M / I2M instead of a gap cost, HapAligner.cpp:266-279), and that one sits in

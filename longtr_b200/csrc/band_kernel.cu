@@ -44,7 +44,9 @@ viterbi_band_kernel(const VitConsts C, const DevBatch B, const BandArgs A) {
   SmemTable T;
   T.base = tb;
   constexpr int W = 2 * K * G;
-  const uint32_t n_rounds = (A.n_pairs + (uint32_t)PPR - 1u) / (uint32_t)PPR;
+  const uint2* __restrict__ pairs = A.pairs + A.info[0];
+  const uint32_t n_pairs = A.info[1];
+  const uint32_t n_rounds = (n_pairs + (uint32_t)PPR - 1u) / (uint32_t)PPR;
   while (true) {
     uint32_t round = 0, att = 0, fl = 0;
     if (lane == 0) {
@@ -57,8 +59,8 @@ viterbi_band_kernel(const VitConsts C, const DevBatch B, const BandArgs A) {
     att = __shfl_sync(kFull, att, 0);
     fl = __shfl_sync(kFull, fl, 0);
     const uint32_t base = round * (uint32_t)PPR;
-    const bool active = (base + (uint32_t)grp) < A.n_pairs;
-    const uint2 pr = A.pairs[active ? base + (uint32_t)grp : base];  // idle groups shadow the round's first pair
+    const bool active = (base + (uint32_t)grp) < n_pairs;
+    const uint2 pr = pairs[active ? base + (uint32_t)grp : base];  // idle groups shadow the round's first pair
     const uint32_t g = pr.x, u = pr.y;
     const uint32_t hoff = B.hap_off[g];
     const int32_t hlen = (int32_t)(B.hap_off[g + 1] - hoff);
@@ -177,9 +179,11 @@ __global__ void band_expand_kernel(const BandTask* __restrict__ tasks, const uin
 // together, like on the plan's own sorted list): pass 0 counts the runs per (row class, cost bucket = floor(log2 cost)),
 // band_bucket_scan_kernel turns the counts into list positions, pass 1 writes the tasks.
 __global__ void band_collect_kernel(const VitConsts C, const DevBatch B, const BandTask* __restrict__ tasks,
-                                    uint32_t n_tasks, const BandCollect S, int pass) {
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_tasks) return;
+                                    const uint32_t* __restrict__ n_tasks_ptr, uint32_t task_cap, const BandCollect S,
+                                    int pass) {
+  uint32_t n_tasks = *n_tasks_ptr;
+  n_tasks = n_tasks < task_cap ? n_tasks : task_cap;
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n_tasks; t += gridDim.x * blockDim.x) {
   const BandTask bt = tasks[t];
   const uint32_t g = bt.hap;
   const uint32_t l = B.hap_locus[g];
@@ -228,6 +232,7 @@ __global__ void band_collect_kernel(const VitConsts C, const DevBatch B, const B
   if (pass == 0 && n_bad) {
     atomicAdd(S.n_uncertified, (unsigned long long)n_bad);
     atomicAdd(S.cells_uncertified, cells);
+  }
   }
 }
 
@@ -291,12 +296,15 @@ cudaError_t launch_band_expand(const BandTask* tasks, const uint32_t* cum, uint3
   return cudaGetLastError();
 }
 
-cudaError_t launch_band_collect(const VitConsts& C, const DevBatch& B, const BandTask* tasks, uint32_t n_tasks,
-                                const BandCollect& S, cudaStream_t stream) {
-  if (n_tasks == 0) return cudaSuccess;
-  band_collect_kernel<<<(n_tasks + 127) / 128, 128, 0, stream>>>(C, B, tasks, n_tasks, S, 0);
+cudaError_t launch_band_collect(const VitConsts& C, const DevBatch& B, const BandTask* tasks, const uint32_t* n_tasks_ptr,
+                                uint32_t task_cap, const BandCollect& S, int sm_count, cudaStream_t stream) {
+  if (task_cap == 0) return cudaSuccess;
+  uint32_t grid = (task_cap + 127u) / 128u;
+  const uint32_t grid_max = (uint32_t)sm_count * 16u;
+  grid = grid < grid_max ? grid : grid_max;
+  band_collect_kernel<<<grid, 128, 0, stream>>>(C, B, tasks, n_tasks_ptr, task_cap, S, 0);
   band_bucket_scan_kernel<<<1, 32, 0, stream>>>(S);
-  band_collect_kernel<<<(n_tasks + 127) / 128, 128, 0, stream>>>(C, B, tasks, n_tasks, S, 1);
+  band_collect_kernel<<<grid, 128, 0, stream>>>(C, B, tasks, n_tasks_ptr, task_cap, S, 1);
   return cudaGetLastError();
 }
 

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <string>
+#include <vector>
 
 #include "longtr_b200.h"
 
@@ -52,20 +53,33 @@ struct DeviceBuffer {
 
 }  // namespace ltr
 
+namespace ltr {
+// Streams of one job in flight.  Jobs of a context take the lanes in turn, so the upload of job k+1 (h2d) and the
+// download of job k-1 (d2h) overlap the kernels of job k (main + one stream per row / band class).
+const int kLanes = 3;
+struct JobLane {
+  cudaStream_t main = nullptr, h2d = nullptr, d2h = nullptr;
+  cudaStream_t cls[kNumStreams] = {nullptr};
+  cudaEvent_t ev_cls[kNumStreams] = {nullptr};
+  cudaEvent_t ev_init = nullptr, ev_collect = nullptr;  // band phase ordering (no timing)
+};
+}  // namespace ltr
+
 struct ltr_ctx {
   int device = 0;
   int sm_count = 0;
-  cudaStream_t main_stream = nullptr;
-  cudaStream_t streams[ltr::kNumStreams] = {nullptr};
-  cudaEvent_t ev_start = nullptr, ev_vit = nullptr, ev_end = nullptr;
-  cudaEvent_t ev_stream[ltr::kNumStreams] = {nullptr};
-  cudaEvent_t ev_init = nullptr, ev_collect = nullptr;  // band phase ordering (no timing)
-  int blocks_per_sm[2][32] = {{0}};
+  cudaStream_t main_stream = nullptr;                    // one-shot entry points (ltr_posteriors, ltr_stutter_ll)
+  cudaEvent_t ev_start = nullptr, ev_end = nullptr;      // ... and their timing
+  ltr::JobLane lanes[ltr::kLanes];
+  unsigned next_lane = 0;
+  int blocks_per_sm[4][32] = {{0}};
   int band_blocks_per_sm[16] = {0};  // by band class index
   int band_w = 0;                    // ltr_ctx_set_band: < 0 off, 0 automatic margin, > 0 margin in diagonals
+  int plan_mode = 0;                 // ltr_ctx_set_plan: 0 automatic, 1 host plan (make_plan), 2 device plan (plan_kernels.cu)
   std::string last_error;
-  void* stage[4] = {nullptr, nullptr, nullptr, nullptr};  // pinned host staging for the plan's large arrays (grow-only)
+  void* stage[4] = {nullptr, nullptr, nullptr, nullptr};  // pinned host staging for the host plan's large arrays (grow-only)
   size_t stage_bytes[4] = {0, 0, 0, 0};
+  std::vector<void*> result_blocks;  // pinned host blocks for per-job statistics, recycled
 };
 
 namespace ltr {

@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include "band_core.cuh"
+#include "plan_device.cuh"
 #include "viterbi_core.cuh"
 
 namespace ltr {
@@ -19,8 +20,9 @@ cudaError_t launch_viterbi(int k, int mode, int grid_blocks, cudaStream_t stream
 
 // Banded anti-diagonal Viterbi (band_kernel.cu, band_core.cuh): rounds of 32 / G pairs per warp.
 struct BandArgs {
-  const uint2* pairs;       // (haplotype, unique read) pairs of one band class, haplotype-major
-  uint32_t n_pairs;
+  const uint2* pairs;       // (haplotype, unique read) pairs of ALL band classes, class after class
+  const uint32_t* info;     // device words {first pair, number of pairs} of this launch's band class (written by the
+                            // host plan's upload or by the device plan: the launch needs no count on the host)
   uint32_t* cursor;         // round cursor of the persistent grid
   uint32_t* counters;       // [0] pairs evaluated, [1] of which not certified (shared by all band classes of a job)
   unsigned long long* cells_evaluated;  // interior band cells of the pairs evaluated (statistics)
@@ -44,8 +46,12 @@ cudaError_t launch_band(int cls, int grid_blocks, cudaStream_t stream, const Vit
                         const BandArgs& A);
 cudaError_t launch_band_expand(const BandTask* tasks, const uint32_t* cum, uint32_t n_tasks, uint2* pairs,
                                cudaStream_t stream);
-cudaError_t launch_band_collect(const VitConsts& C, const DevBatch& B, const BandTask* tasks, uint32_t n_tasks,
-                                const BandCollect& S, cudaStream_t stream);
+// n_tasks_ptr: device word holding the number of band tasks (<= task_cap)
+cudaError_t launch_band_collect(const VitConsts& C, const DevBatch& B, const BandTask* tasks, const uint32_t* n_tasks_ptr,
+                                uint32_t task_cap, const BandCollect& S, int sm_count, cudaStream_t stream);
+
+// The job plan on the device (plan_kernels.cu, plan_device.cuh): five small kernels in stream order.
+cudaError_t launch_device_plan(const PlanDev& P, int sm_count, cudaStream_t stream);
 
 // Fan-out of the unique LL matrices (one row per distinct trimmed read of a locus) to the reference's
 // aln_probs[read*H + hap] layout (HapAligner.cpp:549): out[ll_off(l) + (p-rb0)*H + h] = uniq[ull_off(l) + u(p)*H + h].
@@ -60,6 +66,7 @@ struct ExpandArgs {
   const unsigned long long* ull_off;
   const double* uniq_ll;
   double* out_ll;
+  const uint32_t* err;  // device plan: != 0 -> malformed batch, nothing to expand (may be NULL)
 };
 cudaError_t launch_expand_ll(const ExpandArgs& E, cudaStream_t stream);
 
@@ -67,6 +74,7 @@ cudaError_t launch_expand_ll(const ExpandArgs& E, cudaStream_t stream);
 struct DevPosterior {
   uint32_t n_loci;
   const uint32_t* locus_hap_begin;    // H_l
+  const uint32_t* locus_read_begin;   // pooled reads of locus l (bounds of pool_index)
   const uint32_t* locus_sread_begin;  // sample-reads of locus l
   const uint32_t* pool_index;         // pooled read (relative to the locus) of each sample-read
   const int32_t* sample_label;
@@ -83,8 +91,12 @@ struct DevPosterior {
   double log_one_half;                // host libm log(0.5) (mathops.cpp:10)
   double* post;
   double* totals;
+  const uint32_t* err;                // != 0: malformed batch, nothing is computed (may be NULL)
 };
 cudaError_t launch_posteriors(const DevPosterior& P, cudaStream_t stream);
+// Sets bit 2 of *err when a sample-read points outside its locus' pooled reads or names a sample that does not exist
+// (jobs planned on the device: the host never walks the per-read arrays).
+cudaError_t launch_posterior_validate(const DevPosterior& P, uint32_t* err, cudaStream_t stream);
 
 // Homopolymer / --stutter-align-len path (stutter_kernel.cu): one warp per (read, allele) pair.
 struct StutConsts;

@@ -16,7 +16,19 @@
 
 namespace ltr {
 
+__global__ void __launch_bounds__(128) posterior_validate_kernel(const DevPosterior P, uint32_t* err) {
+  bool bad = false;
+  for (uint32_t l = blockIdx.x; l < P.n_loci; l += gridDim.x) {
+    const uint32_t S = P.locus_n_samples[l];
+    const uint32_t np = P.locus_read_begin[l + 1] - P.locus_read_begin[l];
+    for (uint32_t r = P.locus_sread_begin[l] + threadIdx.x; r < P.locus_sread_begin[l + 1]; r += blockDim.x)
+      bad |= (P.pool_index[r] >= np) || (P.sample_label[r] < 0) || ((uint32_t)P.sample_label[r] >= S);
+  }
+  if (bad) atomicOr(err, 4u);
+}
+
 __global__ void __launch_bounds__(128) posterior_kernel(const DevPosterior P) {
+  if (P.err && *P.err != 0u) return;
   for (uint32_t l = blockIdx.x; l < P.n_loci; l += gridDim.x) {
     const uint32_t H = P.locus_hap_begin[l + 1] - P.locus_hap_begin[l];
     const uint32_t S = P.locus_n_samples[l];
@@ -67,6 +79,7 @@ __global__ void __launch_bounds__(128) posterior_kernel(const DevPosterior P) {
 // 8 lanes per pooled read walk its H haplotype columns (H is 2-12 in practice): coalesced within the row.
 __global__ void __launch_bounds__(256) expand_ll_kernel(const ExpandArgs E) {
   const uint32_t sub = threadIdx.x & 7u;
+  if (E.err && *E.err != 0u) return;
   for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; r < E.n_reads; r += (gridDim.x * blockDim.x) >> 3) {
     const uint32_t l = E.read_locus[r];
     const uint32_t H = E.locus_hap_begin[l + 1] - E.locus_hap_begin[l];
@@ -81,6 +94,13 @@ cudaError_t launch_expand_ll(const ExpandArgs& E, cudaStream_t stream) {
   const uint64_t want = ((uint64_t)E.n_reads * 8u + 255u) / 256u;
   const uint32_t grid = (uint32_t)(want < 148u * 32u ? want : 148u * 32u);
   expand_ll_kernel<<<grid, 256, 0, stream>>>(E);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_posterior_validate(const DevPosterior& P, uint32_t* err, cudaStream_t stream) {
+  if (P.n_loci == 0) return cudaSuccess;
+  const uint32_t grid = P.n_loci < 148u * 16u ? P.n_loci : 148u * 16u;
+  posterior_validate_kernel<<<grid, 128, 0, stream>>>(P, err);
   return cudaGetLastError();
 }
 

@@ -98,13 +98,6 @@ struct PodArray {
   const T& operator[](size_t i) const { return data()[i]; }
 };
 
-// Banded evaluation (band_core.cuh): which pairs go to the band kernel, and with which band class.
-struct BandPolicy {
-  bool on = false;
-  BandGap gap = {0.0, 0.0};  // open = min(|M2D|, |M2I|), ext = min(|D2D|, |I2I|) (open >= ext enforced)
-  int w_fixed = 0;           // > 0: margin requested with ltr_ctx_set_band
-  double budget0 = 0.0, budget_per_row = 0.0;  // automatic margin: error budget B(n) = budget0 + n * budget_per_row
-};
 // band_w < 0: banding off; 0: automatic margin; > 0: that many diagonals.  The band certificate needs every transition
 // parameter <= 0 and the same parameter condition as the final-score certificate (the bail-out is certified from F as well).
 inline BandPolicy band_policy(const ltr_params& p, int band_w) {
@@ -130,25 +123,6 @@ inline BandPolicy band_policy(const ltr_params& p, int band_w) {
   b.on = true;
   return b;
 }
-inline int band_margin_needed(const BandPolicy& bp, int n) {
-  if (bp.w_fixed > 0) return bp.w_fixed;
-  const double B = bp.budget0 + bp.budget_per_row * (double)n;
-  const int w = (int)std::ceil(((B - bp.gap.open) / bp.gap.ext + 1.0) / 2.0);
-  return std::max(2, std::min(w, 255));
-}
-// Band class of a pair (index into band_class_k) or -1: not banded (too short, band not narrower than ~half the matrix,
-// length difference beyond the widest class).
-inline int band_class_of(int hlen, int n, int m, const BandPolicy& bp) {
-  if (!bp.on || hlen <= 60 || n < 2 || m < 2) return -1;
-  const int w_need = band_margin_needed(bp, n);
-  for (int c = 0; c < kBandClasses; ++c) {
-    const int W = band_class_w(c);
-    if (band_geometry(n, m, W).w < w_need) continue;
-    return ((uint64_t)(n + m) * (uint64_t)(W / 2) * 100u <= 55ull * (uint64_t)n * (uint64_t)m) ? c : -1;
-  }
-  return -1;
-}
-
 struct Plan {
   std::vector<std::vector<BandTask>> band_tasks;  // [kBandClasses] tasks of the band kernel; read ranges index unique reads
   std::vector<uint64_t> band_pairs_by_rows;       // [K] band pairs whose haplotype has row class K (capacity of the

@@ -55,6 +55,17 @@ class Job:
         self._e.lib.ltr_job_get_stats(self._h, C.byref(s))
         return s
 
+    def wait(self):
+        """ltr_job_wait of a job started with Engine.submit_job: blocks until the results are in the caller's arrays."""
+        _check(self._e.lib, self._e.ctx, self._e.lib.ltr_job_wait(self._e.ctx, self._h), "ltr_job_wait")
+        return self.stats()
+
+    def poll(self):
+        rc = self._e.lib.ltr_job_poll(self._e.ctx, self._h)
+        if rc < 0:
+            _check(self._e.lib, self._e.ctx, rc, "ltr_job_poll")
+        return rc == 1
+
     def close(self):
         if self._h is not None:
             if self._e.ctx:
@@ -138,6 +149,10 @@ class Engine:
         """ltr_ctx_set_band: < 0 disables the banded kernel, 0 = automatic margin, > 0 = margin in diagonals.
         Results never depend on it (uncertified pairs are re-run over the full matrix)."""
         _check(self.lib, self.ctx, self.lib.ltr_ctx_set_band(self.ctx, int(half_width)), "ltr_ctx_set_band")
+
+    def set_plan(self, mode):
+        """ltr_ctx_set_plan: 0 automatic, 1 plan on the host, 2 plan on the device.  Results never depend on it."""
+        _check(self.lib, self.ctx, self.lib.ltr_ctx_set_plan(self.ctx, int(mode)), "ltr_ctx_set_plan")
 
     def __del__(self):
         try:
@@ -229,6 +244,26 @@ class Engine:
         rc = self.lib.ltr_job_create(self.ctx, C.byref(p), C.byref(vb), pb_ref, C.byref(h))
         _check(self.lib, self.ctx, rc, "ltr_job_create")
         return Job(self, h, (keep, keep2))
+
+    def submit_job(self, batch, post=None, aln_params=None, indel_flank_len=5, out_ll=None, out_post=None, out_totals=None,
+                   prepared=None):
+        """ltr_job_submit: enqueue upload + plan + kernels + posteriors + download and return at once; the arrays of
+        ``batch`` / ``post`` and the output arrays must stay alive and untouched until ``Job.wait()``.
+        ``prepared`` = (ViterbiBatch, PosteriorBatch or None, keepalive) skips the per-call struct building."""
+        if prepared is None:
+            vb, keep = abi.make_viterbi_batch(batch)
+            pb, keep2 = (abi.make_posterior_batch(post) if post is not None else (None, None))
+        else:
+            vb, pb, keep = prepared
+            keep2 = None
+        p = abi.make_params(aln_params, indel_flank_len)
+        h = C.c_void_p()
+        rc = self.lib.ltr_job_submit(self.ctx, C.byref(p), C.byref(vb), C.byref(pb) if pb is not None else None,
+                                     None if out_ll is None else abi.ptr(out_ll, abi._dp),
+                                     None if out_post is None else abi.ptr(out_post, abi._dp),
+                                     None if out_totals is None else abi.ptr(out_totals, abi._dp), C.byref(h))
+        _check(self.lib, self.ctx, rc, "ltr_job_submit")
+        return Job(self, h, (keep, keep2, vb, pb, out_ll, out_post, out_totals))
 
     def process_reads_flat(self, locus, n_reads, n_alleles, fill=0.0):
         ll = np.full((n_reads, n_alleles), fill, dtype=np.float64)

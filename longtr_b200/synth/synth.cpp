@@ -27,7 +27,7 @@
 #include <thread>
 #include <vector>
 
-#include "longtr_b200.h"
+#include "longtr_synth.h"
 
 namespace {
 
@@ -208,7 +208,10 @@ void ltr_synth_free(ltr_synth_batch* b) {
 
 // --alignment-params recommended for the configuration (ONT-like for config 4).
 void ltr_synth_params(int config, ltr_params* p) {
-  ltr_params_default(p);
+  // Dindel defaults, reference HapAligner.h:118 (set here: this library does not link the product)
+  p->ins_ins = -1.0f; p->ins_match = (float)-0.458675; p->del_del = -1.0f; p->del_match = (float)-0.458675;
+  p->match_match = (float)-0.00005800168; p->match_ins = (float)-10.448214728; p->match_del = (float)-10.448214728;
+  p->indel_flank_len = 5;
   if (config == 4) {
     p->ins_ins = -1.0f; p->ins_match = (float)-0.458675; p->del_del = -1.0f; p->del_match = (float)-0.458675;
     p->match_match = (float)-0.0202027; p->match_ins = (float)-4.60517; p->match_del = (float)-4.60517;

@@ -1,5 +1,7 @@
-"""Synthetic workloads of BASELINE.json (configs 3-5), generated by the C++ generator in
-csrc/synth.cpp.  Returns numpy views over library-owned memory."""
+"""Synthetic workloads of BASELINE.json (configs 3-5).  Configs 3 and 4 come from the generator
+library synth/libltr_synth.so (plain C++, no product code: the reference arm of bench.py maps only this), config 5 from
+the product library (its pooled reads and seeds go through the host mirror).  Returns numpy views over library-owned
+memory."""
 import ctypes as C
 import os
 
@@ -71,8 +73,21 @@ class Workload:
             self.batch = self.post = None
 
 
+_synth_lib = None
+
+
+def synth_lib():
+    global _synth_lib
+    if _synth_lib is None:
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "synth", "libltr_synth.so")
+        if not os.path.exists(path):
+            raise RuntimeError("libltr_synth.so is not built (run `python -m longtr_b200.build`)")
+        _synth_lib = C.CDLL(path)
+    return _synth_lib
+
+
 def generate(config, n_loci, first_locus=0, base_seed=None, n_threads=None):
-    lib = abi.load()
+    lib = synth_lib()
     lib.ltr_synth_generate.argtypes = [C.c_int, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int,
                                        C.POINTER(C.POINTER(SynthBatch))]
     lib.ltr_synth_generate.restype = C.c_int

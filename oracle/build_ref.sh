@@ -56,6 +56,21 @@ for o in $objs; do case "$o" in *fasta_reader.o) ;; *) base_objs="$base_objs $o"
 $CXX -o "$out/ltr_ref_full" "$out/obj/full_driver.o" "$out/obj/hts_stubs.o" "$out/obj/fasta_reader.o" \
      $base_objs $fobjs -lm -lpthread
 echo "built $out/ltr_ref_full"
+# ---- ltr_ref_trace: all-CPU reference with a recording wrapper around Genotyper::calc_log_sample_posteriors ---------
+objcopy --redefine-sym _ZN9Genotyper26calc_log_sample_posteriorsERSt6vectorIiSaIiEE=ltr_orig_calc_log_sample_posteriors \
+        "$out/obj/genotyper.o" "$out/obj/genotyper_trace.o"
+$CXX -O2 -g -std=c++11 -fPIC -w -DLTR_FULL_MAIN -DLTR_TRACE_POSTERIORS -I"$here/shim" -I"$ref/src" -I"$here" \
+     -c "$here/full_driver.cpp" -o "$out/obj/full_driver_trace.o"
+trace_objs=""
+for o in $base_objs; do
+  case "$o" in
+    *genotyper.o) trace_objs="$trace_objs $out/obj/genotyper_trace.o";;
+    *) trace_objs="$trace_objs $o";;
+  esac
+done
+$CXX -o "$out/ltr_ref_trace" "$out/obj/full_driver_trace.o" "$out/obj/hts_stubs.o" "$out/obj/fasta_reader.o" \
+     $trace_objs $fobjs -lm -lpthread
+echo "built $out/ltr_ref_trace"
 lib="$here/../longtr_b200/csrc"
 if [ -f "$lib/liblongtr_b200.so" ]; then
   objcopy --weaken-symbol=_ZN10HapAligner13process_readsERKSt6vectorI9AlignmentSaIS1_EEiPK11BaseQualityRKS0_IbSaIbEEPdPi \

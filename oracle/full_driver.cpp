@@ -9,6 +9,8 @@
 //   ltr_ref_full   every object is the reference's own           -> golden VCF records
 //   ltr_ref_gpu    same objects, but HapAligner::process_reads and Genotyper::calc_log_sample_posteriors
 //                        come from integration/reference_binding.cpp (C ABI -> GPU)   -> drop-in check
+//   ltr_ref_trace  the reference's objects with a recording wrapper around calc_log_sample_posteriors
+//                        (-DLTR_TRACE_POSTERIORS): LL matrix, posteriors and MAP pairs of both passes of genotype()
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -16,6 +18,14 @@
 #include <string>
 #include <vector>
 
+#ifdef LTR_TRACE_POSTERIORS
+// The trace build looks inside the reference's genotyper objects (layout is unaffected by access specifiers).
+#include <iostream>
+#include <map>
+#include <set>
+#define private public
+#define protected public
+#endif
 #include "SeqAlignment/AlignmentData.h"
 #include "mathops.h"
 #include "region.h"
@@ -57,6 +67,54 @@ void BamAlignment::ExtractSequenceFields() { unreachable_full("BamAlignment::Ext
 bool VCF::VCFReader::get_next_variant(VCF::Variant&) { unreachable_full("VCFReader::get_next_variant"); return false; }
 const std::vector<std::string>& VCF::Variant::get_samples() const { unreachable_full("Variant::get_samples"); static std::vector<std::string> v; return v; }
 
+#ifdef LTR_TRACE_POSTERIORS
+// ltr_ref_trace: oracle/build_ref.sh renames the reference's Genotyper::calc_log_sample_posteriors(std::vector<int>&)
+// (src/genotyper.cpp:45-83) to ltr_orig_calc_log_sample_posteriors in a COPY of its object file; the definition below
+// takes its place, records what goes in and what comes out of every call, and runs the original in between.  genotype()
+// calls it twice (src/seq_stutter_genotyper.cpp:635 and, through remove_alleles, :643): before and after the uncalled
+// alleles are dropped.
+extern "C" double ltr_orig_calc_log_sample_posteriors(Genotyper* self, std::vector<int>& read_weights);
+static std::string g_trace;
+static void trace_doubles(std::ostringstream& o, const char* tag, const double* v, size_t n) {
+  o << tag << " " << n;
+  char buf[64];
+  for (size_t i = 0; i < n; ++i) {
+    std::snprintf(buf, sizeof(buf), " %a", v[i]);
+    o << buf;
+  }
+  o << "\n";
+}
+double Genotyper::calc_log_sample_posteriors(std::vector<int>& read_weights) {
+  std::ostringstream o;
+  SeqStutterGenotyper* g = dynamic_cast<SeqStutterGenotyper*>(this);
+  o << "CALL " << num_alleles_ << " " << num_reads_ << " " << num_samples_ << "\n";
+  o << "ALLELES";
+  if (g != NULL && g->haplotype_ != NULL && g->haplotype_->num_blocks() == 3)
+    for (int a = 0; a < g->hap_blocks_[1]->num_options(); ++a) o << " " << (g->hap_blocks_[1]->get_seq(a).empty() ? "-" : g->hap_blocks_[1]->get_seq(a));
+  o << "\n";
+  o << "SEEDS";
+  if (g != NULL && g->seed_positions_ != NULL)
+    for (int r = 0; r < num_reads_; ++r) o << " " << g->seed_positions_[r];
+  o << "\n";
+  o << "LABELS";
+  for (int r = 0; r < num_reads_; ++r) o << " " << sample_label_[r];
+  o << "\n";
+  trace_doubles(o, "LL", log_aln_probs_, (size_t)num_reads_ * num_alleles_);
+  trace_doubles(o, "P1", log_p1_, (size_t)num_reads_);
+  trace_doubles(o, "P2", log_p2_, (size_t)num_reads_);
+  const double total = ltr_orig_calc_log_sample_posteriors(this, read_weights);
+  trace_doubles(o, "POST", log_sample_posteriors_, (size_t)num_samples_ * num_alleles_ * num_alleles_);
+  trace_doubles(o, "TOTALS", sample_total_LLs_, (size_t)num_samples_);
+  std::vector<std::pair<int, int> > gts;
+  get_optimal_haplotypes(gts);
+  o << "GTS";
+  for (size_t s = 0; s < gts.size(); ++s) o << " " << gts[s].first << " " << gts[s].second;
+  o << "\n";
+  g_trace += o.str();
+  return total;
+}
+#endif
+
 static void parse_cigar(const char* cigar, Alignment& aln) {
   int num = 0;
   for (const char* p = cigar; *p; ++p) {
@@ -69,6 +127,9 @@ extern "C" int32_t ltr_ref_full_locus(const ltr_full_locus* L, char* out, int32_
   static bool logs_ready = false;
   if (!logs_ready) { precompute_integer_logs(); logs_ready = true; }
   g_capture.clear();
+#ifdef LTR_TRACE_POSTERIORS
+  g_trace.clear();
+#endif
   const std::string chrom_seq(L->chrom_seq);
   Region region(L->chrom_name, L->region_start, L->region_stop, L->motif, L->region_name);
   RegionGroup rg(region);
@@ -156,6 +217,9 @@ int main() {
     const int32_t n = ltr_ref_full_locus(&L, out, (int32_t)sizeof(out));
     if (n < 0) return 3;
     std::printf("RECORD %d\n%s\n", n, out);
+#ifdef LTR_TRACE_POSTERIORS
+    std::printf("TRACE %d\n%s", (int)g_trace.size(), g_trace.c_str());
+#endif
     std::fflush(stdout);
   }
   return 0;

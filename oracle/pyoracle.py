@@ -262,6 +262,48 @@ def log_sample_posteriors(ll, log_p1, log_p2, sample_label, n_samples, haploid=F
 
 
 # ---- IO-less per-locus genotyper of the reference (full_driver.cpp): VCF record text ---------------------------
+def full_locus_traces(cases):
+    """ltr_ref_trace: per case (VCF record text, [calls]) where every call of Genotyper::calc_log_sample_posteriors inside
+    SeqStutterGenotyper::genotype is a dict H, R, S, alleles, seeds, labels, ll, p1, p2, post, totals, gts (doubles as
+    hex-float strings, exactly as the reference held them)."""
+    build()
+    exe = os.path.join(_HERE, "_ref", "ltr_ref_trace")
+    p = subprocess.run([exe], input="".join(_case_text(c) for c in cases).encode(), stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, timeout=600)
+    if p.returncode != 0:
+        raise RuntimeError("ltr_ref_trace failed rc=%d: %s" % (p.returncode, p.stderr.decode()[-400:]))
+    out, res, pos = p.stdout.decode(), [], 0
+    while pos < len(out):
+        assert out.startswith("RECORD ", pos)
+        nl = out.index("\n", pos)
+        n = int(out[pos + 7:nl])
+        rec = out[nl + 1:nl + 1 + n].rstrip("\n")
+        pos = nl + 1 + n + 1
+        assert out.startswith("TRACE ", pos)
+        nl = out.index("\n", pos)
+        n = int(out[pos + 6:nl])
+        body = out[nl + 1:nl + 1 + n]
+        pos = nl + 1 + n
+        calls, cur = [], None
+        for line in body.split("\n"):
+            f = line.split()
+            if not f:
+                continue
+            if f[0] == "CALL":
+                cur = dict(H=int(f[1]), R=int(f[2]), S=int(f[3]))
+                calls.append(cur)
+            elif f[0] == "ALLELES":
+                cur["alleles"] = ["" if a == "-" else a for a in f[1:]]
+            elif f[0] in ("SEEDS", "LABELS", "GTS"):
+                cur[f[0].lower()] = [int(x) for x in f[1:]]
+            else:
+                assert int(f[1]) == len(f) - 2
+                cur[f[0].lower()] = f[2:]
+        res.append((rec, calls))
+    assert len(res) == len(cases)
+    return res
+
+
 def full_available(which):
     """which = 'full' (all-CPU reference) or 'gpu' (reference + integration/reference_binding.cpp -> GPU)."""
     return os.path.exists(os.path.join(_HERE, "_ref", "ltr_ref_%s" % which))

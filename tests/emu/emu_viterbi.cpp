@@ -447,3 +447,136 @@ extern "C" int ltr_emu_plan_check(const ltr_viterbi_batch* b, const ltr_params* 
   }
   return 0;
 }
+
+// ---- device plan (plan_device.cuh) run serially on the host, held against make_plan ------------------------------------
+#include "plan_device.cuh"
+
+#include <map>
+#include <set>
+#include <tuple>
+
+// Returns 0 when the device plan's products are identical to make_plan's (numbering of the distinct reads, offsets,
+// bytes, read map, statistics, and the SETS of band / stream tasks per class; the order inside a list may differ),
+// otherwise the number of the first difference.  -1: make_plan rejected the batch (the device plan must flag it too,
+// which is then reported as -2 if it did not).  pad: readable bytes around the string buffers, as on the device.
+extern "C" int ltr_emu_device_plan_check(const ltr_viterbi_batch* b, const ltr_params* p, int kmax, int band_w,
+                                         uint64_t* counts) {
+  Plan plan;
+  const int rc_host = make_plan(*b, *p, kmax, plan, 1, nullptr, nullptr, band_w);
+  const uint32_t n_loci = b->n_loci;
+  const uint32_t n_haps = b->locus_hap_begin[n_loci], n_reads = b->locus_read_begin[n_loci];
+  const size_t pad = 512;
+  const uint32_t raw_total = n_reads ? b->read_off[n_reads] : 0u;
+  std::vector<uint8_t> raw(pad + raw_total + pad, 0), ubytes_buf(pad + raw_total + pad, 0);
+  if (raw_total) std::memcpy(raw.data() + pad, b->read_bytes, raw_total);
+  std::vector<unsigned long long> rhash(n_reads + 1), ull_off(n_loci + 1), stat(PLAN_STAT_WORDS, 0);
+  std::vector<uint32_t> rlen(n_reads + 1), rep(n_reads + 1), rank_of(n_reads + 1), tmp_len(n_reads + 1), tmp_rep(n_reads + 1),
+      ucount(n_loci + 1), ubytes(n_loci + 1), ubyte_off(n_loci + 1), local_u(n_reads + 1), read_locus(n_reads + 1),
+      hap_locus(n_haps + 1), lub(n_loci + 1), uread_off(n_reads + 2), r2u(n_reads + 1), ctl(PLAN_CTL_WORDS, 0),
+      band_task_pos((size_t)kBandClasses * n_loci + 1, 0), band_pair_pos((size_t)kBandClasses * n_loci + 1, 0);
+  uint64_t n_pairs = 0;
+  for (uint32_t l = 0; l < n_loci; ++l)
+    n_pairs += (uint64_t)(b->locus_hap_begin[l + 1] - b->locus_hap_begin[l]) * (b->locus_read_begin[l + 1] - b->locus_read_begin[l]);
+  std::vector<BandTask> band_tasks(n_pairs + 1);
+  std::vector<PlanPair> band_pairs(n_pairs + 1);
+  std::vector<std::vector<Task> > st(kPlanMaxK + 1, std::vector<Task>(n_pairs + 1));
+  std::vector<uint32_t> st_n(kPlanMaxK + 1, 0);
+  PlanDev P;
+  P.n_loci = n_loci; P.n_haps = n_haps; P.n_reads = n_reads; P.raw_total = raw_total;
+  P.cut = 35 - p->indel_flank_len; P.kmax = kmax; P.band = band_policy(*p, band_w);
+  P.lhb = b->locus_hap_begin; P.lrb = b->locus_read_begin; P.hap_off = b->hap_off; P.read_off = b->read_off;
+  P.read_bytes = raw.data() + pad;
+  P.rhash = rhash.data(); P.rlen = rlen.data(); P.rep = rep.data(); P.rank_of = rank_of.data();
+  P.tmp_len = tmp_len.data(); P.tmp_rep = tmp_rep.data(); P.ucount = ucount.data(); P.ubytes = ubytes.data();
+  P.ubyte_off = ubyte_off.data(); P.band_task_pos = band_task_pos.data(); P.band_pair_pos = band_pair_pos.data();
+  P.local_u = local_u.data(); P.read_locus = read_locus.data();
+  P.hap_locus = hap_locus.data(); P.lub = lub.data(); P.ull_off = ull_off.data(); P.uread_off = uread_off.data();
+  P.uread_bytes = ubytes_buf.data() + pad; P.r2u = r2u.data(); P.ctl = ctl.data(); P.stat = stat.data();
+  P.band_tasks = band_tasks.data(); P.band_pairs = band_pairs.data(); P.band_cap = (uint32_t)n_pairs;
+  for (int k = 0; k <= kPlanMaxK; ++k) {
+    P.st_tasks[k] = st[(size_t)k].data();
+    P.st_cap[k] = (uint32_t)n_pairs;
+    P.st_ntasks[k] = &st_n[(size_t)k];
+  }
+  for (uint32_t l = 0; l < n_loci; ++l) plan_locus_dedupe(P, l, 0, 1);
+  plan_scan_serial(P);
+  for (uint32_t l = 0; l < n_loci; ++l) plan_locus_fill(P, l, 0, 1);
+  for (uint32_t l = 0; l < n_loci; ++l) plan_locus_tasks(P, l, 0);
+  plan_band_scan_serial(P);
+  plan_task_scan(P);
+  for (uint32_t l = 0; l < n_loci; ++l) plan_locus_tasks(P, l, 1);
+  if (rc_host != LTR_OK) return ctl[PLAN_CTL_ERR] ? -1 : -2;
+  if (ctl[PLAN_CTL_ERR]) return 1;
+  if (ctl[PLAN_CTL_N_UREADS] != plan.locus_uread_begin[n_loci]) return 2;
+  for (uint32_t l = 0; l <= n_loci; ++l)
+    if (lub[l] != plan.locus_uread_begin[l] || ull_off[l] != plan.ull_off[l]) return 3;
+  for (uint32_t u = 0; u <= plan.locus_uread_begin[n_loci]; ++u)
+    if (uread_off[u] != plan.uread_off[u]) return 4;
+  if (plan.uread_nbytes && std::memcmp(P.uread_bytes, plan.uread_bytes, plan.uread_nbytes) != 0) return 5;
+  for (uint32_t r = 0; r < n_reads; ++r)
+    if (r2u[r] != plan.read_to_uread[r] || read_locus[r] != plan.read_locus[r]) return 6;
+  for (uint32_t h = 0; h < n_haps; ++h)
+    if (hap_locus[h] != plan.hap_locus[h]) return 7;
+  if (stat[PLAN_STAT_CELLS] != plan.n_cells || stat[PLAN_STAT_CELLS_STREAM] != plan.n_cells_computed ||
+      stat[PLAN_STAT_PAIRS_COMPUTED] != plan.n_pairs_computed || (int)stat[PLAN_STAT_MAX_M] != plan.max_m) return 8;
+  if (ctl[PLAN_CTL_N_BAND_PAIRS] != plan.n_band_pairs) return 9;
+  typedef std::tuple<uint32_t, uint32_t, uint32_t> T3;
+  for (int c = 0; c < kBandClasses; ++c) {
+    // same tasks in the same order as make_plan (run single-threaded): locus by locus, haplotype by haplotype
+    std::vector<T3> a, d;
+    for (const BandTask& t : plan.band_tasks[(size_t)c]) a.push_back(T3(t.hap, t.read_begin, t.read_end));
+    const uint32_t t0 = ctl[PLAN_CTL_BAND_TASK_BASE + c], nt = ctl[PLAN_CTL_BAND_TASK_COUNT + c];
+    uint32_t np = 0;
+    for (uint32_t t = t0; t < t0 + nt; ++t) {
+      d.push_back(T3(band_tasks[t].hap, band_tasks[t].read_begin, band_tasks[t].read_end));
+      np += band_tasks[t].read_end - band_tasks[t].read_begin;
+    }
+    if (a != d) return 10;
+    if (np != ctl[PLAN_CTL_BAND_INFO + 2 * c + 1]) return 11;
+    // the pair list of the class holds exactly the pairs of its tasks
+    std::vector<std::pair<uint32_t, uint32_t> > pa, pd;
+    for (const BandTask& t : plan.band_tasks[(size_t)c])
+      for (uint32_t u = t.read_begin; u < t.read_end; ++u) pa.push_back(std::make_pair(t.hap, u));
+    const uint32_t p0 = ctl[PLAN_CTL_BAND_INFO + 2 * c];
+    for (uint32_t i = p0; i < p0 + np; ++i) pd.push_back(std::make_pair(band_pairs[i].x, band_pairs[i].y));
+    if (pa != pd) return 12;
+  }
+  uint64_t n_stream_tasks = 0, host_stream_tasks = 0;
+  for (int k = 1; k <= kmax; ++k) host_stream_tasks += plan.tasks[(size_t)k].size();
+  for (int k = 1; k <= kmax; ++k) {
+    std::multiset<T3> a, d;
+    for (const Task& t : plan.tasks[(size_t)k]) a.insert(T3(t.hap, t.read_begin, t.read_end));
+    for (uint32_t i = 0; i < st_n[(size_t)k]; ++i)
+      d.insert(T3(st[(size_t)k][i].hap, st[(size_t)k][i].read_begin, st[(size_t)k][i].read_end));
+    {  // the covered (haplotype, distinct read) pairs agree; so do the tasks themselves unless make_plan cut its tasks
+       // into pieces (kWantTasks, small batches only)
+      std::multiset<std::pair<uint32_t, uint32_t> > pa, pd;
+      for (const T3& t : a) for (uint32_t u = std::get<1>(t); u < std::get<2>(t); ++u) pa.insert(std::make_pair(std::get<0>(t), u));
+      for (const T3& t : d) for (uint32_t u = std::get<1>(t); u < std::get<2>(t); ++u) pd.insert(std::make_pair(std::get<0>(t), u));
+      if (pa != pd) return 13;
+      if (host_stream_tasks >= 2048 && a != d) return 13;
+    }
+    n_stream_tasks += d.size();
+    // heaviest cost bucket first
+    uint64_t prev_bucket = 64;
+    for (uint32_t i = 0; i < st_n[(size_t)k]; ++i) {
+      const Task& t = st[(size_t)k][i];
+      const int hlen = (int)(b->hap_off[t.hap + 1] - b->hap_off[t.hap]), n = hlen - 2 * P.cut;
+      const bool real = hlen > 60 && n >= 1;
+      const int strips = real ? std::max(1, (n - 1 + 32 * k - 1) / (32 * k)) : 1;
+      const uint64_t q = uread_off[t.read_end] - uread_off[t.read_begin];
+      const uint64_t cost = real ? (uint64_t)k * strips * (q + 32) : (uint64_t)(t.read_end - t.read_begin);
+      uint64_t bucket = 0;
+      for (uint64_t v = cost; v > 1; v >>= 1) ++bucket;
+      if (bucket > 31) bucket = 31;
+      if (bucket > prev_bucket) return 14;
+      prev_bucket = bucket;
+    }
+  }
+  if (counts) {
+    counts[0] = ctl[PLAN_CTL_N_UREADS];
+    counts[1] = ctl[PLAN_CTL_N_BAND_PAIRS];
+    counts[2] = n_stream_tasks;
+  }
+  return 0;
+}

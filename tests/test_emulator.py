@@ -324,3 +324,55 @@ def test_pathological_batches(emu, seed):
     want, _ = po.viterbi_batch(b)
     out, _stats = run_band(emu, b, None, 16, 0)
     assert np.array_equal(out, want)
+
+
+def _device_plan_check(emu, b, params, kmax, band_w):
+    emu.ltr_emu_device_plan_check.argtypes = [C.POINTER(abi.ViterbiBatch), C.POINTER(abi.Params), C.c_int, C.c_int,
+                                              C.POINTER(C.c_uint64)]
+    emu.ltr_emu_device_plan_check.restype = C.c_int
+    vb, keep = abi.make_viterbi_batch(b)
+    p = abi.make_params(params)
+    counts = (C.c_uint64 * 3)()
+    return emu.ltr_emu_device_plan_check(C.byref(vb), C.byref(p), kmax, band_w, counts), list(counts)
+
+
+@pytest.mark.parametrize("seed,kw,kmax,params", CASES)
+@pytest.mark.parametrize("band_w", [-1, 0, 3, 90])
+def test_device_plan_matches_host_plan(emu, seed, kw, kmax, params, band_w):
+    """plan_device.cuh (the plan kernels' per-item functions, run serially on the host) gives make_plan's numbering of the
+    distinct reads, offsets, bytes, read map, statistics and task sets."""
+    b = synth.make_pair_batch(seed, **kw)
+    rc, _ = _device_plan_check(emu, b, params, kmax, band_w)
+    assert rc == 0
+
+
+def test_device_plan_with_duplicate_reads(emu):
+    from longtr_b200 import workloads
+    w = workloads.generate(3, 300)
+    b, _ = w.subset(300)
+    rc, counts = _device_plan_check(emu, b, w.aln_params, 16, 0)
+    assert rc == 0
+    assert counts[0] < 0.8 * int(b["locus_read_begin"][-1])
+    w4 = workloads.generate(4, 12)
+    b4, _ = w4.subset(12)
+    rc, counts = _device_plan_check(emu, b4, w4.aln_params, 16, 0)
+    assert rc == 0
+    w.close()
+    w4.close()
+
+
+@pytest.mark.parametrize("seed", range(15))
+def test_device_plan_pathological_batches(emu, seed):
+    b = synth.make_pathological_batch(seed)
+    for band_w in (-1, 0, 3):
+        rc, _ = _device_plan_check(emu, b, None, 16, band_w)
+        assert rc == 0
+
+
+def test_device_plan_flags_malformed_read_offsets(emu):
+    b = synth.make_pair_batch(11, n_loci=6)
+    off = b["read_off"].copy()
+    off[3] = off[2]  # an empty read
+    b2 = dict(b, read_off=off)
+    rc, _ = _device_plan_check(emu, b2, None, 16, 0)
+    assert rc == -1  # both plans reject it
