@@ -366,7 +366,7 @@ int setup_posteriors(ltr_ctx* ctx, ltr_job* job, const ltr_viterbi_batch& bb, co
     const uint32_t S = post->locus_n_samples[l];
     max_h = std::max(max_h, H);
     const unsigned long long shh = (unsigned long long)S * H * H;
-    if (S > (1u << 20) || shh > (1ull << 40)) return LTR_ERR_INVALID;
+    if (S > (1u << 20) || shh > (1ull << 31)) return LTR_ERR_INVALID;  // the kernels index a locus' entries with 32 bits
     post_off[l + 1] = post_off[l] + shh;
     tot_off[l + 1] = tot_off[l] + S;
     if (validate_reads_on_host) {
@@ -568,7 +568,8 @@ int setup_device_plan(ltr_ctx* ctx, ltr_job* job, const ltr_viterbi_batch& bb, c
   LTR_CUDA(ctx, job->plan_stat.alloc(PLAN_STAT_WORDS * 8));
   // scratch of the plan kernels, one allocation
   const size_t nr = ((size_t)n_reads + 2 + 1) & ~(size_t)1, nl = ((size_t)n_loci + 2 + 1) & ~(size_t)1;
-  LTR_CUDA(ctx, job->plan_scratch.alloc(nr * 8 + nr * 4 * 6 + nl * 4 * 3 + nl * 4 * 2 * kBandClasses));
+  const size_t n_partial = 3 * ((size_t)kBandClasses * nl / 1024 + 2) + 8;  // tile sums of the scans (plan_kernels.cu)
+  LTR_CUDA(ctx, job->plan_scratch.alloc(nr * 8 + n_partial * 8 + nr * 4 * 6 + nl * 4 * 3 + nl * 4 * 2 * kBandClasses));
   PlanDev& P = job->pd;
   P.n_loci = n_loci; P.n_haps = n_haps; P.n_reads = n_reads; P.raw_total = job->raw_bytes;
   P.cut = cut; P.kmax = kmax; P.band = job->band;
@@ -578,6 +579,7 @@ int setup_device_plan(ltr_ctx* ctx, ltr_job* job, const ltr_viterbi_batch& bb, c
   {
     char* s = job->plan_scratch.as<char>();
     P.rhash = reinterpret_cast<unsigned long long*>(s); s += nr * 8;
+    P.scan_partial = reinterpret_cast<unsigned long long*>(s); s += n_partial * 8;
     P.rlen = reinterpret_cast<uint32_t*>(s); s += nr * 4;
     P.rep = reinterpret_cast<uint32_t*>(s); s += nr * 4;
     P.rank_of = reinterpret_cast<uint32_t*>(s); s += nr * 4;
@@ -813,7 +815,7 @@ int job_enqueue_compute(ltr_ctx* ctx, ltr_job* job) {
     LTR_CUDA(ctx, cudaMemsetAsync(job->plan_stat.p, 0, PLAN_STAT_WORDS * 8, L.main));
     LTR_CUDA(ctx, cudaMemsetAsync(job->pd.band_task_pos, 0, plan_band_counter_bytes(job), L.main));
     LTR_CUDA(ctx, launch_device_plan(job->pd, ctx->sm_count, L.main));
-    if (job->n_loci) job->stats.n_launches += 6;
+    if (job->n_loci) job->stats.n_launches += 11;
   }
   LTR_CUDA(ctx, cudaEventRecord(job->ev_plan, L.main));
   const int n_used = (int)std::min<size_t>(kNumStreams, job->classes.size());  // streams run_classes touches

@@ -76,6 +76,7 @@ struct PlanDev {
   uint32_t* ubyte_off;        // [n_loci+1]
   uint32_t* band_task_pos;    // [kBandClasses][n_loci] pass 0: band tasks of (class, locus); after the scan: list position
   uint32_t* band_pair_pos;    // [kBandClasses][n_loci] the same for their pairs
+  unsigned long long* scan_partial;  // tile sums of the multi-block scans: 3 * ceil(kBandClasses * n_loci / 1024) + 8 words
   // products
   uint32_t* local_u;          // [n_reads] rank | kPlanRep
   uint32_t* read_locus;       // [n_reads]
@@ -172,19 +173,24 @@ LTR_HD bool plan_equal(const uint8_t* a, const uint8_t* b, uint32_t len) {
 }
 
 // ---- step 1: one locus, nl lanes: distinct reads, their order, per-locus counts ----------------------------------------
-LTR_HD void plan_locus_dedupe(const PlanDev& P, uint32_t l, uint32_t lane, uint32_t nl) {
+// bytes / origin: where the raw read bytes are read from -- byte at raw offset o is bytes[o - origin].  The device kernel
+// passes a shared-memory copy of the locus' bytes when it fits (coalesced staging instead of 32 lanes streaming 32
+// different reads through L1), otherwise (and on the host) the raw buffer itself with origin 0.
+// limit: no read of the locus may end behind it (end of the staged span, or of the upload).
+LTR_HD void plan_locus_dedupe(const PlanDev& P, uint32_t l, uint32_t lane, uint32_t nl, const uint8_t* bytes, uint32_t origin,
+                              uint32_t limit) {
   const uint32_t r0 = P.lrb[l], r1 = P.lrb[l + 1];
   for (uint32_t h = P.lhb[l] + lane; h < P.lhb[l + 1]; h += nl) P.hap_locus[h] = l;
   uint32_t bad = 0, max_m = 0;
   for (uint32_t r = r0 + lane; r < r1; r += nl) {
     const uint32_t o0 = P.read_off[r], o1 = P.read_off[r + 1];
-    const bool ok = (o1 > o0) && (o1 <= P.raw_total);  // reads are not empty, offsets stay inside the upload
+    const bool ok = (o1 > o0) && (o1 <= limit) && (o0 >= origin);  // not empty, inside the upload / the staged span
     const uint32_t len = ok ? o1 - o0 : 0u;
     bad |= ok ? 0u : 1u;
     max_m = len > max_m ? len : max_m;
     P.read_locus[r] = l;
     P.rlen[r] = len;
-    P.rhash[r] = plan_hash(P.read_bytes + (ok ? o0 : 0u), len);
+    P.rhash[r] = plan_hash(bytes + ((ok ? o0 : origin) - origin), len);
   }
   if (bad) plan_atomic_or(P.ctl + PLAN_CTL_ERR, 1u);
   if (max_m) plan_atomic_max64(P.stat + PLAN_STAT_MAX_M, (unsigned long long)max_m);
@@ -193,11 +199,11 @@ LTR_HD void plan_locus_dedupe(const PlanDev& P, uint32_t l, uint32_t lane, uint3
   for (uint32_t r = r0 + lane; r < r1; r += nl) {
     const unsigned long long h = P.rhash[r];
     const uint32_t len = P.rlen[r];
-    const uint8_t* s = P.read_bytes + P.read_off[r];
+    const uint8_t* s = bytes + (P.read_off[r] - origin);  // (len == 0: never dereferenced)
     uint32_t rep = r;
     for (uint32_t q = r0; q < r; ++q) {
       if (P.rhash[q] != h || P.rlen[q] != len) continue;
-      if (len == 0 || plan_equal(P.read_bytes + P.read_off[q], s, len)) {
+      if (len == 0 || plan_equal(bytes + (P.read_off[q] - origin), s, len)) {
         rep = q;
         break;
       }

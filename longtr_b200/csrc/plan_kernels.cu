@@ -1,5 +1,5 @@
 // plan_kernels.cu -- the job plan on the device (plan_device.cuh): de-duplication of the trimmed reads of every locus,
-// offsets, compaction and the task lists of the banded / full-matrix Viterbi kernels, as five small kernels that run in
+// offsets, compaction and the task lists of the banded / full-matrix Viterbi kernels, as a handful of small kernels that run in
 // stream order between the upload of a batch and its DP kernels.  HBM-bound integer / byte work: one warp per locus
 // (its reads are contiguous, so the lanes read neighbouring lines), one thread per haplotype for the task passes.
 #include <cuda_runtime.h>
@@ -12,67 +12,231 @@ namespace ltr {
 
 static constexpr int kPlanBlock = 128;
 
+// One warp per locus.  The raw reads of a locus are contiguous: the warp copies them into shared memory with coalesced
+// 16-byte loads (kStageBytes per warp; loci that do not fit, e.g. 30 reads of a 1 kb VNTR, are read in place) and hashes /
+// compares them there.
+static constexpr uint32_t kStageBytes = 16384;
 __global__ void __launch_bounds__(kPlanBlock) plan_dedupe_kernel(const PlanDev P) {
+  extern __shared__ __align__(16) uint8_t plan_smem[];
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t l = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; l < P.n_loci; l += warps)
-    plan_locus_dedupe(P, l, lane, 32u);
+  uint8_t* stage = plan_smem + (size_t)(threadIdx.x >> 5) * kStageBytes;
+  for (uint32_t l = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; l < P.n_loci; l += warps) {
+    const uint32_t o0 = P.read_off[P.lrb[l]], o1 = P.read_off[P.lrb[l + 1]];
+    const uint32_t origin = o0 & ~15u;
+    const bool fits = (o1 >= o0) && (o1 <= P.raw_total) && (o1 - origin + 32u <= kStageBytes);
+    if (fits) {
+      __syncwarp();  // the previous locus' readers are done with the buffer
+      const uint4* src = reinterpret_cast<const uint4*>(P.read_bytes + origin);  // buffer base + 512-byte pad: 16-aligned
+      uint4* dst = reinterpret_cast<uint4*>(stage);
+      const uint32_t n16 = (o1 - origin + 16u + 15u) >> 4;  // one word past the end for plan_load32
+      for (uint32_t i = lane; i < n16; i += 32u) dst[i] = src[i];
+      __syncwarp();
+      plan_locus_dedupe(P, l, lane, 32u, stage, origin, o1);
+    } else {
+      plan_locus_dedupe(P, l, lane, 32u, P.read_bytes, 0u, P.raw_total);
+    }
+  }
 }
 
-// Exclusive scans over the loci: distinct reads, their bytes, rows of the distinct LL matrices.  One CTA; every thread
-// sums a contiguous chunk of loci, the chunk totals are scanned in shared memory, the chunk is then written out.
-__global__ void __launch_bounds__(1024) plan_scan_kernel(const PlanDev P) {
-  __shared__ unsigned long long s_u[1024], s_b[1024], s_l[1024];
-  const uint32_t t = threadIdx.x;
-  const bool err = P.ctl[PLAN_CTL_ERR] != 0;
-  const uint32_t chunk = (P.n_loci + 1023u) / 1024u;
-  const uint32_t l0 = min(P.n_loci, t * chunk), l1 = min(P.n_loci, l0 + chunk);
-  unsigned long long su = 0, sb = 0, sl = 0;
-  if (!err)
-    for (uint32_t l = l0; l < l1; ++l) {
-      const uint32_t c = P.ucount[l];
-      su += c;
-      sb += P.ubytes[l];
-      sl += (unsigned long long)c * (P.lhb[l + 1] - P.lhb[l]);
+// ---- multi-block exclusive scans -----------------------------------------------------------------------------------------
+// Three small kernels per scan: (1) every CTA reduces a tile of kScanTile elements, (2) one CTA scans the tile sums,
+// (3) every CTA scans its tile in shared memory on top of its tile offset and writes the results.  IO is a policy:
+//   COLS columns scanned together; load(i, v[COLS]); store(i, prefix[COLS]); total(prefix[COLS]) once, at the end.
+static constexpr int kScanThreads = 256, kScanPer = 4, kScanTile = kScanThreads * kScanPer;
+
+struct LocusScanIO {  // distinct reads, their bytes, rows of the distinct LL matrices: per locus -> prefix sums
+  static constexpr int COLS = 3;
+  PlanDev P;
+  __device__ uint32_t size() const { return P.n_loci; }
+  __device__ void load(uint32_t l, unsigned long long* v) const {
+    const bool err = P.ctl[PLAN_CTL_ERR] != 0;
+    const uint32_t c = err ? 0u : P.ucount[l];
+    v[0] = c;
+    v[1] = err ? 0u : P.ubytes[l];
+    v[2] = (unsigned long long)c * (P.lhb[l + 1] - P.lhb[l]);
+  }
+  __device__ void store(uint32_t l, const unsigned long long* v) const {
+    P.lub[l] = (uint32_t)v[0];
+    P.ubyte_off[l] = (uint32_t)v[1];
+    P.ull_off[l] = v[2];
+  }
+  __device__ void total(const unsigned long long* v) const {
+    store(P.n_loci, v);
+    P.ctl[PLAN_CTL_N_UREADS] = (uint32_t)v[0];
+    P.stat[PLAN_STAT_PAIRS_COMPUTED] = v[2];
+    if (v[1] > 0xFFFFFFF0ull) atomicOr(P.ctl + PLAN_CTL_ERR, 2u);
+    if (v[0] == 0) P.uread_off[0] = 0u;
+  }
+};
+
+struct BandScanIO {  // [class][locus] band counters (tasks, pairs) -> list positions, class after class, in place
+  static constexpr int COLS = 2;
+  PlanDev P;
+  __device__ uint32_t size() const { return (uint32_t)kBandClasses * P.n_loci; }
+  __device__ void load(uint32_t i, unsigned long long* v) const {
+    v[0] = P.band_task_pos[i];
+    v[1] = P.band_pair_pos[i];
+  }
+  __device__ void store(uint32_t i, const unsigned long long* v) const {
+    P.band_task_pos[i] = (uint32_t)v[0];
+    P.band_pair_pos[i] = (uint32_t)v[1];
+    if (i % P.n_loci == 0) {  // first entry of a band class: where its lists start
+      const uint32_t c = i / P.n_loci;
+      P.ctl[PLAN_CTL_BAND_TASK_BASE + c] = (uint32_t)v[0];
+      P.ctl[PLAN_CTL_BAND_INFO + 2 * c] = (uint32_t)v[1];
     }
-  s_u[t] = su;
-  s_b[t] = sb;
-  s_l[t] = sl;
+  }
+  __device__ void total(const unsigned long long* v) const {
+    P.ctl[PLAN_CTL_N_BAND_TASKS] = v[0] < P.band_cap ? (uint32_t)v[0] : P.band_cap;
+    P.ctl[PLAN_CTL_N_BAND_PAIRS] = (uint32_t)v[1];
+  }
+};
+
+template <typename IO>
+__global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const IO io, unsigned long long* __restrict__ partial) {
+  __shared__ unsigned long long s_w[IO::COLS][kScanThreads / 32];
+  const uint32_t n = io.size(), base = blockIdx.x * (uint32_t)kScanTile;
+  unsigned long long acc[IO::COLS];
+#pragma unroll
+  for (int c = 0; c < IO::COLS; ++c) acc[c] = 0;
+  for (int j = 0; j < kScanPer; ++j) {
+    const uint32_t i = base + (uint32_t)j * kScanThreads + threadIdx.x;
+    if (i < n) {
+      unsigned long long v[IO::COLS];
+      io.load(i, v);
+#pragma unroll
+      for (int c = 0; c < IO::COLS; ++c) acc[c] += v[c];
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < IO::COLS; ++c) {
+    for (int d = 16; d > 0; d >>= 1) acc[c] += __shfl_down_sync(0xFFFFFFFFu, acc[c], d);
+    if ((threadIdx.x & 31) == 0) s_w[c][threadIdx.x >> 5] = acc[c];
+  }
+  __syncthreads();
+  if (threadIdx.x < IO::COLS) {
+    unsigned long long t = 0;
+    for (int w = 0; w < kScanThreads / 32; ++w) t += s_w[threadIdx.x][w];
+    partial[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = t;
+  }
+}
+
+// One CTA: exclusive scan of the n_tiles tile sums of every column in place; the grand totals go to io.total().
+template <typename IO>
+__global__ void __launch_bounds__(1024) scan_partials_kernel(const IO io, unsigned long long* __restrict__ partial, uint32_t n_tiles) {
+  __shared__ unsigned long long s_v[IO::COLS][1024];
+  const uint32_t t = threadIdx.x;
+  const uint32_t chunk = (n_tiles + 1023u) / 1024u;
+  const uint32_t i0 = min(n_tiles, t * chunk), i1 = min(n_tiles, i0 + chunk);
+  unsigned long long own[IO::COLS];
+#pragma unroll
+  for (int c = 0; c < IO::COLS; ++c) {
+    unsigned long long a = 0;
+    for (uint32_t i = i0; i < i1; ++i) a += partial[(size_t)c * n_tiles + i];
+    own[c] = a;
+    s_v[c][t] = a;
+  }
   __syncthreads();
   for (uint32_t d = 1; d < 1024u; d <<= 1) {  // inclusive Hillis-Steele scan of the chunk totals
-    unsigned long long a = 0, b = 0, c = 0;
-    if (t >= d) {
-      a = s_u[t - d];
-      b = s_b[t - d];
-      c = s_l[t - d];
-    }
+    unsigned long long a[IO::COLS];
+#pragma unroll
+    for (int c = 0; c < IO::COLS; ++c) a[c] = (t >= d) ? s_v[c][t - d] : 0ull;
     __syncthreads();
-    s_u[t] += a;
-    s_b[t] += b;
-    s_l[t] += c;
+#pragma unroll
+    for (int c = 0; c < IO::COLS; ++c) s_v[c][t] += a[c];
     __syncthreads();
   }
-  unsigned long long nu = s_u[t] - su, nb = s_b[t] - sb, nll = s_l[t] - sl;  // exclusive prefix of the chunk
-  for (uint32_t l = l0; l < l1; ++l) {
-    P.lub[l] = (uint32_t)nu;
-    P.ubyte_off[l] = (uint32_t)nb;
-    P.ull_off[l] = nll;
-    if (!err) {
-      const uint32_t c = P.ucount[l];
-      nu += c;
-      nb += P.ubytes[l];
-      nll += (unsigned long long)c * (P.lhb[l + 1] - P.lhb[l]);
+#pragma unroll
+  for (int c = 0; c < IO::COLS; ++c) {
+    unsigned long long run = s_v[c][t] - own[c];
+    for (uint32_t i = i0; i < i1; ++i) {
+      const unsigned long long v = partial[(size_t)c * n_tiles + i];
+      partial[(size_t)c * n_tiles + i] = run;
+      run += v;
     }
   }
   if (t == 1023u) {
-    const unsigned long long tu = s_u[1023], tb = s_b[1023], tl = s_l[1023];
-    P.lub[P.n_loci] = (uint32_t)tu;
-    P.ubyte_off[P.n_loci] = (uint32_t)tb;
-    P.ull_off[P.n_loci] = tl;
-    P.ctl[PLAN_CTL_N_UREADS] = (uint32_t)tu;
-    P.stat[PLAN_STAT_PAIRS_COMPUTED] = tl;
-    if (tb > 0xFFFFFFF0ull) atomicOr(P.ctl + PLAN_CTL_ERR, 2u);
-    if (P.n_loci == 0 || tu == 0) P.uread_off[0] = 0u;
+    unsigned long long tot[IO::COLS];
+#pragma unroll
+    for (int c = 0; c < IO::COLS; ++c) tot[c] = s_v[c][1023];
+    io.total(tot);
+  }
+}
+
+template <typename IO>
+__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const IO io, const unsigned long long* __restrict__ partial) {
+  __shared__ unsigned long long s_e[IO::COLS][kScanTile + kScanTile / 32];  // padded: thread t scans elements kScanPer * t ...
+  __shared__ unsigned long long s_w[IO::COLS][kScanThreads / 32];
+  const uint32_t n = io.size(), base = blockIdx.x * (uint32_t)kScanTile;
+  auto slot = [](uint32_t e) { return e + (e >> 5); };
+  for (int j = 0; j < kScanPer; ++j) {
+    const uint32_t e = (uint32_t)j * kScanThreads + threadIdx.x, i = base + e;
+    unsigned long long v[IO::COLS];
+#pragma unroll
+    for (int c = 0; c < IO::COLS; ++c) v[c] = 0;
+    if (i < n) io.load(i, v);
+#pragma unroll
+    for (int c = 0; c < IO::COLS; ++c) s_e[c][slot(e)] = v[c];
+  }
+  __syncthreads();
+  unsigned long long sum[IO::COLS];
+#pragma unroll
+  for (int c = 0; c < IO::COLS; ++c) {
+    unsigned long long a = 0;
+    for (int j = 0; j < kScanPer; ++j) a += s_e[c][slot(threadIdx.x * kScanPer + j)];
+    sum[c] = a;
+    unsigned long long inc = a;  // inclusive scan of the thread sums inside the warp
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned long long up = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+      if ((threadIdx.x & 31) >= d) inc += up;
+    }
+    if ((threadIdx.x & 31) == 31) s_w[c][threadIdx.x >> 5] = inc;
+    sum[c] = inc - a;  // exclusive inside the warp
+  }
+  __syncthreads();
+#pragma unroll
+  for (int c = 0; c < IO::COLS; ++c) {
+    unsigned long long off = partial[(size_t)c * gridDim.x + blockIdx.x];
+    for (uint32_t w = 0; w < (threadIdx.x >> 5); ++w) off += s_w[c][w];
+    unsigned long long run = off + sum[c];
+    for (int j = 0; j < kScanPer; ++j) {
+      const uint32_t sl = slot(threadIdx.x * kScanPer + j);
+      const unsigned long long v = s_e[c][sl];
+      s_e[c][sl] = run;
+      run += v;
+    }
+  }
+  __syncthreads();
+  for (int j = 0; j < kScanPer; ++j) {
+    const uint32_t e = (uint32_t)j * kScanThreads + threadIdx.x, i = base + e;
+    if (i < n) {
+      unsigned long long v[IO::COLS];
+#pragma unroll
+      for (int c = 0; c < IO::COLS; ++c) v[c] = s_e[c][slot(e)];
+      io.store(i, v);
+    }
+  }
+}
+
+template <typename IO>
+static void launch_scan(const IO& io, uint32_t n, unsigned long long* partial, cudaStream_t stream) {
+  const uint32_t n_tiles = (n + kScanTile - 1) / kScanTile;
+  scan_reduce_kernel<IO><<<n_tiles, kScanThreads, 0, stream>>>(io, partial);
+  scan_partials_kernel<IO><<<1, 1024, 0, stream>>>(io, partial, n_tiles);
+  scan_apply_kernel<IO><<<n_tiles, kScanThreads, 0, stream>>>(io, partial);
+}
+
+// Positions of the cost buckets of the stream lists + band class sizes from the scanned class bases (one small CTA).
+__global__ void plan_task_finish_kernel(const PlanDev P) {
+  if (threadIdx.x == 0) plan_task_scan(P);
+  if (threadIdx.x < (uint32_t)kBandClasses) {
+    const uint32_t c = threadIdx.x;
+    const uint32_t t0 = P.ctl[PLAN_CTL_BAND_TASK_BASE + c], p0 = P.ctl[PLAN_CTL_BAND_INFO + 2 * c];
+    const uint32_t t1 = (c + 1 < (uint32_t)kBandClasses) ? P.ctl[PLAN_CTL_BAND_TASK_BASE + c + 1] : P.ctl[PLAN_CTL_N_BAND_TASKS];
+    const uint32_t p1 = (c + 1 < (uint32_t)kBandClasses) ? P.ctl[PLAN_CTL_BAND_INFO + 2 * c + 2] : P.ctl[PLAN_CTL_N_BAND_PAIRS];
+    P.ctl[PLAN_CTL_BAND_TASK_COUNT + c] = t1 - t0;
+    P.ctl[PLAN_CTL_BAND_INFO + 2 * c + 1] = p1 - p0;
   }
 }
 
@@ -88,65 +252,6 @@ __global__ void __launch_bounds__(kPlanBlock) plan_tasks_kernel(const PlanDev P,
   for (uint32_t l = blockIdx.x * blockDim.x + threadIdx.x; l < P.n_loci; l += stride) plan_locus_tasks(P, l, pass);
 }
 
-// Exclusive scan of the [class][locus] band counters (tasks and pairs), class after class, into list positions; one CTA,
-// same scheme as plan_scan_kernel.  Thread 0 also places the cost buckets of the stream lists.
-__global__ void __launch_bounds__(1024) plan_task_scan_kernel(const PlanDev P) {
-  __shared__ unsigned long long s_t[1024], s_p[1024];
-  __shared__ uint32_t s_cls_t[kBandClasses + 1], s_cls_p[kBandClasses + 1];
-  const uint32_t t = threadIdx.x;
-  if (t == 0) plan_task_scan(P);
-  const uint32_t N = (uint32_t)kBandClasses * P.n_loci;
-  const uint32_t chunk = (N + 1023u) / 1024u;
-  const uint32_t i0 = min(N, t * chunk), i1 = min(N, i0 + chunk);
-  unsigned long long st = 0, sp = 0;
-  for (uint32_t i = i0; i < i1; ++i) {
-    st += P.band_task_pos[i];
-    sp += P.band_pair_pos[i];
-  }
-  s_t[t] = st;
-  s_p[t] = sp;
-  __syncthreads();
-  for (uint32_t d = 1; d < 1024u; d <<= 1) {
-    unsigned long long a = 0, b = 0;
-    if (t >= d) {
-      a = s_t[t - d];
-      b = s_p[t - d];
-    }
-    __syncthreads();
-    s_t[t] += a;
-    s_p[t] += b;
-    __syncthreads();
-  }
-  unsigned long long nt = s_t[t] - st, np = s_p[t] - sp;
-  for (uint32_t i = i0; i < i1; ++i) {
-    if (i % P.n_loci == 0) {  // first entry of a band class: where its lists start
-      s_cls_t[i / P.n_loci] = (uint32_t)nt;
-      s_cls_p[i / P.n_loci] = (uint32_t)np;
-    }
-    const uint32_t a = P.band_task_pos[i], b = P.band_pair_pos[i];
-    P.band_task_pos[i] = (uint32_t)nt;
-    P.band_pair_pos[i] = (uint32_t)np;
-    nt += a;
-    np += b;
-  }
-  if (t == 1023u) {
-    s_cls_t[kBandClasses] = (uint32_t)s_t[1023];
-    s_cls_p[kBandClasses] = (uint32_t)s_p[1023];
-  }
-  __syncthreads();
-  if (t < (uint32_t)kBandClasses) {
-    P.ctl[PLAN_CTL_BAND_TASK_BASE + t] = s_cls_t[t];
-    P.ctl[PLAN_CTL_BAND_TASK_COUNT + t] = s_cls_t[t + 1] - s_cls_t[t];
-    P.ctl[PLAN_CTL_BAND_INFO + 2 * t] = s_cls_p[t];
-    P.ctl[PLAN_CTL_BAND_INFO + 2 * t + 1] = s_cls_p[t + 1] - s_cls_p[t];
-  }
-  if (t == 0) {
-    const uint32_t total_t = s_cls_t[kBandClasses];
-    P.ctl[PLAN_CTL_N_BAND_TASKS] = total_t < P.band_cap ? total_t : P.band_cap;
-    P.ctl[PLAN_CTL_N_BAND_PAIRS] = s_cls_p[kBandClasses];
-  }
-}
-
 // The steps in stream order.  ctl / stat / the band counters must be zero on entry (the caller memsets them on the same
 // stream).
 cudaError_t launch_device_plan(const PlanDev& P, int sm_count, cudaStream_t stream) {
@@ -157,11 +262,18 @@ cudaError_t launch_device_plan(const PlanDev& P, int sm_count, cudaStream_t stre
   locus_blocks = locus_blocks < max_blocks ? locus_blocks : max_blocks;
   uint32_t task_blocks = (P.n_loci + kPlanBlock - 1) / kPlanBlock;
   task_blocks = task_blocks < max_blocks ? task_blocks : max_blocks;
-  plan_dedupe_kernel<<<locus_blocks, kPlanBlock, 0, stream>>>(P);
-  plan_scan_kernel<<<1, 1024, 0, stream>>>(P);
+  const size_t dedupe_smem = (size_t)warps_per_block * kStageBytes;
+  cudaFuncSetAttribute(plan_dedupe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dedupe_smem);  // per device
+  plan_dedupe_kernel<<<locus_blocks, kPlanBlock, dedupe_smem, stream>>>(P);
+  LocusScanIO lio;
+  lio.P = P;
+  launch_scan(lio, P.n_loci, P.scan_partial, stream);
   plan_fill_kernel<<<locus_blocks, kPlanBlock, 0, stream>>>(P);
   plan_tasks_kernel<<<task_blocks, kPlanBlock, 0, stream>>>(P, 0);
-  plan_task_scan_kernel<<<1, 1024, 0, stream>>>(P);
+  BandScanIO bio;
+  bio.P = P;
+  launch_scan(bio, (uint32_t)kBandClasses * P.n_loci, P.scan_partial, stream);
+  plan_task_finish_kernel<<<1, 32, 0, stream>>>(P);
   plan_tasks_kernel<<<task_blocks, kPlanBlock, 0, stream>>>(P, 1);
   return cudaGetLastError();
 }

@@ -5,7 +5,7 @@
 //                   log( exp(LL[r][a] + log_p1[r] + log(1/2)) + exp(LL[r][b] + log_p2[r] + log(1/2)) )
 // with LL clamped to >= -600 (:57-58), then per sample total = log_sum_exp over the H*H
 // entries in storage order (mathops.cpp:45-51) and post -= total.
-// One CTA per locus; each thread owns whole (s,a,b) entries so every sum runs in the
+// One warp per locus; each lane owns whole (s,a,b) entries so every sum runs in the
 // reference's order.  Priors use the host's libm log table (genotyper.cpp:21-33 use INT_LOGS).
 // Floating point: CUDA exp/log are within 1 ulp of libm's -> parity tolerance 1e-12 relative.
 #include <cuda_runtime.h>
@@ -27,12 +27,25 @@ __global__ void __launch_bounds__(128) posterior_validate_kernel(const DevPoster
   if (bad) atomicOr(err, 4u);
 }
 
-__global__ void __launch_bounds__(128) posterior_kernel(const DevPosterior P) {
+// One warp per locus.  exp(LL[r][a] + log_p1[r] + log 1/2) depends on (read, allele) only and the term
+// log(e1[r][a] + e2[r][b]) on (read, a, b) only, so the warp first tabulates the 2 R H exponentials and the R H^2 logarithms
+// with all lanes (shared memory, kPostDoubles per warp), and every (sample, a, b) entry is then summed by one lane over its
+// sample's reads in storage order -- the reference's order of summation, on values that are bit for bit what the
+// straightforward loop computes.  Loci whose tables do not fit fall back to fewer tables and finally to that loop.
+static constexpr int kPostWarps = 4;
+static constexpr uint32_t kPostDoubles = 2048;
+
+__global__ void __launch_bounds__(kPostWarps * 32) posterior_kernel(const DevPosterior P) {
+  extern __shared__ __align__(16) double post_smem[];
   if (P.err && *P.err != 0u) return;
-  for (uint32_t l = blockIdx.x; l < P.n_loci; l += gridDim.x) {
+  const uint32_t lane = threadIdx.x & 31u;
+  double* buf = post_smem + (size_t)(threadIdx.x >> 5) * kPostDoubles;
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t l = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; l < P.n_loci; l += warps) {
     const uint32_t H = P.locus_hap_begin[l + 1] - P.locus_hap_begin[l];
     const uint32_t S = P.locus_n_samples[l];
     const uint32_t r0 = P.locus_sread_begin[l], r1 = P.locus_sread_begin[l + 1];
+    const uint32_t R = r1 - r0;
     const bool haploid = P.locus_haploid ? (P.locus_haploid[l] != 0) : false;
     const double* ll = P.ll + P.ll_off[l];
     double* post = P.post + P.post_off[l];
@@ -48,21 +61,50 @@ __global__ void __launch_bounds__(128) posterior_kernel(const DevPosterior P) {
       hom = P.int_logs[2] - lH - lH1;
       het = -lH - lH1;
     }
-    for (uint32_t idx = threadIdx.x; idx < S * HH; idx += blockDim.x) {
+    const unsigned long long n_e = 2ull * R * H, n_t = (unsigned long long)R * HH;
+    const bool have_e = n_e <= kPostDoubles, have_t = have_e && (n_e + n_t <= kPostDoubles);
+    double* E1 = buf;
+    double* E2 = buf + (size_t)R * H;
+    double* T = buf + 2 * (size_t)R * H;
+    __syncwarp();
+    if (have_e) {
+      for (uint32_t i = lane; i < R * H; i += 32u) {
+        const uint32_t r = i / H, a = i - r * H;
+        double v = ll[(size_t)P.pool_index[r0 + r] * H + a];
+        v = (v < -600.0) ? -600.0 : v;  // genotyper.cpp:57-58
+        E1[i] = exp(v + P.log_p1[r0 + r] + P.log_one_half);
+        E2[i] = exp(v + P.log_p2[r0 + r] + P.log_one_half);
+      }
+      __syncwarp();
+    }
+    if (have_t) {
+      for (uint32_t i = lane; i < R * HH; i += 32u) {
+        const uint32_t r = i / HH, ab = i - r * HH, a = ab / H, b = ab - a * H;
+        T[i] = log(E1[r * H + a] + E2[r * H + b]);
+      }
+      __syncwarp();
+    }
+    for (uint32_t idx = lane; idx < S * HH; idx += 32u) {
       const uint32_t s = idx / HH, ab = idx - s * HH, a = ab / H, b = ab - a * H;
       double acc = (a == b) ? hom : het;
-      for (uint32_t r = r0; r < r1; ++r) {
-        if ((uint32_t)P.sample_label[r] != s) continue;
-        const double* row = ll + (size_t)P.pool_index[r] * H;
-        double la = row[a], lb = row[b];
-        la = (la < -600.0) ? -600.0 : la;
-        lb = (lb < -600.0) ? -600.0 : lb;
-        acc += log(exp(la + P.log_p1[r] + P.log_one_half) + exp(lb + P.log_p2[r] + P.log_one_half));
+      for (uint32_t r = 0; r < R; ++r) {
+        if ((uint32_t)P.sample_label[r0 + r] != s) continue;
+        if (have_t) {
+          acc += T[r * HH + ab];
+        } else if (have_e) {
+          acc += log(E1[r * H + a] + E2[r * H + b]);
+        } else {
+          const double* row = ll + (size_t)P.pool_index[r0 + r] * H;
+          double la = row[a], lb = row[b];
+          la = (la < -600.0) ? -600.0 : la;
+          lb = (lb < -600.0) ? -600.0 : lb;
+          acc += log(exp(la + P.log_p1[r0 + r] + P.log_one_half) + exp(lb + P.log_p2[r0 + r] + P.log_one_half));
+        }
       }
       post[idx] = acc;
     }
-    __syncthreads();
-    for (uint32_t s = threadIdx.x; s < S; s += blockDim.x) {
+    __syncwarp();
+    for (uint32_t s = lane; s < S; s += 32u) {  // log_sum_exp in storage order (mathops.cpp:45-51)
       const double* v = post + (size_t)s * HH;
       double mx = v[0];
       for (uint32_t k = 1; k < HH; ++k) mx = (mx < v[k]) ? v[k] : mx;
@@ -70,9 +112,8 @@ __global__ void __launch_bounds__(128) posterior_kernel(const DevPosterior P) {
       for (uint32_t k = 0; k < HH; ++k) sum += exp(v[k] - mx);
       tot[s] = mx + log(sum);
     }
-    __syncthreads();
-    for (uint32_t idx = threadIdx.x; idx < S * HH; idx += blockDim.x) post[idx] -= tot[idx / HH];
-    __syncthreads();
+    __syncwarp();
+    for (uint32_t idx = lane; idx < S * HH; idx += 32u) post[idx] -= tot[idx / HH];
   }
 }
 
@@ -106,8 +147,11 @@ cudaError_t launch_posterior_validate(const DevPosterior& P, uint32_t* err, cuda
 
 cudaError_t launch_posteriors(const DevPosterior& P, cudaStream_t stream) {
   if (P.n_loci == 0) return cudaSuccess;
-  const uint32_t grid = P.n_loci < 148u * 16u ? P.n_loci : 148u * 16u;
-  posterior_kernel<<<grid, 128, 0, stream>>>(P);
+  const size_t smem = (size_t)kPostWarps * kPostDoubles * sizeof(double);
+  cudaFuncSetAttribute(posterior_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  // per device
+  const uint32_t want = (P.n_loci + kPostWarps - 1) / kPostWarps;
+  const uint32_t grid = want < 148u * 8u ? want : 148u * 8u;
+  posterior_kernel<<<grid, kPostWarps * 32, smem, stream>>>(P);
   return cudaGetLastError();
 }
 

@@ -28,8 +28,10 @@ class MT19937:
 
 
 def make_case(name, chrom, motif, units, sample_offsets, reads_per_sample=14, lo=800, span=200, qual="I",
-              haploid=False, params=None):
-    """chrom = left(1000) + motif*units + right(1000); sample_offsets[s] = (k_hp0, k_hp1) repeat-unit offsets."""
+              haploid=False, params=None, extra=None):
+    """chrom = left(1000) + motif*units + right(1000); sample_offsets[s] = (k_hp0, k_hp1) repeat-unit offsets.
+    extra[s] = (k, count): the last `count` reads of sample s carry a third allele (offset k) and no phase information --
+    enough support to become a candidate haplotype, not enough to be called (the allele-pruning cases)."""
     p = len(motif)
     rs, re = 1000, 1000 + p * units
     reads, n1, n2 = [], [], []
@@ -38,6 +40,9 @@ def make_case(name, chrom, motif, units, sample_offsets, reads_per_sample=14, lo
         for r in range(reads_per_sample):
             hp = r % 2
             k = k0 if hp == 0 else k1
+            unphased = False
+            if extra is not None and extra[s] is not None and r >= reads_per_sample - extra[s][1]:
+                k, unphased = extra[s][0], True
             seq = chrom[lo:rs] + motif * (units + k) + chrom[re:re + span]
             left, right = rs - lo, span
             if k > 0:
@@ -51,7 +56,8 @@ def make_case(name, chrom, motif, units, sample_offsets, reads_per_sample=14, lo
             # left-aligned indel placement: the indel sits at the first repeat unit
             reads.append(dict(start=lo, stop=re + span - 1, rev=(r % 3 == 0), sample=s, name="read%d_%d" % (s, r),
                               seq=seq, qual=qual * len(seq), aln=aln, cigar=cigar,
-                              log_p1=-1e-6 if hp == 0 else -1000.0, log_p2=-1000.0 if hp == 0 else -1e-6))
+                              log_p1=(-0.6931471805599453 if unphased else (-1e-6 if hp == 0 else -1000.0)),
+                              log_p2=(-0.6931471805599453 if unphased else (-1000.0 if hp == 0 else -1e-6))))
             c1 += hp == 0
             c2 += hp == 1
         n1.append(c1)
@@ -94,4 +100,30 @@ def seeded_cases():
         offs = [(max(a, 2 - units), max(b, 2 - units)) for a, b in offs]
         out.append(make_case("dropin%02d" % seed, chrom, motif, units, offs, reads_per_sample=int(rng.integers(10, 17)),
                              params=ONT if seed % 4 == 3 else None))
+    return out
+
+
+def pruning_cases():
+    """Loci in which some candidate allele ends up in no sample's optimal pair: SeqStutterGenotyper::genotype drops it
+    and recomputes the posteriors (src/seq_stutter_genotyper.cpp:636-645)."""
+    out = []
+    for seed in range(8):
+        rng = np.random.default_rng(5500 + seed)
+        rnd = lambda n: "".join("ACGT"[int(x)] for x in rng.integers(0, 4, size=n))
+        p = int(rng.integers(2, 6))
+        while True:
+            motif = rnd(p)
+            if all(motif != motif[:q] * (p // q) for q in range(1, p) if p % q == 0):
+                break
+        units = int(rng.integers(8, 24))
+        chrom = rnd(1000) + motif * units + rnd(1000)
+        S = int(rng.integers(1, 4))
+        offs = [(int(rng.integers(-2, 3)), int(rng.integers(-2, 3))) for _ in range(S)]
+        used = {k for o in offs for k in o}
+        extra = []
+        for s in range(S):
+            cand = [k for k in range(-4, 5) if k not in used and k != 0 and units + k >= 2]
+            extra.append((int(rng.choice(cand)), int(rng.integers(3, 5))) if (s == 0 or rng.random() < 0.5) else None)
+        out.append(make_case("prune%02d" % seed, chrom, motif, units, offs, reads_per_sample=int(rng.integers(14, 20)),
+                             extra=extra))
     return out

@@ -498,7 +498,7 @@ extern "C" int ltr_emu_device_plan_check(const ltr_viterbi_batch* b, const ltr_p
     P.st_cap[k] = (uint32_t)n_pairs;
     P.st_ntasks[k] = &st_n[(size_t)k];
   }
-  for (uint32_t l = 0; l < n_loci; ++l) plan_locus_dedupe(P, l, 0, 1);
+  for (uint32_t l = 0; l < n_loci; ++l) plan_locus_dedupe(P, l, 0, 1, P.read_bytes, 0u, P.raw_total);
   plan_scan_serial(P);
   for (uint32_t l = 0; l < n_loci; ++l) plan_locus_fill(P, l, 0, 1);
   for (uint32_t l = 0; l < n_loci; ++l) plan_locus_tasks(P, l, 0);

@@ -133,3 +133,20 @@ def test_genotype_locus_pruned_drops_uncalled_alleles(engine):
         K = len(kept)
         np.testing.assert_allclose(got["log_sample_posteriors"].ravel()[:S * K * K], wpost.ravel(), rtol=RTOL, atol=ATOL)
         assert list(got["best_gts"].ravel()) == list(wbest.ravel())
+
+
+@pytest.mark.parametrize("case", gu.load("pruning"), ids=lambda c: c["name"])
+def test_genotype_locus_pruned_matches_reference_genotype(engine, case):
+    """ltr_genotype_locus_pruned against what the reference's SeqStutterGenotyper::genotype did on the same LL matrix
+    (tests/golden/pruning.json, recorded by oracle/_ref/ltr_ref_trace from src/seq_stutter_genotyper.cpp:634-645): same
+    surviving alleles, same second-pass posteriors (1e-12: CUDA exp/log vs libm), same optimal pairs."""
+    S, H, R = case["S"], case["H"], case["R"]
+    got = engine.genotype_locus_pruned(gu.unhex(case["ll"], (R, H)), gu.unhex(case["log_p1"]), gu.unhex(case["log_p2"]),
+                                       case["reads_per_sample"], haploid=case["haploid"],
+                                       seeds=np.array(case["seeds"], np.int32))
+    assert list(got["kept"]) == case["kept"]
+    K = len(case["kept"])
+    np.testing.assert_allclose(got["log_sample_posteriors"].ravel()[:S * K * K], gu.unhex(case["out_post"]),
+                               rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(got["sample_total_lls"].ravel()[:S], gu.unhex(case["out_totals"]), rtol=RTOL, atol=ATOL)
+    assert list(got["best_gts"].ravel()) == case["out_gts"]

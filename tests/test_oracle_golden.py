@@ -74,3 +74,31 @@ def test_posteriors_match_reference(case):
     assert np.array_equal(tot, gu.unhex(case["totals"]))
     assert total == float.fromhex(case["total"])
     assert list(best.ravel()) == case["best"]
+
+
+@pytest.mark.parametrize("case", gu.load("pruning"), ids=lambda c: c["name"])
+def test_both_posterior_passes_of_genotype_match_reference(case):
+    """tests/golden/pruning.json: the two calls of Genotyper::calc_log_sample_posteriors inside the reference's
+    SeqStutterGenotyper::genotype (before / after the uncalled alleles are removed), recorded by oracle/_ref/ltr_ref_trace.
+    The restatement reproduces both passes bit for bit, and the surviving alleles are exactly the reference allele plus
+    those in some voting sample's optimal pair (src/seq_stutter_genotyper.cpp:250-311)."""
+    S, H, R = case["S"], case["H"], case["R"]
+    lab = np.repeat(np.arange(S), case["reads_per_sample"]).astype(np.int32)
+    p1, p2 = gu.unhex(case["log_p1"]), gu.unhex(case["log_p2"])
+    ll = gu.unhex(case["ll"], (R, H))
+    _cl, post, _tot, _total, best = po.log_sample_posteriors(ll, p1, p2, lab, S, haploid=case["haploid"])
+    assert np.array_equal(post.ravel(), gu.unhex(case["first_post"]))
+    assert list(best.ravel()) == case["first_gts"]
+    seeds = np.array(case["seeds"])
+    voters = [s for s in range(S) if np.any(seeds[lab == s] >= 0)]
+    kept = sorted({0} | {int(a) for s in voters for a in best[s]})
+    assert kept == case["kept"]
+    K = len(kept)
+    out_ll = gu.unhex(case["out_ll"], (R, K))
+    if case["n_calls"] > 1:
+        # the kept columns are carried over after the first pass clamped them (genotyper.cpp:57-58)
+        assert np.array_equal(out_ll, np.maximum(ll, -600.0)[:, kept])
+        _cl2, post2, tot2, _t2, best2 = po.log_sample_posteriors(out_ll, p1, p2, lab, S, haploid=case["haploid"])
+        assert np.array_equal(post2.ravel(), gu.unhex(case["out_post"]))
+        assert np.array_equal(tot2, gu.unhex(case["out_totals"]))
+        assert list(best2.ravel()) == case["out_gts"]

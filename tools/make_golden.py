@@ -200,13 +200,44 @@ def vcf_record_cases():
     return [dict(name=c["name"], record=r) for c, r in zip(cases, recs)]
 
 
+def pruning_cases():
+    """Both passes of SeqStutterGenotyper::genotype (src/seq_stutter_genotyper.cpp:634-645) as the reference ran them
+    (oracle/_ref/ltr_ref_trace records every call of Genotyper::calc_log_sample_posteriors): the LL matrix of all candidate
+    alleles going in, and -- after get_unused_alleles / remove_alleles -- the surviving alleles, their LL columns, the
+    recomputed posteriors and the optimal pairs.  Seeded loci with an uncalled third allele + the shipped-data loci in
+    which the reference pruned something + two loci in which it did not."""
+    import dropin_cases as dc
+    import golden_util as gu
+    cases = dc.pruning_cases() + [dc.case_a4()] + dc.seeded_cases()[:1] + gu.load_real_cases()
+    out = []
+    for c, (rec, calls) in zip(cases, po.full_locus_traces(cases)):
+        if not calls:
+            continue
+        real = not c["name"].startswith(("prune", "A4", "dropin"))
+        if real and len(calls) < 2:
+            continue
+        first, last = calls[0], calls[-1]
+        assert len(set(first["alleles"])) == len(first["alleles"])
+        kept = [first["alleles"].index(a) for a in last["alleles"]]
+        labels = first["labels"]
+        S = first["S"]
+        out.append(dict(name=c["name"], S=S, H=first["H"], R=first["R"], n_calls=len(calls), haploid=bool(c.get("haploid")),
+                        reads_per_sample=[labels.count(s) for s in range(S)], seeds=first["seeds"],
+                        ll=first["ll"], log_p1=first["p1"], log_p2=first["p2"], first_gts=first["gts"],
+                        first_post=first["post"], kept=kept, out_ll=last["ll"], out_post=last["post"],
+                        out_totals=last["totals"], out_gts=last["gts"]))
+    return out
+
+
 def main():
     if not po.ref_available():
         raise SystemExit("oracle/_ref is not built (needs /root/reference)")
     os.makedirs(GOLD, exist_ok=True)
-    sets = dict(appendix_a=[run_ref(c) for c in appendix_a()], process_reads_long=long_path_cases(),
-                process_reads_short=short_path_cases(),
-                posteriors=posterior_cases(), pair_batches=pair_batch_cases(), calls=calls_cases(), vcf_records=vcf_record_cases())
+    makers = dict(appendix_a=lambda: [run_ref(c) for c in appendix_a()], process_reads_long=long_path_cases,
+                  process_reads_short=short_path_cases, posteriors=posterior_cases, pair_batches=pair_batch_cases,
+                  calls=calls_cases, vcf_records=vcf_record_cases, pruning=pruning_cases)
+    only = [a for a in sys.argv[1:] if not a.startswith("-")]  # `python tools/make_golden.py pruning`: that set only
+    sets = {k: f() for k, f in makers.items() if not only or k in only}
     for name, cases in sets.items():
         path = os.path.join(GOLD, name + ".json")
         with open(path, "w") as f:
