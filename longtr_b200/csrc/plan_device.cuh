@@ -271,6 +271,19 @@ LTR_HD void plan_locus_fill(const PlanDev& P, uint32_t l, uint32_t lane, uint32_
   if (P.ctl[PLAN_CTL_ERR] != 0) return;
   const uint32_t r0 = P.lrb[l], r1 = P.lrb[l + 1];
   const uint32_t u0 = P.lub[l], nu = P.lub[l + 1] - u0;
+#ifdef LTR_DEVICE_CODE
+  if (nu <= nl) {  // one distinct read per lane: offsets by a warp scan of the lengths
+    const uint32_t len = lane < nu ? P.tmp_len[r0 + lane] : 0u;
+    uint32_t inc = len;
+    for (uint32_t d = 1; d < 32u; d <<= 1) {
+      const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+      if (lane >= d) inc += up;
+    }
+    const uint32_t base = P.ubyte_off[l];
+    if (lane < nu) P.uread_off[u0 + lane] = base + inc - len;
+    if (l + 1 == P.n_loci && lane == (nu ? nu - 1 : 0)) P.uread_off[u0 + nu] = base + (nu ? inc : 0u);
+  } else
+#endif
   if (lane == 0) {
     uint32_t off = P.ubyte_off[l];
     for (uint32_t k = 0; k < nu; ++k) {

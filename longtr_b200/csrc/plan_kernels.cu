@@ -12,6 +12,59 @@ namespace ltr {
 
 static constexpr int kPlanBlock = 128;
 
+// Loci of at most 32 pooled reads (the common case): one read per lane, everything the lanes need from each other travels
+// through shuffles instead of the global scratch arrays of plan_locus_dedupe -- same numbering, same outputs.
+__device__ __forceinline__ void plan_locus_dedupe_warp(const PlanDev& P, uint32_t l, uint32_t lane, const uint8_t* bytes,
+                                                       uint32_t origin, uint32_t limit) {
+  const uint32_t r0 = P.lrb[l], R = P.lrb[l + 1] - r0;
+  for (uint32_t h = P.lhb[l] + lane; h < P.lhb[l + 1]; h += 32u) P.hap_locus[h] = l;
+  const bool have = lane < R;
+  const uint32_t r = r0 + lane;
+  uint32_t o0 = origin, len = 0;
+  bool ok = true;
+  if (have) {
+    o0 = P.read_off[r];
+    const uint32_t o1 = P.read_off[r + 1];
+    ok = (o1 > o0) && (o1 <= limit) && (o0 >= origin);
+    len = ok ? o1 - o0 : 0u;
+    if (!ok) o0 = origin;
+    P.read_locus[r] = l;
+  }
+  const uint8_t* s = bytes + (o0 - origin);
+  const unsigned long long h = have ? plan_hash(s, len) : 0ull;
+  if (__any_sync(0xFFFFFFFFu, !ok) && lane == 0) atomicOr(P.ctl + PLAN_CTL_ERR, 1u);
+  const uint32_t max_m = __reduce_max_sync(0xFFFFFFFFu, len);
+  if (lane == 0 && max_m) atomicMax(P.stat + PLAN_STAT_MAX_M, (unsigned long long)max_m);
+  uint32_t rep = lane;  // first read of the locus with the same sequence
+  for (uint32_t q = 0; q + 1 < R; ++q) {
+    const unsigned long long hq = __shfl_sync(0xFFFFFFFFu, h, q);
+    const uint32_t lq = __shfl_sync(0xFFFFFFFFu, len, q), oq = __shfl_sync(0xFFFFFFFFu, o0, q);
+    if (have && q < lane && rep == lane && hq == h && lq == len)
+      if (len == 0 || plan_equal(bytes + (oq - origin), s, len)) rep = q;
+  }
+  const bool is_rep = have && rep == lane;
+  uint32_t rank = 0;  // by (length, first occurrence) among the representatives
+  for (uint32_t q = 0; q < R; ++q) {
+    const bool iq = __shfl_sync(0xFFFFFFFFu, is_rep ? 1u : 0u, q) != 0u;
+    const uint32_t lq = __shfl_sync(0xFFFFFFFFu, len, q);
+    rank += (iq && (lq < len || (lq == len && q < lane))) ? 1u : 0u;
+  }
+  const uint32_t k = __shfl_sync(0xFFFFFFFFu, rank, rep);
+  if (have) {
+    P.local_u[r] = k | (is_rep ? kPlanRep : 0u);
+    if (is_rep) {
+      P.tmp_len[r0 + k] = len;
+      P.tmp_rep[r0 + k] = r;
+    }
+  }
+  const uint32_t n_rep = __popc(__ballot_sync(0xFFFFFFFFu, is_rep));
+  const uint32_t n_bytes = __reduce_add_sync(0xFFFFFFFFu, is_rep ? len : 0u);
+  if (lane == 0) {
+    P.ucount[l] = n_rep;
+    P.ubytes[l] = n_bytes;
+  }
+}
+
 // One warp per locus.  The raw reads of a locus are contiguous: the warp copies them into shared memory with coalesced
 // 16-byte loads (kStageBytes per warp; loci that do not fit, e.g. 30 reads of a 1 kb VNTR, are read in place) and hashes /
 // compares them there.
@@ -32,9 +85,11 @@ __global__ void __launch_bounds__(kPlanBlock) plan_dedupe_kernel(const PlanDev P
       const uint32_t n16 = (o1 - origin + 16u + 15u) >> 4;  // one word past the end for plan_load32
       for (uint32_t i = lane; i < n16; i += 32u) dst[i] = src[i];
       __syncwarp();
-      plan_locus_dedupe(P, l, lane, 32u, stage, origin, o1);
+      if (P.lrb[l + 1] - P.lrb[l] <= 32u) plan_locus_dedupe_warp(P, l, lane, stage, origin, o1);
+      else plan_locus_dedupe(P, l, lane, 32u, stage, origin, o1);
     } else {
-      plan_locus_dedupe(P, l, lane, 32u, P.read_bytes, 0u, P.raw_total);
+      if (P.lrb[l + 1] - P.lrb[l] <= 32u) plan_locus_dedupe_warp(P, l, lane, P.read_bytes, 0u, P.raw_total);
+      else plan_locus_dedupe(P, l, lane, 32u, P.read_bytes, 0u, P.raw_total);
     }
   }
 }

@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(128) posterior_validate_kernel(const DevPoster
 // sample's reads in storage order -- the reference's order of summation, on values that are bit for bit what the
 // straightforward loop computes.  Loci whose tables do not fit fall back to fewer tables and finally to that loop.
 static constexpr int kPostWarps = 4;
-static constexpr uint32_t kPostDoubles = 2048;
+static constexpr uint32_t kPostDoubles = 1024;
 
 __global__ void __launch_bounds__(kPostWarps * 32) posterior_kernel(const DevPosterior P) {
   extern __shared__ __align__(16) double post_smem[];

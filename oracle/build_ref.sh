@@ -39,7 +39,8 @@ echo "built $out/libltr_ref.so"
 #   ltr_ref_full : every object is the reference's own (golden VCF records)
 #   ltr_ref_gpu  : HapAligner::process_reads and Genotyper::calc_log_sample_posteriors are taken from
 #                        integration/reference_binding.cpp (C ABI -> liblongtr_b200.so); the reference's own
-#                        definitions are weakened in COPIES of its objects under oracle/_ref/obj.
+#                        definitions are weakened in COPIES of its objects under oracle/_ref/obj.  Haplotype::aln_haps_to_ref
+#                        is elided as in ltr_ref_lazy (integration/lazy_haplotype_alignment.cpp).
 FULL_TUS="seq_stutter_genotyper SeqAlignment/HaplotypeGenerator SeqAlignment/AlignmentOps vcf_writer vcf_input
           debruijn_graph directed_graph extract_indels zalgorithm"
 fobjs=""
@@ -71,6 +72,22 @@ done
 $CXX -o "$out/ltr_ref_trace" "$out/obj/full_driver_trace.o" "$out/obj/hts_stubs.o" "$out/obj/fasta_reader.o" \
      $trace_objs $fobjs -lm -lpthread
 echo "built $out/ltr_ref_trace"
+# ---- ltr_ref_lazy: all-CPU reference with Haplotype::aln_haps_to_ref elided (integration/lazy_haplotype_alignment.cpp);
+#      the reference's own definition is renamed in a copy of its object and stays reachable through an env switch.
+objcopy --redefine-sym _ZN9Haplotype15aln_haps_to_refEv=ltr_orig_aln_haps_to_ref \
+        "$out/obj/Haplotype.o" "$out/obj/Haplotype_lazy.o"
+$CXX -O2 -g -std=c++11 -fPIC -w -I"$here/shim" -I"$ref/src" \
+     -c "$here/../integration/lazy_haplotype_alignment.cpp" -o "$out/obj/lazy_haplotype_alignment.o"
+lazy_objs=""
+for o in $base_objs; do
+  case "$o" in
+    *obj/Haplotype.o) lazy_objs="$lazy_objs $out/obj/Haplotype_lazy.o";;
+    *) lazy_objs="$lazy_objs $o";;
+  esac
+done
+$CXX -o "$out/ltr_ref_lazy" "$out/obj/full_driver.o" "$out/obj/lazy_haplotype_alignment.o" "$out/obj/hts_stubs.o" \
+     "$out/obj/fasta_reader.o" $lazy_objs $fobjs -lm -lpthread
+echo "built $out/ltr_ref_lazy"
 lib="$here/../longtr_b200/csrc"
 if [ -f "$lib/liblongtr_b200.so" ]; then
   objcopy --weaken-symbol=_ZN10HapAligner13process_readsERKSt6vectorI9AlignmentSaIS1_EEiPK11BaseQualityRKS0_IbSaIbEEPdPi \
@@ -83,11 +100,12 @@ if [ -f "$lib/liblongtr_b200.so" ]; then
   for o in $base_objs; do
     case "$o" in
       *HapAligner.o) gpu_objs="$gpu_objs $out/obj/HapAligner_weak.o";;
+      *obj/Haplotype.o) gpu_objs="$gpu_objs $out/obj/Haplotype_lazy.o";;
       *genotyper.o) gpu_objs="$gpu_objs $out/obj/genotyper_weak.o";;
       *) gpu_objs="$gpu_objs $o";;
     esac
   done
-  $CXX -o "$out/ltr_ref_gpu" "$out/obj/reference_binding.o" "$out/obj/full_driver.o" "$out/obj/hts_stubs.o" \
+  $CXX -o "$out/ltr_ref_gpu" "$out/obj/reference_binding.o" "$out/obj/lazy_haplotype_alignment.o" "$out/obj/full_driver.o" "$out/obj/hts_stubs.o" \
        "$out/obj/fasta_reader.o" $gpu_objs $fobjs -L"$lib" -llongtr_b200 \
        -Wl,-rpath,'$ORIGIN/../../longtr_b200/csrc' -lm -lpthread
   echo "built $out/ltr_ref_gpu"

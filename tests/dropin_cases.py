@@ -28,7 +28,7 @@ class MT19937:
 
 
 def make_case(name, chrom, motif, units, sample_offsets, reads_per_sample=14, lo=800, span=200, qual="I",
-              haploid=False, params=None, extra=None):
+              haploid=False, params=None, extra=None, exact_cigar=False):
     """chrom = left(1000) + motif*units + right(1000); sample_offsets[s] = (k_hp0, k_hp1) repeat-unit offsets.
     extra[s] = (k, count): the last `count` reads of sample s carry a third allele (offset k) and no phase information --
     enough support to become a candidate haplotype, not enough to be called (the allele-pruning cases)."""
@@ -46,7 +46,9 @@ def make_case(name, chrom, motif, units, sample_offsets, reads_per_sample=14, lo
             seq = chrom[lo:rs] + motif * (units + k) + chrom[re:re + span]
             left, right = rs - lo, span
             if k > 0:
-                cigar, aln = "%d=%dI%d=" % (left, p * k, right), seq
+                # (the historical form stops the last '=' after `span` bases -- the recorded fixtures, SURVEY A4 included,
+                # were made with it and short repeats never notice; exact_cigar covers the whole read)
+                cigar, aln = "%d=%dI%d=" % (left, p * k, right + (p * units if exact_cigar else 0)), seq
             elif k < 0:
                 cigar = "%d=%dD%d=" % (left, -p * k, right + p * k + (p * units - (-p * k)) - (p * units + p * k) + 0)
                 cigar = "%d=%dD%d=" % (left, -p * k, len(seq) - left)
