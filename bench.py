@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-loci", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra.c4 / extra.c5 sub-lines of the default run")
+    ap.add_argument("--no-raw", action="store_true", help="skip the e2e_from_flat_loci arm (raw loci -> calls)")
     return ap.parse_args()
 
 
@@ -492,6 +493,7 @@ def measure_long(args, config, n_loci, steps, warmup, torch, rank, world, local,
         barrier(torch, world)
         e2e_by_depth[depth] = max_over_ranks(torch, world, (time.perf_counter() - t0) * 1e3 / steps)
     e2e_same = bool(np.array_equal(outs[0][0]["ll"], ll))  # the asynchronous path delivers the resident job's bits
+    raw = None if args.no_raw else measure_from_raw_loci(args, config, n_loci, steps, torch, rank, world, local)
     in_flight = min(e2e_by_depth, key=e2e_by_depth.get)
     e2e_ms = e2e_by_depth[in_flight]
     if rank != 0:
@@ -521,6 +523,7 @@ def measure_long(args, config, n_loci, steps, warmup, torch, rank, world, local,
                 "host_threads_per_gpu": 1, "api": "ltr_job_submit / ltr_job_wait",
                 "jobs_in_flight": in_flight, "results_equal_resident_job": e2e_same,
                 "ms_per_step_by_jobs_in_flight": {str(k): v for k, v in e2e_by_depth.items()}},
+        "e2e_from_flat_loci": raw,
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "fp64_issue", "achieved": achieved, "peak": peak_gcups, "unit": "GCUPS",
@@ -553,11 +556,48 @@ def measure_long(args, config, n_loci, steps, warmup, torch, rank, world, local,
     return line
 
 
+def measure_from_raw_loci(args, config, n_loci, steps, torch, rank, world, local):
+    """The host front half inside the clock: raw loci (whole reads with CIGARs, flank blocks, candidate alleles; pageable
+    host memory) -> ltr_genotyper_run = pooling + trimming + flattening on the host threads, asynchronous GPU jobs
+    (Viterbi, posteriors, removal of uncalled alleles), call extraction -> GT / Q / PQ / GL / PL per sample."""
+    from longtr_b200 import Genotyper, workloads
+    threads = max(1, (os.cpu_count() or 1) // max(1, world))
+    work = workloads.generate_loci(config, n_loci, first_locus=rank * n_loci)
+    gen = Genotyper(devices=(local,), host_threads=threads)
+    n_steps = max(1, min(steps, 3))
+    calls = gen.run_struct(work.struct, work.aln_params)   # warm-up: pinned buffers, memory pool
+    gen.free(calls)
+    barrier(torch, world)
+    t0 = time.perf_counter()
+    prep = wait = post = 0.0
+    n_ok = 0
+    for _ in range(n_steps):
+        calls = gen.run_struct(work.struct, work.aln_params)
+        c = calls.contents
+        prep += c.prep_ms
+        wait += c.gpu_wait_ms
+        post += c.post_ms
+        n_ok = int(np.sum(np.ctypeslib.as_array(c.status, (n_loci,)) == 0))
+        gen.free(calls)
+    barrier(torch, world)
+    ms = max_over_ranks(torch, world, (time.perf_counter() - t0) * 1e3 / n_steps)
+    total_loci = sum_over_ranks(torch, world, float(n_loci))
+    out = {"value": total_loci / (ms * 1e-3), "unit": "loci/s", "ms_per_step": ms, "steps": n_steps,
+           "api": "ltr_genotyper_run (raw loci in pageable host memory -> calls)", "host_threads_per_gpu": threads,
+           "host_prepare_ms_per_step": prep / n_steps, "host_wait_for_gpu_ms_per_step": wait / n_steps,
+           "host_extract_calls_ms_per_step": post / n_steps, "loci_genotyped": n_ok,
+           "input_bytes_per_step": work.input_bytes, "reads_per_step": int(work.n_reads)}
+    gen.close()
+    work.close()
+    return out
+
+
 def compact(line):
     """Sub-line of another configuration inside the default run (extra.c4 / extra.c5)."""
     if line is None:
         return None
-    keep = ("metric", "value", "unit", "ms_per_step", "gcups", "steps", "warmup", "e2e", "roofline", "cpu_baseline",
+    keep = ("metric", "value", "unit", "ms_per_step", "gcups", "steps", "warmup", "e2e", "e2e_from_flat_loci", "roofline",
+            "cpu_baseline",
             "parity_on_bench_sample", "gpu_launches", "clocks")
     out = {k: line[k] for k in keep if k in line}
     out["config"] = {k: line["config"][k] for k in ("workload", "loci_per_gpu", "pairs_per_gpu", "pairs_aligned_per_gpu",

@@ -88,6 +88,17 @@ typedef struct ltr_posterior_batch {
   const double* log_p2;              /* [n_sreads]  */
   const uint32_t* locus_n_samples;   /* [n_loci]    */
   const uint8_t* locus_haploid;      /* [n_loci] or NULL (all diploid) */
+  /* -- optional (zero / NULL = off), appended in version 0.2 -- */
+  const uint8_t* second_mate;        /* [n_sreads] or NULL: sample-read r is the second mate of read r-1 (same read name,
+                                        src/seq_stutter_genotyper.cpp:494): the LL rows of the two are summed before the
+                                        posteriors are formed (:546-559)                                              */
+  const uint8_t* read_aligned;       /* [n_sreads] or NULL (all): seed_positions >= 0, i.e. the read lets its sample vote
+                                        when uncalled alleles are removed (get_unused_alleles, :262-265)              */
+  int32_t prune_uncalled;            /* != 0: after the posteriors, non-reference alleles that are in no voting sample's
+                                        optimal pair are dropped and the posteriors recomputed on the K surviving alleles
+                                        (SeqStutterGenotyper::genotype, :636-645).  post of locus l is then [S][K][K],
+                                        compact, at the locus' usual offset; the surviving alleles come back through
+                                        ltr_job_outputs.kept_mask                                                      */
 } ltr_posterior_batch;
 
 typedef struct ltr_job_stats {
@@ -183,8 +194,17 @@ void ltr_job_sizes(const ltr_job* job, uint64_t* n_ll, uint64_t* n_post, uint64_
 /* Any output pointer may be NULL. out_post is [sum_l S_l*H_l*H_l], out_totals [sum_l S_l]. */
 int ltr_job_download(ltr_ctx* ctx, ltr_job* job, double* out_ll, double* out_post,
                      double* out_totals);
+/* kept_mask [n_haps] of a job created with post->prune_uncalled (all ones otherwise). */
+int ltr_job_download_kept(ltr_ctx* ctx, ltr_job* job, uint8_t* out_kept_mask);
 void ltr_job_get_stats(const ltr_job* job, ltr_job_stats* stats);
 void ltr_job_destroy(ltr_ctx* ctx, ltr_job* job);
+/* The posterior stage alone for many loci whose LL matrices the caller already holds (e.g. the output of ltr_stutter_ll):
+ * ll = the pooled aln_probs matrices back to back (P_l x H_l, layout of ltr_viterbi_batch), P_l = locus_read_begin[l+1] -
+ * locus_read_begin[l], H_l likewise; post as for ltr_job_create, including mate pairs and the removal of uncalled
+ * alleles.  out_kept_mask may be NULL.  Genotyper::calc_log_sample_posteriors (src/genotyper.cpp:45-83) per locus.  */
+int ltr_posteriors_batch(ltr_ctx* ctx, uint32_t n_loci, const uint32_t* locus_hap_begin, const uint32_t* locus_read_begin,
+                         const double* ll, const ltr_posterior_batch* post, double* out_post, double* out_totals,
+                         uint8_t* out_kept_mask);
 
 /* ---- asynchronous jobs: many batches in flight from ONE host thread ------------------------------------------------ */
 /* ltr_job_submit enqueues a whole job -- upload of the batch, plan, kernels, posteriors, download of the results into
@@ -200,6 +220,16 @@ void ltr_job_destroy(ltr_ctx* ctx, ltr_job* job);
 int ltr_job_submit(ltr_ctx* ctx, const ltr_params* params, const ltr_viterbi_batch* batch,
                    const ltr_posterior_batch* post, double* out_ll, double* out_post, double* out_totals,
                    ltr_job** out);
+/* The same with every output named in one struct (any may be NULL); kept_mask [n_haps] receives 1 for every candidate
+ * allele that survives post->prune_uncalled (all ones when it is off). */
+typedef struct ltr_job_outputs {
+  double* ll;          /* [sum_l P_l*H_l]   */
+  double* post;        /* [sum_l S_l*H_l*H_l] (locus l uses the first S_l*K_l*K_l entries of its slice when pruned) */
+  double* totals;      /* [sum_l S_l]       */
+  uint8_t* kept_mask;  /* [n_haps]          */
+} ltr_job_outputs;
+int ltr_job_submit_outputs(ltr_ctx* ctx, const ltr_params* params, const ltr_viterbi_batch* batch,
+                           const ltr_posterior_batch* post, const ltr_job_outputs* outputs, ltr_job** out);
 int ltr_job_wait(ltr_ctx* ctx, ltr_job* job);
 int ltr_job_poll(ltr_ctx* ctx, ltr_job* job);
 
@@ -253,6 +283,81 @@ int ltr_pipeline_flush(ltr_pipeline* p);
 int ltr_pipeline_next(ltr_pipeline* p, int wait, uint64_t* tag, int32_t* n_reads, int32_t* n_alleles, const double** ll,
                       const int32_t** seeds, int* status);
 void ltr_pipeline_destroy(ltr_pipeline* p);
+
+/* ---- many raw loci -> genotype calls: the front half of SeqStutterGenotyper::genotype, batched -------------------------- */
+/* What LongTR does per locus between "the reads of the region are decoded" and "the record can be written"
+ * (src/seq_stutter_genotyper.cpp:485-497, 599-645): pool the reads by sequence (ReadPooler, src/read_pooler.cpp:3-20), trim
+ * every pool to the repeat +- INDEL_FLANK_LEN with its CIGAR (HapAligner::trim_alignment, HapAligner.cpp:346-465), align
+ * the pools to every candidate haplotype (GPU), scatter the pool rows to the reads, form the posteriors (GPU), drop the
+ * uncalled alleles and recompute (GPU), extract GT / Q / PQ / GL / PL (Genotyper::extract_genotypes_and_likelihoods,
+ * src/genotyper.cpp:132-256) -- for a whole batch of loci in structure-of-arrays form, with no per-read objects.
+ * Candidate alleles come from the caller (HaplotypeGenerator, out of scope); loci are independent.
+ * Reads of a locus are SAMPLE-MAJOR (all reads of sample 0, then sample 1, ...), as in the reference.
+ * CIGARs are BAM-encoded (length << 4 | op, op in MIDNSHP=X = 0..8; N and P are rejected like the reference does).   */
+typedef struct ltr_locus_batch {
+  uint32_t n_loci;
+  const uint32_t* lflank_off;          /* [n_loci+1] block 0 of the haplotype (left flank, 35 bp in LongTR)            */
+  const uint8_t* lflank_bytes;
+  const uint32_t* rflank_off;          /* [n_loci+1] block 2                                                             */
+  const uint8_t* rflank_bytes;
+  const uint32_t* locus_allele_begin;  /* [n_loci+1] block 1: candidate alleles, reference allele first                  */
+  const uint32_t* allele_off;          /* [n_alleles+1]                                                                  */
+  const uint8_t* allele_bytes;
+  const int32_t* repeat_start;         /* [n_loci] reference coordinates of block 1 (RepeatBlock start / end)            */
+  const int32_t* repeat_end;
+  const uint32_t* locus_read_begin;    /* [n_loci+1] raw reads                                                           */
+  const int32_t* read_start;           /* [n_reads] Alignment::get_start(): 0-based reference start                      */
+  const int32_t* read_stop;            /* [n_reads] Alignment::get_stop(): 0-based inclusive reference stop              */
+  const uint32_t* read_off;            /* [n_reads+1]                                                                    */
+  const uint8_t* read_bytes;
+  const uint32_t* cigar_off;           /* [n_reads+1] offsets into cigar_ops                                             */
+  const uint32_t* cigar_ops;
+  const int32_t* read_sample;          /* [n_reads] 0 .. locus_n_samples[l]-1, non-decreasing inside a locus             */
+  const double* log_p1;                /* [n_reads] phasing terms (src/snp_bam_processor.h:16-18)                        */
+  const double* log_p2;
+  const uint8_t* second_mate;          /* [n_reads] or NULL                                                              */
+  const uint32_t* locus_n_samples;     /* [n_loci]                                                                       */
+  const uint8_t* locus_haploid;        /* [n_loci] or NULL                                                               */
+} ltr_locus_batch;
+
+/* Calls of a batch, structure of arrays, owned by the library (ltr_batch_calls_free).  Sample (l, s) has the global
+ * index locus_sample_begin[l] + s.  Allele indices are indices into the CALLER's allele list of the locus.            */
+typedef struct ltr_batch_calls {
+  uint32_t n_loci;
+  const int32_t* status;                   /* [n_loci] LTR_OK, or why this locus (alone) was not genotyped               */
+  const uint32_t* locus_sample_begin;      /* [n_loci+1]                                                                 */
+  const uint32_t* locus_allele_begin;      /* [n_loci+1]                                                                 */
+  const uint8_t* kept_mask;                /* [n_alleles] allele survives the removal of uncalled alleles                */
+  const int32_t* n_kept;                   /* [n_loci]                                                                   */
+  const int32_t* n_pools;                  /* [n_loci] distinct read sequences (ReadPooler::num_pools)                   */
+  const int32_t* gts;                      /* [2 * n_samples] optimal allele pair (GT)                                   */
+  const double* log_phased_posteriors;     /* [n_samples] -> PQ = exp(.)                                                 */
+  const double* log_unphased_posteriors;   /* [n_samples] -> Q = exp(.)                                                  */
+  const double* gl_diffs;                  /* [n_samples] GLDIFF                                                         */
+  const double* sample_total_lls;          /* [n_samples]                                                                */
+  const int32_t* n_reads;                  /* [n_samples] DP                                                             */
+  const uint64_t* gl_begin;                /* [n_samples+1] slice of gls / pls; K(K+1)/2 (haploid: K) entries are used   */
+  const double* gls;                       /* log10 genotype likelihoods over the KEPT alleles (GL)                      */
+  const int32_t* pls;                      /* PL                                                                         */
+  double prep_ms, gpu_wait_ms, post_ms, total_ms;  /* host timing of the call                                           */
+} ltr_batch_calls;
+
+typedef struct ltr_genotyper ltr_genotyper;
+/* devices: CUDA device indices (one context each; loci are sharded over them in chunks of chunk_loci, results come back in
+ * input order -- the host-side gather of SURVEY.md section 8e); host_threads <= 0: all hardware threads; chunk_loci <= 0:
+ * default (20 000).  No CPU fallback: fails with LTR_ERR_NO_DEVICE when a device cannot be used.                       */
+int ltr_genotyper_create(const int32_t* devices, int32_t n_devices, int32_t host_threads, int32_t chunk_loci,
+                         ltr_genotyper** out);
+void ltr_genotyper_destroy(ltr_genotyper* g);
+/* Genotypes every locus of the batch.  A malformed locus (CIGAR the reference dies on, reads that do not fit their CIGAR,
+ * missing flanks) fails alone: its status is the error, the rest of the batch is unaffected.                          */
+int ltr_genotyper_run(ltr_genotyper* g, const ltr_params* params, const ltr_locus_batch* batch, ltr_batch_calls** out);
+void ltr_batch_calls_free(ltr_batch_calls* calls);
+/* Host only: HapAligner::trim_alignment on read r of the batch (its locus is looked up); writes the trimmed read (or the
+ * 10 bp pseudo read of HapAligner.cpp:820-823 when nothing is left) into out[cap] and returns its length, negative =
+ * error.  What the genotyper aligns; exposed for parity tests.                                                        */
+int32_t ltr_locus_batch_trim_read(const ltr_locus_batch* batch, const ltr_params* params, uint32_t locus, uint32_t read,
+                                  uint8_t* out, int32_t cap);
 
 /* Genotype calls of one locus from its read x haplotype LL matrix: what SeqStutterGenotyper::genotype +
  * write_vcf_record obtain from Genotyper::calc_log_sample_posteriors (GPU) followed by

@@ -5,3 +5,4 @@ C++ host mirror of LongTR's HapAligner / Genotyper interfaces) and thin ctypes b
 """
 from .abi import DEFAULT_ALN_PARAMS, EXPORTED_SYMBOLS, LIB_PATH  # noqa: F401
 from .engine import Engine, Job, LongTRError, Pipeline  # noqa: F401
+from .locus_batch import Genotyper, build_locus_batch  # noqa: F401,E402

@@ -37,7 +37,12 @@ class ViterbiBatch(C.Structure):
 
 class PosteriorBatch(C.Structure):
     _fields_ = [("locus_sread_begin", _u32p), ("pool_index", _u32p), ("sample_label", _i32p),
-                ("log_p1", _dp), ("log_p2", _dp), ("locus_n_samples", _u32p), ("locus_haploid", _u8p)]
+                ("log_p1", _dp), ("log_p2", _dp), ("locus_n_samples", _u32p), ("locus_haploid", _u8p),
+                ("second_mate", _u8p), ("read_aligned", _u8p), ("prune_uncalled", C.c_int32)]
+
+
+class JobOutputs(C.Structure):
+    _fields_ = [("ll", _dp), ("post", _dp), ("totals", _dp), ("kept_mask", _u8p)]
 
 
 class JobStats(C.Structure):
@@ -130,6 +135,11 @@ def make_posterior_batch(post):
     if post.get("locus_haploid") is not None:
         keep["hap"] = np.ascontiguousarray(post["locus_haploid"], dtype=np.uint8)
         b.locus_haploid = ptr(keep["hap"], _u8p)
+    for key in ("second_mate", "read_aligned"):
+        if post.get(key) is not None:
+            keep[key] = np.ascontiguousarray(post[key], dtype=np.uint8)
+            setattr(b, key, ptr(keep[key], _u8p))
+    b.prune_uncalled = 1 if post.get("prune_uncalled") else 0
     return b, keep
 
 
@@ -177,6 +187,13 @@ def load():
     lib.ltr_job_submit.argtypes = [vp, C.POINTER(Params), C.POINTER(ViterbiBatch), C.POINTER(PosteriorBatch), _dp, _dp, _dp,
                                    C.POINTER(vp)]
     lib.ltr_job_submit.restype = C.c_int
+    lib.ltr_job_submit_outputs.argtypes = [vp, C.POINTER(Params), C.POINTER(ViterbiBatch), C.POINTER(PosteriorBatch),
+                                           C.POINTER(JobOutputs), C.POINTER(vp)]
+    lib.ltr_job_submit_outputs.restype = C.c_int
+    lib.ltr_job_download_kept.argtypes = [vp, vp, _u8p]
+    lib.ltr_job_download_kept.restype = C.c_int
+    lib.ltr_posteriors_batch.argtypes = [vp, C.c_uint32, _u32p, _u32p, _dp, C.POINTER(PosteriorBatch), _dp, _dp, _u8p]
+    lib.ltr_posteriors_batch.restype = C.c_int
     lib.ltr_job_wait.argtypes = [vp, vp]
     lib.ltr_job_wait.restype = C.c_int
     lib.ltr_job_poll.argtypes = [vp, vp]
@@ -222,7 +239,8 @@ EXPORTED_SYMBOLS = [
     "ltr_process_reads_flat_batch", "ltr_pipeline_create", "ltr_pipeline_submit", "ltr_pipeline_flush", "ltr_pipeline_next",
     "ltr_pipeline_destroy", "ltr_flatten_loci", "ltr_flat_batch_free",
     "ltr_fp64_issue_rate", "ltr_genotype_locus", "ltr_extract_calls", "ltr_trim_read_flat", "ltr_seed_base_flat",
-    "ltr_stutter_ll", "ltr_genotype_locus_pruned", "ltr_ctx_set_plan", "ltr_job_submit", "ltr_job_wait", "ltr_job_poll",
+    "ltr_stutter_ll", "ltr_genotype_locus_pruned", "ltr_ctx_set_plan", "ltr_job_submit", "ltr_job_submit_outputs", "ltr_job_wait", "ltr_job_poll", "ltr_job_download_kept", "ltr_posteriors_batch", "ltr_genotyper_create", "ltr_genotyper_destroy",
+    "ltr_genotyper_run", "ltr_batch_calls_free", "ltr_locus_batch_trim_read",
 ]
 
 

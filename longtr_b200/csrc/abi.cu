@@ -80,6 +80,8 @@ struct ltr_job {
   // posterior inputs
   bool has_post = false;
   DeviceBuffer lsb, pool, label, p1, p2, nsamp, haploid, post_off, tot_off, post, totals, int_logs;
+  DeviceBuffer mate, aligned, kept_mask, kept_index;  // optional: mate pairs, voting reads, removal of uncalled alleles
+  bool prune = false;
   uint32_t n_int_logs = 0, n_sreads = 0;
   std::vector<ClassState> classes;
   DeviceBuffer cls_ctrl;  // u32[(kPlanMaxK+1)*4]
@@ -294,7 +296,7 @@ void ltr_job_destroy(ltr_ctx* ctx, ltr_job* job) {
                           &job->raw_bytes_d, &job->raw_off_d, &job->plan_scratch, &job->plan_ctl, &job->plan_stat,
                           &job->lsb, &job->pool, &job->label, &job->p1, &job->p2, &job->nsamp,
                           &job->haploid, &job->post_off, &job->tot_off, &job->post, &job->totals,
-                          &job->int_logs, &job->cls_ctrl, &job->band_tasks, &job->band_cum, &job->band_pairs,
+                          &job->int_logs, &job->mate, &job->aligned, &job->kept_mask, &job->kept_index, &job->cls_ctrl, &job->band_tasks, &job->band_cum, &job->band_pairs,
                           &job->band_ctrl, &job->band_meta};
   for (DeviceBuffer* b : bufs) b->free();
   for (ClassState& c : job->classes) {
@@ -392,6 +394,13 @@ int setup_posteriors(ltr_ctx* ctx, ltr_job* job, const ltr_viterbi_batch& bb, co
   LTR_TRY(upload(ctx, st, job->p2, post->log_p2, n_sreads, 0, h2d));
   LTR_TRY(upload(ctx, st, job->nsamp, post->locus_n_samples, n_loci, 0, h2d));
   if (post->locus_haploid) LTR_TRY(upload(ctx, st, job->haploid, post->locus_haploid, n_loci, 0, h2d));
+  if (post->second_mate) LTR_TRY(upload(ctx, st, job->mate, post->second_mate, n_sreads, 0, h2d));
+  if (post->read_aligned) LTR_TRY(upload(ctx, st, job->aligned, post->read_aligned, n_sreads, 0, h2d));
+  job->prune = post->prune_uncalled != 0;
+  if (job->prune) {
+    LTR_CUDA(ctx, job->kept_mask.alloc((size_t)job->n_haps));
+    LTR_CUDA(ctx, job->kept_index.alloc((size_t)job->n_haps * 4));
+  }
   LTR_TRY(upload(ctx, st, job->post_off, post_off.data(), post_off.size(), 0, h2d));
   LTR_TRY(upload(ctx, st, job->tot_off, tot_off.data(), tot_off.size(), 0, h2d));
   LTR_CUDA(ctx, job->post.alloc(job->n_post * sizeof(double)));
@@ -871,6 +880,11 @@ int job_enqueue_compute(ltr_ctx* ctx, ltr_job* job) {
     P.post = job->post.as<double>();
     P.totals = job->totals.as<double>();
     P.err = job->device_plan ? job->plan_ctl.as<uint32_t>() + PLAN_CTL_ERR : nullptr;
+    P.second_mate = job->mate.p ? job->mate.as<uint8_t>() : nullptr;
+    P.read_aligned = job->aligned.p ? job->aligned.as<uint8_t>() : nullptr;
+    P.kept_mask = job->prune ? job->kept_mask.as<uint8_t>() : nullptr;
+    P.kept_index = job->prune ? job->kept_index.as<uint32_t>() : nullptr;
+    if (job->prune && job->n_haps) LTR_CUDA(ctx, cudaMemsetAsync(job->kept_mask.p, 1, job->n_haps, L.main));
     if (job->device_plan) {
       LTR_CUDA(ctx, launch_posterior_validate(P, job->plan_ctl.as<uint32_t>() + PLAN_CTL_ERR, L.main));
       job->stats.n_launches += 1;
@@ -1004,9 +1018,10 @@ int ltr_job_run(ltr_ctx* ctx, ltr_job* job) {
   return job_collect(ctx, job);
 }
 
-int ltr_job_submit(ltr_ctx* ctx, const ltr_params* params, const ltr_viterbi_batch* batch,
-                   const ltr_posterior_batch* post, double* out_ll, double* out_post, double* out_totals,
-                   ltr_job** out) {
+int ltr_job_submit_outputs(ltr_ctx* ctx, const ltr_params* params, const ltr_viterbi_batch* batch,
+                           const ltr_posterior_batch* post, const ltr_job_outputs* outputs, ltr_job** out) {
+  static const ltr_job_outputs kNone = {nullptr, nullptr, nullptr, nullptr};
+  const ltr_job_outputs& O = outputs ? *outputs : kNone;
   ltr_job* job = nullptr;
   int rc = job_new(ctx, params, batch, post, &job);
   if (rc != LTR_OK) return rc;
@@ -1015,17 +1030,25 @@ int ltr_job_submit(ltr_ctx* ctx, const ltr_params* params, const ltr_viterbi_bat
   if (rc == LTR_OK) {
     cudaError_t e = cudaStreamWaitEvent(L.d2h, job->ev_stats, 0);
     job->stats.d2h_bytes = 0;
-    if (e == cudaSuccess && out_ll && job->n_ll) {
-      e = cudaMemcpyAsync(out_ll, job->out_ll.p, job->n_ll * sizeof(double), cudaMemcpyDeviceToHost, L.d2h);
+    if (e == cudaSuccess && O.ll && job->n_ll) {
+      e = cudaMemcpyAsync(O.ll, job->out_ll.p, job->n_ll * sizeof(double), cudaMemcpyDeviceToHost, L.d2h);
       job->stats.d2h_bytes += job->n_ll * sizeof(double);
     }
-    if (e == cudaSuccess && out_post && job->has_post && job->n_post) {
-      e = cudaMemcpyAsync(out_post, job->post.p, job->n_post * sizeof(double), cudaMemcpyDeviceToHost, L.d2h);
+    if (e == cudaSuccess && O.post && job->has_post && job->n_post) {
+      e = cudaMemcpyAsync(O.post, job->post.p, job->n_post * sizeof(double), cudaMemcpyDeviceToHost, L.d2h);
       job->stats.d2h_bytes += job->n_post * sizeof(double);
     }
-    if (e == cudaSuccess && out_totals && job->has_post && job->n_tot) {
-      e = cudaMemcpyAsync(out_totals, job->totals.p, job->n_tot * sizeof(double), cudaMemcpyDeviceToHost, L.d2h);
+    if (e == cudaSuccess && O.totals && job->has_post && job->n_tot) {
+      e = cudaMemcpyAsync(O.totals, job->totals.p, job->n_tot * sizeof(double), cudaMemcpyDeviceToHost, L.d2h);
       job->stats.d2h_bytes += job->n_tot * sizeof(double);
+    }
+    if (e == cudaSuccess && O.kept_mask && job->n_haps) {
+      if (job->prune) {
+        e = cudaMemcpyAsync(O.kept_mask, job->kept_mask.p, job->n_haps, cudaMemcpyDeviceToHost, L.d2h);
+        job->stats.d2h_bytes += job->n_haps;
+      } else {
+        std::memset(O.kept_mask, 1, job->n_haps);
+      }
     }
     if (e == cudaSuccess) e = cudaEventRecord(job->ev_done, L.d2h);
     if (e != cudaSuccess) rc = fail_cuda(ctx, e, "ltr_job_submit: download");
@@ -1035,14 +1058,24 @@ int ltr_job_submit(ltr_ctx* ctx, const ltr_params* params, const ltr_viterbi_bat
     cudaError_t e = cudaStreamSynchronize(L.h2d);
     if (e != cudaSuccess) rc = fail_cuda(ctx, e, "ltr_job_submit: upload");
   }
+  job->pending = true;
   if (rc != LTR_OK) {
-    job->pending = true;
     ltr_job_destroy(ctx, job);
     return rc;
   }
-  job->pending = true;
   *out = job;
   return LTR_OK;
+}
+
+int ltr_job_submit(ltr_ctx* ctx, const ltr_params* params, const ltr_viterbi_batch* batch,
+                   const ltr_posterior_batch* post, double* out_ll, double* out_post, double* out_totals,
+                   ltr_job** out) {
+  ltr_job_outputs O;
+  O.ll = out_ll;
+  O.post = out_post;
+  O.totals = out_totals;
+  O.kept_mask = nullptr;
+  return ltr_job_submit_outputs(ctx, params, batch, post, &O, out);
 }
 
 int ltr_job_wait(ltr_ctx* ctx, ltr_job* job) {
@@ -1087,6 +1120,96 @@ int ltr_job_download(ltr_ctx* ctx, ltr_job* job, double* out_ll, double* out_pos
   }
   LTR_CUDA(ctx, cudaStreamSynchronize(L.main));
   return LTR_OK;
+}
+
+int ltr_job_download_kept(ltr_ctx* ctx, ltr_job* job, uint8_t* out_kept_mask) {
+  if (!ctx || !job || !out_kept_mask) return LTR_ERR_INVALID;
+  LTR_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!job->prune) {
+    std::memset(out_kept_mask, 1, job->n_haps);
+    return LTR_OK;
+  }
+  JobLane& L = ctx->lanes[job->lane];
+  if (job->n_haps) LTR_CUDA(ctx, cudaMemcpyAsync(out_kept_mask, job->kept_mask.p, job->n_haps, cudaMemcpyDeviceToHost, L.main));
+  LTR_CUDA(ctx, cudaStreamSynchronize(L.main));
+  return LTR_OK;
+}
+
+// Posterior stage on LL matrices the caller already holds (e.g. from ltr_stutter_ll): one upload, one launch, one download.
+int ltr_posteriors_batch(ltr_ctx* ctx, uint32_t n_loci, const uint32_t* locus_hap_begin, const uint32_t* locus_read_begin,
+                         const double* ll, const ltr_posterior_batch* post, double* out_post, double* out_totals,
+                         uint8_t* out_kept_mask) {
+  if (!ctx || !post || !out_post || !out_totals) return LTR_ERR_INVALID;
+  if (n_loci == 0) return LTR_OK;
+  if (!locus_hap_begin || !locus_read_begin || !ll) return LTR_ERR_INVALID;
+  LTR_CUDA(ctx, cudaSetDevice(ctx->device));
+  ltr_job* job = new ltr_job();
+  std::memset(&job->stats, 0, sizeof(job->stats));
+  job->ctx = ctx;
+  job->lane = (int)(ctx->next_lane++ % (unsigned)kLanes);
+  JobLane& L = ctx->lanes[job->lane];
+  AllocScope alloc_scope(L.h2d);
+  ltr_viterbi_batch bb;
+  std::memset(&bb, 0, sizeof(bb));
+  bb.n_loci = n_loci;
+  bb.locus_hap_begin = locus_hap_begin;
+  bb.locus_read_begin = locus_read_begin;
+  int rc = LTR_OK;
+  std::vector<unsigned long long> ll_off((size_t)n_loci + 1, 0);
+  for (uint32_t l = 0; l < n_loci && rc == LTR_OK; ++l) {
+    if (locus_hap_begin[l + 1] < locus_hap_begin[l] || locus_read_begin[l + 1] < locus_read_begin[l]) rc = LTR_ERR_INVALID;
+    ll_off[l + 1] = ll_off[l] + (unsigned long long)(locus_hap_begin[l + 1] - locus_hap_begin[l]) *
+                                    (locus_read_begin[l + 1] - locus_read_begin[l]);
+  }
+  job->n_loci = n_loci;
+  job->n_haps = locus_hap_begin[n_loci];
+  job->n_ll = ll_off[n_loci];
+  uint64_t* h2d = &job->stats.h2d_bytes;
+  if (rc == LTR_OK) rc = upload(ctx, L.h2d, job->lhb, locus_hap_begin, (size_t)n_loci + 1, 0, h2d);
+  if (rc == LTR_OK) rc = upload(ctx, L.h2d, job->lrb, locus_read_begin, (size_t)n_loci + 1, 0, h2d);
+  if (rc == LTR_OK) rc = upload(ctx, L.h2d, job->ll_off, ll_off.data(), ll_off.size(), 0, h2d);
+  if (rc == LTR_OK) rc = upload(ctx, L.h2d, job->out_ll, ll, (size_t)job->n_ll, 0, h2d);
+  if (rc == LTR_OK) rc = setup_posteriors(ctx, job, bb, post, L.h2d, true);
+  if (rc == LTR_OK) {
+    DevPosterior P;
+    P.n_loci = n_loci;
+    P.locus_hap_begin = job->lhb.as<uint32_t>();
+    P.locus_read_begin = job->lrb.as<uint32_t>();
+    P.locus_sread_begin = job->lsb.as<uint32_t>();
+    P.pool_index = job->pool.as<uint32_t>();
+    P.sample_label = job->label.as<int32_t>();
+    P.log_p1 = job->p1.as<double>();
+    P.log_p2 = job->p2.as<double>();
+    P.locus_n_samples = job->nsamp.as<uint32_t>();
+    P.locus_haploid = job->haploid.p ? job->haploid.as<uint8_t>() : nullptr;
+    P.ll_off = job->ll_off.as<unsigned long long>();
+    P.post_off = job->post_off.as<unsigned long long>();
+    P.tot_off = job->tot_off.as<unsigned long long>();
+    P.ll = job->out_ll.as<double>();
+    P.int_logs = job->int_logs.as<double>();
+    P.n_int_logs = job->n_int_logs;
+    P.log_one_half = log(0.5);
+    P.post = job->post.as<double>();
+    P.totals = job->totals.as<double>();
+    P.err = nullptr;
+    P.second_mate = job->mate.p ? job->mate.as<uint8_t>() : nullptr;
+    P.read_aligned = job->aligned.p ? job->aligned.as<uint8_t>() : nullptr;
+    P.kept_mask = job->prune ? job->kept_mask.as<uint8_t>() : nullptr;
+    P.kept_index = job->prune ? job->kept_index.as<uint32_t>() : nullptr;
+    cudaError_t e = cudaSuccess;
+    if (job->prune && job->n_haps) e = cudaMemsetAsync(job->kept_mask.p, 1, job->n_haps, L.h2d);
+    if (e == cudaSuccess) e = launch_posteriors(P, L.h2d);
+    if (e == cudaSuccess && job->n_post) e = cudaMemcpyAsync(out_post, job->post.p, job->n_post * 8, cudaMemcpyDeviceToHost, L.h2d);
+    if (e == cudaSuccess && job->n_tot) e = cudaMemcpyAsync(out_totals, job->totals.p, job->n_tot * 8, cudaMemcpyDeviceToHost, L.h2d);
+    if (e == cudaSuccess && out_kept_mask && job->n_haps) {
+      if (job->prune) e = cudaMemcpyAsync(out_kept_mask, job->kept_mask.p, job->n_haps, cudaMemcpyDeviceToHost, L.h2d);
+      else std::memset(out_kept_mask, 1, job->n_haps);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(L.h2d);
+    if (e != cudaSuccess) rc = fail_cuda(ctx, e, "ltr_posteriors_batch");
+  }
+  ltr_job_destroy(ctx, job);
+  return rc;
 }
 
 void ltr_job_get_stats(const ltr_job* job, ltr_job_stats* stats) {
@@ -1161,6 +1284,10 @@ int ltr_posteriors(ltr_ctx* ctx, int haploid, int32_t n_samples, int32_t n_reads
     P.post = d_post.as<double>();
     P.totals = d_tot.as<double>();
     P.err = nullptr;
+    P.second_mate = nullptr;
+    P.read_aligned = nullptr;
+    P.kept_mask = nullptr;
+    P.kept_index = nullptr;
     cudaError_t e = launch_posteriors(P, ctx->main_stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(post, d_post.p, S * H * H * 8, cudaMemcpyDeviceToHost, ctx->main_stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(totals, d_tot.p, S * 8, cudaMemcpyDeviceToHost, ctx->main_stream);

@@ -92,6 +92,10 @@ struct DevPosterior {
   double* post;
   double* totals;
   const uint32_t* err;                // != 0: malformed batch, nothing is computed (may be NULL)
+  const uint8_t* second_mate;         // [n_sreads] or NULL: read r is the second mate of read r-1 (LL rows are summed)
+  const uint8_t* read_aligned;        // [n_sreads] or NULL (all): seed_positions >= 0 -- whether the read lets its sample vote
+  uint8_t* kept_mask;                 // [n_haps] or NULL: != NULL turns on the removal of uncalled alleles + second pass;
+  uint32_t* kept_index;               //   kept_mask[h] = allele survives; kept_index: scratch, [n_haps]
 };
 cudaError_t launch_posteriors(const DevPosterior& P, cudaStream_t stream);
 // Sets bit 2 of *err when a sample-read points outside its locus' pooled reads or names a sample that does not exist

@@ -27,6 +27,21 @@ __global__ void __launch_bounds__(128) posterior_validate_kernel(const DevPoster
   if (bad) atomicOr(err, 4u);
 }
 
+// LL of (sample-read r, allele a): its pool's row, or -- when reads come in mate pairs (consecutive reads with the same
+// name, P.second_mate) -- what src/seq_stutter_genotyper.cpp:546-559 leaves in the two rows: the sum of both mates,
+// accumulated in read order along a run of flagged reads.
+__device__ __forceinline__ double read_ll(const DevPosterior& P, const double* ll, uint32_t H, uint32_t r0, uint32_t r1,
+                                          uint32_t r, uint32_t a) {
+  if (P.second_mate == nullptr) return ll[(size_t)P.pool_index[r] * H + a];
+  uint32_t c0 = r;
+  while (c0 > r0 && P.second_mate[c0]) --c0;  // first read of the run
+  uint32_t last = r;                          // the row of read r is last rewritten when read r+1 is a second mate
+  if (r + 1 < r1 && P.second_mate[r + 1]) last = r + 1;
+  double s = ll[(size_t)P.pool_index[c0] * H + a];
+  for (uint32_t j = c0 + 1; j <= last; ++j) s = s + ll[(size_t)P.pool_index[j] * H + a];
+  return s;
+}
+
 // One warp per locus.  exp(LL[r][a] + log_p1[r] + log 1/2) depends on (read, allele) only and the term
 // log(e1[r][a] + e2[r][b]) on (read, a, b) only, so the warp first tabulates the 2 R H exponentials and the R H^2 logarithms
 // with all lanes (shared memory, kPostDoubles per warp), and every (sample, a, b) entry is then summed by one lane over its
@@ -70,7 +85,7 @@ __global__ void __launch_bounds__(kPostWarps * 32) posterior_kernel(const DevPos
     if (have_e) {
       for (uint32_t i = lane; i < R * H; i += 32u) {
         const uint32_t r = i / H, a = i - r * H;
-        double v = ll[(size_t)P.pool_index[r0 + r] * H + a];
+        double v = read_ll(P, ll, H, r0, r1, r0 + r, a);
         v = (v < -600.0) ? -600.0 : v;  // genotyper.cpp:57-58
         E1[i] = exp(v + P.log_p1[r0 + r] + P.log_one_half);
         E2[i] = exp(v + P.log_p2[r0 + r] + P.log_one_half);
@@ -94,8 +109,7 @@ __global__ void __launch_bounds__(kPostWarps * 32) posterior_kernel(const DevPos
         } else if (have_e) {
           acc += log(E1[r * H + a] + E2[r * H + b]);
         } else {
-          const double* row = ll + (size_t)P.pool_index[r0 + r] * H;
-          double la = row[a], lb = row[b];
+          double la = read_ll(P, ll, H, r0, r1, r0 + r, a), lb = read_ll(P, ll, H, r0, r1, r0 + r, b);
           la = (la < -600.0) ? -600.0 : la;
           lb = (lb < -600.0) ? -600.0 : lb;
           acc += log(exp(la + P.log_p1[r0 + r] + P.log_one_half) + exp(lb + P.log_p2[r0 + r] + P.log_one_half));
@@ -114,6 +128,81 @@ __global__ void __launch_bounds__(kPostWarps * 32) posterior_kernel(const DevPos
     }
     __syncwarp();
     for (uint32_t idx = lane; idx < S * HH; idx += 32u) post[idx] -= tot[idx / HH];
+    if (P.kept_mask == nullptr) continue;
+    // ---- what SeqStutterGenotyper::genotype does next (src/seq_stutter_genotyper.cpp:636-645): non-reference alleles in
+    // no voting sample's optimal pair are dropped and the posteriors recomputed on the surviving ones ------------------
+    __syncwarp();
+    const uint32_t h0 = P.locus_hap_begin[l];
+    uint8_t* kept = P.kept_mask + h0;
+    uint32_t* kidx = P.kept_index + h0;
+    for (uint32_t a = lane; a < H; a += 32u) kept[a] = (a == 0) ? 1 : 0;
+    __syncwarp();
+    for (uint32_t s = lane; s < S; s += 32u) {
+      bool votes = false;  // the sample has an aligned read (get_unused_alleles, :262-265)
+      for (uint32_t r = r0; r < r1 && !votes; ++r)
+        votes = ((uint32_t)P.sample_label[r] == s) && (P.read_aligned == nullptr || P.read_aligned[r] != 0);
+      if (!votes) continue;
+      const double* v = post + (size_t)s * HH;  // get_optimal_haplotypes (genotyper.cpp:85-100): first maximum
+      double best = -DBL_MAX;
+      uint32_t arg = 0;
+      for (uint32_t k = 0; k < HH; ++k)
+        if (v[k] > best) {
+          best = v[k];
+          arg = k;
+        }
+      kept[arg / H] = 1;
+      kept[arg % H] = 1;
+    }
+    __syncwarp();
+    uint32_t K = 0;
+    if (lane == 0) {
+      for (uint32_t a = 0; a < H; ++a)
+        if (kept[a]) kidx[K++] = a;
+    }
+    K = __shfl_sync(0xFFFFFFFFu, K, 0);
+    __syncwarp();
+    if (K == H) continue;  // nothing removed: the first pass stands
+    const uint32_t KK = K * K;
+    const double lK = P.int_logs[K < P.n_int_logs ? K : 0], lK1 = P.int_logs[K + 1 < P.n_int_logs ? K + 1 : 0];
+    const double hom2 = haploid ? -lK : P.int_logs[2] - lK - lK1;
+    const double het2 = haploid ? -DBL_MAX / 2 : -lK - lK1;
+    // every lane computes its entries from the tables / the LL rows first, the compact array is written afterwards
+    // (it overlaps the first pass' array, which the LL rows do not depend on)
+    for (uint32_t base = 0; base < S * KK; base += 32u) {
+      const uint32_t idx = base + lane;
+      double acc = 0.0;
+      if (idx < S * KK) {
+        const uint32_t s = idx / KK, ab = idx - s * KK, a2 = ab / K, b2 = ab - a2 * K;
+        const uint32_t a = kidx[a2], b = kidx[b2], abo = a * H + b;
+        acc = (a2 == b2) ? hom2 : het2;
+        for (uint32_t r = 0; r < R; ++r) {
+          if ((uint32_t)P.sample_label[r0 + r] != s) continue;
+          if (have_t) {
+            acc += T[r * HH + abo];
+          } else if (have_e) {
+            acc += log(E1[r * H + a] + E2[r * H + b]);
+          } else {
+            double la = read_ll(P, ll, H, r0, r1, r0 + r, a), lb = read_ll(P, ll, H, r0, r1, r0 + r, b);
+            la = (la < -600.0) ? -600.0 : la;
+            lb = (lb < -600.0) ? -600.0 : lb;
+            acc += log(exp(la + P.log_p1[r0 + r] + P.log_one_half) + exp(lb + P.log_p2[r0 + r] + P.log_one_half));
+          }
+        }
+      }
+      __syncwarp();
+      if (idx < S * KK) post[idx] = acc;
+    }
+    __syncwarp();
+    for (uint32_t s = lane; s < S; s += 32u) {
+      const double* v = post + (size_t)s * KK;
+      double mx = v[0];
+      for (uint32_t k = 1; k < KK; ++k) mx = (mx < v[k]) ? v[k] : mx;
+      double sum = 0.0;
+      for (uint32_t k = 0; k < KK; ++k) sum += exp(v[k] - mx);
+      tot[s] = mx + log(sum);
+    }
+    __syncwarp();
+    for (uint32_t idx = lane; idx < S * KK; idx += 32u) post[idx] -= tot[idx / KK];
   }
 }
 

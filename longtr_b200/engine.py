@@ -265,6 +265,24 @@ class Engine:
         _check(self.lib, self.ctx, rc, "ltr_job_submit")
         return Job(self, h, (keep, keep2, vb, pb, out_ll, out_post, out_totals))
 
+    def posteriors_batch(self, locus_hap_begin, locus_read_begin, ll, post):
+        """ltr_posteriors_batch: posteriors (optionally mate pairs / removal of uncalled alleles) for many loci from LL
+        matrices the caller holds.  Returns (post flat, totals flat, kept_mask[n_haps])."""
+        lhb = np.ascontiguousarray(locus_hap_begin, dtype=np.uint32)
+        lrb = np.ascontiguousarray(locus_read_begin, dtype=np.uint32)
+        ll = np.ascontiguousarray(ll, dtype=np.float64)
+        pb, keep = abi.make_posterior_batch(post)
+        H = np.diff(lhb).astype(np.int64)
+        S = np.asarray(post["locus_n_samples"], dtype=np.int64)
+        out_post = np.zeros(int(np.sum(S * H * H)), dtype=np.float64)
+        out_tot = np.zeros(int(np.sum(S)), dtype=np.float64)
+        kept = np.zeros(int(lhb[-1]), dtype=np.uint8)
+        rc = self.lib.ltr_posteriors_batch(self.ctx, len(lhb) - 1, abi.ptr(lhb, abi._u32p), abi.ptr(lrb, abi._u32p),
+                                           abi.ptr(ll, abi._dp), C.byref(pb), abi.ptr(out_post, abi._dp),
+                                           abi.ptr(out_tot, abi._dp), abi.ptr(kept, abi._u8p))
+        _check(self.lib, self.ctx, rc, "ltr_posteriors_batch")
+        return out_post, out_tot, kept
+
     def process_reads_flat(self, locus, n_reads, n_alleles, fill=0.0):
         ll = np.full((n_reads, n_alleles), fill, dtype=np.float64)
         seeds = np.full(n_reads, -12345, dtype=np.int32)

@@ -1,0 +1,192 @@
+"""Python side of ltr_genotyper_* (include/longtr_b200.h): many raw loci -> genotype calls.
+
+``build_locus_batch`` turns a list of plain-Python loci into the structure-of-arrays ``ltr_locus_batch``;
+``Genotyper`` owns an ``ltr_genotyper`` (one context per device + host worker threads).  ctypes only: nothing here
+computes on the CPU beyond packing arrays, and there is no fallback without a GPU."""
+import ctypes as C
+import re
+
+import numpy as np
+
+from . import abi
+
+_u32p, _u8p, _i32p, _dp = abi._u32p, abi._u8p, abi._i32p, abi._dp
+_u64p = C.POINTER(C.c_uint64)
+
+
+class LocusBatch(C.Structure):
+    _fields_ = [("n_loci", C.c_uint32), ("lflank_off", _u32p), ("lflank_bytes", _u8p), ("rflank_off", _u32p),
+                ("rflank_bytes", _u8p), ("locus_allele_begin", _u32p), ("allele_off", _u32p), ("allele_bytes", _u8p),
+                ("repeat_start", _i32p), ("repeat_end", _i32p), ("locus_read_begin", _u32p), ("read_start", _i32p),
+                ("read_stop", _i32p), ("read_off", _u32p), ("read_bytes", _u8p), ("cigar_off", _u32p),
+                ("cigar_ops", _u32p), ("read_sample", _i32p), ("log_p1", _dp), ("log_p2", _dp), ("second_mate", _u8p),
+                ("locus_n_samples", _u32p), ("locus_haploid", _u8p)]
+
+
+class BatchCalls(C.Structure):
+    _fields_ = [("n_loci", C.c_uint32), ("status", _i32p), ("locus_sample_begin", _u32p), ("locus_allele_begin", _u32p),
+                ("kept_mask", _u8p), ("n_kept", _i32p), ("n_pools", _i32p), ("gts", _i32p),
+                ("log_phased_posteriors", _dp), ("log_unphased_posteriors", _dp), ("gl_diffs", _dp),
+                ("sample_total_lls", _dp), ("n_reads", _i32p), ("gl_begin", _u64p), ("gls", _dp), ("pls", _i32p),
+                ("prep_ms", C.c_double), ("gpu_wait_ms", C.c_double), ("post_ms", C.c_double), ("total_ms", C.c_double)]
+
+
+BAM_OPS = "MIDNSHP=X"
+_CIGAR_RE = re.compile(r"(\d+)(.)")
+
+
+def pack_cigar(cigar):
+    """'110=4I90=' -> BAM-encoded uint32 list (length << 4 | op).  Unknown operations get code 15 (rejected by the library
+    like the reference rejects them)."""
+    out = []
+    for n, op in _CIGAR_RE.findall(cigar):
+        k = BAM_OPS.find(op)
+        out.append((int(n) << 4) | (k if k >= 0 else 15))
+    return out
+
+
+def build_locus_batch(loci):
+    """loci: list of dicts with lflank, rflank, alleles (list of str), repeat_start, repeat_end, n_samples, haploid (opt),
+    reads: list of dicts start, stop, seq, cigar (str), sample, log_p1, log_p2, second_mate (opt) -- sample-major.
+    Returns a dict of numpy arrays (the fields of ltr_locus_batch)."""
+    def offs(strs):
+        return np.concatenate([[0], np.cumsum([len(s) for s in strs])]).astype(np.uint32)
+
+    def cat(strs):
+        return np.frombuffer("".join(strs).encode(), dtype=np.uint8).copy()
+    lf, rf = [l["lflank"] for l in loci], [l["rflank"] for l in loci]
+    alleles = [a for l in loci for a in l["alleles"]]
+    reads = [r for l in loci for r in l["reads"]]
+    cig = [pack_cigar(r["cigar"]) for r in reads]
+    any_mate = any(r.get("second_mate") for r in reads)
+    b = dict(
+        lflank_off=offs(lf), lflank_bytes=cat(lf), rflank_off=offs(rf), rflank_bytes=cat(rf),
+        locus_allele_begin=np.concatenate([[0], np.cumsum([len(l["alleles"]) for l in loci])]).astype(np.uint32),
+        allele_off=offs(alleles), allele_bytes=cat(alleles),
+        repeat_start=np.array([l["repeat_start"] for l in loci], np.int32),
+        repeat_end=np.array([l["repeat_end"] for l in loci], np.int32),
+        locus_read_begin=np.concatenate([[0], np.cumsum([len(l["reads"]) for l in loci])]).astype(np.uint32),
+        read_start=np.array([r["start"] for r in reads], np.int32), read_stop=np.array([r["stop"] for r in reads], np.int32),
+        read_off=offs([r["seq"] for r in reads]), read_bytes=cat([r["seq"] for r in reads]),
+        cigar_off=np.concatenate([[0], np.cumsum([len(c) for c in cig])]).astype(np.uint32),
+        cigar_ops=np.array([x for c in cig for x in c], np.uint32),
+        read_sample=np.array([r["sample"] for r in reads], np.int32),
+        log_p1=np.array([r["log_p1"] for r in reads], np.float64), log_p2=np.array([r["log_p2"] for r in reads], np.float64),
+        second_mate=(np.array([1 if r.get("second_mate") else 0 for r in reads], np.uint8) if any_mate else None),
+        locus_n_samples=np.array([l["n_samples"] for l in loci], np.uint32),
+        locus_haploid=np.array([1 if l.get("haploid") else 0 for l in loci], np.uint8))
+    return b
+
+
+_PTR = dict(lflank_off=_u32p, lflank_bytes=_u8p, rflank_off=_u32p, rflank_bytes=_u8p, locus_allele_begin=_u32p,
+            allele_off=_u32p, allele_bytes=_u8p, repeat_start=_i32p, repeat_end=_i32p, locus_read_begin=_u32p,
+            read_start=_i32p, read_stop=_i32p, read_off=_u32p, read_bytes=_u8p, cigar_off=_u32p, cigar_ops=_u32p,
+            read_sample=_i32p, log_p1=_dp, log_p2=_dp, second_mate=_u8p, locus_n_samples=_u32p, locus_haploid=_u8p)
+_DT = {_u32p: np.uint32, _u8p: np.uint8, _i32p: np.int32, _dp: np.float64}
+
+
+def make_locus_batch(b):
+    """dict of numpy arrays -> (LocusBatch, keepalive)."""
+    s = LocusBatch()
+    keep = {}
+    s.n_loci = len(b["locus_read_begin"]) - 1
+    for k, t in _PTR.items():
+        v = b.get(k)
+        if v is None:
+            continue
+        a = np.ascontiguousarray(v, dtype=_DT[t])
+        if a.size == 0:
+            a = np.zeros(1, dtype=_DT[t])
+        keep[k] = a
+        setattr(s, k, a.ctypes.data_as(t))
+    return s, keep
+
+
+def _declare(lib):
+    vp = C.c_void_p
+    lib.ltr_genotyper_create.argtypes = [_i32p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(vp)]
+    lib.ltr_genotyper_create.restype = C.c_int
+    lib.ltr_genotyper_destroy.argtypes = [vp]
+    lib.ltr_genotyper_destroy.restype = None
+    lib.ltr_genotyper_run.argtypes = [vp, C.POINTER(abi.Params), C.POINTER(LocusBatch), C.POINTER(C.POINTER(BatchCalls))]
+    lib.ltr_genotyper_run.restype = C.c_int
+    lib.ltr_batch_calls_free.argtypes = [C.POINTER(BatchCalls)]
+    lib.ltr_batch_calls_free.restype = None
+    lib.ltr_locus_batch_trim_read.argtypes = [C.POINTER(LocusBatch), C.POINTER(abi.Params), C.c_uint32, C.c_uint32, _u8p,
+                                              C.c_int32]
+    lib.ltr_locus_batch_trim_read.restype = C.c_int32
+
+
+def trim_read(batch_struct, locus, read, aln_params=None, indel_flank_len=5, cap=1 << 16):
+    """ltr_locus_batch_trim_read (host only)."""
+    lib = abi.load()
+    _declare(lib)
+    p = abi.make_params(aln_params, indel_flank_len)
+    buf = np.zeros(cap, np.uint8)
+    n = lib.ltr_locus_batch_trim_read(C.byref(batch_struct), C.byref(p), locus, read, buf.ctypes.data_as(_u8p), cap)
+    if n < 0:
+        raise RuntimeError("ltr_locus_batch_trim_read failed: %d" % n)
+    return bytes(buf[:n])
+
+
+class Genotyper:
+    """``ltr_genotyper``: contexts on the given devices + host worker threads."""
+
+    def __init__(self, devices=(0,), host_threads=0, chunk_loci=0):
+        from .engine import LongTRError
+        self.lib = abi.load()
+        _declare(self.lib)
+        self.h = C.c_void_p()
+        dev = np.array(list(devices), np.int32)
+        rc = self.lib.ltr_genotyper_create(dev.ctypes.data_as(_i32p), len(dev), host_threads, chunk_loci, C.byref(self.h))
+        if rc != abi.LTR_OK:
+            self.h = None
+            raise LongTRError("ltr_genotyper_create: %s" % self.lib.ltr_strerror(rc).decode())
+
+    def run_struct(self, batch_struct, aln_params=None, indel_flank_len=5):
+        """Runs on a prepared LocusBatch; returns the raw BatchCalls pointer (free with ``free``)."""
+        from .engine import LongTRError
+        p = abi.make_params(aln_params, indel_flank_len)
+        out = C.POINTER(BatchCalls)()
+        rc = self.lib.ltr_genotyper_run(self.h, C.byref(p), C.byref(batch_struct), C.byref(out))
+        if rc != abi.LTR_OK:
+            raise LongTRError("ltr_genotyper_run: %s" % self.lib.ltr_strerror(rc).decode())
+        return out
+
+    def free(self, calls):
+        self.lib.ltr_batch_calls_free(calls)
+
+    def run(self, batch, aln_params=None, indel_flank_len=5):
+        """batch: dict of numpy arrays (build_locus_batch).  Returns a dict of numpy copies of ltr_batch_calls."""
+        s, keep = make_locus_batch(batch)
+        calls = self.run_struct(s, aln_params, indel_flank_len)
+        c = calls.contents
+        n = c.n_loci
+        arr = np.ctypeslib.as_array
+
+        def take(ptr, count):
+            return arr(ptr, (max(1, count),))[:count].copy()
+        lsb = take(c.locus_sample_begin, n + 1)
+        lab = take(c.locus_allele_begin, n + 1)
+        ns, na = int(lsb[-1]), int(lab[-1])
+        glb = take(c.gl_begin, ns + 1)
+        out = dict(status=take(c.status, n), locus_sample_begin=lsb, locus_allele_begin=lab, kept_mask=take(c.kept_mask, na),
+                   n_kept=take(c.n_kept, n), n_pools=take(c.n_pools, n), gts=take(c.gts, 2 * ns).reshape(ns, 2),
+                   log_phased_posteriors=take(c.log_phased_posteriors, ns),
+                   log_unphased_posteriors=take(c.log_unphased_posteriors, ns), gl_diffs=take(c.gl_diffs, ns),
+                   sample_total_lls=take(c.sample_total_lls, ns), n_reads=take(c.n_reads, ns), gl_begin=glb,
+                   gls=take(c.gls, int(glb[-1])), pls=take(c.pls, int(glb[-1])),
+                   timing=dict(prep_ms=c.prep_ms, gpu_wait_ms=c.gpu_wait_ms, post_ms=c.post_ms, total_ms=c.total_ms))
+        self.free(calls)
+        return out
+
+    def close(self):
+        if self.h:
+            self.lib.ltr_genotyper_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

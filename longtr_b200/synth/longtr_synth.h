@@ -23,6 +23,17 @@ int ltr_synth_generate(int config, uint64_t base_seed, uint32_t first_locus, uin
 void ltr_synth_params(int config, ltr_params* p);
 void ltr_synth_free(ltr_synth_batch* b);
 
+/* The same loci in raw form (configs 3 and 4): whole reads with CIGARs, flank blocks and candidate alleles, ready for
+ * ltr_genotyper_run (include/longtr_b200.h).  Same seeds and read bases as ltr_synth_generate.                      */
+typedef struct ltr_synth_loci {
+  ltr_locus_batch batch;
+  uint32_t n_alleles, n_reads, n_cigar_ops;
+  uint64_t allele_nbytes, read_nbytes;
+} ltr_synth_loci;
+int ltr_synth_generate_loci(int config, uint64_t base_seed, uint32_t first_locus, uint32_t n_loci, int n_threads,
+                            ltr_synth_loci** out);
+void ltr_synth_loci_free(ltr_synth_loci* loci);
+
 
 #ifdef __cplusplus
 }

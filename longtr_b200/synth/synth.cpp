@@ -102,7 +102,62 @@ struct LocusOut {
   std::vector<std::string> reads;   // pooled, trimmed
   std::vector<uint32_t> pool_index; // per sample-read
   std::vector<double> p1, p2;
+  // raw form (ltr_synth_generate_loci): the same reads whole, with CIGARs against the reference window
+  bool want_raw = false;
+  std::string lflank, rflank;
+  std::vector<std::string> alleles;            // repeat-block alleles (pads inside), reference first
+  std::vector<std::string> raw_reads;
+  std::vector<std::vector<uint32_t>> raw_cigars;  // BAM encoding
+  std::vector<int32_t> raw_start, raw_stop;
+  int32_t repeat_start = 0, repeat_end = 0;
 };
+
+// CIGAR under construction: per read base / reference base operations, merged into runs.
+struct CigarBuilder {
+  std::vector<uint32_t> ops;  // len << 4 | op (BAM: M0 I1 D2 =7 X8)
+  void add(uint32_t op, uint32_t n = 1) {
+    if (n == 0) return;
+    if (!ops.empty() && (ops.back() & 15u) == op) ops.back() += n << 4;
+    else ops.push_back((n << 4) | op);
+  }
+};
+
+// add_errors with the operations it performed, for a stretch of the TRUE haplotype whose bases are either aligned to the
+// reference (ref_aligned[i] != 0) or part of an insertion relative to it.  Consumes the generator exactly like add_errors,
+// so the read bases are identical to the flattened workload's.
+std::string add_errors_ops(Rng& r, const std::string& s, const std::vector<uint8_t>& ref_aligned, size_t a0, double sub,
+                           double indel, double homop_mult, CigarBuilder& cg) {
+  std::string out;
+  out.reserve(s.size() + 8);
+  const int L = (int)s.size();
+  for (int i = 0; i < L; ++i) {
+    double ind = indel;
+    if (homop_mult != 1.0) {
+      int a = i, b = i;
+      while (a > 0 && s[a - 1] == s[i]) --a;
+      while (b + 1 < L && s[b + 1] == s[i]) ++b;
+      if (b - a + 1 >= 4) ind *= homop_mult;
+    }
+    const bool al = ref_aligned[a0 + (size_t)i] != 0;
+    const double u = r.unif();
+    if (u < sub) {
+      out.push_back(kBases[(uint32_t)(std::strchr(kBases, s[i]) - kBases + 1 + r.below(3)) & 3]);
+      cg.add(al ? 8u : 1u);
+    } else if (u < sub + ind * 0.5) {
+      if (al) cg.add(2u);  // deletion
+      continue;
+    } else if (u < sub + ind) {
+      out.push_back(s[i]);
+      out.push_back(r.base());  // insertion
+      cg.add(al ? 7u : 1u);
+      cg.add(1u);
+    } else {
+      out.push_back(s[i]);
+      cg.add(al ? 7u : 1u);
+    }
+  }
+  return out;
+}
 
 void gen_locus(int config, uint64_t seed, LocusOut& o) {
   Rng r(seed);
@@ -137,6 +192,7 @@ void gen_locus(int config, uint64_t seed, LocusOut& o) {
   std::vector<std::string> truth;
   truth.push_back(allele_of(ref_units + k1, motif));
   truth.push_back(allele_of(ref_units + k2, motif));
+  const int truth_units[2] = {std::max(1, ref_units + k1), std::max(1, ref_units + k2)};
   // candidate set: reference first, then alternates sorted by (length, sequence)
   // (HaplotypeGenerator.cpp:475); decoys are +-1 unit neighbours / motif-level variants
   const int want_h = r.range(hmin, hmax);
@@ -168,11 +224,80 @@ void gen_locus(int config, uint64_t seed, LocusOut& o) {
   // 30 reads, allele chosen with p = 1/2, HP tag follows the allele (snp_bam_processor.h:16-18)
   std::map<std::string, uint32_t> pools;
   o.reads.clear(); o.pool_index.clear(); o.p1.clear(); o.p2.clear();
+  if (o.want_raw) {
+    o.lflank = lflank; o.rflank = rflank;
+    o.alleles.clear();
+    for (const std::string& h : o.haps) o.alleles.push_back(h.substr(35, h.size() - 70));
+    o.repeat_start = 1000;
+    o.repeat_end = 1000 + (int32_t)ref_allele.size();
+    o.raw_reads.clear(); o.raw_cigars.clear(); o.raw_start.clear(); o.raw_stop.clear();
+  }
   for (int i = 0; i < 30; ++i) {
     const int a = (int)(r.g() & 1);
-    const std::string left = add_errors(r, lctx + lflank.substr(0, 30), sub, indel, homop_mult);
-    const std::string mid = add_errors(r, lflank.substr(30) + truth[a] + rflank.substr(0, 5), sub, indel, homop_mult);
-    const std::string right = add_errors(r, rflank.substr(5) + rctx, sub, indel, homop_mult);
+    std::string left, mid, right;
+    if (!o.want_raw) {
+      left = add_errors(r, lctx + lflank.substr(0, 30), sub, indel, homop_mult);
+      mid = add_errors(r, lflank.substr(30) + truth[a] + rflank.substr(0, 5), sub, indel, homop_mult);
+      right = add_errors(r, rflank.substr(5) + rctx, sub, indel, homop_mult);
+    } else {
+      // true haplotype = window with the allele in place of the reference allele; against the reference it carries one
+      // indel of |d| repeat bases right behind the left pad (left-aligned), everything else is aligned
+      const std::string seg1 = lctx + lflank.substr(0, 30), seg2 = lflank.substr(30) + truth[a] + rflank.substr(0, 5),
+                        seg3 = rflank.substr(5) + rctx;
+      const int d = (truth_units[a] - ref_units) * period;  // > 0: insertion, < 0: deletion
+      std::vector<uint8_t> al1(seg1.size(), 1), al2(seg2.size(), 1), al3(seg3.size(), 1);
+      const size_t rep0 = 5 + lpad.size();  // first repeat base inside seg2
+      if (d > 0)
+        for (int k = 0; k < d; ++k) al2[rep0 + (size_t)k] = 0;
+      CigarBuilder cg;
+      left = add_errors_ops(r, seg1, al1, 0, sub, indel, homop_mult, cg);
+      if (d >= 0) {
+        mid = add_errors_ops(r, seg2, al2, 0, sub, indel, homop_mult, cg);
+      } else {  // the deleted reference bases sit between the left pad and the first repeat base of the read
+        const std::string head = seg2.substr(0, rep0), tail = seg2.substr(rep0);
+        // (split only for the CIGAR: the generator is consumed base by base in the same order; the homopolymer context of
+        // add_errors is evaluated on the whole segment, hence the offsets into seg2)
+        CigarBuilder c_mid;
+        mid = add_errors_ops(r, seg2, al2, 0, sub, indel, homop_mult, c_mid);
+        // re-walk c_mid, inserting the deletion after the operations that consumed the first rep0 haplotype bases
+        size_t consumed = 0;
+        bool placed = false;
+        for (uint32_t op : c_mid.ops) {
+          uint32_t n = op >> 4;
+          const uint32_t code = op & 15u;
+          const bool uses_hap = (code == 7u || code == 8u || code == 2u);  // '=' 'X' 'D' consume an aligned haplotype base
+          while (n > 0) {
+            if (!placed && consumed == rep0) {
+              cg.add(2u, (uint32_t)(-d));
+              placed = true;
+            }
+            uint32_t take = n;
+            if (!placed && uses_hap) take = (uint32_t)std::min<size_t>(n, rep0 - consumed);
+            if (!placed && !uses_hap) take = n;  // error insertions before the boundary stay where they are
+            cg.add(code, take);
+            if (uses_hap) consumed += take;
+            n -= take;
+          }
+        }
+        if (!placed) cg.add(2u, (uint32_t)(-d));
+        (void)head; (void)tail;
+      }
+      right = add_errors_ops(r, seg3, al3, 0, sub, indel, homop_mult, cg);
+      // leading / trailing deletions are not part of an alignment: drop them and move the ends
+      int32_t start = 1000 - 200;
+      int32_t ref_len = 0;
+      std::vector<uint32_t> ops = cg.ops;
+      size_t b0 = 0, b1 = ops.size();
+      while (b0 < b1 && (ops[b0] & 15u) == 2u) { start += (int32_t)(ops[b0] >> 4); ++b0; }
+      while (b1 > b0 && (ops[b1 - 1] & 15u) == 2u) --b1;
+      ops.assign(ops.begin() + (long)b0, ops.begin() + (long)b1);
+      for (uint32_t op : ops)
+        if ((op & 15u) == 7u || (op & 15u) == 8u || (op & 15u) == 2u) ref_len += (int32_t)(op >> 4);
+      o.raw_reads.push_back(left + mid + right);
+      o.raw_cigars.push_back(ops);
+      o.raw_start.push_back(start);
+      o.raw_stop.push_back(start + ref_len - 1);
+    }
     const std::string key = left + "|" + mid + "|" + right;
     auto it = pools.find(key);
     uint32_t idx;
@@ -268,6 +393,82 @@ int ltr_synth_generate(int config, uint64_t base_seed, uint32_t first_locus, uin
   b->n_haps = ih; b->n_reads = ir; b->n_sreads = is; b->hap_nbytes = ob; b->read_nbytes = orb;
   *out = b;
   return LTR_OK;
+}
+
+
+// Raw form of the same workload: whole reads (+-200 bp around the repeat) with CIGARs, flank blocks, candidate alleles --
+// what ltr_genotyper_run takes.  Same seeds, same read bases as ltr_synth_generate (the reads there are these reads pooled
+// and cut to the repeat +- 5 bp).  One sample per locus.
+int ltr_synth_generate_loci(int config, uint64_t base_seed, uint32_t first_locus, uint32_t n_loci, int n_threads,
+                            ltr_synth_loci** out) {
+  if (!out || (config != 3 && config != 4)) return LTR_ERR_INVALID;
+  std::vector<LocusOut> loci(n_loci);
+  if (n_threads < 1) n_threads = 1;
+  std::vector<std::thread> th;
+  for (int t = 0; t < n_threads; ++t)
+    th.emplace_back([&, t]() {
+      for (uint32_t l = (uint32_t)t; l < n_loci; l += (uint32_t)n_threads) {
+        loci[l].want_raw = true;
+        gen_locus(config, base_seed + first_locus + l, loci[l]);
+      }
+    });
+  for (auto& x : th) x.join();
+  uint64_t na = 0, nr = 0, ab = 0, rb = 0, nc = 0;
+  for (const LocusOut& o : loci) {
+    na += o.alleles.size(); nr += o.raw_reads.size();
+    for (const auto& s : o.alleles) ab += s.size();
+    for (const auto& s : o.raw_reads) rb += s.size();
+    for (const auto& c : o.raw_cigars) nc += c.size();
+  }
+  if (ab >= 0xFFFFFFF0ull || rb >= 0xFFFFFFF0ull || nc >= 0xFFFFFFF0ull) return LTR_ERR_INVALID;
+  ltr_synth_loci* S = (ltr_synth_loci*)std::calloc(1, sizeof(ltr_synth_loci));
+  auto u32 = [](uint64_t n) { return (uint32_t*)std::malloc(sizeof(uint32_t) * (n + 1)); };
+  auto i32 = [](uint64_t n) { return (int32_t*)std::calloc(n + 1, sizeof(int32_t)); };
+  uint32_t *lfo = u32(n_loci), *rfo = u32(n_loci), *lab = u32(n_loci), *ao = u32(na), *lrb = u32(n_loci), *ro = u32(nr),
+           *co = u32(nr), *cops = u32(nc), *nsamp = u32(n_loci);
+  int32_t *rs = i32(n_loci), *re = i32(n_loci), *rstart = i32(nr), *rstop = i32(nr), *rsample = i32(nr);
+  uint8_t* lfb = (uint8_t*)std::malloc((size_t)n_loci * 35 + 16);
+  uint8_t* rfb = (uint8_t*)std::malloc((size_t)n_loci * 35 + 16);
+  uint8_t* abytes = (uint8_t*)std::malloc(ab + 16);
+  uint8_t* rbytes = (uint8_t*)std::malloc(rb + 16);
+  double* p1 = (double*)std::malloc(sizeof(double) * (nr + 1));
+  double* p2 = (double*)std::malloc(sizeof(double) * (nr + 1));
+  lfo[0] = rfo[0] = lab[0] = ao[0] = lrb[0] = ro[0] = co[0] = 0;
+  uint32_t ia = 0, ir = 0, oa = 0, orb = 0, oc = 0;
+  for (uint32_t l = 0; l < n_loci; ++l) {
+    const LocusOut& o = loci[l];
+    std::memcpy(lfb + lfo[l], o.lflank.data(), o.lflank.size()); lfo[l + 1] = lfo[l] + (uint32_t)o.lflank.size();
+    std::memcpy(rfb + rfo[l], o.rflank.data(), o.rflank.size()); rfo[l + 1] = rfo[l] + (uint32_t)o.rflank.size();
+    for (const auto& s : o.alleles) { std::memcpy(abytes + oa, s.data(), s.size()); oa += (uint32_t)s.size(); ao[++ia] = oa; }
+    for (size_t i = 0; i < o.raw_reads.size(); ++i) {
+      const std::string& s = o.raw_reads[i];
+      std::memcpy(rbytes + orb, s.data(), s.size()); orb += (uint32_t)s.size();
+      for (uint32_t op : o.raw_cigars[i]) cops[oc++] = op;
+      rstart[ir] = o.raw_start[i]; rstop[ir] = o.raw_stop[i]; p1[ir] = o.p1[i]; p2[ir] = o.p2[i];
+      ++ir; ro[ir] = orb; co[ir] = oc;
+    }
+    lab[l + 1] = ia; lrb[l + 1] = ir; rs[l] = o.repeat_start; re[l] = o.repeat_end; nsamp[l] = 1;
+  }
+  ltr_locus_batch& B = S->batch;
+  B.n_loci = n_loci;
+  B.lflank_off = lfo; B.lflank_bytes = lfb; B.rflank_off = rfo; B.rflank_bytes = rfb;
+  B.locus_allele_begin = lab; B.allele_off = ao; B.allele_bytes = abytes; B.repeat_start = rs; B.repeat_end = re;
+  B.locus_read_begin = lrb; B.read_start = rstart; B.read_stop = rstop; B.read_off = ro; B.read_bytes = rbytes;
+  B.cigar_off = co; B.cigar_ops = cops; B.read_sample = rsample; B.log_p1 = p1; B.log_p2 = p2; B.second_mate = nullptr;
+  B.locus_n_samples = nsamp; B.locus_haploid = nullptr;
+  S->n_alleles = ia; S->n_reads = ir; S->n_cigar_ops = oc; S->allele_nbytes = oa; S->read_nbytes = orb;
+  *out = S;
+  return LTR_OK;
+}
+
+void ltr_synth_loci_free(ltr_synth_loci* S) {
+  if (!S) return;
+  const ltr_locus_batch& B = S->batch;
+  const void* ptrs[] = {B.lflank_off, B.lflank_bytes, B.rflank_off, B.rflank_bytes, B.locus_allele_begin, B.allele_off,
+                        B.allele_bytes, B.repeat_start, B.repeat_end, B.locus_read_begin, B.read_start, B.read_stop, B.read_off,
+                        B.read_bytes, B.cigar_off, B.cigar_ops, B.read_sample, B.log_p1, B.log_p2, B.locus_n_samples};
+  for (const void* p : ptrs) std::free(const_cast<void*>(p));
+  std::free(S);
 }
 
 }  // extern "C"

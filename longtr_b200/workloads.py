@@ -104,6 +104,64 @@ def generate(config, n_loci, first_locus=0, base_seed=None, n_threads=None):
     return Workload(lib, h, config, first_locus)
 
 
+_SynthLoci = None
+
+
+def _synth_loci_type():
+    """ltr_synth_loci (synth/longtr_synth.h): the raw form of configs 3 / 4 for ltr_genotyper_run."""
+    global _SynthLoci
+    if _SynthLoci is None:
+        from . import locus_batch
+
+        class SynthLoci(C.Structure):
+            _fields_ = [("batch", locus_batch.LocusBatch), ("n_alleles", C.c_uint32), ("n_reads", C.c_uint32),
+                        ("n_cigar_ops", C.c_uint32), ("allele_nbytes", C.c_uint64), ("read_nbytes", C.c_uint64)]
+        _SynthLoci = SynthLoci
+    return _SynthLoci
+
+
+class RawWorkload:
+    """Raw loci (whole reads with CIGARs, flank blocks, candidate alleles) owned by the generator library; ``.struct`` is
+    the ltr_locus_batch to hand to Genotyper.run_struct."""
+
+    def __init__(self, lib, handle, config, n_loci):
+        self._lib, self._h = lib, handle
+        self.config, self.n_loci = config, n_loci
+        s = handle.contents
+        self.struct = s.batch
+        self.n_reads, self.read_nbytes, self.n_alleles = s.n_reads, s.read_nbytes, s.n_alleles
+        self.input_bytes = int(s.read_nbytes + s.allele_nbytes + 70 * n_loci + 4 * s.n_cigar_ops + 36 * s.n_reads)
+        p = abi.Params()
+        lib.ltr_synth_params(config, C.byref(p))
+        self.aln_params = (p.ins_ins, p.ins_match, p.del_del, p.del_match, p.match_match, p.match_ins, p.match_del)
+
+    def close(self):
+        if self._h is not None:
+            self._lib.ltr_synth_loci_free(self._h)
+            self._h = None
+            self.struct = None
+
+
+def generate_loci(config, n_loci, first_locus=0, base_seed=None, n_threads=None):
+    """ltr_synth_generate_loci: same seeds and read bases as ``generate``, in raw form."""
+    lib = synth_lib()
+    SynthLoci = _synth_loci_type()
+    lib.ltr_synth_generate_loci.argtypes = [C.c_int, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int,
+                                            C.POINTER(C.POINTER(SynthLoci))]
+    lib.ltr_synth_generate_loci.restype = C.c_int
+    lib.ltr_synth_loci_free.argtypes = [C.POINTER(SynthLoci)]
+    lib.ltr_synth_params.argtypes = [C.c_int, C.POINTER(abi.Params)]
+    if base_seed is None:
+        base_seed = BASE_SEEDS[config]
+    if n_threads is None:
+        n_threads = min(32, os.cpu_count() or 1)
+    h = C.POINTER(SynthLoci)()
+    rc = lib.ltr_synth_generate_loci(config, base_seed, first_locus, n_loci, n_threads, C.byref(h))
+    if rc != 0:
+        raise RuntimeError("ltr_synth_generate_loci failed: %d" % rc)
+    return RawWorkload(lib, h, config, n_loci)
+
+
 class SynthStutterBatch(C.Structure):
     _fields_ = [("batch", abi.StutterBatch), ("post", abi.PosteriorBatch), ("read_start", abi._i32p),
                 ("read_stop", abi._i32p), ("cigar_off", abi._u32p), ("cigar_bytes", abi._u8p),

@@ -92,6 +92,9 @@ double Genotyper::calc_log_sample_posteriors(std::vector<int>& read_weights) {
   if (g != NULL && g->haplotype_ != NULL && g->haplotype_->num_blocks() == 3)
     for (int a = 0; a < g->hap_blocks_[1]->num_options(); ++a) o << " " << (g->hap_blocks_[1]->get_seq(a).empty() ? "-" : g->hap_blocks_[1]->get_seq(a));
   o << "\n";
+  if (g != NULL && g->haplotype_ != NULL && g->haplotype_->num_blocks() == 3)  // flank blocks and repeat coordinates
+    o << "BLOCKS " << g->hap_blocks_[1]->start() << " " << g->hap_blocks_[1]->end() << " "
+      << g->hap_blocks_[0]->get_seq(0) << " " << g->hap_blocks_[2]->get_seq(0) << "\n";
   o << "SEEDS";
   if (g != NULL && g->seed_positions_ != NULL)
     for (int r = 0; r < num_reads_; ++r) o << " " << g->seed_positions_[r];

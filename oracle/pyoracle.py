@@ -294,6 +294,8 @@ def full_locus_traces(cases):
                 calls.append(cur)
             elif f[0] == "ALLELES":
                 cur["alleles"] = ["" if a == "-" else a for a in f[1:]]
+            elif f[0] == "BLOCKS":
+                cur["repeat_start"], cur["repeat_end"], cur["lflank"], cur["rflank"] = int(f[1]), int(f[2]), f[3], f[4]
             elif f[0] in ("SEEDS", "LABELS", "GTS"):
                 cur[f[0].lower()] = [int(x) for x in f[1:]]
             else:

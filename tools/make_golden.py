@@ -225,7 +225,14 @@ def pruning_cases():
                         reads_per_sample=[labels.count(s) for s in range(S)], seeds=first["seeds"],
                         ll=first["ll"], log_p1=first["p1"], log_p2=first["p2"], first_gts=first["gts"],
                         first_post=first["post"], kept=kept, out_ll=last["ll"], out_post=last["post"],
-                        out_totals=last["totals"], out_gts=last["gts"]))
+                        out_totals=last["totals"], out_gts=last["gts"],
+                        # what the reference's HaplotypeGenerator built for the locus: the input of ltr_genotyper_run
+                        lflank=first["lflank"], rflank=first["rflank"], repeat_start=first["repeat_start"],
+                        repeat_end=first["repeat_end"], alleles=first["alleles"],
+                        aln_params=list(c["aln_params"]) if c.get("aln_params") else None,
+                        reads=[dict(start=r["start"], stop=r["stop"], seq=r["seq"], cigar=r["cigar"], sample=r["sample"],
+                                    log_p1=r["log_p1"], log_p2=r["log_p2"]) for r in c["reads"]] if not real else None,
+                        real_case=c["name"] if real else None))
     return out
 
 
