@@ -216,17 +216,131 @@ LTS_HD double stutter_region_ll(const StutConsts& C, const FlankView& F, int32_t
   return lse_finish(mv.mx, sv.total);
 }
 
+// ---- all six insertion sizes of a column in one walk -------------------------------------------------------------------
+// align_pcr_insertion_reverse (StutterAlignerClass.cpp:59-104) for D = 1..6 walks the block with the SAME lag-1 run table
+// and the same skips; only how far it walks (lim_D, non-increasing in D) and how many read bases each position update
+// touches (D of them: idx = i-1 .. i-D) differ, and the updates of size D are a prefix of those of size D+1.  One walk
+// therefore serves all six: every emission pair is loaded once instead of once per size, and the six running sums are
+// independent chains of additions (each the reference's own sequence of operations, so every term is bit-identical).
+// visit(d, v): term v of artifact size D = d + 1.
+template <typename Visit>
+LTS_HD void stutter_insertion_terms(const StutConsts& C, const FlankView& F, int32_t j, Visit& visit) {
+  const int32_t B = F.B;
+  const int32_t last = (int32_t)F.blk[B - 1];
+  const int32_t avail = j + 1;
+  double lp[6];
+  int32_t lim[6];
+  {
+    double ins = 0.0;  // ins_probs_[offset][D-1]: D read bases ending at j against the block's last base
+#pragma unroll
+    for (int32_t d = 0; d < 6; ++d) {
+      const int32_t D = d + 1;
+      if (d < avail) ins += emit_at(F, j - d, last);
+      int32_t base_len = B + D;
+      base_len = (base_len < avail) ? base_len : avail;
+      lp[d] = (-C.int_logs[B + 1] + ins) + ((base_len > D) ? F.match[j - D] : 0.0);
+      visit(d, lp[d]);
+      int32_t l = base_len - D;
+      l = l < 0 ? 0 : l;
+      lim[d] = l > B ? B : l;
+    }
+  }
+  // sizes 1 .. m are still walking (lim is non-increasing in D); a size that stops at position i adds its closing term
+  // (every array index below is a compile-time constant after unrolling: the six sums stay in registers)
+  int32_t m = 6;
+  int32_t i = 0;
+#define LTS_CLOSE_FINISHED_SIZES()                                         \
+  _Pragma("unroll") for (int32_t d = 5; d >= 0; --d) {                     \
+    if (m == d + 1 && !(i > -lim[d])) {                                    \
+      if (i > -B) visit(d, C.int_logs[B + i] + lp[d]);                     \
+      m = d;                                                               \
+    }                                                                      \
+  }
+  LTS_CLOSE_FINISHED_SIZES()
+  while (m > 0) {
+    int32_t step = 1;
+    if (-i + 1 < B) {
+      const int32_t run = F.um[B - 1 + i];  // lag-1 table
+      if (run == 0) {
+        const int32_t c_old = (int32_t)F.blk[B - 1 + i], c_new = (int32_t)F.blk[B - 2 + i];
+#pragma unroll
+        for (int32_t k = 1; k <= 6; ++k) {
+          if (k <= m) {
+            const double eo = emit_at(F, j + i - k, c_old), en = emit_at(F, j + i - k, c_new);
+#pragma unroll
+            for (int32_t d = 0; d < 6; ++d)
+              if (d + 1 >= k && d < m) {
+                lp[d] -= eo;
+                lp[d] += en;
+              }
+          }
+        }
+#pragma unroll
+        for (int32_t d = 0; d < 6; ++d)
+          if (d < m) visit(d, lp[d]);
+      } else {
+        const double lr = C.int_logs[run];
+#pragma unroll
+        for (int32_t d = 0; d < 6; ++d)
+          if (d < m) visit(d, lr + lp[d]);
+        step = run;
+      }
+    } else {
+#pragma unroll
+      for (int32_t d = 0; d < 6; ++d)
+        if (d < m) visit(d, lp[d]);
+    }
+    i -= step;
+    LTS_CLOSE_FINISHED_SIZES()
+  }
+#undef LTS_CLOSE_FINISHED_SIZES
+}
+
+struct MaxVisit6 {
+  double mx[6];
+  uint32_t any;
+  LTS_HD void operator()(int32_t d, double v) {
+    mx[d] = ((any >> d) & 1u) ? smax(mx[d], v) : v;
+    any |= 1u << d;
+  }
+};
+struct SumVisit6 {
+  const StutConsts* C;
+  double mx[6], total[6];
+  LTS_HD void operator()(int32_t d, double v) { total[d] += lse_term(*C, v, mx[d]); }
+};
+// out[d] = align_stutter_region_reverse(base_len, j, D = d + 1), all six at once (two walks: maxima, then sums).
+LTS_HD void stutter_insertion_lls(const StutConsts& C, const FlankView& F, int32_t j, double* out) {
+  MaxVisit6 mv;
+  mv.any = 0u;
+#pragma unroll
+  for (int32_t d = 0; d < 6; ++d) mv.mx[d] = 0.0;
+  stutter_insertion_terms(C, F, j, mv);
+  SumVisit6 sv;
+  sv.C = &C;
+#pragma unroll
+  for (int32_t d = 0; d < 6; ++d) {
+    sv.mx[d] = mv.mx[d];
+    sv.total[d] = 0.0;
+  }
+  stutter_insertion_terms(C, F, j, sv);
+#pragma unroll
+  for (int32_t d = 0; d < 6; ++d) out[d] = lse_finish(mv.mx[d], sv.total[d]);
+}
+
 // The stutter row at column j (HapAligner.cpp:79-107): 13 artifact sizes combined by fast_log_sum_exp.
 // prevM = match row of the haplotype base preceding the block.
 LTS_HD double stutter_row_cell(const StutConsts& C, const FlankView& F, const double* prevM, int32_t j) {
   double probs[13];
+  double ins_ll[6];
+  stutter_insertion_lls(C, F, j, ins_ll);
 #pragma unroll 1
   for (int32_t a = 0; a < 13; ++a) {
     const int32_t D = a - 6;
     int32_t base_len = F.B + D;
     base_len = (base_len < j + 1) ? base_len : (j + 1);
     if (base_len >= 0) {
-      const double prob = stutter_region_ll(C, F, base_len, j, D);
+      const double prob = (D > 0) ? ins_ll[D - 1] : stutter_region_ll(C, F, base_len, j, D);
       const double pre = (j - base_len < 0) ? 0.0 : prevM[j - base_len];
       probs[a] = (F.art_lp[a] + prob) + pre;
     } else {

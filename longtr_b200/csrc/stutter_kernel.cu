@@ -25,6 +25,20 @@ namespace ltr {
 static constexpr unsigned kFull = 0xFFFFFFFFu;
 static constexpr int kStutWarps = 4;
 
+// Everything a phase touches lives in shared memory, but the phases are separate (noinline) functions that receive
+// their pointers through structs, so the compiler sees generic pointers: generic LD + 64-bit address arithmetic
+// (profiles/r2a: 8.5 % LD, 9 % R2UR, no LDS in the hot loops).  Telling it the address space turns them into LDS / STS
+// with 32-bit addresses.
+#define LTR_ASSUME_SHARED(p) __builtin_assume(__isShared(p))
+#define LTR_ASSUME_GLOBAL(p) __builtin_assume(__isGlobal(p))
+__device__ __forceinline__ void assume_shared(const FlankView& F) {
+  LTR_ASSUME_SHARED(F.seq); LTR_ASSUME_SHARED(F.qual); LTR_ASSUME_SHARED(F.tlc); LTR_ASSUME_SHARED(F.tlw);
+  LTR_ASSUME_SHARED(F.blk); LTR_ASSUME_SHARED(F.um); LTR_ASSUME_SHARED(F.match); LTR_ASSUME_SHARED(F.art_lp);
+}
+__device__ __forceinline__ void assume_shared(const StutConsts& C) {
+  LTR_ASSUME_SHARED(C.int_logs); LTR_ASSUME_SHARED(C.qual_lc); LTR_ASSUME_SHARED(C.qual_lw);
+}
+
 struct SideGeom {  // one pair
   const uint8_t* read;  // whole read
   const uint8_t* qual;
@@ -92,10 +106,14 @@ __device__ __forceinline__ WarpCtx* carve(unsigned char* base, uint32_t max_flan
 __device__ __noinline__ double wavefront_rows(const StutConsts* Cs, const WarpCtx* X, double* last, int32_t row0,
                                               int32_t nrows, int32_t first_type, const uint8_t* chars, int32_t dir,
                                               int lane) {
+  LTR_ASSUME_SHARED(Cs); LTR_ASSUME_SHARED(X); LTR_ASSUME_SHARED(last); LTR_ASSUME_GLOBAL(chars);
   const StutConsts C = *Cs;  // registers
   const FlankView F = X->F;
+  assume_shared(C);
+  assume_shared(F);
   double* lineM = X->lineM;
   double* lineD = X->lineD;
+  LTR_ASSUME_SHARED(lineM); LTR_ASSUME_SHARED(lineD);
   double left_prob = 0.0;
   const int32_t per_strip = 32 * kStutRows;
   for (int32_t s0 = 0; s0 < nrows; s0 += per_strip) {
@@ -143,14 +161,30 @@ __device__ __noinline__ double wavefront_rows(const StutConsts* Cs, const WarpCt
 // The stutter row (HapAligner.cpp:64-111): one read column per lane, 13 artifact sizes each; prevM = lineM,
 // result -> lineD.
 __device__ __noinline__ void stutter_row(const StutConsts* Cs, const WarpCtx* X, int lane) {
+  LTR_ASSUME_SHARED(Cs); LTR_ASSUME_SHARED(X);
   const StutConsts C = *Cs;
   const FlankView F = X->F;
+  assume_shared(C);
+  assume_shared(F);
   const double* prevM = X->lineM;
   double* out = X->lineD;
   double* probs = X->probs + lane;  // stride 32: conflict free
+  LTR_ASSUME_SHARED(prevM); LTR_ASSUME_SHARED(out); LTR_ASSUME_SHARED(probs);
   for (int32_t j = lane; j < F.L; j += 32) {
+    {  // insertions: the six sizes share one walk over the block (stutter_insertion_terms)
+      double ins_ll[6];
+      stutter_insertion_lls(C, F, j, ins_ll);
+#pragma unroll
+      for (int32_t d = 0; d < 6; ++d) {
+        const int32_t D = d + 1;
+        int32_t base_len = F.B + D;
+        base_len = (base_len < j + 1) ? base_len : (j + 1);
+        const double pre = (j - base_len < 0) ? 0.0 : prevM[j - base_len];
+        probs[(7 + d) * 32] = (F.art_lp[7 + d] + ins_ll[d]) + pre;
+      }
+    }
 #pragma unroll 1
-    for (int32_t a = 0; a < 13; ++a) {
+    for (int32_t a = 0; a <= 6; ++a) {  // deletions and the artifact-free alignment
       const int32_t D = a - 6;
       int32_t base_len = F.B + D;
       base_len = (base_len < j + 1) ? base_len : (j + 1);
@@ -175,20 +209,26 @@ __device__ __noinline__ void stutter_row(const StutConsts* Cs, const WarpCtx* X,
 // Runs one flank (side 0 = left of the seed against the forward haplotype, side 1 = right of the seed, reversed,
 // against the reversed haplotype).  Fills last[] (last-column M of every reachable hap row), returns left_prob.
 __device__ __noinline__ double run_side(const StutConsts* Cs, WarpCtx* X, int side, int lane) {
+  LTR_ASSUME_SHARED(Cs); LTR_ASSUME_SHARED(X);
   const SideGeom G = X->G;
+  LTR_ASSUME_GLOBAL(G.read); LTR_ASSUME_GLOBAL(G.qual); LTR_ASSUME_GLOBAL(G.allele); LTR_ASSUME_GLOBAL(G.lflank);
+  LTR_ASSUME_GLOBAL(G.rflank);
   const int32_t L = side == 0 ? G.seed : (G.N - G.seed - 1);
   const int32_t B = G.B;
   double* last = side ? X->lastR : X->lastL;
+  LTR_ASSUME_SHARED(last);
   // ---- stage the flank, the allele and the tables ---------------------------------------------------------
   {
     uint8_t* seq = X->seq;
     uint8_t* qual = X->qual;
+    LTR_ASSUME_SHARED(seq); LTR_ASSUME_SHARED(qual);
     for (int32_t j = lane; j < L; j += 32) {
       const int32_t p = side == 0 ? j : (G.N - 1 - j);
       seq[j] = G.read[p];
       qual[j] = G.qual[p];
     }
     uint8_t* blk = X->blk;
+    LTR_ASSUME_SHARED(blk);
     for (int32_t i = lane; i < B; i += 32) blk[i] = side == 0 ? G.allele[i] : G.allele[B - 1 - i];
   }
   __syncwarp();
@@ -197,6 +237,7 @@ __device__ __noinline__ double run_side(const StutConsts* Cs, WarpCtx* X, int si
     const int32_t lag = lane + 1;
     const uint8_t* blk = X->blk;
     int32_t* ml = X->um + (size_t)lane * B;
+    LTR_ASSUME_SHARED(blk); LTR_ASSUME_SHARED(ml);
     int32_t run = 0;
     for (int32_t i = 0; i < B; ++i) {
       if (i < lag) run = 0;
@@ -222,7 +263,9 @@ __device__ __noinline__ double run_side(const StutConsts* Cs, WarpCtx* X, int si
   __syncwarp();
   {
     const FlankView F = X->F;
+    assume_shared(F);
     double* match = X->match;
+    LTR_ASSUME_SHARED(match);
     for (int32_t p = lane; p < L; p += 32) match[p] = stutter_match_prob(F, p);
   }
   __syncwarp();
@@ -300,8 +343,10 @@ __global__ void __launch_bounds__(kStutWarps * 32) stutter_pair_kernel(const Stu
 
   // ---- seed join (compute_aln_logprob, HapAligner.cpp:165-233) ----------------------------------------------------
   const SideGeom G = X->G;
+  LTR_ASSUME_GLOBAL(G.read); LTR_ASSUME_GLOBAL(G.qual); LTR_ASSUME_GLOBAL(G.lflank); LTR_ASSUME_GLOBAL(G.rflank);
   const double* lastL = X->lastL;
   const double* lastR = X->lastR;
+  LTR_ASSUME_SHARED(lastL); LTR_ASSUME_SHARED(lastR);
   const double log_thresh = Cs->log_thresh;
   StutConsts Cj;  // only log_thresh is used by lse_term
   Cj.log_thresh = log_thresh;
