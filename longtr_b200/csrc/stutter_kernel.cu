@@ -55,7 +55,7 @@ struct WarpCtx {  // per warp, in shared memory
   double* lineD;
   double* lastL;
   double* lastR;
-  double* probs;  // [13][32] artifact terms of the stutter row, one column per lane
+  double* probs;  // [7][32] artifact terms D = -6..0 of the stutter row, one column per lane
   int32_t* um;
   uint8_t* seq;
   uint8_t* qual;
@@ -69,7 +69,7 @@ __host__ __device__ inline size_t stutter_warp_smem_bytes(uint32_t max_flank, ui
   size_t b = (sizeof(WarpCtx) + 15) / 16 * 16;
   b += 3 * (size_t)max_flank * sizeof(double);  // match lineM lineD
   b += 2 * (size_t)max_hap * sizeof(double);    // lastL lastR
-  b += 13 * 32 * sizeof(double);                // probs
+  b += 7 * 32 * sizeof(double);                 // probs (deletion sizes and D = 0; the insertion sizes stay in registers)
   b += 6 * (size_t)max_block * sizeof(int32_t); // um
   b += 2 * (((size_t)max_flank + 15) / 16 * 16);  // seq, qual
   b += ((size_t)max_block + 15) / 16 * 16;      // blk
@@ -89,7 +89,7 @@ __device__ __forceinline__ WarpCtx* carve(unsigned char* base, uint32_t max_flan
     X->lineD = d; d += max_flank;
     X->lastL = d; d += max_hap;
     X->lastR = d; d += max_hap;
-    X->probs = d; d += 13 * 32;
+    X->probs = d; d += 7 * 32;
     X->um = reinterpret_cast<int32_t*>(d);
     uint8_t* u = reinterpret_cast<uint8_t*>(X->um + 6 * (size_t)max_block);
     X->seq = u;
@@ -171,7 +171,8 @@ __device__ __noinline__ void stutter_row(const StutConsts* Cs, const WarpCtx* X,
   double* probs = X->probs + lane;  // stride 32: conflict free
   LTR_ASSUME_SHARED(prevM); LTR_ASSUME_SHARED(out); LTR_ASSUME_SHARED(probs);
   for (int32_t j = lane; j < F.L; j += 32) {
-    {  // insertions: the six sizes share one walk over the block (stutter_insertion_terms)
+    double vi[6];  // insertions: the six sizes share one walk over the block (stutter_insertion_terms); kept in registers
+    {
       double ins_ll[6];
       stutter_insertion_lls(C, F, j, ins_ll);
 #pragma unroll
@@ -180,11 +181,11 @@ __device__ __noinline__ void stutter_row(const StutConsts* Cs, const WarpCtx* X,
         int32_t base_len = F.B + D;
         base_len = (base_len < j + 1) ? base_len : (j + 1);
         const double pre = (j - base_len < 0) ? 0.0 : prevM[j - base_len];
-        probs[(7 + d) * 32] = (F.art_lp[7 + d] + ins_ll[d]) + pre;
+        vi[d] = (F.art_lp[7 + d] + ins_ll[d]) + pre;
       }
     }
 #pragma unroll 1
-    for (int32_t a = 0; a <= 6; ++a) {  // deletions and the artifact-free alignment
+    for (int32_t a = 0; a <= 6; ++a) {  // deletions and the artifact-free alignment: one copy of the code, values in smem
       const int32_t D = a - 6;
       int32_t base_len = F.B + D;
       base_len = (base_len < j + 1) ? base_len : (j + 1);
@@ -198,10 +199,14 @@ __device__ __noinline__ void stutter_row(const StutConsts* Cs, const WarpCtx* X,
     }
     double mx = probs[0];
 #pragma unroll
-    for (int32_t a = 1; a < 13; ++a) mx = smax(mx, probs[a * 32]);
+    for (int32_t a = 1; a <= 6; ++a) mx = smax(mx, probs[a * 32]);
+#pragma unroll
+    for (int32_t d = 0; d < 6; ++d) mx = smax(mx, vi[d]);
     double total = 0.0;
 #pragma unroll
-    for (int32_t a = 0; a < 13; ++a) total += lse_term(C, probs[a * 32], mx);
+    for (int32_t a = 0; a <= 6; ++a) total += lse_term(C, probs[a * 32], mx);
+#pragma unroll
+    for (int32_t d = 0; d < 6; ++d) total += lse_term(C, vi[d], mx);
     out[j] = lse_finish(mx, total);
   }
 }
