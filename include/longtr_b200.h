@@ -182,6 +182,14 @@ typedef struct ltr_stutter_batch {
  * SURVEY.md section 8d (flank rows x columns + 13 x block length per column, both flanks).            */
 int ltr_stutter_ll(ltr_ctx* ctx, const ltr_params* params, const ltr_stutter_batch* batch, double* out_ll,
                    ltr_job_stats* stats);
+/* The same, but a locus that cannot be processed fails ALONE: locus_status[l] (non-NULL, [n_loci]) receives LTR_OK or the
+ * locus' error -- LTR_ERR_UNSUPPORTED for an empty (<DEL>) allele (in the reference the stutter row of an empty block
+ * overwrites the row before it, HapAligner.cpp:64-111 with bn = 0) or for read flanks / alleles too long for the kernel's
+ * shared-memory staging, LTR_ERR_INVALID for a malformed stutter model, flank or seed -- its rows of out_ll stay untouched,
+ * and every other locus is computed.  ltr_stutter_ll is this call with locus_status = NULL: the first such locus fails
+ * the whole call and out_ll is not modified.                                                                          */
+int ltr_stutter_ll_status(ltr_ctx* ctx, const ltr_params* params, const ltr_stutter_batch* batch, double* out_ll,
+                          int32_t* locus_status, ltr_job_stats* stats);
 
 /* ---- resident jobs: upload once, run many times, download ------------------------- */
 /* post may be NULL (Viterbi only).  Host arrays may be released after the call.       */
@@ -403,6 +411,14 @@ int ltr_extract_calls(int haploid, int32_t n_samples, int32_t n_alleles, const d
  * ltr_seed_base_flat  = HapAligner::calc_seed_base (HapAligner.cpp:493-542): seed index or -1 (none);
  *                       LTR_ERR_INVALID for a CIGAR operation the reference dies on.                       */
 int32_t ltr_trim_read_flat(const ltr_flat_locus* locus, int32_t read_index, char* out, int32_t cap);
+/* ltr_pool_reads      = ReadPooler::add_alignment for every read + ReadPooler::pool (src/read_pooler.cpp:3-20,
+ *                       src/read_pooler.h:42-48): pool_index[r] = pool of read r (reads with identical sequence share a
+ *                       pool, pools are numbered by first appearance), *n_pools, and the pooled reads' qualities -- the
+ *                       per-position upper median of BaseQuality::median_base_qualities (src/base_quality.cpp:11-28) --
+ *                       back to back in pool order in pooled_quals[cap] (may be NULL).  Returns the bytes of pooled
+ *                       qualities, negative = error.                                                                */
+int64_t ltr_pool_reads(int32_t n_reads, const char* const* seqs, const char* const* quals, int32_t* pool_index,
+                       int32_t* n_pools, char* pooled_quals, int64_t cap);
 int32_t ltr_seed_base_flat(const ltr_flat_locus* locus, int32_t read_index);
 
 /* ---- diagnostics --------------------------------------------------------------------- */

@@ -226,6 +226,8 @@ def load():
     lib.ltr_seed_base_flat.restype = C.c_int32
     lib.ltr_stutter_ll.argtypes = [vp, C.POINTER(Params), C.c_void_p, _dp, C.POINTER(JobStats)]
     lib.ltr_stutter_ll.restype = C.c_int
+    lib.ltr_stutter_ll_status.argtypes = [vp, C.POINTER(Params), C.c_void_p, _dp, _i32p, C.POINTER(JobStats)]
+    lib.ltr_stutter_ll_status.restype = C.c_int
     lib.ltr_fp64_issue_rate.argtypes = [C.c_int, C.c_int, _dp, _dp]
     lib.ltr_fp64_issue_rate.restype = C.c_int
     _lib = lib
@@ -240,7 +242,7 @@ EXPORTED_SYMBOLS = [
     "ltr_pipeline_destroy", "ltr_flatten_loci", "ltr_flat_batch_free",
     "ltr_fp64_issue_rate", "ltr_genotype_locus", "ltr_extract_calls", "ltr_trim_read_flat", "ltr_seed_base_flat",
     "ltr_stutter_ll", "ltr_genotype_locus_pruned", "ltr_ctx_set_plan", "ltr_job_submit", "ltr_job_submit_outputs", "ltr_job_wait", "ltr_job_poll", "ltr_job_download_kept", "ltr_posteriors_batch", "ltr_genotyper_create", "ltr_genotyper_destroy",
-    "ltr_genotyper_run", "ltr_batch_calls_free", "ltr_locus_batch_trim_read",
+    "ltr_genotyper_run", "ltr_batch_calls_free", "ltr_locus_batch_trim_read", "ltr_stutter_ll_status", "ltr_pool_reads",
 ]
 
 
@@ -256,6 +258,35 @@ def extract_calls(post, totals, haploid=False):
         raise RuntimeError("ltr_extract_calls failed: %d" % rc)
     arrays["total_ll"] = c.total_ll
     return arrays
+
+
+def pool_reads(seqs, quals, lib=None, fn="ltr_pool_reads"):
+    """ReadPooler on plain strings; returns (pool_index list, [median quality string per pool]).  ``lib`` / ``fn`` let the
+    tests call the same signature in oracle/_ref (the reference's own ReadPooler)."""
+    lib = lib or load()
+    f = getattr(lib, fn)
+    n = len(seqs)
+    sp = (C.c_char_p * max(1, n))(*[s.encode() for s in seqs])
+    qp = (C.c_char_p * max(1, n))(*[q.encode() for q in quals])
+    pool = np.zeros(max(1, n), np.int32)
+    npools = C.c_int32(0)
+    cap = sum(len(s) for s in seqs) + 16
+    buf = C.create_string_buffer(cap)
+    f.argtypes = [C.c_int32, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), _i32p, C.POINTER(C.c_int32), C.c_char_p, C.c_int64]
+    f.restype = C.c_int64
+    got = f(n, sp, qp, ptr(pool, _i32p), C.byref(npools), buf, cap)
+    if got < 0:
+        raise RuntimeError("%s failed: %d" % (fn, got))
+    raw = buf.raw[:got].decode()
+    meds, off = [], 0
+    first = {}
+    for r in range(n):
+        first.setdefault(int(pool[r]), r)
+    for k in range(npools.value):
+        ln = len(seqs[first[k]])
+        meds.append(raw[off:off + ln])
+        off += ln
+    return [int(x) for x in pool[:n]], meds
 
 
 def trim_read(locus, read_index):

@@ -265,3 +265,32 @@ extern "C" int ltr_flatten_loci(int32_t n_loci, const ltr_flat_locus* loci, ltr_
 extern "C" void ltr_flat_batch_free(ltr_flat_batch* b) {
   if (b) delete reinterpret_cast<FlatBatchOwner*>(b);
 }
+
+// ReadPooler + BaseQuality::median_base_qualities on plain strings (host only): pool index per read, number of pools and
+// the pooled reads' median qualities back to back in pool order.  Returns the bytes written, negative = error.
+extern "C" int64_t ltr_pool_reads(int32_t n_reads, const char* const* seqs, const char* const* quals, int32_t* pool_index,
+                                  int32_t* n_pools, char* pooled_quals, int64_t cap) {
+  using namespace ltr;
+  if (n_reads < 0 || !n_pools || (n_reads > 0 && (!seqs || !quals || !pool_index))) return LTR_ERR_INVALID;
+  ReadPooler pooler;
+  BaseQuality bq;
+  for (int32_t r = 0; r < n_reads; ++r) {
+    if (!seqs[r] || !quals[r] || strlen(seqs[r]) != strlen(quals[r])) return LTR_ERR_INVALID;
+    const Alignment aln(100, 100 + (int32_t)strlen(seqs[r]) - 1, false, false, "read", std::string(quals[r]), std::string(seqs[r]),
+                        std::string(seqs[r]));
+    pool_index[r] = pooler.add_alignment(aln);
+  }
+  if (!pooler.pool(bq)) return LTR_ERR_INVALID;
+  *n_pools = pooler.num_pools();
+  int64_t off = 0;
+  std::vector<Alignment>& alns = pooler.get_alignments();
+  for (size_t i = 0; i < alns.size(); ++i) {
+    const std::string& q = alns[i].get_base_qualities();
+    if (pooled_quals) {
+      if (off + (int64_t)q.size() > cap) return LTR_ERR_INVALID;
+      memcpy(pooled_quals + off, q.data(), q.size());
+    }
+    off += (int64_t)q.size();
+  }
+  return off;
+}

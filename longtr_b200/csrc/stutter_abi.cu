@@ -40,8 +40,19 @@ struct Buffers {
 
 }  // namespace
 
+extern "C" int ltr_stutter_ll_status(ltr_ctx* ctx, const ltr_params* params, const ltr_stutter_batch* b, double* out_ll,
+                                     int32_t* locus_status, ltr_job_stats* stats);
+
+// The whole batch or nothing: the first locus that cannot be processed fails the call (nothing is computed).
 extern "C" int ltr_stutter_ll(ltr_ctx* ctx, const ltr_params* params, const ltr_stutter_batch* b, double* out_ll,
                               ltr_job_stats* stats) {
+  return ltr_stutter_ll_status(ctx, params, b, out_ll, NULL, stats);
+}
+
+// locus_status != NULL: a locus that cannot be processed (empty allele, flanks too long for the shared-memory staging,
+// malformed stutter model / seeds) gets its error code there, its rows stay untouched, and the other loci are computed.
+extern "C" int ltr_stutter_ll_status(ltr_ctx* ctx, const ltr_params* params, const ltr_stutter_batch* b, double* out_ll,
+                                     int32_t* locus_status, ltr_job_stats* stats) {
   if (!ctx || !params || !b || !out_ll) return LTR_ERR_INVALID;
   if (stats) memset(stats, 0, sizeof(*stats));
   if (b->n_loci == 0) return LTR_OK;
@@ -59,38 +70,72 @@ extern "C" int ltr_stutter_ll(ltr_ctx* ctx, const ltr_params* params, const ltr_
   std::vector<double> art((size_t)n_alleles * 13);
   uint32_t max_flank = 1, max_block = 1, max_hap = 2;
   uint64_t n_pairs = 0, n_cells = 0;
+  // validation first (offsets must be monotone before anything is sized), then one pass per locus that either commits
+  // the locus' tasks or records why it cannot be processed
+  for (uint32_t l = 0; l < n_loci; ++l) {
+    if (b->locus_allele_begin[l + 1] < b->locus_allele_begin[l] || b->locus_read_begin[l + 1] < b->locus_read_begin[l])
+      return LTR_ERR_INVALID;
+    const uint32_t H = b->locus_allele_begin[l + 1] - b->locus_allele_begin[l];
+    ll_off[l + 1] = ll_off[l] + (unsigned long long)H * (b->locus_read_begin[l + 1] - b->locus_read_begin[l]);
+    if (locus_status) locus_status[l] = LTR_OK;
+  }
+  std::vector<uint32_t> zero_rows;  // reads without a seed: LL 0 for every haplotype (written once validation is through)
   for (uint32_t l = 0; l < n_loci; ++l) {
     const uint32_t a0 = b->locus_allele_begin[l], a1 = b->locus_allele_begin[l + 1];
     const uint32_t r0 = b->locus_read_begin[l], r1 = b->locus_read_begin[l + 1];
-    if (a1 < a0 || r1 < r0) return LTR_ERR_INVALID;
     const uint32_t H = a1 - a0;
-    ll_off[l + 1] = ll_off[l] + (unsigned long long)H * (r1 - r0);
     const uint32_t n0 = b->lflank_off[l + 1] - b->lflank_off[l], n2 = b->rflank_off[l + 1] - b->rflank_off[l];
-    if (n0 < 1 || n2 < 1 || b->motif_len[l] < 1) return LTR_ERR_INVALID;
+    int st = LTR_OK;
+    uint32_t l_flank = 1, l_block = 1, l_hap = 2;
+    if (b->lflank_off[l + 1] < b->lflank_off[l] || b->rflank_off[l + 1] < b->rflank_off[l] || n0 < 1 || n2 < 1 ||
+        b->motif_len[l] < 1)
+      st = LTR_ERR_INVALID;
     StutterModel model(b->stutter[6 * l], b->stutter[6 * l + 1], b->stutter[6 * l + 2], b->stutter[6 * l + 3],
-                       b->stutter[6 * l + 4], b->stutter[6 * l + 5], std::string((size_t)b->motif_len[l], 'N'));
-    if (!model.valid()) return LTR_ERR_INVALID;
+                       b->stutter[6 * l + 4], b->stutter[6 * l + 5],
+                       std::string((size_t)std::max(1, b->motif_len[l]), 'N'));
+    if (st == LTR_OK && !model.valid()) st = LTR_ERR_INVALID;
+    for (uint32_t a = a0; a < a1 && st == LTR_OK; ++a) {
+      if (b->allele_off[a + 1] < b->allele_off[a]) st = LTR_ERR_INVALID;
+      // empty allele (<DEL>): the reference's stutter row would overwrite its predecessor
+      else if (b->allele_off[a + 1] == b->allele_off[a]) st = LTR_ERR_UNSUPPORTED;
+      else {
+        const uint32_t B = b->allele_off[a + 1] - b->allele_off[a];
+        l_block = std::max(l_block, B);
+        l_hap = std::max(l_hap, n0 + B + n2);
+      }
+    }
+    for (uint32_t r = r0; r < r1 && st == LTR_OK; ++r) {
+      if (b->realign_read && !b->realign_read[r]) continue;
+      if (b->read_off[r + 1] < b->read_off[r]) { st = LTR_ERR_INVALID; break; }
+      const int32_t N = (int32_t)(b->read_off[r + 1] - b->read_off[r]);
+      const int32_t seed = b->read_seed[r];
+      if (seed < 0) continue;
+      if (seed < 1 || seed >= N - 1) { st = LTR_ERR_INVALID; break; }
+      l_flank = std::max<uint32_t>(l_flank, (uint32_t)std::max(seed, N - seed - 1));
+    }
+    // read flank / allele too long for the shared-memory staging of the kernel
+    if (st == LTR_OK && stutter_block_smem_bytes(l_flank, l_block, l_hap) > 220 * 1024) st = LTR_ERR_UNSUPPORTED;
+    if (st != LTR_OK) {
+      if (!locus_status) return st;
+      locus_status[l] = st;
+      continue;
+    }
+    max_flank = std::max(max_flank, l_flank);
+    max_block = std::max(max_block, l_block);
+    max_hap = std::max(max_hap, l_hap);
     for (uint32_t a = a0; a < a1; ++a) {
       const uint32_t B = b->allele_off[a + 1] - b->allele_off[a];
-      if (b->allele_off[a + 1] <= b->allele_off[a]) return LTR_ERR_UNSUPPORTED;  // empty allele
-      max_block = std::max(max_block, B);
-      max_hap = std::max(max_hap, n0 + B + n2);
       // RepeatStutterInfo(period = 1, ...): artifacts of -6..+6 bases (RepeatStutterInfo.h:10-11, 53-61)
       RepeatStutterInfo info(1, std::string((size_t)B, 'N'), model);
       for (int D = -6; D <= 6; ++D) art[(size_t)a * 13 + (D + 6)] = info.log_prob_pcr_artifact(0, D);
     }
     for (uint32_t r = r0; r < r1; ++r) {
       if (b->realign_read && !b->realign_read[r]) continue;
-      if (b->read_off[r + 1] < b->read_off[r]) return LTR_ERR_INVALID;
       const int32_t N = (int32_t)(b->read_off[r + 1] - b->read_off[r]);
-      const int32_t seed = b->read_seed[r];
-      double* row = out_ll + ll_off[l] + (size_t)(r - r0) * H;
-      if (seed < 0) {  // HapAligner.cpp:570-574: no seed -> LL 0 for every haplotype of the read
-        for (uint32_t h = 0; h < H; ++h) row[h] = 0.0;
+      if (b->read_seed[r] < 0) {  // HapAligner.cpp:570-574: no seed -> LL 0 for every haplotype of the read
+        zero_rows.push_back(r);
         continue;
       }
-      if (seed < 1 || seed >= N - 1) return LTR_ERR_INVALID;
-      max_flank = std::max<uint32_t>(max_flank, (uint32_t)std::max(seed, N - seed - 1));
       for (uint32_t a = a0; a < a1; ++a) {
         if (b->realign_allele && !b->realign_allele[a]) continue;
         StutterTask t;
@@ -104,13 +149,26 @@ extern "C" int ltr_stutter_ll(ltr_ctx* ctx, const ltr_params* params, const ltr_
       }
     }
   }
+  // nothing of the caller's array was touched up to here (a call that fails as a whole leaves out_ll as it was)
+  {
+    std::vector<uint32_t> read_locus;
+    if (!zero_rows.empty()) {
+      read_locus.resize(n_reads);
+      for (uint32_t l = 0; l < n_loci; ++l)
+        for (uint32_t r = b->locus_read_begin[l]; r < b->locus_read_begin[l + 1]; ++r) read_locus[r] = l;
+    }
+    for (uint32_t r : zero_rows) {
+      const uint32_t l = read_locus[r];
+      const uint32_t H = b->locus_allele_begin[l + 1] - b->locus_allele_begin[l];
+      double* row = out_ll + ll_off[l] + (size_t)(r - b->locus_read_begin[l]) * H;
+      for (uint32_t h = 0; h < H; ++h) row[h] = 0.0;
+    }
+  }
   if (stats) {
     stats->n_pairs = n_pairs;
     stats->n_cells = n_cells;
   }
   if (tasks.empty()) return LTR_OK;
-  const size_t smem = stutter_block_smem_bytes(max_flank, max_block, max_hap);
-  if (smem > 220 * 1024) return LTR_ERR_UNSUPPORTED;  // read flank / allele too long for the shared-memory staging
 
   // ---- constants from the host's libm ---------------------------------------------------------------------------------
   std::vector<double> int_logs((size_t)std::max(max_block, max_hap) + 16);

@@ -187,12 +187,20 @@ class Engine:
         return ll, post, tot, total.value
 
     # -- HapAligner::process_reads, homopolymer / --stutter-align-len path, for a batch of loci ---------
-    def stutter_ll(self, batch, aln_params=None, out=None):
+    def stutter_ll(self, batch, aln_params=None, out=None, per_locus_status=False):
+        """ltr_stutter_ll; with per_locus_status=True ltr_stutter_ll_status: returns (out, stats, status[n_loci]) and a
+        locus that cannot be processed fails alone."""
         sb, keep = abi.make_stutter_batch(batch)
         p = abi.make_params(aln_params, 5)
         if out is None:
             out = np.zeros(abi.stutter_ll_size(batch), dtype=np.float64)
         st = abi.JobStats()
+        if per_locus_status:
+            status = np.zeros(len(batch["locus_read_begin"]) - 1, dtype=np.int32)
+            rc = self.lib.ltr_stutter_ll_status(self.ctx, C.byref(p), C.byref(sb), abi.ptr(out, abi._dp),
+                                                abi.ptr(status, abi._i32p), C.byref(st))
+            _check(self.lib, self.ctx, rc, "ltr_stutter_ll_status")
+            return out, st, status
         rc = self.lib.ltr_stutter_ll(self.ctx, C.byref(p), C.byref(sb), abi.ptr(out, abi._dp), C.byref(st))
         _check(self.lib, self.ctx, rc, "ltr_stutter_ll")
         return out, st

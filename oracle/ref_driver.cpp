@@ -25,6 +25,7 @@
 #include "base_quality.h"
 #include "genotyper.h"
 #include "mathops.h"
+#include "read_pooler.h"
 #include "stutter_model.h"
 
 #include "longtr_b200.h"
@@ -340,4 +341,29 @@ int ltr_ref_seed_bases(const ltr_flat_locus* L, int32_t* out_seeds) {
 
 const char* ltr_ref_version(void) { return "LongTR reference sources, compiled in place (oracle/_ref)"; }
 
+
+// ReadPooler (src/read_pooler.cpp:3-20, read_pooler.h:42-48) on n reads given as sequence / quality strings: pool index of
+// every read, number of pools and, back to back in pool order, the median qualities BaseQuality::median_base_qualities
+// (src/base_quality.cpp:11-28) leaves on the pooled alignments.  Returns the bytes written to pooled_quals, < 0 on error.
+int64_t ltr_ref_pool_reads(int32_t n_reads, const char* const* seqs, const char* const* quals, int32_t* pool_index,
+                           int32_t* n_pools, char* pooled_quals, int64_t cap) {
+  ReadPooler pooler;
+  BaseQuality bq;
+  for (int32_t r = 0; r < n_reads; ++r) {
+    Alignment aln(100, 100 + (int32_t)strlen(seqs[r]) - 1, false, false, "read", std::string(quals[r]), std::string(seqs[r]),
+                  std::string(seqs[r]));
+    pool_index[r] = pooler.add_alignment(aln);
+  }
+  pooler.pool(bq);
+  *n_pools = pooler.num_pools();
+  int64_t off = 0;
+  std::vector<Alignment>& alns = pooler.get_alignments();
+  for (size_t i = 0; i < alns.size(); ++i) {
+    const std::string& q = alns[i].get_base_qualities();
+    if (off + (int64_t)q.size() > cap) return -1;
+    memcpy(pooled_quals + off, q.data(), q.size());
+    off += (int64_t)q.size();
+  }
+  return off;
+}
 }  // extern "C"

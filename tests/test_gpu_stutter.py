@@ -50,3 +50,44 @@ def test_stutter_batch_config5_matches_oracle(engine):
         assert np.array_equal(got[off:off + P * H].reshape(P, H), want), l
         off += P * H
     assert off == len(got)
+
+
+def test_bad_locus_fails_alone_on_the_short_path(engine):
+    """ltr_stutter_ll_status: an empty (<DEL>) allele, a seed outside the read and a broken stutter model each fail their own
+    locus only; the rows of the other loci equal an undisturbed run bit for bit, the rows of the failed loci stay untouched.
+    ltr_stutter_ll (all or nothing) fails as a whole on the same batch and leaves the output array as it was."""
+    from longtr_b200 import workloads
+    from longtr_b200.engine import LongTRError
+    work = workloads.generate_stutter(24)
+    good, _st = engine.stutter_ll(work.batch)
+    b = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in work.batch.items()}
+    lab, lrb = b["locus_allele_begin"], b["locus_read_begin"]
+    # locus 3: its second allele becomes empty (shift nothing: just make two offsets equal by emptying that allele)
+    a = int(lab[3]) + 1
+    cut = int(b["allele_off"][a + 1] - b["allele_off"][a])
+    b["allele_bytes"] = np.concatenate([b["allele_bytes"][:b["allele_off"][a]], b["allele_bytes"][b["allele_off"][a + 1]:]])
+    b["allele_off"] = b["allele_off"].copy()
+    b["allele_off"][a + 1:] -= cut
+    # locus 7: a seed beyond the read; locus 11: a stutter model that is not a probability distribution
+    b["read_seed"] = b["read_seed"].copy()
+    b["read_seed"][lrb[7]] = 10 ** 6
+    b["stutter"] = b["stutter"].copy()
+    b["stutter"][6 * 11 + 1] = 0.99
+    sentinel = 123.25
+    out = np.full(len(good), sentinel)
+    got, st, status = engine.stutter_ll(b, out=out, per_locus_status=True)
+    assert status[3] == -5 and status[7] == -3 and status[11] == -3
+    assert (np.delete(status, [3, 7, 11]) == 0).all()
+    H = np.diff(lab).astype(np.int64)
+    P = np.diff(lrb).astype(np.int64)
+    off = np.concatenate([[0], np.cumsum(H * P)])
+    for l in range(work.n_loci):
+        rows = got[off[l]:off[l + 1]]
+        if l in (3, 7, 11):
+            assert (rows == sentinel).all()
+        else:
+            assert np.array_equal(rows, good[off[l]:off[l + 1]]), l
+    out2 = np.full(len(good), sentinel)
+    with pytest.raises(LongTRError):
+        engine.stutter_ll(b, out=out2)
+    assert (out2 == sentinel).all()

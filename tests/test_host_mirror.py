@@ -137,3 +137,14 @@ def test_flatten_loci_matches_the_oracle_flattening_on_fresh_loci(seed):
             for hh in range(H):
                 got[read_row[r0 + rr], hap_col[h0 + hh]] = block[rr, hh]
         assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("case", gu.load("pooling"), ids=lambda c: c["name"])
+def test_read_pooler_matches_reference(case):
+    """ltr::ReadPooler + BaseQuality::median_base_qualities (csrc/host/host_types.cpp) against the reference's ReadPooler
+    (src/read_pooler.cpp:3-20, src/read_pooler.h:42-48, src/base_quality.cpp:11-28; fixture tests/golden/pooling.json
+    recorded through oracle/_ref): same pool of every read, same per-position median qualities."""
+    from longtr_b200 import abi
+    pool, meds = abi.pool_reads(case["seqs"], case["quals"])
+    assert pool == case["pool_index"]
+    assert meds == case["median_quals"]

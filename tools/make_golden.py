@@ -200,6 +200,25 @@ def vcf_record_cases():
     return [dict(name=c["name"], record=r) for c, r in zip(cases, recs)]
 
 
+def pooling_cases():
+    """ReadPooler + median base qualities as the reference computes them (oracle/_ref: ltr_ref_pool_reads)."""
+    from longtr_b200 import abi
+    out = []
+    for seed in range(12):
+        rng = np.random.default_rng(7700 + seed)
+        n_distinct = int(rng.integers(1, 8))
+        seqs_d = ["".join("ACGT"[int(x)] for x in rng.integers(0, 4, size=int(rng.integers(5, 60)))) for _ in range(n_distinct)]
+        if seed % 4 == 0 and n_distinct > 1:
+            seqs_d[1] = seqs_d[0][:-1] + ("A" if seqs_d[0][-1] != "A" else "C")   # differs in one base only
+        n = int(rng.integers(1, 30))
+        pick = rng.integers(0, n_distinct, size=n)
+        seqs = [seqs_d[int(k)] for k in pick]
+        quals = ["".join(chr(int(q)) for q in rng.integers(33, 75, size=len(s))) for s in seqs]
+        pool, meds = abi.pool_reads(seqs, quals, lib=po.ref_lib(), fn="ltr_ref_pool_reads")
+        out.append(dict(name="pool%02d" % seed, seqs=seqs, quals=quals, pool_index=pool, median_quals=meds))
+    return out
+
+
 def pruning_cases():
     """Both passes of SeqStutterGenotyper::genotype (src/seq_stutter_genotyper.cpp:634-645) as the reference ran them
     (oracle/_ref/ltr_ref_trace records every call of Genotyper::calc_log_sample_posteriors): the LL matrix of all candidate
@@ -242,7 +261,7 @@ def main():
     os.makedirs(GOLD, exist_ok=True)
     makers = dict(appendix_a=lambda: [run_ref(c) for c in appendix_a()], process_reads_long=long_path_cases,
                   process_reads_short=short_path_cases, posteriors=posterior_cases, pair_batches=pair_batch_cases,
-                  calls=calls_cases, vcf_records=vcf_record_cases, pruning=pruning_cases)
+                  calls=calls_cases, vcf_records=vcf_record_cases, pruning=pruning_cases, pooling=pooling_cases)
     only = [a for a in sys.argv[1:] if not a.startswith("-")]  # `python tools/make_golden.py pruning`: that set only
     sets = {k: f() for k, f in makers.items() if not only or k in only}
     for name, cases in sets.items():
