@@ -9,6 +9,9 @@
 // CPU fallback: without a B200 the process exits through LongTR's own printErrorAndDie.
 // tests/test_gpu_dropin.py links this file into the reference's per-locus genotyper (oracle/build_ref.sh,
 // libltr_ref_gpu.so) and checks that the VCF records it writes are identical to the all-CPU reference's.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -19,6 +22,30 @@
 #include "stutter_model.h"
 
 #include "longtr_b200.h"
+
+// LONGTR_B200_TIMING=1: time spent inside the two replaced functions, printed when the process exits.
+namespace {
+struct BindingTimer {
+  double process_reads_s, posteriors_s;
+  long process_reads_n, posteriors_n;
+  bool on;
+  BindingTimer() : process_reads_s(0), posteriors_s(0), process_reads_n(0), posteriors_n(0),
+                   on(std::getenv("LONGTR_B200_TIMING") != NULL) {}
+  ~BindingTimer() {
+    if (on)
+      std::fprintf(stderr, "[longtr_b200 binding] process_reads: %ld calls, %.3f ms each; calc_log_sample_posteriors: %ld calls, "
+                           "%.3f ms each\n", process_reads_n, 1e3 * process_reads_s / (process_reads_n ? process_reads_n : 1),
+                   posteriors_n, 1e3 * posteriors_s / (posteriors_n ? posteriors_n : 1));
+  }
+};
+BindingTimer g_timer;
+struct Scope {
+  double* acc; long* n;
+  std::chrono::steady_clock::time_point t0;
+  Scope(double* a, long* c) : acc(a), n(c), t0(std::chrono::steady_clock::now()) {}
+  ~Scope() { *acc += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); ++*n; }
+};
+}  // namespace
 
 static ltr_ctx* longtr_b200_ctx() {
   static ltr_ctx* ctx = NULL;  // LongTR is single-threaded: one context per process
@@ -33,6 +60,9 @@ void HapAligner::process_reads(const std::vector<Alignment>& alignments, int ini
                                const BaseQuality* base_quality, const std::vector<bool>& realign_read,
                                double* aln_probs, int* seed_positions) {
   assert(alignments.size() == realign_read.size());
+  ltr_ctx* ctx_first = longtr_b200_ctx();  // (context creation stays outside the timer)
+  (void)ctx_first;
+  Scope timer(&g_timer.process_reads_s, &g_timer.process_reads_n);
   if (fw_haplotype_->num_blocks() != 3) printErrorAndDie("longtr_b200: expected flank / repeat / flank haplotype blocks");
   HapBlock* left = fw_haplotype_->get_block(0);
   HapBlock* rep = fw_haplotype_->get_block(1);
@@ -99,6 +129,9 @@ void HapAligner::process_reads(const std::vector<Alignment>& alignments, int ini
 
 double Genotyper::calc_log_sample_posteriors(std::vector<int>& read_weights) {
   assert(read_weights.size() == num_reads_);  // accepted but unused, as in the reference (genotyper.cpp:45-83)
+  ltr_ctx* ctx_first = longtr_b200_ctx();
+  (void)ctx_first;
+  Scope timer(&g_timer.posteriors_s, &g_timer.posteriors_n);
   double total_LL = 0.0;
   const int rc = ltr_posteriors(longtr_b200_ctx(), haploid_ ? 1 : 0, num_samples_, (int32_t)num_reads_, num_alleles_,
                                 log_aln_probs_ /* clamped in place like :57-58 */, log_p1_, log_p2_, sample_label_,

@@ -103,6 +103,8 @@ struct ltr_job {
   JobResult* res = nullptr;
   bool pending = false;  // submitted, not yet waited for
   bool ran = false;
+  bool drained = true;   // nothing of this job is queued on the device any more (destroy need not wait)
+  cudaStream_t st_h2d = nullptr, st_d2h = nullptr;  // device plan: the lane's copy streams; host plan (small jobs): main
   ltr_job_stats stats;
 };
 
@@ -135,6 +137,16 @@ JobResult* take_result_block(ltr_ctx* ctx) {
     return nullptr;
   }
   return static_cast<JobResult*>(p);
+}
+
+cudaError_t take_event(ltr_ctx* ctx, bool timing, cudaEvent_t* out) {
+  std::vector<cudaEvent_t>& pool = timing ? ctx->timing_events : ctx->plain_events;
+  if (!pool.empty()) {
+    *out = pool.back();
+    pool.pop_back();
+    return cudaSuccess;
+  }
+  return timing ? cudaEventCreate(out) : cudaEventCreateWithFlags(out, cudaEventDisableTiming);
 }
 
 void destroy_lane(JobLane& L) {
@@ -273,6 +285,8 @@ void ltr_ctx_destroy(ltr_ctx* ctx) {
   for (int i = 0; i < 4; ++i)
     if (ctx->stage[i]) cudaFreeHost(ctx->stage[i]);
   for (void* p : ctx->result_blocks) cudaFreeHost(p);
+  for (cudaEvent_t e : ctx->timing_events) cudaEventDestroy(e);
+  for (cudaEvent_t e : ctx->plain_events) cudaEventDestroy(e);
   delete ctx;
 }
 
@@ -280,15 +294,13 @@ void ltr_job_destroy(ltr_ctx* ctx, ltr_job* job) {
   if (!job) return;
   if (!ctx) ctx = job->ctx;
   if (ctx) cudaSetDevice(ctx->device);
-  if (ctx) {
+  if (ctx && !job->drained) {
     // a job may be destroyed while its work is still queued (error paths, a caller that gives up): drain its lane first
     JobLane& L = ctx->lanes[job->lane];
     cudaStreamSynchronize(L.h2d);
-    if (job->pending || job->ran) {
-      cudaStreamSynchronize(L.main);
-      for (int i = 0; i < kNumStreams; ++i) cudaStreamSynchronize(L.cls[i]);
-      cudaStreamSynchronize(L.d2h);
-    }
+    cudaStreamSynchronize(L.main);
+    for (int i = 0; i < kNumStreams; ++i) cudaStreamSynchronize(L.cls[i]);
+    cudaStreamSynchronize(L.d2h);
   }
   DeviceBuffer* bufs[] = {&job->hap_bytes, &job->hap_off, &job->hap_locus, &job->read_bytes, &job->read_off,
                           &job->lhb, &job->lrb, &job->ll_off, &job->out_ll, &job->tabI, &job->tabD,
@@ -302,9 +314,12 @@ void ltr_job_destroy(ltr_ctx* ctx, ltr_job* job) {
   for (ClassState& c : job->classes) {
     c.tasks.free(); c.fails.free(); c.sxy.free(); c.sb.free();
   }
-  cudaEvent_t evs[] = {job->ev_h2d, job->ev_start, job->ev_plan, job->ev_vit, job->ev_end, job->ev_stats, job->ev_done};
-  for (cudaEvent_t e : evs)
-    if (e) cudaEventDestroy(e);
+  cudaEvent_t tev[] = {job->ev_start, job->ev_plan, job->ev_vit, job->ev_end};
+  cudaEvent_t pev[] = {job->ev_h2d, job->ev_stats, job->ev_done};
+  for (cudaEvent_t e : tev)
+    if (e) { if (ctx) ctx->timing_events.push_back(e); else cudaEventDestroy(e); }
+  for (cudaEvent_t e : pev)
+    if (e) { if (ctx) ctx->plain_events.push_back(e); else cudaEventDestroy(e); }
   if (job->res && ctx) ctx->result_blocks.push_back(job->res);
   delete job;
 }
@@ -649,22 +664,20 @@ int job_setup(ltr_ctx* ctx, const ltr_params* params, const ltr_viterbi_batch* b
   ltr_viterbi_batch bb = *b;
   if (bb.n_loci == 0) bb.locus_hap_begin = bb.locus_read_begin = bb.hap_off = bb.read_off = kZero;
   if (!plan_offsets_valid(bb)) return LTR_ERR_INVALID;
-  job->ctx = ctx;
-  job->lane = (int)(ctx->next_lane++ % (unsigned)kLanes);
   job->params = *params;
   job->n_loci = bb.n_loci;
   job->n_haps = bb.locus_hap_begin[bb.n_loci];
   job->n_reads = bb.locus_read_begin[bb.n_loci];
   job->raw_bytes = job->n_reads ? bb.read_off[job->n_reads] : 0u;
   if ((job->n_haps && bb.hap_off[job->n_haps] && !bb.hap_bytes) || (job->raw_bytes && !bb.read_bytes)) return LTR_ERR_INVALID;
-  job->device_plan = ctx->plan_mode == 2 || (ctx->plan_mode == 0 && job->n_reads >= kDevicePlanMinReads);
   JobLane& L = ctx->lanes[job->lane];
-  cudaStream_t st = L.h2d;
+  cudaStream_t st = job->st_h2d;
+  job->drained = false;
   cudaEvent_t* evs[] = {&job->ev_start, &job->ev_plan, &job->ev_vit, &job->ev_end};
-  for (cudaEvent_t* e : evs) LTR_CUDA(ctx, cudaEventCreate(e));
-  LTR_CUDA(ctx, cudaEventCreateWithFlags(&job->ev_h2d, cudaEventDisableTiming));
-  LTR_CUDA(ctx, cudaEventCreateWithFlags(&job->ev_stats, cudaEventDisableTiming));
-  LTR_CUDA(ctx, cudaEventCreateWithFlags(&job->ev_done, cudaEventDisableTiming));
+  for (cudaEvent_t* e : evs) LTR_CUDA(ctx, take_event(ctx, true, e));
+  LTR_CUDA(ctx, take_event(ctx, false, &job->ev_h2d));
+  LTR_CUDA(ctx, take_event(ctx, false, &job->ev_stats));
+  LTR_CUDA(ctx, take_event(ctx, false, &job->ev_done));
   job->res = take_result_block(ctx);
   if (!job->res) return LTR_ERR_OOM;
   std::memset(job->res, 0, sizeof(JobResult));
@@ -805,10 +818,12 @@ int job_enqueue_compute(ltr_ctx* ctx, ltr_job* job) {
   job->stats.n_launches = 0;
   job->stats.n_fallback = 0;
   job->stats.n_band_uncertified = 0;
-  LTR_CUDA(ctx, cudaStreamWaitEvent(L.main, job->ev_h2d, 0));
-  // ev_h2d only covers the copies; the clears behind it on the h2d stream are ordered with a second event
-  LTR_CUDA(ctx, cudaEventRecord(L.ev_init, L.h2d));
-  LTR_CUDA(ctx, cudaStreamWaitEvent(L.main, L.ev_init, 0));
+  if (job->st_h2d != L.main) {
+    // (ev_h2d only covers the copies; the clears behind it on the h2d stream are ordered with a second event)
+    LTR_CUDA(ctx, cudaEventRecord(L.ev_init, job->st_h2d));
+    LTR_CUDA(ctx, cudaStreamWaitEvent(L.main, L.ev_init, 0));
+  }
+  job->drained = false;
   LTR_CUDA(ctx, cudaEventRecord(job->ev_start, L.main));
   // a kernel that silently skipped work must not go unnoticed: results start out as NaN
   if (job->n_upairs_cap) LTR_CUDA(ctx, cudaMemsetAsync(job->uniq_ll.p, 0xFF, job->n_upairs_cap * sizeof(double), L.main));
@@ -944,8 +959,16 @@ int job_new(ltr_ctx* ctx, const ltr_params* params, const ltr_viterbi_batch* b, 
   ltr_job* job = new ltr_job();
   std::memset(&job->stats, 0, sizeof(job->stats));
   job->ctx = ctx;
-  job->lane = (int)(ctx->next_lane % (unsigned)kLanes);
-  AllocScope alloc_scope(ctx->lanes[job->lane].h2d);
+  job->lane = (int)(ctx->next_lane++ % (unsigned)kLanes);
+  // Large batches are planned on the device and use the lane's copy streams so that uploads and downloads overlap other
+  // jobs' kernels; the small batches of the per-locus entry points are planned on the host and keep everything on the
+  // lane's main stream (fewer cross-stream waits per call).
+  const uint32_t n_reads_hint = (b->n_loci && b->locus_read_begin) ? b->locus_read_begin[b->n_loci] : 0u;
+  job->device_plan = ctx->plan_mode == 2 || (ctx->plan_mode == 0 && n_reads_hint >= kDevicePlanMinReads);
+  JobLane& lane = ctx->lanes[job->lane];
+  job->st_h2d = job->device_plan ? lane.h2d : lane.main;
+  job->st_d2h = job->device_plan ? lane.d2h : lane.main;
+  AllocScope alloc_scope(job->st_h2d);
   const int rc = job_setup(ctx, params, b, post, job);
   if (rc != LTR_OK) {
     ltr_job_destroy(ctx, job);  // drains the lane's copies first: the caller may release its arrays
@@ -991,13 +1014,14 @@ int ltr_job_create(ltr_ctx* ctx, const ltr_params* params, const ltr_viterbi_bat
   }
   // every copy from host memory has to be finished: the caller may release its arrays when we return
   if (rc2 == LTR_OK) {
-    cudaError_t e = cudaStreamSynchronize(L.h2d);
+    cudaError_t e = cudaStreamSynchronize(job->st_h2d);
     if (e != cudaSuccess) rc2 = fail_cuda(ctx, e, "ltr_job_create: upload");
   }
   if (rc2 != LTR_OK) {
     ltr_job_destroy(ctx, job);
     return rc2;
   }
+  job->drained = true;
   if (timing) {
     auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point c) {
       return std::chrono::duration<double, std::milli>(c - a).count();
@@ -1015,6 +1039,7 @@ int ltr_job_run(ltr_ctx* ctx, ltr_job* job) {
   LTR_CUDA(ctx, cudaSetDevice(ctx->device));
   LTR_TRY(job_enqueue_compute(ctx, job));
   LTR_CUDA(ctx, cudaEventSynchronize(job->ev_stats));
+  job->drained = true;  // the uploads were awaited by ltr_job_create, every kernel and the statistics copy by this
   return job_collect(ctx, job);
 }
 
@@ -1028,34 +1053,35 @@ int ltr_job_submit_outputs(ltr_ctx* ctx, const ltr_params* params, const ltr_vit
   JobLane& L = ctx->lanes[job->lane];
   rc = job_enqueue_compute(ctx, job);
   if (rc == LTR_OK) {
-    cudaError_t e = cudaStreamWaitEvent(L.d2h, job->ev_stats, 0);
+    cudaStream_t sd = job->st_d2h;
+    cudaError_t e = (sd != L.main) ? cudaStreamWaitEvent(sd, job->ev_stats, 0) : cudaSuccess;
     job->stats.d2h_bytes = 0;
     if (e == cudaSuccess && O.ll && job->n_ll) {
-      e = cudaMemcpyAsync(O.ll, job->out_ll.p, job->n_ll * sizeof(double), cudaMemcpyDeviceToHost, L.d2h);
+      e = cudaMemcpyAsync(O.ll, job->out_ll.p, job->n_ll * sizeof(double), cudaMemcpyDeviceToHost, sd);
       job->stats.d2h_bytes += job->n_ll * sizeof(double);
     }
     if (e == cudaSuccess && O.post && job->has_post && job->n_post) {
-      e = cudaMemcpyAsync(O.post, job->post.p, job->n_post * sizeof(double), cudaMemcpyDeviceToHost, L.d2h);
+      e = cudaMemcpyAsync(O.post, job->post.p, job->n_post * sizeof(double), cudaMemcpyDeviceToHost, sd);
       job->stats.d2h_bytes += job->n_post * sizeof(double);
     }
     if (e == cudaSuccess && O.totals && job->has_post && job->n_tot) {
-      e = cudaMemcpyAsync(O.totals, job->totals.p, job->n_tot * sizeof(double), cudaMemcpyDeviceToHost, L.d2h);
+      e = cudaMemcpyAsync(O.totals, job->totals.p, job->n_tot * sizeof(double), cudaMemcpyDeviceToHost, sd);
       job->stats.d2h_bytes += job->n_tot * sizeof(double);
     }
     if (e == cudaSuccess && O.kept_mask && job->n_haps) {
       if (job->prune) {
-        e = cudaMemcpyAsync(O.kept_mask, job->kept_mask.p, job->n_haps, cudaMemcpyDeviceToHost, L.d2h);
+        e = cudaMemcpyAsync(O.kept_mask, job->kept_mask.p, job->n_haps, cudaMemcpyDeviceToHost, sd);
         job->stats.d2h_bytes += job->n_haps;
       } else {
         std::memset(O.kept_mask, 1, job->n_haps);
       }
     }
-    if (e == cudaSuccess) e = cudaEventRecord(job->ev_done, L.d2h);
+    if (e == cudaSuccess) e = cudaEventRecord(job->ev_done, sd);
     if (e != cudaSuccess) rc = fail_cuda(ctx, e, "ltr_job_submit: download");
   }
   if (rc == LTR_OK && !job->device_plan) {
     // host plan: its arrays sit in the context's staging buffers, which the next job will overwrite
-    cudaError_t e = cudaStreamSynchronize(L.h2d);
+    cudaError_t e = cudaEventSynchronize(job->ev_h2d);
     if (e != cudaSuccess) rc = fail_cuda(ctx, e, "ltr_job_submit: upload");
   }
   job->pending = true;
@@ -1084,6 +1110,7 @@ int ltr_job_wait(ltr_ctx* ctx, ltr_job* job) {
   LTR_CUDA(ctx, cudaSetDevice(ctx->device));
   LTR_CUDA(ctx, cudaEventSynchronize(job->ev_done));
   job->pending = false;
+  job->drained = true;
   return job_collect(ctx, job);
 }
 

@@ -29,6 +29,12 @@ struct SmemTable {  // the lane's closed-form boundary cells, [2K][3][32] double
 #ifndef LTR_BAND_MINBLOCKS
 #define LTR_BAND_MINBLOCKS 4
 #endif
+// Unroll factor of the steady-state loop (one iteration = one double step).  Unrolling removes the register moves of
+// the sliding character windows on the loop's back edge (2.75 of 27 issue slots per cell) at the price of code size.
+#ifndef LTR_BAND_UNROLL
+#define LTR_BAND_UNROLL 2
+#endif
+static constexpr int kBandUnroll = LTR_BAND_UNROLL;
 #ifndef LTR_BAND_MINBLOCKS_G4
 #define LTR_BAND_MINBLOCKS_G4 4
 #endif
@@ -134,7 +140,7 @@ viterbi_band_kernel(const VitConsts C, const DevBatch B, const BandArgs A) {
         band_fast_odd<K, SYM>(L, C, yr, nh, nr);
         band_fixup<K, 1>(L, R, T, s + 1);
       }
-#pragma unroll 1
+#pragma unroll kBandUnroll
       for (; s + 1 < s_end_min; s += 2) {
         const int32_t nh = (int32_t)*hp, nr = (int32_t)*rp;  // consumed after both steps
         ++hp;

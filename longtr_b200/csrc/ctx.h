@@ -80,6 +80,8 @@ struct ltr_ctx {
   void* stage[4] = {nullptr, nullptr, nullptr, nullptr};  // pinned host staging for the host plan's large arrays (grow-only)
   size_t stage_bytes[4] = {0, 0, 0, 0};
   std::vector<void*> result_blocks;  // pinned host blocks for per-job statistics, recycled
+  std::vector<cudaEvent_t> timing_events, plain_events;  // events of finished jobs, recycled (creation costs microseconds
+                                                         // that the per-locus entry points would pay on every call)
 };
 
 namespace ltr {

@@ -151,6 +151,9 @@ __device__ __noinline__ double wavefront_rows(const StutConsts* Cs, const WarpCt
             if (Ln.type[k] != ROW_OFF) last[row0 + s0 + lane * kStutRows + k] = Mout[k];
         }
       }
+      // lane 0 read entry `step` of the hand-off line in this step, lane t_last overwrites it t_last steps from now: the
+      // shuffles keep the lanes in step, this orders the shared-memory accesses as well (compute-sanitizer racecheck)
+      __syncwarp();
     }
     if (first_type == ROW_FIRST && s0 == 0) left_prob = __shfl_sync(kFull, Ln.left, 0);
     __syncwarp();

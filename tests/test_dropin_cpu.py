@@ -39,3 +39,20 @@ def test_reference_reproduces_real_data_records():
     recs = po.full_locus_records(cases, "full")
     for c, r in zip(cases, recs):
         assert r == c["record"], c["name"]
+
+
+@pytest.mark.skipif(not po.full_available("lazy"), reason="oracle/_ref/ltr_ref_lazy not built")
+def test_eliding_the_haplotype_alignment_changes_no_record():
+    """N1 (SURVEY.md section 8f): the reference's per-locus genotyper with Haplotype::aln_haps_to_ref replaced by
+    integration/lazy_haplotype_alignment.cpp (no Needleman-Wunsch of the haplotypes against the reference allele,
+    src/SeqAlignment/Haplotype.cpp:58-86) writes the very same VCF records -- seeded loci, the allele-pruning loci and the
+    shipped HG002 / trio loci -- and so does the same binary with the original re-enabled through its env switch."""
+    import os
+    cases = [dc.case_a4()] + dc.seeded_cases() + dc.pruning_cases() + gu.load_real_cases()
+    want = po.full_locus_records(cases, "full")
+    assert po.full_locus_records(cases, "lazy") == want
+    os.environ["LONGTR_B200_EAGER_HAP_ALIGNMENT"] = "1"
+    try:
+        assert po.full_locus_records(cases, "lazy") == want
+    finally:
+        del os.environ["LONGTR_B200_EAGER_HAP_ALIGNMENT"]

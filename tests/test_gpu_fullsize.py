@@ -26,7 +26,7 @@ def _sub_batch(b, l0, l1):
                 read_bytes=b["read_bytes"][b["read_off"][r0]:b["read_off"][r1]])
 
 
-@pytest.mark.parametrize("config,n_loci,n_check", [(3, 100000, 120), (4, 10000, 6)])
+@pytest.mark.parametrize("config,n_loci,n_check", [(3, 100000, 2400), (4, 10000, 208)])
 def test_full_size_properties(engine, config, n_loci, n_check):
     from longtr_b200 import workloads
     work = workloads.generate(config, n_loci)
@@ -68,10 +68,21 @@ def test_full_size_properties(engine, config, n_loci, n_check):
             if s in first:
                 assert np.array_equal(mat[i], mat[first[s]])
             first.setdefault(s, i)
-    # (6) oracle spot check, bit for bit, on random loci of the full batch
-    for l in rng.integers(0, n_loci, size=n_check):
-        want, _ = po.viterbi_batch(_sub_batch(b, l, l + 1), aln_params=work.aln_params)
-        assert np.array_equal(ll[off[l]:off[l + 1]], want), l
+    # (6) bit for bit against the CPU checkers on n_check loci of the full batch (random runs of consecutive loci, all
+    #     host threads): the reference's own process_reads (oracle/_ref) where it is built, the restatement otherwise --
+    #     and the restatement on every other run anyway
+    import os
+    threads = os.cpu_count() or 1
+    run = 8 if config == 4 else 100
+    for k, l0 in enumerate(rng.integers(0, n_loci - run, size=n_check // run)):
+        sb = _sub_batch(b, int(l0), int(l0) + run)
+        if po.ref_available() and k % 2 == 0:
+            want, _sec = po.ref_viterbi_batch(sb, work.aln_params, n_threads=threads)
+        else:
+            want, _ = po.viterbi_batch(sb, aln_params=work.aln_params, n_threads=threads)
+        got = ll[off[l0]:off[l0 + run]]
+        bad = np.nonzero(got != want)[0]
+        assert len(bad) == 0, (config, int(l0), bad[:5], got[bad[:5]], want[bad[:5]])
 
 
 def test_full_size_homopolymer_path(engine):
@@ -85,7 +96,17 @@ def test_full_size_homopolymer_path(engine):
     a = work.batch["locus_allele_begin"].astype(np.int64)
     r = work.batch["locus_read_begin"].astype(np.int64)
     off = np.concatenate([[0], np.cumsum((a[1:] - a[:-1]) * (r[1:] - r[:-1]))])
-    for l in rng.integers(0, work.n_loci, size=12):       # oracle spot check, bit for bit
-        (L, keep), (P, H) = work.flat_locus(int(l))
-        want, _seeds, _ = po.process_reads(L, P, H)
-        assert np.array_equal(out[off[l]:off[l + 1]].reshape(P, H), want), l
+    # bit for bit against the CPU checkers on 512 random loci (reference where built, restatement otherwise / alternating)
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    loci = [int(l) for l in rng.integers(0, work.n_loci, size=512)]
+
+    def check(args):
+        k, l = args
+        (L, keep), (P, H) = work.flat_locus(l)
+        which = "ref" if (po.ref_available() and k % 2 == 0) else "oracle"
+        want, _seeds, _ = po.process_reads(L, P, H, which=which)
+        return l, bool(np.array_equal(out[off[l]:off[l + 1]].reshape(P, H), want))
+    with ThreadPoolExecutor(max_workers=os.cpu_count() or 1) as ex:
+        res = list(ex.map(check, enumerate(loci)))
+    assert all(ok for _l, ok in res), [l for l, ok in res if not ok][:10]

@@ -11,37 +11,70 @@ import time
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, ".."))
 sys.path.insert(0, os.path.join(HERE, "..", "tests"))
+sys.path.insert(0, HERE)
 import dropin_cases  # noqa: E402
 from oracle import pyoracle as po  # noqa: E402
 
 
-def run(which, text):
+def run(which, text, env=None):
     exe = os.path.join(HERE, "..", "oracle", "_ref", "ltr_ref_%s" % which)
+    e = dict(os.environ)
+    e.update(env or {})
     t0 = time.perf_counter()
-    p = subprocess.run([exe], input=text, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=3000)
+    p = subprocess.run([exe], input=text, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=3000, env=e)
     dt = time.perf_counter() - t0
     if p.returncode != 0:
         raise RuntimeError(p.stderr.decode()[-300:])
     return dt, p.stdout
 
 
+def per_locus(which, env, cases, reps=(1, 5)):
+    """Seconds per locus as a difference quotient: (T(5N) - T(N)) / 4N, best of two runs each -- the CUDA start-up of
+    the GPU build (1-3 s, varies from box to box and run to run) cancels instead of being estimated separately."""
+    t = {}
+    out = None
+    for r in reps:
+        text = "".join(po._case_text(c) for c in cases * r).encode()
+        t[r], out = min((run(which, text, env) for _ in range(2)), key=lambda x: x[0])
+    n = len(cases)
+    return (t[reps[1]] - t[reps[0]]) / (n * (reps[1] - reps[0])), t, out
+
+
 def main():
-    n = int(sys.argv[1]) if len(sys.argv) > 1 else 200
     import golden_util
     cases = [dropin_cases.case_a4()] + dropin_cases.seeded_cases() + golden_util.load_real_cases()
-    cases = (cases * (n // len(cases) + 1))[:n]  # 11 seeded + 47 real (HG002 / trio) loci, repeated
-    text = "".join(po._case_text(c) for c in cases).encode()
-    one = po._case_text(cases[0]).encode()
+    eager = {"LONGTR_B200_EAGER_HAP_ALIGNMENT": "1"}
+    timing = {"LONGTR_B200_TIMING": "1"}
+    rows = (("all-CPU reference (ltr_ref_full)", "full", None), ("GPU drop-in, NW as in the reference", "gpu", eager),
+            ("GPU drop-in, NW elided", "gpu", None))
+    print("11 seeded + 47 real HG002 / trio loci, N = %d and 5N loci per run, per-locus time = (T(5N) - T(N)) / 4N" % len(cases))
     res = {}
-    for which in ("full", "gpu"):
-        t_one, _ = run(which, one)              # process start-up (+ CUDA context for the GPU build)
-        t_all, out = run(which, text)
-        res[which] = (t_one, t_all, out)
-        print("%-4s: %d loci in %.3f s (start-up run with 1 locus: %.3f s) -> %.2f ms per locus after start-up" %
-              (which, n, t_all, t_one, 1e3 * (t_all - t_one) / max(1, n - 1)))
-    print("identical VCF records: %s" % (res["full"][2] == res["gpu"][2]))
-    print("per-locus speed-up of the unbatched drop-in: %.1fx" %
-          ((res["full"][1] - res["full"][0]) / max(1e-9, res["gpu"][1] - res["gpu"][0])))
+    for label, which, env in rows:
+        dt, t, out = per_locus(which, env, cases)
+        res[label] = (dt, out)
+        print("%-38s %7.3f ms per locus   (runs: %.3f s / %.3f s)" % (label, 1e3 * dt, t[1], t[5]))
+    outs = [v[1] for v in res.values()]
+    print("identical VCF records: %s" % (outs[0] == outs[1] == outs[2]))
+    base = res[rows[0][0]][0]
+    for label, _w, _e in rows[1:]:
+        print("per-locus speed-up of the unbatched drop-in (%s): %.2fx" % (label, base / res[label][0]))
+    text = "".join(po._case_text(c) for c in cases * 5).encode()
+    e = dict(os.environ)
+    e.update(timing)
+    p = subprocess.run([os.path.join(HERE, "..", "oracle", "_ref", "ltr_ref_gpu")], input=text, stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, env=e)
+    print(p.stderr.decode().strip().splitlines()[-1])
+    # VNTR-sized loci (~1 kb repeats, ONT-like parameters): where Haplotype::aln_haps_to_ref is what is left on the host
+    import nw_elision_timing as nw
+    v = nw.vntr_cases(4)
+    print("VNTR ~1 kb loci, N = 4 and 3N loci per run")
+    vres = {}
+    for label, which, env in rows:
+        dt, t, out = per_locus(which, env, v, reps=(1, 3))
+        vres[label] = out
+        print("%-38s %7.1f ms per locus   (runs: %.3f s / %.3f s)" % (label, 1e3 * dt, t[1], t[3]))
+    outs = list(vres.values())
+    print("VNTR identical VCF records: %s" % (outs[0] == outs[1] == outs[2]))
 
 
 if __name__ == "__main__":

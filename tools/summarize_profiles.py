@@ -26,7 +26,11 @@ KEYS = ("gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_
         "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "dram__bytes_read.sum",
         "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum",
         "smsp__average_warps_issue_stalled", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
-        "smsp__thread_inst_executed_per_inst_executed.ratio", "sm__cycles_active.avg")
+        "smsp__thread_inst_executed_per_inst_executed.ratio", "sm__cycles_active.avg",
+        "smsp__average_warps_issue_stalled", "sm__icc_request_hit_rate.pct", "sm__icc_requests.sum",
+        "gcc__cache_requests_type_instruction.sum", "launch__shared_mem_per_block_dynamic",
+        "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum")
 
 
 def launch_list(tag, lines):
@@ -62,14 +66,20 @@ def launch_list(tag, lines):
     open(os.path.join(P, tag + "_launch_summary.txt"), "w").write("\n".join(lines) + "\n")
 
 
-def full_capture(tag):
-    rep = os.path.join(G, tag + "_full.ncu-rep")
-    if not os.path.exists(rep):
+def full_capture(tag, which="full", dest="ncu_full"):
+    """Selected metrics of a full capture: from the report itself, or from its raw page exported on the box
+    (<tag>_<which>_raw.csv) when the report was too large to bring back."""
+    rep = os.path.join(G, "%s_%s.ncu-rep" % (tag, which))
+    raw_csv = os.path.join(G, "%s_%s_raw.csv" % (tag, which))
+    if os.path.exists(raw_csv) and os.path.getsize(raw_csv) > 0:
+        raw = open(raw_csv).read()
+    elif os.path.exists(rep):
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    else:
         return
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
-    out = ["`ncu --set full --clock-control none --import-source on` (%s), selected metrics" % tag]
+    out = ["`ncu --set full --clock-control none --import-source on` (%s, %s), selected metrics" % (tag, which)]
     for r in rows[2:]:
         out.append("")
         out.append("KERNEL %s grid=%s block=%s" % (r[4].split("(")[0], r[8], r[7]))
@@ -80,7 +90,7 @@ def full_capture(tag):
                         out.append("  %-95s %s %s" % (h, v, u))
                 except ValueError:
                     pass
-    open(os.path.join(P, tag + "_ncu_full.txt"), "w").write("\n".join(out) + "\n")
+    open(os.path.join(P, "%s_%s.txt" % (tag, dest)), "w").write("\n".join(out) + "\n")
 
 
 def main():
@@ -89,6 +99,18 @@ def main():
     lines = []
     launch_list(tag, lines)
     full_capture(tag)
+    full_capture(tag, "stutter", "ncu_stutter")   # kernel 2 (config 5)
+    full_capture(tag, "c4stream", "ncu_c4_stream")  # full-matrix stream kernel on config 4
+    for extra in ("memcheck.log", "racecheck.log", "dropin_timing.txt", "latency.txt"):
+        src = os.path.join(G, "%s_%s" % (tag, extra))
+        if os.path.exists(src) and os.path.getsize(src):
+            if extra == "racecheck.log":  # keep the verdict lines, not the progress dots
+                keep = [l for l in open(src, errors="ignore").read().splitlines()
+                        if "RACECHECK SUMMARY" in l or "passed" in l or "rc=" in l or l.startswith("real")]
+                hz = [l for l in open(src, errors="ignore").read().splitlines() if "Race reported" in l]
+                open(os.path.join(P, "%s_%s" % (tag, extra)), "w").write("\n".join(sorted(set(hz))[:20] + keep) + "\n")
+            else:
+                shutil.copy(src, os.path.join(P, "%s_%s" % (tag, extra)))
     for fn in sorted(os.listdir(G)):
         if fn.startswith(tag + "_") and fn.endswith((".json", "probe.log", "pytest.log")):
             s = os.path.join(G, fn)
