@@ -37,6 +37,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", type=int, default=3, choices=[3, 4, 5])
+    ap.add_argument("--n2", action="store_true", help="only the extra.n2 line (clustering kernels)")
     ap.add_argument("--loci", type=int, default=0, help="loci per GPU per step (default: config size)")
     ap.add_argument("--cpu-sample-loci", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -510,6 +511,7 @@ def measure_long(args, config, n_loci, steps, warmup, torch, rank, world, local,
                    "pairs_per_gpu": int(st.n_pairs), "cells_per_gpu": int(st.n_cells),
                    "pairs_aligned_per_gpu": int(st.n_pairs_computed), "cells_evaluated_per_gpu": int(st.n_cells_computed),
                    "pairs_banded_per_gpu": int(st.n_band_pairs), "pairs_band_uncertified_per_gpu": int(st.n_band_uncertified),
+                   "pairs_band_second_round_per_gpu": int(st.n_band_retried),
                    "value_includes": "device plan (read de-duplication, band classes, task lists) + Viterbi kernels + "
                                      "fan-out + posteriors, every step; results start as NaN every step",
                    "plan_ms_per_step": plan_ms / steps, "viterbi_ms_per_step": vit_ms / steps,
@@ -592,6 +594,79 @@ def measure_from_raw_loci(args, config, n_loci, steps, torch, rank, world, local
     return out
 
 
+CLUSTER_THRESHOLDS = [20, 50, 80, 100, 150, 200, 300, 400, 500, 600, 700]  # HaplotypeGenerator.cpp:403
+
+
+def measure_cluster(args, eng, n_sets, steps, warmup, with_cpu_baseline):
+    """extra.n2: greedy clustering of the skipped sequences of n_sets (locus, sample) pairs at every threshold of the
+    reference's ladder in one call (ltr_cluster_greedy), host buffers in, assignments out.  The reference walks the ladder
+    until greedy_clustering succeeds; the CPU arm does exactly that on a bounded sample."""
+    from longtr_b200.workloads import generate_cluster_sets
+    seq_bytes, seq_off, begin = generate_cluster_sets(n_sets)
+    nT = len(CLUSTER_THRESHOLDS)
+    items, set_begin, set_T = [], [0], []
+    for k in range(n_sets):
+        ids = np.arange(begin[k], begin[k + 1], dtype=np.uint32)
+        for T in CLUSTER_THRESHOLDS:
+            items.append(ids)
+            set_begin.append(set_begin[-1] + len(ids))
+            set_T.append(T)
+    items = np.concatenate(items)
+    ms, kms = [], []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        cent, ncent, ok, st = eng.cluster_greedy(seq_bytes, seq_off, set_begin, items, set_T)
+        if it >= warmup:
+            ms.append((time.perf_counter() - t0) * 1e3)
+            kms.append(st.kernel_ms)
+    ok = ok.reshape(n_sets, nT)
+    first_ok = np.where(ok.any(axis=1), ok.argmax(axis=1), -1)
+    # comparisons the rounds made: every item behind each centroid of its set
+    lens = np.diff(seq_off.astype(np.int64))
+    line = {"metric": "cluster_sets_per_sec", "value": n_sets / (np.mean(ms) / 1e3), "unit": "sets/s",
+            "ms_per_step": float(np.mean(ms)), "kernel_ms_per_step": float(np.mean(kms)), "steps": steps, "warmup": warmup,
+            "api": "ltr_cluster_greedy (host buffers in, assignments out; all 11 thresholds of a set in one call)",
+            "gpu_launches": int(st.n_launches),
+            "config": {"workload": "N2: skipped sequences of (locus, sample) pairs, config-4-like VNTR alleles (500-1000 bp, "
+                                   "2-4 alleles, ~40 distinct noisy copies), thresholds 20..700",
+                       "sets": n_sets, "sequences": int(len(lens)), "set_thresholds": int(n_sets * nT),
+                       "mean_len": float(lens.mean()), "sets_clustered_at_first_threshold_index": np.bincount(
+                           first_ok[first_ok >= 0], minlength=nT).tolist()}}
+    if with_cpu_baseline:
+        from oracle import pyoracle as po
+        import concurrent.futures as cf
+        threads = os.cpu_count() or 1
+        n_sample = min(n_sets, threads * 2)
+        which = "ref" if po.ref_available() else "oracle"
+
+        def ladder(k):
+            ids = np.arange(begin[k], begin[k + 1], dtype=np.uint32)
+            for ti, T in enumerate(CLUSTER_THRESHOLDS):
+                okk, c, n = po.greedy_cluster(seq_bytes, seq_off, ids, T, which)
+                if okk:
+                    return ti, c
+            return -1, None
+        t0 = time.perf_counter()
+        with cf.ThreadPoolExecutor(threads) as ex:
+            res = list(ex.map(ladder, range(n_sample)))
+        sec = time.perf_counter() - t0
+        same, n_diff = True, 0
+        for k, (ti, c) in enumerate(res):
+            ok_k = (ti == int(first_ok[k]))
+            if ok_k and ti >= 0:
+                b0 = set_begin[k * nT + ti]
+                ok_k = bool(np.array_equal(c, cent[b0:b0 + len(c)]))
+            same &= ok_k
+            n_diff += (not ok_k)
+        line["cpu_baseline"] = {"value": n_sample / sec, "unit": "sets/s", "cores": threads,
+                                "kind": "reference" if which == "ref" else "port",
+                                "sample": "first %d sets, threshold ladder until greedy_clustering succeeds "
+                                          "(HaplotypeGenerator.cpp:403-409), all host threads" % n_sample}
+        line["parity_on_bench_sample"] = {"sets": n_sample, "first_threshold_and_assignments_equal": bool(same),
+                                          "sets_that_differ": int(n_diff)}
+    return line
+
+
 def compact(line):
     """Sub-line of another configuration inside the default run (extra.c4 / extra.c5)."""
     if line is None:
@@ -602,7 +677,8 @@ def compact(line):
     out = {k: line[k] for k in keep if k in line}
     out["config"] = {k: line["config"][k] for k in ("workload", "loci_per_gpu", "pairs_per_gpu", "pairs_aligned_per_gpu",
                                                      "cells_evaluated_per_gpu", "pairs_banded_per_gpu",
-                                                     "pairs_band_uncertified_per_gpu", "cell_equivalents_per_gpu")
+                                                     "pairs_band_uncertified_per_gpu", "pairs_band_second_round_per_gpu",
+                                                     "cell_equivalents_per_gpu")
                      if k in line["config"]}
     return out
 
@@ -618,7 +694,9 @@ def main():
     torch, rank, world, local = dist_setup(args.gpus)
     from longtr_b200 import Engine
     eng = Engine(local)
-    if args.config == 5:
+    if args.n2:
+        line = measure_cluster(args, eng, args.loci or 512, args.steps, args.warmup, not args.no_cpu_baseline)
+    elif args.config == 5:
         line = run_stutter(args, torch, rank, world, local, eng, args.loci or CONFIG_LOCI[5], args.steps, args.warmup,
                            world == 1 and not args.no_cpu_baseline)
     else:
@@ -636,6 +714,7 @@ def main():
                                                    fp64_rate, not args.no_cpu_baseline))
                 extra["c5"] = compact(run_stutter(args, torch, rank, world, local, eng, CONFIG_LOCI[5], 2, 3,
                                                   not args.no_cpu_baseline))
+                extra["n2"] = measure_cluster(args, eng, 512, 3, 3, not args.no_cpu_baseline)
             except Exception as e:  # the headline line must not be lost to a sub-line
                 extra["error"] = repr(e)
             line["extra"] = extra

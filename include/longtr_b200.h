@@ -117,6 +117,8 @@ typedef struct ltr_job_stats {
   uint64_t n_band_uncertified; /* ... of which the band could not certify (re-run over the full matrix)  */
   float plan_ms;               /* device time of the plan kernels (de-duplication of the trimmed reads, band classes,
                                   task lists: plan_kernels.cu) inside kernel_ms; 0 when the plan was built on the host */
+  uint64_t n_band_retried;     /* of n_band_uncertified: pairs whose banded score proved that a wider band class certifies
+                                  them and that ran a second time there instead of over the full matrix             */
 } ltr_job_stats;
 
 /* ---- context --------------------------------------------------------------------- */
@@ -420,6 +422,28 @@ int32_t ltr_trim_read_flat(const ltr_flat_locus* locus, int32_t read_index, char
 int64_t ltr_pool_reads(int32_t n_reads, const char* const* seqs, const char* const* quals, int32_t* pool_index,
                        int32_t* n_pools, char* pooled_quals, int64_t cap);
 int32_t ltr_seed_base_flat(const ltr_flat_locus* locus, int32_t read_index);
+
+/* ---- candidate-haplotype clustering ------------------------------------------------
+ * ltr_edit_distances  HaplotypeGenerator::needleman_wunsch (src/SeqAlignment/HaplotypeGenerator.cpp:201-235) for
+ *                     many pairs at once: out_score[p] is what that function leaves in `score` for
+ *                     cent_seq = sequence pair_a[p], read_seq = sequence pair_b[p], T = pair_T[p] -- the unit-cost
+ *                     edit distance when it is below T, T + 1 when it is above or the lengths differ by more than T,
+ *                     and T or T + 1 as the reference's row test decides when it equals T.  Sequence s is
+ *                     seq_bytes[seq_off[s] .. seq_off[s+1]); bytes are compared as bytes.  0 <= T <= 999.
+ * ltr_cluster_greedy  HaplotypeGenerator::greedy_clustering (:238-271) for many sets at once.  Set k is the item list
+ *                     set_items[set_begin[k] .. set_begin[k+1]) of sequence indices (the reference's `seqs`, in its
+ *                     order; the same sequences may appear in several sets, e.g. one set per threshold of :403) and
+ *                     set_T[k] its threshold.  out_centroid_of[i] = position, inside its set, of the centroid the
+ *                     item was assigned to (centroids name themselves): clusters[seqs[c]] of the reference is the
+ *                     items with out_centroid_of == c, in item order.  out_n_centroids[k]; out_ok[k] = 0 when the
+ *                     reference returns false (more than 15 centroids), in which case the set's assignments are
+ *                     unspecified.                                                                                  */
+int ltr_edit_distances(ltr_ctx* ctx, const uint8_t* seq_bytes, const uint32_t* seq_off, uint32_t n_seqs,
+                       const uint32_t* pair_a, const uint32_t* pair_b, const int32_t* pair_T, uint32_t n_pairs,
+                       int32_t* out_score, ltr_job_stats* stats);
+int ltr_cluster_greedy(ltr_ctx* ctx, const uint8_t* seq_bytes, const uint32_t* seq_off, uint32_t n_seqs,
+                       const uint32_t* set_begin, const uint32_t* set_items, const int32_t* set_T, uint32_t n_sets,
+                       int32_t* out_centroid_of, int32_t* out_n_centroids, uint8_t* out_ok, ltr_job_stats* stats);
 
 /* ---- diagnostics --------------------------------------------------------------------- */
 /* Sustained FP64-pipe issue rate of the device in lane-operations per second (the roofline

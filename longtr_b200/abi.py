@@ -50,7 +50,7 @@ class JobStats(C.Structure):
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("n_launches", C.c_uint32),
                 ("kernel_ms", C.c_float), ("viterbi_ms", C.c_float), ("n_pairs_computed", C.c_uint64),
                 ("n_cells_computed", C.c_uint64), ("n_band_pairs", C.c_uint64), ("n_band_uncertified", C.c_uint64),
-                ("plan_ms", C.c_float)]
+                ("plan_ms", C.c_float), ("n_band_retried", C.c_uint64)]
 
 
 class LocusCalls(C.Structure):
@@ -230,6 +230,12 @@ def load():
     lib.ltr_stutter_ll_status.restype = C.c_int
     lib.ltr_fp64_issue_rate.argtypes = [C.c_int, C.c_int, _dp, _dp]
     lib.ltr_fp64_issue_rate.restype = C.c_int
+    lib.ltr_edit_distances.argtypes = [vp, _u8p, _u32p, C.c_uint32, _u32p, _u32p, _i32p, C.c_uint32, _i32p,
+                                       C.POINTER(JobStats)]
+    lib.ltr_edit_distances.restype = C.c_int
+    lib.ltr_cluster_greedy.argtypes = [vp, _u8p, _u32p, C.c_uint32, _u32p, _u32p, _i32p, C.c_uint32, _i32p, _i32p, _u8p,
+                                       C.POINTER(JobStats)]
+    lib.ltr_cluster_greedy.restype = C.c_int
     _lib = lib
     return lib
 
@@ -243,7 +249,17 @@ EXPORTED_SYMBOLS = [
     "ltr_fp64_issue_rate", "ltr_genotype_locus", "ltr_extract_calls", "ltr_trim_read_flat", "ltr_seed_base_flat",
     "ltr_stutter_ll", "ltr_genotype_locus_pruned", "ltr_ctx_set_plan", "ltr_job_submit", "ltr_job_submit_outputs", "ltr_job_wait", "ltr_job_poll", "ltr_job_download_kept", "ltr_posteriors_batch", "ltr_genotyper_create", "ltr_genotyper_destroy",
     "ltr_genotyper_run", "ltr_batch_calls_free", "ltr_locus_batch_trim_read", "ltr_stutter_ll_status", "ltr_pool_reads",
+    "ltr_edit_distances", "ltr_cluster_greedy",
 ]
+
+
+def pack_seqs(seqs):
+    """Strings / bytes -> (seq_bytes uint8[], seq_off uint32[n+1])."""
+    raw = [s.encode() if isinstance(s, str) else bytes(s) for s in seqs]
+    off = np.zeros(len(raw) + 1, dtype=np.uint32)
+    off[1:] = np.cumsum([len(r) for r in raw], dtype=np.uint64)
+    data = np.frombuffer(b"".join(raw) + b"\0", dtype=np.uint8).copy()
+    return data, off
 
 
 def extract_calls(post, totals, haploid=False):

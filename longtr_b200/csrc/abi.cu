@@ -43,14 +43,29 @@ struct ClassState {
 // What comes back from the device with every run (pinned host memory, one block per job).
 struct JobResult {
   uint32_t cls_ctrl[(kPlanMaxK + 1) * 4];  // per row class: fast cursor, tasks, fail count, full cursor
-  unsigned long long band_words[9];        // band_ctrl: cursors, counters, statistics
+  unsigned long long band_words[11];       // band_ctrl: cursors, counters, statistics
   uint32_t plan_ctl[PLAN_CTL_BAND_TASK_COUNT];
   unsigned long long plan_stat[PLAN_STAT_WORDS];
 };
 
-static const size_t kBandCtrlBytes = 72;  // u32[12], u64 uncertified pairs, u64 their n*m cells, u64 band cells evaluated
+// u32[12], u64 uncertified pairs, u64 n*m cells of those re-run over the full matrix, u64 band cells evaluated, u64 pairs given
+// a second band round, u64 of which still uncertified
+static const size_t kBandCtrlBytes = 88;
 static const size_t kBandBucketOff = 128, kBandBucketWords = 17 * 32;  // then count / base / fill of band_collect_kernel
-static const size_t kBandCtrlAlloc = kBandBucketOff + 3 * kBandBucketWords * sizeof(uint32_t);
+// second band round: retry_count[8], retry_fill[8], retry_info[16], cursors[8]
+static const size_t kBandRetryOff = kBandBucketOff + 3 * kBandBucketWords * sizeof(uint32_t), kBandRetryWords = 40;
+static const size_t kBandCtrlAlloc = kBandRetryOff + kBandRetryWords * sizeof(uint32_t);
+
+// Second band round (band_retry_class): a retry must cost less than this percentage of the full matrix; 0 switches the
+// second round off (LTR_BAND_RETRY_RHO, diagnostics).
+static int band_retry_rho() {
+  static const int rho = [] {
+    const char* e = getenv("LTR_BAND_RETRY_RHO");
+    const int v = e ? atoi(e) : 80;
+    return v < 0 ? 0 : (v > 100 ? 100 : v);
+  }();
+  return rho;
+}
 
 // The string buffers (haplotypes, reads) carry kStringPad readable bytes on either side: the stream kernel prefetches one
 // byte ahead, the band kernel's character windows run up to W/2 + K bytes (W <= 512) ahead of a string's end and,
@@ -93,6 +108,8 @@ struct ltr_job {
   std::vector<BandLaunch> band_launches;
   uint32_t band_cap = 0;  // capacity of band_tasks / band_pairs
   DeviceBuffer band_tasks, band_cum, band_pairs, band_ctrl, band_meta;  // band_meta (host plan): info[16], n_band_tasks
+  DeviceBuffer band_retry;  // pair lists of the second band round (band_collect_kernel)
+  uint32_t band_retry_cap = 0;
   const uint32_t* band_info_dev = nullptr;
   const uint32_t* n_band_tasks_dev = nullptr;
   uint64_t plan_cells_computed = 0;
@@ -309,7 +326,7 @@ void ltr_job_destroy(ltr_ctx* ctx, ltr_job* job) {
                           &job->lsb, &job->pool, &job->label, &job->p1, &job->p2, &job->nsamp,
                           &job->haploid, &job->post_off, &job->tot_off, &job->post, &job->totals,
                           &job->int_logs, &job->mate, &job->aligned, &job->kept_mask, &job->kept_index, &job->cls_ctrl, &job->band_tasks, &job->band_cum, &job->band_pairs,
-                          &job->band_ctrl, &job->band_meta};
+                          &job->band_ctrl, &job->band_meta, &job->band_retry};
   for (DeviceBuffer* b : bufs) b->free();
   for (ClassState& c : job->classes) {
     c.tasks.free(); c.fails.free(); c.sxy.free(); c.sb.free();
@@ -517,6 +534,10 @@ int setup_host_plan(ltr_ctx* ctx, ltr_job* job, const ltr_viterbi_batch& bb, cud
     LTR_TRY(upload(ctx, st, job->band_meta, meta, 17, 0, h2d));
     LTR_CUDA(ctx, job->band_pairs.alloc((size_t)npairs * sizeof(uint2)));
     LTR_CUDA(ctx, job->band_ctrl.alloc(kBandCtrlAlloc));
+    if (band_retry_rho() > 0) {
+      job->band_retry_cap = (uint32_t)npairs;
+      LTR_CUDA(ctx, job->band_retry.alloc((size_t)npairs * sizeof(uint2)));
+    }
     job->band_info_dev = job->band_meta.as<uint32_t>();
     job->n_band_tasks_dev = job->band_meta.as<uint32_t>() + 16;
   }
@@ -639,6 +660,10 @@ int setup_device_plan(ltr_ctx* ctx, ltr_job* job, const ltr_viterbi_batch& bb, c
     LTR_CUDA(ctx, job->band_tasks.alloc((size_t)job->band_cap * sizeof(BandTask)));
     LTR_CUDA(ctx, job->band_pairs.alloc((size_t)job->band_cap * sizeof(uint2)));
     LTR_CUDA(ctx, job->band_ctrl.alloc(kBandCtrlAlloc));
+    if (band_retry_rho() > 0) {
+      job->band_retry_cap = job->band_cap;
+      LTR_CUDA(ctx, job->band_retry.alloc((size_t)job->band_cap * sizeof(uint2)));
+    }
     P.band_tasks = job->band_tasks.as<BandTask>();
     P.band_pairs = reinterpret_cast<PlanPair*>(job->band_pairs.p);
     P.band_cap = job->band_cap;
@@ -805,9 +830,46 @@ int run_band_phase(ltr_ctx* ctx, ltr_job* job, JobLane& L) {
   S.bucket_count = reinterpret_cast<uint32_t*>(job->band_ctrl.as<char>() + kBandBucketOff);
   S.bucket_base = S.bucket_count + kBandBucketWords;
   S.bucket_fill = S.bucket_base + kBandBucketWords;
+  uint32_t* rctrl = reinterpret_cast<uint32_t*>(job->band_ctrl.as<char>() + kBandRetryOff);
+  S.retry_pairs = job->band_retry_cap ? job->band_retry.as<uint2>() : nullptr;
+  S.retry_cap = job->band_retry_cap;
+  S.retry_count = rctrl;
+  S.retry_fill = rctrl + 8;
+  S.retry_info = rctrl + 16;
+  S.n_retried = reinterpret_cast<unsigned long long*>(job->band_ctrl.as<char>() + 72);
+  S.n_retry_failed = reinterpret_cast<unsigned long long*>(job->band_ctrl.as<char>() + 80);
+  S.gap = job->band.gap;
+  S.retry_rho_pct = band_retry_rho();
   LTR_CUDA(ctx, launch_band_collect(job->hc.C, B, job->band_tasks.as<BandTask>(), job->n_band_tasks_dev, job->band_cap, S,
                                     ctx->sm_count, L.main));
   job->stats.n_launches += 3;
+  if (S.retry_pairs) {
+    // second band round: the pairs band_retry_class found a wider, still worthwhile class for (certain to be certified)
+    LTR_CUDA(ctx, cudaEventRecord(L.ev_init, L.main));
+    int used = 0;
+    for (int cls = 1; cls < kBandClasses; ++cls) {  // nothing is retried into the narrowest class
+      ltr_job::BandLaunch bl;
+      bl.cls = cls;
+      cudaStream_t st = L.cls[used % kNumStreams];
+      LTR_CUDA(ctx, cudaStreamWaitEvent(st, L.ev_init, 0));
+      BandArgs A;
+      A.pairs = job->band_retry.as<uint2>();
+      A.info = S.retry_info + 2 * bl.cls;
+      A.cursor = rctrl + 32 + bl.cls;
+      A.counters = bctrl + 10;  // scratch words: the statistics of the first round stay as they are
+      A.cells_evaluated = reinterpret_cast<unsigned long long*>(job->band_ctrl.as<char>() + 64);
+      A.gap = job->band.gap;
+      A.abandon_after = 0u;
+      const uint32_t full_grid = (uint32_t)(ctx->sm_count * ctx->band_blocks_per_sm[bl.cls]);
+      LTR_CUDA(ctx, launch_band(bl.cls, (int)full_grid, st, job->hc.C, B, A));
+      job->stats.n_launches += 1;
+      LTR_CUDA(ctx, cudaEventRecord(L.ev_cls[used % kNumStreams], st));
+      LTR_CUDA(ctx, cudaStreamWaitEvent(L.main, L.ev_cls[used % kNumStreams], 0));
+      ++used;
+    }
+    LTR_CUDA(ctx, launch_band_retry_check(job->hc.C, B, S, ctx->sm_count, L.main));
+    job->stats.n_launches += 1;
+  }
   LTR_CUDA(ctx, cudaEventRecord(L.ev_collect, L.main));
   return LTR_OK;
 }
@@ -933,6 +995,8 @@ int job_collect(ltr_ctx* ctx, ltr_job* job) {
     job->stats.n_band_pairs = R.plan_ctl[PLAN_CTL_N_BAND_PAIRS];
   }
   job->stats.n_band_uncertified = band ? R.band_words[6] : 0;
+  job->stats.n_band_retried = band ? R.band_words[9] : 0;
+  if (band && R.band_words[10] != 0) ctx->last_error = "band retry: a pair was not certified by its second round (re-run over the full matrix)";
   // cells evaluated: full matrices of the stream-kernel pairs (planned + uncertified) + the bands actually evaluated
   job->stats.n_cells_computed = job->plan_cells_computed + (band ? R.band_words[7] + R.band_words[8] : 0);
   job->stats.n_fallback = 0;

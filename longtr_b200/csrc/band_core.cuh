@@ -33,7 +33,14 @@
 
 namespace ltr {
 
-static constexpr double kBandUncertified = 2.0;      // marker in the LL matrix (log-likelihoods are <= 0)
+// A pair the band could not certify is marked in the LL matrix with kBandUncertified - F_band (>= 2: log-likelihoods are
+// <= 0).  F_band is a lower bound of the pair's true score -- exactly the best chain inside the band -- so it tells which
+// wider band is certain to certify the pair (band_retry_class).
+static constexpr double kBandUncertified = 2.0;
+static constexpr double kBandAbandoned = -4.0e9;     // "F_band" of a pair that was not evaluated at all
+LTR_HD double band_mark(double f_band) { return kBandUncertified - f_band; }
+LTR_HD bool band_marked(double v) { return v >= kBandUncertified; }
+LTR_HD double band_unmark(double v) { return kBandUncertified - v; }
 
 // Band classes: G lanes per pair, K cells per lane per step, W = 2 K G diagonals.  The narrowest class spreads its 32
 // diagonals over 4 lanes (8 pairs per warp) so that the loop overhead of a double step is shared by 8 cells.
@@ -130,6 +137,23 @@ LTR_HD double band_threshold(const VitConsts& C, const BandGap& gap, int32_t n, 
   const double len = (double)n + (double)m;
   const double u = -(2.0 * gap.open + gap.ext * (double)(de + 2 * w - 1)) + 1e-3 + 1e-14 * len * len;
   return u > C.fast_thr ? u : C.fast_thr;
+}
+
+// Second chance of a pair whose banded score f_band failed the certificate.  The band of a wider class contains the band
+// just evaluated (band_geometry centres both on the same diagonals), so its score F' satisfies f_band <= F' <= F; a class
+// whose threshold lies below f_band therefore certifies the pair for sure.  Returns the narrowest such class when its band
+// is cheaper than rho_pct % of the full matrix, else -1 (full matrix).  f_band comes out of band_unmark: 1e-6 covers the
+// rounding of the marker.
+LTR_HD int band_retry_class(const VitConsts& C, const BandGap& gap, int32_t n, int32_t m, double f_band, int rho_pct) {
+  for (int c = 0; c < kBandClasses; ++c) {
+    const int W = band_class_w(c);
+    const BandGeom geo = band_geometry(n, m, W);
+    if (geo.w < 0) continue;
+    if (!(f_band - 1e-6 > band_threshold(C, gap, n, m, geo.w))) continue;
+    return ((unsigned long long)(n + m) * (unsigned long long)(W / 2) * 100ull <=
+            (unsigned long long)rho_pct * (unsigned long long)n * (unsigned long long)m) ? c : -1;
+  }
+  return -1;
 }
 
 struct BandPair {       // one (haplotype, read) pair as seen by a lane of its group

@@ -85,7 +85,7 @@ viterbi_band_kernel(const VitConsts C, const DevBatch B, const BandArgs A) {
     // Most pairs so far could not be certified (noisy reads, band too narrow): stop trying, hand the rest to the
     // full-matrix kernel.  Performance heuristic only -- both routes give the reference's bits.
     if (A.abandon_after && att >= A.abandon_after && 2u * fl > att) {
-      if (active && lg == 0) *out = kBandUncertified;
+      if (active && lg == 0) *out = band_mark(kBandAbandoned);
       continue;
     }
     // ---- per-lane closed forms of the boundary cells of its diagonals, initial state -----------------------------
@@ -159,7 +159,7 @@ viterbi_band_kernel(const VitConsts C, const DevBatch B, const BandArgs A) {
     const double thr = band_threshold(C, A.gap, R.n, R.m, geo.w);
     const bool mine = got && active;
     const bool ok = mine && (F > thr);
-    if (mine) *out = ok ? F : kBandUncertified;
+    if (mine) *out = ok ? F : band_mark(F);
     const unsigned done = __ballot_sync(kFull, mine), good = __ballot_sync(kFull, ok);
     const uint32_t cells = __reduce_add_sync(kFull, mine ? (uint32_t)band_cells(R.n, R.m, W, geo.dlo) : 0u);
     if (lane == 0) {
@@ -180,10 +180,12 @@ __global__ void band_expand_kernel(const BandTask* __restrict__ tasks, const uin
   for (uint32_t r = bt.read_begin; r < bt.read_end; ++r) dst[r - bt.read_begin] = make_uint2(bt.hap, r);
 }
 
-// One thread per band task: runs of uncertified pairs become tasks of the stream kernel of the haplotype's row class.
-// Two passes so that the appended tasks end up heaviest first (the persistent warps of the stream kernel then finish
-// together, like on the plan's own sorted list): pass 0 counts the runs per (row class, cost bucket = floor(log2 cost)),
-// band_bucket_scan_kernel turns the counts into list positions, pass 1 writes the tasks.
+// One thread per band task.  An uncertified pair either gets a second chance in a wider band class that is certain to
+// certify it (band_retry_class: S.retry_pairs, one list per class) or joins a run of consecutive reads that becomes ONE
+// task of the stream kernel of the haplotype's row class.  Two passes so that the appended tasks end up heaviest first
+// (the persistent warps of the stream kernel then finish together, like on the plan's own sorted list): pass 0 counts the
+// runs per (row class, cost bucket = floor(log2 cost)) and the retries per band class, band_bucket_scan_kernel turns the
+// counts into list positions, pass 1 writes the tasks and the retry pairs.
 __global__ void band_collect_kernel(const VitConsts C, const DevBatch B, const BandTask* __restrict__ tasks,
                                     const uint32_t* __restrict__ n_tasks_ptr, uint32_t task_cap, const BandCollect S,
                                     int pass) {
@@ -201,11 +203,28 @@ __global__ void band_collect_kernel(const VitConsts C, const DevBatch B, const B
   int strips = (n - 1 + 32 * kr - 1) / (32 * kr);
   if (strips < 1) strips = 1;
   const double* col = B.out_ll + B.ll_off[l] + (g - hb0);
-  uint32_t run_begin = 0, n_bad = 0;
+  uint32_t run_begin = 0, n_bad = 0, n_retry = 0;
   unsigned long long cells = 0;
   bool in_run = false;
   for (uint32_t r = bt.read_begin; r <= bt.read_end; ++r) {
-    const bool bad = (r < bt.read_end) && (col[(unsigned long long)(r - rb0) * H] == kBandUncertified);
+    bool bad = false;
+    if (r < bt.read_end) {
+      const double v = col[(unsigned long long)(r - rb0) * H];
+      bad = band_marked(v);
+      if (bad && S.retry_pairs) {
+        const int rc = band_retry_class(C, S.gap, n, (int32_t)(B.read_off[r + 1] - B.read_off[r]), band_unmark(v), S.retry_rho_pct);
+        if (rc >= 0) {
+          bad = false;
+          ++n_retry;
+          if (pass == 0) {
+            atomicAdd(S.retry_count + rc, 1u);
+          } else {
+            const uint32_t k = S.retry_info[2 * rc] + atomicAdd(S.retry_fill + rc, 1u);
+            if (k < S.retry_cap) S.retry_pairs[k] = make_uint2(g, r);
+          }
+        }
+      }
+    }
     if (bad) {
       ++n_bad;
       cells += (unsigned long long)n * (unsigned long long)(B.read_off[r + 1] - B.read_off[r]);
@@ -235,16 +254,28 @@ __global__ void band_collect_kernel(const VitConsts C, const DevBatch B, const B
       }
     }
   }
-  if (pass == 0 && n_bad) {
-    atomicAdd(S.n_uncertified, (unsigned long long)n_bad);
+  if (pass == 0 && (n_bad || n_retry)) {
+    atomicAdd(S.n_uncertified, (unsigned long long)(n_bad + n_retry));
     atomicAdd(S.cells_uncertified, cells);
+    if (n_retry) atomicAdd(S.n_retried, (unsigned long long)n_retry);
   }
   }
 }
 
 // One thread per row class: positions of the cost buckets behind the plan's tasks, heaviest bucket first; new task count.
+// Thread 31: segments of the retry lists, {first pair, number of pairs} per band class for the second band round.
 __global__ void band_bucket_scan_kernel(const BandCollect S) {
   const int kr = threadIdx.x;
+  if (kr == 31 && S.retry_pairs) {
+    uint32_t running = 0;
+    for (int c = 0; c < kBandClasses; ++c) {
+      uint32_t cnt = S.retry_count[c];
+      if (running + cnt > S.retry_cap) cnt = S.retry_cap - running;
+      S.retry_info[2 * c] = running;
+      S.retry_info[2 * c + 1] = cnt;
+      running += cnt;
+    }
+  }
   if (kr > 16) return;
   uint32_t running = *S.count[kr];
   for (int bkt = 31; bkt >= 0; --bkt) {
@@ -252,6 +283,32 @@ __global__ void band_bucket_scan_kernel(const BandCollect S) {
     running += S.bucket_count[kr * 32 + bkt];
   }
   if (S.cap[kr]) *S.count[kr] = running < S.cap[kr] ? running : S.cap[kr];
+}
+
+// After the second band round: a retried pair that is still marked (the containment argument says there is none) becomes
+// a one-read task of the stream kernel.
+__global__ void band_retry_check_kernel(const VitConsts C, const DevBatch B, const BandCollect S) {
+  const uint32_t n = S.retry_info[2 * (kBandClasses - 1)] + S.retry_info[2 * (kBandClasses - 1) + 1];
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint2 pr = S.retry_pairs[i];
+    const uint32_t g = pr.x, r = pr.y;
+    const uint32_t l = B.hap_locus[g];
+    const uint32_t hb0 = B.locus_hap_begin[l];
+    const uint32_t H = B.locus_hap_begin[l + 1] - hb0;
+    const double v = B.out_ll[B.ll_off[l] + (unsigned long long)(r - B.locus_read_begin[l]) * H + (g - hb0)];
+    if (!band_marked(v)) continue;
+    const int32_t nrow = (int32_t)(B.hap_off[g + 1] - B.hap_off[g]) - 2 * C.cut;
+    const int kr = rows_per_lane_hd(nrow, S.kmax);
+    const uint32_t k = atomicAdd(S.count[kr], 1u);
+    if (k < S.cap[kr]) {
+      Task T;
+      T.hap = g;
+      T.read_begin = r;
+      T.read_end = r + 1;
+      S.tasks[kr][k] = T;
+    }
+    atomicAdd(S.n_retry_failed, 1ull);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -311,6 +368,13 @@ cudaError_t launch_band_collect(const VitConsts& C, const DevBatch& B, const Ban
   band_collect_kernel<<<grid, 128, 0, stream>>>(C, B, tasks, n_tasks_ptr, task_cap, S, 0);
   band_bucket_scan_kernel<<<1, 32, 0, stream>>>(S);
   band_collect_kernel<<<grid, 128, 0, stream>>>(C, B, tasks, n_tasks_ptr, task_cap, S, 1);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_band_retry_check(const VitConsts& C, const DevBatch& B, const BandCollect& S, int sm_count,
+                                    cudaStream_t stream) {
+  if (!S.retry_pairs) return cudaSuccess;
+  band_retry_check_kernel<<<sm_count * 2, 128, 0, stream>>>(C, B, S);
   return cudaGetLastError();
 }
 

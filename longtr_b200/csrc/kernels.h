@@ -39,6 +39,16 @@ struct BandCollect {        // where band_collect_kernel appends the uncertified
   uint32_t* bucket_count;   // [17*32] runs per (row class, floor(log2 cost)); zeroed before the collect
   uint32_t* bucket_base;    // [17*32] list position of each bucket (band_bucket_scan_kernel)
   uint32_t* bucket_fill;    // [17*32] zeroed before the collect
+  // second chance in a wider band (band_retry_class); retry_pairs == NULL: every uncertified pair goes to the stream kernel
+  uint2* retry_pairs;       // pair lists of the second band round, class after class
+  uint32_t retry_cap;
+  uint32_t* retry_count;    // [8] zeroed before the collect
+  uint32_t* retry_fill;     // [8] zeroed before the collect
+  uint32_t* retry_info;     // [16] {first pair, number of pairs} per band class (band_bucket_scan_kernel)
+  unsigned long long* n_retried;       // statistics: pairs given a second band round ...
+  unsigned long long* n_retry_failed;  // ... and not certified by it (expected: 0)
+  BandGap gap;
+  int retry_rho_pct;        // a retry must cost less than this share of the full matrix
 };
 int band_block_threads();
 int band_blocks_per_sm(int cls);  // cls: band class index (band_core.cuh)
@@ -49,6 +59,8 @@ cudaError_t launch_band_expand(const BandTask* tasks, const uint32_t* cum, uint3
 // n_tasks_ptr: device word holding the number of band tasks (<= task_cap)
 cudaError_t launch_band_collect(const VitConsts& C, const DevBatch& B, const BandTask* tasks, const uint32_t* n_tasks_ptr,
                                 uint32_t task_cap, const BandCollect& S, int sm_count, cudaStream_t stream);
+cudaError_t launch_band_retry_check(const VitConsts& C, const DevBatch& B, const BandCollect& S, int sm_count,
+                                    cudaStream_t stream);
 
 // The job plan on the device (plan_kernels.cu, plan_device.cuh): five small kernels in stream order.
 cudaError_t launch_device_plan(const PlanDev& P, int sm_count, cudaStream_t stream);
@@ -127,5 +139,49 @@ struct StutterDevBatch {
 };
 size_t stutter_block_smem_bytes(uint32_t max_flank, uint32_t max_block, uint32_t max_hap);
 cudaError_t launch_stutter(const StutConsts& C, const StutterDevBatch& B, cudaStream_t stream);
+
+// Thresholded unit-cost edit distances and greedy clustering (edit_kernel.cu, edit_core.cuh): one warp per pair.
+struct EditArgs {
+  const uint8_t* seq_bytes;
+  const uint32_t* seq_off;      // [n_seqs+1]
+  const uint32_t* pair_a;       // rows    (cent_seq of HaplotypeGenerator::needleman_wunsch)
+  const uint32_t* pair_b;       // columns (read_seq)
+  const int32_t* pair_T;        // threshold of each pair
+  uint32_t n_pairs;             // used when n_pairs_ptr == NULL
+  const uint32_t* n_pairs_ptr;  // device word holding the number of pairs
+  int32_t* out;                 // [n_pairs]
+  uint32_t* cursor;             // pair ticket of the persistent grid (zero before the launch)
+  int8_t* lines;                // Myers kernel: line_stride bytes per warp (only read when a string exceeds 1024 bases)
+  int32_t* dp_lines;            // exact kernel: line_stride words per warp
+  uint32_t line_stride;
+  uint32_t* flagged;            // pairs with ED == T, listed by the Myers kernel for the exact kernel (may be NULL)
+  uint32_t* n_flagged;
+};
+uint32_t edit_myers_warps(int sm_count);
+uint32_t edit_exact_warps(int sm_count);
+cudaError_t launch_edit_myers(const EditArgs& A, uint32_t pair_cap, int sm_count, cudaStream_t stream);
+cudaError_t launch_edit_exact(const EditArgs& A, uint32_t pair_cap, int sm_count, cudaStream_t stream);
+
+struct ClusterDev {
+  uint32_t n_sets, n_items;
+  const uint32_t* set_begin;   // [n_sets+1] items of each set
+  const int32_t* set_T;        // [n_sets]
+  const uint32_t* item_set;    // [n_items]
+  const uint32_t* item_seq;    // [n_items] sequence of each item
+  int32_t* best_score;         // [n_items]
+  int32_t* centroid_of;        // [n_items] centroid of the item, as an index into its set
+  uint32_t* cur_centroid;      // [n_sets] item that is the centroid of the current round
+  uint32_t* next_centroid;     // [n_sets]
+  int32_t* n_centroids;        // [n_sets]
+  uint8_t* state;              // [n_sets] 0 running, 1 finished, 2 more than 15 centroids (greedy_clustering returns false)
+  uint32_t* pair_item;         // [n_items] round pair list (pair_a / pair_b / pair_T / score live in EditArgs)
+  uint32_t* pair_a;
+  uint32_t* pair_b;
+  int32_t* pair_T;
+  const int32_t* score;
+  uint32_t* n_pairs;
+  uint32_t* cursor;
+};
+cudaError_t launch_cluster(const ClusterDev& C, const EditArgs& A, int sm_count, cudaStream_t stream);
 
 }  // namespace ltr

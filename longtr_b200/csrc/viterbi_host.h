@@ -100,6 +100,16 @@ struct PodArray {
 
 // band_w < 0: banding off; 0: automatic margin; > 0: that many diagonals.  The band certificate needs every transition
 // parameter <= 0 and the same parameter condition as the final-score certificate (the bail-out is certified from F as well).
+// Share of the announced error cost per base that the automatic margin budgets for (LTR_BAND_BUDGET overrides: tuning).
+inline double band_budget_factor() {
+  static const double f = [] {
+    const char* e = getenv("LTR_BAND_BUDGET");
+    const double v = e ? atof(e) : 0.6;
+    return (v > 0.0 && v < 10.0) ? v : 0.6;
+  }();
+  return f;
+}
+
 inline BandPolicy band_policy(const ltr_params& p, int band_w) {
   BandPolicy b;
   if (band_w < 0 || !fast_certificate_valid(p)) return b;
@@ -118,7 +128,7 @@ inline BandPolicy band_policy(const ltr_params& p, int band_w) {
   const double p_gap = 1.0 - std::exp((double)p.match_match);
   const double close = std::min(std::fabs((double)p.del_match), std::fabs((double)p.ins_match));
   b.budget0 = 23.0;
-  b.budget_per_row = 0.6 * p_gap * (b.gap.open + close + b.gap.ext + 9.0);
+  b.budget_per_row = band_budget_factor() * p_gap * (b.gap.open + close + b.gap.ext + 9.0);
   b.w_fixed = band_w > 0 ? band_w : 0;
   b.on = true;
   return b;

@@ -313,6 +313,37 @@ class Engine:
         _check(self.lib, self.ctx, rc, "ltr_process_reads_flat_batch")
         return lls, seeds
 
+    # -- HaplotypeGenerator::needleman_wunsch / greedy_clustering for many pairs / sets ------------------
+    def edit_distances(self, seq_bytes, seq_off, pair_a, pair_b, pair_T):
+        """ltr_edit_distances on packed sequences (abi.pack_seqs); returns (scores int32[n_pairs], stats)."""
+        pair_a = np.ascontiguousarray(pair_a, dtype=np.uint32)
+        pair_b = np.ascontiguousarray(pair_b, dtype=np.uint32)
+        pair_T = np.ascontiguousarray(pair_T, dtype=np.int32)
+        out = np.full(len(pair_a), -1, dtype=np.int32)
+        st = abi.JobStats()
+        rc = self.lib.ltr_edit_distances(self.ctx, abi.ptr(seq_bytes, abi._u8p), abi.ptr(seq_off, abi._u32p),
+                                         len(seq_off) - 1, abi.ptr(pair_a, abi._u32p), abi.ptr(pair_b, abi._u32p),
+                                         abi.ptr(pair_T, abi._i32p), len(pair_a), abi.ptr(out, abi._i32p), C.byref(st))
+        _check(self.lib, self.ctx, rc, "ltr_edit_distances")
+        return out, st
+
+    def cluster_greedy(self, seq_bytes, seq_off, set_begin, set_items, set_T):
+        """ltr_cluster_greedy; returns (centroid_of int32[n_items], n_centroids int32[n_sets], ok uint8[n_sets], stats)."""
+        set_begin = np.ascontiguousarray(set_begin, dtype=np.uint32)
+        set_items = np.ascontiguousarray(set_items, dtype=np.uint32)
+        set_T = np.ascontiguousarray(set_T, dtype=np.int32)
+        n_sets = len(set_begin) - 1
+        cent = np.full(max(1, len(set_items)), -2, dtype=np.int32)
+        ncent = np.full(max(1, n_sets), -2, dtype=np.int32)
+        ok = np.full(max(1, n_sets), 255, dtype=np.uint8)
+        st = abi.JobStats()
+        rc = self.lib.ltr_cluster_greedy(self.ctx, abi.ptr(seq_bytes, abi._u8p), abi.ptr(seq_off, abi._u32p),
+                                         len(seq_off) - 1, abi.ptr(set_begin, abi._u32p), abi.ptr(set_items, abi._u32p),
+                                         abi.ptr(set_T, abi._i32p), n_sets, abi.ptr(cent, abi._i32p),
+                                         abi.ptr(ncent, abi._i32p), abi.ptr(ok, abi._u8p), C.byref(st))
+        _check(self.lib, self.ctx, rc, "ltr_cluster_greedy")
+        return cent[:len(set_items)], ncent[:n_sets], ok[:n_sets], st
+
     def fp64_issue_rate(self, kind=0):
         rate, ms = C.c_double(0.0), C.c_double(0.0)
         rc = self.lib.ltr_fp64_issue_rate(self.device, kind, C.byref(rate), C.byref(ms))

@@ -253,3 +253,40 @@ def generate_stutter(n_loci, first_locus=0, base_seed=None, n_threads=None):
     if rc != 0:
         raise RuntimeError("ltr_synth_stutter_generate failed: %d" % rc)
     return StutterWorkload(lib, h, first_locus)
+
+
+# ---- N2: sets of distinct allele-like strings for the clustering kernels (numpy, seeded) --------------------------------
+def generate_cluster_sets(n_sets, seed=20260106, seqs_per_set=40, lo=500, hi=1000):
+    """The skipped sequences of n_sets (locus, sample) pairs, config-4-like: 2-4 repeat alleles of lo..hi bases that differ
+    by whole motifs, each seen as distinct noisy copies (ONT-like 1 % substitutions, 1.5 % indels), ordered like the
+    reference orders them before greedy_clustering (first string of the std::map in front, the rest by length and
+    sequence: HaplotypeGenerator.cpp:399-401).  Returns (seq_bytes, seq_off, set_begin) with one copy of every string."""
+    rng = np.random.default_rng(seed)
+    code = np.frombuffer(b"ACGT", dtype=np.uint8)
+    chunks, set_begin = [], [0]
+    n_total = 0
+    for _ in range(n_sets):
+        motif = code[rng.integers(0, 4, size=int(rng.integers(10, 61)))]
+        copies = int(rng.integers(lo, hi + 1)) // len(motif)
+        strings = set()
+        n_alleles = int(rng.integers(2, 5))
+        for a in range(n_alleles):
+            allele = np.tile(motif, max(2, copies + int(rng.integers(-4, 5))))
+            for _ in range(max(2, seqs_per_set // n_alleles)):
+                s = allele.copy()
+                sub = rng.random(len(s)) < 0.01
+                s[sub] = code[rng.integers(0, 4, size=int(sub.sum()))]
+                keep = rng.random(len(s)) >= 0.0075
+                s = s[keep]
+                ins = np.flatnonzero(rng.random(len(s)) < 0.0075)
+                s = np.insert(s, ins, code[rng.integers(0, 4, size=len(ins))])
+                strings.add(s.tobytes())
+        strings = sorted(strings)
+        ordered = [strings[0]] + sorted(strings[1:], key=lambda x: (len(x), x))
+        chunks += ordered
+        n_total += len(ordered)
+        set_begin.append(n_total)
+    seq_off = np.zeros(n_total + 1, dtype=np.uint32)
+    seq_off[1:] = np.cumsum([len(c) for c in chunks], dtype=np.uint64)
+    seq_bytes = np.frombuffer(b"".join(chunks) + b"\0", dtype=np.uint8).copy()
+    return seq_bytes, seq_off, np.array(set_begin, dtype=np.uint32)

@@ -32,7 +32,15 @@ done
 $CXX -O2 -g -std=c++11 -fPIC -w -I"$here/shim" -I"$ref/src" -I"$here/../include" \
      -c "$here/ref_driver.cpp" -o "$out/obj/ref_driver.o"
 $CXX -O2 -std=c++11 -fPIC -w -I"$here/shim" -c "$here/shim/hts_stubs.cpp" -o "$out/obj/hts_stubs.o"
-$CXX -shared -o "$out/libltr_ref.so" "$out/obj/ref_driver.o" "$out/obj/hts_stubs.o" $objs -Wl,--no-undefined -lm -lpthread
+# candidate-haplotype clustering (N2): the reference's HaplotypeGenerator behind oracle/edit_driver.cpp
+o="$out/obj/HaplotypeGenerator.o"
+if [ ! -f "$o" ] || [ "$ref/src/SeqAlignment/HaplotypeGenerator.cpp" -nt "$o" ]; then
+  $CXX $FLAGS -I"$here/shim" -c "$ref/src/SeqAlignment/HaplotypeGenerator.cpp" -o "$o"
+fi
+$CXX -O2 -g -std=c++11 -fPIC -w -fno-access-control -I"$here/shim" -I"$ref/src" \
+     -c "$here/edit_driver.cpp" -o "$out/obj/edit_driver.o"
+$CXX -shared -o "$out/libltr_ref.so" "$out/obj/ref_driver.o" "$out/obj/edit_driver.o" "$out/obj/HaplotypeGenerator.o" \
+     "$out/obj/hts_stubs.o" $objs -Wl,--no-undefined -lm -lpthread
 echo "built $out/libltr_ref.so"
 
 # ---- IO-less per-locus genotyper (SeqStutterGenotyper ctor -> genotype -> write_vcf_record), twice ------------

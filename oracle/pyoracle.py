@@ -29,7 +29,7 @@ def build(force=False):
     """Compile the restatement (and oracle/_ref when /root/reference exists)."""
     if force or not os.path.exists(_ORACLE_SO) or \
             os.path.getmtime(_ORACLE_SO) < max(os.path.getmtime(os.path.join(_HERE, f)) for f in
-                                              ("longtr_oracle.c", "longtr_oracle_short.c", "longtr_oracle.h")):
+                                              ("longtr_oracle.c", "longtr_oracle_short.c", "longtr_oracle_edit.c", "longtr_oracle.h")):
         subprocess.check_call(["make", "-C", _HERE, "liblongtr_oracle.so"], stdout=subprocess.DEVNULL)
     if os.path.isdir(os.environ.get("LONGTR_REFERENCE", "/root/reference") + "/src"):
         if force or not os.path.exists(_REF_SO):
@@ -69,6 +69,10 @@ def oracle_lib():
         lib.ltr_oracle_log_sample_posteriors.argtypes = [C.c_int, C.c_int32, C.c_int32, C.c_int32, _dp,
                                                          _dp, _dp, _ip, _dp, _dp]
         lib.ltr_oracle_optimal_haplotypes.argtypes = [C.c_int32, C.c_int32, _dp, _ip]
+        lib.ltr_oracle_edit_score.restype = C.c_int32
+        lib.ltr_oracle_edit_score.argtypes = [C.c_char_p, C.c_int32, C.c_char_p, C.c_int32, C.c_int32]
+        lib.ltr_oracle_greedy_cluster.restype = C.c_int32
+        lib.ltr_oracle_greedy_cluster.argtypes = [_u8p, _u32p, _u32p, C.c_int32, C.c_int32, _ip, _ip]
         _oracle = lib
     return _oracle
 
@@ -97,6 +101,10 @@ def ref_lib():
         lib.ltr_ref_genotype_locus.argtypes = [C.c_int, C.c_int, _ip, C.c_int, _dp, _dp, _dp, _dp, C.POINTER(LocusCalls)]
         lib.ltr_ref_seed_bases.restype = C.c_int
         lib.ltr_ref_seed_bases.argtypes = [C.POINTER(FlatLocus), _ip]
+        lib.ltr_ref_edit_score.restype = C.c_int32
+        lib.ltr_ref_edit_score.argtypes = [C.c_char_p, C.c_int32, C.c_char_p, C.c_int32, C.c_int32]
+        lib.ltr_ref_greedy_cluster.restype = C.c_int32
+        lib.ltr_ref_greedy_cluster.argtypes = [_u8p, _u32p, _u32p, C.c_int32, C.c_int32, _ip, _ip]
         _ref = lib
     return _ref
 
@@ -344,3 +352,23 @@ def full_locus_records(cases, which="full"):
         pos = nl + 1 + n + 1
     assert len(recs) == len(cases)
     return recs
+
+
+# ---- candidate-haplotype clustering (HaplotypeGenerator::needleman_wunsch / greedy_clustering) ------------------------
+def edit_score(cent, read, T, which="oracle"):
+    """Score HaplotypeGenerator::needleman_wunsch(cent, read, score, T) leaves behind."""
+    a = cent.encode() if isinstance(cent, str) else bytes(cent)
+    b = read.encode() if isinstance(read, str) else bytes(read)
+    if which == "ref":
+        return int(ref_lib().ltr_ref_edit_score(a, len(a), b, len(b), T))
+    return int(oracle_lib().ltr_oracle_edit_score(a, len(a), b, len(b), T))
+
+
+def greedy_cluster(seq_bytes, seq_off, items, T, which="oracle"):
+    """greedy_clustering over the sequences items[] -> (ok, centroid_of[len(items)], n_centroids)."""
+    items = np.ascontiguousarray(items, dtype=np.uint32)
+    cent = np.full(max(1, len(items)), -1, dtype=np.int32)
+    n = C.c_int32(0)
+    fn = ref_lib().ltr_ref_greedy_cluster if which == "ref" else oracle_lib().ltr_oracle_greedy_cluster
+    ok = fn(_ptr(seq_bytes, _u8p), _ptr(seq_off, _u32p), _ptr(items, _u32p), len(items), T, _ptr(cent, _ip), C.byref(n))
+    return int(ok), cent[:len(items)], n.value

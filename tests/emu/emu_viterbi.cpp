@@ -240,7 +240,7 @@ static void emu_band_round(const VitConsts& C, const DevBatch& B, const uint32_t
         const double rec[6] = {(double)R[g][t].n, (double)R[g][t].m, (double)W, (double)geo[g].w, F[g][t], ok ? 1.0 : 0.0};
         g_band_dump->insert(g_band_dump->end(), rec, rec + 6);
       }
-      *out[g] = ok ? F[g][t] : kBandUncertified;
+      *out[g] = ok ? F[g][t] : band_mark(F[g][t]);
       if (!ok) ++*n_uncert;
     }
     if (owners != 1) { std::fprintf(stderr, "emu band: %d owners\n", owners); std::abort(); }
@@ -271,6 +271,12 @@ static void emu_band_dispatch(int cls, const VitConsts& C, const DevBatch& B, co
 
 extern "C" int ltr_emu_viterbi_batch_band(const ltr_viterbi_batch* b, const ltr_params* p, int kmax, int use_fast,
                                           int band_w, double* out_ll, uint64_t* n_fallback, uint64_t* band_stats);
+static uint64_t g_band_retried = 0;  // pairs that went through the second band round since the last reset
+extern "C" uint64_t ltr_emu_band_retried(int reset) {
+  const uint64_t v = g_band_retried;
+  if (reset) g_band_retried = 0;
+  return v;
+}
 
 extern "C" int ltr_emu_viterbi_batch(const ltr_viterbi_batch* b, const ltr_params* p, int kmax,
                                      int use_fast, double* out_ll, uint64_t* n_fallback) {
@@ -306,6 +312,8 @@ extern "C" int ltr_emu_viterbi_batch_band(const ltr_viterbi_batch* b, const ltr_
   std::memcpy(hbytes.data() + kPad, b->hap_bytes, hbytes.size() - 2 * kPad);
   B.hap_bytes = hbytes.data() + kPad;
   uint64_t bstats[3] = {plan.n_band_pairs, 0, 0};
+  static const int retry_rho = [] { const char* e = getenv("LTR_BAND_RETRY_RHO"); return e ? atoi(e) : 80; }();  // as abi.cu
+  std::vector<std::array<uint32_t, 2>> retry[kBandClasses];
   for (int c = 0; c < kBandClasses; ++c) {
     std::vector<std::array<uint32_t, 2>> pairs;
     for (const BandTask& bt : plan.band_tasks[(size_t)c])
@@ -323,7 +331,20 @@ extern "C" int ltr_emu_viterbi_batch_band(const ltr_viterbi_batch* b, const ltr_
       bool in_run = false;
       uint32_t run_begin = 0;
       for (uint32_t r = bt.read_begin; r <= bt.read_end; ++r) {
-        const bool bad = r < bt.read_end && col[(size_t)(r - rb0) * H] == kBandUncertified;
+        bool bad = false;
+        if (r < bt.read_end) {
+          const double v = col[(size_t)(r - rb0) * H];
+          bad = band_marked(v);
+          if (bad && retry_rho > 0) {
+            const int rc = band_retry_class(hc.C, plan.band.gap, n, (int32_t)(plan.uread_off[r + 1] - plan.uread_off[r]),
+                                            band_unmark(v), retry_rho);
+            if (rc >= 0) {
+              if (rc <= c) { std::fprintf(stderr, "emu band: retry class %d not wider than %d\n", rc, c); std::abort(); }
+              bad = false;
+              retry[rc].push_back({bt.hap, r});
+            }
+          }
+        }
         if (bad && !in_run) { in_run = true; run_begin = r; }
         if (!bad && in_run) {
           in_run = false;
@@ -333,6 +354,15 @@ extern "C" int ltr_emu_viterbi_batch_band(const ltr_viterbi_batch* b, const ltr_
         }
       }
     }
+  }
+  // second band round + band_retry_check_kernel: every retried pair must come back certified
+  for (int c = 1; c < kBandClasses; ++c) {
+    const uint32_t np = (uint32_t)retry[c].size();
+    uint64_t still = 0;
+    for (uint32_t base = 0; base < np; base += 32u / (uint32_t)band_class_g(c))
+      emu_band_dispatch(c, hc.C, B, reinterpret_cast<const uint32_t(*)[2]>(retry[c].data()), np, base, plan.band.gap, &still);
+    if (still) { std::fprintf(stderr, "emu band: %llu retried pairs not certified\n", (unsigned long long)still); std::abort(); }
+    g_band_retried += np;
   }
   if (band_stats) std::memcpy(band_stats, bstats, sizeof(bstats));
   const bool sym = (hc.C.d2m == hc.C.i2m) && (hc.C.m2i == hc.C.m2d);  // as launch_viterbi

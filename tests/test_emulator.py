@@ -376,3 +376,21 @@ def test_device_plan_flags_malformed_read_offsets(emu):
     b2 = dict(b, read_off=off)
     rc, _ = _device_plan_check(emu, b2, None, 16, 0)
     assert rc == -1  # both plans reject it
+
+
+def test_band_second_round_certifies(emu):
+    """Second band round (band_retry_class): an uncertified pair whose banded score F_band lies above the threshold of a
+    wider class is re-run there and MUST come back certified (the emulator aborts otherwise); results stay the oracle's.
+    Narrow margins on long noisy pairs make sure the round is exercised."""
+    emu.ltr_emu_band_retried.restype = C.c_uint64
+    emu.ltr_emu_band_retried.argtypes = [C.c_int]
+    emu.ltr_emu_band_retried(1)
+    cases = [(ONT, synth.make_pair_batch(61, n_loci=3, n_lo=500, n_hi=900, reads_hi=3, haps_hi=3, sub=0.02, indel=0.03)),
+             (ONT, synth.make_pair_batch(62, n_loci=4, n_lo=200, n_hi=500, reads_hi=4, haps_hi=3, sub=0.01, indel=0.015)),
+             (None, synth.make_pair_batch(63, n_loci=6, n_lo=100, n_hi=300, reads_hi=5, haps_hi=4, sub=0.01, indel=0.02))]
+    for params, b in cases:
+        want, _ = po.viterbi_batch(b, aln_params=params, n_threads=4)
+        for band_w in (1, 3, 12, 30):
+            out, stats = run_band(emu, b, params, 16, band_w)
+            assert np.array_equal(out, want)
+    assert emu.ltr_emu_band_retried(0) > 20
