@@ -49,7 +49,10 @@ typedef struct ltr_job ltr_job;
 typedef struct ltr_params {
   float ins_ins, ins_match, del_del, del_match, match_match, match_ins, match_del;
   int32_t indel_flank_len; /* INDEL_FLANK_LEN; haplotypes are cut by 35-indel_flank_len
-                              on each side (HapAligner.cpp:245-246)                  */
+                              on each side (HapAligner.cpp:245-246).  5 .. 35; values below
+                              5 (where the reference's substr length underflows for
+                              haplotypes of 61 .. 2*(35-flank) bases) are answered with
+                              LTR_ERR_UNSUPPORTED                                     */
 } ltr_params;
 
 /* Fills the Dindel defaults of HapAligner.h:118 and indel_flank_len = 5. */

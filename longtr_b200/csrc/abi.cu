@@ -43,17 +43,19 @@ struct ClassState {
 // What comes back from the device with every run (pinned host memory, one block per job).
 struct JobResult {
   uint32_t cls_ctrl[(kPlanMaxK + 1) * 4];  // per row class: fast cursor, tasks, fail count, full cursor
-  unsigned long long band_words[11];       // band_ctrl: cursors, counters, statistics
+  unsigned long long band_words[13];       // band_ctrl: cursors, counters, statistics
   uint32_t plan_ctl[PLAN_CTL_BAND_TASK_COUNT];
   unsigned long long plan_stat[PLAN_STAT_WORDS];
 };
 
-// u32[12], u64 uncertified pairs, u64 n*m cells of those re-run over the full matrix, u64 band cells evaluated, u64 pairs given
-// a second band round, u64 of which still uncertified
-static const size_t kBandCtrlBytes = 88;
+// u32[16] (round cursor per band class, [12] pairs evaluated, [13] of which uncertified, [14] [15] scratch), then from
+// byte 64: u64 uncertified pairs, u64 n*m cells of those re-run over the full matrix, u64 band cells evaluated, u64 pairs
+// given a second band round, u64 of which still uncertified
+static_assert(kBandClasses <= 12, "band_ctrl layout");
+static const size_t kBandStatOff = 64, kBandCtrlBytes = kBandStatOff + 5 * 8;
 static const size_t kBandBucketOff = 128, kBandBucketWords = 17 * 32;  // then count / base / fill of band_collect_kernel
-// second band round: retry_count[8], retry_fill[8], retry_info[16], cursors[8]
-static const size_t kBandRetryOff = kBandBucketOff + 3 * kBandBucketWords * sizeof(uint32_t), kBandRetryWords = 40;
+// second band round: retry_count[16], retry_fill[16], retry_info[32], cursors[16]
+static const size_t kBandRetryOff = kBandBucketOff + 3 * kBandBucketWords * sizeof(uint32_t), kBandRetryWords = 80;
 static const size_t kBandCtrlAlloc = kBandRetryOff + kBandRetryWords * sizeof(uint32_t);
 
 // Second band round (band_retry_class): a retry must cost less than this percentage of the full matrix; 0 switches the
@@ -504,7 +506,7 @@ int setup_host_plan(ltr_ctx* ctx, ltr_job* job, const ltr_viterbi_batch& bb, cud
   if (plan.n_band_pairs) {
     std::vector<BandTask> all;
     std::vector<uint32_t> cum;
-    uint32_t meta[17];
+    uint32_t meta[2 * kBandClasses + 1];
     std::memset(meta, 0, sizeof(meta));
     uint64_t npairs = 0;
     for (int c = 0; c < kBandClasses; ++c) {
@@ -527,11 +529,11 @@ int setup_host_plan(ltr_ctx* ctx, ltr_job* job, const ltr_viterbi_batch& bb, cud
                                    (uint32_t)(ctx->sm_count * ctx->band_blocks_per_sm[c]));
       job->band_launches.push_back(bl);
     }
-    meta[16] = (uint32_t)all.size();
+    meta[2 * kBandClasses] = (uint32_t)all.size();
     job->band_cap = (uint32_t)all.size();
     LTR_TRY(upload(ctx, st, job->band_tasks, all.data(), all.size(), 0, h2d));
     LTR_TRY(upload(ctx, st, job->band_cum, cum.data(), cum.size(), 0, h2d));
-    LTR_TRY(upload(ctx, st, job->band_meta, meta, 17, 0, h2d));
+    LTR_TRY(upload(ctx, st, job->band_meta, meta, 2 * kBandClasses + 1, 0, h2d));
     LTR_CUDA(ctx, job->band_pairs.alloc((size_t)npairs * sizeof(uint2)));
     LTR_CUDA(ctx, job->band_ctrl.alloc(kBandCtrlAlloc));
     if (band_retry_rho() > 0) {
@@ -539,7 +541,7 @@ int setup_host_plan(ltr_ctx* ctx, ltr_job* job, const ltr_viterbi_batch& bb, cud
       LTR_CUDA(ctx, job->band_retry.alloc((size_t)npairs * sizeof(uint2)));
     }
     job->band_info_dev = job->band_meta.as<uint32_t>();
-    job->n_band_tasks_dev = job->band_meta.as<uint32_t>() + 16;
+    job->n_band_tasks_dev = job->band_meta.as<uint32_t>() + 2 * kBandClasses;
   }
   return LTR_OK;
 }
@@ -804,8 +806,8 @@ int run_band_phase(ltr_ctx* ctx, ltr_job* job, JobLane& L) {
     A.pairs = job->band_pairs.as<uint2>();
     A.info = job->band_info_dev + 2 * bl.cls;
     A.cursor = bctrl + bl.cls;
-    A.counters = bctrl + 8;
-    A.cells_evaluated = reinterpret_cast<unsigned long long*>(job->band_ctrl.as<char>() + 64);
+    A.counters = bctrl + 12;
+    A.cells_evaluated = reinterpret_cast<unsigned long long*>(job->band_ctrl.as<char>() + kBandStatOff + 16);
     A.gap = job->band.gap;
     A.abandon_after = no_abandon ? 0u : 4096u;
     LTR_CUDA(ctx, launch_band(bl.cls, (int)bl.grid, st, job->hc.C, B, A));
@@ -816,7 +818,7 @@ int run_band_phase(ltr_ctx* ctx, ltr_job* job, JobLane& L) {
   BandCollect S;
   for (int k = 0; k < 17; ++k) {
     S.tasks[k] = nullptr;
-    S.count[k] = bctrl + 10;  // never read: capacity 0
+    S.count[k] = bctrl + 15;  // never read: capacity 0
     S.cap[k] = 0;
   }
   for (ClassState& cs : job->classes) {
@@ -825,8 +827,8 @@ int run_band_phase(ltr_ctx* ctx, ltr_job* job, JobLane& L) {
     S.cap[cs.k] = cs.task_cap;
   }
   S.kmax = viterbi_max_rows_per_lane();
-  S.n_uncertified = reinterpret_cast<unsigned long long*>(job->band_ctrl.as<char>() + 48);
-  S.cells_uncertified = reinterpret_cast<unsigned long long*>(job->band_ctrl.as<char>() + 56);
+  S.n_uncertified = reinterpret_cast<unsigned long long*>(job->band_ctrl.as<char>() + kBandStatOff);
+  S.cells_uncertified = reinterpret_cast<unsigned long long*>(job->band_ctrl.as<char>() + kBandStatOff + 8);
   S.bucket_count = reinterpret_cast<uint32_t*>(job->band_ctrl.as<char>() + kBandBucketOff);
   S.bucket_base = S.bucket_count + kBandBucketWords;
   S.bucket_fill = S.bucket_base + kBandBucketWords;
@@ -834,10 +836,10 @@ int run_band_phase(ltr_ctx* ctx, ltr_job* job, JobLane& L) {
   S.retry_pairs = job->band_retry_cap ? job->band_retry.as<uint2>() : nullptr;
   S.retry_cap = job->band_retry_cap;
   S.retry_count = rctrl;
-  S.retry_fill = rctrl + 8;
-  S.retry_info = rctrl + 16;
-  S.n_retried = reinterpret_cast<unsigned long long*>(job->band_ctrl.as<char>() + 72);
-  S.n_retry_failed = reinterpret_cast<unsigned long long*>(job->band_ctrl.as<char>() + 80);
+  S.retry_fill = rctrl + 16;
+  S.retry_info = rctrl + 32;
+  S.n_retried = reinterpret_cast<unsigned long long*>(job->band_ctrl.as<char>() + kBandStatOff + 24);
+  S.n_retry_failed = reinterpret_cast<unsigned long long*>(job->band_ctrl.as<char>() + kBandStatOff + 32);
   S.gap = job->band.gap;
   S.retry_rho_pct = band_retry_rho();
   LTR_CUDA(ctx, launch_band_collect(job->hc.C, B, job->band_tasks.as<BandTask>(), job->n_band_tasks_dev, job->band_cap, S,
@@ -855,9 +857,9 @@ int run_band_phase(ltr_ctx* ctx, ltr_job* job, JobLane& L) {
       BandArgs A;
       A.pairs = job->band_retry.as<uint2>();
       A.info = S.retry_info + 2 * bl.cls;
-      A.cursor = rctrl + 32 + bl.cls;
-      A.counters = bctrl + 10;  // scratch words: the statistics of the first round stay as they are
-      A.cells_evaluated = reinterpret_cast<unsigned long long*>(job->band_ctrl.as<char>() + 64);
+      A.cursor = rctrl + 64 + bl.cls;
+      A.counters = bctrl + 14;  // scratch words: the statistics of the first round stay as they are
+      A.cells_evaluated = reinterpret_cast<unsigned long long*>(job->band_ctrl.as<char>() + kBandStatOff + 16);
       A.gap = job->band.gap;
       A.abandon_after = 0u;
       const uint32_t full_grid = (uint32_t)(ctx->sm_count * ctx->band_blocks_per_sm[bl.cls]);
@@ -994,11 +996,11 @@ int job_collect(ltr_ctx* ctx, ltr_job* job) {
     job->plan_cells_computed = R.plan_stat[PLAN_STAT_CELLS_STREAM];
     job->stats.n_band_pairs = R.plan_ctl[PLAN_CTL_N_BAND_PAIRS];
   }
-  job->stats.n_band_uncertified = band ? R.band_words[6] : 0;
-  job->stats.n_band_retried = band ? R.band_words[9] : 0;
-  if (band && R.band_words[10] != 0) ctx->last_error = "band retry: a pair was not certified by its second round (re-run over the full matrix)";
+  job->stats.n_band_uncertified = band ? R.band_words[8] : 0;
+  job->stats.n_band_retried = band ? R.band_words[11] : 0;
+  if (band && R.band_words[12] != 0) ctx->last_error = "band retry: a pair was not certified by its second round (re-run over the full matrix)";
   // cells evaluated: full matrices of the stream-kernel pairs (planned + uncertified) + the bands actually evaluated
-  job->stats.n_cells_computed = job->plan_cells_computed + (band ? R.band_words[7] + R.band_words[8] : 0);
+  job->stats.n_cells_computed = job->plan_cells_computed + (band ? R.band_words[9] + R.band_words[10] : 0);
   job->stats.n_fallback = 0;
   for (const ClassState& cs : job->classes)
     if (!cs.force_full) job->stats.n_fallback += R.cls_ctrl[4 * cs.k + 2];
@@ -1019,6 +1021,9 @@ int job_new(ltr_ctx* ctx, const ltr_params* params, const ltr_viterbi_batch* b, 
   if (b->n_loci && (!b->locus_hap_begin || !b->locus_read_begin || !b->hap_off || !b->read_off))
     return LTR_ERR_INVALID;
   if (params->indel_flank_len < 0 || params->indel_flank_len > 35) return LTR_ERR_INVALID;
+  // below 5 the reference's substr(cut, size - 2 cut) underflows for haplotypes of 61 .. 2 (35 - flank) bases
+  // (HapAligner.cpp:245-246) and aligns against hap.substr(cut): not reproduced
+  if (params->indel_flank_len < 5) return LTR_ERR_UNSUPPORTED;
   LTR_CUDA(ctx, cudaSetDevice(ctx->device));
   ltr_job* job = new ltr_job();
   std::memset(&job->stats, 0, sizeof(job->stats));

@@ -44,10 +44,13 @@ LTR_HD double band_unmark(double v) { return kBandUncertified - v; }
 
 // Band classes: G lanes per pair, K cells per lane per step, W = 2 K G diagonals.  The narrowest class spreads its 32
 // diagonals over 4 lanes (8 pairs per warp) so that the loop overhead of a double step is shared by 8 cells.
-// The three widest classes give a whole warp to one pair (noisy reads, long repeats: W = 256, 384, 512).
-static constexpr int kBandClasses = 8;
-LTR_HHD int band_class_k(int c) { return c == 0 ? 4 : c == 1 ? 3 : c == 2 ? 4 : c == 3 ? 6 : c == 4 ? 8 : c == 5 ? 4 : c == 6 ? 6 : 8; }
-LTR_HHD int band_class_g(int c) { return c == 0 ? 4 : (c <= 4 ? 8 : 32); }
+// The widest classes give half a warp (W = 192) or a whole warp (W = 256 .. 512 in steps of 64) to one pair (noisy
+// reads, long repeats): a pair pays for the band of its class, so the steps between classes are what it wastes.
+static constexpr int kBandClasses = 11;
+LTR_HHD int band_class_k(int c) {
+  return c == 0 ? 4 : c == 1 ? 3 : c == 2 ? 4 : c == 3 ? 6 : c == 4 ? 8 : c == 5 ? 6 : c == 6 ? 4 : c == 7 ? 5 : c == 8 ? 6 : c == 9 ? 7 : 8;
+}
+LTR_HHD int band_class_g(int c) { return c == 0 ? 4 : (c <= 4 ? 8 : (c == 5 ? 16 : 32)); }
 LTR_HHD int band_class_w(int c) { return 2 * band_class_k(c) * band_class_g(c); }
 
 struct BandGeom {

@@ -321,9 +321,12 @@ static BandKernel band_kernel_for(int cls, bool sym) {  // cls: band class index
     case 2: return sym ? viterbi_band_kernel<4, 8, true> : viterbi_band_kernel<4, 8, false>;
     case 3: return sym ? viterbi_band_kernel<6, 8, true> : viterbi_band_kernel<6, 8, false>;
     case 4: return sym ? viterbi_band_kernel<8, 8, true> : viterbi_band_kernel<8, 8, false>;
-    case 5: return sym ? viterbi_band_kernel<4, 32, true> : viterbi_band_kernel<4, 32, false>;
-    case 6: return sym ? viterbi_band_kernel<6, 32, true> : viterbi_band_kernel<6, 32, false>;
-    case 7: return sym ? viterbi_band_kernel<8, 32, true> : viterbi_band_kernel<8, 32, false>;
+    case 5: return sym ? viterbi_band_kernel<6, 16, true> : viterbi_band_kernel<6, 16, false>;
+    case 6: return sym ? viterbi_band_kernel<4, 32, true> : viterbi_band_kernel<4, 32, false>;
+    case 7: return sym ? viterbi_band_kernel<5, 32, true> : viterbi_band_kernel<5, 32, false>;
+    case 8: return sym ? viterbi_band_kernel<6, 32, true> : viterbi_band_kernel<6, 32, false>;
+    case 9: return sym ? viterbi_band_kernel<7, 32, true> : viterbi_band_kernel<7, 32, false>;
+    case 10: return sym ? viterbi_band_kernel<8, 32, true> : viterbi_band_kernel<8, 32, false>;
     default: return nullptr;
   }
 }

@@ -39,6 +39,7 @@ int build_flat_locus(ltr_ctx* ctx, const ltr_flat_locus* L, const int32_t* in_se
   if (!L || !L->lflank || !L->rflank || !L->alleles || L->n_alleles < 1 || L->n_reads < 0 || !L->motif) return LTR_ERR_INVALID;
   if (L->n_reads > 0 && !L->reads) return LTR_ERR_INVALID;
   if (L->period < 1 || L->indel_flank_len < 0 || L->indel_flank_len > 35) return LTR_ERR_INVALID;
+  if (L->indel_flank_len < 5) return LTR_ERR_UNSUPPORTED;  // see job_new (abi.cu)
   if (L->n_aln_params != 0 && L->n_aln_params != 7) return LTR_ERR_INVALID;
   o.model.reset(new StutterModel(L->stutter[0], L->stutter[1], L->stutter[2], L->stutter[3], L->stutter[4], L->stutter[5],
                                  std::string(L->motif)));

@@ -594,6 +594,7 @@ int ltr_genotyper_run(ltr_genotyper* g, const ltr_params* params, const ltr_locu
                  !B.locus_read_begin || !B.read_off || !B.cigar_off || !B.locus_n_samples))
     return LTR_ERR_INVALID;
   if (params->indel_flank_len < 0 || params->indel_flank_len > 35) return LTR_ERR_INVALID;
+  if (params->indel_flank_len < 5) return LTR_ERR_UNSUPPORTED;  // see job_new (abi.cu)
   const auto t_begin = Clock::now();
   static const uint32_t kZero[1] = {0};
   const uint32_t* lab = n_loci ? B.locus_allele_begin : kZero;

@@ -131,8 +131,9 @@ void worker_main(ltr_pipeline* p) {
         seeds[i] = batch[i]->seeds.data();
       }
       rc = ltr_process_reads_flat_batch(ctx, (int32_t)batch.size(), loci.data(), lls.data(), seeds.data());
-      if (rc != LTR_OK && batch.size() > 1) {
-        // one malformed locus must not fail its neighbours: fall back to one call per locus for this batch
+      if ((rc == LTR_ERR_INVALID || rc == LTR_ERR_UNSUPPORTED) && batch.size() > 1) {
+        // one malformed locus must not fail its neighbours: fall back to one call per locus for this batch (device
+        // errors -- LTR_ERR_CUDA, LTR_ERR_OOM -- go to every locus of the batch as they are: retrying would repeat them)
         for (size_t i = 0; i < batch.size(); ++i)
           batch[i]->status = ltr_process_reads_flat(ctx, &loci[i], lls[i], seeds[i]);
         rc = LTR_OK;
@@ -203,7 +204,9 @@ int ltr_pipeline_next(ltr_pipeline* p, int wait, uint64_t* tag, int32_t* n_reads
   if (!p) return LTR_ERR_INVALID;
   std::unique_lock<std::mutex> lk(p->mu);
   if (wait) {
-    if (p->done.empty() && p->pending > 0 && !p->filling.empty() && p->ready.empty()) queue_filling_locked(p);
+    // a partial batch is only pushed out when nothing else can produce a result (every pending locus sits in it):
+    // flushing while workers still hold batches would cut the GPU jobs short
+    if (p->done.empty() && !p->filling.empty() && p->pending == p->filling.size()) queue_filling_locked(p);
     p->cv_done.wait(lk, [&] { return !p->done.empty() || p->pending == 0; });
   }
   if (p->done.empty()) return 0;

@@ -33,9 +33,9 @@ enum {  // words of PlanDev::ctl
   PLAN_CTL_N_BAND_TASKS = 2,
   PLAN_CTL_N_BAND_PAIRS = 3,
   PLAN_CTL_BAND_INFO = 4,                                  // [kBandClasses][2]: first pair, number of pairs
-  PLAN_CTL_BAND_TASK_COUNT = PLAN_CTL_BAND_INFO + 16,      // [kBandClasses] tasks per band class
-  PLAN_CTL_BAND_TASK_BASE = PLAN_CTL_BAND_TASK_COUNT + 8,  // [kBandClasses] first task of the class
-  PLAN_CTL_ST_COUNT = PLAN_CTL_BAND_TASK_BASE + 8,         // [kPlanSlots] pass 0: stream tasks per (row class, bucket)
+  PLAN_CTL_BAND_TASK_COUNT = PLAN_CTL_BAND_INFO + 2 * kBandClasses,     // [kBandClasses] tasks per band class
+  PLAN_CTL_BAND_TASK_BASE = PLAN_CTL_BAND_TASK_COUNT + kBandClasses,    // [kBandClasses] first task of the class
+  PLAN_CTL_ST_COUNT = PLAN_CTL_BAND_TASK_BASE + kBandClasses,           // [kPlanSlots] pass 0: stream tasks per (row class, bucket)
   PLAN_CTL_ST_BASE = PLAN_CTL_ST_COUNT + kPlanSlots,
   PLAN_CTL_ST_FILL = PLAN_CTL_ST_BASE + kPlanSlots,
   PLAN_CTL_WORDS = PLAN_CTL_ST_FILL + kPlanSlots

@@ -104,8 +104,8 @@ struct PodArray {
 inline double band_budget_factor() {
   static const double f = [] {
     const char* e = getenv("LTR_BAND_BUDGET");
-    const double v = e ? atof(e) : 0.6;
-    return (v > 0.0 && v < 10.0) ? v : 0.6;
+    const double v = e ? atof(e) : 0.45;
+    return (v > 0.0 && v < 10.0) ? v : 0.45;
   }();
   return f;
 }

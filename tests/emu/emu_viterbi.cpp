@@ -261,9 +261,12 @@ static void emu_band_dispatch(int cls, const VitConsts& C, const DevBatch& B, co
     case 2: EMU_BAND(4, 8); break;
     case 3: EMU_BAND(6, 8); break;
     case 4: EMU_BAND(8, 8); break;
-    case 5: EMU_BAND(4, 32); break;
-    case 6: EMU_BAND(6, 32); break;
-    case 7: EMU_BAND(8, 32); break;
+    case 5: EMU_BAND(6, 16); break;
+    case 6: EMU_BAND(4, 32); break;
+    case 7: EMU_BAND(5, 32); break;
+    case 8: EMU_BAND(6, 32); break;
+    case 9: EMU_BAND(7, 32); break;
+    case 10: EMU_BAND(8, 32); break;
     default: std::abort();
   }
 #undef EMU_BAND
