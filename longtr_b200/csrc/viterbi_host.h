@@ -130,6 +130,12 @@ inline BandPolicy band_policy(const ltr_params& p, int band_w) {
   b.budget0 = 23.0;
   b.budget_per_row = band_budget_factor() * p_gap * (b.gap.open + close + b.gap.ext + 9.0);
   b.w_fixed = band_w > 0 ? band_w : 0;
+  static const int share = [] {  // LTR_BAND_MAX_SHARE: tuning
+    const char* e = getenv("LTR_BAND_MAX_SHARE");
+    const int v = e ? atoi(e) : 80;
+    return (v >= 10 && v <= 100) ? v : 80;
+  }();
+  b.max_share_pct = share;
   b.on = true;
   return b;
 }

@@ -267,7 +267,8 @@ def test_band_policy_margins(emu):
     assert emu.ltr_emu_band_margin(C.byref(dindel), 0, 200) == 7              # automatic, HiFi-like parameters
     assert emu.ltr_emu_band_margin(C.byref(dindel), 0, 600) in (7, 8)
     w300, w760 = emu.ltr_emu_band_margin(C.byref(ont), 0, 300), emu.ltr_emu_band_margin(C.byref(ont), 0, 760)
-    assert 30 <= w300 < w760 and 70 <= w760 <= 90                            # ONT-like: margin follows the expected errors
+    assert 25 <= w300 < w760 and 55 <= w760 <= 70                            # ONT-like: margin follows the expected errors
+    # (budget factor 0.45 since the second band round exists: a narrow first attempt costs little when it fails)
     bad = abi.make_params((-1.0, -0.4, -1.0, -0.4, 0.01, -10.0, -10.0))       # a positive parameter: no certificate
     assert emu.ltr_emu_band_margin(C.byref(bad), 0, 200) == -1
     odd = abi.make_params(ODD)                                                # |I2I| < |D2D| ... condition of section 4 fails?
