@@ -448,6 +448,98 @@ int ltr_cluster_greedy(ltr_ctx* ctx, const uint8_t* seq_bytes, const uint32_t* s
                        const uint32_t* set_begin, const uint32_t* set_items, const int32_t* set_T, uint32_t n_sets,
                        int32_t* out_centroid_of, int32_t* out_n_centroids, uint8_t* out_ok, ltr_job_stats* stats);
 
+/* ---- alignment input ------------------------------------------------------------------
+ * A from-scratch BGZF / BAM / BAI reader (zlib only) for what LongTR reads through htslib (src/bam_io.h:313-420
+ * BamCramReader; src/bam_io.cpp:94-214 sam_open / sam_hdr_read / sam_index_load / sam_itr_querys / sam_itr_next).
+ * ltr_bam_open     maps the file, parses header and reference dictionary and loads index_path (NULL: "<path>.bai" when it
+ *                  exists; without an index region queries scan the file).
+ * ltr_bam_fetch    the records that overlap [beg, end) (0-based, half open) of reference tid, in file order, as a structure
+ *                  of arrays owned by the library; tid < 0: every record.  keep_raw != 0 also keeps each record's BAM bytes
+ *                  (what follows block_size: the layout of htslib's bam1_t core + data).  Thread safe on one ltr_bam.  */
+typedef struct ltr_bam ltr_bam;
+typedef struct ltr_bam_reads {
+  uint32_t n;
+  const int32_t* tid;         /* [n] reference id, -1 unplaced                                         */
+  const int32_t* pos;         /* [n] 0-based leftmost reference position                               */
+  const int32_t* end;         /* [n] one past the last reference base (htslib bam_endpos)              */
+  const uint16_t* flag;       /* [n]                                                                   */
+  const uint8_t* mapq;        /* [n]                                                                   */
+  const int32_t* mate_tid;    /* [n]                                                                   */
+  const int32_t* mate_pos;    /* [n]                                                                   */
+  const uint32_t* name_off;   /* [n+1] names: NUL-terminated, back to back                             */
+  const char* names;
+  const uint32_t* seq_off;    /* [n+1] bases (ASCII, "=ACMGRSVTWYHKDBN") and qualities (Phred+33)      */
+  const uint8_t* seq;
+  const uint8_t* qual;
+  const uint32_t* cigar_off;  /* [n+1] BAM-encoded operations (length << 4 | op, op in MIDNSHP=X)      */
+  const uint32_t* cigar_ops;
+  const int32_t* hp;          /* [n] integer value of the HP tag, 0 when absent                        */
+  const uint32_t* raw_off;    /* [n+1] raw record bytes (empty unless keep_raw)                        */
+  const uint8_t* raw;
+  void* owner;
+} ltr_bam_reads;
+int ltr_bam_open(const char* path, const char* index_path, ltr_bam** out);
+void ltr_bam_close(ltr_bam* bam);
+int32_t ltr_bam_n_refs(const ltr_bam* bam);
+const char* ltr_bam_ref_name(const ltr_bam* bam, int32_t tid);
+int64_t ltr_bam_ref_len(const ltr_bam* bam, int32_t tid);
+int32_t ltr_bam_ref_id(const ltr_bam* bam, const char* name);
+const char* ltr_bam_header_text(const ltr_bam* bam);
+int ltr_bam_has_index(const ltr_bam* bam);
+int ltr_bam_fetch(const ltr_bam* bam, int32_t tid, int64_t beg, int64_t end, int32_t keep_raw, ltr_bam_reads** out);
+void ltr_bam_reads_free(ltr_bam_reads* reads);
+
+/* ltr_region_collect   the reads of ONE region from one BAM file per sample, prepared the way LongTR's region loop hands
+ *                      them to its genotyper -- single-end (long) reads only:
+ *                      window of the query (BamProcessor::process_regions, src/bam_processor.cpp:584-596), read filters and
+ *                      the order of reads and samples (read_and_filter_reads, :188-487), phasing terms from the HP tag
+ *                      (SNPBamProcessor::process_phased_reads, src/snp_bam_processor.cpp:141-232), spanning test, cut to
+ *                      +- flank_size bp around the region and '=XID' CIGAR against the reference sequence
+ *                      (GenotyperBamProcessor::left_align_reads, src/genotyper_bam_processor.cpp:38-168;
+ *                      BamAlignment::TrimAlignment, src/bam_io.cpp:267-372).  start / stop: 0-based region as LongTR's
+ *                      Region holds it.  ref_seq[0] is reference position ref_seq_start of `chrom` (the whole chromosome or
+ *                      a slice that covers the reads).  The arrays have the layout of ltr_locus_batch's read fields.     */
+typedef struct ltr_region_params {
+  int32_t max_mate_dist;     /* MAX_MATE_DIST (1000): the fetched window is [start - d, stop + d]          */
+  double min_mean_qual;      /* --min-mean-qual (30): mean Phred quality below it -> LOW_BASE_QUALS         */
+  double min_mapq;           /* --min-mapq (20)                                                              */
+  int32_t require_spanning;  /* REQUIRE_SPANNING (1)                                                         */
+  int32_t min_flank;         /* MIN_FLANK (5): reads covering less are not used for haplotype generation     */
+  int32_t flank_size;        /* FLANK_SIZE (200, src/bam_io.h:28)                                            */
+  int32_t phased_bam;        /* --phased-bam: phasing terms from the HP tag, otherwise 0 / 0                 */
+  int32_t check_hard_clips;  /* BASE_QUAL_TRIM > ' ' (default): hard-clipped reads are dropped               */
+} ltr_region_params;
+typedef struct ltr_region_reads {
+  uint32_t n_samples;                 /* samples that contributed a read, in the reference's order (first appearance
+                                         when its read list is emptied from the back: src/bam_processor.cpp:453-483) */
+  const uint32_t* sample_file;        /* [n_samples] index into bams                                           */
+  const uint32_t* sample_read_begin;  /* [n_samples+1]                                                         */
+  uint32_t n_reads;
+  const int32_t* read_start;          /* [n_reads] Alignment::get_start()                                      */
+  const int32_t* read_stop;           /* [n_reads] Alignment::get_stop(), inclusive                            */
+  const uint32_t* read_off;           /* [n_reads+1] bases (upper case) and qualities (Phred+33)               */
+  const uint8_t* read_bytes;
+  const uint8_t* qual_bytes;
+  const uint32_t* cigar_off;          /* [n_reads+1] BAM-encoded '=XID' operations                             */
+  const uint32_t* cigar_ops;
+  const int32_t* read_sample;         /* [n_reads]                                                             */
+  const double* log_p1;               /* [n_reads]                                                             */
+  const double* log_p2;
+  const uint8_t* hap_gen_ok;          /* [n_reads] usable for haplotype generation (passes_filters)            */
+  const uint8_t* deleted;             /* [n_reads] the repeat is deleted in the read (BamAlignment::GetDeleted) */
+  const uint32_t* name_off;           /* [n_reads+1] NUL-terminated read names                                 */
+  const char* names;
+  /* the counters read_and_filter_reads / left_align_reads log */
+  uint32_t n_overlapping, n_hard_clipped, n_has_n, n_low_qual, n_low_mapq, n_not_spanning, n_not_unique, n_passed,
+      n_trim_failed;
+  void* owner;
+} ltr_region_reads;
+void ltr_region_params_default(ltr_region_params* p);
+int ltr_region_collect(const ltr_bam* const* bams, int32_t n_bams, const char* chrom, int32_t start, int32_t stop,
+                       const uint8_t* ref_seq, int64_t ref_seq_start, int64_t ref_seq_len, const ltr_region_params* params,
+                       ltr_region_reads** out);
+void ltr_region_reads_free(ltr_region_reads* reads);
+
 /* ---- diagnostics --------------------------------------------------------------------- */
 /* Sustained FP64-pipe issue rate of the device in lane-operations per second (the roofline
  * denominator of SURVEY.md section 8d): kind 0 = DADD, 1 = DSETP, 2 = the DADD,DADD,DSETP,

@@ -53,6 +53,113 @@ class JobStats(C.Structure):
                 ("plan_ms", C.c_float), ("n_band_retried", C.c_uint64)]
 
 
+class BamReads(C.Structure):
+    """ltr_bam_reads (include/longtr_b200.h)."""
+    _fields_ = [("n", C.c_uint32), ("tid", _i32p), ("pos", _i32p), ("end", _i32p), ("flag", C.POINTER(C.c_uint16)),
+                ("mapq", _u8p), ("mate_tid", _i32p), ("mate_pos", _i32p), ("name_off", _u32p), ("names", C.c_void_p),
+                ("seq_off", _u32p), ("seq", _u8p), ("qual", _u8p), ("cigar_off", _u32p), ("cigar_ops", _u32p),
+                ("hp", _i32p), ("raw_off", _u32p), ("raw", _u8p), ("owner", C.c_void_p)]
+
+
+class RegionParams(C.Structure):
+    _fields_ = [("max_mate_dist", C.c_int32), ("min_mean_qual", C.c_double), ("min_mapq", C.c_double),
+                ("require_spanning", C.c_int32), ("min_flank", C.c_int32), ("flank_size", C.c_int32),
+                ("phased_bam", C.c_int32), ("check_hard_clips", C.c_int32)]
+
+
+class RegionReads(C.Structure):
+    _fields_ = [("n_samples", C.c_uint32), ("sample_file", _u32p), ("sample_read_begin", _u32p), ("n_reads", C.c_uint32),
+                ("read_start", _i32p), ("read_stop", _i32p), ("read_off", _u32p), ("read_bytes", _u8p), ("qual_bytes", _u8p),
+                ("cigar_off", _u32p), ("cigar_ops", _u32p), ("read_sample", _i32p), ("log_p1", _dp), ("log_p2", _dp),
+                ("hap_gen_ok", _u8p), ("deleted", _u8p), ("name_off", _u32p), ("names", C.c_void_p),
+                ("n_overlapping", C.c_uint32), ("n_hard_clipped", C.c_uint32), ("n_has_n", C.c_uint32),
+                ("n_low_qual", C.c_uint32), ("n_low_mapq", C.c_uint32), ("n_not_spanning", C.c_uint32),
+                ("n_not_unique", C.c_uint32), ("n_passed", C.c_uint32), ("n_trim_failed", C.c_uint32), ("owner", C.c_void_p)]
+
+
+def region_collect(bams, chrom, start, stop, ref_seq, ref_seq_start=0, **overrides):
+    """ltr_region_collect -> dict(samples=[file index], reads=[dict per read, sample-major], counters)."""
+    lib = load()
+    prm = RegionParams()
+    lib.ltr_region_params_default(C.byref(prm))
+    for k, v in overrides.items():
+        setattr(prm, k, v)
+    handles = (C.c_void_p * len(bams))(*[b.h for b in bams])
+    ref = np.frombuffer(ref_seq.encode() if isinstance(ref_seq, str) else bytes(ref_seq), dtype=np.uint8)
+    out = C.POINTER(RegionReads)()
+    rc = lib.ltr_region_collect(handles, len(bams), chrom.encode(), start, stop, ptr(ref, _u8p), ref_seq_start, len(ref),
+                                C.byref(prm), C.byref(out))
+    if rc != 0:
+        raise RuntimeError("ltr_region_collect failed: %d" % rc)
+    r = out.contents
+    n = r.n_reads
+    seq = C.string_at(r.read_bytes, r.read_off[n]) if n else b""
+    qual = C.string_at(r.qual_bytes, r.read_off[n]) if n else b""
+    names = C.string_at(r.names, r.name_off[n]) if n else b""
+    reads = []
+    for i in range(n):
+        cig = "".join("%d%s" % (r.cigar_ops[k] >> 4, "MIDNSHP=X"[r.cigar_ops[k] & 15])
+                      for k in range(r.cigar_off[i], r.cigar_off[i + 1]))
+        reads.append(dict(name=names[r.name_off[i]:r.name_off[i + 1] - 1].decode(), start=r.read_start[i], stop=r.read_stop[i],
+                          seq=seq[r.read_off[i]:r.read_off[i + 1]].decode(), qual=qual[r.read_off[i]:r.read_off[i + 1]].decode(),
+                          cigar=cig, sample=r.read_sample[i], log_p1=r.log_p1[i], log_p2=r.log_p2[i],
+                          hap_gen_ok=int(r.hap_gen_ok[i]), deleted=int(r.deleted[i])))
+    res = dict(samples=[r.sample_file[s] for s in range(r.n_samples)], reads=reads,
+               counters={k: getattr(r, k) for k in ("n_overlapping", "n_hard_clipped", "n_has_n", "n_low_qual", "n_low_mapq",
+                                                    "n_not_spanning", "n_not_unique", "n_passed", "n_trim_failed")})
+    lib.ltr_region_reads_free(out)
+    return res
+
+
+class BamFile:
+    """ltr_bam_*: BGZF / BAM / BAI reader of the library (host only)."""
+
+    def __init__(self, path, index_path=None):
+        self.lib = load()
+        h = C.c_void_p()
+        rc = self.lib.ltr_bam_open(path.encode(), index_path.encode() if index_path else None, C.byref(h))
+        if rc != 0:
+            raise RuntimeError("ltr_bam_open(%s) failed: %d" % (path, rc))
+        self.h = h
+        self.refs = [(self.lib.ltr_bam_ref_name(h, t).decode(), self.lib.ltr_bam_ref_len(h, t))
+                     for t in range(self.lib.ltr_bam_n_refs(h))]
+        self.has_index = bool(self.lib.ltr_bam_has_index(h))
+
+    def fetch(self, tid=-1, beg=0, end=1 << 29, keep_raw=False):
+        """Records overlapping [beg, end) of reference tid (tid < 0: all) as a list of dicts."""
+        p = C.POINTER(BamReads)()
+        rc = self.lib.ltr_bam_fetch(self.h, tid, beg, end, 1 if keep_raw else 0, C.byref(p))
+        if rc != 0:
+            raise RuntimeError("ltr_bam_fetch failed: %d" % rc)
+        r = p.contents
+        n = r.n
+        out = []
+        names = C.string_at(r.names, r.name_off[n]) if n else b""
+        seq = C.string_at(r.seq, r.seq_off[n]) if n else b""
+        qual = C.string_at(r.qual, r.seq_off[n]) if n else b""
+        raw = C.string_at(r.raw, r.raw_off[n]) if n and r.raw_off[n] else b""
+        for i in range(n):
+            cig = [("MIDNSHP=X"[r.cigar_ops[k] & 15], r.cigar_ops[k] >> 4) for k in range(r.cigar_off[i], r.cigar_off[i + 1])]
+            out.append(dict(name=names[r.name_off[i]:r.name_off[i + 1] - 1].decode(), flag=r.flag[i], tid=r.tid[i],
+                            pos=r.pos[i], end=r.end[i], mapq=r.mapq[i], cigar=cig, mate_tid=r.mate_tid[i],
+                            mate_pos=r.mate_pos[i], seq=seq[r.seq_off[i]:r.seq_off[i + 1]].decode(),
+                            qual=qual[r.seq_off[i]:r.seq_off[i + 1]].decode(), hp=r.hp[i],
+                            raw=raw[r.raw_off[i]:r.raw_off[i + 1]]))
+        self.lib.ltr_bam_reads_free(p)
+        return out
+
+    def close(self):
+        if self.h:
+            self.lib.ltr_bam_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class LocusCalls(C.Structure):
     """ltr_locus_calls (include/longtr_b200.h)."""
     _fields_ = [("best_gts", _i32p), ("log_phased_posteriors", _dp), ("log_unphased_posteriors", _dp),
@@ -230,6 +337,33 @@ def load():
     lib.ltr_stutter_ll_status.restype = C.c_int
     lib.ltr_fp64_issue_rate.argtypes = [C.c_int, C.c_int, _dp, _dp]
     lib.ltr_fp64_issue_rate.restype = C.c_int
+    lib.ltr_bam_open.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(vp)]
+    lib.ltr_bam_open.restype = C.c_int
+    lib.ltr_bam_close.argtypes = [vp]
+    lib.ltr_bam_close.restype = None
+    lib.ltr_bam_n_refs.argtypes = [vp]
+    lib.ltr_bam_n_refs.restype = C.c_int32
+    lib.ltr_bam_ref_name.argtypes = [vp, C.c_int32]
+    lib.ltr_bam_ref_name.restype = C.c_char_p
+    lib.ltr_bam_ref_len.argtypes = [vp, C.c_int32]
+    lib.ltr_bam_ref_len.restype = C.c_int64
+    lib.ltr_bam_ref_id.argtypes = [vp, C.c_char_p]
+    lib.ltr_bam_ref_id.restype = C.c_int32
+    lib.ltr_bam_header_text.argtypes = [vp]
+    lib.ltr_bam_header_text.restype = C.c_char_p
+    lib.ltr_bam_has_index.argtypes = [vp]
+    lib.ltr_bam_has_index.restype = C.c_int
+    lib.ltr_bam_fetch.argtypes = [vp, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.POINTER(C.POINTER(BamReads))]
+    lib.ltr_bam_fetch.restype = C.c_int
+    lib.ltr_bam_reads_free.argtypes = [C.POINTER(BamReads)]
+    lib.ltr_bam_reads_free.restype = None
+    lib.ltr_region_params_default.argtypes = [C.POINTER(RegionParams)]
+    lib.ltr_region_params_default.restype = None
+    lib.ltr_region_collect.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_char_p, C.c_int32, C.c_int32, _u8p, C.c_int64,
+                                       C.c_int64, C.POINTER(RegionParams), C.POINTER(C.POINTER(RegionReads))]
+    lib.ltr_region_collect.restype = C.c_int
+    lib.ltr_region_reads_free.argtypes = [C.POINTER(RegionReads)]
+    lib.ltr_region_reads_free.restype = None
     lib.ltr_edit_distances.argtypes = [vp, _u8p, _u32p, C.c_uint32, _u32p, _u32p, _i32p, C.c_uint32, _i32p,
                                        C.POINTER(JobStats)]
     lib.ltr_edit_distances.restype = C.c_int
@@ -250,6 +384,9 @@ EXPORTED_SYMBOLS = [
     "ltr_stutter_ll", "ltr_genotype_locus_pruned", "ltr_ctx_set_plan", "ltr_job_submit", "ltr_job_submit_outputs", "ltr_job_wait", "ltr_job_poll", "ltr_job_download_kept", "ltr_posteriors_batch", "ltr_genotyper_create", "ltr_genotyper_destroy",
     "ltr_genotyper_run", "ltr_batch_calls_free", "ltr_locus_batch_trim_read", "ltr_stutter_ll_status", "ltr_pool_reads",
     "ltr_edit_distances", "ltr_cluster_greedy",
+    "ltr_bam_open", "ltr_bam_close", "ltr_bam_n_refs", "ltr_bam_ref_name", "ltr_bam_ref_len", "ltr_bam_ref_id",
+    "ltr_bam_header_text", "ltr_bam_has_index", "ltr_bam_fetch", "ltr_bam_reads_free",
+    "ltr_region_params_default", "ltr_region_collect", "ltr_region_reads_free",
 ]
 
 

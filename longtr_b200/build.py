@@ -21,7 +21,7 @@ OBJ = os.path.join(CSRC, "build")
 CU_SOURCES = ["viterbi_kernels.cu", "band_kernel.cu", "plan_kernels.cu", "posterior_kernel.cu", "stutter_kernel.cu", "abi.cu", "stutter_abi.cu",
               "edit_kernel.cu", "edit_abi.cu", "microbench.cu"]
 CPP_SOURCES = ["host/flat_api.cpp", "host/host_types.cpp", "host/hap_aligner.cpp", "host/stutter_host.cpp",
-               "host/genotyper.cpp", "host/pipeline.cpp", "host/locus_batcher.cpp", "synth_stutter.cpp"]
+               "host/genotyper.cpp", "host/pipeline.cpp", "host/locus_batcher.cpp", "host/bam_reader.cpp", "host/region_loader.cpp", "synth_stutter.cpp"]
 HEADERS = ["viterbi_core.cuh", "band_core.cuh", "viterbi_host.h", "kernels.h", "stutter_core.cuh", "ctx.h", "plan_device.cuh", "edit_core.cuh"]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -66,7 +66,7 @@ def build(force=False, verbose=False):
     with ThreadPoolExecutor(max_workers=4) as ex:
         list(ex.map(run, jobs))
     if jobs or force or not os.path.exists(OUT):
-        run([NVCC, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"])
+        run([NVCC, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-lz"])
     synth_src = [os.path.join(SYNTH_DIR, "synth.cpp"), os.path.join(SYNTH_DIR, "longtr_synth.h")]
     if force or _stale(SYNTH_OUT, synth_src + [os.path.join(INCLUDE, "longtr_b200.h")]):
         run([os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-I" + INCLUDE,

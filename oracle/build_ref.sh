@@ -43,6 +43,23 @@ $CXX -shared -o "$out/libltr_ref.so" "$out/obj/ref_driver.o" "$out/obj/edit_driv
      "$out/obj/hts_stubs.o" $objs -Wl,--no-undefined -lm -lpthread
 echo "built $out/libltr_ref.so"
 
+# ---- libltr_ref_io.so: the reference's alignment input (bam_io.cpp, compiled in place) on top of the library's BAM reader
+#      through integration/hts_compat.cpp (the htslib names LongTR binds, implemented on ltr_bam_*) ----------------------
+#      (bam_reader.cpp is plain C++: it is compiled into this library, which therefore does not pull liblongtr_b200.so and a
+#      second C++ runtime into the test process)
+o="$out/obj/bam_io.o"
+if [ ! -f "$o" ] || [ "$ref/src/bam_io.cpp" -nt "$o" ]; then
+  $CXX $FLAGS -I"$here/shim" -c "$ref/src/bam_io.cpp" -o "$o"
+fi
+$CXX -O2 -g -std=c++11 -fPIC -w -I"$here/shim" -I"$here/../include" -c "$here/../integration/hts_compat.cpp" -o "$out/obj/hts_compat.o"
+$CXX -O2 -g -std=c++11 -fPIC -w -I"$here/../include" -c "$here/../longtr_b200/csrc/host/bam_reader.cpp" -o "$out/obj/bam_reader.o"
+$CXX -O2 -g -std=c++11 -fPIC -w -I"$here/shim" -I"$ref/src" -c "$here/io_driver.cpp" -o "$out/obj/io_driver.o"
+# linked against the shared C++ runtime (a private static copy next to the process's own breaks iostream's locale facets)
+LINKXX="$CXX"; [ -x /usr/bin/g++ ] && LINKXX=/usr/bin/g++
+$LINKXX -shared -o "$out/libltr_ref_io.so" "$out/obj/io_driver.o" "$out/obj/bam_io.o" "$out/obj/hts_compat.o" "$out/obj/bam_reader.o" \
+     "$out/obj/error.o" "$out/obj/stringops.o" -Wl,--no-undefined -lz -lm -lpthread
+echo "built $out/libltr_ref_io.so"
+
 # ---- IO-less per-locus genotyper (SeqStutterGenotyper ctor -> genotype -> write_vcf_record), twice ------------
 #   ltr_ref_full : every object is the reference's own (golden VCF records)
 #   ltr_ref_gpu  : HapAligner::process_reads and Genotyper::calc_log_sample_posteriors are taken from
