@@ -540,6 +540,42 @@ int ltr_region_collect(const ltr_bam* const* bams, int32_t n_bams, const char* c
                        ltr_region_reads** out);
 void ltr_region_reads_free(ltr_region_reads* reads);
 
+/* ltr_candidate_alleles  the candidate haplotype block of one region from the reads ltr_region_collect prepared:
+ *                        HaplotypeGenerator::add_haplotype_block + fuse_haplotype_blocks without --ref-vcf alleles
+ *                        (src/SeqAlignment/HaplotypeGenerator.cpp:14-164, 296-481, 521-607; called from
+ *                        SeqStutterGenotyper::build_haplotype, src/seq_stutter_genotyper.cpp:416-476).  Alleles: reference
+ *                        allele first, then by (length, sequence); block_start / block_end: the RepeatBlock's region after
+ *                        the trim; lflank / rflank: the reference-only blocks on either side (lflank starts at lflank_start).
+ *                        status LTR_CAND_NEEDS_ASSEMBLY: some sample leaves more than a quarter of its reads without a
+ *                        candidate; the reference then clusters them (ltr_cluster_greedy) and takes a partial-order
+ *                        consensus per cluster (spoa; not reproduced).  The alleles found so far are still returned and
+ *                        cluster_* lists, per such sample, the sequences to be clustered in the reference's order with their
+ *                        read counts.                                                                                    */
+#define LTR_CAND_OK 0
+#define LTR_CAND_NEAR_CHROM_END 1  /* "Haplotype blocks are too near to the chromosome ends" */
+#define LTR_CAND_NO_SPANNING 2     /* "No spanning alignments"                               */
+#define LTR_CAND_NEEDS_ASSEMBLY 3
+typedef struct ltr_candidates {
+  int32_t status;
+  int32_t block_start, block_end;
+  int32_t n_alleles;
+  const uint32_t* allele_off;   /* [n_alleles+1] */
+  const uint8_t* allele_bytes;
+  int32_t lflank_start;
+  const char* lflank;           /* NUL-terminated */
+  const char* rflank;
+  uint32_t n_cluster_samples;
+  const uint32_t* cluster_sample_begin;  /* [n_cluster_samples+1] */
+  const uint32_t* cluster_off;           /* [n_cluster_seqs+1]    */
+  const uint8_t* cluster_bytes;
+  const int32_t* cluster_count;          /* [n_cluster_seqs] reads carrying the sequence */
+  void* owner;
+} ltr_candidates;
+int ltr_candidate_alleles(const ltr_region_reads* reads, int32_t region_start, int32_t region_stop, int32_t period,
+                          const uint8_t* ref_seq, int64_t ref_seq_start, int64_t ref_seq_len, int32_t indel_flank_len,
+                          ltr_candidates** out);
+void ltr_candidates_free(ltr_candidates* c);
+
 /* ---- diagnostics --------------------------------------------------------------------- */
 /* Sustained FP64-pipe issue rate of the device in lane-operations per second (the roofline
  * denominator of SURVEY.md section 8d): kind 0 = DADD, 1 = DSETP, 2 = the DADD,DADD,DSETP,

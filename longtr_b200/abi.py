@@ -77,8 +77,16 @@ class RegionReads(C.Structure):
                 ("n_not_unique", C.c_uint32), ("n_passed", C.c_uint32), ("n_trim_failed", C.c_uint32), ("owner", C.c_void_p)]
 
 
-def region_collect(bams, chrom, start, stop, ref_seq, ref_seq_start=0, **overrides):
-    """ltr_region_collect -> dict(samples=[file index], reads=[dict per read, sample-major], counters)."""
+class Candidates(C.Structure):
+    _fields_ = [("status", C.c_int32), ("block_start", C.c_int32), ("block_end", C.c_int32), ("n_alleles", C.c_int32),
+                ("allele_off", _u32p), ("allele_bytes", _u8p), ("lflank_start", C.c_int32), ("lflank", C.c_char_p),
+                ("rflank", C.c_char_p), ("n_cluster_samples", C.c_uint32), ("cluster_sample_begin", _u32p),
+                ("cluster_off", _u32p), ("cluster_bytes", _u8p), ("cluster_count", _i32p), ("owner", C.c_void_p)]
+
+
+def region_collect(bams, chrom, start, stop, ref_seq, ref_seq_start=0, candidates=None, **overrides):
+    """ltr_region_collect -> dict(samples=[file index], reads=[dict per read, sample-major], counters).
+    candidates=dict(period=.., indel_flank_len=5): also ltr_candidate_alleles on the same reads -> res["candidates"]."""
     lib = load()
     prm = RegionParams()
     lib.ltr_region_params_default(C.byref(prm))
@@ -107,6 +115,25 @@ def region_collect(bams, chrom, start, stop, ref_seq, ref_seq_start=0, **overrid
     res = dict(samples=[r.sample_file[s] for s in range(r.n_samples)], reads=reads,
                counters={k: getattr(r, k) for k in ("n_overlapping", "n_hard_clipped", "n_has_n", "n_low_qual", "n_low_mapq",
                                                     "n_not_spanning", "n_not_unique", "n_passed", "n_trim_failed")})
+    if candidates is not None:
+        cp = C.POINTER(Candidates)()
+        rc = lib.ltr_candidate_alleles(out, start, stop, candidates["period"], ptr(ref, _u8p), ref_seq_start, len(ref),
+                                       candidates.get("indel_flank_len", 5), C.byref(cp))
+        if rc != 0:
+            lib.ltr_region_reads_free(out)
+            raise RuntimeError("ltr_candidate_alleles failed: %d" % rc)
+        c = cp.contents
+        ab = C.string_at(c.allele_bytes, c.allele_off[c.n_alleles]) if c.n_alleles else b""
+        ncs = c.cluster_sample_begin[c.n_cluster_samples] if c.n_cluster_samples else 0
+        cb = C.string_at(c.cluster_bytes, c.cluster_off[ncs]) if ncs else b""
+        res["candidates"] = dict(
+            status=c.status, block_start=c.block_start, block_end=c.block_end, lflank_start=c.lflank_start,
+            alleles=[ab[c.allele_off[k]:c.allele_off[k + 1]].decode() for k in range(c.n_alleles)],
+            lflank=(c.lflank or b"").decode(), rflank=(c.rflank or b"").decode(),
+            cluster_sets=[[(cb[c.cluster_off[k]:c.cluster_off[k + 1]].decode(), c.cluster_count[k])
+                           for k in range(c.cluster_sample_begin[s], c.cluster_sample_begin[s + 1])]
+                          for s in range(c.n_cluster_samples)])
+        lib.ltr_candidates_free(cp)
     lib.ltr_region_reads_free(out)
     return res
 
@@ -364,6 +391,11 @@ def load():
     lib.ltr_region_collect.restype = C.c_int
     lib.ltr_region_reads_free.argtypes = [C.POINTER(RegionReads)]
     lib.ltr_region_reads_free.restype = None
+    lib.ltr_candidate_alleles.argtypes = [C.POINTER(RegionReads), C.c_int32, C.c_int32, C.c_int32, _u8p, C.c_int64, C.c_int64,
+                                          C.c_int32, C.POINTER(C.POINTER(Candidates))]
+    lib.ltr_candidate_alleles.restype = C.c_int
+    lib.ltr_candidates_free.argtypes = [C.POINTER(Candidates)]
+    lib.ltr_candidates_free.restype = None
     lib.ltr_edit_distances.argtypes = [vp, _u8p, _u32p, C.c_uint32, _u32p, _u32p, _i32p, C.c_uint32, _i32p,
                                        C.POINTER(JobStats)]
     lib.ltr_edit_distances.restype = C.c_int
@@ -387,6 +419,7 @@ EXPORTED_SYMBOLS = [
     "ltr_bam_open", "ltr_bam_close", "ltr_bam_n_refs", "ltr_bam_ref_name", "ltr_bam_ref_len", "ltr_bam_ref_id",
     "ltr_bam_header_text", "ltr_bam_has_index", "ltr_bam_fetch", "ltr_bam_reads_free",
     "ltr_region_params_default", "ltr_region_collect", "ltr_region_reads_free",
+    "ltr_candidate_alleles", "ltr_candidates_free",
 ]
 
 

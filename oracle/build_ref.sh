@@ -60,6 +60,15 @@ $LINKXX -shared -o "$out/libltr_ref_io.so" "$out/obj/io_driver.o" "$out/obj/bam_
      "$out/obj/error.o" "$out/obj/stringops.o" -Wl,--no-undefined -lz -lm -lpthread
 echo "built $out/libltr_ref_io.so"
 
+# ---- libltr_ref_hapgen.so: the reference's HaplotypeGenerator (compiled with the spoa stand-in throwing) behind
+#      oracle/hapgen_driver.cpp: candidate alleles of a region from flat reads ---------------------------------------------
+$CXX $FLAGS -DLTR_SPOA_THROW -I"$here/shim" -c "$ref/src/SeqAlignment/HaplotypeGenerator.cpp" -o "$out/obj/HaplotypeGenerator_throw.o"
+$CXX -O2 -g -std=c++11 -fPIC -w -fno-access-control -I"$here/shim" -I"$ref/src" -c "$here/hapgen_driver.cpp" -o "$out/obj/hapgen_driver.o"
+$LINKXX -shared -o "$out/libltr_ref_hapgen.so" "$out/obj/hapgen_driver.o" "$out/obj/HaplotypeGenerator_throw.o" \
+     "$out/obj/HapBlock.o" "$out/obj/error.o" "$out/obj/stringops.o" "$out/obj/stutter_model.o" "$out/obj/mathops.o" \
+     "$out/obj/region.o" -Wl,--no-undefined -lm -lpthread
+echo "built $out/libltr_ref_hapgen.so"
+
 # ---- IO-less per-locus genotyper (SeqStutterGenotyper ctor -> genotype -> write_vcf_record), twice ------------
 #   ltr_ref_full : every object is the reference's own (golden VCF records)
 #   ltr_ref_gpu  : HapAligner::process_reads and Genotyper::calc_log_sample_posteriors are taken from

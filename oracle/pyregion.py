@@ -243,3 +243,51 @@ def ref_io_region(path, chrom, start, end, span=None, trim=None):
             d["deleted"] = int(f[9])
         out.append(d)
     return out
+
+
+# ---- the reference's own HaplotypeGenerator on flat reads (oracle/hapgen_driver.cpp) ------------------------------------
+_HAPGEN_SO = os.path.join(_HERE, "_ref", "libltr_ref_hapgen.so")
+
+
+def ref_hapgen_available():
+    return os.path.exists(_HAPGEN_SO)
+
+
+def ref_candidate_alleles(reads, n_samples, region_start, region_stop, motif, chrom_seq, indel_flank_len=5):
+    """reads: dicts as longtr_b200.abi.region_collect returns them.  -> dict(status) or dict(block, lstart, lflank, rflank,
+    alleles) from HaplotypeGenerator::add_haplotype_block + fuse_haplotype_blocks."""
+    import re
+
+    import numpy as np
+    lib = C.CDLL(_HAPGEN_SO)
+    u32p, i32p, u8p = C.POINTER(C.c_uint32), C.POINTER(C.c_int32), C.POINTER(C.c_uint8)
+    lib.ltr_ref_candidate_alleles.restype = C.c_void_p
+    lib.ltr_ref_candidate_alleles.argtypes = [C.c_uint32, C.c_uint32, i32p, i32p, i32p, u32p, u8p, u32p, u32p, u8p, u8p,
+                                              C.c_int32, C.c_int32, C.c_char_p, C.c_char_p, C.c_int32]
+    n = len(reads)
+    sample = np.array([r["sample"] for r in reads] + [0], dtype=np.int32)
+    start = np.array([r["start"] for r in reads] + [0], dtype=np.int32)
+    stop = np.array([r["stop"] for r in reads] + [0], dtype=np.int32)
+    roff = np.zeros(n + 1, dtype=np.uint32)
+    roff[1:] = np.cumsum([len(r["seq"]) for r in reads])
+    rbytes = np.frombuffer(("".join(r["seq"] for r in reads) + "\0").encode(), dtype=np.uint8).copy()
+    ops, coff = [], [0]
+    for r in reads:
+        for num, op in re.findall(r"(\d+)([MIDNSHP=X])", r["cigar"]):
+            ops.append((int(num) << 4) | "MIDNSHP=X".index(op))
+        coff.append(len(ops))
+    ops = np.array(ops + [0], dtype=np.uint32)
+    coff = np.array(coff, dtype=np.uint32)
+    ok = np.array([r["hap_gen_ok"] for r in reads] + [0], dtype=np.uint8)
+    dele = np.array([r["deleted"] for r in reads] + [0], dtype=np.uint8)
+    P = lambda a, t: a.ctypes.data_as(t)
+    p = lib.ltr_ref_candidate_alleles(n_samples, n, P(sample, i32p), P(start, i32p), P(stop, i32p), P(roff, u32p),
+                                      P(rbytes, u8p), P(coff, u32p), P(ops, u32p), P(ok, u8p), P(dele, u8p), region_start,
+                                      region_stop, motif.encode(), chrom_seq.encode(), indel_flank_len)
+    text = C.string_at(p).decode()
+    C.CDLL(None).free(C.c_void_p(p))
+    if text.startswith("status="):
+        return dict(status=text[7:])
+    m = re.match(r"ok block=(-?\d+),(-?\d+) lstart=(-?\d+) lflank=(\S*) rflank=(\S*) alleles=(.*)$", text)
+    return dict(status="ok", block_start=int(m.group(1)), block_end=int(m.group(2)), lflank_start=int(m.group(3)),
+                lflank=m.group(4), rflank=m.group(5), alleles=re.findall(r"\[([^\]]*)\]", m.group(6)))
