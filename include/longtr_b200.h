@@ -486,6 +486,9 @@ int64_t ltr_bam_ref_len(const ltr_bam* bam, int32_t tid);
 int32_t ltr_bam_ref_id(const ltr_bam* bam, const char* name);
 const char* ltr_bam_header_text(const ltr_bam* bam);
 int ltr_bam_has_index(const ltr_bam* bam);
+/* Builds the index of a coordinate-sorted file in memory (one scan) when no .bai was loaded; not to be called while other
+ * threads fetch from the same handle.  LTR_ERR_UNSUPPORTED: the file is not coordinate sorted.                         */
+int ltr_bam_build_index(ltr_bam* bam);
 int ltr_bam_fetch(const ltr_bam* bam, int32_t tid, int64_t beg, int64_t end, int32_t keep_raw, ltr_bam_reads** out);
 void ltr_bam_reads_free(ltr_bam_reads* reads);
 
@@ -575,6 +578,53 @@ int ltr_candidate_alleles(const ltr_region_reads* reads, int32_t region_start, i
                           const uint8_t* ref_seq, int64_t ref_seq_start, int64_t ref_seq_len, int32_t indel_flank_len,
                           ltr_candidates** out);
 void ltr_candidates_free(ltr_candidates* c);
+
+/* ltr_regions_run   BAM files (one per sample) + regions of ONE chromosome -> genotype calls: LongTR's region loop
+ *                   (BamProcessor::process_regions, src/bam_processor.cpp:536-628; GenotyperBamProcessor::
+ *                   analyze_reads_and_phasing, src/genotyper_bam_processor.cpp:227-351) with the default stutter model, re-cut
+ *                   for the GPU: host threads prepare reads (ltr_region_collect) and candidate alleles
+ *                   (ltr_candidate_alleles) of all regions, the survivors become one ltr_locus_batch, ltr_genotyper_run does
+ *                   the rest.  status[r] says why a region did not enter the batch; locus_index[r] is its locus in `calls`
+ *                   (or -1).  Alleles, block coordinates and the sample order (file index per sample: the order differs from
+ *                   region to region exactly as in the reference) are kept per region for whoever writes the records.     */
+#define LTR_REGION_OK 0
+#define LTR_REGION_INVALID 1
+#define LTR_REGION_TOO_LONG 2         /* reference allele longer than --max-tr-len                       */
+#define LTR_REGION_NEAR_CONTIG_END 3
+#define LTR_REGION_TOO_FEW_READS 4    /* fewer than --min-reads reads passed the filters                  */
+#define LTR_REGION_NO_SPANNING 5
+#define LTR_REGION_NEEDS_ASSEMBLY 6   /* candidate alleles would come from the partial-order assembly    */
+#define LTR_REGION_PAIRED_READS 7     /* paired-end reads: mate logic not reproduced                      */
+#define LTR_REGION_DELETED_READ 8     /* a read in which the whole window is deleted (empty sequence)     */
+typedef struct ltr_region {
+  int32_t start, stop;  /* 0-based, as LongTR's Region holds a BED line */
+  int32_t period;
+} ltr_region;
+typedef struct ltr_regions_opts {
+  int32_t host_threads;     /* <= 0: all hardware threads */
+  int32_t max_tr_len;       /* --max-tr-len (1000)        */
+  int32_t min_total_reads;  /* --min-reads (10)           */
+} ltr_regions_opts;
+typedef struct ltr_regions_result {
+  uint32_t n_regions;
+  const int32_t* status;               /* [n_regions] LTR_REGION_*                                             */
+  const int32_t* locus_index;          /* [n_regions] locus in calls, -1 when the region was not genotyped     */
+  uint32_t n_loci;
+  ltr_batch_calls* calls;              /* NULL when no region was genotyped                                    */
+  const int32_t* block_start;          /* [n_regions] the RepeatBlock's coordinates                            */
+  const int32_t* block_end;
+  const uint32_t* region_allele_begin; /* [n_regions+1] candidate alleles (reference allele first)             */
+  const uint32_t* allele_off;
+  const uint8_t* allele_bytes;
+  const uint32_t* region_sample_begin; /* [n_regions+1]                                                        */
+  const uint32_t* sample_file;         /* index into bams of each sample of the region                         */
+  void* owner;
+} ltr_regions_result;
+void ltr_regions_opts_default(ltr_regions_opts* o);
+int ltr_regions_run(ltr_genotyper* g, const ltr_params* params, const ltr_bam* const* bams, int32_t n_bams, const char* chrom,
+                    const ltr_region* regions, uint32_t n_regions, const uint8_t* ref_seq, int64_t ref_seq_start,
+                    int64_t ref_seq_len, const ltr_region_params* rp, const ltr_regions_opts* opts, ltr_regions_result** out);
+void ltr_regions_result_free(ltr_regions_result* r);
 
 /* ---- diagnostics --------------------------------------------------------------------- */
 /* Sustained FP64-pipe issue rate of the device in lane-operations per second (the roofline

@@ -152,6 +152,12 @@ class BamFile:
                      for t in range(self.lib.ltr_bam_n_refs(h))]
         self.has_index = bool(self.lib.ltr_bam_has_index(h))
 
+    def build_index(self):
+        rc = self.lib.ltr_bam_build_index(self.h)
+        if rc != 0:
+            raise RuntimeError("ltr_bam_build_index failed: %d" % rc)
+        self.has_index = True
+
     def fetch(self, tid=-1, beg=0, end=1 << 29, keep_raw=False):
         """Records overlapping [beg, end) of reference tid (tid < 0: all) as a list of dicts."""
         p = C.POINTER(BamReads)()
@@ -380,6 +386,8 @@ def load():
     lib.ltr_bam_header_text.restype = C.c_char_p
     lib.ltr_bam_has_index.argtypes = [vp]
     lib.ltr_bam_has_index.restype = C.c_int
+    lib.ltr_bam_build_index.argtypes = [vp]
+    lib.ltr_bam_build_index.restype = C.c_int
     lib.ltr_bam_fetch.argtypes = [vp, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.POINTER(C.POINTER(BamReads))]
     lib.ltr_bam_fetch.restype = C.c_int
     lib.ltr_bam_reads_free.argtypes = [C.POINTER(BamReads)]
@@ -417,9 +425,10 @@ EXPORTED_SYMBOLS = [
     "ltr_genotyper_run", "ltr_batch_calls_free", "ltr_locus_batch_trim_read", "ltr_stutter_ll_status", "ltr_pool_reads",
     "ltr_edit_distances", "ltr_cluster_greedy",
     "ltr_bam_open", "ltr_bam_close", "ltr_bam_n_refs", "ltr_bam_ref_name", "ltr_bam_ref_len", "ltr_bam_ref_id",
-    "ltr_bam_header_text", "ltr_bam_has_index", "ltr_bam_fetch", "ltr_bam_reads_free",
+    "ltr_bam_header_text", "ltr_bam_has_index", "ltr_bam_build_index", "ltr_bam_fetch", "ltr_bam_reads_free",
     "ltr_region_params_default", "ltr_region_collect", "ltr_region_reads_free",
-    "ltr_candidate_alleles", "ltr_candidates_free",
+    "ltr_candidate_alleles", "ltr_candidates_free", "ltr_regions_opts_default", "ltr_regions_run",
+    "ltr_regions_result_free",
 ]
 
 

@@ -374,6 +374,79 @@ extern "C" int ltr_bam_open(const char* path, const char* index_path, ltr_bam** 
   return LTR_OK;
 }
 
+// reg2bin of the SAM specification (5.3): the smallest bin that contains [beg, end)
+static uint32_t reg2bin(int64_t beg, int64_t end) {
+  --end;
+  if (beg >> 14 == end >> 14) return (uint32_t)(((1 << 15) - 1) / 7 + (beg >> 14));
+  if (beg >> 17 == end >> 17) return (uint32_t)(((1 << 12) - 1) / 7 + (beg >> 17));
+  if (beg >> 20 == end >> 20) return (uint32_t)(((1 << 9) - 1) / 7 + (beg >> 20));
+  if (beg >> 23 == end >> 23) return (uint32_t)(((1 << 6) - 1) / 7 + (beg >> 23));
+  if (beg >> 26 == end >> 26) return (uint32_t)(((1 << 3) - 1) / 7 + (beg >> 26));
+  return 0;
+}
+
+// Builds the binning + linear index of a coordinate-sorted file in memory (what `samtools index` writes to a .bai), for
+// files that come without one.  Not thread safe against concurrent fetches on the same handle.
+extern "C" int ltr_bam_build_index(ltr_bam* b) {
+  if (!b) return LTR_ERR_INVALID;
+  if (b->has_index) return LTR_OK;
+  std::vector<RefIndex> idx(b->ref_names.size());
+  std::vector<std::vector<std::pair<uint32_t, Chunk>>> raw(b->ref_names.size());
+  Cursor c(&b->file);
+  c.seek(b->first_record);
+  std::vector<uint8_t> rec;
+  int32_t last_tid = 0, last_pos = -1;
+  for (;;) {
+    const uint64_t v0 = c.tell();
+    uint8_t w[4];
+    if (!c.read(w, 4)) break;
+    const uint32_t bs = le32(w);
+    if (bs < 32 || bs > (1u << 28)) return LTR_ERR_INVALID;
+    rec.resize(bs);
+    if (!c.read(rec.data(), bs)) return LTR_ERR_INVALID;
+    const uint64_t v1 = c.tell();
+    const int32_t tid = (int32_t)le32(rec.data()), pos = (int32_t)le32(rec.data() + 4);
+    if (tid < 0) continue;
+    if ((size_t)tid >= idx.size() || pos < 0) return LTR_ERR_INVALID;
+    if (tid < last_tid || (tid == last_tid && pos < last_pos)) return LTR_ERR_UNSUPPORTED;  // not coordinate sorted
+    last_tid = tid;
+    last_pos = pos;
+    const uint32_t l_name = rec[8], n_cig = le16(rec.data() + 12);
+    if (32 + (size_t)l_name + 4 * (size_t)n_cig > bs) return LTR_ERR_INVALID;
+    int64_t ref_len = 0;
+    for (uint32_t k = 0; k < n_cig; ++k) {
+      const uint32_t v = le32(rec.data() + 32 + l_name + 4 * k), op = v & 15;
+      if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) ref_len += v >> 4;
+    }
+    const int64_t end = (int64_t)pos + (ref_len ? ref_len : 1);
+    const uint32_t bin = reg2bin(pos, end);
+    std::vector<std::pair<uint32_t, Chunk>>& rv = raw[(size_t)tid];
+    if (!rv.empty() && rv.back().first == bin && rv.back().second.end == v0) rv.back().second.end = v1;  // consecutive records
+    else rv.push_back(std::make_pair(bin, Chunk{v0, v1}));
+    std::vector<uint64_t>& lin = idx[(size_t)tid].linear;
+    const size_t w0 = (size_t)(pos >> 14), w1 = (size_t)((end - 1) >> 14);
+    if (lin.size() <= w1) lin.resize(w1 + 1, 0);
+    for (size_t k = w0; k <= w1; ++k)
+      if (lin[k] == 0) lin[k] = v0;
+  }
+  for (size_t t = 0; t < idx.size(); ++t) {
+    std::stable_sort(raw[t].begin(), raw[t].end(),
+                     [](const std::pair<uint32_t, Chunk>& a, const std::pair<uint32_t, Chunk>& d) { return a.first < d.first; });
+    for (const std::pair<uint32_t, Chunk>& e : raw[t]) {
+      if (idx[t].bins.empty() || idx[t].bins.back().first != e.first)
+        idx[t].bins.emplace_back(e.first, std::vector<Chunk>());
+      idx[t].bins.back().second.push_back(e.second);
+    }
+    // windows no record starts in inherit the offset of the next one that has one (as htslib fills its linear index)
+    std::vector<uint64_t>& lin = idx[t].linear;
+    for (size_t k = lin.size(); k-- > 0;)
+      if (lin[k] == 0 && k + 1 < lin.size()) lin[k] = lin[k + 1];
+  }
+  b->index.swap(idx);
+  b->has_index = true;
+  return LTR_OK;
+}
+
 extern "C" void ltr_bam_close(ltr_bam* b) { delete b; }
 extern "C" int32_t ltr_bam_n_refs(const ltr_bam* b) { return b ? (int32_t)b->ref_names.size() : 0; }
 extern "C" const char* ltr_bam_ref_name(const ltr_bam* b, int32_t tid) {

@@ -1,0 +1,205 @@
+// region_pipeline.cpp -- ltr_regions_run: BAM files + regions of one chromosome -> genotype calls.
+// The region loop of LongTR (reference BamProcessor::process_regions, src/bam_processor.cpp:536-628, and
+// GenotyperBamProcessor::analyze_reads_and_phasing, src/genotyper_bam_processor.cpp:227-351) re-cut for a GPU: instead of
+// one locus at a time through seek -> filter -> trim -> candidate alleles -> align -> posteriors, the host threads prepare the
+// reads (ltr_region_collect) and candidate alleles (ltr_candidate_alleles) of MANY regions, the survivors are laid out as one
+// ltr_locus_batch, and ltr_genotyper_run aligns and genotypes them as a few asynchronous GPU jobs.
+// Regions the reference skips (too long, too near the contig ends, too few reads, no spanning alignments) or that need the
+// partial-order assembly (not reproduced) are reported with their reason and do not enter the batch.
+#include <string.h>
+
+#include <atomic>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "longtr_b200.h"
+
+namespace {
+
+struct RegionWork {
+  ltr_region_reads* reads = nullptr;
+  ltr_candidates* cand = nullptr;
+  int32_t status = LTR_REGION_OK;
+};
+
+struct Owner {
+  ltr_regions_result pub;
+  std::vector<int32_t> status, locus_index, block_start, block_end;
+  std::vector<uint32_t> region_allele_begin, allele_off, region_sample_begin, sample_file;
+  std::vector<uint8_t> allele_bytes;
+};
+
+}  // namespace
+
+extern "C" int ltr_regions_run(ltr_genotyper* g, const ltr_params* params, const ltr_bam* const* bams, int32_t n_bams,
+                               const char* chrom, const ltr_region* regions, uint32_t n_regions, const uint8_t* ref_seq,
+                               int64_t ref_seq_start, int64_t ref_seq_len, const ltr_region_params* rp,
+                               const ltr_regions_opts* opts, ltr_regions_result** out) {
+  if (!g || !params || !bams || n_bams < 1 || !chrom || (n_regions && !regions) || !ref_seq || !rp || !opts || !out)
+    return LTR_ERR_INVALID;
+  *out = nullptr;
+  std::vector<RegionWork> work(n_regions);
+  int n_threads = opts->host_threads > 0 ? opts->host_threads : (int)std::thread::hardware_concurrency();
+  if (n_threads < 1) n_threads = 1;
+  if ((uint32_t)n_threads > n_regions) n_threads = n_regions ? (int)n_regions : 1;
+  std::atomic<uint32_t> next(0);
+  std::atomic<int> fatal(LTR_OK);
+  auto prepare = [&]() {
+    for (;;) {
+      const uint32_t r = next.fetch_add(1);
+      if (r >= n_regions) break;
+      RegionWork& W = work[r];
+      const ltr_region& R = regions[r];
+      if (R.stop <= R.start || R.period < 1) { W.status = LTR_REGION_INVALID; continue; }
+      if (R.stop - R.start > opts->max_tr_len) { W.status = LTR_REGION_TOO_LONG; continue; }  // bam_processor.cpp:568-574
+      if (R.start < 50 || (int64_t)R.stop + 50 >= ref_seq_start + ref_seq_len) {               // :583-586
+        W.status = LTR_REGION_NEAR_CONTIG_END;
+        continue;
+      }
+      int rc = ltr_region_collect(bams, n_bams, chrom, R.start, R.stop, ref_seq, ref_seq_start, ref_seq_len, rp, &W.reads);
+      if (rc == LTR_ERR_UNSUPPORTED) { W.status = LTR_REGION_PAIRED_READS; continue; }
+      if (rc != LTR_OK) { W.status = LTR_REGION_INVALID; continue; }
+      if ((int32_t)W.reads->n_passed < opts->min_total_reads) {  // genotyper_bam_processor.cpp:231-238
+        W.status = LTR_REGION_TOO_FEW_READS;
+        continue;
+      }
+      if (W.reads->n_reads == 0) { W.status = LTR_REGION_NO_SPANNING; continue; }
+      for (uint32_t i = 0; i < W.reads->n_reads && W.status == LTR_REGION_OK; ++i)
+        if (W.reads->read_off[i + 1] == W.reads->read_off[i]) W.status = LTR_REGION_DELETED_READ;  // empty (deleted) reads: not batched
+      if (W.status != LTR_REGION_OK) continue;
+      rc = ltr_candidate_alleles(W.reads, R.start, R.stop, R.period, ref_seq, ref_seq_start, ref_seq_len,
+                                 params->indel_flank_len, &W.cand);
+      if (rc != LTR_OK) { W.status = LTR_REGION_INVALID; continue; }
+      switch (W.cand->status) {
+        case LTR_CAND_OK: break;
+        case LTR_CAND_NEAR_CHROM_END: W.status = LTR_REGION_NEAR_CONTIG_END; break;
+        case LTR_CAND_NO_SPANNING: W.status = LTR_REGION_NO_SPANNING; break;
+        default: W.status = LTR_REGION_NEEDS_ASSEMBLY; break;
+      }
+    }
+  };
+  {
+    std::vector<std::thread> th;
+    for (int t = 1; t < n_threads; ++t) th.emplace_back(prepare);
+    prepare();
+    for (std::thread& t : th) t.join();
+  }
+  // ---- lay the surviving regions out as one ltr_locus_batch ------------------------------------------------------------
+  Owner* O = new Owner();
+  memset(&O->pub, 0, sizeof(O->pub));
+  O->status.resize(n_regions);
+  O->locus_index.assign(n_regions, -1);
+  O->block_start.assign(n_regions, 0);
+  O->block_end.assign(n_regions, 0);
+  O->region_allele_begin.push_back(0);
+  O->allele_off.push_back(0);
+  O->region_sample_begin.push_back(0);
+  std::vector<uint32_t> lflank_off(1, 0), rflank_off(1, 0), lab(1, 0), aoff(1, 0), lrb(1, 0), roff(1, 0), coff(1, 0), cops, lns;
+  std::vector<uint8_t> lfb, rfb, ab, rb;
+  std::vector<int32_t> rstart, rend, read_start, read_stop, read_sample;
+  std::vector<double> p1, p2;
+  uint32_t n_loci = 0;
+  for (uint32_t r = 0; r < n_regions; ++r) {
+    RegionWork& W = work[r];
+    O->status[r] = W.status;
+    if (W.reads) {
+      for (uint32_t s = 0; s < W.reads->n_samples; ++s) O->sample_file.push_back(W.reads->sample_file[s]);
+    }
+    O->region_sample_begin.push_back((uint32_t)O->sample_file.size());
+    if (W.cand && W.cand->n_alleles > 0) {
+      O->block_start[r] = W.cand->block_start;
+      O->block_end[r] = W.cand->block_end;
+      for (int32_t a = 0; a < W.cand->n_alleles; ++a) {
+        O->allele_bytes.insert(O->allele_bytes.end(), W.cand->allele_bytes + W.cand->allele_off[a],
+                               W.cand->allele_bytes + W.cand->allele_off[a + 1]);
+        O->allele_off.push_back((uint32_t)O->allele_bytes.size());
+      }
+    }
+    O->region_allele_begin.push_back((uint32_t)O->allele_off.size() - 1);
+    if (W.status != LTR_REGION_OK) continue;
+    const ltr_region_reads& RR = *W.reads;
+    const ltr_candidates& C = *W.cand;
+    O->locus_index[r] = (int32_t)n_loci++;
+    lfb.insert(lfb.end(), C.lflank, C.lflank + strlen(C.lflank));
+    lflank_off.push_back((uint32_t)lfb.size());
+    rfb.insert(rfb.end(), C.rflank, C.rflank + strlen(C.rflank));
+    rflank_off.push_back((uint32_t)rfb.size());
+    for (int32_t a = 0; a < C.n_alleles; ++a) {
+      ab.insert(ab.end(), C.allele_bytes + C.allele_off[a], C.allele_bytes + C.allele_off[a + 1]);
+      aoff.push_back((uint32_t)ab.size());
+    }
+    lab.push_back((uint32_t)aoff.size() - 1);
+    rstart.push_back(C.block_start);
+    rend.push_back(C.block_end);
+    for (uint32_t i = 0; i < RR.n_reads; ++i) {
+      read_start.push_back(RR.read_start[i]);
+      read_stop.push_back(RR.read_stop[i]);
+      rb.insert(rb.end(), RR.read_bytes + RR.read_off[i], RR.read_bytes + RR.read_off[i + 1]);
+      roff.push_back((uint32_t)rb.size());
+      cops.insert(cops.end(), RR.cigar_ops + RR.cigar_off[i], RR.cigar_ops + RR.cigar_off[i + 1]);
+      coff.push_back((uint32_t)cops.size());
+      read_sample.push_back(RR.read_sample[i]);
+      p1.push_back(RR.log_p1[i]);
+      p2.push_back(RR.log_p2[i]);
+    }
+    lrb.push_back((uint32_t)read_start.size());
+    lns.push_back(RR.n_samples);
+  }
+  for (RegionWork& W : work) {
+    ltr_candidates_free(W.cand);
+    ltr_region_reads_free(W.reads);
+  }
+  int rc = LTR_OK;
+  ltr_batch_calls* calls = nullptr;
+  if (n_loci) {
+    lfb.push_back(0); rfb.push_back(0); ab.push_back(0); rb.push_back(0); cops.push_back(0);
+    ltr_locus_batch B;
+    memset(&B, 0, sizeof(B));
+    B.n_loci = n_loci;
+    B.lflank_off = lflank_off.data(); B.lflank_bytes = lfb.data();
+    B.rflank_off = rflank_off.data(); B.rflank_bytes = rfb.data();
+    B.locus_allele_begin = lab.data(); B.allele_off = aoff.data(); B.allele_bytes = ab.data();
+    B.repeat_start = rstart.data(); B.repeat_end = rend.data();
+    B.locus_read_begin = lrb.data(); B.read_start = read_start.data(); B.read_stop = read_stop.data();
+    B.read_off = roff.data(); B.read_bytes = rb.data(); B.cigar_off = coff.data(); B.cigar_ops = cops.data();
+    B.read_sample = read_sample.data(); B.log_p1 = p1.data(); B.log_p2 = p2.data();
+    B.second_mate = nullptr;
+    B.locus_n_samples = lns.data();
+    B.locus_haploid = nullptr;
+    rc = ltr_genotyper_run(g, params, &B, &calls);
+  }
+  if (rc != LTR_OK) {
+    delete O;
+    return rc;
+  }
+  ltr_regions_result& P = O->pub;
+  P.n_regions = n_regions;
+  P.status = O->status.data();
+  P.locus_index = O->locus_index.data();
+  P.n_loci = n_loci;
+  P.calls = calls;
+  P.block_start = O->block_start.data();
+  P.block_end = O->block_end.data();
+  P.region_allele_begin = O->region_allele_begin.data();
+  P.allele_off = O->allele_off.data();
+  P.allele_bytes = O->allele_bytes.data();
+  P.region_sample_begin = O->region_sample_begin.data();
+  P.sample_file = O->sample_file.data();
+  P.owner = O;
+  *out = &O->pub;
+  return LTR_OK;
+}
+
+extern "C" void ltr_regions_opts_default(ltr_regions_opts* o) {
+  if (!o) return;
+  o->host_threads = 0;
+  o->max_tr_len = 1000;      // MAX_STR_LENGTH (--max-tr-len), bam_processor.h:94
+  o->min_total_reads = 10;   // MIN_TOTAL_READS (--min-reads), genotyper_bam_processor.h:110
+}
+
+extern "C" void ltr_regions_result_free(ltr_regions_result* r) {
+  if (!r) return;
+  ltr_batch_calls_free(r->calls);
+  delete static_cast<Owner*>(r->owner);
+}

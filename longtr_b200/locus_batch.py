@@ -35,6 +35,21 @@ BAM_OPS = "MIDNSHP=X"
 _CIGAR_RE = re.compile(r"(\d+)(.)")
 
 
+class Region(C.Structure):
+    _fields_ = [("start", C.c_int32), ("stop", C.c_int32), ("period", C.c_int32)]
+
+
+class RegionsOpts(C.Structure):
+    _fields_ = [("host_threads", C.c_int32), ("max_tr_len", C.c_int32), ("min_total_reads", C.c_int32)]
+
+
+class RegionsResult(C.Structure):
+    _fields_ = [("n_regions", C.c_uint32), ("status", _i32p), ("locus_index", _i32p), ("n_loci", C.c_uint32),
+                ("calls", C.POINTER(BatchCalls)), ("block_start", _i32p), ("block_end", _i32p),
+                ("region_allele_begin", _u32p), ("allele_off", _u32p), ("allele_bytes", _u8p),
+                ("region_sample_begin", _u32p), ("sample_file", _u32p), ("owner", C.c_void_p)]
+
+
 def pack_cigar(cigar):
     """'110=4I90=' -> BAM-encoded uint32 list (length << 4 | op).  Unknown operations get code 15 (rejected by the library
     like the reference rejects them)."""
@@ -115,6 +130,12 @@ def _declare(lib):
     lib.ltr_locus_batch_trim_read.argtypes = [C.POINTER(LocusBatch), C.POINTER(abi.Params), C.c_uint32, C.c_uint32, _u8p,
                                               C.c_int32]
     lib.ltr_locus_batch_trim_read.restype = C.c_int32
+    lib.ltr_regions_run.argtypes = [vp, C.POINTER(abi.Params), C.POINTER(C.c_void_p), C.c_int32, C.c_char_p,
+                                    C.POINTER(Region), C.c_uint32, _u8p, C.c_int64, C.c_int64, C.POINTER(abi.RegionParams),
+                                    C.POINTER(RegionsOpts), C.POINTER(C.POINTER(RegionsResult))]
+    lib.ltr_regions_run.restype = C.c_int
+    lib.ltr_regions_result_free.argtypes = [C.POINTER(RegionsResult)]
+    lib.ltr_regions_result_free.restype = None
 
 
 def trim_read(batch_struct, locus, read, aln_params=None, indel_flank_len=5, cap=1 << 16):
@@ -160,6 +181,12 @@ class Genotyper:
         """batch: dict of numpy arrays (build_locus_batch).  Returns a dict of numpy copies of ltr_batch_calls."""
         s, keep = make_locus_batch(batch)
         calls = self.run_struct(s, aln_params, indel_flank_len)
+        out = self._calls_dict(calls)
+        self.free(calls)
+        return out
+
+    @staticmethod
+    def _calls_dict(calls):
         c = calls.contents
         n = c.n_loci
         arr = np.ctypeslib.as_array
@@ -177,8 +204,40 @@ class Genotyper:
                    sample_total_lls=take(c.sample_total_lls, ns), n_reads=take(c.n_reads, ns), gl_begin=glb,
                    gls=take(c.gls, int(glb[-1])), pls=take(c.pls, int(glb[-1])),
                    timing=dict(prep_ms=c.prep_ms, gpu_wait_ms=c.gpu_wait_ms, post_ms=c.post_ms, total_ms=c.total_ms))
-        self.free(calls)
         return out
+
+    def run_regions(self, bams, chrom, regions, ref_seq, ref_seq_start=0, aln_params=None, indel_flank_len=5,
+                    host_threads=0, max_tr_len=1000, min_total_reads=10, **region_overrides):
+        """ltr_regions_run: bams = [abi.BamFile], regions = [(start, stop, period)] on `chrom`.  Returns dict(status,
+        locus_index, alleles [per region], block [(start, end)], samples [per region: file indices], calls (as ``run``))."""
+        from .engine import LongTRError
+        lib = self.lib
+        prm = abi.make_params(aln_params, indel_flank_len)
+        rp = abi.RegionParams()
+        lib.ltr_region_params_default(C.byref(rp))
+        for k, v in region_overrides.items():
+            setattr(rp, k, v)
+        opts = RegionsOpts(host_threads, max_tr_len, min_total_reads)
+        regs = (Region * max(1, len(regions)))(*[Region(*r) for r in regions])
+        handles = (C.c_void_p * len(bams))(*[b.h for b in bams])
+        ref = np.frombuffer(ref_seq.encode() if isinstance(ref_seq, str) else bytes(ref_seq), dtype=np.uint8)
+        out = C.POINTER(RegionsResult)()
+        rc = lib.ltr_regions_run(self.h, C.byref(prm), handles, len(bams), chrom.encode(), regs, len(regions),
+                                 ref.ctypes.data_as(_u8p), ref_seq_start, len(ref), C.byref(rp), C.byref(opts), C.byref(out))
+        if rc != abi.LTR_OK:
+            raise LongTRError("ltr_regions_run: %s" % lib.ltr_strerror(rc).decode())
+        r = out.contents
+        n = r.n_regions
+        ab = C.string_at(r.allele_bytes, r.allele_off[r.region_allele_begin[n]]) if n and r.region_allele_begin[n] else b""
+        res = dict(status=[r.status[i] for i in range(n)], locus_index=[r.locus_index[i] for i in range(n)],
+                   block=[(r.block_start[i], r.block_end[i]) for i in range(n)],
+                   alleles=[[ab[r.allele_off[a]:r.allele_off[a + 1]].decode()
+                             for a in range(r.region_allele_begin[i], r.region_allele_begin[i + 1])] for i in range(n)],
+                   samples=[[r.sample_file[k] for k in range(r.region_sample_begin[i], r.region_sample_begin[i + 1])]
+                            for i in range(n)],
+                   calls=self._calls_dict(r.calls) if r.n_loci else None)
+        lib.ltr_regions_result_free(out)
+        return res
 
     def close(self):
         if self.h:

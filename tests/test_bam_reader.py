@@ -94,6 +94,32 @@ def test_without_index_and_raw_bytes(tmp_path):
     indexed.close()
 
 
+def test_index_built_in_memory_equals_the_bai(tmp_path):
+    """ltr_bam_build_index on a file without .bai answers region queries like the shipped index does."""
+    src = bam_path("HG003")
+    link = tmp_path / "noindex.bam"
+    os.symlink(src, link)
+    built, shipped = abi.BamFile(str(link)), abi.BamFile(src)
+    assert not built.has_index
+    built.build_index()
+    assert built.has_index
+    allr = shipped.fetch()
+    rng = np.random.default_rng(9)
+    n = 0
+    for tid in sorted({r["tid"] for r in allr if r["tid"] >= 0}):
+        recs = [r for r in allr if r["tid"] == tid]
+        lo, hi = min(r["pos"] for r in recs), max(r["end"] for r in recs)
+        for _ in range(60):
+            a = int(rng.integers(lo - 1000, hi + 1000))
+            b = a + int(rng.choice([1, 200, 3000, 60000]))
+            want = [(r["name"], r["pos"]) for r in shipped.fetch(tid, a, b)]
+            assert [(r["name"], r["pos"]) for r in built.fetch(tid, a, b)] == want
+            n += len(want)
+    assert n > 500
+    built.close()
+    shipped.close()
+
+
 def test_open_errors(tmp_path):
     with pytest.raises(RuntimeError):
         abi.BamFile(str(tmp_path / "missing.bam"))

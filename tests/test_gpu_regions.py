@@ -1,0 +1,74 @@
+"""N3 end to end on the GPU: synthetic BAM files (tests/bam_writer.py, rebuilt here from the generator's seeds) ->
+ltr_regions_run (BAM reader, region loop, candidate alleles on host threads; alignment, posteriors, removal of uncalled
+alleles on the device) against what the reference's own genotyper made of the same reads (tests/golden/regions.json,
+recorded by tools/make_region_golden.py from oracle/_ref/ltr_ref_trace): same verdict per region, same candidate alleles,
+same surviving alleles, same optimal pairs, same posteriors."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import bam_writer as bw
+import golden_util as gu
+from longtr_b200 import abi
+from longtr_b200.locus_batch import Genotyper
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "regions.json")
+
+
+@pytest.fixture(scope="module")
+def genotyper():
+    g = Genotyper(devices=(0,), host_threads=8, chunk_loci=16)
+    yield g
+    g.close()
+
+
+@pytest.mark.parametrize("wi", [0, 1])
+def test_regions_run_matches_the_reference(genotyper, tmp_path, wi):
+    W = json.load(open(GOLD))["worlds"][wi]
+    world = bw.synthetic_world(W["n_loci"], config=3, first_locus=W["first_locus"], n_samples=W["n_samples"])
+    bams = [abi.BamFile(p) for p in bw.write_world(world, str(tmp_path))]
+    for b in bams:
+        b.build_index()
+    out = genotyper.run_regions(bams, "chrS", world["regions"], world["chrom_seq"], 0)
+    calls = out["calls"]
+    n_checked = 0
+    for g in W["regions"]:
+        r = g["region"]
+        if g["status"] != 0:
+            assert out["status"][r] == {2: 5, 3: 6, 1: 3}[g["status"]], (r, out["status"][r], g["status"])
+            assert out["locus_index"][r] == -1
+            continue
+        assert out["status"][r] == 0
+        assert out["alleles"][r] == g["alleles"] and list(out["block"][r]) == g["block"] and out["samples"][r] == g["samples"]
+        if g.get("reference_failed"):
+            continue
+        l = out["locus_index"][r]
+        assert calls["status"][l] == 0
+        a0, a1 = calls["locus_allele_begin"][l], calls["locus_allele_begin"][l + 1]
+        kept = list(np.nonzero(calls["kept_mask"][a0:a1])[0])
+        assert kept == g["kept"], r
+        s0, s1 = calls["locus_sample_begin"][l], calls["locus_sample_begin"][l + 1]
+        S, K = g["S"], len(kept)
+        assert s1 - s0 == S
+        assert list(calls["gts"][s0:s1].ravel()) == [kept[x] for x in g["out_gts"]], r
+        post = gu.unhex(g["out_post"], (S, K, K))
+        want = [post[s, g["out_gts"][2 * s], g["out_gts"][2 * s + 1]] for s in range(S)]
+        np.testing.assert_allclose(calls["log_phased_posteriors"][s0:s1], want, rtol=1e-10, atol=1e-9, err_msg=str(r))
+        np.testing.assert_allclose(calls["sample_total_lls"][s0:s1], gu.unhex(g["out_totals"]), rtol=1e-10, atol=1e-9)
+        n_checked += 1
+    assert n_checked >= (30 if wi == 0 else 10)
+
+
+def test_regions_run_reports_skipped_regions(genotyper, tmp_path):
+    world = bw.synthetic_world(6, config=3, n_samples=1)
+    bams = [abi.BamFile(p) for p in bw.write_world(world, str(tmp_path))]
+    s, e, per = world["regions"][2]
+    regions = [(s, e, per), (s, s + 2000, per), (10, 40, 2), (s + 1500, s + 1600, 3), (e, s, per)]
+    out = genotyper.run_regions(bams, "chrS", regions, world["chrom_seq"], 0)  # files without index: scanned
+    assert out["status"][1] == 2 and out["status"][2] == 3 and out["status"][3] == 4 and out["status"][4] == 1
+    assert out["status"][0] in (0, 6)
+    strict = genotyper.run_regions(bams, "chrS", regions[:1], world["chrom_seq"], 0, min_total_reads=31)
+    assert strict["status"] == [4] and strict["calls"] is None
