@@ -594,6 +594,7 @@ def measure_from_raw_loci(args, config, n_loci, steps, torch, rank, world, local
     return out
 
 
+N2_PEAK_GCUPS = 148 * 2 * 1.965e9 / 17.0 * 1024 / 1e9
 CLUSTER_THRESHOLDS = [20, 50, 80, 100, 150, 200, 300, 400, 500, 600, 700]  # HaplotypeGenerator.cpp:403
 
 
@@ -626,6 +627,14 @@ def measure_cluster(args, eng, n_sets, steps, warmup, with_cpu_baseline):
     line = {"metric": "cluster_sets_per_sec", "value": n_sets / (np.mean(ms) / 1e3), "unit": "sets/s",
             "ms_per_step": float(np.mean(ms)), "kernel_ms_per_step": float(np.mean(kms)), "steps": steps, "warmup": warmup,
             "api": "ltr_cluster_greedy (host buffers in, assignments out; all 11 thresholds of a set in one call)",
+            "gcups": float(st.n_cells) / (np.mean(kms) * 1e-3) / 1e9, "comparisons_per_step": int(st.n_pairs),
+            "roofline": {"bound": "alu_issue", "achieved": float(st.n_cells) / (np.mean(kms) * 1e-3) / 1e9,
+                         "peak": N2_PEAK_GCUPS, "unit": "GCUPS", "frac": float(st.n_cells) / (np.mean(kms) * 1e-3) / 1e9 / N2_PEAK_GCUPS,
+                         "traffic": None,
+                         "peak_source": "148 SMs x 2 ALU-pipe warp instructions per clock x 1.965 GHz / 17 word operations of "
+                                        "Myers' recurrence per 32-row word x 1024 cells per warp step; achieved counts the "
+                                        "reference-defined n*m cells of every comparison over the device time of the call "
+                                        "(15 rounds, 61 launches)"},
             "gpu_launches": int(st.n_launches),
             "config": {"workload": "N2: skipped sequences of (locus, sample) pairs, config-4-like VNTR alleles (500-1000 bp, "
                                    "2-4 alleles, ~40 distinct noisy copies), thresholds 20..700",

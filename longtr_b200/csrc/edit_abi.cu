@@ -190,10 +190,15 @@ extern "C" int ltr_cluster_greedy(ltr_ctx* ctx, const uint8_t* seq_bytes, const 
   if (rc == LTR_OK) rc = scratch(ctx, pool, (size_t)n_items, &C.pair_T);
   if (rc == LTR_OK) rc = scratch(ctx, pool, (size_t)n_items, &A.out);
   if (rc == LTR_OK) rc = scratch(ctx, pool, 4, &d_words);
+  unsigned long long* d_stat = nullptr;
+  if (rc == LTR_OK) rc = scratch(ctx, pool, 2, &d_stat);
   A.line_stride = (max_len + 4 + 15) & ~15u;
   if (rc == LTR_OK && max_len > (uint32_t)kEditStripRows)
     rc = scratch(ctx, pool, (size_t)edit_myers_warps(ctx->sm_count) * A.line_stride, &A.lines);
   if (rc != LTR_OK) return rc;
+  LTR_CUDA(ctx, cudaMemsetAsync(d_stat, 0, 2 * sizeof(unsigned long long), st));
+  C.seq_off = d_off;
+  C.stat = d_stat;
   C.n_sets = n_sets;
   C.n_items = n_items;
   C.set_begin = d_set_begin;
@@ -217,12 +222,16 @@ extern "C" int ltr_cluster_greedy(ltr_ctx* ctx, const uint8_t* seq_bytes, const 
   LTR_CUDA(ctx, cudaMemcpyAsync(out_centroid_of, C.centroid_of, (size_t)n_items * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   LTR_CUDA(ctx, cudaMemcpyAsync(out_n_centroids, C.n_centroids, (size_t)n_sets * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   LTR_CUDA(ctx, cudaMemcpyAsync(state.data(), C.state, (size_t)n_sets, cudaMemcpyDeviceToHost, st));
+  unsigned long long h_stat[2] = {0, 0};
+  LTR_CUDA(ctx, cudaMemcpyAsync(h_stat, d_stat, sizeof(h_stat), cudaMemcpyDeviceToHost, st));
   LTR_CUDA(ctx, cudaStreamSynchronize(st));
   for (uint32_t k = 0; k < n_sets; ++k) out_ok[k] = state[k] == 1 ? 1 : 0;
   if (stats) {
     float ms = 0.f;
     LTR_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_end));
     stats->kernel_ms = ms;
+    stats->n_pairs = h_stat[0];
+    stats->n_cells = h_stat[1];
     stats->n_launches = 1 + 15 * 4;
     stats->h2d_bytes = h2d;
     stats->d2h_bytes = (uint64_t)n_items * sizeof(int32_t) + (uint64_t)n_sets * (sizeof(int32_t) + 1);

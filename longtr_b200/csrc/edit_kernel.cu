@@ -206,6 +206,11 @@ __global__ void cluster_pairs_kernel(const ClusterDev C) {
   const uint32_t cur = C.cur_centroid[s];
   if (C.state[s] != 0 || i <= cur) return;
   const uint32_t slot = atomicAdd(C.n_pairs, 1u);
+  if (C.stat) {  // statistics: comparisons made and their matrix cells, as the reference would fill them
+    const uint32_t sa = C.item_seq[i], sb = C.item_seq[cur];
+    atomicAdd(C.stat + 0, 1ull);
+    atomicAdd(C.stat + 1, (unsigned long long)(C.seq_off[sa + 1] - C.seq_off[sa]) * (unsigned long long)(C.seq_off[sb + 1] - C.seq_off[sb]));
+  }
   C.pair_item[slot] = i;
   C.pair_a[slot] = C.item_seq[i];  // needleman_wunsch(seqs[i], centroids[j], ...) (:249)
   C.pair_b[slot] = C.item_seq[cur];

@@ -181,6 +181,8 @@ struct ClusterDev {
   const int32_t* score;
   uint32_t* n_pairs;
   uint32_t* cursor;
+  const uint32_t* seq_off;       // statistics only
+  unsigned long long* stat;      // [2] comparisons, their n*m cells (may be NULL)
 };
 cudaError_t launch_cluster(const ClusterDev& C, const EditArgs& A, int sm_count, cudaStream_t stream);
 
