@@ -38,6 +38,7 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", type=int, default=3, choices=[3, 4, 5])
     ap.add_argument("--n2", action="store_true", help="only the extra.n2 line (clustering kernels)")
+    ap.add_argument("--n3", action="store_true", help="only the extra.n3 line (BAM files -> calls)")
     ap.add_argument("--loci", type=int, default=0, help="loci per GPU per step (default: config size)")
     ap.add_argument("--cpu-sample-loci", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -153,12 +154,40 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi"}
 
 
+NUMA_CPUS = None  # CPUs this rank was bound to (None: not bound)
+
+
+def bind_to_gpu_numa_node(local):
+    """With several ranks on one box every rank pins ~0.75 GB of host buffers per step for its GPU; bound to the CPUs next to
+    that GPU (NVML's affinity mask) the buffers are first touched -- and therefore placed -- on the GPU's own NUMA node, and
+    the copies of eight ranks do not cross the socket interconnect.  What `numactl --cpunodebind` would do for a production
+    launch; LTR_BENCH_NO_BIND=1 switches it off."""
+    global NUMA_CPUS
+    if os.environ.get("LTR_BENCH_NO_BIND"):
+        return
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * w + b for w, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus and len(cpus) < len(os.sched_getaffinity(0)):
+            os.sched_setaffinity(0, cpus)
+            NUMA_CPUS = len(cpus)
+    except Exception:
+        pass
+
+
 def dist_setup(n_gpus):
     """One process per GPU; NCCL only for the barrier and the max-over-ranks of the timings."""
-    import torch
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        bind_to_gpu_numa_node(local)
+    import torch
     torch.cuda.set_device(local)
     if world > 1:
         import torch.distributed as dist
@@ -373,7 +402,8 @@ def run_stutter(args, torch, rank, world, local, eng, n_loci, steps, warmup, wit
                    "cell_equivalents_per_gpu": int(st.n_cells),
                    "l2": "inputs (%.0f MB) streamed once per step; per-warp working set lives in shared memory" %
                          (work.input_bytes / 1e6),
-                   "parallelism": "locus-sharded, no collective", "ll_checksum": float(np.sum(out))},
+                   "parallelism": "locus-sharded, no collective",
+                   "rank_bound_to_cpus_of_its_gpu": NUMA_CPUS, "ll_checksum": float(np.sum(out))},
         "e2e": {"value": total_loci / (e2e_ms * 1e-3), "unit": "loci/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(st.h2d_bytes), "d2h_bytes_per_step": int(st.d2h_bytes)},
         "gpu_launches": launches, "clocks": clocks,
@@ -518,7 +548,8 @@ def measure_long(args, config, n_loci, steps, warmup, torch, rank, world, local,
                    "gcups_note": "gcups = reference-defined cells (every pooled read x haplotype) / Viterbi time; "
                                  "roofline.achieved = cells actually evaluated / Viterbi time",
                    "l2": "inputs (%.0f MB) + outputs larger than L2; no flush needed" % (work.input_bytes / 1e6),
-                   "parallelism": "locus-sharded, no collective", "wall_ms_per_step": wall_step_ms,
+                   "parallelism": "locus-sharded, no collective",
+                   "rank_bound_to_cpus_of_its_gpu": NUMA_CPUS, "wall_ms_per_step": wall_step_ms,
                    "fallback_pairs": int(st.n_fallback), "ll_checksum": checksum},
         "e2e": {"value": total_loci / (e2e_ms * 1e-3), "unit": "loci/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(es.h2d_bytes), "d2h_bytes_per_step": int(es.d2h_bytes),
@@ -676,6 +707,53 @@ def measure_cluster(args, eng, n_sets, steps, warmup, with_cpu_baseline):
     return line
 
 
+def measure_regions(args, n_loci, steps, warmup):
+    """extra.n3: BAM files -> calls through ltr_regions_run (BGZF / BAM / BAI reader, read filters, trimming, candidate
+    alleles on host threads; alignment, posteriors, call extraction through ltr_genotyper_run).  The BAM file is written
+    here from the raw loci of the config-3 generator (tests/bam_writer.py); regions whose candidate alleles would need the
+    partial-order assembly are reported, not genotyped."""
+    import tempfile
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests"))
+    import bam_writer as bw
+    from longtr_b200 import abi
+    from longtr_b200.locus_batch import Genotyper
+    t0 = time.perf_counter()
+    world = bw.synthetic_world(n_loci, config=3, n_samples=1)
+    d = tempfile.mkdtemp(prefix="ltr_n3_")
+    paths = bw.write_world(world, d)
+    gen_s = time.perf_counter() - t0
+    bams = [abi.BamFile(p) for p in paths]
+    t0 = time.perf_counter()
+    for b in bams:
+        b.build_index()
+    index_ms = (time.perf_counter() - t0) * 1e3
+    g = Genotyper(devices=(0,), host_threads=0, chunk_loci=0)
+    ms, out = [], None
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        out = g.run_regions(bams, "chrS", world["regions"], world["chrom_seq"], 0)
+        if it >= warmup:
+            ms.append((time.perf_counter() - t0) * 1e3)
+    g.close()
+    status = np.array(out["status"])
+    bam_bytes = sum(os.path.getsize(p) for p in paths)
+    for p in paths:
+        os.remove(p)
+    os.rmdir(d)
+    t = out["calls"]["timing"] if out["calls"] else {}
+    return {"metric": "regions_per_sec", "value": n_loci / (np.mean(ms) / 1e3), "unit": "regions/s",
+            "ms_per_step": float(np.mean(ms)), "steps": steps, "warmup": warmup,
+            "api": "ltr_regions_run (BAM file + regions + reference sequence in, calls out)",
+            "host_threads_per_gpu": os.cpu_count(),
+            "genotyper_ms": {k: float(v) for k, v in t.items()},
+            "config": {"workload": "N3: %d config-3 loci as one coordinate-sorted BAM file (30 spanning reads per region, "
+                                   "1.5 kb each), one sample" % n_loci, "regions": n_loci,
+                       "regions_genotyped": int((status == 0).sum()), "regions_needing_assembly": int((status == 6).sum()),
+                       "regions_other": int(((status != 0) & (status != 6)).sum()), "bam_bytes": int(bam_bytes),
+                       "reads": int(sum(len(r) for r in world["records"])), "index_build_ms": index_ms,
+                       "bam_written_in_s": gen_s}}
+
+
 def compact(line):
     """Sub-line of another configuration inside the default run (extra.c4 / extra.c5)."""
     if line is None:
@@ -705,6 +783,8 @@ def main():
     eng = Engine(local)
     if args.n2:
         line = measure_cluster(args, eng, args.loci or 512, args.steps, args.warmup, not args.no_cpu_baseline)
+    elif args.n3:
+        line = measure_regions(args, args.loci or 1500, args.steps, args.warmup)
     elif args.config == 5:
         line = run_stutter(args, torch, rank, world, local, eng, args.loci or CONFIG_LOCI[5], args.steps, args.warmup,
                            world == 1 and not args.no_cpu_baseline)
@@ -724,6 +804,7 @@ def main():
                 extra["c5"] = compact(run_stutter(args, torch, rank, world, local, eng, CONFIG_LOCI[5], 2, 3,
                                                   not args.no_cpu_baseline))
                 extra["n2"] = measure_cluster(args, eng, 512, 3, 3, not args.no_cpu_baseline)
+                extra["n3"] = measure_regions(args, 1500, 2, 1)
             except Exception as e:  # the headline line must not be lost to a sub-line
                 extra["error"] = repr(e)
             line["extra"] = extra
