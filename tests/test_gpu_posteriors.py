@@ -38,6 +38,28 @@ def test_posteriors_match_oracle(engine):
         assert abs(g_total - w_total) <= ATOL + RTOL * abs(w_total)
 
 
+@pytest.mark.parametrize("S,H,reads", [(1, 24, 40), (3, 48, 30), (2, 120, 25), (1, 300, 12)])
+def test_posteriors_many_haplotypes(engine, S, H, reads):
+    """Loci far beyond the synthetic configurations (the reference allows up to 1 000 haplotypes,
+    src/seq_stutter_genotyper.cpp:622): the kernel's tables no longer fit its shared-memory budget and it falls back to
+    fewer tables / the plain loop.  Same values, same tolerance."""
+    rng = np.random.default_rng(100 + H)
+    lab = np.repeat(np.arange(S), reads).astype(np.int32)
+    R = len(lab)
+    ll = -rng.exponential(30, size=(R, H))
+    ll[rng.random((R, H)) < 0.03] = -700
+    hp = rng.integers(0, 3, size=R)
+    p1 = np.where(hp == 0, -1e-6, np.where(hp == 1, -1000.0, 0.0))
+    p2 = np.where(hp == 0, -1000.0, np.where(hp == 1, -1e-6, 0.0))
+    for haploid in (False, True):
+        w_ll, w_post, w_tot, w_total, _ = po.log_sample_posteriors(ll, p1, p2, lab, S, haploid=haploid)
+        g_ll, g_post, g_tot, g_total = engine.posteriors(ll, p1, p2, lab, S, haploid=haploid)
+        assert np.array_equal(g_ll, w_ll)
+        np.testing.assert_allclose(g_post, w_post, rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(g_tot, w_tot, rtol=RTOL, atol=ATOL)
+        assert abs(g_total - w_total) <= ATOL + RTOL * abs(w_total)
+
+
 def test_job_posteriors_multi_sample_trio(engine):
     """Resident-job path with three samples per locus (the trio configuration of BASELINE.json configs[1]):
     Viterbi LLs of the pooled reads -> per-sample posteriors, against the oracle locus by locus."""
