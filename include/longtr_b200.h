@@ -549,15 +549,28 @@ void ltr_region_reads_free(ltr_region_reads* reads);
  *                        SeqStutterGenotyper::build_haplotype, src/seq_stutter_genotyper.cpp:416-476).  Alleles: reference
  *                        allele first, then by (length, sequence); block_start / block_end: the RepeatBlock's region after
  *                        the trim; lflank / rflank: the reference-only blocks on either side (lflank starts at lflank_start).
- *                        status LTR_CAND_NEEDS_ASSEMBLY: some sample leaves more than a quarter of its reads without a
- *                        candidate; the reference then clusters them (ltr_cluster_greedy) and takes a partial-order
- *                        consensus per cluster (spoa; not reproduced).  The alleles found so far are still returned and
- *                        cluster_* lists, per such sample, the sequences to be clustered in the reference's order with their
- *                        read counts.                                                                                    */
+ *                        When some sample leaves more than a quarter of its reads without a candidate the reference
+ *                        clusters them (greedy_clustering, thresholds 20 ... 700: :238-271, :403-407), replaces every cluster
+ *                        by a partial-order consensus (spoa: :167-199), merges clusters with close consensus sequences
+ *                        (:274-292) and adds the consensus of every well-supported cluster as an "inexact" allele
+ *                        (:397-471, INEXACT_ALLELE in the VCF record).  ltr_candidate_alleles does the same on the calling
+ *                        thread; the consensus restates spoa's published algorithm (spoa is un-vendored and unpinned in the
+ *                        reference: parity of the consensus itself is unpinned, csrc/host/poa.cpp); clusters of 30 or more
+ *                        sequences, which the reference samples with std::random_device, are sampled with a fixed seed.
+ *                        allele_inexact[a] marks consensus alleles, n_consensus counts the consensus computations,
+ *                        assembly_threshold is the highest clustering threshold a sample ended on (0: no assembly).
+ *                        cluster_* lists, per sample that triggered the assembly, the sequences that were clustered in the
+ *                        reference's order with their read counts.
+ * ltr_candidate_alleles_flags  the same with LTR_CAND_FLAG_NO_ASSEMBLY: stop before the assembly with status
+ *                        LTR_CAND_NEEDS_ASSEMBLY; the alleles found so far are returned and cluster_* holds the sets to
+ *                        cluster (e.g. with ltr_cluster_greedy on the device, all thresholds in one call).
+ * ltr_poa_consensus      the consensus alone: sequences in the order they are to be added; LTR_ERR_INVALID with *out_len set
+ *                        when out_capacity is too small.                                                                 */
 #define LTR_CAND_OK 0
 #define LTR_CAND_NEAR_CHROM_END 1  /* "Haplotype blocks are too near to the chromosome ends" */
 #define LTR_CAND_NO_SPANNING 2     /* "No spanning alignments"                               */
 #define LTR_CAND_NEEDS_ASSEMBLY 3
+#define LTR_CAND_FLAG_NO_ASSEMBLY 1u
 typedef struct ltr_candidates {
   int32_t status;
   int32_t block_start, block_end;
@@ -572,11 +585,19 @@ typedef struct ltr_candidates {
   const uint32_t* cluster_off;           /* [n_cluster_seqs+1]    */
   const uint8_t* cluster_bytes;
   const int32_t* cluster_count;          /* [n_cluster_seqs] reads carrying the sequence */
+  const uint8_t* allele_inexact;         /* [n_alleles] 1: consensus of a read cluster   */
+  uint32_t n_consensus;
+  int32_t assembly_threshold;
   void* owner;
 } ltr_candidates;
 int ltr_candidate_alleles(const ltr_region_reads* reads, int32_t region_start, int32_t region_stop, int32_t period,
                           const uint8_t* ref_seq, int64_t ref_seq_start, int64_t ref_seq_len, int32_t indel_flank_len,
                           ltr_candidates** out);
+int ltr_candidate_alleles_flags(const ltr_region_reads* reads, int32_t region_start, int32_t region_stop, int32_t period,
+                                const uint8_t* ref_seq, int64_t ref_seq_start, int64_t ref_seq_len, int32_t indel_flank_len,
+                                uint32_t flags, ltr_candidates** out);
+int ltr_poa_consensus(const uint8_t* seq_bytes, const uint32_t* seq_off, uint32_t n_seqs, uint8_t* out, uint32_t out_capacity,
+                      uint32_t* out_len);
 void ltr_candidates_free(ltr_candidates* c);
 
 /* ltr_regions_run   BAM files (one per sample) + regions of ONE chromosome -> genotype calls: LongTR's region loop
@@ -593,7 +614,7 @@ void ltr_candidates_free(ltr_candidates* c);
 #define LTR_REGION_NEAR_CONTIG_END 3
 #define LTR_REGION_TOO_FEW_READS 4    /* fewer than --min-reads reads passed the filters                  */
 #define LTR_REGION_NO_SPANNING 5
-#define LTR_REGION_NEEDS_ASSEMBLY 6   /* candidate alleles would come from the partial-order assembly    */
+#define LTR_REGION_NEEDS_ASSEMBLY 6   /* only with opts->no_assembly: alleles would come from the assembly */
 #define LTR_REGION_PAIRED_READS 7     /* paired-end reads: mate logic not reproduced                      */
 #define LTR_REGION_DELETED_READ 8     /* a read in which the whole window is deleted (empty sequence)     */
 typedef struct ltr_region {
@@ -604,6 +625,7 @@ typedef struct ltr_regions_opts {
   int32_t host_threads;     /* <= 0: all hardware threads */
   int32_t max_tr_len;       /* --max-tr-len (1000)        */
   int32_t min_total_reads;  /* --min-reads (10)           */
+  int32_t no_assembly;      /* 1: report regions that need consensus alleles as LTR_REGION_NEEDS_ASSEMBLY (default 0) */
 } ltr_regions_opts;
 typedef struct ltr_regions_result {
   uint32_t n_regions;
@@ -618,6 +640,8 @@ typedef struct ltr_regions_result {
   const uint8_t* allele_bytes;
   const uint32_t* region_sample_begin; /* [n_regions+1]                                                        */
   const uint32_t* sample_file;         /* index into bams of each sample of the region                         */
+  const uint8_t* allele_inexact;       /* per allele (indexed like allele_off): 1 = consensus of a read cluster */
+  uint32_t n_assembled;                /* regions whose candidate alleles went through the assembly branch      */
   void* owner;
 } ltr_regions_result;
 void ltr_regions_opts_default(ltr_regions_opts* o);

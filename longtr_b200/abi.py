@@ -81,12 +81,14 @@ class Candidates(C.Structure):
     _fields_ = [("status", C.c_int32), ("block_start", C.c_int32), ("block_end", C.c_int32), ("n_alleles", C.c_int32),
                 ("allele_off", _u32p), ("allele_bytes", _u8p), ("lflank_start", C.c_int32), ("lflank", C.c_char_p),
                 ("rflank", C.c_char_p), ("n_cluster_samples", C.c_uint32), ("cluster_sample_begin", _u32p),
-                ("cluster_off", _u32p), ("cluster_bytes", _u8p), ("cluster_count", _i32p), ("owner", C.c_void_p)]
+                ("cluster_off", _u32p), ("cluster_bytes", _u8p), ("cluster_count", _i32p), ("allele_inexact", _u8p),
+                ("n_consensus", C.c_uint32), ("assembly_threshold", C.c_int32), ("owner", C.c_void_p)]
 
 
 def region_collect(bams, chrom, start, stop, ref_seq, ref_seq_start=0, candidates=None, **overrides):
     """ltr_region_collect -> dict(samples=[file index], reads=[dict per read, sample-major], counters).
-    candidates=dict(period=.., indel_flank_len=5): also ltr_candidate_alleles on the same reads -> res["candidates"]."""
+    candidates=dict(period=.., indel_flank_len=5, flags=0): also ltr_candidate_alleles_flags on the same reads ->
+    res["candidates"] (flags=1: stop before the assembly)."""
     lib = load()
     prm = RegionParams()
     lib.ltr_region_params_default(C.byref(prm))
@@ -117,8 +119,8 @@ def region_collect(bams, chrom, start, stop, ref_seq, ref_seq_start=0, candidate
                                                     "n_not_spanning", "n_not_unique", "n_passed", "n_trim_failed")})
     if candidates is not None:
         cp = C.POINTER(Candidates)()
-        rc = lib.ltr_candidate_alleles(out, start, stop, candidates["period"], ptr(ref, _u8p), ref_seq_start, len(ref),
-                                       candidates.get("indel_flank_len", 5), C.byref(cp))
+        rc = lib.ltr_candidate_alleles_flags(out, start, stop, candidates["period"], ptr(ref, _u8p), ref_seq_start, len(ref),
+                                             candidates.get("indel_flank_len", 5), candidates.get("flags", 0), C.byref(cp))
         if rc != 0:
             lib.ltr_region_reads_free(out)
             raise RuntimeError("ltr_candidate_alleles failed: %d" % rc)
@@ -130,6 +132,8 @@ def region_collect(bams, chrom, start, stop, ref_seq, ref_seq_start=0, candidate
             status=c.status, block_start=c.block_start, block_end=c.block_end, lflank_start=c.lflank_start,
             alleles=[ab[c.allele_off[k]:c.allele_off[k + 1]].decode() for k in range(c.n_alleles)],
             lflank=(c.lflank or b"").decode(), rflank=(c.rflank or b"").decode(),
+            inexact=[int(c.allele_inexact[k]) for k in range(c.n_alleles)], n_consensus=c.n_consensus,
+            assembly_threshold=c.assembly_threshold,
             cluster_sets=[[(cb[c.cluster_off[k]:c.cluster_off[k + 1]].decode(), c.cluster_count[k])
                            for k in range(c.cluster_sample_begin[s], c.cluster_sample_begin[s + 1])]
                           for s in range(c.n_cluster_samples)])
@@ -402,6 +406,11 @@ def load():
     lib.ltr_candidate_alleles.argtypes = [C.POINTER(RegionReads), C.c_int32, C.c_int32, C.c_int32, _u8p, C.c_int64, C.c_int64,
                                           C.c_int32, C.POINTER(C.POINTER(Candidates))]
     lib.ltr_candidate_alleles.restype = C.c_int
+    lib.ltr_candidate_alleles_flags.argtypes = [C.POINTER(RegionReads), C.c_int32, C.c_int32, C.c_int32, _u8p, C.c_int64,
+                                                C.c_int64, C.c_int32, C.c_uint32, C.POINTER(C.POINTER(Candidates))]
+    lib.ltr_candidate_alleles_flags.restype = C.c_int
+    lib.ltr_poa_consensus.argtypes = [_u8p, _u32p, C.c_uint32, _u8p, C.c_uint32, _u32p]
+    lib.ltr_poa_consensus.restype = C.c_int
     lib.ltr_candidates_free.argtypes = [C.POINTER(Candidates)]
     lib.ltr_candidates_free.restype = None
     lib.ltr_edit_distances.argtypes = [vp, _u8p, _u32p, C.c_uint32, _u32p, _u32p, _i32p, C.c_uint32, _i32p,
@@ -427,9 +436,26 @@ EXPORTED_SYMBOLS = [
     "ltr_bam_open", "ltr_bam_close", "ltr_bam_n_refs", "ltr_bam_ref_name", "ltr_bam_ref_len", "ltr_bam_ref_id",
     "ltr_bam_header_text", "ltr_bam_has_index", "ltr_bam_build_index", "ltr_bam_fetch", "ltr_bam_reads_free",
     "ltr_region_params_default", "ltr_region_collect", "ltr_region_reads_free",
-    "ltr_candidate_alleles", "ltr_candidates_free", "ltr_regions_opts_default", "ltr_regions_run",
+    "ltr_candidate_alleles", "ltr_candidate_alleles_flags", "ltr_poa_consensus", "ltr_candidates_free", "ltr_regions_opts_default", "ltr_regions_run",
     "ltr_regions_result_free",
 ]
+
+
+def poa_consensus(seqs):
+    """ltr_poa_consensus: partial-order consensus of the sequences, added in the given order."""
+    lib = load()
+    data, off = pack_seqs(seqs)
+    cap = 2 * max([len(x) for x in seqs] + [1]) + 16
+    out = np.zeros(cap, dtype=np.uint8)
+    n = C.c_uint32(0)
+    rc = lib.ltr_poa_consensus(ptr(data, _u8p), ptr(off, _u32p), len(seqs), ptr(out, _u8p), cap, C.byref(n))
+    if rc != 0 and n.value > cap:
+        cap = n.value
+        out = np.zeros(cap, dtype=np.uint8)
+        rc = lib.ltr_poa_consensus(ptr(data, _u8p), ptr(off, _u32p), len(seqs), ptr(out, _u8p), cap, C.byref(n))
+    if rc != 0:
+        raise RuntimeError("ltr_poa_consensus failed: %d" % rc)
+    return out[:n.value].tobytes().decode()
 
 
 def pack_seqs(seqs):

@@ -5,10 +5,14 @@
 //   HaplotypeGenerator::extract_sequence        :98-164   (the region's bases of one alignment)
 //   HaplotypeGenerator::trim                    :14-96    (identical allele ends are clipped)
 //   HaplotypeGenerator::fuse_haplotype_blocks   :572-607  (reference flanks of up to 35 bp)
+//   HaplotypeGenerator::greedy_clustering / merge_clusters / poa   :167-292  (the assembly branch of gen_candidate_seqs)
 // SURVEY.md section 8f, N2.  When a sample leaves more than a quarter of its reads without a candidate the reference
-// clusters those reads (greedy_clustering: ltr_cluster_greedy on the device) and replaces every cluster by a partial-order
-// consensus (spoa, un-vendored: :167-199); that consensus is not reproduced -- such a region is answered with
-// LTR_CAND_NEEDS_ASSEMBLY and the sequences that would be clustered are not turned into alleles.
+// clusters those reads (greedy_clustering, thresholds 20 ... 700), replaces every cluster by a partial-order consensus (spoa),
+// merges clusters whose consensus sequences are close, and adds the consensus of every well-supported cluster as an "inexact"
+// allele (:397-471).  That branch runs here on the host thread that prepares the region (north star: candidate-haplotype
+// construction stays on host threads), with poa.cpp standing in for the un-vendored spoa (parity of the consensus itself
+// unpinned, see there).  With LTR_CAND_FLAG_NO_ASSEMBLY the region is answered with LTR_CAND_NEEDS_ASSEMBLY instead and the
+// sets that would be clustered are listed (for ltr_cluster_greedy on the device).
 #include <limits.h>
 #include <string.h>
 
@@ -19,6 +23,7 @@
 #include <vector>
 
 #include "longtr_b200.h"
+#include "poa.h"
 
 namespace {
 
@@ -155,8 +160,137 @@ void trim(int ideal_min_length, int left_pad, int right_pad, int32_t& region_sta
   region_end -= rt;
 }
 
+typedef std::map<std::string, std::vector<std::string> > Clusters;  // centroid -> members; iteration in key order matters
+
+// :238-271.  false: more than 15 centroids at this threshold.
+bool greedy_clustering(const std::vector<std::string>& seqs, Clusters& clusters, int T) {
+  std::vector<const std::string*> centroids(1, &seqs[0]);
+  clusters[seqs[0]].push_back(seqs[0]);
+  for (size_t i = 1; i < seqs.size(); ++i) {
+    int min_score = INT_MAX, min_cntr = -1;
+    for (size_t j = 0; j < centroids.size(); ++j) {
+      const int score = ltr::thresholded_edit_distance(seqs[i], *centroids[j], T);
+      if (score < T && score < min_score) {
+        min_cntr = (int)j;
+        min_score = score;
+      }
+    }
+    if (min_cntr != -1) {
+      clusters[*centroids[(size_t)min_cntr]].push_back(seqs[i]);
+    } else {
+      centroids.push_back(&seqs[i]);
+      if (centroids.size() > 15) return false;
+      clusters[seqs[i]].push_back(seqs[i]);
+    }
+  }
+  return true;
+}
+
+// :274-292 (the inner index starts at 1 there as well)
+bool merge_clusters(const std::vector<std::string>& cent, Clusters& clusters, int T) {
+  bool updated = false;
+  for (size_t i = 0; i < cent.size(); ++i)
+    for (size_t j = 1; j < cent.size(); ++j) {
+      if (i == j || clusters.find(cent[i]) == clusters.end() || clusters.find(cent[j]) == clusters.end()) continue;
+      if (ltr::thresholded_edit_distance(cent[i], cent[j], T) < T) {
+        updated = true;
+        const std::vector<std::string> moved = clusters[cent[j]];
+        std::vector<std::string>& into = clusters[cent[i]];
+        into.insert(into.end(), moved.begin(), moved.end());
+        clusters.erase(cent[j]);
+      }
+    }
+  return updated;
+}
+
+// :167-199.  Fewer than 30 sequences: all of them in order.  Otherwise the reference draws 30 distinct indices from
+// std::random_device (not reproducible by construction); here the same rejection loop runs on a generator with a fixed seed,
+// so that a region always gets the same alleles.
+struct Lcg {  // minimal standard generator: the draw must not depend on the C++ library's distribution code
+  uint64_t x;
+  uint32_t next(uint32_t n) {
+    x = x * 6364136223846793005ull + 1442695040888963407ull;
+    return (uint32_t)((x >> 33) % n);
+  }
+};
+void poa(ltr::PoaGraph& graph, const std::vector<std::string>& seqs, std::string& consensus, uint32_t& n_poa) {
+  const size_t kLimit = 30;
+  graph.clear();
+  ++n_poa;
+  if (seqs.size() < kLimit) {
+    for (const std::string& s : seqs) graph.add((const uint8_t*)s.data(), (uint32_t)s.size());
+  } else {
+    std::vector<uint32_t> idx;
+    Lcg gen = {0x4c6f6e675452ull + seqs.size()};
+    while (idx.size() < kLimit) {
+      const uint32_t r = gen.next((uint32_t)seqs.size());
+      if (std::find(idx.begin(), idx.end(), r) == idx.end()) idx.push_back(r);
+    }
+    for (uint32_t k : idx) graph.add((const uint8_t*)seqs[k].data(), (uint32_t)seqs[k].size());
+  }
+  graph.consensus(consensus);
+}
+
+// :397-471 for one sample: ladder of thresholds, clustering, consensus / merge until nothing merges, support tests.
+void assemble_sample(const std::map<std::string, int>& not_added, int n_ignored, std::vector<Seq>& seqs, uint32_t& n_poa,
+                     int32_t& threshold_used) {
+  std::vector<std::string> uniq;
+  for (auto it = not_added.begin(); it != not_added.end(); ++it) uniq.push_back(it->first);
+  std::sort(uniq.begin() + 1, uniq.end(), [](const std::string& a, const std::string& b) {
+    return a.size() != b.size() ? a.size() < b.size() : a.compare(b) < 0;
+  });
+  static const int kThresholds[] = {20, 50, 80, 100, 150, 200, 300, 400, 500, 600, 700};
+  ltr::PoaGraph graph;
+  for (int t : kThresholds) {
+    Clusters clusters;
+    if (!greedy_clustering(uniq, clusters, t)) continue;
+    bool not_converged = true;
+    while (not_converged) {
+      Clusters updated;
+      std::vector<std::string> cent;
+      for (auto it = clusters.begin(); it != clusters.end(); ++it) {
+        std::string consensus;
+        poa(graph, it->second, consensus, n_poa);
+        if (std::find(cent.begin(), cent.end(), consensus) == cent.end()) {
+          cent.push_back(consensus);
+          updated[consensus] = it->second;
+        } else {
+          std::vector<std::string>& into = updated[consensus];
+          into.insert(into.end(), it->second.begin(), it->second.end());
+        }
+      }
+      std::sort(cent.begin() + 1, cent.end(), [](const std::string& a, const std::string& b) {
+        return a.size() != b.size() ? a.size() < b.size() : a.compare(b) < 0;
+      });
+      not_converged = merge_clusters(cent, updated, t);
+      clusters.swap(updated);
+    }
+    int covered = 0;
+    std::vector<Seq> potential;
+    for (auto it = clusters.begin(); it != clusters.end(); ++it) {
+      int sum = 0;
+      for (const std::string& s : it->second) {
+        auto f = not_added.find(s);
+        if (f != not_added.end()) sum += f->second;  // (the reference's operator[] would insert a zero)
+      }
+      if (sum > std::min((int)(n_ignored * 0.10), 10)) {
+        covered += sum;
+        if (std::find(seqs.begin(), seqs.end(), Seq(it->first, false)) == seqs.end() &&
+            std::find(seqs.begin(), seqs.end(), Seq(it->first, true)) == seqs.end())
+          potential.push_back(Seq(it->first, true));
+      }
+    }
+    if (covered >= (int)(0.80 * n_ignored)) {
+      for (const Seq& s : potential) seqs.push_back(s);
+      threshold_used = t;
+      return;
+    }
+  }
+}
+
 struct Owner {
   ltr_candidates pub;
+  std::vector<uint8_t> allele_inexact;
   std::vector<uint32_t> allele_off;
   std::vector<uint8_t> allele_bytes;
   std::string lflank, rflank;
@@ -167,9 +301,9 @@ struct Owner {
 
 }  // namespace
 
-extern "C" int ltr_candidate_alleles(const ltr_region_reads* reads, int32_t region_start, int32_t region_stop, int32_t period,
-                                     const uint8_t* ref_seq, int64_t ref_seq_start, int64_t ref_seq_len,
-                                     int32_t indel_flank_len, ltr_candidates** out) {
+extern "C" int ltr_candidate_alleles_flags(const ltr_region_reads* reads, int32_t region_start, int32_t region_stop,
+                                           int32_t period, const uint8_t* ref_seq, int64_t ref_seq_start, int64_t ref_seq_len,
+                                           int32_t indel_flank_len, uint32_t flags, ltr_candidates** out) {
   if (!reads || !ref_seq || !out || region_stop < region_start || period < 1 || indel_flank_len < 0) return LTR_ERR_INVALID;
   *out = nullptr;
   Owner* O = new Owner();
@@ -272,6 +406,7 @@ extern "C" int ltr_candidate_alleles(const ltr_region_reads* reads, int32_t regi
   // :377-395 -- reads without a candidate, per sample; a sample with more than a quarter of them triggers the assembly
   O->cluster_sample_begin.push_back(0);
   O->cluster_off.push_back(0);
+  std::vector<std::pair<std::map<std::string, int>, int> > pending;
   for (size_t s = 0; s < by_sample.size(); ++s) {
     std::map<std::string, int> not_added;
     int samp_reads = 0, samp_ignored = 0;
@@ -285,8 +420,7 @@ extern "C" int ltr_candidate_alleles(const ltr_region_reads* reads, int32_t regi
       }
     }
     if (samp_ignored > samp_reads * 0.25) {
-      C.status = LTR_CAND_NEEDS_ASSEMBLY;
-      // the sequences greedy_clustering would see, in the reference's order (:398-401), with their read counts
+      // the sequences greedy_clustering sees, in the reference's order (:398-403), with their read counts
       std::vector<std::string> uniq;
       for (auto it = not_added.begin(); it != not_added.end(); ++it) uniq.push_back(it->first);
       if (uniq.size() > 1)
@@ -299,6 +433,18 @@ extern "C" int ltr_candidate_alleles(const ltr_region_reads* reads, int32_t regi
         O->cluster_count.push_back(not_added[u]);
       }
       O->cluster_sample_begin.push_back((uint32_t)O->cluster_count.size());
+      pending.push_back(std::make_pair(not_added, samp_ignored));
+    }
+  }
+  if (!pending.empty()) {
+    if (flags & LTR_CAND_FLAG_NO_ASSEMBLY) {
+      C.status = LTR_CAND_NEEDS_ASSEMBLY;
+    } else {
+      for (const auto& p : pending) {  // :397-471, sample after sample on the growing allele list
+        int32_t t_used = 0;
+        assemble_sample(p.first, p.second, seqs, C.n_consensus, t_used);
+        C.assembly_threshold = std::max(C.assembly_threshold, t_used);
+      }
     }
   }
   std::sort(seqs.begin() + 1, seqs.end(), by_length_and_sequence);  // :475
@@ -313,12 +459,14 @@ extern "C" int ltr_candidate_alleles(const ltr_region_reads* reads, int32_t regi
   for (const Seq& s : seqs) {
     O->allele_bytes.insert(O->allele_bytes.end(), s.first.begin(), s.first.end());
     O->allele_off.push_back((uint32_t)O->allele_bytes.size());
+    O->allele_inexact.push_back(s.second ? 1 : 0);
   }
   C.block_start = rs;
   C.block_end = re;
   C.n_alleles = (int32_t)seqs.size();
   C.allele_off = O->allele_off.data();
   C.allele_bytes = O->allele_bytes.data();
+  C.allele_inexact = O->allele_inexact.data();
   C.lflank_start = min_start;
   C.lflank = O->lflank.c_str();
   C.rflank = O->rflank.c_str();
@@ -327,6 +475,29 @@ extern "C" int ltr_candidate_alleles(const ltr_region_reads* reads, int32_t regi
   C.cluster_off = O->cluster_off.data();
   C.cluster_bytes = O->cluster_bytes.data();
   C.cluster_count = O->cluster_count.data();
+  return LTR_OK;
+}
+
+extern "C" int ltr_candidate_alleles(const ltr_region_reads* reads, int32_t region_start, int32_t region_stop, int32_t period,
+                                     const uint8_t* ref_seq, int64_t ref_seq_start, int64_t ref_seq_len,
+                                     int32_t indel_flank_len, ltr_candidates** out) {
+  return ltr_candidate_alleles_flags(reads, region_start, region_stop, period, ref_seq, ref_seq_start, ref_seq_len,
+                                     indel_flank_len, 0u, out);
+}
+
+// The consensus alone (diagnostics, tests, hosts that cluster elsewhere): sequences in the order they are to be added.
+extern "C" int ltr_poa_consensus(const uint8_t* seq_bytes, const uint32_t* seq_off, uint32_t n_seqs, uint8_t* out,
+                                 uint32_t out_capacity, uint32_t* out_len) {
+  if ((n_seqs && (!seq_bytes || !seq_off)) || !out_len || (out_capacity && !out)) return LTR_ERR_INVALID;
+  for (uint32_t i = 0; i < n_seqs; ++i)
+    if (seq_off[i + 1] < seq_off[i]) return LTR_ERR_INVALID;
+  ltr::PoaGraph graph;
+  for (uint32_t i = 0; i < n_seqs; ++i) graph.add(seq_bytes + seq_off[i], seq_off[i + 1] - seq_off[i]);
+  std::string c;
+  graph.consensus(c);
+  *out_len = (uint32_t)c.size();
+  if (c.size() > out_capacity) return LTR_ERR_INVALID;
+  if (!c.empty()) memcpy(out, c.data(), c.size());
   return LTR_OK;
 }
 

@@ -4,8 +4,10 @@
 // one locus at a time through seek -> filter -> trim -> candidate alleles -> align -> posteriors, the host threads prepare the
 // reads (ltr_region_collect) and candidate alleles (ltr_candidate_alleles) of MANY regions, the survivors are laid out as one
 // ltr_locus_batch, and ltr_genotyper_run aligns and genotypes them as a few asynchronous GPU jobs.
-// Regions the reference skips (too long, too near the contig ends, too few reads, no spanning alignments) or that need the
-// partial-order assembly (not reproduced) are reported with their reason and do not enter the batch.
+// Regions the reference skips (too long, too near the contig ends, too few reads, no spanning alignments) are reported with
+// their reason and do not enter the batch.  Regions whose reads are not explained by exact candidates get consensus alleles
+// from the assembly branch of ltr_candidate_alleles (clustering + partial-order consensus on the preparing host thread);
+// opts->no_assembly reports them as LTR_REGION_NEEDS_ASSEMBLY instead.
 #include <string.h>
 
 #include <atomic>
@@ -27,7 +29,7 @@ struct Owner {
   ltr_regions_result pub;
   std::vector<int32_t> status, locus_index, block_start, block_end;
   std::vector<uint32_t> region_allele_begin, allele_off, region_sample_begin, sample_file;
-  std::vector<uint8_t> allele_bytes;
+  std::vector<uint8_t> allele_bytes, allele_inexact;
 };
 
 }  // namespace
@@ -68,8 +70,8 @@ extern "C" int ltr_regions_run(ltr_genotyper* g, const ltr_params* params, const
       for (uint32_t i = 0; i < W.reads->n_reads && W.status == LTR_REGION_OK; ++i)
         if (W.reads->read_off[i + 1] == W.reads->read_off[i]) W.status = LTR_REGION_DELETED_READ;  // empty (deleted) reads: not batched
       if (W.status != LTR_REGION_OK) continue;
-      rc = ltr_candidate_alleles(W.reads, R.start, R.stop, R.period, ref_seq, ref_seq_start, ref_seq_len,
-                                 params->indel_flank_len, &W.cand);
+      rc = ltr_candidate_alleles_flags(W.reads, R.start, R.stop, R.period, ref_seq, ref_seq_start, ref_seq_len,
+                                       params->indel_flank_len, opts->no_assembly ? LTR_CAND_FLAG_NO_ASSEMBLY : 0u, &W.cand);
       if (rc != LTR_OK) { W.status = LTR_REGION_INVALID; continue; }
       switch (W.cand->status) {
         case LTR_CAND_OK: break;
@@ -114,7 +116,9 @@ extern "C" int ltr_regions_run(ltr_genotyper* g, const ltr_params* params, const
         O->allele_bytes.insert(O->allele_bytes.end(), W.cand->allele_bytes + W.cand->allele_off[a],
                                W.cand->allele_bytes + W.cand->allele_off[a + 1]);
         O->allele_off.push_back((uint32_t)O->allele_bytes.size());
+        O->allele_inexact.push_back(W.cand->allele_inexact[a]);
       }
+      if (W.cand->status == LTR_CAND_OK && W.cand->n_cluster_samples > 0) ++O->pub.n_assembled;
     }
     O->region_allele_begin.push_back((uint32_t)O->allele_off.size() - 1);
     if (W.status != LTR_REGION_OK) continue;
@@ -184,6 +188,7 @@ extern "C" int ltr_regions_run(ltr_genotyper* g, const ltr_params* params, const
   P.region_allele_begin = O->region_allele_begin.data();
   P.allele_off = O->allele_off.data();
   P.allele_bytes = O->allele_bytes.data();
+  P.allele_inexact = O->allele_inexact.data();
   P.region_sample_begin = O->region_sample_begin.data();
   P.sample_file = O->sample_file.data();
   P.owner = O;
@@ -196,6 +201,7 @@ extern "C" void ltr_regions_opts_default(ltr_regions_opts* o) {
   o->host_threads = 0;
   o->max_tr_len = 1000;      // MAX_STR_LENGTH (--max-tr-len), bam_processor.h:94
   o->min_total_reads = 10;   // MIN_TOTAL_READS (--min-reads), genotyper_bam_processor.h:110
+  o->no_assembly = 0;
 }
 
 extern "C" void ltr_regions_result_free(ltr_regions_result* r) {

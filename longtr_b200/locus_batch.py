@@ -40,14 +40,16 @@ class Region(C.Structure):
 
 
 class RegionsOpts(C.Structure):
-    _fields_ = [("host_threads", C.c_int32), ("max_tr_len", C.c_int32), ("min_total_reads", C.c_int32)]
+    _fields_ = [("host_threads", C.c_int32), ("max_tr_len", C.c_int32), ("min_total_reads", C.c_int32),
+                ("no_assembly", C.c_int32)]
 
 
 class RegionsResult(C.Structure):
     _fields_ = [("n_regions", C.c_uint32), ("status", _i32p), ("locus_index", _i32p), ("n_loci", C.c_uint32),
                 ("calls", C.POINTER(BatchCalls)), ("block_start", _i32p), ("block_end", _i32p),
                 ("region_allele_begin", _u32p), ("allele_off", _u32p), ("allele_bytes", _u8p),
-                ("region_sample_begin", _u32p), ("sample_file", _u32p), ("owner", C.c_void_p)]
+                ("region_sample_begin", _u32p), ("sample_file", _u32p), ("allele_inexact", _u8p),
+                ("n_assembled", C.c_uint32), ("owner", C.c_void_p)]
 
 
 def pack_cigar(cigar):
@@ -207,7 +209,7 @@ class Genotyper:
         return out
 
     def run_regions(self, bams, chrom, regions, ref_seq, ref_seq_start=0, aln_params=None, indel_flank_len=5,
-                    host_threads=0, max_tr_len=1000, min_total_reads=10, **region_overrides):
+                    host_threads=0, max_tr_len=1000, min_total_reads=10, no_assembly=0, **region_overrides):
         """ltr_regions_run: bams = [abi.BamFile], regions = [(start, stop, period)] on `chrom`.  Returns dict(status,
         locus_index, alleles [per region], block [(start, end)], samples [per region: file indices], calls (as ``run``))."""
         from .engine import LongTRError
@@ -217,7 +219,7 @@ class Genotyper:
         lib.ltr_region_params_default(C.byref(rp))
         for k, v in region_overrides.items():
             setattr(rp, k, v)
-        opts = RegionsOpts(host_threads, max_tr_len, min_total_reads)
+        opts = RegionsOpts(host_threads, max_tr_len, min_total_reads, no_assembly)
         regs = (Region * max(1, len(regions)))(*[Region(*r) for r in regions])
         handles = (C.c_void_p * len(bams))(*[b.h for b in bams])
         ref = np.frombuffer(ref_seq.encode() if isinstance(ref_seq, str) else bytes(ref_seq), dtype=np.uint8)
@@ -235,6 +237,9 @@ class Genotyper:
                              for a in range(r.region_allele_begin[i], r.region_allele_begin[i + 1])] for i in range(n)],
                    samples=[[r.sample_file[k] for k in range(r.region_sample_begin[i], r.region_sample_begin[i + 1])]
                             for i in range(n)],
+                   inexact=[[int(r.allele_inexact[a]) for a in range(r.region_allele_begin[i], r.region_allele_begin[i + 1])]
+                            for i in range(n)],
+                   n_assembled=r.n_assembled,
                    calls=self._calls_dict(r.calls) if r.n_loci else None)
         lib.ltr_regions_result_free(out)
         return res

@@ -68,6 +68,13 @@ $LINKXX -shared -o "$out/libltr_ref_hapgen.so" "$out/obj/hapgen_driver.o" "$out/
      "$out/obj/HapBlock.o" "$out/obj/error.o" "$out/obj/stringops.o" "$out/obj/stutter_model.o" "$out/obj/mathops.o" \
      "$out/obj/region.o" -Wl,--no-undefined -lm -lpthread
 echo "built $out/libltr_ref_hapgen.so"
+# the same with the spoa names served by oracle/poa_restatement.hpp: the reference's assembly branch runs to completion
+$CXX $FLAGS -DLTR_SPOA_RESTATEMENT -I"$here/shim" -c "$ref/src/SeqAlignment/HaplotypeGenerator.cpp" -o "$out/obj/HaplotypeGenerator_poa.o"
+$CXX -O2 -g -std=c++11 -fPIC -w -fno-access-control -DLTR_SPOA_RESTATEMENT -I"$here/shim" -I"$ref/src" -c "$here/hapgen_driver.cpp" -o "$out/obj/hapgen_driver_poa.o"
+$LINKXX -shared -o "$out/libltr_ref_hapgen_poa.so" "$out/obj/hapgen_driver_poa.o" "$out/obj/HaplotypeGenerator_poa.o" \
+     "$out/obj/HapBlock.o" "$out/obj/error.o" "$out/obj/stringops.o" "$out/obj/stutter_model.o" "$out/obj/mathops.o" \
+     "$out/obj/region.o" -Wl,--no-undefined -lm -lpthread
+echo "built $out/libltr_ref_hapgen_poa.so"
 
 # ---- IO-less per-locus genotyper (SeqStutterGenotyper ctor -> genotype -> write_vcf_record), twice ------------
 #   ltr_ref_full : every object is the reference's own (golden VCF records)
@@ -80,6 +87,8 @@ FULL_TUS="seq_stutter_genotyper SeqAlignment/HaplotypeGenerator SeqAlignment/Ali
 fobjs=""
 for tu in $FULL_TUS; do
   o="$out/obj/$(basename "$tu").o"
+  # the generator of the full binaries is the build whose spoa names are served by oracle/poa_restatement.hpp (above)
+  if [ "$tu" = "SeqAlignment/HaplotypeGenerator" ]; then fobjs="$fobjs $out/obj/HaplotypeGenerator_poa.o"; continue; fi
   if [ ! -f "$o" ] || [ "$ref/src/$tu.cpp" -nt "$o" ]; then
     $CXX $FLAGS -I"$here/shim" -c "$ref/src/$tu.cpp" -o "$o"
   fi

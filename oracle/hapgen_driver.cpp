@@ -1,6 +1,9 @@
 // TEST INFRASTRUCTURE ONLY -- the reference's own HaplotypeGenerator (add_haplotype_block + fuse_haplotype_blocks,
-// src/SeqAlignment/HaplotypeGenerator.cpp:521-607, compiled IN PLACE with the spoa stand-in throwing instead of aborting)
-// on the flat reads ltr_region_collect produces.  Private members are reached with -fno-access-control; the reference's
+// src/SeqAlignment/HaplotypeGenerator.cpp:521-607, compiled IN PLACE) on the flat reads ltr_region_collect produces.  Built
+// twice (oracle/build_ref.sh): libltr_ref_hapgen.so with the spoa stand-in throwing instead of aborting ("needs assembly" is
+// an answer), libltr_ref_hapgen_poa.so with the spoa names served by oracle/poa_restatement.hpp, so that the reference's own
+// clustering / merging / support logic around the consensus (:397-471) runs to completion; that build also exports the
+// restated consensus alone (ltr_oracle_poa_consensus).  Private members are reached with -fno-access-control; the reference's
 // sources are not touched.  Output: one text record, see tests/test_candidate_alleles.py.
 #include <limits.h>
 #include <stdint.h>
@@ -64,6 +67,8 @@ extern "C" char* ltr_ref_candidate_alleles(uint32_t n_samples, uint32_t n_reads,
       out << "ok block=" << blocks[1]->start() << ',' << blocks[1]->end() << " lstart=" << blocks[0]->start()
           << " lflank=" << blocks[0]->get_seq(0) << " rflank=" << blocks[2]->get_seq(0) << " alleles=";
       for (int k = 0; k < blocks[1]->num_options(); ++k) out << (k ? "," : "") << '[' << blocks[1]->get_seq(k) << ']';
+      out << " inexact=";
+      for (int k = 0; k < blocks[1]->num_options(); ++k) out << (k == 0 ? 0 : (int)blocks[1]->get_inexact(k));
     }
   } catch (const int&) {
     out << "status=needs assembly";
@@ -73,3 +78,17 @@ extern "C" char* ltr_ref_candidate_alleles(uint32_t n_samples, uint32_t n_reads,
   memcpy(r, s.c_str(), s.size() + 1);
   return r;
 }
+
+#ifdef LTR_SPOA_RESTATEMENT
+// HaplotypeGenerator::poa (:167-199) itself on a list of sequences (fewer than 30: no random sampling).
+extern "C" char* ltr_ref_poa(uint32_t n_seqs, const uint32_t* seq_off, const uint8_t* seq_bytes) {
+  std::vector<std::string> seqs;
+  for (uint32_t i = 0; i < n_seqs; ++i) seqs.push_back(std::string((const char*)seq_bytes + seq_off[i], seq_off[i + 1] - seq_off[i]));
+  HaplotypeGenerator gen(0, 1, 5);
+  std::string consensus;
+  gen.poa(seqs, consensus);
+  char* r = (char*)malloc(consensus.size() + 1);
+  memcpy(r, consensus.c_str(), consensus.size() + 1);
+  return r;
+}
+#endif

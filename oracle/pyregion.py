@@ -247,19 +247,41 @@ def ref_io_region(path, chrom, start, end, span=None, trim=None):
 
 # ---- the reference's own HaplotypeGenerator on flat reads (oracle/hapgen_driver.cpp) ------------------------------------
 _HAPGEN_SO = os.path.join(_HERE, "_ref", "libltr_ref_hapgen.so")
+_HAPGEN_POA_SO = os.path.join(_HERE, "_ref", "libltr_ref_hapgen_poa.so")  # spoa names served by oracle/poa_restatement.hpp
 
 
 def ref_hapgen_available():
     return os.path.exists(_HAPGEN_SO)
 
 
-def ref_candidate_alleles(reads, n_samples, region_start, region_stop, motif, chrom_seq, indel_flank_len=5):
+def ref_hapgen_poa_available():
+    return os.path.exists(_HAPGEN_POA_SO)
+
+
+def ref_poa(seqs):
+    """HaplotypeGenerator::poa (reference, compiled in place) on top of the restated spoa; fewer than 30 sequences."""
+    import numpy as np
+    assert len(seqs) < 30
+    lib = C.CDLL(_HAPGEN_POA_SO)
+    lib.ltr_ref_poa.restype = C.c_void_p
+    lib.ltr_ref_poa.argtypes = [C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint8)]
+    off = np.zeros(len(seqs) + 1, dtype=np.uint32)
+    off[1:] = np.cumsum([len(x) for x in seqs])
+    data = np.frombuffer(("".join(seqs) + "\0").encode(), dtype=np.uint8).copy()
+    p = lib.ltr_ref_poa(len(seqs), off.ctypes.data_as(C.POINTER(C.c_uint32)), data.ctypes.data_as(C.POINTER(C.c_uint8)))
+    text = C.string_at(p).decode()
+    C.CDLL(None).free(C.c_void_p(p))
+    return text
+
+
+def ref_candidate_alleles(reads, n_samples, region_start, region_stop, motif, chrom_seq, indel_flank_len=5, assemble=False):
     """reads: dicts as longtr_b200.abi.region_collect returns them.  -> dict(status) or dict(block, lstart, lflank, rflank,
-    alleles) from HaplotypeGenerator::add_haplotype_block + fuse_haplotype_blocks."""
+    alleles, inexact) from HaplotypeGenerator::add_haplotype_block + fuse_haplotype_blocks.  assemble: the build whose spoa
+    names are served by the restatement (otherwise a region that reaches the consensus answers "needs assembly")."""
     import re
 
     import numpy as np
-    lib = C.CDLL(_HAPGEN_SO)
+    lib = C.CDLL(_HAPGEN_POA_SO if assemble else _HAPGEN_SO)
     u32p, i32p, u8p = C.POINTER(C.c_uint32), C.POINTER(C.c_int32), C.POINTER(C.c_uint8)
     lib.ltr_ref_candidate_alleles.restype = C.c_void_p
     lib.ltr_ref_candidate_alleles.argtypes = [C.c_uint32, C.c_uint32, i32p, i32p, i32p, u32p, u8p, u32p, u32p, u8p, u8p,
@@ -288,6 +310,7 @@ def ref_candidate_alleles(reads, n_samples, region_start, region_stop, motif, ch
     C.CDLL(None).free(C.c_void_p(p))
     if text.startswith("status="):
         return dict(status=text[7:])
-    m = re.match(r"ok block=(-?\d+),(-?\d+) lstart=(-?\d+) lflank=(\S*) rflank=(\S*) alleles=(.*)$", text)
+    m = re.match(r"ok block=(-?\d+),(-?\d+) lstart=(-?\d+) lflank=(\S*) rflank=(\S*) alleles=(\S*) inexact=(\d*)$", text)
     return dict(status="ok", block_start=int(m.group(1)), block_end=int(m.group(2)), lflank_start=int(m.group(3)),
-                lflank=m.group(4), rflank=m.group(5), alleles=re.findall(r"\[([^\]]*)\]", m.group(6)))
+                lflank=m.group(4), rflank=m.group(5), alleles=re.findall(r"\[([^\]]*)\]", m.group(6)),
+                inexact=[int(ch) for ch in m.group(7)])

@@ -31,8 +31,13 @@ def world():
     return dict(bams=bams, ref=ref, ref_start=lo, regions=[r for r in real_cases.regions() if r["chrom"] == "chr1"])
 
 
-@pytest.mark.parametrize("which,flank", [("trio", 5), ("single", 5), ("trio", 12)])
-def test_candidates_match_the_reference(world, which, flank):
+@pytest.mark.parametrize("which,flank,assemble", [("trio", 5, False), ("single", 5, False), ("trio", 12, False),
+                                                  ("trio", 5, True), ("single", 5, True)])
+def test_candidates_match_the_reference(world, which, flank, assemble):
+    """assemble=False: the reference build whose spoa stand-in throws, against LTR_CAND_FLAG_NO_ASSEMBLY (same verdict "needs
+    assembly"); assemble=True: the build on the restated spoa against the default call (same alleles, inexact flags)."""
+    if assemble and not pr.ref_hapgen_poa_available():
+        pytest.skip("oracle/_ref/libltr_ref_hapgen_poa.so not built")
     bams = world["bams"] if which == "trio" else world["bams"][:1]
     # the driver sees a chromosome that starts at position 0: pad the slice in front
     chrom = "N" * world["ref_start"] + world["ref"]
@@ -41,20 +46,24 @@ def test_candidates_match_the_reference(world, which, flank):
     for reg in world["regions"]:
         motif = reg["motif"].split(",")[0]
         got = abi.region_collect(bams, "chr1", reg["start"], reg["stop"], world["ref"], world["ref_start"],
-                                 candidates=dict(period=len(motif), indel_flank_len=flank))
+                                 candidates=dict(period=len(motif), indel_flank_len=flank, flags=0 if assemble else 1))
         if not got["reads"]:
             continue
         c = got["candidates"]
-        want = pr.ref_candidate_alleles(got["reads"], len(got["samples"]), reg["start"], reg["stop"], motif, chrom, flank)
+        want = pr.ref_candidate_alleles(got["reads"], len(got["samples"]), reg["start"], reg["stop"], motif, chrom, flank,
+                                        assemble=assemble)
         if want["status"] != "ok":
             assert STATUS.get(c["status"]) == want["status"], (reg["name"], c["status"], want["status"])
             seen["needs assembly" if want["status"] == "needs assembly" else "other"] += 1
             continue
         assert c["status"] == 0, (reg["name"], c["status"])
-        assert c["alleles"] == want["alleles"], reg["name"]
+        assert c["alleles"] == want["alleles"] and c["inexact"] == want["inexact"], reg["name"]
+        seen["assembled"] = seen.get("assembled", 0) + (c["assembly_threshold"] > 0)
         assert (c["block_start"], c["block_end"], c["lflank_start"]) == \
                (want["block_start"], want["block_end"], want["lflank_start"])
         assert c["lflank"] == want["lflank"] and c["rflank"] == want["rflank"]
         seen["ok"] += 1
         n_multi += len(c["alleles"]) > 1
     assert seen["ok"] >= 15 and n_multi >= 8, seen
+    if assemble:
+        assert seen["needs assembly"] == 0 and seen["assembled"] >= (3 if which == "trio" else 0), seen

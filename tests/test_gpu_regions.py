@@ -2,7 +2,8 @@
 ltr_regions_run (BAM reader, region loop, candidate alleles on host threads; alignment, posteriors, removal of uncalled
 alleles on the device) against what the reference's own genotyper made of the same reads (tests/golden/regions.json,
 recorded by tools/make_region_golden.py from oracle/_ref/ltr_ref_trace): same verdict per region, same candidate alleles,
-same surviving alleles, same optimal pairs, same posteriors."""
+same surviving alleles, same optimal pairs, same posteriors -- including the regions whose candidate alleles come from the
+assembly branch (clustering + partial-order consensus; the reference ran it on the restated spoa, see tools/make_region_golden.py)."""
 import json
 import os
 
@@ -43,6 +44,7 @@ def test_regions_run_matches_the_reference(genotyper, tmp_path, wi):
             continue
         assert out["status"][r] == 0
         assert out["alleles"][r] == g["alleles"] and list(out["block"][r]) == g["block"] and out["samples"][r] == g["samples"]
+        assert out["inexact"][r] == g["inexact"]
         if g.get("reference_failed"):
             continue
         l = out["locus_index"][r]
@@ -59,7 +61,12 @@ def test_regions_run_matches_the_reference(genotyper, tmp_path, wi):
         np.testing.assert_allclose(calls["log_phased_posteriors"][s0:s1], want, rtol=1e-10, atol=1e-9, err_msg=str(r))
         np.testing.assert_allclose(calls["sample_total_lls"][s0:s1], gu.unhex(g["out_totals"]), rtol=1e-10, atol=1e-9)
         n_checked += 1
-    assert n_checked >= (30 if wi == 0 else 10)
+    assert n_checked >= (100 if wi == 0 else 60)
+    assert out["n_assembled"] >= 40 and sum(map(sum, out["inexact"])) >= 10
+    # the same regions with the assembly switched off: those that needed it are reported, the others are unchanged
+    off = genotyper.run_regions(bams, "chrS", world["regions"], world["chrom_seq"], 0, no_assembly=1)
+    n_needs = sum(1 for st in off["status"] if st == 6)
+    assert n_needs == out["n_assembled"] and off["n_assembled"] == 0
 
 
 def test_regions_run_reports_skipped_regions(genotyper, tmp_path):

@@ -1,6 +1,8 @@
 """Records tests/golden/regions.json: what the REFERENCE's genotyper (SeqStutterGenotyper ctor -> genotype(), oracle/_ref/
 ltr_ref_trace: its own HaplotypeGenerator, HapAligner and posteriors) makes of the reads that the library's region loop
-(ltr_bam_* -> ltr_region_collect) prepares from synthetic BAM files (tests/bam_writer.py).  The GPU test
+(ltr_bam_* -> ltr_region_collect) prepares from synthetic BAM files (tests/bam_writer.py).  The reference's generator runs its
+assembly branch on the restated spoa (oracle/poa_restatement.hpp: spoa is un-vendored, the consensus itself is unpinned); the
+candidate alleles it arrives at must equal ltr_candidate_alleles' (asserted below) before anything is recorded.  The GPU test
 tests/test_gpu_regions.py rebuilds the same BAM files from the same seeds and holds ltr_regions_run to these answers.
 
     python tools/make_region_golden.py          (needs /root/reference for oracle/_ref; no GPU)"""
@@ -58,6 +60,7 @@ def main():
                               n_p1s=[0] * S, n_p2s=[0] * S, reads=reads, stutter_motif="A", stutter_period=per))
             meta[-1]["case"] = len(cases) - 1
             meta[-1]["alleles"] = c["alleles"]
+            meta[-1]["inexact"] = c["inexact"]
             meta[-1]["samples"] = got["samples"]
         traces = po.full_locus_traces(cases)
         regions = []
@@ -71,7 +74,8 @@ def main():
                 continue
             first, last = calls[0], calls[-1]
             assert first["alleles"] == m["alleles"], (m["region"], first["alleles"], m["alleles"])
-            regions.append(dict(region=m["region"], status=0, alleles=m["alleles"], samples=m["samples"], S=first["S"],
+            regions.append(dict(region=m["region"], status=0, alleles=m["alleles"], inexact=m["inexact"], samples=m["samples"],
+                                S=first["S"],
                                 block=[first["repeat_start"], first["repeat_end"]], lflank=first["lflank"], rflank=first["rflank"],
                                 kept=[first["alleles"].index(a) for a in last["alleles"]], out_gts=last["gts"],
                                 out_post=last["post"], out_totals=last["totals"]))
