@@ -162,14 +162,30 @@ void trim(int ideal_min_length, int left_pad, int right_pad, int32_t& region_sta
 
 typedef std::map<std::string, std::vector<std::string> > Clusters;  // centroid -> members; iteration in key order matters
 
+// The ladder of thresholds and the consensus / merge rounds compare the same pairs of sequences again and again, and only the
+// threshold changes: the distance itself is remembered per region.
+struct DistanceMemo {
+  std::map<std::pair<std::string, std::string>, int> known;
+  int operator()(const std::string& cent_seq, const std::string& read_seq, int T) {
+    const int n = (int)cent_seq.size(), m = (int)read_seq.size();
+    if (std::abs(n - m) > T || n == 0 || m == 0) return ltr::thresholded_from_distance(n, m, 0, T);
+    auto key = std::make_pair(cent_seq, read_seq);
+    auto hit = known.find(key);
+    int d;
+    if (hit != known.end()) d = hit->second;
+    else known[key] = d = ltr::edit_distance(cent_seq, read_seq);
+    return ltr::thresholded_from_distance(n, m, d, T);
+  }
+};
+
 // :238-271.  false: more than 15 centroids at this threshold.
-bool greedy_clustering(const std::vector<std::string>& seqs, Clusters& clusters, int T) {
+bool greedy_clustering(const std::vector<std::string>& seqs, Clusters& clusters, int T, DistanceMemo& dist) {
   std::vector<const std::string*> centroids(1, &seqs[0]);
   clusters[seqs[0]].push_back(seqs[0]);
   for (size_t i = 1; i < seqs.size(); ++i) {
     int min_score = INT_MAX, min_cntr = -1;
     for (size_t j = 0; j < centroids.size(); ++j) {
-      const int score = ltr::thresholded_edit_distance(seqs[i], *centroids[j], T);
+      const int score = dist(seqs[i], *centroids[j], T);
       if (score < T && score < min_score) {
         min_cntr = (int)j;
         min_score = score;
@@ -187,12 +203,12 @@ bool greedy_clustering(const std::vector<std::string>& seqs, Clusters& clusters,
 }
 
 // :274-292 (the inner index starts at 1 there as well)
-bool merge_clusters(const std::vector<std::string>& cent, Clusters& clusters, int T) {
+bool merge_clusters(const std::vector<std::string>& cent, Clusters& clusters, int T, DistanceMemo& dist) {
   bool updated = false;
   for (size_t i = 0; i < cent.size(); ++i)
     for (size_t j = 1; j < cent.size(); ++j) {
       if (i == j || clusters.find(cent[i]) == clusters.end() || clusters.find(cent[j]) == clusters.end()) continue;
-      if (ltr::thresholded_edit_distance(cent[i], cent[j], T) < T) {
+      if (dist(cent[i], cent[j], T) < T) {
         updated = true;
         const std::vector<std::string> moved = clusters[cent[j]];
         std::vector<std::string>& into = clusters[cent[i]];
@@ -213,8 +229,22 @@ struct Lcg {  // minimal standard generator: the draw must not depend on the C++
     return (uint32_t)((x >> 33) % n);
   }
 };
-void poa(ltr::PoaGraph& graph, const std::vector<std::string>& seqs, std::string& consensus, uint32_t& n_poa) {
+// The consensus is a function of the list of sequences alone, and the ladder of thresholds and the consensus / merge rounds
+// keep asking for the same lists: answers are remembered per region (key: the sequences with their lengths).
+typedef std::map<std::string, std::string> PoaMemo;
+void poa(ltr::PoaGraph& graph, PoaMemo& memo, const std::vector<std::string>& seqs, std::string& consensus, uint32_t& n_poa) {
   const size_t kLimit = 30;
+  std::string key;
+  for (const std::string& s : seqs) {
+    const uint32_t n = (uint32_t)s.size();
+    key.append((const char*)&n, sizeof(n));
+    key.append(s);
+  }
+  auto hit = memo.find(key);
+  if (hit != memo.end()) {
+    consensus = hit->second;
+    return;
+  }
   graph.clear();
   ++n_poa;
   if (seqs.size() < kLimit) {
@@ -229,6 +259,7 @@ void poa(ltr::PoaGraph& graph, const std::vector<std::string>& seqs, std::string
     for (uint32_t k : idx) graph.add((const uint8_t*)seqs[k].data(), (uint32_t)seqs[k].size());
   }
   graph.consensus(consensus);
+  memo[key] = consensus;
 }
 
 // :397-471 for one sample: ladder of thresholds, clustering, consensus / merge until nothing merges, support tests.
@@ -241,16 +272,18 @@ void assemble_sample(const std::map<std::string, int>& not_added, int n_ignored,
   });
   static const int kThresholds[] = {20, 50, 80, 100, 150, 200, 300, 400, 500, 600, 700};
   ltr::PoaGraph graph;
+  PoaMemo memo;
+  DistanceMemo dist;
   for (int t : kThresholds) {
     Clusters clusters;
-    if (!greedy_clustering(uniq, clusters, t)) continue;
+    if (!greedy_clustering(uniq, clusters, t, dist)) continue;
     bool not_converged = true;
     while (not_converged) {
       Clusters updated;
       std::vector<std::string> cent;
       for (auto it = clusters.begin(); it != clusters.end(); ++it) {
         std::string consensus;
-        poa(graph, it->second, consensus, n_poa);
+        poa(graph, memo, it->second, consensus, n_poa);
         if (std::find(cent.begin(), cent.end(), consensus) == cent.end()) {
           cent.push_back(consensus);
           updated[consensus] = it->second;
@@ -262,7 +295,7 @@ void assemble_sample(const std::map<std::string, int>& not_added, int n_ignored,
       std::sort(cent.begin() + 1, cent.end(), [](const std::string& a, const std::string& b) {
         return a.size() != b.size() ? a.size() < b.size() : a.compare(b) < 0;
       });
-      not_converged = merge_clusters(cent, updated, t);
+      not_converged = merge_clusters(cent, updated, t, dist);
       clusters.swap(updated);
     }
     int covered = 0;

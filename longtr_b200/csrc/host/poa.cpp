@@ -110,42 +110,99 @@ void PoaGraph::sort_nodes() {
   for (uint32_t i = 0; i < N; ++i) rank_[order_[i]] = i;
 }
 
-void PoaGraph::align(const uint8_t* seq, uint32_t len, std::vector<int32_t>& aln_node, std::vector<int32_t>& aln_pos) {
+// One matrix row: columns 1 .. len of `row` from the predecessor rows (`preds`: n_pred row pointers, the first one first),
+//   row[j] = max over predecessors p of max(p[j-1] + (seq[j-1] == c ? +1 : -1), p[j] - 1), then row[j] = max(row[j], row[j-1] - 1).
+// The second pass is a running maximum of row[j] + j.  Plain version and an AVX2 version (8 columns per step, the running
+// maximum as a three-step in-register scan plus a carried lane); same integers either way.
+static void poa_row_plain(int32_t* row, const int32_t* const* preds, size_t n_pred, const uint8_t* seq, size_t len, uint8_t c) {
+  const int32_t* p0 = preds[0];
+  for (size_t j = 1; j <= len; ++j) row[j] = std::max(p0[j - 1] + (seq[j - 1] == c ? 1 : -1), p0[j] - 1);
+  for (size_t k = 1; k < n_pred; ++k) {
+    const int32_t* pk = preds[k];
+    for (size_t j = 1; j <= len; ++j) row[j] = std::max(pk[j - 1] + (seq[j - 1] == c ? 1 : -1), std::max(row[j], pk[j] - 1));
+  }
+  for (size_t j = 1; j <= len; ++j) row[j] = std::max(row[j - 1] - 1, row[j]);
+}
+
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+#define LTR_POA_AVX2 1
+// Rows are padded: columns up to the next multiple of 8 past len exist in every row and in seq (their values are never used).
+__attribute__((target("avx2"))) static void poa_row_avx2(int32_t* row, const int32_t* const* preds, size_t n_pred,
+                                                          const uint8_t* seq, size_t len, uint8_t c) {
+  const __m256i vc = _mm256_set1_epi32((int)c), one = _mm256_set1_epi32(1), two = _mm256_set1_epi32(2);
+  const __m256i neg = _mm256_set1_epi32(INT32_MIN / 2);
+  const __m256i sh1 = _mm256_setr_epi32(0, 0, 1, 2, 3, 4, 5, 6), sh2 = _mm256_setr_epi32(0, 0, 0, 1, 2, 3, 4, 5),
+                sh4 = _mm256_setr_epi32(0, 0, 0, 0, 0, 1, 2, 3), last = _mm256_set1_epi32(7);
+  __m256i jv = _mm256_setr_epi32(1, 2, 3, 4, 5, 6, 7, 8);
+  __m256i carry = _mm256_set1_epi32(row[0]);  // running maximum of row[j] + j, starting from column 0
+  const __m256i eight = _mm256_set1_epi32(8);
+  for (size_t j = 1; j <= len; j += 8) {
+    const __m256i ch = _mm256_cvtepu8_epi32(_mm_loadl_epi64((const __m128i*)(seq + j - 1)));
+    const __m256i s = _mm256_sub_epi32(_mm256_and_si256(_mm256_cmpeq_epi32(ch, vc), two), one);  // +1 / -1
+    __m256i r = _mm256_max_epi32(_mm256_add_epi32(_mm256_loadu_si256((const __m256i*)(preds[0] + j - 1)), s),
+                                 _mm256_sub_epi32(_mm256_loadu_si256((const __m256i*)(preds[0] + j)), one));
+    for (size_t k = 1; k < n_pred; ++k) {
+      const __m256i d = _mm256_add_epi32(_mm256_loadu_si256((const __m256i*)(preds[k] + j - 1)), s);
+      const __m256i u = _mm256_sub_epi32(_mm256_loadu_si256((const __m256i*)(preds[k] + j)), one);
+      r = _mm256_max_epi32(d, _mm256_max_epi32(r, u));
+    }
+    __m256i x = _mm256_add_epi32(r, jv);
+    x = _mm256_max_epi32(x, _mm256_blend_epi32(_mm256_permutevar8x32_epi32(x, sh1), neg, 0x01));
+    x = _mm256_max_epi32(x, _mm256_blend_epi32(_mm256_permutevar8x32_epi32(x, sh2), neg, 0x03));
+    x = _mm256_max_epi32(x, _mm256_blend_epi32(_mm256_permutevar8x32_epi32(x, sh4), neg, 0x0f));
+    x = _mm256_max_epi32(x, carry);
+    carry = _mm256_permutevar8x32_epi32(x, last);
+    _mm256_storeu_si256((__m256i*)(row + j), _mm256_sub_epi32(x, jv));
+    jv = _mm256_add_epi32(jv, eight);
+  }
+}
+#endif
+
+void PoaGraph::align(const uint8_t* seq_in, uint32_t len, std::vector<int32_t>& aln_node, std::vector<int32_t>& aln_pos) {
   aln_node.clear();
   aln_pos.clear();
   const uint32_t N = n_nodes();
   if (N == 0 || len == 0) return;
-  const size_t W = (size_t)len + 1;
+  const size_t W = ((size_t)len + 8) / 8 * 8 + 8;  // row stride: column 0, len columns, padding to whole steps of 8
   const int32_t gap = -1, hit = 1, miss = -1;
   if (H_.size() < (size_t)(N + 1) * W) H_.resize((size_t)(N + 1) * W);
   int32_t* H = H_.data();
-  for (size_t j = 0; j < W; ++j) H[j] = (int32_t)j * gap;
+  std::vector<uint8_t> padded(W + 8, 0);
+  std::copy(seq_in, seq_in + len, padded.begin());
+  const uint8_t* seq = padded.data();
+#ifdef LTR_POA_AVX2
+  static const bool use_avx2 = __builtin_cpu_supports("avx2");
+#endif
+  for (size_t j = 0; j < W; ++j) H[j] = -(int32_t)j;
   auto row_of_tail = [&](uint32_t e) { return (size_t)rank_[tail_[e]] + 1; };
   int32_t best = std::numeric_limits<int32_t>::min();
   uint32_t best_row = 0;
+  std::vector<const int32_t*> preds;
   for (uint32_t r = 0; r < N; ++r) {
     const uint32_t v = order_[r];
     int32_t* row = H + (size_t)(r + 1) * W;
     const std::vector<uint32_t>& in = in_[v];
-    const uint8_t c = code_[v];
     // column 0: one graph step below the best predecessor
+    preds.clear();
     if (in.empty()) {
       row[0] = gap;
+      preds.push_back(H);
     } else {
       int32_t top = std::numeric_limits<int32_t>::min() + 1024;
-      for (uint32_t e : in) top = std::max(top, H[row_of_tail(e) * W]);
+      for (uint32_t e : in) {
+        preds.push_back(H + row_of_tail(e) * W);
+        top = std::max(top, preds.back()[0]);
+      }
       row[0] = top + gap;
     }
-    const int32_t* p0 = H + (in.empty() ? 0 : row_of_tail(in[0])) * W;
-    for (size_t j = 1; j < W; ++j) row[j] = std::max(p0[j - 1] + (seq[j - 1] == c ? hit : miss), p0[j] + gap);
-    for (size_t k = 1; k < in.size(); ++k) {
-      const int32_t* pk = H + row_of_tail(in[k]) * W;
-      for (size_t j = 1; j < W; ++j)
-        row[j] = std::max(pk[j - 1] + (seq[j - 1] == c ? hit : miss), std::max(row[j], pk[j] + gap));
-    }
-    for (size_t j = 1; j < W; ++j) row[j] = std::max(row[j - 1] + gap, row[j]);
-    if (out_[v].empty() && best < row[W - 1]) {
-      best = row[W - 1];
+#ifdef LTR_POA_AVX2
+    if (use_avx2) poa_row_avx2(row, preds.data(), preds.size(), seq, len, code_[v]);
+    else
+#endif
+      poa_row_plain(row, preds.data(), preds.size(), seq, len, code_[v]);
+    if (out_[v].empty() && best < row[len]) {
+      best = row[len];
       best_row = r + 1;
     }
   }
@@ -301,13 +358,14 @@ void PoaGraph::consensus(std::string& out) {
 // ---- thresholded edit distance ------------------------------------------------------------------------------------------
 // Bit-vector recurrence of the unit-cost edit distance matrix (rows = cent_seq, columns = read_seq, first row and column
 // 0, 1, 2, ...), 64 rows per word, blocks chained through the horizontal delta of their last row.
-int thresholded_edit_distance(const std::string& a, const std::string& b, int T) {
+int edit_distance(const std::string& a, const std::string& b) {
   const int n = (int)a.size(), m = (int)b.size();
-  if (std::abs(n - m) > T) return T + 1;  // :203-206
-  if (n == 0) return m;                   // no row is visited
-  if (m == 0) return T + 1;               // every row's minimum keeps its starting value of 1000 (> T)
+  if (n == 0 || m == 0) return n + m;
   const int nb = (n + 63) / 64;
-  std::vector<uint64_t> peq((size_t)nb * 256, 0), pv((size_t)nb, ~0ull), mv((size_t)nb, 0ull);
+  static thread_local std::vector<uint64_t> peq, pv, mv;
+  peq.assign((size_t)nb * 256, 0);
+  pv.assign((size_t)nb, ~0ull);
+  mv.assign((size_t)nb, 0ull);
   for (int i = 0; i < n; ++i) peq[(size_t)(i / 64) * 256 + (uint8_t)a[(size_t)i]] |= 1ull << (i % 64);
   const int last_bit = (n - 1) % 64;
   int score = n;
@@ -332,7 +390,20 @@ int thresholded_edit_distance(const std::string& a, const std::string& b, int T)
     }
     score += hin;
   }
-  return score < T ? score : (score == T ? T : T + 1);
+  return score;
+}
+
+int thresholded_from_distance(int n, int m, int distance, int T) {
+  if (std::abs(n - m) > T) return T + 1;  // :203-206
+  if (n == 0) return m;                   // no row is visited
+  if (m == 0) return T + 1;               // every row's minimum keeps its starting value of 1000 (> T)
+  return distance < T ? distance : (distance == T ? T : T + 1);
+}
+
+int thresholded_edit_distance(const std::string& a, const std::string& b, int T) {
+  const int n = (int)a.size(), m = (int)b.size();
+  if (std::abs(n - m) > T || n == 0 || m == 0) return thresholded_from_distance(n, m, 0, T);
+  return thresholded_from_distance(n, m, edit_distance(a, b), T);
 }
 
 }  // namespace ltr

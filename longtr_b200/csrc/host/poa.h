@@ -44,5 +44,9 @@ class PoaGraph {
 // is below T and some value >= T otherwise (bit-vector recurrence on 64-bit words).  Empty strings as in the reference:
 // an empty cent_seq gives |read_seq|, an empty read_seq with a non-empty cent_seq gives T + 1.
 int thresholded_edit_distance(const std::string& cent_seq, const std::string& read_seq, int T);
+// The two halves of it: the unit-cost edit distance itself (independent of T, so a caller that walks the ladder of
+// thresholds can remember it), and the reference's answer for (|cent_seq|, |read_seq|, distance, T).
+int edit_distance(const std::string& a, const std::string& b);
+int thresholded_from_distance(int n, int m, int distance, int T);
 
 }  // namespace ltr
