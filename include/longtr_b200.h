@@ -650,6 +650,49 @@ int ltr_regions_run(ltr_genotyper* g, const ltr_params* params, const ltr_bam* c
                     int64_t ref_seq_len, const ltr_region_params* rp, const ltr_regions_opts* opts, ltr_regions_result** out);
 void ltr_regions_result_free(ltr_regions_result* r);
 
+/* ---- reference sequence, region file, the whole run ---------------------------------
+ * ltr_fasta_*   indexed FASTA access in place of htslib's faidx behind the reference's FastaReader (src/fasta_reader.{h,cpp}):
+ *               `path` is one FASTA file or a directory whose *.fa files are all loaded; the .fai index next to a file is
+ *               used when present and built in memory otherwise; a sequence name occurring twice is LTR_ERR_INVALID,
+ *               compressed FASTA LTR_ERR_UNSUPPORTED.  ltr_fasta_fetch copies bases [start, end) as they stand in the file.
+ * ltr_bed_read  readRegions + orderRegions (src/region.cpp:26-75): lines CHROM START STOP MOTIF [NAME] with 1-based START;
+ *               regions come back 0-based, sorted by (chromosome, start, stop), grouped by chromosome; period = the motif
+ *               length, -1 when comma-separated motifs differ in length (Region::computePeriod, src/region.h:36-43);
+ *               chrom_limit (may be NULL) keeps one chromosome; max_regions 0 = no limit.  A malformed line is
+ *               LTR_ERR_INVALID (the reference exits).
+ * ltr_run_bed   BamProcessor::process_regions (src/bam_processor.cpp:536-628): chromosomes of the region file are checked
+ *               against the FASTA and the alignment files (verify_chromosomes :490-531, LTR_ERR_INVALID when one is
+ *               missing), then every chromosome's sequence is fetched once and its regions go through ltr_regions_run.
+ *               per_chrom[c] covers bed->regions[chrom_region_begin[c] .. chrom_region_begin[c+1]).                   */
+typedef struct ltr_fasta ltr_fasta;
+int ltr_fasta_open(const char* path, ltr_fasta** out);
+void ltr_fasta_close(ltr_fasta* fa);
+int32_t ltr_fasta_n_seqs(const ltr_fasta* fa);
+const char* ltr_fasta_seq_name(const ltr_fasta* fa, int32_t i);
+int64_t ltr_fasta_seq_len(const ltr_fasta* fa, const char* name); /* -1: no such sequence */
+int ltr_fasta_fetch(const ltr_fasta* fa, const char* name, int64_t start, int64_t end, uint8_t* out);
+typedef struct ltr_bed {
+  uint32_t n_regions;
+  const ltr_region* regions;      /* [n_regions] sorted, grouped by chromosome */
+  const int32_t* region_chrom;    /* [n_regions] index into chroms             */
+  const char* const* names;       /* [n_regions] "" when the line has no name  */
+  const char* const* motifs;      /* [n_regions]                               */
+  uint32_t n_chroms;
+  const char* const* chroms;      /* [n_chroms] in order of appearance         */
+  void* owner;
+} ltr_bed;
+int ltr_bed_read(const char* path, uint32_t max_regions, const char* chrom_limit, ltr_bed** out);
+void ltr_bed_free(ltr_bed* b);
+typedef struct ltr_bed_run_result {
+  uint32_t n_chroms;
+  ltr_regions_result* const* per_chrom;  /* [n_chroms]   */
+  const uint32_t* chrom_region_begin;    /* [n_chroms+1] */
+  void* owner;
+} ltr_bed_run_result;
+int ltr_run_bed(ltr_genotyper* g, const ltr_params* params, const ltr_bam* const* bams, int32_t n_bams, const ltr_fasta* fasta,
+                const ltr_bed* bed, const ltr_region_params* rp, const ltr_regions_opts* opts, ltr_bed_run_result** out);
+void ltr_bed_run_result_free(ltr_bed_run_result* r);
+
 /* ---- diagnostics --------------------------------------------------------------------- */
 /* Sustained FP64-pipe issue rate of the device in lane-operations per second (the roofline
  * denominator of SURVEY.md section 8d): kind 0 = DADD, 1 = DSETP, 2 = the DADD,DADD,DSETP,

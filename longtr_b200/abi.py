@@ -142,6 +142,71 @@ def region_collect(bams, chrom, start, stop, ref_seq, ref_seq_start=0, candidate
     return res
 
 
+class Region(C.Structure):
+    _fields_ = [("start", C.c_int32), ("stop", C.c_int32), ("period", C.c_int32)]
+
+
+class Bed(C.Structure):
+    _fields_ = [("n_regions", C.c_uint32), ("regions", C.POINTER(Region)), ("region_chrom", _i32p),
+                ("names", C.POINTER(C.c_char_p)), ("motifs", C.POINTER(C.c_char_p)), ("n_chroms", C.c_uint32),
+                ("chroms", C.POINTER(C.c_char_p)), ("owner", C.c_void_p)]
+
+
+class FastaFile:
+    """ltr_fasta_*: indexed FASTA access (one file or a directory of *.fa files; host only)."""
+
+    def __init__(self, path):
+        self.lib = load()
+        h = C.c_void_p()
+        rc = self.lib.ltr_fasta_open(path.encode(), C.byref(h))
+        if rc != 0:
+            raise RuntimeError("ltr_fasta_open(%s) failed: %d" % (path, rc))
+        self.h = h
+        self.names = [self.lib.ltr_fasta_seq_name(h, i).decode() for i in range(self.lib.ltr_fasta_n_seqs(h))]
+
+    def length(self, name):
+        return self.lib.ltr_fasta_seq_len(self.h, name.encode())
+
+    def fetch(self, name, start=0, end=None):
+        if end is None:
+            end = self.length(name)
+        buf = np.zeros(max(1, end - start), dtype=np.uint8)
+        rc = self.lib.ltr_fasta_fetch(self.h, name.encode(), start, end, ptr(buf, _u8p))
+        if rc != 0:
+            raise RuntimeError("ltr_fasta_fetch failed: %d" % rc)
+        return buf[:max(0, end - start)].tobytes().decode()
+
+    def close(self):
+        if self.h:
+            self.lib.ltr_fasta_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def bed_read(path, max_regions=0, chrom_limit=None, keep_handle=False):
+    """ltr_bed_read -> dict(chroms, regions=[(chrom index, start, stop, period, name, motif)]) (+ handle with keep_handle;
+    free it with load().ltr_bed_free)."""
+    lib = load()
+    bp = C.POINTER(Bed)()
+    rc = lib.ltr_bed_read(path.encode(), max_regions, chrom_limit.encode() if chrom_limit else None, C.byref(bp))
+    if rc != 0:
+        raise RuntimeError("ltr_bed_read failed: %d" % rc)
+    b = bp.contents
+    res = dict(chroms=[b.chroms[i].decode() for i in range(b.n_chroms)],
+               regions=[(b.region_chrom[i], b.regions[i].start, b.regions[i].stop, b.regions[i].period, b.names[i].decode(),
+                         b.motifs[i].decode()) for i in range(b.n_regions)])
+    if keep_handle:
+        res["handle"] = bp
+    else:
+        lib.ltr_bed_free(bp)
+    return res
+
+
 class BamFile:
     """ltr_bam_*: BGZF / BAM / BAI reader of the library (host only)."""
 
@@ -396,6 +461,22 @@ def load():
     lib.ltr_bam_fetch.restype = C.c_int
     lib.ltr_bam_reads_free.argtypes = [C.POINTER(BamReads)]
     lib.ltr_bam_reads_free.restype = None
+    lib.ltr_fasta_open.argtypes = [C.c_char_p, C.POINTER(vp)]
+    lib.ltr_fasta_open.restype = C.c_int
+    lib.ltr_fasta_close.argtypes = [vp]
+    lib.ltr_fasta_close.restype = None
+    lib.ltr_fasta_n_seqs.argtypes = [vp]
+    lib.ltr_fasta_n_seqs.restype = C.c_int32
+    lib.ltr_fasta_seq_name.argtypes = [vp, C.c_int32]
+    lib.ltr_fasta_seq_name.restype = C.c_char_p
+    lib.ltr_fasta_seq_len.argtypes = [vp, C.c_char_p]
+    lib.ltr_fasta_seq_len.restype = C.c_int64
+    lib.ltr_fasta_fetch.argtypes = [vp, C.c_char_p, C.c_int64, C.c_int64, _u8p]
+    lib.ltr_fasta_fetch.restype = C.c_int
+    lib.ltr_bed_read.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p, C.POINTER(C.POINTER(Bed))]
+    lib.ltr_bed_read.restype = C.c_int
+    lib.ltr_bed_free.argtypes = [C.POINTER(Bed)]
+    lib.ltr_bed_free.restype = None
     lib.ltr_region_params_default.argtypes = [C.POINTER(RegionParams)]
     lib.ltr_region_params_default.restype = None
     lib.ltr_region_collect.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_char_p, C.c_int32, C.c_int32, _u8p, C.c_int64,
@@ -437,7 +518,8 @@ EXPORTED_SYMBOLS = [
     "ltr_bam_header_text", "ltr_bam_has_index", "ltr_bam_build_index", "ltr_bam_fetch", "ltr_bam_reads_free",
     "ltr_region_params_default", "ltr_region_collect", "ltr_region_reads_free",
     "ltr_candidate_alleles", "ltr_candidate_alleles_flags", "ltr_poa_consensus", "ltr_candidates_free", "ltr_regions_opts_default", "ltr_regions_run",
-    "ltr_regions_result_free",
+    "ltr_regions_result_free", "ltr_fasta_open", "ltr_fasta_close", "ltr_fasta_n_seqs", "ltr_fasta_seq_name",
+    "ltr_fasta_seq_len", "ltr_fasta_fetch", "ltr_bed_read", "ltr_bed_free", "ltr_run_bed", "ltr_bed_run_result_free",
 ]
 
 

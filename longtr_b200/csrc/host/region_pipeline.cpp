@@ -196,6 +196,66 @@ extern "C" int ltr_regions_run(ltr_genotyper* g, const ltr_params* params, const
   return LTR_OK;
 }
 
+// ---- the whole run: BAM files + FASTA + region file -> calls (BamProcessor::process_regions, src/bam_processor.cpp:536-628) ----
+namespace {
+struct RunOwner {
+  ltr_bed_run_result pub;
+  std::vector<ltr_regions_result*> per_chrom;
+  std::vector<uint32_t> begin;
+};
+}  // namespace
+
+extern "C" int ltr_run_bed(ltr_genotyper* g, const ltr_params* params, const ltr_bam* const* bams, int32_t n_bams,
+                           const ltr_fasta* fasta, const ltr_bed* bed, const ltr_region_params* rp, const ltr_regions_opts* opts,
+                           ltr_bed_run_result** out) {
+  if (!g || !params || !bams || n_bams < 1 || !fasta || !bed || !rp || !opts || !out) return LTR_ERR_INVALID;
+  *out = nullptr;
+  // verify_chromosomes (:490-531): every chromosome of the region file must exist in the FASTA and in the alignment files
+  for (uint32_t c = 0; c < bed->n_chroms; ++c) {
+    if (ltr_fasta_seq_len(fasta, bed->chroms[c]) < 0) return LTR_ERR_INVALID;
+    for (int32_t b = 0; b < n_bams; ++b)
+      if (ltr_bam_ref_id(bams[b], bed->chroms[c]) < 0) return LTR_ERR_INVALID;
+  }
+  RunOwner* O = new RunOwner();
+  memset(&O->pub, 0, sizeof(O->pub));
+  O->begin.push_back(0);
+  int rc = LTR_OK;
+  std::vector<uint8_t> chrom_seq;
+  uint32_t r = 0;
+  for (uint32_t c = 0; c < bed->n_chroms && rc == LTR_OK; ++c) {
+    uint32_t e = r;
+    while (e < bed->n_regions && bed->region_chrom[e] == (int32_t)c) ++e;
+    const int64_t len = ltr_fasta_seq_len(fasta, bed->chroms[c]);
+    chrom_seq.resize((size_t)len + 1);
+    rc = ltr_fasta_fetch(fasta, bed->chroms[c], 0, len, chrom_seq.data());
+    ltr_regions_result* res = nullptr;
+    if (rc == LTR_OK)
+      rc = ltr_regions_run(g, params, bams, n_bams, bed->chroms[c], bed->regions + r, e - r, chrom_seq.data(), 0, len, rp, opts,
+                           &res);
+    O->per_chrom.push_back(res);
+    O->begin.push_back(e);
+    r = e;
+  }
+  if (rc != LTR_OK) {
+    for (ltr_regions_result* p : O->per_chrom) ltr_regions_result_free(p);
+    delete O;
+    return rc;
+  }
+  O->pub.n_chroms = bed->n_chroms;
+  O->pub.per_chrom = O->per_chrom.data();
+  O->pub.chrom_region_begin = O->begin.data();
+  O->pub.owner = O;
+  *out = &O->pub;
+  return LTR_OK;
+}
+
+extern "C" void ltr_bed_run_result_free(ltr_bed_run_result* r) {
+  if (!r) return;
+  RunOwner* O = static_cast<RunOwner*>(r->owner);
+  for (ltr_regions_result* p : O->per_chrom) ltr_regions_result_free(p);
+  delete O;
+}
+
 extern "C" void ltr_regions_opts_default(ltr_regions_opts* o) {
   if (!o) return;
   o->host_threads = 0;

@@ -52,6 +52,11 @@ class RegionsResult(C.Structure):
                 ("n_assembled", C.c_uint32), ("owner", C.c_void_p)]
 
 
+class BedRunResult(C.Structure):
+    _fields_ = [("n_chroms", C.c_uint32), ("per_chrom", C.POINTER(C.POINTER(RegionsResult))), ("chrom_region_begin", _u32p),
+                ("owner", C.c_void_p)]
+
+
 def pack_cigar(cigar):
     """'110=4I90=' -> BAM-encoded uint32 list (length << 4 | op).  Unknown operations get code 15 (rejected by the library
     like the reference rejects them)."""
@@ -138,6 +143,11 @@ def _declare(lib):
     lib.ltr_regions_run.restype = C.c_int
     lib.ltr_regions_result_free.argtypes = [C.POINTER(RegionsResult)]
     lib.ltr_regions_result_free.restype = None
+    lib.ltr_run_bed.argtypes = [vp, C.POINTER(abi.Params), C.POINTER(C.c_void_p), C.c_int32, vp, C.POINTER(abi.Bed),
+                                C.POINTER(abi.RegionParams), C.POINTER(RegionsOpts), C.POINTER(C.POINTER(BedRunResult))]
+    lib.ltr_run_bed.restype = C.c_int
+    lib.ltr_bed_run_result_free.argtypes = [C.POINTER(BedRunResult)]
+    lib.ltr_bed_run_result_free.restype = None
 
 
 def trim_read(batch_struct, locus, read, aln_params=None, indel_flank_len=5, cap=1 << 16):
@@ -208,6 +218,20 @@ class Genotyper:
                    timing=dict(prep_ms=c.prep_ms, gpu_wait_ms=c.gpu_wait_ms, post_ms=c.post_ms, total_ms=c.total_ms))
         return out
 
+    def _regions_dict(self, r):
+        n = r.n_regions
+        ab = C.string_at(r.allele_bytes, r.allele_off[r.region_allele_begin[n]]) if n and r.region_allele_begin[n] else b""
+        return dict(status=[r.status[i] for i in range(n)], locus_index=[r.locus_index[i] for i in range(n)],
+                   block=[(r.block_start[i], r.block_end[i]) for i in range(n)],
+                   alleles=[[ab[r.allele_off[a]:r.allele_off[a + 1]].decode()
+                             for a in range(r.region_allele_begin[i], r.region_allele_begin[i + 1])] for i in range(n)],
+                   samples=[[r.sample_file[k] for k in range(r.region_sample_begin[i], r.region_sample_begin[i + 1])]
+                            for i in range(n)],
+                   inexact=[[int(r.allele_inexact[a]) for a in range(r.region_allele_begin[i], r.region_allele_begin[i + 1])]
+                            for i in range(n)],
+                   n_assembled=r.n_assembled,
+                   calls=self._calls_dict(r.calls) if r.n_loci else None)
+
     def run_regions(self, bams, chrom, regions, ref_seq, ref_seq_start=0, aln_params=None, indel_flank_len=5,
                     host_threads=0, max_tr_len=1000, min_total_reads=10, no_assembly=0, **region_overrides):
         """ltr_regions_run: bams = [abi.BamFile], regions = [(start, stop, period)] on `chrom`.  Returns dict(status,
@@ -228,20 +252,36 @@ class Genotyper:
                                  ref.ctypes.data_as(_u8p), ref_seq_start, len(ref), C.byref(rp), C.byref(opts), C.byref(out))
         if rc != abi.LTR_OK:
             raise LongTRError("ltr_regions_run: %s" % lib.ltr_strerror(rc).decode())
-        r = out.contents
-        n = r.n_regions
-        ab = C.string_at(r.allele_bytes, r.allele_off[r.region_allele_begin[n]]) if n and r.region_allele_begin[n] else b""
-        res = dict(status=[r.status[i] for i in range(n)], locus_index=[r.locus_index[i] for i in range(n)],
-                   block=[(r.block_start[i], r.block_end[i]) for i in range(n)],
-                   alleles=[[ab[r.allele_off[a]:r.allele_off[a + 1]].decode()
-                             for a in range(r.region_allele_begin[i], r.region_allele_begin[i + 1])] for i in range(n)],
-                   samples=[[r.sample_file[k] for k in range(r.region_sample_begin[i], r.region_sample_begin[i + 1])]
-                            for i in range(n)],
-                   inexact=[[int(r.allele_inexact[a]) for a in range(r.region_allele_begin[i], r.region_allele_begin[i + 1])]
-                            for i in range(n)],
-                   n_assembled=r.n_assembled,
-                   calls=self._calls_dict(r.calls) if r.n_loci else None)
+        res = self._regions_dict(out.contents)
         lib.ltr_regions_result_free(out)
+        return res
+
+    def run_bed(self, bams, fasta, bed_path, aln_params=None, indel_flank_len=5, host_threads=0, max_tr_len=1000,
+                min_total_reads=10, no_assembly=0, chrom_limit=None, **region_overrides):
+        """ltr_run_bed: bams = [abi.BamFile], fasta = abi.FastaFile, bed_path = region file (CHROM START STOP MOTIF [NAME]).
+        Returns dict(chroms, bed=[(chrom index, start, stop, period, name, motif)], per_chrom=[as run_regions])."""
+        from .engine import LongTRError
+        lib = self.lib
+        bed = abi.bed_read(bed_path, 0, chrom_limit, keep_handle=True)
+        prm = abi.make_params(aln_params, indel_flank_len)
+        rp = abi.RegionParams()
+        lib.ltr_region_params_default(C.byref(rp))
+        for k, v in region_overrides.items():
+            setattr(rp, k, v)
+        opts = RegionsOpts(host_threads, max_tr_len, min_total_reads, no_assembly)
+        handles = (C.c_void_p * len(bams))(*[b.h for b in bams])
+        out = C.POINTER(BedRunResult)()
+        rc = lib.ltr_run_bed(self.h, C.byref(prm), handles, len(bams), fasta.h, bed["handle"], C.byref(rp), C.byref(opts),
+                             C.byref(out))
+        if rc != abi.LTR_OK:
+            lib.ltr_bed_free(bed["handle"])
+            raise LongTRError("ltr_run_bed: %s" % lib.ltr_strerror(rc).decode())
+        r = out.contents
+        res = dict(chroms=bed["chroms"], bed=bed["regions"],
+                   chrom_region_begin=[r.chrom_region_begin[c] for c in range(r.n_chroms + 1)],
+                   per_chrom=[self._regions_dict(r.per_chrom[c].contents) for c in range(r.n_chroms)])
+        lib.ltr_bed_run_result_free(out)
+        lib.ltr_bed_free(bed["handle"])
         return res
 
     def close(self):

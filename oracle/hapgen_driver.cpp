@@ -79,6 +79,21 @@ extern "C" char* ltr_ref_candidate_alleles(uint32_t n_samples, uint32_t n_reads,
   return r;
 }
 
+// readRegions + orderRegions (src/region.cpp:26-75) on a well-formed region file (a malformed one makes the reference exit).
+extern "C" char* ltr_ref_read_regions(const char* path, uint32_t max_regions, const char* chrom_limit) {
+  std::vector<Region> regions;
+  std::ostringstream log, out;
+  readRegions(path, max_regions, chrom_limit ? chrom_limit : "", regions, log);
+  orderRegions(regions);
+  for (const Region& r : regions)
+    out << r.chrom() << ' ' << r.start() << ' ' << r.stop() << ' ' << r.period() << ' ' << (r.name().empty() ? "." : r.name())
+        << ' ' << r.motif() << '\n';
+  const std::string s = out.str();
+  char* res = (char*)malloc(s.size() + 1);
+  memcpy(res, s.c_str(), s.size() + 1);
+  return res;
+}
+
 #ifdef LTR_SPOA_RESTATEMENT
 // HaplotypeGenerator::poa (:167-199) itself on a list of sequences (fewer than 30: no random sampling).
 extern "C" char* ltr_ref_poa(uint32_t n_seqs, const uint32_t* seq_off, const uint8_t* seq_bytes) {

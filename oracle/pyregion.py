@@ -258,6 +258,21 @@ def ref_hapgen_poa_available():
     return os.path.exists(_HAPGEN_POA_SO)
 
 
+def ref_read_regions(path, max_regions=1000000000, chrom_limit=None):
+    """readRegions + orderRegions of the reference -> [(chrom, start, stop, period, name, motif)]."""
+    lib = C.CDLL(_HAPGEN_SO)
+    lib.ltr_ref_read_regions.restype = C.c_void_p
+    lib.ltr_ref_read_regions.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p]
+    p = lib.ltr_ref_read_regions(path.encode(), max_regions, chrom_limit.encode() if chrom_limit else None)
+    text = C.string_at(p).decode()
+    C.CDLL(None).free(C.c_void_p(p))
+    out = []
+    for line in text.splitlines():
+        c, s, e, per, name, motif = line.split(" ")
+        out.append((c, int(s), int(e), int(per), "" if name == "." else name, motif))
+    return out
+
+
 def ref_poa(seqs):
     """HaplotypeGenerator::poa (reference, compiled in place) on top of the restated spoa; fewer than 30 sequences."""
     import numpy as np

@@ -79,3 +79,37 @@ def test_regions_run_reports_skipped_regions(genotyper, tmp_path):
     assert out["status"][0] in (0, 6)
     strict = genotyper.run_regions(bams, "chrS", regions[:1], world["chrom_seq"], 0, min_total_reads=31)
     assert strict["status"] == [4] and strict["calls"] is None
+
+
+def test_run_bed_equals_regions_run(genotyper, tmp_path):
+    """ltr_run_bed (FASTA file + region file + BAM files -> calls) against ltr_regions_run on the same
+    regions with the sequence handed over directly."""
+    world = bw.synthetic_world(12, config=3, first_locus=40, n_samples=1)
+    paths = bw.write_world(world, str(tmp_path))
+    bams = [abi.BamFile(p) for p in paths]
+    for b in bams:
+        b.build_index()
+    fa = tmp_path / "ref.fa"
+    with open(fa, "w") as f:
+        f.write(">chrOther\n" + "ACGT" * 50 + "\n>chrS description\n")
+        s = world["chrom_seq"]
+        for k in range(0, len(s), 60):
+            f.write(s[k:k + 60] + "\n")
+    bed = tmp_path / "regions.bed"
+    order = list(range(len(world["regions"])))[::-1]                  # unsorted on purpose
+    with open(bed, "w") as f:
+        for r in order:
+            s0, e0, per = world["regions"][r]
+            f.write("chrS\t%d\t%d\t%s\tR%d\n" % (s0 + 1, e0, world["chrom_seq"][s0:s0 + per], r))
+    want = genotyper.run_regions(bams, "chrS", world["regions"], world["chrom_seq"], 0)
+    got = genotyper.run_bed(bams, abi.FastaFile(str(fa)), str(bed))
+    assert got["chroms"] == ["chrS"] and [b[4] for b in got["bed"]] == ["R%d" % r for r in range(len(order))]
+    g = got["per_chrom"][0]
+    for key in ("status", "locus_index", "block", "alleles", "samples", "inexact"):
+        assert g[key] == want[key], key
+    for key in ("gts", "kept_mask", "log_phased_posteriors", "gl_diffs"):
+        np.testing.assert_array_equal(g["calls"][key], want["calls"][key])
+    with open(bed, "a") as f:
+        f.write("chrMissing\t100\t130\tAC\n")
+    with pytest.raises(Exception):
+        genotyper.run_bed(bams, abi.FastaFile(str(fa)), str(bed))     # chromosome absent from the FASTA / BAM files
