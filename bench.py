@@ -39,6 +39,8 @@ def parse_args():
     ap.add_argument("--config", type=int, default=3, choices=[3, 4, 5])
     ap.add_argument("--n2", action="store_true", help="only the extra.n2 line (clustering kernels)")
     ap.add_argument("--n3", action="store_true", help="only the extra.n3 line (BAM files -> calls)")
+    ap.add_argument("--one-process-devices", type=int, default=0,
+                    help="only the raw-loci arm (ltr_genotyper_run) with ONE process driving this many devices")
     ap.add_argument("--loci", type=int, default=0, help="loci per GPU per step (default: config size)")
     ap.add_argument("--cpu-sample-loci", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -589,14 +591,14 @@ def measure_long(args, config, n_loci, steps, warmup, torch, rank, world, local,
     return line
 
 
-def measure_from_raw_loci(args, config, n_loci, steps, torch, rank, world, local):
+def measure_from_raw_loci(args, config, n_loci, steps, torch, rank, world, local, devices=None):
     """The host front half inside the clock: raw loci (whole reads with CIGARs, flank blocks, candidate alleles; pageable
     host memory) -> ltr_genotyper_run = pooling + trimming + flattening on the host threads, asynchronous GPU jobs
     (Viterbi, posteriors, removal of uncalled alleles), call extraction -> GT / Q / PQ / GL / PL per sample."""
     from longtr_b200 import Genotyper, workloads
     threads = max(1, (os.cpu_count() or 1) // max(1, world))
     work = workloads.generate_loci(config, n_loci, first_locus=rank * n_loci)
-    gen = Genotyper(devices=(local,), host_threads=threads)
+    gen = Genotyper(devices=tuple(devices) if devices else (local,), host_threads=threads)
     n_steps = max(1, min(steps, 3))
     calls = gen.run_struct(work.struct, work.aln_params)   # warm-up: pinned buffers, memory pool
     gen.free(calls)
@@ -783,7 +785,17 @@ def main():
     torch, rank, world, local = dist_setup(args.gpus)
     from longtr_b200 import Engine
     eng = Engine(local)
-    if args.n2:
+    if args.one_process_devices:
+        # the product-level multi-GPU form: one process, one context per device, chunks round robin, results in input order
+        nd = args.one_process_devices
+        line = {"metric": "loci_per_sec", "unit": "loci/s", "n_gpus": nd, "one_process": True}
+        for k in (1, nd):
+            r = measure_from_raw_loci(args, args.config, (args.loci or CONFIG_LOCI[args.config]) * k, args.steps, torch, rank,
+                                      world, local, devices=range(k))
+            line["devices_%d" % k] = r
+        line["value"] = line["devices_%d" % nd]["value"]
+        line["speedup_over_one_device"] = line["value"] / line["devices_1"]["value"]
+    elif args.n2:
         line = measure_cluster(args, eng, args.loci or 512, args.steps, args.warmup, not args.no_cpu_baseline)
     elif args.n3:
         line = measure_regions(args, args.loci or 1500, args.steps, args.warmup)

@@ -140,3 +140,29 @@ def test_batch_calls_match_the_reference_genotyper(genotyper):
             np.testing.assert_allclose(out["sample_total_lls"][s0:s1], gu.unhex(c["out_totals"]), rtol=1e-10, atol=1e-9)
             n_checked += 1
     assert n_checked == len(cases)
+
+
+def _n_devices():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.skipif(_n_devices() < 2, reason="needs two GPUs (one process driving several devices)")
+def test_one_process_two_devices_same_calls_in_input_order(genotyper):
+    """ltr_genotyper_create(devices = {0, 1}): chunks of the batch go round robin over the devices and every result is written
+    at its input index -- identical to what one device returns."""
+    loci = [_sampled_locus(1000 + s, 1 + s % 3) for s in range(96)]
+    batch = build_locus_batch(loci)
+    want = genotyper.run(batch)
+    two = Genotyper(devices=(0, 1), host_threads=8, chunk_loci=8)   # 12 chunks, 6 per device
+    try:
+        got = two.run(batch)
+    finally:
+        two.close()
+    for key in ("status", "kept_mask", "n_kept", "n_pools", "gts", "n_reads", "pls", "locus_sample_begin", "locus_allele_begin"):
+        np.testing.assert_array_equal(got[key], want[key], err_msg=key)
+    for key in ("log_phased_posteriors", "log_unphased_posteriors", "gl_diffs", "sample_total_lls", "gls"):
+        np.testing.assert_array_equal(got[key], want[key], err_msg=key)   # same kernels on the same inputs: same doubles
