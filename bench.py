@@ -604,11 +604,13 @@ def measure_from_raw_loci(args, config, n_loci, steps, torch, rank, world, local
     gen.free(calls)
     barrier(torch, world)
     t0 = time.perf_counter()
-    prep = wait = post = 0.0
-    n_ok = 0
+    prep = wait = post = submit = 0.0
+    n_ok = n_chunks = 0
     for _ in range(n_steps):
         calls = gen.run_struct(work.struct, work.aln_params)
         c = calls.contents
+        submit += c.submit_ms
+        n_chunks = c.n_chunks
         prep += c.prep_ms
         wait += c.gpu_wait_ms
         post += c.post_ms
@@ -620,7 +622,8 @@ def measure_from_raw_loci(args, config, n_loci, steps, torch, rank, world, local
     out = {"value": total_loci / (ms * 1e-3), "unit": "loci/s", "ms_per_step": ms, "steps": n_steps,
            "api": "ltr_genotyper_run (raw loci in pageable host memory -> calls)", "host_threads_per_gpu": threads,
            "host_prepare_ms_per_step": prep / n_steps, "host_wait_for_gpu_ms_per_step": wait / n_steps,
-           "host_extract_calls_ms_per_step": post / n_steps, "loci_genotyped": n_ok,
+           "host_extract_calls_ms_per_step": post / n_steps, "host_submit_ms_per_step": submit / n_steps,
+           "jobs_per_step": int(n_chunks), "loci_genotyped": n_ok,
            "input_bytes_per_step": work.input_bytes, "reads_per_step": int(work.n_reads)}
     gen.close()
     work.close()

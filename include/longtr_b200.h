@@ -353,6 +353,8 @@ typedef struct ltr_batch_calls {
   const double* gls;                       /* log10 genotype likelihoods over the KEPT alleles (GL)                      */
   const int32_t* pls;                      /* PL                                                                         */
   double prep_ms, gpu_wait_ms, post_ms, total_ms;  /* host timing of the call                                           */
+  double submit_ms;                        /* of which inside ltr_job_submit_outputs                                     */
+  uint32_t n_chunks;                       /* jobs the batch was cut into                                                */
 } ltr_batch_calls;
 
 typedef struct ltr_genotyper ltr_genotyper;

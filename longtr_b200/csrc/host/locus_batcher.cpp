@@ -624,7 +624,7 @@ int ltr_genotyper_run(ltr_genotyper* g, const ltr_params* params, const ltr_locu
   O->gls.assign(O->glb[n_samples], 0.0);
   O->pls.assign(O->glb[n_samples], 0);
 
-  double prep_ms = 0, wait_ms = 0, post_ms = 0;
+  double prep_ms = 0, wait_ms = 0, post_ms = 0, submit_ms = 0;
   int rc_all = LTR_OK;
   std::deque<Chunk*> inflight;
   std::vector<Chunk*> free_chunks(g->chunks.begin(), g->chunks.end());
@@ -646,23 +646,68 @@ int ltr_genotyper_run(ltr_genotyper* g, const ltr_params* params, const ltr_locu
     post_ms += ms_since(t1);
     free_chunks.push_back(c);
   };
-  uint32_t chunk_no = 0;
-  for (uint32_t l0 = 0; l0 < n_loci && rc_all == LTR_OK; l0 += g->chunk_loci, ++chunk_no) {
-    while (free_chunks.empty() || inflight.size() >= 2 * n_dev) {
-      retire(inflight.front());
-      inflight.pop_front();
+  // Chunk boundaries.  One device: chunk_loci loci per chunk.  Several devices: chunks of about equal estimated work (reads x
+  // allele bytes x allele length: VNTR loci differ by two orders of magnitude), at least four per device so that every device
+  // has a chunk running and one queued; a new chunk goes to the device with the fewest chunks in flight and whichever chunk
+  // finishes first is retired first.
+  std::vector<uint32_t> cuts;
+  if (n_dev <= 1 || n_loci == 0) {
+    for (uint32_t l0 = 0; l0 < n_loci; l0 += g->chunk_loci) cuts.push_back(std::min(n_loci, l0 + g->chunk_loci));
+  } else {
+    std::vector<double> cost(n_loci);
+    double total = 0;
+    for (uint32_t l = 0; l < n_loci; ++l) {
+      const double H = (double)(lab[l + 1] - lab[l]);
+      const double sumA = B.allele_off ? (double)(B.allele_off[lab[l + 1]] - B.allele_off[lab[l]]) : 0.0;
+      const double R = (double)(lrb[l + 1] - lrb[l]);
+      cost[l] = 1.0 + R * (sumA + 70.0 * H) * (H > 0 ? sumA / H + 70.0 : 0.0);
+      total += cost[l];
     }
+    const double target = total / (4.0 * (double)n_dev);
+    const uint32_t min_loci = 64;
+    double acc = 0;
+    uint32_t begin = 0;
+    for (uint32_t l = 0; l < n_loci; ++l) {
+      acc += cost[l];
+      const uint32_t n = l + 1 - begin;
+      if (n >= g->chunk_loci || (acc >= target && n >= min_loci)) {
+        cuts.push_back(l + 1);
+        begin = l + 1;
+        acc = 0;
+      }
+    }
+    if (begin < n_loci) cuts.push_back(n_loci);
+  }
+  std::vector<int> dev_load(n_dev, 0);
+  auto retire_one = [&]() {  // a finished chunk if there is one, else the oldest
+    size_t pick = 0;
+    if (n_dev > 1)
+      for (size_t k = 0; k < inflight.size(); ++k)
+        if (ltr_job_poll(g->ctxs[(size_t)inflight[k]->device_slot], inflight[k]->job) == 1) {
+          pick = k;
+          break;
+        }
+    Chunk* c = inflight[pick];
+    inflight.erase(inflight.begin() + (long)pick);
+    --dev_load[(size_t)c->device_slot];
+    retire(c);
+  };
+  uint32_t l0 = 0;
+  for (size_t ci = 0; ci < cuts.size() && rc_all == LTR_OK; l0 = cuts[ci], ++ci) {
+    while (free_chunks.empty() || inflight.size() >= 2 * n_dev) retire_one();
     Chunk* c = free_chunks.back();
     free_chunks.pop_back();
     c->l0 = l0;
-    c->l1 = std::min(n_loci, l0 + g->chunk_loci);
-    c->device_slot = (int)(chunk_no % n_dev);
+    c->l1 = cuts[ci];
+    c->device_slot = (int)(std::min_element(dev_load.begin(), dev_load.end()) - dev_load.begin());
+    ++dev_load[(size_t)c->device_slot];
     const auto t0 = Clock::now();
     prepare_pass1(B, *params, *c, *g->pool);
     const bool ok = prepare_pass2(B, *c, *g->pool);
     prep_ms += ms_since(t0);
     if (!ok) {
       rc_all = LTR_ERR_OOM;
+      --dev_load[(size_t)c->device_slot];
       free_chunks.push_back(c);
       break;
     }
@@ -678,21 +723,21 @@ int ltr_genotyper_run(ltr_genotyper* g, const ltr_params* params, const ltr_locu
     pb.prune_uncalled = 1;
     ltr_job_outputs outs;
     outs.ll = nullptr; outs.post = c->post.p; outs.totals = c->totals.p; outs.kept_mask = c->kept.p;
+    const auto t_submit = Clock::now();
     const int rc = ltr_job_submit_outputs(g->ctxs[(size_t)c->device_slot], params, &vb, &pb, &outs, &c->job);
+    submit_ms += ms_since(t_submit);
     if (rc != LTR_OK) {
       for (int32_t& s : c->status)
         if (s == LTR_OK) s = rc;
       if (rc == LTR_ERR_CUDA || rc == LTR_ERR_OOM) rc_all = rc;
       for (uint32_t i = 0; i < c->l1 - c->l0; ++i) O->status[c->l0 + i] = c->status[i];
+      --dev_load[(size_t)c->device_slot];
       free_chunks.push_back(c);
       continue;
     }
     inflight.push_back(c);
   }
-  while (!inflight.empty()) {
-    retire(inflight.front());
-    inflight.pop_front();
-  }
+  while (!inflight.empty()) retire_one();
   ltr_batch_calls& V = O->view;
   V.n_loci = n_loci;
   V.status = O->status.data(); V.locus_sample_begin = O->lsb.data(); V.locus_allele_begin = O->lab.data();
@@ -701,6 +746,7 @@ int ltr_genotyper_run(ltr_genotyper* g, const ltr_params* params, const ltr_locu
   V.sample_total_lls = O->stl.data(); V.n_reads = O->n_reads.data(); V.gl_begin = O->glb.data(); V.gls = O->gls.data();
   V.pls = O->pls.data();
   V.prep_ms = prep_ms; V.gpu_wait_ms = wait_ms; V.post_ms = post_ms; V.total_ms = ms_since(t_begin);
+  V.submit_ms = submit_ms; V.n_chunks = (uint32_t)cuts.size();
   if (rc_all != LTR_OK) {
     delete O;
     return rc_all;

@@ -28,7 +28,8 @@ class BatchCalls(C.Structure):
                 ("kept_mask", _u8p), ("n_kept", _i32p), ("n_pools", _i32p), ("gts", _i32p),
                 ("log_phased_posteriors", _dp), ("log_unphased_posteriors", _dp), ("gl_diffs", _dp),
                 ("sample_total_lls", _dp), ("n_reads", _i32p), ("gl_begin", _u64p), ("gls", _dp), ("pls", _i32p),
-                ("prep_ms", C.c_double), ("gpu_wait_ms", C.c_double), ("post_ms", C.c_double), ("total_ms", C.c_double)]
+                ("prep_ms", C.c_double), ("gpu_wait_ms", C.c_double), ("post_ms", C.c_double), ("total_ms", C.c_double),
+                ("submit_ms", C.c_double), ("n_chunks", C.c_uint32)]
 
 
 BAM_OPS = "MIDNSHP=X"
@@ -215,7 +216,8 @@ class Genotyper:
                    log_unphased_posteriors=take(c.log_unphased_posteriors, ns), gl_diffs=take(c.gl_diffs, ns),
                    sample_total_lls=take(c.sample_total_lls, ns), n_reads=take(c.n_reads, ns), gl_begin=glb,
                    gls=take(c.gls, int(glb[-1])), pls=take(c.pls, int(glb[-1])),
-                   timing=dict(prep_ms=c.prep_ms, gpu_wait_ms=c.gpu_wait_ms, post_ms=c.post_ms, total_ms=c.total_ms))
+                   timing=dict(prep_ms=c.prep_ms, gpu_wait_ms=c.gpu_wait_ms, post_ms=c.post_ms, total_ms=c.total_ms, submit_ms=c.submit_ms,
+                               n_chunks=c.n_chunks))
         return out
 
     def _regions_dict(self, r):
