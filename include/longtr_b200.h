@@ -695,6 +695,38 @@ int ltr_run_bed(ltr_genotyper* g, const ltr_params* params, const ltr_bam* const
                 const ltr_bed* bed, const ltr_region_params* rp, const ltr_regions_opts* opts, ltr_bed_run_result** out);
 void ltr_bed_run_result_free(ltr_bed_run_result* r);
 
+/* ---- length-based EM of the stutter model ----------------------------------------------
+ * ltr_em_stutter_train  EMStutterGenotyper(...).train(...) (src/em_stutter_genotyper.{h,cpp}) for many loci at once, as
+ *                       GenotyperBamProcessor::learn_stutter_model calls it (src/genotyper_bam_processor.cpp:170-225): per
+ *                       read the observed size difference to the reference in bp (ExtractCigar) and its phasing terms; the
+ *                       allele sizes of a locus are the distinct observed differences, the reference allele (0) first.
+ *                       One warp per locus runs the whole EM loop on the device.  out_params[6 * l ..] = in-frame geometric
+ *                       parameter, P(up), P(down), out-of-frame geometric parameter, P(up), P(down) of the last model;
+ *                       out_trained[l] = what train() returns; out_n_iter[l] = E steps done; out_ll[l] = last total
+ *                       log-likelihood; out_log_gt_priors (optional) = the allele log-frequencies, prior_stride entries per
+ *                       locus (alleles beyond it are dropped).  Phasing terms must be <= 0 (the reference asserts it).  In the
+ *                       reference's CLI this path is switched off by the default stutter model (hipstr_main.cpp:140, 362);
+ *                       the class is the oracle (oracle/em_driver.cpp).                                                   */
+typedef struct ltr_em_batch {
+  uint32_t n_loci;
+  const uint32_t* locus_sample_begin;  /* [n_loci+1]    samples of the locus                           */
+  const uint32_t* sample_read_begin;   /* [n_samples+1] reads of the sample (reads are sample-major)   */
+  const int32_t* read_bp_diff;         /* [n_reads]                                                    */
+  const double* log_p1;                /* [n_reads]                                                    */
+  const double* log_p2;                /* [n_reads]                                                    */
+  const int32_t* locus_motif_len;      /* [n_loci]                                                     */
+  const uint8_t* locus_haploid;        /* [n_loci] or NULL                                             */
+} ltr_em_batch;
+typedef struct ltr_em_opts {
+  int32_t max_iter;          /* MAX_EM_ITER (100)       */
+  double abs_ll_converge;    /* ABS_LL_CONVERGE (0.01)  */
+  double frac_ll_converge;   /* FRAC_LL_CONVERGE (0.001) */
+} ltr_em_opts;
+void ltr_em_opts_default(ltr_em_opts* o);
+int ltr_em_stutter_train(ltr_ctx* ctx, const ltr_em_batch* batch, const ltr_em_opts* opts, double* out_params,
+                         int32_t* out_trained, int32_t* out_n_iter, double* out_ll, double* out_log_gt_priors,
+                         uint32_t prior_stride);
+
 /* ---- diagnostics --------------------------------------------------------------------- */
 /* Sustained FP64-pipe issue rate of the device in lane-operations per second (the roofline
  * denominator of SURVEY.md section 8d): kind 0 = DADD, 1 = DSETP, 2 = the DADD,DADD,DSETP,

@@ -492,6 +492,10 @@ def load():
     lib.ltr_candidate_alleles_flags.restype = C.c_int
     lib.ltr_poa_consensus.argtypes = [_u8p, _u32p, C.c_uint32, _u8p, C.c_uint32, _u32p]
     lib.ltr_poa_consensus.restype = C.c_int
+    lib.ltr_em_opts_default.argtypes = [C.POINTER(EmOpts)]
+    lib.ltr_em_opts_default.restype = None
+    lib.ltr_em_stutter_train.argtypes = [vp, C.POINTER(EmBatch), C.POINTER(EmOpts), _dp, _i32p, _i32p, _dp, _dp, C.c_uint32]
+    lib.ltr_em_stutter_train.restype = C.c_int
     lib.ltr_candidates_free.argtypes = [C.POINTER(Candidates)]
     lib.ltr_candidates_free.restype = None
     lib.ltr_edit_distances.argtypes = [vp, _u8p, _u32p, C.c_uint32, _u32p, _u32p, _i32p, C.c_uint32, _i32p,
@@ -520,7 +524,56 @@ EXPORTED_SYMBOLS = [
     "ltr_candidate_alleles", "ltr_candidate_alleles_flags", "ltr_poa_consensus", "ltr_candidates_free", "ltr_regions_opts_default", "ltr_regions_run",
     "ltr_regions_result_free", "ltr_fasta_open", "ltr_fasta_close", "ltr_fasta_n_seqs", "ltr_fasta_seq_name",
     "ltr_fasta_seq_len", "ltr_fasta_fetch", "ltr_bed_read", "ltr_bed_free", "ltr_run_bed", "ltr_bed_run_result_free",
+    "ltr_em_opts_default", "ltr_em_stutter_train",
 ]
+
+
+class EmBatch(C.Structure):
+    _fields_ = [("n_loci", C.c_uint32), ("locus_sample_begin", _u32p), ("sample_read_begin", _u32p), ("read_bp_diff", _i32p),
+                ("log_p1", _dp), ("log_p2", _dp), ("locus_motif_len", _i32p), ("locus_haploid", _u8p)]
+
+
+class EmOpts(C.Structure):
+    _fields_ = [("max_iter", C.c_int32), ("abs_ll_converge", C.c_double), ("frac_ll_converge", C.c_double)]
+
+
+def em_stutter_train(ctx, loci, max_iter=None, abs_conv=None, frac_conv=None, prior_stride=32):
+    """ltr_em_stutter_train.  loci: [dict(reads_per_sample, bp_diff, log_p1, log_p2, motif_len, haploid=False)], reads
+    sample-major.  -> dict(params [n, 6], trained, n_iter, ll, log_gt_priors [n, prior_stride])."""
+    lib = load()
+    n = len(loci)
+    lsb = np.zeros(n + 1, dtype=np.uint32)
+    srb, bd, p1, p2 = [0], [], [], []
+    for k, L in enumerate(loci):
+        for c in L["reads_per_sample"]:
+            srb.append(srb[-1] + int(c))
+        lsb[k + 1] = len(srb) - 1
+        bd += list(L["bp_diff"]); p1 += list(L["log_p1"]); p2 += list(L["log_p2"])
+    srb = np.array(srb, dtype=np.uint32)
+    bd = np.array(bd + [0], dtype=np.int32)
+    p1 = np.array(p1 + [0.0], dtype=np.float64)
+    p2 = np.array(p2 + [0.0], dtype=np.float64)
+    ml = np.array([L["motif_len"] for L in loci] + [1], dtype=np.int32)
+    hp = np.array([1 if L.get("haploid") else 0 for L in loci] + [0], dtype=np.uint8)
+    B = EmBatch(n, ptr(lsb, _u32p), ptr(srb, _u32p), ptr(bd, _i32p), ptr(p1, _dp), ptr(p2, _dp), ptr(ml, _i32p), ptr(hp, _u8p))
+    O = EmOpts()
+    lib.ltr_em_opts_default(C.byref(O))
+    if max_iter is not None:
+        O.max_iter = max_iter
+    if abs_conv is not None:
+        O.abs_ll_converge = abs_conv
+    if frac_conv is not None:
+        O.frac_ll_converge = frac_conv
+    params = np.zeros((max(n, 1), 6))
+    trained = np.zeros(max(n, 1), dtype=np.int32)
+    n_iter = np.zeros(max(n, 1), dtype=np.int32)
+    ll = np.zeros(max(n, 1))
+    pri = np.zeros((max(n, 1), prior_stride))
+    rc = lib.ltr_em_stutter_train(ctx, C.byref(B), C.byref(O), ptr(params, _dp), ptr(trained, _i32p), ptr(n_iter, _i32p),
+                                  ptr(ll, _dp), ptr(pri, _dp), prior_stride)
+    if rc != 0:
+        raise RuntimeError("ltr_em_stutter_train failed: %d" % rc)
+    return dict(params=params[:n], trained=trained[:n], n_iter=n_iter[:n], ll=ll[:n], log_gt_priors=pri[:n])
 
 
 def poa_consensus(seqs):

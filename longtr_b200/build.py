@@ -19,7 +19,7 @@ SYNTH_OUT = os.path.join(SYNTH_DIR, "libltr_synth.so")  # workload generator of 
 OBJ = os.path.join(CSRC, "build")
 
 CU_SOURCES = ["viterbi_kernels.cu", "band_kernel.cu", "plan_kernels.cu", "posterior_kernel.cu", "stutter_kernel.cu", "abi.cu", "stutter_abi.cu",
-              "edit_kernel.cu", "edit_abi.cu", "microbench.cu"]
+              "edit_kernel.cu", "edit_abi.cu", "em_kernel.cu", "microbench.cu"]
 CPP_SOURCES = ["host/flat_api.cpp", "host/host_types.cpp", "host/hap_aligner.cpp", "host/stutter_host.cpp",
                "host/genotyper.cpp", "host/pipeline.cpp", "host/locus_batcher.cpp", "host/bam_reader.cpp", "host/region_loader.cpp", "host/candidate_alleles.cpp", "host/poa.cpp", "host/fasta_reader.cpp", "host/region_pipeline.cpp", "synth_stutter.cpp"]
 HEADERS = ["viterbi_core.cuh", "band_core.cuh", "viterbi_host.h", "kernels.h", "stutter_core.cuh", "ctx.h", "plan_device.cuh", "edit_core.cuh"]

@@ -76,6 +76,15 @@ $LINKXX -shared -o "$out/libltr_ref_hapgen_poa.so" "$out/obj/hapgen_driver_poa.o
      "$out/obj/region.o" -Wl,--no-undefined -lm -lpthread
 echo "built $out/libltr_ref_hapgen_poa.so"
 
+# ---- libltr_ref_em.so: the reference's EMStutterGenotyper (length-based EM of the stutter model) behind oracle/em_driver.cpp ----
+$CXX $FLAGS -I"$here/shim" -c "$ref/src/em_stutter_genotyper.cpp" -o "$out/obj/em_stutter_genotyper.o"
+$CXX -O2 -g -std=c++11 -fPIC -w -fno-access-control -I"$here/shim" -I"$ref/src" -c "$here/em_driver.cpp" -o "$out/obj/em_driver.o"
+$LINKXX -shared -o "$out/libltr_ref_em.so" "$out/obj/em_driver.o" "$out/obj/em_stutter_genotyper.o" "$out/obj/genotyper.o" \
+     "$out/obj/stutter_model.o" "$out/obj/mathops.o" "$out/obj/error.o" "$out/obj/stringops.o" "$out/obj/region.o" \
+     "$out/obj/fasta_reader.o" "$out/obj/hts_stubs.o" \
+     -Wl,--no-undefined -lm -lpthread
+echo "built $out/libltr_ref_em.so"
+
 # ---- IO-less per-locus genotyper (SeqStutterGenotyper ctor -> genotype -> write_vcf_record), twice ------------
 #   ltr_ref_full : every object is the reference's own (golden VCF records)
 #   ltr_ref_gpu  : HapAligner::process_reads and Genotyper::calc_log_sample_posteriors are taken from

@@ -372,3 +372,38 @@ def greedy_cluster(seq_bytes, seq_off, items, T, which="oracle"):
     fn = ref_lib().ltr_ref_greedy_cluster if which == "ref" else oracle_lib().ltr_oracle_greedy_cluster
     ok = fn(_ptr(seq_bytes, _u8p), _ptr(seq_off, _u32p), _ptr(items, _u32p), len(items), T, _ptr(cent, _ip), C.byref(n))
     return int(ok), cent[:len(items)], n.value
+
+
+# ---- the reference's EMStutterGenotyper compiled in place (oracle/em_driver.cpp -> oracle/_ref/libltr_ref_em.so) ----------
+_EM_SO = os.path.join(_HERE, "_ref", "libltr_ref_em.so")
+
+
+def ref_em_available():
+    return os.path.exists(_EM_SO)
+
+
+def ref_em_train(reads_per_sample, bp_diff, log_p1, log_p2, motif_len, haploid=False, max_iter=100, abs_conv=0.01,
+                 frac_conv=0.001):
+    """EMStutterGenotyper(...).train(...) of the reference on one locus (reads sample-major).
+    -> dict(trained, params[6] = in_geom, in_up, in_down, out_geom, out_up, out_down, n_iter, lls[n_iter], log_gt_priors)."""
+    import ctypes as C
+
+    import numpy as np
+    lib = C.CDLL(_EM_SO)
+    i32p, dp = C.POINTER(C.c_int32), C.POINTER(C.c_double)
+    lib.ltr_ref_em_train.restype = C.c_int
+    lib.ltr_ref_em_train.argtypes = [C.c_uint32, i32p, i32p, dp, dp, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double,
+                                     dp, i32p, dp, dp, i32p]
+    rps = np.ascontiguousarray(reads_per_sample, dtype=np.int32)
+    bd = np.ascontiguousarray(bp_diff, dtype=np.int32)
+    p1 = np.ascontiguousarray(log_p1, dtype=np.float64)
+    p2 = np.ascontiguousarray(log_p2, dtype=np.float64)
+    params = np.zeros(6)
+    lls = np.zeros(max_iter + 2)
+    pri = np.zeros(64)
+    n_iter, n_all = C.c_int32(0), C.c_int32(0)
+    P = lambda a, t: a.ctypes.data_as(t)
+    trained = lib.ltr_ref_em_train(len(rps), P(rps, i32p), P(bd, i32p), P(p1, dp), P(p2, dp), motif_len, int(haploid), max_iter,
+                                   abs_conv, frac_conv, P(params, dp), C.byref(n_iter), P(lls, dp), P(pri, dp), C.byref(n_all))
+    return dict(trained=bool(trained), params=params, n_iter=n_iter.value, lls=lls[:n_iter.value],
+                log_gt_priors=pri[:min(64, n_all.value)], n_alleles=n_all.value)
