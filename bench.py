@@ -39,6 +39,7 @@ def parse_args():
     ap.add_argument("--config", type=int, default=3, choices=[3, 4, 5])
     ap.add_argument("--n2", action="store_true", help="only the extra.n2 line (clustering kernels)")
     ap.add_argument("--n3", action="store_true", help="only the extra.n3 line (BAM files -> calls)")
+    ap.add_argument("--em", action="store_true", help="only the extra.em line (stutter-model EM kernel)")
     ap.add_argument("--one-process-devices", type=int, default=0,
                     help="only the raw-loci arm (ltr_genotyper_run) with ONE process driving this many devices")
     ap.add_argument("--loci", type=int, default=0, help="loci per GPU per step (default: config size)")
@@ -761,6 +762,44 @@ def measure_regions(args, n_loci, steps, warmup):
                        "bam_written_in_s": gen_s}}
 
 
+def measure_em(args, eng, n_loci, steps, warmup, with_cpu_baseline):
+    """extra.em: length-based EM of the stutter model (ltr_em_stutter_train, one warp per locus) on seeded loci of 1-3 samples
+    with 3-40 reads each, host buffers in, parameters out; the reference's EMStutterGenotyper (compiled in place) on one host
+    thread over a bounded sample beside it, and the parameters of that sample compared."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests"))
+    import em_cases
+    from longtr_b200 import abi
+    base = [em_cases.em_locus(100000 + k) for k in range(min(n_loci, 2000))]
+    loci = [base[k % len(base)] for k in range(n_loci)]
+    packed = abi.em_pack(loci)
+    ms, got = [], None
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        got = abi.em_stutter_train(eng.ctx, packed)
+        if it >= warmup:
+            ms.append((time.perf_counter() - t0) * 1e3)
+    n_reads = sum(sum(L["reads_per_sample"]) for L in loci)
+    line = {"metric": "loci_per_sec", "value": n_loci / (np.mean(ms) / 1e3), "unit": "loci/s", "ms_per_step": float(np.mean(ms)),
+            "steps": steps, "warmup": warmup, "api": "ltr_em_stutter_train (host buffers in, parameters out)", "config": {"workload": "N4: stutter-model EM, %d loci, %d reads" % (n_loci, n_reads)},
+            "iterations_mean": float(np.mean(got["n_iter"])), "trained_fraction": float(np.mean(got["trained"]))}
+    if with_cpu_baseline:
+        from oracle import pyoracle as po
+        if po.ref_em_available():
+            n_s = min(400, len(base))
+            t0 = time.perf_counter()
+            ref = [po.ref_em_train(L["reads_per_sample"], L["bp_diff"], L["log_p1"], L["log_p2"], L["motif_len"], L["haploid"])
+                   for L in base[:n_s]]
+            sec = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": n_s / sec, "unit": "loci/s", "cores": 1, "kind": "reference",
+                                    "sample": "first %d loci, EMStutterGenotyper compiled in place, one thread" % n_s}
+            err = max(float(np.max(np.abs(got["params"][k] - ref[k]["params"]) / np.maximum(np.abs(ref[k]["params"]), 1e-300)))
+                      for k in range(n_s))
+            line["parity_on_bench_sample"] = {"loci": n_s, "max_rel_err_params": err,
+                                              "same_iterations": bool(all(got["n_iter"][k] == ref[k]["n_iter"] for k in range(n_s))),
+                                              "same_trained": bool(all(bool(got["trained"][k]) == ref[k]["trained"] for k in range(n_s)))}
+    return line
+
+
 def compact(line):
     """Sub-line of another configuration inside the default run (extra.c4 / extra.c5)."""
     if line is None:
@@ -802,6 +841,8 @@ def main():
         line = measure_cluster(args, eng, args.loci or 512, args.steps, args.warmup, not args.no_cpu_baseline)
     elif args.n3:
         line = measure_regions(args, args.loci or 1500, args.steps, args.warmup)
+    elif args.em:
+        line = measure_em(args, eng, args.loci or 20000, args.steps, args.warmup, not args.no_cpu_baseline)
     elif args.config == 5:
         line = run_stutter(args, torch, rank, world, local, eng, args.loci or CONFIG_LOCI[5], args.steps, args.warmup,
                            world == 1 and not args.no_cpu_baseline)
@@ -822,6 +863,7 @@ def main():
                                                   not args.no_cpu_baseline))
                 extra["n2"] = measure_cluster(args, eng, 512, 3, 3, not args.no_cpu_baseline)
                 extra["n3"] = measure_regions(args, 1500, 2, 1)
+                extra["em"] = measure_em(args, eng, 20000, 2, 1, not args.no_cpu_baseline)
             except Exception as e:  # the headline line must not be lost to a sub-line
                 extra["error"] = repr(e)
             line["extra"] = extra

@@ -537,10 +537,9 @@ class EmOpts(C.Structure):
     _fields_ = [("max_iter", C.c_int32), ("abs_ll_converge", C.c_double), ("frac_ll_converge", C.c_double)]
 
 
-def em_stutter_train(ctx, loci, max_iter=None, abs_conv=None, frac_conv=None, prior_stride=32):
-    """ltr_em_stutter_train.  loci: [dict(reads_per_sample, bp_diff, log_p1, log_p2, motif_len, haploid=False)], reads
-    sample-major.  -> dict(params [n, 6], trained, n_iter, ll, log_gt_priors [n, prior_stride])."""
-    lib = load()
+def em_pack(loci):
+    """[dict(reads_per_sample, bp_diff, log_p1, log_p2, motif_len, haploid=False)] (reads sample-major) -> the arrays of an
+    ltr_em_batch (kept alive by the returned dict)."""
     n = len(loci)
     lsb = np.zeros(n + 1, dtype=np.uint32)
     srb, bd, p1, p2 = [0], [], [], []
@@ -548,14 +547,24 @@ def em_stutter_train(ctx, loci, max_iter=None, abs_conv=None, frac_conv=None, pr
         for c in L["reads_per_sample"]:
             srb.append(srb[-1] + int(c))
         lsb[k + 1] = len(srb) - 1
-        bd += list(L["bp_diff"]); p1 += list(L["log_p1"]); p2 += list(L["log_p2"])
-    srb = np.array(srb, dtype=np.uint32)
-    bd = np.array(bd + [0], dtype=np.int32)
-    p1 = np.array(p1 + [0.0], dtype=np.float64)
-    p2 = np.array(p2 + [0.0], dtype=np.float64)
-    ml = np.array([L["motif_len"] for L in loci] + [1], dtype=np.int32)
-    hp = np.array([1 if L.get("haploid") else 0 for L in loci] + [0], dtype=np.uint8)
-    B = EmBatch(n, ptr(lsb, _u32p), ptr(srb, _u32p), ptr(bd, _i32p), ptr(p1, _dp), ptr(p2, _dp), ptr(ml, _i32p), ptr(hp, _u8p))
+        bd.extend(L["bp_diff"])
+        p1.extend(L["log_p1"])
+        p2.extend(L["log_p2"])
+    P = dict(n=n, lsb=lsb, srb=np.array(srb, dtype=np.uint32), bd=np.array(bd + [0], dtype=np.int32),
+             p1=np.array(p1 + [0.0], dtype=np.float64), p2=np.array(p2 + [0.0], dtype=np.float64),
+             ml=np.array([L["motif_len"] for L in loci] + [1], dtype=np.int32),
+             hp=np.array([1 if L.get("haploid") else 0 for L in loci] + [0], dtype=np.uint8))
+    P["struct"] = EmBatch(n, ptr(P["lsb"], _u32p), ptr(P["srb"], _u32p), ptr(P["bd"], _i32p), ptr(P["p1"], _dp),
+                          ptr(P["p2"], _dp), ptr(P["ml"], _i32p), ptr(P["hp"], _u8p))
+    return P
+
+
+def em_stutter_train(ctx, loci, max_iter=None, abs_conv=None, frac_conv=None, prior_stride=32):
+    """ltr_em_stutter_train.  loci: a list as em_pack takes it, or what em_pack returned.
+    -> dict(params [n, 6], trained, n_iter, ll, log_gt_priors [n, prior_stride])."""
+    lib = load()
+    P = loci if isinstance(loci, dict) else em_pack(loci)
+    n = P["n"]
     O = EmOpts()
     lib.ltr_em_opts_default(C.byref(O))
     if max_iter is not None:
@@ -569,8 +578,8 @@ def em_stutter_train(ctx, loci, max_iter=None, abs_conv=None, frac_conv=None, pr
     n_iter = np.zeros(max(n, 1), dtype=np.int32)
     ll = np.zeros(max(n, 1))
     pri = np.zeros((max(n, 1), prior_stride))
-    rc = lib.ltr_em_stutter_train(ctx, C.byref(B), C.byref(O), ptr(params, _dp), ptr(trained, _i32p), ptr(n_iter, _i32p),
-                                  ptr(ll, _dp), ptr(pri, _dp), prior_stride)
+    rc = lib.ltr_em_stutter_train(ctx, C.byref(P["struct"]), C.byref(O), ptr(params, _dp), ptr(trained, _i32p),
+                                  ptr(n_iter, _i32p), ptr(ll, _dp), ptr(pri, _dp), prior_stride)
     if rc != 0:
         raise RuntimeError("ltr_em_stutter_train failed: %d" % rc)
     return dict(params=params[:n], trained=trained[:n], n_iter=n_iter[:n], ll=ll[:n], log_gt_priors=pri[:n])
