@@ -32,7 +32,13 @@ def build(force=False):
                                               ("longtr_oracle.c", "longtr_oracle_short.c", "longtr_oracle_edit.c", "longtr_oracle.h")):
         subprocess.check_call(["make", "-C", _HERE, "liblongtr_oracle.so"], stdout=subprocess.DEVNULL)
     if os.path.isdir(os.environ.get("LONGTR_REFERENCE", "/root/reference") + "/src"):
-        if force or not os.path.exists(_REF_SO):
+        outs = [os.path.join(_HERE, "_ref", f) for f in
+                ("libltr_ref.so", "libltr_ref_io.so", "libltr_ref_hapgen.so", "libltr_ref_hapgen_poa.so", "libltr_ref_em.so",
+                 "ltr_ref_full", "ltr_ref_trace", "ltr_ref_lazy")]
+        srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".cpp", ".hpp", ".sh"))]
+        srcs += [os.path.join(_HERE, "shim", "spoa", "spoa.hpp"), os.path.join(_HERE, "shim", "hts_stubs.cpp")]
+        newest = max(os.path.getmtime(f) for f in srcs if os.path.exists(f))
+        if force or any(not os.path.exists(o) or os.path.getmtime(o) < newest for o in outs):
             subprocess.check_call([os.path.join(_HERE, "build_ref.sh")], stdout=subprocess.DEVNULL)
 
 
