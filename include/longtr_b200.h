@@ -135,6 +135,11 @@ int ltr_ctx_set_band(ltr_ctx* ctx, int32_t half_width);
  * 0 (default) on the device for batches of >= 4096 pooled reads and on the host below that (per-locus calls: fewer
  * launches), 1 always on the host, 2 always on the device.  Results do not depend on it. */
 int ltr_ctx_set_plan(ltr_ctx* ctx, int32_t mode);
+/* How read_bytes of the batches submitted afterwards is encoded (ltr_job_create / ltr_job_submit*): 0 = one byte per base
+ * (default), 1 = ONE 4-bit stream over all reads, BAM's own sequence encoding ("=ACMGRSVTWYHKDBN"): base b of the batch sits
+ * in byte b / 2, even b in the high nibble; read_off keeps counting bases.  Halves the largest host-to-device copy; the
+ * plan's first kernel expands the stream on the device.  Results do not depend on it.                                     */
+int ltr_ctx_set_read_encoding(ltr_ctx* ctx, int32_t encoding);
 const char* ltr_strerror(int code);
 const char* ltr_last_error(const ltr_ctx* ctx); /* CUDA error text of the last failure */
 const char* ltr_version(void);

@@ -393,6 +393,8 @@ def load():
     lib.ltr_job_destroy.argtypes = [vp, vp]
     lib.ltr_ctx_set_plan.argtypes = [vp, C.c_int32]
     lib.ltr_ctx_set_plan.restype = C.c_int
+    lib.ltr_ctx_set_read_encoding.argtypes = [vp, C.c_int32]
+    lib.ltr_ctx_set_read_encoding.restype = C.c_int
     lib.ltr_job_submit.argtypes = [vp, C.POINTER(Params), C.POINTER(ViterbiBatch), C.POINTER(PosteriorBatch), _dp, _dp, _dp,
                                    C.POINTER(vp)]
     lib.ltr_job_submit.restype = C.c_int
@@ -515,7 +517,7 @@ EXPORTED_SYMBOLS = [
     "ltr_process_reads_flat_batch", "ltr_pipeline_create", "ltr_pipeline_submit", "ltr_pipeline_flush", "ltr_pipeline_next",
     "ltr_pipeline_destroy", "ltr_flatten_loci", "ltr_flat_batch_free",
     "ltr_fp64_issue_rate", "ltr_genotype_locus", "ltr_extract_calls", "ltr_trim_read_flat", "ltr_seed_base_flat",
-    "ltr_stutter_ll", "ltr_genotype_locus_pruned", "ltr_ctx_set_plan", "ltr_job_submit", "ltr_job_submit_outputs", "ltr_job_wait", "ltr_job_poll", "ltr_job_download_kept", "ltr_posteriors_batch", "ltr_genotyper_create", "ltr_genotyper_destroy",
+    "ltr_stutter_ll", "ltr_genotype_locus_pruned", "ltr_ctx_set_plan", "ltr_ctx_set_read_encoding", "ltr_job_submit", "ltr_job_submit_outputs", "ltr_job_wait", "ltr_job_poll", "ltr_job_download_kept", "ltr_posteriors_batch", "ltr_genotyper_create", "ltr_genotyper_destroy",
     "ltr_genotyper_run", "ltr_batch_calls_free", "ltr_locus_batch_trim_read", "ltr_stutter_ll_status", "ltr_pool_reads",
     "ltr_edit_distances", "ltr_cluster_greedy",
     "ltr_bam_open", "ltr_bam_close", "ltr_bam_n_refs", "ltr_bam_ref_name", "ltr_bam_ref_len", "ltr_bam_ref_id",
@@ -600,6 +602,23 @@ def poa_consensus(seqs):
     if rc != 0:
         raise RuntimeError("ltr_poa_consensus failed: %d" % rc)
     return out[:n.value].tobytes().decode()
+
+
+_NIBBLE = np.full(256, 15, dtype=np.uint8)   # BAM's 4-bit codes; anything else becomes N
+for _k, _c in enumerate("=ACMGRSVTWYHKDBN"):
+    _NIBBLE[ord(_c)] = _k
+
+
+def pack_reads_4bit(read_bytes, n_bases=None):
+    """Bytes of a batch's reads (uint8 array, one byte per base) -> the 4-bit stream ltr_ctx_set_read_encoding(1) expects:
+    base b in byte b // 2, even b in the high nibble."""
+    a = np.asarray(read_bytes, dtype=np.uint8)
+    if n_bases is not None:
+        a = a[:n_bases]
+    codes = _NIBBLE[a]
+    if len(codes) % 2:
+        codes = np.concatenate([codes, np.zeros(1, dtype=np.uint8)])
+    return ((codes[0::2] << 4) | codes[1::2]).astype(np.uint8)
 
 
 def pack_seqs(seqs):

@@ -93,6 +93,8 @@ struct ltr_job {
   DeviceBuffer hap_bytes, hap_off, hap_locus, read_bytes, read_off, lhb, lrb, ll_off, out_ll, tabI, tabD;
   DeviceBuffer lub, r2u, rlocus, ull_off, uniq_ll;  // distinct-read bookkeeping (host or device plan)
   DeviceBuffer raw_bytes_d, raw_off_d, plan_scratch, plan_ctl, plan_stat;  // device plan only
+  DeviceBuffer raw_packed_d;           // device plan, read encoding 1: the 4-bit stream as uploaded
+  std::vector<uint8_t> host_unpacked;  // host plan, read encoding 1: the reads as bytes
   PlanDev pd;
   // posterior inputs
   bool has_post = false;
@@ -287,6 +289,12 @@ int ltr_ctx_set_band(ltr_ctx* ctx, int32_t half_width) {
   return LTR_OK;
 }
 
+int ltr_ctx_set_read_encoding(ltr_ctx* ctx, int32_t encoding) {
+  if (!ctx || encoding < 0 || encoding > 1) return LTR_ERR_INVALID;
+  ctx->read_encoding = encoding;
+  return LTR_OK;
+}
+
 int ltr_ctx_set_plan(ltr_ctx* ctx, int32_t mode) {
   if (!ctx || mode < 0 || mode > 2) return LTR_ERR_INVALID;
   ctx->plan_mode = mode;
@@ -324,7 +332,7 @@ void ltr_job_destroy(ltr_ctx* ctx, ltr_job* job) {
   DeviceBuffer* bufs[] = {&job->hap_bytes, &job->hap_off, &job->hap_locus, &job->read_bytes, &job->read_off,
                           &job->lhb, &job->lrb, &job->ll_off, &job->out_ll, &job->tabI, &job->tabD,
                           &job->lub, &job->r2u, &job->rlocus, &job->ull_off, &job->uniq_ll,
-                          &job->raw_bytes_d, &job->raw_off_d, &job->plan_scratch, &job->plan_ctl, &job->plan_stat,
+                          &job->raw_bytes_d, &job->raw_packed_d, &job->raw_off_d, &job->plan_scratch, &job->plan_ctl, &job->plan_stat,
                           &job->lsb, &job->pool, &job->label, &job->p1, &job->p2, &job->nsamp,
                           &job->haploid, &job->post_off, &job->tot_off, &job->post, &job->totals,
                           &job->int_logs, &job->mate, &job->aligned, &job->kept_mask, &job->kept_index, &job->cls_ctrl, &job->band_tasks, &job->band_cum, &job->band_pairs,
@@ -597,7 +605,15 @@ int setup_device_plan(ltr_ctx* ctx, ltr_job* job, const ltr_viterbi_batch& bb, c
   // every pair with |n - m| > 600 is answered before any table is read (HapAligner.cpp:249-252): columns up to
   // max_n + 600 are the most a table entry can be asked for
   make_consts(job->params, max_n + 604, job->hc);
-  LTR_TRY(upload(ctx, st, job->raw_bytes_d, bb.read_bytes, (size_t)job->raw_bytes, kStringPad, h2d, &job->deferred_zero));
+  if (ctx->read_encoding == 1) {
+    // the reads travel as one 4-bit stream (half the bytes); the plan's first kernel expands them into raw_bytes_d
+    LTR_CUDA(ctx, job->raw_bytes_d.alloc(kStringPad + (size_t)job->raw_bytes + kStringPad));
+    job->deferred_zero.push_back(std::make_pair(job->raw_bytes_d.p, kStringPad));
+    job->deferred_zero.push_back(std::make_pair((void*)((char*)job->raw_bytes_d.p + kStringPad + job->raw_bytes), kStringPad));
+    LTR_TRY(upload(ctx, st, job->raw_packed_d, bb.read_bytes, ((size_t)job->raw_bytes + 1) / 2, 0, h2d));
+  } else {
+    LTR_TRY(upload(ctx, st, job->raw_bytes_d, bb.read_bytes, (size_t)job->raw_bytes, kStringPad, h2d, &job->deferred_zero));
+  }
   LTR_TRY(upload(ctx, st, job->raw_off_d, bb.read_off, (size_t)n_reads + 1, 0, h2d));
   LTR_TRY(upload(ctx, st, job->ll_off, ll_off.data(), ll_off.size(), 0, h2d));
   // products of the plan kernels
@@ -623,6 +639,7 @@ int setup_device_plan(ltr_ctx* ctx, ltr_job* job, const ltr_viterbi_batch& bb, c
   P.lhb = job->lhb.as<uint32_t>(); P.lrb = job->lrb.as<uint32_t>(); P.hap_off = job->hap_off.as<uint32_t>();
   P.read_off = job->raw_off_d.as<uint32_t>();
   P.read_bytes = job->raw_bytes_d.as<uint8_t>() + kStringPad;
+  P.packed = (ctx->read_encoding == 1) ? job->raw_packed_d.as<uint8_t>() : nullptr;
   {
     char* s = job->plan_scratch.as<char>();
     P.rhash = reinterpret_cast<unsigned long long*>(s); s += nr * 8;
@@ -697,6 +714,15 @@ int job_setup(ltr_ctx* ctx, const ltr_params* params, const ltr_viterbi_batch* b
   job->n_reads = bb.locus_read_begin[bb.n_loci];
   job->raw_bytes = job->n_reads ? bb.read_off[job->n_reads] : 0u;
   if ((job->n_haps && bb.hap_off[job->n_haps] && !bb.hap_bytes) || (job->raw_bytes && !bb.read_bytes)) return LTR_ERR_INVALID;
+  if (ctx->read_encoding == 1 && !job->device_plan && job->raw_bytes) {
+    // small batch, host plan: the 4-bit stream is expanded here (the device plan does it in its first kernel)
+    job->host_unpacked.resize(job->raw_bytes);
+    for (uint32_t i = 0; i < job->raw_bytes; ++i) {
+      const uint8_t byte = bb.read_bytes[i >> 1];
+      job->host_unpacked[i] = (uint8_t)"=ACMGRSVTWYHKDBN"[(i & 1u) ? (byte & 15u) : (byte >> 4)];
+    }
+    bb.read_bytes = job->host_unpacked.data();
+  }
   JobLane& L = ctx->lanes[job->lane];
   cudaStream_t st = job->st_h2d;
   job->drained = false;

@@ -74,6 +74,7 @@ struct ltr_ctx {
   unsigned next_lane = 0;
   int blocks_per_sm[4][32] = {{0}};
   int band_blocks_per_sm[16] = {0};  // by band class index
+  int read_encoding = 0;             // ltr_ctx_set_read_encoding: 0 bytes, 1 one 4-bit stream (BAM nibble codes)
   int band_w = 0;                    // ltr_ctx_set_band: < 0 off, 0 automatic margin, > 0 margin in diagonals
   int plan_mode = 0;                 // ltr_ctx_set_plan: 0 automatic, 1 host plan (make_plan), 2 device plan (plan_kernels.cu)
   std::string last_error;

@@ -64,6 +64,8 @@ struct PlanDev {
   const uint32_t* hap_off;    // [n_haps+1]
   const uint32_t* read_off;   // [n_reads+1] raw
   const uint8_t* read_bytes;  // raw, padded on both sides
+  const uint8_t* packed;      // NULL, or the raw reads as one 4-bit stream (base b in byte b / 2, even b in the high nibble):
+                              // unpacked into read_bytes by the first kernel of the plan
   // scratch
   unsigned long long* rhash;  // [n_reads]
   uint32_t* rlen;             // [n_reads] length of every raw read (0: malformed offsets)

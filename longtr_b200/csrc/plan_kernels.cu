@@ -307,6 +307,44 @@ __global__ void __launch_bounds__(kPlanBlock) plan_tasks_kernel(const PlanDev P,
   for (uint32_t l = blockIdx.x * blockDim.x + threadIdx.x; l < P.n_loci; l += stride) plan_locus_tasks(P, l, pass);
 }
 
+// Reads handed over as a 4-bit stream (BAM's sequence encoding, ltr_ctx_set_read_encoding): every thread expands 8 packed
+// bytes into 16 bases.  HBM-bound: n / 2 bytes in, n bytes out.
+__global__ void __launch_bounds__(256) plan_unpack_kernel(const uint8_t* __restrict__ packed, uint8_t* __restrict__ out,
+                                                          uint32_t n_bases) {
+  const uint32_t n_groups = (n_bases + 15u) >> 4;
+  for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < n_groups; g += gridDim.x * blockDim.x) {
+    const uint32_t b0 = g << 4;
+    const uint32_t n_in = ((n_bases + 1u) >> 1) - (b0 >> 1);  // packed bytes left from this group on
+    uint32_t w[2] = {0u, 0u};
+    if (n_in >= 8u) {
+      const uint2 v = *reinterpret_cast<const uint2*>(packed + (b0 >> 1));
+      w[0] = v.x;
+      w[1] = v.y;
+    } else {
+      for (uint32_t k = 0; k < n_in; ++k) w[k >> 2] |= (uint32_t)packed[(b0 >> 1) + k] << (8u * (k & 3u));
+    }
+    uint32_t o[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint32_t word = 0u;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t b = (uint32_t)(4 * q + k);               // base within the group
+        const uint32_t byte = (w[b >> 3] >> (8u * ((b >> 1) & 3u))) & 0xFFu;
+        const uint32_t nib = (b & 1u) ? (byte & 15u) : (byte >> 4);
+        const uint32_t ch = (b0 + b < n_bases) ? (uint32_t)(uint8_t)"=ACMGRSVTWYHKDBN"[nib] : 0u;
+        word |= ch << (8 * k);
+      }
+      o[q] = word;
+    }
+    if (b0 + 16u <= n_bases) {
+      *reinterpret_cast<uint4*>(out + b0) = make_uint4(o[0], o[1], o[2], o[3]);
+    } else {
+      for (uint32_t b = 0; b0 + b < n_bases; ++b) out[b0 + b] = (uint8_t)(o[b >> 2] >> (8u * (b & 3u)));
+    }
+  }
+}
+
 // The steps in stream order.  ctl / stat / the band counters must be zero on entry (the caller memsets them on the same
 // stream).
 cudaError_t launch_device_plan(const PlanDev& P, int sm_count, cudaStream_t stream) {
@@ -317,6 +355,11 @@ cudaError_t launch_device_plan(const PlanDev& P, int sm_count, cudaStream_t stre
   locus_blocks = locus_blocks < max_blocks ? locus_blocks : max_blocks;
   uint32_t task_blocks = (P.n_loci + kPlanBlock - 1) / kPlanBlock;
   task_blocks = task_blocks < max_blocks ? task_blocks : max_blocks;
+  if (P.packed && P.raw_total) {
+    uint32_t blocks = ((P.raw_total + 15u) / 16u + 255u) / 256u;
+    blocks = blocks < max_blocks ? blocks : max_blocks;
+    plan_unpack_kernel<<<blocks, 256, 0, stream>>>(P.packed, const_cast<uint8_t*>(P.read_bytes), P.raw_total);
+  }
   const size_t dedupe_smem = (size_t)warps_per_block * kStageBytes;
   cudaFuncSetAttribute(plan_dedupe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dedupe_smem);  // per device
   plan_dedupe_kernel<<<locus_blocks, kPlanBlock, dedupe_smem, stream>>>(P);

@@ -150,6 +150,10 @@ class Engine:
         Results never depend on it (uncertified pairs are re-run over the full matrix)."""
         _check(self.lib, self.ctx, self.lib.ltr_ctx_set_band(self.ctx, int(half_width)), "ltr_ctx_set_band")
 
+    def set_read_encoding(self, encoding):
+        """ltr_ctx_set_read_encoding: 0 = one byte per base, 1 = one 4-bit stream over all reads (abi.pack_reads_4bit)."""
+        _check(self.lib, self.ctx, self.lib.ltr_ctx_set_read_encoding(self.ctx, int(encoding)), "ltr_ctx_set_read_encoding")
+
     def set_plan(self, mode):
         """ltr_ctx_set_plan: 0 automatic, 1 plan on the host, 2 plan on the device.  Results never depend on it."""
         _check(self.lib, self.ctx, self.lib.ltr_ctx_set_plan(self.ctx, int(mode)), "ltr_ctx_set_plan")

@@ -30,6 +30,7 @@ def plan_engine(engine):
     yield engine
     engine.set_plan(0)
     engine.set_band(0)
+    engine.set_read_encoding(0)
 
 
 def _stats_tuple(st):
@@ -194,3 +195,45 @@ def test_posterior_batch_validation(plan_engine, mode):
     assert eng.lib.ltr_job_create(eng.ctx, C.byref(prm), C.byref(vb), C.byref(pb), C.byref(h)) == -3
     attempt(p)   # the well-formed batch still runs
     w.close()
+
+
+@pytest.mark.parametrize("seed,kw,params", [CASES[0], CASES[1], CASES[2], CASES[5]])
+@pytest.mark.parametrize("plan", [1, 2])
+def test_reads_as_4bit_stream_same_results(plan_engine, seed, kw, params, plan):
+    """ltr_ctx_set_read_encoding(1): the reads of the batch travel as one 4-bit stream (half the bytes) and are expanded by the
+    first kernel of the device plan (on the host for the small batches of the host plan) -- same bits, same statistics."""
+    eng = plan_engine
+    b = synth.make_pair_batch(seed, **kw)
+    n_bases = int(np.asarray(b["read_off"])[-1])
+    assert set(np.unique(np.asarray(b["read_bytes"])[:n_bases]).tolist()) <= set(b"ACGTN")
+    eng.set_plan(plan)
+    want, st_b = eng.viterbi_ll(b, aln_params=params)
+    packed = dict(b, read_bytes=abi.pack_reads_4bit(b["read_bytes"], n_bases))
+    assert len(packed["read_bytes"]) == (n_bases + 1) // 2
+    eng.set_read_encoding(1)
+    got, st_p = eng.viterbi_ll(packed, aln_params=params)
+    eng.set_read_encoding(0)
+    assert np.array_equal(got, want)
+    assert _stats_tuple(st_p) == _stats_tuple(st_b)
+    if plan == 2:
+        assert st_b.h2d_bytes - st_p.h2d_bytes == n_bases - (n_bases + 1) // 2
+    with pytest.raises(LongTRError):
+        eng.set_read_encoding(2)
+
+
+def test_4bit_stream_through_submit_wait(plan_engine):
+    """The asynchronous pair with the packed encoding, odd total length, posteriors attached."""
+    eng = plan_engine
+    b = synth.make_pair_batch(77, n_loci=300)
+    n_bases = int(np.asarray(b["read_off"])[-1])
+    post = synth.make_posterior_inputs(b, 77) if hasattr(synth, "make_posterior_inputs") else None
+    eng.set_plan(2)
+    want, _ = eng.viterbi_ll(b)
+    packed = dict(b, read_bytes=abi.pack_reads_4bit(b["read_bytes"], n_bases))
+    eng.set_read_encoding(1)
+    out = np.zeros(abi.ll_size(b))
+    j = eng.submit_job(packed, None, out_ll=out)
+    j.wait()
+    j.close()
+    eng.set_read_encoding(0)
+    assert np.array_equal(out, want)
