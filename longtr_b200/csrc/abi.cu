@@ -723,7 +723,6 @@ int job_setup(ltr_ctx* ctx, const ltr_params* params, const ltr_viterbi_batch* b
     }
     bb.read_bytes = job->host_unpacked.data();
   }
-  JobLane& L = ctx->lanes[job->lane];
   cudaStream_t st = job->st_h2d;
   job->drained = false;
   cudaEvent_t* evs[] = {&job->ev_start, &job->ev_plan, &job->ev_vit, &job->ev_end};

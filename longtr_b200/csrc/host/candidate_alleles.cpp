@@ -163,18 +163,28 @@ void trim(int ideal_min_length, int left_pad, int right_pad, int32_t& region_sta
 typedef std::map<std::string, std::vector<std::string> > Clusters;  // centroid -> members; iteration in key order matters
 
 // The ladder of thresholds and the consensus / merge rounds compare the same pairs of sequences again and again, and only the
-// threshold changes: the distance itself is remembered per region.
+// threshold changes.  Per region a pair's distance is remembered -- exactly when it was found below the cut-off it was computed
+// with (ltr::bounded_edit_distance evaluates only the diagonals within the cut-off), as a lower bound otherwise; a larger
+// threshold later recomputes with a doubled cut-off.  The callers only test `score < T` and compare scores below T.
 struct DistanceMemo {
-  std::map<std::pair<std::string, std::string>, int> known;
+  struct Entry {
+    int value;    // the distance if exact, else a value the distance is known to exceed or equal
+    bool exact;
+  };
+  std::map<std::pair<std::string, std::string>, Entry> known;
   int operator()(const std::string& cent_seq, const std::string& read_seq, int T) {
     const int n = (int)cent_seq.size(), m = (int)read_seq.size();
     if (std::abs(n - m) > T || n == 0 || m == 0) return ltr::thresholded_from_distance(n, m, 0, T);
-    auto key = std::make_pair(cent_seq, read_seq);
-    auto hit = known.find(key);
-    int d;
-    if (hit != known.end()) d = hit->second;
-    else known[key] = d = ltr::edit_distance(cent_seq, read_seq);
-    return ltr::thresholded_from_distance(n, m, d, T);
+    Entry& e = known.insert(std::make_pair(std::make_pair(cent_seq, read_seq), Entry{0, false})).first->second;
+    if (!e.exact && e.value < T) {
+      int k = std::max(T, 2 * e.value);
+      k = std::min(std::max(n, m), (k + 63) / 64 * 64);
+      const int d = ltr::bounded_edit_distance(cent_seq, read_seq, k);
+      e.exact = d <= k;
+      e.value = d;  // k + 1 when not exact: the distance is at least that
+    }
+    if (e.exact) return ltr::thresholded_from_distance(n, m, e.value, T);
+    return T + 1;  // distance >= e.value >= T
   }
 };
 

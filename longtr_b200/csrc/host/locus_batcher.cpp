@@ -49,7 +49,6 @@ class WorkerPool {
     cv_.notify_all();
     for (std::thread& t : threads_) t.join();
   }
-  int size() const { return n_threads_; }
   // f(begin, end, thread); blocks of `grain` items are handed out dynamically (loci differ a lot in cost)
   void parallel_for(uint32_t n, uint32_t grain, const std::function<void(uint32_t, uint32_t, int)>& f) {
     if (n == 0) return;

@@ -112,24 +112,27 @@ void PoaGraph::sort_nodes() {
 
 // One matrix row: columns 1 .. len of `row` from the predecessor rows (`preds`: n_pred row pointers, the first one first),
 //   row[j] = max over predecessors p of max(p[j-1] + (seq[j-1] == c ? +1 : -1), p[j] - 1), then row[j] = max(row[j], row[j-1] - 1).
-// The second pass is a running maximum of row[j] + j.  Plain version and an AVX2 version (8 columns per step, the running
-// maximum as a three-step in-register scan plus a carried lane); same integers either way.
-static void poa_row_plain(int32_t* row, const int32_t* const* preds, size_t n_pred, const uint8_t* seq, size_t len, uint8_t c) {
-  const int32_t* p0 = preds[0];
-  for (size_t j = 1; j <= len; ++j) row[j] = std::max(p0[j - 1] + (seq[j - 1] == c ? 1 : -1), p0[j] - 1);
+// The second pass is a running maximum of row[j] + j.  A plain version for either cell type and two AVX2 versions (runtime
+// dispatch): 8 int32 columns per step, or 16 int16 columns per step when every score of the matrix fits (see align); the
+// running maximum is an in-register scan plus a carried lane.  Same integers either way.
+template <typename T>
+static void poa_row_plain(T* row, const T* const* preds, size_t n_pred, const uint8_t* seq, size_t len, uint8_t c) {
+  const T* p0 = preds[0];
+  for (size_t j = 1; j <= len; ++j) row[j] = (T)std::max(p0[j - 1] + (seq[j - 1] == c ? 1 : -1), p0[j] - 1);
   for (size_t k = 1; k < n_pred; ++k) {
-    const int32_t* pk = preds[k];
-    for (size_t j = 1; j <= len; ++j) row[j] = std::max(pk[j - 1] + (seq[j - 1] == c ? 1 : -1), std::max(row[j], pk[j] - 1));
+    const T* pk = preds[k];
+    for (size_t j = 1; j <= len; ++j)
+      row[j] = (T)std::max(pk[j - 1] + (seq[j - 1] == c ? 1 : -1), std::max((int)row[j], pk[j] - 1));
   }
-  for (size_t j = 1; j <= len; ++j) row[j] = std::max(row[j - 1] - 1, row[j]);
+  for (size_t j = 1; j <= len; ++j) row[j] = (T)std::max(row[j - 1] - 1, (int)row[j]);
 }
 
 #if defined(__x86_64__) && defined(__GNUC__)
 #include <immintrin.h>
 #define LTR_POA_AVX2 1
-// Rows are padded: columns up to the next multiple of 8 past len exist in every row and in seq (their values are never used).
+// Rows are padded: columns up to the next multiple of 16 past len exist in every row and in seq (their values are never used).
 __attribute__((target("avx2"))) static void poa_row_avx2(int32_t* row, const int32_t* const* preds, size_t n_pred,
-                                                          const uint8_t* seq, size_t len, uint8_t c) {
+                                                          const uint8_t* seq, size_t len, uint8_t c, int32_t) {
   const __m256i vc = _mm256_set1_epi32((int)c), one = _mm256_set1_epi32(1), two = _mm256_set1_epi32(2);
   const __m256i neg = _mm256_set1_epi32(INT32_MIN / 2);
   const __m256i sh1 = _mm256_setr_epi32(0, 0, 1, 2, 3, 4, 5, 6), sh2 = _mm256_setr_epi32(0, 0, 0, 1, 2, 3, 4, 5),
@@ -157,51 +160,88 @@ __attribute__((target("avx2"))) static void poa_row_avx2(int32_t* row, const int
     jv = _mm256_add_epi32(jv, eight);
   }
 }
+// 16 columns per step.  The scan runs on row[j] + j + bias with bias > |lowest score|, so that the zeros shifted in by the
+// lane shifts act as minus infinity; the caller guarantees bias + 2 len < 2^15.
+__attribute__((target("avx2"))) static void poa_row_avx2(int16_t* row, const int16_t* const* preds, size_t n_pred,
+                                                          const uint8_t* seq, size_t len, uint8_t c, int32_t bias) {
+  const __m128i vc = _mm_set1_epi8((char)c);
+  const __m256i one = _mm256_set1_epi16(1), minus1 = _mm256_set1_epi16(-1), sixteen = _mm256_set1_epi16(16);
+  const __m256i vbias = _mm256_set1_epi16((short)bias);
+  const __m256i top = _mm256_setr_epi8(14, 15, 14, 15, 14, 15, 14, 15, 14, 15, 14, 15, 14, 15, 14, 15,
+                                       14, 15, 14, 15, 14, 15, 14, 15, 14, 15, 14, 15, 14, 15, 14, 15);
+  __m256i jv = _mm256_setr_epi16(1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16);
+  __m256i carry = _mm256_set1_epi16((short)(row[0] + bias));
+  for (size_t j = 1; j <= len; j += 16) {
+    const __m128i eq = _mm_cmpeq_epi8(_mm_loadu_si128((const __m128i*)(seq + j - 1)), vc);  // 0xff where the base matches
+    const __m256i m = _mm256_cvtepi8_epi16(eq);                                               // -1 / 0
+    const __m256i s = _mm256_sub_epi16(minus1, _mm256_add_epi16(m, m));                       // +1 / -1
+    __m256i r = _mm256_max_epi16(_mm256_add_epi16(_mm256_loadu_si256((const __m256i*)(preds[0] + j - 1)), s),
+                                 _mm256_sub_epi16(_mm256_loadu_si256((const __m256i*)(preds[0] + j)), one));
+    for (size_t k = 1; k < n_pred; ++k) {
+      const __m256i d = _mm256_add_epi16(_mm256_loadu_si256((const __m256i*)(preds[k] + j - 1)), s);
+      const __m256i u = _mm256_sub_epi16(_mm256_loadu_si256((const __m256i*)(preds[k] + j)), one);
+      r = _mm256_max_epi16(d, _mm256_max_epi16(r, u));
+    }
+    __m256i x = _mm256_add_epi16(_mm256_add_epi16(r, jv), vbias);  // > 0
+    __m256i lo = _mm256_permute2x128_si256(x, x, 0x08);            // [0, x.low]
+    x = _mm256_max_epi16(x, _mm256_alignr_epi8(x, lo, 14));        // shifted by 1 lane, zeros in
+    lo = _mm256_permute2x128_si256(x, x, 0x08);
+    x = _mm256_max_epi16(x, _mm256_alignr_epi8(x, lo, 12));        // by 2
+    lo = _mm256_permute2x128_si256(x, x, 0x08);
+    x = _mm256_max_epi16(x, _mm256_alignr_epi8(x, lo, 8));         // by 4
+    lo = _mm256_permute2x128_si256(x, x, 0x08);
+    x = _mm256_max_epi16(x, lo);                                   // by 8
+    x = _mm256_max_epi16(x, carry);
+    carry = _mm256_shuffle_epi8(_mm256_permute2x128_si256(x, x, 0x11), top);  // lane 15 everywhere
+    _mm256_storeu_si256((__m256i*)(row + j), _mm256_sub_epi16(_mm256_sub_epi16(x, jv), vbias));
+    jv = _mm256_add_epi16(jv, sixteen);
+  }
+}
 #endif
 
-void PoaGraph::align(const uint8_t* seq_in, uint32_t len, std::vector<int32_t>& aln_node, std::vector<int32_t>& aln_pos) {
-  aln_node.clear();
-  aln_pos.clear();
+template <typename T>
+void PoaGraph::align_cells(const uint8_t* seq_in, uint32_t len, std::vector<int32_t>& aln_node, std::vector<int32_t>& aln_pos) {
   const uint32_t N = n_nodes();
-  if (N == 0 || len == 0) return;
-  const size_t W = ((size_t)len + 8) / 8 * 8 + 8;  // row stride: column 0, len columns, padding to whole steps of 8
+  const size_t W = ((size_t)len + 16) / 16 * 16 + 16;  // row stride: column 0, len columns, padding to whole steps of 16
   const int32_t gap = -1, hit = 1, miss = -1;
-  if (H_.size() < (size_t)(N + 1) * W) H_.resize((size_t)(N + 1) * W);
-  int32_t* H = H_.data();
-  std::vector<uint8_t> padded(W + 8, 0);
+  const size_t need = ((size_t)(N + 1) * W * sizeof(T) + sizeof(int32_t) - 1) / sizeof(int32_t);
+  if (H_.size() < need) H_.resize(need);
+  T* H = reinterpret_cast<T*>(H_.data());
+  std::vector<uint8_t> padded(W + 16, 0);
   std::copy(seq_in, seq_in + len, padded.begin());
   const uint8_t* seq = padded.data();
+  const int32_t bias = (int32_t)N + (int32_t)len + 2;  // every score is >= -(N + len)
 #ifdef LTR_POA_AVX2
   static const bool use_avx2 = __builtin_cpu_supports("avx2");
 #endif
-  for (size_t j = 0; j < W; ++j) H[j] = -(int32_t)j;
+  for (size_t j = 0; j < W; ++j) H[j] = (T)(-(int32_t)j);
   auto row_of_tail = [&](uint32_t e) { return (size_t)rank_[tail_[e]] + 1; };
   int32_t best = std::numeric_limits<int32_t>::min();
   uint32_t best_row = 0;
-  std::vector<const int32_t*> preds;
+  std::vector<const T*> preds;
   for (uint32_t r = 0; r < N; ++r) {
     const uint32_t v = order_[r];
-    int32_t* row = H + (size_t)(r + 1) * W;
+    T* row = H + (size_t)(r + 1) * W;
     const std::vector<uint32_t>& in = in_[v];
     // column 0: one graph step below the best predecessor
     preds.clear();
     if (in.empty()) {
-      row[0] = gap;
+      row[0] = (T)gap;
       preds.push_back(H);
     } else {
       int32_t top = std::numeric_limits<int32_t>::min() + 1024;
       for (uint32_t e : in) {
         preds.push_back(H + row_of_tail(e) * W);
-        top = std::max(top, preds.back()[0]);
+        top = std::max(top, (int32_t)preds.back()[0]);
       }
-      row[0] = top + gap;
+      row[0] = (T)(top + gap);
     }
 #ifdef LTR_POA_AVX2
-    if (use_avx2) poa_row_avx2(row, preds.data(), preds.size(), seq, len, code_[v]);
+    if (use_avx2) poa_row_avx2(row, preds.data(), preds.size(), seq, len, code_[v], bias);
     else
 #endif
-      poa_row_plain(row, preds.data(), preds.size(), seq, len, code_[v]);
-    if (out_[v].empty() && best < row[len]) {
+      poa_row_plain<T>(row, preds.data(), preds.size(), seq, len, code_[v]);
+    if (out_[v].empty() && best < (int32_t)row[len]) {
       best = row[len];
       best_row = r + 1;
     }
@@ -220,7 +260,7 @@ void PoaGraph::align(const uint8_t* seq_in, uint32_t len, std::vector<int32_t>& 
         const int32_t s = seq[j - 1] == code_[v] ? hit : miss;
         for (size_t k = 0; k < n_pred && !found; ++k) {
           const size_t p = in.empty() ? 0 : row_of_tail(in[k]);
-          if (here == H[p * W + (j - 1)] + s) {
+          if (here == (int32_t)H[p * W + (j - 1)] + s) {
             pi = p;
             pj = j - 1;
             found = true;
@@ -229,14 +269,14 @@ void PoaGraph::align(const uint8_t* seq_in, uint32_t len, std::vector<int32_t>& 
       }
       for (size_t k = 0; k < n_pred && !found; ++k) {
         const size_t p = in.empty() ? 0 : row_of_tail(in[k]);
-        if (here == H[p * W + j] + gap) {
+        if (here == (int32_t)H[p * W + j] + gap) {
           pi = p;
           pj = j;
           found = true;
         }
       }
     }
-    if (!found && j != 0 && here == H[i * W + j - 1] + gap) {
+    if (!found && j != 0 && here == (int32_t)H[i * W + j - 1] + gap) {
       pj = j - 1;
       found = true;
     }
@@ -252,6 +292,16 @@ void PoaGraph::align(const uint8_t* seq_in, uint32_t len, std::vector<int32_t>& 
   }
   std::reverse(aln_node.begin(), aln_node.end());
   std::reverse(aln_pos.begin(), aln_pos.end());
+}
+
+void PoaGraph::align(const uint8_t* seq, uint32_t len, std::vector<int32_t>& aln_node, std::vector<int32_t>& aln_pos) {
+  aln_node.clear();
+  aln_pos.clear();
+  const uint32_t N = n_nodes();
+  if (N == 0 || len == 0) return;
+  // scores lie in [-(N + len), len]; the 16-bit row kernel also forms score + column + bias with bias = N + len + 2
+  if ((uint64_t)N + 3ull * len + 64 < 32000ull && !force_wide_) align_cells<int16_t>(seq, len, aln_node, aln_pos);
+  else align_cells<int32_t>(seq, len, aln_node, aln_pos);
 }
 
 void PoaGraph::add(const uint8_t* seq, uint32_t len) {
@@ -391,6 +441,61 @@ int edit_distance(const std::string& a, const std::string& b) {
     score += hin;
   }
   return score;
+}
+
+// The same distance when it is at most k, k + 1 otherwise (Ukkonen's cut-off on the block recurrence).  A cell (i, j) with
+// a value <= k has |i - j| <= k, and so has every cell of an optimal path to it: column j only needs the blocks that hold
+// rows j - k .. j + k.  Blocks above the band are dropped (the first kept block is fed the horizontal delta +1), blocks below
+// it are switched on when the band reaches them, with all vertical deltas +1; both model cells outside the band by values that
+// are not below the true ones, which leaves every value <= k inside the band exact.
+int bounded_edit_distance(const std::string& a, const std::string& b, int k) {
+  const int n = (int)a.size(), m = (int)b.size();
+  if (std::abs(n - m) > k) return k + 1;
+  if (n == 0 || m == 0) return n + m;
+  const int nb = (n + 63) / 64;
+  static thread_local std::vector<uint64_t> peq, pv, mv;
+  peq.assign((size_t)nb * 256, 0);
+  pv.assign((size_t)nb, ~0ull);
+  mv.assign((size_t)nb, 0ull);
+  for (int i = 0; i < n; ++i) peq[(size_t)(uint8_t)a[(size_t)i] * (size_t)nb + (size_t)(i / 64)] |= 1ull << (i % 64);
+  int y = (std::min(n, std::max(k, 1)) - 1) / 64;  // last block switched on (rows 1 .. k of column 0)
+  long long score = 64ll * (y + 1);                // value at the bottom row of block y
+  for (int j = 1; j <= m; ++j) {
+    const uint64_t* eqc = peq.data() + (size_t)(uint8_t)b[(size_t)j - 1] * (size_t)nb;
+    const int f = (std::max(1, j - k) - 1) / 64;
+    const int want = (int)((std::min<long long>(n, (long long)j + k) - 1) / 64);
+    while (y < want) {
+      ++y;
+      pv[(size_t)y] = ~0ull;
+      mv[(size_t)y] = 0ull;
+      score += 64;
+    }
+    int hin = 1;
+    for (int blk = f; blk <= y; ++blk) {
+      uint64_t eq = eqc[blk];
+      const uint64_t pvk = pv[(size_t)blk], mvk = mv[(size_t)blk];
+      const uint64_t xv = eq | mvk;
+      if (hin < 0) eq |= 1ull;
+      const uint64_t xh = (((eq & pvk) + pvk) ^ pvk) | eq;
+      uint64_t ph = mvk | ~(xh | pvk);
+      uint64_t mh = pvk & xh;
+      const int hout = (int)(ph >> 63) - (int)(mh >> 63);
+      ph = (ph << 1) | (hin > 0 ? 1ull : 0ull);
+      mh = (mh << 1) | (hin < 0 ? 1ull : 0ull);
+      pv[(size_t)blk] = mh | ~(xv | ph);
+      mv[(size_t)blk] = ph & xv;
+      hin = hout;
+    }
+    score += hin;
+  }
+  // y == nb - 1: |n - m| <= k.  Rows n + 1 .. 64 nb of the last block are padding: take their vertical deltas off again.
+  const int pad = 64 * nb - n;
+  if (pad > 0) {
+    const uint64_t mask = ~0ull << (64 - pad);
+    score -= __builtin_popcountll(pv[(size_t)nb - 1] & mask);
+    score += __builtin_popcountll(mv[(size_t)nb - 1] & mask);
+  }
+  return score <= k ? (int)score : k + 1;
 }
 
 int thresholded_from_distance(int n, int m, int distance, int T) {

@@ -17,12 +17,15 @@ class PoaGraph {
   void add(const uint8_t* seq, uint32_t len);
   void consensus(std::string& out);
   uint32_t n_nodes() const { return (uint32_t)code_.size(); }
+  void force_wide_cells(bool on) { force_wide_ = on; }  // tests: 32-bit matrix cells even where 16 bits are enough
 
  private:
   uint32_t new_node(uint8_t code);
   void link(uint32_t tail, uint32_t head, uint32_t weight);
   void sort_nodes();
   void align(const uint8_t* seq, uint32_t len, std::vector<int32_t>& aln_node, std::vector<int32_t>& aln_pos);
+  template <typename T>
+  void align_cells(const uint8_t* seq, uint32_t len, std::vector<int32_t>& aln_node, std::vector<int32_t>& aln_pos);
   uint32_t complete_branch(uint32_t rank, std::vector<int64_t>& score, std::vector<int32_t>& pred) const;
 
   // nodes
@@ -37,6 +40,7 @@ class PoaGraph {
   // scratch
   std::vector<int32_t> H_;
   std::vector<int32_t> aln_node_, aln_pos_;
+  bool force_wide_ = false;
 };
 
 // HaplotypeGenerator::needleman_wunsch (:201-235) as far as its callers (greedy_clustering :238-271, merge_clusters
@@ -47,6 +51,8 @@ int thresholded_edit_distance(const std::string& cent_seq, const std::string& re
 // The two halves of it: the unit-cost edit distance itself (independent of T, so a caller that walks the ladder of
 // thresholds can remember it), and the reference's answer for (|cent_seq|, |read_seq|, distance, T).
 int edit_distance(const std::string& a, const std::string& b);
+// the distance when it is <= k, k + 1 otherwise: only the blocks within k diagonals of the main one are evaluated
+int bounded_edit_distance(const std::string& a, const std::string& b, int k);
 int thresholded_from_distance(int n, int m, int distance, int T);
 
 }  // namespace ltr

@@ -46,7 +46,6 @@ extern "C" int ltr_regions_run(ltr_genotyper* g, const ltr_params* params, const
   if (n_threads < 1) n_threads = 1;
   if ((uint32_t)n_threads > n_regions) n_threads = n_regions ? (int)n_regions : 1;
   std::atomic<uint32_t> next(0);
-  std::atomic<int> fatal(LTR_OK);
   auto prepare = [&]() {
     for (;;) {
       const uint32_t r = next.fetch_add(1);

@@ -133,3 +133,38 @@ def test_consensus_matches_the_restatement_on_fresh_clusters():
         if not any(seqs):
             continue
         assert abi.poa_consensus(seqs) == pr.ref_poa(seqs)
+
+
+def test_host_edit_distances_fuzz(tmp_path):
+    """ltr::edit_distance / ltr::bounded_edit_distance (the clustering's distances, host) against the plain recurrence."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "host_edit_fuzz")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-I" + os.path.join(root, "longtr_b200", "csrc", "host"),
+                           os.path.join(root, "tests", "emu", "host_edit_fuzz.cpp"),
+                           os.path.join(root, "longtr_b200", "csrc", "host", "poa.cpp"), "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and " bad 0" in out.stdout, out.stdout[-400:]
+
+
+def test_consensus_with_wide_cells():
+    """Sequences long enough that the alignment matrix needs 32-bit cells (16-bit cells serve N + 3 len < 32 000)."""
+    if not pr.ref_hapgen_poa_available():
+        pytest.skip("oracle/_ref/libltr_ref_hapgen_poa.so not built")
+    rng = random.Random(3)
+    truth = "".join(rng.choice("ACGT") for _ in range(9000))
+    seqs = []
+    for _ in range(3):
+        out = []
+        for ch in truth:
+            r = rng.random()
+            if r < 0.002:
+                out.append(rng.choice("ACGT"))
+            elif r < 0.003:
+                continue
+            elif r < 0.004:
+                out.append(ch + rng.choice("ACGT"))
+            else:
+                out.append(ch)
+        seqs.append("".join(out))
+    assert abi.poa_consensus(seqs) == pr.ref_poa(seqs)
