@@ -85,6 +85,61 @@ class Candidates(C.Structure):
                 ("n_consensus", C.c_uint32), ("assembly_threshold", C.c_int32), ("owner", C.c_void_p)]
 
 
+def _candidates_dict(c):
+    ab = C.string_at(c.allele_bytes, c.allele_off[c.n_alleles]) if c.n_alleles else b""
+    ncs = c.cluster_sample_begin[c.n_cluster_samples] if c.n_cluster_samples else 0
+    cb = C.string_at(c.cluster_bytes, c.cluster_off[ncs]) if ncs else b""
+    return dict(
+        status=c.status, block_start=c.block_start, block_end=c.block_end, lflank_start=c.lflank_start,
+        alleles=[ab[c.allele_off[k]:c.allele_off[k + 1]].decode() for k in range(c.n_alleles)],
+        lflank=(c.lflank or b"").decode(), rflank=(c.rflank or b"").decode(),
+        inexact=[int(c.allele_inexact[k]) for k in range(c.n_alleles)], n_consensus=c.n_consensus,
+        assembly_threshold=c.assembly_threshold,
+        cluster_sets=[[(cb[c.cluster_off[k]:c.cluster_off[k + 1]].decode(), c.cluster_count[k])
+                       for k in range(c.cluster_sample_begin[s], c.cluster_sample_begin[s + 1])]
+                      for s in range(c.n_cluster_samples)])
+
+
+def candidate_alleles_from_reads(reads, n_samples, region_start, region_stop, period, ref_seq, ref_seq_start=0,
+                                 indel_flank_len=5, flags=0):
+    """ltr_candidate_alleles_flags on reads the caller holds (dicts with start, stop, seq, cigar, sample; optional hap_gen_ok,
+    deleted; sample-major) instead of reads ltr_region_collect prepared.  Host only."""
+    import re
+    lib = load()
+    n = len(reads)
+    start = np.array([r["start"] for r in reads] + [0], dtype=np.int32)
+    stop = np.array([r["stop"] for r in reads] + [0], dtype=np.int32)
+    sample = np.array([r["sample"] for r in reads] + [0], dtype=np.int32)
+    roff = np.zeros(n + 1, dtype=np.uint32)
+    roff[1:] = np.cumsum([len(r["seq"]) for r in reads])
+    rbytes = np.frombuffer(("".join(r["seq"] for r in reads) + "\0").encode(), dtype=np.uint8).copy()
+    ops, coff = [], [0]
+    for r in reads:
+        for num, op in re.findall(r"(\d+)([MIDNSHP=X])", r["cigar"]):
+            ops.append((int(num) << 4) | "MIDNSHP=X".index(op))
+        coff.append(len(ops))
+    ops = np.array(ops + [0], dtype=np.uint32)
+    coff = np.array(coff, dtype=np.uint32)
+    ok = np.array([r.get("hap_gen_ok", 1) for r in reads] + [0], dtype=np.uint8)
+    dele = np.array([r.get("deleted", 0) for r in reads] + [0], dtype=np.uint8)
+    R = RegionReads()
+    R.n_samples = n_samples
+    R.n_reads = n
+    R.read_start, R.read_stop, R.read_sample = ptr(start, _i32p), ptr(stop, _i32p), ptr(sample, _i32p)
+    R.read_off, R.read_bytes = ptr(roff, _u32p), ptr(rbytes, _u8p)
+    R.cigar_off, R.cigar_ops = ptr(coff, _u32p), ptr(ops, _u32p)
+    R.hap_gen_ok, R.deleted = ptr(ok, _u8p), ptr(dele, _u8p)
+    ref = np.frombuffer(ref_seq.encode() if isinstance(ref_seq, str) else bytes(ref_seq), dtype=np.uint8)
+    cp = C.POINTER(Candidates)()
+    rc = lib.ltr_candidate_alleles_flags(C.byref(R), region_start, region_stop, period, ptr(ref, _u8p), ref_seq_start, len(ref),
+                                         indel_flank_len, flags, C.byref(cp))
+    if rc != 0:
+        raise RuntimeError("ltr_candidate_alleles failed: %d" % rc)
+    out = _candidates_dict(cp.contents)
+    lib.ltr_candidates_free(cp)
+    return out
+
+
 def region_collect(bams, chrom, start, stop, ref_seq, ref_seq_start=0, candidates=None, **overrides):
     """ltr_region_collect -> dict(samples=[file index], reads=[dict per read, sample-major], counters).
     candidates=dict(period=.., indel_flank_len=5, flags=0): also ltr_candidate_alleles_flags on the same reads ->
@@ -124,19 +179,7 @@ def region_collect(bams, chrom, start, stop, ref_seq, ref_seq_start=0, candidate
         if rc != 0:
             lib.ltr_region_reads_free(out)
             raise RuntimeError("ltr_candidate_alleles failed: %d" % rc)
-        c = cp.contents
-        ab = C.string_at(c.allele_bytes, c.allele_off[c.n_alleles]) if c.n_alleles else b""
-        ncs = c.cluster_sample_begin[c.n_cluster_samples] if c.n_cluster_samples else 0
-        cb = C.string_at(c.cluster_bytes, c.cluster_off[ncs]) if ncs else b""
-        res["candidates"] = dict(
-            status=c.status, block_start=c.block_start, block_end=c.block_end, lflank_start=c.lflank_start,
-            alleles=[ab[c.allele_off[k]:c.allele_off[k + 1]].decode() for k in range(c.n_alleles)],
-            lflank=(c.lflank or b"").decode(), rflank=(c.rflank or b"").decode(),
-            inexact=[int(c.allele_inexact[k]) for k in range(c.n_alleles)], n_consensus=c.n_consensus,
-            assembly_threshold=c.assembly_threshold,
-            cluster_sets=[[(cb[c.cluster_off[k]:c.cluster_off[k + 1]].decode(), c.cluster_count[k])
-                           for k in range(c.cluster_sample_begin[s], c.cluster_sample_begin[s + 1])]
-                          for s in range(c.n_cluster_samples)])
+        res["candidates"] = _candidates_dict(cp.contents)
         lib.ltr_candidates_free(cp)
     lib.ltr_region_reads_free(out)
     return res

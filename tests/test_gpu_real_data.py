@@ -1,0 +1,66 @@
+"""BASELINE.json configs[0] / configs[1] through the library's OWN pipeline (not through LongTR's classes as the drop-in test
+does): the reads of the shipped HG002 / trio BAMs on the shipped regions (tests/golden/real_cases.json.gz, decoded by
+tools/real_cases.py) -> ltr_candidate_alleles (exact candidates + assembly branch) -> ltr_genotyper_run (pooling, trimming,
+Viterbi, posteriors, removal of uncalled alleles, call extraction) against the VCF record the all-CPU reference wrote for the
+same reads: per sample the genotype as base-pair differences (GB), Q, PQ, DP and GLDIFF."""
+import numpy as np
+import pytest
+
+import golden_util as gu
+from longtr_b200 import Genotyper, abi, build_locus_batch
+
+pytestmark = pytest.mark.gpu
+
+
+def _fields(record):
+    f = record.split("\t")
+    fmt = f[8].split(":")
+    return f, [dict(zip(fmt, s.split(":"))) if s != "." else None for s in f[9:]]
+
+
+def test_real_loci_through_the_library_pipeline():
+    cases = gu.load_real_cases()
+    loci, keep = [], []
+    for c in cases:
+        cand = abi.candidate_alleles_from_reads(c["reads"], len(c["samples"]), c["region_start"], c["region_stop"],
+                                                len(c["motif"]), c["chrom_seq"])
+        assert cand["status"] == 0, c["name"]
+        loci.append(dict(lflank=cand["lflank"], rflank=cand["rflank"], alleles=cand["alleles"], repeat_start=cand["block_start"],
+                         repeat_end=cand["block_end"], n_samples=len(c["samples"]),
+                         reads=[dict(start=r["start"], stop=r["stop"], seq=r["seq"], cigar=r["cigar"], sample=r["sample"],
+                                     log_p1=r["log_p1"], log_p2=r["log_p2"]) for r in c["reads"]]))
+        keep.append(cand)
+    g = Genotyper(devices=(0,), host_threads=8, chunk_loci=16)
+    try:
+        out = g.run(build_locus_batch(loci))
+    finally:
+        g.close()
+    assert (out["status"] == 0).all()
+    n_samples = n_het = n_inexact = 0
+    for l, (c, cand) in enumerate(zip(cases, keep)):
+        f, samples = _fields(c["record"])
+        info = dict(kv.split("=") for kv in f[7].split(";"))
+        s0 = out["locus_sample_begin"][l]
+        lens = [len(a) for a in cand["alleles"]]
+        n_inexact += sum(cand["inexact"])
+        # INFO/INEXACT_ALLELE lists the alternate alleles that survive, in order of length
+        a0, a1 = out["locus_allele_begin"][l], out["locus_allele_begin"][l + 1]
+        kept = [k for k in range(a1 - a0) if out["kept_mask"][a0 + k]]
+        want_inexact = [] if info["INEXACT_ALLELE"] == "." else [int(x) for x in info["INEXACT_ALLELE"].split(",")]
+        alts = sorted((k for k in kept if k != 0), key=lambda k: (lens[k], cand["alleles"][k]))
+        assert [cand["inexact"][k] for k in alts] == want_inexact, c["name"]
+        if "BPDIFFS" in info:
+            assert [lens[k] - lens[0] for k in alts] == [int(x) for x in info["BPDIFFS"].split(",")], c["name"]
+        for s, want in enumerate(samples):
+            if want is None:
+                continue
+            ga, gb = out["gts"][s0 + s]
+            assert "%d|%d" % (lens[ga] - lens[0], lens[gb] - lens[0]) == want["GB"], (c["name"], s)
+            assert abs(np.exp(out["log_unphased_posteriors"][s0 + s]) - float(want["Q"])) <= 0.0051, (c["name"], s)
+            assert abs(np.exp(out["log_phased_posteriors"][s0 + s]) - float(want["PQ"])) <= 0.0051, (c["name"], s)
+            assert int(out["n_reads"][s0 + s]) == int(want["DP"]), (c["name"], s)
+            if want["GLDIFF"] != ".":
+                assert abs(out["gl_diffs"][s0 + s] - float(want["GLDIFF"])) <= 0.0051 + 1e-4 * abs(float(want["GLDIFF"])), (c["name"], s)
+            n_samples += 1
+            n_het += ga != gb
+    assert len(cases) >= 50 and n_samples >= 100 and n_het >= 10 and n_inexact >= 2
