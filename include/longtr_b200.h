@@ -360,6 +360,8 @@ typedef struct ltr_batch_calls {
   double prep_ms, gpu_wait_ms, post_ms, total_ms;  /* host timing of the call                                           */
   double submit_ms;                        /* of which inside ltr_job_submit_outputs                                     */
   uint32_t n_chunks;                       /* jobs the batch was cut into                                                */
+  const int32_t* read_allele;              /* [n_reads] or NULL (ltr_genotyper_set_read_alleles): the allele of its sample's
+                                              genotype each read supports -- what MALLREADS counts                         */
 } ltr_batch_calls;
 
 typedef struct ltr_genotyper ltr_genotyper;
@@ -369,6 +371,10 @@ typedef struct ltr_genotyper ltr_genotyper;
 int ltr_genotyper_create(const int32_t* devices, int32_t n_devices, int32_t host_threads, int32_t chunk_loci,
                          ltr_genotyper** out);
 void ltr_genotyper_destroy(ltr_genotyper* g);
+/* on != 0: the calls of later runs carry read_allele (the LL matrices are then downloaded as well: ~8 bytes per pooled read and
+ * allele).  As write_vcf_record assigns reads (src/seq_stutter_genotyper.cpp:954-970): the first allele of the genotype unless
+ * log_p2 + LL[second] >= log_p1 + LL[first].                                                                              */
+int ltr_genotyper_set_read_alleles(ltr_genotyper* g, int32_t on);
 /* Genotypes every locus of the batch.  A malformed locus (CIGAR the reference dies on, reads that do not fit their CIGAR,
  * missing flanks) fails alone: its status is the error, the rest of the batch is unaffected.                          */
 int ltr_genotyper_run(ltr_genotyper* g, const ltr_params* params, const ltr_locus_batch* batch, ltr_batch_calls** out);
@@ -699,6 +705,52 @@ typedef struct ltr_bed_run_result {
 int ltr_run_bed(ltr_genotyper* g, const ltr_params* params, const ltr_bam* const* bams, int32_t n_bams, const ltr_fasta* fasta,
                 const ltr_bed* bed, const ltr_region_params* rp, const ltr_regions_opts* opts, ltr_bed_run_result** out);
 void ltr_bed_run_result_free(ltr_bed_run_result* r);
+
+/* ---- VCF records (the output side of the path) ---------------------------------------------------
+ * ltr_vcf_record   the text of one record as SeqStutterGenotyper::write_vcf_record composes it (src/seq_stutter_genotyper.cpp:
+ *                  894-1402; get_alleles :688-781, reorder_alleles :667-686) with the reference's default output switches
+ *                  (ALLREADS, MALLREADS on; GL / PL / PHASEDGL / FILTER off) on the long-read path: CHROM POS ID REF ALT . .
+ *                  INFO (START END MOTIF PERIOD NSKIP NFILT INEXACT_ALLELE BPDIFFS DP DSNP DFLANKINDEL AN REFAC AC) FORMAT and
+ *                  one column per entry of column_sample ("." for -1 or a sample without reads).  Alleles are the candidates
+ *                  that survive (kept_mask; NULL = all), genotypes are candidate indices; read_allele (needed when a sample is
+ *                  heterozygous) is the allele each read is assigned to (ltr_batch_calls.read_allele); read_bp_diff is
+ *                  ltr_extract_cigar_bp_diff of the read over [region_start - 5, region_stop + 5], INT32_MIN where it returns
+ *                  0.  No trailing newline; LTR_ERR_INVALID with *out_len set when the buffer is too small; empty ("<DEL>")
+ *                  alleles are LTR_ERR_UNSUPPORTED.  The header lines of the file are not produced.
+ * ltr_extract_cigar_bp_diff  ExtractCigar (src/extract_indels.cpp:18-93) on BAM-encoded CIGAR operations.                  */
+typedef struct ltr_vcf_locus {
+  const char* chrom;
+  const char* name;               /* NULL or "": "."                                                    */
+  const char* motif;              /* the region's motif column (comma separated list)                   */
+  int32_t region_start, region_stop;  /* 0-based start as LongTR's Region holds it                      */
+  const uint8_t* chrom_seq;       /* reference bases [chrom_seq_start, chrom_seq_start + chrom_seq_len) */
+  int64_t chrom_seq_start, chrom_seq_len;
+  int32_t block_start, block_end; /* the candidate block (ltr_candidates)                               */
+  int32_t n_alleles;
+  const uint32_t* allele_off;     /* [n_alleles+1] */
+  const uint8_t* allele_bytes;
+  const uint8_t* allele_inexact;  /* [n_alleles] or NULL */
+  const uint8_t* kept_mask;       /* [n_alleles] or NULL */
+  int32_t haploid;
+  int32_t n_samples;              /* samples of the locus, in the locus' order                          */
+  const int32_t* gts;             /* [2 * n_samples] candidate indices                                  */
+  const double* log_unphased_posteriors;
+  const double* log_phased_posteriors;
+  const double* gl_diffs;
+  const int32_t* n_p1;            /* [n_samples] reads tagged HP = 1 / 2 (PDP), NULL = zeros            */
+  const int32_t* n_p2;
+  int32_t n_reads;
+  const int32_t* read_sample;     /* [n_reads] */
+  const double* log_p1;
+  const double* log_p2;
+  const int32_t* read_bp_diff;    /* [n_reads] or NULL (ALLREADS "."), INT32_MIN = none for this read   */
+  const int32_t* read_allele;     /* [n_reads] or NULL when no sample is heterozygous                   */
+  int32_t n_columns;
+  const int32_t* column_sample;   /* [n_columns] sample of the locus shown in the column, -1 = none     */
+} ltr_vcf_locus;
+int ltr_vcf_record(const ltr_vcf_locus* locus, char* out, uint32_t capacity, uint32_t* out_len);
+int ltr_extract_cigar_bp_diff(const uint32_t* cigar_ops, uint32_t n_ops, int32_t cigar_start, int32_t region_start,
+                              int32_t region_end, int32_t* bp_diff);
 
 /* ---- length-based EM of the stutter model ----------------------------------------------
  * ltr_em_stutter_train  EMStutterGenotyper(...).train(...) (src/em_stutter_genotyper.{h,cpp}) for many loci at once, as

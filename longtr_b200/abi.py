@@ -537,6 +537,10 @@ def load():
     lib.ltr_candidate_alleles_flags.restype = C.c_int
     lib.ltr_poa_consensus.argtypes = [_u8p, _u32p, C.c_uint32, _u8p, C.c_uint32, _u32p]
     lib.ltr_poa_consensus.restype = C.c_int
+    lib.ltr_vcf_record.argtypes = [C.POINTER(VcfLocus), C.c_char_p, C.c_uint32, _u32p]
+    lib.ltr_vcf_record.restype = C.c_int
+    lib.ltr_extract_cigar_bp_diff.argtypes = [_u32p, C.c_uint32, C.c_int32, C.c_int32, C.c_int32, _i32p]
+    lib.ltr_extract_cigar_bp_diff.restype = C.c_int
     lib.ltr_em_opts_default.argtypes = [C.POINTER(EmOpts)]
     lib.ltr_em_opts_default.restype = None
     lib.ltr_em_stutter_train.argtypes = [vp, C.POINTER(EmBatch), C.POINTER(EmOpts), _dp, _i32p, _i32p, _dp, _dp, C.c_uint32]
@@ -569,8 +573,74 @@ EXPORTED_SYMBOLS = [
     "ltr_candidate_alleles", "ltr_candidate_alleles_flags", "ltr_poa_consensus", "ltr_candidates_free", "ltr_regions_opts_default", "ltr_regions_run",
     "ltr_regions_result_free", "ltr_fasta_open", "ltr_fasta_close", "ltr_fasta_n_seqs", "ltr_fasta_seq_name",
     "ltr_fasta_seq_len", "ltr_fasta_fetch", "ltr_bed_read", "ltr_bed_free", "ltr_run_bed", "ltr_bed_run_result_free",
-    "ltr_em_opts_default", "ltr_em_stutter_train",
+    "ltr_em_opts_default", "ltr_em_stutter_train", "ltr_vcf_record", "ltr_extract_cigar_bp_diff", "ltr_genotyper_set_read_alleles",
 ]
+
+
+class VcfLocus(C.Structure):
+    _fields_ = [("chrom", C.c_char_p), ("name", C.c_char_p), ("motif", C.c_char_p), ("region_start", C.c_int32),
+                ("region_stop", C.c_int32), ("chrom_seq", _u8p), ("chrom_seq_start", C.c_int64), ("chrom_seq_len", C.c_int64),
+                ("block_start", C.c_int32), ("block_end", C.c_int32), ("n_alleles", C.c_int32), ("allele_off", _u32p),
+                ("allele_bytes", _u8p), ("allele_inexact", _u8p), ("kept_mask", _u8p), ("haploid", C.c_int32),
+                ("n_samples", C.c_int32), ("gts", _i32p), ("log_unphased_posteriors", _dp), ("log_phased_posteriors", _dp),
+                ("gl_diffs", _dp), ("n_p1", _i32p), ("n_p2", _i32p), ("n_reads", C.c_int32), ("read_sample", _i32p),
+                ("log_p1", _dp), ("log_p2", _dp), ("read_bp_diff", _i32p), ("read_allele", _i32p), ("n_columns", C.c_int32),
+                ("column_sample", _i32p)]
+
+
+INT32_MIN = -2147483648
+
+
+def extract_cigar_bp_diff(cigar, cigar_start, region_start, region_end):
+    """ltr_extract_cigar_bp_diff on a CIGAR string -> bp difference or None."""
+    import re
+    lib = load()
+    ops = np.array([(int(n) << 4) | "MIDNSHP=X".index(o) for n, o in re.findall(r"(\d+)([MIDNSHP=X])", cigar)] + [0],
+                   dtype=np.uint32)
+    d = C.c_int32(0)
+    ok = lib.ltr_extract_cigar_bp_diff(ptr(ops, _u32p), len(ops) - 1, cigar_start, region_start, region_end, C.byref(d))
+    return d.value if ok else None
+
+
+def vcf_record(chrom, name, motif, region_start, region_stop, chrom_seq, chrom_seq_start, block_start, block_end, alleles,
+               inexact, kept_mask, gts, log_unphased, log_phased, gl_diffs, n_p1, n_p2, read_sample, log_p1, log_p2,
+               read_bp_diff, read_allele, column_sample, haploid=False):
+    """ltr_vcf_record -> str.  read_bp_diff entries may be None; read_allele may be None."""
+    lib = load()
+    seq = np.frombuffer(chrom_seq.encode() if isinstance(chrom_seq, str) else bytes(chrom_seq), dtype=np.uint8)
+    ab, aoff = pack_seqs(alleles)
+    inex = np.array(list(inexact) + [0], dtype=np.uint8)
+    kept = np.array(list(kept_mask) + [0], dtype=np.uint8)
+    S = len(gts) // 2 if not hasattr(gts, "shape") else int(np.asarray(gts).size // 2)
+    g = np.array(list(np.asarray(gts).ravel()) + [0], dtype=np.int32)
+    lu = np.array(list(log_unphased) + [0.0], dtype=np.float64)
+    lp = np.array(list(log_phased) + [0.0], dtype=np.float64)
+    gd = np.array(list(gl_diffs) + [0.0], dtype=np.float64)
+    p1c = np.array(list(n_p1) + [0], dtype=np.int32)
+    p2c = np.array(list(n_p2) + [0], dtype=np.int32)
+    rs = np.array(list(read_sample) + [0], dtype=np.int32)
+    l1 = np.array(list(log_p1) + [0.0], dtype=np.float64)
+    l2 = np.array(list(log_p2) + [0.0], dtype=np.float64)
+    bd = np.array([INT32_MIN if x is None else x for x in read_bp_diff] + [0], dtype=np.int64).astype(np.int32)
+    ra = None if read_allele is None else np.array(list(read_allele) + [0], dtype=np.int32)
+    cs = np.array(list(column_sample) + [0], dtype=np.int32)
+    L = VcfLocus(chrom.encode(), (name or "").encode(), motif.encode(), region_start, region_stop, ptr(seq, _u8p),
+                 chrom_seq_start, len(seq), block_start, block_end, len(alleles), ptr(aoff, _u32p), ptr(ab, _u8p),
+                 ptr(inex, _u8p), ptr(kept, _u8p), int(haploid), S, ptr(g, _i32p), ptr(lu, _dp), ptr(lp, _dp), ptr(gd, _dp),
+                 ptr(p1c, _i32p), ptr(p2c, _i32p), len(read_sample), ptr(rs, _i32p), ptr(l1, _dp), ptr(l2, _dp), ptr(bd, _i32p),
+                 None if ra is None else ptr(ra, _i32p), len(column_sample), ptr(cs, _i32p))
+    cap = 1 << 16
+    for _ in range(2):
+        buf = C.create_string_buffer(cap)
+        n = C.c_uint32(0)
+        rc = lib.ltr_vcf_record(C.byref(L), buf, cap, C.byref(n))
+        if rc == 0:
+            return buf.value.decode()
+        if n.value + 1 > cap:
+            cap = n.value + 16
+            continue
+        break
+    raise RuntimeError("ltr_vcf_record failed: %d" % rc)
 
 
 class EmBatch(C.Structure):

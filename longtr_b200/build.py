@@ -21,7 +21,7 @@ OBJ = os.path.join(CSRC, "build")
 CU_SOURCES = ["viterbi_kernels.cu", "band_kernel.cu", "plan_kernels.cu", "posterior_kernel.cu", "stutter_kernel.cu", "abi.cu", "stutter_abi.cu",
               "edit_kernel.cu", "edit_abi.cu", "em_kernel.cu", "microbench.cu"]
 CPP_SOURCES = ["host/flat_api.cpp", "host/host_types.cpp", "host/hap_aligner.cpp", "host/stutter_host.cpp",
-               "host/genotyper.cpp", "host/pipeline.cpp", "host/locus_batcher.cpp", "host/bam_reader.cpp", "host/region_loader.cpp", "host/candidate_alleles.cpp", "host/poa.cpp", "host/fasta_reader.cpp", "host/region_pipeline.cpp", "synth_stutter.cpp"]
+               "host/genotyper.cpp", "host/pipeline.cpp", "host/locus_batcher.cpp", "host/bam_reader.cpp", "host/region_loader.cpp", "host/candidate_alleles.cpp", "host/poa.cpp", "host/fasta_reader.cpp", "host/vcf_writer.cpp", "host/region_pipeline.cpp", "synth_stutter.cpp"]
 HEADERS = ["viterbi_core.cuh", "band_core.cuh", "viterbi_host.h", "kernels.h", "stutter_core.cuh", "ctx.h", "plan_device.cuh", "edit_core.cuh"]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

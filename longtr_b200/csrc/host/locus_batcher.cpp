@@ -280,12 +280,14 @@ struct Chunk {
   Pinned<uint8_t> hap_bytes, read_bytes, haploid, mate, kept;
   Pinned<int32_t> label;
   Pinned<double> p1, p2, post, totals;
+  Pinned<double> ll;                          // LL of (pool, allele), only when the per-read allele assignment is wanted
+  std::vector<unsigned long long> ll_off;     // per locus of the chunk: pools x alleles prefix
   std::vector<unsigned long long> post_off, tot_off;
   uint32_t n_haps = 0, n_preads = 0, n_sreads = 0;
   void release() {
     lhb.release(); lrb.release(); hap_off.release(); read_off.release(); lsb.release(); pool_index.release(); nsamp.release();
     hap_bytes.release(); read_bytes.release(); haploid.release(); mate.release(); kept.release(); label.release();
-    p1.release(); p2.release(); post.release(); totals.release();
+    p1.release(); p2.release(); post.release(); totals.release(); ll.release();
   }
 };
 
@@ -295,6 +297,7 @@ struct ltr_genotyper {
   std::vector<ltr_ctx*> ctxs;
   WorkerPool* pool = nullptr;
   uint32_t chunk_loci = 20000;
+  bool want_read_alleles = false;  // ltr_genotyper_set_read_alleles
   std::vector<Chunk*> chunks;  // 2 per device + 1 being prepared
 };
 
@@ -485,6 +488,7 @@ struct CallsOwner {  // storage behind an ltr_batch_calls
   std::vector<uint8_t> kept;
   std::vector<double> lpp, lup, gld, stl, gls;
   std::vector<uint64_t> glb;
+  std::vector<int32_t> read_allele;  // per raw read of the batch, -1 = not assigned
 };
 
 // Genotyper::extract_genotypes_and_likelihoods per locus on the surviving alleles (parallel over loci).
@@ -538,6 +542,23 @@ void finish_chunk(const ltr_locus_batch& B, Chunk& C, CallsOwner& O, WorkerPool&
           O.pls[g0 + k] = pls[s * n_gl + k];
         }
       }
+      if (!O.read_allele.empty() && !C.ll_off.empty()) {
+        // which allele of its sample's genotype a read supports (write_vcf_record, seq_stutter_genotyper.cpp:954-970): the
+        // first unless log_p2 + LL[second] >= log_p1 + LL[first]; LLs clamped at -600 like the posterior pass leaves them
+        const double* ll = C.ll.p + C.ll_off[i];
+        const uint32_t r_first = B.locus_read_begin[C.l0];
+        for (uint32_t r = B.locus_read_begin[l]; r < B.locus_read_begin[l + 1]; ++r) {
+          const uint32_t s = (uint32_t)B.read_sample[r];
+          const int32_t ga = O.gts[2 * (s0 + s)], gb = O.gts[2 * (s0 + s) + 1];
+          int32_t best = ga;
+          if (!haploid && ga != gb) {
+            const double* row = ll + (size_t)C.pool_of[r - r_first] * H;
+            const double la = row[ga] < -600 ? -600 : row[ga], lb = row[gb] < -600 ? -600 : row[gb];
+            best = (B.log_p1[r] + la > B.log_p2[r] + lb) ? ga : gb;
+          }
+          O.read_allele[r] = best;
+        }
+      }
     }
   });
 }
@@ -565,6 +586,12 @@ int ltr_genotyper_create(const int32_t* devices, int32_t n_devices, int32_t host
   if (chunk_loci > 0) g->chunk_loci = (uint32_t)chunk_loci;
   for (size_t k = 0; k < 2 * g->ctxs.size() + 1; ++k) g->chunks.push_back(new Chunk());
   *out = g;
+  return LTR_OK;
+}
+
+int ltr_genotyper_set_read_alleles(ltr_genotyper* g, int32_t on) {
+  if (!g) return LTR_ERR_INVALID;
+  g->want_read_alleles = on != 0;
   return LTR_OK;
 }
 
@@ -622,6 +649,7 @@ int ltr_genotyper_run(ltr_genotyper* g, const ltr_params* params, const ltr_locu
   }
   O->gls.assign(O->glb[n_samples], 0.0);
   O->pls.assign(O->glb[n_samples], 0);
+  if (g->want_read_alleles) O->read_allele.assign((size_t)n_reads + 1, -1);
 
   double prep_ms = 0, wait_ms = 0, post_ms = 0, submit_ms = 0;
   int rc_all = LTR_OK;
@@ -722,6 +750,20 @@ int ltr_genotyper_run(ltr_genotyper* g, const ltr_params* params, const ltr_locu
     pb.prune_uncalled = 1;
     ltr_job_outputs outs;
     outs.ll = nullptr; outs.post = c->post.p; outs.totals = c->totals.p; outs.kept_mask = c->kept.p;
+    c->ll_off.clear();
+    if (g->want_read_alleles) {
+      const uint32_t nc = c->l1 - c->l0;
+      c->ll_off.assign((size_t)nc + 1, 0);
+      for (uint32_t i = 0; i < nc; ++i)
+        c->ll_off[i + 1] = c->ll_off[i] + (unsigned long long)(c->lrb.p[i + 1] - c->lrb.p[i]) * (c->lhb.p[i + 1] - c->lhb.p[i]);
+      if (!c->ll.reserve((size_t)c->ll_off[nc] + 1)) {
+        rc_all = LTR_ERR_OOM;
+        --dev_load[(size_t)c->device_slot];
+        free_chunks.push_back(c);
+        break;
+      }
+      outs.ll = c->ll.p;
+    }
     const auto t_submit = Clock::now();
     const int rc = ltr_job_submit_outputs(g->ctxs[(size_t)c->device_slot], params, &vb, &pb, &outs, &c->job);
     submit_ms += ms_since(t_submit);
@@ -746,6 +788,7 @@ int ltr_genotyper_run(ltr_genotyper* g, const ltr_params* params, const ltr_locu
   V.pls = O->pls.data();
   V.prep_ms = prep_ms; V.gpu_wait_ms = wait_ms; V.post_ms = post_ms; V.total_ms = ms_since(t_begin);
   V.submit_ms = submit_ms; V.n_chunks = (uint32_t)cuts.size();
+  V.read_allele = O->read_allele.empty() ? nullptr : O->read_allele.data();
   if (rc_all != LTR_OK) {
     delete O;
     return rc_all;

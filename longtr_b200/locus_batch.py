@@ -29,7 +29,7 @@ class BatchCalls(C.Structure):
                 ("log_phased_posteriors", _dp), ("log_unphased_posteriors", _dp), ("gl_diffs", _dp),
                 ("sample_total_lls", _dp), ("n_reads", _i32p), ("gl_begin", _u64p), ("gls", _dp), ("pls", _i32p),
                 ("prep_ms", C.c_double), ("gpu_wait_ms", C.c_double), ("post_ms", C.c_double), ("total_ms", C.c_double),
-                ("submit_ms", C.c_double), ("n_chunks", C.c_uint32)]
+                ("submit_ms", C.c_double), ("n_chunks", C.c_uint32), ("read_allele", _i32p)]
 
 
 BAM_OPS = "MIDNSHP=X"
@@ -131,6 +131,8 @@ def _declare(lib):
     lib.ltr_genotyper_create.restype = C.c_int
     lib.ltr_genotyper_destroy.argtypes = [vp]
     lib.ltr_genotyper_destroy.restype = None
+    lib.ltr_genotyper_set_read_alleles.argtypes = [vp, C.c_int32]
+    lib.ltr_genotyper_set_read_alleles.restype = C.c_int
     lib.ltr_genotyper_run.argtypes = [vp, C.POINTER(abi.Params), C.POINTER(LocusBatch), C.POINTER(C.POINTER(BatchCalls))]
     lib.ltr_genotyper_run.restype = C.c_int
     lib.ltr_batch_calls_free.argtypes = [C.POINTER(BatchCalls)]
@@ -194,12 +196,16 @@ class Genotyper:
         """batch: dict of numpy arrays (build_locus_batch).  Returns a dict of numpy copies of ltr_batch_calls."""
         s, keep = make_locus_batch(batch)
         calls = self.run_struct(s, aln_params, indel_flank_len)
-        out = self._calls_dict(calls)
+        out = self._calls_dict(calls, int(np.asarray(batch["locus_read_begin"])[-1]))
         self.free(calls)
         return out
 
+    def set_read_alleles(self, on=True):
+        """ltr_genotyper_set_read_alleles: later runs also return read_allele (what MALLREADS counts)."""
+        self.lib.ltr_genotyper_set_read_alleles(self.h, 1 if on else 0)
+
     @staticmethod
-    def _calls_dict(calls):
+    def _calls_dict(calls, nr=0):
         c = calls.contents
         n = c.n_loci
         arr = np.ctypeslib.as_array
@@ -216,6 +222,7 @@ class Genotyper:
                    log_unphased_posteriors=take(c.log_unphased_posteriors, ns), gl_diffs=take(c.gl_diffs, ns),
                    sample_total_lls=take(c.sample_total_lls, ns), n_reads=take(c.n_reads, ns), gl_begin=glb,
                    gls=take(c.gls, int(glb[-1])), pls=take(c.pls, int(glb[-1])),
+                   read_allele=(None if not c.read_allele or not nr else take(c.read_allele, nr)),
                    timing=dict(prep_ms=c.prep_ms, gpu_wait_ms=c.gpu_wait_ms, post_ms=c.post_ms, total_ms=c.total_ms, submit_ms=c.submit_ms,
                                n_chunks=c.n_chunks))
         return out

@@ -32,10 +32,24 @@ def test_real_loci_through_the_library_pipeline():
         keep.append(cand)
     g = Genotyper(devices=(0,), host_threads=8, chunk_loci=16)
     try:
+        g.set_read_alleles(True)
         out = g.run(build_locus_batch(loci))
     finally:
         g.close()
     assert (out["status"] == 0).all()
+    # ---- the whole record as text: ltr_vcf_record on the device's numbers = the reference's record, character for character
+    import test_vcf_writer as tw
+    rb = np.concatenate([[0], np.cumsum([len(c["reads"]) for c in cases])])
+    n_text = 0
+    for l, (c, cand) in enumerate(zip(cases, keep)):
+        s0, s1 = out["locus_sample_begin"][l], out["locus_sample_begin"][l + 1]
+        a0, a1 = out["locus_allele_begin"][l], out["locus_allele_begin"][l + 1]
+        calls = dict(gts=out["gts"][s0:s1], lup=out["log_unphased_posteriors"][s0:s1], lpp=out["log_phased_posteriors"][s0:s1],
+                     gld=out["gl_diffs"][s0:s1], kept=out["kept_mask"][a0:a1], read_allele=out["read_allele"][rb[l]:rb[l + 1]])
+        got = abi.vcf_record(**tw.record_inputs(c, cand, calls))
+        assert got == c["record"], c["name"]
+        n_text += 1
+    assert n_text == len(cases)
     n_samples = n_het = n_inexact = 0
     for l, (c, cand) in enumerate(zip(cases, keep)):
         f, samples = _fields(c["record"])
