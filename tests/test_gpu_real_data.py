@@ -78,3 +78,37 @@ def test_real_loci_through_the_library_pipeline():
             n_samples += 1
             n_het += ga != gb
     assert len(cases) >= 50 and n_samples >= 100 and n_het >= 10 and n_inexact >= 2
+
+
+def test_seeded_loci_records_character_for_character():
+    """SURVEY Appendix A4 and the ten seeded drop-in loci (tests/dropin_cases.py; haploid loci and custom alignment parameters
+    among them) through the same route: the library's record = the reference's (tests/golden/vcf_records.json)."""
+    import dropin_cases as dc
+    import test_vcf_writer as tw
+    want = {c["name"]: c["record"] for c in gu.load("vcf_records")}
+    cases = [dc.case_a4()] + dc.seeded_cases()
+    g = Genotyper(devices=(0,), host_threads=4, chunk_loci=16)
+    g.set_read_alleles(True)
+    n = 0
+    try:
+        for c in cases:
+            if c["name"] not in want:
+                continue
+            cand = abi.candidate_alleles_from_reads(c["reads"], len(c["samples"]), c["region_start"], c["region_stop"],
+                                                    len(c["motif"]), c["chrom_seq"])
+            assert cand["status"] == 0, c["name"]
+            locus = dict(lflank=cand["lflank"], rflank=cand["rflank"], alleles=cand["alleles"], repeat_start=cand["block_start"],
+                         repeat_end=cand["block_end"], n_samples=len(c["samples"]), haploid=bool(c.get("haploid")),
+                         reads=[dict(start=r["start"], stop=r["stop"], seq=r["seq"], cigar=r["cigar"], sample=r["sample"],
+                                     log_p1=r["log_p1"], log_p2=r["log_p2"]) for r in c["reads"]])
+            out = g.run(build_locus_batch([locus]), aln_params=c.get("aln_params"))
+            assert out["status"][0] == 0, c["name"]
+            calls = dict(gts=out["gts"], lup=out["log_unphased_posteriors"], lpp=out["log_phased_posteriors"],
+                         gld=out["gl_diffs"], kept=out["kept_mask"], read_allele=out["read_allele"])
+            inp = tw.record_inputs(dict(c, record=want[c["name"]]), cand, calls)
+            got = abi.vcf_record(haploid=bool(c.get("haploid")), **inp)
+            assert got == want[c["name"]], c["name"]
+            n += 1
+    finally:
+        g.close()
+    assert n >= 10
