@@ -548,6 +548,7 @@ typedef struct ltr_region_reads {
   /* the counters read_and_filter_reads / left_align_reads log */
   uint32_t n_overlapping, n_hard_clipped, n_has_n, n_low_qual, n_low_mapq, n_not_spanning, n_not_unique, n_passed,
       n_trim_failed;
+  const int32_t* read_hp;             /* [n_reads] value of the HP tag, 0 without one (PDP of the VCF record)   */
   void* owner;
 } ltr_region_reads;
 void ltr_region_params_default(ltr_region_params* p);
@@ -639,6 +640,10 @@ typedef struct ltr_regions_opts {
   int32_t max_tr_len;       /* --max-tr-len (1000)        */
   int32_t min_total_reads;  /* --min-reads (10)           */
   int32_t no_assembly;      /* 1: report regions that need consensus alleles as LTR_REGION_NEEDS_ASSEMBLY (default 0) */
+  int32_t vcf_records;      /* 1: also compose the VCF record of every genotyped region (ltr_vcf_record), one sample column
+                               per BAM file; needs region_motifs                                                          */
+  const char* const* region_names;   /* [n_regions] or NULL ("."): ID column                                              */
+  const char* const* region_motifs;  /* [n_regions] MOTIF / PERIOD of the record                                          */
 } ltr_regions_opts;
 typedef struct ltr_regions_result {
   uint32_t n_regions;
@@ -655,6 +660,9 @@ typedef struct ltr_regions_result {
   const uint32_t* sample_file;         /* index into bams of each sample of the region                         */
   const uint8_t* allele_inexact;       /* per allele (indexed like allele_off): 1 = consensus of a read cluster */
   uint32_t n_assembled;                /* regions whose candidate alleles went through the assembly branch      */
+  const uint32_t* record_off;          /* [n_regions+1] or NULL (opts->vcf_records): record r = records[record_off[r] ..
+                                          record_off[r+1]), empty for a region that was not genotyped; no newlines       */
+  const char* records;
   void* owner;
 } ltr_regions_result;
 void ltr_regions_opts_default(ltr_regions_opts* o);

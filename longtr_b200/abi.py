@@ -74,7 +74,8 @@ class RegionReads(C.Structure):
                 ("hap_gen_ok", _u8p), ("deleted", _u8p), ("name_off", _u32p), ("names", C.c_void_p),
                 ("n_overlapping", C.c_uint32), ("n_hard_clipped", C.c_uint32), ("n_has_n", C.c_uint32),
                 ("n_low_qual", C.c_uint32), ("n_low_mapq", C.c_uint32), ("n_not_spanning", C.c_uint32),
-                ("n_not_unique", C.c_uint32), ("n_passed", C.c_uint32), ("n_trim_failed", C.c_uint32), ("owner", C.c_void_p)]
+                ("n_not_unique", C.c_uint32), ("n_passed", C.c_uint32), ("n_trim_failed", C.c_uint32), ("read_hp", _i32p),
+                ("owner", C.c_void_p)]
 
 
 class Candidates(C.Structure):
@@ -168,7 +169,7 @@ def region_collect(bams, chrom, start, stop, ref_seq, ref_seq_start=0, candidate
         reads.append(dict(name=names[r.name_off[i]:r.name_off[i + 1] - 1].decode(), start=r.read_start[i], stop=r.read_stop[i],
                           seq=seq[r.read_off[i]:r.read_off[i + 1]].decode(), qual=qual[r.read_off[i]:r.read_off[i + 1]].decode(),
                           cigar=cig, sample=r.read_sample[i], log_p1=r.log_p1[i], log_p2=r.log_p2[i],
-                          hap_gen_ok=int(r.hap_gen_ok[i]), deleted=int(r.deleted[i])))
+                          hap_gen_ok=int(r.hap_gen_ok[i]), deleted=int(r.deleted[i]), hp=int(r.read_hp[i])))
     res = dict(samples=[r.sample_file[s] for s in range(r.n_samples)], reads=reads,
                counters={k: getattr(r, k) for k in ("n_overlapping", "n_hard_clipped", "n_has_n", "n_low_qual", "n_low_mapq",
                                                     "n_not_spanning", "n_not_unique", "n_passed", "n_trim_failed")})

@@ -133,7 +133,7 @@ void trim_alignment(Aln& a, int32_t min_read_start, int32_t max_read_stop, int32
 struct Owner {
   ltr_region_reads pub;
   std::vector<uint32_t> sample_file, sample_read_begin, read_off, cigar_off, cigar_ops, name_off;
-  std::vector<int32_t> read_start, read_stop, read_sample;
+  std::vector<int32_t> read_start, read_stop, read_sample, read_hp;
   std::vector<uint8_t> read_bytes, qual_bytes, hap_gen_ok, deleted;
   std::vector<double> log_p1, log_p2;
   std::vector<char> names;
@@ -381,6 +381,7 @@ extern "C" int ltr_region_collect(const ltr_bam* const* bams, int32_t n_bams, co
       O->log_p2.push_back(p2[s][j]);
       O->hap_gen_ok.push_back(a.deleted && a.bases.empty() ? 1 : ((a.flag & 0x8000) ? 1 : 0));
       O->deleted.push_back(a.deleted ? 1 : 0);
+      O->read_hp.push_back(a.has_hp ? a.hp : 0);  // left_align_reads counts these per sample (:146-151): PDP of the record
       O->names.insert(O->names.end(), a.name.begin(), a.name.end());
       O->names.push_back('\0');
       O->name_off.push_back((uint32_t)O->names.size());
@@ -407,6 +408,7 @@ extern "C" int ltr_region_collect(const ltr_bam* const* bams, int32_t n_bams, co
   S.log_p2 = O->log_p2.data();
   S.hap_gen_ok = O->hap_gen_ok.data();
   S.deleted = O->deleted.data();
+  S.read_hp = O->read_hp.data();
   S.name_off = O->name_off.data();
   S.names = O->names.data();
   S.owner = O;

@@ -8,6 +8,8 @@
 // their reason and do not enter the batch.  Regions whose reads are not explained by exact candidates get consensus alleles
 // from the assembly branch of ltr_candidate_alleles (clustering + partial-order consensus on the preparing host thread);
 // opts->no_assembly reports them as LTR_REGION_NEEDS_ASSEMBLY instead.
+#include <limits.h>
+#include <stdint.h>
 #include <string.h>
 
 #include <atomic>
@@ -30,6 +32,8 @@ struct Owner {
   std::vector<int32_t> status, locus_index, block_start, block_end;
   std::vector<uint32_t> region_allele_begin, allele_off, region_sample_begin, sample_file;
   std::vector<uint8_t> allele_bytes, allele_inexact;
+  std::vector<uint32_t> record_off;
+  std::string records;
 };
 
 }  // namespace
@@ -40,6 +44,7 @@ extern "C" int ltr_regions_run(ltr_genotyper* g, const ltr_params* params, const
                                const ltr_regions_opts* opts, ltr_regions_result** out) {
   if (!g || !params || !bams || n_bams < 1 || !chrom || (n_regions && !regions) || !ref_seq || !rp || !opts || !out)
     return LTR_ERR_INVALID;
+  if (opts->vcf_records && n_regions && !opts->region_motifs) return LTR_ERR_INVALID;
   *out = nullptr;
   std::vector<RegionWork> work(n_regions);
   int n_threads = opts->host_threads > 0 ? opts->host_threads : (int)std::thread::hardware_concurrency();
@@ -100,6 +105,9 @@ extern "C" int ltr_regions_run(ltr_genotyper* g, const ltr_params* params, const
   std::vector<uint8_t> lfb, rfb, ab, rb;
   std::vector<int32_t> rstart, rend, read_start, read_stop, read_sample;
   std::vector<double> p1, p2;
+  std::vector<int32_t> read_bp_diff, n_hp1, n_hp2;   // for the records: ExtractCigar per read, HP counts per (locus, sample)
+  std::vector<uint32_t> locus_sample_begin(1, 0), locus_region;
+  const bool want_records = opts->vcf_records != 0;
   uint32_t n_loci = 0;
   for (uint32_t r = 0; r < n_regions; ++r) {
     RegionWork& W = work[r];
@@ -146,6 +154,21 @@ extern "C" int ltr_regions_run(ltr_genotyper* g, const ltr_params* params, const
       p1.push_back(RR.log_p1[i]);
       p2.push_back(RR.log_p2[i]);
     }
+    if (want_records) {
+      const size_t h0 = n_hp1.size();
+      n_hp1.resize(h0 + RR.n_samples, 0);
+      n_hp2.resize(h0 + RR.n_samples, 0);
+      for (uint32_t i = 0; i < RR.n_reads; ++i) {
+        int32_t d = 0;  // write_vcf_record (:1017-1023): ExtractCigar over the region +- 5 bp
+        const int got = ltr_extract_cigar_bp_diff(RR.cigar_ops + RR.cigar_off[i], RR.cigar_off[i + 1] - RR.cigar_off[i],
+                                                  RR.read_start[i], regions[r].start - 5, regions[r].stop + 5, &d);
+        read_bp_diff.push_back(got ? d : INT32_MIN);
+        if (RR.read_hp[i] == 1) ++n_hp1[h0 + (size_t)RR.read_sample[i]];
+        if (RR.read_hp[i] == 2) ++n_hp2[h0 + (size_t)RR.read_sample[i]];
+      }
+      locus_sample_begin.push_back((uint32_t)n_hp1.size());
+      locus_region.push_back(r);
+    }
     lrb.push_back((uint32_t)read_start.size());
     lns.push_back(RR.n_samples);
   }
@@ -170,9 +193,66 @@ extern "C" int ltr_regions_run(ltr_genotyper* g, const ltr_params* params, const
     B.second_mate = nullptr;
     B.locus_n_samples = lns.data();
     B.locus_haploid = nullptr;
+    if (want_records) ltr_genotyper_set_read_alleles(g, 1);
     rc = ltr_genotyper_run(g, params, &B, &calls);
+    if (want_records) ltr_genotyper_set_read_alleles(g, 0);
+  }
+  if (rc == LTR_OK && want_records) {
+    O->record_off.assign((size_t)n_regions + 1, 0);
+    std::vector<std::string> text(n_regions);
+    std::vector<char> buf(1 << 16);
+    for (uint32_t l = 0; l < n_loci && rc == LTR_OK; ++l) {
+      const uint32_t r = locus_region[l];
+      if (calls->status[l] != LTR_OK) continue;
+      const uint32_t a0 = O->region_allele_begin[r], na = O->region_allele_begin[r + 1] - a0;
+      const uint32_t s0 = calls->locus_sample_begin[l], ns = calls->locus_sample_begin[l + 1] - s0;
+      std::vector<uint32_t> aoff(na + 1);
+      for (uint32_t a = 0; a <= na; ++a) aoff[a] = O->allele_off[a0 + a] - O->allele_off[a0];
+      std::vector<int32_t> column((size_t)n_bams, -1);
+      for (uint32_t s = 0; s < ns; ++s) {
+        const uint32_t f = O->sample_file[O->region_sample_begin[r] + s];
+        if (f < (uint32_t)n_bams) column[f] = (int32_t)s;
+      }
+      ltr_vcf_locus V;
+      memset(&V, 0, sizeof(V));
+      V.chrom = chrom;
+      V.name = opts->region_names ? opts->region_names[r] : "";
+      V.motif = opts->region_motifs[r];
+      V.region_start = regions[r].start; V.region_stop = regions[r].stop;
+      V.chrom_seq = ref_seq; V.chrom_seq_start = ref_seq_start; V.chrom_seq_len = ref_seq_len;
+      V.block_start = O->block_start[r]; V.block_end = O->block_end[r];
+      V.n_alleles = (int32_t)na; V.allele_off = aoff.data(); V.allele_bytes = O->allele_bytes.data() + O->allele_off[a0];
+      V.allele_inexact = O->allele_inexact.data() + a0;
+      V.kept_mask = calls->kept_mask + calls->locus_allele_begin[l];
+      V.haploid = 0;
+      V.n_samples = (int32_t)ns;
+      V.gts = calls->gts + 2 * (size_t)s0;
+      V.log_unphased_posteriors = calls->log_unphased_posteriors + s0;
+      V.log_phased_posteriors = calls->log_phased_posteriors + s0;
+      V.gl_diffs = calls->gl_diffs + s0;
+      V.n_p1 = n_hp1.data() + locus_sample_begin[l]; V.n_p2 = n_hp2.data() + locus_sample_begin[l];
+      V.n_reads = (int32_t)(lrb[l + 1] - lrb[l]);
+      V.read_sample = read_sample.data() + lrb[l];
+      V.log_p1 = p1.data() + lrb[l]; V.log_p2 = p2.data() + lrb[l];
+      V.read_bp_diff = read_bp_diff.data() + lrb[l];
+      V.read_allele = calls->read_allele ? calls->read_allele + lrb[l] : nullptr;
+      V.n_columns = n_bams; V.column_sample = column.data();
+      uint32_t len = 0;
+      int vrc = ltr_vcf_record(&V, buf.data(), (uint32_t)buf.size(), &len);
+      if (vrc == LTR_ERR_INVALID && (size_t)len + 1 > buf.size()) {
+        buf.resize((size_t)len + 16);
+        vrc = ltr_vcf_record(&V, buf.data(), (uint32_t)buf.size(), &len);
+      }
+      if (vrc == LTR_OK) text[r].assign(buf.data(), len);
+      else if (vrc != LTR_ERR_UNSUPPORTED) rc = vrc;
+    }
+    for (uint32_t r = 0; r < n_regions; ++r) {
+      O->records += text[r];
+      O->record_off[r + 1] = (uint32_t)O->records.size();
+    }
   }
   if (rc != LTR_OK) {
+    ltr_batch_calls_free(calls);
     delete O;
     return rc;
   }
@@ -188,6 +268,8 @@ extern "C" int ltr_regions_run(ltr_genotyper* g, const ltr_params* params, const
   P.allele_off = O->allele_off.data();
   P.allele_bytes = O->allele_bytes.data();
   P.allele_inexact = O->allele_inexact.data();
+  P.record_off = want_records ? O->record_off.data() : nullptr;
+  P.records = want_records ? O->records.c_str() : nullptr;
   P.region_sample_begin = O->region_sample_begin.data();
   P.sample_file = O->sample_file.data();
   P.owner = O;
@@ -228,8 +310,11 @@ extern "C" int ltr_run_bed(ltr_genotyper* g, const ltr_params* params, const ltr
     chrom_seq.resize((size_t)len + 1);
     rc = ltr_fasta_fetch(fasta, bed->chroms[c], 0, len, chrom_seq.data());
     ltr_regions_result* res = nullptr;
+    ltr_regions_opts o = *opts;  // names and motifs of this chromosome's regions for the records
+    o.region_names = bed->names + r;
+    o.region_motifs = bed->motifs + r;
     if (rc == LTR_OK)
-      rc = ltr_regions_run(g, params, bams, n_bams, bed->chroms[c], bed->regions + r, e - r, chrom_seq.data(), 0, len, rp, opts,
+      rc = ltr_regions_run(g, params, bams, n_bams, bed->chroms[c], bed->regions + r, e - r, chrom_seq.data(), 0, len, rp, &o,
                            &res);
     O->per_chrom.push_back(res);
     O->begin.push_back(e);
@@ -261,6 +346,9 @@ extern "C" void ltr_regions_opts_default(ltr_regions_opts* o) {
   o->max_tr_len = 1000;      // MAX_STR_LENGTH (--max-tr-len), bam_processor.h:94
   o->min_total_reads = 10;   // MIN_TOTAL_READS (--min-reads), genotyper_bam_processor.h:110
   o->no_assembly = 0;
+  o->vcf_records = 0;
+  o->region_names = nullptr;
+  o->region_motifs = nullptr;
 }
 
 extern "C" void ltr_regions_result_free(ltr_regions_result* r) {

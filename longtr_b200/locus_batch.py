@@ -42,7 +42,8 @@ class Region(C.Structure):
 
 class RegionsOpts(C.Structure):
     _fields_ = [("host_threads", C.c_int32), ("max_tr_len", C.c_int32), ("min_total_reads", C.c_int32),
-                ("no_assembly", C.c_int32)]
+                ("no_assembly", C.c_int32), ("vcf_records", C.c_int32), ("region_names", C.POINTER(C.c_char_p)),
+                ("region_motifs", C.POINTER(C.c_char_p))]
 
 
 class RegionsResult(C.Structure):
@@ -50,7 +51,7 @@ class RegionsResult(C.Structure):
                 ("calls", C.POINTER(BatchCalls)), ("block_start", _i32p), ("block_end", _i32p),
                 ("region_allele_begin", _u32p), ("allele_off", _u32p), ("allele_bytes", _u8p),
                 ("region_sample_begin", _u32p), ("sample_file", _u32p), ("allele_inexact", _u8p),
-                ("n_assembled", C.c_uint32), ("owner", C.c_void_p)]
+                ("n_assembled", C.c_uint32), ("record_off", _u32p), ("records", C.c_void_p), ("owner", C.c_void_p)]
 
 
 class BedRunResult(C.Structure):
@@ -239,12 +240,17 @@ class Genotyper:
                    inexact=[[int(r.allele_inexact[a]) for a in range(r.region_allele_begin[i], r.region_allele_begin[i + 1])]
                             for i in range(n)],
                    n_assembled=r.n_assembled,
+                   records=(None if not r.record_off else
+                            [C.string_at(r.records + r.record_off[i], r.record_off[i + 1] - r.record_off[i]).decode()
+                             for i in range(n)]),
                    calls=self._calls_dict(r.calls) if r.n_loci else None)
 
     def run_regions(self, bams, chrom, regions, ref_seq, ref_seq_start=0, aln_params=None, indel_flank_len=5,
-                    host_threads=0, max_tr_len=1000, min_total_reads=10, no_assembly=0, **region_overrides):
+                    host_threads=0, max_tr_len=1000, min_total_reads=10, no_assembly=0, motifs=None, names=None,
+                    **region_overrides):
         """ltr_regions_run: bams = [abi.BamFile], regions = [(start, stop, period)] on `chrom`.  Returns dict(status,
-        locus_index, alleles [per region], block [(start, end)], samples [per region: file indices], calls (as ``run``))."""
+        locus_index, alleles [per region], block [(start, end)], samples [per region: file indices], calls (as ``run``)).
+        motifs = [str per region] (+ names): also the VCF record of every genotyped region (``records``)."""
         from .engine import LongTRError
         lib = self.lib
         prm = abi.make_params(aln_params, indel_flank_len)
@@ -253,6 +259,12 @@ class Genotyper:
         for k, v in region_overrides.items():
             setattr(rp, k, v)
         opts = RegionsOpts(host_threads, max_tr_len, min_total_reads, no_assembly)
+        if motifs is not None:
+            m_arr = (C.c_char_p * max(1, len(regions)))(*[m.encode() for m in motifs])
+            n_arr = (C.c_char_p * max(1, len(regions)))(*[(x or "").encode() for x in (names or [""] * len(regions))])
+            opts.vcf_records = 1
+            opts.region_motifs = m_arr
+            opts.region_names = n_arr
         regs = (Region * max(1, len(regions)))(*[Region(*r) for r in regions])
         handles = (C.c_void_p * len(bams))(*[b.h for b in bams])
         ref = np.frombuffer(ref_seq.encode() if isinstance(ref_seq, str) else bytes(ref_seq), dtype=np.uint8)
@@ -266,7 +278,7 @@ class Genotyper:
         return res
 
     def run_bed(self, bams, fasta, bed_path, aln_params=None, indel_flank_len=5, host_threads=0, max_tr_len=1000,
-                min_total_reads=10, no_assembly=0, chrom_limit=None, **region_overrides):
+                min_total_reads=10, no_assembly=0, chrom_limit=None, vcf_records=False, **region_overrides):
         """ltr_run_bed: bams = [abi.BamFile], fasta = abi.FastaFile, bed_path = region file (CHROM START STOP MOTIF [NAME]).
         Returns dict(chroms, bed=[(chrom index, start, stop, period, name, motif)], per_chrom=[as run_regions])."""
         from .engine import LongTRError
@@ -278,6 +290,7 @@ class Genotyper:
         for k, v in region_overrides.items():
             setattr(rp, k, v)
         opts = RegionsOpts(host_threads, max_tr_len, min_total_reads, no_assembly)
+        opts.vcf_records = 1 if vcf_records else 0
         handles = (C.c_void_p * len(bams))(*[b.h for b in bams])
         out = C.POINTER(BedRunResult)()
         rc = lib.ltr_run_bed(self.h, C.byref(prm), handles, len(bams), fasta.h, bed["handle"], C.byref(rp), C.byref(opts),

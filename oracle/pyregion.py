@@ -182,7 +182,8 @@ def left_align(samples, by_sample, terms, start, stop, ref, ref_start, flank=200
                 continue
             t = trim_alignment(r, start - flank if start > flank else 1, stop + flank, flank)
             hap_ok = int(not (min_flank > 0 and (r["pos"] > start - min_flank or r["end"] < stop + min_flank)))
-            base = dict(name=r["name"], sample=s, log_p1=terms[s][j][0], log_p2=terms[s][j][1])
+            base = dict(name=r["name"], sample=s, log_p1=terms[s][j][0], log_p2=terms[s][j][1],
+                        hp=(r["hp"] if has_tag(r["raw"], "HP") else 0))   # genotyper_bam_processor.cpp:146-151 counts these
             if not t["seq"]:
                 out.append(dict(base, start=start, stop=stop, seq="", qual="", cigar="", hap_gen_ok=1, deleted=1))
                 continue

@@ -33,9 +33,11 @@ def test_regions_run_matches_the_reference(genotyper, tmp_path, wi):
     bams = [abi.BamFile(p) for p in bw.write_world(world, str(tmp_path))]
     for b in bams:
         b.build_index()
-    out = genotyper.run_regions(bams, "chrS", world["regions"], world["chrom_seq"], 0)
+    motifs = [world["chrom_seq"][s0:s0 + per] for s0, _e, per in world["regions"]]
+    names = ["R%d" % k for k in range(len(world["regions"]))]
+    out = genotyper.run_regions(bams, "chrS", world["regions"], world["chrom_seq"], 0, motifs=motifs, names=names)
     calls = out["calls"]
-    n_checked = 0
+    n_checked = n_records = 0
     for g in W["regions"]:
         r = g["region"]
         if g["status"] != 0:
@@ -61,7 +63,13 @@ def test_regions_run_matches_the_reference(genotyper, tmp_path, wi):
         np.testing.assert_allclose(calls["log_phased_posteriors"][s0:s1], want, rtol=1e-10, atol=1e-9, err_msg=str(r))
         np.testing.assert_allclose(calls["sample_total_lls"][s0:s1], gu.unhex(g["out_totals"]), rtol=1e-10, atol=1e-9)
         n_checked += 1
-    assert n_checked >= (100 if wi == 0 else 60)
+        # the VCF record: the reference lists the samples in the region's order, the library one column per BAM file
+        f = g["record"].split("\t")
+        by_file = {g["samples"][k]: f[9 + k] for k in range(S)}
+        want_rec = "\t".join(f[:9] + [by_file.get(b, ".") for b in range(len(bams))])
+        assert out["records"][r] == want_rec, r
+        n_records += 1
+    assert n_checked >= (100 if wi == 0 else 60) and n_records == n_checked
     assert out["n_assembled"] >= 40 and sum(map(sum, out["inexact"])) >= 10
     # the same regions with the assembly switched off: those that needed it are reported, the others are unchanged
     off = genotyper.run_regions(bams, "chrS", world["regions"], world["chrom_seq"], 0, no_assembly=1)
@@ -101,12 +109,15 @@ def test_run_bed_equals_regions_run(genotyper, tmp_path):
         for r in order:
             s0, e0, per = world["regions"][r]
             f.write("chrS\t%d\t%d\t%s\tR%d\n" % (s0 + 1, e0, world["chrom_seq"][s0:s0 + per], r))
-    want = genotyper.run_regions(bams, "chrS", world["regions"], world["chrom_seq"], 0)
-    got = genotyper.run_bed(bams, abi.FastaFile(str(fa)), str(bed))
+    motifs = [world["chrom_seq"][s0:s0 + per] for s0, _e, per in world["regions"]]
+    want = genotyper.run_regions(bams, "chrS", world["regions"], world["chrom_seq"], 0, motifs=motifs,
+                                 names=["R%d" % r for r in range(len(order))])
+    got = genotyper.run_bed(bams, abi.FastaFile(str(fa)), str(bed), vcf_records=True)
     assert got["chroms"] == ["chrS"] and [b[4] for b in got["bed"]] == ["R%d" % r for r in range(len(order))]
     g = got["per_chrom"][0]
-    for key in ("status", "locus_index", "block", "alleles", "samples", "inexact"):
+    for key in ("status", "locus_index", "block", "alleles", "samples", "inexact", "records"):
         assert g[key] == want[key], key
+    assert sum(1 for x in g["records"] if x.startswith("chrS\t")) == sum(1 for st in g["status"] if st == 0) >= 8
     for key in ("gts", "kept_mask", "log_phased_posteriors", "gl_diffs"):
         np.testing.assert_array_equal(g["calls"][key], want["calls"][key])
     with open(bed, "a") as f:

@@ -57,7 +57,8 @@ def main():
                           log_p2=r["log_p2"]) for r in got["reads"]]
             cases.append(dict(name="%s_%d" % (W["name"], ri), chrom_name="chrS", chrom_seq=world["chrom_seq"], region_start=s,
                               region_stop=e, motif=motif, region_name="R%d" % ri, samples=["S%d" % f for f in got["samples"]],
-                              n_p1s=[0] * S, n_p2s=[0] * S, reads=reads, stutter_motif="A", stutter_period=per))
+                              n_p1s=[sum(1 for r in got["reads"] if r["sample"] == k and r["hp"] == 1) for k in range(S)],
+                              n_p2s=[sum(1 for r in got["reads"] if r["sample"] == k and r["hp"] == 2) for k in range(S)], reads=reads, stutter_motif="A", stutter_period=per))
             meta[-1]["case"] = len(cases) - 1
             meta[-1]["alleles"] = c["alleles"]
             meta[-1]["inexact"] = c["inexact"]
@@ -78,6 +79,7 @@ def main():
                                 S=first["S"],
                                 block=[first["repeat_start"], first["repeat_end"]], lflank=first["lflank"], rflank=first["rflank"],
                                 kept=[first["alleles"].index(a) for a in last["alleles"]], out_gts=last["gts"],
+                                record=rec, motif=world["chrom_seq"][world["regions"][m["region"]][0]:world["regions"][m["region"]][0] + world["regions"][m["region"]][2]],
                                 out_post=last["post"], out_totals=last["totals"]))
         gold["worlds"].append(dict(W, regions=regions))
         print(W["name"], "regions", len(regions), "genotyped by the reference", sum(1 for r in regions if "kept" in r))
