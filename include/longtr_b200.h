@@ -759,6 +759,11 @@ typedef struct ltr_vcf_locus {
 int ltr_vcf_record(const ltr_vcf_locus* locus, char* out, uint32_t capacity, uint32_t* out_len);
 int ltr_extract_cigar_bp_diff(const uint32_t* cigar_ops, uint32_t n_ops, int32_t cigar_start, int32_t region_start,
                               int32_t region_end, int32_t* bp_diff);
+/* The header lines of the file (Genotyper::get_vcf_header, src/genotyper.cpp:258-336, default output switches): file format,
+ * command, reference, one contig line per sequence of the FASTA, the INFO / FORMAT descriptions, the #CHROM line with the
+ * sample columns.  Ends with a newline.  LTR_ERR_INVALID with *out_len set when the buffer is too small.                   */
+int ltr_vcf_header(const ltr_fasta* fasta, const char* fasta_path, const char* command, const char* const* sample_names,
+                   uint32_t n_samples, char* out, uint32_t capacity, uint32_t* out_len);
 
 /* ---- length-based EM of the stutter model ----------------------------------------------
  * ltr_em_stutter_train  EMStutterGenotyper(...).train(...) (src/em_stutter_genotyper.{h,cpp}) for many loci at once, as

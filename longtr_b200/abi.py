@@ -538,6 +538,8 @@ def load():
     lib.ltr_candidate_alleles_flags.restype = C.c_int
     lib.ltr_poa_consensus.argtypes = [_u8p, _u32p, C.c_uint32, _u8p, C.c_uint32, _u32p]
     lib.ltr_poa_consensus.restype = C.c_int
+    lib.ltr_vcf_header.argtypes = [vp, C.c_char_p, C.c_char_p, C.POINTER(C.c_char_p), C.c_uint32, C.c_char_p, C.c_uint32, _u32p]
+    lib.ltr_vcf_header.restype = C.c_int
     lib.ltr_vcf_record.argtypes = [C.POINTER(VcfLocus), C.c_char_p, C.c_uint32, _u32p]
     lib.ltr_vcf_record.restype = C.c_int
     lib.ltr_extract_cigar_bp_diff.argtypes = [_u32p, C.c_uint32, C.c_int32, C.c_int32, C.c_int32, _i32p]
@@ -574,7 +576,7 @@ EXPORTED_SYMBOLS = [
     "ltr_candidate_alleles", "ltr_candidate_alleles_flags", "ltr_poa_consensus", "ltr_candidates_free", "ltr_regions_opts_default", "ltr_regions_run",
     "ltr_regions_result_free", "ltr_fasta_open", "ltr_fasta_close", "ltr_fasta_n_seqs", "ltr_fasta_seq_name",
     "ltr_fasta_seq_len", "ltr_fasta_fetch", "ltr_bed_read", "ltr_bed_free", "ltr_run_bed", "ltr_bed_run_result_free",
-    "ltr_em_opts_default", "ltr_em_stutter_train", "ltr_vcf_record", "ltr_extract_cigar_bp_diff", "ltr_genotyper_set_read_alleles",
+    "ltr_em_opts_default", "ltr_em_stutter_train", "ltr_vcf_record", "ltr_vcf_header", "ltr_extract_cigar_bp_diff", "ltr_genotyper_set_read_alleles",
 ]
 
 
@@ -642,6 +644,21 @@ def vcf_record(chrom, name, motif, region_start, region_stop, chrom_seq, chrom_s
             continue
         break
     raise RuntimeError("ltr_vcf_record failed: %d" % rc)
+
+
+def vcf_header(fasta, fasta_path, command, sample_names):
+    """ltr_vcf_header -> str (fasta: FastaFile)."""
+    lib = load()
+    names = (C.c_char_p * max(1, len(sample_names)))(*[x.encode() for x in sample_names])
+    cap = 1 << 16
+    for _ in range(2):
+        buf = C.create_string_buffer(cap)
+        n = C.c_uint32(0)
+        rc = lib.ltr_vcf_header(fasta.h, fasta_path.encode(), command.encode(), names, len(sample_names), buf, cap, C.byref(n))
+        if rc == 0:
+            return buf.value.decode()
+        cap = n.value + 16
+    raise RuntimeError("ltr_vcf_header failed: %d" % rc)
 
 
 class EmBatch(C.Structure):

@@ -8,7 +8,8 @@
 //   ExtractCigar        src/extract_indels.cpp:18-93   (the caller supplies its result per read: ltr_extract_cigar_bp_diff)
 //   condense_read_counts  src/genotyper.h:50-64
 // Inputs are the outputs of the library's own pipeline (ltr_candidate_alleles, ltr_genotyper_run with read alleles, the
-// per-read bookkeeping of ltr_regions_run); the header lines of the file are not produced here.
+// per-read bookkeeping of ltr_regions_run); ltr_vcf_header gives the header lines
+// (Genotyper::get_vcf_header, src/genotyper.cpp:258-336).
 #include <limits.h>
 #include <math.h>
 #include <stdio.h>
@@ -295,6 +296,73 @@ extern "C" int ltr_vcf_record(const ltr_vcf_locus* L, char* out, uint32_t capaci
     }
     o += ":" + condense(bps[(size_t)s]) + ":" + condense(ml_bps[(size_t)s]);
   }
+  *out_len = (uint32_t)o.size();
+  if (o.size() + 1 > capacity) return LTR_ERR_INVALID;
+  memcpy(out, o.c_str(), o.size() + 1);
+  return LTR_OK;
+}
+
+// ---- header lines (Genotyper::get_vcf_header, src/genotyper.cpp:258-336; contigs: FastaReader::write_all_contigs_to_vcf,
+//      src/fasta_reader.cpp:64-73) with the default output switches.  The descriptions are part of the file format LongTR's
+//      users parse, so they are reproduced verbatim, as a table.
+namespace {
+struct FieldLine {
+  const char* id;
+  const char* number;
+  const char* type;
+  const char* description;
+};
+const FieldLine kInfo[] = {
+    {"START", "1", "Integer", "Inclusive start coodinate for the repetitive portion of the reference allele"},
+    {"END", "1", "Integer", "Inclusive end coordinate for the repetitive portion of the reference allele"},
+    {"MOTIF", ".", "String", "TR motif(s)"},
+    {"PERIOD", ".", "Integer", "Length of TR motif(s)"},
+    {"NSKIP", "1", "Integer", "Number of samples not genotyped due to various issues"},
+    {"NFILT", "1", "Integer", "Number of samples whose genotypes were filtered due to various issues"},
+    {"INEXACT_ALLELE", "A", "Integer",
+     "Boolean showing if each alternate allele is exact or approximated by POA, 0 for exact 1 for approximated."},
+    {"BPDIFFS", "A", "Integer", "Base pair difference of each alternate allele from the reference allele"},
+    {"DP", "1", "Integer", "Total number of valid reads used to genotype all samples"},
+    {"DSNP", "1", "Integer", "Total number of reads with SNP phasing information"},
+    {"DFLANKINDEL", "1", "Integer", "Total number of reads with an indel in the regions flanking the STR"},
+    {"AN", "1", "Integer", "Total number of alleles in called genotypes"},
+    {"REFAC", "1", "Integer", "Reference allele count"},
+    {"AC", "A", "Integer", "Alternate allele counts"},
+};
+const FieldLine kFormat[] = {
+    {"GT", "1", "String", "Genotype"},
+    {"GB", "1", "String", "Base pair differences of genotype from reference"},
+    {"Q", "1", "Float", "Posterior probability of unphased genotype"},
+    {"PQ", "1", "Float", "Posterior probability of phased genotype"},
+    {"DP", "1", "Integer", "Number of valid reads used for sample's genotype"},
+    {"DSNP", "1", "Integer", "Number of reads with SNP phasing information"},
+    {"PSNP", "1", "String", "Number of reads with SNPs supporting each haploid genotype"},
+    {"PDP", "1", "String", "Fractional reads supporting each haploid genotype"},
+    {"GLDIFF", "1", "Float", "Difference in likelihood between the reported and next best genotypes"},
+    {"ALLREADS", "1", "String", "Base pair difference observed in each read's Needleman-Wunsch alignment"},
+    {"MALLREADS", "1", "String",
+     "Maximum likelihood bp diff in each read based on haplotype alignments for reads that span the repeat region by at least 5 "
+     "base pairs"},
+};
+}  // namespace
+
+extern "C" int ltr_vcf_header(const ltr_fasta* fasta, const char* fasta_path, const char* command,
+                              const char* const* sample_names, uint32_t n_samples, char* out, uint32_t capacity,
+                              uint32_t* out_len) {
+  if (!fasta || !fasta_path || !command || !out_len || (n_samples && !sample_names) || (capacity && !out)) return LTR_ERR_INVALID;
+  std::string o = "##fileformat=VCFv4.1\n";
+  o += std::string("##command=") + command + "\n##reference=" + fasta_path + "\n";
+  for (int32_t i = 0; i < ltr_fasta_n_seqs(fasta); ++i) {
+    const char* name = ltr_fasta_seq_name(fasta, i);
+    o += std::string("##contig=<ID=") + name + ",length=" + std::to_string(ltr_fasta_seq_len(fasta, name)) + ">\n";
+  }
+  for (const FieldLine& f : kInfo)
+    o += std::string("##INFO=<ID=") + f.id + ",Number=" + f.number + ",Type=" + f.type + ",Description=\"" + f.description + "\">\n";
+  for (const FieldLine& f : kFormat)
+    o += std::string("##FORMAT=<ID=") + f.id + ",Number=" + f.number + ",Type=" + f.type + ",Description=\"" + f.description + "\">\n";
+  o += "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT";
+  for (uint32_t i = 0; i < n_samples; ++i) o += std::string("\t") + sample_names[i];
+  o += "\n";
   *out_len = (uint32_t)o.size();
   if (o.size() + 1 > capacity) return LTR_ERR_INVALID;
   memcpy(out, o.c_str(), o.size() + 1);

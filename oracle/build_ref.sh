@@ -76,6 +76,15 @@ $LINKXX -shared -o "$out/libltr_ref_hapgen_poa.so" "$out/obj/hapgen_driver_poa.o
      "$out/obj/region.o" -Wl,--no-undefined -lm -lpthread
 echo "built $out/libltr_ref_hapgen_poa.so"
 
+# ---- libltr_ref_fasta.so: the reference's FastaReader + Genotyper::get_vcf_header on integration/faidx_compat.cpp -> ltr_fasta_* ----
+$CXX -O2 -g -std=c++11 -fPIC -w -I"$here/../include" -c "$here/../integration/faidx_compat.cpp" -o "$out/obj/faidx_compat.o"
+$CXX -O2 -g -std=c++17 -fPIC -w -I"$here/../include" -c "$here/../longtr_b200/csrc/host/fasta_reader.cpp" -o "$out/obj/ltr_fasta_reader.o"
+$CXX -O2 -g -std=c++11 -fPIC -w -I"$here/shim" -I"$ref/src" -c "$here/fasta_driver.cpp" -o "$out/obj/fasta_driver.o"
+$LINKXX -shared -o "$out/libltr_ref_fasta.so" "$out/obj/fasta_driver.o" "$out/obj/fasta_reader.o" "$out/obj/genotyper.o" \
+     "$out/obj/faidx_compat.o" "$out/obj/ltr_fasta_reader.o" "$out/obj/mathops.o" "$out/obj/error.o" "$out/obj/stringops.o" \
+     -Wl,--no-undefined -lm -lpthread
+echo "built $out/libltr_ref_fasta.so"
+
 # ---- libltr_ref_em.so: the reference's EMStutterGenotyper (length-based EM of the stutter model) behind oracle/em_driver.cpp ----
 $CXX $FLAGS -I"$here/shim" -c "$ref/src/em_stutter_genotyper.cpp" -o "$out/obj/em_stutter_genotyper.o"
 $CXX -O2 -g -std=c++11 -fPIC -w -fno-access-control -I"$here/shim" -I"$ref/src" -c "$here/em_driver.cpp" -o "$out/obj/em_driver.o"

@@ -33,7 +33,7 @@ def build(force=False):
         subprocess.check_call(["make", "-C", _HERE, "liblongtr_oracle.so"], stdout=subprocess.DEVNULL)
     if os.path.isdir(os.environ.get("LONGTR_REFERENCE", "/root/reference") + "/src"):
         outs = [os.path.join(_HERE, "_ref", f) for f in
-                ("libltr_ref.so", "libltr_ref_io.so", "libltr_ref_hapgen.so", "libltr_ref_hapgen_poa.so", "libltr_ref_em.so",
+                ("libltr_ref.so", "libltr_ref_io.so", "libltr_ref_hapgen.so", "libltr_ref_hapgen_poa.so", "libltr_ref_em.so", "libltr_ref_fasta.so",
                  "ltr_ref_full", "ltr_ref_trace", "ltr_ref_lazy")]
         srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".cpp", ".hpp", ".sh"))]
         srcs += [os.path.join(_HERE, "shim", "spoa", "spoa.hpp"), os.path.join(_HERE, "shim", "hts_stubs.cpp")]

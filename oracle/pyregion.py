@@ -274,6 +274,36 @@ def ref_read_regions(path, max_regions=1000000000, chrom_limit=None):
     return out
 
 
+_FASTA_SO = os.path.join(_HERE, "_ref", "libltr_ref_fasta.so")  # FastaReader + get_vcf_header on integration/faidx_compat.cpp
+
+
+def ref_fasta_available():
+    return os.path.exists(_FASTA_SO)
+
+
+def ref_fasta_sequence(path, chrom):
+    """FastaReader(path).get_sequence(chrom) of the reference, running on the library's FASTA reader -> (sequence, length)."""
+    lib = C.CDLL(_FASTA_SO)
+    lib.ltr_ref_fasta_sequence.restype = C.c_void_p
+    lib.ltr_ref_fasta_sequence.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_longlong)]
+    n = C.c_longlong(0)
+    p = lib.ltr_ref_fasta_sequence(path.encode(), chrom.encode(), C.byref(n))
+    text = C.string_at(p).decode()
+    C.CDLL(None).free(C.c_void_p(p))
+    return text, n.value
+
+
+def ref_vcf_header(fasta_path, command, samples):
+    """Genotyper::get_vcf_header of the reference (contigs through its FastaReader on the library's reader)."""
+    lib = C.CDLL(_FASTA_SO)
+    lib.ltr_ref_vcf_header.restype = C.c_void_p
+    lib.ltr_ref_vcf_header.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p]
+    p = lib.ltr_ref_vcf_header(fasta_path.encode(), command.encode(), "\n".join(samples).encode())
+    text = C.string_at(p).decode()
+    C.CDLL(None).free(C.c_void_p(p))
+    return text
+
+
 def ref_poa(seqs):
     """HaplotypeGenerator::poa (reference, compiled in place) on top of the restated spoa; fewer than 30 sequences."""
     import numpy as np

@@ -136,3 +136,22 @@ def test_bed_read_matches_the_reference(tmp_path):
             flat = [(got["chroms"][c], s, e, per, name, motif) for c, s, e, per, name, motif in got["regions"]]
             assert [key(r) for r in flat] == [key(r) for r in want]      # ties are in unspecified order in std::sort
             assert sorted(flat) == sorted(want)
+
+
+@pytest.mark.skipif(not pr.ref_fasta_available(), reason="oracle/_ref/libltr_ref_fasta.so not built")
+def test_reference_fasta_reader_runs_on_our_reader_and_header_matches(tmp_path):
+    """integration/faidx_compat.cpp serves the faidx names LongTR binds: its own FastaReader (compiled in place) returns the
+    sequences of the file, and Genotyper::get_vcf_header -- contig lines through that reader -- equals ltr_vcf_header."""
+    rng = random.Random(21)
+    seqs = _seqs(rng, 4)
+    path = str(tmp_path / "ref.fa")
+    _write_fasta(path, seqs, 70)
+    for name, s in seqs:
+        got, n = pr.ref_fasta_sequence(path, name)
+        assert n == len(s) and got == s
+    assert pr.ref_fasta_sequence(path, "chrNope")[1] == -1
+    fa = abi.FastaFile(path)
+    for samples in (["HG002"], ["HG002", "HG003", "HG004"], []):
+        cmd = "LongTR --bams a.bam --fasta ref.fa --regions r.bed"
+        assert abi.vcf_header(fa, path, cmd, samples) == pr.ref_vcf_header(path, cmd, samples)
+    fa.close()
