@@ -124,3 +124,28 @@ def test_run_bed_equals_regions_run(genotyper, tmp_path):
         f.write("chrMissing\t100\t130\tAC\n")
     with pytest.raises(Exception):
         genotyper.run_bed(bams, abi.FastaFile(str(fa)), str(bed))     # chromosome absent from the FASTA / BAM files
+
+
+def test_example_flow_writes_the_vcf_file(tmp_path):
+    """tools/run_bed_to_vcf.py: BAM + FASTA + region file -> VCF file; its records are the golden ones of the world."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import run_bed_to_vcf
+    W = json.load(open(GOLD))["worlds"][0]
+    world = bw.synthetic_world(W["n_loci"], config=3, first_locus=W["first_locus"], n_samples=W["n_samples"])
+    paths = bw.write_world(world, str(tmp_path))
+    fa, bed, vcf = tmp_path / "ref.fa", tmp_path / "regions.bed", tmp_path / "calls.vcf"
+    with open(fa, "w") as f:
+        f.write(">chrS\n")
+        for k in range(0, len(world["chrom_seq"]), 80):
+            f.write(world["chrom_seq"][k:k + 80] + "\n")
+    with open(bed, "w") as f:
+        for r, (s0, e0, per) in enumerate(world["regions"]):
+            f.write("chrS\t%d\t%d\t%s\tR%d\n" % (s0 + 1, e0, world["chrom_seq"][s0:s0 + per], r))
+    n = run_bed_to_vcf.main(["--bams", ",".join(paths), "--fasta", str(fa), "--regions", str(bed), "--out", str(vcf),
+                             "--samples", "S0"])
+    lines = open(vcf).read().splitlines()
+    body = [x for x in lines if not x.startswith("#")]
+    assert lines[0] == "##fileformat=VCFv4.1" and lines[len(lines) - len(body) - 1].endswith("FORMAT\tS0")
+    want = [g["record"] for g in W["regions"] if g["status"] == 0]
+    assert n == len(body) == len(want) and body == want

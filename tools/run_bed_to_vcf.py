@@ -1,0 +1,54 @@
+#!/usr/bin/env python
+"""The whole flow through the C ABI, as a few calls (an example, not a command-line tool: LongTR's CLI is out of scope):
+
+    python tools/run_bed_to_vcf.py --bams a.bam,b.bam --fasta ref.fa --regions regions.bed --out calls.vcf [--samples A,B]
+
+BAM files (one per sample) + indexed FASTA + region file (CHROM START STOP MOTIF [NAME]) -> VCF text: ltr_bam_open,
+ltr_fasta_open, ltr_run_bed with vcf_records (host threads: read filters, trimming, candidate alleles; GPU: alignment,
+posteriors, removal of uncalled alleles), ltr_vcf_header + the records in region order."""
+import argparse
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--bams", required=True)
+    ap.add_argument("--fasta", required=True)
+    ap.add_argument("--regions", required=True)
+    ap.add_argument("--out", required=True)
+    ap.add_argument("--samples", default="")
+    ap.add_argument("--devices", default="0")
+    ap.add_argument("--phased-bam", action="store_true")
+    a = ap.parse_args(argv)
+    from longtr_b200 import Genotyper, abi
+    paths = a.bams.split(",")
+    samples = a.samples.split(",") if a.samples else [os.path.basename(p).split(".")[0] for p in paths]
+    bams = [abi.BamFile(p) for p in paths]
+    for b in bams:
+        if not b.has_index:
+            b.build_index()
+    fasta = abi.FastaFile(a.fasta)
+    g = Genotyper(devices=tuple(int(d) for d in a.devices.split(",")))
+    try:
+        run = g.run_bed(bams, fasta, a.regions, vcf_records=True, phased_bam=1 if a.phased_bam else 0)
+    finally:
+        g.close()
+    n = 0
+    with open(a.out, "w") as f:
+        f.write(abi.vcf_header(fasta, a.fasta, " ".join(["run_bed_to_vcf.py"] + (argv if argv is not None else sys.argv[1:])),
+                               samples))
+        for res in run["per_chrom"]:
+            for rec in res["records"] or []:
+                if rec:
+                    f.write(rec + "\n")
+                    n += 1
+    print("%d records -> %s" % (n, a.out))
+    return n
+
+
+if __name__ == "__main__":
+    main()
