@@ -22,7 +22,7 @@ def main(argv=None):
     ap.add_argument("--out", required=True)
     ap.add_argument("--samples", default="")
     ap.add_argument("--devices", default="0")
-    ap.add_argument("--phased-bam", action="store_true")
+    ap.add_argument("--no-phased-bam", action="store_true", help="ignore HP tags (the library's default is --phased-bam)")
     a = ap.parse_args(argv)
     from longtr_b200 import Genotyper, abi
     paths = a.bams.split(",")
@@ -34,7 +34,7 @@ def main(argv=None):
     fasta = abi.FastaFile(a.fasta)
     g = Genotyper(devices=tuple(int(d) for d in a.devices.split(",")))
     try:
-        run = g.run_bed(bams, fasta, a.regions, vcf_records=True, phased_bam=1 if a.phased_bam else 0)
+        run = g.run_bed(bams, fasta, a.regions, vcf_records=True, **(dict(phased_bam=0) if a.no_phased_bam else {}))
     finally:
         g.close()
     n = 0
