@@ -599,6 +599,7 @@ def measure_long(args, config, n_loci, steps, warmup, torch, rank, world, local,
         "roofline": {"bound": "fp64_issue", "achieved": achieved, "peak": peak_gcups, "unit": "GCUPS",
                      "frac": achieved / peak_gcups, "traffic": ncu_traffic("traffic"),
                      "traffic_source": ncu_traffic("source"), "traffic_kernel": ncu_traffic("kernel"),
+                     "pipe_utilisation_ncu": ncu_traffic("pipe_utilisation_ncu"),
                      "peak_source": "ltr_fp64_issue_rate (DADD lane-ops/s measured in this run) / 17 FP64 ops per cell",
                      "fp64_lane_ops_per_s": fp64_rate,
                      "hbm_gbs_algorithmic": (work.input_bytes + 8.0 * st.n_pairs) / (vit_ms / steps) / 1e6},
