@@ -644,6 +644,7 @@ typedef struct ltr_regions_opts {
                                per BAM file; needs region_motifs                                                          */
   const char* const* region_names;   /* [n_regions] or NULL ("."): ID column                                              */
   const char* const* region_motifs;  /* [n_regions] MOTIF / PERIOD of the record                                          */
+  int32_t haploid;          /* 1: the chromosome is haploid in every sample (--haploid-chrs): haploid priors and records  */
 } ltr_regions_opts;
 typedef struct ltr_regions_result {
   uint32_t n_regions;

@@ -192,7 +192,9 @@ extern "C" int ltr_regions_run(ltr_genotyper* g, const ltr_params* params, const
     B.read_sample = read_sample.data(); B.log_p1 = p1.data(); B.log_p2 = p2.data();
     B.second_mate = nullptr;
     B.locus_n_samples = lns.data();
-    B.locus_haploid = nullptr;
+    std::vector<uint8_t> haploid_flags;
+    if (opts->haploid) haploid_flags.assign((size_t)n_loci + 1, 1);
+    B.locus_haploid = opts->haploid ? haploid_flags.data() : nullptr;
     if (want_records) ltr_genotyper_set_read_alleles(g, 1);
     rc = ltr_genotyper_run(g, params, &B, &calls);
     if (want_records) ltr_genotyper_set_read_alleles(g, 0);
@@ -224,7 +226,7 @@ extern "C" int ltr_regions_run(ltr_genotyper* g, const ltr_params* params, const
       V.n_alleles = (int32_t)na; V.allele_off = aoff.data(); V.allele_bytes = O->allele_bytes.data() + O->allele_off[a0];
       V.allele_inexact = O->allele_inexact.data() + a0;
       V.kept_mask = calls->kept_mask + calls->locus_allele_begin[l];
-      V.haploid = 0;
+      V.haploid = opts->haploid ? 1 : 0;
       V.n_samples = (int32_t)ns;
       V.gts = calls->gts + 2 * (size_t)s0;
       V.log_unphased_posteriors = calls->log_unphased_posteriors + s0;
@@ -349,6 +351,7 @@ extern "C" void ltr_regions_opts_default(ltr_regions_opts* o) {
   o->vcf_records = 0;
   o->region_names = nullptr;
   o->region_motifs = nullptr;
+  o->haploid = 0;
 }
 
 extern "C" void ltr_regions_result_free(ltr_regions_result* r) {

@@ -43,7 +43,7 @@ class Region(C.Structure):
 class RegionsOpts(C.Structure):
     _fields_ = [("host_threads", C.c_int32), ("max_tr_len", C.c_int32), ("min_total_reads", C.c_int32),
                 ("no_assembly", C.c_int32), ("vcf_records", C.c_int32), ("region_names", C.POINTER(C.c_char_p)),
-                ("region_motifs", C.POINTER(C.c_char_p))]
+                ("region_motifs", C.POINTER(C.c_char_p)), ("haploid", C.c_int32)]
 
 
 class RegionsResult(C.Structure):
@@ -247,7 +247,7 @@ class Genotyper:
 
     def run_regions(self, bams, chrom, regions, ref_seq, ref_seq_start=0, aln_params=None, indel_flank_len=5,
                     host_threads=0, max_tr_len=1000, min_total_reads=10, no_assembly=0, motifs=None, names=None,
-                    **region_overrides):
+                    haploid=False, **region_overrides):
         """ltr_regions_run: bams = [abi.BamFile], regions = [(start, stop, period)] on `chrom`.  Returns dict(status,
         locus_index, alleles [per region], block [(start, end)], samples [per region: file indices], calls (as ``run``)).
         motifs = [str per region] (+ names): also the VCF record of every genotyped region (``records``)."""
@@ -259,6 +259,7 @@ class Genotyper:
         for k, v in region_overrides.items():
             setattr(rp, k, v)
         opts = RegionsOpts(host_threads, max_tr_len, min_total_reads, no_assembly)
+        opts.haploid = 1 if haploid else 0
         if motifs is not None:
             m_arr = (C.c_char_p * max(1, len(regions)))(*[m.encode() for m in motifs])
             n_arr = (C.c_char_p * max(1, len(regions)))(*[(x or "").encode() for x in (names or [""] * len(regions))])

@@ -149,3 +149,23 @@ def test_example_flow_writes_the_vcf_file(tmp_path):
     assert lines[0] == "##fileformat=VCFv4.1" and lines[len(lines) - len(body) - 1].endswith("FORMAT\tS0")
     want = [g["record"] for g in W["regions"] if g["status"] == 0]
     assert n == len(body) == len(want) and body == want
+
+
+def test_haploid_chromosome(genotyper, tmp_path):
+    """opts->haploid (--haploid-chrs): homozygous calls only, haploid FORMAT of the records."""
+    world = bw.synthetic_world(10, config=3, first_locus=300, n_samples=1)
+    bams = [abi.BamFile(p) for p in bw.write_world(world, str(tmp_path))]
+    motifs = [world["chrom_seq"][s0:s0 + per] for s0, _e, per in world["regions"]]
+    out = genotyper.run_regions(bams, "chrS", world["regions"], world["chrom_seq"], 0, motifs=motifs, haploid=True)
+    calls = out["calls"]
+    n = 0
+    for r, st in enumerate(out["status"]):
+        if st != 0:
+            continue
+        l = out["locus_index"][r]
+        s0 = calls["locus_sample_begin"][l]
+        assert calls["gts"][s0][0] == calls["gts"][s0][1]
+        f = out["records"][r].split("\t")
+        assert f[8] == "GT:GB:Q:DP:DFLANKINDEL:GLDIFF:ALLREADS:MALLREADS" and "|" not in f[9].split(":")[0]
+        n += 1
+    assert n >= 8
