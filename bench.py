@@ -553,13 +553,11 @@ def measure_long(args, config, n_loci, steps, warmup, torch, rank, world, local,
     raw = None if args.no_raw else measure_from_raw_loci(args, config, n_loci, steps, torch, rank, world, local)
     in_flight = min(e2e_by_depth, key=e2e_by_depth.get)
     e2e_ms = e2e_by_depth[in_flight]
+    # The headline end-to-end number is the plain form (one byte per base, nothing done to the caller's buffers); the 4-bit
+    # stream -- packed by the caller outside the clock, as a caller that reads BAM records holds its reads -- is reported
+    # beside it.
     e2e_encoding = "one byte per base"
-    e2e_bytes_ms = e2e_ms
-    if e2e_packed_by_depth and packed_same and min(e2e_packed_by_depth.values()) < e2e_ms:
-        in_flight = min(e2e_packed_by_depth, key=e2e_packed_by_depth.get)
-        e2e_ms = e2e_packed_by_depth[in_flight]
-        es = es4
-        e2e_encoding = "4-bit stream (BAM nibble codes), packed by the caller outside the clock"
+    e2e_4bit_ms = min(e2e_packed_by_depth.values()) if (e2e_packed_by_depth and packed_same) else None
     if rank != 0:
         work.close()
         return None
@@ -591,7 +589,10 @@ def measure_long(args, config, n_loci, steps, warmup, torch, rank, world, local,
                 "read_encoding": e2e_encoding,
                 "ms_per_step_by_jobs_in_flight": {str(k): v for k, v in e2e_by_depth.items()},
                 "ms_per_step_by_jobs_in_flight_4bit_reads": {str(k): v for k, v in e2e_packed_by_depth.items()},
-                "value_one_byte_per_base": total_loci / (e2e_bytes_ms * 1e-3),
+                "value_4bit_reads": (None if e2e_4bit_ms is None else total_loci / (e2e_4bit_ms * 1e-3)),
+                "h2d_bytes_per_step_4bit_reads": (None if es4 is None else int(es4.h2d_bytes)),
+                "note_4bit_reads": "ltr_ctx_set_read_encoding(1): reads as one 4-bit stream (BAM nibble codes), packed by the "
+                                   "caller outside the clock; not the headline",
                 "results_equal_resident_job_4bit_reads": packed_same},
         "e2e_from_flat_loci": raw,
         "gpu_launches": launches,

@@ -8,5 +8,5 @@ python - <<PY
 import json
 d=json.loads([l for l in open('gpurun_out/r2N_scale$n.json') if l.startswith('{')][-1])
 e=d["e2e"]
-print("N", d["n_gpus"], "value", round(d["value"]), "ms", round(d["ms_per_step"],2), "e2e", round(e["value"]), e["read_encoding"][:12], "bytes", round(e["value_one_byte_per_base"]))
+print("N", d["n_gpus"], "value", round(d["value"]), "ms", round(d["ms_per_step"],2), "e2e", round(e["value"]), "4-bit", e.get("value_4bit_reads"))
 PY
