@@ -18,6 +18,7 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <atomic>
 #include <string>
 #include <utility>
 #include <vector>
@@ -29,7 +30,10 @@ namespace {
 struct Mapped {
   const uint8_t* p = nullptr;
   size_t n = 0;
+  uint64_t id = 0;  // unique per opened file (key of the per-thread block cache)
   bool open(const char* path) {
+    static std::atomic<uint64_t> next_id(1);
+    id = next_id.fetch_add(1);
     const int fd = ::open(path, O_RDONLY);
     if (fd < 0) return false;
     struct stat st;
@@ -78,21 +82,44 @@ size_t bgzf_inflate(const Mapped& f, uint64_t coff, std::vector<uint8_t>& out) {
   const uint32_t isize = le32(h + bsize - 4);
   out.resize(isize);
   if (isize) {
-    z_stream zs;
-    memset(&zs, 0, sizeof(zs));
-    if (inflateInit2(&zs, -15) != Z_OK) return 0;
-    zs.next_in = const_cast<Bytef*>(h + 12 + xlen);
-    zs.avail_in = bsize - 12 - xlen - 8;
-    zs.next_out = out.data();
-    zs.avail_out = isize;
-    const int rc = inflate(&zs, Z_FINISH);
-    inflateEnd(&zs);
-    if (rc != Z_STREAM_END || zs.total_out != isize) return 0;
+    // one inflate state per thread, reset per block (inflateInit2 allocates the 32 KB window every time)
+    struct State {
+      z_stream zs;
+      bool ok;
+      State() {
+        memset(&zs, 0, sizeof(zs));
+        ok = inflateInit2(&zs, -15) == Z_OK;
+      }
+      ~State() {
+        if (ok) inflateEnd(&zs);
+      }
+    };
+    static thread_local State st;
+    if (!st.ok || inflateReset(&st.zs) != Z_OK) return 0;
+    st.zs.next_in = const_cast<Bytef*>(h + 12 + xlen);
+    st.zs.avail_in = bsize - 12 - xlen - 8;
+    st.zs.next_out = out.data();
+    st.zs.avail_out = isize;
+    const int rc = inflate(&st.zs, Z_FINISH);
+    if (rc != Z_STREAM_END || st.zs.total_out != isize) return 0;
   }
   return bsize;
 }
 
-// Sequential reader over virtual offsets with a one-block cache.
+// The last two blocks a thread inflated, whatever query they were for: consecutive regions of a sorted region list start in
+// the block the previous one ended in.
+struct ThreadBlocks {
+  uint64_t id[2] = {0, 0}, coff[2] = {0, 0};
+  size_t csize[2] = {0, 0};
+  std::vector<uint8_t> blk[2];
+  int victim = 0;
+};
+static ThreadBlocks& thread_blocks() {
+  static thread_local ThreadBlocks t;
+  return t;
+}
+
+// Sequential reader over virtual offsets with a one-block cache (backed by the thread's last two blocks).
 struct Cursor {
   const Mapped* f;
   std::vector<uint8_t> blk;
@@ -104,7 +131,23 @@ struct Cursor {
   bool load(uint64_t c) {
     if (c == coff) return csize != 0;
     coff = c;
+    ThreadBlocks& T = thread_blocks();
+    for (int k = 0; k < 2; ++k)
+      if (T.id[k] == f->id && T.coff[k] == c && T.csize[k] != 0) {
+        blk = T.blk[k];
+        csize = T.csize[k];
+        T.victim = 1 - k;
+        return true;
+      }
     csize = bgzf_inflate(*f, c, blk);
+    if (csize != 0) {
+      const int k = T.victim;
+      T.id[k] = f->id;
+      T.coff[k] = c;
+      T.csize[k] = csize;
+      T.blk[k] = blk;
+      T.victim = 1 - k;
+    }
     return csize != 0;
   }
   void seek(uint64_t voff) {

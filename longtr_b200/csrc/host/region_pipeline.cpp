@@ -12,6 +12,7 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 #include <string>
 #include <thread>
@@ -52,9 +53,11 @@ extern "C" int ltr_regions_run(ltr_genotyper* g, const ltr_params* params, const
   if ((uint32_t)n_threads > n_regions) n_threads = n_regions ? (int)n_regions : 1;
   std::atomic<uint32_t> next(0);
   auto prepare = [&]() {
-    for (;;) {
-      const uint32_t r = next.fetch_add(1);
-      if (r >= n_regions) break;
+    // a few consecutive regions per grab: neighbours of a sorted region list share BGZF blocks (the reader keeps the last two
+    // blocks a thread inflated)
+    const uint32_t kGrab = 4;
+    for (uint32_t r0 = next.fetch_add(kGrab); r0 < n_regions; r0 = next.fetch_add(kGrab))
+    for (uint32_t r = r0; r < std::min(n_regions, r0 + kGrab); ++r) {
       RegionWork& W = work[r];
       const ltr_region& R = regions[r];
       if (R.stop <= R.start || R.period < 1) { W.status = LTR_REGION_INVALID; continue; }

@@ -1,6 +1,7 @@
 // Host-only timing of the per-region preparation of ltr_regions_run (ltr_region_collect + ltr_candidate_alleles) on T threads.
 //   g++ -O2 -std=c++17 -Iinclude tools/region_prepare_bench.cpp -Llongtr_b200/csrc -llongtr_b200 -Wl,-rpath,$PWD/longtr_b200/csrc -pthread -o /tmp/region_prepare_bench
 //   /tmp/region_prepare_bench <bam> <regions.txt: start stop period per line> <chrom.txt> <threads> [no_assembly]
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cstdio>
@@ -43,9 +44,8 @@ int main(int argc, char** argv) {
     const double t0 = now_ms();
     auto work = [&](int t) {
       const ltr_bam* bams[1] = {bam};
-      for (;;) {
-        const uint32_t r = next.fetch_add(1);
-        if (r >= regions.size()) break;
+      for (uint32_t r0 = next.fetch_add(4); r0 < regions.size(); r0 = next.fetch_add(4))
+      for (uint32_t r = r0; r < std::min<uint32_t>((uint32_t)regions.size(), r0 + 4); ++r) {
         ltr_region_reads* reads = nullptr;
         double a = now_ms();
         int rc = ltr_region_collect(bams, 1, "chrS", regions[r].start, regions[r].stop, (const uint8_t*)chrom.data(), 0,
