@@ -270,11 +270,15 @@ class Genotyper:
         handles = (C.c_void_p * len(bams))(*[b.h for b in bams])
         ref = np.frombuffer(ref_seq.encode() if isinstance(ref_seq, str) else bytes(ref_seq), dtype=np.uint8)
         out = C.POINTER(RegionsResult)()
+        import time
+        t0 = time.perf_counter()
         rc = lib.ltr_regions_run(self.h, C.byref(prm), handles, len(bams), chrom.encode(), regs, len(regions),
                                  ref.ctypes.data_as(_u8p), ref_seq_start, len(ref), C.byref(rp), C.byref(opts), C.byref(out))
+        call_ms = (time.perf_counter() - t0) * 1e3
         if rc != abi.LTR_OK:
             raise LongTRError("ltr_regions_run: %s" % lib.ltr_strerror(rc).decode())
         res = self._regions_dict(out.contents)
+        res["call_ms"] = call_ms   # the ltr_regions_run call alone (the conversion into Python objects is harness time)
         lib.ltr_regions_result_free(out)
         return res
 
