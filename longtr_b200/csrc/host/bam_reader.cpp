@@ -11,6 +11,7 @@
 // The file is mapped once; queries are read-only on the mapping and keep their own block cache, so several host threads
 // can fetch different regions from one ltr_bam concurrently.
 #include <fcntl.h>
+#include <stdint.h>
 #include <string.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -18,6 +19,7 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <new>
 #include <atomic>
 #include <string>
 #include <utility>
@@ -306,16 +308,18 @@ bool append_record(ReadsOwner& R, const uint8_t* rec, size_t n, bool keep_raw) {
   R.names.insert(R.names.end(), (const char*)q, (const char*)q + l_name);  // NUL included
   R.name_off.push_back((uint32_t)R.names.size());
   q += l_name;
-  int32_t ref_len = 0;
+  int64_t ref_len = 0;
   for (uint32_t k = 0; k < n_cig; ++k) {
     const uint32_t v = le32(q + 4 * k);
     R.cigar_ops.push_back(v);
     const uint32_t op = v & 15;
-    if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) ref_len += (int32_t)(v >> 4);  // M D N = X
+    if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) ref_len += (int64_t)(v >> 4);  // M D N = X
   }
   R.cigar_off.push_back((uint32_t)R.cigar_ops.size());
   q += 4 * (size_t)n_cig;
-  R.end.push_back(pos + (ref_len ? ref_len : 1));  // as htslib's bam_endpos: an unaligned record covers one base
+  // as htslib's bam_endpos: an unaligned record covers one base (positions of a damaged record saturate instead of wrapping)
+  const int64_t end64 = (int64_t)pos + (ref_len ? ref_len : 1);
+  R.end.push_back(end64 > INT32_MAX ? INT32_MAX : (int32_t)end64);
   const size_t s0 = R.seq.size();
   R.seq.resize(s0 + l_seq);
   for (uint32_t i = 0; i < l_seq; ++i) R.seq[s0 + i] = (uint8_t)kSeqCodes[(q[i >> 1] >> ((~i & 1) << 2)) & 0xf];
@@ -372,7 +376,7 @@ bool load_index(ltr_bam* b, const char* path) {
 
 }  // namespace
 
-extern "C" int ltr_bam_open(const char* path, const char* index_path, ltr_bam** out) {
+static int ltr_bam_open_impl(const char* path, const char* index_path, ltr_bam** out) {
   if (!path || !out) return LTR_ERR_INVALID;
   *out = nullptr;
   ltr_bam* b = new ltr_bam();
@@ -417,6 +421,17 @@ extern "C" int ltr_bam_open(const char* path, const char* index_path, ltr_bam** 
   return LTR_OK;
 }
 
+// C ABI boundary: no exception leaves the library (malformed input and exhausted memory become error codes)
+extern "C" int ltr_bam_open(const char* path, const char* index_path, ltr_bam** out) {
+  try {
+    return ltr_bam_open_impl(path, index_path, out);
+  } catch (const std::bad_alloc&) {
+    return LTR_ERR_OOM;
+  } catch (...) {
+    return LTR_ERR_INVALID;
+  }
+}
+
 // reg2bin of the SAM specification (5.3): the smallest bin that contains [beg, end)
 static uint32_t reg2bin(int64_t beg, int64_t end) {
   --end;
@@ -430,7 +445,7 @@ static uint32_t reg2bin(int64_t beg, int64_t end) {
 
 // Builds the binning + linear index of a coordinate-sorted file in memory (what `samtools index` writes to a .bai), for
 // files that come without one.  Not thread safe against concurrent fetches on the same handle.
-extern "C" int ltr_bam_build_index(ltr_bam* b) {
+static int ltr_bam_build_index_impl(ltr_bam* b) {
   if (!b) return LTR_ERR_INVALID;
   if (b->has_index) return LTR_OK;
   std::vector<RefIndex> idx(b->ref_names.size());
@@ -490,6 +505,17 @@ extern "C" int ltr_bam_build_index(ltr_bam* b) {
   return LTR_OK;
 }
 
+// C ABI boundary: no exception leaves the library (malformed input and exhausted memory become error codes)
+extern "C" int ltr_bam_build_index(ltr_bam* b) {
+  try {
+    return ltr_bam_build_index_impl(b);
+  } catch (const std::bad_alloc&) {
+    return LTR_ERR_OOM;
+  } catch (...) {
+    return LTR_ERR_INVALID;
+  }
+}
+
 extern "C" void ltr_bam_close(ltr_bam* b) { delete b; }
 extern "C" int32_t ltr_bam_n_refs(const ltr_bam* b) { return b ? (int32_t)b->ref_names.size() : 0; }
 extern "C" const char* ltr_bam_ref_name(const ltr_bam* b, int32_t tid) {
@@ -508,7 +534,7 @@ extern "C" const char* ltr_bam_header_text(const ltr_bam* b) { return b ? b->tex
 extern "C" int ltr_bam_has_index(const ltr_bam* b) { return b && b->has_index; }
 
 // Records that overlap [beg, end) on reference tid (tid < 0: every record of the file, in file order).
-extern "C" int ltr_bam_fetch(const ltr_bam* b, int32_t tid, int64_t beg, int64_t end, int32_t keep_raw, ltr_bam_reads** out) {
+static int ltr_bam_fetch_impl(const ltr_bam* b, int32_t tid, int64_t beg, int64_t end, int32_t keep_raw, ltr_bam_reads** out) {
   if (!b || !out) return LTR_ERR_INVALID;
   *out = nullptr;
   if (tid >= (int32_t)b->ref_names.size()) return LTR_ERR_INVALID;
@@ -583,6 +609,17 @@ extern "C" int ltr_bam_fetch(const ltr_bam* b, int32_t tid, int64_t beg, int64_t
   R->publish();
   *out = &R->pub;
   return LTR_OK;
+}
+
+// C ABI boundary: no exception leaves the library (malformed input and exhausted memory become error codes)
+extern "C" int ltr_bam_fetch(const ltr_bam* b, int32_t tid, int64_t beg, int64_t end, int32_t keep_raw, ltr_bam_reads** out) {
+  try {
+    return ltr_bam_fetch_impl(b, tid, beg, end, keep_raw, out);
+  } catch (const std::bad_alloc&) {
+    return LTR_ERR_OOM;
+  } catch (...) {
+    return LTR_ERR_INVALID;
+  }
 }
 
 extern "C" void ltr_bam_reads_free(ltr_bam_reads* r) {

@@ -17,6 +17,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <new>
 #include <map>
 #include <string>
 #include <utility>
@@ -344,7 +345,7 @@ struct Owner {
 
 }  // namespace
 
-extern "C" int ltr_candidate_alleles_flags(const ltr_region_reads* reads, int32_t region_start, int32_t region_stop,
+static int ltr_candidate_alleles_flags_impl(const ltr_region_reads* reads, int32_t region_start, int32_t region_stop,
                                            int32_t period, const uint8_t* ref_seq, int64_t ref_seq_start, int64_t ref_seq_len,
                                            int32_t indel_flank_len, uint32_t flags, ltr_candidates** out) {
   if (!reads || !ref_seq || !out || region_stop < region_start || period < 1 || indel_flank_len < 0) return LTR_ERR_INVALID;
@@ -519,6 +520,19 @@ extern "C" int ltr_candidate_alleles_flags(const ltr_region_reads* reads, int32_
   C.cluster_bytes = O->cluster_bytes.data();
   C.cluster_count = O->cluster_count.data();
   return LTR_OK;
+}
+
+// C ABI boundary: no exception leaves the library (malformed input and exhausted memory become error codes)
+extern "C" int ltr_candidate_alleles_flags(const ltr_region_reads* reads, int32_t region_start, int32_t region_stop,
+                                           int32_t period, const uint8_t* ref_seq, int64_t ref_seq_start, int64_t ref_seq_len,
+                                           int32_t indel_flank_len, uint32_t flags, ltr_candidates** out) {
+  try {
+    return ltr_candidate_alleles_flags_impl(reads, region_start, region_stop, period, ref_seq, ref_seq_start, ref_seq_len, indel_flank_len, flags, out);
+  } catch (const std::bad_alloc&) {
+    return LTR_ERR_OOM;
+  } catch (...) {
+    return LTR_ERR_INVALID;
+  }
 }
 
 extern "C" int ltr_candidate_alleles(const ltr_region_reads* reads, int32_t region_start, int32_t region_stop, int32_t period,

@@ -11,6 +11,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <new>
 #include <map>
 #include <string>
 #include <vector>
@@ -160,7 +161,7 @@ extern "C" void ltr_region_params_default(ltr_region_params* p) {
   p->check_hard_clips = 1;   // BASE_QUAL_TRIM > ' ' (bam_processor.h:101)
 }
 
-extern "C" int ltr_region_collect(const ltr_bam* const* bams, int32_t n_bams, const char* chrom, int32_t start, int32_t stop,
+static int ltr_region_collect_impl(const ltr_bam* const* bams, int32_t n_bams, const char* chrom, int32_t start, int32_t stop,
                                   const uint8_t* ref_seq, int64_t ref_seq_start, int64_t ref_seq_len,
                                   const ltr_region_params* params, ltr_region_reads** out) {
   if (!bams || n_bams < 1 || !chrom || !ref_seq || !params || !out || stop < start) return LTR_ERR_INVALID;
@@ -230,6 +231,21 @@ extern "C" int ltr_region_collect(const ltr_bam* const* bams, int32_t n_bams, co
         a.cigar[k].type = "MIDNSHP=X"[(cg[k] & 15) > 8 ? 8 : (cg[k] & 15)];
         a.cigar[k].len = (int32_t)(cg[k] >> 4);
       }
+      {
+        // a record whose CIGAR does not describe its sequence and end position (a damaged file: the reference would read past
+        // its strings) refuses the region instead
+        int64_t q_len = 0, r_len = 0;
+        bool ok = true;
+        for (const Op& c : a.cigar) {
+          if (c.len < 1) ok = false;
+          if (c.type == 'M' || c.type == '=' || c.type == 'X' || c.type == 'I' || c.type == 'S') q_len += c.len;
+          if (c.type == 'M' || c.type == '=' || c.type == 'X' || c.type == 'D' || c.type == 'N') r_len += c.len;
+        }
+        if (!ok || q_len != (int64_t)l_seq || (int64_t)pos + r_len != (int64_t)end_pos) {
+          rc = LTR_ERR_INVALID;
+          break;
+        }
+      }
       a.pos = pos;
       a.end_pos = end_pos;
       a.flag = flag;
@@ -249,6 +265,7 @@ extern "C" int ltr_region_collect(const ltr_bam* const* bams, int32_t n_bams, co
       potential_strs.insert(std::make_pair(key, a));  // a second alignment of the same name is ignored, as std::map::insert does
     }
     ltr_bam_reads_free(R);
+    if (rc != LTR_OK) break;  // (a refusal found in this file must not be overwritten by the next file's fetch)
   }
   if (rc != LTR_OK) {
     delete O;
@@ -414,6 +431,19 @@ extern "C" int ltr_region_collect(const ltr_bam* const* bams, int32_t n_bams, co
   S.owner = O;
   *out = &O->pub;
   return LTR_OK;
+}
+
+// C ABI boundary: no exception leaves the library (malformed input and exhausted memory become error codes)
+extern "C" int ltr_region_collect(const ltr_bam* const* bams, int32_t n_bams, const char* chrom, int32_t start, int32_t stop,
+                                  const uint8_t* ref_seq, int64_t ref_seq_start, int64_t ref_seq_len,
+                                  const ltr_region_params* params, ltr_region_reads** out) {
+  try {
+    return ltr_region_collect_impl(bams, n_bams, chrom, start, stop, ref_seq, ref_seq_start, ref_seq_len, params, out);
+  } catch (const std::bad_alloc&) {
+    return LTR_ERR_OOM;
+  } catch (...) {
+    return LTR_ERR_INVALID;
+  }
 }
 
 extern "C" void ltr_region_reads_free(ltr_region_reads* r) {

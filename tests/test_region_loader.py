@@ -112,3 +112,23 @@ def test_region_collect_options_and_errors(world):
         abi.region_collect(bams, "chrNope", reg["start"], reg["stop"], world["ref"], world["ref_start"])
     with pytest.raises(RuntimeError):  # reference slice that does not cover the reads
         abi.region_collect(bams, "chr1", reg["start"], reg["stop"], "ACGT", world["ref_start"])
+
+
+def test_a_record_whose_cigar_does_not_fit_its_sequence_refuses_the_region(tmp_path):
+    """Damaged files must end in an error code, not in an exception across the C ABI: a record whose CIGAR describes more bases
+    than it carries (the reference would read past its strings) makes ltr_region_collect return LTR_ERR_INVALID."""
+    import bam_writer as bw
+    seq = "ACGT" * 300
+    good = bw.encode_record(0, 1000, "r1", 0, 60, [("=", 1200)], seq, "I" * 1200)
+    bad = bw.encode_record(0, 1000, "r2", 0, 60, [("=", 2000)], seq, "I" * 1200)   # CIGAR longer than the sequence
+    ref = "ACGT" * 2000
+    for k, recs in enumerate(([good], [good, bad])):
+        path = str(tmp_path / ("f%d.bam" % k))
+        bw.write_bam(path, [("chrS", 8000)], recs)
+        b = abi.BamFile(path)
+        b.build_index()
+        if k == 0:
+            assert len(abi.region_collect([b], "chrS", 1500, 1560, ref, 0)["reads"]) == 1
+        else:
+            with pytest.raises(RuntimeError):
+                abi.region_collect([b], "chrS", 1500, 1560, ref, 0)
