@@ -362,6 +362,9 @@ typedef struct ltr_batch_calls {
   uint32_t n_chunks;                       /* jobs the batch was cut into                                                */
   const int32_t* read_allele;              /* [n_reads] or NULL (ltr_genotyper_set_read_alleles): the allele of its sample's
                                               genotype each read supports -- what MALLREADS counts                         */
+  const uint64_t* pgl_begin;               /* [n_samples+1] or NULL (ltr_genotyper_set_phased_gls): slice of phased_gls;
+                                              K*K (haploid: K) entries are used, [a*K + b] over the KEPT alleles          */
+  const double* phased_gls;                /* log10 likelihoods of the phased genotypes (PHASEDGL)                       */
 } ltr_batch_calls;
 
 typedef struct ltr_genotyper ltr_genotyper;
@@ -375,6 +378,8 @@ void ltr_genotyper_destroy(ltr_genotyper* g);
  * allele).  As write_vcf_record assigns reads (src/seq_stutter_genotyper.cpp:954-970): the first allele of the genotype unless
  * log_p2 + LL[second] >= log_p1 + LL[first].                                                                              */
 int ltr_genotyper_set_read_alleles(ltr_genotyper* g, int32_t on);
+/* on != 0: later runs also return phased_gls / pgl_begin (the PHASEDGL field behind --output-phased-gls). */
+int ltr_genotyper_set_phased_gls(ltr_genotyper* g, int32_t on);
 /* Genotypes every locus of the batch.  A malformed locus (CIGAR the reference dies on, reads that do not fit their CIGAR,
  * missing flanks) fails alone: its status is the error, the rest of the batch is unaffected.                          */
 int ltr_genotyper_run(ltr_genotyper* g, const ltr_params* params, const ltr_locus_batch* batch, ltr_batch_calls** out);
@@ -645,6 +650,7 @@ typedef struct ltr_regions_opts {
   const char* const* region_names;   /* [n_regions] or NULL ("."): ID column                                              */
   const char* const* region_motifs;  /* [n_regions] MOTIF / PERIOD of the record                                          */
   int32_t haploid;          /* 1: the chromosome is haploid in every sample (--haploid-chrs): haploid priors and records  */
+  uint32_t vcf_switches;    /* LTR_VCF_* output switches of the records (ltr_regions_opts_default: LTR_VCF_DEFAULT)       */
 } ltr_regions_opts;
 typedef struct ltr_regions_result {
   uint32_t n_regions;
@@ -758,6 +764,30 @@ typedef struct ltr_vcf_locus {
   const int32_t* column_sample;   /* [n_columns] sample of the locus shown in the column, -1 = none     */
 } ltr_vcf_locus;
 int ltr_vcf_record(const ltr_vcf_locus* locus, char* out, uint32_t capacity, uint32_t* out_len);
+/* The reference's output switches (Genotyper::OUTPUT_*, src/genotyper.cpp:339-346; command line --hide-allreads,
+ * --hide-mallreads, --output-gls, --output-pls, --output-phased-gls, --output-filters: src/hipstr_main.cpp:178-183).
+ * ltr_vcf_record_ex composes the record under any combination of them (write_vcf_record :1182-1229, :1304-1365):
+ * GL / PL in the order of the record's alleles (pairs (j <= i) of the re-ordered alleles), PHASEDGL [i * K + j], FILTER =
+ * PASS, and "NO_READS" behind the empty fields for a column without reads.  gls / pls / phased_gls are what
+ * ltr_batch_calls delivers: per sample of the locus a slice over the KEPT alleles in candidate order (gls / pls: pair
+ * (a <= b) at b(b+1)/2 + a, haploid: [a]; phased_gls: [a * K + b], haploid: [a]); a slice holds at least that many
+ * entries.  extras == NULL or switches == LTR_VCF_DEFAULT: ltr_vcf_record.                                           */
+#define LTR_VCF_ALLREADS 1u
+#define LTR_VCF_MALLREADS 2u
+#define LTR_VCF_GLS 4u
+#define LTR_VCF_PLS 8u
+#define LTR_VCF_PHASED_GLS 16u
+#define LTR_VCF_FILTERS 32u
+#define LTR_VCF_DEFAULT (LTR_VCF_ALLREADS | LTR_VCF_MALLREADS)
+typedef struct ltr_vcf_extras {
+  uint32_t switches;          /* LTR_VCF_*                                                  */
+  const uint64_t* gl_begin;   /* [n_samples+1] slices of gls / pls (GL or PL switched on)   */
+  const double* gls;
+  const int32_t* pls;
+  const uint64_t* pgl_begin;  /* [n_samples+1] slices of phased_gls (PHASEDGL switched on, diploid) */
+  const double* phased_gls;
+} ltr_vcf_extras;
+int ltr_vcf_record_ex(const ltr_vcf_locus* locus, const ltr_vcf_extras* extras, char* out, uint32_t capacity, uint32_t* out_len);
 int ltr_extract_cigar_bp_diff(const uint32_t* cigar_ops, uint32_t n_ops, int32_t cigar_start, int32_t region_start,
                               int32_t region_end, int32_t* bp_diff);
 /* The header lines of the file (Genotyper::get_vcf_header, src/genotyper.cpp:258-336, default output switches): file format,
@@ -765,6 +795,9 @@ int ltr_extract_cigar_bp_diff(const uint32_t* cigar_ops, uint32_t n_ops, int32_t
  * sample columns.  Ends with a newline.  LTR_ERR_INVALID with *out_len set when the buffer is too small.                   */
 int ltr_vcf_header(const ltr_fasta* fasta, const char* fasta_path, const char* command, const char* const* sample_names,
                    uint32_t n_samples, char* out, uint32_t capacity, uint32_t* out_len);
+/* The same under the output switches `switches` (LTR_VCF_*): the FORMAT lines of the switched fields (:313-327). */
+int ltr_vcf_header_ex(const ltr_fasta* fasta, const char* fasta_path, const char* command, const char* const* sample_names,
+                      uint32_t n_samples, uint32_t switches, char* out, uint32_t capacity, uint32_t* out_len);
 
 /* ---- length-based EM of the stutter model ----------------------------------------------
  * ltr_em_stutter_train  EMStutterGenotyper(...).train(...) (src/em_stutter_genotyper.{h,cpp}) for many loci at once, as

@@ -542,6 +542,11 @@ def load():
     lib.ltr_vcf_header.restype = C.c_int
     lib.ltr_vcf_record.argtypes = [C.POINTER(VcfLocus), C.c_char_p, C.c_uint32, _u32p]
     lib.ltr_vcf_record.restype = C.c_int
+    lib.ltr_vcf_record_ex.argtypes = [C.POINTER(VcfLocus), C.POINTER(VcfExtras), C.c_char_p, C.c_uint32, _u32p]
+    lib.ltr_vcf_record_ex.restype = C.c_int
+    lib.ltr_vcf_header_ex.argtypes = [vp, C.c_char_p, C.c_char_p, C.POINTER(C.c_char_p), C.c_uint32, C.c_uint32, C.c_char_p,
+                                      C.c_uint32, _u32p]
+    lib.ltr_vcf_header_ex.restype = C.c_int
     lib.ltr_extract_cigar_bp_diff.argtypes = [_u32p, C.c_uint32, C.c_int32, C.c_int32, C.c_int32, _i32p]
     lib.ltr_extract_cigar_bp_diff.restype = C.c_int
     lib.ltr_em_opts_default.argtypes = [C.POINTER(EmOpts)]
@@ -577,6 +582,7 @@ EXPORTED_SYMBOLS = [
     "ltr_regions_result_free", "ltr_fasta_open", "ltr_fasta_close", "ltr_fasta_n_seqs", "ltr_fasta_seq_name",
     "ltr_fasta_seq_len", "ltr_fasta_fetch", "ltr_bed_read", "ltr_bed_free", "ltr_run_bed", "ltr_bed_run_result_free",
     "ltr_em_opts_default", "ltr_em_stutter_train", "ltr_vcf_record", "ltr_vcf_header", "ltr_extract_cigar_bp_diff", "ltr_genotyper_set_read_alleles",
+    "ltr_vcf_record_ex", "ltr_vcf_header_ex", "ltr_genotyper_set_phased_gls",
 ]
 
 
@@ -591,6 +597,16 @@ class VcfLocus(C.Structure):
                 ("column_sample", _i32p)]
 
 
+_u64p = C.POINTER(C.c_uint64)
+
+
+class VcfExtras(C.Structure):
+    _fields_ = [("switches", C.c_uint32), ("gl_begin", _u64p), ("gls", _dp), ("pls", _i32p), ("pgl_begin", _u64p),
+                ("phased_gls", _dp)]
+
+
+VCF_ALLREADS, VCF_MALLREADS, VCF_GLS, VCF_PLS, VCF_PHASED_GLS, VCF_FILTERS = 1, 2, 4, 8, 16, 32
+VCF_DEFAULT = VCF_ALLREADS | VCF_MALLREADS
 INT32_MIN = -2147483648
 
 
@@ -607,8 +623,10 @@ def extract_cigar_bp_diff(cigar, cigar_start, region_start, region_end):
 
 def vcf_record(chrom, name, motif, region_start, region_stop, chrom_seq, chrom_seq_start, block_start, block_end, alleles,
                inexact, kept_mask, gts, log_unphased, log_phased, gl_diffs, n_p1, n_p2, read_sample, log_p1, log_p2,
-               read_bp_diff, read_allele, column_sample, haploid=False):
-    """ltr_vcf_record -> str.  read_bp_diff entries may be None; read_allele may be None."""
+               read_bp_diff, read_allele, column_sample, haploid=False, switches=None, gl_begin=None, gls=None, pls=None,
+               pgl_begin=None, phased_gls=None):
+    """ltr_vcf_record -> str.  read_bp_diff entries may be None; read_allele may be None.  switches (VCF_* mask) with the
+    per-sample slices gl_begin / gls / pls / pgl_begin / phased_gls (ltr_batch_calls layout): ltr_vcf_record_ex."""
     lib = load()
     seq = np.frombuffer(chrom_seq.encode() if isinstance(chrom_seq, str) else bytes(chrom_seq), dtype=np.uint8)
     ab, aoff = pack_seqs(alleles)
@@ -636,7 +654,16 @@ def vcf_record(chrom, name, motif, region_start, region_stop, chrom_seq, chrom_s
     for _ in range(2):
         buf = C.create_string_buffer(cap)
         n = C.c_uint32(0)
-        rc = lib.ltr_vcf_record(C.byref(L), buf, cap, C.byref(n))
+        if switches is None:
+            rc = lib.ltr_vcf_record(C.byref(L), buf, cap, C.byref(n))
+        else:
+            def arr(x, dt):
+                return None if x is None else np.ascontiguousarray(list(x) + [0], dtype=dt)
+            xa = [arr(gl_begin, np.uint64), arr(gls, np.float64), arr(pls, np.int32), arr(pgl_begin, np.uint64),
+                  arr(phased_gls, np.float64)]
+            pt = [_u64p, _dp, _i32p, _u64p, _dp]
+            X = VcfExtras(int(switches), *[None if a is None else ptr(a, t) for a, t in zip(xa, pt)])
+            rc = lib.ltr_vcf_record_ex(C.byref(L), C.byref(X), buf, cap, C.byref(n))
         if rc == 0:
             return buf.value.decode()
         if n.value + 1 > cap:
@@ -646,15 +673,19 @@ def vcf_record(chrom, name, motif, region_start, region_stop, chrom_seq, chrom_s
     raise RuntimeError("ltr_vcf_record failed: %d" % rc)
 
 
-def vcf_header(fasta, fasta_path, command, sample_names):
-    """ltr_vcf_header -> str (fasta: FastaFile)."""
+def vcf_header(fasta, fasta_path, command, sample_names, switches=None):
+    """ltr_vcf_header (switches: ltr_vcf_header_ex) -> str (fasta: FastaFile)."""
     lib = load()
     names = (C.c_char_p * max(1, len(sample_names)))(*[x.encode() for x in sample_names])
     cap = 1 << 16
     for _ in range(2):
         buf = C.create_string_buffer(cap)
         n = C.c_uint32(0)
-        rc = lib.ltr_vcf_header(fasta.h, fasta_path.encode(), command.encode(), names, len(sample_names), buf, cap, C.byref(n))
+        if switches is None:
+            rc = lib.ltr_vcf_header(fasta.h, fasta_path.encode(), command.encode(), names, len(sample_names), buf, cap, C.byref(n))
+        else:
+            rc = lib.ltr_vcf_header_ex(fasta.h, fasta_path.encode(), command.encode(), names, len(sample_names), int(switches),
+                                       buf, cap, C.byref(n))
         if rc == 0:
             return buf.value.decode()
         cap = n.value + 16

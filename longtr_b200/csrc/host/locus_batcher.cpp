@@ -298,6 +298,7 @@ struct ltr_genotyper {
   WorkerPool* pool = nullptr;
   uint32_t chunk_loci = 20000;
   bool want_read_alleles = false;  // ltr_genotyper_set_read_alleles
+  bool want_phased_gls = false;    // ltr_genotyper_set_phased_gls
   std::vector<Chunk*> chunks;  // 2 per device + 1 being prepared
 };
 
@@ -489,6 +490,8 @@ struct CallsOwner {  // storage behind an ltr_batch_calls
   std::vector<double> lpp, lup, gld, stl, gls;
   std::vector<uint64_t> glb;
   std::vector<int32_t> read_allele;  // per raw read of the batch, -1 = not assigned
+  std::vector<uint64_t> pglb;        // only with ltr_genotyper_set_phased_gls
+  std::vector<double> pgls;
 };
 
 // Genotyper::extract_genotypes_and_likelihoods per locus on the surviving alleles (parallel over loci).
@@ -541,6 +544,7 @@ void finish_chunk(const ltr_locus_batch& B, Chunk& C, CallsOwner& O, WorkerPool&
           O.gls[g0 + k] = gls[s * n_gl + k];
           O.pls[g0 + k] = pls[s * n_gl + k];
         }
+        if (!O.pglb.empty()) std::copy(pgl.begin() + (ptrdiff_t)(s * n_pgl), pgl.begin() + (ptrdiff_t)((s + 1) * n_pgl), O.pgls.begin() + (ptrdiff_t)O.pglb[s0 + s]);
       }
       if (!O.read_allele.empty() && !C.ll_off.empty()) {
         // which allele of its sample's genotype a read supports (write_vcf_record, seq_stutter_genotyper.cpp:954-970): the
@@ -586,6 +590,12 @@ int ltr_genotyper_create(const int32_t* devices, int32_t n_devices, int32_t host
   if (chunk_loci > 0) g->chunk_loci = (uint32_t)chunk_loci;
   for (size_t k = 0; k < 2 * g->ctxs.size() + 1; ++k) g->chunks.push_back(new Chunk());
   *out = g;
+  return LTR_OK;
+}
+
+int ltr_genotyper_set_phased_gls(ltr_genotyper* g, int32_t on) {
+  if (!g) return LTR_ERR_INVALID;
+  g->want_phased_gls = on != 0;
   return LTR_OK;
 }
 
@@ -650,6 +660,15 @@ int ltr_genotyper_run(ltr_genotyper* g, const ltr_params* params, const ltr_locu
   O->gls.assign(O->glb[n_samples], 0.0);
   O->pls.assign(O->glb[n_samples], 0);
   if (g->want_read_alleles) O->read_allele.assign((size_t)n_reads + 1, -1);
+  if (g->want_phased_gls) {
+    O->pglb.assign((size_t)n_samples + 1, 0);
+    for (uint32_t l = 0; l < n_loci; ++l) {
+      const uint64_t H = lab[l + 1] - lab[l];
+      const bool hap = B.locus_haploid && B.locus_haploid[l];
+      for (uint32_t s = O->lsb[l]; s < O->lsb[l + 1]; ++s) O->pglb[s + 1] = O->pglb[s] + (hap ? H : H * H);
+    }
+    O->pgls.assign(O->pglb[n_samples], 0.0);
+  }
 
   double prep_ms = 0, wait_ms = 0, post_ms = 0, submit_ms = 0;
   int rc_all = LTR_OK;
@@ -789,6 +808,8 @@ int ltr_genotyper_run(ltr_genotyper* g, const ltr_params* params, const ltr_locu
   V.prep_ms = prep_ms; V.gpu_wait_ms = wait_ms; V.post_ms = post_ms; V.total_ms = ms_since(t_begin);
   V.submit_ms = submit_ms; V.n_chunks = (uint32_t)cuts.size();
   V.read_allele = O->read_allele.empty() ? nullptr : O->read_allele.data();
+  V.pgl_begin = O->pglb.empty() ? nullptr : O->pglb.data();
+  V.phased_gls = O->pglb.empty() ? nullptr : O->pgls.data();
   if (rc_all != LTR_OK) {
     delete O;
     return rc_all;

@@ -111,6 +111,7 @@ extern "C" int ltr_regions_run(ltr_genotyper* g, const ltr_params* params, const
   std::vector<int32_t> read_bp_diff, n_hp1, n_hp2;   // for the records: ExtractCigar per read, HP counts per (locus, sample)
   std::vector<uint32_t> locus_sample_begin(1, 0), locus_region;
   const bool want_records = opts->vcf_records != 0;
+  const bool want_pgl = want_records && !opts->haploid && (opts->vcf_switches & LTR_VCF_PHASED_GLS);
   uint32_t n_loci = 0;
   for (uint32_t r = 0; r < n_regions; ++r) {
     RegionWork& W = work[r];
@@ -199,8 +200,10 @@ extern "C" int ltr_regions_run(ltr_genotyper* g, const ltr_params* params, const
     if (opts->haploid) haploid_flags.assign((size_t)n_loci + 1, 1);
     B.locus_haploid = opts->haploid ? haploid_flags.data() : nullptr;
     if (want_records) ltr_genotyper_set_read_alleles(g, 1);
+    if (want_pgl) ltr_genotyper_set_phased_gls(g, 1);
     rc = ltr_genotyper_run(g, params, &B, &calls);
     if (want_records) ltr_genotyper_set_read_alleles(g, 0);
+    if (want_pgl) ltr_genotyper_set_phased_gls(g, 0);
   }
   if (rc == LTR_OK && want_records) {
     O->record_off.assign((size_t)n_regions + 1, 0);
@@ -242,11 +245,21 @@ extern "C" int ltr_regions_run(ltr_genotyper* g, const ltr_params* params, const
       V.read_bp_diff = read_bp_diff.data() + lrb[l];
       V.read_allele = calls->read_allele ? calls->read_allele + lrb[l] : nullptr;
       V.n_columns = n_bams; V.column_sample = column.data();
+      ltr_vcf_extras X;  // slices re-based to the locus' first sample
+      memset(&X, 0, sizeof(X));
+      X.switches = opts->vcf_switches;
+      std::vector<uint64_t> glb(ns + 1), pglb(ns + 1, 0);
+      for (uint32_t s = 0; s <= ns; ++s) glb[s] = calls->gl_begin[s0 + s] - calls->gl_begin[s0];
+      X.gl_begin = glb.data(); X.gls = calls->gls + calls->gl_begin[s0]; X.pls = calls->pls + calls->gl_begin[s0];
+      if (calls->pgl_begin) {
+        for (uint32_t s = 0; s <= ns; ++s) pglb[s] = calls->pgl_begin[s0 + s] - calls->pgl_begin[s0];
+        X.pgl_begin = pglb.data(); X.phased_gls = calls->phased_gls + calls->pgl_begin[s0];
+      }
       uint32_t len = 0;
-      int vrc = ltr_vcf_record(&V, buf.data(), (uint32_t)buf.size(), &len);
+      int vrc = ltr_vcf_record_ex(&V, &X, buf.data(), (uint32_t)buf.size(), &len);
       if (vrc == LTR_ERR_INVALID && (size_t)len + 1 > buf.size()) {
         buf.resize((size_t)len + 16);
-        vrc = ltr_vcf_record(&V, buf.data(), (uint32_t)buf.size(), &len);
+        vrc = ltr_vcf_record_ex(&V, &X, buf.data(), (uint32_t)buf.size(), &len);
       }
       if (vrc == LTR_OK) text[r].assign(buf.data(), len);
       else if (vrc != LTR_ERR_UNSUPPORTED) rc = vrc;
@@ -355,6 +368,7 @@ extern "C" void ltr_regions_opts_default(ltr_regions_opts* o) {
   o->region_names = nullptr;
   o->region_motifs = nullptr;
   o->haploid = 0;
+  o->vcf_switches = LTR_VCF_DEFAULT;
 }
 
 extern "C" void ltr_regions_result_free(ltr_regions_result* r) {

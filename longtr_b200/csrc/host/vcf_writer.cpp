@@ -1,6 +1,7 @@
 // vcf_writer.cpp -- ltr_vcf_record: the VCF record of one genotyped locus, the way SeqStutterGenotyper::write_vcf_record
-// composes it (reference src/seq_stutter_genotyper.cpp:894-1402) with the default output switches (ALLREADS and MALLREADS on;
-// GL / PL / PHASEDGL / FILTER / haplotype fields off: src/genotyper.cpp:339-346) on the long-read path
+// composes it (reference src/seq_stutter_genotyper.cpp:894-1402) under the reference's output switches (ltr_vcf_record: the
+// defaults, ALLREADS and MALLREADS on, src/genotyper.cpp:339-346; ltr_vcf_record_ex: any combination of ALLREADS / MALLREADS /
+// GL / PL / PHASEDGL / FILTER; the haplotype fields HQ / PHQ have no command-line switch) on the long-read path
 // (--stutter-align-len 0: no retraced alignments, DFLANKINDEL = 0, MALLREADS = size of the allele a read is assigned to).
 //   get_alleles         :688-781   alleles of the record: trimmed to the region, flanks re-attached, 1 bp pad when an
 //                                   alternate allele would otherwise start differently from the reference allele
@@ -94,12 +95,25 @@ extern "C" int ltr_extract_cigar_bp_diff(const uint32_t* cigar_ops, uint32_t n_o
 }
 
 extern "C" int ltr_vcf_record(const ltr_vcf_locus* L, char* out, uint32_t capacity, uint32_t* out_len) {
+  return ltr_vcf_record_ex(L, nullptr, out, capacity, out_len);
+}
+
+extern "C" int ltr_vcf_record_ex(const ltr_vcf_locus* L, const ltr_vcf_extras* X, char* out, uint32_t capacity,
+                                 uint32_t* out_len) {
+  const uint32_t sw = X ? X->switches : LTR_VCF_DEFAULT;
+  if (sw & ~(LTR_VCF_ALLREADS | LTR_VCF_MALLREADS | LTR_VCF_GLS | LTR_VCF_PLS | LTR_VCF_PHASED_GLS | LTR_VCF_FILTERS))
+    return LTR_ERR_INVALID;
   if (!L || !out_len || (capacity && !out) || !L->chrom || !L->motif || !L->chrom_seq || L->n_alleles < 1 || !L->allele_off ||
       !L->allele_bytes || L->n_samples < 0 || (L->n_samples && (!L->gts || !L->log_unphased_posteriors || !L->gl_diffs)) ||
       L->n_reads < 0 || (L->n_reads && (!L->read_sample || !L->log_p1 || !L->log_p2)) || (L->n_columns && !L->column_sample))
     return LTR_ERR_INVALID;
   const bool haploid = L->haploid != 0;
   if (!haploid && L->n_samples && !L->log_phased_posteriors) return LTR_ERR_INVALID;
+  const bool show_gl = (sw & LTR_VCF_GLS) != 0, show_pl = (sw & LTR_VCF_PLS) != 0;
+  const bool show_pgl = !haploid && (sw & LTR_VCF_PHASED_GLS) != 0, show_filter = (sw & LTR_VCF_FILTERS) != 0;
+  if (L->n_samples && ((show_gl && (!X->gl_begin || !X->gls)) || (show_pl && (!X->gl_begin || !X->pls)) ||
+                       (show_pgl && (!X->pgl_begin || !X->phased_gls))))
+    return LTR_ERR_INVALID;
   auto ref_sub = [&](int64_t a, int64_t b) {  // uppercase(chrom_seq.substr(a, b - a))
     std::string s;
     for (int64_t p = a; p < b; ++p) {
@@ -272,12 +286,48 @@ extern "C" int ltr_vcf_record(const ltr_vcf_locus* L, char* out, uint32_t capaci
     for (int i = 1; i < K; ++i) o += std::to_string(allele_counts[(size_t)new_to_old[(size_t)i]]) + (i + 1 < K ? "," : "");
   }
   o += haploid ? "\tGT:GB:Q:DP:DFLANKINDEL:GLDIFF" : "\tGT:GB:Q:PQ:DP:DSNP:DFLANKINDEL:PDP:PSNP:GLDIFF";
-  o += ":ALLREADS:MALLREADS";
+  int n_fields = haploid ? 6 : 10;  // :1172-1194; FILTER is not counted
+  if (sw & LTR_VCF_ALLREADS) o += ":ALLREADS", ++n_fields;
+  if (sw & LTR_VCF_MALLREADS) o += ":MALLREADS", ++n_fields;
+  if (show_gl) o += ":GL", ++n_fields;
+  if (show_pl) o += ":PL", ++n_fields;
+  if (show_pgl) o += ":PHASEDGL", ++n_fields;
+  if (show_filter) o += ":FILTER";
+  std::string no_reads = ".";  // a column without (realigned) reads (:1203-1215)
+  if (show_filter) {
+    no_reads.clear();
+    for (int f = 0; f < n_fields; ++f) no_reads += ".:";
+    no_reads += "NO_READS";
+  }
+  // GL / PL / PHASEDGL slices hold the kept alleles in candidate order; the record lists them in its own allele order
+  // (:1311-1358): pairs (j <= i) of the re-ordered alleles, phased pairs [i][j]
+  auto gl_list = [&](int s, auto&& value_at) {
+    std::string t;
+    const uint64_t g0 = X->gl_begin[s];
+    if (haploid) {
+      for (int i = 0; i < K; ++i) t += (i ? "," : "") + value_at(g0 + (uint64_t)new_to_old[(size_t)i]);
+    } else {
+      for (int i = 0; i < K; ++i)
+        for (int j = 0; j <= i; ++j) {
+          const int lo = std::min(new_to_old[(size_t)i], new_to_old[(size_t)j]), hi = std::max(new_to_old[(size_t)i], new_to_old[(size_t)j]);
+          t += ((i || j) ? "," : "") + value_at(g0 + (uint64_t)hi * (uint64_t)(hi + 1) / 2 + (uint64_t)lo);
+        }
+    }
+    return t;
+  };
+  if (show_gl || show_pl)
+    for (int s = 0; s < S; ++s)
+      if (X->gl_begin[s + 1] < X->gl_begin[s] || X->gl_begin[s + 1] - X->gl_begin[s] < (uint64_t)(haploid ? K : K * (K + 1) / 2))
+        return LTR_ERR_INVALID;
+  if (show_pgl)
+    for (int s = 0; s < S; ++s)
+      if (X->pgl_begin[s + 1] < X->pgl_begin[s] || X->pgl_begin[s + 1] - X->pgl_begin[s] < (uint64_t)K * (uint64_t)K)
+        return LTR_ERR_INVALID;
   for (int c = 0; c < L->n_columns; ++c) {
     o += "\t";
     const int s = L->column_sample[c];
     if (s < 0 || n_aligned[(size_t)s] == 0) {
-      o += ".";
+      o += no_reads;
       continue;
     }
     const int a = kept_of[(size_t)L->gts[2 * s]], b = kept_of[(size_t)L->gts[2 * s + 1]];
@@ -294,7 +344,19 @@ extern "C" int ltr_vcf_record(const ltr_vcf_locus* L, char* out, uint32_t capaci
       o += std::to_string(old_to_new[(size_t)a]) + ":" + std::to_string(bp_diffs[(size_t)a]);
       o += ":" + fixed2(exp(L->log_unphased_posteriors[s])) + ":" + std::to_string(n_aligned[(size_t)s]) + ":0:" + gldiff;
     }
-    o += ":" + condense(bps[(size_t)s]) + ":" + condense(ml_bps[(size_t)s]);
+    if (sw & LTR_VCF_ALLREADS) o += ":" + condense(bps[(size_t)s]);
+    if (sw & LTR_VCF_MALLREADS) o += ":" + condense(ml_bps[(size_t)s]);
+    if (show_gl) o += ":" + gl_list(s, [&](uint64_t k) { return fixed2(X->gls[k]); });
+    if (show_pl) o += ":" + gl_list(s, [&](uint64_t k) { return std::to_string(X->pls[k]); });
+    if (show_pgl) {
+      o += ":";
+      const uint64_t g0 = X->pgl_begin[s];
+      for (int i = 0; i < K; ++i)
+        for (int j = 0; j < K; ++j)
+          o += std::string((i || j) ? "," : "") +
+               fixed2(X->phased_gls[g0 + (uint64_t)new_to_old[(size_t)i] * (uint64_t)K + (uint64_t)new_to_old[(size_t)j]]);
+    }
+    if (show_filter) o += ":PASS";
   }
   *out_len = (uint32_t)o.size();
   if (o.size() + 1 > capacity) return LTR_ERR_INVALID;
@@ -339,16 +401,36 @@ const FieldLine kFormat[] = {
     {"PSNP", "1", "String", "Number of reads with SNPs supporting each haploid genotype"},
     {"PDP", "1", "String", "Fractional reads supporting each haploid genotype"},
     {"GLDIFF", "1", "Float", "Difference in likelihood between the reported and next best genotypes"},
-    {"ALLREADS", "1", "String", "Base pair difference observed in each read's Needleman-Wunsch alignment"},
-    {"MALLREADS", "1", "String",
-     "Maximum likelihood bp diff in each read based on haplotype alignments for reads that span the repeat region by at least 5 "
-     "base pairs"},
+};
+struct SwitchedLine {
+  uint32_t flag;
+  FieldLine line;
+};
+const SwitchedLine kSwitched[] = {  // in the order get_vcf_header writes them (:313-327)
+    {LTR_VCF_ALLREADS, {"ALLREADS", "1", "String", "Base pair difference observed in each read's Needleman-Wunsch alignment"}},
+    {LTR_VCF_MALLREADS,
+     {"MALLREADS", "1", "String",
+      "Maximum likelihood bp diff in each read based on haplotype alignments for reads that span the repeat region by at least 5 "
+      "base pairs"}},
+    {LTR_VCF_GLS, {"GL", "G", "Float", "log10 genotype likelihoods"}},
+    {LTR_VCF_PLS, {"PL", "G", "Integer", "Phred-scaled genotype likelihoods"}},
+    {LTR_VCF_PHASED_GLS,
+     {"PHASEDGL", ".", "Float",
+      "log10 genotype likelihood for each phased genotype. Value for phased genotype X|Y is stored at a 0-based index of X*A + Y, "
+      "where A is the number of alleles. Not applicable to haploid genotypes"}},
+    {LTR_VCF_FILTERS, {"FILTER", "1", "String", "Reason for filtering the current call, or PASS if the call was not filtered"}},
 };
 }  // namespace
 
 extern "C" int ltr_vcf_header(const ltr_fasta* fasta, const char* fasta_path, const char* command,
                               const char* const* sample_names, uint32_t n_samples, char* out, uint32_t capacity,
                               uint32_t* out_len) {
+  return ltr_vcf_header_ex(fasta, fasta_path, command, sample_names, n_samples, LTR_VCF_DEFAULT, out, capacity, out_len);
+}
+
+extern "C" int ltr_vcf_header_ex(const ltr_fasta* fasta, const char* fasta_path, const char* command,
+                                 const char* const* sample_names, uint32_t n_samples, uint32_t switches, char* out,
+                                 uint32_t capacity, uint32_t* out_len) {
   if (!fasta || !fasta_path || !command || !out_len || (n_samples && !sample_names) || (capacity && !out)) return LTR_ERR_INVALID;
   std::string o = "##fileformat=VCFv4.1\n";
   o += std::string("##command=") + command + "\n##reference=" + fasta_path + "\n";
@@ -360,6 +442,10 @@ extern "C" int ltr_vcf_header(const ltr_fasta* fasta, const char* fasta_path, co
     o += std::string("##INFO=<ID=") + f.id + ",Number=" + f.number + ",Type=" + f.type + ",Description=\"" + f.description + "\">\n";
   for (const FieldLine& f : kFormat)
     o += std::string("##FORMAT=<ID=") + f.id + ",Number=" + f.number + ",Type=" + f.type + ",Description=\"" + f.description + "\">\n";
+  for (const SwitchedLine& w : kSwitched)
+    if (switches & w.flag)
+      o += std::string("##FORMAT=<ID=") + w.line.id + ",Number=" + w.line.number + ",Type=" + w.line.type + ",Description=\"" +
+           w.line.description + "\">\n";
   o += "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT";
   for (uint32_t i = 0; i < n_samples; ++i) o += std::string("\t") + sample_names[i];
   o += "\n";

@@ -29,7 +29,8 @@ class BatchCalls(C.Structure):
                 ("log_phased_posteriors", _dp), ("log_unphased_posteriors", _dp), ("gl_diffs", _dp),
                 ("sample_total_lls", _dp), ("n_reads", _i32p), ("gl_begin", _u64p), ("gls", _dp), ("pls", _i32p),
                 ("prep_ms", C.c_double), ("gpu_wait_ms", C.c_double), ("post_ms", C.c_double), ("total_ms", C.c_double),
-                ("submit_ms", C.c_double), ("n_chunks", C.c_uint32), ("read_allele", _i32p)]
+                ("submit_ms", C.c_double), ("n_chunks", C.c_uint32), ("read_allele", _i32p), ("pgl_begin", _u64p),
+                ("phased_gls", _dp)]
 
 
 BAM_OPS = "MIDNSHP=X"
@@ -43,7 +44,7 @@ class Region(C.Structure):
 class RegionsOpts(C.Structure):
     _fields_ = [("host_threads", C.c_int32), ("max_tr_len", C.c_int32), ("min_total_reads", C.c_int32),
                 ("no_assembly", C.c_int32), ("vcf_records", C.c_int32), ("region_names", C.POINTER(C.c_char_p)),
-                ("region_motifs", C.POINTER(C.c_char_p)), ("haploid", C.c_int32)]
+                ("region_motifs", C.POINTER(C.c_char_p)), ("haploid", C.c_int32), ("vcf_switches", C.c_uint32)]
 
 
 class RegionsResult(C.Structure):
@@ -134,6 +135,8 @@ def _declare(lib):
     lib.ltr_genotyper_destroy.restype = None
     lib.ltr_genotyper_set_read_alleles.argtypes = [vp, C.c_int32]
     lib.ltr_genotyper_set_read_alleles.restype = C.c_int
+    lib.ltr_genotyper_set_phased_gls.argtypes = [vp, C.c_int32]
+    lib.ltr_genotyper_set_phased_gls.restype = C.c_int
     lib.ltr_genotyper_run.argtypes = [vp, C.POINTER(abi.Params), C.POINTER(LocusBatch), C.POINTER(C.POINTER(BatchCalls))]
     lib.ltr_genotyper_run.restype = C.c_int
     lib.ltr_batch_calls_free.argtypes = [C.POINTER(BatchCalls)]
@@ -205,6 +208,10 @@ class Genotyper:
         """ltr_genotyper_set_read_alleles: later runs also return read_allele (what MALLREADS counts)."""
         self.lib.ltr_genotyper_set_read_alleles(self.h, 1 if on else 0)
 
+    def set_phased_gls(self, on=True):
+        """ltr_genotyper_set_phased_gls: later runs also return pgl_begin / phased_gls (PHASEDGL)."""
+        self.lib.ltr_genotyper_set_phased_gls(self.h, 1 if on else 0)
+
     @staticmethod
     def _calls_dict(calls, nr=0):
         c = calls.contents
@@ -226,6 +233,9 @@ class Genotyper:
                    read_allele=(None if not c.read_allele or not nr else take(c.read_allele, nr)),
                    timing=dict(prep_ms=c.prep_ms, gpu_wait_ms=c.gpu_wait_ms, post_ms=c.post_ms, total_ms=c.total_ms, submit_ms=c.submit_ms,
                                n_chunks=c.n_chunks))
+        if c.pgl_begin:
+            out["pgl_begin"] = take(c.pgl_begin, ns + 1)
+            out["phased_gls"] = take(c.phased_gls, int(out["pgl_begin"][-1]))
         return out
 
     def _regions_dict(self, r):
@@ -247,7 +257,7 @@ class Genotyper:
 
     def run_regions(self, bams, chrom, regions, ref_seq, ref_seq_start=0, aln_params=None, indel_flank_len=5,
                     host_threads=0, max_tr_len=1000, min_total_reads=10, no_assembly=0, motifs=None, names=None,
-                    haploid=False, **region_overrides):
+                    haploid=False, vcf_switches=None, **region_overrides):
         """ltr_regions_run: bams = [abi.BamFile], regions = [(start, stop, period)] on `chrom`.  Returns dict(status,
         locus_index, alleles [per region], block [(start, end)], samples [per region: file indices], calls (as ``run``)).
         motifs = [str per region] (+ names): also the VCF record of every genotyped region (``records``)."""
@@ -260,6 +270,7 @@ class Genotyper:
             setattr(rp, k, v)
         opts = RegionsOpts(host_threads, max_tr_len, min_total_reads, no_assembly)
         opts.haploid = 1 if haploid else 0
+        opts.vcf_switches = abi.VCF_DEFAULT if vcf_switches is None else int(vcf_switches)   # ltr_regions_opts_default
         if motifs is not None:
             m_arr = (C.c_char_p * max(1, len(regions)))(*[m.encode() for m in motifs])
             n_arr = (C.c_char_p * max(1, len(regions)))(*[(x or "").encode() for x in (names or [""] * len(regions))])
@@ -283,7 +294,7 @@ class Genotyper:
         return res
 
     def run_bed(self, bams, fasta, bed_path, aln_params=None, indel_flank_len=5, host_threads=0, max_tr_len=1000,
-                min_total_reads=10, no_assembly=0, chrom_limit=None, vcf_records=False, **region_overrides):
+                min_total_reads=10, no_assembly=0, chrom_limit=None, vcf_records=False, vcf_switches=None, **region_overrides):
         """ltr_run_bed: bams = [abi.BamFile], fasta = abi.FastaFile, bed_path = region file (CHROM START STOP MOTIF [NAME]).
         Returns dict(chroms, bed=[(chrom index, start, stop, period, name, motif)], per_chrom=[as run_regions])."""
         from .engine import LongTRError
@@ -296,6 +307,7 @@ class Genotyper:
             setattr(rp, k, v)
         opts = RegionsOpts(host_threads, max_tr_len, min_total_reads, no_assembly)
         opts.vcf_records = 1 if vcf_records else 0
+        opts.vcf_switches = abi.VCF_DEFAULT if vcf_switches is None else int(vcf_switches)
         handles = (C.c_void_p * len(bams))(*[b.h for b in bams])
         out = C.POINTER(BedRunResult)()
         rc = lib.ltr_run_bed(self.h, C.byref(prm), handles, len(bams), fasta.h, bed["handle"], C.byref(rp), C.byref(opts),

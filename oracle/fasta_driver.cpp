@@ -35,3 +35,18 @@ extern "C" char* ltr_ref_vcf_header(const char* fasta_path, const char* command,
     if (!item.empty()) names.push_back(item);
   return dup(Genotyper::get_vcf_header(fasta_path, command, chroms, names));
 }
+
+// The same under the output switches `mask` (the library's LTR_VCF_* bits: 1 ALLREADS, 2 MALLREADS, 4 GL, 8 PL, 16 PHASEDGL,
+// 32 FILTER -> Genotyper::OUTPUT_*, what src/hipstr_main.cpp:178-183 sets); the defaults are restored afterwards.
+extern "C" char* ltr_ref_vcf_header_switches(const char* fasta_path, const char* command, const char* samples, unsigned mask) {
+  int* sw[6] = {&Genotyper::OUTPUT_ALLREADS, &Genotyper::OUTPUT_MALLREADS,  &Genotyper::OUTPUT_GLS,
+                &Genotyper::OUTPUT_PLS,      &Genotyper::OUTPUT_PHASED_GLS, &Genotyper::OUTPUT_FILTERS};
+  int saved[6];
+  for (int i = 0; i < 6; ++i) {
+    saved[i] = *sw[i];
+    *sw[i] = (mask >> i) & 1;
+  }
+  char* text = ltr_ref_vcf_header(fasta_path, command, samples);
+  for (int i = 0; i < 6; ++i) *sw[i] = saved[i];
+  return text;
+}

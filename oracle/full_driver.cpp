@@ -187,6 +187,18 @@ extern "C" int32_t ltr_ref_full_locus(const ltr_full_locus* L, char* out, int32_
 int main() {
   std::string chrom_name, chrom_seq, motif, region_name;
   static char out[1 << 20];
+  // LTR_REF_OUTPUT_SWITCHES: the reference's output switches as a bit mask in the order of the library's LTR_VCF_* flags
+  // (1 ALLREADS, 2 MALLREADS, 4 GL, 8 PL, 16 PHASEDGL, 32 FILTER): what --hide-allreads / --hide-mallreads / --output-gls /
+  // --output-pls / --output-phased-gls / --output-filters set (src/hipstr_main.cpp:178-183).  Unset = the defaults.
+  if (const char* sw = std::getenv("LTR_REF_OUTPUT_SWITCHES")) {
+    const unsigned m = (unsigned)std::strtoul(sw, NULL, 0);
+    Genotyper::OUTPUT_ALLREADS = (m & 1) ? 1 : 0;
+    Genotyper::OUTPUT_MALLREADS = (m & 2) ? 1 : 0;
+    Genotyper::OUTPUT_GLS = (m & 4) ? 1 : 0;
+    Genotyper::OUTPUT_PLS = (m & 8) ? 1 : 0;
+    Genotyper::OUTPUT_PHASED_GLS = (m & 16) ? 1 : 0;
+    Genotyper::OUTPUT_FILTERS = (m & 32) ? 1 : 0;
+  }
   while (std::cin >> chrom_name >> chrom_seq) {
     ltr_full_locus L;
     std::memset(&L, 0, sizeof(L));

@@ -340,13 +340,18 @@ def _case_text(case):
     return " ".join(str(x) for x in t) + "\n"
 
 
-def full_locus_records(cases, which="full"):
+def full_locus_records(cases, which="full", switches=None):
     """SeqStutterGenotyper ctor -> genotype -> write_vcf_record for every case; returns the VCF record texts
-    ('' where genotype() failed)."""
+    ('' where genotype() failed).  switches: the reference's output switches as a mask of the library's LTR_VCF_* bits
+    (None = the reference's defaults)."""
     build()
     exe = os.path.join(_HERE, "_ref", "ltr_ref_%s" % which)
+    env = dict(os.environ)
+    env.pop("LTR_REF_OUTPUT_SWITCHES", None)
+    if switches is not None:
+        env["LTR_REF_OUTPUT_SWITCHES"] = str(int(switches))
     p = subprocess.run([exe], input="".join(_case_text(c) for c in cases).encode(), stdout=subprocess.PIPE,
-                       stderr=subprocess.PIPE, timeout=600)
+                       stderr=subprocess.PIPE, timeout=600, env=env)
     if p.returncode != 0:
         raise RuntimeError("ltr_ref_%s failed rc=%d: %s" % (which, p.returncode, p.stderr.decode()[-400:]))
     out, recs, pos = p.stdout.decode(), [], 0

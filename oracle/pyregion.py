@@ -293,12 +293,18 @@ def ref_fasta_sequence(path, chrom):
     return text, n.value
 
 
-def ref_vcf_header(fasta_path, command, samples):
-    """Genotyper::get_vcf_header of the reference (contigs through its FastaReader on the library's reader)."""
+def ref_vcf_header(fasta_path, command, samples, switches=None):
+    """Genotyper::get_vcf_header of the reference (contigs through its FastaReader on the library's reader); switches: the
+    reference's output switches as a mask of the library's LTR_VCF_* bits."""
     lib = C.CDLL(_FASTA_SO)
     lib.ltr_ref_vcf_header.restype = C.c_void_p
     lib.ltr_ref_vcf_header.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p]
-    p = lib.ltr_ref_vcf_header(fasta_path.encode(), command.encode(), "\n".join(samples).encode())
+    lib.ltr_ref_vcf_header_switches.restype = C.c_void_p
+    lib.ltr_ref_vcf_header_switches.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint]
+    if switches is None:
+        p = lib.ltr_ref_vcf_header(fasta_path.encode(), command.encode(), "\n".join(samples).encode())
+    else:
+        p = lib.ltr_ref_vcf_header_switches(fasta_path.encode(), command.encode(), "\n".join(samples).encode(), int(switches))
     text = C.string_at(p).decode()
     C.CDLL(None).free(C.c_void_p(p))
     return text

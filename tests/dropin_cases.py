@@ -105,6 +105,12 @@ def seeded_cases():
     return out
 
 
+def haploid_cases():
+    """The first five seeded loci genotyped as a haploid chromosome (--haploid-chrs): haploid priors, GT / GL / PL over single
+    alleles, no PHASEDGL."""
+    return [dict(c, name=c["name"] + "_haploid", haploid=True) for c in seeded_cases()[:5]]
+
+
 def pruning_cases():
     """Loci in which some candidate allele ends up in no sample's optimal pair: SeqStutterGenotyper::genotype drops it
     and recomputes the posteriors (src/seq_stutter_genotyper.cpp:636-645)."""

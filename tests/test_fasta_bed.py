@@ -154,4 +154,6 @@ def test_reference_fasta_reader_runs_on_our_reader_and_header_matches(tmp_path):
     for samples in (["HG002"], ["HG002", "HG003", "HG004"], []):
         cmd = "LongTR --bams a.bam --fasta ref.fa --regions r.bed"
         assert abi.vcf_header(fa, path, cmd, samples) == pr.ref_vcf_header(path, cmd, samples)
+    for mask in (0, 3, 7, 60, 63, 37):   # --hide-allreads / --hide-mallreads / --output-gls / -pls / -phased-gls / -filters
+        assert abi.vcf_header(fa, path, cmd, ["HG002"], switches=mask) == pr.ref_vcf_header(path, cmd, ["HG002"], switches=mask)
     fa.close()

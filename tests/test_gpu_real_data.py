@@ -18,6 +18,13 @@ def _fields(record):
     return f, [dict(zip(fmt, s.split(":"))) if s != "." else None for s in f[9:]]
 
 
+def _extras(out, s0, s1):
+    """GL / PL / PHASEDGL slices of samples [s0, s1) of a Genotyper.run result, re-based for ltr_vcf_record_ex."""
+    glb, pglb = out["gl_begin"][s0:s1 + 1], out["pgl_begin"][s0:s1 + 1]
+    return dict(gl_begin=glb - glb[0], gls=out["gls"][glb[0]:glb[-1]], pls=out["pls"][glb[0]:glb[-1]],
+                pgl_begin=pglb - pglb[0], phased_gls=out["phased_gls"][pglb[0]:pglb[-1]])
+
+
 def test_real_loci_through_the_library_pipeline():
     cases = gu.load_real_cases()
     loci, keep = [], []
@@ -33,6 +40,7 @@ def test_real_loci_through_the_library_pipeline():
     g = Genotyper(devices=(0,), host_threads=8, chunk_loci=16)
     try:
         g.set_read_alleles(True)
+        g.set_phased_gls(True)
         out = g.run(build_locus_batch(loci))
     finally:
         g.close()
@@ -40,7 +48,8 @@ def test_real_loci_through_the_library_pipeline():
     # ---- the whole record as text: ltr_vcf_record on the device's numbers = the reference's record, character for character
     import test_vcf_writer as tw
     rb = np.concatenate([[0], np.cumsum([len(c["reads"]) for c in cases])])
-    n_text = 0
+    switch_gold = tw.load_switch_records()
+    n_text = n_switched = 0
     for l, (c, cand) in enumerate(zip(cases, keep)):
         s0, s1 = out["locus_sample_begin"][l], out["locus_sample_begin"][l + 1]
         a0, a1 = out["locus_allele_begin"][l], out["locus_allele_begin"][l + 1]
@@ -49,7 +58,13 @@ def test_real_loci_through_the_library_pipeline():
         got = abi.vcf_record(**tw.record_inputs(c, cand, calls))
         assert got == c["record"], c["name"]
         n_text += 1
-    assert n_text == len(cases)
+        # ... and under the reference's output switches (GL / PL / PHASEDGL computed on the device's posteriors)
+        extras = _extras(out, s0, s1)
+        for mask, recs in switch_gold.items():
+            got = abi.vcf_record(switches=mask, **tw.record_inputs(dict(c, record=recs[c["name"]]), cand, calls), **extras)
+            assert got == recs[c["name"]], (c["name"], mask)
+            n_switched += 1
+    assert n_text == len(cases) and n_switched == 4 * len(cases)
     n_samples = n_het = n_inexact = 0
     for l, (c, cand) in enumerate(zip(cases, keep)):
         f, samples = _fields(c["record"])
@@ -89,7 +104,9 @@ def test_seeded_loci_records_character_for_character():
     cases = [dc.case_a4()] + dc.seeded_cases()
     g = Genotyper(devices=(0,), host_threads=4, chunk_loci=16)
     g.set_read_alleles(True)
-    n = 0
+    g.set_phased_gls(True)
+    switch_gold = tw.load_switch_records()
+    n = n_switched = 0
     try:
         for c in cases:
             if c["name"] not in want:
@@ -109,6 +126,30 @@ def test_seeded_loci_records_character_for_character():
             got = abi.vcf_record(haploid=bool(c.get("haploid")), **inp)
             assert got == want[c["name"]], c["name"]
             n += 1
+            for mask, recs in switch_gold.items():   # the reference's output switches, haploid loci among them
+                inp = tw.record_inputs(dict(c, record=recs[c["name"]]), cand, calls)
+                got = abi.vcf_record(haploid=bool(c.get("haploid")), switches=mask, **inp, **_extras(out, 0, len(c["samples"])))
+                assert got == recs[c["name"]], (c["name"], mask)
+                n_switched += 1
+        # the same loci as a haploid chromosome (--haploid-chrs): GT / GL / PL over single alleles, no PHASEDGL
+        hap_gold = tw.load_switch_records("haploid")
+        n_hap = 0
+        for c in dc.haploid_cases():
+            cand = abi.candidate_alleles_from_reads(c["reads"], len(c["samples"]), c["region_start"], c["region_stop"],
+                                                    len(c["motif"]), c["chrom_seq"])
+            locus = dict(lflank=cand["lflank"], rflank=cand["rflank"], alleles=cand["alleles"], repeat_start=cand["block_start"],
+                         repeat_end=cand["block_end"], n_samples=len(c["samples"]), haploid=True,
+                         reads=[dict(start=r["start"], stop=r["stop"], seq=r["seq"], cigar=r["cigar"], sample=r["sample"],
+                                     log_p1=r["log_p1"], log_p2=r["log_p2"]) for r in c["reads"]])
+            out = g.run(build_locus_batch([locus]), aln_params=c.get("aln_params"))
+            assert out["status"][0] == 0, c["name"]
+            calls = dict(gts=out["gts"], lup=out["log_unphased_posteriors"], lpp=out["log_phased_posteriors"],
+                         gld=out["gl_diffs"], kept=out["kept_mask"], read_allele=out["read_allele"])
+            for mask, recs in hap_gold.items():
+                inp = tw.record_inputs(dict(c, record=recs[c["name"]]), cand, calls)
+                got = abi.vcf_record(haploid=True, switches=mask, **inp, **_extras(out, 0, len(c["samples"])))
+                assert got == recs[c["name"]], (c["name"], mask)
+                n_hap += 1
     finally:
         g.close()
-    assert n >= 10
+    assert n >= 10 and n_switched == 4 * n and n_hap == 25

@@ -151,6 +151,39 @@ def test_example_flow_writes_the_vcf_file(tmp_path):
     assert n == len(body) == len(want) and body == want
 
 
+def test_region_records_under_the_output_switches(genotyper, tmp_path):
+    """opts->vcf_switches: the region loop's records with GL / PL / PHASEDGL / FILTER (the reference's --output-gls ... switches;
+    the record composer itself is pinned by the reference's records in tests/test_vcf_writer.py / test_gpu_real_data.py): the
+    default fields are unchanged, the extra ones have one entry per genotype of the record's alleles, the PL of the most likely
+    genotype is 0, and hiding ALLREADS / MALLREADS removes exactly those."""
+    world = bw.synthetic_world(12, config=3, first_locus=500, n_samples=2)
+    bams = [abi.BamFile(p) for p in bw.write_world(world, str(tmp_path))]
+    motifs = [world["chrom_seq"][s0:s0 + per] for s0, _e, per in world["regions"]]
+    base = genotyper.run_regions(bams, "chrS", world["regions"], world["chrom_seq"], 0, motifs=motifs)
+    full = genotyper.run_regions(bams, "chrS", world["regions"], world["chrom_seq"], 0, motifs=motifs, vcf_switches=63)
+    bare = genotyper.run_regions(bams, "chrS", world["regions"], world["chrom_seq"], 0, motifs=motifs, vcf_switches=0)
+    n = n_multi = 0
+    for r, st in enumerate(base["status"]):
+        if st != 0:
+            continue
+        b, f, z = (x["records"][r].split("\t") for x in (base, full, bare))
+        assert f[:8] == b[:8] == z[:8]
+        assert f[8] == b[8] + ":GL:PL:PHASEDGL:FILTER" and z[8] + ":ALLREADS:MALLREADS" == b[8]
+        K = 1 + (0 if b[4] == "." else b[4].count(",") + 1)
+        for cb, cf, cz in zip(b[9:], f[9:], z[9:]):
+            if cb == ".":
+                assert cf == ".:" * 15 + "NO_READS" and cz == "."
+                continue
+            wb, wf = cb.split(":"), cf.split(":")
+            assert wf[:len(wb)] == wb and wf[-1] == "PASS" and cz.split(":") == wb[:-2]
+            gl, pl, pgl = ([float(x) for x in wf[len(wb) + k].split(",")] for k in range(3))
+            assert len(gl) == len(pl) == K * (K + 1) // 2 and len(pgl) == K * K
+            assert min(pl) == 0 and pl[gl.index(max(gl))] == 0   # PL = min(999, -10 (GL - max GL)), genotyper.cpp:86-89
+            n += 1
+            n_multi += K > 1
+    assert n >= 16 and n_multi >= 8
+
+
 def test_haploid_chromosome(genotyper, tmp_path):
     """opts->haploid (--haploid-chrs): homozygous calls only, haploid FORMAT of the records."""
     world = bw.synthetic_world(10, config=3, first_locus=300, n_samples=1)

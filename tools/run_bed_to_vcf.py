@@ -23,6 +23,9 @@ def main(argv=None):
     ap.add_argument("--samples", default="")
     ap.add_argument("--devices", default="0")
     ap.add_argument("--no-phased-bam", action="store_true", help="ignore HP tags (the library's default is --phased-bam)")
+    # the reference's output switches (src/hipstr_main.cpp:178-183) -> LTR_VCF_* (ltr_regions_opts.vcf_switches, ltr_vcf_header_ex)
+    for flag in ("hide-allreads", "hide-mallreads", "output-gls", "output-pls", "output-phased-gls", "output-filters"):
+        ap.add_argument("--" + flag, action="store_true")
     a = ap.parse_args(argv)
     from longtr_b200 import Genotyper, abi
     paths = a.bams.split(",")
@@ -32,15 +35,19 @@ def main(argv=None):
         if not b.has_index:
             b.build_index()
     fasta = abi.FastaFile(a.fasta)
+    switches = ((0 if a.hide_allreads else abi.VCF_ALLREADS) | (0 if a.hide_mallreads else abi.VCF_MALLREADS) |
+                (abi.VCF_GLS if a.output_gls else 0) | (abi.VCF_PLS if a.output_pls else 0) |
+                (abi.VCF_PHASED_GLS if a.output_phased_gls else 0) | (abi.VCF_FILTERS if a.output_filters else 0))
     g = Genotyper(devices=tuple(int(d) for d in a.devices.split(",")))
     try:
-        run = g.run_bed(bams, fasta, a.regions, vcf_records=True, **(dict(phased_bam=0) if a.no_phased_bam else {}))
+        run = g.run_bed(bams, fasta, a.regions, vcf_records=True, vcf_switches=switches,
+                        **(dict(phased_bam=0) if a.no_phased_bam else {}))
     finally:
         g.close()
     n = 0
     with open(a.out, "w") as f:
         f.write(abi.vcf_header(fasta, a.fasta, " ".join(["run_bed_to_vcf.py"] + (argv if argv is not None else sys.argv[1:])),
-                               samples))
+                               samples, switches=switches))
         for res in run["per_chrom"]:
             for rec in res["records"] or []:
                 if rec:
