@@ -10,6 +10,9 @@
 //         names.
 // The file is mapped once; queries are read-only on the mapping and keep their own block cache, so several host threads
 // can fetch different regions from one ltr_bam concurrently.
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <fcntl.h>
 #include <stdint.h>
 #include <string.h>
@@ -322,10 +325,36 @@ bool append_record(ReadsOwner& R, const uint8_t* rec, size_t n, bool keep_raw) {
   R.end.push_back(end64 > INT32_MAX ? INT32_MAX : (int32_t)end64);
   const size_t s0 = R.seq.size();
   R.seq.resize(s0 + l_seq);
-  for (uint32_t i = 0; i < l_seq; ++i) R.seq[s0 + i] = (uint8_t)kSeqCodes[(q[i >> 1] >> ((~i & 1) << 2)) & 0xf];
+  {
+    // two bases per packed byte through a 256-entry table of letter pairs (high nibble first)
+    static const struct PairTable {
+      uint16_t v[256];
+      PairTable() {
+        for (int b = 0; b < 256; ++b) v[b] = (uint16_t)((uint8_t)kSeqCodes[b >> 4] | ((uint16_t)(uint8_t)kSeqCodes[b & 15] << 8));
+      }
+    } pairs;
+    uint8_t* dst = R.seq.data() + s0;
+    const uint32_t full = l_seq >> 1;
+    for (uint32_t k = 0; k < full; ++k) memcpy(dst + 2 * (size_t)k, &pairs.v[q[k]], 2);
+    if (l_seq & 1) dst[l_seq - 1] = (uint8_t)kSeqCodes[q[full] >> 4];
+  }
   q += (l_seq + 1) / 2;
   R.qual.resize(s0 + l_seq);
-  for (uint32_t i = 0; i < l_seq; ++i) R.qual[s0 + i] = (uint8_t)(q[i] == 0xff ? '!' : (q[i] > 93 ? 126 : q[i] + 33));
+  {
+    // phred + 33, 0xff (missing) -> '!', above 93 -> '~'
+    uint8_t* dst = R.qual.data() + s0;
+    uint32_t i = 0;
+#if defined(__SSE2__)
+    const __m128i c33 = _mm_set1_epi8(33), cap = _mm_set1_epi8(93), ff = _mm_set1_epi8((char)0xff);
+    for (; i + 16 <= l_seq; i += 16) {
+      const __m128i x = _mm_loadu_si128((const __m128i*)(q + i));
+      const __m128i missing = _mm_cmpeq_epi8(x, ff);
+      const __m128i v = _mm_add_epi8(_mm_min_epu8(x, cap), c33);  // min(x, 93) + 33: 126 for everything above 93
+      _mm_storeu_si128((__m128i*)(dst + i), _mm_or_si128(_mm_andnot_si128(missing, v), _mm_and_si128(missing, c33)));
+    }
+#endif
+    for (; i < l_seq; ++i) dst[i] = (uint8_t)(q[i] == 0xff ? '!' : (q[i] > 93 ? 126 : q[i] + 33));
+  }
   R.seq_off.push_back((uint32_t)R.seq.size());
   q += l_seq;
   R.hp.push_back(aux_int(q, rec + n, 'H', 'P'));

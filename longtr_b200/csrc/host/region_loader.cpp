@@ -8,6 +8,9 @@
 //                                        against the reference sequence, soft-clipped reads dropped
 // Paired-end bookkeeping (mate lookup, NO_UNIQUE_MAPPING between mates, PCR duplicates) is not reproduced: a read whose
 // PAIRED flag is set is refused with LTR_ERR_UNSUPPORTED for the region.  Output arrays have the layout of ltr_locus_batch.
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <string.h>
 
 #include <algorithm>
@@ -73,57 +76,69 @@ bool aux_has(const uint8_t* raw, size_t n, char t0, char t1) {
   return false;
 }
 
-// BamAlignment::TrimAlignment(min_read_start, max_read_stop) (bam_io.cpp:267-372), operation by operation.
+// BamAlignment::TrimAlignment(min_read_start, max_read_stop) (bam_io.cpp:267-372).  The reference walks base by base; here
+// every CIGAR operation is consumed in one step (as many of its bases as the reference's loop would take before its
+// condition fails), which leaves the same CIGAR, sequence and positions.
 void trim_alignment(Aln& a, int32_t min_read_start, int32_t max_read_stop, int32_t flank_size) {
-  int ltrim = 0;
+  int64_t ltrim = 0;
   int32_t start_pos = a.pos;
   size_t first = 0;  // cigar[first..) is what is left at the front
   std::vector<Op>& c = a.cigar;
   while (start_pos < min_read_start && first < c.size()) {  // :274-300
-    switch (c[first].type) {
-      case 'M': case '=': case 'X': ++ltrim; ++start_pos; break;
-      case 'D': ++start_pos; break;
-      case 'I': case 'S': ++ltrim; break;
-      default: break;  // 'H'
+    Op& o = c[first];
+    int32_t t = o.len;  // 'I', 'S', 'H', ...: the position does not move, the whole operation goes
+    switch (o.type) {
+      case 'M': case '=': case 'X':
+        t = std::min(o.len, min_read_start - start_pos);
+        ltrim += t;
+        start_pos += t;
+        break;
+      case 'D':
+        t = std::min(o.len, min_read_start - start_pos);
+        start_pos += t;
+        break;
+      case 'I': case 'S': ltrim += t; break;
+      default: break;
     }
-    if (c[first].len == 1) ++first;
-    else --c[first].len;
+    if (t == o.len) ++first;
+    else o.len -= t;
   }
   c.erase(c.begin(), c.begin() + (long)first);
   // :303-338 -- is the repeat deleted in this read?
   {
     int32_t repeat_pointer = start_pos;
     const int32_t repeat_start = min_read_start + flank_size, repeat_end = max_read_stop - flank_size;
-    int32_t deletion_size = 0;
-    size_t k = 0;
-    int32_t left = c.empty() ? 0 : c[0].len;
-    while (repeat_pointer >= min_read_start && repeat_pointer < repeat_end && k < c.size()) {
-      switch (c[k].type) {
-        case 'M': case '=': case 'X': ++repeat_pointer; break;
-        case 'D':
-          if (repeat_pointer >= repeat_start) ++deletion_size;
-          ++repeat_pointer;
-          break;
-        default: break;
+    int64_t deletion_size = 0;
+    if (repeat_pointer >= min_read_start)
+      for (size_t k = 0; k < c.size() && repeat_pointer < repeat_end; ++k) {
+        const bool match = c[k].type == 'M' || c[k].type == '=' || c[k].type == 'X';
+        if (!match && c[k].type != 'D') continue;
+        const int32_t t = std::min(c[k].len, repeat_end - repeat_pointer);
+        if (!match && repeat_pointer + t > repeat_start) deletion_size += repeat_pointer + t - std::max(repeat_pointer, repeat_start);
+        repeat_pointer += t;
       }
-      if (--left == 0) {
-        ++k;
-        left = k < c.size() ? c[k].len : 0;
-      }
-    }
     if (deletion_size >= repeat_end - repeat_start) a.deleted = true;
   }
-  int rtrim = 0;
+  int64_t rtrim = 0;
   int32_t end_pos = a.end_pos;
   while (end_pos > max_read_stop && !c.empty()) {  // :342-364
-    switch (c.back().type) {
-      case 'M': case '=': case 'X': ++rtrim; --end_pos; break;
-      case 'D': --end_pos; break;
-      case 'I': case 'S': ++rtrim; break;
+    Op& o = c.back();
+    int32_t t = o.len;
+    switch (o.type) {
+      case 'M': case '=': case 'X':
+        t = std::min(o.len, end_pos - max_read_stop);
+        rtrim += t;
+        end_pos -= t;
+        break;
+      case 'D':
+        t = std::min(o.len, end_pos - max_read_stop);
+        end_pos -= t;
+        break;
+      case 'I': case 'S': rtrim += t; break;
       default: break;
     }
-    if (c.back().len == 1) c.pop_back();
-    else --c.back().len;
+    if (t == o.len) c.pop_back();
+    else o.len -= t;
   }
   a.bases = a.bases.substr((size_t)ltrim, a.bases.size() - (size_t)ltrim - (size_t)rtrim);
   a.quals = a.quals.substr((size_t)ltrim, a.quals.size() - (size_t)ltrim - (size_t)rtrim);
@@ -206,8 +221,17 @@ static int ltr_region_collect_impl(const ltr_bam* const* bams, int32_t n_bams, c
       bool pass = false;
       if (memchr(sq, 'N', l_seq)) ++S.n_has_n;  // :265-268
       else {
-        double sum = 0.0;
-        for (uint32_t k = 0; k < l_seq; ++k) sum += (double)((int)ql[k] - 33);  // base_quality.h:77-84
+        // base_quality.h:77-84 adds (quality - 33) base by base in double: integer-valued partial sums far below 2^53, so the
+        // integer sum converted once is the same double
+        uint64_t qsum = 0;
+        uint32_t k = 0;
+#if defined(__SSE2__)
+        __m128i acc = _mm_setzero_si128();
+        for (; k + 16 <= l_seq; k += 16) acc = _mm_add_epi64(acc, _mm_sad_epu8(_mm_loadu_si128((const __m128i*)(ql + k)), _mm_setzero_si128()));
+        qsum = (uint64_t)_mm_cvtsi128_si64(acc) + (uint64_t)_mm_cvtsi128_si64(_mm_unpackhi_epi64(acc, acc));
+#endif
+        for (; k < l_seq; ++k) qsum += ql[k];
+        const double sum = (double)((int64_t)qsum - 33 * (int64_t)l_seq);
         if (sum / (double)l_seq < params->min_mean_qual) ++S.n_low_qual;
         else if ((double)R->mapq[i] < params->min_mapq) ++S.n_low_mapq;
         else if (params->require_spanning == 1 && !(pos <= start && end_pos >= stop)) ++S.n_not_spanning;  // :175-186
@@ -262,7 +286,7 @@ static int ltr_region_collect_impl(const ltr_bam* const* bams, int32_t n_bams, c
       a.flag = (uint16_t)((a.flag & 0x7fff) | (hap_ok ? 0x8000 : 0));  // carried in the top bit (not a SAM flag here)
       auto mate = potential_mates.find(key);
       if (mate != potential_mates.end()) potential_mates.erase(mate);  // :324-330 (same mate number: both are "not first")
-      potential_strs.insert(std::make_pair(key, a));  // a second alignment of the same name is ignored, as std::map::insert does
+      potential_strs.emplace(key, std::move(a));  // a second alignment of the same name is ignored, as std::map::insert does
     }
     ltr_bam_reads_free(R);
     if (rc != LTR_OK) break;  // (a refusal found in this file must not be overwritten by the next file's fetch)
@@ -271,7 +295,7 @@ static int ltr_region_collect_impl(const ltr_bam* const* bams, int32_t n_bams, c
     delete O;
     return rc;
   }
-  std::vector<const Aln*> unpaired;  // :420-436
+  std::vector<Aln*> unpaired;  // :420-436
   for (auto it = potential_strs.begin(); it != potential_strs.end(); ++it) {
     if (it->second.has_xa) {
       ++S.n_not_unique;
@@ -281,16 +305,16 @@ static int ltr_region_collect_impl(const ltr_bam* const* bams, int32_t n_bams, c
   }
   S.n_passed = (uint32_t)unpaired.size();
   // :453-483: reads are taken from the BACK of the list; samples (one per file) are numbered by first appearance
-  std::vector<std::vector<const Aln*>> by_sample;
+  std::vector<std::vector<Aln*>> by_sample;
   std::map<uint32_t, size_t> sample_of_file;
   for (size_t k = unpaired.size(); k-- > 0;) {
-    const Aln* a = unpaired[k];
+    Aln* a = unpaired[k];
     auto it = sample_of_file.find(a->file);
     size_t s;
     if (it == sample_of_file.end()) {
       s = by_sample.size();
       sample_of_file[a->file] = s;
-      by_sample.push_back(std::vector<const Aln*>());
+      by_sample.push_back(std::vector<Aln*>());
       O->sample_file.push_back(a->file);
     } else {
       s = it->second;
@@ -330,7 +354,7 @@ static int ltr_region_collect_impl(const ltr_bam* const* bams, int32_t n_bams, c
   O->sample_read_begin.push_back(0);
   for (size_t s = 0; s < by_sample.size() && rc == LTR_OK; ++s) {
     for (size_t j = 0; j < by_sample[s].size() && rc == LTR_OK; ++j) {
-      Aln a = *by_sample[s][j];
+      Aln& a = *by_sample[s][j];  // trimmed in place: every read of potential_strs is visited once
       if (a.pos > start || a.end_pos < stop) {  // :55-58
         ++S.n_trim_failed;
         continue;
@@ -388,7 +412,15 @@ static int ltr_region_collect_impl(const ltr_bam* const* bams, int32_t n_bams, c
       }
       O->read_start.push_back(r_start);
       O->read_stop.push_back(r_stop);
-      for (char ch : a.bases) O->read_bytes.push_back((uint8_t)((ch >= 'a' && ch <= 'z') ? ch - 32 : ch));
+      {
+        const size_t at = O->read_bytes.size();
+        O->read_bytes.resize(at + a.bases.size());
+        uint8_t* dst = O->read_bytes.data() + at;
+        for (size_t k = 0; k < a.bases.size(); ++k) {
+          const char ch = a.bases[k];
+          dst[k] = (uint8_t)((ch >= 'a' && ch <= 'z') ? ch - 32 : ch);
+        }
+      }
       O->qual_bytes.insert(O->qual_bytes.end(), a.quals.begin(), a.quals.end());
       O->read_off.push_back((uint32_t)O->read_bytes.size());
       for (const Op& c : ops) O->cigar_ops.push_back(((uint32_t)c.len << 4) | bam_op(c.type));

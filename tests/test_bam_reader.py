@@ -129,3 +129,28 @@ def test_open_errors(tmp_path):
         abi.BamFile(str(junk))
     with pytest.raises(RuntimeError):
         abi.BamFile(bam_path("HG002"), index_path=str(junk))
+
+
+def test_sequence_and_quality_decoding_edge_cases(tmp_path):
+    """Every 4-bit base code, odd and even lengths around the 16-byte vector width, missing qualities (0xff -> '!') and
+    qualities above 93 (-> '~'), as htslib prints them (SAM specification 4.2.3 / 4.2.4)."""
+    import bam_writer as bw
+    import struct
+    codes = "=ACMGRSVTWYHKDBN"
+    recs, want = [], []
+    for n in (1, 2, 15, 16, 17, 31, 32, 33, 47, 64, 101):
+        seq = "".join(codes[(3 * i + n) % 16] for i in range(n))
+        raw_q = bytes((i * 37 + n) % 256 if i % 5 else 0xff for i in range(n))
+        rec = bytearray(bw.encode_record(0, 100 + n, "r%d" % n, 0, 60, [("M", n)], seq, "!" * n))
+        # overwrite the quality bytes (they sit right behind the packed sequence)
+        l_name = rec[4 + 8]
+        q_at = 4 + 32 + l_name + 4 + (n + 1) // 2
+        rec[q_at:q_at + n] = raw_q
+        recs.append(bytes(rec))
+        want.append((seq, "".join("!" if q == 0xff else chr(126 if q > 93 else q + 33) for q in raw_q)))
+    path = str(tmp_path / "edge.bam")
+    bw.write_bam(path, [("chrE", 10000)], recs)
+    b = abi.BamFile(path)
+    got = b.fetch()
+    assert [(r["seq"], r["qual"]) for r in got] == want
+    b.close()
