@@ -802,6 +802,8 @@ def measure_regions(args, n_loci, steps, warmup):
                                  "note": "ltr_regions_run with opts.vcf_records (LL download, per-read alleles, record text)"},
             "wall_ms_per_step_incl_python_decoding": float(np.mean(wall)),
             "genotyper_ms": {k: float(v) for k, v in t.items()},
+            "host_ms": {k: float(v) for k, v in out.get("host_ms", {}).items()},
+            "host_ms_with_vcf_records": {k: float(v) for k, v in o2.get("host_ms", {}).items()},
             "config": {"workload": "N3: %d config-3 loci as one coordinate-sorted BAM file (30 spanning reads per region, "
                                    "1.5 kb each), one sample" % n_loci, "regions": n_loci,
                        "regions_genotyped": int((status == 0).sum()), "regions_assembled": int(out["n_assembled"]),

@@ -671,6 +671,9 @@ typedef struct ltr_regions_result {
                                           record_off[r+1]), empty for a region that was not genotyped; no newlines       */
   const char* records;
   void* owner;
+  double prepare_ms, layout_ms, genotype_ms, records_ms;  /* host timing of the call: region preparation on the host threads
+                                          (BAM fetch, filters, trimming, candidate alleles), laying the batch out, ltr_genotyper_run,
+                                          composing the records                                                          */
 } ltr_regions_result;
 void ltr_regions_opts_default(ltr_regions_opts* o);
 int ltr_regions_run(ltr_genotyper* g, const ltr_params* params, const ltr_bam* const* bams, int32_t n_bams, const char* chrom,

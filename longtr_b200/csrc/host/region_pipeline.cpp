@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <string>
 #include <thread>
 #include <vector>
@@ -51,6 +52,9 @@ extern "C" int ltr_regions_run(ltr_genotyper* g, const ltr_params* params, const
   int n_threads = opts->host_threads > 0 ? opts->host_threads : (int)std::thread::hardware_concurrency();
   if (n_threads < 1) n_threads = 1;
   if ((uint32_t)n_threads > n_regions) n_threads = n_regions ? (int)n_regions : 1;
+  typedef std::chrono::steady_clock Clock;
+  auto ms_since = [](Clock::time_point t) { return std::chrono::duration<double, std::milli>(Clock::now() - t).count(); };
+  const Clock::time_point t_begin = Clock::now();
   std::atomic<uint32_t> next(0);
   auto prepare = [&]() {
     // a few consecutive regions per grab: neighbours of a sorted region list share BGZF blocks (the reader keeps the last two
@@ -94,94 +98,157 @@ extern "C" int ltr_regions_run(ltr_genotyper* g, const ltr_params* params, const
     prepare();
     for (std::thread& t : th) t.join();
   }
+  const double prepare_ms = ms_since(t_begin);
+  const Clock::time_point t_layout = Clock::now();
   // ---- lay the surviving regions out as one ltr_locus_batch ------------------------------------------------------------
+  // Sizes and offsets first (serial, a few integers per region); the bytes are then copied -- and the per-region work freed --
+  // by the host threads, each region into its own slice.
   Owner* O = new Owner();
   memset(&O->pub, 0, sizeof(O->pub));
   O->status.resize(n_regions);
   O->locus_index.assign(n_regions, -1);
   O->block_start.assign(n_regions, 0);
   O->block_end.assign(n_regions, 0);
-  O->region_allele_begin.push_back(0);
-  O->allele_off.push_back(0);
-  O->region_sample_begin.push_back(0);
-  std::vector<uint32_t> lflank_off(1, 0), rflank_off(1, 0), lab(1, 0), aoff(1, 0), lrb(1, 0), roff(1, 0), coff(1, 0), cops, lns;
+  O->region_allele_begin.assign(1, 0);
+  O->region_sample_begin.assign(1, 0);
+  std::vector<uint32_t> lflank_off(1, 0), rflank_off(1, 0), lab(1, 0), aoff, lrb(1, 0), roff, coff, cops, lns;
   std::vector<uint8_t> lfb, rfb, ab, rb;
   std::vector<int32_t> rstart, rend, read_start, read_stop, read_sample;
   std::vector<double> p1, p2;
   std::vector<int32_t> read_bp_diff, n_hp1, n_hp2;   // for the records: ExtractCigar per read, HP counts per (locus, sample)
   std::vector<uint32_t> locus_sample_begin(1, 0), locus_region;
+  std::vector<uint64_t> o_ab_off(1, 0), ab_off(1, 0), rb_off(1, 0), cop_off(1, 0);  // byte / operation offsets per region / locus
   const bool want_records = opts->vcf_records != 0;
   const bool want_pgl = want_records && !opts->haploid && (opts->vcf_switches & LTR_VCF_PHASED_GLS);
   uint32_t n_loci = 0;
   for (uint32_t r = 0; r < n_regions; ++r) {
-    RegionWork& W = work[r];
+    const RegionWork& W = work[r];
     O->status[r] = W.status;
-    if (W.reads) {
-      for (uint32_t s = 0; s < W.reads->n_samples; ++s) O->sample_file.push_back(W.reads->sample_file[s]);
-    }
-    O->region_sample_begin.push_back((uint32_t)O->sample_file.size());
-    if (W.cand && W.cand->n_alleles > 0) {
+    O->region_sample_begin.push_back(O->region_sample_begin.back() + (W.reads ? W.reads->n_samples : 0u));
+    const bool has_alleles = W.cand && W.cand->n_alleles > 0;
+    const uint32_t na = has_alleles ? (uint32_t)W.cand->n_alleles : 0u;
+    const uint64_t nab = has_alleles ? (uint64_t)(W.cand->allele_off[na] - W.cand->allele_off[0]) : 0u;
+    if (has_alleles) {
       O->block_start[r] = W.cand->block_start;
       O->block_end[r] = W.cand->block_end;
-      for (int32_t a = 0; a < W.cand->n_alleles; ++a) {
-        O->allele_bytes.insert(O->allele_bytes.end(), W.cand->allele_bytes + W.cand->allele_off[a],
-                               W.cand->allele_bytes + W.cand->allele_off[a + 1]);
-        O->allele_off.push_back((uint32_t)O->allele_bytes.size());
-        O->allele_inexact.push_back(W.cand->allele_inexact[a]);
-      }
       if (W.cand->status == LTR_CAND_OK && W.cand->n_cluster_samples > 0) ++O->pub.n_assembled;
     }
-    O->region_allele_begin.push_back((uint32_t)O->allele_off.size() - 1);
+    O->region_allele_begin.push_back(O->region_allele_begin.back() + na);
+    o_ab_off.push_back(o_ab_off.back() + nab);
     if (W.status != LTR_REGION_OK) continue;
     const ltr_region_reads& RR = *W.reads;
     const ltr_candidates& C = *W.cand;
     O->locus_index[r] = (int32_t)n_loci++;
-    lfb.insert(lfb.end(), C.lflank, C.lflank + strlen(C.lflank));
-    lflank_off.push_back((uint32_t)lfb.size());
-    rfb.insert(rfb.end(), C.rflank, C.rflank + strlen(C.rflank));
-    rflank_off.push_back((uint32_t)rfb.size());
-    for (int32_t a = 0; a < C.n_alleles; ++a) {
-      ab.insert(ab.end(), C.allele_bytes + C.allele_off[a], C.allele_bytes + C.allele_off[a + 1]);
-      aoff.push_back((uint32_t)ab.size());
-    }
-    lab.push_back((uint32_t)aoff.size() - 1);
+    locus_region.push_back(r);
+    lflank_off.push_back(lflank_off.back() + (uint32_t)strlen(C.lflank));
+    rflank_off.push_back(rflank_off.back() + (uint32_t)strlen(C.rflank));
+    lab.push_back(lab.back() + na);
+    ab_off.push_back(ab_off.back() + nab);
     rstart.push_back(C.block_start);
     rend.push_back(C.block_end);
-    for (uint32_t i = 0; i < RR.n_reads; ++i) {
-      read_start.push_back(RR.read_start[i]);
-      read_stop.push_back(RR.read_stop[i]);
-      rb.insert(rb.end(), RR.read_bytes + RR.read_off[i], RR.read_bytes + RR.read_off[i + 1]);
-      roff.push_back((uint32_t)rb.size());
-      cops.insert(cops.end(), RR.cigar_ops + RR.cigar_off[i], RR.cigar_ops + RR.cigar_off[i + 1]);
-      coff.push_back((uint32_t)cops.size());
-      read_sample.push_back(RR.read_sample[i]);
-      p1.push_back(RR.log_p1[i]);
-      p2.push_back(RR.log_p2[i]);
-    }
-    if (want_records) {
-      const size_t h0 = n_hp1.size();
-      n_hp1.resize(h0 + RR.n_samples, 0);
-      n_hp2.resize(h0 + RR.n_samples, 0);
-      for (uint32_t i = 0; i < RR.n_reads; ++i) {
-        int32_t d = 0;  // write_vcf_record (:1017-1023): ExtractCigar over the region +- 5 bp
-        const int got = ltr_extract_cigar_bp_diff(RR.cigar_ops + RR.cigar_off[i], RR.cigar_off[i + 1] - RR.cigar_off[i],
-                                                  RR.read_start[i], regions[r].start - 5, regions[r].stop + 5, &d);
-        read_bp_diff.push_back(got ? d : INT32_MIN);
-        if (RR.read_hp[i] == 1) ++n_hp1[h0 + (size_t)RR.read_sample[i]];
-        if (RR.read_hp[i] == 2) ++n_hp2[h0 + (size_t)RR.read_sample[i]];
-      }
-      locus_sample_begin.push_back((uint32_t)n_hp1.size());
-      locus_region.push_back(r);
-    }
-    lrb.push_back((uint32_t)read_start.size());
+    lrb.push_back(lrb.back() + RR.n_reads);
+    rb_off.push_back(rb_off.back() + (RR.read_off[RR.n_reads] - RR.read_off[0]));
+    cop_off.push_back(cop_off.back() + (RR.cigar_off[RR.n_reads] - RR.cigar_off[0]));
     lns.push_back(RR.n_samples);
+    locus_sample_begin.push_back(locus_sample_begin.back() + RR.n_samples);
   }
-  for (RegionWork& W : work) {
-    ltr_candidates_free(W.cand);
-    ltr_region_reads_free(W.reads);
+  if (o_ab_off.back() > 0xFFFFFFF0ull || ab_off.back() > 0xFFFFFFF0ull || rb_off.back() > 0xFFFFFFF0ull || cop_off.back() > 0xFFFFFFF0ull) {
+    for (RegionWork& W : work) {
+      ltr_candidates_free(W.cand);
+      ltr_region_reads_free(W.reads);
+    }
+    delete O;
+    return LTR_ERR_INVALID;  // more than 4 GB of reads in one call: the batch's offsets are 32 bits wide
+  }
+  {
+    const size_t n_reads_all = lrb.back();
+    O->sample_file.resize(O->region_sample_begin.back());
+    O->allele_off.assign((size_t)O->region_allele_begin.back() + 1, 0);
+    O->allele_bytes.resize(o_ab_off.back());
+    O->allele_inexact.resize(O->region_allele_begin.back());
+    // (one spare element each: the batch's byte arrays get a terminator appended below without growing)
+    lfb.reserve((size_t)lflank_off.back() + 1); lfb.resize(lflank_off.back());
+    rfb.reserve((size_t)rflank_off.back() + 1); rfb.resize(rflank_off.back());
+    aoff.assign((size_t)lab.back() + 1, 0);
+    ab.reserve(ab_off.back() + 1); ab.resize(ab_off.back());
+    roff.assign(n_reads_all + 1, 0);
+    coff.assign(n_reads_all + 1, 0);
+    rb.reserve(rb_off.back() + 1); rb.resize(rb_off.back());
+    cops.reserve(cop_off.back() + 1); cops.resize(cop_off.back());
+    read_start.resize(n_reads_all); read_stop.resize(n_reads_all); read_sample.resize(n_reads_all);
+    p1.resize(n_reads_all); p2.resize(n_reads_all);
+    if (want_records) {
+      read_bp_diff.resize(n_reads_all);
+      n_hp1.assign(locus_sample_begin.back(), 0);
+      n_hp2.assign(locus_sample_begin.back(), 0);
+    }
+  }
+  next.store(0);
+  auto fill = [&]() {
+    const uint32_t kGrab = 8;
+    for (uint32_t r0 = next.fetch_add(kGrab); r0 < n_regions; r0 = next.fetch_add(kGrab))
+    for (uint32_t r = r0; r < std::min(n_regions, r0 + kGrab); ++r) {
+      RegionWork& W = work[r];
+      if (W.reads)
+        for (uint32_t s = 0; s < W.reads->n_samples; ++s) O->sample_file[O->region_sample_begin[r] + s] = W.reads->sample_file[s];
+      if (W.cand && W.cand->n_alleles > 0) {
+        const ltr_candidates& C = *W.cand;
+        const uint32_t a0 = O->region_allele_begin[r], c0 = C.allele_off[0];
+        memcpy(O->allele_bytes.data() + o_ab_off[r], C.allele_bytes + c0, C.allele_off[C.n_alleles] - c0);
+        for (int32_t a = 0; a < C.n_alleles; ++a) {
+          O->allele_off[a0 + (uint32_t)a + 1] = (uint32_t)o_ab_off[r] + (C.allele_off[a + 1] - c0);
+          O->allele_inexact[a0 + (uint32_t)a] = C.allele_inexact[a];
+        }
+      }
+      if (W.status == LTR_REGION_OK) {
+        const ltr_region_reads& RR = *W.reads;
+        const ltr_candidates& C = *W.cand;
+        const uint32_t l = (uint32_t)O->locus_index[r];
+        memcpy(lfb.data() + lflank_off[l], C.lflank, lflank_off[l + 1] - lflank_off[l]);
+        memcpy(rfb.data() + rflank_off[l], C.rflank, rflank_off[l + 1] - rflank_off[l]);
+        const uint32_t c0 = C.allele_off[0];
+        memcpy(ab.data() + ab_off[l], C.allele_bytes + c0, C.allele_off[C.n_alleles] - c0);
+        for (int32_t a = 0; a < C.n_alleles; ++a) aoff[lab[l] + (uint32_t)a + 1] = (uint32_t)ab_off[l] + (C.allele_off[a + 1] - c0);
+        const uint32_t i0 = lrb[l], n = RR.n_reads, b0 = RR.read_off[0], g0 = RR.cigar_off[0];
+        memcpy(rb.data() + rb_off[l], RR.read_bytes + b0, RR.read_off[n] - b0);
+        if (RR.cigar_off[n] > g0) memcpy(cops.data() + cop_off[l], RR.cigar_ops + g0, sizeof(uint32_t) * (RR.cigar_off[n] - g0));
+        for (uint32_t i = 0; i < n; ++i) {
+          read_start[i0 + i] = RR.read_start[i];
+          read_stop[i0 + i] = RR.read_stop[i];
+          roff[i0 + i + 1] = (uint32_t)rb_off[l] + (RR.read_off[i + 1] - b0);
+          coff[i0 + i + 1] = (uint32_t)cop_off[l] + (RR.cigar_off[i + 1] - g0);
+          read_sample[i0 + i] = RR.read_sample[i];
+          p1[i0 + i] = RR.log_p1[i];
+          p2[i0 + i] = RR.log_p2[i];
+        }
+        if (want_records) {
+          const size_t h0 = locus_sample_begin[l];
+          for (uint32_t i = 0; i < n; ++i) {
+            int32_t d = 0;  // write_vcf_record (:1017-1023): ExtractCigar over the region +- 5 bp
+            const int got = ltr_extract_cigar_bp_diff(RR.cigar_ops + RR.cigar_off[i], RR.cigar_off[i + 1] - RR.cigar_off[i],
+                                                      RR.read_start[i], regions[r].start - 5, regions[r].stop + 5, &d);
+            read_bp_diff[i0 + i] = got ? d : INT32_MIN;
+            if (RR.read_hp[i] == 1) ++n_hp1[h0 + (size_t)RR.read_sample[i]];
+            if (RR.read_hp[i] == 2) ++n_hp2[h0 + (size_t)RR.read_sample[i]];
+          }
+        }
+      }
+      ltr_candidates_free(W.cand);
+      ltr_region_reads_free(W.reads);
+      W.cand = nullptr;
+      W.reads = nullptr;
+    }
+  };
+  {
+    std::vector<std::thread> th;
+    for (int t = 1; t < n_threads; ++t) th.emplace_back(fill);
+    fill();
+    for (std::thread& t : th) t.join();
   }
   int rc = LTR_OK;
   ltr_batch_calls* calls = nullptr;
+  const double layout_ms = ms_since(t_layout);
+  const Clock::time_point t_geno = Clock::now();
   if (n_loci) {
     lfb.push_back(0); rfb.push_back(0); ab.push_back(0); rb.push_back(0); cops.push_back(0);
     ltr_locus_batch B;
@@ -205,11 +272,18 @@ extern "C" int ltr_regions_run(ltr_genotyper* g, const ltr_params* params, const
     if (want_records) ltr_genotyper_set_read_alleles(g, 0);
     if (want_pgl) ltr_genotyper_set_phased_gls(g, 0);
   }
+  const double genotype_ms = ms_since(t_geno);
+  const Clock::time_point t_rec = Clock::now();
   if (rc == LTR_OK && want_records) {
     O->record_off.assign((size_t)n_regions + 1, 0);
     std::vector<std::string> text(n_regions);
+    std::atomic<int> rec_rc(LTR_OK);
+    next.store(0);
+    auto compose = [&]() {  // the records are independent of each other: composed by the host threads
     std::vector<char> buf(1 << 16);
-    for (uint32_t l = 0; l < n_loci && rc == LTR_OK; ++l) {
+    const uint32_t kGrab = 8;
+    for (uint32_t l0 = next.fetch_add(kGrab); l0 < n_loci; l0 = next.fetch_add(kGrab))
+    for (uint32_t l = l0; l < std::min(n_loci, l0 + kGrab) && rec_rc.load() == LTR_OK; ++l) {
       const uint32_t r = locus_region[l];
       if (calls->status[l] != LTR_OK) continue;
       const uint32_t a0 = O->region_allele_begin[r], na = O->region_allele_begin[r + 1] - a0;
@@ -262,8 +336,16 @@ extern "C" int ltr_regions_run(ltr_genotyper* g, const ltr_params* params, const
         vrc = ltr_vcf_record_ex(&V, &X, buf.data(), (uint32_t)buf.size(), &len);
       }
       if (vrc == LTR_OK) text[r].assign(buf.data(), len);
-      else if (vrc != LTR_ERR_UNSUPPORTED) rc = vrc;
+      else if (vrc != LTR_ERR_UNSUPPORTED) rec_rc.store(vrc);
     }
+    };
+    {
+      std::vector<std::thread> th;
+      for (int t = 1; t < n_threads; ++t) th.emplace_back(compose);
+      compose();
+      for (std::thread& t : th) t.join();
+    }
+    rc = rec_rc.load();
     for (uint32_t r = 0; r < n_regions; ++r) {
       O->records += text[r];
       O->record_off[r + 1] = (uint32_t)O->records.size();
@@ -291,6 +373,7 @@ extern "C" int ltr_regions_run(ltr_genotyper* g, const ltr_params* params, const
   P.region_sample_begin = O->region_sample_begin.data();
   P.sample_file = O->sample_file.data();
   P.owner = O;
+  P.prepare_ms = prepare_ms; P.layout_ms = layout_ms; P.genotype_ms = genotype_ms; P.records_ms = ms_since(t_rec);
   *out = &O->pub;
   return LTR_OK;
 }

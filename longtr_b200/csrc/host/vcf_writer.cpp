@@ -18,6 +18,7 @@
 
 #include <algorithm>
 #include <map>
+#include <new>
 #include <set>
 #include <sstream>
 #include <string>
@@ -98,8 +99,21 @@ extern "C" int ltr_vcf_record(const ltr_vcf_locus* L, char* out, uint32_t capaci
   return ltr_vcf_record_ex(L, nullptr, out, capacity, out_len);
 }
 
+static int vcf_record_impl(const ltr_vcf_locus* L, const ltr_vcf_extras* X, char* out, uint32_t capacity, uint32_t* out_len);
+
+// C ABI boundary: no exception leaves the library (exhausted memory becomes an error code)
 extern "C" int ltr_vcf_record_ex(const ltr_vcf_locus* L, const ltr_vcf_extras* X, char* out, uint32_t capacity,
                                  uint32_t* out_len) {
+  try {
+    return vcf_record_impl(L, X, out, capacity, out_len);
+  } catch (const std::bad_alloc&) {
+    return LTR_ERR_OOM;
+  } catch (...) {
+    return LTR_ERR_INVALID;
+  }
+}
+
+static int vcf_record_impl(const ltr_vcf_locus* L, const ltr_vcf_extras* X, char* out, uint32_t capacity, uint32_t* out_len) {
   const uint32_t sw = X ? X->switches : LTR_VCF_DEFAULT;
   if (sw & ~(LTR_VCF_ALLREADS | LTR_VCF_MALLREADS | LTR_VCF_GLS | LTR_VCF_PLS | LTR_VCF_PHASED_GLS | LTR_VCF_FILTERS))
     return LTR_ERR_INVALID;

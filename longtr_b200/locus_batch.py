@@ -52,7 +52,8 @@ class RegionsResult(C.Structure):
                 ("calls", C.POINTER(BatchCalls)), ("block_start", _i32p), ("block_end", _i32p),
                 ("region_allele_begin", _u32p), ("allele_off", _u32p), ("allele_bytes", _u8p),
                 ("region_sample_begin", _u32p), ("sample_file", _u32p), ("allele_inexact", _u8p),
-                ("n_assembled", C.c_uint32), ("record_off", _u32p), ("records", C.c_void_p), ("owner", C.c_void_p)]
+                ("n_assembled", C.c_uint32), ("record_off", _u32p), ("records", C.c_void_p), ("owner", C.c_void_p),
+                ("prepare_ms", C.c_double), ("layout_ms", C.c_double), ("genotype_ms", C.c_double), ("records_ms", C.c_double)]
 
 
 class BedRunResult(C.Structure):
@@ -253,7 +254,8 @@ class Genotyper:
                    records=(None if not r.record_off else
                             [C.string_at(r.records + r.record_off[i], r.record_off[i + 1] - r.record_off[i]).decode()
                              for i in range(n)]),
-                   calls=self._calls_dict(r.calls) if r.n_loci else None)
+                   calls=self._calls_dict(r.calls) if r.n_loci else None,
+                   host_ms=dict(prepare_ms=r.prepare_ms, layout_ms=r.layout_ms, genotype_ms=r.genotype_ms, records_ms=r.records_ms))
 
     def run_regions(self, bams, chrom, regions, ref_seq, ref_seq_start=0, aln_params=None, indel_flank_len=5,
                     host_threads=0, max_tr_len=1000, min_total_reads=10, no_assembly=0, motifs=None, names=None,
