@@ -14,6 +14,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <memory>
+#include <new>
 #include <chrono>
 #include <string>
 #include <thread>
@@ -23,10 +25,20 @@
 
 namespace {
 
-struct RegionWork {
+struct RegionWork {  // what the preparation leaves behind for one region; freed with it
   ltr_region_reads* reads = nullptr;
   ltr_candidates* cand = nullptr;
   int32_t status = LTR_REGION_OK;
+  RegionWork() {}
+  RegionWork(const RegionWork&) = delete;
+  RegionWork& operator=(const RegionWork&) = delete;
+  void release() {
+    ltr_candidates_free(cand);
+    ltr_region_reads_free(reads);
+    cand = nullptr;
+    reads = nullptr;
+  }
+  ~RegionWork() { release(); }
 };
 
 struct Owner {
@@ -38,12 +50,57 @@ struct Owner {
   std::string records;
 };
 
+// fn(i) for every i in [0, n) on n_threads host threads (the caller's among them), `grab` consecutive items at a time.
+// false when an item threw (exhausted memory): no exception leaves a worker thread or the library.
+template <typename F>
+bool parallel_items(uint32_t n, uint32_t grab, int n_threads, F fn) {
+  std::atomic<uint32_t> next(0);
+  std::atomic<bool> failed(false);
+  auto loop = [&]() {
+    for (uint32_t i0 = next.fetch_add(grab); i0 < n; i0 = next.fetch_add(grab))
+      for (uint32_t i = i0; i < std::min(n, i0 + grab); ++i) {
+        try {
+          fn(i);
+        } catch (...) {
+          failed.store(true);
+        }
+      }
+  };
+  std::vector<std::thread> th;
+  try {
+    for (int t = 1; t < n_threads; ++t) th.emplace_back(loop);
+  } catch (...) {  // no more threads to be had: the ones that started (and this one) do the work
+  }
+  loop();
+  for (std::thread& t : th) t.join();
+  return !failed.load();
+}
+
 }  // namespace
 
+static int regions_run_impl(ltr_genotyper* g, const ltr_params* params, const ltr_bam* const* bams, int32_t n_bams,
+                            const char* chrom, const ltr_region* regions, uint32_t n_regions, const uint8_t* ref_seq,
+                            int64_t ref_seq_start, int64_t ref_seq_len, const ltr_region_params* rp,
+                            const ltr_regions_opts* opts, ltr_regions_result** out);
+
+// C ABI boundary: no exception leaves the library (exhausted memory becomes an error code; what was built is freed)
 extern "C" int ltr_regions_run(ltr_genotyper* g, const ltr_params* params, const ltr_bam* const* bams, int32_t n_bams,
                                const char* chrom, const ltr_region* regions, uint32_t n_regions, const uint8_t* ref_seq,
                                int64_t ref_seq_start, int64_t ref_seq_len, const ltr_region_params* rp,
                                const ltr_regions_opts* opts, ltr_regions_result** out) {
+  try {
+    return regions_run_impl(g, params, bams, n_bams, chrom, regions, n_regions, ref_seq, ref_seq_start, ref_seq_len, rp, opts, out);
+  } catch (const std::bad_alloc&) {
+    return LTR_ERR_OOM;
+  } catch (...) {
+    return LTR_ERR_INVALID;
+  }
+}
+
+static int regions_run_impl(ltr_genotyper* g, const ltr_params* params, const ltr_bam* const* bams, int32_t n_bams,
+                            const char* chrom, const ltr_region* regions, uint32_t n_regions, const uint8_t* ref_seq,
+                            int64_t ref_seq_start, int64_t ref_seq_len, const ltr_region_params* rp,
+                            const ltr_regions_opts* opts, ltr_regions_result** out) {
   if (!g || !params || !bams || n_bams < 1 || !chrom || (n_regions && !regions) || !ref_seq || !rp || !opts || !out)
     return LTR_ERR_INVALID;
   if (opts->vcf_records && n_regions && !opts->region_motifs) return LTR_ERR_INVALID;
@@ -55,55 +112,46 @@ extern "C" int ltr_regions_run(ltr_genotyper* g, const ltr_params* params, const
   typedef std::chrono::steady_clock Clock;
   auto ms_since = [](Clock::time_point t) { return std::chrono::duration<double, std::milli>(Clock::now() - t).count(); };
   const Clock::time_point t_begin = Clock::now();
-  std::atomic<uint32_t> next(0);
-  auto prepare = [&]() {
-    // a few consecutive regions per grab: neighbours of a sorted region list share BGZF blocks (the reader keeps the last two
-    // blocks a thread inflated)
-    const uint32_t kGrab = 4;
-    for (uint32_t r0 = next.fetch_add(kGrab); r0 < n_regions; r0 = next.fetch_add(kGrab))
-    for (uint32_t r = r0; r < std::min(n_regions, r0 + kGrab); ++r) {
-      RegionWork& W = work[r];
-      const ltr_region& R = regions[r];
-      if (R.stop <= R.start || R.period < 1) { W.status = LTR_REGION_INVALID; continue; }
-      if (R.stop - R.start > opts->max_tr_len) { W.status = LTR_REGION_TOO_LONG; continue; }  // bam_processor.cpp:568-574
-      if (R.start < 50 || (int64_t)R.stop + 50 >= ref_seq_start + ref_seq_len) {               // :583-586
-        W.status = LTR_REGION_NEAR_CONTIG_END;
-        continue;
-      }
-      int rc = ltr_region_collect(bams, n_bams, chrom, R.start, R.stop, ref_seq, ref_seq_start, ref_seq_len, rp, &W.reads);
-      if (rc == LTR_ERR_UNSUPPORTED) { W.status = LTR_REGION_PAIRED_READS; continue; }
-      if (rc != LTR_OK) { W.status = LTR_REGION_INVALID; continue; }
-      if ((int32_t)W.reads->n_passed < opts->min_total_reads) {  // genotyper_bam_processor.cpp:231-238
-        W.status = LTR_REGION_TOO_FEW_READS;
-        continue;
-      }
-      if (W.reads->n_reads == 0) { W.status = LTR_REGION_NO_SPANNING; continue; }
-      for (uint32_t i = 0; i < W.reads->n_reads && W.status == LTR_REGION_OK; ++i)
-        if (W.reads->read_off[i + 1] == W.reads->read_off[i]) W.status = LTR_REGION_DELETED_READ;  // empty (deleted) reads: not batched
-      if (W.status != LTR_REGION_OK) continue;
-      rc = ltr_candidate_alleles_flags(W.reads, R.start, R.stop, R.period, ref_seq, ref_seq_start, ref_seq_len,
-                                       params->indel_flank_len, opts->no_assembly ? LTR_CAND_FLAG_NO_ASSEMBLY : 0u, &W.cand);
-      if (rc != LTR_OK) { W.status = LTR_REGION_INVALID; continue; }
-      switch (W.cand->status) {
-        case LTR_CAND_OK: break;
-        case LTR_CAND_NEAR_CHROM_END: W.status = LTR_REGION_NEAR_CONTIG_END; break;
-        case LTR_CAND_NO_SPANNING: W.status = LTR_REGION_NO_SPANNING; break;
-        default: W.status = LTR_REGION_NEEDS_ASSEMBLY; break;
-      }
+  // a few consecutive regions per grab: neighbours of a sorted region list share BGZF blocks (the reader keeps the last two
+  // blocks a thread inflated)
+  const bool prepared = parallel_items(n_regions, 4, n_threads, [&](uint32_t r) {
+    RegionWork& W = work[r];
+    const ltr_region& R = regions[r];
+    if (R.stop <= R.start || R.period < 1) { W.status = LTR_REGION_INVALID; return; }
+    if (R.stop - R.start > opts->max_tr_len) { W.status = LTR_REGION_TOO_LONG; return; }  // bam_processor.cpp:568-574
+    if (R.start < 50 || (int64_t)R.stop + 50 >= ref_seq_start + ref_seq_len) {               // :583-586
+      W.status = LTR_REGION_NEAR_CONTIG_END;
+      return;
     }
-  };
-  {
-    std::vector<std::thread> th;
-    for (int t = 1; t < n_threads; ++t) th.emplace_back(prepare);
-    prepare();
-    for (std::thread& t : th) t.join();
-  }
+    int rc = ltr_region_collect(bams, n_bams, chrom, R.start, R.stop, ref_seq, ref_seq_start, ref_seq_len, rp, &W.reads);
+    if (rc == LTR_ERR_UNSUPPORTED) { W.status = LTR_REGION_PAIRED_READS; return; }
+    if (rc != LTR_OK) { W.status = LTR_REGION_INVALID; return; }
+    if ((int32_t)W.reads->n_passed < opts->min_total_reads) {  // genotyper_bam_processor.cpp:231-238
+      W.status = LTR_REGION_TOO_FEW_READS;
+      return;
+    }
+    if (W.reads->n_reads == 0) { W.status = LTR_REGION_NO_SPANNING; return; }
+    for (uint32_t i = 0; i < W.reads->n_reads && W.status == LTR_REGION_OK; ++i)
+      if (W.reads->read_off[i + 1] == W.reads->read_off[i]) W.status = LTR_REGION_DELETED_READ;  // empty (deleted) reads: not batched
+    if (W.status != LTR_REGION_OK) return;
+    rc = ltr_candidate_alleles_flags(W.reads, R.start, R.stop, R.period, ref_seq, ref_seq_start, ref_seq_len,
+                                     params->indel_flank_len, opts->no_assembly ? LTR_CAND_FLAG_NO_ASSEMBLY : 0u, &W.cand);
+    if (rc != LTR_OK) { W.status = LTR_REGION_INVALID; return; }
+    switch (W.cand->status) {
+      case LTR_CAND_OK: break;
+      case LTR_CAND_NEAR_CHROM_END: W.status = LTR_REGION_NEAR_CONTIG_END; break;
+      case LTR_CAND_NO_SPANNING: W.status = LTR_REGION_NO_SPANNING; break;
+      default: W.status = LTR_REGION_NEEDS_ASSEMBLY; break;
+    }
+  });
+  if (!prepared) return LTR_ERR_OOM;
   const double prepare_ms = ms_since(t_begin);
   const Clock::time_point t_layout = Clock::now();
   // ---- lay the surviving regions out as one ltr_locus_batch ------------------------------------------------------------
   // Sizes and offsets first (serial, a few integers per region); the bytes are then copied -- and the per-region work freed --
   // by the host threads, each region into its own slice.
-  Owner* O = new Owner();
+  std::unique_ptr<Owner> owner(new Owner());  // handed to the result at the end
+  Owner* O = owner.get();
   memset(&O->pub, 0, sizeof(O->pub));
   O->status.resize(n_regions);
   O->locus_index.assign(n_regions, -1);
@@ -153,11 +201,6 @@ extern "C" int ltr_regions_run(ltr_genotyper* g, const ltr_params* params, const
     locus_sample_begin.push_back(locus_sample_begin.back() + RR.n_samples);
   }
   if (o_ab_off.back() > 0xFFFFFFF0ull || ab_off.back() > 0xFFFFFFF0ull || rb_off.back() > 0xFFFFFFF0ull || cop_off.back() > 0xFFFFFFF0ull) {
-    for (RegionWork& W : work) {
-      ltr_candidates_free(W.cand);
-      ltr_region_reads_free(W.reads);
-    }
-    delete O;
     return LTR_ERR_INVALID;  // more than 4 GB of reads in one call: the batch's offsets are 32 bits wide
   }
   {
@@ -183,70 +226,57 @@ extern "C" int ltr_regions_run(ltr_genotyper* g, const ltr_params* params, const
       n_hp2.assign(locus_sample_begin.back(), 0);
     }
   }
-  next.store(0);
-  auto fill = [&]() {
-    const uint32_t kGrab = 8;
-    for (uint32_t r0 = next.fetch_add(kGrab); r0 < n_regions; r0 = next.fetch_add(kGrab))
-    for (uint32_t r = r0; r < std::min(n_regions, r0 + kGrab); ++r) {
-      RegionWork& W = work[r];
-      if (W.reads)
-        for (uint32_t s = 0; s < W.reads->n_samples; ++s) O->sample_file[O->region_sample_begin[r] + s] = W.reads->sample_file[s];
-      if (W.cand && W.cand->n_alleles > 0) {
-        const ltr_candidates& C = *W.cand;
-        const uint32_t a0 = O->region_allele_begin[r], c0 = C.allele_off[0];
-        memcpy(O->allele_bytes.data() + o_ab_off[r], C.allele_bytes + c0, C.allele_off[C.n_alleles] - c0);
-        for (int32_t a = 0; a < C.n_alleles; ++a) {
-          O->allele_off[a0 + (uint32_t)a + 1] = (uint32_t)o_ab_off[r] + (C.allele_off[a + 1] - c0);
-          O->allele_inexact[a0 + (uint32_t)a] = C.allele_inexact[a];
-        }
+  parallel_items(n_regions, 8, n_threads, [&](uint32_t r) {
+    RegionWork& W = work[r];
+    if (W.reads)
+      for (uint32_t s = 0; s < W.reads->n_samples; ++s) O->sample_file[O->region_sample_begin[r] + s] = W.reads->sample_file[s];
+    if (W.cand && W.cand->n_alleles > 0) {
+      const ltr_candidates& C = *W.cand;
+      const uint32_t a0 = O->region_allele_begin[r], c0 = C.allele_off[0];
+      memcpy(O->allele_bytes.data() + o_ab_off[r], C.allele_bytes + c0, C.allele_off[C.n_alleles] - c0);
+      for (int32_t a = 0; a < C.n_alleles; ++a) {
+        O->allele_off[a0 + (uint32_t)a + 1] = (uint32_t)o_ab_off[r] + (C.allele_off[a + 1] - c0);
+        O->allele_inexact[a0 + (uint32_t)a] = C.allele_inexact[a];
       }
-      if (W.status == LTR_REGION_OK) {
-        const ltr_region_reads& RR = *W.reads;
-        const ltr_candidates& C = *W.cand;
-        const uint32_t l = (uint32_t)O->locus_index[r];
-        memcpy(lfb.data() + lflank_off[l], C.lflank, lflank_off[l + 1] - lflank_off[l]);
-        memcpy(rfb.data() + rflank_off[l], C.rflank, rflank_off[l + 1] - rflank_off[l]);
-        const uint32_t c0 = C.allele_off[0];
-        memcpy(ab.data() + ab_off[l], C.allele_bytes + c0, C.allele_off[C.n_alleles] - c0);
-        for (int32_t a = 0; a < C.n_alleles; ++a) aoff[lab[l] + (uint32_t)a + 1] = (uint32_t)ab_off[l] + (C.allele_off[a + 1] - c0);
-        const uint32_t i0 = lrb[l], n = RR.n_reads, b0 = RR.read_off[0], g0 = RR.cigar_off[0];
-        memcpy(rb.data() + rb_off[l], RR.read_bytes + b0, RR.read_off[n] - b0);
-        if (RR.cigar_off[n] > g0) memcpy(cops.data() + cop_off[l], RR.cigar_ops + g0, sizeof(uint32_t) * (RR.cigar_off[n] - g0));
-        for (uint32_t i = 0; i < n; ++i) {
-          read_start[i0 + i] = RR.read_start[i];
-          read_stop[i0 + i] = RR.read_stop[i];
-          roff[i0 + i + 1] = (uint32_t)rb_off[l] + (RR.read_off[i + 1] - b0);
-          coff[i0 + i + 1] = (uint32_t)cop_off[l] + (RR.cigar_off[i + 1] - g0);
-          read_sample[i0 + i] = RR.read_sample[i];
-          p1[i0 + i] = RR.log_p1[i];
-          p2[i0 + i] = RR.log_p2[i];
-        }
-        if (want_records) {
-          const size_t h0 = locus_sample_begin[l];
-          for (uint32_t i = 0; i < n; ++i) {
-            int32_t d = 0;  // write_vcf_record (:1017-1023): ExtractCigar over the region +- 5 bp
-            const int got = ltr_extract_cigar_bp_diff(RR.cigar_ops + RR.cigar_off[i], RR.cigar_off[i + 1] - RR.cigar_off[i],
-                                                      RR.read_start[i], regions[r].start - 5, regions[r].stop + 5, &d);
-            read_bp_diff[i0 + i] = got ? d : INT32_MIN;
-            if (RR.read_hp[i] == 1) ++n_hp1[h0 + (size_t)RR.read_sample[i]];
-            if (RR.read_hp[i] == 2) ++n_hp2[h0 + (size_t)RR.read_sample[i]];
-          }
-        }
-      }
-      ltr_candidates_free(W.cand);
-      ltr_region_reads_free(W.reads);
-      W.cand = nullptr;
-      W.reads = nullptr;
     }
-  };
-  {
-    std::vector<std::thread> th;
-    for (int t = 1; t < n_threads; ++t) th.emplace_back(fill);
-    fill();
-    for (std::thread& t : th) t.join();
-  }
+    if (W.status == LTR_REGION_OK) {
+      const ltr_region_reads& RR = *W.reads;
+      const ltr_candidates& C = *W.cand;
+      const uint32_t l = (uint32_t)O->locus_index[r];
+      memcpy(lfb.data() + lflank_off[l], C.lflank, lflank_off[l + 1] - lflank_off[l]);
+      memcpy(rfb.data() + rflank_off[l], C.rflank, rflank_off[l + 1] - rflank_off[l]);
+      const uint32_t c0 = C.allele_off[0];
+      memcpy(ab.data() + ab_off[l], C.allele_bytes + c0, C.allele_off[C.n_alleles] - c0);
+      for (int32_t a = 0; a < C.n_alleles; ++a) aoff[lab[l] + (uint32_t)a + 1] = (uint32_t)ab_off[l] + (C.allele_off[a + 1] - c0);
+      const uint32_t i0 = lrb[l], n = RR.n_reads, b0 = RR.read_off[0], g0 = RR.cigar_off[0];
+      memcpy(rb.data() + rb_off[l], RR.read_bytes + b0, RR.read_off[n] - b0);
+      if (RR.cigar_off[n] > g0) memcpy(cops.data() + cop_off[l], RR.cigar_ops + g0, sizeof(uint32_t) * (RR.cigar_off[n] - g0));
+      for (uint32_t i = 0; i < n; ++i) {
+        read_start[i0 + i] = RR.read_start[i];
+        read_stop[i0 + i] = RR.read_stop[i];
+        roff[i0 + i + 1] = (uint32_t)rb_off[l] + (RR.read_off[i + 1] - b0);
+        coff[i0 + i + 1] = (uint32_t)cop_off[l] + (RR.cigar_off[i + 1] - g0);
+        read_sample[i0 + i] = RR.read_sample[i];
+        p1[i0 + i] = RR.log_p1[i];
+        p2[i0 + i] = RR.log_p2[i];
+      }
+      if (want_records) {
+        const size_t h0 = locus_sample_begin[l];
+        for (uint32_t i = 0; i < n; ++i) {
+          int32_t d = 0;  // write_vcf_record (:1017-1023): ExtractCigar over the region +- 5 bp
+          const int got = ltr_extract_cigar_bp_diff(RR.cigar_ops + RR.cigar_off[i], RR.cigar_off[i + 1] - RR.cigar_off[i],
+                                                    RR.read_start[i], regions[r].start - 5, regions[r].stop + 5, &d);
+          read_bp_diff[i0 + i] = got ? d : INT32_MIN;
+          if (RR.read_hp[i] == 1) ++n_hp1[h0 + (size_t)RR.read_sample[i]];
+          if (RR.read_hp[i] == 2) ++n_hp2[h0 + (size_t)RR.read_sample[i]];
+        }
+      }
+    }
+    W.release();
+  });
   int rc = LTR_OK;
   ltr_batch_calls* calls = nullptr;
+  std::unique_ptr<ltr_batch_calls, void (*)(ltr_batch_calls*)> calls_guard(nullptr, ltr_batch_calls_free);
   const double layout_ms = ms_since(t_layout);
   const Clock::time_point t_geno = Clock::now();
   if (n_loci) {
@@ -271,6 +301,7 @@ extern "C" int ltr_regions_run(ltr_genotyper* g, const ltr_params* params, const
     rc = ltr_genotyper_run(g, params, &B, &calls);
     if (want_records) ltr_genotyper_set_read_alleles(g, 0);
     if (want_pgl) ltr_genotyper_set_phased_gls(g, 0);
+    calls_guard.reset(calls);
   }
   const double genotype_ms = ms_since(t_geno);
   const Clock::time_point t_rec = Clock::now();
@@ -278,14 +309,11 @@ extern "C" int ltr_regions_run(ltr_genotyper* g, const ltr_params* params, const
     O->record_off.assign((size_t)n_regions + 1, 0);
     std::vector<std::string> text(n_regions);
     std::atomic<int> rec_rc(LTR_OK);
-    next.store(0);
-    auto compose = [&]() {  // the records are independent of each other: composed by the host threads
-    std::vector<char> buf(1 << 16);
-    const uint32_t kGrab = 8;
-    for (uint32_t l0 = next.fetch_add(kGrab); l0 < n_loci; l0 = next.fetch_add(kGrab))
-    for (uint32_t l = l0; l < std::min(n_loci, l0 + kGrab) && rec_rc.load() == LTR_OK; ++l) {
+    // the records are independent of each other: composed by the host threads
+    const bool composed = parallel_items(n_loci, 8, n_threads, [&](uint32_t l) {
+      std::vector<char> buf(4096);
       const uint32_t r = locus_region[l];
-      if (calls->status[l] != LTR_OK) continue;
+      if (calls->status[l] != LTR_OK || rec_rc.load() != LTR_OK) return;
       const uint32_t a0 = O->region_allele_begin[r], na = O->region_allele_begin[r + 1] - a0;
       const uint32_t s0 = calls->locus_sample_begin[l], ns = calls->locus_sample_begin[l + 1] - s0;
       std::vector<uint32_t> aoff(na + 1);
@@ -337,25 +365,14 @@ extern "C" int ltr_regions_run(ltr_genotyper* g, const ltr_params* params, const
       }
       if (vrc == LTR_OK) text[r].assign(buf.data(), len);
       else if (vrc != LTR_ERR_UNSUPPORTED) rec_rc.store(vrc);
-    }
-    };
-    {
-      std::vector<std::thread> th;
-      for (int t = 1; t < n_threads; ++t) th.emplace_back(compose);
-      compose();
-      for (std::thread& t : th) t.join();
-    }
-    rc = rec_rc.load();
+    });
+    rc = composed ? rec_rc.load() : LTR_ERR_OOM;
     for (uint32_t r = 0; r < n_regions; ++r) {
       O->records += text[r];
       O->record_off[r + 1] = (uint32_t)O->records.size();
     }
   }
-  if (rc != LTR_OK) {
-    ltr_batch_calls_free(calls);
-    delete O;
-    return rc;
-  }
+  if (rc != LTR_OK) return rc;
   ltr_regions_result& P = O->pub;
   P.n_regions = n_regions;
   P.status = O->status.data();
@@ -374,6 +391,8 @@ extern "C" int ltr_regions_run(ltr_genotyper* g, const ltr_params* params, const
   P.sample_file = O->sample_file.data();
   P.owner = O;
   P.prepare_ms = prepare_ms; P.layout_ms = layout_ms; P.genotype_ms = genotype_ms; P.records_ms = ms_since(t_rec);
+  owner.release();
+  calls_guard.release();
   *out = &O->pub;
   return LTR_OK;
 }
