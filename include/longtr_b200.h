@@ -723,6 +723,15 @@ typedef struct ltr_bed_run_result {
 int ltr_run_bed(ltr_genotyper* g, const ltr_params* params, const ltr_bam* const* bams, int32_t n_bams, const ltr_fasta* fasta,
                 const ltr_bed* bed, const ltr_region_params* rp, const ltr_regions_opts* opts, ltr_bed_run_result** out);
 void ltr_bed_run_result_free(ltr_bed_run_result* r);
+/* ltr_run_bed in bounded memory (whole-genome region files): a chromosome's regions go through ltr_regions_run
+ * chunk_regions at a time (<= 0: 4096) and every chunk's result is handed to `sink` -- chromosome index, index of the chunk's
+ * first region in bed->regions, the result (valid during the call only; the library frees it) -- in region order, the way the
+ * reference's region loop hands its records to the VCFWriter one region after the other (src/bam_processor.cpp:563-627).
+ * A sink that returns non-zero stops the run (LTR_ERR_INVALID).  Calls and records equal ltr_run_bed's.                     */
+typedef int (*ltr_regions_sink)(void* user, uint32_t chrom, uint32_t first_region, const ltr_regions_result* result);
+int ltr_run_bed_stream(ltr_genotyper* g, const ltr_params* params, const ltr_bam* const* bams, int32_t n_bams, const ltr_fasta* fasta,
+                       const ltr_bed* bed, const ltr_region_params* rp, const ltr_regions_opts* opts, int32_t chunk_regions,
+                       ltr_regions_sink sink, void* user);
 
 /* ---- VCF records (the output side of the path) ---------------------------------------------------
  * ltr_vcf_record   the text of one record as SeqStutterGenotyper::write_vcf_record composes it (src/seq_stutter_genotyper.cpp:

@@ -582,7 +582,7 @@ EXPORTED_SYMBOLS = [
     "ltr_regions_result_free", "ltr_fasta_open", "ltr_fasta_close", "ltr_fasta_n_seqs", "ltr_fasta_seq_name",
     "ltr_fasta_seq_len", "ltr_fasta_fetch", "ltr_bed_read", "ltr_bed_free", "ltr_run_bed", "ltr_bed_run_result_free",
     "ltr_em_opts_default", "ltr_em_stutter_train", "ltr_vcf_record", "ltr_vcf_header", "ltr_extract_cigar_bp_diff", "ltr_genotyper_set_read_alleles",
-    "ltr_vcf_record_ex", "ltr_vcf_header_ex", "ltr_genotyper_set_phased_gls",
+    "ltr_vcf_record_ex", "ltr_vcf_header_ex", "ltr_genotyper_set_phased_gls", "ltr_run_bed_stream",
 ]
 
 

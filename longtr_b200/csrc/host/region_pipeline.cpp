@@ -453,6 +453,49 @@ extern "C" int ltr_run_bed(ltr_genotyper* g, const ltr_params* params, const ltr
   return LTR_OK;
 }
 
+// ltr_run_bed in bounded memory: a chromosome's regions go through ltr_regions_run `chunk_regions` at a time and every chunk's
+// result is handed to the caller's sink in region order, then freed -- what a host writing a whole-genome VCF needs (the
+// reference's VCFWriter receives its records region by region too, src/bam_processor.cpp:563-627).
+extern "C" int ltr_run_bed_stream(ltr_genotyper* g, const ltr_params* params, const ltr_bam* const* bams, int32_t n_bams,
+                                  const ltr_fasta* fasta, const ltr_bed* bed, const ltr_region_params* rp,
+                                  const ltr_regions_opts* opts, int32_t chunk_regions, ltr_regions_sink sink, void* user) {
+  if (!g || !params || !bams || n_bams < 1 || !fasta || !bed || !rp || !opts || !sink) return LTR_ERR_INVALID;
+  for (uint32_t c = 0; c < bed->n_chroms; ++c) {  // verify_chromosomes (:490-531)
+    if (ltr_fasta_seq_len(fasta, bed->chroms[c]) < 0) return LTR_ERR_INVALID;
+    for (int32_t b = 0; b < n_bams; ++b)
+      if (ltr_bam_ref_id(bams[b], bed->chroms[c]) < 0) return LTR_ERR_INVALID;
+  }
+  const uint32_t chunk = chunk_regions > 0 ? (uint32_t)chunk_regions : 4096u;
+  try {
+    std::vector<uint8_t> chrom_seq;
+    uint32_t r = 0;
+    for (uint32_t c = 0; c < bed->n_chroms; ++c) {
+      uint32_t e = r;
+      while (e < bed->n_regions && bed->region_chrom[e] == (int32_t)c) ++e;
+      const int64_t len = ltr_fasta_seq_len(fasta, bed->chroms[c]);
+      chrom_seq.resize((size_t)len + 1);
+      int rc = ltr_fasta_fetch(fasta, bed->chroms[c], 0, len, chrom_seq.data());
+      for (uint32_t r0 = r; r0 < e && rc == LTR_OK; r0 += chunk) {
+        const uint32_t n = std::min(chunk, e - r0);
+        ltr_regions_result* res = nullptr;
+        ltr_regions_opts o = *opts;  // names and motifs of this chunk's regions for the records
+        o.region_names = bed->names + r0;
+        o.region_motifs = bed->motifs + r0;
+        rc = ltr_regions_run(g, params, bams, n_bams, bed->chroms[c], bed->regions + r0, n, chrom_seq.data(), 0, len, rp, &o, &res);
+        if (rc == LTR_OK && sink(user, c, r0, res) != 0) rc = LTR_ERR_INVALID;  // the sink asked to stop
+        ltr_regions_result_free(res);
+      }
+      if (rc != LTR_OK) return rc;
+      r = e;
+    }
+  } catch (const std::bad_alloc&) {
+    return LTR_ERR_OOM;
+  } catch (...) {
+    return LTR_ERR_INVALID;
+  }
+  return LTR_OK;
+}
+
 extern "C" void ltr_bed_run_result_free(ltr_bed_run_result* r) {
   if (!r) return;
   RunOwner* O = static_cast<RunOwner*>(r->owner);

@@ -56,6 +56,9 @@ class RegionsResult(C.Structure):
                 ("prepare_ms", C.c_double), ("layout_ms", C.c_double), ("genotype_ms", C.c_double), ("records_ms", C.c_double)]
 
 
+REGIONS_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(RegionsResult))   # ltr_regions_sink
+
+
 class BedRunResult(C.Structure):
     _fields_ = [("n_chroms", C.c_uint32), ("per_chrom", C.POINTER(C.POINTER(RegionsResult))), ("chrom_region_begin", _u32p),
                 ("owner", C.c_void_p)]
@@ -154,6 +157,9 @@ def _declare(lib):
     lib.ltr_run_bed.argtypes = [vp, C.POINTER(abi.Params), C.POINTER(C.c_void_p), C.c_int32, vp, C.POINTER(abi.Bed),
                                 C.POINTER(abi.RegionParams), C.POINTER(RegionsOpts), C.POINTER(C.POINTER(BedRunResult))]
     lib.ltr_run_bed.restype = C.c_int
+    lib.ltr_run_bed_stream.argtypes = [vp, C.POINTER(abi.Params), C.POINTER(C.c_void_p), C.c_int32, vp, C.POINTER(abi.Bed),
+                                       C.POINTER(abi.RegionParams), C.POINTER(RegionsOpts), C.c_int32, REGIONS_SINK, vp]
+    lib.ltr_run_bed_stream.restype = C.c_int
     lib.ltr_bed_run_result_free.argtypes = [C.POINTER(BedRunResult)]
     lib.ltr_bed_run_result_free.restype = None
 
@@ -324,6 +330,34 @@ class Genotyper:
         lib.ltr_bed_run_result_free(out)
         lib.ltr_bed_free(bed["handle"])
         return res
+
+    def run_bed_stream(self, bams, fasta, bed_path, on_chunk, chunk_regions=0, aln_params=None, indel_flank_len=5, host_threads=0,
+                       max_tr_len=1000, min_total_reads=10, no_assembly=0, chrom_limit=None, vcf_records=False, vcf_switches=None,
+                       **region_overrides):
+        """ltr_run_bed_stream: as run_bed, but the regions go through in chunks and on_chunk(chrom index, first region,
+        result dict as run_regions') is called per chunk (a true return value stops the run)."""
+        from .engine import LongTRError
+        lib = self.lib
+        bed = abi.bed_read(bed_path, 0, chrom_limit, keep_handle=True)
+        prm = abi.make_params(aln_params, indel_flank_len)
+        rp = abi.RegionParams()
+        lib.ltr_region_params_default(C.byref(rp))
+        for k, v in region_overrides.items():
+            setattr(rp, k, v)
+        opts = RegionsOpts(host_threads, max_tr_len, min_total_reads, no_assembly)
+        opts.vcf_records = 1 if vcf_records else 0
+        opts.vcf_switches = abi.VCF_DEFAULT if vcf_switches is None else int(vcf_switches)
+        handles = (C.c_void_p * len(bams))(*[b.h for b in bams])
+
+        def sink(_user, chrom, first, res):
+            return 1 if on_chunk(chrom, first, self._regions_dict(res.contents)) else 0
+        cb = REGIONS_SINK(sink)
+        rc = lib.ltr_run_bed_stream(self.h, C.byref(prm), handles, len(bams), fasta.h, bed["handle"], C.byref(rp), C.byref(opts),
+                                    int(chunk_regions), cb, None)
+        lib.ltr_bed_free(bed["handle"])
+        if rc != abi.LTR_OK:
+            raise LongTRError("ltr_run_bed_stream: %s" % lib.ltr_strerror(rc).decode())
+        return dict(chroms=bed["chroms"], bed=bed["regions"])
 
     def close(self):
         if self.h:

@@ -120,10 +120,24 @@ def test_run_bed_equals_regions_run(genotyper, tmp_path):
     assert sum(1 for x in g["records"] if x.startswith("chrS\t")) == sum(1 for st in g["status"] if st == 0) >= 8
     for key in ("gts", "kept_mask", "log_phased_posteriors", "gl_diffs"):
         np.testing.assert_array_equal(g["calls"][key], want["calls"][key])
+    # ltr_run_bed_stream: the same regions three at a time through a sink -- same status, alleles and records in region order
+    chunks = []
+    genotyper.run_bed_stream(bams, abi.FastaFile(str(fa)), str(bed), lambda c, first, res: chunks.append((c, first, res)) and None,
+                             chunk_regions=3, vcf_records=True)
+    assert [first for _c, first, _r in chunks] == list(range(0, len(order), 3)) and all(c == 0 for c, _f, _r in chunks)
+    for key in ("status", "block", "alleles", "samples", "inexact", "records"):
+        assert [x for _c, _f, res in chunks for x in res[key]] == g[key], key
+    stopped = []
+    with pytest.raises(Exception):   # a sink that returns non-zero stops the run
+        genotyper.run_bed_stream(bams, abi.FastaFile(str(fa)), str(bed), lambda c, first, res: stopped.append(first) or True,
+                                 chunk_regions=3)
+    assert stopped == [0]
     with open(bed, "a") as f:
         f.write("chrMissing\t100\t130\tAC\n")
     with pytest.raises(Exception):
         genotyper.run_bed(bams, abi.FastaFile(str(fa)), str(bed))     # chromosome absent from the FASTA / BAM files
+    with pytest.raises(Exception):
+        genotyper.run_bed_stream(bams, abi.FastaFile(str(fa)), str(bed), lambda *a: None)
 
 
 def test_example_flow_writes_the_vcf_file(tmp_path):
