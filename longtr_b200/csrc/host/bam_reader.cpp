@@ -308,7 +308,9 @@ bool append_record(ReadsOwner& R, const uint8_t* rec, size_t n, bool keep_raw) {
   R.mate_tid.push_back((int32_t)le32(rec + 20));
   R.mate_pos.push_back((int32_t)le32(rec + 24));
   const uint8_t* q = rec + 32;
-  R.names.insert(R.names.end(), (const char*)q, (const char*)q + l_name);  // NUL included
+  // l_name counts the terminating NUL; a damaged record may not have one, so it is written here (readers use strlen)
+  R.names.insert(R.names.end(), (const char*)q, (const char*)q + l_name - 1);
+  R.names.push_back('\0');
   R.name_off.push_back((uint32_t)R.names.size());
   q += l_name;
   int64_t ref_len = 0;

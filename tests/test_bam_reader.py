@@ -154,3 +154,21 @@ def test_sequence_and_quality_decoding_edge_cases(tmp_path):
     got = b.fetch()
     assert [(r["seq"], r["qual"]) for r in got] == want
     b.close()
+
+
+def test_read_name_without_terminator(tmp_path):
+    """A damaged record whose read name lacks its NUL (l_read_name counts it, SAM specification 4.2): the reader writes the
+    terminator itself instead of letting strlen run into the next record's name (found by tools/bam_fuzz.cpp under ASan)."""
+    import bam_writer as bw
+    recs = []
+    for k, name in enumerate(("first", "second", "third")):
+        rec = bytearray(bw.encode_record(0, 100 + k, name, 0, 60, [("M", 8)], "ACGTACGT", "I" * 8))
+        if k < 2:
+            rec[4 + 32 + len(name)] = ord("X")   # the terminator of the name
+        recs.append(bytes(rec))
+    path = str(tmp_path / "noterm.bam")
+    bw.write_bam(path, [("chrE", 10000)], recs)
+    b = abi.BamFile(path)
+    got = b.fetch()
+    assert [r["name"] for r in got] == ["first", "second", "third"] and [r["seq"] for r in got] == ["ACGTACGT"] * 3
+    b.close()

@@ -6,7 +6,9 @@
 //       longtr_b200/csrc/host/{bam_reader,region_loader,candidate_alleles,poa}.cpp -lz -pthread -o /tmp/bam_fuzz
 //   python tools/bam_fuzz_make.py <seed> && /tmp/bam_fuzz
 // Round 2: 1 500 damaged files, no sanitizer report (two findings fixed on the way: a record whose CIGAR does not fit its
-// sequence made the trimming throw across the ABI; an end position overflowed 32 bits).
+// sequence made the trimming throw across the ABI; an end position overflowed 32 bits).  After the reader's decoding loops
+// were vectorised: seeds 101-108 (2 400 files), one more finding fixed -- a read name without its terminating NUL let strlen
+// run past the name buffer (tests/test_bam_reader.py::test_read_name_without_terminator) -- then clean.
 #include <cstdio>
 #include <string>
 #include "longtr_b200.h"
