@@ -316,8 +316,8 @@ static int regions_run_impl(ltr_genotyper* g, const ltr_params* params, const lt
       if (calls->status[l] != LTR_OK || rec_rc.load() != LTR_OK) return;
       const uint32_t a0 = O->region_allele_begin[r], na = O->region_allele_begin[r + 1] - a0;
       const uint32_t s0 = calls->locus_sample_begin[l], ns = calls->locus_sample_begin[l + 1] - s0;
-      std::vector<uint32_t> aoff(na + 1);
-      for (uint32_t a = 0; a <= na; ++a) aoff[a] = O->allele_off[a0 + a] - O->allele_off[a0];
+      std::vector<uint32_t> rec_aoff(na + 1);  // the region's allele offsets, re-based
+      for (uint32_t a = 0; a <= na; ++a) rec_aoff[a] = O->allele_off[a0 + a] - O->allele_off[a0];
       std::vector<int32_t> column((size_t)n_bams, -1);
       for (uint32_t s = 0; s < ns; ++s) {
         const uint32_t f = O->sample_file[O->region_sample_begin[r] + s];
@@ -331,7 +331,7 @@ static int regions_run_impl(ltr_genotyper* g, const ltr_params* params, const lt
       V.region_start = regions[r].start; V.region_stop = regions[r].stop;
       V.chrom_seq = ref_seq; V.chrom_seq_start = ref_seq_start; V.chrom_seq_len = ref_seq_len;
       V.block_start = O->block_start[r]; V.block_end = O->block_end[r];
-      V.n_alleles = (int32_t)na; V.allele_off = aoff.data(); V.allele_bytes = O->allele_bytes.data() + O->allele_off[a0];
+      V.n_alleles = (int32_t)na; V.allele_off = rec_aoff.data(); V.allele_bytes = O->allele_bytes.data() + O->allele_off[a0];
       V.allele_inexact = O->allele_inexact.data() + a0;
       V.kept_mask = calls->kept_mask + calls->locus_allele_begin[l];
       V.haploid = opts->haploid ? 1 : 0;

@@ -301,11 +301,16 @@ static int vcf_record_impl(const ltr_vcf_locus* L, const ltr_vcf_extras* X, char
   }
   o += haploid ? "\tGT:GB:Q:DP:DFLANKINDEL:GLDIFF" : "\tGT:GB:Q:PQ:DP:DSNP:DFLANKINDEL:PDP:PSNP:GLDIFF";
   int n_fields = haploid ? 6 : 10;  // :1172-1194; FILTER is not counted
-  if (sw & LTR_VCF_ALLREADS) o += ":ALLREADS", ++n_fields;
-  if (sw & LTR_VCF_MALLREADS) o += ":MALLREADS", ++n_fields;
-  if (show_gl) o += ":GL", ++n_fields;
-  if (show_pl) o += ":PL", ++n_fields;
-  if (show_pgl) o += ":PHASEDGL", ++n_fields;
+  const struct {
+    bool on;
+    const char* key;
+  } optional[] = {{(sw & LTR_VCF_ALLREADS) != 0, ":ALLREADS"}, {(sw & LTR_VCF_MALLREADS) != 0, ":MALLREADS"}, {show_gl, ":GL"},
+                  {show_pl, ":PL"}, {show_pgl, ":PHASEDGL"}};
+  for (const auto& f : optional)
+    if (f.on) {
+      o += f.key;
+      ++n_fields;
+    }
   if (show_filter) o += ":FILTER";
   std::string no_reads = ".";  // a column without (realigned) reads (:1203-1215)
   if (show_filter) {
