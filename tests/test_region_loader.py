@@ -132,3 +132,86 @@ def test_a_record_whose_cigar_does_not_fit_its_sequence_refuses_the_region(tmp_p
         else:
             with pytest.raises(RuntimeError):
                 abi.region_collect([b], "chrS", 1500, 1560, ref, 0)
+
+
+def _random_cigar_world(tmp_path, seed, n_reads=60):
+    """One BAM file of reads with random CIGARs around the region [3000, 3060): match runs, insertions and deletions of every
+    size -- some exactly at the trimming boundaries (2800 / 3260), some deleting the whole repeat --, soft / hard clips."""
+    import random
+    import bam_writer as bw
+    rng = random.Random(seed)
+    ref = "".join(rng.choice("ACGT") for _ in range(6000))
+    recs = []
+    for k in range(n_reads):
+        pos = rng.randrange(2300, 2990)
+        cigar, seq, p = [], [], pos
+        if rng.random() < 0.2:
+            cigar.append(("H", rng.randrange(1, 30)))
+        if rng.random() < 0.25:
+            n = rng.randrange(1, 25)
+            cigar.append(("S", n))
+            seq.append("".join(rng.choice("ACGT") for _ in range(n)))
+        want_end = rng.randrange(3070, 3700)
+        last = None
+        while p < want_end:
+            x = rng.random()
+            near = min(abs(p - b) for b in (2800, 3000, 3060, 3260)) < 15
+            if last in (None, "I", "D") or x < (0.5 if near else 0.8):
+                n = rng.randrange(1, 12 if near else 90)
+                op = rng.choice("M=X") if rng.random() < 0.5 else "M"
+                s = ref[p:p + n]
+                if op != "=":
+                    s = "".join(c if rng.random() < 0.9 else rng.choice("ACGT") for c in s)
+                seq.append(s)
+                p += n
+            elif x < (0.75 if near else 0.9):
+                op, n = "I", rng.randrange(1, 14)
+                seq.append("".join(rng.choice("ACGT") for _ in range(n)))
+            else:
+                op, n = "D", (rng.randrange(70, 120) if rng.random() < 0.1 else rng.randrange(1, 14))
+                p += n
+            if op == last or (op in "M=X" and last in ("M", "=", "X") and op == cigar[-1][0]):
+                cigar[-1] = (op, cigar[-1][1] + n)
+            else:
+                cigar.append((op, n))
+            last = op
+        if last not in ("M", "=", "X"):
+            cigar.append(("M", 5))
+            seq.append(ref[p:p + 5])
+            p += 5
+        if rng.random() < 0.25:
+            n = rng.randrange(1, 25)
+            cigar.append(("S", n))
+            seq.append("".join(rng.choice("ACGT") for _ in range(n)))
+        if rng.random() < 0.2:
+            cigar.append(("H", rng.randrange(1, 30)))
+        s = "".join(seq)
+        recs.append((pos, bw.encode_record(0, pos, "rd%03d" % k, 16 if k % 3 == 0 else 0, 60, cigar, s, "I" * len(s),
+                                           hp=(1 + k % 2) if k % 4 else None)))
+    recs.sort(key=lambda t: t[0])
+    path = str(tmp_path / ("cigars%d.bam" % seed))
+    bw.write_bam(path, [("chrR", len(ref))], [r for _p, r in recs])
+    return path, ref
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_trimming_on_random_cigars(tmp_path, seed):
+    """The library's trimming consumes whole CIGAR operations where the reference walks base by base: on reads with random
+    CIGARs (indels at the trimming boundaries, deleted repeats, clips) ltr_region_collect must leave the same reads as the
+    base-by-base restatement (oracle/pyregion.trim_alignment, itself pinned by the reference's BamAlignment::TrimAlignment on
+    the shipped reads above; the reference's reader needs a .bai on disk, which these generated files do not have)."""
+    path, ref = _random_cigar_world(tmp_path, seed)
+    bam = abi.BamFile(path)
+    bam.build_index()
+    start, stop = 3000, 3060
+    reads = bam.fetch(0, 0, 1 << 29, keep_raw=True)
+    assert sum(1 for r in reads if r["pos"] <= start and r["end"] >= stop) >= 50
+    got = abi.region_collect([bam], "chrR", start, stop, ref, 0, min_mean_qual=0.0)
+    samples, by_sample, cnt = pr.filter_and_order([reads], start, stop, min_mean_qual=0.0)
+    terms = pr.phasing_terms(by_sample)
+    want, failed = pr.left_align(samples, by_sample, terms, start, stop, ref, 0)
+    cnt["n_trim_failed"] = failed
+    assert got["counters"] == cnt and len(got["reads"]) == len(want) >= 15
+    for g, w in zip(got["reads"], want):
+        assert g == w
+    bam.close()
